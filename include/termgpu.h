@@ -1,0 +1,361 @@
+/*
+ * termgpu.h — C ABI of the B200-native evaluator for term-guard's constraint / analyzer hot path.
+ *
+ * This is the drop-in boundary. Every entry point below replaces the body of one
+ * reference trait method that today lowers to `ctx.sql(..).collect()`; the reference file:line each
+ * one stands in for is cited beside it (paths relative to the reference checkout, term-guard/src/...).
+ * A Rust shim (`term-guard-gpu-sys`) binds these 1:1 and implements
+ * `Constraint::evaluate` (core/constraint.rs:186-225) and `Analyzer::compute_state_from_data`
+ * (analyzers/traits.rs:65-148) on top of them.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch types cross this boundary
+ *   - every function returns tg_status; the message for the last failure on the calling thread is
+ *     tg_last_error(). Data-shape problems found while evaluating (missing column, type mismatch)
+ *     do NOT fail the call: like the reference (core/suite.rs:231-256) they become a failed
+ *     constraint whose message starts with "Error evaluating constraint:".
+ *   - the engine owns device buffers; results are POD copied out; message pointers stay valid
+ *     until the owning plan is destroyed or re-executed.
+ *   - there is no CPU fallback: without a CUDA device tg_engine_create fails with TG_ERR_CUDA.
+ */
+#ifndef TERMGPU_H
+#define TERMGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TG_API __attribute__((visibility("default")))
+
+typedef struct tg_engine tg_engine;
+typedef struct tg_table tg_table;
+typedef struct tg_plan tg_plan;
+
+/* mirrors TermError variants (error.rs:16-140) as codes */
+typedef enum {
+    TG_OK = 0,
+    TG_ERR_INVALID_ARG = 1,
+    TG_ERR_COLUMN_NOT_FOUND = 2,
+    TG_ERR_TYPE_MISMATCH = 3,
+    TG_ERR_SECURITY = 4,      /* TermError::SecurityError (security.rs) */
+    TG_ERR_UNSUPPORTED = 5,   /* syntax outside the declared regex / predicate grammar */
+    TG_ERR_CUDA = 6,
+    TG_ERR_NCCL = 7,
+    TG_ERR_INTERNAL = 8,
+    TG_ERR_TABLE_NOT_FOUND = 9,
+    TG_ERR_VALIDATION = 10,   /* TermError::ValidationFailed at construction (e.g. threshold range) */
+    TG_ERR_CONFIGURATION = 11 /* TermError::Configuration */
+} tg_status;
+
+typedef enum {
+    TG_INT64 = 1,
+    TG_FLOAT64 = 2,
+    TG_UTF8 = 3,   /* Arrow Utf8: int32 offsets + value bytes */
+    TG_INT32 = 4,
+    TG_FLOAT32 = 5,
+    TG_BOOL = 6    /* Arrow Boolean: bit-packed values */
+} tg_dtype;
+
+/* ConstraintStatus (core/constraint.rs:11-20) */
+typedef enum { TG_SUCCESS = 0, TG_FAILURE = 1, TG_SKIPPED = 2 } tg_constraint_status;
+
+/* Assertion (constraints/assertion.rs:13-31) */
+typedef enum {
+    TG_ASSERT_EQUALS = 0,
+    TG_ASSERT_NOT_EQUALS = 1,
+    TG_ASSERT_GREATER_THAN = 2,
+    TG_ASSERT_GREATER_THAN_OR_EQUAL = 3,
+    TG_ASSERT_LESS_THAN = 4,
+    TG_ASSERT_LESS_THAN_OR_EQUAL = 5,
+    TG_ASSERT_BETWEEN = 6,
+    TG_ASSERT_NOT_BETWEEN = 7
+} tg_assertion_kind;
+
+typedef struct {
+    int32_t kind; /* tg_assertion_kind */
+    double a;     /* value, or lower bound */
+    double b;     /* upper bound for (NOT_)BETWEEN */
+} tg_assertion;
+
+/* LogicalOperator (core/logical.rs:16-27) */
+typedef enum { TG_OP_ALL = 0, TG_OP_ANY = 1, TG_OP_EXACTLY = 2, TG_OP_AT_LEAST = 3, TG_OP_AT_MOST = 4 } tg_logical_op;
+
+/* StatisticType (constraints/statistics.rs:24-45) */
+typedef enum {
+    TG_STAT_MIN = 0,
+    TG_STAT_MAX = 1,
+    TG_STAT_MEAN = 2,
+    TG_STAT_SUM = 3,
+    TG_STAT_STDDEV = 4,
+    TG_STAT_VARIANCE = 5,
+    TG_STAT_MEDIAN = 6,     /* APPROX_PERCENTILE_CONT in the reference; KLL-backed here */
+    TG_STAT_PERCENTILE = 7
+} tg_stat_kind;
+
+/* FormatType (constraints/format.rs:189-215) */
+typedef enum {
+    TG_FMT_REGEX = 0,
+    TG_FMT_EMAIL = 1,
+    TG_FMT_URL = 2,          /* flag = allow_localhost */
+    TG_FMT_CREDIT_CARD = 3,  /* flag = detect_only */
+    TG_FMT_PHONE = 4,        /* arg = country or NULL */
+    TG_FMT_POSTAL_CODE = 5,  /* arg = country */
+    TG_FMT_UUID = 6,
+    TG_FMT_IPV4 = 7,
+    TG_FMT_IPV6 = 8,
+    TG_FMT_JSON = 9,
+    TG_FMT_ISO8601 = 10,
+    TG_FMT_SSN = 11
+} tg_format_kind;
+
+/* FormatOptions (constraints/format.rs:367-384) */
+typedef struct {
+    int32_t case_sensitive;    /* default 1 */
+    int32_t trim_before_check; /* default 0 */
+    int32_t null_is_valid;     /* default 1 */
+} tg_format_options;
+
+/* UniquenessType / NullHandling (constraints/uniqueness.rs:40-170) */
+typedef enum {
+    TG_UNIQ_FULL = 0,
+    TG_UNIQ_DISTINCTNESS = 1,
+    TG_UNIQ_UNIQUE_VALUE_RATIO = 2,
+    TG_UNIQ_PRIMARY_KEY = 3,
+    TG_UNIQ_WITH_NULLS = 4,
+    TG_UNIQ_COMPOSITE = 5
+} tg_uniqueness_kind;
+typedef enum { TG_NULLS_EXCLUDE = 0, TG_NULLS_INCLUDE = 1, TG_NULLS_DISTINCT = 2 } tg_null_handling;
+
+/* CorrelationValidation / CorrelationType (constraints/correlation.rs:20-90) */
+typedef enum {
+    TG_CORR_PEARSON = 0,
+    TG_CORR_COVARIANCE = 1,
+    TG_CORR_INDEPENDENCE = 2, /* ABS(CORR) <= max_correlation; assertion.a = max */
+    TG_CORR_SPEARMAN = 3,     /* constraint form is Skipped in the reference (correlation.rs:340-345) */
+    TG_CORR_KENDALL = 4,
+    TG_CORR_MUTUAL_INFORMATION = 5,
+    TG_CORR_RANGE = 6         /* Pearson with Between(a,b), name "correlation_range" */
+} tg_correlation_kind;
+
+/* analyzers (analyzers/basic/ *.rs and analyzers/advanced/{standard_deviation,correlation,kll_sketch}.rs) */
+typedef enum {
+    TG_AN_SIZE = 0,
+    TG_AN_COMPLETENESS = 1,
+    TG_AN_DISTINCTNESS = 2,
+    TG_AN_MEAN = 3,
+    TG_AN_MIN = 4,
+    TG_AN_MAX = 5,
+    TG_AN_SUM = 6,
+    TG_AN_STDDEV = 7,
+    TG_AN_CORR_PEARSON = 8,
+    TG_AN_CORR_SPEARMAN = 9,
+    TG_AN_COVARIANCE = 10,
+    TG_AN_KLL = 11,
+    TG_AN_GROUPED_COMPLETENESS = 12,
+    TG_AN_COMPLIANCE = 13
+} tg_analyzer_kind;
+
+/* ConstraintResult (core/constraint.rs:40-48) */
+typedef struct {
+    int32_t status;      /* tg_constraint_status */
+    int32_t has_metric;  /* Option<f64> discriminant */
+    double metric;
+    const char* message; /* NULL when Option<String> is None */
+    const char* name;    /* Constraint::name() */
+    int32_t error_code;  /* != 0: the reference's evaluate() returns Err(..) here; status is FAILURE and
+                            message is "Error evaluating constraint: ..." as core/suite.rs:231-256 reports it */
+    int32_t reserved;
+} tg_result;
+
+/*
+ * Analyzer state + metric. `u`/`f` hold the reference *State struct fields in declaration order:
+ *   SIZE                u[0]=count                                   (analyzers/basic/size.rs)
+ *   COMPLETENESS        u[0]=total_count u[1]=non_null_count         (basic/completeness.rs:58-62)
+ *   DISTINCTNESS        u[0]=total_count(non-null) u[1]=distinct     (basic/distinctness.rs:57-61)
+ *   MEAN                f[0]=sum u[0]=count                          (basic/mean.rs:58-62)
+ *   MIN/MAX             f[0]=min f[1]=max u[0]=has_min u[1]=has_max  (basic/min_max.rs)
+ *   SUM                 f[0]=sum u[0]=has_values                     (basic/sum.rs)
+ *   STDDEV              u[0]=count f[0]=sum f[1]=sum_squared f[2]=mean   (advanced/standard_deviation.rs:60-75)
+ *   CORR / COVARIANCE   u[0]=n f[0..5]=sum_x,sum_y,sum_x2,sum_y2,sum_xy  (advanced/correlation.rs:42-62)
+ *   KLL                 u[0]=count f[0]=min f[1]=max; quantiles via tg_plan_map_*
+ *   COMPLIANCE          u[0]=satisfied u[1]=total
+ * metric_kind: 0 Double, 1 Long, 2 Map (entries via tg_plan_map_*), 3 none (AnalyzerError::NoData)
+ */
+typedef struct {
+    uint64_t u[4];
+    double f[8];
+    int32_t metric_kind;
+    int32_t error;        /* 0 ok; 1 NoData; 2 InvalidData (message set) */
+    double metric_double;
+    int64_t metric_long;
+    const char* metric_key; /* Analyzer::metric_key() */
+    const char* message;
+} tg_analyzer_result;
+
+/* ---------------------------------------------------------------- engine ---- */
+
+/* Opens CUDA device `device`, creates streams + pinned staging ring. Replaces SessionContext as the
+ * owner of registered data (core/context.rs:16-39). */
+TG_API tg_status tg_engine_create(int device, tg_engine** out);
+TG_API void tg_engine_destroy(tg_engine* eng);
+TG_API const char* tg_last_error(void);
+TG_API const char* tg_version(void);
+/* number of kernels this library has launched on this engine since creation (bench `gpu_launches`) */
+TG_API uint64_t tg_engine_launch_count(const tg_engine* eng);
+/* raw CUDA stream (cudaStream_t) the engine launches scan kernels on; for event timing by the harness */
+TG_API void* tg_engine_stream(tg_engine* eng);
+
+/* ---------------------------------------------------------------- tables ---- */
+
+/* SessionContext::register_table(name, MemTable) — creates an empty table; columns are appended
+ * batch by batch like RecordBatches of a MemTable partition. */
+TG_API tg_status tg_table_create(tg_engine* eng, const char* name, tg_table** out);
+TG_API tg_status tg_table_drop(tg_engine* eng, const char* name);
+TG_API tg_status tg_table_lookup(tg_engine* eng, const char* name, tg_table** out);
+TG_API int64_t tg_table_num_rows(const tg_table* t);
+
+/*
+ * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity
+ * bitmap, LSB bit order, `bit_offset` = Arrow array offset). The call stages them through pinned
+ * memory into HBM (async copies on the engine's copy stream) and returns after the copy is queued and
+ * the caller's buffers are no longer needed. validity may be NULL (no nulls). For TG_UTF8 `values`
+ * is the byte buffer and `offsets` has n_rows+1 entries. First call for a name defines its dtype.
+ */
+TG_API tg_status tg_table_append_host(tg_table* t, const char* name, int32_t dtype, int64_t n_rows,
+                                      const void* values, const int32_t* offsets,
+                                      const uint8_t* validity, int64_t bit_offset);
+
+/*
+ * Adopt DEVICE-resident Arrow buffers without copying (HBM-resident path). Pointers must be 16-byte
+ * aligned and readable up to the next multiple of 16 bytes. The engine does not take ownership.
+ * `n_value_bytes` is the Utf8 byte-buffer length (ignored otherwise).
+ */
+TG_API tg_status tg_table_adopt_device(tg_table* t, const char* name, int32_t dtype, int64_t n_rows,
+                                       const void* d_values, const int32_t* d_offsets,
+                                       const uint8_t* d_validity, int64_t n_value_bytes);
+
+/* Arrow C Data Interface ingestion: `schema`/`array` are struct ArrowSchema* / struct ArrowArray* of a
+ * struct-typed array (a RecordBatch). The engine copies; the caller keeps ownership and releases. */
+TG_API tg_status tg_table_append_arrow(tg_table* t, const void* arrow_schema, const void* arrow_array);
+
+/* ------------------------------------------------------------------ plan ---- */
+
+/* A plan is the fused form of a Check / ValidationSuite / AnalysisRunner: every add_* returns a slot
+ * (>= 0) or a negative tg_status. One tg_plan_execute evaluates all slots with at most one numeric
+ * pass, one pass per string column and one hash job per key set. */
+TG_API tg_status tg_plan_create(tg_plan** out);
+TG_API void tg_plan_destroy(tg_plan* plan);
+TG_API int32_t tg_plan_num_slots(const tg_plan* plan);
+
+/* CompletenessConstraint::new (constraints/completeness.rs:96-110), evaluate_column :137-246,
+ * multi-column combine core/unified.rs:41-123 */
+TG_API int32_t tg_plan_add_completeness(tg_plan* plan, const char* const* columns, int32_t n_columns,
+                                        double threshold, int32_t logical_op, int32_t logical_n);
+/* SizeConstraint::evaluate (constraints/size.rs:53-119) */
+TG_API int32_t tg_plan_add_size(tg_plan* plan, tg_assertion assertion);
+/* StatisticalConstraint::evaluate (constraints/statistics.rs:254-322) */
+TG_API int32_t tg_plan_add_statistic(tg_plan* plan, const char* column, int32_t stat_kind,
+                                     double percentile, tg_assertion assertion);
+/* MultiStatisticalConstraint::evaluate (constraints/statistics.rs:424-504) */
+TG_API int32_t tg_plan_add_multi_statistic(tg_plan* plan, const char* column, const int32_t* stat_kinds,
+                                           const double* percentiles, const tg_assertion* assertions,
+                                           int32_t n);
+/* FormatConstraint::new / evaluate (constraints/format.rs:490-520, 740-843) */
+TG_API int32_t tg_plan_add_format(tg_plan* plan, const char* column, int32_t format_kind,
+                                  const char* arg, int32_t flag, double threshold,
+                                  const tg_format_options* options);
+/* UniquenessConstraint::new / evaluate (constraints/uniqueness.rs:262-308, 449-482) */
+TG_API int32_t tg_plan_add_uniqueness(tg_plan* plan, const char* const* columns, int32_t n_columns,
+                                      int32_t uniqueness_kind, double threshold, tg_assertion assertion,
+                                      int32_t null_handling);
+/* CorrelationConstraint::evaluate (constraints/correlation.rs:299-440) */
+TG_API int32_t tg_plan_add_correlation(tg_plan* plan, const char* column1, const char* column2,
+                                       int32_t correlation_kind, tg_assertion assertion);
+/* CustomSqlConstraint::new / evaluate (constraints/custom_sql.rs:60-98, 195-282); hint may be NULL */
+TG_API int32_t tg_plan_add_custom_sql(tg_plan* plan, const char* expression, const char* hint);
+/* ForeignKeyConstraint::evaluate (constraints/foreign_key.rs:307-410); columns are "table.column" */
+TG_API int32_t tg_plan_add_foreign_key(tg_plan* plan, const char* child_column, const char* parent_column,
+                                       int32_t allow_nulls, int32_t max_violations_reported);
+
+/* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
+TG_API int32_t tg_plan_add_analyzer(tg_plan* plan, int32_t analyzer_kind, const char* column,
+                                    const char* column2, const char* expression);
+/* KllSketch (analyzers/advanced/kll_sketch.rs:142-400) behind the documented KllSketchAnalyzer shape
+ * (docs/reference/analyzers.md:327-356): metric Map{min,max,count,quantile_{p}} */
+TG_API int32_t tg_plan_add_kll(tg_plan* plan, const char* column, int32_t k, const double* quantiles,
+                               int32_t n_quantiles);
+/* CompletenessAnalyzer::with_grouping (analyzers/basic/grouped_completeness.rs:99-239,
+ * analyzers/grouped.rs:17-59) */
+TG_API int32_t tg_plan_add_grouped_completeness(tg_plan* plan, const char* column,
+                                                const char* const* group_columns, int32_t n_group_columns,
+                                                int32_t max_groups, int32_t include_overall);
+
+/*
+ * Evaluate every slot against table `table_name` (the reference's task-local
+ * ValidationContext::table_name, core/validation_context.rs:71-82; default "data"). Blocking.
+ * Equivalent to execute_partial + finalize on one GPU.
+ */
+TG_API tg_status tg_plan_execute(tg_engine* eng, tg_plan* plan, const char* table_name);
+
+/* Multi-GPU (row-partitioned) form: each rank runs execute_partial on its shard, exchanges the
+ * serialised partial aggregates (a small POD blob; NCCL/gloo all-gather is done by the host layer),
+ * merges every rank's blob IN RANK ORDER and finalizes — mirrors AnalyzerState::merge
+ * (analyzers/traits.rs:154-179). */
+TG_API tg_status tg_plan_execute_partial(tg_engine* eng, tg_plan* plan, const char* table_name);
+TG_API tg_status tg_plan_partial_size(const tg_plan* plan, size_t* n_bytes);
+TG_API tg_status tg_plan_partial_export(const tg_plan* plan, void* buf, size_t n_bytes);
+/* host-only: build partials for a plan without a GPU from an exported blob (tests, incremental runs) */
+TG_API tg_status tg_plan_partial_reset(tg_plan* plan);
+TG_API tg_status tg_plan_partial_merge(tg_plan* plan, const void* buf, size_t n_bytes);
+TG_API tg_status tg_plan_finalize(tg_plan* plan);
+
+TG_API tg_status tg_plan_result(const tg_plan* plan, int32_t slot, tg_result* out);
+TG_API tg_status tg_plan_analyzer_result(const tg_plan* plan, int32_t slot, tg_analyzer_result* out);
+/* Map-valued metrics (KLL, grouped completeness, stddev): entry i of slot */
+TG_API int32_t tg_plan_map_size(const tg_plan* plan, int32_t slot);
+TG_API tg_status tg_plan_map_entry(const tg_plan* plan, int32_t slot, int32_t i, const char** key,
+                                   double* value);
+
+/* timings of the last execute, milliseconds (SURVEY §5 metrics row): h2d, scan kernels, total */
+typedef struct {
+    double gpu_ms;        /* CUDA-event time of all kernels of the last execute */
+    double scan_ms;       /* fused numeric scan kernel only */
+    double string_ms;
+    double hash_ms;
+    double sketch_ms;
+    uint64_t bytes_scanned; /* algorithmic bytes of the last execute */
+    uint64_t launches;
+} tg_exec_stats;
+TG_API tg_status tg_plan_exec_stats(const tg_plan* plan, tg_exec_stats* out);
+
+/* -------------------------------------------------- host-side helpers ---- */
+/* These restate O(1) reference host logic so the shim and tests can call it without a GPU. */
+
+/* Assertion::evaluate (constraints/assertion.rs:48-61) */
+TG_API int32_t tg_assertion_evaluate(tg_assertion a, double value);
+/* Assertion::description (assertion.rs:64-75); writes NUL-terminated into buf, returns needed length */
+TG_API int32_t tg_assertion_description(tg_assertion a, char* buf, int32_t cap);
+/* LogicalOperator::evaluate (core/logical.rs:69-89) */
+TG_API int32_t tg_logical_evaluate(int32_t op, int32_t n, const uint8_t* results, int32_t n_results);
+/* SqlSecurity::validate_identifier (security.rs:89-137) */
+TG_API tg_status tg_validate_identifier(const char* identifier);
+/* SqlSecurity::validate_regex_pattern (security.rs:152-183) + our DFA grammar check */
+TG_API tg_status tg_validate_regex_pattern(const char* pattern);
+/* custom_sql.rs:100-190 validate_sql_expression */
+TG_API tg_status tg_validate_sql_expression(const char* expression);
+/* FormatType::get_pattern (constraints/format.rs:217-307) */
+TG_API const char* tg_format_pattern(int32_t format_kind, const char* arg, int32_t flag);
+/* Host DFA matcher used ONLY to unit-test the regex compiler without a GPU (the product path runs the
+ * same table on the device): returns 1/0 match of `pattern` (search semantics of `~`) on bytes. */
+TG_API int32_t tg_regex_host_match(const char* pattern, int32_t case_insensitive, const uint8_t* s,
+                                   int64_t len, int32_t* out_match);
+/* Rust `{}` Display of f64, for message parity; returns needed length */
+TG_API int32_t tg_format_f64(double v, char* buf, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TERMGPU_H */

@@ -1,0 +1,906 @@
+"""CPU oracle — TEST INFRASTRUCTURE ONLY (never imported by term_b200/, never a fallback).
+
+A plain numpy / pure-Python restatement of what the reference (withterm/term, `term-guard` 0.0.2)
+computes on the hot path by lowering each constraint / analyzer to a DataFusion SQL aggregate.
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import it.
+
+The arithmetic itself lives in third-party crates that are NOT vendored under /root/reference
+(datafusion 50.3.0, arrow 56.2.0, regex 1.12.2 / regex-syntax 0.8.8 — Cargo.lock); this file restates
+the published SQL semantics those queries have and the in-tree Rust that follows each
+query. Every function cites the reference file:line it follows (paths under term-guard/src/).
+
+PINNING: the reference cannot be built here (no cargo/rustc), so the oracle is pinned against the
+reference's own known-answer tests, ported to tests/golden/reference_vectors.json with their file:line
+(tests/test_oracle_golden.py). Values no reference test fixes are "parity unpinned" (SURVEY.md §8c last
+row): APPROX_PERCENTILE_CONT, CORR with zero variance / n<2, float MIN/MAX with NaN, FK example choice.
+"""
+import math
+import re
+from dataclasses import dataclass
+from decimal import Decimal
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+SUCCESS, FAILURE, SKIPPED = "success", "failure", "skipped"
+
+
+@dataclass
+class Result:  # core/constraint.rs:40-48
+    status: str
+    metric: Optional[float] = None
+    message: Optional[str] = None
+
+
+# ------------------------------------------------------------------ Rust formatting ----
+def rust_f64(v: float) -> str:
+    """`{}` of an f64: shortest round-trip digits, never scientific, integral values without '.0'."""
+    if math.isnan(v):
+        return "NaN"
+    if math.isinf(v):
+        return "inf" if v > 0 else "-inf"
+    s = format(Decimal(repr(float(v))), "f")
+    if "." in s:
+        s = s.rstrip("0").rstrip(".")
+    if s in ("-0", ""):
+        s = "-0" if s == "-0" else "0"
+    return s
+
+
+def rust_prec(v: float, n: int) -> str:
+    return format(v, f".{n}f")
+
+
+# ------------------------------------------------------------------ Assertion / LogicalOperator ----
+def assertion_eval(a, value: float) -> bool:
+    """constraints/assertion.rs:48-61; a = (kind, x[, y])"""
+    k = a[0]
+    eps = 1e-10
+    if k == "Equals":
+        return abs(value - a[1]) < eps
+    if k == "NotEquals":
+        return abs(value - a[1]) >= eps
+    if k == "GreaterThan":
+        return value > a[1]
+    if k == "GreaterThanOrEqual":
+        return value >= a[1]
+    if k == "LessThan":
+        return value < a[1]
+    if k == "LessThanOrEqual":
+        return value <= a[1]
+    if k == "Between":
+        return a[1] <= value <= a[2]
+    if k == "NotBetween":
+        return value < a[1] or value > a[2]
+    raise ValueError(k)
+
+
+def assertion_desc(a) -> str:
+    """constraints/assertion.rs:64-75"""
+    k = a[0]
+    names = {"Equals": "equals", "NotEquals": "not equals", "GreaterThan": "greater than",
+             "GreaterThanOrEqual": "greater than or equal to", "LessThan": "less than",
+             "LessThanOrEqual": "less than or equal to"}
+    if k in names:
+        return f"{names[k]} {rust_f64(a[1])}"
+    if k == "Between":
+        return f"between {rust_f64(a[1])} and {rust_f64(a[2])}"
+    return f"not between {rust_f64(a[1])} and {rust_f64(a[2])}"
+
+
+def logical_eval(op, results: Sequence[bool]) -> bool:
+    """core/logical.rs:69-89; op = ("All",) | ("Any",) | ("Exactly", n) | ("AtLeast", n) | ("AtMost", n)"""
+    k = op[0]
+    if len(results) == 0:
+        return {"All": True, "Any": False, "AtMost": True}.get(k, (op[1] if len(op) > 1 else 0) == 0)
+    t = sum(1 for r in results if r)
+    if k == "All":
+        return t == len(results)
+    if k == "Any":
+        return t > 0
+    if k == "Exactly":
+        return t == op[1]
+    if k == "AtLeast":
+        return t >= op[1]
+    if k == "AtMost":
+        return t <= op[1]
+    raise ValueError(k)
+
+
+def logical_desc(op) -> str:
+    k = op[0]
+    return {"All": "all", "Any": "any"}.get(k) or {"Exactly": "exactly", "AtLeast": "at least", "AtMost": "at most"}[k] + f" {op[1]}"
+
+
+# ------------------------------------------------------------------ column access ----
+class Col:
+    """values: numpy array (numeric) or list of str; valid: bool mask; kind: 'i64' | 'f64' | 'str' | 'bool'"""
+
+    def __init__(self, values, valid, kind):
+        self.values, self.valid, self.kind = values, np.asarray(valid, dtype=bool), kind
+
+    def __len__(self):
+        return len(self.valid)
+
+
+def col_from_arrow(arr) -> Col:
+    import pyarrow as pa
+    if isinstance(arr, pa.ChunkedArray):
+        arr = arr.combine_chunks()
+    valid = np.asarray(arr.is_valid())
+    t = arr.type
+    if pa.types.is_integer(t):
+        vals = np.asarray(arr.fill_null(0)).astype(np.int64)
+        return Col(vals, valid, "i64")
+    if pa.types.is_floating(t):
+        vals = np.asarray(arr.fill_null(0.0)).astype(np.float64)
+        return Col(vals, valid, "f64")
+    if pa.types.is_boolean(t):
+        return Col(np.asarray(arr.fill_null(False)), valid, "bool")
+    return Col(arr.to_pylist(), valid, "str")
+
+
+def table_cols(table) -> Dict[str, Col]:
+    """table: pyarrow.Table / RecordBatch or dict name -> Col"""
+    if isinstance(table, dict):
+        return table
+    return {n: col_from_arrow(table.column(n)) for n in table.schema.names}
+
+
+def n_rows(cols: Dict[str, Col]) -> int:
+    return len(next(iter(cols.values()))) if cols else 0
+
+
+# ------------------------------------------------------------------ constraints ----
+def completeness_column(col: Col, name: str, threshold: float) -> Result:
+    """constraints/completeness.rs:137-246: SELECT COUNT(*), COUNT(c)"""
+    total = float(len(col))
+    if total == 0.0:
+        return Result(SKIPPED, None, "No data to validate")
+    c = float(int(col.valid.sum())) / total
+    if c >= threshold:
+        return Result(SUCCESS, c)
+    return Result(FAILURE, c, f"Column '{name}' completeness {rust_prec(c * 100.0, 2)}% is below threshold {rust_prec(threshold * 100.0, 2)}%")
+
+
+def completeness(table, columns, threshold=1.0, op=("All",)) -> Result:
+    """core/unified.rs:41-123"""
+    cols = table_cols(table)
+    columns = [columns] if isinstance(columns, str) else list(columns)
+    if len(columns) == 0:
+        return Result(SKIPPED, None, "No columns specified")
+    rs = [completeness_column(cols[c], c, threshold) for c in columns]
+    if len(rs) == 1:
+        return rs[0]
+    bools = [r.status == SUCCESS for r in rs]
+    metrics = [r.metric for r in rs if r.metric is not None]
+    metric = sum(metrics) / len(metrics) if metrics else None
+    ok = logical_eval(op, bools)
+    if ok:
+        if op[0] == "All":
+            msg = f"All {len(columns)} columns satisfy the constraint"
+        elif op[0] == "Any":
+            msg = "Columns " + ", ".join(c for c, b in zip(columns, bools) if b) + " satisfy the constraint"
+        else:
+            msg = None
+        return Result(SUCCESS, metric, msg)
+    failed = ", ".join(c for c, b in zip(columns, bools) if not b)
+    return Result(FAILURE, metric, f"Constraint failed for columns: {failed}. Required: {logical_desc(op)}")
+
+
+def size(table, assertion) -> Result:
+    """constraints/size.rs:53-119: SELECT COUNT(*)"""
+    n = float(n_rows(table_cols(table)))
+    if assertion_eval(assertion, n):
+        return Result(SUCCESS, n)
+    return Result(FAILURE, n, f"Size {rust_f64(n)} does not {assertion_desc(assertion)}")
+
+
+STAT_NAMES = {"Min": "minimum", "Max": "maximum", "Mean": "mean", "Sum": "sum",
+              "StandardDeviation": "standard deviation", "Variance": "variance", "Median": "median"}
+
+
+def wrap_i64(x: int) -> int:
+    x &= (1 << 64) - 1
+    return x - (1 << 64) if x >= (1 << 63) else x
+
+
+def stat_value(col: Col, stat: str) -> Optional[float]:
+    """MIN|MAX|AVG|SUM|STDDEV|VARIANCE with DataFusion typing (constraints/statistics.rs:45-56,278-308):
+    on Int64 columns MIN/MAX/SUM are Int64 (SUM wraps) then cast to f64; AVG/STDDEV/VARIANCE are Float64;
+    STDDEV/VARIANCE are the SAMPLE statistics (tests/property_tests.rs:784-793) and NULL for n < 2."""
+    v = col.values[col.valid]
+    n = len(v)
+    if stat in ("Min", "Max", "Sum", "Mean") and n == 0:
+        return None
+    if stat == "Min":
+        return float(v.min())
+    if stat == "Max":
+        return float(v.max())
+    if stat == "Sum":
+        if col.kind == "i64":
+            return float(wrap_i64(sum(int(x) for x in v)))
+        return math.fsum(float(x) for x in v)
+    if stat == "Mean":
+        return math.fsum(float(x) for x in v) / n
+    if stat in ("StandardDeviation", "Variance"):
+        if n < 2:
+            return None
+        f = [float(x) for x in v]
+        mean = math.fsum(f) / n
+        var = math.fsum((x - mean) ** 2 for x in f) / (n - 1)
+        return math.sqrt(var) if stat == "StandardDeviation" else var
+    raise ValueError(stat)
+
+
+def statistic(table, column, stat, assertion) -> Result:
+    """constraints/statistics.rs:254-322"""
+    col = table_cols(table)[column]
+    v = stat_value(col, stat)
+    name = STAT_NAMES[stat]
+    if v is None:
+        return Result(FAILURE, None, f"{name} is null (no non-null values)")
+    if assertion_eval(assertion, v):
+        return Result(SUCCESS, v)
+    return Result(FAILURE, v, f"{name} {rust_f64(v)} does not {assertion_desc(assertion)}")
+
+
+def multi_statistic(table, column, stats) -> Result:
+    """constraints/statistics.rs:424-504; stats = [(stat, assertion)]"""
+    col = table_cols(table)[column]
+    failures, metrics = [], []
+    for stat, a in stats:
+        v = stat_value(col, stat)
+        name = STAT_NAMES[stat]
+        if v is None:
+            failures.append(f"{name} is null")
+            continue
+        metrics.append(v)
+        if not assertion_eval(a, v):
+            failures.append(f"{name} is {rust_f64(v)} which does not {assertion_desc(a)}")
+    if not failures:
+        return Result(SUCCESS, metrics[0] if metrics else 0.0)
+    return Result(FAILURE, None, "; ".join(failures))
+
+
+# FormatType::get_pattern, constraints/format.rs:217-307 (pattern strings are interface data)
+def format_pattern(kind, arg=None, flag=False) -> str:
+    if kind == "Regex":
+        return arg
+    if kind == "Email":
+        return r"^[a-zA-Z0-9.!#$%&'*+/=?^_`{|}~-]+@[a-zA-Z0-9](?:[a-zA-Z0-9-]{0,61}[a-zA-Z0-9])?(?:\.[a-zA-Z0-9](?:[a-zA-Z0-9-]{0,61}[a-zA-Z0-9])?)*$"
+    if kind == "Url":
+        if flag:
+            return r"^https?://(?:localhost|(?:[a-zA-Z0-9.-]+\.?[a-zA-Z]{2,}|(?:\d{1,3}\.){3}\d{1,3}))(?::\d+)?(?:/[^\s]*)?$"
+        return r"^https?://[a-zA-Z0-9.-]+\.[a-zA-Z]{2,}(?::\d+)?(?:/[^\s]*)?$"
+    if kind == "CreditCard":
+        return r"^(?:4[0-9]{12}(?:[0-9]{3})?|5[1-5][0-9]{14}|3[47][0-9]{13}|3[0-9]{13}|6(?:011|5[0-9]{2})[0-9]{12})$|^(?:\d{4}[-\s]?){3}\d{4}$"
+    if kind == "Phone":
+        return {"US": r"^(\+?1[-.\s]?)?\(?([0-9]{3})\)?[-.\s]?([0-9]{3})[-.\s]?([0-9]{4})$",
+                "CA": r"^(\+?1[-.\s]?)?\(?([0-9]{3})\)?[-.\s]?([0-9]{3})[-.\s]?([0-9]{4})$",
+                "UK": r"^(\+44\s?)?(?:\(?0\d{4}\)?\s?\d{6}|\(?0\d{3}\)?\s?\d{7}|\(?0\d{2}\)?\s?\d{8})$",
+                "DE": r"^(\+49\s?)?(?:\(?0\d{2,5}\)?\s?\d{4,12})$",
+                "FR": r"^(\+33\s?)?(?:\(?0\d{1}\)?\s?\d{8})$"}.get(arg, r"^[\+]?[1-9][\d]{0,15}$")
+    if kind == "PostalCode":
+        return {"US": r"^\d{5}(-\d{4})?$", "CA": r"^[A-Za-z]\d[A-Za-z][ -]?\d[A-Za-z]\d$",
+                "UK": r"^[A-Z]{1,2}\d[A-Z\d]?\s?\d[A-Z]{2}$", "DE": r"^\d{5}$", "FR": r"^\d{5}$",
+                "JP": r"^\d{3}-\d{4}$", "AU": r"^\d{4}$"}.get(arg, r"^[A-Za-z0-9\s-]{3,10}$")
+    if kind == "UUID":
+        return r"^[0-9a-fA-F]{8}-[0-9a-fA-F]{4}-[1-5][0-9a-fA-F]{3}-[89abAB][0-9a-fA-F]{3}-[0-9a-fA-F]{12}$"
+    if kind == "IPv4":
+        return r"^(?:(?:25[0-5]|2[0-4][0-9]|[01]?[0-9][0-9]?)\.){3}(?:25[0-5]|2[0-4][0-9]|[01]?[0-9][0-9]?)$"
+    if kind == "IPv6":
+        return r"^([0-9a-fA-F]{0,4}:){1,7}([0-9a-fA-F]{0,4})?$|^::$|^::1$|^([0-9a-fA-F]{1,4}:)*::([0-9a-fA-F]{1,4}:)*[0-9a-fA-F]{1,4}$"
+    if kind == "Json":
+        return r"^\s*[\{\[].*[\}\]]\s*$"
+    if kind == "Iso8601DateTime":
+        return r"^\d{4}-\d{2}-\d{2}T\d{2}:\d{2}:\d{2}(?:\.\d+)?(?:Z|[+-]\d{2}:\d{2})$"
+    if kind == "SocialSecurityNumber":
+        return r"^(00[1-9]|0[1-9][0-9]|[1-5][0-9]{2}|6[0-5][0-9]|66[0-5]|667|66[89]|6[7-9][0-9]|[7-8][0-9]{2})-?(0[1-9]|[1-9][0-9])-?(000[1-9]|00[1-9][0-9]|0[1-9][0-9]{2}|[1-9][0-9]{3})$"
+    raise ValueError(kind)
+
+
+def format_description(kind, pattern, arg=None, flag=False) -> str:
+    """constraints/format.rs:329-361"""
+    return {
+        "Regex": f"matches pattern '{pattern}'", "Email": "are valid email addresses",
+        "Url": "are valid URLs (including localhost)" if flag else "are valid URLs",
+        "CreditCard": "contain credit card number patterns" if flag else "are valid credit card numbers",
+        "Phone": f"are valid {arg} phone numbers" if arg else "are valid phone numbers",
+        "PostalCode": f"are valid {arg} postal codes", "UUID": "are valid UUIDs",
+        "IPv4": "are valid IPv4 addresses", "IPv6": "are valid IPv6 addresses",
+        "Json": "are valid JSON documents", "Iso8601DateTime": "are valid ISO 8601 date-time strings",
+        "SocialSecurityNumber": "contain Social Security Number patterns"}[kind]
+
+
+def rust_regex_to_python(pattern: str, case_insensitive: bool):
+    """Rust `regex` semantics on top of Python `re`: `$` only at the very end (Python's also matches
+    before a trailing newline -> rewrite unescaped `$` outside classes to `\\Z`); `\\z` -> `\\Z`;
+    `.` already excludes only \\n; Unicode classes by default for str patterns."""
+    out, i, in_class = [], 0, False
+    while i < len(pattern):
+        ch = pattern[i]
+        if ch == "\\" and i + 1 < len(pattern):
+            nxt = pattern[i + 1]
+            if not in_class and nxt == "z":
+                out.append(r"\Z")
+            elif not in_class and nxt == "A":
+                out.append(r"\A")
+            else:
+                out.append(ch + nxt)
+            i += 2
+            continue
+        if in_class:
+            if ch == "]":
+                in_class = False
+            out.append(ch)
+        elif ch == "[":
+            in_class = True
+            out.append(ch)
+            if i + 1 < len(pattern) and pattern[i + 1] == "^":
+                out.append("^")
+                i += 1
+            if i + 1 < len(pattern) and pattern[i + 1] == "]":
+                out.append(r"\]")
+                i += 1
+        elif ch == "$":
+            out.append(r"\Z")
+        else:
+            out.append(ch)
+        i += 1
+    return re.compile("".join(out), re.IGNORECASE if case_insensitive else 0)
+
+
+def regex_matches(col: Col, pattern: str, case_insensitive=False, trim=False) -> List[Optional[bool]]:
+    """`c ~ 'pat'` / `~*` = Regex::is_match = unanchored search; TRIM strips ASCII space only
+    (constraints/format.rs:756-776)"""
+    rx = rust_regex_to_python(pattern, case_insensitive)
+    out = []
+    for s, ok in zip(col.values, col.valid):
+        if not ok:
+            out.append(None)
+            continue
+        if trim:
+            s = s.strip(" ")
+        out.append(rx.search(s) is not None)
+    return out
+
+
+def format_constraint(table, column, kind, threshold, arg=None, flag=False, case_sensitive=True, trim=False,
+                      null_is_valid=True) -> Result:
+    """constraints/format.rs:740-843"""
+    col = table_cols(table)[column]
+    pattern = format_pattern(kind, arg, flag)
+    ms = regex_matches(col, pattern, not case_sensitive, trim)
+    matches = float(sum(1 for m in ms if m is True or (m is None and null_is_valid)))
+    total = float(len(ms))
+    if total == 0.0:
+        return Result(SKIPPED, None, "No data to validate")
+    ratio = matches / total
+    detect = kind == "CreditCard" and flag
+    ok = ratio <= threshold if detect else ratio >= threshold
+    if ok:
+        return Result(SUCCESS, ratio)
+    if detect:
+        msg = f"Credit card detection ratio {rust_prec(ratio, 3)} exceeds threshold {rust_prec(threshold, 3)}"
+    else:
+        msg = (f"Format validation ratio {rust_prec(ratio, 3)} is below threshold {rust_prec(threshold, 3)}"
+               f" - values that {format_description(kind, pattern, arg, flag)}")
+    return Result(FAILURE, ratio, msg)
+
+
+def _keys(cols: Dict[str, Col], columns):
+    """row keys with None for NULL components"""
+    cs = [cols[c] for c in columns]
+    n = len(cs[0]) if cs else 0
+    out = []
+    for i in range(n):
+        out.append(tuple((c.values[i].item() if hasattr(c.values[i], "item") else c.values[i]) if c.valid[i] else None for c in cs))
+    return out
+
+
+def distinct_counts(table, columns):
+    """The five counts every uniqueness flavour needs (constraints/uniqueness.rs:549-718)."""
+    cols = table_cols(table)
+    keys = _keys(cols, columns)
+    from collections import Counter
+    cnt = Counter(keys)
+    return dict(
+        rows=len(keys),
+        distinct_nonnull=sum(1 for k in cnt if all(x is not None for x in k)),
+        distinct_all=len(cnt),
+        singletons=sum(1 for k, v in cnt.items() if v == 1),
+        any_null_rows=sum(1 for k in keys if any(x is None for x in k)),
+    )
+
+
+UNIQ_NAMES = {"FullUniqueness": "full_uniqueness", "Distinctness": "distinctness",
+              "UniqueValueRatio": "unique_value_ratio", "PrimaryKey": "primary_key",
+              "UniqueWithNulls": "unique_with_nulls", "UniqueComposite": "unique_composite"}
+
+
+def uniqueness(table, columns, kind, threshold=1.0, assertion=None, null_handling="Exclude") -> Result:
+    """constraints/uniqueness.rs:449-482 + SQL generators :549-718 + evaluators :721-852.
+    COUNT(DISTINCT c) ignores NULL; COUNT(DISTINCT (a, b)) counts struct values (never NULL);
+    multi-column distinctness concatenates COALESCE(..,'<NULL>'); GROUP BY keeps a NULL group."""
+    columns = [columns] if isinstance(columns, str) else list(columns)
+    d = distinct_counts(table, columns)
+    multi = len(columns) > 1
+    total = float(d["rows"])
+    cde = d["distinct_all"] if multi else d["distinct_nonnull"]
+    cols_s = ", ".join(columns)
+    if kind in ("FullUniqueness", "UniqueWithNulls", "UniqueComposite"):
+        unique = cde
+        if kind == "UniqueWithNulls" and not multi:
+            if null_handling == "Include":
+                unique = d["distinct_all"]
+            elif null_handling == "Distinct":
+                unique = d["distinct_nonnull"] + d["any_null_rows"]
+        if total == 0.0:
+            return Result(SKIPPED, None, "No data to validate")
+        ratio = float(unique) / total
+        if ratio >= threshold:
+            return Result(SUCCESS, ratio)
+        return Result(FAILURE, ratio, f"Uniqueness ratio {rust_prec(ratio, 3)} is below threshold {rust_prec(threshold, 3)} for columns: {cols_s}")
+    if kind in ("Distinctness", "UniqueValueRatio"):
+        count = float((d["distinct_all"] if multi else d["distinct_nonnull"]) if kind == "Distinctness" else d["singletons"])
+        if total == 0.0:
+            return Result(SKIPPED, None, "No data to validate")
+        ratio = count / total
+        if assertion_eval(assertion, ratio):
+            return Result(SUCCESS, ratio)
+        return Result(FAILURE, ratio, f"{UNIQ_NAMES[kind]} ratio {rust_prec(ratio, 3)} does not satisfy {assertion_desc(assertion)} for columns: {cols_s}")
+    if total == 0.0:
+        return Result(SKIPPED, None, "No data to validate")
+    nulls = float(d["any_null_rows"])
+    if nulls > 0.0:
+        return Result(FAILURE, nulls / total, f"Primary key columns contain {rust_f64(nulls)} NULL values: {cols_s}")
+    if float(cde) != total:
+        return Result(FAILURE, (total - cde) / total, f"Primary key columns contain {rust_f64(total - cde)} duplicate values: {cols_s}")
+    return Result(SUCCESS, 1.0)
+
+
+def pair_values(table, c1, c2):
+    cols = table_cols(table)
+    a, b = cols[c1], cols[c2]
+    m = a.valid & b.valid
+    return np.asarray(a.values, dtype=np.float64)[m], np.asarray(b.values, dtype=np.float64)[m]
+
+
+def pearson(x, y) -> Optional[float]:
+    """CORR(x, y): population-moment Pearson over pairwise-complete rows; NULL for n < 2 or zero variance
+    (parity unpinned there; the constraint reads NULL as 0.0, constraints/correlation.rs:355-362)."""
+    n = len(x)
+    if n < 2:
+        return None
+    mx, my = math.fsum(x) / n, math.fsum(y) / n
+    sxy = math.fsum((a - mx) * (b - my) for a, b in zip(x, y))
+    sxx = math.fsum((a - mx) ** 2 for a in x)
+    syy = math.fsum((b - my) ** 2 for b in y)
+    den = math.sqrt(sxx * syy)
+    if not den > 0.0:
+        return None
+    return sxy / den
+
+
+def covar_samp(x, y) -> Optional[float]:
+    n = len(x)
+    if n < 2:
+        return None
+    mx, my = math.fsum(x) / n, math.fsum(y) / n
+    return math.fsum((a - mx) * (b - my) for a, b in zip(x, y)) / (n - 1)
+
+
+def correlation(table, c1, c2, kind, assertion) -> Result:
+    """constraints/correlation.rs:299-440"""
+    if kind in ("Spearman", "KendallTau", "MutualInformation"):
+        return Result(SKIPPED, None, "Correlation type not yet implemented")
+    x, y = pair_values(table, c1, c2)
+    if kind == "Independence":
+        v = abs(pearson(x, y) or 0.0)
+        if v <= assertion[1]:
+            return Result(SUCCESS, v)
+        return Result(FAILURE, v, f"Columns {c1} and {c2} have correlation {rust_f64(v)} exceeding independence threshold {rust_f64(assertion[1])}")
+    cov = kind == "Covariance"
+    v = (covar_samp(x, y) if cov else pearson(x, y)) or 0.0
+    if assertion_eval(assertion, v):
+        return Result(SUCCESS, v)
+    nm = "covariance" if cov else "Pearson correlation"
+    return Result(FAILURE, v, f"{nm} between {c1} and {c2} is {rust_f64(v)} which does not {assertion_desc(assertion)}")
+
+
+# ---- a tiny independent SQL-predicate evaluator (Python objects, None = NULL) for `satisfies` ----
+_TOK = re.compile(r"\s*(?:(\d+\.\d*(?:[eE][+-]?\d+)?|\.\d+(?:[eE][+-]?\d+)?|\d+[eE][+-]?\d+)|(\d+)|'((?:[^']|'')*)'|\"((?:[^\"]|\"\")*)\"|([A-Za-z_][A-Za-z0-9_.]*)|(<=|>=|<>|!=|==|[-+*/%<>=(),]))")
+
+
+def _tokenize(s):
+    out, pos = [], 0
+    s = s.rstrip()
+    while pos < len(s):
+        m = _TOK.match(s, pos)
+        if not m:
+            raise ValueError(f"bad SQL near {s[pos:]!r}")
+        pos = m.end()
+        if m.group(1) is not None:
+            out.append(("f", float(m.group(1))))
+        elif m.group(2) is not None:
+            out.append(("i", int(m.group(2))))
+        elif m.group(3) is not None:
+            out.append(("s", m.group(3).replace("''", "'")))
+        elif m.group(4) is not None:
+            out.append(("c", m.group(4).replace('""', '"')))
+        elif m.group(5) is not None:
+            w = m.group(5)
+            up = w.upper()
+            if up in ("AND", "OR", "NOT", "IS", "NULL", "TRUE", "FALSE", "BETWEEN", "IN"):
+                out.append(("k", up))
+            else:
+                out.append(("c", w.lower().split(".")[-1]))
+        else:
+            out.append(("o", m.group(6)))
+    out.append(("e", None))
+    return out
+
+
+class _P:
+    def __init__(self, toks):
+        self.t, self.i = toks, 0
+
+    def peek(self):
+        return self.t[self.i]
+
+    def eat(self, kind=None, val=None):
+        k, v = self.t[self.i]
+        if (kind and k != kind) or (val is not None and v != val):
+            raise ValueError(f"unexpected token {k} {v}")
+        self.i += 1
+        return v
+
+    def is_(self, kind, val=None):
+        k, v = self.t[self.i]
+        return k == kind and (val is None or v == val)
+
+    def or_(self):
+        l = self.and_()
+        while self.is_("k", "OR"):
+            self.eat()
+            l = ("or", l, self.and_())
+        return l
+
+    def and_(self):
+        l = self.not_()
+        while self.is_("k", "AND"):
+            self.eat()
+            l = ("and", l, self.not_())
+        return l
+
+    def not_(self):
+        if self.is_("k", "NOT"):
+            self.eat()
+            return ("not", self.not_())
+        return self.cmp()
+
+    def cmp(self):
+        l = self.add()
+        while True:
+            if self.peek()[0] == "o" and self.peek()[1] in ("=", "==", "<>", "!=", "<", "<=", ">", ">="):
+                op = self.eat()
+                op = {"==": "=", "!=": "<>"}.get(op, op)
+                l = ("cmp", op, l, self.add())
+            elif self.is_("k", "IS"):
+                self.eat()
+                neg = False
+                if self.is_("k", "NOT"):
+                    self.eat()
+                    neg = True
+                w = self.eat("k")
+                l = ("is", w, neg, l)
+            elif self.is_("k", "BETWEEN") or (self.is_("k", "NOT") and self.t[self.i + 1] in (("k", "BETWEEN"), ("k", "IN"))):
+                neg = False
+                if self.is_("k", "NOT"):
+                    self.eat()
+                    neg = True
+                if self.is_("k", "BETWEEN"):
+                    self.eat()
+                    lo = self.add()
+                    self.eat("k", "AND")
+                    hi = self.add()
+                    e = ("and", ("cmp", ">=", l, lo), ("cmp", "<=", l, hi))
+                else:
+                    self.eat("k", "IN")
+                    self.eat("o", "(")
+                    e = None
+                    while True:
+                        it = ("cmp", "=", l, self.add())
+                        e = it if e is None else ("or", e, it)
+                        if self.is_("o", ","):
+                            self.eat()
+                            continue
+                        break
+                    self.eat("o", ")")
+                l = ("not", e) if neg else e
+            elif self.is_("k", "IN"):
+                self.eat()
+                self.eat("o", "(")
+                e = None
+                while True:
+                    it = ("cmp", "=", l, self.add())
+                    e = it if e is None else ("or", e, it)
+                    if self.is_("o", ","):
+                        self.eat()
+                        continue
+                    break
+                self.eat("o", ")")
+                l = e
+            else:
+                return l
+
+    def add(self):
+        l = self.mul()
+        while self.peek()[0] == "o" and self.peek()[1] in "+-":
+            op = self.eat()
+            l = ("ar", op, l, self.mul())
+        return l
+
+    def mul(self):
+        l = self.unary()
+        while self.peek()[0] == "o" and self.peek()[1] in ("*", "/", "%"):
+            op = self.eat()
+            l = ("ar", op, l, self.unary())
+        return l
+
+    def unary(self):
+        if self.is_("o", "-"):
+            self.eat()
+            return ("neg", self.unary())
+        if self.is_("o", "+"):
+            self.eat()
+            return self.unary()
+        return self.prim()
+
+    def prim(self):
+        k, v = self.peek()
+        if k in ("f", "i", "s"):
+            self.eat()
+            return ("lit", v)
+        if k == "k" and v in ("TRUE", "FALSE", "NULL"):
+            self.eat()
+            return ("lit", {"TRUE": True, "FALSE": False, "NULL": None}[v])
+        if k == "o" and v == "(":
+            self.eat()
+            e = self.or_()
+            self.eat("o", ")")
+            return e
+        if k == "c":
+            self.eat()
+            if self.is_("o", "("):
+                self.eat()
+                args = []
+                if not self.is_("o", ")"):
+                    while True:
+                        args.append(self.or_())
+                        if self.is_("o", ","):
+                            self.eat()
+                            continue
+                        break
+                self.eat("o", ")")
+                return ("fn", v.upper(), args)
+            return ("col", v)
+        raise ValueError(f"unexpected token {k} {v}")
+
+
+class DivideByZero(Exception):
+    pass
+
+
+def _ev(e, row):
+    k = e[0]
+    if k == "lit":
+        return e[1]
+    if k == "col":
+        return row[e[1]]
+    if k == "neg":
+        v = _ev(e[1], row)
+        return None if v is None else (wrap_i64(-v) if isinstance(v, int) and not isinstance(v, bool) else -v)
+    if k == "fn":
+        if e[1] == "ABS":
+            v = _ev(e[2][0], row)
+            return None if v is None else abs(v)
+        raise ValueError(e[1])
+    if k == "ar":
+        a, b = _ev(e[2], row), _ev(e[3], row)
+        if a is None or b is None:
+            return None
+        ints = isinstance(a, int) and isinstance(b, int)
+        if e[1] == "+":
+            return wrap_i64(a + b) if ints else float(a) + float(b)
+        if e[1] == "-":
+            return wrap_i64(a - b) if ints else float(a) - float(b)
+        if e[1] == "*":
+            return wrap_i64(a * b) if ints else float(a) * float(b)
+        if e[1] == "/":
+            if ints:
+                if b == 0:
+                    raise DivideByZero()
+                q = abs(a) // abs(b)
+                return wrap_i64(q if (a >= 0) == (b >= 0) else -q)
+            fb = float(b)
+            fa = float(a)
+            if fb == 0.0:
+                return math.nan if fa == 0.0 or math.isnan(fa) else math.copysign(math.inf, fa) * math.copysign(1.0, fb)
+            return fa / fb
+        if e[1] == "%":
+            if b == 0:
+                raise DivideByZero()
+            return int(math.fmod(a, b))
+    if k == "cmp":
+        a, b = _ev(e[2], row), _ev(e[3], row)
+        if a is None or b is None:
+            return None
+        if not (isinstance(a, int) and isinstance(b, int)) and not isinstance(a, str):
+            a, b = float(a), float(b)
+        return {"=": a == b, "<>": a != b, "<": a < b, "<=": a <= b, ">": a > b, ">=": a >= b}[e[1]]
+    if k == "and":
+        a, b = _ev(e[1], row), _ev(e[2], row)
+        if a is False or b is False:
+            return False
+        if a is None or b is None:
+            return None
+        return True
+    if k == "or":
+        a, b = _ev(e[1], row), _ev(e[2], row)
+        if a is True or b is True:
+            return True
+        if a is None or b is None:
+            return None
+        return False
+    if k == "not":
+        a = _ev(e[1], row)
+        return None if a is None else (not a)
+    if k == "is":
+        a = _ev(e[3], row)
+        r = {"NULL": a is None, "TRUE": a is True, "FALSE": a is False}[e[1]]
+        return (not r) if e[2] else r
+    raise ValueError(k)
+
+
+def predicate_counts(table, expression):
+    """COUNT(CASE WHEN expr THEN 1 END), COUNT(*) — rows where expr is NULL are not counted
+    (constraints/custom_sql.rs:203-209)"""
+    cols = table_cols(table)
+    ast = _P(_tokenize(expression)).or_()
+    n = n_rows(cols)
+    names = list(cols)
+    sat = 0
+    for i in range(n):
+        row = {}
+        for nm in names:
+            c = cols[nm]
+            if not c.valid[i]:
+                row[nm] = None
+            else:
+                v = c.values[i]
+                row[nm] = v.item() if hasattr(v, "item") else v
+        if _ev(ast, row) is True:
+            sat += 1
+    return sat, n
+
+
+def custom_sql(table, expression, hint=None) -> Result:
+    """constraints/custom_sql.rs:195-282"""
+    try:
+        sat, total = predicate_counts(table, expression)
+    except DivideByZero:
+        return Result(FAILURE, None, f"SQL execution error: Arrow error: Divide by zero error. Expression: '{expression}'")
+    if total == 0:
+        return Result(SKIPPED, None, "No data to validate")
+    ratio = float(sat) / float(total)
+    if ratio == 1.0:
+        return Result(SUCCESS, ratio)
+    failed = int(float(total) - float(sat))
+    msg = f"{hint} ({failed} rows failed the condition)" if hint is not None else f"Custom SQL condition not satisfied for {failed} rows. Expression: '{expression}'"
+    return Result(FAILURE, ratio, msg)
+
+
+def foreign_key(tables, child, parent, allow_nulls=False, max_examples=100):
+    """constraints/foreign_key.rs:307-410: LEFT JOIN child->parent WHERE parent.col IS NULL [AND child.col IS
+    NOT NULL] -> COUNT(*), COUNT(DISTINCT child.col). Returns (Result, total, unique)."""
+    ct, cc = child.split(".")
+    pt, pc = parent.split(".")
+    ccol = table_cols(tables[ct])[cc]
+    pcol = table_cols(tables[pt])[pc]
+    pset = set((v.item() if hasattr(v, "item") else v) for v, ok in zip(pcol.values, pcol.valid) if ok)
+    total, uniq = 0, set()
+    for v, ok in zip(ccol.values, ccol.valid):
+        if not ok:
+            if not allow_nulls:
+                total += 1
+            continue
+        v = v.item() if hasattr(v, "item") else v
+        if v not in pset:
+            total += 1
+            uniq.add(v)
+    if total == 0:
+        return Result(SUCCESS, None, None), 0, 0
+    msg = (f"Foreign key constraint violation: {total} values in '{child}' do not exist in '{parent}' "
+           f"(total: {total}, unique: {len(uniq)})")  # examples are an unordered DISTINCT..LIMIT: unpinned
+    return Result(FAILURE, float(total), msg), total, len(uniq)
+
+
+# ------------------------------------------------------------------ analyzers ----
+def an_completeness(table, column):
+    """analyzers/basic/completeness.rs:58-146 -> (total, non_null, metric)"""
+    c = table_cols(table)[column]
+    t, nn = len(c), int(c.valid.sum())
+    return t, nn, (1.0 if t == 0 else nn / t)
+
+
+def an_distinctness(table, column):
+    """analyzers/basic/distinctness.rs:105-153: COUNT(c), COUNT(DISTINCT c)"""
+    d = distinct_counts(table, [column])
+    nn = d["rows"] - d["any_null_rows"]
+    return nn, d["distinct_nonnull"], (1.0 if nn == 0 else d["distinct_nonnull"] / nn)
+
+
+def an_stddev(table, column):
+    """analyzers/advanced/standard_deviation.rs:163-279 (state -> metric map)"""
+    c = table_cols(table)[column]
+    v = [float(x) for x in c.values[c.valid]]
+    n = len(v)
+    if n == 0:
+        return None
+    s, ss = math.fsum(v), math.fsum(x * x for x in v)
+    mean = s / n
+    m2 = math.fsum((x - mean) ** 2 for x in v)
+    out = {"count": float(n), "mean": mean, "std_dev": math.sqrt(m2 / n), "variance": m2 / n}
+    if n > 1:
+        out["sample_std_dev"] = math.sqrt(m2 / (n - 1))
+        out["sample_variance"] = m2 / (n - 1)
+    if abs(mean) >= 2.220446049250313e-16:
+        out["coefficient_of_variation"] = math.sqrt(m2 / n) / abs(mean)
+    return dict(count=n, sum=s, sum_squared=ss, mean=mean, metric=out)
+
+
+def an_correlation(table, c1, c2, kind="pearson"):
+    """analyzers/advanced/correlation.rs:227-435. Spearman = Pearson over RANK() (competition/min ranks)."""
+    x, y = pair_values(table, c1, c2)
+    if kind == "spearman":
+        from scipy.stats import rankdata
+        x = rankdata(x, method="min").astype(np.float64)
+        y = rankdata(y, method="min").astype(np.float64)
+    n = len(x)
+    if n < 2:
+        return math.nan
+    if kind == "covariance":
+        return covar_samp(x, y)
+    r = pearson(x, y)
+    return 0.0 if r is None else r
+
+
+def grouped_completeness(table, column, group_columns):
+    """analyzers/basic/grouped_completeness.rs:131-239: GROUP BY g.. -> {key: (total, non_null)}"""
+    cols = table_cols(table)
+    tgt = cols[column]
+    keys = _keys(cols, group_columns)
+    out = {}
+    for k, ok in zip(keys, tgt.valid):
+        t = out.setdefault(k, [0, 0])
+        t[0] += 1
+        t[1] += int(ok)
+    return out
+
+
+def exact_quantile(values: np.ndarray, q: float) -> float:
+    """the reference's own accuracy harness: sorted[min(floor(n*q), n-1)] (tests/tpc_integration_tests.rs:533-551)"""
+    s = np.sort(values)
+    return float(s[min(int(len(s) * q), len(s) - 1)])
+
+
+def rank_error(values_sorted: np.ndarray, estimate: float, q: float) -> float:
+    """|rank(estimate)/n - q| with the most favourable rank among ties"""
+    n = len(values_sorted)
+    lo = np.searchsorted(values_sorted, estimate, side="left") / n
+    hi = np.searchsorted(values_sorted, estimate, side="right") / n
+    if lo <= q <= hi:
+        return 0.0
+    return min(abs(lo - q), abs(hi - q))

@@ -1,0 +1,918 @@
+"""Host-side mirror of the reference's plugin interface for the hot path.
+
+Names, argument meaning and error behaviour follow term-guard so parity tests read like the reference's
+own tests:
+
+    ctx = SessionContext()                                   # datafusion::SessionContext (core/context.rs)
+    ctx.register_table("data", pyarrow_table)                # MemTable registration
+    c = CompletenessConstraint.with_threshold("col", 0.8)    # constraints/completeness.rs:112
+    r = c.evaluate(ctx)                                      # Constraint::evaluate (core/constraint.rs:186)
+    suite = ValidationSuite.builder("s").check(Check.builder("c").has_size(Assertion.GreaterThan(0)).build()).build()
+    suite.run(ctx)                                           # core/suite.rs:399 — here ONE fused GPU plan
+
+Everything numeric happens behind the C ABI (libtermgpu.so); this file only marshals Arrow buffers and
+reproduces the orchestration of `ValidationSuite::run_sequential` (core/suite.rs:67-258).
+"""
+import ctypes as C
+import enum
+import time
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import _ffi as F
+
+try:  # pyarrow is the Arrow implementation of the harness; the C ABI itself only sees raw buffers
+    import pyarrow as pa
+except Exception:  # pragma: no cover
+    pa = None
+
+
+# ----------------------------------------------------------------------------- value types ----
+class ConstraintStatus(enum.Enum):  # core/constraint.rs:11-20
+    Success = 0
+    Failure = 1
+    Skipped = 2
+
+    def is_success(self):
+        return self is ConstraintStatus.Success
+
+    def is_failure(self):
+        return self is ConstraintStatus.Failure
+
+    def is_skipped(self):
+        return self is ConstraintStatus.Skipped
+
+
+@dataclass
+class ConstraintResult:  # core/constraint.rs:40-48
+    status: ConstraintStatus
+    metric: Optional[float] = None
+    message: Optional[str] = None
+    name: str = ""
+    error_code: int = 0
+
+
+class Assertion:  # constraints/assertion.rs:13-31
+    KINDS = ["Equals", "NotEquals", "GreaterThan", "GreaterThanOrEqual", "LessThan", "LessThanOrEqual",
+             "Between", "NotBetween"]
+
+    def __init__(self, kind: int, a: float, b: float = 0.0):
+        self.kind, self.a, self.b = kind, float(a), float(b)
+
+    def c(self):
+        return F.tg_assertion(self.kind, self.a, self.b)
+
+    def evaluate(self, value: float) -> bool:
+        return bool(F.lib().tg_assertion_evaluate(self.c(), float(value)))
+
+    def description(self) -> str:
+        buf = C.create_string_buffer(256)
+        F.lib().tg_assertion_description(self.c(), buf, 256)
+        return buf.value.decode()
+
+    def __str__(self):
+        return self.description()
+
+    def __repr__(self):
+        return f"Assertion.{self.KINDS[self.kind]}({self.a}" + (f", {self.b})" if self.kind >= 6 else ")")
+
+
+for _i, _n in enumerate(Assertion.KINDS):
+    if _i < 6:
+        setattr(Assertion, _n, staticmethod(lambda v, _k=_i: Assertion(_k, v)))
+    else:
+        setattr(Assertion, _n, staticmethod(lambda lo, hi, _k=_i: Assertion(_k, lo, hi)))
+
+
+class LogicalOperator:  # core/logical.rs:16-27
+    def __init__(self, op: int, n: int = 0):
+        self.op, self.n = op, n
+
+    def evaluate(self, results: Sequence[bool]) -> bool:
+        arr = (C.c_uint8 * max(1, len(results)))(*[1 if r else 0 for r in results])
+        return bool(F.lib().tg_logical_evaluate(self.op, self.n, arr, len(results)))
+
+    @staticmethod
+    def Exactly(n):
+        return LogicalOperator(2, n)
+
+    @staticmethod
+    def AtLeast(n):
+        return LogicalOperator(3, n)
+
+    @staticmethod
+    def AtMost(n):
+        return LogicalOperator(4, n)
+
+
+LogicalOperator.All = LogicalOperator(0)
+LogicalOperator.Any = LogicalOperator(1)
+
+
+class Level(enum.Enum):  # core/level.rs:76-84
+    Info = 0
+    Warning = 1
+    Error = 2
+
+
+class StatisticType(enum.Enum):  # constraints/statistics.rs:24-45
+    Min = 0
+    Max = 1
+    Mean = 2
+    Sum = 3
+    StandardDeviation = 4
+    Variance = 5
+    Median = 6
+    Percentile = 7
+
+
+class FormatType(enum.Enum):  # constraints/format.rs:189-215
+    Regex = 0
+    Email = 1
+    Url = 2
+    CreditCard = 3
+    Phone = 4
+    PostalCode = 5
+    UUID = 6
+    IPv4 = 7
+    IPv6 = 8
+    Json = 9
+    Iso8601DateTime = 10
+    SocialSecurityNumber = 11
+
+
+@dataclass
+class FormatOptions:  # constraints/format.rs:367-480
+    case_sensitive: bool = True
+    trim_before_check: bool = False
+    null_is_valid: bool = True
+
+    @staticmethod
+    def strict():
+        return FormatOptions(True, False, False)
+
+    @staticmethod
+    def lenient():
+        return FormatOptions(False, True, True)
+
+    @staticmethod
+    def case_insensitive():
+        return FormatOptions(False, False, True)
+
+    @staticmethod
+    def with_trimming():
+        return FormatOptions(True, True, True)
+
+
+class UniquenessType(enum.Enum):  # constraints/uniqueness.rs:44-60
+    FullUniqueness = 0
+    Distinctness = 1
+    UniqueValueRatio = 2
+    PrimaryKey = 3
+    UniqueWithNulls = 4
+    UniqueComposite = 5
+
+
+class NullHandling(enum.Enum):
+    Exclude = 0
+    Include = 1
+    Distinct = 2
+
+
+class CorrelationType(enum.Enum):  # constraints/correlation.rs:20-30 (+ validation kinds)
+    Pearson = 0
+    Covariance = 1
+    Independence = 2
+    Spearman = 3
+    KendallTau = 4
+    MutualInformation = 5
+    Range = 6
+
+
+# ----------------------------------------------------------------------------- context ----
+_NP_DTYPES = {np.dtype("int64"): F.TG_INT64, np.dtype("float64"): F.TG_FLOAT64,
+              np.dtype("int32"): F.TG_INT32, np.dtype("float32"): F.TG_FLOAT32}
+
+
+class SessionContext:
+    """Owner of registered tables; stands where datafusion's SessionContext stands in the reference."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        F.check(F.lib().tg_engine_create(device, C.byref(self._h)))
+        self.device = device
+        self._keepalive = {}
+
+    def close(self):
+        if self._h:
+            F.lib().tg_engine_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def launch_count(self) -> int:
+        return int(F.lib().tg_engine_launch_count(self._h))
+
+    def stream(self) -> int:
+        return int(F.lib().tg_engine_stream(self._h) or 0)
+
+    def _create(self, name):
+        t = C.c_void_p()
+        F.check(F.lib().tg_table_create(self._h, name.encode(), C.byref(t)))
+        return t
+
+    def deregister_table(self, name: str):
+        F.check(F.lib().tg_table_drop(self._h, name.encode()))
+        self._keepalive.pop(name, None)
+
+    def num_rows(self, name: str) -> int:
+        t = C.c_void_p()
+        F.check(F.lib().tg_table_lookup(self._h, name.encode(), C.byref(t)))
+        return int(F.lib().tg_table_num_rows(t))
+
+    def register_table(self, name: str, data, use_c_data_interface: bool = False):
+        """Register host data: a pyarrow Table / RecordBatch / list of RecordBatches, or a dict
+        column -> numpy array | (numpy array, validity bool mask) | list of str/None."""
+        t = self._create(name)
+        try:
+            if pa is not None and isinstance(data, (pa.Table, pa.RecordBatch)):
+                batches = data.to_batches() if isinstance(data, pa.Table) else [data]
+                if isinstance(data, pa.Table) and not batches:
+                    batches = [pa.RecordBatch.from_arrays([pa.array([], type=f.type) for f in data.schema], schema=data.schema)]
+                for b in batches:
+                    self._append_batch(t, b, use_c_data_interface)
+            elif isinstance(data, list) and pa is not None and all(isinstance(b, pa.RecordBatch) for b in data):
+                for b in data:
+                    self._append_batch(t, b, use_c_data_interface)
+            elif isinstance(data, dict):
+                arrays = {}
+                for col, v in data.items():
+                    arrays[col] = _to_arrow(v)
+                self._append_batch(t, pa.RecordBatch.from_arrays(list(arrays.values()), names=list(arrays.keys())),
+                                   use_c_data_interface)
+            else:
+                raise TypeError(f"cannot register {type(data)}")
+        except Exception:
+            F.lib().tg_table_drop(self._h, name.encode())
+            raise
+        return t
+
+    def _append_batch(self, t, batch, use_c):
+        if use_c:
+            return self._append_batch_c(t, batch)
+        for col_name, arr in zip(batch.schema.names, batch.columns):
+            typ = arr.type
+            if pa.types.is_large_string(typ):
+                arr = arr.cast(pa.string())
+                typ = arr.type
+            bufs = arr.buffers()
+            validity = bufs[0].address if (bufs[0] is not None and arr.null_count > 0) else None
+            n, off = len(arr), arr.offset
+            if pa.types.is_int64(typ) or pa.types.is_float64(typ) or pa.types.is_int32(typ) or pa.types.is_float32(typ):
+                dt = {pa.int64(): F.TG_INT64, pa.float64(): F.TG_FLOAT64, pa.int32(): F.TG_INT32, pa.float32(): F.TG_FLOAT32}[typ]
+                w = 8 if dt in (F.TG_INT64, F.TG_FLOAT64) else 4
+                vals = (bufs[1].address + off * w) if bufs[1] is not None else None
+                F.check(F.lib().tg_table_append_host(t, col_name.encode(), dt, n, vals, None, validity, off))
+            elif pa.types.is_string(typ):
+                offs = (bufs[1].address + off * 4) if bufs[1] is not None else None
+                if offs is None:  # zero-length array without buffers
+                    zero = (C.c_int32 * 1)(0)
+                    offs = C.addressof(zero)
+                vals = bufs[2].address if bufs[2] is not None else None
+                F.check(F.lib().tg_table_append_host(t, col_name.encode(), F.TG_UTF8, n, vals, offs, validity, off))
+            elif pa.types.is_boolean(typ):
+                vals = bufs[1].address if bufs[1] is not None else None
+                F.check(F.lib().tg_table_append_host(t, col_name.encode(), F.TG_BOOL, n, vals, None, validity, off))
+            else:
+                raise TypeError(f"column {col_name}: unsupported Arrow type {typ}")
+
+    def _append_batch_c(self, t, batch):
+        # Arrow C Data Interface: export the batch as a struct array, hand the two structs to the engine
+        schema_buf = (C.c_uint8 * 72)()
+        array_buf = (C.c_uint8 * 80)()
+        batch._export_to_c(C.addressof(array_buf), C.addressof(schema_buf))
+        try:
+            F.check(F.lib().tg_table_append_arrow(t, C.addressof(schema_buf), C.addressof(array_buf)))
+        finally:
+            # caller keeps ownership: call the release callbacks (offset 56 in ArrowSchema, 64 in ArrowArray)
+            rel_s = C.cast(C.addressof(schema_buf) + 56, C.POINTER(C.c_void_p))[0]
+            rel_a = C.cast(C.addressof(array_buf) + 64, C.POINTER(C.c_void_p))[0]
+            if rel_a:
+                C.CFUNCTYPE(None, C.c_void_p)(rel_a)(C.addressof(array_buf))
+            if rel_s:
+                C.CFUNCTYPE(None, C.c_void_p)(rel_s)(C.addressof(schema_buf))
+
+    def register_device_table(self, name: str, columns: Dict[str, dict], keepalive=None):
+        """Adopt HBM-resident Arrow buffers without copying. columns[name] = dict(dtype=TG_*, n_rows=,
+        values=ptr, validity=ptr|None, offsets=ptr|None, n_value_bytes=int). Pointers are device addresses."""
+        t = self._create(name)
+        for col, d in columns.items():
+            F.check(F.lib().tg_table_adopt_device(t, col.encode(), d["dtype"], d["n_rows"], d.get("values"),
+                                                  d.get("offsets"), d.get("validity"), d.get("n_value_bytes", 0)))
+        self._keepalive[name] = keepalive
+        return t
+
+
+def _to_arrow(v):
+    if pa is not None and isinstance(v, (pa.Array, pa.ChunkedArray)):
+        return v.combine_chunks() if isinstance(v, pa.ChunkedArray) else v
+    if isinstance(v, tuple):
+        vals, mask = v
+        return pa.array(np.asarray(vals), mask=~np.asarray(mask, dtype=bool))
+    if isinstance(v, np.ndarray):
+        return pa.array(v)
+    return pa.array(v)
+
+
+# ----------------------------------------------------------------------------- plan ----
+class Plan:
+    """Thin RAII wrapper of tg_plan."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        F.check(F.lib().tg_plan_create(C.byref(self._h)))
+
+    def __del__(self):
+        try:
+            if self._h:
+                F.lib().tg_plan_destroy(self._h)
+                self._h = C.c_void_p()
+        except Exception:
+            pass
+
+    @property
+    def handle(self):
+        return self._h
+
+    def execute(self, ctx: SessionContext, table: str = "data"):
+        F.check(F.lib().tg_plan_execute(ctx.handle, self._h, table.encode()))
+
+    def execute_partial(self, ctx: SessionContext, table: str = "data"):
+        F.check(F.lib().tg_plan_execute_partial(ctx.handle, self._h, table.encode()))
+
+    def partial_export(self) -> bytes:
+        n = C.c_size_t()
+        F.check(F.lib().tg_plan_partial_size(self._h, C.byref(n)))
+        buf = C.create_string_buffer(n.value)
+        F.check(F.lib().tg_plan_partial_export(self._h, buf, n.value))
+        return buf.raw
+
+    def partial_reset(self):
+        F.check(F.lib().tg_plan_partial_reset(self._h))
+
+    def partial_merge(self, blob: bytes):
+        F.check(F.lib().tg_plan_partial_merge(self._h, blob, len(blob)))
+
+    def finalize(self):
+        F.check(F.lib().tg_plan_finalize(self._h))
+
+    def result(self, slot: int) -> ConstraintResult:
+        r = F.tg_result()
+        F.check(F.lib().tg_plan_result(self._h, slot, C.byref(r)))
+        return ConstraintResult(ConstraintStatus(r.status), r.metric if r.has_metric else None,
+                                r.message.decode("utf-8", "replace") if r.message else None,
+                                r.name.decode() if r.name else "", r.error_code)
+
+    def analyzer_result(self, slot: int):
+        r = F.tg_analyzer_result()
+        F.check(F.lib().tg_plan_analyzer_result(self._h, slot, C.byref(r)))
+        m = {}
+        n = F.lib().tg_plan_map_size(self._h, slot)
+        for i in range(max(n, 0)):
+            k, v = C.c_char_p(), C.c_double()
+            F.check(F.lib().tg_plan_map_entry(self._h, slot, i, C.byref(k), C.byref(v)))
+            m[k.value.decode()] = v.value
+        return AnalyzerOutput(list(r.u), list(r.f), r.metric_kind, r.error, r.metric_double, r.metric_long,
+                              r.metric_key.decode() if r.metric_key else "",
+                              r.message.decode("utf-8", "replace") if r.message else None, m)
+
+    def stats(self):
+        s = F.tg_exec_stats()
+        F.check(F.lib().tg_plan_exec_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in F.tg_exec_stats._fields_}
+
+
+@dataclass
+class AnalyzerOutput:
+    u: List[int]
+    f: List[float]
+    metric_kind: int   # 0 Double, 1 Long, 2 Map, 3 none
+    error: int         # 0 ok, 1 NoData, 2 InvalidData
+    metric_double: float
+    metric_long: int
+    metric_key: str
+    message: Optional[str]
+    map: Dict[str, float]
+
+    @property
+    def metric(self):
+        if self.error:
+            return None
+        return {0: self.metric_double, 1: self.metric_long, 2: self.map}.get(self.metric_kind)
+
+
+def _strs(cols):
+    arr = (C.c_char_p * max(1, len(cols)))(*[c.encode() for c in cols])
+    return arr, len(cols)
+
+
+def _opt(s):
+    return s.encode() if s is not None else None
+
+
+# ----------------------------------------------------------------------------- constraints ----
+class Constraint:
+    """core/constraint.rs:186-225 — evaluate(ctx) -> ConstraintResult; name(); column()."""
+
+    def _add_to(self, plan: Plan) -> int:
+        raise NotImplementedError
+
+    def evaluate(self, ctx: SessionContext, table: str = "data") -> ConstraintResult:
+        plan = Plan()
+        slot = self._add_to(plan)
+        plan.execute(ctx, table)
+        return plan.result(slot)
+
+    def name(self):
+        plan = Plan()
+        slot = self._add_to(plan)
+        plan.finalize()
+        return plan.result(slot).name
+
+
+class CompletenessConstraint(Constraint):  # constraints/completeness.rs
+    def __init__(self, columns, threshold=1.0, operator=None):
+        self.columns = [columns] if isinstance(columns, str) else list(columns)
+        self.threshold = threshold
+        self.operator = operator or LogicalOperator.All
+        self._validate()
+
+    def _validate(self):
+        self._add_to(Plan())
+
+    @staticmethod
+    def with_threshold(columns, threshold):
+        return CompletenessConstraint(columns, threshold)
+
+    @staticmethod
+    def complete(columns):
+        return CompletenessConstraint(columns, 1.0)
+
+    @staticmethod
+    def with_operator(columns, operator, threshold):
+        return CompletenessConstraint(columns, threshold, operator)
+
+    def _add_to(self, plan):
+        arr, n = _strs(self.columns)
+        return F.check_slot(F.lib().tg_plan_add_completeness(plan.handle, arr, n, self.threshold,
+                                                             self.operator.op, self.operator.n))
+
+
+class SizeConstraint(Constraint):  # constraints/size.rs
+    def __init__(self, assertion: Assertion):
+        self.assertion = assertion
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_size(plan.handle, self.assertion.c()))
+
+
+class StatisticalConstraint(Constraint):  # constraints/statistics.rs:120-322
+    def __init__(self, column, statistic: StatisticType, assertion: Assertion, percentile: float = 0.0):
+        self.column, self.statistic, self.assertion, self.percentile = column, statistic, assertion, percentile
+        self._add_to(Plan())
+
+    @staticmethod
+    def min(c, a): return StatisticalConstraint(c, StatisticType.Min, a)
+    @staticmethod
+    def max(c, a): return StatisticalConstraint(c, StatisticType.Max, a)
+    @staticmethod
+    def mean(c, a): return StatisticalConstraint(c, StatisticType.Mean, a)
+    @staticmethod
+    def sum(c, a): return StatisticalConstraint(c, StatisticType.Sum, a)
+    @staticmethod
+    def standard_deviation(c, a): return StatisticalConstraint(c, StatisticType.StandardDeviation, a)
+    @staticmethod
+    def variance(c, a): return StatisticalConstraint(c, StatisticType.Variance, a)
+    @staticmethod
+    def median(c, a): return StatisticalConstraint(c, StatisticType.Median, a)
+    @staticmethod
+    def percentile_(c, p, a): return StatisticalConstraint(c, StatisticType.Percentile, a, p)
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_statistic(plan.handle, self.column.encode(), self.statistic.value,
+                                                          self.percentile, self.assertion.c()))
+
+
+class MultiStatisticalConstraint(Constraint):  # constraints/statistics.rs:385-504
+    def __init__(self, column, statistics):
+        self.column, self.statistics = column, list(statistics)
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        n = len(self.statistics)
+        kinds = (C.c_int32 * max(1, n))(*[s[0].value if isinstance(s[0], StatisticType) else s[0][0].value for s in self.statistics])
+        pcts = (C.c_double * max(1, n))(*[0.0 if isinstance(s[0], StatisticType) else s[0][1] for s in self.statistics])
+        asr = (F.tg_assertion * max(1, n))(*[s[1].c() for s in self.statistics])
+        return F.check_slot(F.lib().tg_plan_add_multi_statistic(plan.handle, self.column.encode(), kinds, pcts, asr, n))
+
+
+class FormatConstraint(Constraint):  # constraints/format.rs:482-843
+    def __init__(self, column, format: FormatType, threshold, options: FormatOptions = None, arg=None, flag=False):
+        self.column, self.format, self.threshold = column, format, threshold
+        self.options = options or FormatOptions()
+        self.arg, self.flag = arg, flag
+        self._add_to(Plan())
+
+    @staticmethod
+    def new(column, format, threshold, options, arg=None, flag=False):
+        return FormatConstraint(column, format, threshold, options, arg, flag)
+
+    @staticmethod
+    def email(c, t): return FormatConstraint(c, FormatType.Email, t)
+    @staticmethod
+    def url(c, t, allow_localhost): return FormatConstraint(c, FormatType.Url, t, flag=allow_localhost)
+    @staticmethod
+    def credit_card(c, t, detect_only): return FormatConstraint(c, FormatType.CreditCard, t, flag=detect_only)
+    @staticmethod
+    def phone(c, t, country=None): return FormatConstraint(c, FormatType.Phone, t, FormatOptions(trim_before_check=True), arg=country)
+    @staticmethod
+    def postal_code(c, t, country): return FormatConstraint(c, FormatType.PostalCode, t, FormatOptions(trim_before_check=True), arg=country)
+    @staticmethod
+    def uuid(c, t): return FormatConstraint(c, FormatType.UUID, t)
+    @staticmethod
+    def ipv4(c, t): return FormatConstraint(c, FormatType.IPv4, t)
+    @staticmethod
+    def ipv6(c, t): return FormatConstraint(c, FormatType.IPv6, t)
+    @staticmethod
+    def json(c, t): return FormatConstraint(c, FormatType.Json, t)
+    @staticmethod
+    def iso8601_datetime(c, t): return FormatConstraint(c, FormatType.Iso8601DateTime, t)
+    @staticmethod
+    def regex(c, pattern, t): return FormatConstraint(c, FormatType.Regex, t, arg=pattern)
+    @staticmethod
+    def social_security_number(c, t): return FormatConstraint(c, FormatType.SocialSecurityNumber, t, FormatOptions(trim_before_check=True))
+
+    def _add_to(self, plan):
+        o = F.tg_format_options(int(self.options.case_sensitive), int(self.options.trim_before_check),
+                                int(self.options.null_is_valid))
+        return F.check_slot(F.lib().tg_plan_add_format(plan.handle, self.column.encode(), self.format.value,
+                                                       _opt(self.arg), int(bool(self.flag)), self.threshold, C.byref(o)))
+
+
+class UniquenessConstraint(Constraint):  # constraints/uniqueness.rs
+    def __init__(self, columns, uniqueness_type: UniquenessType, threshold=1.0, assertion: Assertion = None,
+                 null_handling: NullHandling = NullHandling.Exclude):
+        self.columns = [columns] if isinstance(columns, str) else list(columns)
+        self.uniqueness_type, self.threshold = uniqueness_type, threshold
+        self.assertion = assertion or Assertion.Equals(0.0)
+        self.null_handling = null_handling
+        self._add_to(Plan())
+
+    @staticmethod
+    def full_uniqueness(column, threshold): return UniquenessConstraint([column], UniquenessType.FullUniqueness, threshold)
+    @staticmethod
+    def full_uniqueness_multi(columns, threshold): return UniquenessConstraint(columns, UniquenessType.FullUniqueness, threshold)
+    @staticmethod
+    def distinctness(columns, assertion): return UniquenessConstraint(columns, UniquenessType.Distinctness, assertion=assertion)
+    @staticmethod
+    def unique_value_ratio(columns, assertion): return UniquenessConstraint(columns, UniquenessType.UniqueValueRatio, assertion=assertion)
+    @staticmethod
+    def primary_key(columns): return UniquenessConstraint(columns, UniquenessType.PrimaryKey)
+    @staticmethod
+    def unique_with_nulls(columns, threshold, null_handling): return UniquenessConstraint(columns, UniquenessType.UniqueWithNulls, threshold, null_handling=null_handling)
+    @staticmethod
+    def unique_composite(columns, threshold, null_handling, case_sensitive=True): return UniquenessConstraint(columns, UniquenessType.UniqueComposite, threshold, null_handling=null_handling)
+
+    def column(self):
+        return self.columns[0] if len(self.columns) == 1 else None
+
+    def _add_to(self, plan):
+        arr, n = _strs(self.columns)
+        return F.check_slot(F.lib().tg_plan_add_uniqueness(plan.handle, arr, n, self.uniqueness_type.value,
+                                                           self.threshold, self.assertion.c(), self.null_handling.value))
+
+
+class CorrelationConstraint(Constraint):  # constraints/correlation.rs
+    def __init__(self, column1, column2, kind: CorrelationType, assertion: Assertion):
+        self.column1, self.column2, self.kind, self.assertion = column1, column2, kind, assertion
+        self._add_to(Plan())
+
+    @staticmethod
+    def pearson(c1, c2, assertion): return CorrelationConstraint(c1, c2, CorrelationType.Pearson, assertion)
+    @staticmethod
+    def spearman(c1, c2, assertion): return CorrelationConstraint(c1, c2, CorrelationType.Spearman, assertion)
+    @staticmethod
+    def covariance(c1, c2, assertion): return CorrelationConstraint(c1, c2, CorrelationType.Covariance, assertion)
+    @staticmethod
+    def independence(c1, c2, max_correlation): return CorrelationConstraint(c1, c2, CorrelationType.Independence, Assertion(0, max_correlation))
+    @staticmethod
+    def correlation_range(c1, c2, lo, hi): return CorrelationConstraint(c1, c2, CorrelationType.Range, Assertion.Between(lo, hi))
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_correlation(plan.handle, self.column1.encode(), self.column2.encode(),
+                                                            self.kind.value, self.assertion.c()))
+
+
+class CustomSqlConstraint(Constraint):  # constraints/custom_sql.rs
+    def __init__(self, expression: str, hint: Optional[str] = None):
+        self.expression, self.hint = expression, hint
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_custom_sql(plan.handle, self.expression.encode(), _opt(self.hint)))
+
+
+class ForeignKeyConstraint(Constraint):  # constraints/foreign_key.rs
+    def __init__(self, child_column: str, parent_column: str):
+        self.child_column, self.parent_column = child_column, parent_column
+        self._allow_nulls, self._max = False, 100
+
+    def allow_nulls(self, allow: bool):
+        self._allow_nulls = allow
+        return self
+
+    def max_violations_reported(self, n: int):
+        self._max = n
+        return self
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_foreign_key(plan.handle, self.child_column.encode(),
+                                                            self.parent_column.encode(), int(self._allow_nulls), self._max))
+
+
+# ----------------------------------------------------------------------------- Check / Suite ----
+@dataclass
+class Check:  # core/check.rs
+    name: str
+    level: Level = Level.Error
+    description: Optional[str] = None
+    constraints: List[Constraint] = field(default_factory=list)
+
+    @staticmethod
+    def builder(name):
+        return CheckBuilder(name)
+
+
+class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
+    def __init__(self, name):
+        self._c = Check(name)
+
+    def level(self, lvl: Level):
+        self._c.level = lvl
+        return self
+
+    def description(self, d):
+        self._c.description = d
+        return self
+
+    def constraint(self, c: Constraint):
+        self._c.constraints.append(c)
+        return self
+
+    def has_size(self, assertion): return self.constraint(SizeConstraint(assertion))
+    def completeness(self, columns, threshold=1.0, operator=None): return self.constraint(CompletenessConstraint(columns, threshold, operator))
+    def validates_uniqueness(self, columns, threshold=1.0): return self.constraint(UniquenessConstraint(columns, UniquenessType.FullUniqueness, threshold))
+    def validates_distinctness(self, columns, assertion): return self.constraint(UniquenessConstraint.distinctness(columns, assertion))
+    def validates_unique_value_ratio(self, columns, assertion): return self.constraint(UniquenessConstraint.unique_value_ratio(columns, assertion))
+    def validates_primary_key(self, columns): return self.constraint(UniquenessConstraint.primary_key(columns))
+    def validates_uniqueness_with_nulls(self, columns, threshold, null_handling): return self.constraint(UniquenessConstraint.unique_with_nulls(columns, threshold, null_handling))
+    def validates_regex(self, column, pattern, threshold): return self.constraint(FormatConstraint.regex(column, pattern, threshold))
+    def validates_email(self, column, threshold): return self.constraint(FormatConstraint.email(column, threshold))
+    def validates_url(self, column, threshold, allow_localhost=False): return self.constraint(FormatConstraint.url(column, threshold, allow_localhost))
+    def validates_credit_card(self, column, threshold, detect_only): return self.constraint(FormatConstraint.credit_card(column, threshold, detect_only))
+    def contains_ssn(self, column, threshold): return self.constraint(FormatConstraint.social_security_number(column, threshold))
+    def has_format(self, column, format, threshold, options=None, arg=None, flag=False): return self.constraint(FormatConstraint(column, format, threshold, options, arg, flag))
+    def statistic(self, column, stat, assertion, percentile=0.0): return self.constraint(StatisticalConstraint(column, stat, assertion, percentile))
+    def has_min(self, column, assertion): return self.statistic(column, StatisticType.Min, assertion)
+    def has_max(self, column, assertion): return self.statistic(column, StatisticType.Max, assertion)
+    def has_mean(self, column, assertion): return self.statistic(column, StatisticType.Mean, assertion)
+    def has_sum(self, column, assertion): return self.statistic(column, StatisticType.Sum, assertion)
+    def has_standard_deviation(self, column, assertion): return self.statistic(column, StatisticType.StandardDeviation, assertion)
+    def has_variance(self, column, assertion): return self.statistic(column, StatisticType.Variance, assertion)
+    def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
+    def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
+    def foreign_key(self, child, parent): return self.constraint(ForeignKeyConstraint(child, parent))
+
+    def build(self) -> Check:
+        return self._c
+
+
+@dataclass
+class ValidationIssue:  # core/result.rs:49-70
+    check_name: str
+    constraint_name: str
+    level: Level
+    message: str
+    metric: Optional[float] = None
+
+
+@dataclass
+class ValidationMetrics:  # core/result.rs:8-46
+    total_checks: int = 0
+    passed_checks: int = 0
+    failed_checks: int = 0
+    skipped_checks: int = 0
+    execution_time_ms: int = 0
+    custom_metrics: Dict[str, float] = field(default_factory=dict)
+
+
+@dataclass
+class ValidationReport:  # core/result.rs:72-118
+    suite_name: str
+    metrics: ValidationMetrics = field(default_factory=ValidationMetrics)
+    issues: List[ValidationIssue] = field(default_factory=list)
+    results: List[ConstraintResult] = field(default_factory=list)
+
+
+@dataclass
+class ValidationResult:  # core/result.rs:120-136
+    success: bool
+    report: ValidationReport
+
+    def is_success(self):
+        return self.success
+
+    def is_failure(self):
+        return not self.success
+
+
+class ValidationSuite:  # core/suite.rs
+    def __init__(self, name, checks=None, table_name="data"):
+        self.name, self.checks, self.table_name = name, list(checks or []), table_name
+
+    @staticmethod
+    def builder(name):
+        return ValidationSuiteBuilder(name)
+
+    def build_plan(self):
+        plan = Plan()
+        slots = []
+        for check in self.checks:
+            for c in check.constraints:
+                slots.append((check, c, c._add_to(plan)))
+        return plan, slots
+
+    def run(self, ctx: SessionContext, distributed: bool = False) -> ValidationResult:
+        """core/suite.rs:399-501 with run_sequential's reporting (:67-258) over ONE fused plan."""
+        t0 = time.perf_counter()
+        plan, slots = self.build_plan()
+        if distributed:
+            from .distributed import execute_distributed
+            execute_distributed(plan, ctx, self.table_name)
+        else:
+            plan.execute(ctx, self.table_name)
+        report = ValidationReport(self.name)
+        m = report.metrics
+        has_errors = False
+        for check, c, slot in slots:
+            r = plan.result(slot)
+            report.results.append(r)
+            m.total_checks += 1
+            if r.status is ConstraintStatus.Success:
+                m.passed_checks += 1
+            elif r.status is ConstraintStatus.Skipped:
+                m.skipped_checks += 1
+            else:
+                m.failed_checks += 1
+                if check.level is Level.Error:
+                    has_errors = True
+                report.issues.append(ValidationIssue(check.name, r.name, check.level,
+                                                     r.message or "Constraint failed", r.metric))
+            if r.metric is not None:
+                m.custom_metrics[f"{check.name}.{r.name}"] = r.metric  # suite.rs:203-209
+        m.execution_time_ms = int((time.perf_counter() - t0) * 1000)
+        self.last_plan = plan
+        return ValidationResult(not has_errors, report)
+
+
+class ValidationSuiteBuilder:
+    def __init__(self, name):
+        self._s = ValidationSuite(name)
+
+    def table_name(self, t):
+        self._s.table_name = t
+        return self
+
+    def check(self, c: Check):
+        self._s.checks.append(c)
+        return self
+
+    def build(self):
+        return self._s
+
+
+# ----------------------------------------------------------------------------- analyzers ----
+class Analyzer:
+    """analyzers/traits.rs:65-148: compute_state_from_data + compute_metric_from_state, fused in a plan."""
+    KIND = None
+
+    def __init__(self, column=None, column2=None, expression=None):
+        self.column, self.column2, self.expression = column, column2, expression
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_analyzer(plan.handle, self.KIND, _opt(self.column),
+                                                         _opt(self.column2), _opt(self.expression)))
+
+    def compute(self, ctx, table="data") -> AnalyzerOutput:
+        plan = Plan()
+        slot = self._add_to(plan)
+        plan.execute(ctx, table)
+        return plan.analyzer_result(slot)
+
+
+def _mk(kind, doc):
+    return type(doc, (Analyzer,), {"KIND": kind, "__doc__": doc})
+
+
+class SizeAnalyzer(Analyzer):
+    KIND = 0
+
+    def __init__(self):
+        super().__init__()
+
+
+CompletenessAnalyzer = _mk(1, "CompletenessAnalyzer")
+DistinctnessAnalyzer = _mk(2, "DistinctnessAnalyzer")
+MeanAnalyzer = _mk(3, "MeanAnalyzer")
+MinAnalyzer = _mk(4, "MinAnalyzer")
+MaxAnalyzer = _mk(5, "MaxAnalyzer")
+SumAnalyzer = _mk(6, "SumAnalyzer")
+StandardDeviationAnalyzer = _mk(7, "StandardDeviationAnalyzer")
+
+
+class CorrelationAnalyzer(Analyzer):
+    def __init__(self, c1, c2, kind=8):
+        super().__init__(c1, c2)
+        self.KIND = kind
+
+    @staticmethod
+    def pearson(c1, c2): return CorrelationAnalyzer(c1, c2, 8)
+    @staticmethod
+    def spearman(c1, c2): return CorrelationAnalyzer(c1, c2, 9)
+    @staticmethod
+    def covariance(c1, c2): return CorrelationAnalyzer(c1, c2, 10)
+
+
+class ComplianceAnalyzer(Analyzer):
+    KIND = 13
+
+    def __init__(self, name, predicate):
+        super().__init__(expression=predicate)
+        self.instance = name
+
+
+class KllSketchAnalyzer(Analyzer):
+    def __init__(self, column, k=200, quantiles=(0.25, 0.5, 0.75, 0.9, 0.95, 0.99)):
+        super().__init__(column)
+        self.k, self.quantiles = k, list(quantiles)
+
+    def _add_to(self, plan):
+        q = (C.c_double * max(1, len(self.quantiles)))(*self.quantiles)
+        return F.check_slot(F.lib().tg_plan_add_kll(plan.handle, self.column.encode(), self.k, q, len(self.quantiles)))
+
+
+class GroupedCompletenessAnalyzer(Analyzer):
+    """CompletenessAnalyzer::new(c).with_grouping(GroupingConfig::new(cols)) (analyzers/grouped.rs:198-203)"""
+
+    def __init__(self, column, group_columns, max_groups=10000, include_overall=True):
+        super().__init__(column)
+        self.group_columns, self.max_groups, self.include_overall = list(group_columns), max_groups, include_overall
+
+    def _add_to(self, plan):
+        arr, n = _strs(self.group_columns)
+        return F.check_slot(F.lib().tg_plan_add_grouped_completeness(plan.handle, self.column.encode(), arr, n,
+                                                                     self.max_groups, int(self.include_overall)))
+
+
+class AnalysisRunner:  # analyzers/runner.rs:149-202 — all analyzers in one plan instead of one scan each
+    def __init__(self):
+        self.analyzers = []
+
+    def add(self, a: Analyzer):
+        self.analyzers.append(a)
+        return self
+
+    def run(self, ctx, table="data", distributed=False) -> Dict[str, AnalyzerOutput]:
+        plan = Plan()
+        slots = [a._add_to(plan) for a in self.analyzers]
+        if distributed:
+            from .distributed import execute_distributed
+            execute_distributed(plan, ctx, table)
+        else:
+            plan.execute(ctx, table)
+        out = {}
+        for a, s in zip(self.analyzers, slots):
+            r = plan.analyzer_result(s)
+            out[r.metric_key] = r
+        self.last_plan = plan
+        return out

@@ -1,0 +1,405 @@
+// extern "C" surface declared in include/termgpu.h
+#include <cstring>
+
+#include "engine.hpp"
+#include "regex_dfa.hpp"
+
+namespace tg {
+const char* last_error_cstr();
+Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype);
+void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* values,
+                       const int32_t* offsets, const uint8_t* validity, int64_t bit_offset);
+void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* d_values,
+                        const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes);
+void table_append_arrow(Table& t, const void* schema_p, const void* array_p);
+}  // namespace tg
+
+using namespace tg;
+
+struct tg_engine {
+    Engine e;
+};
+struct tg_table {
+    Table t;
+};
+struct tg_plan {
+    Plan p;
+    std::string msg_scratch;
+};
+
+template <typename F>
+static tg_status guard(F&& f) {
+    try {
+        f();
+        return TG_OK;
+    } catch (Error& e) {
+        return fail(e.code, e.msg);
+    } catch (std::exception& e) {
+        return fail(TG_ERR_INTERNAL, e.what());
+    }
+}
+template <typename F>
+static int32_t guard_slot(F&& f) {
+    try {
+        return f();
+    } catch (Error& e) {
+        fail(e.code, e.msg);
+        return -(int32_t)e.code;
+    } catch (std::exception& e) {
+        fail(TG_ERR_INTERNAL, e.what());
+        return -(int32_t)TG_ERR_INTERNAL;
+    }
+}
+
+extern "C" {
+
+const char* tg_last_error(void) { return last_error_cstr(); }
+const char* tg_version(void) { return "termgpu 0.1.0 (sm_100a)"; }
+
+tg_status tg_engine_create(int device, tg_engine** out) {
+    return guard([&] {
+        if (!out) throw Error(TG_ERR_INVALID_ARG, "out is NULL");
+        int n = 0;
+        cudaError_t ce = cudaGetDeviceCount(&n);
+        if (ce != cudaSuccess || n == 0)
+            throw Error(TG_ERR_CUDA, std::string("no CUDA device available (termgpu has no CPU fallback): ") +
+                                         cudaGetErrorString(ce));
+        if (device < 0 || device >= n) throw Error(TG_ERR_INVALID_ARG, "device index out of range");
+        TG_CUDA(cudaSetDevice(device));
+        auto* h = new tg_engine();
+        Engine& e = h->e;
+        e.device = device;
+        cudaDeviceProp prop{};
+        TG_CUDA(cudaGetDeviceProperties(&prop, device));
+        e.sm_count = prop.multiProcessorCount;
+        TG_CUDA(cudaStreamCreateWithFlags(&e.stream, cudaStreamNonBlocking));
+        TG_CUDA(cudaStreamCreateWithFlags(&e.copy_stream, cudaStreamNonBlocking));
+        for (auto& ev : e.ev) TG_CUDA(cudaEventCreate(&ev));
+        e.pinned_bytes = 32u << 20;
+        for (int i = 0; i < 2; ++i) {
+            TG_CUDA(cudaMallocHost(&e.pinned[i], e.pinned_bytes));
+            TG_CUDA(cudaEventCreateWithFlags(&e.pinned_free[i], cudaEventDisableTiming));
+        }
+        *out = h;
+    });
+}
+
+void tg_engine_destroy(tg_engine* h) {
+    if (!h) return;
+    Engine& e = h->e;
+    cudaSetDevice(e.device);
+    cudaDeviceSynchronize();
+    for (auto& kv : e.tables) {
+        for (auto& c : kv.second->cols) {
+            if (c->values.owned && c->values.p) cudaFree(c->values.p);
+            if (c->offsets.owned && c->offsets.p) cudaFree(c->offsets.p);
+            if (c->validity.owned && c->validity.p) cudaFree(c->validity.p);
+        }
+    }
+    e.tables.clear();
+    if (e.d_scratch) cudaFree(e.d_scratch);
+    if (e.h_scratch) cudaFreeHost(e.h_scratch);
+    for (int i = 0; i < 2; ++i) {
+        if (e.pinned[i]) cudaFreeHost(e.pinned[i]);
+        if (e.pinned_free[i]) cudaEventDestroy(e.pinned_free[i]);
+    }
+    for (auto& ev : e.ev)
+        if (ev) cudaEventDestroy(ev);
+    if (e.stream) cudaStreamDestroy(e.stream);
+    if (e.copy_stream) cudaStreamDestroy(e.copy_stream);
+    delete h;
+}
+
+uint64_t tg_engine_launch_count(const tg_engine* h) { return h ? h->e.launches : 0; }
+void* tg_engine_stream(tg_engine* h) { return h ? (void*)h->e.stream : nullptr; }
+
+// tables are owned by the engine's registry; tg_table* is a borrowed handle
+tg_status tg_table_create(tg_engine* h, const char* name, tg_table** out) {
+    return guard([&] {
+        if (!h || !name || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        validate_identifier(name);
+        std::lock_guard<std::mutex> g(h->e.mu);
+        if (h->e.tables.count(name)) throw Error(TG_ERR_INVALID_ARG, std::string("table '") + name + "' already exists");
+        auto t = std::make_unique<Table>();
+        t->eng = &h->e;
+        t->name = name;
+        Table* raw = t.get();
+        h->e.tables[name] = std::move(t);
+        *out = reinterpret_cast<tg_table*>(raw);
+    });
+}
+
+tg_status tg_table_drop(tg_engine* h, const char* name) {
+    return guard([&] {
+        if (!h || !name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        auto it = h->e.tables.find(name);
+        if (it == h->e.tables.end()) throw Error(TG_ERR_TABLE_NOT_FOUND, std::string("table '") + name + "' not found");
+        cudaSetDevice(h->e.device);
+        cudaStreamSynchronize(h->e.copy_stream);
+        cudaStreamSynchronize(h->e.stream);
+        for (auto& c : it->second->cols) {
+            if (c->values.owned && c->values.p) cudaFree(c->values.p);
+            if (c->offsets.owned && c->offsets.p) cudaFree(c->offsets.p);
+            if (c->validity.owned && c->validity.p) cudaFree(c->validity.p);
+        }
+        h->e.tables.erase(it);
+    });
+}
+
+tg_status tg_table_lookup(tg_engine* h, const char* name, tg_table** out) {
+    return guard([&] {
+        if (!h || !name || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        auto it = h->e.tables.find(name);
+        if (it == h->e.tables.end()) throw Error(TG_ERR_TABLE_NOT_FOUND, std::string("table '") + name + "' not found");
+        *out = reinterpret_cast<tg_table*>(it->second.get());
+    });
+}
+
+int64_t tg_table_num_rows(const tg_table* t) { return t ? reinterpret_cast<const Table*>(t)->n_rows : -1; }
+
+tg_status tg_table_append_host(tg_table* t, const char* name, int32_t dtype, int64_t n_rows, const void* values,
+                               const int32_t* offsets, const uint8_t* validity, int64_t bit_offset) {
+    return guard([&] {
+        if (!t || !name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        table_append_host(*reinterpret_cast<Table*>(t), name, dtype, n_rows, values, offsets, validity, bit_offset);
+    });
+}
+
+tg_status tg_table_adopt_device(tg_table* t, const char* name, int32_t dtype, int64_t n_rows, const void* d_values,
+                                const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes) {
+    return guard([&] {
+        if (!t || !name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        table_adopt_device(*reinterpret_cast<Table*>(t), name, dtype, n_rows, d_values, d_offsets, d_validity,
+                           n_value_bytes);
+    });
+}
+
+tg_status tg_table_append_arrow(tg_table* t, const void* schema, const void* array) {
+    return guard([&] {
+        if (!t) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        table_append_arrow(*reinterpret_cast<Table*>(t), schema, array);
+    });
+}
+
+// ------------------------------------------------------------------ plan ----
+tg_status tg_plan_create(tg_plan** out) {
+    return guard([&] {
+        if (!out) throw Error(TG_ERR_INVALID_ARG, "out is NULL");
+        *out = new tg_plan();
+    });
+}
+void tg_plan_destroy(tg_plan* p) { delete p; }
+int32_t tg_plan_num_slots(const tg_plan* p) { return p ? (int32_t)p->p.slots.size() : 0; }
+
+static std::vector<std::string> strvec(const char* const* a, int32_t n) {
+    std::vector<std::string> v;
+    for (int32_t i = 0; i < n; ++i) v.emplace_back(a[i] ? a[i] : "");
+    return v;
+}
+
+int32_t tg_plan_add_completeness(tg_plan* p, const char* const* columns, int32_t n, double threshold, int32_t op,
+                                 int32_t op_n) {
+    return guard_slot([&] { return plan_add_completeness(p->p, strvec(columns, n), threshold, op, op_n); });
+}
+int32_t tg_plan_add_size(tg_plan* p, tg_assertion a) {
+    return guard_slot([&] { return plan_add_size(p->p, a); });
+}
+int32_t tg_plan_add_statistic(tg_plan* p, const char* column, int32_t kind, double pct, tg_assertion a) {
+    return guard_slot([&] { return plan_add_statistic(p->p, column ? column : "", kind, pct, a); });
+}
+int32_t tg_plan_add_multi_statistic(tg_plan* p, const char* column, const int32_t* kinds, const double* pcts,
+                                    const tg_assertion* as, int32_t n) {
+    return guard_slot([&] {
+        std::vector<StatReq> v;
+        for (int32_t i = 0; i < n; ++i) v.push_back(StatReq{kinds[i], pcts ? pcts[i] : 0.0, as[i], -1});
+        return plan_add_multi_statistic(p->p, column ? column : "", v);
+    });
+}
+int32_t tg_plan_add_format(tg_plan* p, const char* column, int32_t kind, const char* arg, int32_t flag,
+                           double threshold, const tg_format_options* opt) {
+    return guard_slot([&] {
+        tg_format_options o{1, 0, 1};
+        if (opt) o = *opt;
+        return plan_add_format(p->p, column ? column : "", kind, arg, flag, threshold, o);
+    });
+}
+int32_t tg_plan_add_uniqueness(tg_plan* p, const char* const* columns, int32_t n, int32_t kind, double threshold,
+                               tg_assertion a, int32_t null_handling) {
+    return guard_slot([&] { return plan_add_uniqueness(p->p, strvec(columns, n), kind, threshold, a, null_handling); });
+}
+int32_t tg_plan_add_correlation(tg_plan* p, const char* c1, const char* c2, int32_t kind, tg_assertion a) {
+    return guard_slot([&] { return plan_add_correlation(p->p, c1 ? c1 : "", c2 ? c2 : "", kind, a); });
+}
+int32_t tg_plan_add_custom_sql(tg_plan* p, const char* expr, const char* hint) {
+    return guard_slot([&] { return plan_add_custom_sql(p->p, expr ? expr : "", hint); });
+}
+int32_t tg_plan_add_foreign_key(tg_plan* p, const char* child, const char* parent, int32_t allow_nulls,
+                                int32_t max_examples) {
+    return guard_slot([&] { return plan_add_foreign_key(p->p, child ? child : "", parent ? parent : "", allow_nulls, max_examples); });
+}
+int32_t tg_plan_add_analyzer(tg_plan* p, int32_t kind, const char* column, const char* column2, const char* expr) {
+    return guard_slot([&] { return plan_add_analyzer(p->p, kind, column, column2, expr); });
+}
+int32_t tg_plan_add_kll(tg_plan* p, const char* column, int32_t k, const double* q, int32_t nq) {
+    return guard_slot([&] {
+        std::vector<double> v(q, q + (nq > 0 ? nq : 0));
+        return plan_add_kll(p->p, column ? column : "", k, v);
+    });
+}
+int32_t tg_plan_add_grouped_completeness(tg_plan* p, const char* column, const char* const* groups, int32_t n,
+                                         int32_t max_groups, int32_t include_overall) {
+    return guard_slot([&] {
+        return plan_add_grouped_completeness(p->p, column ? column : "", strvec(groups, n), max_groups, include_overall);
+    });
+}
+
+tg_status tg_plan_execute_partial(tg_engine* h, tg_plan* p, const char* table_name) {
+    return guard([&] {
+        if (!h || !p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        execute_partial(h->e, p->p, table_name ? table_name : "data");
+    });
+}
+tg_status tg_plan_execute(tg_engine* h, tg_plan* p, const char* table_name) {
+    return guard([&] {
+        if (!h || !p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        execute_partial(h->e, p->p, table_name ? table_name : "data");
+        p->p.finalize();
+    });
+}
+tg_status tg_plan_partial_size(const tg_plan* p, size_t* n) {
+    return guard([&] {
+        if (!p || !n) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        *n = p->p.partial_size();
+    });
+}
+tg_status tg_plan_partial_export(const tg_plan* p, void* buf, size_t n) {
+    return guard([&] {
+        if (!p || !buf) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        if (n < p->p.partial_size()) throw Error(TG_ERR_INVALID_ARG, "buffer too small");
+        p->p.partial_export((uint8_t*)buf);
+    });
+}
+tg_status tg_plan_partial_reset(tg_plan* p) {
+    return guard([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        p->p.reset_partials();
+    });
+}
+tg_status tg_plan_partial_merge(tg_plan* p, const void* buf, size_t n) {
+    return guard([&] {
+        if (!p || !buf) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        p->p.partial_merge((const uint8_t*)buf, n);
+    });
+}
+tg_status tg_plan_finalize(tg_plan* p) {
+    return guard([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        p->p.finalize();
+    });
+}
+
+tg_status tg_plan_result(const tg_plan* p, int32_t slot, tg_result* out) {
+    return guard([&] {
+        if (!p || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        if (slot < 0 || slot >= (int32_t)p->p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
+        if (!p->p.executed) throw Error(TG_ERR_INVALID_ARG, "plan has not been executed");
+        const Slot& s = p->p.slots[slot];
+        out->status = s.status;
+        out->has_metric = s.has_metric;
+        out->metric = s.metric;
+        out->message = s.has_message ? s.message.c_str() : nullptr;
+        out->name = s.name.c_str();
+        out->error_code = 0;
+        for (int a : s.aggs)
+            if (p->p.aggs[a].err != TG_OK && s.kind != SL_SQL) out->error_code = p->p.aggs[a].err;
+        out->reserved = 0;
+    });
+}
+
+tg_status tg_plan_analyzer_result(const tg_plan* p, int32_t slot, tg_analyzer_result* out) {
+    return guard([&] {
+        if (!p || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        if (slot < 0 || slot >= (int32_t)p->p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
+        if (!p->p.executed) throw Error(TG_ERR_INVALID_ARG, "plan has not been executed");
+        const Slot& s = p->p.slots[slot];
+        if (s.kind != SL_ANALYZER && s.kind != SL_KLL && s.kind != SL_GROUPED)
+            throw Error(TG_ERR_INVALID_ARG, "slot is not an analyzer");
+        *out = s.ares;
+        out->metric_key = s.metric_key.c_str();
+        out->message = s.has_message ? s.message.c_str() : nullptr;
+    });
+}
+
+int32_t tg_plan_map_size(const tg_plan* p, int32_t slot) {
+    if (!p || slot < 0 || slot >= (int32_t)p->p.slots.size()) return -1;
+    return (int32_t)p->p.slots[slot].map.size();
+}
+tg_status tg_plan_map_entry(const tg_plan* p, int32_t slot, int32_t i, const char** key, double* value) {
+    return guard([&] {
+        if (!p || slot < 0 || slot >= (int32_t)p->p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
+        const Slot& s = p->p.slots[slot];
+        if (i < 0 || i >= (int32_t)s.map.size()) throw Error(TG_ERR_INVALID_ARG, "map index out of range");
+        if (key) *key = s.map[i].first.c_str();
+        if (value) *value = s.map[i].second;
+    });
+}
+
+tg_status tg_plan_exec_stats(const tg_plan* p, tg_exec_stats* out) {
+    return guard([&] {
+        if (!p || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        *out = p->p.stats;
+    });
+}
+
+// ------------------------------------------------------------------ host helpers ----
+int32_t tg_assertion_evaluate(tg_assertion a, double value) { return assertion_evaluate(a, value) ? 1 : 0; }
+static int32_t copy_out(const std::string& s, char* buf, int32_t cap) {
+    if (buf && cap > 0) {
+        size_t n = std::min((size_t)cap - 1, s.size());
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int32_t)s.size();
+}
+int32_t tg_assertion_description(tg_assertion a, char* buf, int32_t cap) {
+    return copy_out(assertion_description(a), buf, cap);
+}
+int32_t tg_logical_evaluate(int32_t op, int32_t n, const uint8_t* results, int32_t n_results) {
+    std::vector<bool> v;
+    for (int32_t i = 0; i < n_results; ++i) v.push_back(results[i] != 0);
+    return logical_evaluate(op, n, v) ? 1 : 0;
+}
+tg_status tg_validate_identifier(const char* id) {
+    return guard([&] { validate_identifier(id ? id : ""); });
+}
+tg_status tg_validate_regex_pattern(const char* pattern) {
+    return guard([&] {
+        std::string p = pattern ? pattern : "";
+        validate_regex_pattern_text(p);
+        (void)compile_regex(p, false);
+    });
+}
+tg_status tg_validate_sql_expression(const char* e) {
+    return guard([&] { validate_sql_expression(e ? e : ""); });
+}
+const char* tg_format_pattern(int32_t kind, const char* arg, int32_t flag) {
+    static thread_local std::string s;
+    try {
+        s = format_pattern(kind, arg, flag);
+    } catch (Error& e) {
+        fail(e.code, e.msg);
+        return nullptr;
+    }
+    return s.c_str();
+}
+int32_t tg_regex_host_match(const char* pattern, int32_t icase, const uint8_t* s, int64_t len, int32_t* out) {
+    return (int32_t)guard([&] {
+        Dfa d = compile_regex(pattern ? pattern : "", icase != 0);
+        if (out) *out = d.match(s, len) ? 1 : 0;
+    });
+}
+int32_t tg_format_f64(double v, char* buf, int32_t cap) { return copy_out(fmt_f64(v), buf, cap); }
+
+}  // extern "C"

@@ -1,0 +1,501 @@
+// Engine: device memory, Arrow buffer marshalling (pinned double-buffered H2D), job dispatch, and the
+// planner of the fused numeric scan (which units run on which consumer warp of scan_kernel).
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+namespace tg {
+
+constexpr size_t PINNED_CHUNK = 32u << 20;
+constexpr size_t PAD = 256;
+
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+uint8_t* Engine::scratch(size_t bytes) {
+    if (bytes > scratch_cap) {
+        TG_CUDA(cudaStreamSynchronize(stream));
+        if (d_scratch) TG_CUDA(cudaFree(d_scratch));
+        scratch_cap = round_up(std::max(bytes, (size_t)1 << 20), 1 << 20);
+        TG_CUDA(cudaMalloc(&d_scratch, scratch_cap));
+    }
+    return d_scratch;
+}
+
+uint8_t* Engine::host_scratch(size_t bytes) {
+    if (bytes > h_scratch_cap) {
+        if (h_scratch) TG_CUDA(cudaFreeHost(h_scratch));
+        h_scratch_cap = round_up(std::max(bytes, (size_t)1 << 16), 1 << 16);
+        TG_CUDA(cudaMallocHost(&h_scratch, h_scratch_cap));
+    }
+    return h_scratch;
+}
+
+// grow a device buffer to hold `need` bytes (+ zeroed padding), preserving the first keep_bytes
+void Engine::dev_reserve(DevBuf& b, size_t need, size_t keep_bytes) {
+    need = round_up(need + PAD, PAD);
+    if (b.p && need <= b.cap) return;
+    size_t ncap = std::max(need, b.cap + b.cap / 2);
+    ncap = round_up(ncap, PAD);
+    uint8_t* np = nullptr;
+    TG_CUDA(cudaMalloc(&np, ncap));
+    TG_CUDA(cudaMemsetAsync(np, 0, ncap, copy_stream));
+    if (b.p && keep_bytes) TG_CUDA(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, copy_stream));
+    if (b.p) {
+        TG_CUDA(cudaStreamSynchronize(copy_stream));
+        TG_CUDA(cudaStreamSynchronize(stream));
+        if (b.owned) TG_CUDA(cudaFree(b.p));
+    }
+    b.p = np;
+    b.cap = ncap;
+    b.owned = true;
+}
+
+void Engine::h2d(void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return;
+    cudaPointerAttributes attr{};
+    bool pinned_src = false;
+    if (cudaPointerGetAttributes(&attr, src) == cudaSuccess) pinned_src = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    if (pinned_src) {
+        TG_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, copy_stream));
+        return;
+    }
+    // pageable source: stage through the pinned ring so the CPU memcpy of chunk i+1 overlaps the DMA of chunk i
+    size_t off = 0;
+    while (off < bytes) {
+        size_t n = std::min(PINNED_CHUNK, bytes - off);
+        int k = pinned_next;
+        pinned_next ^= 1;
+        TG_CUDA(cudaEventSynchronize(pinned_free[k]));
+        memcpy(pinned[k], (const uint8_t*)src + off, n);
+        TG_CUDA(cudaMemcpyAsync((uint8_t*)dst + off, pinned[k], n, cudaMemcpyHostToDevice, copy_stream));
+        TG_CUDA(cudaEventRecord(pinned_free[k], copy_stream));
+        off += n;
+    }
+}
+
+void Engine::sync_copies() { TG_CUDA(cudaStreamSynchronize(copy_stream)); }
+
+// ------------------------------------------------------------------ scan planning ----
+
+struct ScanOp {
+    int kind;  // UNIT_*
+    int agg;
+    Column* c0 = nullptr;
+    Column* c1 = nullptr;
+    double cost = 1.0;
+    std::vector<PredInstr> code;
+    std::vector<Column*> pred_cols;
+};
+
+struct TileCol {
+    Column* col;
+    bool need_values;
+};
+
+static int tile_col_index(std::vector<TileCol>& tc, Column* c, bool need_values) {
+    for (size_t i = 0; i < tc.size(); ++i)
+        if (tc[i].col == c) {
+            tc[i].need_values |= need_values;
+            return (int)i;
+        }
+    tc.push_back(TileCol{c, need_values});
+    return (int)tc.size() - 1;
+}
+
+static std::string no_field_msg(const Table& t, const std::string& col) {
+    return "Schema error: No field named " + col + ". Valid fields are " + t.valid_fields() + ".";
+}
+
+static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops) {
+    if (ops.empty()) return;
+    auto P = std::make_unique<ScanParams>();
+    memset(P.get(), 0, sizeof(ScanParams));
+    std::vector<TileCol> tcols;
+    // tile columns
+    struct OpCols {
+        int c0 = -1, c1 = -1;
+    };
+    std::vector<OpCols> oc(ops.size());
+    for (size_t i = 0; i < ops.size(); ++i) {
+        ScanOp& o = ops[i];
+        if (o.kind == UNIT_COUNT) oc[i].c0 = tile_col_index(tcols, o.c0, false);
+        else if (o.kind == UNIT_NUM_F64 || o.kind == UNIT_NUM_I64) oc[i].c0 = tile_col_index(tcols, o.c0, true);
+        else if (o.kind == UNIT_PAIR) {
+            oc[i].c0 = tile_col_index(tcols, o.c0, true);
+            oc[i].c1 = tile_col_index(tcols, o.c1, true);
+        } else if (o.kind == UNIT_PRED) {
+            for (auto* c : o.pred_cols) tile_col_index(tcols, c, true);
+        }
+    }
+    if (tcols.size() > (size_t)SCAN_MAX_COLS) throw Error(TG_ERR_UNSUPPORTED, "too many columns in one scan pass");
+    // predicate code was compiled against per-op column order; remap to tile indices
+    int code_len_total = 0;
+    for (auto& o : ops) code_len_total += (int)o.code.size();
+    if (code_len_total > SCAN_MAX_CODE) throw Error(TG_ERR_UNSUPPORTED, "predicates too long for one scan pass");
+
+    // bytes per row -> tile rows / stages
+    auto stage_bytes_for = [&](int tile_rows, std::vector<uint32_t>* val_off, std::vector<uint32_t>* bit_off) {
+        size_t off = 0;
+        for (size_t i = 0; i < tcols.size(); ++i) {
+            if (tcols[i].need_values) {
+                if (val_off) (*val_off)[i] = (uint32_t)off;
+                size_t b = tcols[i].col->dtype == TG_BOOL ? (size_t)tile_rows / 8 : (size_t)tile_rows * 8;
+                off += round_up(b, 128);
+            }
+            if (tcols[i].col->validity.p) {
+                if (bit_off) (*bit_off)[i] = (uint32_t)off;
+                off += round_up((size_t)tile_rows / 8, 128);
+            }
+        }
+        return off;
+    };
+    // units: replicate ops over row slices so ~SCAN_CONSUMER_WARPS units of similar cost exist
+    double total_cost = 0;
+    for (auto& o : ops) total_cost += o.cost;
+    int tile_rows = 4096;
+    int n_stages = 0;
+    std::vector<int> reps(ops.size(), 1);
+    size_t stage_bytes = 0, state_bytes = 0;
+    const size_t smem_budget = 227 * 1024 - 256;
+    for (; tile_rows >= 128; tile_rows /= 2) {
+        int n_units = 0;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            double share = ops[i].cost / total_cost * SCAN_CONSUMER_WARPS;
+            int r = 1;
+            while (r * 2 <= share + 0.5 && r * 2 <= tile_rows / 64) r *= 2;
+            if (ops[i].kind == UNIT_COUNT) r = 1;
+            reps[i] = r;
+            n_units += r;
+        }
+        if (n_units > SCAN_MAX_UNITS) throw Error(TG_ERR_UNSUPPORTED, "too many aggregates in one scan pass");
+        state_bytes = (size_t)n_units * SCAN_STATE_SLOTS * 32 * 8;
+        stage_bytes = stage_bytes_for(tile_rows, nullptr, nullptr);
+        if (stage_bytes == 0) stage_bytes = 128;
+        if (state_bytes + 3 * stage_bytes + 2 * SCAN_MAX_STAGES * 8 <= smem_budget) {
+            n_stages = (int)std::min<size_t>(SCAN_MAX_STAGES, (smem_budget - state_bytes - 2 * SCAN_MAX_STAGES * 8) / stage_bytes);
+            break;
+        }
+    }
+    if (n_stages < 2) throw Error(TG_ERR_UNSUPPORTED, "scan pass does not fit in shared memory");
+
+    std::vector<uint32_t> val_off(tcols.size(), 0), bit_off(tcols.size(), 0);
+    stage_bytes_for(tile_rows, &val_off, &bit_off);
+    P->n_rows = t.n_rows;
+    P->tile_rows = tile_rows;
+    P->n_tiles = (t.n_rows + tile_rows - 1) / tile_rows;
+    P->n_cols = (int)tcols.size();
+    P->n_stages = n_stages;
+    P->stage_bytes = (uint32_t)stage_bytes;
+    for (size_t i = 0; i < tcols.size(); ++i) {
+        Column* c = tcols[i].col;
+        ScanColDesc& d = P->cols[i];
+        d.values = tcols[i].need_values ? c->values.p : nullptr;
+        d.validity = c->validity.p;
+        d.kind = c->dtype == TG_FLOAT64 ? SC_F64 : c->dtype == TG_INT64 ? SC_I64 : c->dtype == TG_BOOL ? SC_BOOL : SC_BITS;
+        if (!tcols[i].need_values) d.kind = SC_BITS;
+        d.smem_val_off = val_off[i];
+        d.smem_bits_off = bit_off[i];
+        d.pivot = c->pivot;
+    }
+    // units + code
+    struct UnitTmp {
+        ScanUnitDesc d;
+        double cost;
+    };
+    std::vector<UnitTmp> units;
+    int code_off = 0;
+    for (size_t i = 0; i < ops.size(); ++i) {
+        ScanOp& o = ops[i];
+        int this_code_off = code_off;
+        if (o.kind == UNIT_PRED) {
+            for (auto ins : o.code) {
+                // operands referencing columns carry an index into o.pred_cols; translate to tile columns
+                auto fix = [&](uint8_t kind, uint16_t& idx) {
+                    if (kind == PK_COL_F64 || kind == PK_COL_I64 || kind == PK_COL_I64_AS_F64 || kind == PK_COL_BOOL)
+                        idx = (uint16_t)tile_col_index(tcols, o.pred_cols[idx], true);
+                };
+                fix(ins.a_kind, ins.a_idx);
+                fix(ins.b_kind, ins.b_idx);
+                P->code[code_off++] = ins;
+            }
+        }
+        const int r = reps[i];
+        const int slice = tile_rows / r;
+        for (int k = 0; k < r; ++k) {
+            UnitTmp u{};
+            u.d.kind = o.kind;
+            u.d.c0 = oc[i].c0;
+            u.d.c1 = oc[i].c1;
+            u.d.row0 = k * slice;
+            u.d.nrows = slice;
+            u.d.agg = (int)i;  // local aggregate index within this pass
+            u.d.code_off = this_code_off;
+            u.d.code_len = (int)o.code.size();
+            u.d.c0_is_i64 = o.c0 && o.c0->dtype == TG_INT64;
+            u.d.c1_is_i64 = o.c1 && o.c1->dtype == TG_INT64;
+            u.cost = o.cost / r;
+            units.push_back(u);
+        }
+    }
+    // LPT assignment of units to consumer warps
+    std::vector<int> order(units.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return units[a].cost > units[b].cost; });
+    double load[SCAN_CONSUMER_WARPS] = {0};
+    for (int idx : order) {
+        int best = 0;
+        for (int w = 1; w < SCAN_CONSUMER_WARPS; ++w)
+            if (load[w] < load[best]) best = w;
+        units[idx].d.warp = best;
+        load[best] += units[idx].cost;
+    }
+    P->n_units = (int)units.size();
+    P->n_aggs = (int)ops.size();
+    for (size_t i = 0; i < units.size(); ++i) P->units[i] = units[i].d;
+
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(P->n_tiles, 1), e.sm_count);
+    const size_t partial_bytes = (size_t)grid * P->n_units * SCAN_STATE_SLOTS * 8;
+    const size_t out_bytes = ops.size() * sizeof(ScanAggOut);
+    uint8_t* scr = e.scratch(round_up(partial_bytes, 256) + out_bytes);
+    P->partials = reinterpret_cast<uint64_t*>(scr);
+    ScanAggOut* d_out = reinterpret_cast<ScanAggOut*>(scr + round_up(partial_bytes, 256));
+
+    TG_CUDA(cudaEventRecord(e.ev[0], e.stream));
+    TG_CUDA(scan_launch(*P, grid, d_out, e.stream));
+    TG_CUDA(cudaEventRecord(e.ev[1], e.stream));
+    e.launches += 2;
+    p.stats.launches += 2;
+    ScanAggOut* h_out = reinterpret_cast<ScanAggOut*>(e.host_scratch(out_bytes));
+    TG_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    float ms = 0;
+    TG_CUDA(cudaEventElapsedTime(&ms, e.ev[0], e.ev[1]));
+    p.stats.scan_ms += ms;
+    p.stats.gpu_ms += ms;
+
+    auto u2d = [](uint64_t u) {
+        double d;
+        memcpy(&d, &u, 8);
+        return d;
+    };
+    for (size_t i = 0; i < ops.size(); ++i) {
+        Agg& a = p.aggs[ops[i].agg];
+        const uint64_t* s = h_out[i].s;
+        switch (ops[i].kind) {
+            case UNIT_COUNT:
+                a.u[0] = (uint64_t)t.n_rows;
+                a.u[1] = s[S_N];
+                break;
+            case UNIT_NUM_F64:
+            case UNIT_NUM_I64:
+                a.u[0] = s[S_N];
+                a.f[0] = ops[i].c0->pivot;
+                a.f[1] = u2d(s[S_SD]);
+                a.f[2] = u2d(s[S_SDD]);
+                a.f[5] = u2d(s[S_SX]);
+                if (ops[i].kind == UNIT_NUM_I64) {
+                    a.u[1] = s[S_ISUM];
+                    a.u[2] = s[S_MIN];
+                    a.u[3] = s[S_MAX];
+                    a.u[4] = 1;
+                } else {
+                    a.f[3] = u2d(s[S_MIN]);
+                    a.f[4] = u2d(s[S_MAX]);
+                }
+                break;
+            case UNIT_PAIR:
+                a.u[0] = s[P_N];
+                a.f[0] = ops[i].c0->pivot;
+                a.f[1] = ops[i].c1->pivot;
+                a.f[2] = u2d(s[P_SX]);
+                a.f[3] = u2d(s[P_SY]);
+                a.f[4] = u2d(s[P_SXX]);
+                a.f[5] = u2d(s[P_SYY]);
+                a.f[6] = u2d(s[P_SXY]);
+                break;
+            case UNIT_PRED:
+                a.u[0] = s[0];
+                a.u[1] = s[1];
+                a.u[2] = (uint64_t)t.n_rows;
+                break;
+        }
+    }
+}
+
+void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids) {
+    std::vector<ScanOp> ops;
+    uint64_t bytes = 0;
+    std::vector<Column*> counted_vals, counted_bits;
+    auto count_bytes = [&](Column* c, bool values) {
+        if (values && std::find(counted_vals.begin(), counted_vals.end(), c) == counted_vals.end()) {
+            counted_vals.push_back(c);
+            bytes += c->dtype == TG_BOOL ? (uint64_t)(t.n_rows + 7) / 8 : (uint64_t)t.n_rows * 8;
+        }
+        if (c->validity.p && std::find(counted_bits.begin(), counted_bits.end(), c) == counted_bits.end()) {
+            counted_bits.push_back(c);
+            bytes += (uint64_t)(t.n_rows + 7) / 8;
+        }
+    };
+    for (int id : agg_ids) {
+        Agg& a = p.aggs[id];
+        if (a.err != TG_OK) continue;
+        ScanOp o;
+        o.agg = id;
+        auto col = [&](const std::string& name) -> Column* {
+            Column* c = t.find(name);
+            if (!c) {
+                a.err = TG_ERR_COLUMN_NOT_FOUND;
+                a.err_msg = no_field_msg(t, name);
+            }
+            return c;
+        };
+        auto numeric = [&](Column* c) {
+            if (c->dtype == TG_INT64 || c->dtype == TG_FLOAT64) return true;
+            a.err = TG_ERR_TYPE_MISMATCH;
+            a.err_msg = "Error during planning: numeric aggregate is not supported for column '" + c->name +
+                        "' of this type";
+            return false;
+        };
+        switch (a.kind) {
+            case A_VALID: {
+                Column* c = col(a.cols[0]);
+                if (!c) break;
+                if (!c->validity.p) {  // no nulls: COUNT(c) == COUNT(*) without touching the device
+                    a.u[0] = (uint64_t)t.n_rows;
+                    a.u[1] = (uint64_t)t.n_rows;
+                    break;
+                }
+                o.kind = UNIT_COUNT;
+                o.c0 = c;
+                o.cost = 0.05;
+                count_bytes(c, false);
+                ops.push_back(std::move(o));
+            } break;
+            case A_NUM: {
+                Column* c = col(a.cols[0]);
+                if (!c || !numeric(c)) break;
+                o.kind = c->dtype == TG_INT64 ? UNIT_NUM_I64 : UNIT_NUM_F64;
+                o.c0 = c;
+                o.cost = c->dtype == TG_INT64 ? 1.4 : 1.0;
+                count_bytes(c, true);
+                ops.push_back(std::move(o));
+            } break;
+            case A_PAIR: {
+                Column* x = col(a.cols[0]);
+                if (!x) break;
+                Column* y = col(a.cols[1]);
+                if (!y || !numeric(x) || !numeric(y)) break;
+                o.kind = UNIT_PAIR;
+                o.c0 = x;
+                o.c1 = y;
+                o.cost = 1.5;
+                count_bytes(x, true);
+                count_bytes(y, true);
+                ops.push_back(std::move(o));
+            } break;
+            case A_PRED: {
+                if (!a.expr) break;
+                try {
+                    ColumnResolver res = [&](const std::string& name) -> ColumnBinding {
+                        Column* c = t.find(name);
+                        if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, no_field_msg(t, name));
+                        for (size_t i = 0; i < o.pred_cols.size(); ++i)
+                            if (o.pred_cols[i] == c) return ColumnBinding{(int)i, c->dtype};
+                        o.pred_cols.push_back(c);
+                        return ColumnBinding{(int)o.pred_cols.size() - 1, c->dtype};
+                    };
+                    compile_predicate(a.expr, res, o.code);
+                } catch (Error& er) {
+                    a.err = er.code;
+                    a.err_msg = er.msg;
+                    break;
+                }
+                o.kind = UNIT_PRED;
+                o.cost = 0.6 + 0.5 * (double)o.code.size();
+                for (auto* c : o.pred_cols) count_bytes(c, true);
+                ops.push_back(std::move(o));
+            } break;
+            default: break;
+        }
+    }
+    p.stats.bytes_scanned += bytes;
+    if (t.n_rows == 0) {
+        // nothing to scan: aggregates keep their zero state (COUNT(*) = 0)
+        for (auto& o : ops)
+            if (p.aggs[o.agg].kind == A_PRED) p.aggs[o.agg].u[2] = 0;
+        return;
+    }
+    // split into passes that fit the kernel's descriptor limits
+    size_t i = 0;
+    while (i < ops.size()) {
+        std::vector<ScanOp> pass;
+        int code = 0;
+        std::vector<Column*> cols;
+        while (i < ops.size() && pass.size() < 24) {
+            int add_code = (int)ops[i].code.size();
+            if (code + add_code > SCAN_MAX_CODE && !pass.empty()) break;
+            code += add_code;
+            pass.push_back(std::move(ops[i]));
+            ++i;
+        }
+        run_scan_pass(e, t, p, pass);
+    }
+}
+
+// ------------------------------------------------------------------ execute ----
+
+void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    p.reset_partials();
+    p.stats = tg_exec_stats{};
+    p.executed = false;
+    e.sync_copies();
+    auto it = e.tables.find(table_name);
+    Table* t = it == e.tables.end() ? nullptr : it->second.get();
+    std::vector<int> scan_ids, string_ids;
+    for (size_t i = 0; i < p.aggs.size(); ++i) {
+        Agg& a = p.aggs[i];
+        if (a.err != TG_OK) continue;
+        if (a.kind == A_FK) continue;  // uses its own tables
+        if (!t) {
+            a.err = TG_ERR_TABLE_NOT_FOUND;
+            a.err_msg = "Error during planning: table 'datafusion.public." + table_name + "' not found";
+            continue;
+        }
+        switch (a.kind) {
+            case A_ROWS: a.u[0] = (uint64_t)t->n_rows; break;
+            case A_VALID:
+            case A_NUM:
+            case A_PAIR:
+            case A_PRED: scan_ids.push_back((int)i); break;
+            case A_REGEX: string_ids.push_back((int)i); break;
+            default: break;
+        }
+    }
+    if (t && !scan_ids.empty()) exec_scan_jobs(e, *t, p, scan_ids);
+    if (t && !string_ids.empty()) exec_string_jobs(e, *t, p, string_ids);
+    for (size_t i = 0; i < p.aggs.size(); ++i) {
+        Agg& a = p.aggs[i];
+        if (a.err != TG_OK) continue;
+        try {
+            switch (a.kind) {
+                case A_DISTINCT: exec_distinct_job(e, *t, p, (int)i); break;
+                case A_FK: exec_fk_job(e, p, (int)i); break;
+                case A_KLL: exec_kll_job(e, *t, p, (int)i); break;
+                case A_GROUPED: exec_grouped_job(e, *t, p, (int)i); break;
+                case A_SPEARMAN: exec_spearman_job(e, *t, p, (int)i); break;
+                default: break;
+            }
+        } catch (Error& er) {
+            if (er.code == TG_ERR_CUDA) throw;
+            a.err = er.code;
+            a.err_msg = er.msg;
+        }
+    }
+}
+
+}  // namespace tg

@@ -1,0 +1,120 @@
+// Engine / table / column objects behind the C ABI. Device memory layout:
+// every column is ONE contiguous Arrow-layout buffer set in HBM (values, validity bitmap LSB-first,
+// int32 offsets for Utf8), 256-byte aligned, zero padded to a multiple of 256 bytes so TMA bulk copies
+// and 128-bit loads may over-read the tail.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "plan.hpp"
+#include "scan_defs.h"
+
+namespace tg {
+
+#define TG_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess)                                                                          \
+            throw ::tg::Error(TG_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));         \
+    } while (0)
+
+struct Engine;
+
+struct DevBuf {
+    uint8_t* p = nullptr;
+    size_t cap = 0;
+    bool owned = true;
+};
+
+struct Column {
+    std::string name;
+    int32_t dtype = 0;
+    int64_t n_rows = 0;
+    DevBuf values;      // fixed width: n*w bytes; Utf8: value bytes; Bool: bit-packed
+    DevBuf offsets;     // Utf8: (n+1) int32
+    DevBuf validity;    // p == nullptr: no nulls so far
+    int64_t value_bytes = 0;
+    int64_t null_count = 0;
+    uint8_t tail_byte = 0;   // host mirror of the last, partially filled validity byte
+    uint8_t tail_vbyte = 0;  // same for bit-packed Bool values
+    int32_t last_offset = 0;
+    bool pivot_set = false;
+    double pivot = 0.0;
+    bool adopted = false;
+    int elem_bytes() const {
+        switch (dtype) {
+            case TG_INT64: case TG_FLOAT64: return 8;
+            case TG_INT32: case TG_FLOAT32: return 4;
+            default: return 0;
+        }
+    }
+};
+
+struct Table {
+    Engine* eng = nullptr;
+    std::string name;
+    std::vector<std::unique_ptr<Column>> cols;
+    int64_t n_rows = 0;
+    Column* find(const std::string& n) {
+        for (auto& c : cols)
+            if (c->name == n) return c.get();
+        return nullptr;
+    }
+    std::string valid_fields() const {
+        std::string s;
+        for (size_t i = 0; i < cols.size(); ++i) {
+            if (i) s += ", ";
+            s += name + "." + cols[i]->name;
+        }
+        return s;
+    }
+};
+
+struct Engine {
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr;       // kernels
+    cudaStream_t copy_stream = nullptr;  // H2D staging
+    cudaEvent_t ev[8] = {};
+    uint8_t* pinned[2] = {nullptr, nullptr};
+    cudaEvent_t pinned_free[2] = {};
+    size_t pinned_bytes = 0;
+    int pinned_next = 0;
+    std::map<std::string, std::unique_ptr<Table>> tables;
+    std::mutex mu;
+    uint64_t launches = 0;
+    // scratch
+    uint8_t* d_scratch = nullptr;
+    size_t scratch_cap = 0;
+    uint8_t* h_scratch = nullptr;  // pinned
+    size_t h_scratch_cap = 0;
+
+    uint8_t* scratch(size_t bytes);
+    uint8_t* host_scratch(size_t bytes);
+    void dev_reserve(DevBuf& b, size_t need, size_t keep_bytes);
+    void h2d(void* dst, const void* src, size_t bytes);  // staged through the pinned ring unless src is pinned
+    void sync_copies();
+};
+
+// jobs (each fills the partial state of the aggregates it owns)
+void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);   // engine.cu + scan.cu
+void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // strings.cu
+void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id);                     // hashing.cu
+void exec_fk_job(Engine& e, Plan& p, int agg_id);                                     // hashing.cu
+void exec_kll_job(Engine& e, Table& t, Plan& p, int agg_id);                          // sketch.cu
+void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                      // hashing.cu
+void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
+
+void execute_partial(Engine& e, Plan& p, const std::string& table_name);
+
+// scan.cu
+size_t scan_smem_bytes(const ScanParams& P);
+cudaError_t scan_launch(const ScanParams& P, int grid, ScanAggOut* d_out, cudaStream_t stream);
+
+}  // namespace tg

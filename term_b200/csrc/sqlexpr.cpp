@@ -1,0 +1,588 @@
+#include "sqlexpr.hpp"
+
+#include <cmath>
+#include <cstdlib>
+
+namespace tg {
+
+namespace {
+
+struct Tok {
+    enum K { END, NUM_I, NUM_F, STR, IDENT, QIDENT, OP, LP, RP, COMMA } k;
+    std::string s;
+    int64_t i = 0;
+    double f = 0;
+};
+
+static std::string upper(std::string s) {
+    for (auto& c : s) c = (char)toupper((unsigned char)c);
+    return s;
+}
+
+struct Lexer {
+    const std::string& t;
+    size_t p = 0;
+    explicit Lexer(const std::string& text) : t(text) {}
+    [[noreturn]] void err(const std::string& m) { throw Error(TG_ERR_UNSUPPORTED, "SQL parser error: " + m); }
+    Tok next() {
+        while (p < t.size() && isspace((unsigned char)t[p])) ++p;
+        Tok k;
+        if (p >= t.size()) {
+            k.k = Tok::END;
+            return k;
+        }
+        char c = t[p];
+        if (isdigit((unsigned char)c) || (c == '.' && p + 1 < t.size() && isdigit((unsigned char)t[p + 1]))) {
+            size_t s = p;
+            bool is_f = false;
+            while (p < t.size() && isdigit((unsigned char)t[p])) ++p;
+            if (p < t.size() && t[p] == '.') {
+                is_f = true;
+                ++p;
+                while (p < t.size() && isdigit((unsigned char)t[p])) ++p;
+            }
+            if (p < t.size() && (t[p] == 'e' || t[p] == 'E')) {
+                size_t q = p + 1;
+                if (q < t.size() && (t[q] == '+' || t[q] == '-')) ++q;
+                if (q < t.size() && isdigit((unsigned char)t[q])) {
+                    is_f = true;
+                    p = q;
+                    while (p < t.size() && isdigit((unsigned char)t[p])) ++p;
+                }
+            }
+            std::string num = t.substr(s, p - s);
+            if (is_f) {
+                k.k = Tok::NUM_F;
+                k.f = strtod(num.c_str(), nullptr);
+            } else {
+                errno = 0;
+                long long v = strtoll(num.c_str(), nullptr, 10);
+                if (errno == ERANGE) {
+                    k.k = Tok::NUM_F;
+                    k.f = strtod(num.c_str(), nullptr);
+                } else {
+                    k.k = Tok::NUM_I;
+                    k.i = v;
+                }
+            }
+            return k;
+        }
+        if (isalpha((unsigned char)c) || c == '_') {
+            size_t s = p;
+            while (p < t.size() && (isalnum((unsigned char)t[p]) || t[p] == '_' || t[p] == '.')) ++p;
+            k.k = Tok::IDENT;
+            k.s = t.substr(s, p - s);
+            return k;
+        }
+        if (c == '"') {
+            ++p;
+            std::string s;
+            while (p < t.size()) {
+                if (t[p] == '"') {
+                    if (p + 1 < t.size() && t[p + 1] == '"') {
+                        s += '"';
+                        p += 2;
+                        continue;
+                    }
+                    break;
+                }
+                s += t[p++];
+            }
+            if (p >= t.size()) err("unterminated quoted identifier");
+            ++p;
+            k.k = Tok::QIDENT;
+            k.s = s;
+            return k;
+        }
+        if (c == '\'') {
+            ++p;
+            std::string s;
+            while (p < t.size()) {
+                if (t[p] == '\'') {
+                    if (p + 1 < t.size() && t[p + 1] == '\'') {
+                        s += '\'';
+                        p += 2;
+                        continue;
+                    }
+                    break;
+                }
+                s += t[p++];
+            }
+            if (p >= t.size()) err("unterminated string literal");
+            ++p;
+            k.k = Tok::STR;
+            k.s = s;
+            return k;
+        }
+        if (c == '(') { ++p; k.k = Tok::LP; return k; }
+        if (c == ')') { ++p; k.k = Tok::RP; return k; }
+        if (c == ',') { ++p; k.k = Tok::COMMA; return k; }
+        static const char* ops2[] = {"<=", ">=", "<>", "!=", "=="};
+        for (const char* o : ops2) {
+            if (t.compare(p, 2, o) == 0) {
+                p += 2;
+                k.k = Tok::OP;
+                k.s = o;
+                return k;
+            }
+        }
+        if (strchr("+-*/%<>=", c)) {
+            ++p;
+            k.k = Tok::OP;
+            k.s = std::string(1, c);
+            return k;
+        }
+        err(std::string("unexpected character '") + c + "'");
+    }
+};
+
+struct Parser {
+    Lexer lx;
+    Tok cur;
+    explicit Parser(const std::string& t) : lx(t) { cur = lx.next(); }
+    void adv() { cur = lx.next(); }
+    bool is_kw(const char* kw) const { return cur.k == Tok::IDENT && upper(cur.s) == kw; }
+    bool is_op(const char* o) const { return cur.k == Tok::OP && cur.s == o; }
+    [[noreturn]] void err(const std::string& m) { throw Error(TG_ERR_UNSUPPORTED, "SQL parser error: " + m); }
+
+    static ExprP mk(Expr::Kind k) {
+        auto e = std::make_shared<Expr>();
+        e->kind = k;
+        return e;
+    }
+    static ExprP bin(const std::string& op, ExprP a, ExprP b) {
+        auto e = mk(Expr::BINARY);
+        e->s = op;
+        e->args = {a, b};
+        return e;
+    }
+    static ExprP un(const std::string& op, ExprP a) {
+        auto e = mk(Expr::UNARY);
+        e->s = op;
+        e->args = {a};
+        return e;
+    }
+
+    ExprP parse_or() {
+        ExprP l = parse_and();
+        while (is_kw("OR")) {
+            adv();
+            l = bin("OR", l, parse_and());
+        }
+        return l;
+    }
+    ExprP parse_and() {
+        ExprP l = parse_not();
+        while (is_kw("AND")) {
+            adv();
+            l = bin("AND", l, parse_not());
+        }
+        return l;
+    }
+    ExprP parse_not() {
+        if (is_kw("NOT")) {
+            adv();
+            return un("NOT", parse_not());
+        }
+        return parse_cmp();
+    }
+    ExprP parse_cmp() {
+        ExprP l = parse_add();
+        while (true) {
+            if (cur.k == Tok::OP && (cur.s == "=" || cur.s == "==" || cur.s == "<>" || cur.s == "!=" ||
+                                     cur.s == "<" || cur.s == "<=" || cur.s == ">" || cur.s == ">=")) {
+                std::string op = cur.s;
+                if (op == "==") op = "=";
+                if (op == "!=") op = "<>";
+                adv();
+                l = bin(op, l, parse_add());
+                continue;
+            }
+            if (is_kw("IS")) {
+                adv();
+                bool neg = false;
+                if (is_kw("NOT")) {
+                    neg = true;
+                    adv();
+                }
+                auto e = mk(Expr::IS);
+                if (is_kw("NULL")) e->s = neg ? "NOTNULL" : "NULL";
+                else if (is_kw("TRUE")) e->s = neg ? "NOTTRUE" : "TRUE";
+                else if (is_kw("FALSE")) e->s = neg ? "NOTFALSE" : "FALSE";
+                else err("expected NULL, TRUE or FALSE after IS");
+                adv();
+                e->args = {l};
+                l = e;
+                continue;
+            }
+            bool neg = false;
+            if (is_kw("NOT")) {
+                // lookahead: NOT BETWEEN / NOT IN
+                size_t save_p = lx.p;
+                Tok save = cur;
+                adv();
+                if (is_kw("BETWEEN") || is_kw("IN")) neg = true;
+                else {
+                    lx.p = save_p;
+                    cur = save;
+                    break;
+                }
+            }
+            if (is_kw("BETWEEN")) {
+                adv();
+                ExprP lo = parse_add();
+                if (!is_kw("AND")) err("expected AND in BETWEEN");
+                adv();
+                ExprP hi = parse_add();
+                ExprP e = bin("AND", bin(">=", l, lo), bin("<=", l, hi));
+                l = neg ? un("NOT", e) : e;
+                continue;
+            }
+            if (is_kw("IN")) {
+                adv();
+                if (cur.k != Tok::LP) err("expected ( after IN");
+                adv();
+                ExprP e;
+                while (true) {
+                    ExprP item = parse_add();
+                    ExprP eq = bin("=", l, item);
+                    e = e ? bin("OR", e, eq) : eq;
+                    if (cur.k == Tok::COMMA) {
+                        adv();
+                        continue;
+                    }
+                    break;
+                }
+                if (cur.k != Tok::RP) err("expected ) after IN list");
+                adv();
+                l = neg ? un("NOT", e) : e;
+                continue;
+            }
+            break;
+        }
+        return l;
+    }
+    ExprP parse_add() {
+        ExprP l = parse_mul();
+        while (is_op("+") || is_op("-")) {
+            std::string op = cur.s;
+            adv();
+            l = bin(op, l, parse_mul());
+        }
+        return l;
+    }
+    ExprP parse_mul() {
+        ExprP l = parse_unary();
+        while (is_op("*") || is_op("/") || is_op("%")) {
+            std::string op = cur.s;
+            adv();
+            l = bin(op, l, parse_unary());
+        }
+        return l;
+    }
+    ExprP parse_unary() {
+        if (is_op("-")) {
+            adv();
+            ExprP a = parse_unary();
+            if (a->kind == Expr::LIT_I) {
+                a->i = (int64_t)(0 - (uint64_t)a->i);
+                return a;
+            }
+            if (a->kind == Expr::LIT_F) {
+                a->f = -a->f;
+                return a;
+            }
+            return un("NEG", a);
+        }
+        if (is_op("+")) {
+            adv();
+            return parse_unary();
+        }
+        return parse_primary();
+    }
+    ExprP parse_primary() {
+        if (cur.k == Tok::NUM_I) {
+            auto e = mk(Expr::LIT_I);
+            e->i = cur.i;
+            adv();
+            return e;
+        }
+        if (cur.k == Tok::NUM_F) {
+            auto e = mk(Expr::LIT_F);
+            e->f = cur.f;
+            adv();
+            return e;
+        }
+        if (cur.k == Tok::STR) {
+            auto e = mk(Expr::LIT_S);
+            e->s = cur.s;
+            adv();
+            return e;
+        }
+        if (cur.k == Tok::LP) {
+            adv();
+            ExprP e = parse_or();
+            if (cur.k != Tok::RP) err("expected )");
+            adv();
+            return e;
+        }
+        if (cur.k == Tok::QIDENT) {
+            auto e = mk(Expr::COL);
+            e->s = cur.s;
+            adv();
+            return e;
+        }
+        if (cur.k == Tok::IDENT) {
+            std::string name = cur.s, up = upper(cur.s);
+            if (up == "TRUE" || up == "FALSE") {
+                auto e = mk(Expr::LIT_B);
+                e->b = up == "TRUE";
+                adv();
+                return e;
+            }
+            if (up == "NULL") {
+                adv();
+                return mk(Expr::LIT_NULL);
+            }
+            adv();
+            if (cur.k == Tok::LP) {
+                adv();
+                auto e = mk(Expr::FUNC);
+                e->s = up;
+                if (cur.k != Tok::RP) {
+                    while (true) {
+                        e->args.push_back(parse_or());
+                        if (cur.k == Tok::COMMA) {
+                            adv();
+                            continue;
+                        }
+                        break;
+                    }
+                }
+                if (cur.k != Tok::RP) err("expected ) after function arguments");
+                adv();
+                return e;
+            }
+            auto e = mk(Expr::COL);
+            // unquoted identifiers are folded to lower case by the SQL parser (DataFusion normalises)
+            std::string low = name;
+            for (auto& ch : low) ch = (char)tolower((unsigned char)ch);
+            // qualified name t.c -> keep the column part
+            size_t dot = low.rfind('.');
+            e->s = dot == std::string::npos ? low : low.substr(dot + 1);
+            return e;
+        }
+        err("unexpected token");
+    }
+};
+
+// ---------------- compiler ----------------
+struct Operand {
+    uint8_t kind;   // PK_*
+    uint16_t idx;   // temp or tile column
+    uint64_t imm;
+    PredType type;
+};
+
+struct Compiler {
+    const ColumnResolver& resolve;
+    std::vector<PredInstr>& code;
+    bool temp_used[4] = {false, false, false, false};
+
+    int alloc_temp() {
+        for (int k = 0; k < 4; ++k)
+            if (!temp_used[k]) {
+                temp_used[k] = true;
+                return k;
+            }
+        throw Error(TG_ERR_UNSUPPORTED, "SQL expression too deeply nested for the predicate engine");
+    }
+    void release(const Operand& o) {
+        if (o.kind == PK_TEMP) temp_used[o.idx] = false;
+    }
+    static uint64_t d2u(double d) {
+        uint64_t u;
+        memcpy(&u, &d, 8);
+        return u;
+    }
+    static double u2d(uint64_t u) {
+        double d;
+        memcpy(&d, &u, 8);
+        return d;
+    }
+
+    Operand emit(uint8_t op, Operand a, Operand b, PredType type) {
+        // at most one immediate per instruction: spill `a` into a temp if both are immediates
+        if (a.kind == PK_IMM && b.kind == PK_IMM) a = emit(PO_MOV, a, Operand{PK_NULL, 0, 0, PT_NULL}, a.type);
+        release(a);
+        release(b);
+        int dst = alloc_temp();
+        PredInstr ins{};
+        ins.op = op;
+        ins.dst = (uint8_t)dst;
+        ins.a_kind = a.kind;
+        ins.a_idx = a.idx;
+        ins.b_kind = b.kind;
+        ins.b_idx = b.idx;
+        ins.imm = a.kind == PK_IMM ? a.imm : b.imm;
+        if ((int)code.size() >= SCAN_MAX_CODE) throw Error(TG_ERR_UNSUPPORTED, "SQL expression too long");
+        code.push_back(ins);
+        return Operand{PK_TEMP, (uint16_t)dst, 0, type};
+    }
+    Operand none() { return Operand{PK_NULL, 0, 0, PT_NULL}; }
+
+    Operand to_f64(Operand o) {
+        if (o.type == PT_F64 || o.type == PT_NULL) return o;
+        if (o.type != PT_I64) throw Error(TG_ERR_TYPE_MISMATCH, "cannot use a boolean value in arithmetic");
+        if (o.kind == PK_IMM) return Operand{PK_IMM, 0, d2u((double)(int64_t)o.imm), PT_F64};
+        if (o.kind == PK_COL_I64) return Operand{PK_COL_I64_AS_F64, o.idx, 0, PT_F64};
+        return emit(PO_I2F, o, none(), PT_F64);
+    }
+
+    Operand gen(const ExprP& e) {
+        switch (e->kind) {
+            case Expr::LIT_I: return Operand{PK_IMM, 0, (uint64_t)e->i, PT_I64};
+            case Expr::LIT_F: return Operand{PK_IMM, 0, d2u(e->f), PT_F64};
+            case Expr::LIT_B: return Operand{PK_IMM, 0, e->b ? 1ull : 0ull, PT_BOOL};
+            case Expr::LIT_NULL: return none();
+            case Expr::LIT_S:
+                throw Error(TG_ERR_UNSUPPORTED, "string literals are not supported by the predicate engine yet");
+            case Expr::COL: {
+                ColumnBinding b = resolve(e->s);
+                if (b.dtype == TG_INT64) return Operand{PK_COL_I64, (uint16_t)b.tile_col, 0, PT_I64};
+                if (b.dtype == TG_FLOAT64) return Operand{PK_COL_F64, (uint16_t)b.tile_col, 0, PT_F64};
+                if (b.dtype == TG_BOOL) return Operand{PK_COL_BOOL, (uint16_t)b.tile_col, 0, PT_BOOL};
+                throw Error(TG_ERR_UNSUPPORTED, "column '" + e->s + "' has a type the predicate engine does not support");
+            }
+            case Expr::UNARY: {
+                Operand a = gen(e->args[0]);
+                if (e->s == "NOT") {
+                    if (a.type != PT_BOOL && a.type != PT_NULL)
+                        throw Error(TG_ERR_TYPE_MISMATCH, "NOT requires a boolean operand");
+                    return emit(PO_NOT, a, none(), PT_BOOL);
+                }
+                if (a.type == PT_I64) return emit(PO_NEG_I, a, none(), PT_I64);
+                if (a.type == PT_F64) return emit(PO_NEG_F, a, none(), PT_F64);
+                if (a.type == PT_NULL) return a;
+                throw Error(TG_ERR_TYPE_MISMATCH, "unary minus requires a numeric operand");
+            }
+            case Expr::IS: {
+                Operand a = gen(e->args[0]);
+                if (e->s == "NULL") return emit(PO_ISNULL, a, none(), PT_BOOL);
+                if (e->s == "NOTNULL") return emit(PO_ISNOTNULL, a, none(), PT_BOOL);
+                if (a.type != PT_BOOL && a.type != PT_NULL)
+                    throw Error(TG_ERR_TYPE_MISMATCH, "IS TRUE/FALSE requires a boolean operand");
+                if (e->s == "TRUE") return emit(PO_ISTRUE, a, none(), PT_BOOL);
+                if (e->s == "FALSE") return emit(PO_ISFALSE, a, none(), PT_BOOL);
+                // IS NOT TRUE / IS NOT FALSE
+                Operand t = emit(e->s == "NOTTRUE" ? PO_ISTRUE : PO_ISFALSE, a, none(), PT_BOOL);
+                return emit(PO_NOT, t, none(), PT_BOOL);
+            }
+            case Expr::FUNC: {
+                if (e->s == "ABS" && e->args.size() == 1) {
+                    Operand a = gen(e->args[0]);
+                    if (a.type == PT_I64) return emit(PO_ABS_I, a, none(), PT_I64);
+                    if (a.type == PT_F64) return emit(PO_ABS_F, a, none(), PT_F64);
+                    if (a.type == PT_NULL) return a;
+                    throw Error(TG_ERR_TYPE_MISMATCH, "ABS requires a numeric operand");
+                }
+                throw Error(TG_ERR_UNSUPPORTED, "function " + e->s + " is not supported by the predicate engine");
+            }
+            case Expr::BINARY: {
+                const std::string& op = e->s;
+                if (op == "AND" || op == "OR") {
+                    Operand a = gen(e->args[0]);
+                    Operand b = gen(e->args[1]);
+                    if ((a.type != PT_BOOL && a.type != PT_NULL) || (b.type != PT_BOOL && b.type != PT_NULL))
+                        throw Error(TG_ERR_TYPE_MISMATCH, op + " requires boolean operands");
+                    return emit(op == "AND" ? PO_AND : PO_OR, a, b, PT_BOOL);
+                }
+                Operand a = gen(e->args[0]);
+                Operand b = gen(e->args[1]);
+                const bool arith = op == "+" || op == "-" || op == "*" || op == "/" || op == "%";
+                if (a.type == PT_NULL || b.type == PT_NULL) {
+                    // NULL op x -> NULL (typed as the result type)
+                    release(a);
+                    release(b);
+                    Operand n = none();
+                    n.type = arith ? PT_NULL : PT_BOOL;
+                    if (!arith) return emit(PO_MOV, none(), none(), PT_BOOL);
+                    return n;
+                }
+                if (a.type == PT_BOOL || b.type == PT_BOOL) {
+                    if (arith || a.type != b.type)
+                        throw Error(TG_ERR_TYPE_MISMATCH, "cannot apply '" + op + "' to boolean and numeric operands");
+                    // boolean comparison: payloads are 0/1 integers
+                    uint8_t o = op == "=" ? PO_EQ_I : op == "<>" ? PO_NE_I : op == "<" ? PO_LT_I
+                              : op == "<=" ? PO_LE_I : op == ">" ? PO_GT_I : PO_GE_I;
+                    return emit(o, a, b, PT_BOOL);
+                }
+                const bool use_f = a.type == PT_F64 || b.type == PT_F64;
+                if (use_f) {
+                    a = to_f64(a);
+                    b = to_f64(b);
+                }
+                if (arith) {
+                    uint8_t o;
+                    if (use_f) {
+                        if (op == "%") throw Error(TG_ERR_UNSUPPORTED, "% on floating point operands is not supported");
+                        o = op == "+" ? PO_ADD_F : op == "-" ? PO_SUB_F : op == "*" ? PO_MUL_F : PO_DIV_F;
+                    } else {
+                        o = op == "+" ? PO_ADD_I : op == "-" ? PO_SUB_I : op == "*" ? PO_MUL_I
+                          : op == "/" ? PO_DIV_I : PO_MOD_I;
+                    }
+                    return emit(o, a, b, use_f ? PT_F64 : PT_I64);
+                }
+                uint8_t o;
+                if (use_f)
+                    o = op == "=" ? PO_EQ_F : op == "<>" ? PO_NE_F : op == "<" ? PO_LT_F
+                      : op == "<=" ? PO_LE_F : op == ">" ? PO_GT_F : PO_GE_F;
+                else
+                    o = op == "=" ? PO_EQ_I : op == "<>" ? PO_NE_I : op == "<" ? PO_LT_I
+                      : op == "<=" ? PO_LE_I : op == ">" ? PO_GT_I : PO_GE_I;
+                return emit(o, a, b, PT_BOOL);
+            }
+        }
+        throw Error(TG_ERR_INTERNAL, "bad expression node");
+    }
+};
+
+}  // namespace
+
+ExprP parse_sql_expr(const std::string& text) {
+    Parser p(text);
+    ExprP e = p.parse_or();
+    if (p.cur.k != Tok::END) p.err("unexpected trailing input");
+    return e;
+}
+
+void collect_columns(const ExprP& e, std::vector<std::string>& out) {
+    if (!e) return;
+    if (e->kind == Expr::COL) {
+        for (auto& c : out)
+            if (c == e->s) return;
+        out.push_back(e->s);
+    }
+    for (auto& a : e->args) collect_columns(a, out);
+}
+
+void compile_predicate(const ExprP& e, const ColumnResolver& resolve, std::vector<PredInstr>& code) {
+    Compiler c{resolve, code};
+    Operand r = c.gen(e);
+    if (r.type != PT_BOOL && r.type != PT_NULL)
+        throw Error(TG_ERR_TYPE_MISMATCH, "predicate must be a boolean expression");
+    // result must end in temp 0
+    if (!(r.kind == PK_TEMP && r.idx == 0)) {
+        c.release(r);
+        PredInstr ins{};
+        ins.op = PO_MOV;
+        ins.dst = 0;
+        ins.a_kind = r.kind;
+        ins.a_idx = r.idx;
+        ins.b_kind = PK_NULL;
+        ins.imm = r.imm;
+        code.push_back(ins);
+    }
+}
+
+}  // namespace tg

@@ -1,0 +1,43 @@
+// Predicate grammar for `satisfies` / ComplianceAnalyzer: parser + compiler to the scan kernel's
+// 3-address code. Declared subset of SQL (SURVEY §7 hard part d): column refs, numeric / boolean /
+// NULL literals, + - * / %, unary -, comparisons, AND / OR / NOT, IS [NOT] NULL, IS [NOT] TRUE|FALSE,
+// [NOT] BETWEEN, [NOT] IN (...), ABS(). Anything else -> TG_ERR_UNSUPPORTED.
+#pragma once
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "common.hpp"
+#include "scan_defs.h"
+
+namespace tg {
+
+struct Expr;
+using ExprP = std::shared_ptr<Expr>;
+
+struct Expr {
+    enum Kind { LIT_I, LIT_F, LIT_S, LIT_B, LIT_NULL, COL, UNARY, BINARY, IS, FUNC } kind;
+    int64_t i = 0;
+    double f = 0;
+    bool b = false;
+    std::string s;   // column name, string literal, operator or function name
+    std::vector<ExprP> args;
+};
+
+ExprP parse_sql_expr(const std::string& text);                 // throws Error(TG_ERR_UNSUPPORTED,...)
+void collect_columns(const ExprP& e, std::vector<std::string>& out);
+
+enum PredType { PT_I64, PT_F64, PT_BOOL, PT_NULL };
+
+struct ColumnBinding {
+    int tile_col;  // index in the scan tile
+    int dtype;     // tg_dtype
+};
+// resolve(name) returns the binding or throws Error(TG_ERR_COLUMN_NOT_FOUND,...)
+using ColumnResolver = std::function<ColumnBinding(const std::string&)>;
+
+// Appends instructions to `code`; result of the predicate ends in temp 0.
+void compile_predicate(const ExprP& e, const ColumnResolver& resolve, std::vector<PredInstr>& code);
+
+}  // namespace tg

@@ -1,0 +1,283 @@
+// Arrow buffer marshalling: values, validity bitmaps and Utf8 offsets staged into HBM.
+// Replaces MemTable registration on a SessionContext (e.g. constraints/completeness.rs:389-391 in the
+// reference tests, sources/mod.rs:48-66 in production) for the GPU path.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace tg {
+
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+__global__ void pick_pivot_kernel(const uint8_t* values, const uint32_t* validity, int64_t n_rows, int is_i64,
+                                  double* out) {
+    // one warp: first valid row -> pivot
+    const int lane = threadIdx.x;
+    const int64_t n_words = (n_rows + 31) / 32;
+    int64_t found = -1;
+    for (int64_t base = 0; base < n_words && found < 0; base += 32) {
+        const int64_t w = base + lane;
+        uint32_t bits = 0;
+        if (w < n_words) {
+            bits = validity ? validity[w] : 0xffffffffu;
+            const int64_t rem = n_rows - w * 32;
+            if (rem < 32) bits &= (1u << rem) - 1u;
+        }
+        const uint32_t any = __ballot_sync(0xffffffffu, bits != 0);
+        if (any) {
+            const int src = __ffs(any) - 1;
+            const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
+            found = (base + src) * 32 + (__ffs(b) - 1);
+        }
+    }
+    if (lane == 0) {
+        double v = 0.0;
+        if (found >= 0) {
+            if (is_i64) v = (double)reinterpret_cast<const int64_t*>(values)[found];
+            else v = reinterpret_cast<const double*>(values)[found];
+            if (!(v == v) || v - v != 0.0) v = 0.0;  // NaN / inf pivots would poison the shifted sums
+        }
+        *out = v;
+    }
+}
+
+static void set_pivot_host(Column& c, int32_t dtype, int64_t n, const void* values, const uint8_t* validity,
+                           int64_t bit_offset) {
+    if (c.pivot_set || (dtype != TG_INT64 && dtype != TG_FLOAT64)) return;
+    for (int64_t i = 0; i < n; ++i) {
+        bool ok = !validity || ((validity[(bit_offset + i) >> 3] >> ((bit_offset + i) & 7)) & 1);
+        if (!ok) continue;
+        double v = dtype == TG_INT64 ? (double)reinterpret_cast<const int64_t*>(values)[i]
+                                     : reinterpret_cast<const double*>(values)[i];
+        if (v == v && v - v == 0.0) {
+            c.pivot = v;
+            c.pivot_set = true;
+            return;
+        }
+        if (i > 4096) return;  // give up: keep 0.0 until a later batch
+    }
+}
+
+// append `n` bits taken from src starting at bit `src_off` (or all-ones when src == nullptr) to a device
+// bitmap that currently holds `have` bits; tail = host mirror of its last partial byte
+static void append_bits(Engine& e, DevBuf& buf, uint8_t& tail, int64_t have, const uint8_t* src, int64_t src_off,
+                        int64_t n, int64_t* zeros) {
+    const int64_t total = have + n;
+    e.dev_reserve(buf, (size_t)(total + 7) / 8, (size_t)(have + 7) / 8);
+    const int64_t first_byte = have / 8;
+    const int shift = (int)(have % 8);
+    const size_t out_bytes = (size_t)((total + 7) / 8 - first_byte);
+    std::vector<uint8_t> tmp(out_bytes + 8, 0);
+    if (shift) tmp[0] = tail & (uint8_t)((1u << shift) - 1);
+    int64_t z = 0;
+    if (!src) {
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t o = shift + i;
+            tmp[o >> 3] |= (uint8_t)(1u << (o & 7));
+        }
+    } else if (shift == 0 && (src_off & 7) == 0) {
+        memcpy(tmp.data(), src + src_off / 8, (size_t)(n + 7) / 8);
+        if (n & 7) tmp[(n - 1) / 8] &= (uint8_t)((1u << (n & 7)) - 1);
+        for (size_t i = 0; i < (size_t)(n + 7) / 8; ++i) z += 8 - __builtin_popcount(tmp[i]);
+        z -= (8 - (n & 7)) & 7;
+    } else {
+        for (int64_t i = 0; i < n; ++i) {
+            const int64_t s = src_off + i;
+            const int bit = (src[s >> 3] >> (s & 7)) & 1;
+            const int64_t o = shift + i;
+            tmp[o >> 3] |= (uint8_t)(bit << (o & 7));
+            z += !bit;
+        }
+    }
+    if (zeros) *zeros = z;
+    tail = (total & 7) ? tmp[out_bytes - 1] : 0;
+    // staged copy (tmp is pageable; h2d copies it into the pinned ring before returning)
+    e.h2d(buf.p + first_byte, tmp.data(), out_bytes);
+}
+
+Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype) {
+    Column* c = t.find(name);
+    if (c) {
+        if (c->dtype != dtype) throw Error(TG_ERR_TYPE_MISMATCH, "column '" + name + "' was registered with a different type");
+        return c;
+    }
+    validate_identifier(name);
+    auto nc = std::make_unique<Column>();
+    nc->name = name;
+    nc->dtype = dtype;
+    t.cols.push_back(std::move(nc));
+    return t.cols.back().get();
+}
+
+void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* values,
+                       const int32_t* offsets, const uint8_t* validity, int64_t bit_offset) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (n < 0) throw Error(TG_ERR_INVALID_ARG, "negative row count");
+    Column& c = *table_get_or_add(t, name, dtype);
+    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
+    const int64_t have = c.n_rows;
+    if (n == 0) {
+        t.n_rows = std::max(t.n_rows, c.n_rows);
+        return;
+    }
+    // ---- validity ----
+    bool has_nulls = false;
+    if (validity) {
+        // does the batch actually contain a null?
+        for (int64_t i = 0; i < n && !has_nulls;) {
+            const int64_t s = bit_offset + i;
+            if ((s & 7) == 0 && i + 8 <= n) {
+                has_nulls = validity[s >> 3] != 0xff;
+                i += 8;
+            } else {
+                has_nulls = !((validity[s >> 3] >> (s & 7)) & 1);
+                i += 1;
+            }
+        }
+    }
+    if (has_nulls && !c.validity.p && have > 0) {
+        // earlier batches had no bitmap: materialise all-ones for them
+        append_bits(e, c.validity, c.tail_byte, 0, nullptr, 0, have, nullptr);
+    }
+    if (has_nulls || c.validity.p) {
+        int64_t zeros = 0;
+        append_bits(e, c.validity, c.tail_byte, have, validity, bit_offset, n, &zeros);
+        c.null_count += zeros;
+    }
+    // ---- values ----
+    switch (dtype) {
+        case TG_INT64:
+        case TG_FLOAT64:
+        case TG_INT32:
+        case TG_FLOAT32: {
+            const size_t w = (size_t)c.elem_bytes();
+            e.dev_reserve(c.values, (size_t)(have + n) * w, (size_t)have * w);
+            e.h2d(c.values.p + (size_t)have * w, values, (size_t)n * w);
+            c.value_bytes = (have + n) * (int64_t)w;
+            set_pivot_host(c, dtype, n, values, validity, bit_offset);
+        } break;
+        case TG_BOOL: {
+            append_bits(e, c.values, c.tail_vbyte, have, (const uint8_t*)values, bit_offset, n, nullptr);
+            c.value_bytes = (have + n + 7) / 8;
+        } break;
+        case TG_UTF8: {
+            if (!offsets) throw Error(TG_ERR_INVALID_ARG, "Utf8 column requires offsets");
+            const int32_t o0 = offsets[0], o1 = offsets[n];
+            const int64_t nbytes = (int64_t)o1 - o0;
+            if (nbytes < 0) throw Error(TG_ERR_INVALID_ARG, "Utf8 offsets are not monotonic");
+            if (c.value_bytes + nbytes > INT32_MAX)
+                throw Error(TG_ERR_UNSUPPORTED, "Utf8 column exceeds 2 GiB of value bytes (use LargeUtf8 sharding)");
+            e.dev_reserve(c.values, (size_t)(c.value_bytes + nbytes), (size_t)c.value_bytes);
+            e.h2d(c.values.p + c.value_bytes, (const uint8_t*)values + o0, (size_t)nbytes);
+            // rebase offsets onto the concatenated byte buffer
+            e.dev_reserve(c.offsets, (size_t)(have + n + 1) * 4, (size_t)(have + 1) * 4);
+            std::vector<int32_t> tmp((size_t)n + 1);
+            const int32_t delta = (int32_t)c.value_bytes - o0;
+            for (int64_t i = 0; i <= n; ++i) tmp[i] = offsets[i] + delta;
+            e.h2d(c.offsets.p + (size_t)have * 4, tmp.data(), (size_t)(n + 1) * 4);
+            c.value_bytes += nbytes;
+        } break;
+        default: throw Error(TG_ERR_INVALID_ARG, "unknown dtype");
+    }
+    c.n_rows = have + n;
+    t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* d_values,
+                        const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (t.find(name)) throw Error(TG_ERR_INVALID_ARG, "column '" + name + "' already exists");
+    if (((uintptr_t)d_values & 15) || ((uintptr_t)d_validity & 15) || ((uintptr_t)d_offsets & 15))
+        throw Error(TG_ERR_INVALID_ARG, "adopted device buffers must be 16-byte aligned");
+    Column& c = *table_get_or_add(t, name, dtype);
+    c.adopted = true;
+    c.n_rows = n;
+    c.values.p = (uint8_t*)d_values;
+    c.values.owned = false;
+    c.values.cap = 0;
+    c.validity.p = (uint8_t*)d_validity;
+    c.validity.owned = false;
+    c.offsets.p = (uint8_t*)d_offsets;
+    c.offsets.owned = false;
+    c.value_bytes = dtype == TG_UTF8 ? n_value_bytes : n * c.elem_bytes();
+    c.null_count = -1;
+    if ((dtype == TG_INT64 || dtype == TG_FLOAT64) && n > 0) {
+        double* d_p = reinterpret_cast<double*>(e.scratch(256));
+        pick_pivot_kernel<<<1, 32, 0, e.stream>>>((const uint8_t*)d_values, (const uint32_t*)d_validity, n,
+                                                  dtype == TG_INT64, d_p);
+        TG_CUDA(cudaGetLastError());
+        e.launches += 1;
+        double h = 0;
+        TG_CUDA(cudaMemcpyAsync(&h, d_p, 8, cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        c.pivot = h;
+        c.pivot_set = true;
+    }
+    t.n_rows = std::max(t.n_rows, n);
+}
+
+// ---- Arrow C Data Interface (https://arrow.apache.org/docs/format/CDataInterface.html) ----
+struct ArrowSchema {
+    const char* format;
+    const char* name;
+    const char* metadata;
+    int64_t flags;
+    int64_t n_children;
+    struct ArrowSchema** children;
+    struct ArrowSchema* dictionary;
+    void (*release)(struct ArrowSchema*);
+    void* private_data;
+};
+struct ArrowArray {
+    int64_t length;
+    int64_t null_count;
+    int64_t offset;
+    int64_t n_buffers;
+    int64_t n_children;
+    const void** buffers;
+    struct ArrowArray** children;
+    struct ArrowArray* dictionary;
+    void (*release)(struct ArrowArray*);
+    void* private_data;
+};
+
+void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
+    const ArrowSchema* sc = (const ArrowSchema*)schema_p;
+    const ArrowArray* ar = (const ArrowArray*)array_p;
+    if (!sc || !ar || !sc->format || strcmp(sc->format, "+s") != 0)
+        throw Error(TG_ERR_INVALID_ARG, "expected a struct-typed ArrowArray (a RecordBatch)");
+    if (ar->offset != 0) throw Error(TG_ERR_UNSUPPORTED, "sliced struct arrays are not supported");
+    for (int64_t i = 0; i < sc->n_children; ++i) {
+        const ArrowSchema* cs = sc->children[i];
+        const ArrowArray* ca = ar->children[i];
+        const std::string fmt = cs->format;
+        int32_t dtype;
+        if (fmt == "l") dtype = TG_INT64;
+        else if (fmt == "g") dtype = TG_FLOAT64;
+        else if (fmt == "u") dtype = TG_UTF8;
+        else if (fmt == "i") dtype = TG_INT32;
+        else if (fmt == "f") dtype = TG_FLOAT32;
+        else if (fmt == "b") dtype = TG_BOOL;
+        else throw Error(TG_ERR_UNSUPPORTED, std::string("Arrow format '") + fmt + "' of column '" + cs->name + "' is not supported");
+        const uint8_t* validity = (const uint8_t*)ca->buffers[0];
+        if (ca->null_count == 0) validity = nullptr;
+        const int64_t off = ca->offset, n = ca->length;
+        if (dtype == TG_UTF8) {
+            const int32_t* offs = (const int32_t*)ca->buffers[1] + off;
+            table_append_host(t, cs->name, dtype, n, ca->buffers[2], offs, validity, off);
+        } else if (dtype == TG_BOOL) {
+            // values bitmap shares the array offset; append_bits takes one bit offset for both
+            table_append_host(t, cs->name, dtype, n, ca->buffers[1], nullptr, validity, off);
+        } else {
+            const int w = dtype == TG_INT64 || dtype == TG_FLOAT64 ? 8 : 4;
+            table_append_host(t, cs->name, dtype, n, (const uint8_t*)ca->buffers[1] + off * w, nullptr, validity, off);
+        }
+    }
+}
+
+}  // namespace tg

@@ -1,0 +1,31 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with `-m gpu`)")
+
+
+@pytest.fixture(scope="session")
+def built_lib():
+    """The C-ABI library must exist (built by __graft_entry__.build()); build it if it is missing."""
+    from term_b200 import _ffi
+    if not os.path.exists(_ffi.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    return _ffi.lib()
+
+
+@pytest.fixture(scope="session")
+def ctx(built_lib):
+    """One engine on cuda:0 for the GPU tests (fails loudly without a device: no CPU fallback)."""
+    import term_b200 as T
+    c = T.SessionContext(0)
+    yield c
+    c.close()

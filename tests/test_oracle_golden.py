@@ -1,0 +1,138 @@
+"""Pins the CPU oracle against every known-answer test the reference holds for the hot path
+(tests/golden/reference_vectors.json, each case citing its Rust test). CPU only."""
+import math
+
+import numpy as np
+import pytest
+
+from . import helpers as H
+
+CASES = H.load_golden()
+CONSTRAINT_CASES = [c for c in CASES if c["op"]["kind"] not in ("analyzer", "assertion", "logical")]
+ANALYZER_CASES = [c for c in CASES if c["op"]["kind"] == "analyzer"]
+
+
+@pytest.mark.parametrize("case", CONSTRAINT_CASES, ids=[c["id"] for c in CONSTRAINT_CASES])
+def test_oracle_constraint_matches_reference_vector(case):
+    r = H.oracle_eval(case)
+    H.check_expect(r.status, r.metric, r.message, case["expect"], case["ref"])
+
+
+@pytest.mark.parametrize("case", ANALYZER_CASES, ids=[c["id"] for c in ANALYZER_CASES])
+def test_oracle_analyzer_matches_reference_vector(case):
+    got = H.oracle_analyzer(case)
+    exp = case["expect"]
+    if exp.get("no_data"):
+        assert got.get("no_data")
+        return
+    for key in ("u", "f"):
+        if key in exp:
+            assert list(got[key][: len(exp[key])]) == exp[key], (key, got, exp)
+    if "metric" in exp:
+        tol = exp.get("metric_tol", 0.0)
+        assert abs(got["metric"] - exp["metric"]) <= tol, (got, exp)
+    if "metric_long" in exp:
+        assert got["metric_long"] == exp["metric_long"]
+    if "metric_gt" in exp:
+        assert exp["metric_gt"] < got["metric"] < exp["metric_lt"]
+    if "map" in exp:
+        assert got["map"] == exp["map"] and got["n_groups"] == exp["n_groups"]
+
+
+def test_oracle_assertion_and_logical_vectors():
+    from oracle import term_oracle as O
+    for c in CASES:
+        if c["op"]["kind"] == "assertion":
+            for a, v, want in c["op"]["cases"]:
+                assert O.assertion_eval(tuple(a), v) is want, (a, v)
+            for a, want in c["op"]["descriptions"]:
+                assert O.assertion_desc(tuple(a)) == want
+        if c["op"]["kind"] == "logical":
+            for op, vals, want in c["op"]["cases"]:
+                assert O.logical_eval(tuple(op), vals) is want, (op, vals)
+
+
+def test_rust_f64_display():
+    from oracle.term_oracle import rust_f64
+    assert rust_f64(20.0) == "20"
+    assert rust_f64(0.1) == "0.1"
+    assert rust_f64(1e21) == "1000000000000000000000"
+    assert rust_f64(1e-7) == "0.0000001"
+    assert rust_f64(-2.5) == "-2.5"
+    assert rust_f64(float("nan")) == "NaN" and rust_f64(float("inf")) == "inf"
+
+
+# ---- the reference's in-tree KllSketch restated (oracle/kll_ref.py) against its own unit tests ----
+def test_kll_ref_basic_operations():  # kll_sketch.rs:406-425
+    from oracle.kll_ref import KllSketch
+    s = KllSketch(100)
+    assert s.n == 0
+    for i in range(1000):
+        s.update(float(i))
+    assert s.count() == 1000
+    med = s.get_quantile(0.5)
+    assert 0.0 <= med <= 999.0
+    assert s.get_quantile(0.0) == 0.0 and s.get_quantile(1.0) == 999.0
+
+
+def test_kll_ref_single_value_nan_and_merge():  # kll_sketch.rs:427-458, 520-558
+    from oracle.kll_ref import KllSketch
+    s = KllSketch(50)
+    s.update(42.0)
+    assert s.get_quantile(0.0) == 42.0 and s.get_quantile(0.5) == 42.0 and s.get_quantile(1.0) == 42.0
+    s = KllSketch(50)
+    s.update(1.0)
+    s.update(float("nan"))
+    s.update(2.0)
+    assert s.count() == 2
+    a, b = KllSketch(100), KllSketch(100)
+    for i in range(500):
+        a.update(float(i))
+    for i in range(500, 1000):
+        b.update(float(i))
+    a.merge(b)
+    assert a.count() == 1000
+    assert a.get_quantile(0.0) == 0.0 and a.get_quantile(1.0) == 999.0
+    assert abs(KllSketch(200).relative_error_bound() - 1.65 / math.sqrt(200)) < 1e-12
+
+
+def test_kll_ref_compactor_halves():  # kll_sketch.rs:497-518: 4 items -> 2 kept + 2 promoted
+    from oracle.kll_ref import Compactor
+    c = Compactor(4)
+    c.items = [1.0, 2.0, 3.0, 4.0]
+    promoted = c.compact()
+    assert len(promoted) == 2 and len(c.items) == 2
+    assert sorted(promoted + c.items) == [1.0, 2.0, 3.0, 4.0]
+
+
+def test_siphash13_known_answer():
+    # SipHash-1-3 of the empty message with zero keys (Rust: DefaultHasher::new().finish())
+    from oracle.kll_ref import siphash13
+    assert siphash13([]) == 0xD1FBA762150C532C
+
+
+# ---- oracle self-consistency on the property-test generator (tests/property_tests.rs:102-145) ----
+def _property_column(n, null_fraction, lo, rng_range):
+    nulls = round(n * null_fraction)
+    vals = [None] * nulls + [lo + (j / max(1, n - nulls)) * rng_range for j in range(n - nulls)]
+    return vals
+
+
+@pytest.mark.parametrize("n,frac", [(10, 0.0), (100, 0.25), (1000, 0.5), (7, 1.0)])
+def test_oracle_property_generators(n, frac):
+    from oracle import term_oracle as O
+    import pyarrow as pa
+    vals = _property_column(n, frac, -50.0, 100.0)
+    t = pa.table({"c": pa.array(vals, type=pa.float64())})
+    nn = sum(v is not None for v in vals)
+    r = O.completeness(t, "c", 0.0)
+    assert r.metric == nn / n  # property_tests.rs:215-257
+    r = O.size(t, ("Equals", float(n)))
+    assert r.status == "success" and r.metric == float(n)  # :309-365
+    if nn:
+        arr = np.array([v for v in vals if v is not None])
+        assert abs(O.stat_value(O.table_cols(t)["c"], "Mean") - arr.mean()) < 1e-9  # :378-425
+        assert O.stat_value(O.table_cols(t)["c"], "Min") == arr.min()  # :430-480
+        assert O.stat_value(O.table_cols(t)["c"], "Max") == arr.max()
+    if nn > 1:
+        assert abs(O.stat_value(O.table_cols(t)["c"], "StandardDeviation") - arr.std(ddof=1)) < 1e-9  # :776-825
