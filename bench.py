@@ -1,0 +1,430 @@
+#!/usr/bin/env python3
+"""bench.py — headline benchmark of the hot path (contract in the task prompt).
+
+Workload (BASELINE.json configs[1], C2): the numeric business-rules suite
+    has_size, has_min(f0), has_mean(f1), has_correlation(f0, f1), satisfies("f2 > 0 AND i0 < 1000000")
+on a synthetic 100 M-row x 8-column (4 f64 + 4 i64) table with 5 % nulls per column, per GPU
+(row-partitioned, weak scaling). A "step" is one evaluation of the whole suite over one table.
+
+    value      rows/s with the table already resident in HBM (adopted device buffers), whole job
+    roofline   algorithmic bytes of the suite / average duration of the fused scan kernel (CUDA events
+               recorded by the engine on its own stream around the launch) vs MEASURED_PEAKS.json hbm_gbs
+    e2e        same metric through the public API from pinned HOST Arrow buffers: H2D staging of the
+               referenced columns + scan + result read-back inside the timed region, every step
+    cpu_baseline   oracle C restatement of the reference's one-scan-per-constraint DataFusion schedule,
+               all host cores, on a bounded row sample (rank 0, N=1 only)
+    --impl reference   times that CPU restatement alone (the reference itself is Rust + DataFusion and
+               cannot be built in this image: no cargo/rustc)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ROWS_PER_GPU = int(os.environ.get("TG_BENCH_ROWS", 100_000_000))
+NULL_FRACTION = 0.05
+METRIC = "rows/sec scanned per suite (numeric business-rules suite, 100M rows x 8 cols per GPU)"
+UNIT = "rows/s"
+SUITE_COLUMNS = ("f0", "f1", "f2", "i0")  # columns the literal suite references
+
+
+def algorithmic_bytes(n_rows, columns=SUITE_COLUMNS):
+    """8 B value + 1/8 B validity per referenced, nullable column, each counted once."""
+    return len(columns) * (n_rows * 8 + (n_rows + 7) // 8)
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu, self.proc, self.lines = gpu_index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                smax.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ data ----
+def make_device_table(torch, n, seed, device):
+    """Synthetic C2 table generated on the device: f0..f3 f64, i0..i3 i64, 5 % nulls, f1 = 0.8 f0 + noise.
+    Buffers carry 64 elements of slack so TMA tiles may over-read the tail."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cols, keep = {}, []
+    pad = 64
+
+    def buf(dtype):
+        t = torch.zeros(n + pad, dtype=dtype, device=device)
+        keep.append(t)
+        return t
+
+    def validity():
+        words = (n + 63) // 64 * 8 + 64
+        bits = torch.zeros(words, dtype=torch.uint8, device=device)
+        chunk = 1 << 26
+        w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=device)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            m = (torch.rand(e - s, generator=g, device=device) >= NULL_FRACTION)
+            padn = (-(e - s)) % 8
+            if padn:
+                m = torch.cat([m, torch.zeros(padn, dtype=torch.bool, device=device)])
+            packed = (m.view(-1, 8).to(torch.uint8) * w).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+            bits[s // 8: s // 8 + packed.numel()] = packed
+        keep.append(bits)
+        return bits
+
+    f0 = buf(torch.float64)
+    f0[:n].normal_(100.0, 15.0, generator=g)
+    f1 = buf(torch.float64)
+    f1[:n].normal_(0.0, 9.0, generator=g)
+    f1[:n].add_(f0[:n], alpha=0.8)
+    f2 = buf(torch.float64)
+    f2[:n].uniform_(0.0, 1000.0, generator=g)
+    f3 = buf(torch.float64)
+    f3[:n].normal_(0.0, 1.0, generator=g).exp_()
+    floats = {"f0": f0, "f1": f1, "f2": f2, "f3": f3}
+    ints = {}
+    for k in range(4):
+        t = buf(torch.int64)
+        t[:n].random_(-10**6, 10**6 + 1, generator=g)
+        ints[f"i{k}"] = t
+    from term_b200 import _ffi as F
+    for name, t in list(floats.items()) + list(ints.items()):
+        v = validity()
+        cols[name] = dict(dtype=F.TG_FLOAT64 if name[0] == "f" else F.TG_INT64, n_rows=n, values=t.data_ptr(),
+                          validity=v.data_ptr(), tensor=t, bits=v)
+    return cols, keep
+
+
+def build_suite(T, table_name):
+    A = T.Assertion
+    check = (T.Check.builder("business_rules")
+             .has_size(A.GreaterThan(0.0))
+             .has_min("f0", A.GreaterThan(-1000.0))
+             .has_mean("f1", A.Between(50.0, 110.0))
+             .has_correlation("f0", "f1", A.GreaterThan(0.5))
+             .satisfies("f2 > 0 AND i0 < 1000000")
+             .build())
+    return T.ValidationSuite.builder("numeric_business_rules").table_name(table_name).check(check).build()
+
+
+def build_full_suite(T, table_name):
+    """'full numeric set' variant of SURVEY §8d: {completeness,min,max,mean,sum,stddev} x 8 cols + 4 pairs"""
+    A = T.Assertion
+    cb = T.Check.builder("full_numeric_set").has_size(A.GreaterThan(0.0))
+    names = [f"f{k}" for k in range(4)] + [f"i{k}" for k in range(4)]
+    for c in names:
+        cb.completeness(c, 0.9)
+        for s in ("Min", "Max", "Mean", "Sum", "StandardDeviation"):
+            cb.statistic(c, T.StatisticType[s], A.GreaterThan(-1e300))
+    for a, b in (("f0", "f1"), ("f2", "f3"), ("i0", "i1"), ("f0", "i2")):
+        cb.has_correlation(a, b, A.GreaterThan(-2.0))
+    return T.ValidationSuite.builder("full_numeric_set").table_name(table_name).check(cb.build()).build()
+
+
+# ------------------------------------------------------------------------------ CPU arm ----
+def cpu_suite_rate(sample_rows, repeats=1, seed=1234):
+    """Times the oracle's C restatement (all host cores) of the literal suite on `sample_rows` rows."""
+    import numpy as np
+    from oracle import cpu_scan as S
+    rng = np.random.default_rng(seed)
+    cols = {}
+    f0 = rng.normal(100.0, 15.0, sample_rows)
+    cols["f0"] = (f0, S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
+    cols["f1"] = (0.8 * f0 + rng.normal(0.0, 9.0, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
+    cols["f2"] = (rng.uniform(0.0, 1000.0, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
+    cols["i0"] = (rng.integers(-10**6, 10**6 + 1, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
+    S.numeric_suite(cols, sample_rows)  # warm caches / thread pool
+    times = []
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        S.numeric_suite(cols, sample_rows)
+        times.append(time.perf_counter() - t0)
+    return sample_rows / (sum(times) / len(times)), S.num_threads(), times
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = int(os.environ.get("TG_BENCH_CPU_ROWS", 20_000_000))
+    import numpy as np  # noqa: F401
+    from oracle import cpu_scan as S
+    rate, cores, _ = cpu_suite_rate(sample, repeats=1)  # warm-up incl. data generation
+    times = []
+    # re-use one dataset for all steps
+    rng_rows = sample
+    import numpy as np
+    rng = np.random.default_rng(1234)
+    cols = {}
+    f0 = rng.normal(100.0, 15.0, rng_rows)
+    cols["f0"] = (f0, S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
+    cols["f1"] = (0.8 * f0 + rng.normal(0.0, 9.0, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
+    cols["f2"] = (rng.uniform(0.0, 1000.0, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
+    cols["i0"] = (rng.integers(-10**6, 10**6 + 1, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
+    for _ in range(args.warmup):
+        S.numeric_suite(cols, rng_rows)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        S.numeric_suite(cols, rng_rows)
+    dt = time.perf_counter() - t0
+    value = rng_rows * args.steps / dt
+    sample_desc = (f"{rng_rows} rows x 4 referenced cols per step (of the 100M-row workload), one full scan per "
+                   f"constraint as ValidationSuite::run_sequential does, OpenMP over all host cores")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C2 numeric business-rules suite (has_size, has_min, has_mean, has_correlation, satisfies)",
+                   "rows_per_step": rng_rows, "columns": 8, "null_fraction": NULL_FRACTION},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "note": "CPU restatement of the reference's DataFusion path (oracle/cpu_scan.c); the Rust reference cannot be built in this image",
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm ----
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="termgpu")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--variants", action="store_true", help="also time the full numeric set variant")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl != "reference" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import term_b200 as T
+    from term_b200 import _ffi as F
+    from term_b200.distributed import execute_distributed
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    n = ROWS_PER_GPU
+    ctx = T.SessionContext(local_rank)
+    cols, keep = make_device_table(torch, n, seed=42 + 2 + rank, device=device)
+    ctx.register_device_table("data", {k: {kk: vv for kk, vv in v.items() if kk not in ("tensor", "bits")} for k, v in cols.items()},
+                              keepalive=keep)
+    torch.cuda.synchronize()
+
+    suite = build_suite(T, "data")
+    plan, slots = suite.build_plan()
+    engine_stream = torch.cuda.ExternalStream(ctx.stream(), device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        if world > 1:
+            execute_distributed(plan, ctx, "data")
+        else:
+            plan.execute(ctx, "data")
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = ctx.launch_count()
+    scan_ms = []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(engine_stream)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+        scan_ms.append(plan.stats()["scan_ms"])
+    ev1.record(engine_stream)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    # max over ranks of the device-side time
+    t_ms = torch.tensor([dev_ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+    total_ms = float(t_ms.item())
+    ms_per_step = total_ms / args.steps
+    value = n * world * args.steps / (total_ms / 1e3)
+
+    results = [plan.result(s) for _, _, s in slots]
+    kernel_ms = sum(scan_ms) / len(scan_ms)
+    alg_bytes = algorithmic_bytes(n)
+    peak, peak_src = measured_peak_gbs()
+    achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "kernel": "scan_kernel (+ scan_finalize_kernel)", "kernel_ms": kernel_ms,
+                "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "step_gbs": alg_bytes * world / (ms_per_step / 1e3) / 1e9}
+
+    variants = {}
+    if args.variants and world == 1:
+        fs = build_full_suite(T, "data")
+        fplan, _ = fs.build_plan()
+        for _ in range(3):
+            fplan.execute(ctx, "data")
+        ks = []
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(engine_stream)
+        for _ in range(max(5, args.steps // 2)):
+            fplan.execute(ctx, "data")
+            ks.append(fplan.stats()["scan_ms"])
+        e1.record(engine_stream)
+        torch.cuda.synchronize()
+        fb = algorithmic_bytes(n, ("f0", "f1", "f2", "f3", "i0", "i1", "i2", "i3"))
+        km = sum(ks) / len(ks)
+        variants["full_numeric_set"] = {"rows_per_s": n * len(ks) / (e0.elapsed_time(e1) / 1e3), "kernel_ms": km,
+                                        "achieved_gbs": fb / (km / 1e3) / 1e9, "frac": fb / (km / 1e3) / 1e9 / peak,
+                                        "algorithmic_bytes": fb}
+
+    # ---------------- e2e: host Arrow buffers -> H2D -> scan -> results, every step ----------------
+    e2e = None
+    if not args.no_e2e:
+        e2e_rows = int(os.environ.get("TG_BENCH_E2E_ROWS", n))
+        host = {}
+        for name in SUITE_COLUMNS:
+            vt = cols[name]["tensor"][:e2e_rows].cpu().pin_memory()
+            bt = cols[name]["bits"][: (e2e_rows + 7) // 8].cpu().pin_memory()
+            host[name] = (vt, bt)
+        h2d_bytes = sum(v.numel() * v.element_size() + b.numel() for v, b in host.values())
+        esuite = build_suite(T, "e2e")
+        eplan, eslots = esuite.build_plan()
+
+        def e2e_step():
+            t = ctx._create("e2e")
+            for name, (vt, bt) in host.items():
+                dt = F.TG_FLOAT64 if name[0] == "f" else F.TG_INT64
+                F.check(F.lib().tg_table_append_host(t, name.encode(), dt, e2e_rows, vt.data_ptr(), None, bt.data_ptr(), 0))
+            if world > 1:
+                execute_distributed(eplan, ctx, "e2e")
+            else:
+                eplan.execute(ctx, "e2e")
+            out = [eplan.result(s) for _, _, s in eslots]
+            ctx.deregister_table("e2e")
+            return out
+
+        e2e_steps = max(3, min(args.steps, 5))
+        for _ in range(2):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            eres = e2e_step()
+        barrier()
+        e2e_wall = time.perf_counter() - t0
+        tw = torch.tensor([e2e_wall], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(tw, op=dist.ReduceOp.MAX)
+        e2e_value = e2e_rows * world * e2e_steps / float(tw.item())
+        d2h = 5 * 8 + 64  # one ScanAggOut record per aggregate + 5 result structs
+        e2e = {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d_bytes, "d2h_bytes_per_step": d2h * 4,
+               "steps": e2e_steps, "rows_per_step_per_gpu": e2e_rows, "ms_per_step": float(tw.item()) / e2e_steps * 1e3,
+               "note": "pinned host Arrow buffers -> tg_table_append_host (async H2D) -> tg_plan_execute -> tg_plan_result"}
+        assert [r.status for r in eres] == [r.status for r in results] or e2e_rows != n
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        sample = int(os.environ.get("TG_BENCH_CPU_ROWS", 20_000_000))
+        rate, cores, times = cpu_suite_rate(sample, repeats=3)
+        cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{sample} rows of the same synthetic table, 3 repeats after warm-up; oracle/cpu_scan.c: one "
+                                  f"full scan per constraint (run_sequential schedule), OpenMP over {cores} host threads"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C2 numeric business-rules suite (has_size, has_min(f0), has_mean(f1), has_correlation(f0,f1), "
+                                   "satisfies(f2 > 0 AND i0 < 1000000)) on 100M rows x 8 f64/i64 cols, 5% nulls, per GPU",
+                       "rows_per_gpu": n, "columns": 8, "referenced_columns": list(SUITE_COLUMNS), "null_fraction": NULL_FRACTION,
+                       "parallelism": f"row-partitioned x{world}", "l2": "inputs (3.25 GB/step) are larger than L2; no flush needed",
+                       "merge": "all-gather of partial aggregates via torch.distributed (NCCL)" if world > 1 else "single GPU"},
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": clocks, "wall_ms_per_step": wall / args.steps * 1e3,
+            "results": [{"name": r.name, "status": r.status.name, "metric": r.metric} for r in results],
+        }
+        if variants:
+            line["variants"] = variants
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()

@@ -86,7 +86,9 @@ struct ScanOp {
     Column* c0 = nullptr;
     Column* c1 = nullptr;
     double cost = 1.0;
+    int flags = 0;
     std::vector<PredInstr> code;
+    std::vector<ScanTerm> terms;
     std::vector<Column*> pred_cols;
 };
 
@@ -126,8 +128,16 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
         else if (o.kind == UNIT_PAIR) {
             oc[i].c0 = tile_col_index(tcols, o.c0, true);
             oc[i].c1 = tile_col_index(tcols, o.c1, true);
-        } else if (o.kind == UNIT_PRED) {
-            for (auto* c : o.pred_cols) tile_col_index(tcols, c, true);
+        } else if (o.kind == UNIT_PRED || o.kind == UNIT_TERMS) {
+            for (size_t k = 0; k < o.pred_cols.size(); ++k) {
+                bool need_values = true;
+                if (o.kind == UNIT_TERMS) {  // IS [NOT] NULL terms only need the validity bitmap
+                    need_values = false;
+                    for (auto& tm : o.terms)
+                        if (tm.col == (int)k && tm.kind != TK_ISNULL && tm.kind != TK_NOTNULL) need_values = true;
+                }
+                tile_col_index(tcols, o.pred_cols[k], need_values);
+            }
         }
     }
     if (tcols.size() > (size_t)SCAN_MAX_COLS) throw Error(TG_ERR_UNSUPPORTED, "too many columns in one scan pass");
@@ -159,13 +169,16 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     int n_stages = 0;
     std::vector<int> reps(ops.size(), 1);
     size_t stage_bytes = 0, state_bytes = 0;
-    const size_t smem_budget = 227 * 1024 - 256;
-    for (; tile_rows >= 128; tile_rows /= 2) {
+    const size_t smem_budget = 227 * 1024 - 256 - sizeof(ScanTables);
+    bool has_terms = false;
+    for (auto& o : ops) has_terms |= o.kind == UNIT_TERMS;
+    for (; tile_rows >= (has_terms ? 256 : 128); tile_rows /= 2) {
         int n_units = 0;
         for (size_t i = 0; i < ops.size(); ++i) {
             double share = ops[i].cost / total_cost * SCAN_CONSUMER_WARPS;
             int r = 1;
-            while (r * 2 <= share + 0.5 && r * 2 <= tile_rows / 64) r *= 2;
+            const int min_slice = ops[i].kind == UNIT_TERMS ? 256 : 64;
+            while (r * 2 <= share + 0.5 && r * 2 <= tile_rows / min_slice) r *= 2;
             if (ops[i].kind == UNIT_COUNT) r = 1;
             reps[i] = r;
             n_units += r;
@@ -191,7 +204,7 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     P->stage_bytes = (uint32_t)stage_bytes;
     for (size_t i = 0; i < tcols.size(); ++i) {
         Column* c = tcols[i].col;
-        ScanColDesc& d = P->cols[i];
+        ScanColDesc& d = P->tab.cols[i];
         d.values = tcols[i].need_values ? c->values.p : nullptr;
         d.validity = c->validity.p;
         d.kind = c->dtype == TG_FLOAT64 ? SC_F64 : c->dtype == TG_INT64 ? SC_I64 : c->dtype == TG_BOOL ? SC_BOOL : SC_BITS;
@@ -199,8 +212,11 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
         d.smem_val_off = val_off[i];
         d.smem_bits_off = bit_off[i];
         d.pivot = c->pivot;
+        d.ipivot = c->ipivot;
+        d.pivot_is_element = c->pivot_set ? 1 : 0;
     }
-    // units + code
+    // units + code / terms
+    int term_off = 0;
     struct UnitTmp {
         ScanUnitDesc d;
         double cost;
@@ -219,7 +235,15 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 };
                 fix(ins.a_kind, ins.a_idx);
                 fix(ins.b_kind, ins.b_idx);
-                P->code[code_off++] = ins;
+                P->tab.code[code_off++] = ins;
+            }
+        }
+        if (o.kind == UNIT_TERMS) {
+            this_code_off = term_off;
+            for (auto tm : o.terms) {
+                tm.col = tile_col_index(tcols, o.pred_cols[tm.col], false);
+                if (term_off >= SCAN_MAX_TERMS) throw Error(TG_ERR_UNSUPPORTED, "too many predicate terms in one scan pass");
+                P->tab.terms[term_off++] = tm;
             }
         }
         const int r = reps[i];
@@ -233,9 +257,10 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
             u.d.nrows = slice;
             u.d.agg = (int)i;  // local aggregate index within this pass
             u.d.code_off = this_code_off;
-            u.d.code_len = (int)o.code.size();
+            u.d.code_len = o.kind == UNIT_TERMS ? (int)o.terms.size() : (int)o.code.size();
             u.d.c0_is_i64 = o.c0 && o.c0->dtype == TG_INT64;
             u.d.c1_is_i64 = o.c1 && o.c1->dtype == TG_INT64;
+            u.d.flags = o.flags;
             u.cost = o.cost / r;
             units.push_back(u);
         }
@@ -245,16 +270,22 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return units[a].cost > units[b].cost; });
     double load[SCAN_CONSUMER_WARPS] = {0};
+    int owned[SCAN_CONSUMER_WARPS] = {0};
     for (int idx : order) {
-        int best = 0;
-        for (int w = 1; w < SCAN_CONSUMER_WARPS; ++w)
-            if (load[w] < load[best]) best = w;
+        int best = -1;
+        for (int w = 0; w < SCAN_CONSUMER_WARPS; ++w)
+            if (owned[w] < SCAN_WARP_UNITS && (best < 0 || load[w] < load[best])) best = w;
+        if (best < 0) throw Error(TG_ERR_UNSUPPORTED, "too many aggregates in one scan pass");
         units[idx].d.warp = best;
         load[best] += units[idx].cost;
+        P->tab.warp_units[best][1 + owned[best]] = idx;
+        P->tab.warp_units[best][0] = ++owned[best];
     }
     P->n_units = (int)units.size();
     P->n_aggs = (int)ops.size();
-    for (size_t i = 0; i < units.size(); ++i) P->units[i] = units[i].d;
+    P->n_code = code_off;
+    P->n_terms = term_off;
+    for (size_t i = 0; i < units.size(); ++i) P->tab.units[i] = units[i].d;
 
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(P->n_tiles, 1), e.sm_count);
     const size_t partial_bytes = (size_t)grid * P->n_units * SCAN_STATE_SLOTS * 8;
@@ -295,9 +326,15 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 a.f[0] = ops[i].c0->pivot;
                 a.f[1] = u2d(s[S_SD]);
                 a.f[2] = u2d(s[S_SDD]);
-                a.f[5] = u2d(s[S_SX]);
+                a.f[5] = (double)s[S_N] * ops[i].c0->pivot + u2d(s[S_SD]);  // sum(x) = n*K + sum(x-K)
                 if (ops[i].kind == UNIT_NUM_I64) {
-                    a.u[1] = s[S_ISUM];
+                    // NULL / padding rows were summed as K: remove them (exact in wrapping arithmetic)
+                    uint64_t isum = s[S_ISUM];
+                    if (ops[i].c0->pivot_set) {
+                        const uint64_t padded = (uint64_t)P->n_tiles * (uint64_t)P->tile_rows;
+                        isum -= (padded - s[S_N]) * (uint64_t)ops[i].c0->ipivot;
+                    }
+                    a.u[1] = isum;
                     a.u[2] = s[S_MIN];
                     a.u[3] = s[S_MAX];
                     a.u[4] = 1;
@@ -317,8 +354,9 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 a.f[6] = u2d(s[P_SXY]);
                 break;
             case UNIT_PRED:
+            case UNIT_TERMS:
                 a.u[0] = s[0];
-                a.u[1] = s[1];
+                a.u[1] = ops[i].kind == UNIT_PRED ? s[1] : 0;
                 a.u[2] = (uint64_t)t.n_rows;
                 break;
         }
@@ -379,7 +417,10 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 if (!c || !numeric(c)) break;
                 o.kind = c->dtype == TG_INT64 ? UNIT_NUM_I64 : UNIT_NUM_F64;
                 o.c0 = c;
-                o.cost = c->dtype == TG_INT64 ? 1.4 : 1.0;
+                o.flags = a.flags ? a.flags : 7;
+                if (c->dtype != TG_INT64) o.flags &= ~4;
+                o.cost = 0.3 + ((o.flags & 1) ? 0.5 : 0.0) + ((o.flags & 2) ? 0.4 : 0.0) + ((o.flags & 4) ? 0.2 : 0.0) +
+                         ((o.flags & 1) && c->dtype == TG_INT64 ? 0.3 : 0.0);
                 count_bytes(c, true);
                 ops.push_back(std::move(o));
             } break;
@@ -407,14 +448,22 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                         o.pred_cols.push_back(c);
                         return ColumnBinding{(int)o.pred_cols.size() - 1, c->dtype};
                     };
-                    compile_predicate(a.expr, res, o.code);
+                    bool is_or = false;
+                    if (try_compile_terms(a.expr, res, o.terms, is_or)) {
+                        o.kind = UNIT_TERMS;
+                        o.flags = is_or ? 1 : 0;
+                        o.cost = 0.15 + 0.45 * (double)o.terms.size();
+                    } else {
+                        o.pred_cols.clear();
+                        compile_predicate(a.expr, res, o.code);
+                        o.kind = UNIT_PRED;
+                        o.cost = 0.5 + 0.6 * (double)o.code.size();
+                    }
                 } catch (Error& er) {
                     a.err = er.code;
                     a.err_msg = er.msg;
                     break;
                 }
-                o.kind = UNIT_PRED;
-                o.cost = 0.6 + 0.5 * (double)o.code.size();
                 for (auto* c : o.pred_cols) count_bytes(c, true);
                 ops.push_back(std::move(o));
             } break;

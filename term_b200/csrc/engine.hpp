@@ -44,8 +44,9 @@ struct Column {
     uint8_t tail_byte = 0;   // host mirror of the last, partially filled validity byte
     uint8_t tail_vbyte = 0;  // same for bit-packed Bool values
     int32_t last_offset = 0;
-    bool pivot_set = false;
-    double pivot = 0.0;
+    bool pivot_set = false;       // a finite, valid element of the column was found
+    double pivot = 0.0;           // shift K of the moment sums (== (double)ipivot for Int64 columns)
+    int64_t ipivot = 0;
     bool adopted = false;
     int elem_bytes() const {
         switch (dtype) {

@@ -12,7 +12,10 @@ namespace tg {
 
 int Plan::add_agg(Agg a) {
     for (size_t i = 0; i < aggs.size(); ++i)
-        if (aggs[i].key == a.key) return (int)i;
+        if (aggs[i].key == a.key) {
+            if (a.kind == A_NUM) aggs[i].flags |= a.flags;  // union of the statistics requested on the column
+            return (int)i;
+        }
     aggs.push_back(std::move(a));
     return (int)aggs.size() - 1;
 }
@@ -35,11 +38,21 @@ static Agg mk_valid(const std::string& c) {
     a.cols = {c};
     return a;
 }
-static Agg mk_num(const std::string& c) {
+// NUM aggregate flags (scan_defs.h UF_*): 1 moments (mean/sum/stddev/variance), 2 min/max, 4 wrapping i64 sum
+static int stat_flags(int stat) {
+    switch (stat) {
+        case TG_STAT_MIN: case TG_STAT_MAX: return 2;
+        case TG_STAT_MEAN: case TG_STAT_STDDEV: case TG_STAT_VARIANCE: return 1;
+        case TG_STAT_SUM: return 1 | 4;
+        default: return 2;  // median / percentile: min and max come with the sketch
+    }
+}
+static Agg mk_num(const std::string& c, int flags) {
     Agg a;
     a.kind = A_NUM;
     a.key = "num|" + c;
     a.cols = {c};
+    a.flags = flags;
     return a;
 }
 static Agg mk_pair(const std::string& x, const std::string& y) {
@@ -170,7 +183,7 @@ int plan_add_statistic(Plan& p, const std::string& col, int stat, double pct, tg
     s.name = stat_constraint_name(stat);
     s.columns = {col};
     StatReq r{stat, stat == TG_STAT_MEDIAN ? 0.5 : pct, a, -1};
-    s.aggs.push_back(p.add_agg(mk_num(col)));
+    s.aggs.push_back(p.add_agg(mk_num(col, stat_flags(stat))));
     if (stat == TG_STAT_MEDIAN || stat == TG_STAT_PERCENTILE) r.agg_kll = p.add_agg(mk_kll(col, KLL_K_FOR_PERCENTILE));
     s.stats.push_back(r);
     p.slots.push_back(std::move(s));
@@ -183,7 +196,9 @@ int plan_add_multi_statistic(Plan& p, const std::string& col, const std::vector<
     s.kind = SL_MULTISTAT;
     s.name = "multi_statistical";
     s.columns = {col};
-    s.aggs.push_back(p.add_agg(mk_num(col)));
+    int fl = 0;
+    for (auto& r : stats) fl |= stat_flags(r.kind);
+    s.aggs.push_back(p.add_agg(mk_num(col, fl)));
     for (auto r : stats) {
         if (r.kind == TG_STAT_PERCENTILE && !(r.percentile >= 0.0 && r.percentile <= 1.0))
             throw Error(TG_ERR_SECURITY, "Percentile must be between 0.0 and 1.0");
@@ -393,7 +408,7 @@ int plan_add_analyzer(Plan& p, int kind, const char* col, const char* col2, cons
             // StandardDeviationAnalyzer has no metric_key override
             s.metric_key = kind == TG_AN_STDDEV ? std::string(nm) : std::string(nm) + "." + c;
             s.columns = {c};
-            s.aggs.push_back(p.add_agg(mk_num(c)));
+            s.aggs.push_back(p.add_agg(mk_num(c, kind == TG_AN_MIN || kind == TG_AN_MAX ? 2 : kind == TG_AN_STDDEV ? 1 : (1 | 4))));
         } break;
         case TG_AN_CORR_PEARSON:
         case TG_AN_COVARIANCE:

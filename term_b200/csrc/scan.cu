@@ -16,13 +16,16 @@
 //     tile); they read the tile from shared memory conflict-free (lane-contiguous 8-byte elements),
 //     keep per-lane accumulators in shared memory between tiles, and release the stage through an
 //     "empty" mbarrier, so fast warps run up to n_stages-1 tiles ahead of slow ones.
-//   * moments are accumulated as shifted sums Σ(x-K), Σ(x-K)² (K = a value of the column), which
-//     merge by plain addition across lanes/CTAs/GPUs and lose at most ~n·eps relative accuracy.
+//   * descriptor tables (columns, units, predicate code) are copied to shared memory once; every
+//     kind / flag decision is hoisted out of the row loops (template specialisations).
+//   * moments are accumulated as shifted sums Σ(x-K), Σ(x-K)² with K an element of the column; NULL rows
+//     are replaced by K (contributing exactly 0), so the inner loops have no predicated accumulates.
 //   * per-CTA partials go to global memory; scan_finalize_kernel reduces them in a fixed order, so a
 //     given (grid, plan) is bit-reproducible run to run.
 #include <cfloat>
-#include <math_constants.h>
+#include <cstddef>
 #include <cstdio>
+#include <math_constants.h>
 
 #include "ptx.cuh"
 #include "scan_defs.h"
@@ -32,87 +35,156 @@ namespace tg {
 extern __shared__ __align__(128) uint8_t scan_smem[];
 
 __device__ __forceinline__ uint32_t tail_mask(int base_row, int rows_in_tile) {
-    int rem = rows_in_tile - base_row;
+    const int rem = rows_in_tile - base_row;
     return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
 }
-
-// ---- per-lane state in shared memory: state[unit][slot][lane] ----
-struct LaneState {
-    uint64_t s[SCAN_STATE_SLOTS];
-};
-__device__ __forceinline__ void state_load(const uint64_t* st, int lane, LaneState& v, int nslots) {
-#pragma unroll
-    for (int k = 0; k < SCAN_STATE_SLOTS; ++k)
-        if (k < nslots) v.s[k] = st[k * 32 + lane];
-}
-__device__ __forceinline__ void state_store(uint64_t* st, int lane, const LaneState& v, int nslots) {
-#pragma unroll
-    for (int k = 0; k < SCAN_STATE_SLOTS; ++k)
-        if (k < nslots) st[k * 32 + lane] = v.s[k];
-}
-
 __device__ __forceinline__ double u2d(uint64_t u) { return __longlong_as_double((long long)u); }
 __device__ __forceinline__ uint64_t d2u(double d) { return (uint64_t)__double_as_longlong(d); }
 
-__device__ void unit_init(const ScanUnitDesc& u, uint64_t* st, int lane) {
-    LaneState v;
+// per-lane state in shared memory: st[slot * 32 + lane]
+__device__ __forceinline__ void unit_init(const ScanUnitDesc& u, uint64_t* st, int lane) {
 #pragma unroll
-    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) v.s[k] = 0;
+    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) st[k * 32 + lane] = 0;
     if (u.kind == UNIT_NUM_F64) {
-        v.s[S_MIN] = d2u(CUDART_INF);
-        v.s[S_MAX] = d2u(-CUDART_INF);
+        st[S_MIN * 32 + lane] = d2u(CUDART_INF);
+        st[S_MAX * 32 + lane] = d2u(-CUDART_INF);
     } else if (u.kind == UNIT_NUM_I64) {
-        v.s[S_MIN] = (uint64_t)INT64_MAX;
-        v.s[S_MAX] = (uint64_t)INT64_MIN;
+        st[S_MIN * 32 + lane] = (uint64_t)INT64_MAX;
+        st[S_MAX * 32 + lane] = (uint64_t)INT64_MIN;
     }
-    state_store(st, lane, v, SCAN_STATE_SLOTS);
 }
 
-// validity word j (32 rows) of a column inside the stage; all-ones when the column has no bitmap
+// validity word (32 rows) of a column inside the stage; all-ones when the column has no bitmap
 __device__ __forceinline__ uint32_t vword(const ScanColDesc& c, const uint8_t* stage, int word) {
     return c.validity ? reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off)[word] : 0xffffffffu;
 }
 
-__device__ void unit_count(const ScanParams& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
-                           int lane, int rows_in_tile) {
-    const ScanColDesc& c = P.cols[u.c0];
-    uint64_t n = st[S_N * 32 + lane];
+// valid rows of a slice: each lane popcounts different validity words, so the element loops never count
+__device__ __forceinline__ uint64_t slice_valid_count(const ScanColDesc& cx, const ScanColDesc* cy,
+                                                      const ScanUnitDesc& u, const uint8_t* stage, int lane,
+                                                      int rows_in_tile) {
+    uint64_t n = 0;
     const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
     for (int j = lane; j < nw; j += 32) {
-        uint32_t w = vword(c, stage, w0 + j) & tail_mask(u.row0 + 32 * j, rows_in_tile);
+        uint32_t w = vword(cx, stage, w0 + j) & tail_mask(u.row0 + 32 * j, rows_in_tile);
+        if (cy) w &= vword(*cy, stage, w0 + j);
         n += __popc(w);
     }
-    st[S_N * 32 + lane] = n;
+    return n;
 }
 
-template <bool IS_I64>
-__device__ void unit_num(const ScanParams& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
-                         int lane, int rows_in_tile, bool partial) {
-    const ScanColDesc& c = P.cols[u.c0];
+__device__ __forceinline__ void unit_count(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
+                                           uint64_t* st, int lane, int rows_in_tile) {
+    st[S_N * 32 + lane] += slice_valid_count(T.cols[u.c0], nullptr, u, stage, lane, rows_in_tile);
+}
+
+// ---- NUM unit -------------------------------------------------------------------------------------
+// NULL rows (and rows past the end of the table) are replaced by the pivot element K: they add 0 to Σd and
+// Σd², cannot change min/max (K is a value of the column), and the wrapping integer sum is corrected on
+// the host by (rows_processed - n)·K. MASK: 0 dense full tile, 1 validity bitmap, 2 bitmap and/or tail.
+template <bool IS_I64, int FLAGS, int MASK>
+__device__ __forceinline__ void num_loop(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
+                                         uint64_t* st, int lane, int rows_in_tile) {
+    constexpr bool MOM = (FLAGS & UF_MOMENTS) != 0, MM = (FLAGS & UF_MINMAX) != 0, ISUM = IS_I64 && (FLAGS & UF_ISUM) != 0;
     const double K = c.pivot;
-    LaneState v;
-    state_load(st, lane, v, 7);
-    uint64_t n = v.s[S_N];
-    double sd = u2d(v.s[S_SD]), sdd = u2d(v.s[S_SDD]), sx = u2d(v.s[S_SX]);
-    double fmn = u2d(v.s[S_MIN]), fmx = u2d(v.s[S_MAX]);
-    int64_t imn = (int64_t)v.s[S_MIN], imx = (int64_t)v.s[S_MAX];
-    uint64_t isum = v.s[S_ISUM];
-    const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
+    const uint64_t Kbits = IS_I64 ? (uint64_t)c.ipivot : d2u(c.pivot);
+    double sd = 0, sdd = 0, fmn = 0, fmx = 0;
+    int64_t imn = 0, imx = 0;
+    uint64_t isum = 0;
+    if (MOM) {
+        sd = u2d(st[S_SD * 32 + lane]);
+        sdd = u2d(st[S_SDD * 32 + lane]);
+    }
+    if (MM) {
+        if (IS_I64) {
+            imn = (int64_t)st[S_MIN * 32 + lane];
+            imx = (int64_t)st[S_MAX * 32 + lane];
+        } else {
+            fmn = u2d(st[S_MIN * 32 + lane]);
+            fmx = u2d(st[S_MAX * 32 + lane]);
+        }
+    }
+    if (ISUM) isum = st[S_ISUM * 32 + lane];
+    const int nw = u.nrows >> 5;
     const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + u.row0 + lane;
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off) + (u.row0 >> 5);
+    const uint32_t lanebit = 1u << lane;
+    const bool has_bits = c.validity != nullptr;
 #pragma unroll 4
     for (int j = 0; j < nw; ++j) {
-        uint32_t w = vword(c, stage, w0 + j);
-        if (partial) w &= tail_mask(u.row0 + 32 * j, rows_in_tile);
-        const bool ok = (w >> lane) & 1u;
-        const uint64_t raw = vals[32 * j];
-        n += ok;
+        uint64_t raw = vals[32 * j];
+        if (MASK == 1) {
+            raw = (bits[j] & lanebit) ? raw : Kbits;
+        } else if (MASK == 2) {
+            uint32_t w = has_bits ? bits[j] : 0xffffffffu;
+            w &= tail_mask(u.row0 + 32 * j, rows_in_tile);
+            raw = (w & lanebit) ? raw : Kbits;
+        }
         if (IS_I64) {
             const int64_t xi = (int64_t)raw;
-            const double x = (double)xi;
-            const double d = ok ? x - K : 0.0;
+            if (MOM) {
+                const double d = (double)xi - K;
+                sd += d;
+                sdd = fma(d, d, sdd);
+            }
+            if (ISUM) isum += (uint64_t)xi;
+            if (MM) {
+                imn = xi < imn ? xi : imn;
+                imx = xi > imx ? xi : imx;
+            }
+        } else {
+            const double x = u2d(raw);
+            if (MOM) {
+                const double d = x - K;
+                sd += d;
+                sdd = fma(d, d, sdd);
+            }
+            if (MM) {
+                fmn = x < fmn ? x : fmn;
+                fmx = x > fmx ? x : fmx;
+            }
+        }
+    }
+    if (MOM) {
+        st[S_SD * 32 + lane] = d2u(sd);
+        st[S_SDD * 32 + lane] = d2u(sdd);
+    }
+    if (MM) {
+        st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
+        st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
+    }
+    if (ISUM) st[S_ISUM * 32 + lane] = isum;
+}
+
+template <bool IS_I64, int FLAGS>
+__device__ __forceinline__ void num_mask(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
+                                         uint64_t* st, int lane, int rows, bool partial) {
+    if (partial) num_loop<IS_I64, FLAGS, 2>(c, u, stage, st, lane, rows);
+    else if (c.validity) num_loop<IS_I64, FLAGS, 1>(c, u, stage, st, lane, rows);
+    else num_loop<IS_I64, FLAGS, 0>(c, u, stage, st, lane, rows);
+}
+
+// slow path: the pivot is not an element of the column (no finite valid value was found when the column was
+// registered, e.g. all NULL): rows are masked explicitly
+template <bool IS_I64>
+__device__ __noinline__ void unit_num_slow(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
+                                           uint64_t* st, int lane, int rows_in_tile) {
+    const double K = c.pivot;
+    double sd = u2d(st[S_SD * 32 + lane]), sdd = u2d(st[S_SDD * 32 + lane]);
+    double fmn = u2d(st[S_MIN * 32 + lane]), fmx = u2d(st[S_MAX * 32 + lane]);
+    int64_t imn = (int64_t)st[S_MIN * 32 + lane], imx = (int64_t)st[S_MAX * 32 + lane];
+    uint64_t isum = st[S_ISUM * 32 + lane];
+    const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
+    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + u.row0 + lane;
+    for (int j = 0; j < nw; ++j) {
+        const uint32_t w = vword(c, stage, w0 + j) & tail_mask(u.row0 + 32 * j, rows_in_tile);
+        const bool ok = (w >> lane) & 1u;
+        const uint64_t raw = vals[32 * j];
+        if (IS_I64) {
+            const int64_t xi = (int64_t)raw;
+            const double d = ok ? (double)xi - K : 0.0;
             sd += d;
             sdd = fma(d, d, sdd);
-            sx += ok ? x : 0.0;
             isum += ok ? (uint64_t)xi : 0ull;
             imn = min(imn, ok ? xi : INT64_MAX);
             imx = max(imx, ok ? xi : INT64_MIN);
@@ -121,234 +193,377 @@ __device__ void unit_num(const ScanParams& P, const ScanUnitDesc& u, const uint8
             const double d = ok ? x - K : 0.0;
             sd += d;
             sdd = fma(d, d, sdd);
-            sx += ok ? x : 0.0;
             fmn = fmin(fmn, ok ? x : CUDART_INF);
             fmx = fmax(fmx, ok ? x : -CUDART_INF);
         }
     }
-    v.s[S_N] = n;
-    v.s[S_SD] = d2u(sd);
-    v.s[S_SDD] = d2u(sdd);
-    v.s[S_SX] = d2u(sx);
-    if (IS_I64) {
-        v.s[S_MIN] = (uint64_t)imn;
-        v.s[S_MAX] = (uint64_t)imx;
-        v.s[S_ISUM] = isum;
-    } else {
-        v.s[S_MIN] = d2u(fmn);
-        v.s[S_MAX] = d2u(fmx);
-    }
-    state_store(st, lane, v, 7);
+    st[S_SD * 32 + lane] = d2u(sd);
+    st[S_SDD * 32 + lane] = d2u(sdd);
+    st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
+    st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
+    st[S_ISUM * 32 + lane] = isum;
 }
 
-__device__ void unit_pair(const ScanParams& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
-                          int lane, int rows_in_tile, bool partial) {
-    const ScanColDesc& cx = P.cols[u.c0];
-    const ScanColDesc& cy = P.cols[u.c1];
+template <bool IS_I64>
+__device__ __forceinline__ void unit_num(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
+                                         uint64_t* st, int lane, int rows, bool partial) {
+    const ScanColDesc& c = T.cols[u.c0];
+    st[S_N * 32 + lane] += slice_valid_count(c, nullptr, u, stage, lane, rows);
+    if (!c.pivot_is_element) {
+        unit_num_slow<IS_I64>(c, u, stage, st, lane, rows);
+        return;
+    }
+    switch (u.flags & 7) {
+        case 0: break;
+        case 1: num_mask<IS_I64, 1>(c, u, stage, st, lane, rows, partial); break;
+        case 2: num_mask<IS_I64, 2>(c, u, stage, st, lane, rows, partial); break;
+        case 3: num_mask<IS_I64, 3>(c, u, stage, st, lane, rows, partial); break;
+        case 4: num_mask<IS_I64, 4>(c, u, stage, st, lane, rows, partial); break;
+        case 5: num_mask<IS_I64, 5>(c, u, stage, st, lane, rows, partial); break;
+        case 6: num_mask<IS_I64, 6>(c, u, stage, st, lane, rows, partial); break;
+        default: num_mask<IS_I64, 7>(c, u, stage, st, lane, rows, partial); break;
+    }
+}
+
+// ---- PAIR unit: rows where either side is NULL are replaced by (Kx, Ky) => dx = dy = 0 -------------
+template <bool XI, bool YI, bool MASKED>
+__device__ __forceinline__ void pair_loop(const ScanColDesc& cx, const ScanColDesc& cy, const ScanUnitDesc& u,
+                                          const uint8_t* stage, uint64_t* st, int lane, int rows_in_tile) {
     const double Kx = cx.pivot, Ky = cy.pivot;
-    LaneState v;
-    state_load(st, lane, v, 6);
-    uint64_t n = v.s[P_N];
-    double sx = u2d(v.s[P_SX]), sy = u2d(v.s[P_SY]), sxx = u2d(v.s[P_SXX]), syy = u2d(v.s[P_SYY]),
-           sxy = u2d(v.s[P_SXY]);
+    double sx = u2d(st[P_SX * 32 + lane]), sy = u2d(st[P_SY * 32 + lane]), sxx = u2d(st[P_SXX * 32 + lane]),
+           syy = u2d(st[P_SYY * 32 + lane]), sxy = u2d(st[P_SXY * 32 + lane]);
     const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
     const uint64_t* vx = reinterpret_cast<const uint64_t*>(stage + cx.smem_val_off) + u.row0 + lane;
     const uint64_t* vy = reinterpret_cast<const uint64_t*>(stage + cy.smem_val_off) + u.row0 + lane;
-    const bool xi = u.c0_is_i64, yi = u.c1_is_i64;
+    const uint32_t lanebit = 1u << lane;
 #pragma unroll 4
     for (int j = 0; j < nw; ++j) {
-        uint32_t w = vword(cx, stage, w0 + j) & vword(cy, stage, w0 + j);
-        if (partial) w &= tail_mask(u.row0 + 32 * j, rows_in_tile);
-        const bool ok = (w >> lane) & 1u;
         const uint64_t rx = vx[32 * j], ry = vy[32 * j];
-        const double x = xi ? (double)(int64_t)rx : u2d(rx);
-        const double y = yi ? (double)(int64_t)ry : u2d(ry);
-        const double dx = ok ? x - Kx : 0.0, dy = ok ? y - Ky : 0.0;
-        n += ok;
+        double x = XI ? (double)(int64_t)rx : u2d(rx);
+        double y = YI ? (double)(int64_t)ry : u2d(ry);
+        if (MASKED) {
+            const uint32_t w = vword(cx, stage, w0 + j) & vword(cy, stage, w0 + j) &
+                               tail_mask(u.row0 + 32 * j, rows_in_tile);
+            const bool ok = w & lanebit;
+            x = ok ? x : Kx;
+            y = ok ? y : Ky;
+        }
+        const double dx = x - Kx, dy = y - Ky;
         sx += dx;
         sy += dy;
         sxx = fma(dx, dx, sxx);
         syy = fma(dy, dy, syy);
         sxy = fma(dx, dy, sxy);
     }
-    v.s[P_N] = n;
-    v.s[P_SX] = d2u(sx);
-    v.s[P_SY] = d2u(sy);
-    v.s[P_SXX] = d2u(sxx);
-    v.s[P_SYY] = d2u(syy);
-    v.s[P_SXY] = d2u(sxy);
-    state_store(st, lane, v, 6);
+    st[P_SX * 32 + lane] = d2u(sx);
+    st[P_SY * 32 + lane] = d2u(sy);
+    st[P_SXX * 32 + lane] = d2u(sxx);
+    st[P_SYY * 32 + lane] = d2u(syy);
+    st[P_SXY * 32 + lane] = d2u(sxy);
 }
 
-// ---- predicate interpreter: 4 temporaries x PR rows per lane, SQL three-valued logic ----
-constexpr int PR = 2;
+__device__ __forceinline__ void unit_pair(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
+                                          uint64_t* st, int lane, int rows, bool partial) {
+    const ScanColDesc& cx = T.cols[u.c0];
+    const ScanColDesc& cy = T.cols[u.c1];
+    st[P_N * 32 + lane] += slice_valid_count(cx, &cy, u, stage, lane, rows);
+    const bool masked = cx.validity || cy.validity || partial;
+    const int sel = (u.c0_is_i64 ? 1 : 0) | (u.c1_is_i64 ? 2 : 0) | (masked ? 4 : 0);
+    switch (sel) {
+        case 0: pair_loop<false, false, false>(cx, cy, u, stage, st, lane, rows); break;
+        case 1: pair_loop<true, false, false>(cx, cy, u, stage, st, lane, rows); break;
+        case 2: pair_loop<false, true, false>(cx, cy, u, stage, st, lane, rows); break;
+        case 3: pair_loop<true, true, false>(cx, cy, u, stage, st, lane, rows); break;
+        case 4: pair_loop<false, false, true>(cx, cy, u, stage, st, lane, rows); break;
+        case 5: pair_loop<true, false, true>(cx, cy, u, stage, st, lane, rows); break;
+        case 6: pair_loop<false, true, true>(cx, cy, u, stage, st, lane, rows); break;
+        default: pair_loop<true, true, true>(cx, cy, u, stage, st, lane, rows); break;
+    }
+}
 
-struct PVal {
-    uint64_t v[PR];
-    bool nul[PR];
+// ---- TERMS unit: AND / OR of <= 4 comparison terms ---------------------------------------------------
+// One specialised pass per term over a chunk of TG groups (32 rows each); the running TRUE masks of the
+// chunk stay in registers. A comparison is two compares + selects + one ballot per 32 rows.
+constexpr int TG = 8;  // 256 rows per chunk
+
+template <int KIND>
+__device__ __forceinline__ void term_pass(const ScanTerm& t, const ScanColDesc& c, const uint8_t* stage, int row0,
+                                          int lane, bool is_or, uint32_t (&m)[TG]) {
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off) + (row0 >> 5);
+    const bool has_bits = c.validity != nullptr;
+    if (KIND == TK_ISNULL || KIND == TK_NOTNULL) {
+#pragma unroll
+        for (int g = 0; g < TG; ++g) {
+            const uint32_t valid = has_bits ? bits[g] : 0xffffffffu;
+            const uint32_t tm = KIND == TK_ISNULL ? ~valid : valid;
+            m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
+        }
+        return;
+    }
+    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + row0 + lane;
+    // result of the comparison by outcome: lt / eq / otherwise (gt; for floats also unordered, which
+    // matches Arrow's total order where NaN sorts above every number)
+    const bool r_lt = t.cmp_mask & 1, r_eq = (t.cmp_mask >> 1) & 1, r_gt = (t.cmp_mask >> 2) & 1;
+    const uint64_t imm = t.imm;
+#pragma unroll
+    for (int g = 0; g < TG; ++g) {
+        const uint64_t raw = vals[32 * g];
+        bool r;
+        if (KIND == TK_I64) {
+            const int64_t x = (int64_t)raw, cst = (int64_t)imm;
+            r = x < cst ? r_lt : (x == cst ? r_eq : r_gt);
+        } else {
+            const double x = KIND == TK_F64 ? u2d(raw) : (double)(int64_t)raw, cst = u2d(imm);
+            r = x < cst ? r_lt : (x == cst ? r_eq : r_gt);
+        }
+        uint32_t tm = __ballot_sync(0xffffffffu, r);
+        if (has_bits) tm &= bits[g];
+        m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
+    }
+}
+
+__device__ __forceinline__ void unit_terms(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
+                                           uint64_t* st, int lane, int rows_in_tile) {
+    const bool is_or = u.flags & 1;
+    uint64_t cnt = 0;
+    for (int base = u.row0; base < u.row0 + u.nrows; base += 32 * TG) {
+        uint32_t m[TG];
+#pragma unroll
+        for (int g = 0; g < TG; ++g) m[g] = is_or ? 0u : 0xffffffffu;
+        for (int k = 0; k < u.code_len; ++k) {
+            const ScanTerm& t = T.terms[u.code_off + k];
+            const ScanColDesc& c = T.cols[t.col];
+            switch (t.kind) {
+                case TK_F64: term_pass<TK_F64>(t, c, stage, base, lane, is_or, m); break;
+                case TK_I64: term_pass<TK_I64>(t, c, stage, base, lane, is_or, m); break;
+                case TK_I64_AS_F64: term_pass<TK_I64_AS_F64>(t, c, stage, base, lane, is_or, m); break;
+                case TK_ISNULL: term_pass<TK_ISNULL>(t, c, stage, base, lane, is_or, m); break;
+                default: term_pass<TK_NOTNULL>(t, c, stage, base, lane, is_or, m); break;
+            }
+        }
+#pragma unroll
+        for (int g = 0; g < TG; ++g) cnt += __popc(m[g] & tail_mask(base + 32 * g, rows_in_tile));
+    }
+    if (lane == 0) st[0] += cnt;
+}
+
+// ---- general predicate evaluator: per-lane numeric temporaries, warp-uniform NULL/TRUE/FALSE masks ----
+constexpr int PG = PRED_GROUPS;
+
+struct NumVal {
+    uint64_t v[PG];    // per-lane payload, group g = tile row (base + 32 g + lane)
+    uint32_t nul[PG];  // warp-uniform NULL masks
+};
+struct BoolVal {
+    uint32_t t[PG], f[PG];  // warp-uniform TRUE / FALSE masks (neither bit set = NULL)
 };
 
-__device__ __forceinline__ void pred_fetch(const ScanParams& P, const uint8_t* stage, uint8_t kind, uint16_t idx,
-                                           uint64_t imm, const uint64_t (&t)[4][PR], const bool (&tn)[4][PR],
-                                           int row, int lane, PVal& out) {
-    if (kind == PK_TEMP) {
+__device__ __forceinline__ void fetch_num(const ScanTables& P, const uint8_t* stage, uint8_t kind, uint16_t idx,
+                                          uint64_t imm, const NumVal (&nt)[4], int row, NumVal& out) {
+    if (kind == PK_NTEMP) {
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-            if (k == idx) {
-#pragma unroll
-                for (int r = 0; r < PR; ++r) {
-                    out.v[r] = t[k][r];
-                    out.nul[r] = tn[k][r];
-                }
-            }
+            if (k == idx) out = nt[k];
     } else if (kind == PK_IMM) {
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            out.v[r] = imm;
-            out.nul[r] = false;
+        for (int g = 0; g < PG; ++g) {
+            out.v[g] = imm;
+            out.nul[g] = 0u;
         }
-    } else if (kind == PK_NULL) {
+    } else if (kind == PK_NNULL) {
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            out.v[r] = 0;
-            out.nul[r] = true;
+        for (int g = 0; g < PG; ++g) {
+            out.v[g] = 0;
+            out.nul[g] = 0xffffffffu;
         }
     } else {
         const ScanColDesc& c = P.cols[idx];
+        const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + row;
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const int rr = row + 32 * r;  // tile row of this lane
-            const uint32_t w = vword(c, stage, rr >> 5);
-            out.nul[r] = !((w >> lane) & 1u);
-            if (kind == PK_COL_BOOL) {
-                const uint32_t bw = reinterpret_cast<const uint32_t*>(stage + c.smem_val_off)[rr >> 5];
-                out.v[r] = (bw >> lane) & 1u;
-            } else {
-                const uint64_t raw = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off)[rr];
-                out.v[r] = (kind == PK_COL_I64_AS_F64) ? d2u((double)(int64_t)raw) : raw;
-            }
+        for (int g = 0; g < PG; ++g) {
+            const uint64_t raw = vals[32 * g];
+            out.v[g] = (kind == PK_COL_I64_AS_F64) ? d2u((double)(int64_t)raw) : raw;
+            out.nul[g] = ~vword(c, stage, (row >> 5) + g);
         }
     }
 }
 
-__device__ void unit_pred(const ScanParams& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
-                          int lane, int rows_in_tile) {
-    uint64_t cnt = st[0 * 32 + lane];
-    uint64_t div0 = st[1 * 32 + lane];
+__device__ __forceinline__ void fetch_bool(const ScanTables& P, const uint8_t* stage, uint8_t kind, uint16_t idx,
+                                           uint64_t imm, const BoolVal (&bt)[4], int row, BoolVal& out) {
+    if (kind == PK_BTEMP) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            if (k == idx) out = bt[k];
+    } else if (kind == PK_BIMM) {
+#pragma unroll
+        for (int g = 0; g < PG; ++g) {
+            out.t[g] = imm ? 0xffffffffu : 0u;
+            out.f[g] = imm ? 0u : 0xffffffffu;
+        }
+    } else if (kind == PK_COL_BOOL) {
+        const ScanColDesc& c = P.cols[idx];
+        const uint32_t* vals = reinterpret_cast<const uint32_t*>(stage + c.smem_val_off);
+#pragma unroll
+        for (int g = 0; g < PG; ++g) {
+            const uint32_t ok = vword(c, stage, (row >> 5) + g), b = vals[(row >> 5) + g];
+            out.t[g] = b & ok;
+            out.f[g] = ~b & ok;
+        }
+    } else {  // PK_BNULL / PK_NONE
+#pragma unroll
+        for (int g = 0; g < PG; ++g) out.t[g] = out.f[g] = 0u;
+    }
+}
+
+__device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
+                                       int lane, int rows_in_tile) {
+    uint64_t cnt = 0;
+    uint32_t div0 = 0;
     const int nw = u.nrows >> 5;
-    for (int j = 0; j < nw; j += PR) {
-        uint64_t t[4][PR];
-        bool tn[4][PR];
+    for (int j = 0; j < nw; j += PG) {
+        NumVal nt[4];
+        BoolVal bt[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k)
 #pragma unroll
-            for (int r = 0; r < PR; ++r) {
-                t[k][r] = 0;
-                tn[k][r] = true;
+            for (int g = 0; g < PG; ++g) {
+                nt[k].v[g] = 0;
+                nt[k].nul[g] = 0xffffffffu;
+                bt[k].t[g] = bt[k].f[g] = 0u;
             }
-        const int row = u.row0 + 32 * j + lane;
+        const int row = u.row0 + 32 * j + lane;  // this lane's row in group 0
         for (int pc = 0; pc < u.code_len; ++pc) {
             const PredInstr ins = P.code[u.code_off + pc];
-            PVal a, b;
-            pred_fetch(P, stage, ins.a_kind, ins.a_idx, ins.imm, t, tn, row, lane, a);
-            pred_fetch(P, stage, ins.b_kind, ins.b_idx, ins.imm, t, tn, row, lane, b);
-            uint64_t res[PR];
-            bool rn[PR];
+            if (ins.op < PO_ISNULL_N) {
+                NumVal a, b;
+                fetch_num(P, stage, ins.a_kind, ins.a_idx, ins.imm, nt, row, a);
+                if (ins.b_kind != PK_NONE) fetch_num(P, stage, ins.b_kind, ins.b_idx, ins.imm, nt, row, b);
+                else b = a;
+                if (ins.op < PO_EQ_F) {
+                    NumVal r;
 #pragma unroll
-            for (int r = 0; r < PR; ++r) {
-                const double af = u2d(a.v[r]), bf = u2d(b.v[r]);
-                const int64_t ai = (int64_t)a.v[r], bi = (int64_t)b.v[r];
-                const bool an = a.nul[r], bn = b.nul[r];
-                uint64_t o = 0;
-                bool on = an || bn;
-                switch (ins.op) {
-                    case PO_MOV: o = a.v[r]; on = an; break;
-                    case PO_ADD_F: o = d2u(af + bf); break;
-                    case PO_SUB_F: o = d2u(af - bf); break;
-                    case PO_MUL_F: o = d2u(af * bf); break;
-                    case PO_DIV_F: o = d2u(af / bf); break;
-                    case PO_NEG_F: o = d2u(-af); on = an; break;
-                    case PO_ABS_F: o = d2u(fabs(af)); on = an; break;
-                    case PO_ADD_I: o = (uint64_t)ai + (uint64_t)bi; break;
-                    case PO_SUB_I: o = (uint64_t)ai - (uint64_t)bi; break;
-                    case PO_MUL_I: o = (uint64_t)ai * (uint64_t)bi; break;
-                    case PO_DIV_I:
-                        if (!on && bi == 0) {
-                            div0 = 1;
-                            on = true;
-                        } else if (!on) {
-                            o = (bi == -1) ? (uint64_t)0 - (uint64_t)ai : (uint64_t)(ai / bi);
+                    for (int g = 0; g < PG; ++g) {
+                        const double af = u2d(a.v[g]), bf = u2d(b.v[g]);
+                        const int64_t ai = (int64_t)a.v[g], bi = (int64_t)b.v[g];
+                        uint32_t nm = a.nul[g] | b.nul[g];
+                        uint64_t o = 0;
+                        switch (ins.op) {
+                            case PO_MOVN: o = a.v[g]; break;
+                            case PO_ADD_F: o = d2u(af + bf); break;
+                            case PO_SUB_F: o = d2u(af - bf); break;
+                            case PO_MUL_F: o = d2u(af * bf); break;
+                            case PO_DIV_F: o = d2u(af / bf); break;
+                            case PO_NEG_F: o = d2u(-af); break;
+                            case PO_ABS_F: o = d2u(fabs(af)); break;
+                            case PO_ADD_I: o = (uint64_t)ai + (uint64_t)bi; break;
+                            case PO_SUB_I: o = (uint64_t)ai - (uint64_t)bi; break;
+                            case PO_MUL_I: o = (uint64_t)ai * (uint64_t)bi; break;
+                            case PO_DIV_I:
+                            case PO_MOD_I: {
+                                const uint32_t z = __ballot_sync(0xffffffffu, bi == 0) & ~nm;
+                                div0 |= z;
+                                nm |= z;
+                                const int64_t sb = bi == 0 ? 1 : bi;
+                                if (ins.op == PO_DIV_I) o = sb == -1 ? (uint64_t)0 - (uint64_t)ai : (uint64_t)(ai / sb);
+                                else o = sb == -1 ? 0 : (uint64_t)(ai % sb);
+                            } break;
+                            case PO_NEG_I: o = (uint64_t)0 - (uint64_t)ai; break;
+                            case PO_ABS_I: o = ai < 0 ? (uint64_t)0 - (uint64_t)ai : (uint64_t)ai; break;
+                            case PO_I2F: o = d2u((double)ai); break;
+                            default: break;
                         }
-                        break;
-                    case PO_MOD_I:
-                        if (!on && bi == 0) {
-                            div0 = 1;
-                            on = true;
-                        } else if (!on) {
-                            o = (bi == -1) ? 0 : (uint64_t)(ai % bi);
-                        }
-                        break;
-                    case PO_NEG_I: o = (uint64_t)0 - (uint64_t)ai; on = an; break;
-                    case PO_ABS_I: o = ai < 0 ? (uint64_t)0 - (uint64_t)ai : (uint64_t)ai; on = an; break;
-                    case PO_EQ_F: o = af == bf; break;
-                    case PO_NE_F: o = af != bf; break;
-                    case PO_LT_F: o = af < bf; break;
-                    case PO_LE_F: o = af <= bf; break;
-                    case PO_GT_F: o = af > bf; break;
-                    case PO_GE_F: o = af >= bf; break;
-                    case PO_EQ_I: o = ai == bi; break;
-                    case PO_NE_I: o = ai != bi; break;
-                    case PO_LT_I: o = ai < bi; break;
-                    case PO_LE_I: o = ai <= bi; break;
-                    case PO_GT_I: o = ai > bi; break;
-                    case PO_GE_I: o = ai >= bi; break;
-                    case PO_AND: {
-                        const bool af0 = !an && a.v[r] == 0, bf0 = !bn && b.v[r] == 0;
-                        if (af0 || bf0) { o = 0; on = false; }
-                        else if (an || bn) { on = true; }
-                        else { o = 1; on = false; }
-                    } break;
-                    case PO_OR: {
-                        const bool at = !an && a.v[r] != 0, bt = !bn && b.v[r] != 0;
-                        if (at || bt) { o = 1; on = false; }
-                        else if (an || bn) { on = true; }
-                        else { o = 0; on = false; }
-                    } break;
-                    case PO_NOT: o = a.v[r] == 0; on = an; break;
-                    case PO_ISNULL: o = an; on = false; break;
-                    case PO_ISNOTNULL: o = !an; on = false; break;
-                    case PO_ISTRUE: o = !an && a.v[r] != 0; on = false; break;
-                    case PO_ISFALSE: o = !an && a.v[r] == 0; on = false; break;
-                    case PO_I2F: o = d2u((double)ai); on = an; break;
-                    default: break;
-                }
-                res[r] = o;
-                rn[r] = on;
-            }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                if (k == ins.dst) {
-#pragma unroll
-                    for (int r = 0; r < PR; ++r) {
-                        t[k][r] = res[r];
-                        tn[k][r] = rn[r];
+                        r.v[g] = o;
+                        r.nul[g] = nm;
                     }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k == ins.dst) nt[k] = r;
+                } else {
+                    BoolVal r;
+#pragma unroll
+                    for (int g = 0; g < PG; ++g) {
+                        const double af = u2d(a.v[g]), bf = u2d(b.v[g]);
+                        const int64_t ai = (int64_t)a.v[g], bi = (int64_t)b.v[g];
+                        bool c = false;
+                        switch (ins.op) {
+                            case PO_EQ_F: c = af == bf; break;
+                            case PO_NE_F: c = af != bf; break;
+                            case PO_LT_F: c = af < bf; break;
+                            case PO_LE_F: c = af <= bf; break;
+                            case PO_GT_F: c = af > bf; break;
+                            case PO_GE_F: c = af >= bf; break;
+                            case PO_EQ_I: c = ai == bi; break;
+                            case PO_NE_I: c = ai != bi; break;
+                            case PO_LT_I: c = ai < bi; break;
+                            case PO_LE_I: c = ai <= bi; break;
+                            case PO_GT_I: c = ai > bi; break;
+                            case PO_GE_I: c = ai >= bi; break;
+                            default: break;
+                        }
+                        const uint32_t m = __ballot_sync(0xffffffffu, c), known = ~(a.nul[g] | b.nul[g]);
+                        r.t[g] = m & known;
+                        r.f[g] = ~m & known;
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        if (k == ins.dst) bt[k] = r;
                 }
+            } else if (ins.op <= PO_ISNOTNULL_N) {
+                NumVal a;
+                fetch_num(P, stage, ins.a_kind, ins.a_idx, ins.imm, nt, row, a);
+                BoolVal r;
+#pragma unroll
+                for (int g = 0; g < PG; ++g) {
+                    r.t[g] = ins.op == PO_ISNULL_N ? a.nul[g] : ~a.nul[g];
+                    r.f[g] = ~r.t[g];
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k == ins.dst) bt[k] = r;
+            } else {
+                BoolVal a, b, r;
+                fetch_bool(P, stage, ins.a_kind, ins.a_idx, ins.imm, bt, row, a);
+                fetch_bool(P, stage, ins.b_kind, ins.b_idx, ins.imm, bt, row, b);
+#pragma unroll
+                for (int g = 0; g < PG; ++g) {
+                    const uint32_t at = a.t[g], af = a.f[g], btt = b.t[g], bf = b.f[g];
+                    uint32_t t = 0, f = 0;
+                    switch (ins.op) {
+                        case PO_MOVB: t = at; f = af; break;
+                        case PO_AND: t = at & btt; f = af | bf; break;
+                        case PO_OR: t = at | btt; f = af & bf; break;
+                        case PO_NOT: t = af; f = at; break;
+                        case PO_ISNULL_B: t = ~(at | af); f = at | af; break;
+                        case PO_ISNOTNULL_B: t = at | af; f = ~(at | af); break;
+                        case PO_ISTRUE: t = at; f = ~at; break;
+                        case PO_ISFALSE: t = af; f = ~af; break;
+                        case PO_EQ_B: t = (at & btt) | (af & bf); f = (at & bf) | (af & btt); break;
+                        case PO_NE_B: t = (at & bf) | (af & btt); f = (at & btt) | (af & bf); break;
+                        default: break;
+                    }
+                    r.t[g] = t;
+                    r.f[g] = f;
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k == ins.dst) bt[k] = r;
+            }
         }
 #pragma unroll
-        for (int r = 0; r < PR; ++r) {
-            const bool in_range = (row + 32 * r) < rows_in_tile;
-            cnt += (in_range && !tn[0][r] && t[0][r] != 0) ? 1 : 0;
-        }
+        for (int g = 0; g < PG; ++g) cnt += __popc(bt[0].t[g] & tail_mask(u.row0 + 32 * (j + g), rows_in_tile));
     }
-    st[0 * 32 + lane] = cnt;
-    st[1 * 32 + lane] = div0;
+    // masks are warp-uniform: lane 0 carries the counts
+    if (lane == 0) {
+        st[0 * 32] += cnt;
+        st[1 * 32] |= (uint64_t)(div0 != 0);
+    }
 }
 
 // reduce op of a state slot: 0 u64 add, 1 f64 add, 2 f64 min, 3 f64 max, 4 i64 min, 5 i64 max, 6 or
 __host__ __device__ __forceinline__ int slot_op(int kind, int slot) {
     switch (kind) {
         case UNIT_COUNT: return 0;
+        case UNIT_TERMS: return 0;
         case UNIT_PRED: return slot == 1 ? 6 : 0;
         case UNIT_PAIR: return slot == P_N ? 0 : 1;
         case UNIT_NUM_F64:
@@ -378,8 +593,8 @@ __device__ __forceinline__ uint64_t slot_combine(int op, uint64_t a, uint64_t b)
 __host__ __device__ __forceinline__ uint64_t slot_identity(int kind, int slot) {
     int op = slot_op(kind, slot);
     switch (op) {
-        case 2: return 0x7ff0000000000000ull;   // +inf
-        case 3: return 0xfff0000000000000ull;   // -inf
+        case 2: return 0x7ff0000000000000ull;  // +inf
+        case 3: return 0xfff0000000000000ull;  // -inf
         case 4: return (uint64_t)INT64_MAX;
         case 5: return (uint64_t)INT64_MIN;
         default: return 0;
@@ -392,7 +607,21 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     uint64_t* state = reinterpret_cast<uint64_t*>(scan_smem + (size_t)P.n_stages * P.stage_bytes);
     uint64_t* full = state + (size_t)P.n_units * SCAN_STATE_SLOTS * 32;
     uint64_t* empty = full + P.n_stages;
+    ScanTables* T = reinterpret_cast<ScanTables*>(empty + P.n_stages);
 
+    // descriptor tables -> shared memory (only the used prefix of each array)
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(&P.tab);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(T);
+        auto copy = [&](size_t off, size_t bytes) {
+            for (uint32_t i = threadIdx.x; i < bytes / 4; i += blockDim.x) dst[off / 4 + i] = src[off / 4 + i];
+        };
+        copy(offsetof(ScanTables, cols), sizeof(ScanColDesc) * P.n_cols);
+        copy(offsetof(ScanTables, units), sizeof(ScanUnitDesc) * P.n_units);
+        copy(offsetof(ScanTables, code), sizeof(PredInstr) * P.n_code);
+        copy(offsetof(ScanTables, terms), sizeof(ScanTerm) * P.n_terms);
+        copy(offsetof(ScanTables, warp_units), sizeof(T->warp_units));
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < P.n_stages; ++s) {
             mbar_init(&full[s], 1);
@@ -400,87 +629,93 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         }
         mbar_fence_init();
     }
-    if (warp > 0) {
-        for (int u = 0; u < P.n_units; ++u)
-            if (P.units[u].warp == warp - 1) unit_init(P.units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane);
-    }
     __syncthreads();
+    const int n_stages = P.n_stages, tile_rows = P.tile_rows;
+    const int64_t n_tiles = P.n_tiles, n_rows = P.n_rows;
+    const uint32_t stage_bytes = P.stage_bytes;
 
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x, ++it) {
-            const int s = it % P.n_stages;
-            const uint32_t ph = (uint32_t)(it / P.n_stages) & 1u;
+        // ---------------- TMA producer: lane c moves column c ----------------
+        const bool active = lane < P.n_cols;
+        const ScanColDesc c = T->cols[active ? lane : 0];
+        const bool has_v = active && c.values != nullptr, has_b = active && c.validity != nullptr;
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             mbar_wait(&empty[s], ph ^ 1u);
-            const int64_t row_base = t * P.tile_rows;
-            const int rows = (int)min((int64_t)P.tile_rows, P.n_rows - row_base);
-            uint8_t* stage = stages + (size_t)s * P.stage_bytes;
-            // lane c moves column c; bytes are padded to 16 (buffers are allocated with that slack)
-            uint32_t vbytes = 0, bbytes = 0;
-            if (lane < P.n_cols) {
-                const ScanColDesc& c = P.cols[lane];
-                if (c.values) {
-                    if (c.kind == SC_BOOL) vbytes = (uint32_t)(((rows + 7) / 8 + 15) & ~15);
-                    else vbytes = (uint32_t)((rows * 8 + 15) & ~15);
-                }
-                if (c.validity) bbytes = (uint32_t)(((rows + 7) / 8 + 15) & ~15);
-            }
+            const int64_t row_base = t * tile_rows;
+            const int rows = (int)min((int64_t)tile_rows, n_rows - row_base);
+            uint8_t* stage = stages + (size_t)s * stage_bytes;
+            // byte counts padded to 16 (buffers are allocated with that slack)
+            const uint32_t bbytes = has_b ? (uint32_t)(((rows + 7) / 8 + 15) & ~15) : 0u;
+            const uint32_t vbytes = !has_v ? 0u : (c.kind == SC_BOOL ? (uint32_t)(((rows + 7) / 8 + 15) & ~15)
+                                                                      : (uint32_t)((rows * 8 + 15) & ~15));
             uint32_t total = vbytes + bbytes;
 #pragma unroll
             for (int m = 16; m > 0; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
             if (lane == 0) mbar_arrive_expect_tx(&full[s], total);
             __syncwarp();
-            if (lane < P.n_cols) {
-                const ScanColDesc& c = P.cols[lane];
-                if (vbytes) {
-                    const uint8_t* src = c.kind == SC_BOOL ? c.values + row_base / 8 : c.values + row_base * 8;
-                    bulk_g2s(stage + c.smem_val_off, src, vbytes, &full[s]);
-                }
-                if (bbytes) bulk_g2s(stage + c.smem_bits_off, c.validity + row_base / 8, bbytes, &full[s]);
+            if (vbytes) {
+                const uint8_t* src = c.kind == SC_BOOL ? c.values + row_base / 8 : c.values + row_base * 8;
+                bulk_g2s(stage + c.smem_val_off, src, vbytes, &full[s]);
+            }
+            if (bbytes) bulk_g2s(stage + c.smem_bits_off, c.validity + row_base / 8, bbytes, &full[s]);
+            if (++s == n_stages) {
+                s = 0;
+                ph ^= 1u;
             }
         }
     } else {
         // ---------------- consumers ----------------
         const int cw = warp - 1;
-        int it = 0;
-        for (int64_t t = blockIdx.x; t < P.n_tiles; t += gridDim.x, ++it) {
-            const int s = it % P.n_stages;
-            const uint32_t ph = (uint32_t)(it / P.n_stages) & 1u;
+        const int n_mine = T->warp_units[cw][0];
+        for (int k = 0; k < n_mine; ++k) {
+            const int u = T->warp_units[cw][1 + k];
+            unit_init(T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane);
+        }
+        __syncwarp();
+        int s = 0;
+        uint32_t ph = 0;
+        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
             mbar_wait(&full[s], ph);
-            const int64_t row_base = t * P.tile_rows;
-            const int rows = (int)min((int64_t)P.tile_rows, P.n_rows - row_base);
-            const bool partial = rows < P.tile_rows;
-            const uint8_t* stage = stages + (size_t)s * P.stage_bytes;
-            for (int u = 0; u < P.n_units; ++u) {
-                const ScanUnitDesc& ud = P.units[u];
-                if (ud.warp != cw) continue;
-                if (ud.row0 >= rows) continue;
+            const int64_t row_base = t * tile_rows;
+            const int rows = (int)min((int64_t)tile_rows, n_rows - row_base);
+            const bool partial = rows < tile_rows;
+            const uint8_t* stage = stages + (size_t)s * stage_bytes;
+            for (int k = 0; k < n_mine; ++k) {
+                const int u = T->warp_units[cw][1 + k];
+                const ScanUnitDesc& ud = T->units[u];
                 uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
                 switch (ud.kind) {
-                    case UNIT_COUNT: unit_count(P, ud, stage, st, lane, rows); break;
-                    case UNIT_NUM_F64: unit_num<false>(P, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_NUM_I64: unit_num<true>(P, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_PAIR: unit_pair(P, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_PRED: unit_pred(P, ud, stage, st, lane, rows); break;
+                    case UNIT_COUNT: unit_count(*T, ud, stage, st, lane, rows); break;
+                    case UNIT_NUM_F64: unit_num<false>(*T, ud, stage, st, lane, rows, partial); break;
+                    case UNIT_NUM_I64: unit_num<true>(*T, ud, stage, st, lane, rows, partial); break;
+                    case UNIT_PAIR: unit_pair(*T, ud, stage, st, lane, rows, partial); break;
+                    case UNIT_PRED: unit_pred(*T, ud, stage, st, lane, rows); break;
+                    case UNIT_TERMS: unit_terms(*T, ud, stage, st, lane, rows); break;
                 }
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == n_stages) {
+                s = 0;
+                ph ^= 1u;
+            }
         }
+        __syncwarp();
         // cross-lane reduction in a fixed butterfly order, then one record per (CTA, unit)
-        for (int u = 0; u < P.n_units; ++u) {
-            const ScanUnitDesc& ud = P.units[u];
-            if (ud.warp != cw) continue;
+        for (int k = 0; k < n_mine; ++k) {
+            const int u = T->warp_units[cw][1 + k];
+            const int kind = T->units[u].kind;
             const uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
             uint64_t* out = P.partials + ((size_t)blockIdx.x * P.n_units + u) * SCAN_STATE_SLOTS;
 #pragma unroll
-            for (int k = 0; k < SCAN_STATE_SLOTS; ++k) {
-                const int op = slot_op(ud.kind, k);
-                uint64_t v = st[k * 32 + lane];
+            for (int sl = 0; sl < SCAN_STATE_SLOTS; ++sl) {
+                const int op = slot_op(kind, sl);
+                uint64_t v = st[sl * 32 + lane];
 #pragma unroll
                 for (int m = 16; m > 0; m >>= 1) v = slot_combine(op, v, shfl_xor_u64(v, m));
-                if (lane == 0) out[k] = v;
+                if (lane == 0) out[sl] = v;
             }
         }
     }
@@ -492,14 +727,14 @@ __global__ void scan_finalize_kernel(const __grid_constant__ ScanParams P, int n
     if (warp >= P.n_aggs) return;
     int kind = -1;
     for (int u = 0; u < P.n_units; ++u)
-        if (P.units[u].agg == warp) kind = P.units[u].kind;
+        if (P.tab.units[u].agg == warp) kind = P.tab.units[u].kind;
     if (kind < 0) return;
     for (int k = 0; k < SCAN_STATE_SLOTS; ++k) {
         const int op = slot_op(kind, k);
         uint64_t acc = slot_identity(kind, k);
         for (int b = lane; b < n_ctas; b += 32) {
             for (int u = 0; u < P.n_units; ++u) {
-                if (P.units[u].agg != warp) continue;
+                if (P.tab.units[u].agg != warp) continue;
                 acc = slot_combine(op, acc, P.partials[((size_t)b * P.n_units + u) * SCAN_STATE_SLOTS + k]);
             }
         }
@@ -512,7 +747,7 @@ __global__ void scan_finalize_kernel(const __grid_constant__ ScanParams P, int n
 // ---- host launchers (called from engine.cu) ----
 size_t scan_smem_bytes(const ScanParams& P) {
     return (size_t)P.n_stages * P.stage_bytes + (size_t)P.n_units * SCAN_STATE_SLOTS * 32 * 8 +
-           (size_t)2 * P.n_stages * 8;
+           (size_t)2 * P.n_stages * 8 + sizeof(ScanTables);
 }
 
 cudaError_t scan_launch(const ScanParams& P, int grid, ScanAggOut* d_out, cudaStream_t stream) {

@@ -387,36 +387,41 @@ struct Operand {
 struct Compiler {
     const ColumnResolver& resolve;
     std::vector<PredInstr>& code;
-    bool temp_used[4] = {false, false, false, false};
+    bool ntemp_used[4] = {false, false, false, false};
+    bool btemp_used[4] = {false, false, false, false};
 
-    int alloc_temp() {
+    int alloc(bool* used) {
         for (int k = 0; k < 4; ++k)
-            if (!temp_used[k]) {
-                temp_used[k] = true;
+            if (!used[k]) {
+                used[k] = true;
                 return k;
             }
         throw Error(TG_ERR_UNSUPPORTED, "SQL expression too deeply nested for the predicate engine");
     }
     void release(const Operand& o) {
-        if (o.kind == PK_TEMP) temp_used[o.idx] = false;
+        if (o.kind == PK_NTEMP) ntemp_used[o.idx] = false;
+        if (o.kind == PK_BTEMP) btemp_used[o.idx] = false;
     }
     static uint64_t d2u(double d) {
         uint64_t u;
         memcpy(&u, &d, 8);
         return u;
     }
-    static double u2d(uint64_t u) {
-        double d;
-        memcpy(&d, &u, 8);
-        return d;
-    }
+    static bool is_imm(const Operand& o) { return o.kind == PK_IMM || o.kind == PK_BIMM; }
+    Operand none() { return Operand{PK_NONE, 0, 0, PT_NULL}; }
+    Operand null_num() { return Operand{PK_NNULL, 0, 0, PT_NULL}; }
+    Operand null_bool() { return Operand{PK_BNULL, 0, 0, PT_BOOL}; }
 
+    // result_bool: destination register file
     Operand emit(uint8_t op, Operand a, Operand b, PredType type) {
-        // at most one immediate per instruction: spill `a` into a temp if both are immediates
-        if (a.kind == PK_IMM && b.kind == PK_IMM) a = emit(PO_MOV, a, Operand{PK_NULL, 0, 0, PT_NULL}, a.type);
+        const bool result_bool = type == PT_BOOL;
+        if (is_imm(a) && is_imm(b)) {
+            // at most one immediate per instruction: materialise `a`
+            a = emit(a.kind == PK_BIMM ? PO_MOVB : PO_MOVN, a, none(), a.type);
+        }
         release(a);
         release(b);
-        int dst = alloc_temp();
+        int dst = alloc(result_bool ? btemp_used : ntemp_used);
         PredInstr ins{};
         ins.op = op;
         ins.dst = (uint8_t)dst;
@@ -424,12 +429,11 @@ struct Compiler {
         ins.a_idx = a.idx;
         ins.b_kind = b.kind;
         ins.b_idx = b.idx;
-        ins.imm = a.kind == PK_IMM ? a.imm : b.imm;
+        ins.imm = is_imm(a) ? a.imm : b.imm;
         if ((int)code.size() >= SCAN_MAX_CODE) throw Error(TG_ERR_UNSUPPORTED, "SQL expression too long");
         code.push_back(ins);
-        return Operand{PK_TEMP, (uint16_t)dst, 0, type};
+        return Operand{(uint8_t)(result_bool ? PK_BTEMP : PK_NTEMP), (uint16_t)dst, 0, type};
     }
-    Operand none() { return Operand{PK_NULL, 0, 0, PT_NULL}; }
 
     Operand to_f64(Operand o) {
         if (o.type == PT_F64 || o.type == PT_NULL) return o;
@@ -438,15 +442,21 @@ struct Compiler {
         if (o.kind == PK_COL_I64) return Operand{PK_COL_I64_AS_F64, o.idx, 0, PT_F64};
         return emit(PO_I2F, o, none(), PT_F64);
     }
+    // a NULL literal adopts the register file its context needs
+    Operand as_bool(Operand o) {
+        if (o.type == PT_NULL) return null_bool();
+        if (o.type != PT_BOOL) throw Error(TG_ERR_TYPE_MISMATCH, "expected a boolean operand");
+        return o;
+    }
 
     Operand gen(const ExprP& e) {
         switch (e->kind) {
             case Expr::LIT_I: return Operand{PK_IMM, 0, (uint64_t)e->i, PT_I64};
             case Expr::LIT_F: return Operand{PK_IMM, 0, d2u(e->f), PT_F64};
-            case Expr::LIT_B: return Operand{PK_IMM, 0, e->b ? 1ull : 0ull, PT_BOOL};
-            case Expr::LIT_NULL: return none();
+            case Expr::LIT_B: return Operand{PK_BIMM, 0, e->b ? 1ull : 0ull, PT_BOOL};
+            case Expr::LIT_NULL: return null_num();
             case Expr::LIT_S:
-                throw Error(TG_ERR_UNSUPPORTED, "string literals are not supported by the predicate engine yet");
+                throw Error(TG_ERR_UNSUPPORTED, "string literals are only supported in comparisons with a Utf8 column");
             case Expr::COL: {
                 ColumnBinding b = resolve(e->s);
                 if (b.dtype == TG_INT64) return Operand{PK_COL_I64, (uint16_t)b.tile_col, 0, PT_I64};
@@ -456,11 +466,7 @@ struct Compiler {
             }
             case Expr::UNARY: {
                 Operand a = gen(e->args[0]);
-                if (e->s == "NOT") {
-                    if (a.type != PT_BOOL && a.type != PT_NULL)
-                        throw Error(TG_ERR_TYPE_MISMATCH, "NOT requires a boolean operand");
-                    return emit(PO_NOT, a, none(), PT_BOOL);
-                }
+                if (e->s == "NOT") return emit(PO_NOT, as_bool(a), none(), PT_BOOL);
                 if (a.type == PT_I64) return emit(PO_NEG_I, a, none(), PT_I64);
                 if (a.type == PT_F64) return emit(PO_NEG_F, a, none(), PT_F64);
                 if (a.type == PT_NULL) return a;
@@ -468,13 +474,12 @@ struct Compiler {
             }
             case Expr::IS: {
                 Operand a = gen(e->args[0]);
-                if (e->s == "NULL") return emit(PO_ISNULL, a, none(), PT_BOOL);
-                if (e->s == "NOTNULL") return emit(PO_ISNOTNULL, a, none(), PT_BOOL);
-                if (a.type != PT_BOOL && a.type != PT_NULL)
-                    throw Error(TG_ERR_TYPE_MISMATCH, "IS TRUE/FALSE requires a boolean operand");
+                const bool is_b = a.type == PT_BOOL;
+                if (e->s == "NULL") return emit(is_b ? PO_ISNULL_B : PO_ISNULL_N, a, none(), PT_BOOL);
+                if (e->s == "NOTNULL") return emit(is_b ? PO_ISNOTNULL_B : PO_ISNOTNULL_N, a, none(), PT_BOOL);
+                a = as_bool(a);
                 if (e->s == "TRUE") return emit(PO_ISTRUE, a, none(), PT_BOOL);
                 if (e->s == "FALSE") return emit(PO_ISFALSE, a, none(), PT_BOOL);
-                // IS NOT TRUE / IS NOT FALSE
                 Operand t = emit(e->s == "NOTTRUE" ? PO_ISTRUE : PO_ISFALSE, a, none(), PT_BOOL);
                 return emit(PO_NOT, t, none(), PT_BOOL);
             }
@@ -491,31 +496,25 @@ struct Compiler {
             case Expr::BINARY: {
                 const std::string& op = e->s;
                 if (op == "AND" || op == "OR") {
-                    Operand a = gen(e->args[0]);
-                    Operand b = gen(e->args[1]);
-                    if ((a.type != PT_BOOL && a.type != PT_NULL) || (b.type != PT_BOOL && b.type != PT_NULL))
-                        throw Error(TG_ERR_TYPE_MISMATCH, op + " requires boolean operands");
+                    Operand a = as_bool(gen(e->args[0]));
+                    Operand b = as_bool(gen(e->args[1]));
                     return emit(op == "AND" ? PO_AND : PO_OR, a, b, PT_BOOL);
                 }
                 Operand a = gen(e->args[0]);
                 Operand b = gen(e->args[1]);
                 const bool arith = op == "+" || op == "-" || op == "*" || op == "/" || op == "%";
                 if (a.type == PT_NULL || b.type == PT_NULL) {
-                    // NULL op x -> NULL (typed as the result type)
                     release(a);
                     release(b);
-                    Operand n = none();
-                    n.type = arith ? PT_NULL : PT_BOOL;
-                    if (!arith) return emit(PO_MOV, none(), none(), PT_BOOL);
-                    return n;
+                    if (arith) return null_num();
+                    return null_bool();  // comparison with NULL is NULL
                 }
                 if (a.type == PT_BOOL || b.type == PT_BOOL) {
                     if (arith || a.type != b.type)
                         throw Error(TG_ERR_TYPE_MISMATCH, "cannot apply '" + op + "' to boolean and numeric operands");
-                    // boolean comparison: payloads are 0/1 integers
-                    uint8_t o = op == "=" ? PO_EQ_I : op == "<>" ? PO_NE_I : op == "<" ? PO_LT_I
-                              : op == "<=" ? PO_LE_I : op == ">" ? PO_GT_I : PO_GE_I;
-                    return emit(o, a, b, PT_BOOL);
+                    if (op == "=") return emit(PO_EQ_B, a, b, PT_BOOL);
+                    if (op == "<>") return emit(PO_NE_B, a, b, PT_BOOL);
+                    throw Error(TG_ERR_UNSUPPORTED, "ordering comparison of booleans is not supported");
                 }
                 const bool use_f = a.type == PT_F64 || b.type == PT_F64;
                 if (use_f) {
@@ -566,20 +565,83 @@ void collect_columns(const ExprP& e, std::vector<std::string>& out) {
     for (auto& a : e->args) collect_columns(a, out);
 }
 
+static void flatten(const ExprP& e, const std::string& op, std::vector<ExprP>& out) {
+    if (e->kind == Expr::BINARY && e->s == op) {
+        flatten(e->args[0], op, out);
+        flatten(e->args[1], op, out);
+    } else {
+        out.push_back(e);
+    }
+}
+
+bool try_compile_terms(const ExprP& e, const ColumnResolver& resolve, std::vector<ScanTerm>& terms, bool& is_or) {
+    std::vector<ExprP> leaves;
+    is_or = e->kind == Expr::BINARY && e->s == "OR";
+    flatten(e, is_or ? "OR" : "AND", leaves);
+    if (leaves.size() > (size_t)SCAN_UNIT_TERMS) return false;
+    auto d2u = [](double d) {
+        uint64_t u;
+        memcpy(&u, &d, 8);
+        return u;
+    };
+    std::vector<ScanTerm> out;
+    for (auto& l : leaves) {
+        ScanTerm t{};
+        if (l->kind == Expr::IS && (l->s == "NULL" || l->s == "NOTNULL") && l->args[0]->kind == Expr::COL) {
+            ColumnBinding b = resolve(l->args[0]->s);
+            t.col = b.tile_col;
+            t.kind = l->s == "NULL" ? TK_ISNULL : TK_NOTNULL;
+            out.push_back(t);
+            continue;
+        }
+        if (l->kind != Expr::BINARY) return false;
+        const std::string& op = l->s;
+        int mask = op == "<" ? 1 : op == "<=" ? 3 : op == "=" ? 2 : op == ">=" ? 6 : op == ">" ? 4 : op == "<>" ? 13 : -1;
+        if (mask < 0) return false;
+        ExprP c = l->args[0], v = l->args[1];
+        if (c->kind != Expr::COL) {
+            std::swap(c, v);
+            // literal op col  ==  col (flipped op) literal
+            mask = (mask & 2) | ((mask & 1) << 2) | ((mask & 4) >> 2) | (mask & 8);
+        }
+        if (c->kind != Expr::COL || (v->kind != Expr::LIT_I && v->kind != Expr::LIT_F)) return false;
+        ColumnBinding b = resolve(c->s);
+        t.col = b.tile_col;
+        t.cmp_mask = mask;
+        if (b.dtype == TG_FLOAT64) {
+            t.kind = TK_F64;
+            t.imm = d2u(v->kind == Expr::LIT_I ? (double)v->i : v->f);
+        } else if (b.dtype == TG_INT64) {
+            if (v->kind == Expr::LIT_I) {
+                t.kind = TK_I64;
+                t.imm = (uint64_t)v->i;
+            } else {
+                t.kind = TK_I64_AS_F64;
+                t.imm = d2u(v->f);
+            }
+        } else {
+            return false;
+        }
+        out.push_back(t);
+    }
+    terms = out;
+    return true;
+}
+
 void compile_predicate(const ExprP& e, const ColumnResolver& resolve, std::vector<PredInstr>& code) {
     Compiler c{resolve, code};
     Operand r = c.gen(e);
-    if (r.type != PT_BOOL && r.type != PT_NULL)
-        throw Error(TG_ERR_TYPE_MISMATCH, "predicate must be a boolean expression");
-    // result must end in temp 0
-    if (!(r.kind == PK_TEMP && r.idx == 0)) {
+    if (r.type == PT_NULL) r = c.null_bool();
+    if (r.type != PT_BOOL) throw Error(TG_ERR_TYPE_MISMATCH, "predicate must be a boolean expression");
+    // the predicate's value must end in B0
+    if (!(r.kind == PK_BTEMP && r.idx == 0)) {
         c.release(r);
         PredInstr ins{};
-        ins.op = PO_MOV;
+        ins.op = PO_MOVB;
         ins.dst = 0;
         ins.a_kind = r.kind;
         ins.a_idx = r.idx;
-        ins.b_kind = PK_NULL;
+        ins.b_kind = PK_NONE;
         ins.imm = r.imm;
         code.push_back(ins);
     }

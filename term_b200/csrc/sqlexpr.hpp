@@ -37,6 +37,11 @@ struct ColumnBinding {
 // resolve(name) returns the binding or throws Error(TG_ERR_COLUMN_NOT_FOUND,...)
 using ColumnResolver = std::function<ColumnBinding(const std::string&)>;
 
+// Fast path: if the predicate is an AND (or an OR) of at most SCAN_UNIT_TERMS terms of the form
+// `col cmp literal`, `literal cmp col`, `col IS [NOT] NULL`, fills `terms` (col = resolver's tile_col) and
+// returns true; otherwise returns false and the caller compiles the general code.
+bool try_compile_terms(const ExprP& e, const ColumnResolver& resolve, std::vector<ScanTerm>& terms, bool& is_or);
+
 // Appends instructions to `code`; result of the predicate ends in temp 0.
 void compile_predicate(const ExprP& e, const ColumnResolver& resolve, std::vector<PredInstr>& code);
 

@@ -10,53 +10,40 @@ namespace tg {
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-__global__ void pick_pivot_kernel(const uint8_t* values, const uint32_t* validity, int64_t n_rows, int is_i64,
-                                  double* out) {
-    // one warp: first valid row -> pivot
-    const int lane = threadIdx.x;
-    const int64_t n_words = (n_rows + 31) / 32;
-    int64_t found = -1;
-    for (int64_t base = 0; base < n_words && found < 0; base += 32) {
-        const int64_t w = base + lane;
-        uint32_t bits = 0;
-        if (w < n_words) {
-            bits = validity ? validity[w] : 0xffffffffu;
-            const int64_t rem = n_rows - w * 32;
-            if (rem < 32) bits &= (1u << rem) - 1u;
-        }
-        const uint32_t any = __ballot_sync(0xffffffffu, bits != 0);
-        if (any) {
-            const int src = __ffs(any) - 1;
-            const uint32_t b = __shfl_sync(0xffffffffu, bits, src);
-            found = (base + src) * 32 + (__ffs(b) - 1);
-        }
-    }
-    if (lane == 0) {
-        double v = 0.0;
-        if (found >= 0) {
-            if (is_i64) v = (double)reinterpret_cast<const int64_t*>(values)[found];
-            else v = reinterpret_cast<const double*>(values)[found];
-            if (!(v == v) || v - v != 0.0) v = 0.0;  // NaN / inf pivots would poison the shifted sums
-        }
-        *out = v;
-    }
-}
-
+// Pivot K of the shifted moment sums: the median of the first (up to) five finite, valid values of the
+// column. It must be an ELEMENT of the column (the scan replaces NULL rows by K), and a typical one, so
+// that sum(x) = n*K + sum(x-K) keeps full accuracy; a median of five is robust to isolated outliers.
 static void set_pivot_host(Column& c, int32_t dtype, int64_t n, const void* values, const uint8_t* validity,
                            int64_t bit_offset) {
     if (c.pivot_set || (dtype != TG_INT64 && dtype != TG_FLOAT64)) return;
-    for (int64_t i = 0; i < n; ++i) {
+    double cand[5];
+    int64_t icand[5];
+    int m = 0;
+    for (int64_t i = 0; i < n && i < 65536 && m < 5; ++i) {
         bool ok = !validity || ((validity[(bit_offset + i) >> 3] >> ((bit_offset + i) & 7)) & 1);
         if (!ok) continue;
-        double v = dtype == TG_INT64 ? (double)reinterpret_cast<const int64_t*>(values)[i]
-                                     : reinterpret_cast<const double*>(values)[i];
-        if (v == v && v - v == 0.0) {
-            c.pivot = v;
-            c.pivot_set = true;
-            return;
+        if (dtype == TG_INT64) {
+            icand[m] = reinterpret_cast<const int64_t*>(values)[i];
+            cand[m] = (double)icand[m];
+            ++m;
+        } else {
+            double v = reinterpret_cast<const double*>(values)[i];
+            if (v == v && v - v == 0.0) {
+                cand[m] = v;
+                icand[m] = 0;
+                ++m;
+            }
         }
-        if (i > 4096) return;  // give up: keep 0.0 until a later batch
     }
+    if (m == 0) return;
+    for (int i = 1; i < m; ++i)
+        for (int j = i; j > 0 && (dtype == TG_INT64 ? icand[j] < icand[j - 1] : cand[j] < cand[j - 1]); --j) {
+            std::swap(cand[j], cand[j - 1]);
+            std::swap(icand[j], icand[j - 1]);
+        }
+    c.pivot = cand[m / 2];
+    c.ipivot = icand[m / 2];
+    c.pivot_set = true;
 }
 
 // append `n` bits taken from src starting at bit `src_off` (or all-ones when src == nullptr) to a device
@@ -207,16 +194,11 @@ void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_
     c.value_bytes = dtype == TG_UTF8 ? n_value_bytes : n * c.elem_bytes();
     c.null_count = -1;
     if ((dtype == TG_INT64 || dtype == TG_FLOAT64) && n > 0) {
-        double* d_p = reinterpret_cast<double*>(e.scratch(256));
-        pick_pivot_kernel<<<1, 32, 0, e.stream>>>((const uint8_t*)d_values, (const uint32_t*)d_validity, n,
-                                                  dtype == TG_INT64, d_p);
-        TG_CUDA(cudaGetLastError());
-        e.launches += 1;
-        double h = 0;
-        TG_CUDA(cudaMemcpyAsync(&h, d_p, 8, cudaMemcpyDeviceToHost, e.stream));
-        TG_CUDA(cudaStreamSynchronize(e.stream));
-        c.pivot = h;
-        c.pivot_set = true;
+        const int64_t head = std::min<int64_t>(n, 65536);
+        std::vector<uint8_t> hv((size_t)head * 8), hb((size_t)(head + 7) / 8);
+        TG_CUDA(cudaMemcpy(hv.data(), d_values, hv.size(), cudaMemcpyDeviceToHost));
+        if (d_validity) TG_CUDA(cudaMemcpy(hb.data(), d_validity, hb.size(), cudaMemcpyDeviceToHost));
+        set_pivot_host(c, dtype, head, hv.data(), d_validity ? hb.data() : nullptr, 0);
     }
     t.n_rows = std::max(t.n_rows, n);
 }
