@@ -363,7 +363,86 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     }
 }
 
+// ---- string-literal comparisons inside predicates --------------------------------------------------
+// `utf8_col = 'lit'` / `<>` (and IN lists, which desugar to them) are materialised by a small kernel into a
+// bit-packed BOOLEAN virtual column (validity = the string column's validity) that the fused scan then
+// reads like any other column; e.g. `status = 'active' AND price >= 10` (constraints/custom_sql.rs:440-456).
+__global__ void str_eq_kernel(const int32_t* offsets, const uint8_t* bytes, int64_t n, const uint8_t* lit, int32_t lit_len,
+                              uint32_t* out_bits) {
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < n;
+         base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = base + (threadIdx.x & 31);
+        bool eq = false;
+        if (row < n) {
+            const int32_t b = offsets[row], e = offsets[row + 1];
+            eq = (e - b) == lit_len;
+            for (int32_t k = 0; eq && k < lit_len; ++k) eq = bytes[b + k] == lit[k];
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, eq);
+        if ((threadIdx.x & 31) == 0) out_bits[base >> 5] = w;
+    }
+}
+
+struct VirtualCols {
+    Engine& e;
+    std::vector<std::unique_ptr<Column>> cols;
+    explicit VirtualCols(Engine& e_) : e(e_) {}
+    ~VirtualCols() {
+        cudaStreamSynchronize(e.stream);
+        for (auto& c : cols)
+            if (c->values.p) cudaFree(c->values.p);
+    }
+};
+
+static ExprP rewrite_string_compares(const ExprP& ex, Engine& e, Table& t, Plan& p, VirtualCols& vc) {
+    if (!ex) return ex;
+    if (ex->kind == Expr::BINARY && (ex->s == "=" || ex->s == "<>")) {
+        ExprP c = ex->args[0], l = ex->args[1];
+        if (c->kind != Expr::COL) std::swap(c, l);
+        if (c->kind == Expr::COL && l->kind == Expr::LIT_S) {
+            Column* col = t.find(c->s);
+            if (col && col->dtype == TG_UTF8) {
+                auto v = std::make_unique<Column>();
+                v->name = std::string("\x01str") + std::to_string(vc.cols.size());
+                v->dtype = TG_BOOL;
+                v->n_rows = t.n_rows;
+                v->validity = col->validity;
+                v->validity.owned = false;
+                const size_t words = (size_t)(t.n_rows + 31) / 32;
+                const size_t bytes = round_up(words * 4 + PAD, PAD), lit_b = round_up(l->s.size() + 1, 256);
+                TG_CUDA(cudaMalloc(&v->values.p, bytes + lit_b));
+                TG_CUDA(cudaMemsetAsync(v->values.p, 0, bytes + lit_b, e.stream));
+                uint8_t* d_lit = v->values.p + bytes;
+                if (!l->s.empty()) TG_CUDA(cudaMemcpyAsync(d_lit, l->s.data(), l->s.size(), cudaMemcpyHostToDevice, e.stream));
+                if (t.n_rows > 0) {
+                    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t.n_rows + 255) / 256, (int64_t)e.sm_count * 8));
+                    str_eq_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, t.n_rows, d_lit,
+                                                              (int32_t)l->s.size(), (uint32_t*)v->values.p);
+                    TG_CUDA(cudaGetLastError());
+                    e.launches += 1;
+                    p.stats.launches += 1;
+                }
+                p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)col->value_bytes;
+                auto node = std::make_shared<Expr>();
+                node->kind = Expr::COL;
+                node->s = v->name;
+                vc.cols.push_back(std::move(v));
+                if (ex->s == "=") return node;
+                auto neg = std::make_shared<Expr>();
+                neg->kind = Expr::UNARY;
+                neg->s = "NOT";
+                neg->args = {node};
+                return neg;
+            }
+        }
+    }
+    auto copy = std::make_shared<Expr>(*ex);
+    for (auto& a : copy->args) a = rewrite_string_compares(a, e, t, p, vc);
+    return copy;
+}
+
 void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids) {
+    VirtualCols virtuals(e);
     std::vector<ScanOp> ops;
     uint64_t bytes = 0;
     std::vector<Column*> counted_vals, counted_bits;
@@ -440,8 +519,12 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
             case A_PRED: {
                 if (!a.expr) break;
                 try {
+                    const ExprP expr = rewrite_string_compares(a.expr, e, t, p, virtuals);
                     ColumnResolver res = [&](const std::string& name) -> ColumnBinding {
                         Column* c = t.find(name);
+                        if (!c && !name.empty() && name[0] == '\x01')
+                            for (auto& v : virtuals.cols)
+                                if (v->name == name) c = v.get();
                         if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, no_field_msg(t, name));
                         for (size_t i = 0; i < o.pred_cols.size(); ++i)
                             if (o.pred_cols[i] == c) return ColumnBinding{(int)i, c->dtype};
@@ -449,13 +532,13 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                         return ColumnBinding{(int)o.pred_cols.size() - 1, c->dtype};
                     };
                     bool is_or = false;
-                    if (try_compile_terms(a.expr, res, o.terms, is_or)) {
+                    if (try_compile_terms(expr, res, o.terms, is_or)) {
                         o.kind = UNIT_TERMS;
                         o.flags = is_or ? 1 : 0;
                         o.cost = 0.15 + 0.45 * (double)o.terms.size();
                     } else {
                         o.pred_cols.clear();
-                        compile_predicate(a.expr, res, o.code);
+                        compile_predicate(expr, res, o.code);
                         o.kind = UNIT_PRED;
                         o.cost = 0.5 + 0.6 * (double)o.code.size();
                     }

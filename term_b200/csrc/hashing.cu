@@ -1,0 +1,761 @@
+// K3 / K5 — GPU hash tables for distinct / unique / primary-key counts, foreign-key anti-joins and grouped
+// completeness.
+//
+// Replaces  COUNT(DISTINCT c), COUNT(DISTINCT (a, b)), GROUP BY .. COUNT(*)     constraints/uniqueness.rs:549-718
+//           COUNT(c), COUNT(DISTINCT c)                                          analyzers/basic/distinctness.rs:113
+//           LEFT JOIN .. WHERE parent IS NULL -> COUNT(*), COUNT(DISTINCT child)  constraints/foreign_key.rs:165-172
+//           GROUP BY g.. COUNT(*), COUNT(c)                                      analyzers/basic/grouped_completeness.rs:131
+//
+// Keys: a single Int64 / Float64 column is keyed EXACTLY by its 64-bit value (open addressing, linear
+// probing, 64-bit atomicCAS). Utf8 and multi-column keys are keyed by a 128-bit fingerprint of the tuple
+// (two independent 64-bit hashes; NULL components hash as a tag so NULL is "a value" where SQL makes it
+// one). Counting is incremental: the first insert of a key adds one distinct and one singleton, the
+// second removes the singleton, so no pass over the table is needed afterwards.
+// Round-1 layout: one table in HBM (capacity = next pow2 >= 2n); the radix-partitioned shared-memory
+// variant is the planned optimisation.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace tg {
+
+constexpr unsigned long long EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr int HASH_THREADS = 256;
+
+__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+__device__ __forceinline__ uint64_t canon_f64(uint64_t bits) {
+    // -0.0 == +0.0 and all NaNs compare as one value when grouping
+    if ((bits << 1) == 0) return 0;
+    if ((bits & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (bits & 0x000fffffffffffffull)) return 0x7ff8000000000000ull;
+    return bits;
+}
+__device__ __forceinline__ bool row_valid(const uint32_t* validity, int64_t row) {
+    return !validity || ((validity[row >> 5] >> (row & 31)) & 1u);
+}
+
+struct HashCounters {
+    unsigned long long distinct_all;      // groups, NULL as a value
+    unsigned long long distinct_nonnull;  // groups whose key has no NULL component
+    unsigned long long singles_plus;      // +1 on first insert
+    unsigned long long singles_minus;     // +1 on second insert
+    unsigned long long any_null_rows;
+    unsigned long long special;           // rows whose exact key equals the EMPTY sentinel (path A)
+    unsigned long long violations;        // FK
+    unsigned long long null_children;     // FK
+    unsigned long long n_examples;
+    unsigned long long pad[7];
+};
+
+// block-level reduction of per-thread counters, one atomic per counter per CTA
+__device__ __forceinline__ void flush_counter(unsigned long long v, unsigned long long* dst) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+// ---------------------------------------------------------------- path A: exact 64-bit keys ----
+__global__ void __launch_bounds__(HASH_THREADS) insert64_kernel(const uint64_t* values, const uint32_t* validity,
+                                                                int64_t n, int is_f64, unsigned long long* keys,
+                                                                uint32_t* counts, uint64_t mask, HashCounters* ctr) {
+    unsigned long long d = 0, sp = 0, sm = 0, nulls = 0, special = 0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        if (!row_valid(validity, row)) {
+            ++nulls;
+            continue;
+        }
+        uint64_t key = values[row];
+        if (is_f64) key = canon_f64(key);
+        if (key == EMPTY64) {
+            ++special;
+            continue;
+        }
+        uint64_t slot = fmix64(key) & mask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, (unsigned long long)key);
+            if (prev == EMPTY64 || prev == key) {
+                const uint32_t old = atomicAdd(&counts[slot], 1u);
+                if (old == 0) {
+                    ++d;
+                    ++sp;
+                } else if (old == 1) {
+                    ++sm;
+                }
+                break;
+            }
+            slot = (slot + 1) & mask;
+        }
+    }
+    flush_counter(d, &ctr->distinct_nonnull);
+    flush_counter(sp, &ctr->singles_plus);
+    flush_counter(sm, &ctr->singles_minus);
+    flush_counter(nulls, &ctr->any_null_rows);
+    flush_counter(special, &ctr->special);
+}
+
+// ---------------------------------------------------------------- path B: 128-bit fingerprints ----
+struct Fp {
+    uint64_t h1, h2;
+};
+constexpr uint64_t NULL_TAG1 = 0x9ae16a3b2f90404full, NULL_TAG2 = 0xc3a5c85c97cb3127ull;
+
+__device__ __forceinline__ void fp_combine(Fp& acc, uint64_t a, uint64_t b, bool first) {
+    if (first) {
+        acc.h1 = fmix64(a ^ 0x2545f4914f6cdd1dull);
+        acc.h2 = fmix64(b + 0x9e3779b97f4a7c15ull);
+    } else {
+        acc.h1 = fmix64(acc.h1 * 0x9e3779b97f4a7c15ull + a);
+        acc.h2 = fmix64((acc.h2 ^ b) * 0xd6e8feb86659fd93ull + 0x632be59bd9b4e019ull);
+    }
+}
+
+// fixed-width column -> fingerprint update; nullflag[row] |= 1 when the component is NULL
+__global__ void fp_fixed_kernel(const uint8_t* values, const uint32_t* validity, int64_t n, int dtype, int first,
+                                Fp* fp, uint8_t* nullflag) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        Fp acc = first ? Fp{0, 0} : fp[row];
+        if (!row_valid(validity, row)) {
+            fp_combine(acc, NULL_TAG1, NULL_TAG2, first);
+            nullflag[row] = first ? 1 : (nullflag[row] | 1);
+        } else {
+            uint64_t v;
+            switch (dtype) {
+                case TG_INT64: v = reinterpret_cast<const uint64_t*>(values)[row]; break;
+                case TG_FLOAT64: v = canon_f64(reinterpret_cast<const uint64_t*>(values)[row]); break;
+                case TG_INT32: v = (uint64_t)(int64_t)reinterpret_cast<const int32_t*>(values)[row]; break;
+                case TG_FLOAT32: v = canon_f64((uint64_t)__double_as_longlong((double)reinterpret_cast<const float*>(values)[row])); break;
+                default: v = (reinterpret_cast<const uint32_t*>(values)[row >> 5] >> (row & 31)) & 1u; break;  // TG_BOOL
+            }
+            fp_combine(acc, v, v ^ 0x5851f42d4c957f2dull, first);
+            if (first) nullflag[row] = 0;
+        }
+        fp[row] = acc;
+    }
+}
+
+// Utf8 column: two independent multiplicative hashes over the bytes (8 at a time), length-seeded
+__global__ void fp_utf8_kernel(const int32_t* offsets, const uint8_t* bytes, const uint32_t* validity, int64_t n, int first,
+                               Fp* fp, uint8_t* nullflag) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        Fp acc = first ? Fp{0, 0} : fp[row];
+        if (!row_valid(validity, row)) {
+            fp_combine(acc, NULL_TAG1, NULL_TAG2, first);
+            nullflag[row] = first ? 1 : (nullflag[row] | 1);
+        } else {
+            const int32_t b = offsets[row], e = offsets[row + 1];
+            uint64_t a = 0x736f6d6570736575ull ^ (uint64_t)(e - b), c = 0x646f72616e646f6dull + (uint64_t)(e - b) * 0x100000001b3ull;
+            int32_t p = b;
+            for (; p + 8 <= e; p += 8) {
+                uint64_t w = 0;
+#pragma unroll
+                for (int k = 0; k < 8; ++k) w |= (uint64_t)bytes[p + k] << (8 * k);
+                a = (a ^ w) * 0x9fb21c651e98df25ull;
+                a ^= a >> 29;
+                c = (c + w) * 0xc2b2ae3d27d4eb4full;
+                c ^= c >> 31;
+            }
+            uint64_t w = 0;
+            for (int k = 0; p + k < e; ++k) w |= (uint64_t)bytes[p + k] << (8 * k);
+            a = (a ^ w) * 0x9fb21c651e98df25ull;
+            c = (c + w) * 0xc2b2ae3d27d4eb4full;
+            fp_combine(acc, fmix64(a), fmix64(c), first);
+            if (first) nullflag[row] = 0;
+        }
+        fp[row] = acc;
+    }
+}
+
+struct Table128 {
+    unsigned long long* h1;
+    unsigned long long* h2;
+    uint32_t* counts;
+    uint64_t mask;
+};
+
+// find-or-insert a fingerprint; returns the slot and whether this call created it
+__device__ __forceinline__ uint64_t upsert128(const Table128& t, Fp f, bool& created) {
+    uint64_t a = f.h1 == EMPTY64 ? 0 : f.h1, b = f.h2 == EMPTY64 ? 0 : f.h2;
+    uint64_t slot = (a ^ (b >> 32)) & t.mask;
+    created = false;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&t.h1[slot], EMPTY64, (unsigned long long)a);
+        if (prev == EMPTY64) {
+            // claimed: publish the second word
+            atomicExch(&t.h2[slot], (unsigned long long)b);
+            created = true;
+            return slot;
+        }
+        if (prev == a) {
+            unsigned long long v;
+            do {
+                v = *reinterpret_cast<volatile unsigned long long*>(&t.h2[slot]);
+            } while (v == EMPTY64);
+            if (v == b) return slot;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+__global__ void __launch_bounds__(HASH_THREADS) insert128_kernel(const Fp* fp, const uint8_t* nullflag, int64_t n,
+                                                                 Table128 t, HashCounters* ctr) {
+    unsigned long long da = 0, dn = 0, sp = 0, sm = 0, nulls = 0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        const bool has_null = nullflag[row] != 0;
+        nulls += has_null;
+        bool created;
+        const uint64_t slot = upsert128(t, fp[row], created);
+        const uint32_t old = atomicAdd(&t.counts[slot], 1u);
+        if (old == 0) {
+            ++da;
+            dn += !has_null;
+            ++sp;
+        } else if (old == 1) {
+            ++sm;
+        }
+    }
+    flush_counter(da, &ctr->distinct_all);
+    flush_counter(dn, &ctr->distinct_nonnull);
+    flush_counter(sp, &ctr->singles_plus);
+    flush_counter(sm, &ctr->singles_minus);
+    flush_counter(nulls, &ctr->any_null_rows);
+}
+
+// ---------------------------------------------------------------- foreign key ----
+// parent set: keys only (64-bit exact or the h1/h2 pair)
+__global__ void __launch_bounds__(HASH_THREADS) build_set64_kernel(const uint64_t* values, const uint32_t* validity,
+                                                                   int64_t n, int is_f64, unsigned long long* keys,
+                                                                   uint64_t mask, unsigned long long* has_special) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        if (!row_valid(validity, row)) continue;
+        uint64_t key = values[row];
+        if (is_f64) key = canon_f64(key);
+        if (key == EMPTY64) {
+            *has_special = 1;
+            continue;
+        }
+        uint64_t slot = fmix64(key) & mask;
+        while (true) {
+            const unsigned long long prev = atomicCAS(&keys[slot], EMPTY64, (unsigned long long)key);
+            if (prev == EMPTY64 || prev == key) break;
+            slot = (slot + 1) & mask;
+        }
+    }
+}
+
+__device__ __forceinline__ bool set64_contains(const unsigned long long* keys, uint64_t mask, uint64_t key) {
+    uint64_t slot = fmix64(key) & mask;
+    while (true) {
+        const unsigned long long v = keys[slot];
+        if (v == key) return true;
+        if (v == EMPTY64) return false;
+        slot = (slot + 1) & mask;
+    }
+}
+
+// pass 1: count violating child rows; pass 2 (collect != 0): also dedupe violators into vkeys/vcounts and record
+// up to max_examples row indices of first occurrences
+__global__ void __launch_bounds__(HASH_THREADS) fk_probe64_kernel(const uint64_t* child, const uint32_t* validity, int64_t n,
+                                                                  int is_f64, const unsigned long long* pkeys, uint64_t pmask,
+                                                                  const unsigned long long* parent_has_special, int allow_nulls,
+                                                                  int collect, unsigned long long* vkeys, uint32_t* vcounts,
+                                                                  uint64_t vmask, int64_t* examples, int max_examples,
+                                                                  HashCounters* ctr) {
+    unsigned long long viol = 0, nullc = 0, dist = 0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        if (!row_valid(validity, row)) {
+            ++nullc;
+            if (!allow_nulls) ++viol;
+            continue;
+        }
+        uint64_t key = child[row];
+        if (is_f64) key = canon_f64(key);
+        const bool found = key == EMPTY64 ? (*parent_has_special != 0) : set64_contains(pkeys, pmask, key);
+        if (found) continue;
+        ++viol;
+        if (collect) {
+            if (key == EMPTY64) {
+                if (atomicAdd(&ctr->special, 1ull) == 0) {
+                    ++dist;
+                    const unsigned long long idx = atomicAdd(&ctr->n_examples, 1ull);
+                    if (idx < (unsigned long long)max_examples) examples[idx] = row;
+                }
+                continue;
+            }
+            uint64_t slot = fmix64(key) & vmask;
+            while (true) {
+                const unsigned long long prev = atomicCAS(&vkeys[slot], EMPTY64, (unsigned long long)key);
+                if (prev == EMPTY64 || prev == key) {
+                    if (atomicAdd(&vcounts[slot], 1u) == 0) {
+                        ++dist;
+                        const unsigned long long idx = atomicAdd(&ctr->n_examples, 1ull);
+                        if (idx < (unsigned long long)max_examples) examples[idx] = row;
+                    }
+                    break;
+                }
+                slot = (slot + 1) & vmask;
+            }
+        }
+    }
+    flush_counter(viol, &ctr->violations);
+    flush_counter(nullc, &ctr->null_children);
+    if (collect) flush_counter(dist, &ctr->distinct_all);
+}
+
+// fingerprint variants (Utf8 keys)
+__global__ void __launch_bounds__(HASH_THREADS) build_set128_kernel(const Fp* fp, const uint8_t* nullflag, int64_t n, Table128 t) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        if (nullflag[row]) continue;
+        bool created;
+        upsert128(t, fp[row], created);
+    }
+}
+__device__ __forceinline__ bool set128_contains(const Table128& t, Fp f) {
+    uint64_t a = f.h1 == EMPTY64 ? 0 : f.h1, b = f.h2 == EMPTY64 ? 0 : f.h2;
+    uint64_t slot = (a ^ (b >> 32)) & t.mask;
+    while (true) {
+        const unsigned long long v = t.h1[slot];
+        if (v == EMPTY64) return false;
+        if (v == a && t.h2[slot] == b) return true;
+        slot = (slot + 1) & t.mask;
+    }
+}
+__global__ void __launch_bounds__(HASH_THREADS) fk_probe128_kernel(const Fp* fp, const uint8_t* nullflag, int64_t n, Table128 parent,
+                                                                   int allow_nulls, int collect, Table128 viol_t, int64_t* examples,
+                                                                   int max_examples, HashCounters* ctr) {
+    unsigned long long viol = 0, nullc = 0, dist = 0;
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        if (nullflag[row]) {
+            ++nullc;
+            if (!allow_nulls) ++viol;
+            continue;
+        }
+        if (set128_contains(parent, fp[row])) continue;
+        ++viol;
+        if (collect) {
+            bool created;
+            const uint64_t slot = upsert128(viol_t, fp[row], created);
+            if (atomicAdd(&viol_t.counts[slot], 1u) == 0) {
+                ++dist;
+                const unsigned long long idx = atomicAdd(&ctr->n_examples, 1ull);
+                if (idx < (unsigned long long)max_examples) examples[idx] = row;
+            }
+        }
+    }
+    flush_counter(viol, &ctr->violations);
+    flush_counter(nullc, &ctr->null_children);
+    if (collect) flush_counter(dist, &ctr->distinct_all);
+}
+
+// ---------------------------------------------------------------- grouped completeness ----
+// table entry: fingerprint of the group tuple -> (total rows, non-null target rows, first row index)
+__global__ void __launch_bounds__(HASH_THREADS) group_count_kernel(const Fp* fp, int64_t n, const uint32_t* target_validity,
+                                                                   Table128 t, unsigned long long* totals, unsigned long long* nonnull,
+                                                                   long long* first_row, unsigned long long* n_groups) {
+    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = base + threadIdx.x;
+        const bool active = row < n;
+        uint64_t slot = ~0ull;
+        bool created = false;
+        if (active) slot = upsert128(t, fp[row], created);
+        if (created) {
+            atomicAdd(n_groups, 1ull);
+            atomicMin(&first_row[slot], (long long)row);
+        } else if (active) {
+            atomicMin(&first_row[slot], (long long)row);
+        }
+        // warp-aggregated counting: one atomic per distinct slot per warp
+        const unsigned amask = __ballot_sync(0xffffffffu, active);
+        if (active) {
+            const unsigned peers = __match_any_sync(amask, slot);
+            const bool ok = row_valid(target_validity, row);
+            const unsigned ok_peers = __ballot_sync(peers, ok) & peers;
+            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
+                atomicAdd(&totals[slot], (unsigned long long)__popc(peers));
+                const int c = __popc(ok_peers);
+                if (c) atomicAdd(&nonnull[slot], (unsigned long long)c);
+            }
+        }
+    }
+}
+
+__global__ void group_collect_kernel(Table128 t, const unsigned long long* totals, const unsigned long long* nonnull,
+                                     const long long* first_row, uint64_t cap, unsigned long long* out_n, uint64_t max_out,
+                                     unsigned long long* out /* [max_out][3] = first_row, total, nonnull */) {
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        if (t.h1[s] == EMPTY64) continue;
+        const unsigned long long i = atomicAdd(out_n, 1ull);
+        if (i < max_out) {
+            out[i * 3 + 0] = (unsigned long long)first_row[s];
+            out[i * 3 + 1] = totals[s];
+            out[i * 3 + 2] = nonnull[s];
+        }
+    }
+}
+
+// ================================================================== host side ==================
+static uint64_t pow2_at_least(uint64_t x) {
+    uint64_t p = 1024;
+    while (p < x) p <<= 1;
+    return p;
+}
+static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+static int grid_for(Engine& e, int64_t n) {
+    const int64_t blocks = (n + HASH_THREADS - 1) / HASH_THREADS;
+    return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)e.sm_count * 8));
+}
+
+struct Timer {
+    Engine& e;
+    Plan& p;
+    Timer(Engine& e_, Plan& p_) : e(e_), p(p_) { cudaEventRecord(e.ev[4], e.stream); }
+    void stop(int launches) {
+        cudaEventRecord(e.ev[5], e.stream);
+        cudaStreamSynchronize(e.stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e.ev[4], e.ev[5]);
+        p.stats.hash_ms += ms;
+        p.stats.gpu_ms += ms;
+        p.stats.launches += launches;
+        e.launches += launches;
+    }
+};
+
+static Column* need_col(Table& t, const std::string& name) {
+    Column* c = t.find(name);
+    if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + name + ". Valid fields are " + t.valid_fields() + ".");
+    return c;
+}
+
+static uint64_t col_bytes(const Column& c, int64_t n) {
+    uint64_t b = c.validity.p ? (uint64_t)(n + 7) / 8 : 0;
+    if (c.dtype == TG_UTF8) return b + (uint64_t)(n + 1) * 4 + (uint64_t)c.value_bytes;
+    if (c.dtype == TG_BOOL) return b + (uint64_t)(n + 7) / 8;
+    return b + (uint64_t)n * c.elem_bytes();
+}
+
+// fingerprints of a tuple of columns into scratch; returns launches
+static int compute_fingerprints(Engine& e, Table& t, const std::vector<Column*>& cols, Fp* d_fp, uint8_t* d_null) {
+    const int64_t n = t.n_rows;
+    const int grid = grid_for(e, n);
+    int launches = 0;
+    for (size_t i = 0; i < cols.size(); ++i) {
+        Column* c = cols[i];
+        if (c->dtype == TG_UTF8)
+            fp_utf8_kernel<<<grid, HASH_THREADS, 0, e.stream>>>((const int32_t*)c->offsets.p, c->values.p,
+                                                                (const uint32_t*)c->validity.p, n, i == 0, d_fp, d_null);
+        else
+            fp_fixed_kernel<<<grid, HASH_THREADS, 0, e.stream>>>(c->values.p, (const uint32_t*)c->validity.p, n, c->dtype,
+                                                                 i == 0, d_fp, d_null);
+        TG_CUDA(cudaGetLastError());
+        ++launches;
+    }
+    return launches;
+}
+
+void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
+    Agg& a = p.aggs[agg_id];
+    std::vector<Column*> cols;
+    for (auto& name : a.cols) cols.push_back(need_col(t, name));
+    const int64_t n = t.n_rows;
+    a.u[0] = (uint64_t)n;
+    for (auto* c : cols) p.stats.bytes_scanned += col_bytes(*c, n);
+    if (n == 0) return;
+    const bool exact64 = cols.size() == 1 && (cols[0]->dtype == TG_INT64 || cols[0]->dtype == TG_FLOAT64);
+    const uint64_t cap = pow2_at_least((uint64_t)n * 2);
+    HashCounters h{};
+    Timer tm(e, p);
+    int launches = 0;
+    if (exact64) {
+        const size_t keys_b = cap * 8, cnt_b = cap * 4;
+        uint8_t* scr = e.scratch(keys_b + cnt_b + 256);
+        unsigned long long* keys = (unsigned long long*)scr;
+        uint32_t* counts = (uint32_t*)(scr + keys_b);
+        HashCounters* d_ctr = (HashCounters*)(scr + keys_b + cnt_b);
+        TG_CUDA(cudaMemsetAsync(keys, 0xFF, keys_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(counts, 0, cnt_b + 256, e.stream));
+        insert64_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>((const uint64_t*)cols[0]->values.p,
+                                                                       (const uint32_t*)cols[0]->validity.p, n,
+                                                                       cols[0]->dtype == TG_FLOAT64, keys, counts, cap - 1, d_ctr);
+        TG_CUDA(cudaGetLastError());
+        launches = 1;
+        TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+        tm.stop(launches);
+        uint64_t distinct_nonnull = h.distinct_nonnull, singles = h.singles_plus - h.singles_minus;
+        if (h.special) {
+            distinct_nonnull += 1;
+            singles += h.special == 1;
+        }
+        const uint64_t nulls = h.any_null_rows;
+        a.u[1] = distinct_nonnull;
+        a.u[2] = singles + (nulls == 1 ? 1 : 0);  // the NULL group of GROUP BY
+        a.u[3] = nulls;
+        a.u[4] = nulls;
+        a.u[5] = distinct_nonnull + (nulls > 0 ? 1 : 0);
+        return;
+    }
+    const size_t fp_b = round_up((size_t)n * 16, 256), nf_b = round_up((size_t)n, 256);
+    const size_t h_b = cap * 8, cnt_b = cap * 4;
+    uint8_t* scr = e.scratch(fp_b + nf_b + 2 * h_b + cnt_b + 256);
+    Fp* d_fp = (Fp*)scr;
+    uint8_t* d_null = scr + fp_b;
+    Table128 tb{(unsigned long long*)(scr + fp_b + nf_b), (unsigned long long*)(scr + fp_b + nf_b + h_b),
+                (uint32_t*)(scr + fp_b + nf_b + 2 * h_b), cap - 1};
+    HashCounters* d_ctr = (HashCounters*)(scr + fp_b + nf_b + 2 * h_b + cnt_b);
+    TG_CUDA(cudaMemsetAsync(tb.h1, 0xFF, 2 * h_b, e.stream));
+    TG_CUDA(cudaMemsetAsync(tb.counts, 0, cnt_b + 256, e.stream));
+    launches += compute_fingerprints(e, t, cols, d_fp, d_null);
+    insert128_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>(d_fp, d_null, n, tb, d_ctr);
+    TG_CUDA(cudaGetLastError());
+    ++launches;
+    TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+    tm.stop(launches);
+    a.u[1] = h.distinct_nonnull;
+    a.u[2] = h.singles_plus - h.singles_minus;
+    a.u[3] = h.any_null_rows;
+    a.u[4] = h.any_null_rows;
+    a.u[5] = h.distinct_all;
+}
+
+// value of a row as the reference prints violation examples (foreign_key.rs:250-290)
+static std::string row_to_string(Engine& e, Column& c, int64_t row) {
+    if (c.dtype == TG_UTF8) {
+        int32_t off[2];
+        TG_CUDA(cudaMemcpy(off, c.offsets.p + (size_t)row * 4, 8, cudaMemcpyDeviceToHost));
+        std::string s((size_t)(off[1] - off[0]), '\0');
+        if (!s.empty()) TG_CUDA(cudaMemcpy(&s[0], c.values.p + off[0], s.size(), cudaMemcpyDeviceToHost));
+        return s;
+    }
+    if (c.dtype == TG_INT64) {
+        int64_t v;
+        TG_CUDA(cudaMemcpy(&v, c.values.p + (size_t)row * 8, 8, cudaMemcpyDeviceToHost));
+        return fmt_i64(v);
+    }
+    if (c.dtype == TG_FLOAT64) {
+        double v;
+        TG_CUDA(cudaMemcpy(&v, c.values.p + (size_t)row * 8, 8, cudaMemcpyDeviceToHost));
+        return fmt_f64(v);
+    }
+    if (c.dtype == TG_INT32) {
+        int32_t v;
+        TG_CUDA(cudaMemcpy(&v, c.values.p + (size_t)row * 4, 4, cudaMemcpyDeviceToHost));
+        return fmt_i64(v);
+    }
+    return "";
+}
+
+void exec_fk_job(Engine& e, Plan& p, int agg_id) {
+    Agg& a = p.aggs[agg_id];
+    auto find_table = [&](const std::string& name) -> Table& {
+        auto it = e.tables.find(name);
+        if (it == e.tables.end())
+            throw Error(TG_ERR_TABLE_NOT_FOUND, "Constraint evaluation failed for 'foreign_key': Foreign key validation query failed: "
+                                                "Error during planning: table 'datafusion.public." + name + "' not found");
+        return *it->second;
+    };
+    Table& ct = find_table(a.cols[0]);
+    Table& pt = find_table(a.cols[2]);
+    Column* cc = need_col(ct, a.cols[1]);
+    Column* pc = need_col(pt, a.cols[3]);
+    if (cc->dtype != pc->dtype)
+        throw Error(TG_ERR_TYPE_MISMATCH, "foreign key columns have different types");
+    const int64_t nc = ct.n_rows, np = pt.n_rows;
+    p.stats.bytes_scanned += col_bytes(*cc, nc) + col_bytes(*pc, np);
+    const int allow_nulls = a.flags, max_examples = std::max(0, a.iparam);
+    if (nc == 0) return;
+    const bool exact64 = cc->dtype == TG_INT64 || cc->dtype == TG_FLOAT64;
+    const uint64_t pcap = pow2_at_least((uint64_t)std::max<int64_t>(np, 1) * 2);
+    HashCounters h{};
+    Timer tm(e, p);
+    int launches = 0;
+    std::vector<int64_t> ex_rows;
+    if (exact64) {
+        const size_t pk_b = pcap * 8;
+        uint8_t* scr = e.scratch(pk_b + 512);
+        unsigned long long* pkeys = (unsigned long long*)scr;
+        HashCounters* d_ctr = (HashCounters*)(scr + pk_b);
+        unsigned long long* d_special = (unsigned long long*)(scr + pk_b + 256);
+        TG_CUDA(cudaMemsetAsync(pkeys, 0xFF, pk_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(d_ctr, 0, 512, e.stream));
+        if (np > 0) {
+            build_set64_kernel<<<grid_for(e, np), HASH_THREADS, 0, e.stream>>>((const uint64_t*)pc->values.p, (const uint32_t*)pc->validity.p,
+                                                                               np, pc->dtype == TG_FLOAT64, pkeys, pcap - 1, d_special);
+            ++launches;
+        }
+        fk_probe64_kernel<<<grid_for(e, nc), HASH_THREADS, 0, e.stream>>>((const uint64_t*)cc->values.p, (const uint32_t*)cc->validity.p, nc,
+                                                                          cc->dtype == TG_FLOAT64, pkeys, pcap - 1, d_special, allow_nulls, 0,
+                                                                          nullptr, nullptr, 0, nullptr, 0, d_ctr);
+        TG_CUDA(cudaGetLastError());
+        ++launches;
+        TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        const uint64_t viol = h.violations;
+        const uint64_t key_viol = viol - (allow_nulls ? 0 : h.null_children);
+        if (key_viol > 0) {
+            // second pass: dedupe the violating keys (table sized from the known count)
+            const uint64_t vcap = pow2_at_least(key_viol * 2);
+            const size_t vk_b = vcap * 8, vc_b = vcap * 4, ex_b = round_up((size_t)std::max(max_examples, 1) * 8, 256);
+            // scratch may move: re-derive every pointer after growing
+            scr = e.scratch(pk_b + 512 + vk_b + vc_b + ex_b);
+            pkeys = (unsigned long long*)scr;
+            d_ctr = (HashCounters*)(scr + pk_b);
+            d_special = (unsigned long long*)(scr + pk_b + 256);
+            unsigned long long* vkeys = (unsigned long long*)(scr + pk_b + 512);
+            uint32_t* vcounts = (uint32_t*)(scr + pk_b + 512 + vk_b);
+            int64_t* d_ex = (int64_t*)(scr + pk_b + 512 + vk_b + vc_b);
+            TG_CUDA(cudaMemsetAsync(pkeys, 0xFF, pk_b, e.stream));
+            TG_CUDA(cudaMemsetAsync(d_ctr, 0, 512, e.stream));
+            TG_CUDA(cudaMemsetAsync(vkeys, 0xFF, vk_b, e.stream));
+            TG_CUDA(cudaMemsetAsync(vcounts, 0, vc_b + ex_b, e.stream));
+            if (np > 0) {
+                build_set64_kernel<<<grid_for(e, np), HASH_THREADS, 0, e.stream>>>((const uint64_t*)pc->values.p, (const uint32_t*)pc->validity.p,
+                                                                                   np, pc->dtype == TG_FLOAT64, pkeys, pcap - 1, d_special);
+                ++launches;
+            }
+            fk_probe64_kernel<<<grid_for(e, nc), HASH_THREADS, 0, e.stream>>>((const uint64_t*)cc->values.p, (const uint32_t*)cc->validity.p, nc,
+                                                                              cc->dtype == TG_FLOAT64, pkeys, pcap - 1, d_special, allow_nulls, 1,
+                                                                              vkeys, vcounts, vcap - 1, d_ex, max_examples, d_ctr);
+            TG_CUDA(cudaGetLastError());
+            ++launches;
+            TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+            TG_CUDA(cudaStreamSynchronize(e.stream));
+            const size_t ne = (size_t)std::min<uint64_t>(h.n_examples, (uint64_t)max_examples);
+            ex_rows.resize(ne);
+            if (ne) TG_CUDA(cudaMemcpy(ex_rows.data(), d_ex, ne * 8, cudaMemcpyDeviceToHost));
+        }
+    } else if (cc->dtype == TG_UTF8) {
+        const size_t cfp_b = round_up((size_t)nc * 16, 256), cnf_b = round_up((size_t)nc, 256);
+        const size_t pfp_b = round_up((size_t)std::max<int64_t>(np, 1) * 16, 256), pnf_b = round_up((size_t)std::max<int64_t>(np, 1), 256);
+        const size_t ph_b = pcap * 8;
+        const uint64_t vcap = pow2_at_least((uint64_t)nc * 2);  // worst case: every child row violates
+        const size_t vh_b = vcap * 8, vc_b = vcap * 4, ex_b = round_up((size_t)std::max(max_examples, 1) * 8, 256);
+        uint8_t* scr = e.scratch(cfp_b + cnf_b + pfp_b + pnf_b + 2 * ph_b + 2 * vh_b + vc_b + ex_b + 512);
+        uint8_t* q = scr;
+        Fp* cfp = (Fp*)q; q += cfp_b;
+        uint8_t* cnf = q; q += cnf_b;
+        Fp* pfp = (Fp*)q; q += pfp_b;
+        uint8_t* pnf = q; q += pnf_b;
+        Table128 ptab{(unsigned long long*)q, (unsigned long long*)(q + ph_b), nullptr, pcap - 1}; q += 2 * ph_b;
+        Table128 vtab{(unsigned long long*)q, (unsigned long long*)(q + vh_b), (uint32_t*)(q + 2 * vh_b), vcap - 1}; q += 2 * vh_b + vc_b;
+        int64_t* d_ex = (int64_t*)q; q += ex_b;
+        HashCounters* d_ctr = (HashCounters*)q;
+        TG_CUDA(cudaMemsetAsync(ptab.h1, 0xFF, 2 * ph_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(vtab.h1, 0xFF, 2 * vh_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(vtab.counts, 0, vc_b + ex_b + 512, e.stream));
+        launches += compute_fingerprints(e, ct, {cc}, cfp, cnf);
+        if (np > 0) {
+            launches += compute_fingerprints(e, pt, {pc}, pfp, pnf);
+            build_set128_kernel<<<grid_for(e, np), HASH_THREADS, 0, e.stream>>>(pfp, pnf, np, ptab);
+            ++launches;
+        }
+        fk_probe128_kernel<<<grid_for(e, nc), HASH_THREADS, 0, e.stream>>>(cfp, cnf, nc, ptab, allow_nulls, 1, vtab, d_ex, max_examples, d_ctr);
+        TG_CUDA(cudaGetLastError());
+        ++launches;
+        TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        const size_t ne = (size_t)std::min<uint64_t>(h.n_examples, (uint64_t)max_examples);
+        ex_rows.resize(ne);
+        if (ne) TG_CUDA(cudaMemcpy(ex_rows.data(), d_ex, ne * 8, cudaMemcpyDeviceToHost));
+    } else {
+        throw Error(TG_ERR_UNSUPPORTED, "foreign key columns of this type are not supported");
+    }
+    tm.stop(launches);
+    a.u[0] = h.violations;
+    a.u[1] = h.distinct_all;
+    a.u[2] = h.null_children;
+    // examples blob: [count u64][u32 len, bytes]...
+    uint64_t cnt = ex_rows.size();
+    a.blob.resize(8);
+    memcpy(a.blob.data(), &cnt, 8);
+    std::sort(ex_rows.begin(), ex_rows.end());
+    for (int64_t r : ex_rows) {
+        std::string s = row_to_string(e, *cc, r);
+        uint32_t L = (uint32_t)s.size();
+        size_t o = a.blob.size();
+        a.blob.resize(o + 4 + L);
+        memcpy(a.blob.data() + o, &L, 4);
+        memcpy(a.blob.data() + o + 4, s.data(), L);
+    }
+}
+
+void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id) {
+    Agg& a = p.aggs[agg_id];
+    Column* target = need_col(t, a.cols[0]);
+    std::vector<Column*> gcols;
+    for (size_t i = 1; i < a.cols.size(); ++i) gcols.push_back(need_col(t, a.cols[i]));
+    const int64_t n = t.n_rows;
+    for (auto* c : gcols) p.stats.bytes_scanned += col_bytes(*c, n);
+    if (target->validity.p) p.stats.bytes_scanned += (uint64_t)(n + 7) / 8;
+    uint64_t zero = 0;
+    a.blob.assign((uint8_t*)&zero, (uint8_t*)&zero + 8);
+    if (n == 0) return;
+    const uint64_t max_groups_dev = 1u << 20;
+    const uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, max_groups_dev * 4));
+    const size_t fp_b = round_up((size_t)n * 16, 256), nf_b = round_up((size_t)n, 256), h_b = cap * 8;
+    const size_t out_b = round_up((size_t)max_groups_dev * 24, 256);
+    uint8_t* scr = e.scratch(fp_b + nf_b + 5 * h_b + out_b + 256);
+    uint8_t* q = scr;
+    Fp* d_fp = (Fp*)q; q += fp_b;
+    uint8_t* d_null = q; q += nf_b;
+    Table128 tb{(unsigned long long*)q, (unsigned long long*)(q + h_b), nullptr, cap - 1}; q += 2 * h_b;
+    unsigned long long* totals = (unsigned long long*)q; q += h_b;
+    unsigned long long* nonnull = (unsigned long long*)q; q += h_b;
+    long long* first_row = (long long*)q; q += h_b;
+    unsigned long long* d_out = (unsigned long long*)q; q += out_b;
+    unsigned long long* d_n = (unsigned long long*)q;
+    Timer tm(e, p);
+    TG_CUDA(cudaMemsetAsync(tb.h1, 0xFF, 2 * h_b, e.stream));
+    TG_CUDA(cudaMemsetAsync(totals, 0, 2 * h_b, e.stream));
+    TG_CUDA(cudaMemsetAsync(first_row, 0x7F, h_b, e.stream));
+    TG_CUDA(cudaMemsetAsync(d_n, 0, 256, e.stream));
+    int launches = compute_fingerprints(e, t, gcols, d_fp, d_null);
+    group_count_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>(d_fp, n, (const uint32_t*)target->validity.p, tb, totals, nonnull,
+                                                                      first_row, d_n);
+    TG_CUDA(cudaGetLastError());
+    unsigned long long n_groups = 0;
+    TG_CUDA(cudaMemcpyAsync(&n_groups, d_n, 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    if (n_groups > max_groups_dev) {
+        tm.stop(launches + 1);
+        throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 1048576 groups");
+    }
+    group_collect_kernel<<<grid_for(e, (int64_t)cap), HASH_THREADS, 0, e.stream>>>(tb, totals, nonnull, first_row, cap, d_n + 1,
+                                                                                  max_groups_dev, d_out);
+    TG_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> out((size_t)n_groups * 3);
+    if (n_groups) TG_CUDA(cudaMemcpyAsync(out.data(), d_out, out.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+    tm.stop(launches + 2);
+    // group keys: string value of each group column at the group's first row, joined by \x1f
+    a.blob.resize(8);
+    memcpy(a.blob.data(), &n_groups, 8);
+    for (unsigned long long g = 0; g < n_groups; ++g) {
+        const int64_t row = (int64_t)out[g * 3];
+        std::string key;
+        for (size_t i = 0; i < gcols.size(); ++i) {
+            if (i) key += '\x1f';
+            bool valid = true;
+            if (gcols[i]->validity.p) {
+                uint8_t b;
+                TG_CUDA(cudaMemcpy(&b, gcols[i]->validity.p + (row >> 3), 1, cudaMemcpyDeviceToHost));
+                valid = (b >> (row & 7)) & 1;
+            }
+            key += valid ? row_to_string(e, *gcols[i], row) : std::string("NULL");
+        }
+        uint32_t L = (uint32_t)key.size();
+        size_t o = a.blob.size();
+        a.blob.resize(o + 4 + L + 16);
+        memcpy(a.blob.data() + o, &L, 4);
+        memcpy(a.blob.data() + o + 4, key.data(), L);
+        memcpy(a.blob.data() + o + 4 + L, &out[g * 3 + 1], 8);
+        memcpy(a.blob.data() + o + 4 + L + 8, &out[g * 3 + 2], 8);
+    }
+}
+
+}  // namespace tg

@@ -270,3 +270,158 @@ def test_string_suite_matches_oracle(ctx, n):
             assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (g, o)
     finally:
         ctx.deregister_table(name)
+
+
+# ---------------------------------------------------------------- hash jobs: distinct / unique / FK / grouped ----
+def _uniq_all_kinds(ctx, name, t, cols):
+    A = T.Assertion
+    variants = [
+        dict(uniqueness="FullUniqueness", threshold=0.5),
+        dict(uniqueness="Distinctness", assertion=["GreaterThan", 0.1]),
+        dict(uniqueness="UniqueValueRatio", assertion=["GreaterThan", 0.1]),
+        dict(uniqueness="PrimaryKey"),
+        dict(uniqueness="UniqueWithNulls", threshold=0.5, null_handling="Include"),
+        dict(uniqueness="UniqueWithNulls", threshold=0.5, null_handling="Distinct"),
+    ]
+    for v in variants:
+        op = dict(kind="uniqueness", columns=cols, **v)
+        g = H.build_constraint(T, op).evaluate(ctx, name)
+        o = O.uniqueness(t, cols, v["uniqueness"], v.get("threshold", 1.0),
+                         tuple(v["assertion"]) if "assertion" in v else None, v.get("null_handling", "Exclude"))
+        assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (cols, v, g, o)
+
+
+@pytest.mark.parametrize("n", [1, 33, 1000, 300_000])
+def test_uniqueness_matches_oracle(ctx, n):
+    rng = np.random.default_rng(n)
+    ints = rng.integers(0, max(2, n // 2), n)
+    ints[rng.random(n) < 0.01] = -1  # 0xFFFF..FFFF: the table's EMPTY sentinel must still count as a key
+    floats = rng.integers(0, max(2, n // 3), n).astype(np.float64) / 4.0
+    floats[rng.random(n) < 0.01] = -0.0
+    strs = [f"k{v}" if v % 7 else "" for v in rng.integers(0, max(2, n // 2), n)]
+    small = rng.integers(0, 5, n)
+    t = pa.table({
+        "i": pa.array(ints, mask=rng.random(n) < 0.03), "f": pa.array(floats, mask=rng.random(n) < 0.03),
+        "s": pa.array(strs, type=pa.string(), mask=rng.random(n) < 0.03), "g": pa.array(small),
+        "pk": pa.array(np.arange(n, dtype=np.int64)),
+    })
+    name = f"uniq_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=7001))
+    try:
+        for cols in (["i"], ["f"], ["s"], ["pk"], ["i", "g"], ["s", "f"]):
+            _uniq_all_kinds(ctx, name, t, cols)
+        a = T.DistinctnessAnalyzer("s").compute(ctx, name)
+        nn, d, m = O.an_distinctness(t, "s")
+        assert a.u[:2] == [nn, d] and a.metric_double == m
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.parametrize("kind", ["i64", "str"])
+def test_foreign_key_matches_oracle(ctx, kind):
+    rng = np.random.default_rng(11)
+    n_parent, n_child = 5000, 200_000
+    parents = rng.permutation(n_parent * 2)[:n_parent]
+    children = rng.integers(0, n_parent * 2 + 50, n_child)
+    cmask = rng.random(n_child) < 0.01
+    if kind == "str":
+        pt = pa.table({"id": pa.array([f"c{v}" for v in parents], type=pa.string())})
+        ct = pa.table({"cid": pa.array([f"c{v}" for v in children], type=pa.string(), mask=cmask)})
+    else:
+        pt = pa.table({"id": pa.array(parents.astype(np.int64))})
+        ct = pa.table({"cid": pa.array(children.astype(np.int64), mask=cmask)})
+    ctx.register_table("fkp", pt)
+    ctx.register_table("fkc", ct)
+    try:
+        for allow in (False, True):
+            g = T.ForeignKeyConstraint("fkc.cid", "fkp.id").allow_nulls(allow).evaluate(ctx)
+            o, total, uniq = O.foreign_key({"fkc": ct, "fkp": pt}, "fkc.cid", "fkp.id", allow)
+            assert g.status.name.lower() == o.status and g.metric == o.metric
+            assert g.message.startswith(o.message), (g.message, o.message)
+            # examples: any valid subset of the violating values (unordered DISTINCT .. LIMIT in the reference)
+            ex = g.message.split("Examples: [")[1].split("]")[0].split(", ")[:5]
+            pset = set(pt.column("id").to_pylist())
+            assert all((e if kind == "str" else int(e)) not in pset for e in ex)
+        ok = T.ForeignKeyConstraint("fkp.id", "fkp.id").evaluate(ctx)
+        assert ok.status is T.ConstraintStatus.Success and ok.metric is None and ok.message is None
+    finally:
+        ctx.deregister_table("fkp")
+        ctx.deregister_table("fkc")
+
+
+def test_grouped_completeness_matches_oracle(ctx):
+    rng = np.random.default_rng(5)
+    n = 100_000
+    g1 = [f"region{v}" for v in rng.integers(0, 16, n)]
+    g2 = [f"cat{v}" for v in rng.integers(0, 200, n)]
+    vals = rng.normal(0, 1, n)
+    t = pa.table({"g1": pa.array(g1), "g2": pa.array(g2), "v": pa.array(vals, mask=rng.random(n) < 0.2)})
+    ctx.register_table("grp", t)
+    try:
+        for groups in (["g1"], ["g2"], ["g1", "g2"]):
+            r = T.GroupedCompletenessAnalyzer("v", groups).compute(ctx, "grp")
+            want = O.grouped_completeness(t, "v", groups)
+            got = {k: v for k, v in r.map.items() if not k.startswith("__")}
+            assert got == {"_".join(k): nn / tt for k, (tt, nn) in want.items()}
+            tot = sum(tt for tt, _ in want.values())
+            nnn = sum(nn for _, nn in want.values())
+            assert r.map["__overall__"] == nnn / tot
+    finally:
+        ctx.deregister_table("grp")
+
+
+# ---------------------------------------------------------------- quantile sketch ----
+@pytest.mark.parametrize("n,k", [(1, 50), (100, 200), (5000, 256), (3_000_000, 256)])
+def test_kll_rank_error_within_reference_bound(ctx, n, k):
+    """contract: rank error <= 1.65/sqrt(k) against exact quantiles (kll_sketch.rs:397-399); min/max/count
+    exact (:260-265); NaN ignored (:197-199)"""
+    rng = np.random.default_rng(n)
+    vals = rng.lognormal(0.0, 1.0, n)
+    if n > 10:
+        vals[3] = np.nan
+    mask = rng.random(n) < 0.05 if n > 10 else np.zeros(n, dtype=bool)
+    t = pa.table({"x": pa.array(vals, mask=mask)})
+    name = f"kll_{n}"
+    ctx.register_table(name, t)
+    try:
+        qs = [0.0, 0.01, 0.25, 0.5, 0.75, 0.95, 0.99, 1.0]
+        r = T.KllSketchAnalyzer("x", k=k, quantiles=qs).compute(ctx, name)
+        clean = np.sort(vals[~mask & ~np.isnan(vals)])
+        assert r.u[0] == len(clean) and r.map["count"] == len(clean)
+        assert r.map["min"] == clean[0] and r.map["max"] == clean[-1]
+        bound = 1.65 / math.sqrt(k)
+        prev = -math.inf
+        for q in qs:
+            est = r.map["quantile_" + O.rust_f64(q)]
+            assert clean[0] <= est <= clean[-1] and est >= prev  # monotone, inside [min, max]
+            prev = est
+            err = O.rank_error(clean, est, q)
+            assert err <= bound, (q, est, err, bound)
+            if n <= 8 * k:  # fewer items than the sketch capacity: exact order statistics
+                target = max(1, math.ceil(q * len(clean)))
+                assert est == (clean[0] if q == 0.0 else clean[-1] if q == 1.0 else clean[target - 1])
+    finally:
+        ctx.deregister_table(name)
+
+
+# ---------------------------------------------------------------- Spearman ----
+@pytest.mark.parametrize("n", [2, 101, 200_000])
+def test_spearman_matches_scipy_min_ranks(ctx, n):
+    rng = np.random.default_rng(n)
+    x = np.round(rng.normal(0, 10, n), 0)  # heavy ties
+    y = 0.5 * x + rng.normal(0, 5, n)
+    yi = rng.integers(-50, 50, n)
+    t = pa.table({"x": pa.array(x, mask=rng.random(n) < 0.05 if n > 2 else None), "y": pa.array(y), "yi": pa.array(yi)})
+    name = f"spear_{n}"
+    ctx.register_table(name, t)
+    try:
+        for c2 in ("y", "yi"):
+            r = T.CorrelationAnalyzer.spearman("x", c2).compute(ctx, name)
+            want = O.an_correlation(t, "x", c2, "spearman")
+            if math.isnan(want):
+                assert math.isnan(r.metric_double)
+            else:
+                assert abs(r.metric_double - want) <= 1e-6, (r.metric_double, want)
+            assert r.metric_key == f"correlation_spearman_x_{c2}"
+    finally:
+        ctx.deregister_table(name)
