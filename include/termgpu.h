@@ -311,6 +311,12 @@ TG_API tg_status tg_plan_partial_export(const tg_plan* plan, void* buf, size_t n
 TG_API tg_status tg_plan_partial_reset(tg_plan* plan);
 TG_API tg_status tg_plan_partial_merge(tg_plan* plan, const void* buf, size_t n_bytes);
 TG_API tg_status tg_plan_finalize(tg_plan* plan);
+/* The de-duplicated device aggregates behind the slots, in partial-blob order: kind is one of
+ * 0 ROWS, 1 VALID, 2 NUM, 3 PAIR, 4 PRED, 5 REGEX, 6 DISTINCT, 7 FK, 8 KLL, 9 GROUPED, 10 SPEARMAN; key is a
+ * stable textual identity such as "num|price" (valid until the plan is destroyed). Lets a host that computed a
+ * shard elsewhere (another engine, a stored IncrementalAnalysisRunner state) assemble a partial blob. */
+TG_API int32_t tg_plan_num_aggregates(const tg_plan* plan);
+TG_API tg_status tg_plan_aggregate_info(const tg_plan* plan, int32_t i, int32_t* kind, const char** key);
 
 TG_API tg_status tg_plan_result(const tg_plan* plan, int32_t slot, tg_result* out);
 TG_API tg_status tg_plan_analyzer_result(const tg_plan* plan, int32_t slot, tg_analyzer_result* out);

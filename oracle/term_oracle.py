@@ -17,6 +17,11 @@ row): APPROX_PERCENTILE_CONT, CORR with zero variance / n<2, float MIN/MAX with 
 import math
 import re
 from dataclasses import dataclass
+
+try:  # the `regex` module implements UTS#18 \w (Alphabetic + M + Nd + Pc + Join_Control) and simple case
+    import regex as _rx  # folding exactly like the Rust regex crate; stdlib `re` differs on combining marks
+except Exception:  # pragma: no cover
+    _rx = re
 from decimal import Decimal
 from typing import Dict, List, Optional, Sequence
 
@@ -348,7 +353,7 @@ def rust_regex_to_python(pattern: str, case_insensitive: bool):
         else:
             out.append(ch)
         i += 1
-    return re.compile("".join(out), re.IGNORECASE if case_insensitive else 0)
+    return _rx.compile("".join(out), _rx.IGNORECASE if case_insensitive else 0)
 
 
 def regex_matches(col: Col, pattern: str, case_insensitive=False, trim=False) -> List[Optional[bool]]:

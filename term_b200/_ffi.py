@@ -100,6 +100,8 @@ SIGNATURES = {
     "tg_plan_partial_reset": (C.c_int, [P]),
     "tg_plan_partial_merge": (C.c_int, [P, P, C.c_size_t]),
     "tg_plan_finalize": (C.c_int, [P]),
+    "tg_plan_num_aggregates": (C.c_int32, [P]),
+    "tg_plan_aggregate_info": (C.c_int, [P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]),
     "tg_plan_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_result)]),
     "tg_plan_analyzer_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_analyzer_result)]),
     "tg_plan_map_size": (C.c_int32, [P, C.c_int32]),

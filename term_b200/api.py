@@ -376,6 +376,15 @@ class Plan:
     def finalize(self):
         F.check(F.lib().tg_plan_finalize(self._h))
 
+    def aggregates(self):
+        """[(kind, key)] of the plan's device aggregates, in partial-blob order."""
+        out = []
+        for i in range(F.lib().tg_plan_num_aggregates(self._h)):
+            k, key = C.c_int32(), C.c_char_p()
+            F.check(F.lib().tg_plan_aggregate_info(self._h, i, C.byref(k), C.byref(key)))
+            out.append((k.value, key.value.decode()))
+        return out
+
     def result(self, slot: int) -> ConstraintResult:
         r = F.tg_result()
         F.check(F.lib().tg_plan_result(self._h, slot, C.byref(r)))

@@ -300,6 +300,15 @@ tg_status tg_plan_finalize(tg_plan* p) {
     });
 }
 
+int32_t tg_plan_num_aggregates(const tg_plan* p) { return p ? (int32_t)p->p.aggs.size() : 0; }
+tg_status tg_plan_aggregate_info(const tg_plan* p, int32_t i, int32_t* kind, const char** key) {
+    return guard([&] {
+        if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
+        if (kind) *kind = p->p.aggs[i].kind;
+        if (key) *key = p->p.aggs[i].key.c_str();
+    });
+}
+
 tg_status tg_plan_result(const tg_plan* p, int32_t slot, tg_result* out) {
     return guard([&] {
         if (!p || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");

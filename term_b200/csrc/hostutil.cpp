@@ -23,10 +23,40 @@ const char* last_error_cstr() { return g_last_error.c_str(); }
 std::string fmt_f64(double v) {
     if (std::isnan(v)) return "NaN";
     if (std::isinf(v)) return v > 0 ? "inf" : "-inf";
-    char buf[512];
-    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::fixed);
-    std::string s(buf, r.ptr);
-    return s;
+    // shortest round-trip digits (scientific), then laid out positionally with zero padding — Rust pads the
+    // shortest digits with zeros instead of printing the exact binary expansion of huge / tiny values
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    std::string sci(buf, r.ptr);
+    bool neg = false;
+    size_t i = 0;
+    if (sci[0] == '-') {
+        neg = true;
+        i = 1;
+    }
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t k = i; k < epos; ++k)
+        if (sci[k] != '.') digits += sci[k];
+    const int exp10 = std::stoi(sci.substr(epos + 1));
+    std::string out;
+    const int point = exp10 + 1;  // digits before the decimal point
+    if (point <= 0) {
+        out = "0.";
+        out.append((size_t)(-point), '0');
+        out += digits;
+    } else if ((size_t)point >= digits.size()) {
+        out = digits;
+        out.append((size_t)point - digits.size(), '0');
+    } else {
+        out = digits.substr(0, (size_t)point) + "." + digits.substr((size_t)point);
+    }
+    if (out.find('.') != std::string::npos) {
+        while (!out.empty() && out.back() == '0') out.pop_back();
+        if (!out.empty() && out.back() == '.') out.pop_back();
+    }
+    if (out.empty()) out = "0";
+    return neg ? "-" + out : out;
 }
 
 // `{:.N}`: exact decimal expansion rounded half-to-even at N places — what glibc printf does.

@@ -802,7 +802,7 @@ static Dfa compile_regex_uncached(const std::string& pattern, bool case_insensit
     // block ids: 0 DEAD, 1 MATCH, then by accept_end
     std::vector<uint32_t> block(n);
     for (size_t i = 0; i < n; ++i) block[i] = !live[i] ? 0 : (acc_end[i] ? 3 : 2);
-    uint32_t nblocks = 4;
+    uint32_t nblocks = 0;  // forces a second pass: the seed partition may have fewer than 2 live blocks
     while (true) {
         std::map<std::vector<uint32_t>, uint32_t> sig_ids;
         std::vector<uint32_t> nb(n);

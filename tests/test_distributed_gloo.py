@@ -1,0 +1,145 @@
+"""N>1 host path on CPU: world_size-2 `gloo` ranks each hold a row shard, assemble the shard's partial
+aggregate blob (here from numpy — on a GPU box tg_plan_execute_partial produces it), all-gather the
+blobs with term_b200.distributed, merge them in rank order through the C ABI and finalize. Every rank must
+reproduce the oracle's single-table answer (AnalyzerState::merge semantics, analyzers/traits.rs:154-179)."""
+import math
+import os
+import struct
+
+import numpy as np
+import pyarrow as pa
+import pytest
+import torch.multiprocessing as mp
+
+N_ROWS = 20_001
+
+
+def make_table():
+    rng = np.random.default_rng(99)
+    x = rng.normal(50.0, 7.0, N_ROWS)
+    y = 0.3 * x + rng.normal(0, 2.0, N_ROWS)
+    k = rng.integers(-2**62, 2**62, N_ROWS)
+    return pa.table({"x": pa.array(x, mask=rng.random(N_ROWS) < 0.1), "y": pa.array(y, mask=rng.random(N_ROWS) < 0.1),
+                     "k": pa.array(k, mask=rng.random(N_ROWS) < 0.1)})
+
+
+def build_plan(T):
+    A = T.Assertion
+    cb = (T.Check.builder("c").has_size(A.Equals(float(N_ROWS))).completeness("x", 0.95)
+          .has_mean("x", A.Between(49.0, 51.0)).has_standard_deviation("x", A.LessThan(100.0))
+          .has_min("x", A.GreaterThan(-1e9)).has_max("x", A.LessThan(1e9)).has_sum("k", A.LessThan(1e300))
+          .has_min("k", A.LessThan(0.0)).has_correlation("x", "y", A.GreaterThan(0.5)).satisfies("x > 45", "x must exceed 45"))
+    suite = T.ValidationSuite.builder("dist").check(cb.build()).build()
+    return suite.build_plan()
+
+
+def shard_blob(plan, t):
+    """Partial blob of one row shard, layout documented in term_b200/csrc/plan.cpp (partial_export)."""
+    cols = {n: (np.asarray(t.column(n).fill_null(0)), np.asarray(t.column(n).is_valid())) for n in t.schema.names}
+    n = t.num_rows
+    out = [struct.pack("<Q", len(plan.aggregates()))]
+    for kind, key in plan.aggregates():
+        u, f = [0] * 8, [0.0] * 8
+        parts = key.split("|")
+        if kind == 0:
+            u[0] = n
+        elif kind == 1:
+            u[0], u[1] = n, int(cols[parts[1]][1].sum())
+        elif kind == 2:
+            v, ok = cols[parts[1]]
+            vv = v[ok]
+            u[0] = len(vv)
+            if len(vv):
+                K = float(vv[0])
+                d = vv.astype(np.float64) - K
+                f[0], f[1], f[2] = K, math.fsum(d), math.fsum(d * d)
+                f[5] = math.fsum(vv.astype(np.float64))
+                if v.dtype == np.int64:
+                    u[1] = int(sum(int(a) for a in vv)) & (2**64 - 1)
+                    u[2], u[3], u[4] = int(vv.min()) & (2**64 - 1), int(vv.max()) & (2**64 - 1), 1
+                else:
+                    f[3], f[4] = float(vv.min()), float(vv.max())
+        elif kind == 3:
+            (vx, okx), (vy, oky) = cols[parts[1]], cols[parts[2]]
+            m = okx & oky
+            a, b = vx[m].astype(np.float64), vy[m].astype(np.float64)
+            u[0] = int(m.sum())
+            if u[0]:
+                Kx, Ky = float(a[0]), float(b[0])
+                dx, dy = a - Kx, b - Ky
+                f[0], f[1] = Kx, Ky
+                f[2], f[3], f[4], f[5], f[6] = math.fsum(dx), math.fsum(dy), math.fsum(dx * dx), math.fsum(dy * dy), math.fsum(dx * dy)
+        elif kind == 4:
+            v, ok = cols["x"]
+            u[0], u[2] = int(((v > 45) & ok).sum()), n
+        else:
+            raise AssertionError(f"unexpected aggregate {kind} {key}")
+        out.append(struct.pack("<QQ", kind, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *f) + struct.pack("<QQ", 0, 0))
+    return b"".join(out)
+
+
+def worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import term_b200 as T
+        from term_b200.distributed import allgather_blobs, merge_partials
+        t = make_table()
+        lo, hi = N_ROWS * rank // world, N_ROWS * (rank + 1) // world
+        plan, slots = build_plan(T)
+        blobs = allgather_blobs(shard_blob(plan, t.slice(lo, hi - lo)))
+        assert len(blobs) == world
+        merge_partials(plan, blobs)
+        res = [plan.result(s) for _, _, s in slots]
+        q.put((rank, [(r.name, r.status.name, r.metric, r.message) for r in res]))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_merge_matches_oracle(built_lib):
+    from oracle import term_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0] == results[1], "ranks disagree after the ordered merge"
+    t = make_table()
+    want = [O.size(t, ("Equals", float(N_ROWS))), O.completeness(t, "x", 0.95), O.statistic(t, "x", "Mean", ("Between", 49.0, 51.0)),
+            O.statistic(t, "x", "StandardDeviation", ("LessThan", 100.0)), O.statistic(t, "x", "Min", ("GreaterThan", -1e9)),
+            O.statistic(t, "x", "Max", ("LessThan", 1e9)), O.statistic(t, "k", "Sum", ("LessThan", 1e300)),
+            O.statistic(t, "k", "Min", ("LessThan", 0.0)), O.correlation(t, "x", "y", "Pearson", ("GreaterThan", 0.5)),
+            O.custom_sql(t, "x > 45", "x must exceed 45")]
+    exact = {"size", "completeness", "min", "max", "sum", "custom_sql"}
+    for (name, status, metric, message), o in zip(results[0], want):
+        assert status.lower() == o.status, (name, status, o)
+        if name in exact:
+            assert metric == o.metric and message == o.message, (name, metric, o)
+        else:
+            assert abs(metric - o.metric) <= 1e-9 * max(1.0, abs(o.metric)), (name, metric, o.metric)
+
+
+def test_partial_blob_roundtrip_and_rejects_foreign_blobs(built_lib):
+    import term_b200 as T
+    t = make_table()
+    plan, _ = build_plan(T)
+    plan.partial_reset()
+    plan.partial_merge(shard_blob(plan, t))
+    blob = plan.partial_export()
+    other, _ = build_plan(T)
+    other.partial_reset()
+    other.partial_merge(blob)
+    assert other.partial_export() == blob
+    small = T.Plan()
+    T.SizeConstraint(T.Assertion.Equals(1.0))._add_to(small)
+    with pytest.raises(T.TermGpuError):
+        small.partial_merge(blob)
+    with pytest.raises(T.TermGpuError):
+        plan.partial_merge(blob[: len(blob) // 2])

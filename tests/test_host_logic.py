@@ -1,0 +1,197 @@
+"""CPU-only tests of the host side of the drop-in: the C-ABI library loads and exports every symbol
+include/termgpu.h declares, the O(1) reference logic restated in C++ (Assertion, LogicalOperator,
+SqlSecurity, pattern strings, Rust number formatting), the regex -> DFA compiler against Python `re`, and
+the predicate grammar. No compute entry point is called (there is no GPU here)."""
+import ctypes as C
+import os
+import random
+import re
+
+import pytest
+
+import term_b200 as T
+from term_b200 import _ffi as F
+from oracle import term_oracle as O
+
+from . import helpers as H
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "termgpu.h")).read()
+    declared = set(re.findall(r"TG_API\s+[\w\s\*]+?\b(tg_\w+)\s*\(", hdr))
+    assert len(declared) >= 45
+    for name in declared:
+        assert hasattr(built_lib, name), f"{name} declared in termgpu.h but not exported"
+        assert name in F.SIGNATURES, f"{name} has no ctypes signature"
+    assert set(F.SIGNATURES) <= declared
+    assert b"sm_100a" in built_lib.tg_version()
+
+
+def test_engine_creation_fails_loudly_without_gpu(built_lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(T.TermGpuError) as e:
+        T.SessionContext(0)
+    assert e.value.code == F.TG_ERR_CUDA and "no CPU fallback" in str(e.value)
+
+
+def test_assertion_and_logical_golden(built_lib):
+    for c in H.load_golden():
+        if c["op"]["kind"] == "assertion":
+            for a, v, want in c["op"]["cases"]:
+                assert H._assertion(T, a).evaluate(v) is want
+            for a, want in c["op"]["descriptions"]:
+                assert H._assertion(T, a).description() == want
+        if c["op"]["kind"] == "logical":
+            for op, vals, want in c["op"]["cases"]:
+                assert H._operator(T, op).evaluate(vals) is want
+
+
+@pytest.mark.parametrize("v", [0.0, 20.0, 0.1, -2.5, 1e21, 1e-7, 123456789.125, 2.0 / 3.0, 1e15, 5e-324, 1.7976931348623157e308])
+def test_rust_f64_display_matches_oracle(built_lib, v):
+    buf = C.create_string_buffer(512)
+    built_lib.tg_format_f64(v, buf, 512)
+    assert buf.value.decode() == O.rust_f64(v)
+
+
+def test_identifier_validation(built_lib):  # security.rs:89-137 + tests :300-420
+    ok = ["col", "_x", "user_id", "t.c", "created_at", "updated_by", '"quoted"', "a1.b2.c3", "selection"]
+    bad = ["", "1abc", "a b", "a;b", "a--b", "xp_cmdshell", "sp_help", "drop_table", "x/*y", "a" * 129, "select_x", "a.", ".a"]
+    for s in ok:
+        assert built_lib.tg_validate_identifier(s.encode()) == 0, s
+    for s in bad:
+        assert built_lib.tg_validate_identifier(s.encode()) == F.TG_ERR_SECURITY, s
+
+
+def test_sql_expression_validation(built_lib):  # custom_sql.rs:344-392
+    ok = ["price > 0", "quantity BETWEEN 1 AND 100", "status = 'active' AND price < 1000", "LENGTH(name) > 3",
+          "order_date <= ship_date", "updated_at > '2024-01-01'", "is_deleted = false", "created_by = 'admin'"]
+    bad = ["DROP TABLE users", "DELETE FROM t WHERE 1=1", "UPDATE data SET price = 0", "price > 0; DROP TABLE data",
+           "INSERT INTO data VALUES (1, 2, 3)", "CREATE TABLE new_table (id INT)", "ALTER TABLE data ADD COLUMN c",
+           "TRUNCATE TABLE data", "-- comment\nprice > 0", "price > 0 /* comment */", "drop table users", "DeLeTe FROM t",
+           "UpDaTe data SET x = 1"]
+    for s in ok:
+        assert built_lib.tg_validate_sql_expression(s.encode()) == 0, s
+    for s in bad:
+        assert built_lib.tg_validate_sql_expression(s.encode()) != 0, s
+    with pytest.raises(T.TermGpuError) as e:
+        T.CustomSqlConstraint("DROP TABLE data")
+    assert "forbidden operation: DROP" in str(e.value)
+
+
+def test_constructor_validation_matches_reference(built_lib):
+    with pytest.raises(T.TermGpuError, match="Threshold must be between 0.0 and 1.0"):
+        T.CompletenessConstraint.with_threshold("col", 1.5)  # completeness.rs:535-539
+    with pytest.raises(T.TermGpuError, match="Threshold must be between 0.0 and 1.0"):
+        T.FormatConstraint.email("col", 1.5)  # format.rs:1279-1287
+    with pytest.raises(T.TermGpuError, match="Threshold must be between 0.0 and 1.0"):
+        T.UniquenessConstraint.full_uniqueness("col", 1.5)  # uniqueness.rs:1072-1080
+    with pytest.raises(T.TermGpuError, match="At least one column must be specified"):
+        T.UniquenessConstraint([], T.UniquenessType.FullUniqueness, 1.0)  # uniqueness.rs:1082-1095
+    with pytest.raises(T.TermGpuError, match="Percentile must be between 0.0 and 1.0"):
+        T.StatisticalConstraint("value", T.StatisticType.Percentile, T.Assertion.LessThan(100.0), 1.5)  # statistics.rs:682-690
+    with pytest.raises(T.TermGpuError, match="Max correlation must be between 0.0 and 1.0"):
+        T.CorrelationConstraint.independence("x", "y", 1.5)  # correlation.rs:633-641
+    with pytest.raises(T.TermGpuError, match="ReDoS"):
+        T.FormatConstraint.regex("c", "(a+)+b", 0.5)  # security.rs:258-281
+    with pytest.raises(T.TermGpuError, match="Invalid regex pattern"):
+        T.FormatConstraint.regex("c", "([a-z", 0.5)
+    assert T.FormatConstraint.email("c", 0.5).name() == "email"
+    assert T.StatisticalConstraint.standard_deviation("c", T.Assertion.GreaterThan(0)).name() == "standard_deviation"
+    assert T.UniquenessConstraint.primary_key(["a", "b"]).name() == "primary_key"
+    assert T.CorrelationConstraint.correlation_range("a", "b", 0.1, 0.9).name() == "correlation_range"
+
+
+def test_format_patterns_match_oracle(built_lib):
+    kinds = [("Email", None, 0), ("Url", None, 0), ("Url", None, 1), ("CreditCard", None, 0), ("Phone", None, 0),
+             ("Phone", "US", 0), ("Phone", "UK", 0), ("Phone", "DE", 0), ("Phone", "FR", 0), ("PostalCode", "US", 0),
+             ("PostalCode", "CA", 0), ("PostalCode", "UK", 0), ("PostalCode", "JP", 0), ("PostalCode", "ZZ", 0),
+             ("UUID", None, 0), ("IPv4", None, 0), ("IPv6", None, 0), ("Json", None, 0), ("Iso8601DateTime", None, 0),
+             ("SocialSecurityNumber", None, 0)]
+    for kind, arg, flag in kinds:
+        got = built_lib.tg_format_pattern(T.FormatType[kind].value, arg.encode() if arg else None, flag).decode()
+        assert got == O.format_pattern(kind, arg, bool(flag)), kind
+        assert built_lib.tg_validate_regex_pattern(got.encode()) == 0, kind  # every built-in compiles to a DFA
+
+
+def _dfa_match(lib, pattern, s, icase=False):
+    out = C.c_int32()
+    b = s.encode("utf-8")
+    rc = lib.tg_regex_host_match(pattern.encode("utf-8"), int(icase), b, len(b), C.byref(out))
+    assert rc == 0, (pattern, F.last_error())
+    return bool(out.value)
+
+
+CORPUS = ["", "a", "abc", "ABC123", "abc123", "test@example.com", "user.name+tag@sub.domain.org", "invalid-email", "@", "a@b",
+          "123-45-6789", "123456789", "000-12-3456", "666-12-3456", "4111-1111-1111-1111", "4111111111111111",
+          "5555 5555 5555 4444", "https://example.com", "http://localhost:3000/path?q=1", "ftp://x", "192.168.1.1",
+          "256.256.256.256", "::1", "2001:db8:85a3::8a2e:370:7334", '{"k": [1, 2]}', " [1] ", "not json",
+          "2023-12-25T10:30:00Z", "2023-12-25T10:30:00.123+05:30", "550e8400-e29b-41d4-a716-446655440000", "(555) 123-4567",
+          "+1 555.123.4567", "12345-6789", "K1A 0B1", "héllo wörld", "日本語テキスト", "٣٤٥", "a\nb", "tab\there", "x" * 300,
+          "trailing\n", " lead", "UPPER lower", "a.b.c", "aaa", "ab" * 40, "ſ", "K", "é"]
+
+PATTERNS = [r"@", r"^[A-Z]{3}\d{3}$", r"^\d+$", r"\d{3}-\d{2}-\d{4}", r"^[^\s]*$", r"^.+$", r"^$", r"a|b|c$", r"^(a|b)*c?$",
+            r"[a-z]+@[a-z]+\.(com|org)", r"^\w+$", r"\W", r"\s", r"^\S+\s\S+$", r"(ab){2,3}", r"a{0,2}b", r"^a.c", r"x{250,}",
+            r"^[\+]?[1-9][\d]{0,15}$", r"[[:alpha:]]+[[:digit:]]", r"^[-a-c]+$", r"^[]a]$", r"[^a-z]", r"\.", r"\x41", r"é",
+            r"(?i)upper", r"(?i:ABC)1", r"(?s)a.b", r"e.", r"日本", r"^\d{4}-\d{2}", r"\A\w", r"c\z", r"^(?:\d{1,3}\.){3}\d{1,3}$",
+            r"(|a)b", r"a*?b+?", r"[\d\s-]{5,}", r"^[^@]+@[^@]+$", r"k", r"s$"]
+
+
+def test_regex_dfa_matches_python_re_on_corpus(built_lib):
+    for pat in PATTERNS + [O.format_pattern(k) for k in ("Email", "CreditCard", "SocialSecurityNumber", "UUID", "IPv4", "IPv6",
+                                                         "Json", "Iso8601DateTime")] + [O.format_pattern("Url", None, True)]:
+        for ic in (False, True):
+            py_pat = pat.replace("[[:alpha:]]", "[a-zA-Z]").replace("[[:digit:]]", "[0-9]").replace(r"é", "é")
+            rx = O.rust_regex_to_python(py_pat, ic)
+            for s in CORPUS:
+                want = rx.search(s) is not None
+                if ic and any(ch in s for ch in "ſK") and re.search(r"[ks]", pat, re.I):
+                    continue  # Python's IGNORECASE and Rust's simple case folding differ on these two code points
+                assert _dfa_match(built_lib, pat, s, ic) == want, (pat, s, ic)
+
+
+def test_regex_dfa_random_fuzz(built_lib):
+    rnd = random.Random(1234)
+    atoms = ["a", "b", "c", "\\d", "\\w", "\\s", ".", "[ab]", "[^c]", "[a-c0-2]", "(ab|c)", "(?:a|bc)", "@", "-"]
+    quants = ["", "", "", "*", "+", "?", "{2}", "{1,3}", "{0,2}"]
+    alphabet = "abc012 @-_\n"
+    for _ in range(300):
+        pat = "".join(rnd.choice(atoms) + rnd.choice(quants) for _ in range(rnd.randint(1, 5)))
+        if rnd.random() < 0.3:
+            pat = "^" + pat
+        if rnd.random() < 0.3:
+            pat = pat + "$"
+        if rnd.random() < 0.15:
+            pat = pat + "|" + rnd.choice(atoms)
+        rx = O.rust_regex_to_python(pat, False)
+        for _ in range(25):
+            s = "".join(rnd.choice(alphabet) for _ in range(rnd.randint(0, 8)))
+            assert _dfa_match(built_lib, pat, s) == (rx.search(s) is not None), (pat, s)
+
+
+def test_regex_unsupported_and_invalid_are_reported(built_lib):
+    for pat in [r"\bword\b", r"(?m)^a$", r"\p{L}+", r"[a-z&&[^b]]"]:
+        assert built_lib.tg_validate_regex_pattern(pat.encode()) == F.TG_ERR_UNSUPPORTED, pat
+    for pat in [r"(", r"a{2,1}", r"*a", r"[z-a]", r"\1", r"(?<!a)b", r"a{99999999}"]:
+        assert built_lib.tg_validate_regex_pattern(pat.encode()) == F.TG_ERR_SECURITY, pat
+    assert built_lib.tg_validate_regex_pattern(("a" * 1001).encode()) == F.TG_ERR_SECURITY
+
+
+def test_plan_deduplicates_aggregates(built_lib):
+    p = T.Plan()
+    T.StatisticalConstraint.min("x", T.Assertion.GreaterThan(0))._add_to(p)
+    T.StatisticalConstraint.max("x", T.Assertion.LessThan(9))._add_to(p)
+    T.StatisticalConstraint.mean("x", T.Assertion.LessThan(9))._add_to(p)
+    T.CompletenessConstraint("x", 0.5)._add_to(p)
+    T.CompletenessConstraint(["x", "y"], 0.5)._add_to(p)
+    T.FormatConstraint.email("s", 0.5)._add_to(p)
+    T.FormatConstraint.email("s", 0.9)._add_to(p)
+    T.CustomSqlConstraint("x > 1")._add_to(p)
+    T.CustomSqlConstraint("x > 1", "hint")._add_to(p)
+    keys = [k for _, k in p.aggregates()]
+    assert keys.count("num|x") == 1 and keys.count("valid|x") == 1 and keys.count("valid|y") == 1
+    assert sum(k.startswith("regex|s") for k in keys) == 1 and keys.count("pred|x > 1") == 1
+    assert F.lib().tg_plan_num_slots(p.handle) == 9
