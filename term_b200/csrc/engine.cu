@@ -173,15 +173,26 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     bool has_terms = false;
     for (auto& o : ops) has_terms |= o.kind == UNIT_TERMS;
     for (; tile_rows >= (has_terms ? 256 : 128); tile_rows /= 2) {
-        int n_units = 0;
-        for (size_t i = 0; i < ops.size(); ++i) {
-            double share = ops[i].cost / total_cost * SCAN_CONSUMER_WARPS;
-            int r = 1;
-            const int min_slice = ops[i].kind == UNIT_TERMS ? 256 : 64;
-            while (r * 2 <= share + 0.5 && r * 2 <= tile_rows / min_slice) r *= 2;
-            if (ops[i].kind == UNIT_COUNT) r = 1;
-            reps[i] = r;
-            n_units += r;
+        // replicate ops over row slices until exactly SCAN_CONSUMER_WARPS units exist (every warp owns one unit and
+        // keeps it in registers): repeatedly halve the slice of the op whose per-slice cost is largest
+        int n_units = (int)ops.size();
+        for (size_t i = 0; i < ops.size(); ++i) reps[i] = 1;
+        while (true) {
+            int best = -1;
+            double best_cost = 0;
+            for (size_t i = 0; i < ops.size(); ++i) {
+                const int min_slice = ops[i].kind == UNIT_TERMS ? 256 : 64;
+                if (ops[i].kind == UNIT_COUNT || tile_rows / (reps[i] * 2) < min_slice) continue;
+                if (n_units + reps[i] > SCAN_CONSUMER_WARPS) continue;
+                const double c = ops[i].cost / reps[i];
+                if (c > best_cost) {
+                    best_cost = c;
+                    best = (int)i;
+                }
+            }
+            if (best < 0) break;
+            n_units += reps[best];
+            reps[best] *= 2;
         }
         if (n_units > SCAN_MAX_UNITS) throw Error(TG_ERR_UNSUPPORTED, "too many aggregates in one scan pass");
         state_bytes = (size_t)n_units * SCAN_STATE_SLOTS * 32 * 8;
@@ -456,9 +467,24 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
             bytes += (uint64_t)(t.n_rows + 7) / 8;
         }
     };
+    // COUNT(c) of a column that also has a NUM aggregate in this plan comes for free from that unit's n
+    std::vector<std::pair<int, int>> valid_from_num;  // (valid agg, num agg)
     for (int id : agg_ids) {
         Agg& a = p.aggs[id];
         if (a.err != TG_OK) continue;
+        if (a.kind == A_VALID) {
+            bool folded = false;
+            for (int id2 : agg_ids) {
+                const Agg& b = p.aggs[id2];
+                Column* bc = b.kind == A_NUM && b.err == TG_OK ? t.find(b.cols[0]) : nullptr;
+                if (bc && b.cols[0] == a.cols[0] && (bc->dtype == TG_INT64 || bc->dtype == TG_FLOAT64) && bc->validity.p) {
+                    valid_from_num.emplace_back(id, id2);
+                    folded = true;
+                    break;
+                }
+            }
+            if (folded) continue;
+        }
         ScanOp o;
         o.agg = id;
         auto col = [&](const std::string& name) -> Column* {
@@ -487,7 +513,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 }
                 o.kind = UNIT_COUNT;
                 o.c0 = c;
-                o.cost = 0.05;
+                o.cost = 0.2;
                 count_bytes(c, false);
                 ops.push_back(std::move(o));
             } break;
@@ -498,8 +524,9 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 o.c0 = c;
                 o.flags = a.flags ? a.flags : 7;
                 if (c->dtype != TG_INT64) o.flags &= ~4;
-                o.cost = 0.3 + ((o.flags & 1) ? 0.5 : 0.0) + ((o.flags & 2) ? 0.4 : 0.0) + ((o.flags & 4) ? 0.2 : 0.0) +
-                         ((o.flags & 1) && c->dtype == TG_INT64 ? 0.3 : 0.0);
+                // warp-instructions per 32 rows: load + mask, then moments / min-max / integer sum
+                o.cost = 5.0 + ((o.flags & 1) ? 3.0 : 0.0) + ((o.flags & 2) ? (c->dtype == TG_INT64 ? 8.0 : 6.0) : 0.0) +
+                         ((o.flags & 4) ? 2.0 : 0.0) + ((o.flags & 1) && c->dtype == TG_INT64 ? 1.0 : 0.0);
                 count_bytes(c, true);
                 ops.push_back(std::move(o));
             } break;
@@ -511,7 +538,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 o.kind = UNIT_PAIR;
                 o.c0 = x;
                 o.c1 = y;
-                o.cost = 1.5;
+                o.cost = 20.0 + (x->dtype == TG_INT64 ? 1.0 : 0.0) + (y->dtype == TG_INT64 ? 1.0 : 0.0);
                 count_bytes(x, true);
                 count_bytes(y, true);
                 ops.push_back(std::move(o));
@@ -535,12 +562,12 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                     if (try_compile_terms(expr, res, o.terms, is_or)) {
                         o.kind = UNIT_TERMS;
                         o.flags = is_or ? 1 : 0;
-                        o.cost = 0.15 + 0.45 * (double)o.terms.size();
+                        o.cost = 3.0 + 7.0 * (double)o.terms.size();
                     } else {
                         o.pred_cols.clear();
                         compile_predicate(expr, res, o.code);
                         o.kind = UNIT_PRED;
-                        o.cost = 0.5 + 0.6 * (double)o.code.size();
+                        o.cost = 10.0 + 25.0 * (double)o.code.size();
                     }
                 } catch (Error& er) {
                     a.err = er.code;
@@ -554,6 +581,17 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
         }
     }
     p.stats.bytes_scanned += bytes;
+    struct FoldFill {
+        Plan& p;
+        Table& t;
+        std::vector<std::pair<int, int>>& v;
+        ~FoldFill() {
+            for (auto& pr : v) {
+                p.aggs[pr.first].u[0] = (uint64_t)t.n_rows;
+                p.aggs[pr.first].u[1] = p.aggs[pr.second].u[0];
+            }
+        }
+    } fold_fill{p, t, valid_from_num};
     if (t.n_rows == 0) {
         // nothing to scan: aggregates keep their zero state (COUNT(*) = 0)
         for (auto& o : ops)

@@ -59,293 +59,379 @@ __device__ __forceinline__ uint32_t vword(const ScanColDesc& c, const uint8_t* s
     return c.validity ? reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off)[word] : 0xffffffffu;
 }
 
-// valid rows of a slice: each lane popcounts different validity words, so the element loops never count
-__device__ __forceinline__ uint64_t slice_valid_count(const ScanColDesc& cx, const ScanColDesc* cy,
-                                                      const ScanUnitDesc& u, const uint8_t* stage, int lane,
-                                                      int rows_in_tile) {
-    uint64_t n = 0;
-    const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
-    for (int j = lane; j < nw; j += 32) {
-        uint32_t w = vword(cx, stage, w0 + j) & tail_mask(u.row0 + 32 * j, rows_in_tile);
-        if (cy) w &= vword(*cy, stage, w0 + j);
-        n += __popc(w);
+// ======================================================================================================
+// Units. Every unit kind is a small object with begin(state) / tile(stage) / end(state): a warp that owns ONE
+// unit keeps the object (descriptor fields + accumulators) in registers across its whole tile loop; a warp that
+// owns several runs begin/tile/end per tile against the per-lane state in shared memory.
+// ======================================================================================================
+
+// ---- COUNT: popcount of validity words ----
+struct CountUnit {
+    uint32_t bits_off;
+    int w0, nw, row0, lane;
+    uint64_t n;
+    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+        const ScanColDesc& c = T.cols[u.c0];
+        bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
+        w0 = u.row0 >> 5;
+        nw = u.nrows >> 5;
+        row0 = u.row0;
+        lane = lane_;
+        n = st[S_N * 32 + lane];
     }
-    return n;
-}
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) {
+        for (int j = lane; j < nw; j += 32) {
+            uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[w0 + j] : 0xffffffffu;
+            n += __popc(w & tail_mask(row0 + 32 * j, rows));
+        }
+    }
+    __device__ __forceinline__ void end(uint64_t* st) { st[S_N * 32 + lane] = n; }
+};
 
-__device__ __forceinline__ void unit_count(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
-                                           uint64_t* st, int lane, int rows_in_tile) {
-    st[S_N * 32 + lane] += slice_valid_count(T.cols[u.c0], nullptr, u, stage, lane, rows_in_tile);
-}
-
-// ---- NUM unit -------------------------------------------------------------------------------------
+// ---- NUM ----
 // NULL rows (and rows past the end of the table) are replaced by the pivot element K: they add 0 to Σd and
-// Σd², cannot change min/max (K is a value of the column), and the wrapping integer sum is corrected on
-// the host by (rows_processed - n)·K. MASK: 0 dense full tile, 1 validity bitmap, 2 bitmap and/or tail.
-template <bool IS_I64, int FLAGS, int MASK>
-__device__ __forceinline__ void num_loop(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
-                                         uint64_t* st, int lane, int rows_in_tile) {
-    constexpr bool MOM = (FLAGS & UF_MOMENTS) != 0, MM = (FLAGS & UF_MINMAX) != 0, ISUM = IS_I64 && (FLAGS & UF_ISUM) != 0;
-    const double K = c.pivot;
-    const uint64_t Kbits = IS_I64 ? (uint64_t)c.ipivot : d2u(c.pivot);
-    double sd = 0, sdd = 0, fmn = 0, fmx = 0;
-    int64_t imn = 0, imx = 0;
-    uint64_t isum = 0;
-    if (MOM) {
+// Σd², cannot change min/max (K is a value of the column), and the wrapping integer sum is corrected on the
+// host by (rows_processed - n)·K. Valid rows are counted by popcounting validity words (one word per lane).
+template <bool IS_I64, int FLAGS>
+struct NumUnit {
+    static constexpr bool MOM = (FLAGS & UF_MOMENTS) != 0, MM = (FLAGS & UF_MINMAX) != 0, ISUM = IS_I64 && (FLAGS & UF_ISUM) != 0;
+    uint32_t val_off, bits_off;  // bits_off == ~0u: no bitmap
+    int row0, nw, lane;
+    double K;
+    uint64_t Kbits, n, isum;
+    double sd, sdd, fmn, fmx;
+    int64_t imn, imx;
+
+    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+        const ScanColDesc& c = T.cols[u.c0];
+        val_off = c.smem_val_off;
+        bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
+        row0 = u.row0;
+        nw = u.nrows >> 5;
+        lane = lane_;
+        K = c.pivot;
+        Kbits = IS_I64 ? (uint64_t)c.ipivot : d2u(c.pivot);
+        n = st[S_N * 32 + lane];
         sd = u2d(st[S_SD * 32 + lane]);
         sdd = u2d(st[S_SDD * 32 + lane]);
+        fmn = u2d(st[S_MIN * 32 + lane]);
+        fmx = u2d(st[S_MAX * 32 + lane]);
+        imn = (int64_t)st[S_MIN * 32 + lane];
+        imx = (int64_t)st[S_MAX * 32 + lane];
+        isum = st[S_ISUM * 32 + lane];
     }
-    if (MM) {
-        if (IS_I64) {
-            imn = (int64_t)st[S_MIN * 32 + lane];
-            imx = (int64_t)st[S_MAX * 32 + lane];
-        } else {
-            fmn = u2d(st[S_MIN * 32 + lane]);
-            fmx = u2d(st[S_MAX * 32 + lane]);
-        }
-    }
-    if (ISUM) isum = st[S_ISUM * 32 + lane];
-    const int nw = u.nrows >> 5;
-    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + u.row0 + lane;
-    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off) + (u.row0 >> 5);
-    const uint32_t lanebit = 1u << lane;
-    const bool has_bits = c.validity != nullptr;
+    template <int MASK>  // 0 dense full tile, 1 bitmap, 2 bitmap and/or tail
+    __device__ __forceinline__ void loop(const uint8_t* stage, int rows) {
+        const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
+        const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off != 0xffffffffu ? bits_off : 0u)) + (row0 >> 5);
+        const uint32_t lanebit = 1u << lane;
+        const bool has_bits = bits_off != 0xffffffffu;
 #pragma unroll 4
-    for (int j = 0; j < nw; ++j) {
-        uint64_t raw = vals[32 * j];
-        if (MASK == 1) {
-            raw = (bits[j] & lanebit) ? raw : Kbits;
-        } else if (MASK == 2) {
-            uint32_t w = has_bits ? bits[j] : 0xffffffffu;
-            w &= tail_mask(u.row0 + 32 * j, rows_in_tile);
-            raw = (w & lanebit) ? raw : Kbits;
+        for (int j = 0; j < nw; ++j) {
+            uint64_t raw = vals[32 * j];
+            if (MASK == 1) {
+                raw = (bits[j] & lanebit) ? raw : Kbits;
+            } else if (MASK == 2) {
+                uint32_t w = has_bits ? bits[j] : 0xffffffffu;
+                w &= tail_mask(row0 + 32 * j, rows);
+                raw = (w & lanebit) ? raw : Kbits;
+            }
+            if (IS_I64) {
+                const int64_t xi = (int64_t)raw;
+                if (MOM) {
+                    const double d = (double)xi - K;
+                    sd += d;
+                    sdd = fma(d, d, sdd);
+                }
+                if (ISUM) isum += (uint64_t)xi;
+                if (MM) {
+                    imn = xi < imn ? xi : imn;
+                    imx = xi > imx ? xi : imx;
+                }
+            } else {
+                const double x = u2d(raw);
+                if (MOM) {
+                    const double d = x - K;
+                    sd += d;
+                    sdd = fma(d, d, sdd);
+                }
+                if (MM) {
+                    fmn = x < fmn ? x : fmn;
+                    fmx = x > fmx ? x : fmx;
+                }
+            }
         }
-        if (IS_I64) {
-            const int64_t xi = (int64_t)raw;
-            if (MOM) {
-                const double d = (double)xi - K;
-                sd += d;
-                sdd = fma(d, d, sdd);
+    }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
+        // valid rows: each lane popcounts different words
+        if (bits_off != 0xffffffffu || partial) {
+            for (int j = lane; j < nw; j += 32) {
+                uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[(row0 >> 5) + j] : 0xffffffffu;
+                n += __popc(w & tail_mask(row0 + 32 * j, rows));
             }
-            if (ISUM) isum += (uint64_t)xi;
-            if (MM) {
-                imn = xi < imn ? xi : imn;
-                imx = xi > imx ? xi : imx;
-            }
-        } else {
-            const double x = u2d(raw);
-            if (MOM) {
-                const double d = x - K;
-                sd += d;
-                sdd = fma(d, d, sdd);
-            }
-            if (MM) {
-                fmn = x < fmn ? x : fmn;
-                fmx = x > fmx ? x : fmx;
-            }
+        } else if (lane == 0) {
+            n += (uint64_t)nw * 32;
         }
+        if (FLAGS == 0) return;
+        if (partial) loop<2>(stage, rows);
+        else if (bits_off != 0xffffffffu) loop<1>(stage, rows);
+        else loop<0>(stage, rows);
     }
-    if (MOM) {
-        st[S_SD * 32 + lane] = d2u(sd);
-        st[S_SDD * 32 + lane] = d2u(sdd);
+    __device__ __forceinline__ void end(uint64_t* st) {
+        st[S_N * 32 + lane] = n;
+        if (MOM) {
+            st[S_SD * 32 + lane] = d2u(sd);
+            st[S_SDD * 32 + lane] = d2u(sdd);
+        }
+        if (MM) {
+            st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
+            st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
+        }
+        if (ISUM) st[S_ISUM * 32 + lane] = isum;
     }
-    if (MM) {
-        st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
-        st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
-    }
-    if (ISUM) st[S_ISUM * 32 + lane] = isum;
-}
-
-template <bool IS_I64, int FLAGS>
-__device__ __forceinline__ void num_mask(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
-                                         uint64_t* st, int lane, int rows, bool partial) {
-    if (partial) num_loop<IS_I64, FLAGS, 2>(c, u, stage, st, lane, rows);
-    else if (c.validity) num_loop<IS_I64, FLAGS, 1>(c, u, stage, st, lane, rows);
-    else num_loop<IS_I64, FLAGS, 0>(c, u, stage, st, lane, rows);
-}
+};
 
 // slow path: the pivot is not an element of the column (no finite valid value was found when the column was
 // registered, e.g. all NULL): rows are masked explicitly
 template <bool IS_I64>
-__device__ __noinline__ void unit_num_slow(const ScanColDesc& c, const ScanUnitDesc& u, const uint8_t* stage,
-                                           uint64_t* st, int lane, int rows_in_tile) {
-    const double K = c.pivot;
-    double sd = u2d(st[S_SD * 32 + lane]), sdd = u2d(st[S_SDD * 32 + lane]);
-    double fmn = u2d(st[S_MIN * 32 + lane]), fmx = u2d(st[S_MAX * 32 + lane]);
-    int64_t imn = (int64_t)st[S_MIN * 32 + lane], imx = (int64_t)st[S_MAX * 32 + lane];
-    uint64_t isum = st[S_ISUM * 32 + lane];
-    const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
-    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + u.row0 + lane;
-    for (int j = 0; j < nw; ++j) {
-        const uint32_t w = vword(c, stage, w0 + j) & tail_mask(u.row0 + 32 * j, rows_in_tile);
-        const bool ok = (w >> lane) & 1u;
-        const uint64_t raw = vals[32 * j];
-        if (IS_I64) {
-            const int64_t xi = (int64_t)raw;
-            const double d = ok ? (double)xi - K : 0.0;
-            sd += d;
-            sdd = fma(d, d, sdd);
-            isum += ok ? (uint64_t)xi : 0ull;
-            imn = min(imn, ok ? xi : INT64_MAX);
-            imx = max(imx, ok ? xi : INT64_MIN);
-        } else {
-            const double x = u2d(raw);
-            const double d = ok ? x - K : 0.0;
-            sd += d;
-            sdd = fma(d, d, sdd);
-            fmn = fmin(fmn, ok ? x : CUDART_INF);
-            fmx = fmax(fmx, ok ? x : -CUDART_INF);
+struct NumSlowUnit {
+    uint32_t val_off, bits_off;
+    int row0, nw, lane;
+    double K;
+    uint64_t n, isum;
+    double sd, sdd, fmn, fmx;
+    int64_t imn, imx;
+    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+        const ScanColDesc& c = T.cols[u.c0];
+        val_off = c.smem_val_off;
+        bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
+        row0 = u.row0;
+        nw = u.nrows >> 5;
+        lane = lane_;
+        K = c.pivot;
+        n = st[S_N * 32 + lane];
+        sd = u2d(st[S_SD * 32 + lane]);
+        sdd = u2d(st[S_SDD * 32 + lane]);
+        fmn = u2d(st[S_MIN * 32 + lane]);
+        fmx = u2d(st[S_MAX * 32 + lane]);
+        imn = (int64_t)st[S_MIN * 32 + lane];
+        imx = (int64_t)st[S_MAX * 32 + lane];
+        isum = st[S_ISUM * 32 + lane];
+    }
+    __device__ __noinline__ void tile(const uint8_t* stage, int rows, bool) {
+        const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
+        for (int j = 0; j < nw; ++j) {
+            uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[(row0 >> 5) + j] : 0xffffffffu;
+            w &= tail_mask(row0 + 32 * j, rows);
+            const bool ok = (w >> lane) & 1u;
+            n += ok;
+            const uint64_t raw = vals[32 * j];
+            if (IS_I64) {
+                const int64_t xi = (int64_t)raw;
+                const double d = ok ? (double)xi - K : 0.0;
+                sd += d;
+                sdd = fma(d, d, sdd);
+                isum += ok ? (uint64_t)xi : 0ull;
+                imn = min(imn, ok ? xi : INT64_MAX);
+                imx = max(imx, ok ? xi : INT64_MIN);
+            } else {
+                const double x = u2d(raw);
+                const double d = ok ? x - K : 0.0;
+                sd += d;
+                sdd = fma(d, d, sdd);
+                fmn = fmin(fmn, ok ? x : CUDART_INF);
+                fmx = fmax(fmx, ok ? x : -CUDART_INF);
+            }
         }
     }
-    st[S_SD * 32 + lane] = d2u(sd);
-    st[S_SDD * 32 + lane] = d2u(sdd);
-    st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
-    st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
-    st[S_ISUM * 32 + lane] = isum;
-}
-
-template <bool IS_I64>
-__device__ __forceinline__ void unit_num(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
-                                         uint64_t* st, int lane, int rows, bool partial) {
-    const ScanColDesc& c = T.cols[u.c0];
-    st[S_N * 32 + lane] += slice_valid_count(c, nullptr, u, stage, lane, rows);
-    if (!c.pivot_is_element) {
-        unit_num_slow<IS_I64>(c, u, stage, st, lane, rows);
-        return;
+    __device__ __forceinline__ void end(uint64_t* st) {
+        st[S_N * 32 + lane] = n;
+        st[S_SD * 32 + lane] = d2u(sd);
+        st[S_SDD * 32 + lane] = d2u(sdd);
+        st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
+        st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
+        st[S_ISUM * 32 + lane] = isum;
     }
-    switch (u.flags & 7) {
-        case 0: break;
-        case 1: num_mask<IS_I64, 1>(c, u, stage, st, lane, rows, partial); break;
-        case 2: num_mask<IS_I64, 2>(c, u, stage, st, lane, rows, partial); break;
-        case 3: num_mask<IS_I64, 3>(c, u, stage, st, lane, rows, partial); break;
-        case 4: num_mask<IS_I64, 4>(c, u, stage, st, lane, rows, partial); break;
-        case 5: num_mask<IS_I64, 5>(c, u, stage, st, lane, rows, partial); break;
-        case 6: num_mask<IS_I64, 6>(c, u, stage, st, lane, rows, partial); break;
-        default: num_mask<IS_I64, 7>(c, u, stage, st, lane, rows, partial); break;
-    }
-}
+};
 
-// ---- PAIR unit: rows where either side is NULL are replaced by (Kx, Ky) => dx = dy = 0 -------------
-template <bool XI, bool YI, bool MASKED>
-__device__ __forceinline__ void pair_loop(const ScanColDesc& cx, const ScanColDesc& cy, const ScanUnitDesc& u,
-                                          const uint8_t* stage, uint64_t* st, int lane, int rows_in_tile) {
-    const double Kx = cx.pivot, Ky = cy.pivot;
-    double sx = u2d(st[P_SX * 32 + lane]), sy = u2d(st[P_SY * 32 + lane]), sxx = u2d(st[P_SXX * 32 + lane]),
-           syy = u2d(st[P_SYY * 32 + lane]), sxy = u2d(st[P_SXY * 32 + lane]);
-    const int w0 = u.row0 >> 5, nw = u.nrows >> 5;
-    const uint64_t* vx = reinterpret_cast<const uint64_t*>(stage + cx.smem_val_off) + u.row0 + lane;
-    const uint64_t* vy = reinterpret_cast<const uint64_t*>(stage + cy.smem_val_off) + u.row0 + lane;
-    const uint32_t lanebit = 1u << lane;
+// ---- PAIR: rows where either side is NULL are replaced by (Kx, Ky) => dx = dy = 0 ----
+template <bool XI, bool YI>
+struct PairUnit {
+    uint32_t vx_off, vy_off, bx_off, by_off;
+    int row0, nw, lane;
+    double Kx, Ky, sx, sy, sxx, syy, sxy;
+    uint64_t n;
+    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+        const ScanColDesc& cx = T.cols[u.c0];
+        const ScanColDesc& cy = T.cols[u.c1];
+        vx_off = cx.smem_val_off;
+        vy_off = cy.smem_val_off;
+        bx_off = cx.validity ? cx.smem_bits_off : 0xffffffffu;
+        by_off = cy.validity ? cy.smem_bits_off : 0xffffffffu;
+        row0 = u.row0;
+        nw = u.nrows >> 5;
+        lane = lane_;
+        Kx = cx.pivot;
+        Ky = cy.pivot;
+        n = st[P_N * 32 + lane];
+        sx = u2d(st[P_SX * 32 + lane]);
+        sy = u2d(st[P_SY * 32 + lane]);
+        sxx = u2d(st[P_SXX * 32 + lane]);
+        syy = u2d(st[P_SYY * 32 + lane]);
+        sxy = u2d(st[P_SXY * 32 + lane]);
+    }
+    __device__ __forceinline__ uint32_t both(const uint8_t* stage, int word) const {
+        uint32_t w = 0xffffffffu;
+        if (bx_off != 0xffffffffu) w &= reinterpret_cast<const uint32_t*>(stage + bx_off)[word];
+        if (by_off != 0xffffffffu) w &= reinterpret_cast<const uint32_t*>(stage + by_off)[word];
+        return w;
+    }
+    template <int MASK>
+    __device__ __forceinline__ void loop(const uint8_t* stage, int rows) {
+        const uint64_t* vx = reinterpret_cast<const uint64_t*>(stage + vx_off) + row0 + lane;
+        const uint64_t* vy = reinterpret_cast<const uint64_t*>(stage + vy_off) + row0 + lane;
+        const uint32_t lanebit = 1u << lane;
+        const int w0 = row0 >> 5;
 #pragma unroll 4
-    for (int j = 0; j < nw; ++j) {
-        const uint64_t rx = vx[32 * j], ry = vy[32 * j];
-        double x = XI ? (double)(int64_t)rx : u2d(rx);
-        double y = YI ? (double)(int64_t)ry : u2d(ry);
-        if (MASKED) {
-            const uint32_t w = vword(cx, stage, w0 + j) & vword(cy, stage, w0 + j) &
-                               tail_mask(u.row0 + 32 * j, rows_in_tile);
-            const bool ok = w & lanebit;
-            x = ok ? x : Kx;
-            y = ok ? y : Ky;
+        for (int j = 0; j < nw; ++j) {
+            const uint64_t rx = vx[32 * j], ry = vy[32 * j];
+            double x = XI ? (double)(int64_t)rx : u2d(rx);
+            double y = YI ? (double)(int64_t)ry : u2d(ry);
+            if (MASK) {
+                uint32_t w = both(stage, w0 + j);
+                if (MASK == 2) w &= tail_mask(row0 + 32 * j, rows);
+                const bool ok = w & lanebit;
+                x = ok ? x : Kx;
+                y = ok ? y : Ky;
+            }
+            const double dx = x - Kx, dy = y - Ky;
+            sx += dx;
+            sy += dy;
+            sxx = fma(dx, dx, sxx);
+            syy = fma(dy, dy, syy);
+            sxy = fma(dx, dy, sxy);
         }
-        const double dx = x - Kx, dy = y - Ky;
-        sx += dx;
-        sy += dy;
-        sxx = fma(dx, dx, sxx);
-        syy = fma(dy, dy, syy);
-        sxy = fma(dx, dy, sxy);
     }
-    st[P_SX * 32 + lane] = d2u(sx);
-    st[P_SY * 32 + lane] = d2u(sy);
-    st[P_SXX * 32 + lane] = d2u(sxx);
-    st[P_SYY * 32 + lane] = d2u(syy);
-    st[P_SXY * 32 + lane] = d2u(sxy);
-}
-
-__device__ __forceinline__ void unit_pair(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
-                                          uint64_t* st, int lane, int rows, bool partial) {
-    const ScanColDesc& cx = T.cols[u.c0];
-    const ScanColDesc& cy = T.cols[u.c1];
-    st[P_N * 32 + lane] += slice_valid_count(cx, &cy, u, stage, lane, rows);
-    const bool masked = cx.validity || cy.validity || partial;
-    const int sel = (u.c0_is_i64 ? 1 : 0) | (u.c1_is_i64 ? 2 : 0) | (masked ? 4 : 0);
-    switch (sel) {
-        case 0: pair_loop<false, false, false>(cx, cy, u, stage, st, lane, rows); break;
-        case 1: pair_loop<true, false, false>(cx, cy, u, stage, st, lane, rows); break;
-        case 2: pair_loop<false, true, false>(cx, cy, u, stage, st, lane, rows); break;
-        case 3: pair_loop<true, true, false>(cx, cy, u, stage, st, lane, rows); break;
-        case 4: pair_loop<false, false, true>(cx, cy, u, stage, st, lane, rows); break;
-        case 5: pair_loop<true, false, true>(cx, cy, u, stage, st, lane, rows); break;
-        case 6: pair_loop<false, true, true>(cx, cy, u, stage, st, lane, rows); break;
-        default: pair_loop<true, true, true>(cx, cy, u, stage, st, lane, rows); break;
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
+        const bool has_bits = bx_off != 0xffffffffu || by_off != 0xffffffffu;
+        if (has_bits || partial) {
+            for (int j = lane; j < nw; j += 32) n += __popc(both(stage, (row0 >> 5) + j) & tail_mask(row0 + 32 * j, rows));
+        } else if (lane == 0) {
+            n += (uint64_t)nw * 32;
+        }
+        if (partial) loop<2>(stage, rows);
+        else if (has_bits) loop<1>(stage, rows);
+        else loop<0>(stage, rows);
     }
-}
+    __device__ __forceinline__ void end(uint64_t* st) {
+        st[P_N * 32 + lane] = n;
+        st[P_SX * 32 + lane] = d2u(sx);
+        st[P_SY * 32 + lane] = d2u(sy);
+        st[P_SXX * 32 + lane] = d2u(sxx);
+        st[P_SYY * 32 + lane] = d2u(syy);
+        st[P_SXY * 32 + lane] = d2u(sxy);
+    }
+};
 
-// ---- TERMS unit: AND / OR of <= 4 comparison terms ---------------------------------------------------
-// One specialised pass per term over a chunk of TG groups (32 rows each); the running TRUE masks of the
-// chunk stay in registers. A comparison is two compares + selects + one ballot per 32 rows.
+// ---- TERMS: AND / OR of <= 4 comparison terms ----
+// One pass per term over a chunk of TG groups (32 rows each); the running TRUE masks of the chunk stay in
+// registers; the comparison operator is selected OUTSIDE the row loop, so a term costs one load, one compare and
+// one ballot per 32 rows.
 constexpr int TG = 8;  // 256 rows per chunk
 
-template <int KIND>
-__device__ __forceinline__ void term_pass(const ScanTerm& t, const ScanColDesc& c, const uint8_t* stage, int row0,
-                                          int lane, bool is_or, uint32_t (&m)[TG]) {
-    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off) + (row0 >> 5);
-    const bool has_bits = c.validity != nullptr;
-    if (KIND == TK_ISNULL || KIND == TK_NOTNULL) {
-#pragma unroll
-        for (int g = 0; g < TG; ++g) {
-            const uint32_t valid = has_bits ? bits[g] : 0xffffffffu;
-            const uint32_t tm = KIND == TK_ISNULL ? ~valid : valid;
-            m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
-        }
-        return;
-    }
-    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + row0 + lane;
-    // result of the comparison by outcome: lt / eq / otherwise (gt; for floats also unordered, which
-    // matches Arrow's total order where NaN sorts above every number)
-    const bool r_lt = t.cmp_mask & 1, r_eq = (t.cmp_mask >> 1) & 1, r_gt = (t.cmp_mask >> 2) & 1;
-    const uint64_t imm = t.imm;
+template <int KIND, int OP>  // OP = cmp_mask: 1 <, 2 ==, 3 <=, 4 >, 5 <> (13 with unordered), 6 >=
+__device__ __forceinline__ void term_cmp_pass(uint64_t imm, uint32_t val_off, uint32_t bits_off, const uint8_t* stage,
+                                              int row0, int lane, bool is_or, uint32_t (&m)[TG]) {
+    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
+    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off != 0xffffffffu ? bits_off : 0u)) + (row0 >> 5);
+    const bool has_bits = bits_off != 0xffffffffu;
 #pragma unroll
     for (int g = 0; g < TG; ++g) {
         const uint64_t raw = vals[32 * g];
         bool r;
         if (KIND == TK_I64) {
-            const int64_t x = (int64_t)raw, cst = (int64_t)imm;
-            r = x < cst ? r_lt : (x == cst ? r_eq : r_gt);
+            const int64_t x = (int64_t)raw, c = (int64_t)imm;
+            r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? x > c : OP == 6 ? x >= c : x != c;
         } else {
-            const double x = KIND == TK_F64 ? u2d(raw) : (double)(int64_t)raw, cst = u2d(imm);
-            r = x < cst ? r_lt : (x == cst ? r_eq : r_gt);
+            // floats: NaN sorts above every number (Arrow total order): > and >= and <> are true for NaN
+            const double x = KIND == TK_F64 ? u2d(raw) : (double)(int64_t)raw, c = u2d(imm);
+            r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? !(x <= c) : OP == 6 ? !(x < c) : x != c;
         }
         uint32_t tm = __ballot_sync(0xffffffffu, r);
         if (has_bits) tm &= bits[g];
         m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
     }
 }
-
-__device__ __forceinline__ void unit_terms(const ScanTables& T, const ScanUnitDesc& u, const uint8_t* stage,
-                                           uint64_t* st, int lane, int rows_in_tile) {
-    const bool is_or = u.flags & 1;
-    uint64_t cnt = 0;
-    for (int base = u.row0; base < u.row0 + u.nrows; base += 32 * TG) {
-        uint32_t m[TG];
-#pragma unroll
-        for (int g = 0; g < TG; ++g) m[g] = is_or ? 0u : 0xffffffffu;
-        for (int k = 0; k < u.code_len; ++k) {
-            const ScanTerm& t = T.terms[u.code_off + k];
-            const ScanColDesc& c = T.cols[t.col];
-            switch (t.kind) {
-                case TK_F64: term_pass<TK_F64>(t, c, stage, base, lane, is_or, m); break;
-                case TK_I64: term_pass<TK_I64>(t, c, stage, base, lane, is_or, m); break;
-                case TK_I64_AS_F64: term_pass<TK_I64_AS_F64>(t, c, stage, base, lane, is_or, m); break;
-                case TK_ISNULL: term_pass<TK_ISNULL>(t, c, stage, base, lane, is_or, m); break;
-                default: term_pass<TK_NOTNULL>(t, c, stage, base, lane, is_or, m); break;
-            }
-        }
-#pragma unroll
-        for (int g = 0; g < TG; ++g) cnt += __popc(m[g] & tail_mask(base + 32 * g, rows_in_tile));
+template <int KIND>
+__device__ __forceinline__ void term_pass(int cmp_mask, uint64_t imm, uint32_t val_off, uint32_t bits_off, const uint8_t* stage,
+                                          int row0, int lane, bool is_or, uint32_t (&m)[TG]) {
+    switch (cmp_mask & 7) {
+        case 1: term_cmp_pass<KIND, 1>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+        case 2: term_cmp_pass<KIND, 2>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+        case 3: term_cmp_pass<KIND, 3>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+        case 4: term_cmp_pass<KIND, 4>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+        case 6: term_cmp_pass<KIND, 6>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+        default: term_cmp_pass<KIND, 5>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
     }
-    if (lane == 0) st[0] += cnt;
 }
+
+struct TermsUnit {
+    uint64_t imm[SCAN_UNIT_TERMS];
+    uint32_t val_off[SCAN_UNIT_TERMS], bits_off[SCAN_UNIT_TERMS];
+    int kind[SCAN_UNIT_TERMS], cmp[SCAN_UNIT_TERMS];
+    int nt, row0, nrows, lane;
+    bool is_or;
+    uint64_t cnt;
+    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+        nt = u.code_len;
+#pragma unroll
+        for (int k = 0; k < SCAN_UNIT_TERMS; ++k) {
+            const ScanTerm& t = T.terms[u.code_off + (k < nt ? k : 0)];
+            const ScanColDesc& c = T.cols[t.col];
+            imm[k] = t.imm;
+            kind[k] = t.kind;
+            cmp[k] = t.cmp_mask;
+            val_off[k] = c.smem_val_off;
+            bits_off[k] = c.validity ? c.smem_bits_off : 0xffffffffu;
+        }
+        row0 = u.row0;
+        nrows = u.nrows;
+        lane = lane_;
+        is_or = u.flags & 1;
+        cnt = st[0];
+    }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) {
+        for (int base = row0; base < row0 + nrows; base += 32 * TG) {
+            uint32_t m[TG];
+#pragma unroll
+            for (int g = 0; g < TG; ++g) m[g] = is_or ? 0u : 0xffffffffu;
+#pragma unroll
+            for (int k = 0; k < SCAN_UNIT_TERMS; ++k) {
+                if (k >= nt) break;
+                if (kind[k] == TK_ISNULL || kind[k] == TK_NOTNULL) {
+                    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off[k] != 0xffffffffu ? bits_off[k] : 0u)) + (base >> 5);
+#pragma unroll
+                    for (int g = 0; g < TG; ++g) {
+                        const uint32_t valid = bits_off[k] != 0xffffffffu ? bits[g] : 0xffffffffu;
+                        const uint32_t tm = kind[k] == TK_ISNULL ? ~valid : valid;
+                        m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
+                    }
+                } else if (kind[k] == TK_F64) {
+                    term_pass<TK_F64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
+                } else if (kind[k] == TK_I64) {
+                    term_pass<TK_I64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
+                } else {
+                    term_pass<TK_I64_AS_F64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < TG; ++g) cnt += __popc(m[g] & tail_mask(base + 32 * g, rows));
+        }
+    }
+    __device__ __forceinline__ void end(uint64_t* st) {
+        if (lane == 0) st[0] = cnt;
+    }
+};
 
 // ---- general predicate evaluator: per-lane numeric temporaries, warp-uniform NULL/TRUE/FALSE masks ----
 constexpr int PG = PRED_GROUPS;
@@ -601,6 +687,106 @@ __host__ __device__ __forceinline__ uint64_t slot_identity(int kind, int slot) {
     }
 }
 
+struct PredUnit {
+    const ScanTables* T;
+    const ScanUnitDesc* u;
+    uint64_t* st;
+    int lane;
+    __device__ __forceinline__ void begin(const ScanTables& T_, const ScanUnitDesc& u_, const uint64_t* st_, int lane_) {
+        T = &T_;
+        u = &u_;
+        st = const_cast<uint64_t*>(st_);
+        lane = lane_;
+    }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) { unit_pred(*T, *u, stage, st, lane, rows); }
+    __device__ __forceinline__ void end(uint64_t*) {}
+};
+
+// consumer-side view of the stage ring
+struct Pipe {
+    uint8_t* stages;
+    uint64_t* full;
+    uint64_t* empty;
+    int n_stages, tile_rows;
+    uint32_t stage_bytes;
+    int64_t n_tiles, n_rows;
+};
+
+// a warp that owns exactly one unit: descriptors and accumulators live in registers for the whole scan
+template <class U>
+__device__ __forceinline__ void run_single(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane) {
+    U unit;
+    unit.begin(T, ud, st, lane);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
+        mbar_wait(&p.full[s], ph);
+        const int64_t row_base = t * p.tile_rows;
+        const int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row_base);
+        unit.tile(p.stages + (size_t)s * p.stage_bytes, rows, rows < p.tile_rows);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p.empty[s]);
+        if (++s == p.n_stages) {
+            s = 0;
+            ph ^= 1u;
+        }
+    }
+    unit.end(st);
+}
+template <class U>
+__device__ __forceinline__ void run_once(const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane, const uint8_t* stage,
+                                         int rows, bool partial) {
+    U unit;
+    unit.begin(T, ud, st, lane);
+    unit.tile(stage, rows, partial);
+    unit.end(st);
+}
+
+// kind / flag dispatch, shared by both execution modes (SINGLE: whole tile loop inside; else one tile)
+template <bool SINGLE, class U>
+__device__ __forceinline__ void run_unit(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane,
+                                         const uint8_t* stage, int rows, bool partial) {
+    if (SINGLE) run_single<U>(p, T, ud, st, lane);
+    else run_once<U>(T, ud, st, lane, stage, rows, partial);
+}
+template <bool SINGLE, bool IS_I64>
+__device__ __forceinline__ void dispatch_num(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane,
+                                             const uint8_t* stage, int rows, bool partial) {
+    if (!T.cols[ud.c0].pivot_is_element) {
+        run_unit<SINGLE, NumSlowUnit<IS_I64>>(p, T, ud, st, lane, stage, rows, partial);
+        return;
+    }
+    switch (ud.flags & 7) {
+        case 0: run_unit<SINGLE, NumUnit<IS_I64, 0>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 1: run_unit<SINGLE, NumUnit<IS_I64, 1>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 2: run_unit<SINGLE, NumUnit<IS_I64, 2>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 3: run_unit<SINGLE, NumUnit<IS_I64, 3>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 4: run_unit<SINGLE, NumUnit<IS_I64, 4>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 5: run_unit<SINGLE, NumUnit<IS_I64, 5>>(p, T, ud, st, lane, stage, rows, partial); break;
+        case 6: run_unit<SINGLE, NumUnit<IS_I64, 6>>(p, T, ud, st, lane, stage, rows, partial); break;
+        default: run_unit<SINGLE, NumUnit<IS_I64, 7>>(p, T, ud, st, lane, stage, rows, partial); break;
+    }
+}
+template <bool SINGLE>
+__device__ __forceinline__ void dispatch_unit(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane,
+                                              const uint8_t* stage, int rows, bool partial) {
+    switch (ud.kind) {
+        case UNIT_COUNT: run_unit<SINGLE, CountUnit>(p, T, ud, st, lane, stage, rows, partial); break;
+        case UNIT_NUM_F64: dispatch_num<SINGLE, false>(p, T, ud, st, lane, stage, rows, partial); break;
+        case UNIT_NUM_I64: dispatch_num<SINGLE, true>(p, T, ud, st, lane, stage, rows, partial); break;
+        case UNIT_PAIR:
+            switch ((ud.c0_is_i64 ? 1 : 0) | (ud.c1_is_i64 ? 2 : 0)) {
+                case 0: run_unit<SINGLE, PairUnit<false, false>>(p, T, ud, st, lane, stage, rows, partial); break;
+                case 1: run_unit<SINGLE, PairUnit<true, false>>(p, T, ud, st, lane, stage, rows, partial); break;
+                case 2: run_unit<SINGLE, PairUnit<false, true>>(p, T, ud, st, lane, stage, rows, partial); break;
+                default: run_unit<SINGLE, PairUnit<true, true>>(p, T, ud, st, lane, stage, rows, partial); break;
+            }
+            break;
+        case UNIT_TERMS: run_unit<SINGLE, TermsUnit>(p, T, ud, st, lane, stage, rows, partial); break;
+        default: run_unit<SINGLE, PredUnit>(p, T, ud, st, lane, stage, rows, partial); break;
+    }
+}
+
 __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_constant__ ScanParams P) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* stages = scan_smem;
@@ -630,9 +816,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         mbar_fence_init();
     }
     __syncthreads();
-    const int n_stages = P.n_stages, tile_rows = P.tile_rows;
-    const int64_t n_tiles = P.n_tiles, n_rows = P.n_rows;
-    const uint32_t stage_bytes = P.stage_bytes;
+    Pipe pipe{stages, full, empty, P.n_stages, P.tile_rows, P.stage_bytes, P.n_tiles, P.n_rows};
 
     if (warp == 0) {
         // ---------------- TMA producer: lane c moves column c ----------------
@@ -641,11 +825,11 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         const bool has_v = active && c.values != nullptr, has_b = active && c.validity != nullptr;
         int s = 0;
         uint32_t ph = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        for (int64_t t = blockIdx.x; t < pipe.n_tiles; t += gridDim.x) {
             mbar_wait(&empty[s], ph ^ 1u);
-            const int64_t row_base = t * tile_rows;
-            const int rows = (int)min((int64_t)tile_rows, n_rows - row_base);
-            uint8_t* stage = stages + (size_t)s * stage_bytes;
+            const int64_t row_base = t * pipe.tile_rows;
+            const int rows = (int)min((int64_t)pipe.tile_rows, pipe.n_rows - row_base);
+            uint8_t* stage = stages + (size_t)s * pipe.stage_bytes;
             // byte counts padded to 16 (buffers are allocated with that slack)
             const uint32_t bbytes = has_b ? (uint32_t)(((rows + 7) / 8 + 15) & ~15) : 0u;
             const uint32_t vbytes = !has_v ? 0u : (c.kind == SC_BOOL ? (uint32_t)(((rows + 7) / 8 + 15) & ~15)
@@ -660,7 +844,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
                 bulk_g2s(stage + c.smem_val_off, src, vbytes, &full[s]);
             }
             if (bbytes) bulk_g2s(stage + c.smem_bits_off, c.validity + row_base / 8, bbytes, &full[s]);
-            if (++s == n_stages) {
+            if (++s == pipe.n_stages) {
                 s = 0;
                 ph ^= 1u;
             }
@@ -674,32 +858,28 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
             unit_init(T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane);
         }
         __syncwarp();
-        int s = 0;
-        uint32_t ph = 0;
-        for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
-            mbar_wait(&full[s], ph);
-            const int64_t row_base = t * tile_rows;
-            const int rows = (int)min((int64_t)tile_rows, n_rows - row_base);
-            const bool partial = rows < tile_rows;
-            const uint8_t* stage = stages + (size_t)s * stage_bytes;
-            for (int k = 0; k < n_mine; ++k) {
-                const int u = T->warp_units[cw][1 + k];
-                const ScanUnitDesc& ud = T->units[u];
-                uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
-                switch (ud.kind) {
-                    case UNIT_COUNT: unit_count(*T, ud, stage, st, lane, rows); break;
-                    case UNIT_NUM_F64: unit_num<false>(*T, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_NUM_I64: unit_num<true>(*T, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_PAIR: unit_pair(*T, ud, stage, st, lane, rows, partial); break;
-                    case UNIT_PRED: unit_pred(*T, ud, stage, st, lane, rows); break;
-                    case UNIT_TERMS: unit_terms(*T, ud, stage, st, lane, rows); break;
+        if (n_mine == 1) {
+            const int u = T->warp_units[cw][1];
+            dispatch_unit<true>(pipe, *T, T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane, nullptr, 0, false);
+        } else {
+            int s = 0;
+            uint32_t ph = 0;
+            for (int64_t t = blockIdx.x; t < pipe.n_tiles; t += gridDim.x) {
+                mbar_wait(&full[s], ph);
+                const int64_t row_base = t * pipe.tile_rows;
+                const int rows = (int)min((int64_t)pipe.tile_rows, pipe.n_rows - row_base);
+                const uint8_t* stage = stages + (size_t)s * pipe.stage_bytes;
+                for (int k = 0; k < n_mine; ++k) {
+                    const int u = T->warp_units[cw][1 + k];
+                    dispatch_unit<false>(pipe, *T, T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane, stage, rows,
+                                         rows < pipe.tile_rows);
                 }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-            if (++s == n_stages) {
-                s = 0;
-                ph ^= 1u;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[s]);
+                if (++s == pipe.n_stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
             }
         }
         __syncwarp();
