@@ -162,28 +162,26 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
         }
         return off;
     };
-    // units: replicate ops over row slices so ~SCAN_CONSUMER_WARPS units of similar cost exist
-    double total_cost = 0;
-    for (auto& o : ops) total_cost += o.cost;
+    // units: ops are replicated over row slices of the tile (multiples of 128 rows) so that every consumer warp
+    // owns one unit of similar cost and keeps it in registers; warps are handed out greedily to the op whose
+    // per-replica cost is largest
     int tile_rows = 4096;
+    if (const char* ev = getenv("TG_SCAN_TILE_ROWS")) tile_rows = std::max(128, atoi(ev) / 128 * 128);
+    int min_stages = 3;
+    if (const char* ev = getenv("TG_SCAN_MIN_STAGES")) min_stages = std::max(2, atoi(ev));
     int n_stages = 0;
     std::vector<int> reps(ops.size(), 1);
     size_t stage_bytes = 0, state_bytes = 0;
     const size_t smem_budget = 227 * 1024 - 256 - sizeof(ScanTables);
-    bool has_terms = false;
-    for (auto& o : ops) has_terms |= o.kind == UNIT_TERMS;
-    for (; tile_rows >= (has_terms ? 256 : 128); tile_rows /= 2) {
-        // replicate ops over row slices until exactly SCAN_CONSUMER_WARPS units exist (every warp owns one unit and
-        // keeps it in registers): repeatedly halve the slice of the op whose per-slice cost is largest
+    for (; tile_rows >= 128; tile_rows /= 2) {
+        const int chunks = tile_rows / 128;
         int n_units = (int)ops.size();
         for (size_t i = 0; i < ops.size(); ++i) reps[i] = 1;
-        while (true) {
+        while (n_units < SCAN_CONSUMER_WARPS) {
             int best = -1;
             double best_cost = 0;
             for (size_t i = 0; i < ops.size(); ++i) {
-                const int min_slice = ops[i].kind == UNIT_TERMS ? 256 : 64;
-                if (ops[i].kind == UNIT_COUNT || tile_rows / (reps[i] * 2) < min_slice) continue;
-                if (n_units + reps[i] > SCAN_CONSUMER_WARPS) continue;
+                if (ops[i].kind == UNIT_COUNT || reps[i] >= chunks) continue;
                 const double c = ops[i].cost / reps[i];
                 if (c > best_cost) {
                     best_cost = c;
@@ -191,14 +189,14 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 }
             }
             if (best < 0) break;
-            n_units += reps[best];
-            reps[best] *= 2;
+            ++reps[best];
+            ++n_units;
         }
         if (n_units > SCAN_MAX_UNITS) throw Error(TG_ERR_UNSUPPORTED, "too many aggregates in one scan pass");
-        state_bytes = (size_t)n_units * SCAN_STATE_SLOTS * 32 * 8;
+        state_bytes = n_units <= SCAN_CONSUMER_WARPS ? 0 : (size_t)n_units * SCAN_STATE_SLOTS * 32 * 8;
         stage_bytes = stage_bytes_for(tile_rows, nullptr, nullptr);
         if (stage_bytes == 0) stage_bytes = 128;
-        if (state_bytes + 3 * stage_bytes + 2 * SCAN_MAX_STAGES * 8 <= smem_budget) {
+        if (state_bytes + (size_t)min_stages * stage_bytes + 2 * SCAN_MAX_STAGES * 8 <= smem_budget) {
             n_stages = (int)std::min<size_t>(SCAN_MAX_STAGES, (smem_budget - state_bytes - 2 * SCAN_MAX_STAGES * 8) / stage_bytes);
             break;
         }
@@ -258,21 +256,21 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
             }
         }
         const int r = reps[i];
-        const int slice = tile_rows / r;
+        const int chunks = tile_rows / 128;
         for (int k = 0; k < r; ++k) {
             UnitTmp u{};
             u.d.kind = o.kind;
             u.d.c0 = oc[i].c0;
             u.d.c1 = oc[i].c1;
-            u.d.row0 = k * slice;
-            u.d.nrows = slice;
+            u.d.row0 = (k * chunks / r) * 128;
+            u.d.nrows = ((k + 1) * chunks / r) * 128 - u.d.row0;
             u.d.agg = (int)i;  // local aggregate index within this pass
             u.d.code_off = this_code_off;
             u.d.code_len = o.kind == UNIT_TERMS ? (int)o.terms.size() : (int)o.code.size();
             u.d.c0_is_i64 = o.c0 && o.c0->dtype == TG_INT64;
             u.d.c1_is_i64 = o.c1 && o.c1->dtype == TG_INT64;
             u.d.flags = o.flags;
-            u.cost = o.cost / r;
+            u.cost = o.cost * u.d.nrows / tile_rows;
             units.push_back(u);
         }
     }
@@ -293,6 +291,7 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
         P->tab.warp_units[best][0] = ++owned[best];
     }
     P->n_units = (int)units.size();
+    P->n_state_units = units.size() <= (size_t)SCAN_CONSUMER_WARPS ? 0 : (int)units.size();
     P->n_aggs = (int)ops.size();
     P->n_code = code_off;
     P->n_terms = term_off;
@@ -339,13 +338,7 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 a.f[2] = u2d(s[S_SDD]);
                 a.f[5] = (double)s[S_N] * ops[i].c0->pivot + u2d(s[S_SD]);  // sum(x) = n*K + sum(x-K)
                 if (ops[i].kind == UNIT_NUM_I64) {
-                    // NULL / padding rows were summed as K: remove them (exact in wrapping arithmetic)
-                    uint64_t isum = s[S_ISUM];
-                    if (ops[i].c0->pivot_set) {
-                        const uint64_t padded = (uint64_t)P->n_tiles * (uint64_t)P->tile_rows;
-                        isum -= (padded - s[S_N]) * (uint64_t)ops[i].c0->ipivot;
-                    }
-                    a.u[1] = isum;
+                    a.u[1] = s[S_ISUM];  // wrapping i64 sum over the valid rows
                     a.u[2] = s[S_MIN];
                     a.u[3] = s[S_MAX];
                     a.u[4] = 1;
@@ -525,8 +518,9 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 o.flags = a.flags ? a.flags : 7;
                 if (c->dtype != TG_INT64) o.flags &= ~4;
                 // warp-instructions per 32 rows: load + mask, then moments / min-max / integer sum
-                o.cost = 5.0 + ((o.flags & 1) ? 3.0 : 0.0) + ((o.flags & 2) ? (c->dtype == TG_INT64 ? 8.0 : 6.0) : 0.0) +
-                         ((o.flags & 4) ? 2.0 : 0.0) + ((o.flags & 1) && c->dtype == TG_INT64 ? 1.0 : 0.0);
+                // warp-instructions per 32 rows of the specialised loops (counted in the SASS)
+                o.cost = 2.5 + ((o.flags & 1) ? 5.5 : 0.0) + ((o.flags & 2) ? (c->dtype == TG_INT64 ? 8.5 : 6.5) : 0.0) +
+                         ((o.flags & 4) ? 3.5 : 0.0) + ((o.flags & 1) && c->dtype == TG_INT64 ? 1.0 : 0.0);
                 count_bytes(c, true);
                 ops.push_back(std::move(o));
             } break;
@@ -538,7 +532,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                 o.kind = UNIT_PAIR;
                 o.c0 = x;
                 o.c1 = y;
-                o.cost = 20.0 + (x->dtype == TG_INT64 ? 1.0 : 0.0) + (y->dtype == TG_INT64 ? 1.0 : 0.0);
+                o.cost = 15.5 + (x->dtype == TG_INT64 ? 1.0 : 0.0) + (y->dtype == TG_INT64 ? 1.0 : 0.0);
                 count_bytes(x, true);
                 count_bytes(y, true);
                 ops.push_back(std::move(o));
@@ -562,7 +556,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                     if (try_compile_terms(expr, res, o.terms, is_or)) {
                         o.kind = UNIT_TERMS;
                         o.flags = is_or ? 1 : 0;
-                        o.cost = 3.0 + 7.0 * (double)o.terms.size();
+                        o.cost = 1.0 + 6.5 * (double)o.terms.size();
                     } else {
                         o.pred_cols.clear();
                         compile_predicate(expr, res, o.code);

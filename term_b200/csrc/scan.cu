@@ -12,14 +12,20 @@
 //     buffer (values and validity words of each column) into a multi-stage shared-memory ring,
 //     completion tracked by mbarrier transaction bytes. Every input byte crosses HBM->SM exactly once
 //     no matter how many constraints reference it.
-//   * 16 consumer warps each own a fixed list of "units" (one aggregate over a row slice of the
-//     tile); they read the tile from shared memory conflict-free (lane-contiguous 8-byte elements),
-//     keep per-lane accumulators in shared memory between tiles, and release the stage through an
-//     "empty" mbarrier, so fast warps run up to n_stages-1 tiles ahead of slow ones.
+//   * 16 consumer warps each own "units" (one aggregate over a row slice of the tile, a multiple of 128
+//     rows); they read the tile from shared memory conflict-free (lane-contiguous 8-byte elements) and
+//     release the stage through an "empty" mbarrier, so fast warps run up to n_stages-1 tiles ahead of
+//     slow ones. When a pass has at most 16 units (the planner replicates aggregates over row slices to
+//     get exactly 16) every warp keeps its unit's descriptor and accumulators in REGISTERS for the whole
+//     scan; with more units a warp runs several per tile against per-lane state in shared memory.
 //   * descriptor tables (columns, units, predicate code) are copied to shared memory once; every
 //     kind / flag decision is hoisted out of the row loops (template specialisations).
-//   * moments are accumulated as shifted sums Σ(x-K), Σ(x-K)² with K an element of the column; NULL rows
-//     are replaced by K (contributing exactly 0), so the inner loops have no predicated accumulates.
+//   * every inner loop handles 128 rows per iteration (4 groups of 32 rows; lane l owns row 32g+l) with
+//     ONE 128-bit load of the four validity words and two independent accumulator sets, so each dependent
+//     FP64 chain has a second one to overlap with.
+//   * moments are accumulated as shifted sums Σ(x-K), Σ(x-K)² with K a typical element of the column; NULL
+//     rows are masked by zeroing the shifted value (2 selects) or by AND-ing the validity predicate into the
+//     compare (min/max, predicates: no extra instruction).
 //   * per-CTA partials go to global memory; scan_finalize_kernel reduces them in a fixed order, so a
 //     given (grid, plan) is bit-reproducible run to run.
 #include <cfloat>
@@ -34,6 +40,8 @@ namespace tg {
 
 extern __shared__ __align__(128) uint8_t scan_smem[];
 
+typedef uint64_t Slots[SCAN_STATE_SLOTS];
+
 __device__ __forceinline__ uint32_t tail_mask(int base_row, int rows_in_tile) {
     const int rem = rows_in_tile - base_row;
     return rem >= 32 ? 0xffffffffu : (rem <= 0 ? 0u : ((1u << rem) - 1u));
@@ -41,28 +49,31 @@ __device__ __forceinline__ uint32_t tail_mask(int base_row, int rows_in_tile) {
 __device__ __forceinline__ double u2d(uint64_t u) { return __longlong_as_double((long long)u); }
 __device__ __forceinline__ uint64_t d2u(double d) { return (uint64_t)__double_as_longlong(d); }
 
-// per-lane state in shared memory: st[slot * 32 + lane]
-__device__ __forceinline__ void unit_init(const ScanUnitDesc& u, uint64_t* st, int lane) {
-#pragma unroll
-    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) st[k * 32 + lane] = 0;
-    if (u.kind == UNIT_NUM_F64) {
-        st[S_MIN * 32 + lane] = d2u(CUDART_INF);
-        st[S_MAX * 32 + lane] = d2u(-CUDART_INF);
-    } else if (u.kind == UNIT_NUM_I64) {
-        st[S_MIN * 32 + lane] = (uint64_t)INT64_MAX;
-        st[S_MAX * 32 + lane] = (uint64_t)INT64_MIN;
-    }
-}
-
 // validity word (32 rows) of a column inside the stage; all-ones when the column has no bitmap
 __device__ __forceinline__ uint32_t vword(const ScanColDesc& c, const uint8_t* stage, int word) {
     return c.validity ? reinterpret_cast<const uint32_t*>(stage + c.smem_bits_off)[word] : 0xffffffffu;
 }
+__device__ __forceinline__ uint32_t word_or_ones(const uint32_t* bits, bool has_bits, int g) { return has_bits ? bits[g] : 0xffffffffu; }
+
+// masked running min / max: the validity predicate is AND-ed into the compare (DSETP.x.AND / ISETP.x.AND.EX), so
+// masking costs no extra instruction
+__device__ __forceinline__ void min_if_f64(double& mn, double x, uint32_t m) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.lt.and.f64 q, %1, %0, p;\n\tselp.f64 %0, %1, %0, q;\n\t}" : "+d"(mn) : "d"(x), "r"(m));
+}
+__device__ __forceinline__ void max_if_f64(double& mx, double x, uint32_t m) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.gt.and.f64 q, %1, %0, p;\n\tselp.f64 %0, %1, %0, q;\n\t}" : "+d"(mx) : "d"(x), "r"(m));
+}
+__device__ __forceinline__ void min_if_i64(int64_t& mn, int64_t x, uint32_t m) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.lt.and.s64 q, %1, %0, p;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(mn) : "l"(x), "r"(m));
+}
+__device__ __forceinline__ void max_if_i64(int64_t& mx, int64_t x, uint32_t m) {
+    asm("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %2, 0;\n\tsetp.gt.and.s64 q, %1, %0, p;\n\tselp.b64 %0, %1, %0, q;\n\t}" : "+l"(mx) : "l"(x), "r"(m));
+}
 
 // ======================================================================================================
-// Units. Every unit kind is a small object with begin(state) / tile(stage) / end(state): a warp that owns ONE
-// unit keeps the object (descriptor fields + accumulators) in registers across its whole tile loop; a warp that
-// owns several runs begin/tile/end per tile against the per-lane state in shared memory.
+// Units. Every unit kind is a small object: setup(descriptors) / load(slots) / tile(stage) / store(slots).
+// `slots` is this lane's SCAN_STATE_SLOTS 64-bit partial state (meaning per kind in scan_defs.h).
+// The last (partial) tile of the table takes a generic masked path (`tail`).
 // ======================================================================================================
 
 // ---- COUNT: popcount of validity words ----
@@ -70,198 +81,185 @@ struct CountUnit {
     uint32_t bits_off;
     int w0, nw, row0, lane;
     uint64_t n;
-    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+    __device__ __forceinline__ void setup(const ScanTables& T, const ScanUnitDesc& u, int lane_) {
         const ScanColDesc& c = T.cols[u.c0];
         bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
         w0 = u.row0 >> 5;
         nw = u.nrows >> 5;
         row0 = u.row0;
         lane = lane_;
-        n = st[S_N * 32 + lane];
     }
-    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) {
+    __device__ __forceinline__ void load(const Slots& r) { n = r[S_N]; }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
+        if (bits_off == 0xffffffffu && !partial) {
+            if (lane == 0) n += (uint64_t)nw * 32;
+            return;
+        }
         for (int j = lane; j < nw; j += 32) {
             uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[w0 + j] : 0xffffffffu;
-            n += __popc(w & tail_mask(row0 + 32 * j, rows));
+            if (partial) w &= tail_mask(row0 + 32 * j, rows);
+            n += __popc(w);
         }
     }
-    __device__ __forceinline__ void end(uint64_t* st) { st[S_N * 32 + lane] = n; }
+    __device__ __forceinline__ void store(Slots& r) {
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = 0;
+        r[S_N] = n;
+    }
 };
 
-// ---- NUM ----
-// NULL rows (and rows past the end of the table) are replaced by the pivot element K: they add 0 to Σd and
-// Σd², cannot change min/max (K is a value of the column), and the wrapping integer sum is corrected on the
-// host by (rows_processed - n)·K. Valid rows are counted by popcounting validity words (one word per lane).
+// ---- NUM: n, Σ(x-K), Σ(x-K)², min, max, wrapping integer sum over the valid rows of one column ----
 template <bool IS_I64, int FLAGS>
 struct NumUnit {
     static constexpr bool MOM = (FLAGS & UF_MOMENTS) != 0, MM = (FLAGS & UF_MINMAX) != 0, ISUM = IS_I64 && (FLAGS & UF_ISUM) != 0;
     uint32_t val_off, bits_off;  // bits_off == ~0u: no bitmap
-    int row0, nw, lane;
+    int row0, nrows, lane;
     double K;
-    uint64_t Kbits, n, isum;
-    double sd, sdd, fmn, fmx;
-    int64_t imn, imx;
+    uint64_t n, isum[2];
+    double sd[2], sdd[2], fmn[2], fmx[2];
+    int64_t imn[2], imx[2];
 
-    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+    __device__ __forceinline__ void setup(const ScanTables& T, const ScanUnitDesc& u, int lane_) {
         const ScanColDesc& c = T.cols[u.c0];
         val_off = c.smem_val_off;
         bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
         row0 = u.row0;
-        nw = u.nrows >> 5;
+        nrows = u.nrows;
         lane = lane_;
         K = c.pivot;
-        Kbits = IS_I64 ? (uint64_t)c.ipivot : d2u(c.pivot);
-        n = st[S_N * 32 + lane];
-        sd = u2d(st[S_SD * 32 + lane]);
-        sdd = u2d(st[S_SDD * 32 + lane]);
-        fmn = u2d(st[S_MIN * 32 + lane]);
-        fmx = u2d(st[S_MAX * 32 + lane]);
-        imn = (int64_t)st[S_MIN * 32 + lane];
-        imx = (int64_t)st[S_MAX * 32 + lane];
-        isum = st[S_ISUM * 32 + lane];
     }
-    template <int MASK>  // 0 dense full tile, 1 bitmap, 2 bitmap and/or tail
-    __device__ __forceinline__ void loop(const uint8_t* stage, int rows) {
+    __device__ __forceinline__ void load(const Slots& r) {
+        n = r[S_N];
+        sd[0] = u2d(r[S_SD]);
+        sdd[0] = u2d(r[S_SDD]);
+        fmn[0] = u2d(r[S_MIN]);
+        fmx[0] = u2d(r[S_MAX]);
+        imn[0] = (int64_t)r[S_MIN];
+        imx[0] = (int64_t)r[S_MAX];
+        isum[0] = r[S_ISUM];
+        sd[1] = sdd[1] = 0.0;
+        fmn[1] = CUDART_INF;
+        fmx[1] = -CUDART_INF;
+        imn[1] = INT64_MAX;
+        imx[1] = INT64_MIN;
+        isum[1] = 0;
+    }
+    // m != 0 <=> the row is valid; MASKED = false: every row is valid (m ignored)
+    template <int A, bool MASKED>
+    __device__ __forceinline__ void acc(uint64_t raw, uint32_t m) {
+        if (IS_I64) {
+            const int64_t xi = (int64_t)raw;
+            if (MOM) {
+                double d = (double)xi - K;
+                if (MASKED) d = m ? d : 0.0;
+                sd[A] += d;
+                sdd[A] = fma(d, d, sdd[A]);
+            }
+            if (ISUM) isum[A] += (MASKED && !m) ? 0ull : raw;
+            if (MM) {
+                if (MASKED) {
+                    min_if_i64(imn[A], xi, m);
+                    max_if_i64(imx[A], xi, m);
+                } else {
+                    imn[A] = xi < imn[A] ? xi : imn[A];
+                    imx[A] = xi > imx[A] ? xi : imx[A];
+                }
+            }
+        } else {
+            const double x = u2d(raw);
+            if (MOM) {
+                double d = x - K;
+                if (MASKED) d = m ? d : 0.0;
+                sd[A] += d;
+                sdd[A] = fma(d, d, sdd[A]);
+            }
+            if (MM) {
+                if (MASKED) {
+                    min_if_f64(fmn[A], x, m);
+                    max_if_f64(fmx[A], x, m);
+                } else {
+                    fmn[A] = x < fmn[A] ? x : fmn[A];
+                    fmx[A] = x > fmx[A] ? x : fmx[A];
+                }
+            }
+        }
+    }
+    template <bool HB>
+    __device__ __forceinline__ void body(const uint8_t* stage) {
         const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
-        const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off != 0xffffffffu ? bits_off : 0u)) + (row0 >> 5);
         const uint32_t lanebit = 1u << lane;
+        const int nq = nrows >> 7;
+        if (HB) {
+            const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + bits_off) + (row0 >> 5);
+            for (int j = lane; j < 4 * nq; j += 32) n += __popc(bits[j]);
+            if (FLAGS == 0) return;
+            const uint4* b4 = reinterpret_cast<const uint4*>(bits);
+#pragma unroll 2
+            for (int q = 0; q < nq; ++q) {
+                const uint4 w = b4[q];
+                const uint64_t r0 = vals[128 * q], r1 = vals[128 * q + 32], r2 = vals[128 * q + 64], r3 = vals[128 * q + 96];
+                acc<0, true>(r0, w.x & lanebit);
+                acc<1, true>(r1, w.y & lanebit);
+                acc<0, true>(r2, w.z & lanebit);
+                acc<1, true>(r3, w.w & lanebit);
+            }
+        } else {
+            if (lane == 0) n += (uint64_t)nrows;
+            if (FLAGS == 0) return;
+#pragma unroll 2
+            for (int q = 0; q < nq; ++q) {
+                const uint64_t r0 = vals[128 * q], r1 = vals[128 * q + 32], r2 = vals[128 * q + 64], r3 = vals[128 * q + 96];
+                acc<0, false>(r0, 1u);
+                acc<1, false>(r1, 1u);
+                acc<0, false>(r2, 1u);
+                acc<1, false>(r3, 1u);
+            }
+        }
+    }
+    // last tile of the table: rows beyond `rows` are masked off
+    __device__ __forceinline__ void tail(const uint8_t* stage, int rows) {
+        const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
         const bool has_bits = bits_off != 0xffffffffu;
-#pragma unroll 4
-        for (int j = 0; j < nw; ++j) {
-            uint64_t raw = vals[32 * j];
-            if (MASK == 1) {
-                raw = (bits[j] & lanebit) ? raw : Kbits;
-            } else if (MASK == 2) {
-                uint32_t w = has_bits ? bits[j] : 0xffffffffu;
-                w &= tail_mask(row0 + 32 * j, rows);
-                raw = (w & lanebit) ? raw : Kbits;
-            }
-            if (IS_I64) {
-                const int64_t xi = (int64_t)raw;
-                if (MOM) {
-                    const double d = (double)xi - K;
-                    sd += d;
-                    sdd = fma(d, d, sdd);
-                }
-                if (ISUM) isum += (uint64_t)xi;
-                if (MM) {
-                    imn = xi < imn ? xi : imn;
-                    imx = xi > imx ? xi : imx;
-                }
-            } else {
-                const double x = u2d(raw);
-                if (MOM) {
-                    const double d = x - K;
-                    sd += d;
-                    sdd = fma(d, d, sdd);
-                }
-                if (MM) {
-                    fmn = x < fmn ? x : fmn;
-                    fmx = x > fmx ? x : fmx;
-                }
-            }
+        const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (has_bits ? bits_off : 0u)) + (row0 >> 5);
+        const int ng = nrows >> 5;
+        for (int j = lane; j < ng; j += 32) n += __popc(word_or_ones(bits, has_bits, j) & tail_mask(row0 + 32 * j, rows));
+        if (FLAGS == 0) return;
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+            const uint32_t w = word_or_ones(bits, has_bits, g) & tail_mask(row0 + 32 * g, rows);
+            acc<0, true>(vals[32 * g], (w >> lane) & 1u);
         }
     }
     __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
-        // valid rows: each lane popcounts different words
-        if (bits_off != 0xffffffffu || partial) {
-            for (int j = lane; j < nw; j += 32) {
-                uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[(row0 >> 5) + j] : 0xffffffffu;
-                n += __popc(w & tail_mask(row0 + 32 * j, rows));
-            }
-        } else if (lane == 0) {
-            n += (uint64_t)nw * 32;
-        }
-        if (FLAGS == 0) return;
-        if (partial) loop<2>(stage, rows);
-        else if (bits_off != 0xffffffffu) loop<1>(stage, rows);
-        else loop<0>(stage, rows);
+        if (partial) tail(stage, rows);
+        else if (bits_off != 0xffffffffu) body<true>(stage);
+        else body<false>(stage);
     }
-    __device__ __forceinline__ void end(uint64_t* st) {
-        st[S_N * 32 + lane] = n;
-        if (MOM) {
-            st[S_SD * 32 + lane] = d2u(sd);
-            st[S_SDD * 32 + lane] = d2u(sdd);
+    __device__ __forceinline__ void store(Slots& r) {
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = 0;
+        r[S_N] = n;
+        r[S_SD] = d2u(sd[0] + sd[1]);
+        r[S_SDD] = d2u(sdd[0] + sdd[1]);
+        if (IS_I64) {
+            r[S_MIN] = (uint64_t)(imn[0] < imn[1] ? imn[0] : imn[1]);
+            r[S_MAX] = (uint64_t)(imx[0] > imx[1] ? imx[0] : imx[1]);
+        } else {
+            r[S_MIN] = d2u(fmn[0] < fmn[1] ? fmn[0] : fmn[1]);
+            r[S_MAX] = d2u(fmx[0] > fmx[1] ? fmx[0] : fmx[1]);
         }
-        if (MM) {
-            st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
-            st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
-        }
-        if (ISUM) st[S_ISUM * 32 + lane] = isum;
+        r[S_ISUM] = isum[0] + isum[1];
     }
 };
 
-// slow path: the pivot is not an element of the column (no finite valid value was found when the column was
-// registered, e.g. all NULL): rows are masked explicitly
-template <bool IS_I64>
-struct NumSlowUnit {
-    uint32_t val_off, bits_off;
-    int row0, nw, lane;
-    double K;
-    uint64_t n, isum;
-    double sd, sdd, fmn, fmx;
-    int64_t imn, imx;
-    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
-        const ScanColDesc& c = T.cols[u.c0];
-        val_off = c.smem_val_off;
-        bits_off = c.validity ? c.smem_bits_off : 0xffffffffu;
-        row0 = u.row0;
-        nw = u.nrows >> 5;
-        lane = lane_;
-        K = c.pivot;
-        n = st[S_N * 32 + lane];
-        sd = u2d(st[S_SD * 32 + lane]);
-        sdd = u2d(st[S_SDD * 32 + lane]);
-        fmn = u2d(st[S_MIN * 32 + lane]);
-        fmx = u2d(st[S_MAX * 32 + lane]);
-        imn = (int64_t)st[S_MIN * 32 + lane];
-        imx = (int64_t)st[S_MAX * 32 + lane];
-        isum = st[S_ISUM * 32 + lane];
-    }
-    __device__ __noinline__ void tile(const uint8_t* stage, int rows, bool) {
-        const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
-        for (int j = 0; j < nw; ++j) {
-            uint32_t w = bits_off != 0xffffffffu ? reinterpret_cast<const uint32_t*>(stage + bits_off)[(row0 >> 5) + j] : 0xffffffffu;
-            w &= tail_mask(row0 + 32 * j, rows);
-            const bool ok = (w >> lane) & 1u;
-            n += ok;
-            const uint64_t raw = vals[32 * j];
-            if (IS_I64) {
-                const int64_t xi = (int64_t)raw;
-                const double d = ok ? (double)xi - K : 0.0;
-                sd += d;
-                sdd = fma(d, d, sdd);
-                isum += ok ? (uint64_t)xi : 0ull;
-                imn = min(imn, ok ? xi : INT64_MAX);
-                imx = max(imx, ok ? xi : INT64_MIN);
-            } else {
-                const double x = u2d(raw);
-                const double d = ok ? x - K : 0.0;
-                sd += d;
-                sdd = fma(d, d, sdd);
-                fmn = fmin(fmn, ok ? x : CUDART_INF);
-                fmx = fmax(fmx, ok ? x : -CUDART_INF);
-            }
-        }
-    }
-    __device__ __forceinline__ void end(uint64_t* st) {
-        st[S_N * 32 + lane] = n;
-        st[S_SD * 32 + lane] = d2u(sd);
-        st[S_SDD * 32 + lane] = d2u(sdd);
-        st[S_MIN * 32 + lane] = IS_I64 ? (uint64_t)imn : d2u(fmn);
-        st[S_MAX * 32 + lane] = IS_I64 ? (uint64_t)imx : d2u(fmx);
-        st[S_ISUM * 32 + lane] = isum;
-    }
-};
-
-// ---- PAIR: rows where either side is NULL are replaced by (Kx, Ky) => dx = dy = 0 ----
+// ---- PAIR: co-moments over the rows where both columns are valid ----
 template <bool XI, bool YI>
 struct PairUnit {
     uint32_t vx_off, vy_off, bx_off, by_off;
-    int row0, nw, lane;
-    double Kx, Ky, sx, sy, sxx, syy, sxy;
+    int row0, nrows, lane;
+    double Kx, Ky, sx[2], sy[2], sxx[2], syy[2], sxy[2];
     uint64_t n;
-    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+    __device__ __forceinline__ void setup(const ScanTables& T, const ScanUnitDesc& u, int lane_) {
         const ScanColDesc& cx = T.cols[u.c0];
         const ScanColDesc& cy = T.cols[u.c1];
         vx_off = cx.smem_val_off;
@@ -269,16 +267,67 @@ struct PairUnit {
         bx_off = cx.validity ? cx.smem_bits_off : 0xffffffffu;
         by_off = cy.validity ? cy.smem_bits_off : 0xffffffffu;
         row0 = u.row0;
-        nw = u.nrows >> 5;
+        nrows = u.nrows;
         lane = lane_;
         Kx = cx.pivot;
         Ky = cy.pivot;
-        n = st[P_N * 32 + lane];
-        sx = u2d(st[P_SX * 32 + lane]);
-        sy = u2d(st[P_SY * 32 + lane]);
-        sxx = u2d(st[P_SXX * 32 + lane]);
-        syy = u2d(st[P_SYY * 32 + lane]);
-        sxy = u2d(st[P_SXY * 32 + lane]);
+    }
+    __device__ __forceinline__ void load(const Slots& r) {
+        n = r[P_N];
+        sx[0] = u2d(r[P_SX]);
+        sy[0] = u2d(r[P_SY]);
+        sxx[0] = u2d(r[P_SXX]);
+        syy[0] = u2d(r[P_SYY]);
+        sxy[0] = u2d(r[P_SXY]);
+        sx[1] = sy[1] = sxx[1] = syy[1] = sxy[1] = 0.0;
+    }
+    template <int A, bool MASKED>
+    __device__ __forceinline__ void acc(uint64_t rx, uint64_t ry, uint32_t m) {
+        double dx = (XI ? (double)(int64_t)rx : u2d(rx)) - Kx;
+        double dy = (YI ? (double)(int64_t)ry : u2d(ry)) - Ky;
+        if (MASKED) {
+            dx = m ? dx : 0.0;
+            dy = m ? dy : 0.0;
+        }
+        sx[A] += dx;
+        sy[A] += dy;
+        sxx[A] = fma(dx, dx, sxx[A]);
+        syy[A] = fma(dy, dy, syy[A]);
+        sxy[A] = fma(dx, dy, sxy[A]);
+    }
+    template <int NB>  // number of bitmaps: 0, 1 (at b1_off) or 2
+    __device__ __forceinline__ void body(const uint8_t* stage, uint32_t b1_off, uint32_t b2_off) {
+        const uint64_t* vx = reinterpret_cast<const uint64_t*>(stage + vx_off) + row0 + lane;
+        const uint64_t* vy = reinterpret_cast<const uint64_t*>(stage + vy_off) + row0 + lane;
+        const uint32_t lanebit = 1u << lane;
+        const int nq = nrows >> 7;
+        const uint32_t* bits1 = reinterpret_cast<const uint32_t*>(stage + (NB ? b1_off : 0u)) + (row0 >> 5);
+        const uint32_t* bits2 = reinterpret_cast<const uint32_t*>(stage + (NB == 2 ? b2_off : 0u)) + (row0 >> 5);
+        if (NB) {
+            for (int j = lane; j < 4 * nq; j += 32) n += __popc(NB == 2 ? (bits1[j] & bits2[j]) : bits1[j]);
+        } else if (lane == 0) {
+            n += (uint64_t)nrows;
+        }
+        const uint4* p1 = reinterpret_cast<const uint4*>(bits1);
+        const uint4* p2 = reinterpret_cast<const uint4*>(bits2);
+#pragma unroll 2
+        for (int q = 0; q < nq; ++q) {
+            uint4 w = make_uint4(lanebit, lanebit, lanebit, lanebit);
+            if (NB >= 1) w = p1[q];
+            if (NB == 2) {
+                const uint4 w2 = p2[q];
+                w.x &= w2.x;
+                w.y &= w2.y;
+                w.z &= w2.z;
+                w.w &= w2.w;
+            }
+            const uint64_t x0 = vx[128 * q], x1 = vx[128 * q + 32], x2 = vx[128 * q + 64], x3 = vx[128 * q + 96];
+            const uint64_t y0 = vy[128 * q], y1 = vy[128 * q + 32], y2 = vy[128 * q + 64], y3 = vy[128 * q + 96];
+            acc<0, NB != 0>(x0, y0, w.x & lanebit);
+            acc<1, NB != 0>(x1, y1, w.y & lanebit);
+            acc<0, NB != 0>(x2, y2, w.z & lanebit);
+            acc<1, NB != 0>(x3, y3, w.w & lanebit);
+        }
     }
     __device__ __forceinline__ uint32_t both(const uint8_t* stage, int word) const {
         uint32_t w = 0xffffffffu;
@@ -286,150 +335,146 @@ struct PairUnit {
         if (by_off != 0xffffffffu) w &= reinterpret_cast<const uint32_t*>(stage + by_off)[word];
         return w;
     }
-    template <int MASK>
-    __device__ __forceinline__ void loop(const uint8_t* stage, int rows) {
+    __device__ __forceinline__ void tail(const uint8_t* stage, int rows) {
         const uint64_t* vx = reinterpret_cast<const uint64_t*>(stage + vx_off) + row0 + lane;
         const uint64_t* vy = reinterpret_cast<const uint64_t*>(stage + vy_off) + row0 + lane;
-        const uint32_t lanebit = 1u << lane;
-        const int w0 = row0 >> 5;
-#pragma unroll 4
-        for (int j = 0; j < nw; ++j) {
-            const uint64_t rx = vx[32 * j], ry = vy[32 * j];
-            double x = XI ? (double)(int64_t)rx : u2d(rx);
-            double y = YI ? (double)(int64_t)ry : u2d(ry);
-            if (MASK) {
-                uint32_t w = both(stage, w0 + j);
-                if (MASK == 2) w &= tail_mask(row0 + 32 * j, rows);
-                const bool ok = w & lanebit;
-                x = ok ? x : Kx;
-                y = ok ? y : Ky;
-            }
-            const double dx = x - Kx, dy = y - Ky;
-            sx += dx;
-            sy += dy;
-            sxx = fma(dx, dx, sxx);
-            syy = fma(dy, dy, syy);
-            sxy = fma(dx, dy, sxy);
+        const int ng = nrows >> 5, w0 = row0 >> 5;
+        for (int j = lane; j < ng; j += 32) n += __popc(both(stage, w0 + j) & tail_mask(row0 + 32 * j, rows));
+#pragma unroll 1
+        for (int g = 0; g < ng; ++g) {
+            const uint32_t w = both(stage, w0 + g) & tail_mask(row0 + 32 * g, rows);
+            acc<0, true>(vx[32 * g], vy[32 * g], (w >> lane) & 1u);
         }
     }
     __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
-        const bool has_bits = bx_off != 0xffffffffu || by_off != 0xffffffffu;
-        if (has_bits || partial) {
-            for (int j = lane; j < nw; j += 32) n += __popc(both(stage, (row0 >> 5) + j) & tail_mask(row0 + 32 * j, rows));
-        } else if (lane == 0) {
-            n += (uint64_t)nw * 32;
-        }
-        if (partial) loop<2>(stage, rows);
-        else if (has_bits) loop<1>(stage, rows);
-        else loop<0>(stage, rows);
+        const bool hx = bx_off != 0xffffffffu, hy = by_off != 0xffffffffu;
+        if (partial) tail(stage, rows);
+        else if (hx && hy) body<2>(stage, bx_off, by_off);
+        else if (hx || hy) body<1>(stage, hx ? bx_off : by_off, 0u);
+        else body<0>(stage, 0u, 0u);
     }
-    __device__ __forceinline__ void end(uint64_t* st) {
-        st[P_N * 32 + lane] = n;
-        st[P_SX * 32 + lane] = d2u(sx);
-        st[P_SY * 32 + lane] = d2u(sy);
-        st[P_SXX * 32 + lane] = d2u(sxx);
-        st[P_SYY * 32 + lane] = d2u(syy);
-        st[P_SXY * 32 + lane] = d2u(sxy);
+    __device__ __forceinline__ void store(Slots& r) {
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = 0;
+        r[P_N] = n;
+        r[P_SX] = d2u(sx[0] + sx[1]);
+        r[P_SY] = d2u(sy[0] + sy[1]);
+        r[P_SXX] = d2u(sxx[0] + sxx[1]);
+        r[P_SYY] = d2u(syy[0] + syy[1]);
+        r[P_SXY] = d2u(sxy[0] + sxy[1]);
     }
 };
 
 // ---- TERMS: AND / OR of <= 4 comparison terms ----
-// One pass per term over a chunk of TG groups (32 rows each); the running TRUE masks of the chunk stay in
-// registers; the comparison operator is selected OUTSIDE the row loop, so a term costs one load, one compare and
-// one ballot per 32 rows.
-constexpr int TG = 8;  // 256 rows per chunk
-
-template <int KIND, int OP>  // OP = cmp_mask: 1 <, 2 ==, 3 <=, 4 >, 5 <> (13 with unordered), 6 >=
-__device__ __forceinline__ void term_cmp_pass(uint64_t imm, uint32_t val_off, uint32_t bits_off, const uint8_t* stage,
-                                              int row0, int lane, bool is_or, uint32_t (&m)[TG]) {
-    const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + val_off) + row0 + lane;
-    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off != 0xffffffffu ? bits_off : 0u)) + (row0 >> 5);
-    const bool has_bits = bits_off != 0xffffffffu;
+// Term-major over blocks of up to 32 row groups: one pass per term leaves, in every lane, a 32-bit mask whose bit g
+// says "term is TRUE for MY row of group g" (row 32g + lane); the validity bit is AND-ed into the compare as a
+// predicate. Masks of the terms are AND-ed / OR-ed and popcounted per lane: no cross-lane traffic at all, and
+// the (kind, operator) dispatch happens once per term per block, outside the row loop.
+template <int KIND, int OP, bool HB>  // OP = cmp_mask: 1 <, 2 ==, 3 <=, 4 >, 5 <> (13 with unordered), 6 >=
+__device__ __forceinline__ uint32_t term_loop(uint64_t imm, const uint64_t* vals, const uint4* b4, int nq, uint32_t lanebit) {
+    uint32_t pm = 0;
+#pragma unroll 2
+    for (int q = 0; q < nq; ++q) {
+        uint4 w = make_uint4(lanebit, lanebit, lanebit, lanebit);
+        if (HB) w = b4[q];
+        const uint64_t raw[4] = {vals[128 * q], vals[128 * q + 32], vals[128 * q + 64], vals[128 * q + 96]};
+        const uint32_t v[4] = {w.x & lanebit, w.y & lanebit, w.z & lanebit, w.w & lanebit};
+        uint32_t nib = 0;
 #pragma unroll
-    for (int g = 0; g < TG; ++g) {
-        const uint64_t raw = vals[32 * g];
-        bool r;
-        if (KIND == TK_I64) {
-            const int64_t x = (int64_t)raw, c = (int64_t)imm;
-            r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? x > c : OP == 6 ? x >= c : x != c;
-        } else {
-            // floats: NaN sorts above every number (Arrow total order): > and >= and <> are true for NaN
-            const double x = KIND == TK_F64 ? u2d(raw) : (double)(int64_t)raw, c = u2d(imm);
-            r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? !(x <= c) : OP == 6 ? !(x < c) : x != c;
+        for (int j = 0; j < 4; ++j) {
+            bool r;
+            if (KIND == TK_I64) {
+                const int64_t x = (int64_t)raw[j], c = (int64_t)imm;
+                r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? x > c : OP == 6 ? x >= c : x != c;
+            } else {
+                // floats: NaN sorts above every number (Arrow total order): > and >= and <> are true for NaN
+                const double x = KIND == TK_F64 ? u2d(raw[j]) : (double)(int64_t)raw[j], c = u2d(imm);
+                r = OP == 1 ? x < c : OP == 2 ? x == c : OP == 3 ? x <= c : OP == 4 ? !(x <= c) : OP == 6 ? !(x < c) : x != c;
+            }
+            if (r && (!HB || v[j])) nib |= 1u << j;
         }
-        uint32_t tm = __ballot_sync(0xffffffffu, r);
-        if (has_bits) tm &= bits[g];
-        m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
+        pm |= nib << (4 * q);
+    }
+    return pm;
+}
+template <int KIND, bool HB>
+__device__ __forceinline__ uint32_t term_ops(int cmp_mask, uint64_t imm, const uint64_t* vals, const uint4* b4, int nq, uint32_t lanebit) {
+    switch (cmp_mask & 7) {
+        case 1: return term_loop<KIND, 1, HB>(imm, vals, b4, nq, lanebit);
+        case 2: return term_loop<KIND, 2, HB>(imm, vals, b4, nq, lanebit);
+        case 3: return term_loop<KIND, 3, HB>(imm, vals, b4, nq, lanebit);
+        case 4: return term_loop<KIND, 4, HB>(imm, vals, b4, nq, lanebit);
+        case 6: return term_loop<KIND, 6, HB>(imm, vals, b4, nq, lanebit);
+        default: return term_loop<KIND, 5, HB>(imm, vals, b4, nq, lanebit);
     }
 }
-template <int KIND>
-__device__ __forceinline__ void term_pass(int cmp_mask, uint64_t imm, uint32_t val_off, uint32_t bits_off, const uint8_t* stage,
-                                          int row0, int lane, bool is_or, uint32_t (&m)[TG]) {
-    switch (cmp_mask & 7) {
-        case 1: term_cmp_pass<KIND, 1>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
-        case 2: term_cmp_pass<KIND, 2>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
-        case 3: term_cmp_pass<KIND, 3>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
-        case 4: term_cmp_pass<KIND, 4>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
-        case 6: term_cmp_pass<KIND, 6>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
-        default: term_cmp_pass<KIND, 5>(imm, val_off, bits_off, stage, row0, lane, is_or, m); break;
+// validity of MY rows of a block: bit g = row (32 g + lane) is valid
+__device__ __forceinline__ uint32_t valid_loop(const uint4* b4, int nq, uint32_t lanebit) {
+    uint32_t pm = 0;
+    for (int q = 0; q < nq; ++q) {
+        const uint4 w = b4[q];
+        const uint32_t nib = ((w.x & lanebit) ? 1u : 0u) | ((w.y & lanebit) ? 2u : 0u) | ((w.z & lanebit) ? 4u : 0u) | ((w.w & lanebit) ? 8u : 0u);
+        pm |= nib << (4 * q);
     }
+    return pm;
 }
 
 struct TermsUnit {
-    uint64_t imm[SCAN_UNIT_TERMS];
-    uint32_t val_off[SCAN_UNIT_TERMS], bits_off[SCAN_UNIT_TERMS];
-    int kind[SCAN_UNIT_TERMS], cmp[SCAN_UNIT_TERMS];
-    int nt, row0, nrows, lane;
+    const ScanTables* T;
+    int t0, nt, row0, nrows, lane;
     bool is_or;
     uint64_t cnt;
-    __device__ __forceinline__ void begin(const ScanTables& T, const ScanUnitDesc& u, const uint64_t* st, int lane_) {
+    __device__ __forceinline__ void setup(const ScanTables& T_, const ScanUnitDesc& u, int lane_) {
+        T = &T_;
+        t0 = u.code_off;
         nt = u.code_len;
-#pragma unroll
-        for (int k = 0; k < SCAN_UNIT_TERMS; ++k) {
-            const ScanTerm& t = T.terms[u.code_off + (k < nt ? k : 0)];
-            const ScanColDesc& c = T.cols[t.col];
-            imm[k] = t.imm;
-            kind[k] = t.kind;
-            cmp[k] = t.cmp_mask;
-            val_off[k] = c.smem_val_off;
-            bits_off[k] = c.validity ? c.smem_bits_off : 0xffffffffu;
-        }
         row0 = u.row0;
         nrows = u.nrows;
         lane = lane_;
         is_or = u.flags & 1;
-        cnt = st[0];
     }
-    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) {
-        for (int base = row0; base < row0 + nrows; base += 32 * TG) {
-            uint32_t m[TG];
-#pragma unroll
-            for (int g = 0; g < TG; ++g) m[g] = is_or ? 0u : 0xffffffffu;
-#pragma unroll
-            for (int k = 0; k < SCAN_UNIT_TERMS; ++k) {
-                if (k >= nt) break;
-                if (kind[k] == TK_ISNULL || kind[k] == TK_NOTNULL) {
-                    const uint32_t* bits = reinterpret_cast<const uint32_t*>(stage + (bits_off[k] != 0xffffffffu ? bits_off[k] : 0u)) + (base >> 5);
-#pragma unroll
-                    for (int g = 0; g < TG; ++g) {
-                        const uint32_t valid = bits_off[k] != 0xffffffffu ? bits[g] : 0xffffffffu;
-                        const uint32_t tm = kind[k] == TK_ISNULL ? ~valid : valid;
-                        m[g] = is_or ? (m[g] | tm) : (m[g] & tm);
-                    }
-                } else if (kind[k] == TK_F64) {
-                    term_pass<TK_F64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
-                } else if (kind[k] == TK_I64) {
-                    term_pass<TK_I64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
+    __device__ __forceinline__ void load(const Slots& r) { cnt = r[0]; }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool partial) {
+        const uint32_t lanebit = 1u << lane;
+        for (int blk = 0; blk < nrows; blk += 1024) {
+            const int base = row0 + blk;
+            const int nq = min(8, (nrows - blk) >> 7);
+            uint32_t m = is_or ? 0u : 0xffffffffu;
+#pragma unroll 1
+            for (int k = 0; k < nt; ++k) {
+                // term descriptors are read from shared memory once per (term, block): a few uniform loads
+                const ScanTerm& t = T->terms[t0 + k];
+                const ScanColDesc& c = T->cols[t.col];
+                const bool hb = c.validity != nullptr;
+                const int kind = t.kind, cmp = t.cmp_mask;
+                const uint64_t imm = t.imm;
+                const uint64_t* vals = reinterpret_cast<const uint64_t*>(stage + c.smem_val_off) + base + lane;
+                const uint4* b4 = reinterpret_cast<const uint4*>(stage + (hb ? c.smem_bits_off : 0u) + (base >> 3));
+                uint32_t pm;
+                if (kind == TK_ISNULL || kind == TK_NOTNULL) {
+                    pm = hb ? valid_loop(b4, nq, lanebit) : 0xffffffffu;
+                    if (kind == TK_ISNULL) pm = ~pm;
+                } else if (kind == TK_F64) {
+                    pm = hb ? term_ops<TK_F64, true>(cmp, imm, vals, b4, nq, lanebit) : term_ops<TK_F64, false>(cmp, imm, vals, b4, nq, lanebit);
+                } else if (kind == TK_I64) {
+                    pm = hb ? term_ops<TK_I64, true>(cmp, imm, vals, b4, nq, lanebit) : term_ops<TK_I64, false>(cmp, imm, vals, b4, nq, lanebit);
                 } else {
-                    term_pass<TK_I64_AS_F64>(cmp[k], imm[k], val_off[k], bits_off[k], stage, base, lane, is_or, m);
+                    pm = hb ? term_ops<TK_I64_AS_F64, true>(cmp, imm, vals, b4, nq, lanebit)
+                            : term_ops<TK_I64_AS_F64, false>(cmp, imm, vals, b4, nq, lanebit);
                 }
+                m = is_or ? (m | pm) : (m & pm);
             }
-#pragma unroll
-            for (int g = 0; g < TG; ++g) cnt += __popc(m[g] & tail_mask(base + 32 * g, rows));
+            // keep the groups of this block whose row (base + 32 g + lane) exists
+            int ng = 4 * nq;
+            if (partial) ng = max(0, min(ng, (rows - base - lane + 31) >> 5));
+            const uint32_t gmask = ng >= 32 ? 0xffffffffu : ((1u << ng) - 1u);
+            cnt += __popc(m & gmask);
         }
     }
-    __device__ __forceinline__ void end(uint64_t* st) {
-        if (lane == 0) st[0] = cnt;
+    __device__ __forceinline__ void store(Slots& r) {
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = 0;
+        r[0] = cnt;
     }
 };
 
@@ -501,8 +546,8 @@ __device__ __forceinline__ void fetch_bool(const ScanTables& P, const uint8_t* s
     }
 }
 
-__device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& u, const uint8_t* stage, uint64_t* st,
-                                       int lane, int rows_in_tile) {
+__device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& u, const uint8_t* stage, int lane,
+                                       int rows_in_tile, uint64_t* cnt_out, uint64_t* div0_out) {
     uint64_t cnt = 0;
     uint32_t div0 = 0;
     const int nw = u.nrows >> 5;
@@ -640,10 +685,34 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
     }
     // masks are warp-uniform: lane 0 carries the counts
     if (lane == 0) {
-        st[0 * 32] += cnt;
-        st[1 * 32] |= (uint64_t)(div0 != 0);
+        *cnt_out += cnt;
+        *div0_out |= (uint64_t)(div0 != 0);
     }
 }
+
+
+struct PredUnit {
+    const ScanTables* T;
+    const ScanUnitDesc* u;
+    int lane;
+    uint64_t cnt, div0;
+    __device__ __forceinline__ void setup(const ScanTables& T_, const ScanUnitDesc& u_, int lane_) {
+        T = &T_;
+        u = &u_;
+        lane = lane_;
+    }
+    __device__ __forceinline__ void load(const Slots& r) {
+        cnt = r[0];
+        div0 = r[1];
+    }
+    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) { unit_pred(*T, *u, stage, lane, rows, &cnt, &div0); }
+    __device__ __forceinline__ void store(Slots& r) {
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = 0;
+        r[0] = cnt;
+        r[1] = div0;
+    }
+};
 
 // reduce op of a state slot: 0 u64 add, 1 f64 add, 2 f64 min, 3 f64 max, 4 i64 min, 5 i64 max, 6 or
 __host__ __device__ __forceinline__ int slot_op(int kind, int slot) {
@@ -687,20 +756,17 @@ __host__ __device__ __forceinline__ uint64_t slot_identity(int kind, int slot) {
     }
 }
 
-struct PredUnit {
-    const ScanTables* T;
-    const ScanUnitDesc* u;
-    uint64_t* st;
-    int lane;
-    __device__ __forceinline__ void begin(const ScanTables& T_, const ScanUnitDesc& u_, const uint64_t* st_, int lane_) {
-        T = &T_;
-        u = &u_;
-        st = const_cast<uint64_t*>(st_);
-        lane = lane_;
+// cross-lane reduction of one unit's per-lane slots in a fixed butterfly order -> one record per (CTA, unit)
+__device__ __forceinline__ void reduce_store(int kind, const Slots& r, uint64_t* out, int lane) {
+#pragma unroll
+    for (int sl = 0; sl < SCAN_STATE_SLOTS; ++sl) {
+        const int op = slot_op(kind, sl);
+        uint64_t v = r[sl];
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v = slot_combine(op, v, shfl_xor_u64(v, m));
+        if (lane == 0) out[sl] = v;
     }
-    __device__ __forceinline__ void tile(const uint8_t* stage, int rows, bool) { unit_pred(*T, *u, stage, st, lane, rows); }
-    __device__ __forceinline__ void end(uint64_t*) {}
-};
+}
 
 // consumer-side view of the stage ring
 struct Pipe {
@@ -709,21 +775,28 @@ struct Pipe {
     uint64_t* empty;
     int n_stages, tile_rows;
     uint32_t stage_bytes;
-    int64_t n_tiles, n_rows;
+    int64_t n_tiles;
+    int64_t t_partial;  // index of the partial last tile, or -1
+    int rows_partial;   // its row count
 };
 
 // a warp that owns exactly one unit: descriptors and accumulators live in registers for the whole scan
 template <class U>
-__device__ __forceinline__ void run_single(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane) {
+__device__ __forceinline__ void run_single(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* out, int lane) {
     U unit;
-    unit.begin(T, ud, st, lane);
+    unit.setup(T, ud, lane);
+    {
+        Slots r;
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = slot_identity(ud.kind, k);
+        unit.load(r);
+    }
     int s = 0;
     uint32_t ph = 0;
     for (int64_t t = blockIdx.x; t < p.n_tiles; t += gridDim.x) {
         mbar_wait(&p.full[s], ph);
-        const int64_t row_base = t * p.tile_rows;
-        const int rows = (int)min((int64_t)p.tile_rows, p.n_rows - row_base);
-        unit.tile(p.stages + (size_t)s * p.stage_bytes, rows, rows < p.tile_rows);
+        const bool partial = t == p.t_partial;
+        unit.tile(p.stages + (size_t)s * p.stage_bytes, partial ? p.rows_partial : p.tile_rows, partial);
         __syncwarp();
         if (lane == 0) mbar_arrive(&p.empty[s]);
         if (++s == p.n_stages) {
@@ -731,15 +804,24 @@ __device__ __forceinline__ void run_single(const Pipe& p, const ScanTables& T, c
             ph ^= 1u;
         }
     }
-    unit.end(st);
+    Slots r;
+    unit.store(r);
+    reduce_store(ud.kind, r, out, lane);
 }
+// a warp that owns several units: per-lane state lives in shared memory between tiles
 template <class U>
 __device__ __forceinline__ void run_once(const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane, const uint8_t* stage,
                                          int rows, bool partial) {
     U unit;
-    unit.begin(T, ud, st, lane);
+    unit.setup(T, ud, lane);
+    Slots r;
+#pragma unroll
+    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) r[k] = st[k * 32 + lane];
+    unit.load(r);
     unit.tile(stage, rows, partial);
-    unit.end(st);
+    unit.store(r);
+#pragma unroll
+    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) st[k * 32 + lane] = r[k];
 }
 
 // kind / flag dispatch, shared by both execution modes (SINGLE: whole tile loop inside; else one tile)
@@ -752,10 +834,6 @@ __device__ __forceinline__ void run_unit(const Pipe& p, const ScanTables& T, con
 template <bool SINGLE, bool IS_I64>
 __device__ __forceinline__ void dispatch_num(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane,
                                              const uint8_t* stage, int rows, bool partial) {
-    if (!T.cols[ud.c0].pivot_is_element) {
-        run_unit<SINGLE, NumSlowUnit<IS_I64>>(p, T, ud, st, lane, stage, rows, partial);
-        return;
-    }
     switch (ud.flags & 7) {
         case 0: run_unit<SINGLE, NumUnit<IS_I64, 0>>(p, T, ud, st, lane, stage, rows, partial); break;
         case 1: run_unit<SINGLE, NumUnit<IS_I64, 1>>(p, T, ud, st, lane, stage, rows, partial); break;
@@ -767,6 +845,7 @@ __device__ __forceinline__ void dispatch_num(const Pipe& p, const ScanTables& T,
         default: run_unit<SINGLE, NumUnit<IS_I64, 7>>(p, T, ud, st, lane, stage, rows, partial); break;
     }
 }
+// st: SINGLE -> global partial record of (CTA, unit); else this unit's per-lane state in shared memory
 template <bool SINGLE>
 __device__ __forceinline__ void dispatch_unit(const Pipe& p, const ScanTables& T, const ScanUnitDesc& ud, uint64_t* st, int lane,
                                               const uint8_t* stage, int rows, bool partial) {
@@ -791,7 +870,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint8_t* stages = scan_smem;
     uint64_t* state = reinterpret_cast<uint64_t*>(scan_smem + (size_t)P.n_stages * P.stage_bytes);
-    uint64_t* full = state + (size_t)P.n_units * SCAN_STATE_SLOTS * 32;
+    uint64_t* full = state + (size_t)P.n_state_units * SCAN_STATE_SLOTS * 32;
     uint64_t* empty = full + P.n_stages;
     ScanTables* T = reinterpret_cast<ScanTables*>(empty + P.n_stages);
 
@@ -816,7 +895,9 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         mbar_fence_init();
     }
     __syncthreads();
-    Pipe pipe{stages, full, empty, P.n_stages, P.tile_rows, P.stage_bytes, P.n_tiles, P.n_rows};
+    const int rows_last = (int)(P.n_rows - (P.n_tiles - 1) * (int64_t)P.tile_rows);
+    Pipe pipe{stages, full, empty, P.n_stages, P.tile_rows, P.stage_bytes, P.n_tiles,
+              rows_last < P.tile_rows ? P.n_tiles - 1 : (int64_t)-1, rows_last};
 
     if (warp == 0) {
         // ---------------- TMA producer: lane c moves column c ----------------
@@ -828,7 +909,7 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         for (int64_t t = blockIdx.x; t < pipe.n_tiles; t += gridDim.x) {
             mbar_wait(&empty[s], ph ^ 1u);
             const int64_t row_base = t * pipe.tile_rows;
-            const int rows = (int)min((int64_t)pipe.tile_rows, pipe.n_rows - row_base);
+            const int rows = t == pipe.t_partial ? pipe.rows_partial : pipe.tile_rows;
             uint8_t* stage = stages + (size_t)s * pipe.stage_bytes;
             // byte counts padded to 16 (buffers are allocated with that slack)
             const uint32_t bbytes = has_b ? (uint32_t)(((rows + 7) / 8 + 15) & ~15) : 0u;
@@ -853,26 +934,43 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
         // ---------------- consumers ----------------
         const int cw = warp - 1;
         const int n_mine = T->warp_units[cw][0];
-        for (int k = 0; k < n_mine; ++k) {
-            const int u = T->warp_units[cw][1 + k];
-            unit_init(T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane);
-        }
-        __syncwarp();
-        if (n_mine == 1) {
-            const int u = T->warp_units[cw][1];
-            dispatch_unit<true>(pipe, *T, T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane, nullptr, 0, false);
+        if (P.n_state_units == 0) {
+            // every warp owns at most one unit: registers only
+            if (n_mine == 1) {
+                const int u = T->warp_units[cw][1];
+                dispatch_unit<true>(pipe, *T, T->units[u], P.partials + ((size_t)blockIdx.x * P.n_units + u) * SCAN_STATE_SLOTS,
+                                    lane, nullptr, 0, false);
+            } else {
+                // idle warp: keep the ring moving
+                int s = 0;
+                uint32_t ph = 0;
+                for (int64_t t = blockIdx.x; t < pipe.n_tiles; t += gridDim.x) {
+                    mbar_wait(&full[s], ph);
+                    if (lane == 0) mbar_arrive(&empty[s]);
+                    if (++s == pipe.n_stages) {
+                        s = 0;
+                        ph ^= 1u;
+                    }
+                }
+            }
         } else {
+            for (int k = 0; k < n_mine; ++k) {
+                const int u = T->warp_units[cw][1 + k];
+                uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
+#pragma unroll
+                for (int sl = 0; sl < SCAN_STATE_SLOTS; ++sl) st[sl * 32 + lane] = slot_identity(T->units[u].kind, sl);
+            }
+            __syncwarp();
             int s = 0;
             uint32_t ph = 0;
             for (int64_t t = blockIdx.x; t < pipe.n_tiles; t += gridDim.x) {
                 mbar_wait(&full[s], ph);
-                const int64_t row_base = t * pipe.tile_rows;
-                const int rows = (int)min((int64_t)pipe.tile_rows, pipe.n_rows - row_base);
+                const bool partial = t == pipe.t_partial;
+                const int rows = partial ? pipe.rows_partial : pipe.tile_rows;
                 const uint8_t* stage = stages + (size_t)s * pipe.stage_bytes;
                 for (int k = 0; k < n_mine; ++k) {
                     const int u = T->warp_units[cw][1 + k];
-                    dispatch_unit<false>(pipe, *T, T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane, stage, rows,
-                                         rows < pipe.tile_rows);
+                    dispatch_unit<false>(pipe, *T, T->units[u], state + (size_t)u * SCAN_STATE_SLOTS * 32, lane, stage, rows, partial);
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&empty[s]);
@@ -881,21 +979,14 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
                     ph ^= 1u;
                 }
             }
-        }
-        __syncwarp();
-        // cross-lane reduction in a fixed butterfly order, then one record per (CTA, unit)
-        for (int k = 0; k < n_mine; ++k) {
-            const int u = T->warp_units[cw][1 + k];
-            const int kind = T->units[u].kind;
-            const uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
-            uint64_t* out = P.partials + ((size_t)blockIdx.x * P.n_units + u) * SCAN_STATE_SLOTS;
+            __syncwarp();
+            for (int k = 0; k < n_mine; ++k) {
+                const int u = T->warp_units[cw][1 + k];
+                const uint64_t* st = state + (size_t)u * SCAN_STATE_SLOTS * 32;
+                Slots r;
 #pragma unroll
-            for (int sl = 0; sl < SCAN_STATE_SLOTS; ++sl) {
-                const int op = slot_op(kind, sl);
-                uint64_t v = st[sl * 32 + lane];
-#pragma unroll
-                for (int m = 16; m > 0; m >>= 1) v = slot_combine(op, v, shfl_xor_u64(v, m));
-                if (lane == 0) out[sl] = v;
+                for (int sl = 0; sl < SCAN_STATE_SLOTS; ++sl) r[sl] = st[sl * 32 + lane];
+                reduce_store(T->units[u].kind, r, P.partials + ((size_t)blockIdx.x * P.n_units + u) * SCAN_STATE_SLOTS, lane);
             }
         }
     }
@@ -926,7 +1017,7 @@ __global__ void scan_finalize_kernel(const __grid_constant__ ScanParams P, int n
 
 // ---- host launchers (called from engine.cu) ----
 size_t scan_smem_bytes(const ScanParams& P) {
-    return (size_t)P.n_stages * P.stage_bytes + (size_t)P.n_units * SCAN_STATE_SLOTS * 32 * 8 +
+    return (size_t)P.n_stages * P.stage_bytes + (size_t)P.n_state_units * SCAN_STATE_SLOTS * 32 * 8 +
            (size_t)2 * P.n_stages * 8 + sizeof(ScanTables);
 }
 

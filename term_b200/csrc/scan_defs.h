@@ -9,7 +9,10 @@ constexpr int SCAN_MAX_UNITS = 48;
 constexpr int SCAN_MAX_CODE = 128;
 constexpr int SCAN_MAX_TERMS = 32;
 constexpr int SCAN_UNIT_TERMS = 4;  // comparison terms a UNIT_TERMS unit keeps in registers
-constexpr int SCAN_CONSUMER_WARPS = 16;
+#ifndef TG_SCAN_CONSUMER_WARPS
+#define TG_SCAN_CONSUMER_WARPS 15  // + 1 producer = 16 warps = 4 per SM sub-partition -> 128 registers per thread
+#endif
+constexpr int SCAN_CONSUMER_WARPS = TG_SCAN_CONSUMER_WARPS;
 constexpr int SCAN_THREADS = (SCAN_CONSUMER_WARPS + 1) * 32;  // warp 0 = TMA producer
 constexpr int SCAN_STATE_SLOTS = 8;                           // 64-bit slots per lane per unit
 constexpr int SCAN_MAX_STAGES = 8;
@@ -141,6 +144,7 @@ struct ScanParams {
     int32_t n_aggs;
     int32_t n_code;
     int32_t n_terms;
+    int32_t n_state_units;  // 0: every consumer warp owns <= 1 unit (state in registers); else n_units
     uint64_t* partials;  // [gridDim.x][n_units][SCAN_STATE_SLOTS]
     ScanTables tab;
 };

@@ -1,0 +1,262 @@
+#!/usr/bin/env python3
+"""Secondary benchmarks: BASELINE.json configs C3 (string/PII formats), C4 (uniqueness + foreign key) and
+C5 (KLL / grouped completeness / Spearman) at the per-GPU shard sizes of SURVEY §8d (1/8 of the config),
+one GPU, HBM-resident. Prints one JSON line per workload with the algorithmic GB/s (SURVEY §8d bytes, each
+input buffer counted once) against MEASURED_PEAKS.json. bench.py stays the headline (C2); these lines are
+the per-kernel rooflines DESIGN.md §6 quotes.
+
+    python tools/bench_suites.py [c3] [c4] [c5] [--scale 1.0] [--steps 5]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+import term_b200 as T  # noqa: E402
+from term_b200 import _ffi as F  # noqa: E402
+
+
+def peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"])
+    return 6650.0
+
+
+def pack_validity(mask):
+    """bool tensor (True = valid) -> LSB-first bitmap bytes, padded with 64 slack bytes"""
+    n = mask.numel()
+    padn = (-n) % 8
+    if padn:
+        mask = torch.cat([mask, torch.zeros(padn, dtype=torch.bool, device=mask.device)])
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=mask.device)
+    packed = (mask.view(-1, 8).to(torch.uint8) * w).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+    out = torch.zeros(packed.numel() + 320 - packed.numel() % 64, dtype=torch.uint8, device=mask.device)
+    out[: packed.numel()] = packed
+    return out
+
+
+def validity(n, g, dev, frac):
+    chunks = []
+    for s in range(0, n, 1 << 26):
+        e = min(n, s + (1 << 26))
+        chunks.append(torch.rand(e - s, generator=g, device=dev) >= frac)
+    return pack_validity(torch.cat(chunks))
+
+
+def make_strings(n, g, dev, null_frac=0.02):
+    """C3 column: lengths ~ clipped Poisson(24) in [8, 64]; 70 % email-shaped, 10 % SSN-shaped (11 bytes),
+    10 % 16-digit card-shaped, 10 % lowercase noise; ASCII. Returns (offsets i32, bytes u8, validity, cats)."""
+    lens = torch.poisson(torch.full((n,), 24.0, device=dev), generator=g).clamp_(8, 64).to(torch.int64)
+    cat = torch.rand(n, generator=g, device=dev)
+    is_ssn = (cat >= 0.7) & (cat < 0.8)
+    is_card = (cat >= 0.8) & (cat < 0.9)
+    is_email = cat < 0.7
+    lens[is_ssn] = 11
+    lens[is_card] = 16
+    offs = torch.zeros(n + 1, dtype=torch.int64, device=dev)
+    torch.cumsum(lens, 0, out=offs[1:])
+    total = int(offs[-1].item())
+    data = torch.randint(97, 123, (total + 256,), generator=g, device=dev, dtype=torch.uint8)
+    digits = torch.randint(48, 58, (total + 256,), generator=g, device=dev, dtype=torch.uint8)
+    # which row each byte belongs to
+    row_of = torch.repeat_interleave(torch.arange(n, device=dev), lens)
+    dig_row = (is_ssn | is_card)[row_of]
+    data[:total][dig_row] = digits[:total][dig_row]
+    del digits, dig_row, row_of
+    start = offs[:-1]
+    # emails: local@domain.com
+    e_idx = torch.nonzero(is_email).squeeze(1)
+    es, el = start[e_idx], lens[e_idx]
+    data[es + el // 2] = 64  # '@'
+    data[es + el - 4] = 46   # '.'
+    s_idx = torch.nonzero(is_ssn).squeeze(1)
+    ss = start[s_idx]
+    # SSN area must not be 000/666/9xx: force first digit 1..5
+    data[ss] = (data[ss] - 48) % 5 + 49
+    data[ss + 3] = 45
+    data[ss + 6] = 45
+    # group/serial not all zero: force one non-zero digit each
+    data[ss + 5] = (data[ss + 5] - 48) % 9 + 49
+    data[ss + 10] = (data[ss + 10] - 48) % 9 + 49
+    c_idx = torch.nonzero(is_card).squeeze(1)
+    data[start[c_idx]] = 52  # '4' (visa-like prefix)
+    v = validity(n, g, dev, null_frac)
+    return offs.to(torch.int32), data, v, (is_email, is_ssn, is_card), total
+
+
+def run_plan(plan, ctx, table, steps, key):
+    for _ in range(2):
+        plan.execute(ctx, table)
+    ms, wall = [], []
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan.execute(ctx, table)
+        wall.append((time.perf_counter() - t0) * 1e3)
+        ms.append(plan.stats()[key])
+    return sum(ms) / len(ms), sum(wall) / len(wall), plan.stats()
+
+
+def report(name, workload, n_rows, alg_bytes, kernel_ms, wall_ms, stats, extra=None):
+    gbs = alg_bytes / (kernel_ms / 1e3) / 1e9
+    line = {"workload": name, "config": workload, "rows": n_rows, "algorithmic_bytes": alg_bytes, "kernel_ms": kernel_ms,
+            "wall_ms": wall_ms, "rows_per_s": n_rows / (wall_ms / 1e3), "achieved_gbs": gbs, "peak_gbs": peak(),
+            "frac": gbs / peak(), "launches": int(stats["launches"]), "engine_bytes_scanned": int(stats["bytes_scanned"])}
+    if extra:
+        line.update(extra)
+    print(json.dumps(line), flush=True)
+
+
+def bench_c3(ctx, dev, scale, steps):
+    n = int(25_000_000 * scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + 3)
+    offs, data, v, cats, total = make_strings(n, g, dev)
+    ctx.register_device_table("pii", {"s": dict(dtype=F.TG_UTF8, n_rows=n, values=data.data_ptr(), offsets=offs.data_ptr(),
+                                                validity=v.data_ptr(), n_value_bytes=total)}, keepalive=[offs, data, v])
+    check = (T.Check.builder("pii").validates_regex("s", "@", 0.5).validates_email("s", 0.5).contains_ssn("s", 0.05)
+             .validates_credit_card("s", 0.5, True).build())
+    suite = T.ValidationSuite.builder("c3").table_name("pii").check(check).build()
+    plan, slots = suite.build_plan()
+    kms, wms, st = run_plan(plan, ctx, "pii", steps, "string_ms")
+    res = {plan.result(s).name: plan.result(s).metric for _, _, s in slots}
+    alg = 4 * (n + 1) + total + (n + 7) // 8
+    exp_email = float((cats[0].sum().item())) / n
+    report("c3_string_formats", "regex('@') + email + ssn + credit_card(detect_only) on one Utf8 column, avg 24 B, 2% null",
+           n, alg, kms, wms, st, {"results": res, "email_shaped_fraction": exp_email})
+    # single-pattern variants for the per-pattern cost
+    for nm, build in (("regex_at", lambda b: b.validates_regex("s", "@", 0.5)), ("email", lambda b: b.validates_email("s", 0.5))):
+        suite = T.ValidationSuite.builder(nm).table_name("pii").check(build(T.Check.builder(nm)).build()).build()
+        plan, _ = suite.build_plan()
+        kms, wms, st = run_plan(plan, ctx, "pii", steps, "string_ms")
+        report("c3_" + nm, "single pattern", n, alg, kms, wms, st)
+    ctx.deregister_table("pii")
+
+
+def bench_c4(ctx, dev, scale, steps):
+    n = int(125_000_000 * scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + 4)
+    keys = torch.randperm(n, generator=g, device=dev, dtype=torch.int64)
+    ndup = max(1, n // 1_000_000)
+    keys[torch.randint(0, n, (ndup,), generator=g, device=dev)] = keys[torch.randint(0, n, (ndup,), generator=g, device=dev)]
+    pad = torch.zeros(64, dtype=torch.int64, device=dev)
+    keys = torch.cat([keys, pad])
+    v = validity(n, g, dev, 0.01)
+    ctx.register_device_table("keys", {"k": dict(dtype=F.TG_INT64, n_rows=n, values=keys.data_ptr(), validity=v.data_ptr())},
+                              keepalive=[keys, v])
+    suite = (T.ValidationSuite.builder("c4u").table_name("keys")
+             .check(T.Check.builder("u").validates_uniqueness(["k"], 0.9).build()).build())
+    plan, slots = suite.build_plan()
+    kms, wms, st = run_plan(plan, ctx, "keys", steps, "hash_ms")
+    r = plan.result(slots[0][2])
+    report("c4_is_unique", "validates_uniqueness on i64 keys (permutation + 1e-6 duplicates, 1% null)", n, 8 * n + (n + 7) // 8,
+           kms, wms, st, {"metric": r.metric})
+    ctx.deregister_table("keys")
+    del keys, v
+    # foreign key: child n rows -> parent n/10 rows
+    m = max(1000, n // 10)
+    parent = torch.cat([torch.randperm(m, generator=g, device=dev, dtype=torch.int64), pad])
+    child = torch.cat([torch.randint(0, int(m * (1 + 1e-4)), (n,), generator=g, device=dev, dtype=torch.int64), pad])
+    cv = validity(n, g, dev, 0.01)
+    ctx.register_device_table("customers", {"id": dict(dtype=F.TG_INT64, n_rows=m, values=parent.data_ptr(), validity=None)},
+                              keepalive=[parent])
+    ctx.register_device_table("orders", {"customer_id": dict(dtype=F.TG_INT64, n_rows=n, values=child.data_ptr(),
+                                                               validity=cv.data_ptr())}, keepalive=[child, cv])
+    suite = (T.ValidationSuite.builder("c4f").table_name("orders")
+             .check(T.Check.builder("fk").foreign_key("orders.customer_id", "customers.id").build()).build())
+    plan, slots = suite.build_plan()
+    kms, wms, st = run_plan(plan, ctx, "orders", steps, "hash_ms")
+    r = plan.result(slots[0][2])
+    report("c4_foreign_key", "foreign_key orders(n) -> customers(n/10), 1e-4 violation headroom, 1% null child keys", n,
+           8 * n + (n + 7) // 8 + 8 * m, kms, wms, st, {"metric": r.metric, "status": r.status.name})
+    ctx.deregister_table("orders")
+    ctx.deregister_table("customers")
+
+
+def bench_c5(ctx, dev, scale, steps):
+    n = int(125_000_000 * scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + 5)
+    cols, keep = {}, []
+    for k in range(4):
+        t = torch.zeros(n + 64, dtype=torch.float64, device=dev)
+        if k == 0:
+            t[:n].normal_(100.0, 15.0, generator=g)
+        elif k == 1:
+            t[:n].normal_(0.0, 9.0, generator=g)
+            t[:n].add_(cols["f0"]["t"][:n], alpha=0.8)
+        elif k == 2:
+            t[:n].normal_(0.0, 1.0, generator=g).exp_()
+        else:
+            t[:n].uniform_(0.0, 1000.0, generator=g)
+        v = validity(n, g, dev, 0.05)
+        cols[f"f{k}"] = dict(dtype=F.TG_FLOAT64, n_rows=n, values=t.data_ptr(), validity=v.data_ptr(), t=t)
+        keep += [t, v]
+    group_bytes = {}
+    for name, card in (("g0", 16), ("g1", 200)):
+        ids = torch.randint(0, card, (n,), generator=g, device=dev)
+        # group value "G<id:03d>" (4 bytes each)
+        offs = (torch.arange(n + 1, device=dev, dtype=torch.int64) * 4).to(torch.int32)
+        data = torch.zeros(4 * n + 256, dtype=torch.uint8, device=dev)
+        d4 = data[: 4 * n].view(n, 4)
+        d4[:, 0] = 71
+        d4[:, 1] = (48 + ids // 100).to(torch.uint8)
+        d4[:, 2] = (48 + (ids // 10) % 10).to(torch.uint8)
+        d4[:, 3] = (48 + ids % 10).to(torch.uint8)
+        cols[name] = dict(dtype=F.TG_UTF8, n_rows=n, values=data.data_ptr(), offsets=offs.data_ptr(), validity=None,
+                          n_value_bytes=4 * n)
+        keep += [offs, data]
+        group_bytes[name] = 4 * (n + 1) + 4 * n
+    ctx.register_device_table("wide", {k: {kk: vv for kk, vv in d.items() if kk != "t"} for k, d in cols.items()}, keepalive=keep)
+
+    r = T.AnalysisRunner()
+    for k in range(4):
+        r.add(T.KllSketchAnalyzer(f"f{k}", 256, (0.5, 0.95, 0.99)))
+    plan = T.Plan()
+    slots = [a._add_to(plan) for a in r.analyzers]
+    kms, wms, st = run_plan(plan, ctx, "wide", steps, "sketch_ms")
+    q = plan.analyzer_result(slots[0])
+    f0 = cols["f0"]["t"][:n]
+    report("c5_kll", "KLL k=256 (p50/p95/p99) on 4 f64 columns, 5% null", n, 4 * (8 * n + (n + 7) // 8), kms, wms, st,
+           {"kll_f0": getattr(q, "map", None) or str(q)[:300], "f0_exact_median_ignoring_nulls": float(f0[: min(n, 20_000_000)].median().item())})
+
+    plan = T.Plan()
+    for gc in (["g0"], ["g1"], ["g0", "g1"]):
+        T.GroupedCompletenessAnalyzer("f0", gc)._add_to(plan)
+    kms, wms, st = run_plan(plan, ctx, "wide", steps, "hash_ms")
+    alg = group_bytes["g0"] + group_bytes["g1"] + (n + 7) // 8
+    report("c5_grouped_completeness", "completeness(f0) grouped by g0 (16), g1 (200), (g0,g1)", n, alg, kms, wms, st)
+
+    plan = T.Plan()
+    s = T.CorrelationAnalyzer.spearman("f0", "f1")._add_to(plan)
+    kms, wms, st = run_plan(plan, ctx, "wide", max(2, steps // 2), "gpu_ms")
+    report("c5_spearman", "Spearman(f0,f1) (min ranks)", n, 2 * (8 * n + (n + 7) // 8), kms, wms, st,
+           {"rho": str(plan.analyzer_result(s))[:200]})
+    ctx.deregister_table("wide")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", nargs="*", default=["c3", "c4", "c5"])
+    ap.add_argument("--scale", type=float, default=1.0)
+    ap.add_argument("--steps", type=int, default=5)
+    a = ap.parse_args()
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    ctx = T.SessionContext(0)
+    for w in a.which:
+        {"c3": bench_c3, "c4": bench_c4, "c5": bench_c5}[w](ctx, dev, a.scale, a.steps)
+        torch.cuda.empty_cache()
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
