@@ -97,6 +97,7 @@ void tg_engine_destroy(tg_engine* h) {
         }
     }
     e.tables.clear();
+    e.dev_trim();
     if (e.d_scratch) cudaFree(e.d_scratch);
     if (e.h_scratch) cudaFreeHost(e.h_scratch);
     for (int i = 0; i < 2; ++i) {
@@ -139,9 +140,9 @@ tg_status tg_table_drop(tg_engine* h, const char* name) {
         cudaStreamSynchronize(h->e.copy_stream);
         cudaStreamSynchronize(h->e.stream);
         for (auto& c : it->second->cols) {
-            if (c->values.owned && c->values.p) cudaFree(c->values.p);
-            if (c->offsets.owned && c->offsets.p) cudaFree(c->offsets.p);
-            if (c->validity.owned && c->validity.p) cudaFree(c->validity.p);
+            if (c->values.owned) h->e.dev_free(c->values.p, c->values.cap);
+            if (c->offsets.owned) h->e.dev_free(c->offsets.p, c->offsets.cap);
+            if (c->validity.owned) h->e.dev_free(c->validity.p, c->validity.cap);
         }
         h->e.tables.erase(it);
     });

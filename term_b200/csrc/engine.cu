@@ -32,24 +32,61 @@ uint8_t* Engine::host_scratch(size_t bytes) {
     return h_scratch;
 }
 
+// Device blocks of tables are recycled through an exact-size free list: registering a table of the same shape
+// again (the steady state of a validation service, and of bench.py's end-to-end loop) costs no cudaMalloc /
+// cudaFree, which for multi-GB buffers are milliseconds each and serialise the device.
+uint8_t* Engine::dev_alloc(size_t bytes) {
+    auto it = free_blocks.find(bytes);
+    if (it != free_blocks.end() && !it->second.empty()) {
+        uint8_t* p = it->second.back();
+        it->second.pop_back();
+        cached_bytes -= bytes;
+        return p;
+    }
+    uint8_t* p = nullptr;
+    cudaError_t err = cudaMalloc(&p, bytes);
+    if (err != cudaSuccess) {
+        cudaGetLastError();
+        dev_trim();
+        TG_CUDA(cudaMalloc(&p, bytes));
+    }
+    return p;
+}
+void Engine::dev_free(uint8_t* p, size_t bytes) {
+    if (!p) return;
+    if (bytes == 0 || cached_bytes + bytes > cache_limit) {
+        cudaFree(p);
+        return;
+    }
+    free_blocks[bytes].push_back(p);
+    cached_bytes += bytes;
+}
+void Engine::dev_trim() {
+    for (auto& kv : free_blocks)
+        for (uint8_t* p : kv.second) cudaFree(p);
+    free_blocks.clear();
+    cached_bytes = 0;
+}
+
 // grow a device buffer to hold `need` bytes (+ zeroed padding), preserving the first keep_bytes
 void Engine::dev_reserve(DevBuf& b, size_t need, size_t keep_bytes) {
-    need = round_up(need + PAD, PAD);
-    if (b.p && need <= b.cap) return;
-    size_t ncap = std::max(need, b.cap + b.cap / 2);
-    ncap = round_up(ncap, PAD);
-    uint8_t* np = nullptr;
-    TG_CUDA(cudaMalloc(&np, ncap));
-    TG_CUDA(cudaMemsetAsync(np, 0, ncap, copy_stream));
-    if (b.p && keep_bytes) TG_CUDA(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, copy_stream));
-    if (b.p) {
-        TG_CUDA(cudaStreamSynchronize(copy_stream));
-        TG_CUDA(cudaStreamSynchronize(stream));
-        if (b.owned) TG_CUDA(cudaFree(b.p));
+    const size_t padded = round_up(need + PAD, PAD);
+    if (!(b.p && padded <= b.cap)) {
+        size_t ncap = b.p ? std::max(padded, b.cap + b.cap / 2) : padded;
+        ncap = round_up(ncap, PAD);
+        uint8_t* np = dev_alloc(ncap);
+        if (b.p && keep_bytes) TG_CUDA(cudaMemcpyAsync(np, b.p, keep_bytes, cudaMemcpyDeviceToDevice, copy_stream));
+        if (b.p) {
+            TG_CUDA(cudaStreamSynchronize(copy_stream));
+            TG_CUDA(cudaStreamSynchronize(stream));
+            if (b.owned) dev_free(b.p, b.cap);
+        }
+        b.p = np;
+        b.cap = ncap;
+        b.owned = true;
     }
-    b.p = np;
-    b.cap = ncap;
-    b.owned = true;
+    // zero the padding behind the new logical end (kernels over-read it with TMA / 128-bit loads)
+    TG_CUDA(cudaMemsetAsync(b.p + need, 0, padded - need, copy_stream));
 }
 
 void Engine::h2d(void* dst, const void* src, size_t bytes) {

@@ -96,6 +96,14 @@ struct Engine {
     uint8_t* h_scratch = nullptr;  // pinned
     size_t h_scratch_cap = 0;
 
+    // recycled device blocks of dropped tables, by exact capacity
+    std::map<size_t, std::vector<uint8_t*>> free_blocks;
+    size_t cached_bytes = 0;
+    size_t cache_limit = (size_t)48 << 30;
+    uint8_t* dev_alloc(size_t bytes);
+    void dev_free(uint8_t* p, size_t bytes);
+    void dev_trim();
+
     uint8_t* scratch(size_t bytes);
     uint8_t* host_scratch(size_t bytes);
     void dev_reserve(DevBuf& b, size_t need, size_t keep_bytes);

@@ -112,16 +112,28 @@ void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t
     }
     // ---- validity ----
     bool has_nulls = false;
+    bool fast_bits = false;
+    int64_t zeros = 0;
     if (validity) {
-        // does the batch actually contain a null?
-        for (int64_t i = 0; i < n && !has_nulls;) {
-            const int64_t s = bit_offset + i;
-            if ((s & 7) == 0 && i + 8 <= n) {
-                has_nulls = validity[s >> 3] != 0xff;
-                i += 8;
-            } else {
+        if ((bit_offset & 7) == 0 && (have & 7) == 0) {
+            // byte-aligned on both sides: count zero bits 64 at a time; the bitmap bytes then go to the device as
+            // they are (direct DMA when the source is pinned)
+            const uint8_t* src = validity + bit_offset / 8;
+            const int64_t full_words = n / 64;
+            int64_t ones = 0;
+            for (int64_t w = 0; w < full_words; ++w) {
+                uint64_t x;
+                memcpy(&x, src + 8 * w, 8);
+                ones += __builtin_popcountll(x);
+            }
+            for (int64_t i = full_words * 64; i < n; ++i) ones += (src[i >> 3] >> (i & 7)) & 1;
+            zeros = n - ones;
+            has_nulls = zeros > 0;
+            fast_bits = true;
+        } else {
+            for (int64_t i = 0; i < n && !has_nulls; ++i) {
+                const int64_t s = bit_offset + i;
                 has_nulls = !((validity[s >> 3] >> (s & 7)) & 1);
-                i += 1;
             }
         }
     }
@@ -130,8 +142,15 @@ void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t
         append_bits(e, c.validity, c.tail_byte, 0, nullptr, 0, have, nullptr);
     }
     if (has_nulls || c.validity.p) {
-        int64_t zeros = 0;
-        append_bits(e, c.validity, c.tail_byte, have, validity, bit_offset, n, &zeros);
+        if (fast_bits && validity) {
+            const size_t nbytes = (size_t)(n + 7) / 8;
+            e.dev_reserve(c.validity, (size_t)(have + n + 7) / 8, (size_t)(have + 7) / 8);
+            e.h2d(c.validity.p + have / 8, validity + bit_offset / 8, nbytes);
+            // host mirror of the last partial byte (bits past the end masked off) for the next unaligned append
+            c.tail_byte = (n & 7) ? (uint8_t)(validity[bit_offset / 8 + nbytes - 1] & ((1u << (n & 7)) - 1)) : 0;
+        } else {
+            append_bits(e, c.validity, c.tail_byte, have, validity, bit_offset, n, &zeros);
+        }
         c.null_count += zeros;
     }
     // ---- values ----
