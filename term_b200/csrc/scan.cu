@@ -993,25 +993,58 @@ __global__ void __launch_bounds__(SCAN_THREADS, 1) scan_kernel(const __grid_cons
 }
 
 // one warp per aggregate: reduce partials[cta][unit] over CTAs and over the units feeding that aggregate
-__global__ void scan_finalize_kernel(const __grid_constant__ ScanParams P, int n_ctas, ScanAggOut* out) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (warp >= P.n_aggs) return;
-    int kind = -1;
-    for (int u = 0; u < P.n_units; ++u)
-        if (P.tab.units[u].agg == warp) kind = P.tab.units[u].kind;
-    if (kind < 0) return;
-    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) {
-        const int op = slot_op(kind, k);
-        uint64_t acc = slot_identity(kind, k);
-        for (int b = lane; b < n_ctas; b += 32) {
-            for (int u = 0; u < P.n_units; ++u) {
-                if (P.tab.units[u].agg != warp) continue;
-                acc = slot_combine(op, acc, P.partials[((size_t)b * P.n_units + u) * SCAN_STATE_SLOTS + k]);
+// One CTA per aggregate: thread i owns the (CTA b, unit u) partial records i, i+128, .. of that aggregate (all
+// SCAN_STATE_SLOTS slots of a record are one 64-byte load, every load independent), then a fixed-shape
+// shuffle + shared-memory tree combines them, so the result is bit-reproducible for a given (grid, plan).
+constexpr int FIN_THREADS = 128;
+__global__ void __launch_bounds__(FIN_THREADS) scan_finalize_kernel(const __grid_constant__ ScanParams P, int n_ctas, ScanAggOut* out) {
+    const int agg = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __shared__ int ulist[SCAN_MAX_UNITS];
+    __shared__ int s_nu, s_kind;
+    __shared__ uint64_t red[FIN_THREADS / 32][SCAN_STATE_SLOTS];
+    if (tid == 0) {
+        int nu = 0, kind = -1;
+        for (int u = 0; u < P.n_units; ++u)
+            if (P.tab.units[u].agg == agg) {
+                ulist[nu++] = u;
+                kind = P.tab.units[u].kind;
             }
-        }
+        s_nu = nu;
+        s_kind = kind;
+    }
+    __syncthreads();
+    const int nu = s_nu, kind = s_kind;
+    if (kind < 0) return;
+    uint64_t acc[SCAN_STATE_SLOTS];
+    int op[SCAN_STATE_SLOTS];
 #pragma unroll
-        for (int m = 16; m > 0; m >>= 1) acc = slot_combine(op, acc, shfl_xor_u64(acc, m));
-        if (lane == 0) out[warp].s[k] = acc;
+    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) {
+        op[k] = slot_op(kind, k);
+        acc[k] = slot_identity(kind, k);
+    }
+    const int total = n_ctas * nu;
+    for (int i = tid; i < total; i += FIN_THREADS) {
+        const int b = i / nu, u = ulist[i - b * nu];
+        const ulonglong2* rec = reinterpret_cast<const ulonglong2*>(P.partials + ((size_t)b * P.n_units + u) * SCAN_STATE_SLOTS);
+#pragma unroll
+        for (int k = 0; k < SCAN_STATE_SLOTS / 2; ++k) {
+            const ulonglong2 v = rec[k];
+            acc[2 * k] = slot_combine(op[2 * k], acc[2 * k], v.x);
+            acc[2 * k + 1] = slot_combine(op[2 * k + 1], acc[2 * k + 1], v.y);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_STATE_SLOTS; ++k) {
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) acc[k] = slot_combine(op[k], acc[k], shfl_xor_u64(acc[k], m));
+        if (lane == 0) red[warp][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < SCAN_STATE_SLOTS) {
+        uint64_t v = red[0][tid];
+        const int o = slot_op(kind, tid);
+        for (int w = 1; w < FIN_THREADS / 32; ++w) v = slot_combine(o, v, red[w][tid]);
+        out[agg].s[tid] = v;
     }
 }
 
@@ -1032,10 +1065,7 @@ cudaError_t scan_launch(const ScanParams& P, int grid, ScanAggOut* d_out, cudaSt
     scan_kernel<<<grid, SCAN_THREADS, smem, stream>>>(P);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    int warps = P.n_aggs;
-    int threads = 128;
-    int blocks = (warps * 32 + threads - 1) / threads;
-    scan_finalize_kernel<<<blocks, threads, 0, stream>>>(P, grid, d_out);
+    scan_finalize_kernel<<<P.n_aggs, FIN_THREADS, 0, stream>>>(P, grid, d_out);
     return cudaGetLastError();
 }
 
