@@ -4,198 +4,414 @@
 // (constraints/format.rs:762-776 -> arrow-string regexp_is_match -> regex crate) for every pattern that a
 // suite applies to the same column, in ONE pass over that column's bytes.
 //
-// Layout / mapping: thread-per-string, 256-thread CTAs walking blocks of consecutive rows (adjacent
-// lanes read adjacent strings, so a warp's loads fall in a handful of contiguous 128-byte lines that L1
-// serves to all lanes); transition tables of up to 4 DFAs live in shared memory and share ONE joint
-// byte-class map so each input byte costs one class lookup plus one table lookup per DFA still alive.
-// A DFA leaves the alive set as soon as it reaches DEAD (no match possible) or MATCH (match found).
+// Host: the DFAs of all patterns on a column (regex_dfa.cpp) are combined into ONE product automaton over a
+// joint byte-class map, so an input byte costs one class lookup and one transition lookup however many
+// patterns are checked. Product states whose components are all decided (DEAD = cannot match any more,
+// MATCH = already matched) are numbered first, so "nothing left to learn from this string" is a single
+// compare. The built-in formats are anchored (^...$) and die within a few bytes on strings of another
+// format, which keeps the product small (the C3 suite '@' + email + SSN + credit card: 669 states x 82
+// classes); when a product would not fit in shared memory the patterns are split into several passes.
+//
+// Device: warp-per-32-strings, thread-per-string. A warp owns blocks of 32 consecutive rows, whose bytes are
+// one contiguous range of the value buffer: lane 0 fetches that range with one TMA bulk copy
+// (cp.async.bulk -> mbarrier) into the warp's private double buffer one block ahead, and the offsets two
+// blocks ahead, so the DFA loop only ever touches shared memory (bytes, class map, transition table).
+// A block whose bytes exceed the warp's stage (very long strings) is walked straight from global memory.
 #include <algorithm>
 #include <cstring>
 #include <map>
+#include <mutex>
 
 #include "engine.hpp"
+#include "ptx.cuh"
 #include "regex_dfa.hpp"
 
 namespace tg {
 
-constexpr int STR_MAX_DFA = 4;
-constexpr int STR_THREADS = 256;
+constexpr int STR_MAX_DFA = 8;          // patterns per product automaton
+constexpr int STR_MAX_WARPS = 32;       // warps per CTA (upper bound; fewer when the table is large)
+constexpr size_t STR_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory available beside the static tables
+constexpr size_t STR_TABLE_BUDGET = 112 * 1024;      // product tables up to this size still leave room for 32 warps
+constexpr uint32_t STR_MAX_ELEMS = 65536 - 256;      // transition entries addressable by the 16-bit row encoding
 
-struct DfaDev {
-    uint32_t n_classes;   // joint classes
-    uint32_t start;
-    uint32_t table_off;   // offset (in uint16) of next[] inside the shared table blob
-    uint32_t accept_off;  // offset (in uint16) of accept_end[] (one uint16 per state)
-    uint32_t trim;
-};
+// Transition table encoding (all uint16). A product state is named by the ELEMENT INDEX of its row. A row has
+// n_classes entries (next state per joint byte class) plus one END entry: the match mask if the string ends in this
+// state. Decided states (every component DEAD or MATCH) come first, so "decided" is E < n_term * (n_classes + 1);
+// their rows loop to themselves. Byte 0xFF — which cannot occur in valid UTF-8 — is a class of its own that maps
+// every state to itself: the kernel pads the last 8-byte window of a string with 0xFF, so the per-byte loop has no
+// end-of-string test and no branch at all; "decided" is tested once per 8 bytes.
 struct StrParams {
     const int32_t* offsets;
     const uint8_t* bytes;
     const uint32_t* validity;
     int64_t n_rows;
-    int32_t n_dfa;
-    uint32_t blob_u16;        // total uint16 entries in the table blob (after the 256-byte class map)
-    const uint16_t* g_blob;   // [128 uint16 = 256-byte joint class map][tables...]
-    unsigned long long* out;  // [n_dfa] match counts, [STR_MAX_DFA] = valid (non-null) rows
-    DfaDev dfa[STR_MAX_DFA];
+    int64_t n_blocks;         // ceil(n_rows / 32)
+    int32_t trim;             // TRIM(c) (ASCII space, both ends) before matching
+    uint32_t n_classes;       // joint byte classes
+    uint32_t term_limit;      // states with E < term_limit are decided
+    uint32_t start;           // encoded start state
+    uint32_t tab_bytes;       // 256-byte class map + transition table (multiple of 16)
+    uint32_t stage;           // bytes per warp stage buffer (multiple of 128)
+    const uint8_t* g_blob;    // [256 B class map (uint8 class)][table]
+    unsigned long long* out;  // [STR_MAX_DFA] match counts, [STR_MAX_DFA] = valid (non-null) rows
 };
 
-extern __shared__ __align__(16) uint16_t str_smem[];
+extern __shared__ __align__(256) uint8_t str_smem[];
 
-__global__ void __launch_bounds__(STR_THREADS) dfa_kernel(const __grid_constant__ StrParams P) {
-    // stage class map + tables
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// 8 automaton steps over the bytes of (lo, hi). cls_base = shared address of the class map (256-byte aligned, so
+// "base + byte" is one PRMT); the 8 class lookups do not depend on the state and issue ahead of the chain.
+__device__ __forceinline__ uint32_t dfa_step8(uint32_t lo, uint32_t hi, uint32_t E, uint32_t cls_base, uint32_t tab_addr) {
+    uint32_t c[8];
+    c[0] = lds_u8(__byte_perm(lo, cls_base, 0x7650));
+    c[1] = lds_u8(__byte_perm(lo, cls_base, 0x7651));
+    c[2] = lds_u8(__byte_perm(lo, cls_base, 0x7652));
+    c[3] = lds_u8(__byte_perm(lo, cls_base, 0x7653));
+    c[4] = lds_u8(__byte_perm(hi, cls_base, 0x7650));
+    c[5] = lds_u8(__byte_perm(hi, cls_base, 0x7651));
+    c[6] = lds_u8(__byte_perm(hi, cls_base, 0x7652));
+    c[7] = lds_u8(__byte_perm(hi, cls_base, 0x7653));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) E = lds_u16(tab_addr + 2u * (E + c[k]));
+    return E;
+}
+
+// Runs the product automaton over bytes [p, e) of the warp's stage (shared address stage_addr).
+__device__ __forceinline__ uint32_t run_dfa_smem(uint32_t stage_addr, uint32_t p, uint32_t e, uint32_t E, uint32_t cls_base,
+                                                 uint32_t tab_addr, uint32_t term_limit) {
+    while (p < e) {
+        const uint32_t a = stage_addr + (p & ~3u);
+        const uint32_t w0 = lds_u32(a), w1 = lds_u32(a + 4), w2 = lds_u32(a + 8);
+        const uint32_t sh = (p & 3u) * 8u;
+        uint32_t lo = __funnelshift_r(w0, w1, sh), hi = __funnelshift_r(w1, w2, sh);
+        const uint32_t rem = e - p;
+        if (rem < 8u) {  // pad the tail with 0xFF (the identity class)
+            const unsigned long long m = ~0ull << (8u * rem);
+            lo |= (uint32_t)m;
+            hi |= (uint32_t)(m >> 32);
+        }
+        E = dfa_step8(lo, hi, E, cls_base, tab_addr);
+        p += 8u;
+        if (E < term_limit) break;
+    }
+    return E;
+}
+// Same over global memory, byte loads (only blocks whose bytes exceed the stage: very long strings).
+__device__ __forceinline__ uint32_t run_dfa_gmem(const uint8_t* bytes, uint32_t p, uint32_t e, uint32_t E, uint32_t cls_base,
+                                                 uint32_t tab_addr, uint32_t term_limit) {
+    for (; p < e && E >= term_limit; ++p) E = lds_u16(tab_addr + 2u * (E + lds_u8(cls_base + __ldg(bytes + p))));
+    return E;
+}
+
+template <int NDFA>
+__global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_constant__ StrParams P) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    // ---- stage class map + transition table ----
     {
-        const uint32_t total = 128 + P.blob_u16;
-        for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) str_smem[i] = P.g_blob[i];
+        const uint4* src = reinterpret_cast<const uint4*>(P.g_blob);
+        uint4* dst = reinterpret_cast<uint4*>(str_smem);
+        for (uint32_t i = threadIdx.x; i < P.tab_bytes / 16; i += blockDim.x) dst[i] = src[i];
     }
+    const uint32_t cls_base = smem_u32(str_smem), tab_addr = cls_base + 256u;
+    const uint32_t term_limit = P.term_limit, n_classes = P.n_classes;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(str_smem + P.tab_bytes) + warp * 2;
+    const uint32_t stage_bytes = P.stage;
+    uint8_t* stage = str_smem + P.tab_bytes + (size_t)n_warps * 16 + (size_t)warp * (2 * stage_bytes);
+    if (lane == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+    }
+    mbar_fence_init();
     __syncthreads();
-    const uint8_t* jclass = reinterpret_cast<const uint8_t*>(str_smem);
-    const uint16_t* tab = str_smem + 128;
 
-    unsigned long long cnt[STR_MAX_DFA] = {0, 0, 0, 0};
-    unsigned long long nvalid = 0;
-    const uint32_t* words = reinterpret_cast<const uint32_t*>(P.bytes);
+    const int64_t total_warps = (int64_t)gridDim.x * n_warps;
+    const int64_t gwarp = (int64_t)blockIdx.x * n_warps + warp;
+    const int64_t n = P.n_rows;
+    uint32_t cnt[NDFA];
+#pragma unroll
+    for (int i = 0; i < NDFA; ++i) cnt[i] = 0;
+    uint32_t nvalid = 0;
+    const uint32_t byte_base_lo = (uint32_t)reinterpret_cast<uint64_t>(P.bytes) & 15u;  // misalignment of the value buffer
 
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < P.n_rows; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = base + threadIdx.x;
-        if (row >= P.n_rows) continue;
-        if (P.validity && !((P.validity[row >> 5] >> (row & 31)) & 1u)) continue;
-        ++nvalid;
-        const int32_t b = P.offsets[row], e = P.offsets[row + 1];
-        // TRIM(c): ASCII space only, both ends
-        int32_t tb = b, te = e;
-        bool any_trim = false;
-#pragma unroll
-        for (int i = 0; i < STR_MAX_DFA; ++i) any_trim |= (i < P.n_dfa) && P.dfa[i].trim;
-        if (any_trim) {
-            while (tb < te && P.bytes[tb] == ' ') ++tb;
-            while (te > tb && P.bytes[te - 1] == ' ') --te;
+    // offsets of a block: lane l holds [o, oe) of row blk*32 + l (rows past the end are empty) and the block's
+    // validity word (32 rows = one word)
+    auto load_offsets = [&](int64_t blk, uint32_t& o, uint32_t& oe, uint32_t& vw) {
+        o = oe = 0;
+        vw = 0;
+        if (blk < P.n_blocks) {
+            const int64_t r = blk * 32 + lane;
+            o = (uint32_t)__ldg(P.offsets + (r < n ? r : n));
+            oe = (uint32_t)__ldg(P.offsets + (r + 1 < n ? r + 1 : n));
+            vw = P.validity ? __ldg(P.validity + blk) : 0xffffffffu;
         }
-        uint32_t st[STR_MAX_DFA];
-        uint32_t alive = 0;
-#pragma unroll
-        for (int i = 0; i < STR_MAX_DFA; ++i) {
-            st[i] = i < P.n_dfa ? P.dfa[i].start : DFA_DEAD;
-            if (i < P.n_dfa && st[i] > DFA_MATCH) alive |= 1u << i;
+    };
+    // block byte range -> TMA bulk copy into stage buffer `buf`. Returns false when the block is empty or does not
+    // fit (then it is read from global memory); org = the byte index (relative to P.bytes, may be "negative" by the
+    // buffer's misalignment, hence wrapping uint32 arithmetic) that maps to stage offset 0. 16 bytes of the stage
+    // stay free: the window loads of the last string may run 11 bytes past its end.
+    auto issue = [&](uint32_t o, uint32_t oe, int buf, uint32_t& org) -> bool {
+        const uint32_t b0 = __shfl_sync(0xffffffffu, o, 0), b1 = __shfl_sync(0xffffffffu, oe, 31);
+        if (b1 <= b0) return false;
+        const uint32_t lead = (byte_base_lo + b0) & 15u;  // bytes between the 16-byte aligned start and b0
+        const uint32_t sz = (lead + (b1 - b0) + 15u) & ~15u;
+        if (sz + 16u > stage_bytes) return false;
+        if (lane == 0) {
+            mbar_arrive_expect_tx(&bars[buf], sz);
+            bulk_g2s(stage + buf * stage_bytes, P.bytes + (int64_t)b0 - (int64_t)lead, sz, &bars[buf]);
         }
-        uint32_t w = 0;
-        int32_t wi = -1;
-        for (int32_t p = b; p < e && alive; ++p) {
-            if ((p >> 2) != wi) {
-                wi = p >> 2;
-                w = __ldg(words + wi);
-            }
-            const uint32_t byte = (w >> ((p & 3) * 8)) & 0xffu;
-            const uint32_t c = jclass[byte];
-#pragma unroll
-            for (int i = 0; i < STR_MAX_DFA; ++i) {
-                if (alive & (1u << i)) {
-                    const bool inside = !P.dfa[i].trim || (p >= tb && p < te);
-                    if (inside) {
-                        st[i] = tab[P.dfa[i].table_off + st[i] * P.dfa[i].n_classes + c];
-                        if (st[i] <= DFA_MATCH) alive &= ~(1u << i);
-                    }
+        org = b0 - lead;
+        return true;
+    };
+
+    uint32_t o0, oe0, o1, oe1, o2, oe2;  // offsets of blocks it, it+1, it+2
+    uint32_t vw0, vw1, vw2;
+    load_offsets(gwarp, o0, oe0, vw0);
+    load_offsets(gwarp + total_warps, o1, oe1, vw1);
+    uint32_t org0 = 0, org1 = 0;  // stage origins of blocks it, it+1
+    bool staged0 = false, staged1 = false;
+    if (gwarp < P.n_blocks) staged0 = issue(o0, oe0, 0, org0);
+    uint32_t phase = 0;  // bit b = parity of the next completion of bars[b]
+    int it = 0;
+    for (int64_t blk = gwarp; blk < P.n_blocks; blk += total_warps, ++it) {
+        const int buf = it & 1;
+        // prefetch: offsets two blocks ahead, bytes one block ahead (its buffer was last read an iteration ago)
+        load_offsets(blk + 2 * total_warps, o2, oe2, vw2);
+        __syncwarp();
+        staged1 = false;
+        if (blk + total_warps < P.n_blocks) staged1 = issue(o1, oe1, buf ^ 1, org1);
+        // ---- this block ----
+        const bool valid = (vw0 >> lane) & 1u;
+        if (staged0) {
+            mbar_wait(&bars[buf], (phase >> buf) & 1u);
+            phase ^= 1u << buf;
+        }
+        if (valid && blk * 32 + lane < n) {
+            ++nvalid;
+            uint32_t E;
+            if (staged0) {
+                const uint8_t* base = stage + buf * stage_bytes;
+                uint32_t p = o0 - org0, e = oe0 - org0;
+                if (P.trim) {
+                    while (p < e && base[p] == ' ') ++p;
+                    while (e > p && base[e - 1] == ' ') --e;
                 }
+                E = run_dfa_smem(smem_u32(base), p, e, P.start, cls_base, tab_addr, term_limit);
+            } else {
+                uint32_t p = o0, e = oe0;
+                if (P.trim) {
+                    while (p < e && P.bytes[p] == ' ') ++p;
+                    while (e > p && P.bytes[e - 1] == ' ') --e;
+                }
+                E = run_dfa_gmem(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
             }
-        }
+            const uint32_t m = lds_u16(tab_addr + 2u * (E + n_classes));  // END entry = match mask
 #pragma unroll
-        for (int i = 0; i < STR_MAX_DFA; ++i) {
-            if (i < P.n_dfa) {
-                const bool m = st[i] == DFA_MATCH || (st[i] != DFA_DEAD && tab[P.dfa[i].accept_off + st[i]] != 0);
-                cnt[i] += m;
-            }
+            for (int i = 0; i < NDFA; ++i) cnt[i] += (m >> i) & 1u;
         }
+        o0 = o1; oe0 = oe1; vw0 = vw1;
+        o1 = o2; oe1 = oe2; vw1 = vw2;
+        org0 = org1;
+        staged0 = staged1;
     }
-    // block reduction -> one atomic per counter per CTA
-    __shared__ unsigned long long red[STR_MAX_DFA + 1][STR_THREADS / 32];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // ---- block reduction -> one atomic per counter per CTA ----
+    __syncthreads();
+    uint32_t* red = reinterpret_cast<uint32_t*>(str_smem + P.tab_bytes + (size_t)n_warps * 16);  // stages are dead now
 #pragma unroll
-    for (int i = 0; i <= STR_MAX_DFA; ++i) {
-        unsigned long long v = i < STR_MAX_DFA ? cnt[i] : nvalid;
+    for (int i = 0; i <= NDFA; ++i) {
+        uint32_t v = i < NDFA ? cnt[i < NDFA ? i : 0] : nvalid;
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        if (lane == 0) red[i][warp] = v;
+        if (lane == 0) red[i * STR_MAX_WARPS + warp] = v;
     }
     __syncthreads();
-    if (threadIdx.x <= STR_MAX_DFA) {
+    if (threadIdx.x <= NDFA) {
         unsigned long long v = 0;
-        for (int k = 0; k < STR_THREADS / 32; ++k) v += red[threadIdx.x][k];
-        if (v) atomicAdd(P.out + threadIdx.x, v);
+        for (int k = 0; k < n_warps; ++k) v += red[threadIdx.x * STR_MAX_WARPS + k];
+        if (v) atomicAdd(P.out + (threadIdx.x < NDFA ? threadIdx.x : STR_MAX_DFA), v);
     }
 }
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::vector<int>& ids) {
-    const int nd = (int)ids.size();
-    std::vector<Dfa> dfas;
-    for (int id : ids) {
-        Agg& a = p.aggs[id];
-        dfas.push_back(compile_regex(a.text, (a.flags & 1) != 0));
-    }
+// ------------------------------------------------------------------ product automaton (host) ----
+struct Product {
+    uint32_t n_classes = 0, n_states = 0, n_term = 0, term_limit = 0, start = 0, tab_bytes = 0;
+    std::vector<uint8_t> blob;  // device image, see StrParams::g_blob
+    bool ok = false;            // false: exceeded the state / size limits
+};
+
+static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_budget) {
+    Product pr;
+    const size_t nd = dfas.size();
     // joint byte classes
-    std::map<std::vector<uint8_t>, uint8_t> sig_ids;
-    uint8_t jclass[256];
+    std::map<std::vector<uint8_t>, uint16_t> sig_ids;
+    uint16_t jclass[256];
     std::vector<uint8_t> rep;
     for (int b = 0; b < 256; ++b) {
         std::vector<uint8_t> sig;
-        for (auto& d : dfas) sig.push_back(d.class_of[b]);
+        for (auto* d : dfas) sig.push_back(d->class_of[b]);
+        sig.push_back(b == 0xFF ? 1 : 0);  // 0xFF (never part of valid UTF-8) is the kernel's padding byte: own class
         auto it = sig_ids.find(sig);
         if (it == sig_ids.end()) {
-            it = sig_ids.emplace(sig, (uint8_t)rep.size()).first;
+            it = sig_ids.emplace(sig, (uint16_t)rep.size()).first;
             rep.push_back((uint8_t)b);
         }
         jclass[b] = it->second;
     }
-    const uint32_t njc = (uint32_t)rep.size();
-    std::vector<uint16_t> blob(128);
-    memcpy(blob.data(), jclass, 256);
-    StrParams P{};
-    P.n_dfa = nd;
-    for (int i = 0; i < nd; ++i) {
-        const Dfa& d = dfas[i];
-        P.dfa[i].n_classes = njc;
-        P.dfa[i].start = d.start;
-        P.dfa[i].trim = (p.aggs[ids[i]].flags & 2) ? 1 : 0;
-        P.dfa[i].table_off = (uint32_t)blob.size() - 128;
-        for (uint32_t s = 0; s < d.n_states; ++s)
-            for (uint32_t jc = 0; jc < njc; ++jc)
-                blob.push_back(d.next[(size_t)s * d.n_classes + d.class_of[rep[jc]]]);
-        P.dfa[i].accept_off = (uint32_t)blob.size() - 128;
-        for (uint32_t s = 0; s < d.n_states; ++s) blob.push_back(d.accept_end[s]);
+    const uint32_t njc = (uint32_t)rep.size(), stride = njc + 1, nop_class = jclass[0xFF];
+    if (njc > 255) return pr;
+    // breadth-first product construction
+    typedef std::vector<uint16_t> Tuple;
+    std::map<Tuple, uint32_t> ids;
+    std::vector<Tuple> states;
+    std::vector<uint32_t> next;  // [state][class] in discovery numbering
+    Tuple st0;
+    for (auto* d : dfas) st0.push_back((uint16_t)d->start);
+    ids[st0] = 0;
+    states.push_back(st0);
+    const size_t max_elems = std::min<size_t>(STR_MAX_ELEMS, table_budget / 2);
+    const size_t max_states = max_elems / stride;
+    for (size_t s = 0; s < states.size(); ++s) {
+        for (uint32_t c = 0; c < njc; ++c) {
+            Tuple t(nd);
+            const Tuple& cur = states[s];
+            if (c == nop_class) {
+                t = cur;  // identity: the padding byte
+            } else {
+                for (size_t i = 0; i < nd; ++i) {
+                    uint16_t x = cur[i];
+                    if (x > DFA_MATCH) x = dfas[i]->next[(size_t)x * dfas[i]->n_classes + dfas[i]->class_of[rep[c]]];
+                    t[i] = x;
+                }
+            }
+            auto it = ids.find(t);
+            if (it == ids.end()) {
+                if (states.size() >= max_states) return pr;
+                it = ids.emplace(t, (uint32_t)states.size()).first;
+                states.push_back(std::move(t));
+            }
+            next.push_back(it->second);
+        }
     }
-    P.blob_u16 = (uint32_t)blob.size() - 128;
-    const size_t smem = blob.size() * 2;
-    if (smem > 200 * 1024) throw Error(TG_ERR_UNSUPPORTED, "DFA tables exceed shared memory");
-    const size_t blob_bytes = round_up(smem, 256);
+    const uint32_t ns = (uint32_t)states.size();
+    // rows: decided tuples (every component DEAD or MATCH) first
+    std::vector<uint32_t> enc(ns);
+    uint32_t n_term = 0;
+    auto decided = [&](const Tuple& t) {
+        for (auto x : t)
+            if (x > DFA_MATCH) return false;
+        return true;
+    };
+    for (uint32_t s = 0; s < ns; ++s)
+        if (decided(states[s])) enc[s] = (n_term++) * stride;
+    uint32_t row = n_term;
+    for (uint32_t s = 0; s < ns; ++s)
+        if (!decided(states[s])) enc[s] = (row++) * stride;
+    if ((size_t)ns * stride > max_elems) return pr;
+    const size_t tab_bytes = round_up(256 + (size_t)ns * stride * 2, 16);
+    pr.n_classes = njc;
+    pr.n_states = ns;
+    pr.n_term = n_term;
+    pr.term_limit = n_term * stride;
+    pr.start = enc[0];
+    pr.tab_bytes = (uint32_t)tab_bytes;
+    pr.blob.assign(tab_bytes, 0);
+    for (int b = 0; b < 256; ++b) pr.blob[b] = (uint8_t)jclass[b];
+    uint16_t* tab = reinterpret_cast<uint16_t*>(pr.blob.data() + 256);
+    for (uint32_t s = 0; s < ns; ++s) {
+        uint8_t m = 0;
+        for (size_t i = 0; i < nd; ++i) {
+            const uint16_t x = states[s][i];
+            if (x == DFA_MATCH || (x != DFA_DEAD && dfas[i]->accept_end[x])) m |= (uint8_t)(1u << i);
+        }
+        uint16_t* r = tab + enc[s];
+        for (uint32_t c = 0; c < njc; ++c) r[c] = (uint16_t)enc[next[(size_t)s * njc + c]];
+        r[njc] = m;  // END entry
+    }
+    pr.ok = true;
+    return pr;
+}
+
+// products are cached by their pattern list, like the reference caches compiled patterns (format.rs:183-184)
+static const Product& cached_product(const std::vector<std::pair<std::string, bool>>& pats, size_t budget) {
+    static std::mutex mu;
+    static std::map<std::pair<std::vector<std::pair<std::string, bool>>, size_t>, Product> cache;
+    std::lock_guard<std::mutex> g(mu);
+    auto key = std::make_pair(pats, budget);
+    auto it = cache.find(key);
+    if (it != cache.end()) return it->second;
+    std::vector<Dfa> dfas;
+    for (auto& p : pats) dfas.push_back(compile_regex(p.first, p.second));
+    std::vector<const Dfa*> ptrs;
+    for (auto& d : dfas) ptrs.push_back(&d);
+    return cache.emplace(key, build_product(ptrs, budget)).first->second;
+}
+
+static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::vector<int>& ids, const Product& pr, bool trim) {
+    const int nd = (int)ids.size();
+    StrParams P{};
+    P.trim = trim ? 1 : 0;
+    P.n_classes = pr.n_classes;
+    P.term_limit = pr.term_limit;
+    P.start = pr.start;
+    P.tab_bytes = pr.tab_bytes;
+    // per-warp stage: 32 rows of ~1.5x the column's mean length, so almost every block is staged by TMA
+    const double mean_len = t.n_rows > 0 ? (double)c.value_bytes / (double)t.n_rows : 0.0;
+    size_t stage = round_up((size_t)(mean_len * 32.0 * 1.5) + 256, 128);
+    stage = std::min<size_t>(std::max<size_t>(stage, 1024), 8192);
+    // warps per CTA: as many as fit beside the table (each owns a double stage + 2 mbarriers)
+    int warps = 0;
+    for (;; stage = std::max<size_t>(1024, stage / 2 / 128 * 128)) {
+        warps = (int)std::min<size_t>(STR_MAX_WARPS, (STR_SMEM_MAX - pr.tab_bytes) / (2 * stage + 16));
+        if (warps >= 8 || stage <= 1024) break;
+    }
+    if (warps < 1) throw Error(TG_ERR_UNSUPPORTED, "DFA tables exceed shared memory");
+    P.stage = (uint32_t)stage;
+    const size_t smem = pr.tab_bytes + (size_t)warps * (2 * stage + 16);
+    const size_t blob_bytes = round_up(pr.blob.size(), 256);
     uint8_t* scr = e.scratch(blob_bytes + 256);
-    TG_CUDA(cudaMemcpyAsync(scr, blob.data(), smem, cudaMemcpyHostToDevice, e.stream));
+    TG_CUDA(cudaMemcpyAsync(scr, pr.blob.data(), pr.blob.size(), cudaMemcpyHostToDevice, e.stream));
     unsigned long long* d_out = reinterpret_cast<unsigned long long*>(scr + blob_bytes);
-    TG_CUDA(cudaMemsetAsync(d_out, 0, 64, e.stream));
-    P.g_blob = reinterpret_cast<const uint16_t*>(scr);
+    TG_CUDA(cudaMemsetAsync(d_out, 0, 128, e.stream));
+    P.g_blob = scr;
     P.out = d_out;
     P.offsets = reinterpret_cast<const int32_t*>(c.offsets.p);
     P.bytes = c.values.p;
     P.validity = reinterpret_cast<const uint32_t*>(c.validity.p);
     P.n_rows = t.n_rows;
-    static bool attr = false;
-    if (!attr) {
-        TG_CUDA(cudaFuncSetAttribute(dfa_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        attr = true;
-    }
+    P.n_blocks = (t.n_rows + 31) / 32;
+    typedef void (*Kernel)(const StrParams);
+    const Kernel kernel = nd <= 1 ? (Kernel)dfa_kernel<1> : nd <= 2 ? (Kernel)dfa_kernel<2> : nd <= 4 ? (Kernel)dfa_kernel<4> : (Kernel)dfa_kernel<8>;
+    TG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STR_SMEM_MAX));
+    const int threads = warps * 32;
     int per_sm = 1;
-    TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, dfa_kernel, STR_THREADS, smem));
+    TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
     per_sm = std::max(per_sm, 1);
-    const int64_t blocks_needed = (t.n_rows + STR_THREADS - 1) / STR_THREADS;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(blocks_needed, (int64_t)e.sm_count * per_sm));
+    const int64_t ctas_needed = (P.n_blocks + warps - 1) / warps;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ctas_needed, (int64_t)e.sm_count * per_sm));
     TG_CUDA(cudaEventRecord(e.ev[2], e.stream));
-    dfa_kernel<<<grid, STR_THREADS, smem, e.stream>>>(P);
+    kernel<<<grid, threads, smem, e.stream>>>(P);
     TG_CUDA(cudaGetLastError());
     TG_CUDA(cudaEventRecord(e.ev[3], e.stream));
     e.launches += 1;
     p.stats.launches += 1;
-    unsigned long long h_out[8];
-    TG_CUDA(cudaMemcpyAsync(h_out, d_out, 64, cudaMemcpyDeviceToHost, e.stream));
+    unsigned long long h_out[16];
+    TG_CUDA(cudaMemcpyAsync(h_out, d_out, 128, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
     float ms = 0;
     TG_CUDA(cudaEventElapsedTime(&ms, e.ev[2], e.ev[3]));
@@ -210,8 +426,10 @@ static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::
 }
 
 void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids) {
-    // group by column, then passes of up to STR_MAX_DFA patterns whose tables fit in shared memory
-    std::map<Column*, std::vector<int>> by_col;
+    // group by (column, TRIM flag): all patterns of a group walk the same byte sequence, so they share one
+    // product automaton (split greedily when the product would not fit in shared memory)
+    std::map<std::pair<Column*, bool>, std::vector<int>> by_col;
+    std::vector<Column*> counted;
     for (int id : agg_ids) {
         Agg& a = p.aggs[id];
         Column* c = t.find(a.cols[0]);
@@ -225,31 +443,47 @@ void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_
             a.err_msg = "Error during planning: regular expression match requires a Utf8 column, '" + c->name + "' is not";
             continue;
         }
-        by_col[c].push_back(id);
+        by_col[{c, (a.flags & 2) != 0}].push_back(id);
+        if (std::find(counted.begin(), counted.end(), c) == counted.end()) {
+            counted.push_back(c);
+            // algorithmic bytes: offsets + value bytes + validity, once per column
+            p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)c->value_bytes +
+                                     (c->validity.p ? (uint64_t)(t.n_rows + 7) / 8 : 0);
+        }
     }
     for (auto& kv : by_col) {
-        Column& c = *kv.first;
-        // algorithmic bytes: offsets + value bytes + validity, once per column
-        p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)c.value_bytes +
-                                 (c.validity.p ? (uint64_t)(t.n_rows + 7) / 8 : 0);
+        Column& c = *kv.first.first;
+        const bool trim = kv.first.second;
         if (t.n_rows == 0) {
             for (int id : kv.second) p.aggs[id].u[2] = 0;
             continue;
         }
         std::vector<int> pass;
-        size_t est = 0;
+        std::vector<std::pair<std::string, bool>> pats;
         auto flush = [&]() {
-            if (!pass.empty()) run_string_pass(e, t, p, c, pass);
+            if (pass.empty()) return;
+            const Product* pr = &cached_product(pats, STR_TABLE_BUDGET);
+            if (!pr->ok && pass.size() == 1) pr = &cached_product(pats, 2 * (size_t)STR_MAX_ELEMS);
+            if (!pr->ok) {
+                for (int id : pass) {
+                    p.aggs[id].err = TG_ERR_UNSUPPORTED;
+                    p.aggs[id].err_msg = "regex pattern compiles to DFA tables that exceed shared memory";
+                }
+            } else {
+                run_string_pass(e, t, p, c, pass, *pr, trim);
+            }
             pass.clear();
-            est = 0;
+            pats.clear();
         };
         for (int id : kv.second) {
-            Dfa d = compile_regex(p.aggs[id].text, (p.aggs[id].flags & 1) != 0);
-            // joint classes can exceed each DFA's own count; bound by 2x as a planning estimate
-            size_t bytes = (size_t)d.n_states * std::min<size_t>(256, (size_t)d.n_classes * 2) * 2 + d.n_states * 2;
-            if (!pass.empty() && (pass.size() >= (size_t)STR_MAX_DFA || est + bytes > 150 * 1024)) flush();
+            const std::pair<std::string, bool> pat{p.aggs[id].text, (p.aggs[id].flags & 1) != 0};
+            if (!pass.empty()) {
+                auto trial = pats;
+                trial.push_back(pat);
+                if (pass.size() >= (size_t)STR_MAX_DFA || !cached_product(trial, STR_TABLE_BUDGET).ok) flush();
+            }
             pass.push_back(id);
-            est += bytes;
+            pats.push_back(pat);
         }
         flush();
     }
