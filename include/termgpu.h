@@ -237,6 +237,19 @@ TG_API tg_status tg_table_adopt_device(tg_table* t, const char* name, int32_t dt
                                        const void* d_values, const int32_t* d_offsets,
                                        const uint8_t* d_validity, int64_t n_value_bytes);
 
+/*
+ * Multi-GPU hash shuffle, step 1 (stands where DataFusion's RepartitionExec(Hash) stands under
+ * COUNT(DISTINCT ..) / the foreign-key LEFT JOIN, constraints/uniqueness.rs:549-718, foreign_key.rs:165-172).
+ * Groups the valid (non-NULL) keys of an Int64 / Float64 column by destination part = f(hash(key)), so that equal
+ * keys of every rank meet on one rank after an all-to-all. *d_keys receives a DEVICE pointer to the keys (raw
+ * 64-bit values, part 0 first; valid until the next call of this function on the engine), counts[n_parts] the
+ * keys per part, *n_null_rows the NULL rows (the host layer sends them to part 0 as a count). The all-to-all
+ * itself is the host layer's (NCCL); the receiving rank adopts the keys as a table (tg_table_adopt_device) and
+ * runs the ordinary plan on it — the partial states of hash-disjoint shards merge by addition.
+ */
+TG_API tg_status tg_table_partition_keys(tg_engine* eng, const char* table, const char* column, int32_t n_parts,
+                                         void** d_keys, int64_t* counts, int64_t* n_null_rows);
+
 /* Arrow C Data Interface ingestion: `schema`/`array` are struct ArrowSchema* / struct ArrowArray* of a
  * struct-typed array (a RecordBatch). The engine copies; the caller keeps ownership and releases. */
 TG_API tg_status tg_table_append_arrow(tg_table* t, const void* arrow_schema, const void* arrow_array);

@@ -76,6 +76,7 @@ SIGNATURES = {
     "tg_table_append_host": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_adopt_device": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_append_arrow": (C.c_int, [P, P, P]),
+    "tg_table_partition_keys": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_int32, PP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tg_plan_create": (C.c_int, [PP]),
     "tg_plan_destroy": (None, [P]),
     "tg_plan_num_slots": (C.c_int32, [P]),

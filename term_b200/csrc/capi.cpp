@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "engine.hpp"
+#include "hashpart.hpp"
 #include "regex_dfa.hpp"
 
 namespace tg {
@@ -99,6 +100,7 @@ void tg_engine_destroy(tg_engine* h) {
     e.tables.clear();
     e.dev_trim();
     if (e.d_scratch) cudaFree(e.d_scratch);
+    if (e.d_shuffle) cudaFree(e.d_shuffle);
     if (e.h_scratch) cudaFreeHost(e.h_scratch);
     for (int i = 0; i < 2; ++i) {
         if (e.pinned[i]) cudaFreeHost(e.pinned[i]);
@@ -145,6 +147,29 @@ tg_status tg_table_drop(tg_engine* h, const char* name) {
             if (c->validity.owned) h->e.dev_free(c->validity.p, c->validity.cap);
         }
         h->e.tables.erase(it);
+    });
+}
+
+tg_status tg_table_partition_keys(tg_engine* h, const char* table, const char* column, int32_t n_parts, void** d_keys,
+                                  int64_t* counts, int64_t* n_null_rows) {
+    return guard([&] {
+        if (!h || !table || !column || !d_keys || !counts || !n_null_rows) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        Engine& e = h->e;
+        std::lock_guard<std::mutex> g(e.mu);
+        TG_CUDA(cudaSetDevice(e.device));
+        e.sync_copies();
+        auto it = e.tables.find(table);
+        if (it == e.tables.end()) throw Error(TG_ERR_TABLE_NOT_FOUND, std::string("table '") + table + "' not found");
+        Table& t = *it->second;
+        Column* c = t.find(column);
+        if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + std::string(column) + ". Valid fields are " + t.valid_fields() + ".");
+        if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64)
+            throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports Int64 / Float64 key columns");
+        uint64_t* keys = nullptr;
+        int launches = 0;
+        partition_keys_by_rank(e, *c, t.n_rows, n_parts, &keys, counts, n_null_rows, launches);
+        e.launches += launches;
+        *d_keys = keys;
     });
 }
 

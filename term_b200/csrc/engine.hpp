@@ -95,6 +95,8 @@ struct Engine {
     size_t scratch_cap = 0;
     uint8_t* h_scratch = nullptr;  // pinned
     size_t h_scratch_cap = 0;
+    uint8_t* d_shuffle = nullptr;  // keys grouped by destination rank (multi-GPU shuffle), grow-only
+    size_t shuffle_cap = 0;
 
     // recycled device blocks of dropped tables, by exact capacity
     std::map<size_t, std::vector<uint8_t*>> free_blocks;

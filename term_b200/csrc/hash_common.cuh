@@ -1,0 +1,58 @@
+// Shared device helpers of the hash jobs (hashing.cu: single-table path for small inputs, Utf8 / composite keys and
+// grouped counts; hashpart.cu: radix-partitioned path for large Int64 / Float64 key columns and the multi-GPU shuffle).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tg {
+
+constexpr unsigned long long EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
+constexpr int HASH_THREADS = 256;
+
+__host__ __device__ __forceinline__ uint64_t fmix64(uint64_t k) {
+    k ^= k >> 33;
+    k *= 0xff51afd7ed558ccdull;
+    k ^= k >> 33;
+    k *= 0xc4ceb9fe1a85ec53ull;
+    k ^= k >> 33;
+    return k;
+}
+__host__ __device__ __forceinline__ uint64_t canon_f64(uint64_t bits) {
+    // -0.0 == +0.0 and all NaNs compare as one value when grouping
+    if ((bits << 1) == 0) return 0;
+    if ((bits & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (bits & 0x000fffffffffffffull)) return 0x7ff8000000000000ull;
+    return bits;
+}
+__device__ __forceinline__ bool row_valid(const uint32_t* validity, int64_t row) {
+    return !validity || ((validity[row >> 5] >> (row & 31)) & 1u);
+}
+
+// How the 64 hash bits of a key are spent (disjoint fields, so the levels are independent):
+//   bits  0..31  slot inside a (bucket-local) hash table
+//   bits 32..41  local radix bucket (<= 1024 buckets per GPU)
+//   bits 42..63  destination rank of the multi-GPU shuffle: (top22 * world) >> 22
+__host__ __device__ __forceinline__ uint32_t hash_bucket(uint64_t h, uint32_t pmask) { return (uint32_t)(h >> 32) & pmask; }
+__host__ __device__ __forceinline__ uint32_t hash_rank(uint64_t h, uint32_t world) { return (uint32_t)(((h >> 42) * world) >> 22); }
+
+struct HashCounters {
+    unsigned long long distinct_all;      // groups, NULL as a value
+    unsigned long long distinct_nonnull;  // groups whose key has no NULL component
+    unsigned long long singles_plus;      // +1 on first insert
+    unsigned long long singles_minus;     // +1 on second insert
+    unsigned long long any_null_rows;
+    unsigned long long special;           // rows whose exact key equals the EMPTY sentinel (path A)
+    unsigned long long violations;        // FK
+    unsigned long long null_children;     // FK
+    unsigned long long n_examples;
+    unsigned long long overflow;          // a bucket table filled up (skewed hash): the caller falls back
+    unsigned long long pad[6];
+};
+
+// block-level reduction of per-thread counters, one atomic per counter per warp
+__device__ __forceinline__ void flush_counter(unsigned long long v, unsigned long long* dst) {
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
+}
+
+}  // namespace tg

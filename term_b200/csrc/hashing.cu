@@ -17,49 +17,10 @@
 #include <cstring>
 
 #include "engine.hpp"
+#include "hash_common.cuh"
+#include "hashpart.hpp"
 
 namespace tg {
-
-constexpr unsigned long long EMPTY64 = 0xFFFFFFFFFFFFFFFFull;
-constexpr int HASH_THREADS = 256;
-
-__device__ __forceinline__ uint64_t fmix64(uint64_t k) {
-    k ^= k >> 33;
-    k *= 0xff51afd7ed558ccdull;
-    k ^= k >> 33;
-    k *= 0xc4ceb9fe1a85ec53ull;
-    k ^= k >> 33;
-    return k;
-}
-__device__ __forceinline__ uint64_t canon_f64(uint64_t bits) {
-    // -0.0 == +0.0 and all NaNs compare as one value when grouping
-    if ((bits << 1) == 0) return 0;
-    if ((bits & 0x7ff0000000000000ull) == 0x7ff0000000000000ull && (bits & 0x000fffffffffffffull)) return 0x7ff8000000000000ull;
-    return bits;
-}
-__device__ __forceinline__ bool row_valid(const uint32_t* validity, int64_t row) {
-    return !validity || ((validity[row >> 5] >> (row & 31)) & 1u);
-}
-
-struct HashCounters {
-    unsigned long long distinct_all;      // groups, NULL as a value
-    unsigned long long distinct_nonnull;  // groups whose key has no NULL component
-    unsigned long long singles_plus;      // +1 on first insert
-    unsigned long long singles_minus;     // +1 on second insert
-    unsigned long long any_null_rows;
-    unsigned long long special;           // rows whose exact key equals the EMPTY sentinel (path A)
-    unsigned long long violations;        // FK
-    unsigned long long null_children;     // FK
-    unsigned long long n_examples;
-    unsigned long long pad[7];
-};
-
-// block-level reduction of per-thread counters, one atomic per counter per CTA
-__device__ __forceinline__ void flush_counter(unsigned long long v, unsigned long long* dst) {
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
-}
 
 // ---------------------------------------------------------------- path A: exact 64-bit keys ----
 __global__ void __launch_bounds__(HASH_THREADS) insert64_kernel(const uint64_t* values, const uint32_t* validity,
@@ -469,6 +430,26 @@ void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
     for (auto* c : cols) p.stats.bytes_scanned += col_bytes(*c, n);
     if (n == 0) return;
     const bool exact64 = cols.size() == 1 && (cols[0]->dtype == TG_INT64 || cols[0]->dtype == TG_FLOAT64);
+    if (exact64 && n > (1 << 20)) {
+        // large key column (hashpart.cu): dense Int64 ranges are counted in bitmaps; anything else is radix-
+        // partitioned and deduplicated bucket by bucket in an L2-resident table
+        Distinct64Result r;
+        Timer tm(e, p);
+        int launches = 0;
+        bool ok = distinct64_dense(e, *cols[0], n, r, launches);
+        if (!ok && (size_t)n > distinct64_min_rows()) ok = distinct64_partitioned(e, *cols[0], n, r, launches);
+        tm.stop(launches);
+        if (ok) {
+            const uint64_t singles = r.distinct - r.dup_keys;
+            a.u[1] = r.distinct;
+            a.u[2] = singles + (r.nulls == 1 ? 1 : 0);  // the NULL group of GROUP BY
+            a.u[3] = r.nulls;
+            a.u[4] = r.nulls;
+            a.u[5] = r.distinct + (r.nulls > 0 ? 1 : 0);
+            return;
+        }
+        // a bucket table overflowed (adversarial hash skew): fall through to the single-table path
+    }
     const uint64_t cap = pow2_at_least((uint64_t)n * 2);
     HashCounters h{};
     Timer tm(e, p);
@@ -576,6 +557,47 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
     Timer tm(e, p);
     int launches = 0;
     std::vector<int64_t> ex_rows;
+    if (exact64 && (nc > (1 << 20) || (size_t)np > distinct64_min_rows())) {
+        // hashpart.cu: a dense Int64 parent range becomes a bitmap; a parent key set too large for an L2-resident
+        // table is radix-partitioned together with the child keys by the same hash bits
+        Fk64Result r;
+        bool ok = fk64_dense(e, *cc, nc, *pc, np, allow_nulls, max_examples, r, launches);
+        if (!ok && (size_t)np > distinct64_min_rows()) ok = fk64_partitioned(e, *cc, nc, *pc, np, allow_nulls, max_examples, r, launches);
+        if (ok) {
+            tm.stop(launches);
+            a.u[0] = r.violations;
+            a.u[1] = r.distinct_violations;
+            a.u[2] = r.null_children;
+            std::vector<std::string> ex;
+            if (cc->dtype == TG_INT64) {
+                std::vector<int64_t> ks;
+                for (uint64_t k : r.example_keys) ks.push_back((int64_t)k);
+                std::sort(ks.begin(), ks.end());
+                for (int64_t k : ks) ex.push_back(fmt_i64(k));
+            } else {
+                std::vector<double> ks;
+                for (uint64_t k : r.example_keys) {
+                    double d;
+                    memcpy(&d, &k, 8);
+                    ks.push_back(d);
+                }
+                std::sort(ks.begin(), ks.end(), [](double x, double y) { return x < y || (y != y && x == x); });
+                for (double d : ks) ex.push_back(fmt_f64(d));
+            }
+            uint64_t cnt = ex.size();
+            a.blob.resize(8);
+            memcpy(a.blob.data(), &cnt, 8);
+            for (auto& s : ex) {
+                uint32_t L = (uint32_t)s.size();
+                size_t o = a.blob.size();
+                a.blob.resize(o + 4 + L);
+                memcpy(a.blob.data() + o, &L, 4);
+                memcpy(a.blob.data() + o + 4, s.data(), L);
+            }
+            return;
+        }
+        launches = 0;  // overflow: redo on the single-table path below
+    }
     if (exact64) {
         const size_t pk_b = pcap * 8;
         uint8_t* scr = e.scratch(pk_b + 512);

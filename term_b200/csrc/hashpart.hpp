@@ -1,0 +1,40 @@
+// Radix-partitioned hash jobs for large Int64 / Float64 key columns (hashpart.cu).
+#pragma once
+#include <cstdint>
+#include <vector>
+
+#include "engine.hpp"
+
+namespace tg {
+
+struct Distinct64Result {
+    uint64_t distinct = 0;   // distinct non-null keys
+    uint64_t dup_keys = 0;   // keys that occur at least twice
+    uint64_t nulls = 0;      // NULL rows
+};
+// COUNT(DISTINCT c) / GROUP BY c HAVING COUNT(*) = 1 over a single 64-bit key column. Returns false when a bucket
+// table overflowed (pathologically skewed hash): the caller falls back to the single-table path.
+bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches);
+size_t distinct64_min_rows();
+// Dense Int64 key range (max - min < 2^28 and < 32 n): exact bitmap counting, no partitioning. Returns false when
+// the column does not qualify (nothing is counted then).
+bool distinct64_dense(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches);
+
+struct Fk64Result {
+    uint64_t violations = 0;           // child rows without a parent (NULL children included when not allowed)
+    uint64_t distinct_violations = 0;  // distinct orphan keys
+    uint64_t null_children = 0;
+    std::vector<uint64_t> example_keys;  // up to max_examples distinct orphan keys (raw 64-bit values)
+};
+bool fk64_partitioned(Engine& e, const Column& child, int64_t nc, const Column& parent, int64_t np, int allow_nulls,
+                      int max_examples, Fk64Result& r, int& launches);
+
+bool fk64_dense(Engine& e, const Column& child, int64_t nc, const Column& parent, int64_t np, int allow_nulls, int max_examples,
+                Fk64Result& r, int& launches);
+
+// Multi-GPU shuffle, step 1: the valid keys of a column grouped by destination rank
+// (hash_rank of the canonical key). d_keys stays valid until the next partition call on this engine.
+void partition_keys_by_rank(Engine& e, const Column& c, int64_t n, int world, uint64_t** d_keys, int64_t* counts,
+                            int64_t* n_nulls, int& launches);
+
+}  // namespace tg

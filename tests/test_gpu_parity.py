@@ -317,6 +317,86 @@ def test_uniqueness_matches_oracle(ctx, n):
         ctx.deregister_table(name)
 
 
+@pytest.mark.parametrize("dtype", ["i64", "i64_sparse", "f64"])
+def test_uniqueness_partitioned_path_large_keys(ctx, dtype):
+    """Large key columns take the dense-bitmap or the radix-partitioned path (hashpart.cu): counts must stay bit-exact.
+    conftest.py lowers the partitioning threshold (TG_HASH_BUCKET_KEYS) so that 1.3 M rows already split into 8
+    buckets. Expected values from np.unique (the oracle's distinct_counts goes through Python sets: 10x slower)."""
+    n = 1_300_000
+    rng = np.random.default_rng(77)
+    if dtype.startswith("i64"):
+        vals = rng.integers(-n // 3, n // 3, n)  # dense range: bitmap path
+        if dtype == "i64_sparse":
+            vals = vals * 1_000_003  # range >> 32 n: radix-partitioned hash path
+        vals[rng.random(n) < 0.001] = -1  # the EMPTY sentinel of the tables is a legitimate key
+    else:
+        vals = rng.integers(0, n // 2, n).astype(np.float64) / 8.0
+        vals[rng.random(n) < 0.001] = -0.0  # groups with +0.0
+    mask = rng.random(n) < 0.02
+    t = pa.table({"k": pa.array(vals, mask=mask)})
+    name = f"uniq_big_{dtype}"
+    ctx.register_table(name, t.to_batches(max_chunksize=1 << 20))
+    try:
+        kept = vals[~mask]
+        if dtype == "f64":
+            kept = kept + 0.0  # -0.0 -> +0.0
+        _, counts = np.unique(kept, return_counts=True)
+        distinct, singles, nulls = len(counts), int((counts == 1).sum()), int(mask.sum())
+        a = T.DistinctnessAnalyzer("k").compute(ctx, name)
+        assert a.u[:2] == [n - nulls, distinct]
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="FullUniqueness", threshold=0.1)).evaluate(ctx, name)
+        assert g.metric == distinct / n
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="UniqueValueRatio",
+                                       assertion=["GreaterThan", 0.0])).evaluate(ctx, name)
+        assert g.metric == (singles + (1 if nulls == 1 else 0)) / n
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="UniqueWithNulls", threshold=0.1,
+                                       null_handling="Include")).evaluate(ctx, name)
+        assert g.metric == (distinct + (1 if nulls else 0)) / n
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.parametrize("keys", ["dense", "sparse"])
+def test_foreign_key_partitioned_path_large_parent(ctx, keys):
+    """large parent key set (hashpart.cu): a dense Int64 parent range becomes a bitmap; sparse keys are radix-
+    partitioned on both sides by the same hash bits (threshold lowered by conftest.py)"""
+    rng = np.random.default_rng(12)
+    n_parent, n_child = 600_000, 1_200_000
+    mul = 1 if keys == "dense" else 1_000_003
+    parents = rng.permutation(n_parent * 2)[:n_parent].astype(np.int64) * mul
+    parents[0] = -1
+    children = rng.integers(0, n_parent * 2 + 50, n_child).astype(np.int64) * mul
+    children[rng.random(n_child) < 0.0001] = -1
+    cmask = rng.random(n_child) < 0.01
+    pt = pa.table({"id": pa.array(parents)})
+    ct = pa.table({"cid": pa.array(children, mask=cmask)})
+    ctx.register_table("fkpb", pt)
+    ctx.register_table("fkcb", ct)
+    try:
+        valid_children = children[~cmask]
+        orphan = ~np.isin(valid_children, parents)
+        n_viol, n_null = int(orphan.sum()), int(cmask.sum())
+        pset = set(parents.tolist())
+        for allow in (False, True):
+            g = T.ForeignKeyConstraint("fkcb.cid", "fkpb.id").allow_nulls(allow).evaluate(ctx)
+            want = n_viol + (0 if allow else n_null)
+            assert g.status is T.ConstraintStatus.Failure and g.metric == float(want)
+            uniq = len(np.unique(valid_children[orphan]))
+            assert g.message.startswith(f"Foreign key constraint violation: {want} values in 'fkcb.cid' do not exist in 'fkpb.id' "
+                                        f"(total: {want}, unique: {uniq})"), g.message[:200]
+            ex = g.message.split("Examples: [")[1].split("]")[0].split(", ")[:5]
+            assert all(int(e) not in pset for e in ex)
+        # now without the -1 parent: the sentinel key itself becomes an orphan
+        ctx.deregister_table("fkpb")
+        parents[0] = parents[1]
+        ctx.register_table("fkpb", pa.table({"id": pa.array(parents)}))
+        g = T.ForeignKeyConstraint("fkcb.cid", "fkpb.id").allow_nulls(True).evaluate(ctx)
+        assert g.metric == float(int((~np.isin(valid_children, parents)).sum()))
+    finally:
+        ctx.deregister_table("fkpb")
+        ctx.deregister_table("fkcb")
+
+
 @pytest.mark.parametrize("kind", ["i64", "str"])
 def test_foreign_key_matches_oracle(ctx, kind):
     rng = np.random.default_rng(11)
