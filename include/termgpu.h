@@ -216,6 +216,8 @@ TG_API tg_status tg_table_create(tg_engine* eng, const char* name, tg_table** ou
 TG_API tg_status tg_table_drop(tg_engine* eng, const char* name);
 TG_API tg_status tg_table_lookup(tg_engine* eng, const char* name, tg_table** out);
 TG_API int64_t tg_table_num_rows(const tg_table* t);
+/* schema lookup (SessionContext::table(..).schema().field_with_name(..).data_type()) -> tg_dtype */
+TG_API tg_status tg_table_column_dtype(const tg_table* t, const char* column, int32_t* dtype);
 
 /*
  * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity
@@ -330,6 +332,12 @@ TG_API tg_status tg_plan_finalize(tg_plan* plan);
  * shard elsewhere (another engine, a stored IncrementalAnalysisRunner state) assemble a partial blob. */
 TG_API int32_t tg_plan_num_aggregates(const tg_plan* plan);
 TG_API tg_status tg_plan_aggregate_info(const tg_plan* plan, int32_t i, int32_t* kind, const char** key);
+
+/* Multi-GPU shuffle, step 3: aggregate i (kind 6 DISTINCT or 7 FK) reads its keys from `table_name` — the table
+ * holding this rank's hash-shuffled shard (tg_table_partition_keys + all-to-all + tg_table_adopt_device) — instead
+ * of the plan's table; which = 0: the DISTINCT table / the FK child table, 1: the FK parent table. NULL or ""
+ * removes the redirection. Shards are hash-disjoint, so tg_plan_partial_merge adds their states exactly. */
+TG_API tg_status tg_plan_redirect_aggregate(tg_plan* plan, int32_t i, int32_t which, const char* table_name);
 
 TG_API tg_status tg_plan_result(const tg_plan* plan, int32_t slot, tg_result* out);
 TG_API tg_status tg_plan_analyzer_result(const tg_plan* plan, int32_t slot, tg_analyzer_result* out);

@@ -73,6 +73,7 @@ SIGNATURES = {
     "tg_table_drop": (C.c_int, [P, C.c_char_p]),
     "tg_table_lookup": (C.c_int, [P, C.c_char_p, PP]),
     "tg_table_num_rows": (C.c_int64, [P]),
+    "tg_table_column_dtype": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_int32)]),
     "tg_table_append_host": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_adopt_device": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_append_arrow": (C.c_int, [P, P, P]),
@@ -103,6 +104,7 @@ SIGNATURES = {
     "tg_plan_finalize": (C.c_int, [P]),
     "tg_plan_num_aggregates": (C.c_int32, [P]),
     "tg_plan_aggregate_info": (C.c_int, [P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]),
+    "tg_plan_redirect_aggregate": (C.c_int, [P, C.c_int32, C.c_int32, C.c_char_p]),
     "tg_plan_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_result)]),
     "tg_plan_analyzer_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_analyzer_result)]),
     "tg_plan_map_size": (C.c_int32, [P, C.c_int32]),

@@ -235,6 +235,23 @@ class SessionContext:
         F.check(F.lib().tg_table_drop(self._h, name.encode()))
         self._keepalive.pop(name, None)
 
+    def partition_keys(self, table: str, column: str, n_parts: int):
+        """tg_table_partition_keys: (device pointer to the valid keys grouped by destination part, keys per part,
+        NULL rows). The pointer stays valid until the next partition_keys call on this context."""
+        ptr = C.c_void_p()
+        counts = (C.c_int64 * n_parts)()
+        nulls = C.c_int64()
+        F.check(F.lib().tg_table_partition_keys(self._h, table.encode(), column.encode(), n_parts, C.byref(ptr), counts,
+                                                C.byref(nulls)))
+        return int(ptr.value or 0), [int(c) for c in counts], int(nulls.value)
+
+    def column_dtype(self, table: str, column: str) -> int:
+        t = C.c_void_p()
+        F.check(F.lib().tg_table_lookup(self._h, table.encode(), C.byref(t)))
+        d = C.c_int32()
+        F.check(F.lib().tg_table_column_dtype(t, column.encode(), C.byref(d)))
+        return int(d.value)
+
     def num_rows(self, name: str) -> int:
         t = C.c_void_p()
         F.check(F.lib().tg_table_lookup(self._h, name.encode(), C.byref(t)))
@@ -375,6 +392,10 @@ class Plan:
 
     def finalize(self):
         F.check(F.lib().tg_plan_finalize(self._h))
+
+    def redirect(self, agg_index: int, which: int, table):
+        """tg_plan_redirect_aggregate: aggregate `agg_index` reads its keys from `table` (None: undo)."""
+        F.check(F.lib().tg_plan_redirect_aggregate(self._h, agg_index, which, table.encode() if table else None))
 
     def aggregates(self):
         """[(kind, key)] of the plan's device aggregates, in partial-blob order."""

@@ -150,6 +150,16 @@ tg_status tg_table_drop(tg_engine* h, const char* name) {
     });
 }
 
+tg_status tg_table_column_dtype(const tg_table* t, const char* column, int32_t* dtype) {
+    return guard([&] {
+        if (!t || !column || !dtype) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        Table* tab = const_cast<Table*>(reinterpret_cast<const Table*>(t));
+        Column* c = tab->find(column);
+        if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + std::string(column) + ". Valid fields are " + tab->valid_fields() + ".");
+        *dtype = c->dtype;
+    });
+}
+
 tg_status tg_table_partition_keys(tg_engine* h, const char* table, const char* column, int32_t n_parts, void** d_keys,
                                   int64_t* counts, int64_t* n_null_rows) {
     return guard([&] {
@@ -332,6 +342,17 @@ tg_status tg_plan_aggregate_info(const tg_plan* p, int32_t i, int32_t* kind, con
         if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
         if (kind) *kind = p->p.aggs[i].kind;
         if (key) *key = p->p.aggs[i].key.c_str();
+    });
+}
+
+tg_status tg_plan_redirect_aggregate(tg_plan* p, int32_t i, int32_t which, const char* table_name) {
+    return guard([&] {
+        if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
+        Agg& a = p->p.aggs[i];
+        if (which < 0 || which > 1 || (which == 1 && a.kind != A_FK) || (a.kind != A_FK && a.kind != A_DISTINCT))
+            throw Error(TG_ERR_INVALID_ARG, "only DISTINCT (which = 0) and FK (which = 0 child, 1 parent) aggregates can be redirected");
+        if (table_name && *table_name) validate_identifier(table_name);
+        a.redirect[which] = table_name ? table_name : "";
     });
 }
 

@@ -541,8 +541,8 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
                                                 "Error during planning: table 'datafusion.public." + name + "' not found");
         return *it->second;
     };
-    Table& ct = find_table(a.cols[0]);
-    Table& pt = find_table(a.cols[2]);
+    Table& ct = find_table(a.redirect[0].empty() ? a.cols[0] : a.redirect[0]);
+    Table& pt = find_table(a.redirect[1].empty() ? a.cols[2] : a.redirect[1]);
     Column* cc = need_col(ct, a.cols[1]);
     Column* pc = need_col(pt, a.cols[3]);
     if (cc->dtype != pc->dtype)

@@ -35,6 +35,9 @@ struct Agg {
     int32_t flags = 0;               // regex: bit0 case-insensitive, bit1 trim ; distinct: see hash job
     int32_t iparam = 0;              // KLL k / FK max examples / grouped max_groups
     ExprP expr;                      // parsed predicate
+    // multi-GPU shuffle: read this aggregate's keys from another registered table (the hash-shuffled shard) instead
+    // of the plan's table; [0] = the table of a DISTINCT aggregate or the child table of an FK, [1] = the FK parent
+    std::string redirect[2];
     // construction-time problem the reference only reports when the constraint is evaluated
     tg_status ctor_err = TG_OK;
     std::string ctor_err_msg;

@@ -1,18 +1,35 @@
-"""Row-partitioned multi-GPU execution: one process per GPU, each rank evaluates the
-plan on its own row shard, the serialised partial aggregates are all-gathered (torch.distributed: NCCL
-on GPUs, gloo in the CPU tests) and merged IN RANK ORDER on every rank, so all ranks finalize to the
-same, deterministic result. Mirrors AnalyzerState::merge (analyzers/traits.rs:154-179) and the
-IncrementalAnalysisRunner's partition -> state -> merge flow (analyzers/incremental/runner.rs:165-358).
+"""Multi-GPU execution: one process per GPU, every rank holds a row shard of each table.
+
+* Scan / string / KLL / grouped aggregates shard by rows: each rank evaluates the plan on its shard, the
+  serialised partial aggregates are all-gathered (torch.distributed: NCCL on GPUs, gloo in the CPU tests) and
+  merged IN RANK ORDER on every rank, so all ranks finalize to the same, deterministic result. Mirrors
+  AnalyzerState::merge (analyzers/traits.rs:154-179) and the IncrementalAnalysisRunner's partition -> state ->
+  merge flow (analyzers/incremental/runner.rs:165-358).
+* COUNT(DISTINCT ..) / uniqueness and the foreign-key anti-join do not merge by rows. Their keys are first hash-
+  shuffled — the step DataFusion's RepartitionExec(Hash) performs under the reference's SQL
+  (constraints/uniqueness.rs:549-718, foreign_key.rs:165-172): every rank groups its keys by destination rank on
+  the device (tg_table_partition_keys), one all-to-all moves them (NCCL over NVLink), the receiving rank adopts
+  its keys as a table and the aggregate is redirected to it (tg_plan_redirect_aggregate). Equal keys now live on
+  exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0.
 """
 import torch
 import torch.distributed as dist
+
+from . import _ffi as F
+
+KIND_DISTINCT, KIND_FK = 6, 7
+
+
+def _device(device=None):
+    if device is not None:
+        return device
+    return torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
 
 
 def allgather_blobs(blob: bytes, device=None):
     """All-gather variable-length byte strings; returns the list ordered by rank."""
     world = dist.get_world_size()
-    backend = dist.get_backend()
-    dev = device if device is not None else (torch.device("cuda", torch.cuda.current_device()) if backend == "nccl" else torch.device("cpu"))
+    dev = _device(device)
     n = torch.tensor([len(blob)], dtype=torch.int64, device=dev)
     sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
     dist.all_gather(sizes, n)
@@ -34,11 +51,104 @@ def merge_partials(plan, blobs):
     plan.finalize()
 
 
+def shuffle_keys(keys: torch.Tensor, counts, n_nulls: int):
+    """All-to-all of hash-partitioned keys. `keys` (int64, grouped by destination rank) holds counts[r] keys for
+    rank r. Returns (the keys this rank owns after the exchange, NULL rows this rank accounts for): every rank's
+    NULL count goes to rank 0. Works on NCCL (device tensors) and gloo (CPU tensors)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = keys.device
+    send = torch.tensor(list(counts), dtype=torch.int64, device=dev)
+    recv = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send)
+    recv_counts = [int(x) for x in recv.tolist()]
+    out = torch.empty(sum(recv_counts), dtype=torch.int64, device=dev)
+    dist.all_to_all_single(out, keys[: sum(counts)].contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(counts))
+    nulls = torch.tensor([int(n_nulls)], dtype=torch.int64, device=dev)
+    dist.all_reduce(nulls)
+    return out, (int(nulls.item()) if rank == 0 else 0)
+
+
+def _adopt_shard(ctx, name, column, dtype, keys: torch.Tensor, n_nulls: int):
+    """Register this rank's shuffled keys (+ n_nulls NULL rows at the end) as a one-column device table."""
+    n = keys.numel() + n_nulls
+    vals = torch.zeros(n + 64, dtype=torch.int64, device=keys.device)
+    vals[: keys.numel()] = keys
+    keep = [vals]
+    validity = None
+    if n_nulls:
+        bits = torch.zeros((n + 7) // 8 + 64, dtype=torch.uint8, device=keys.device)
+        full, rem = divmod(keys.numel(), 8)
+        bits[:full] = 0xFF
+        if rem:
+            bits[full] = (1 << rem) - 1
+        keep.append(bits)
+        validity = bits.data_ptr()
+    ctx.register_device_table(name, {column: dict(dtype=dtype, n_rows=n, values=vals.data_ptr(), validity=validity)}, keepalive=keep)
+
+
+def _column_dtype(ctx, table, column):
+    return ctx.column_dtype(table, column)
+
+
+def _shuffle_column(ctx, table, column, shard_name):
+    """partition -> all-to-all -> adopt as table `shard_name` (column keeps its name)."""
+    world = dist.get_world_size()
+    dtype = _column_dtype(ctx, table, column)
+    if dtype not in (F.TG_INT64, F.TG_FLOAT64):
+        raise NotImplementedError(f"multi-GPU shuffle of column '{table}.{column}': only Int64 / Float64 keys are supported")
+    ptr, counts, nulls = ctx.partition_keys(table, column, world)
+    total = sum(counts)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    # view the engine-owned device buffer as a tensor (no copy); it is consumed before the next partition call
+    if total:
+        keys = _tensor_from_ptr(ptr, total, dev)
+    else:
+        keys = torch.empty(0, dtype=torch.int64, device=dev)
+    mine, my_nulls = shuffle_keys(keys, counts, nulls)
+    _adopt_shard(ctx, shard_name, column, dtype, mine, my_nulls)
+
+
+def _tensor_from_ptr(ptr, n, dev):
+    class _Wrap:  # __cuda_array_interface__ v3
+        pass
+    w = _Wrap()
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+    return torch.as_tensor(w, device=dev)
+
+
 def execute_distributed(plan, ctx, table="data"):
-    """Each rank: partial execute on its shard -> all-gather -> ordered merge -> finalize."""
-    plan.execute_partial(ctx, table)
+    """Each rank: shuffle the keys of DISTINCT / FK aggregates, partial execute on its shard -> all-gather ->
+    ordered merge -> finalize."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
-        plan.finalize()
+        plan.execute(ctx, table)
         return
-    blobs = allgather_blobs(plan.partial_export())
-    merge_partials(plan, blobs)
+    temps, redirected = [], []
+    try:
+        for i, (kind, key) in enumerate(plan.aggregates()):
+            parts = key.split("|")
+            if kind == KIND_DISTINCT:
+                if len(parts) != 2:
+                    raise NotImplementedError("multi-GPU uniqueness over composite keys is not implemented (single Int64 / Float64 key only)")
+                name = f"tg_shuffle_{i}_k"
+                _shuffle_column(ctx, table, parts[1], name)
+                temps.append(name)
+                plan.redirect(i, 0, name)
+                redirected.append((i, 0))
+            elif kind == KIND_FK:
+                (ct, cc), (pt, pc) = parts[1].split("."), parts[2].split(".")
+                cname, pname = f"tg_shuffle_{i}_c", f"tg_shuffle_{i}_p"
+                _shuffle_column(ctx, ct, cc, cname)
+                temps.append(cname)
+                _shuffle_column(ctx, pt, pc, pname)
+                temps.append(pname)
+                plan.redirect(i, 0, cname)
+                plan.redirect(i, 1, pname)
+                redirected += [(i, 0), (i, 1)]
+        plan.execute_partial(ctx, table)
+        blobs = allgather_blobs(plan.partial_export())
+        merge_partials(plan, blobs)
+    finally:
+        for i, which in redirected:
+            plan.redirect(i, which, None)
+        for name in temps:
+            ctx.deregister_table(name)

@@ -185,3 +185,23 @@ def check_expect(result_status, metric, message, expect, what=""):
         assert message is not None and frag in message, f"{what}: message {message!r} lacks {frag!r}"
     if expect.get("message_none"):
         assert message is None, f"{what}: message {message!r}"
+
+
+# ---- numpy restatement of the key hash of term_b200/csrc/hash_common.cuh (test infrastructure) ----
+def fmix64_np(k):
+    import numpy as np
+    k = np.asarray(k).astype(np.uint64)
+    with np.errstate(over="ignore"):
+        k = k ^ (k >> np.uint64(33))
+        k = k * np.uint64(0xff51afd7ed558ccd)
+        k = k ^ (k >> np.uint64(33))
+        k = k * np.uint64(0xc4ceb9fe1a85ec53)
+        k = k ^ (k >> np.uint64(33))
+    return k
+
+
+def hash_rank_np(keys_i64, world):
+    """destination rank of the multi-GPU shuffle: ((hash >> 42) * world) >> 22"""
+    import numpy as np
+    h = fmix64_np(np.asarray(keys_i64).view(np.uint64))
+    return (((h >> np.uint64(42)) * np.uint64(world)) >> np.uint64(22)).astype(np.int64)

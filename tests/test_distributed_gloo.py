@@ -143,3 +143,81 @@ def test_partial_blob_roundtrip_and_rejects_foreign_blobs(built_lib):
         small.partial_merge(blob)
     with pytest.raises(T.TermGpuError):
         plan.partial_merge(blob[: len(blob) // 2])
+
+
+# ---- hash shuffle for uniqueness / foreign key: all-to-all over gloo, states add up exactly ----
+def _shuffle_table():
+    rng = np.random.default_rng(5)
+    n = 30_011
+    k = rng.integers(0, n // 2, n)
+    k[rng.random(n) < 0.01] = -1
+    return pa.table({"k": pa.array(k, mask=rng.random(n) < 0.05)})
+
+
+def _distinct_blob(plan, keys, n_nulls):
+    """partial blob of a hash shard: A_DISTINCT state u0 rows u1 distinct u2 singleton groups u3/u4 NULL rows
+    u5 distinct with NULL as a value (term_b200/csrc/plan.hpp)"""
+    aggs = plan.aggregates()
+    assert [k for k, _ in aggs] == [6]
+    _, counts = np.unique(keys, return_counts=True)
+    d, singles = len(counts), int((counts == 1).sum())
+    u = [len(keys) + n_nulls, d, singles + (1 if n_nulls == 1 else 0), n_nulls, n_nulls, d + (1 if n_nulls else 0), 0, 0]
+    return (struct.pack("<Q", 1) + struct.pack("<QQ", 6, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *([0.0] * 8)) +
+            struct.pack("<QQ", 0, 0))
+
+
+def shuffle_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import term_b200 as T
+        from term_b200.distributed import allgather_blobs, merge_partials, shuffle_keys
+        from tests.helpers import hash_rank_np
+        t = _shuffle_table()
+        n = t.num_rows
+        shard = t.slice(n * rank // world, n * (rank + 1) // world - n * rank // world)
+        vals = np.asarray(shard.column("k").fill_null(0))
+        ok = np.asarray(shard.column("k").is_valid())
+        keys = vals[ok]
+        dest = hash_rank_np(keys, world)  # what tg_table_partition_keys computes on the device
+        order = np.argsort(dest, kind="stable")
+        counts = [int((dest == r).sum()) for r in range(world)]
+        mine, my_nulls = shuffle_keys(torch.from_numpy(keys[order].copy()), counts, int((~ok).sum()))
+        mine = mine.numpy()
+        assert (hash_rank_np(mine, world) == rank).all(), "received a key that hashes to another rank"
+        plan = T.Plan()
+        slot = T.UniquenessConstraint(["k"], T.UniquenessType.UniqueValueRatio, assertion=T.Assertion.GreaterThan(0.0))._add_to(plan)
+        slot2 = T.DistinctnessAnalyzer("k")._add_to(plan)
+        blobs = allgather_blobs(_distinct_blob(plan, mine, my_nulls))
+        merge_partials(plan, blobs)
+        r = plan.result(slot)
+        a = plan.analyzer_result(slot2)
+        q.put((rank, (r.status.name, r.metric, r.message, a.u[:2], a.metric_double, len(mine))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_hash_shuffle_uniqueness(built_lib):
+    from oracle import term_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=shuffle_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert results[0][:5] == results[1][:5], "ranks disagree after the merge"
+    t = _shuffle_table()
+    o = O.uniqueness(t, ["k"], "UniqueValueRatio", 1.0, ("GreaterThan", 0.0))
+    nn, d, m = O.an_distinctness(t, "k")
+    status, metric, message, u, md, _ = results[0]
+    assert status.lower() == o.status and metric == o.metric and message == o.message
+    assert u == [nn, d] and md == m
+    assert results[0][5] + results[1][5] == nn, "every valid key lands on exactly one rank"
+    assert min(results[0][5], results[1][5]) > nn // 4, "the hash split is badly skewed"

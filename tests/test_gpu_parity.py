@@ -429,6 +429,112 @@ def test_foreign_key_matches_oracle(ctx, kind):
         ctx.deregister_table("fkc")
 
 
+# ---------------------------------------------------------------- multi-GPU shuffle pieces on one GPU ----
+def _shard_tables(ctx, table, column, world, prefix):
+    """tg_table_partition_keys, then register part r (+ all NULL rows on part 0) as table f"{prefix}{r}": what every
+    rank holds after the all-to-all of term_b200.distributed when there is a single sender."""
+    import torch
+    from term_b200 import distributed as D
+    ptr, counts, nulls = ctx.partition_keys(table, column, world)
+    dev = torch.device("cuda", 0)
+    keys = D._tensor_from_ptr(ptr, sum(counts), dev).clone() if sum(counts) else torch.empty(0, dtype=torch.int64, device=dev)
+    off = 0
+    parts = []
+    for r in range(world):
+        part = keys[off: off + counts[r]]
+        off += counts[r]
+        D._adopt_shard(ctx, f"{prefix}{r}", column, ctx.column_dtype(table, column), part, nulls if r == 0 else 0)
+        parts.append(part.cpu().numpy())
+    return parts, counts, nulls
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+def test_partition_keys_matches_host_hash_split(ctx, world):
+    n = 400_000
+    rng = np.random.default_rng(world)
+    k = rng.integers(-2**62, 2**62, n)
+    k[rng.random(n) < 0.01] = -1
+    mask = rng.random(n) < 0.03
+    ctx.register_table("pk_src", pa.table({"k": pa.array(k, mask=mask)}))
+    try:
+        parts, counts, nulls = _shard_tables(ctx, "pk_src", "k", world, "pk_part")
+        valid = k[~mask]
+        dest = H.hash_rank_np(valid, world)
+        assert nulls == int(mask.sum()) and sum(counts) == len(valid)
+        for r in range(world):
+            assert counts[r] == int((dest == r).sum())
+            assert np.array_equal(np.sort(parts[r]), np.sort(valid[dest == r]))
+    finally:
+        ctx.deregister_table("pk_src")
+        for r in range(world):
+            ctx.deregister_table(f"pk_part{r}")
+
+
+def test_shuffled_shards_merge_to_single_table_answer(ctx):
+    """uniqueness (every flavour) and foreign key evaluated shard by shard through tg_plan_redirect_aggregate and
+    merged with tg_plan_partial_merge must equal the single-table evaluation bit for bit"""
+    world = 4
+    n = 300_000
+    rng = np.random.default_rng(3)
+    k = rng.integers(0, n // 2, n)
+    k[rng.random(n) < 0.01] = -1
+    f = rng.integers(0, n // 3, n).astype(np.float64) / 4.0
+    parents = rng.permutation(n)[: n // 3].astype(np.int64)
+    ctx.register_table("sh_data", pa.table({"k": pa.array(k, mask=rng.random(n) < 0.03), "f": pa.array(f, mask=rng.random(n) < 0.03)}))
+    ctx.register_table("sh_parent", pa.table({"id": pa.array(parents)}))
+    names = []
+    try:
+        plan = T.Plan()
+        slots = []
+        for col in ("k", "f"):
+            for ut, kw in ((T.UniquenessType.FullUniqueness, dict(threshold=0.5)),
+                           (T.UniquenessType.UniqueValueRatio, dict(assertion=T.Assertion.GreaterThan(0.1))),
+                           (T.UniquenessType.PrimaryKey, {}),
+                           (T.UniquenessType.UniqueWithNulls, dict(threshold=0.5, null_handling=T.NullHandling.Include))):
+                slots.append(T.UniquenessConstraint([col], ut, **kw)._add_to(plan))
+        slots.append(T.ForeignKeyConstraint("sh_data.k", "sh_parent.id")._add_to(plan))
+        plan.execute(ctx, "sh_data")
+        want = [plan.result(s) for s in slots]
+        # shard every key column like the all-to-all would
+        for col, pre in (("k", "sh_k"), ("f", "sh_f")):
+            _shard_tables(ctx, "sh_data", col, world, pre)
+            names += [f"{pre}{r}" for r in range(world)]
+        _shard_tables(ctx, "sh_parent", "id", world, "sh_p")
+        names += [f"sh_p{r}" for r in range(world)]
+        aggs = plan.aggregates()
+        blobs = []
+        for r in range(world):
+            for i, (kind, key) in enumerate(aggs):
+                if kind == 6:
+                    plan.redirect(i, 0, f"sh_{key.split('|')[1]}{r}")
+                elif kind == 7:
+                    plan.redirect(i, 0, f"sh_k{r}")
+                    plan.redirect(i, 1, f"sh_p{r}")
+            # the other ranks' row shards are empty in this single-sender emulation: execute on the full table for
+            # rank 0 only (row-sharded aggregates do not exist in this plan)
+            plan.execute_partial(ctx, "sh_data")
+            blobs.append(plan.partial_export())
+        for i, (kind, _) in enumerate(aggs):
+            plan.redirect(i, 0, None)
+            if kind == 7:
+                plan.redirect(i, 1, None)
+        plan.partial_reset()
+        for b in blobs:
+            plan.partial_merge(b)
+        plan.finalize()
+        got = [plan.result(s) for s in slots]
+        for g, w in zip(got[:-1], want[:-1]):
+            assert (g.status, g.metric, g.message) == (w.status, w.metric, w.message)
+        g, w = got[-1], want[-1]
+        assert g.status == w.status and g.metric == w.metric
+        assert g.message.split("Examples")[0] == w.message.split("Examples")[0]
+    finally:
+        ctx.deregister_table("sh_data")
+        ctx.deregister_table("sh_parent")
+        for nm in names:
+            ctx.deregister_table(nm)
+
+
 def test_grouped_completeness_matches_oracle(ctx):
     rng = np.random.default_rng(5)
     n = 100_000

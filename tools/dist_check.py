@@ -1,0 +1,148 @@
+#!/usr/bin/env python3
+"""Multi-GPU parity + timing check (run under torchrun, one rank per GPU, NCCL):
+every rank holds a row shard; execute_distributed (row-sharded partials + hash shuffle of uniqueness / foreign-key
+keys over NCCL all-to-all) must reproduce, bit for bit, what ONE GPU computes on the concatenated tables.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29611 \
+        tools/dist_check.py [--rows 20000000]
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import term_b200 as T  # noqa: E402
+from term_b200 import _ffi as F  # noqa: E402
+from term_b200.distributed import execute_distributed  # noqa: E402
+
+
+def bitmap(mask):
+    n = mask.numel()
+    padn = (-n) % 8
+    if padn:
+        mask = torch.cat([mask, torch.zeros(padn, dtype=torch.bool, device=mask.device)])
+    w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=mask.device)
+    packed = (mask.view(-1, 8).to(torch.uint8) * w).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+    out = torch.zeros(packed.numel() + 320 - packed.numel() % 64, dtype=torch.uint8, device=mask.device)
+    out[: packed.numel()] = packed
+    return out
+
+
+def pad(t):
+    return torch.cat([t, torch.zeros(64, dtype=t.dtype, device=t.device)])
+
+
+def register(ctx, name, cols):
+    spec, keep = {}, []
+    for c, (vals, valid) in cols.items():
+        v = pad(vals)
+        b = bitmap(valid) if valid is not None else None
+        keep += [v, b]
+        spec[c] = dict(dtype=F.TG_FLOAT64 if vals.dtype == torch.float64 else F.TG_INT64, n_rows=vals.numel(), values=v.data_ptr(),
+                       validity=b.data_ptr() if b is not None else None)
+    ctx.register_device_table(name, spec, keepalive=keep)
+
+
+def gather(t, world):
+    sizes = [torch.zeros(1, dtype=torch.int64, device=t.device) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([t.numel()], dtype=torch.int64, device=t.device))
+    cap = int(max(s.item() for s in sizes))
+    buf = torch.zeros(cap, dtype=t.dtype, device=t.device)
+    buf[: t.numel()] = t
+    outs = [torch.zeros(cap, dtype=t.dtype, device=t.device) for _ in range(world)]
+    dist.all_gather(outs, buf)
+    return torch.cat([o[: int(s.item())] for o, s in zip(outs, sizes)])
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--rows", type=int, default=20_000_000, help="child / key rows per GPU")
+    ap.add_argument("--sparse", action="store_true", help="sparse keys (radix-partitioned hash path instead of bitmaps)")
+    a = ap.parse_args()
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    ctx = T.SessionContext(local)
+    g = torch.Generator(device=dev)
+    g.manual_seed(100 + rank)
+    n, m = a.rows, max(1000, a.rows // 10)
+    mul = 1_000_003 if a.sparse else 1
+    total_parents = m * world
+    # global parent ids = 0..total_parents-1 (x mul), sharded contiguously; children draw from a slightly larger range
+    parent = (torch.arange(rank * m, (rank + 1) * m, device=dev, dtype=torch.int64)[torch.randperm(m, generator=g, device=dev)]) * mul
+    child = torch.randint(0, int(total_parents * 1.0001) + 1, (n,), generator=g, device=dev, dtype=torch.int64) * mul
+    child_valid = torch.rand(n, generator=g, device=dev) >= 0.01
+    keys = (torch.randperm(n, generator=g, device=dev, dtype=torch.int64) + rank * n) * mul
+    dup = torch.randint(0, n, (max(1, n // 1000),), generator=g, device=dev)
+    keys[dup] = (torch.randint(0, n * world, (dup.numel(),), generator=g, device=dev, dtype=torch.int64)) * mul  # cross-rank duplicates
+    keys_valid = torch.rand(n, generator=g, device=dev) >= 0.01
+    x = torch.empty(n, dtype=torch.float64, device=dev).normal_(100.0, 15.0, generator=g)
+    x_valid = torch.rand(n, generator=g, device=dev) >= 0.05
+    register(ctx, "orders", {"customer_id": (child, child_valid), "order_key": (keys, keys_valid), "amount": (x, x_valid)})
+    register(ctx, "customers", {"id": (parent, None)})
+
+    A = T.Assertion
+    check = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
+             .validates_uniqueness(["order_key"], 0.9)
+             .foreign_key("orders.customer_id", "customers.id").build())
+    suite = T.ValidationSuite.builder("dist").table_name("orders").check(check).build()
+    plan, slots = suite.build_plan()
+    extra = T.UniquenessConstraint(["order_key"], T.UniquenessType.UniqueValueRatio, assertion=A.GreaterThan(0.0))._add_to(plan)
+    for _ in range(2):
+        execute_distributed(plan, ctx, "orders")
+    dist.barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    reps = 3
+    for _ in range(reps):
+        execute_distributed(plan, ctx, "orders")
+    dist.barrier()
+    torch.cuda.synchronize()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    got = [plan.result(s) for _, _, s in slots] + [plan.result(extra)]
+    got = [(r.name, r.status.name, r.metric, (r.message or "").split("Examples")[0]) for r in got]
+
+    # reference: everything on rank 0's GPU
+    full = {"customer_id": gather(child, world), "cv": gather(child_valid.to(torch.uint8), world).bool(),
+            "order_key": gather(keys, world), "kv": gather(keys_valid.to(torch.uint8), world).bool(),
+            "amount": gather(x, world), "av": gather(x_valid.to(torch.uint8), world).bool(), "parent": gather(parent, world)}
+    ok = True
+    if rank == 0:
+        register(ctx, "orders_all", {"customer_id": (full["customer_id"], full["cv"]), "order_key": (full["order_key"], full["kv"]),
+                                     "amount": (full["amount"], full["av"])})
+        register(ctx, "customers_all", {"id": (full["parent"], None)})
+        check1 = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
+                  .validates_uniqueness(["order_key"], 0.9)
+                  .foreign_key("orders_all.customer_id", "customers_all.id").build())
+        s1 = T.ValidationSuite.builder("single").table_name("orders_all").check(check1).build()
+        p1, sl1 = s1.build_plan()
+        e1 = T.UniquenessConstraint(["order_key"], T.UniquenessType.UniqueValueRatio, assertion=A.GreaterThan(0.0))._add_to(p1)
+        p1.execute(ctx, "orders_all")
+        want = [p1.result(s) for _, _, s in sl1] + [p1.result(e1)]
+        want = [(r.name, r.status.name, r.metric, (r.message or "").split("Examples")[0].replace("orders_all", "orders").replace("customers_all", "customers"))
+                for r in want]
+        for gg, ww in zip(got, want):
+            exact = gg[0] != "mean"
+            same = gg[1] == ww[1] and gg[3] == ww[3] and (gg[2] == ww[2] if exact else abs(gg[2] - ww[2]) <= 1e-9 * abs(ww[2]))
+            ok = ok and same
+            if not same:
+                print("MISMATCH", gg, ww, flush=True)
+        print(json.dumps({"check": "multi_gpu_parity", "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
+                          "ok": ok, "ms_per_execute": ms, "results": got}), flush=True)
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    dist.broadcast(flag, 0)
+    ctx.close()
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
