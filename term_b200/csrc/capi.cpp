@@ -101,6 +101,7 @@ void tg_engine_destroy(tg_engine* h) {
     e.dev_trim();
     if (e.d_scratch) cudaFree(e.d_scratch);
     if (e.d_shuffle) cudaFree(e.d_shuffle);
+    if (e.d_aux) cudaFree(e.d_aux);
     if (e.h_scratch) cudaFreeHost(e.h_scratch);
     for (int i = 0; i < 2; ++i) {
         if (e.pinned[i]) cudaFreeHost(e.pinned[i]);

@@ -23,6 +23,19 @@ uint8_t* Engine::scratch(size_t bytes) {
     return d_scratch;
 }
 
+uint8_t* Engine::aux(size_t bytes) {
+    if (bytes > aux_cap) {
+        TG_CUDA(cudaStreamSynchronize(stream));
+        if (d_aux) TG_CUDA(cudaFree(d_aux));
+        d_aux = nullptr;
+        aux_cap = 0;
+        const size_t ncap = round_up(std::max(bytes, (size_t)1 << 20), 1 << 20);
+        TG_CUDA(cudaMalloc(&d_aux, ncap));
+        aux_cap = ncap;
+    }
+    return d_aux;
+}
+
 uint8_t* Engine::host_scratch(size_t bytes) {
     if (bytes > h_scratch_cap) {
         if (h_scratch) TG_CUDA(cudaFreeHost(h_scratch));

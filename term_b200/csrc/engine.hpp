@@ -106,6 +106,9 @@ struct Engine {
     void dev_free(uint8_t* p, size_t bytes);
     void dev_trim();
 
+    uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
+    size_t aux_cap = 0;
+    uint8_t* aux(size_t bytes);
     uint8_t* scratch(size_t bytes);
     uint8_t* host_scratch(size_t bytes);
     void dev_reserve(DevBuf& b, size_t need, size_t keep_bytes);

@@ -55,4 +55,53 @@ __device__ __forceinline__ void flush_counter(unsigned long long v, unsigned lon
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
+// ---- 128-bit fingerprints of Utf8 / composite keys ----
+struct Fp {
+    uint64_t h1, h2;
+};
+constexpr uint64_t NULL_TAG1 = 0x9ae16a3b2f90404full, NULL_TAG2 = 0xc3a5c85c97cb3127ull;
+
+__device__ __forceinline__ void fp_combine(Fp& acc, uint64_t a, uint64_t b, bool first) {
+    if (first) {
+        acc.h1 = fmix64(a ^ 0x2545f4914f6cdd1dull);
+        acc.h2 = fmix64(b + 0x9e3779b97f4a7c15ull);
+    } else {
+        acc.h1 = fmix64(acc.h1 * 0x9e3779b97f4a7c15ull + a);
+        acc.h2 = fmix64((acc.h2 ^ b) * 0xd6e8feb86659fd93ull + 0x632be59bd9b4e019ull);
+    }
+}
+
+
+struct Table128 {
+    unsigned long long* h1;
+    unsigned long long* h2;
+    uint32_t* counts;
+    uint64_t mask;
+};
+
+// find-or-insert a fingerprint; returns the slot and whether this call created it
+__device__ __forceinline__ uint64_t upsert128(const Table128& t, Fp f, bool& created) {
+    uint64_t a = f.h1 == EMPTY64 ? 0 : f.h1, b = f.h2 == EMPTY64 ? 0 : f.h2;
+    uint64_t slot = (a ^ (b >> 32)) & t.mask;
+    created = false;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&t.h1[slot], EMPTY64, (unsigned long long)a);
+        if (prev == EMPTY64) {
+            // claimed: publish the second word
+            atomicExch(&t.h2[slot], (unsigned long long)b);
+            created = true;
+            return slot;
+        }
+        if (prev == a) {
+            unsigned long long v;
+            do {
+                v = *reinterpret_cast<volatile unsigned long long*>(&t.h2[slot]);
+            } while (v == EMPTY64);
+            if (v == b) return slot;
+        }
+        slot = (slot + 1) & t.mask;
+    }
+}
+
+
 }  // namespace tg

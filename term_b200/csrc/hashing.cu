@@ -62,21 +62,6 @@ __global__ void __launch_bounds__(HASH_THREADS) insert64_kernel(const uint64_t* 
 }
 
 // ---------------------------------------------------------------- path B: 128-bit fingerprints ----
-struct Fp {
-    uint64_t h1, h2;
-};
-constexpr uint64_t NULL_TAG1 = 0x9ae16a3b2f90404full, NULL_TAG2 = 0xc3a5c85c97cb3127ull;
-
-__device__ __forceinline__ void fp_combine(Fp& acc, uint64_t a, uint64_t b, bool first) {
-    if (first) {
-        acc.h1 = fmix64(a ^ 0x2545f4914f6cdd1dull);
-        acc.h2 = fmix64(b + 0x9e3779b97f4a7c15ull);
-    } else {
-        acc.h1 = fmix64(acc.h1 * 0x9e3779b97f4a7c15ull + a);
-        acc.h2 = fmix64((acc.h2 ^ b) * 0xd6e8feb86659fd93ull + 0x632be59bd9b4e019ull);
-    }
-}
-
 // fixed-width column -> fingerprint update; nullflag[row] |= 1 when the component is NULL
 __global__ void fp_fixed_kernel(const uint8_t* values, const uint32_t* validity, int64_t n, int dtype, int first,
                                 Fp* fp, uint8_t* nullflag) {
@@ -130,37 +115,6 @@ __global__ void fp_utf8_kernel(const int32_t* offsets, const uint8_t* bytes, con
             if (first) nullflag[row] = 0;
         }
         fp[row] = acc;
-    }
-}
-
-struct Table128 {
-    unsigned long long* h1;
-    unsigned long long* h2;
-    uint32_t* counts;
-    uint64_t mask;
-};
-
-// find-or-insert a fingerprint; returns the slot and whether this call created it
-__device__ __forceinline__ uint64_t upsert128(const Table128& t, Fp f, bool& created) {
-    uint64_t a = f.h1 == EMPTY64 ? 0 : f.h1, b = f.h2 == EMPTY64 ? 0 : f.h2;
-    uint64_t slot = (a ^ (b >> 32)) & t.mask;
-    created = false;
-    while (true) {
-        const unsigned long long prev = atomicCAS(&t.h1[slot], EMPTY64, (unsigned long long)a);
-        if (prev == EMPTY64) {
-            // claimed: publish the second word
-            atomicExch(&t.h2[slot], (unsigned long long)b);
-            created = true;
-            return slot;
-        }
-        if (prev == a) {
-            unsigned long long v;
-            do {
-                v = *reinterpret_cast<volatile unsigned long long*>(&t.h2[slot]);
-            } while (v == EMPTY64);
-            if (v == b) return slot;
-        }
-        slot = (slot + 1) & t.mask;
     }
 }
 
@@ -312,52 +266,6 @@ __global__ void __launch_bounds__(HASH_THREADS) fk_probe128_kernel(const Fp* fp,
     flush_counter(viol, &ctr->violations);
     flush_counter(nullc, &ctr->null_children);
     if (collect) flush_counter(dist, &ctr->distinct_all);
-}
-
-// ---------------------------------------------------------------- grouped completeness ----
-// table entry: fingerprint of the group tuple -> (total rows, non-null target rows, first row index)
-__global__ void __launch_bounds__(HASH_THREADS) group_count_kernel(const Fp* fp, int64_t n, const uint32_t* target_validity,
-                                                                   Table128 t, unsigned long long* totals, unsigned long long* nonnull,
-                                                                   long long* first_row, unsigned long long* n_groups) {
-    for (int64_t base = (int64_t)blockIdx.x * blockDim.x; base < n; base += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t row = base + threadIdx.x;
-        const bool active = row < n;
-        uint64_t slot = ~0ull;
-        bool created = false;
-        if (active) slot = upsert128(t, fp[row], created);
-        if (created) {
-            atomicAdd(n_groups, 1ull);
-            atomicMin(&first_row[slot], (long long)row);
-        } else if (active) {
-            atomicMin(&first_row[slot], (long long)row);
-        }
-        // warp-aggregated counting: one atomic per distinct slot per warp
-        const unsigned amask = __ballot_sync(0xffffffffu, active);
-        if (active) {
-            const unsigned peers = __match_any_sync(amask, slot);
-            const bool ok = row_valid(target_validity, row);
-            const unsigned ok_peers = __ballot_sync(peers, ok) & peers;
-            if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-                atomicAdd(&totals[slot], (unsigned long long)__popc(peers));
-                const int c = __popc(ok_peers);
-                if (c) atomicAdd(&nonnull[slot], (unsigned long long)c);
-            }
-        }
-    }
-}
-
-__global__ void group_collect_kernel(Table128 t, const unsigned long long* totals, const unsigned long long* nonnull,
-                                     const long long* first_row, uint64_t cap, unsigned long long* out_n, uint64_t max_out,
-                                     unsigned long long* out /* [max_out][3] = first_row, total, nonnull */) {
-    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
-        if (t.h1[s] == EMPTY64) continue;
-        const unsigned long long i = atomicAdd(out_n, 1ull);
-        if (i < max_out) {
-            out[i * 3 + 0] = (unsigned long long)first_row[s];
-            out[i * 3 + 1] = totals[s];
-            out[i * 3 + 2] = nonnull[s];
-        }
-    }
 }
 
 // ================================================================== host side ==================
@@ -704,79 +612,6 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
         a.blob.resize(o + 4 + L);
         memcpy(a.blob.data() + o, &L, 4);
         memcpy(a.blob.data() + o + 4, s.data(), L);
-    }
-}
-
-void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id) {
-    Agg& a = p.aggs[agg_id];
-    Column* target = need_col(t, a.cols[0]);
-    std::vector<Column*> gcols;
-    for (size_t i = 1; i < a.cols.size(); ++i) gcols.push_back(need_col(t, a.cols[i]));
-    const int64_t n = t.n_rows;
-    for (auto* c : gcols) p.stats.bytes_scanned += col_bytes(*c, n);
-    if (target->validity.p) p.stats.bytes_scanned += (uint64_t)(n + 7) / 8;
-    uint64_t zero = 0;
-    a.blob.assign((uint8_t*)&zero, (uint8_t*)&zero + 8);
-    if (n == 0) return;
-    const uint64_t max_groups_dev = 1u << 20;
-    const uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, max_groups_dev * 4));
-    const size_t fp_b = round_up((size_t)n * 16, 256), nf_b = round_up((size_t)n, 256), h_b = cap * 8;
-    const size_t out_b = round_up((size_t)max_groups_dev * 24, 256);
-    uint8_t* scr = e.scratch(fp_b + nf_b + 5 * h_b + out_b + 256);
-    uint8_t* q = scr;
-    Fp* d_fp = (Fp*)q; q += fp_b;
-    uint8_t* d_null = q; q += nf_b;
-    Table128 tb{(unsigned long long*)q, (unsigned long long*)(q + h_b), nullptr, cap - 1}; q += 2 * h_b;
-    unsigned long long* totals = (unsigned long long*)q; q += h_b;
-    unsigned long long* nonnull = (unsigned long long*)q; q += h_b;
-    long long* first_row = (long long*)q; q += h_b;
-    unsigned long long* d_out = (unsigned long long*)q; q += out_b;
-    unsigned long long* d_n = (unsigned long long*)q;
-    Timer tm(e, p);
-    TG_CUDA(cudaMemsetAsync(tb.h1, 0xFF, 2 * h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(totals, 0, 2 * h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(first_row, 0x7F, h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(d_n, 0, 256, e.stream));
-    int launches = compute_fingerprints(e, t, gcols, d_fp, d_null);
-    group_count_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>(d_fp, n, (const uint32_t*)target->validity.p, tb, totals, nonnull,
-                                                                      first_row, d_n);
-    TG_CUDA(cudaGetLastError());
-    unsigned long long n_groups = 0;
-    TG_CUDA(cudaMemcpyAsync(&n_groups, d_n, 8, cudaMemcpyDeviceToHost, e.stream));
-    TG_CUDA(cudaStreamSynchronize(e.stream));
-    if (n_groups > max_groups_dev) {
-        tm.stop(launches + 1);
-        throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 1048576 groups");
-    }
-    group_collect_kernel<<<grid_for(e, (int64_t)cap), HASH_THREADS, 0, e.stream>>>(tb, totals, nonnull, first_row, cap, d_n + 1,
-                                                                                  max_groups_dev, d_out);
-    TG_CUDA(cudaGetLastError());
-    std::vector<unsigned long long> out((size_t)n_groups * 3);
-    if (n_groups) TG_CUDA(cudaMemcpyAsync(out.data(), d_out, out.size() * 8, cudaMemcpyDeviceToHost, e.stream));
-    tm.stop(launches + 2);
-    // group keys: string value of each group column at the group's first row, joined by \x1f
-    a.blob.resize(8);
-    memcpy(a.blob.data(), &n_groups, 8);
-    for (unsigned long long g = 0; g < n_groups; ++g) {
-        const int64_t row = (int64_t)out[g * 3];
-        std::string key;
-        for (size_t i = 0; i < gcols.size(); ++i) {
-            if (i) key += '\x1f';
-            bool valid = true;
-            if (gcols[i]->validity.p) {
-                uint8_t b;
-                TG_CUDA(cudaMemcpy(&b, gcols[i]->validity.p + (row >> 3), 1, cudaMemcpyDeviceToHost));
-                valid = (b >> (row & 7)) & 1;
-            }
-            key += valid ? row_to_string(e, *gcols[i], row) : std::string("NULL");
-        }
-        uint32_t L = (uint32_t)key.size();
-        size_t o = a.blob.size();
-        a.blob.resize(o + 4 + L + 16);
-        memcpy(a.blob.data() + o, &L, 4);
-        memcpy(a.blob.data() + o + 4, key.data(), L);
-        memcpy(a.blob.data() + o + 4 + L, &out[g * 3 + 1], 8);
-        memcpy(a.blob.data() + o + 4 + L + 8, &out[g * 3 + 2], 8);
     }
 }
 
