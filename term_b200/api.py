@@ -399,11 +399,16 @@ class Plan:
 
     def aggregates(self):
         """[(kind, key)] of the plan's device aggregates, in partial-blob order."""
+        n = F.lib().tg_plan_num_aggregates(self._h)
+        cached = getattr(self, "_aggs_cache", None)
+        if cached is not None and len(cached) == n:  # aggregates are only ever appended
+            return cached
         out = []
-        for i in range(F.lib().tg_plan_num_aggregates(self._h)):
+        for i in range(n):
             k, key = C.c_int32(), C.c_char_p()
             F.check(F.lib().tg_plan_aggregate_info(self._h, i, C.byref(k), C.byref(key)))
             out.append((k.value, key.value.decode()))
+        self._aggs_cache = out
         return out
 
     def result(self, slot: int) -> ConstraintResult:

@@ -51,6 +51,61 @@ def merge_partials(plan, blobs):
     plan.finalize()
 
 
+_FIXED_KINDS = {0, 1, 2, 3, 4, 5, 6, 10}  # aggregates whose partial record has a fixed size (no blob)
+_bufs = {}
+
+
+def allgather_blobs_fixed(blob: bytes, cap: int, device=None):
+    """One-collective all-gather for blobs whose size every rank can bound WITHOUT talking (a plan of fixed-size
+    aggregates): each rank sends [u64 length | payload] padded to `cap` bytes through cached pinned / device
+    buffers. Returns None when some rank's blob did not fit (all ranks see that and take the general path)."""
+    world = dist.get_world_size()
+    dev = _device(device)
+    key = (cap, str(dev), world)
+    b = _bufs.get(key)
+    if b is None:
+        pin = dev.type == "cuda"
+        b = dict(h_send=torch.zeros(cap, dtype=torch.uint8, pin_memory=pin), h_recv=torch.zeros(cap * world, dtype=torch.uint8, pin_memory=pin),
+                 d_send=torch.zeros(cap, dtype=torch.uint8, device=dev), d_recv=torch.zeros(cap * world, dtype=torch.uint8, device=dev))
+        _bufs[key] = b
+    n = len(blob)
+    fits = n + 8 <= cap
+    hs = b["h_send"].numpy()
+    hs[:8] = memoryview((n if fits else 0xFFFFFFFFFFFFFFFF).to_bytes(8, "little"))
+    if fits:
+        hs[8: 8 + n] = memoryview(blob)
+    if dev.type == "cuda":
+        b["d_send"].copy_(b["h_send"], non_blocking=True)
+        dist.all_gather_into_tensor(b["d_recv"], b["d_send"])
+        b["h_recv"].copy_(b["d_recv"], non_blocking=True)
+        torch.cuda.current_stream(dev).synchronize()
+        raw = b["h_recv"].numpy()
+    else:
+        outs = [torch.zeros(cap, dtype=torch.uint8) for _ in range(world)]
+        dist.all_gather(outs, b["h_send"])
+        raw = torch.cat(outs).numpy()
+    out = []
+    for r in range(world):
+        ln = int.from_bytes(raw[r * cap: r * cap + 8].tobytes(), "little")
+        if ln == 0xFFFFFFFFFFFFFFFF:
+            return None
+        out.append(raw[r * cap + 8: r * cap + 8 + ln].tobytes())
+    return out
+
+
+def exchange_partials(plan):
+    """All-gather this rank's partial blob; one collective when the plan's partial records are fixed-size."""
+    blob = plan.partial_export()
+    aggs = plan.aggregates()
+    if all(k in _FIXED_KINDS for k, _ in aggs):
+        # 8 (count) + per aggregate 8 + 8 + 64 + 64 + 8 + 8, plus room for an error message or two
+        cap = (8 + len(aggs) * 160 + 1024 + 4095) // 4096 * 4096
+        got = allgather_blobs_fixed(blob, cap)
+        if got is not None:
+            return got
+    return allgather_blobs(blob)
+
+
 def shuffle_keys(keys: torch.Tensor, counts, n_nulls: int):
     """All-to-all of hash-partitioned keys. `keys` (int64, grouped by destination rank) holds counts[r] keys for
     rank r. Returns (the keys this rank owns after the exchange, NULL rows this rank accounts for): every rank's
@@ -145,8 +200,7 @@ def execute_distributed(plan, ctx, table="data"):
                 plan.redirect(i, 1, pname)
                 redirected += [(i, 0), (i, 1)]
         plan.execute_partial(ctx, table)
-        blobs = allgather_blobs(plan.partial_export())
-        merge_partials(plan, blobs)
+        merge_partials(plan, exchange_partials(plan))
     finally:
         for i, which in redirected:
             plan.redirect(i, which, None)

@@ -85,12 +85,17 @@ def worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         import term_b200 as T
-        from term_b200.distributed import allgather_blobs, merge_partials
+        from term_b200.distributed import allgather_blobs, allgather_blobs_fixed, merge_partials
         t = make_table()
         lo, hi = N_ROWS * rank // world, N_ROWS * (rank + 1) // world
         plan, slots = build_plan(T)
-        blobs = allgather_blobs(shard_blob(plan, t.slice(lo, hi - lo)))
+        mine = shard_blob(plan, t.slice(lo, hi - lo))
+        blobs = allgather_blobs(mine)
         assert len(blobs) == world
+        # the one-collective path used for plans of fixed-size aggregates must deliver the same bytes; a blob that
+        # does not fit makes every rank fall back (None)
+        assert allgather_blobs_fixed(mine, 8192) == blobs
+        assert allgather_blobs_fixed(mine, 64) is None
         merge_partials(plan, blobs)
         res = [plan.result(s) for _, _, s in slots]
         q.put((rank, [(r.name, r.status.name, r.metric, r.message) for r in res]))
