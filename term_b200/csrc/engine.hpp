@@ -121,7 +121,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
 void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // strings.cu
 void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id);                     // hashing.cu
 void exec_fk_job(Engine& e, Plan& p, int agg_id);                                     // hashing.cu
-void exec_kll_job(Engine& e, Table& t, Plan& p, int agg_id);                          // sketch.cu
+void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);  // sketch.cu
 void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                      // hashing.cu
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
 
