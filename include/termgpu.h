@@ -295,6 +295,16 @@ TG_API int32_t tg_plan_add_custom_sql(tg_plan* plan, const char* expression, con
 TG_API int32_t tg_plan_add_foreign_key(tg_plan* plan, const char* child_column, const char* parent_column,
                                        int32_t allow_nulls, int32_t max_violations_reported);
 
+/* LengthConstraint::evaluate (constraints/length.rs:150-226); LengthAssertion (:20-60) as kind: 0 Min(a),
+ * 1 Max(a), 2 Between(a, b), 3 Exactly(a), 4 NotEmpty. LENGTH counts characters, not bytes. */
+typedef enum { TG_LEN_MIN = 0, TG_LEN_MAX = 1, TG_LEN_BETWEEN = 2, TG_LEN_EXACTLY = 3, TG_LEN_NOT_EMPTY = 4 } tg_length_kind;
+TG_API int32_t tg_plan_add_length(tg_plan* plan, const char* column, int32_t length_kind, int64_t a, int64_t b);
+/* ContainmentConstraint::evaluate (constraints/values.rs:232-296) */
+TG_API int32_t tg_plan_add_containment(tg_plan* plan, const char* column, const char* const* allowed_values,
+                                       int32_t n_values);
+/* NonNegativeConstraint::evaluate (constraints/values.rs:357-414) */
+TG_API int32_t tg_plan_add_non_negative(tg_plan* plan, const char* column);
+
 /* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
 TG_API int32_t tg_plan_add_analyzer(tg_plan* plan, int32_t analyzer_kind, const char* column,
                                     const char* column2, const char* expression);
@@ -327,7 +337,7 @@ TG_API tg_status tg_plan_partial_reset(tg_plan* plan);
 TG_API tg_status tg_plan_partial_merge(tg_plan* plan, const void* buf, size_t n_bytes);
 TG_API tg_status tg_plan_finalize(tg_plan* plan);
 /* The de-duplicated device aggregates behind the slots, in partial-blob order: kind is one of
- * 0 ROWS, 1 VALID, 2 NUM, 3 PAIR, 4 PRED, 5 REGEX, 6 DISTINCT, 7 FK, 8 KLL, 9 GROUPED, 10 SPEARMAN; key is a
+ * 0 ROWS, 1 VALID, 2 NUM, 3 PAIR, 4 PRED, 5 REGEX, 6 DISTINCT, 7 FK, 8 KLL, 9 GROUPED, 10 SPEARMAN, 11 LENGTH; key is a
  * stable textual identity such as "num|price" (valid until the plan is destroyed). Lets a host that computed a
  * shard elsewhere (another engine, a stored IncrementalAnalysisRunner state) assemble a partial blob. */
 TG_API int32_t tg_plan_num_aggregates(const tg_plan* plan);

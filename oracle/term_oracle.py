@@ -807,6 +807,62 @@ def custom_sql(table, expression, hint=None) -> Result:
     return Result(FAILURE, ratio, msg)
 
 
+LENGTH_NAMES = {"Min": "min_length", "Max": "max_length", "Between": "length_between", "Exactly": "exact_length", "NotEmpty": "not_empty"}
+
+
+def length_constraint(table, column, kind, a=0, b=0) -> Result:
+    """constraints/length.rs:150-226: COUNT(CASE WHEN <cond on LENGTH(c)> OR c IS NULL THEN 1 END) * 1.0 /
+    NULLIF(COUNT(*), 0); LENGTH counts characters (Unicode scalar values); Success iff ratio >= 1.0."""
+    c = table_cols(table)[column]
+    n = len(c.valid)
+    if n == 0:
+        return Result(SKIPPED, None, "No data to validate")
+    lo, hi, desc = {"Min": (a, None, f"at least {a} characters"), "Max": (0, a, f"at most {a} characters"),
+                    "Between": (a, b, f"between {a} and {b} characters"), "Exactly": (a, a, f"exactly {a} characters"),
+                    "NotEmpty": (1, None, "not empty")}[kind]
+    ok = 0
+    for v, valid in zip(c.values, c.valid):
+        if not valid:
+            ok += 1
+            continue
+        L = len(v)  # Python str: code points == Unicode scalar values for valid UTF-8
+        if L >= lo and (hi is None or L <= hi):
+            ok += 1
+    ratio = float(ok) * 1.0 / float(n)
+    if ratio >= 1.0:
+        return Result(SUCCESS, ratio)
+    return Result(FAILURE, ratio, f"Length constraint failed: {rust_prec(ratio * 100.0, 2)}% of values are {desc}")
+
+
+def containment(table, column, allowed) -> Result:
+    """constraints/values.rs:232-296: valid = COUNT(CASE WHEN c IN (..) ..), total = COUNT(*) WHERE c IS NOT NULL"""
+    c = table_cols(table)[column]
+    allowed = set(str(v) for v in allowed)
+    vals = [v for v, ok in zip(c.values, c.valid) if ok]
+    total = float(len(vals))
+    if total == 0.0:
+        return Result(SKIPPED, None, "No non-null data to validate")
+    valid = float(sum(1 for v in vals if str(v) in allowed))
+    ratio = valid / total
+    if ratio == 1.0:
+        return Result(SUCCESS, ratio)
+    return Result(FAILURE, ratio, f"{rust_f64(total - valid)} values are not in the allowed set")
+
+
+def non_negative(table, column) -> Result:
+    """constraints/values.rs:357-414: COUNT(CASE WHEN CAST(c AS DOUBLE) >= 0 ..), COUNT(*) WHERE c IS NOT NULL"""
+    c = table_cols(table)[column]
+    vals = [float(v) for v, ok in zip(c.values, c.valid) if ok]
+    total = float(len(vals))
+    if total == 0.0:
+        return Result(SKIPPED, None, "No non-null data to validate")
+    nn = float(sum(1 for v in vals if v >= 0))  # NaN >= 0 is false here; Arrow's total order puts NaN last (unpinned)
+    ratio = nn / total
+    if ratio == 1.0:
+        return Result(SUCCESS, ratio)
+    return Result(FAILURE, ratio, f"{rust_f64(total - nn)} values are negative")
+
+
 def foreign_key(tables, child, parent, allow_nulls=False, max_examples=100):
     """constraints/foreign_key.rs:307-410: LEFT JOIN child->parent WHERE parent.col IS NULL [AND child.col IS
     NOT NULL] -> COUNT(*), COUNT(DISTINCT child.col). Returns (Result, total, unique)."""

@@ -521,6 +521,63 @@ class SizeConstraint(Constraint):  # constraints/size.rs
         return F.check_slot(F.lib().tg_plan_add_size(plan.handle, self.assertion.c()))
 
 
+class LengthAssertion:  # constraints/length.rs:20-60
+    """LengthAssertion::{Min, Max, Between, Exactly, NotEmpty}"""
+    def __init__(self, kind, a=0, b=0):
+        self.kind, self.a, self.b = kind, a, b
+
+    @staticmethod
+    def Min(n): return LengthAssertion(0, n)
+    @staticmethod
+    def Max(n): return LengthAssertion(1, n)
+    @staticmethod
+    def Between(a, b): return LengthAssertion(2, a, b)
+    @staticmethod
+    def Exactly(n): return LengthAssertion(3, n)
+    @staticmethod
+    def NotEmpty(): return LengthAssertion(4)
+
+
+class LengthConstraint(Constraint):  # constraints/length.rs:86-232
+    def __init__(self, column, assertion: LengthAssertion):
+        self.column, self.assertion = column, assertion
+        self._add_to(Plan())
+
+    @staticmethod
+    def min(c, n): return LengthConstraint(c, LengthAssertion.Min(n))
+    @staticmethod
+    def max(c, n): return LengthConstraint(c, LengthAssertion.Max(n))
+    @staticmethod
+    def between(c, a, b): return LengthConstraint(c, LengthAssertion.Between(a, b))
+    @staticmethod
+    def exactly(c, n): return LengthConstraint(c, LengthAssertion.Exactly(n))
+    @staticmethod
+    def not_empty(c): return LengthConstraint(c, LengthAssertion.NotEmpty())
+
+    def _add_to(self, plan):
+        a = self.assertion
+        return F.check_slot(F.lib().tg_plan_add_length(plan.handle, self.column.encode(), a.kind, a.a, a.b))
+
+
+class ContainmentConstraint(Constraint):  # constraints/values.rs:205-331
+    def __init__(self, column, allowed_values):
+        self.column, self.allowed_values = column, [str(v) for v in allowed_values]
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        arr = (C.c_char_p * max(1, len(self.allowed_values)))(*[v.encode() for v in self.allowed_values])
+        return F.check_slot(F.lib().tg_plan_add_containment(plan.handle, self.column.encode(), arr, len(self.allowed_values)))
+
+
+class NonNegativeConstraint(Constraint):  # constraints/values.rs:336-440
+    def __init__(self, column):
+        self.column = column
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_non_negative(plan.handle, self.column.encode()))
+
+
 class StatisticalConstraint(Constraint):  # constraints/statistics.rs:120-322
     def __init__(self, column, statistic: StatisticType, assertion: Assertion, percentile: float = 0.0):
         self.column, self.statistic, self.assertion, self.percentile = column, statistic, assertion, percentile
@@ -736,6 +793,13 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_variance(self, column, assertion): return self.statistic(column, StatisticType.Variance, assertion)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
+    # core/check.rs:518-625, 1777-1786
+    def has_min_length(self, column, n): return self.constraint(LengthConstraint.min(column, n))
+    def has_max_length(self, column, n): return self.constraint(LengthConstraint.max(column, n))
+    def has_length_between(self, column, a, b): return self.constraint(LengthConstraint.between(column, a, b))
+    def has_exact_length(self, column, n): return self.constraint(LengthConstraint.exactly(column, n))
+    def is_not_empty(self, column): return self.constraint(LengthConstraint.not_empty(column))
+    def length(self, column, assertion): return self.constraint(LengthConstraint(column, assertion))
     def foreign_key(self, child, parent): return self.constraint(ForeignKeyConstraint(child, parent))
 
     def build(self) -> Check:

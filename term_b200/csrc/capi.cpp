@@ -285,6 +285,15 @@ int32_t tg_plan_add_kll(tg_plan* p, const char* column, int32_t k, const double*
         return plan_add_kll(p->p, column ? column : "", k, v);
     });
 }
+int32_t tg_plan_add_length(tg_plan* p, const char* column, int32_t kind, int64_t a, int64_t b) {
+    return guard_slot([&] { return plan_add_length(p->p, column ? column : "", kind, a, b); });
+}
+int32_t tg_plan_add_containment(tg_plan* p, const char* column, const char* const* allowed, int32_t n) {
+    return guard_slot([&] { return plan_add_containment(p->p, column ? column : "", strvec(allowed, n)); });
+}
+int32_t tg_plan_add_non_negative(tg_plan* p, const char* column) {
+    return guard_slot([&] { return plan_add_non_negative(p->p, column ? column : ""); });
+}
 int32_t tg_plan_add_grouped_completeness(tg_plan* p, const char* column, const char* const* groups, int32_t n,
                                          int32_t max_groups, int32_t include_overall) {
     return guard_slot([&] {

@@ -670,7 +670,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
     e.sync_copies();
     auto it = e.tables.find(table_name);
     Table* t = it == e.tables.end() ? nullptr : it->second.get();
-    std::vector<int> scan_ids, string_ids, kll_ids;
+    std::vector<int> scan_ids, string_ids, kll_ids, length_ids;
     for (size_t i = 0; i < p.aggs.size(); ++i) {
         Agg& a = p.aggs[i];
         if (a.err != TG_OK) continue;
@@ -689,11 +689,13 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
             case A_PRED: scan_ids.push_back((int)i); break;
             case A_REGEX: string_ids.push_back((int)i); break;
             case A_KLL: kll_ids.push_back((int)i); break;
+            case A_LENGTH: length_ids.push_back((int)i); break;
             default: break;
         }
     }
     if (t && !scan_ids.empty()) exec_scan_jobs(e, *t, p, scan_ids);
     if (t && !string_ids.empty()) exec_string_jobs(e, *t, p, string_ids);
+    if (t && !length_ids.empty()) exec_length_jobs(e, *t, p, length_ids);
     if (t && !kll_ids.empty()) exec_kll_jobs(e, *t, p, kll_ids);
     for (size_t i = 0; i < p.aggs.size(); ++i) {
         Agg& a = p.aggs[i];

@@ -119,6 +119,7 @@ struct Engine {
 // jobs (each fills the partial state of the aggregates it owns)
 void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);   // engine.cu + scan.cu
 void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // strings.cu
+void exec_length_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // strings.cu
 void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id);                     // hashing.cu
 void exec_fk_job(Engine& e, Plan& p, int agg_id);                                     // hashing.cu
 void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);  // sketch.cu

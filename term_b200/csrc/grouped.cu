@@ -15,6 +15,7 @@
 
 #include "engine.hpp"
 #include "hash_common.cuh"
+#include "ptx.cuh"
 
 namespace tg {
 
@@ -42,15 +43,6 @@ struct GrpParams {
     long long* first_row;
     unsigned long long* n_groups;
 };
-
-// up to 8 bytes starting at bytes[p] (len <= 8), little endian, without reading past p + len rounded up to 8
-__device__ __forceinline__ uint64_t load_upto8(const uint8_t* bytes, int64_t p, int len) {
-    const int64_t a = p & ~(int64_t)7;
-    const int sh = (int)(p - a) * 8;
-    uint64_t w = __ldg(reinterpret_cast<const unsigned long long*>(bytes + a)) >> sh;
-    if (sh + len * 8 > 64) w |= __ldg(reinterpret_cast<const unsigned long long*>(bytes + a + 8)) << (64 - sh);
-    return len >= 8 ? w : (w & ((1ull << (len * 8)) - 1ull));
-}
 
 constexpr int GRP_ILP = 4;  // rows per thread per iteration: their loads are issued together
 

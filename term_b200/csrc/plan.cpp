@@ -452,6 +452,75 @@ int plan_add_kll(Plan& p, const std::string& col, int k, const std::vector<doubl
     return (int)p.slots.size() - 1;
 }
 
+// constraints/length.rs:20-60 (LengthAssertion), :150-226 (evaluate). kind: 0 Min(a) 1 Max(a) 2 Between(a, b)
+// 3 Exactly(a) 4 NotEmpty
+int plan_add_length(Plan& p, const std::string& col, int kind, int64_t a, int64_t b) {
+    validate_identifier(col);
+    if (kind < 0 || kind > 4 || a < 0 || b < 0) throw Error(TG_ERR_INVALID_ARG, "invalid length assertion");
+    if (kind == 2 && a > b) throw Error(TG_ERR_INVALID_ARG, "min_length must be <= max_length");  // length.rs:136 assert!
+    Slot s;
+    s.kind = SL_LENGTH;
+    s.columns = {col};
+    s.sub_kind = kind;
+    const std::string A = std::to_string(a), B = std::to_string(b);
+    int64_t lo = 0, hi = INT64_MAX;
+    switch (kind) {
+        case 0: s.name = "min_length"; s.arg = "at least " + A + " characters"; lo = a; break;
+        case 1: s.name = "max_length"; s.arg = "at most " + A + " characters"; hi = a; break;
+        case 2: s.name = "length_between"; s.arg = "between " + A + " and " + B + " characters"; lo = a; hi = b; break;
+        case 3: s.name = "exact_length"; s.arg = "exactly " + A + " characters"; lo = hi = a; break;
+        default: s.name = "not_empty"; s.arg = "not empty"; lo = 1; break;
+    }
+    Agg g;
+    g.kind = A_LENGTH;
+    g.key = "length|" + col + "|" + std::to_string(lo) + "|" + std::to_string(hi);
+    g.cols = {col};
+    g.lo = lo;
+    g.hi = hi;
+    s.aggs.push_back(p.add_agg(std::move(g)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
+// constraints/values.rs:217-296: COUNT(CASE WHEN c IN ('v', ..) THEN 1 END), COUNT(*) .. WHERE c IS NOT NULL
+int plan_add_containment(Plan& p, const std::string& col, const std::vector<std::string>& allowed) {
+    validate_identifier(col);
+    Slot s;
+    s.kind = SL_CONTAINMENT;
+    s.name = "containment";
+    s.columns = {col};
+    std::string expr = col + " IN (";
+    for (size_t i = 0; i < allowed.size(); ++i) {
+        if (i) expr += ", ";
+        expr += '\'';
+        for (char c : allowed[i]) {
+            expr += c;
+            if (c == '\'') expr += '\'';  // values.rs:241 doubles single quotes
+        }
+        expr += '\'';
+    }
+    expr += ")";
+    s.arg = expr;
+    s.aggs.push_back(p.add_agg(mk_pred(expr)));
+    s.aggs.push_back(p.add_agg(mk_valid(col)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
+// constraints/values.rs:347-414: COUNT(CASE WHEN CAST(c AS DOUBLE) >= 0 THEN 1 END), COUNT(*) .. WHERE c IS NOT NULL
+int plan_add_non_negative(Plan& p, const std::string& col) {
+    validate_identifier(col);
+    Slot s;
+    s.kind = SL_NON_NEGATIVE;
+    s.name = "non_negative";
+    s.columns = {col};
+    s.arg = col + " >= 0";
+    s.aggs.push_back(p.add_agg(mk_pred(s.arg)));
+    s.aggs.push_back(p.add_agg(mk_valid(col)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall) {
     if (groups.empty()) throw Error(TG_ERR_INVALID_ARG, "at least one grouping column is required");
@@ -558,6 +627,7 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
             case A_ROWS:
             case A_VALID:
             case A_REGEX:
+            case A_LENGTH:
                 for (int i = 0; i < 8; ++i) a.u[i] += u[i];
                 break;
             case A_PRED:
@@ -1067,6 +1137,40 @@ static void finalize_sql(Plan& p, Slot& s) {
     failure_metric(s, ratio, msg);
 }
 
+static void finalize_length(Plan& p, Slot& s) {
+    const Agg& a = p.aggs[s.aggs[0]];
+    if (a.err != TG_OK) {
+        set_error(s, a);
+        return;
+    }
+    const double rows = (double)a.u[2];
+    if (rows == 0.0) {  // NULLIF(COUNT(*), 0) -> NULL ratio
+        skipped(s, "No data to validate");
+        return;
+    }
+    const double ratio = (double)(a.u[0] + a.u[1]) * 1.0 / rows;
+    if (ratio >= 1.0) success_metric(s, ratio);
+    else failure_metric(s, ratio, "Length constraint failed: " + fmt_f64_prec(ratio * 100.0, 2) + "% of values are " + s.arg);
+}
+
+// containment / non_negative share the shape: matching rows / non-null rows (values.rs:245-296, 363-414)
+static void finalize_value_ratio(Plan& p, Slot& s, const char* what) {
+    const Agg& pred = p.aggs[s.aggs[0]];
+    const Agg& valid = p.aggs[s.aggs[1]];
+    if (pred.err != TG_OK || valid.err != TG_OK) {
+        set_error(s, pred.err != TG_OK ? pred : valid);
+        return;
+    }
+    const double ok = (double)pred.u[0], total = (double)valid.u[1];
+    if (total == 0.0) {
+        skipped(s, "No non-null data to validate");
+        return;
+    }
+    const double ratio = ok / total;
+    if (ratio == 1.0) success_metric(s, ratio);
+    else failure_metric(s, ratio, fmt_f64(total - ok) + what);
+}
+
 static void finalize_fk(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     if (a.err != TG_OK) {
@@ -1382,6 +1486,9 @@ void Plan::finalize() {
             case SL_ANALYZER: finalize_analyzer(*this, s); break;
             case SL_KLL: finalize_kll(*this, s); break;
             case SL_GROUPED: finalize_grouped(*this, s); break;
+            case SL_LENGTH: finalize_length(*this, s); break;
+            case SL_CONTAINMENT: finalize_value_ratio(*this, s, " values are not in the allowed set"); break;
+            case SL_NON_NEGATIVE: finalize_value_ratio(*this, s, " values are negative"); break;
         }
     }
     executed = true;

@@ -25,6 +25,7 @@ enum AggKind : int32_t {
     A_KLL = 8,       // blob = sketch
     A_GROUPED = 9,   // blob = group table
     A_SPEARMAN = 10, // same layout as A_PAIR over min-ranks
+    A_LENGTH = 11,   // COUNT(CASE WHEN lo <= LENGTH(c) <= hi ..)  u0 matching non-null rows u1 nulls u2 rows
 };
 
 struct Agg {
@@ -34,6 +35,7 @@ struct Agg {
     std::string text;                // predicate / regex pattern
     int32_t flags = 0;               // regex: bit0 case-insensitive, bit1 trim ; distinct: see hash job
     int32_t iparam = 0;              // KLL k / FK max examples / grouped max_groups
+    int64_t lo = 0, hi = 0;          // A_LENGTH: inclusive character-count range
     ExprP expr;                      // parsed predicate
     // multi-GPU shuffle: read this aggregate's keys from another registered table (the hash-shuffled shard) instead
     // of the plan's table; [0] = the table of a DISTINCT aggregate or the child table of an FK, [1] = the FK parent
@@ -70,6 +72,9 @@ enum SlotKind : int32_t {
     SL_ANALYZER,
     SL_KLL,
     SL_GROUPED,
+    SL_LENGTH,
+    SL_CONTAINMENT,
+    SL_NON_NEGATIVE,
 };
 
 struct StatReq {
@@ -143,6 +148,9 @@ int plan_add_foreign_key(Plan& p, const std::string& child, const std::string& p
                          int max_examples);
 int plan_add_analyzer(Plan& p, int kind, const char* col, const char* col2, const char* expr);
 int plan_add_kll(Plan& p, const std::string& col, int k, const std::vector<double>& q);
+int plan_add_length(Plan& p, const std::string& col, int kind, int64_t a, int64_t b);
+int plan_add_containment(Plan& p, const std::string& col, const std::vector<std::string>& allowed);
+int plan_add_non_negative(Plan& p, const std::string& col);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 

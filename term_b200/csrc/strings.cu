@@ -489,4 +489,149 @@ void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_
     }
 }
 
+// ------------------------------------------------------------------ LENGTH(c) ranges ----
+// Replaces COUNT(CASE WHEN LENGTH(c) >= a [AND LENGTH(c) <= b] OR c IS NULL THEN 1 END) * 1.0 / NULLIF(COUNT(*), 0)
+// (constraints/length.rs:150-170) for every length assertion on a column in one pass. SQL LENGTH counts CHARACTERS:
+// bytes minus UTF-8 continuation bytes. A row's byte length (two offsets) already bounds its character count
+// (ceil(bytes/4) <= chars <= bytes), so the value bytes are only read for rows some range cannot decide from that.
+constexpr int LEN_MAX_RANGES = 8;
+constexpr int LEN_THREADS = 256;
+constexpr int LEN_ILP = 4;
+struct LenParams {
+    const int32_t* offsets;
+    const uint8_t* bytes;
+    const uint32_t* validity;
+    int64_t n_rows;
+    int32_t n_ranges;
+    int32_t pad;
+    long long lo[LEN_MAX_RANGES], hi[LEN_MAX_RANGES];
+    unsigned long long* out;  // [LEN_MAX_RANGES] matching non-null rows, [LEN_MAX_RANGES] = non-null rows
+};
+
+__global__ void __launch_bounds__(LEN_THREADS) length_kernel(const __grid_constant__ LenParams P) {
+    uint32_t cnt[LEN_MAX_RANGES];
+#pragma unroll
+    for (int i = 0; i < LEN_MAX_RANGES; ++i) cnt[i] = 0;
+    uint32_t nvalid = 0;
+    for (int64_t base = (int64_t)blockIdx.x * LEN_THREADS * LEN_ILP; base < P.n_rows; base += (int64_t)gridDim.x * LEN_THREADS * LEN_ILP) {
+        int32_t b[LEN_ILP], e[LEN_ILP];
+        uint32_t vw[LEN_ILP];
+#pragma unroll
+        for (int k = 0; k < LEN_ILP; ++k) {
+            const int64_t row = base + (int64_t)k * LEN_THREADS + threadIdx.x;
+            const int64_t rc = row < P.n_rows ? row : P.n_rows - 1;
+            b[k] = __ldg(P.offsets + rc);
+            e[k] = __ldg(P.offsets + rc + 1);
+            vw[k] = P.validity ? __ldg(P.validity + (rc >> 5)) : 0xffffffffu;
+        }
+#pragma unroll
+        for (int k = 0; k < LEN_ILP; ++k) {
+            const int64_t row = base + (int64_t)k * LEN_THREADS + threadIdx.x;
+            if (row >= P.n_rows || !((vw[k] >> (row & 31)) & 1u)) continue;
+            ++nvalid;
+            const long long nbytes = e[k] - b[k], min_chars = (nbytes + 3) >> 2;
+            bool need_bytes = false;
+            for (int i = 0; i < P.n_ranges; ++i) {
+                const bool surely_out = nbytes < P.lo[i] || min_chars > P.hi[i];
+                const bool surely_in = min_chars >= P.lo[i] && nbytes <= P.hi[i];
+                need_bytes |= !(surely_out || surely_in);
+            }
+            long long chars = nbytes;
+            if (need_bytes) {
+                int cont = 0;
+                for (int32_t q = b[k]; q < e[k]; q += 8) {
+                    const uint64_t w = load_upto8(P.bytes, q, min(8, e[k] - q));
+                    cont += __popcll(w & (~w << 1) & 0x8080808080808080ull);  // 10xxxxxx bytes
+                }
+                chars = nbytes - cont;
+            }
+#pragma unroll
+            for (int i = 0; i < LEN_MAX_RANGES; ++i)
+                if (i < P.n_ranges) {
+                    // when the bytes were skipped every range was decided from the bounds, and `chars = nbytes` agrees
+                    // with that decision only for surely_in / nbytes < lo; the remaining case (min_chars > hi) is out
+                    const bool in = need_bytes ? (chars >= P.lo[i] && chars <= P.hi[i]) : (min_chars >= P.lo[i] && nbytes <= P.hi[i]);
+                    cnt[i] += in;
+                }
+        }
+    }
+    __shared__ unsigned long long red[LEN_MAX_RANGES + 1][LEN_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i <= LEN_MAX_RANGES; ++i) {
+        uint32_t v = i < LEN_MAX_RANGES ? cnt[i < LEN_MAX_RANGES ? i : 0] : nvalid;
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+        if (lane == 0) red[i][warp] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= LEN_MAX_RANGES) {
+        unsigned long long v = 0;
+        for (int k = 0; k < LEN_THREADS / 32; ++k) v += red[threadIdx.x][k];
+        if (v) atomicAdd(P.out + threadIdx.x, v);
+    }
+}
+
+void exec_length_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids) {
+    std::map<Column*, std::vector<int>> by_col;
+    for (int id : agg_ids) {
+        Agg& a = p.aggs[id];
+        Column* c = t.find(a.cols[0]);
+        if (!c) {
+            a.err = TG_ERR_COLUMN_NOT_FOUND;
+            a.err_msg = "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t.valid_fields() + ".";
+            continue;
+        }
+        if (c->dtype != TG_UTF8) {
+            a.err = TG_ERR_TYPE_MISMATCH;
+            a.err_msg = "Error during planning: LENGTH requires a Utf8 column, '" + c->name + "' is not";
+            continue;
+        }
+        by_col[c].push_back(id);
+    }
+    for (auto& kv : by_col) {
+        Column& c = *kv.first;
+        p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)c.value_bytes + (c.validity.p ? (uint64_t)(t.n_rows + 7) / 8 : 0);
+        for (size_t first = 0; first < kv.second.size(); first += LEN_MAX_RANGES) {
+            const size_t cnt = std::min<size_t>(LEN_MAX_RANGES, kv.second.size() - first);
+            unsigned long long h_out[16] = {0};
+            if (t.n_rows > 0) {
+                LenParams P{};
+                P.offsets = reinterpret_cast<const int32_t*>(c.offsets.p);
+                P.bytes = c.values.p;
+                P.validity = reinterpret_cast<const uint32_t*>(c.validity.p);
+                P.n_rows = t.n_rows;
+                P.n_ranges = (int)cnt;
+                for (size_t i = 0; i < cnt; ++i) {
+                    P.lo[i] = p.aggs[kv.second[first + i]].lo;
+                    P.hi[i] = p.aggs[kv.second[first + i]].hi;
+                }
+                uint8_t* scr = e.scratch(256);
+                P.out = reinterpret_cast<unsigned long long*>(scr);
+                TG_CUDA(cudaMemsetAsync(scr, 0, 128, e.stream));
+                const int64_t per_cta = (int64_t)LEN_THREADS * LEN_ILP;
+                const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t.n_rows + per_cta - 1) / per_cta, (int64_t)e.sm_count * 8));
+                TG_CUDA(cudaEventRecord(e.ev[2], e.stream));
+                length_kernel<<<grid, LEN_THREADS, 0, e.stream>>>(P);
+                TG_CUDA(cudaGetLastError());
+                TG_CUDA(cudaEventRecord(e.ev[3], e.stream));
+                TG_CUDA(cudaMemcpyAsync(h_out, scr, 128, cudaMemcpyDeviceToHost, e.stream));
+                TG_CUDA(cudaStreamSynchronize(e.stream));
+                float ms = 0;
+                TG_CUDA(cudaEventElapsedTime(&ms, e.ev[2], e.ev[3]));
+                p.stats.string_ms += ms;
+                p.stats.gpu_ms += ms;
+                p.stats.launches += 1;
+                e.launches += 1;
+            }
+            for (size_t i = 0; i < cnt; ++i) {
+                Agg& a = p.aggs[kv.second[first + i]];
+                a.u[0] = h_out[i];
+                a.u[1] = (uint64_t)t.n_rows - h_out[LEN_MAX_RANGES];
+                a.u[2] = (uint64_t)t.n_rows;
+            }
+        }
+    }
+}
+
 }  // namespace tg

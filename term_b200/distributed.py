@@ -51,7 +51,7 @@ def merge_partials(plan, blobs):
     plan.finalize()
 
 
-_FIXED_KINDS = {0, 1, 2, 3, 4, 5, 6, 10}  # aggregates whose partial record has a fixed size (no blob)
+_FIXED_KINDS = {0, 1, 2, 3, 4, 5, 6, 10, 11}  # aggregates whose partial record has a fixed size (no blob)
 _bufs = {}
 
 

@@ -186,6 +186,55 @@ sql("sql_complex", "constraints/custom_sql.rs:440-456", "status = 'active' AND p
 sql("sql_is_not_null", "constraints/custom_sql.rs:458-469", "price IS NOT NULL", dict(status="failure", metric=0.8))
 sql("sql_invalid_column", "constraints/custom_sql.rs:471-486", "invalid_column > 0", dict(status="failure", message_contains=["SQL expression error", "invalid_column"]))
 
+# ------------------------------------------------------------------ length ----
+def scol(v):
+    return {"data": {"text": col("str", v)}}
+
+
+case("length_min_ok", "constraints/length.rs:244-267", scol(["hello", "world", "testing", "great", None]),
+     {"kind": "length", "column": "text", "assertion": ["Min", 5]}, status="success", metric=1.0)
+case("length_min_failure", "constraints/length.rs:269-288", scol(["hi", "hello", "a", "testing", None]),
+     {"kind": "length", "column": "text", "assertion": ["Min", 5]}, status="failure", metric=0.6,
+     message_contains=["at least 5 characters"])
+case("length_max_ok", "constraints/length.rs:290-302", scol(["hi", "hey", "test", None]),
+     {"kind": "length", "column": "text", "assertion": ["Max", 10]}, status="success", metric=1.0)
+case("length_max_failure", "constraints/length.rs:304-322",
+     scol(["short", "this is a very long string that exceeds the limit", "ok", None]),
+     {"kind": "length", "column": "text", "assertion": ["Max", 10]}, status="failure", metric=0.75,
+     message_contains=["at most 10 characters"])
+case("length_between", "constraints/length.rs:324-347", scol(["hello", "testing", "hi", "this is way too long", None]),
+     {"kind": "length", "column": "text", "assertion": ["Between", 3, 10]}, status="failure", metric=0.6,
+     message_contains=["between 3 and 10 characters"])
+case("length_exactly", "constraints/length.rs:349-369", scol(["hello", "world", "test", "testing", None]),
+     {"kind": "length", "column": "text", "assertion": ["Exactly", 5]}, status="failure", metric=0.6,
+     message_contains=["exactly 5 characters"])
+case("length_not_empty", "constraints/length.rs:371-391", scol(["hello", "a", "", "testing", None]),
+     {"kind": "length", "column": "text", "assertion": ["NotEmpty"]}, status="failure", metric=0.8,
+     message_contains=["not empty"])
+case("length_utf8_characters_not_bytes", "constraints/length.rs:393-412", scol(["hello", "你好", "🦀🔥", "café", None]),
+     {"kind": "length", "column": "text", "assertion": ["Min", 2]}, status="success")
+case("length_all_null", "constraints/length.rs:414-426", scol([None, None, None]),
+     {"kind": "length", "column": "text", "assertion": ["Min", 5]}, status="success", metric=1.0)
+case("length_empty", "constraints/length.rs:428-438", scol([]),
+     {"kind": "length", "column": "text", "assertion": ["Min", 5]}, status="skipped")
+
+# ------------------------------------------------------------------ containment / non-negative ----
+case("containment_failure", "constraints/values.rs:523-543",
+     {"data": {"text_col": col("str", ["active", "inactive", "pending", "invalid_status"])}},
+     {"kind": "containment", "column": "text_col", "allowed": ["active", "inactive", "pending", "archived"]},
+     status="failure", metric=0.75)
+case("containment_ok", "constraints/values.rs:545-560",
+     {"data": {"text_col": col("str", ["active", "inactive", "pending"])}},
+     {"kind": "containment", "column": "text_col", "allowed": ["active", "inactive", "pending", "archived"]},
+     status="success", metric=1.0)
+case("containment_with_nulls", "constraints/values.rs:590-602",
+     {"data": {"text_col": col("str", ["active", None, "inactive", None])}},
+     {"kind": "containment", "column": "text_col", "allowed": ["active", "inactive"]}, status="success", metric=1.0)
+case("non_negative_ok", "constraints/values.rs:562-574", {"data": {"num_col": col("f64", [1.0, 0.0, 5.5, 100.0])}},
+     {"kind": "non_negative", "column": "num_col"}, status="success", metric=1.0)
+case("non_negative_failure", "constraints/values.rs:576-588", {"data": {"num_col": col("f64", [1.0, -2.0, 5.5, 100.0])}},
+     {"kind": "non_negative", "column": "num_col"}, status="failure", metric=0.75)
+
 # ------------------------------------------------------------------ foreign key ----
 def fk(id, ref, parent_ids, child_ids, expect, allow_nulls=False):
     case(id, ref, {"customers": {"id": col("i64", parent_ids)}, "orders": {"customer_id": col("i64", child_ids)}},

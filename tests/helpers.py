@@ -57,6 +57,12 @@ def oracle_eval(case):
             return O.Result("failure", None, f"SQL expression error: Schema error: No field named {e.args[0]}. Expression: '{op['expression']}'")
     if k == "foreign_key":
         return O.foreign_key(tables, op["child"], op["parent"], op.get("allow_nulls", False))[0]
+    if k == "length":
+        return O.length_constraint(t, op["column"], op["assertion"][0], *op["assertion"][1:])
+    if k == "containment":
+        return O.containment(t, op["column"], op["allowed"])
+    if k == "non_negative":
+        return O.non_negative(t, op["column"])
     raise ValueError(k)
 
 
@@ -132,6 +138,12 @@ def build_constraint(T, op):
         return T.CustomSqlConstraint(op["expression"], op.get("hint"))
     if k == "foreign_key":
         return T.ForeignKeyConstraint(op["child"], op["parent"]).allow_nulls(op.get("allow_nulls", False))
+    if k == "length":
+        return T.LengthConstraint(op["column"], getattr(T.LengthAssertion, op["assertion"][0])(*op["assertion"][1:]))
+    if k == "containment":
+        return T.ContainmentConstraint(op["column"], op["allowed"])
+    if k == "non_negative":
+        return T.NonNegativeConstraint(op["column"])
     raise ValueError(k)
 
 

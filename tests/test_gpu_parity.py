@@ -272,6 +272,44 @@ def test_string_suite_matches_oracle(ctx, n):
         ctx.deregister_table(name)
 
 
+# ---------------------------------------------------------------- length / containment / non-negative (§8f.1) ----
+@pytest.mark.parametrize("n", [1, 257, 40_000])
+def test_length_containment_non_negative_match_oracle(ctx, n):
+    rng = np.random.default_rng(n + 5)
+    alphabet = list("ab c") + ["é", "你", "🦀", "ß"]
+    strs = ["".join(rng.choice(alphabet, rng.integers(0, 14))) for _ in range(n)]
+    status = [["active", "inactive", "pending", "it's", "ACTIVE", ""][v] for v in rng.integers(0, 6, n)]
+    nums = rng.normal(0.5, 1.0, n)
+    ints = rng.integers(-3, 50, n)
+    t = pa.table({"s": pa.array(strs, type=pa.string(), mask=rng.random(n) < 0.1),
+                  "status": pa.array(status, type=pa.string(), mask=rng.random(n) < 0.1),
+                  "x": pa.array(nums, mask=rng.random(n) < 0.1), "i": pa.array(ints)})
+    name = f"len_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=1001))
+    try:
+        cb = T.Check.builder("len")
+        asserts = [("Min", 3), ("Max", 6), ("Between", 2, 9), ("Exactly", 4), ("NotEmpty",), ("Min", 0), ("Max", 0), ("Between", 13, 40),
+                   ("Min", 12)]
+        for a in asserts:
+            cb.length("s", getattr(T.LengthAssertion, a[0])(*a[1:]))
+        cb.constraint(T.ContainmentConstraint("status", ["active", "inactive", "it's"]))
+        cb.constraint(T.ContainmentConstraint("status", ["active", "inactive", "pending", "it's", "ACTIVE", ""]))
+        cb.constraint(T.NonNegativeConstraint("x"))
+        cb.constraint(T.NonNegativeConstraint("i"))
+        suite = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build()
+        rs = suite.run(ctx).report.results
+        want = [O.length_constraint(t, "s", a[0], *a[1:]) for a in asserts]
+        want += [O.containment(t, "status", ["active", "inactive", "it's"]),
+                 O.containment(t, "status", ["active", "inactive", "pending", "it's", "ACTIVE", ""]),
+                 O.non_negative(t, "x"), O.non_negative(t, "i")]
+        assert len(rs) == len(want)
+        for g, o in zip(rs, want):
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (g, o)
+        assert [r.name for r in rs[:5]] == ["min_length", "max_length", "length_between", "exact_length", "not_empty"]
+    finally:
+        ctx.deregister_table(name)
+
+
 # ---------------------------------------------------------------- hash jobs: distinct / unique / FK / grouped ----
 def _uniq_all_kinds(ctx, name, t, cols):
     A = T.Assertion
