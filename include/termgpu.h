@@ -155,7 +155,8 @@ typedef enum {
     TG_AN_COVARIANCE = 10,
     TG_AN_KLL = 11,
     TG_AN_GROUPED_COMPLETENESS = 12,
-    TG_AN_COMPLIANCE = 13
+    TG_AN_COMPLIANCE = 13,
+    TG_AN_APPROX_COUNT_DISTINCT = 14 /* analyzers/advanced/approx_count_distinct.rs; answered EXACTLY */
 } tg_analyzer_kind;
 
 /* ConstraintResult (core/constraint.rs:40-48) */
@@ -182,6 +183,7 @@ typedef struct {
  *   CORR / COVARIANCE   u[0]=n f[0..5]=sum_x,sum_y,sum_x2,sum_y2,sum_xy  (advanced/correlation.rs:42-62)
  *   KLL                 u[0]=count f[0]=min f[1]=max; quantiles via tg_plan_map_*
  *   COMPLIANCE          u[0]=satisfied u[1]=total
+ *   APPROX_COUNT_DISTINCT u[0]=approx_distinct_count u[1]=total_count   (advanced/approx_count_distinct.rs:59-64)
  * metric_kind: 0 Double, 1 Long, 2 Map (entries via tg_plan_map_*), 3 none (AnalyzerError::NoData)
  */
 typedef struct {
@@ -304,6 +306,10 @@ TG_API int32_t tg_plan_add_containment(tg_plan* plan, const char* column, const 
                                        int32_t n_values);
 /* NonNegativeConstraint::evaluate (constraints/values.rs:357-414) */
 TG_API int32_t tg_plan_add_non_negative(tg_plan* plan, const char* column);
+
+/* ApproxCountDistinctConstraint::evaluate (constraints/approx_count_distinct.rs:49-134). APPROX_DISTINCT's
+ * HyperLogLog estimate is replaced by the exact distinct count of the hash job. */
+TG_API int32_t tg_plan_add_approx_count_distinct(tg_plan* plan, const char* column, tg_assertion assertion);
 
 /* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
 TG_API int32_t tg_plan_add_analyzer(tg_plan* plan, int32_t analyzer_kind, const char* column,

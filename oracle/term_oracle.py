@@ -863,6 +863,15 @@ def non_negative(table, column) -> Result:
     return Result(FAILURE, ratio, f"{rust_f64(total - nn)} values are negative")
 
 
+def approx_count_distinct(table, column, assertion) -> Result:
+    """constraints/approx_count_distinct.rs:49-134: SELECT APPROX_DISTINCT(c) (HyperLogLog; the reference's tests only
+    assert ranges). This restatement returns the exact distinct count, which every HLL error bound contains."""
+    d = float(distinct_counts(table, [column])["distinct_nonnull"])
+    if assertion_eval(assertion, d):
+        return Result(SUCCESS, d)
+    return Result(FAILURE, d, f"Approximate distinct count {rust_f64(d)} does not satisfy assertion {assertion_desc(assertion)} for column '{column}'")
+
+
 def foreign_key(tables, child, parent, allow_nulls=False, max_examples=100):
     """constraints/foreign_key.rs:307-410: LEFT JOIN child->parent WHERE parent.col IS NULL [AND child.col IS
     NOT NULL] -> COUNT(*), COUNT(DISTINCT child.col). Returns (Result, total, unique)."""

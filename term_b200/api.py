@@ -578,6 +578,15 @@ class NonNegativeConstraint(Constraint):  # constraints/values.rs:336-440
         return F.check_slot(F.lib().tg_plan_add_non_negative(plan.handle, self.column.encode()))
 
 
+class ApproxCountDistinctConstraint(Constraint):  # constraints/approx_count_distinct.rs
+    def __init__(self, column, assertion: Assertion):
+        self.column, self.assertion = column, assertion
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_approx_count_distinct(plan.handle, self.column.encode(), self.assertion.c()))
+
+
 class StatisticalConstraint(Constraint):  # constraints/statistics.rs:120-322
     def __init__(self, column, statistic: StatisticType, assertion: Assertion, percentile: float = 0.0):
         self.column, self.statistic, self.assertion, self.percentile = column, statistic, assertion, percentile
@@ -794,6 +803,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
     # core/check.rs:518-625, 1777-1786
+    def has_approx_count_distinct(self, column, assertion): return self.constraint(ApproxCountDistinctConstraint(column, assertion))
     def has_min_length(self, column, n): return self.constraint(LengthConstraint.min(column, n))
     def has_max_length(self, column, n): return self.constraint(LengthConstraint.max(column, n))
     def has_length_between(self, column, a, b): return self.constraint(LengthConstraint.between(column, a, b))
@@ -942,6 +952,7 @@ class SizeAnalyzer(Analyzer):
 
 CompletenessAnalyzer = _mk(1, "CompletenessAnalyzer")
 DistinctnessAnalyzer = _mk(2, "DistinctnessAnalyzer")
+ApproxCountDistinctAnalyzer = _mk(14, "ApproxCountDistinctAnalyzer")  # advanced/approx_count_distinct.rs (answered exactly)
 MeanAnalyzer = _mk(3, "MeanAnalyzer")
 MinAnalyzer = _mk(4, "MinAnalyzer")
 MaxAnalyzer = _mk(5, "MaxAnalyzer")

@@ -294,6 +294,9 @@ int32_t tg_plan_add_containment(tg_plan* p, const char* column, const char* cons
 int32_t tg_plan_add_non_negative(tg_plan* p, const char* column) {
     return guard_slot([&] { return plan_add_non_negative(p->p, column ? column : ""); });
 }
+int32_t tg_plan_add_approx_count_distinct(tg_plan* p, const char* column, tg_assertion a) {
+    return guard_slot([&] { return plan_add_approx_count_distinct(p->p, column ? column : "", a); });
+}
 int32_t tg_plan_add_grouped_completeness(tg_plan* p, const char* column, const char* const* groups, int32_t n,
                                          int32_t max_groups, int32_t include_overall) {
     return guard_slot([&] {

@@ -396,6 +396,13 @@ int plan_add_analyzer(Plan& p, int kind, const char* col, const char* col2, cons
             s.columns = {c};
             s.aggs.push_back(p.add_agg(mk_distinct({c})));
             break;
+        case TG_AN_APPROX_COUNT_DISTINCT:  // analyzers/advanced/approx_count_distinct.rs:100-176
+            need_col();
+            s.name = "approx_count_distinct";
+            s.metric_key = "approx_count_distinct." + c;
+            s.columns = {c};
+            s.aggs.push_back(p.add_agg(mk_distinct({c})));
+            break;
         case TG_AN_MEAN:
         case TG_AN_MIN:
         case TG_AN_MAX:
@@ -517,6 +524,20 @@ int plan_add_non_negative(Plan& p, const std::string& col) {
     s.arg = col + " >= 0";
     s.aggs.push_back(p.add_agg(mk_pred(s.arg)));
     s.aggs.push_back(p.add_agg(mk_valid(col)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
+// constraints/approx_count_distinct.rs:40-134: SELECT APPROX_DISTINCT(c). The HyperLogLog estimate is replaced by
+// the EXACT distinct count of the hash job (error 0 <= any HLL error bound; the reference's tests assert ranges).
+int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion a) {
+    validate_identifier(col);
+    Slot s;
+    s.kind = SL_APPROX_DISTINCT;
+    s.name = "approx_count_distinct";
+    s.columns = {col};
+    s.assertion = a;
+    s.aggs.push_back(p.add_agg(mk_distinct({col})));
     p.slots.push_back(std::move(s));
     return (int)p.slots.size() - 1;
 }
@@ -1171,6 +1192,18 @@ static void finalize_value_ratio(Plan& p, Slot& s, const char* what) {
     else failure_metric(s, ratio, fmt_f64(total - ok) + what);
 }
 
+static void finalize_approx_distinct(Plan& p, Slot& s) {
+    const Agg& a = p.aggs[s.aggs[0]];
+    if (a.err != TG_OK) {
+        set_error(s, a);
+        return;
+    }
+    const double count = (double)a.u[1];  // 0 for an empty or all-NULL column (approx_count_distinct.rs:300-326)
+    if (assertion_evaluate(s.assertion, count)) success_metric(s, count);
+    else failure_metric(s, count, "Approximate distinct count " + fmt_f64(count) + " does not satisfy assertion " +
+                                      assertion_description(s.assertion) + " for column '" + s.columns[0] + "'");
+}
+
 static void finalize_fk(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     if (a.err != TG_OK) {
@@ -1240,6 +1273,12 @@ static void finalize_analyzer(Plan& p, Slot& s) {
             r.u[1] = a.u[1];
             r.metric_kind = 0;
             r.metric_double = a.u[0] == 0 ? 1.0 : (double)a.u[1] / (double)a.u[0];
+            break;
+        case TG_AN_APPROX_COUNT_DISTINCT:  // state {approx_distinct_count, total_count = COUNT(c)}; metric Long
+            r.u[0] = a.u[1];
+            r.u[1] = a.u[0] - a.u[3];
+            r.metric_kind = 1;
+            r.metric_long = (int64_t)a.u[1];
             break;
         case TG_AN_DISTINCTNESS: {
             // COUNT(c), COUNT(DISTINCT c): denominator is the non-null count (distinctness.rs:113-116)
@@ -1489,6 +1528,7 @@ void Plan::finalize() {
             case SL_LENGTH: finalize_length(*this, s); break;
             case SL_CONTAINMENT: finalize_value_ratio(*this, s, " values are not in the allowed set"); break;
             case SL_NON_NEGATIVE: finalize_value_ratio(*this, s, " values are negative"); break;
+            case SL_APPROX_DISTINCT: finalize_approx_distinct(*this, s); break;
         }
     }
     executed = true;

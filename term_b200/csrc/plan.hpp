@@ -75,6 +75,7 @@ enum SlotKind : int32_t {
     SL_LENGTH,
     SL_CONTAINMENT,
     SL_NON_NEGATIVE,
+    SL_APPROX_DISTINCT,
 };
 
 struct StatReq {
@@ -151,6 +152,7 @@ int plan_add_kll(Plan& p, const std::string& col, int k, const std::vector<doubl
 int plan_add_length(Plan& p, const std::string& col, int kind, int64_t a, int64_t b);
 int plan_add_containment(Plan& p, const std::string& col, const std::vector<std::string>& allowed);
 int plan_add_non_negative(Plan& p, const std::string& col);
+int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion a);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 

@@ -235,6 +235,33 @@ case("non_negative_ok", "constraints/values.rs:562-574", {"data": {"num_col": co
 case("non_negative_failure", "constraints/values.rs:576-588", {"data": {"num_col": col("f64", [1.0, -2.0, 5.5, 100.0])}},
      {"kind": "non_negative", "column": "num_col"}, status="failure", metric=0.75)
 
+# ------------------------------------------------------------------ approx_count_distinct ----
+case("approx_distinct_high_cardinality", "constraints/approx_count_distinct.rs:190-205",
+     {"data": {"test_col": col("i64", list(range(1000)))}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["GreaterThan", 990.0]},
+     status="success", metric_gt=990.0)
+case("approx_distinct_low_cardinality", "constraints/approx_count_distinct.rs:207-226",
+     {"data": {"test_col": col("i64", [1, 2, 3] * 100)}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["LessThan", 10.0]},
+     status="success", metric_lt=10.0)
+case("approx_distinct_with_nulls", "constraints/approx_count_distinct.rs:228-255",
+     {"data": {"test_col": col("i64", [1, None, 2, None, 3, None, 1, 2, 3, None])}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["Between", 2.0, 5.0]},
+     status="success", metric_gt=1.999, metric_lt=5.001)
+case("approx_distinct_failure", "constraints/approx_count_distinct.rs:257-273",
+     {"data": {"test_col": col("i64", [i % 10 for i in range(50)])}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["GreaterThan", 100.0]},
+     status="failure", metric_lt=20.0)
+case("approx_distinct_strings", "constraints/approx_count_distinct.rs:275-297",
+     {"data": {"test_col": col("str", ["apple", "banana", "cherry", "apple", "banana", "date", "elderberry", None])}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["Between", 4.0, 6.0]}, status="success")
+case("approx_distinct_empty", "constraints/approx_count_distinct.rs:299-311",
+     {"data": {"test_col": col("i64", [])}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["Equals", 0.0]}, status="success", metric=0.0)
+case("approx_distinct_all_null", "constraints/approx_count_distinct.rs:313-326",
+     {"data": {"test_col": col("i64", [None, None, None, None, None])}},
+     {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["Equals", 0.0]}, status="success", metric=0.0)
+
 # ------------------------------------------------------------------ foreign key ----
 def fk(id, ref, parent_ids, child_ids, expect, allow_nulls=False):
     case(id, ref, {"customers": {"id": col("i64", parent_ids)}, "orders": {"customer_id": col("i64", child_ids)}},

@@ -63,6 +63,8 @@ def oracle_eval(case):
         return O.containment(t, op["column"], op["allowed"])
     if k == "non_negative":
         return O.non_negative(t, op["column"])
+    if k == "approx_count_distinct":
+        return O.approx_count_distinct(t, op["column"], tuple(op["assertion"]))
     raise ValueError(k)
 
 
@@ -144,6 +146,8 @@ def build_constraint(T, op):
         return T.ContainmentConstraint(op["column"], op["allowed"])
     if k == "non_negative":
         return T.NonNegativeConstraint(op["column"])
+    if k == "approx_count_distinct":
+        return T.ApproxCountDistinctConstraint(op["column"], _assertion(T, op["assertion"]))
     raise ValueError(k)
 
 
