@@ -48,6 +48,17 @@ def measured_peak_gbs():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def measured_traffic(n_rows):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE scan_kernel launch from the committed ncu --set full capture
+    (profiles/scan_traffic.json), scaled by rows when the bench runs at another size; None if the file is absent."""
+    p = os.path.join(ROOT, "profiles", "scan_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        t = json.load(f)
+    return int((t["dram_bytes_read"] + t["dram_bytes_write"]) * (n_rows / t["rows"]))
+
+
 class ClockSampler:
     """SM clock and throttle reasons sampled DURING the timed region. The region is tens of milliseconds, far
     shorter than an `nvidia-smi -lms` period, so the sampler polls NVML directly (nvidia_ml_py) from a thread
@@ -371,7 +382,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     achieved = alg_bytes / (kernel_ms / 1e3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "scan_kernel (+ scan_finalize_kernel)", "kernel_ms": kernel_ms,
+                "traffic": measured_traffic(n), "kernel": "scan_kernel (+ scan_finalize_kernel)", "kernel_ms": kernel_ms,
                 "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "step_gbs": alg_bytes * world / (ms_per_step / 1e3) / 1e9}
 
