@@ -83,7 +83,7 @@ __device__ __forceinline__ void row_fingerprints(const GrpParams& P, const int64
                     y = (y + ww) * 0xc2b2ae3d27d4eb4full;
                     y ^= y >> 31;
                 }
-                fp_combine(acc[k], fmix64(x), fmix64(y), first);
+                fp_combine(acc[k], x, y, first);  // fp_combine applies the finalising mix
             }
         } else {
             uint64_t v[GRP_ILP];

@@ -118,7 +118,10 @@ __device__ __forceinline__ uint32_t run_dfa_gmem(const uint8_t* bytes, uint32_t 
     return E;
 }
 
-template <int NDFA>
+// R = rows per lane per block: a warp's block is 32*R consecutive rows (lane l owns rows base + j*32 + l, j < R).
+// R = 2 halves the per-block bookkeeping (offset prefetch, TMA issue, mbarrier wait) per string and evens out the
+// string-length imbalance between lanes; R = 1 keeps small inputs spread over all SMs.
+template <int NDFA, int R>
 __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_constant__ StrParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     // ---- stage class map + transition table ----
@@ -132,6 +135,7 @@ __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_co
     uint64_t* bars = reinterpret_cast<uint64_t*>(str_smem + P.tab_bytes) + warp * 2;
     const uint32_t stage_bytes = P.stage;
     uint8_t* stage = str_smem + P.tab_bytes + (size_t)n_warps * 16 + (size_t)warp * (2 * stage_bytes);
+    const uint32_t stage_addr = smem_u32(stage);
     if (lane == 0) {
         mbar_init(&bars[0], 1);
         mbar_init(&bars[1], 1);
@@ -148,24 +152,32 @@ __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_co
     uint32_t nvalid = 0;
     const uint32_t byte_base_lo = (uint32_t)reinterpret_cast<uint64_t>(P.bytes) & 15u;  // misalignment of the value buffer
 
-    // offsets of a block: lane l holds [o, oe) of row blk*32 + l (rows past the end are empty) and the block's
-    // validity word (32 rows = one word)
-    auto load_offsets = [&](int64_t blk, uint32_t& o, uint32_t& oe, uint32_t& vw) {
-        o = oe = 0;
-        vw = 0;
+    // a block's per-lane view: [o, oe) of its R rows (rows past the end are empty) and their validity words
+    struct Blk {
+        uint32_t o[R], oe[R], vw[R];
+    };
+    auto load_offsets = [&](int64_t blk, Blk& b) {
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            b.o[j] = b.oe[j] = 0;
+            b.vw[j] = 0;
+        }
         if (blk < P.n_blocks) {
-            const int64_t r = blk * 32 + lane;
-            o = (uint32_t)__ldg(P.offsets + (r < n ? r : n));
-            oe = (uint32_t)__ldg(P.offsets + (r + 1 < n ? r + 1 : n));
-            vw = P.validity ? __ldg(P.validity + blk) : 0xffffffffu;
+#pragma unroll
+            for (int j = 0; j < R; ++j) {
+                const int64_t r = (blk * R + j) * 32 + lane;
+                b.o[j] = (uint32_t)__ldg(P.offsets + (r < n ? r : n));
+                b.oe[j] = (uint32_t)__ldg(P.offsets + (r + 1 < n ? r + 1 : n));
+                b.vw[j] = ((blk * R + j) * 32 < n) ? (P.validity ? __ldg(P.validity + blk * R + j) : 0xffffffffu) : 0u;
+            }
         }
     };
     // block byte range -> TMA bulk copy into stage buffer `buf`. Returns false when the block is empty or does not
     // fit (then it is read from global memory); org = the byte index (relative to P.bytes, may be "negative" by the
     // buffer's misalignment, hence wrapping uint32 arithmetic) that maps to stage offset 0. 16 bytes of the stage
     // stay free: the window loads of the last string may run 11 bytes past its end.
-    auto issue = [&](uint32_t o, uint32_t oe, int buf, uint32_t& org) -> bool {
-        const uint32_t b0 = __shfl_sync(0xffffffffu, o, 0), b1 = __shfl_sync(0xffffffffu, oe, 31);
+    auto issue = [&](const Blk& b, int buf, uint32_t& org) -> bool {
+        const uint32_t b0 = __shfl_sync(0xffffffffu, b.o[0], 0), b1 = __shfl_sync(0xffffffffu, b.oe[R - 1], 31);
         if (b1 <= b0) return false;
         const uint32_t lead = (byte_base_lo + b0) & 15u;  // bytes between the 16-byte aligned start and b0
         const uint32_t sz = (lead + (b1 - b0) + 15u) & ~15u;
@@ -178,53 +190,55 @@ __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_co
         return true;
     };
 
-    uint32_t o0, oe0, o1, oe1, o2, oe2;  // offsets of blocks it, it+1, it+2
-    uint32_t vw0, vw1, vw2;
-    load_offsets(gwarp, o0, oe0, vw0);
-    load_offsets(gwarp + total_warps, o1, oe1, vw1);
+    Blk c0, c1, c2;  // blocks it, it+1, it+2
+    load_offsets(gwarp, c0);
+    load_offsets(gwarp + total_warps, c1);
     uint32_t org0 = 0, org1 = 0;  // stage origins of blocks it, it+1
     bool staged0 = false, staged1 = false;
-    if (gwarp < P.n_blocks) staged0 = issue(o0, oe0, 0, org0);
+    if (gwarp < P.n_blocks) staged0 = issue(c0, 0, org0);
     uint32_t phase = 0;  // bit b = parity of the next completion of bars[b]
     int it = 0;
     for (int64_t blk = gwarp; blk < P.n_blocks; blk += total_warps, ++it) {
         const int buf = it & 1;
         // prefetch: offsets two blocks ahead, bytes one block ahead (its buffer was last read an iteration ago)
-        load_offsets(blk + 2 * total_warps, o2, oe2, vw2);
+        load_offsets(blk + 2 * total_warps, c2);
         __syncwarp();
         staged1 = false;
-        if (blk + total_warps < P.n_blocks) staged1 = issue(o1, oe1, buf ^ 1, org1);
+        if (blk + total_warps < P.n_blocks) staged1 = issue(c1, buf ^ 1, org1);
         // ---- this block ----
-        const bool valid = (vw0 >> lane) & 1u;
         if (staged0) {
             mbar_wait(&bars[buf], (phase >> buf) & 1u);
             phase ^= 1u << buf;
         }
-        if (valid && blk * 32 + lane < n) {
-            ++nvalid;
-            uint32_t E;
-            if (staged0) {
-                const uint8_t* base = stage + buf * stage_bytes;
-                uint32_t p = o0 - org0, e = oe0 - org0;
-                if (P.trim) {
-                    while (p < e && base[p] == ' ') ++p;
-                    while (e > p && base[e - 1] == ' ') --e;
-                }
-                E = run_dfa_smem(smem_u32(base), p, e, P.start, cls_base, tab_addr, term_limit);
-            } else {
-                uint32_t p = o0, e = oe0;
-                if (P.trim) {
-                    while (p < e && P.bytes[p] == ' ') ++p;
-                    while (e > p && P.bytes[e - 1] == ' ') --e;
-                }
-                E = run_dfa_gmem(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
-            }
-            const uint32_t m = lds_u16(tab_addr + 2u * (E + n_classes));  // END entry = match mask
 #pragma unroll
-            for (int i = 0; i < NDFA; ++i) cnt[i] += (m >> i) & 1u;
+        for (int j = 0; j < R; ++j) {
+            const bool valid = (c0.vw[j] >> lane) & 1u;
+            if (valid && (blk * R + j) * 32 + lane < n) {
+                ++nvalid;
+                uint32_t E;
+                if (staged0) {
+                    uint32_t p = c0.o[j] - org0, e = c0.oe[j] - org0;
+                    if (P.trim) {
+                        const uint8_t* base = stage + buf * stage_bytes;
+                        while (p < e && base[p] == ' ') ++p;
+                        while (e > p && base[e - 1] == ' ') --e;
+                    }
+                    E = run_dfa_smem(stage_addr + buf * stage_bytes, p, e, P.start, cls_base, tab_addr, term_limit);
+                } else {
+                    uint32_t p = c0.o[j], e = c0.oe[j];
+                    if (P.trim) {
+                        while (p < e && P.bytes[p] == ' ') ++p;
+                        while (e > p && P.bytes[e - 1] == ' ') --e;
+                    }
+                    E = run_dfa_gmem(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
+                }
+                const uint32_t m = lds_u16(tab_addr + 2u * (E + n_classes));  // END entry = match mask
+#pragma unroll
+                for (int i = 0; i < NDFA; ++i) cnt[i] += (m >> i) & 1u;
+            }
         }
-        o0 = o1; oe0 = oe1; vw0 = vw1;
-        o1 = o2; oe1 = oe2; vw1 = vw2;
+        c0 = c1;
+        c1 = c2;
         org0 = org1;
         staged0 = staged1;
     }
@@ -372,7 +386,9 @@ static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::
     P.tab_bytes = pr.tab_bytes;
     // per-warp stage: 32 rows of ~1.5x the column's mean length, so almost every block is staged by TMA
     const double mean_len = t.n_rows > 0 ? (double)c.value_bytes / (double)t.n_rows : 0.0;
-    size_t stage = round_up((size_t)(mean_len * 32.0 * 1.5) + 256, 128);
+    // two rows per lane once there are enough 64-row blocks to keep every warp of the grid busy several times over
+    const int R = t.n_rows >= ((int64_t)1 << 21) && !getenv("TG_STR_R1") ? 2 : 1;
+    size_t stage = round_up((size_t)(mean_len * 32.0 * R * (R == 2 ? 1.25 : 1.5)) + (R == 2 ? 128 : 256), 128);
     stage = std::min<size_t>(std::max<size_t>(stage, 1024), 8192);
     // warps per CTA: as many as fit beside the table (each owns a double stage + 2 mbarriers)
     int warps = 0;
@@ -394,9 +410,11 @@ static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::
     P.bytes = c.values.p;
     P.validity = reinterpret_cast<const uint32_t*>(c.validity.p);
     P.n_rows = t.n_rows;
-    P.n_blocks = (t.n_rows + 31) / 32;
+    P.n_blocks = (t.n_rows + 32 * R - 1) / (32 * R);
     typedef void (*Kernel)(const StrParams);
-    const Kernel kernel = nd <= 1 ? (Kernel)dfa_kernel<1> : nd <= 2 ? (Kernel)dfa_kernel<2> : nd <= 4 ? (Kernel)dfa_kernel<4> : (Kernel)dfa_kernel<8>;
+    const Kernel k1 = nd <= 1 ? (Kernel)dfa_kernel<1, 1> : nd <= 2 ? (Kernel)dfa_kernel<2, 1> : nd <= 4 ? (Kernel)dfa_kernel<4, 1> : (Kernel)dfa_kernel<8, 1>;
+    const Kernel k2 = nd <= 1 ? (Kernel)dfa_kernel<1, 2> : nd <= 2 ? (Kernel)dfa_kernel<2, 2> : nd <= 4 ? (Kernel)dfa_kernel<4, 2> : (Kernel)dfa_kernel<8, 2>;
+    const Kernel kernel = R == 2 ? k2 : k1;
     TG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STR_SMEM_MAX));
     const int threads = warps * 32;
     int per_sm = 1;
