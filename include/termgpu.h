@@ -311,6 +311,10 @@ TG_API int32_t tg_plan_add_non_negative(tg_plan* plan, const char* column);
  * HyperLogLog estimate is replaced by the exact distinct count of the hash job. */
 TG_API int32_t tg_plan_add_approx_count_distinct(tg_plan* plan, const char* column, tg_assertion assertion);
 
+/* DataTypeConstraint::evaluate (constraints/values.rs:104-165); DataType (:14-37) */
+typedef enum { TG_DT_INTEGER = 0, TG_DT_FLOAT = 1, TG_DT_BOOLEAN = 2, TG_DT_DATE = 3, TG_DT_TIMESTAMP = 4, TG_DT_STRING = 5 } tg_value_type;
+TG_API int32_t tg_plan_add_data_type(tg_plan* plan, const char* column, int32_t value_type, double threshold);
+
 /* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
 TG_API int32_t tg_plan_add_analyzer(tg_plan* plan, int32_t analyzer_kind, const char* column,
                                     const char* column2, const char* expression);

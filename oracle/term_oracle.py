@@ -863,6 +863,23 @@ def non_negative(table, column) -> Result:
     return Result(FAILURE, ratio, f"{rust_f64(total - nn)} values are negative")
 
 
+DATA_TYPE_PATTERNS = {"Integer": r"^-?\d+$", "Float": r"^-?\d*\.?\d+([eE][+-]?\d+)?$", "Boolean": r"^(true|false|TRUE|FALSE|True|False|0|1)$",
+                      "Date": r"^\d{4}-\d{2}-\d{2}$", "Timestamp": r"^\d{4}-\d{2}-\d{2}[ T]\d{2}:\d{2}:\d{2}", "String": r".*"}
+
+
+def data_type(table, column, dtype, threshold) -> Result:
+    """constraints/values.rs:104-165: matches = COUNT(CASE WHEN c ~ pattern ..), total = COUNT(*) WHERE c IS NOT NULL"""
+    ms = [m for m in regex_matches(table_cols(table)[column], DATA_TYPE_PATTERNS[dtype]) if m is not None]
+    total = float(len(ms))
+    if total == 0.0:
+        return Result(SKIPPED, None, "No non-null data to validate")
+    matches = float(sum(1 for m in ms if m))
+    ratio = matches / total
+    if ratio >= threshold:
+        return Result(SUCCESS, ratio)
+    return Result(FAILURE, ratio, f"Data type conformance {rust_f64(ratio)} is below threshold {rust_f64(threshold)}")
+
+
 def approx_count_distinct(table, column, assertion) -> Result:
     """constraints/approx_count_distinct.rs:49-134: SELECT APPROX_DISTINCT(c) (HyperLogLog; the reference's tests only
     assert ranges). This restatement returns the exact distinct count, which every HLL error bound contains."""

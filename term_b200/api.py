@@ -587,6 +587,24 @@ class ApproxCountDistinctConstraint(Constraint):  # constraints/approx_count_dis
         return F.check_slot(F.lib().tg_plan_add_approx_count_distinct(plan.handle, self.column.encode(), self.assertion.c()))
 
 
+class DataType(enum.IntEnum):  # constraints/values.rs:14-26
+    Integer = 0
+    Float = 1
+    Boolean = 2
+    Date = 3
+    Timestamp = 4
+    String = 5
+
+
+class DataTypeConstraint(Constraint):  # constraints/values.rs:69-196
+    def __init__(self, column, data_type: DataType, threshold: float):
+        self.column, self.data_type, self.threshold = column, data_type, threshold
+        self._add_to(Plan())
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_data_type(plan.handle, self.column.encode(), int(self.data_type), float(self.threshold)))
+
+
 class StatisticalConstraint(Constraint):  # constraints/statistics.rs:120-322
     def __init__(self, column, statistic: StatisticType, assertion: Assertion, percentile: float = 0.0):
         self.column, self.statistic, self.assertion, self.percentile = column, statistic, assertion, percentile

@@ -297,6 +297,9 @@ int32_t tg_plan_add_non_negative(tg_plan* p, const char* column) {
 int32_t tg_plan_add_approx_count_distinct(tg_plan* p, const char* column, tg_assertion a) {
     return guard_slot([&] { return plan_add_approx_count_distinct(p->p, column ? column : "", a); });
 }
+int32_t tg_plan_add_data_type(tg_plan* p, const char* column, int32_t data_type, double threshold) {
+    return guard_slot([&] { return plan_add_data_type(p->p, column ? column : "", data_type, threshold); });
+}
 int32_t tg_plan_add_grouped_completeness(tg_plan* p, const char* column, const char* const* groups, int32_t n,
                                          int32_t max_groups, int32_t include_overall) {
     return guard_slot([&] {

@@ -542,6 +542,25 @@ int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion
     return (int)p.slots.size() - 1;
 }
 
+// constraints/values.rs:28-37 (DataType::pattern), :88-165: COUNT(CASE WHEN c ~ 'pattern' ..), COUNT(*) .. WHERE c IS
+// NOT NULL; data_type: 0 Integer 1 Float 2 Boolean 3 Date 4 Timestamp 5 String
+int plan_add_data_type(Plan& p, const std::string& col, int data_type, double threshold) {
+    validate_identifier(col);
+    if (!(threshold >= 0.0 && threshold <= 1.0)) throw Error(TG_ERR_VALIDATION, "Threshold must be between 0.0 and 1.0");
+    static const char* patterns[] = {"^-?\\d+$", "^-?\\d*\\.?\\d+([eE][+-]?\\d+)?$", "^(true|false|TRUE|FALSE|True|False|0|1)$",
+                                     "^\\d{4}-\\d{2}-\\d{2}$", "^\\d{4}-\\d{2}-\\d{2}[ T]\\d{2}:\\d{2}:\\d{2}", ".*"};
+    if (data_type < 0 || data_type > 5) throw Error(TG_ERR_INVALID_ARG, "unknown data type");
+    Slot s;
+    s.kind = SL_DATA_TYPE;
+    s.name = "data_type";
+    s.columns = {col};
+    s.threshold = threshold;
+    s.pattern = patterns[data_type];
+    s.aggs.push_back(p.add_agg(mk_regex(col, s.pattern, false, false)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall) {
     if (groups.empty()) throw Error(TG_ERR_INVALID_ARG, "at least one grouping column is required");
@@ -1204,6 +1223,22 @@ static void finalize_approx_distinct(Plan& p, Slot& s) {
                                       assertion_description(s.assertion) + " for column '" + s.columns[0] + "'");
 }
 
+static void finalize_data_type(Plan& p, Slot& s) {
+    const Agg& a = p.aggs[s.aggs[0]];
+    if (a.err != TG_OK) {
+        set_error(s, a);
+        return;
+    }
+    const double matches = (double)a.u[0], total = (double)(a.u[2] - a.u[1]);  // non-null rows only (WHERE c IS NOT NULL)
+    if (total == 0.0) {
+        skipped(s, "No non-null data to validate");
+        return;
+    }
+    const double ratio = matches / total;
+    if (ratio >= s.threshold) success_metric(s, ratio);
+    else failure_metric(s, ratio, "Data type conformance " + fmt_f64(ratio) + " is below threshold " + fmt_f64(s.threshold));
+}
+
 static void finalize_fk(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     if (a.err != TG_OK) {
@@ -1529,6 +1564,7 @@ void Plan::finalize() {
             case SL_CONTAINMENT: finalize_value_ratio(*this, s, " values are not in the allowed set"); break;
             case SL_NON_NEGATIVE: finalize_value_ratio(*this, s, " values are negative"); break;
             case SL_APPROX_DISTINCT: finalize_approx_distinct(*this, s); break;
+            case SL_DATA_TYPE: finalize_data_type(*this, s); break;
         }
     }
     executed = true;

@@ -76,6 +76,7 @@ enum SlotKind : int32_t {
     SL_CONTAINMENT,
     SL_NON_NEGATIVE,
     SL_APPROX_DISTINCT,
+    SL_DATA_TYPE,
 };
 
 struct StatReq {
@@ -153,6 +154,7 @@ int plan_add_length(Plan& p, const std::string& col, int kind, int64_t a, int64_
 int plan_add_containment(Plan& p, const std::string& col, const std::vector<std::string>& allowed);
 int plan_add_non_negative(Plan& p, const std::string& col);
 int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion a);
+int plan_add_data_type(Plan& p, const std::string& col, int data_type, double threshold);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 

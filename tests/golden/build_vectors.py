@@ -235,6 +235,14 @@ case("non_negative_ok", "constraints/values.rs:562-574", {"data": {"num_col": co
 case("non_negative_failure", "constraints/values.rs:576-588", {"data": {"num_col": col("f64", [1.0, -2.0, 5.5, 100.0])}},
      {"kind": "non_negative", "column": "num_col"}, status="failure", metric=0.75)
 
+# ------------------------------------------------------------------ data type ----
+case("data_type_integer", "constraints/values.rs:480-493", {"data": {"text_col": col("str", ["123", "456", "not_number", "789"])}},
+     {"kind": "data_type", "column": "text_col", "data_type": "Integer", "threshold": 0.7}, status="success", metric=0.75)
+case("data_type_float", "constraints/values.rs:495-507", {"data": {"text_col": col("str", ["123.45", "67.89", "invalid", "100"])}},
+     {"kind": "data_type", "column": "text_col", "data_type": "Float", "threshold": 0.7}, status="success", metric=0.75)
+case("data_type_boolean", "constraints/values.rs:509-521", {"data": {"text_col": col("str", ["true", "false", "invalid", "1"])}},
+     {"kind": "data_type", "column": "text_col", "data_type": "Boolean", "threshold": 0.7}, status="success", metric=0.75)
+
 # ------------------------------------------------------------------ approx_count_distinct ----
 case("approx_distinct_high_cardinality", "constraints/approx_count_distinct.rs:190-205",
      {"data": {"test_col": col("i64", list(range(1000)))}},

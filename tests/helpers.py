@@ -65,6 +65,8 @@ def oracle_eval(case):
         return O.non_negative(t, op["column"])
     if k == "approx_count_distinct":
         return O.approx_count_distinct(t, op["column"], tuple(op["assertion"]))
+    if k == "data_type":
+        return O.data_type(t, op["column"], op["data_type"], op["threshold"])
     raise ValueError(k)
 
 
@@ -148,6 +150,8 @@ def build_constraint(T, op):
         return T.NonNegativeConstraint(op["column"])
     if k == "approx_count_distinct":
         return T.ApproxCountDistinctConstraint(op["column"], _assertion(T, op["assertion"]))
+    if k == "data_type":
+        return T.DataTypeConstraint(op["column"], T.DataType[op["data_type"]], op["threshold"])
     raise ValueError(k)
 
 

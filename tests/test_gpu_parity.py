@@ -281,7 +281,10 @@ def test_length_containment_non_negative_match_oracle(ctx, n):
     status = [["active", "inactive", "pending", "it's", "ACTIVE", ""][v] for v in rng.integers(0, 6, n)]
     nums = rng.normal(0.5, 1.0, n)
     ints = rng.integers(-3, 50, n)
+    numish = [["12", "-7", "3.5", "1e9", "-.5", "2024-01-31", "2024-01-31 10:11:12", "2024-01-31T10:11:12Z", "abc", "", "٣"][v]
+              for v in rng.integers(0, 11, n)]
     t = pa.table({"s": pa.array(strs, type=pa.string(), mask=rng.random(n) < 0.1),
+                  "num": pa.array(numish, type=pa.string(), mask=rng.random(n) < 0.1),
                   "status": pa.array(status, type=pa.string(), mask=rng.random(n) < 0.1),
                   "x": pa.array(nums, mask=rng.random(n) < 0.1), "i": pa.array(ints)})
     name = f"len_{n}"
@@ -296,12 +299,19 @@ def test_length_containment_non_negative_match_oracle(ctx, n):
         cb.constraint(T.ContainmentConstraint("status", ["active", "inactive", "pending", "it's", "ACTIVE", ""]))
         cb.constraint(T.NonNegativeConstraint("x"))
         cb.constraint(T.NonNegativeConstraint("i"))
+        cb.constraint(T.DataTypeConstraint("num", T.DataType.Integer, 0.5))
+        cb.constraint(T.DataTypeConstraint("num", T.DataType.Float, 0.99))
+        cb.constraint(T.DataTypeConstraint("num", T.DataType.Date, 0.01))
+        cb.constraint(T.DataTypeConstraint("num", T.DataType.Timestamp, 0.01))
+        cb.constraint(T.DataTypeConstraint("status", T.DataType.String, 1.0))
         suite = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build()
         rs = suite.run(ctx).report.results
         want = [O.length_constraint(t, "s", a[0], *a[1:]) for a in asserts]
         want += [O.containment(t, "status", ["active", "inactive", "it's"]),
                  O.containment(t, "status", ["active", "inactive", "pending", "it's", "ACTIVE", ""]),
-                 O.non_negative(t, "x"), O.non_negative(t, "i")]
+                 O.non_negative(t, "x"), O.non_negative(t, "i"),
+                 O.data_type(t, "num", "Integer", 0.5), O.data_type(t, "num", "Float", 0.99), O.data_type(t, "num", "Date", 0.01),
+                 O.data_type(t, "num", "Timestamp", 0.01), O.data_type(t, "status", "String", 1.0)]
         assert len(rs) == len(want)
         for g, o in zip(rs, want):
             assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (g, o)
