@@ -102,6 +102,10 @@ void tg_engine_destroy(tg_engine* h) {
     if (e.d_scratch) cudaFree(e.d_scratch);
     if (e.d_shuffle) cudaFree(e.d_shuffle);
     if (e.d_aux) cudaFree(e.d_aux);
+    for (auto& s : e.side)
+        if (s) cudaStreamDestroy(s);
+    for (auto& ev : e.side_ev)
+        if (ev) cudaEventDestroy(ev);
     if (e.h_scratch) cudaFreeHost(e.h_scratch);
     for (int i = 0; i < 2; ++i) {
         if (e.pinned[i]) cudaFreeHost(e.pinned[i]);

@@ -23,6 +23,12 @@ uint8_t* Engine::scratch(size_t bytes) {
     return d_scratch;
 }
 
+void Engine::ensure_side_streams() {
+    if (side[0]) return;
+    for (auto& s : side) TG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    for (auto& ev : side_ev) TG_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+}
+
 uint8_t* Engine::aux(size_t bytes) {
     if (bytes > aux_cap) {
         TG_CUDA(cudaStreamSynchronize(stream));

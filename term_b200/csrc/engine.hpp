@@ -106,6 +106,10 @@ struct Engine {
     void dev_free(uint8_t* p, size_t bytes);
     void dev_trim();
 
+    // side streams: independent bucket pipelines of the partitioned hash jobs run concurrently on them
+    cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void ensure_side_streams();
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
     size_t aux_cap = 0;
     uint8_t* aux(size_t bytes);

@@ -222,15 +222,21 @@ __global__ void fill_kernel(uint4* __restrict__ p, size_t n16, uint32_t word) {
     const uint4 v = make_uint4(word, word, word, word);
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
 }
-static void fill_async(Engine& e, void* p, size_t bytes, uint32_t word) {
-    static const bool use_memset = getenv("TG_HASH_MEMSET") != nullptr;
-    if (use_memset) {
-        TG_CUDA(cudaMemsetAsync(p, (int)(word & 0xff), bytes, e.stream));
-        return;
-    }
+static void fill_async(Engine& e, void* p, size_t bytes, uint32_t word, cudaStream_t stream = nullptr) {
+    if (!stream) stream = e.stream;
     const size_t n16 = bytes / 16;
     const int grid = (int)std::min<size_t>((n16 + 255) / 256, (size_t)e.sm_count * 8);
-    fill_kernel<<<std::max(grid, 1), 256, 0, e.stream>>>((uint4*)p, n16, word);
+    fill_kernel<<<std::max(grid, 1), 256, 0, stream>>>((uint4*)p, n16, word);
+}
+// bucket pipelines run side by side on this many streams, each with its own table: one bucket's kernel is a chain of
+// dependent L2 atomics and does not fill the machine on its own
+static int hash_lanes() {
+    static const int v = [] {
+        const char* e = getenv("TG_HASH_LANES");
+        const int x = e ? atoi(e) : 0;
+        return x >= 1 && x <= 4 ? x : 2;
+    }();
+    return v;
 }
 
 constexpr int BUCKET_ILP = 4;  // independent probe chains per thread (the loop is bound by L2 atomic latency)
@@ -440,7 +446,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
             const int64_t row = base + k * PART_THREADS + threadIdx.x;
             ok[k] = (vw[k] >> (row & 31)) & 1u;
             nulls += (row < n) && !ok[k];
-            const unsigned long long idx = (unsigned long long)(v[k] - lo);
+            const unsigned long long idx = ((unsigned long long)v[k] - (unsigned long long)lo);
             old[k] = 0;
             if (ok[k]) {
                 const uint32_t bit = 1u << (idx & 31);
@@ -456,7 +462,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
                 if (!old[k]) {
                     ++d;
                 } else {
-                    const unsigned long long idx = (unsigned long long)(v[k] - lo);
+                    const unsigned long long idx = ((unsigned long long)v[k] - (unsigned long long)lo);
                     const uint32_t bit = 1u << (idx & 31);
                     if (!(atomicOr(&dup[idx >> 5], bit) & bit)) ++dupk;
                 }
@@ -509,8 +515,10 @@ static int bucket_grid(Engine& e, int64_t expected) {
     const int64_t blocks = (expected + HASH_THREADS - 1) / HASH_THREADS;
     return (int)std::max<int64_t>(1, std::min<int64_t>(blocks, (int64_t)e.sm_count * 8));
 }
-static uint32_t parts_for(int64_t n) {
-    return (uint32_t)std::min<uint64_t>(PART_MAX, pow2_at_least((uint64_t)((n + bucket_target_keys() - 1) / bucket_target_keys()), 1));
+static uint32_t parts_for(int64_t n, int lanes = 1) {
+    // `lanes` tables share the L2, so each bucket gets 1/lanes of the key budget
+    const int64_t target = std::max<int64_t>(1024, bucket_target_keys() / lanes);
+    return (uint32_t)std::min<uint64_t>(PART_MAX, pow2_at_least((uint64_t)((n + target - 1) / target), 1));
 }
 
 // device block: [hist parts][offsets parts+1][cursors parts][PartCounters], 256-byte aligned pieces
@@ -546,24 +554,37 @@ static int partition_column(Engine& e, const Column& c, int64_t n, uint32_t part
 }
 
 bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches) {
-    const uint32_t parts = parts_for(n);
+    const int lanes = hash_lanes();
+    const uint32_t parts = parts_for(n, lanes);
     const uint64_t cap = pow2_at_least(((uint64_t)n + parts - 1) / parts * slots_factor(), 1024);
     const size_t keys_b = round_up((size_t)n * 8, 256), tab_b = cap * 8, bits_b = round_up(cap / 8, 256);
-    uint8_t* scr = e.scratch(keys_b + tab_b + bits_b + PartMeta::bytes() + 256);
+    uint8_t* scr = e.scratch(keys_b + (size_t)lanes * (tab_b + bits_b) + PartMeta::bytes() + 256);
     uint64_t* part_keys = (uint64_t*)scr;
-    unsigned long long* table = (unsigned long long*)(scr + keys_b);
-    uint32_t* bits = (uint32_t*)(scr + keys_b + tab_b);
+    uint8_t* tables = scr + keys_b;
     PartMeta m;
-    m.bind(scr + keys_b + tab_b + bits_b);
-    HashCounters* d_ctr = (HashCounters*)(scr + keys_b + tab_b + bits_b + PartMeta::bytes());
+    m.bind(tables + (size_t)lanes * (tab_b + bits_b));
+    HashCounters* d_ctr = (HashCounters*)(tables + (size_t)lanes * (tab_b + bits_b) + PartMeta::bytes());
     TG_CUDA(cudaMemsetAsync(d_ctr, 0, sizeof(HashCounters), e.stream));
     launches += partition_column<PM_BUCKET>(e, c, n, parts, m, part_keys);
     const int grid = bucket_grid(e, n / parts / BUCKET_ILP + 1);
-    for (uint32_t b = 0; b < parts; ++b) {
-        fill_async(e, table, tab_b, 0xFFFFFFFFu);
-        fill_async(e, bits, bits_b, 0u);
-        insert_bucket_kernel<<<grid, HASH_THREADS, 0, e.stream>>>(part_keys, m.offsets, (int)b, table, (uint32_t)(cap - 1), bits, d_ctr);
-        ++launches;
+    // fan out: lane l handles buckets l, l + lanes, .. on its own stream and table; fan back in before the read-back
+    e.ensure_side_streams();
+    TG_CUDA(cudaEventRecord(e.side_ev[4], e.stream));
+    for (int l = 0; l < lanes; ++l) {
+        cudaStream_t st = lanes == 1 ? e.stream : e.side[l];
+        if (lanes > 1) TG_CUDA(cudaStreamWaitEvent(st, e.side_ev[4], 0));
+        unsigned long long* table = (unsigned long long*)(tables + (size_t)l * (tab_b + bits_b));
+        uint32_t* bits = (uint32_t*)(tables + (size_t)l * (tab_b + bits_b) + tab_b);
+        for (uint32_t b = (uint32_t)l; b < parts; b += (uint32_t)lanes) {
+            fill_async(e, table, tab_b, 0xFFFFFFFFu, st);
+            fill_async(e, bits, bits_b, 0u, st);
+            insert_bucket_kernel<<<grid, HASH_THREADS, 0, st>>>(part_keys, m.offsets, (int)b, table, (uint32_t)(cap - 1), bits, d_ctr);
+            ++launches;
+        }
+        if (lanes > 1) {
+            TG_CUDA(cudaEventRecord(e.side_ev[l], st));
+            TG_CUDA(cudaStreamWaitEvent(e.stream, e.side_ev[l], 0));
+        }
     }
     TG_CUDA(cudaGetLastError());
     HashCounters h{};
