@@ -353,6 +353,19 @@ TG_API tg_status tg_plan_finalize(tg_plan* plan);
 TG_API int32_t tg_plan_num_aggregates(const tg_plan* plan);
 TG_API tg_status tg_plan_aggregate_info(const tg_plan* plan, int32_t i, int32_t* kind, const char** key);
 
+/*
+ * Peer mailboxes: the per-step exchange of partial states over NVLink / NVSwitch peer memory instead of
+ * H2D -> ncclAllGather -> D2H (one node, one process per GPU). Each rank creates a mailbox (a small device buffer;
+ * *handle_out receives its 64-byte cudaIpcMemHandle_t), the host layer all-gathers the handles once (any transport)
+ * and every rank opens them. tg_plan_exchange_and_finalize then replaces
+ * export / all-gather / reset / merge-in-rank-order / finalize: one kernel stores this rank's blob into every peer's
+ * mailbox and raises a flag, a second waits for all flags, one copy brings the collected blobs to the host.
+ * Falls back to the NCCL path of the host layer when a blob exceeds slot_bytes (TG_ERR_INVALID_ARG).
+ */
+TG_API tg_status tg_engine_mailbox_create(tg_engine* eng, int32_t world, int32_t rank, size_t slot_bytes, void* handle_out);
+TG_API tg_status tg_engine_mailbox_open(tg_engine* eng, const void* handles /* world x 64 bytes, rank order */);
+TG_API tg_status tg_plan_exchange_and_finalize(tg_engine* eng, tg_plan* plan);
+
 /* Multi-GPU shuffle, step 3: aggregate i (kind 6 DISTINCT or 7 FK) reads its keys from `table_name` — the table
  * holding this rank's hash-shuffled shard (tg_table_partition_keys + all-to-all + tg_table_adopt_device) — instead
  * of the plan's table; which = 0: the DISTINCT table / the FK child table, 1: the FK parent table. NULL or ""

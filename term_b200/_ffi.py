@@ -109,6 +109,9 @@ SIGNATURES = {
     "tg_plan_finalize": (C.c_int, [P]),
     "tg_plan_num_aggregates": (C.c_int32, [P]),
     "tg_plan_aggregate_info": (C.c_int, [P, C.c_int32, C.POINTER(C.c_int32), C.POINTER(C.c_char_p)]),
+    "tg_engine_mailbox_create": (C.c_int, [P, C.c_int32, C.c_int32, C.c_size_t, P]),
+    "tg_engine_mailbox_open": (C.c_int, [P, P]),
+    "tg_plan_exchange_and_finalize": (C.c_int, [P, P]),
     "tg_plan_redirect_aggregate": (C.c_int, [P, C.c_int32, C.c_int32, C.c_char_p]),
     "tg_plan_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_result)]),
     "tg_plan_analyzer_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_analyzer_result)]),

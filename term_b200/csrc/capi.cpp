@@ -102,6 +102,7 @@ void tg_engine_destroy(tg_engine* h) {
     if (e.d_scratch) cudaFree(e.d_scratch);
     if (e.d_shuffle) cudaFree(e.d_shuffle);
     if (e.d_aux) cudaFree(e.d_aux);
+    mailbox_destroy(e);
     for (auto& s : e.side)
         if (s) cudaStreamDestroy(s);
     for (auto& ev : e.side_ev)
@@ -362,6 +363,36 @@ tg_status tg_plan_aggregate_info(const tg_plan* p, int32_t i, int32_t* kind, con
         if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
         if (kind) *kind = p->p.aggs[i].kind;
         if (key) *key = p->p.aggs[i].key.c_str();
+    });
+}
+
+tg_status tg_engine_mailbox_create(tg_engine* h, int32_t world, int32_t rank, size_t slot_bytes, void* handle_out) {
+    return guard([&] {
+        if (!h || !handle_out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        TG_CUDA(cudaSetDevice(h->e.device));
+        mailbox_create(h->e, world, rank, slot_bytes, handle_out);
+    });
+}
+tg_status tg_engine_mailbox_open(tg_engine* h, const void* handles) {
+    return guard([&] {
+        if (!h || !handles) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        TG_CUDA(cudaSetDevice(h->e.device));
+        mailbox_open(h->e, handles);
+    });
+}
+// publish this plan's partial states to every rank's mailbox, collect everyone's, merge IN RANK ORDER, finalize
+tg_status tg_plan_exchange_and_finalize(tg_engine* h, tg_plan* p) {
+    return guard([&] {
+        if (!h || !p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::vector<uint8_t> blob(p->p.partial_size());
+        p->p.partial_export(blob.data());
+        std::vector<std::vector<uint8_t>> all;
+        mailbox_exchange(h->e, blob.data(), blob.size(), all);
+        p->p.reset_partials();
+        for (auto& b : all) p->p.partial_merge(b.data(), b.size());
+        p->p.finalize();
     });
 }
 

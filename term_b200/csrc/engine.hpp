@@ -77,6 +77,23 @@ struct Table {
     }
 };
 
+// peer mailboxes of the multi-GPU partial-state exchange (mailbox.cu)
+constexpr int MAILBOX_MAX_WORLD = 16;
+struct MailboxPeers {
+    uint8_t* p[MAILBOX_MAX_WORLD];
+};
+struct Mailbox {
+    int world = 0, rank = 0;
+    size_t slot_bytes = 0, bytes = 0;
+    uint8_t* local = nullptr;     // this rank's mailbox (device)
+    MailboxPeers peers{};         // every rank's mailbox as seen from this device (IPC-mapped)
+    uint8_t* d_stage = nullptr;   // this rank's outgoing blob (device) + timeout flag
+    uint8_t* h_stage = nullptr;   // pinned
+    uint8_t* h_all = nullptr;     // pinned landing area of a collected step
+    unsigned long long seq = 0;
+    bool open = false;
+};
+
 struct Engine {
     int device = 0;
     int sm_count = 0;
@@ -110,6 +127,7 @@ struct Engine {
     cudaStream_t side[4] = {nullptr, nullptr, nullptr, nullptr};
     cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void ensure_side_streams();
+    Mailbox mailbox;
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
     size_t aux_cap = 0;
     uint8_t* aux(size_t bytes);
@@ -131,6 +149,12 @@ void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);
+
+// mailbox.cu
+void mailbox_create(Engine& e, int world, int rank, size_t slot_bytes, void* handle_out /* 64 bytes */);
+void mailbox_open(Engine& e, const void* handles /* world x 64 bytes */);
+void mailbox_destroy(Engine& e);
+void mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out);
 
 // scan.cu
 size_t scan_smem_bytes(const ScanParams& P);

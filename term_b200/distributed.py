@@ -12,6 +12,8 @@
   its keys as a table and the aggregate is redirected to it (tg_plan_redirect_aggregate). Equal keys now live on
   exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0.
 """
+import os
+
 import torch
 import torch.distributed as dist
 
@@ -91,6 +93,56 @@ def allgather_blobs_fixed(blob: bytes, cap: int, device=None):
             return None
         out.append(raw[r * cap + 8: r * cap + 8 + ln].tobytes())
     return out
+
+
+MAILBOX_SLOT_BYTES = 64 * 1024
+
+
+def _ensure_mailbox(ctx) -> bool:
+    """One-time setup of the NVLink peer mailboxes (tg_engine_mailbox_*): create, all-gather the 64-byte CUDA IPC
+    handles, open. Returns False (and remembers it) when the platform refuses, so the NCCL all-gather path is used."""
+    import ctypes as C
+    state = getattr(ctx, "_mailbox_state", None)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if state is not None:
+        return state == ("ok", world)
+    ok = True
+    handle = C.create_string_buffer(64)
+    try:
+        if os.environ.get("TG_NO_MAILBOX"):
+            raise RuntimeError("disabled")
+        F.check(F.lib().tg_engine_mailbox_create(ctx.handle, world, rank, MAILBOX_SLOT_BYTES, handle))
+    except Exception:
+        ok = False
+    dev = _device()
+    mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(dev)
+    allh = torch.zeros(64 * world, dtype=torch.uint8, device=dev)
+    dist.all_gather_into_tensor(allh, mine)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = bool(flag.item())
+    if ok:
+        try:
+            raw = bytes(allh.cpu().numpy().tobytes())
+            F.check(F.lib().tg_engine_mailbox_open(ctx.handle, raw))
+        except Exception:
+            ok = False
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    ctx._mailbox_state = ("ok", world) if ok else ("failed", world)
+    return ok
+
+
+def exchange_and_finalize(plan, ctx):
+    """Exchange this rank's partial states with every rank, merge in rank order, finalize. Plans whose partial records
+    are fixed-size go through the peer mailboxes (two tiny kernels + one copy over NVLink peer memory, see
+    term_b200/csrc/mailbox.cu); everything else, and any platform where CUDA IPC is unavailable, takes the NCCL
+    all-gather."""
+    if dist.get_backend() == "nccl" and all(k in _FIXED_KINDS for k, _ in plan.aggregates()) and _ensure_mailbox(ctx):
+        F.check(F.lib().tg_plan_exchange_and_finalize(ctx.handle, plan.handle))
+        return
+    merge_partials(plan, exchange_partials(plan))
 
 
 def exchange_partials(plan):
@@ -200,7 +252,7 @@ def execute_distributed(plan, ctx, table="data"):
                 plan.redirect(i, 1, pname)
                 redirected += [(i, 0), (i, 1)]
         plan.execute_partial(ctx, table)
-        merge_partials(plan, exchange_partials(plan))
+        exchange_and_finalize(plan, ctx)
     finally:
         for i, which in redirected:
             plan.redirect(i, which, None)
