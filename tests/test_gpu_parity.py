@@ -404,6 +404,78 @@ def test_uniqueness_partitioned_path_large_keys(ctx, dtype):
         ctx.deregister_table(name)
 
 
+@pytest.mark.parametrize("shape", ["all_null", "all_equal", "one_null", "two_values_sparse", "no_validity"])
+def test_uniqueness_large_path_edge_cases(ctx, shape):
+    """degenerate key columns through the dense / partitioned paths: no valid key at all, one hot key (every row in the
+    same bucket), exactly one NULL (the NULL group is a singleton), two far-apart values (not dense), no bitmap"""
+    n = 1_200_000
+    rng = np.random.default_rng(8)
+    mask = np.zeros(n, dtype=bool)
+    if shape == "all_null":
+        vals, mask = np.zeros(n, dtype=np.int64), np.ones(n, dtype=bool)
+    elif shape == "all_equal":
+        vals = np.full(n, 7_000_000_007, dtype=np.int64)
+        mask = rng.random(n) < 0.1
+    elif shape == "one_null":
+        vals = rng.permutation(n).astype(np.int64) * 1_000_003
+        mask[12345] = True
+    elif shape == "two_values_sparse":
+        vals = np.where(rng.random(n) < 0.5, np.int64(-(2**62)), np.int64(2**62)).astype(np.int64)
+    else:
+        vals = rng.integers(0, n // 4, n).astype(np.int64) * 1_000_003
+    arr = pa.array(vals, mask=mask) if shape != "no_validity" else pa.array(vals)
+    name = f"uniq_edge_{shape}"
+    ctx.register_table(name, pa.table({"k": arr}))
+    try:
+        kept = vals[~mask]
+        _, counts = np.unique(kept, return_counts=True)
+        distinct, singles, nulls = len(counts), int((counts == 1).sum()), int(mask.sum())
+        a = T.DistinctnessAnalyzer("k").compute(ctx, name)
+        assert a.u[:2] == [n - nulls, distinct]
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="UniqueValueRatio", assertion=["GreaterThanOrEqual", 0.0])).evaluate(ctx, name)
+        assert g.metric == (singles + (1 if nulls == 1 else 0)) / n
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="PrimaryKey")).evaluate(ctx, name)
+        if nulls:
+            assert g.status is T.ConstraintStatus.Failure and g.metric == nulls / n
+        elif distinct != n:
+            assert g.status is T.ConstraintStatus.Failure and g.metric == (n - distinct) / n
+        else:
+            assert g.status is T.ConstraintStatus.Success
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.parametrize("shape", ["empty_parent", "all_null_children", "parent_with_nulls_sparse"])
+def test_foreign_key_large_path_edge_cases(ctx, shape):
+    n_child = 1_200_000
+    rng = np.random.default_rng(9)
+    mul = 1_000_003 if shape == "parent_with_nulls_sparse" else 1
+    children = rng.integers(0, 700_000, n_child).astype(np.int64) * mul
+    cmask = np.ones(n_child, dtype=bool) if shape == "all_null_children" else rng.random(n_child) < 0.01
+    if shape == "empty_parent":
+        parents, pmask = np.zeros(0, dtype=np.int64), np.zeros(0, dtype=bool)
+    else:
+        parents = rng.permutation(700_000)[:600_000].astype(np.int64) * mul
+        pmask = rng.random(len(parents)) < 0.05
+    ctx.register_table("fkpe", pa.table({"id": pa.array(parents, mask=pmask)}))
+    ctx.register_table("fkce", pa.table({"cid": pa.array(children, mask=cmask)}))
+    try:
+        valid_children = children[~cmask]
+        orphan = ~np.isin(valid_children, parents[~pmask])
+        for allow in (False, True):
+            g = T.ForeignKeyConstraint("fkce.cid", "fkpe.id").allow_nulls(allow).evaluate(ctx)
+            want = int(orphan.sum()) + (0 if allow else int(cmask.sum()))
+            if want == 0:
+                assert g.status is T.ConstraintStatus.Success and g.metric is None
+            else:
+                uniq = len(np.unique(valid_children[orphan]))
+                assert g.status is T.ConstraintStatus.Failure and g.metric == float(want)
+                assert f"(total: {want}, unique: {uniq})" in g.message, g.message[:200]
+    finally:
+        ctx.deregister_table("fkpe")
+        ctx.deregister_table("fkce")
+
+
 @pytest.mark.parametrize("keys", ["dense", "sparse"])
 def test_foreign_key_partitioned_path_large_parent(ctx, keys):
     """large parent key set (hashpart.cu): a dense Int64 parent range becomes a bitmap; sparse keys are radix-
