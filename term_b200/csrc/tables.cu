@@ -110,6 +110,16 @@ void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t
         t.n_rows = std::max(t.n_rows, c.n_rows);
         return;
     }
+    // ---- fixed-width values first: their DMA (the bulk of the bytes) is queued before the host walks the validity
+    // bitmap below, so counting NULLs overlaps the copy instead of delaying it ----
+    const bool fixed_width = dtype == TG_INT64 || dtype == TG_FLOAT64 || dtype == TG_INT32 || dtype == TG_FLOAT32;
+    if (fixed_width) {
+        const size_t w = (size_t)c.elem_bytes();
+        e.dev_reserve(c.values, (size_t)(have + n) * w, (size_t)have * w);
+        e.h2d(c.values.p + (size_t)have * w, values, (size_t)n * w);
+        c.value_bytes = (have + n) * (int64_t)w;
+        set_pivot_host(c, dtype, n, values, validity, bit_offset);
+    }
     // ---- validity ----
     bool has_nulls = false;
     bool fast_bits = false;
@@ -158,13 +168,7 @@ void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t
         case TG_INT64:
         case TG_FLOAT64:
         case TG_INT32:
-        case TG_FLOAT32: {
-            const size_t w = (size_t)c.elem_bytes();
-            e.dev_reserve(c.values, (size_t)(have + n) * w, (size_t)have * w);
-            e.h2d(c.values.p + (size_t)have * w, values, (size_t)n * w);
-            c.value_bytes = (have + n) * (int64_t)w;
-            set_pivot_host(c, dtype, n, values, validity, bit_offset);
-        } break;
+        case TG_FLOAT32: break;  // queued above
         case TG_BOOL: {
             append_bits(e, c.values, c.tail_vbyte, have, (const uint8_t*)values, bit_offset, n, nullptr);
             c.value_bytes = (have + n + 7) / 8;
