@@ -10,7 +10,7 @@ constexpr int SCAN_MAX_CODE = 128;
 constexpr int SCAN_MAX_TERMS = 32;
 constexpr int SCAN_UNIT_TERMS = 4;  // comparison terms a UNIT_TERMS unit keeps in registers
 #ifndef TG_SCAN_CONSUMER_WARPS
-#define TG_SCAN_CONSUMER_WARPS 15  // + 1 producer = 16 warps = 4 per SM sub-partition -> 128 registers per thread
+#define TG_SCAN_CONSUMER_WARPS 16  // + 1 producer = 17 warps (96 registers per thread); measured against 15 @128 and 19 @96: best on both C2 suites
 #endif
 constexpr int SCAN_CONSUMER_WARPS = TG_SCAN_CONSUMER_WARPS;
 constexpr int SCAN_THREADS = (SCAN_CONSUMER_WARPS + 1) * 32;  // warp 0 = TMA producer
