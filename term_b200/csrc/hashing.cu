@@ -344,7 +344,7 @@ void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
         Distinct64Result r;
         Timer tm(e, p);
         int launches = 0;
-        bool ok = distinct64_dense(e, *cols[0], n, r, launches);
+        bool ok = distinct64_dense(e, *cols[0], n, (a.flags & 1) != 0, r, launches);
         if (!ok && (size_t)n > distinct64_min_rows()) ok = distinct64_partitioned(e, *cols[0], n, r, launches);
         tm.stop(launches);
         if (ok) {

@@ -420,13 +420,24 @@ __global__ void __launch_bounds__(PART_THREADS) minmax_i64_kernel(const long lon
     }
 }
 
+// number of set bits of a bitmap (distinct count after a non-returning build)
+__global__ void bitmap_popcount_kernel(const uint4* __restrict__ bm, size_t n16, unsigned long long* out) {
+    unsigned long long c = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) {
+        const uint4 v = bm[i];
+        c += __popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w);
+    }
+    flush_counter(c, out);
+}
+
 // mode 0: distinct / seen-twice counting; mode 1: build the parent set (non-returning OR); mode 2: probe
 template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __restrict__ values, const uint32_t* __restrict__ validity,
                                                              int64_t n, long long lo, unsigned long long range, uint32_t* seen,
                                                              uint32_t* dup, unsigned long long* vkeys, uint64_t vmask,
-                                                             unsigned long long* examples, int max_examples, HashCounters* ctr) {
-    unsigned long long d = 0, dupk = 0, viol = 0, dist = 0, nulls = 0, special = 0;
+                                                             unsigned long long* examples, int max_examples, HashCounters* ctr,
+                                                             unsigned long long* nulls_out = nullptr) {
+    unsigned long long d = 0, dupk = 0, viol = 0, dist = 0, nulls = 0, special = 0, nulls_count = 0;
     const int64_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * PART_TILE;
@@ -446,6 +457,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
             const int64_t row = base + k * PART_THREADS + threadIdx.x;
             ok[k] = (vw[k] >> (row & 31)) & 1u;
             nulls += (row < n) && !ok[k];
+            nulls_count += (row < n) && !ok[k];
             const unsigned long long idx = ((unsigned long long)v[k] - (unsigned long long)lo);
             old[k] = 0;
             if (ok[k]) {
@@ -498,6 +510,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
         flush_counter(special, &ctr->special);
     }
     if (MODE != 1) flush_counter(nulls, &ctr->any_null_rows);
+    if (MODE == 1 && nulls_out) flush_counter(nulls_count, nulls_out);
 }
 
 // ================================================================== host side ==================
@@ -733,7 +746,7 @@ static bool dense_enough(const MinMaxOut& h) {
     return range < DENSE_MAX_RANGE && range <= 32ull * h.n_valid + 4096ull;
 }
 
-bool distinct64_dense(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches) {
+bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, Distinct64Result& r, int& launches) {
     if (c.dtype != TG_INT64 || getenv("TG_HASH_NO_DENSE")) return false;
     MinMaxOut mm{};
     if (!minmax_i64(e, c, n, mm, launches)) {
@@ -747,16 +760,29 @@ bool distinct64_dense(Engine& e, const Column& c, int64_t n, Distinct64Result& r
     uint32_t* seen = (uint32_t*)scr;
     uint32_t* dup = (uint32_t*)(scr + bm_b);
     HashCounters* d_ctr = (HashCounters*)(scr + 2 * bm_b);
-    fill_async(e, scr, 2 * bm_b + 256, 0u);
-    dense_kernel<0><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, mm.mn, range,
-                                                                   seen, dup, nullptr, 0, nullptr, 0, d_ctr);
-    TG_CUDA(cudaGetLastError());
-    launches += 2;
     HashCounters h{};
+    if (need_singles) {
+        // one RETURNING atomicOr per key: the old bit tells first from repeated occurrence
+        fill_async(e, scr, 2 * bm_b + 256, 0u);
+        dense_kernel<0><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, mm.mn,
+                                                                       range, seen, dup, nullptr, 0, nullptr, 0, d_ctr);
+        launches += 2;
+    } else {
+        // only COUNT(DISTINCT) is wanted: non-returning ORs (190 vs 126 G/s in L2), then count the set bits
+        fill_async(e, seen, bm_b, 0u);
+        fill_async(e, d_ctr, 256, 0u);
+        dense_kernel<1><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, mm.mn,
+                                                                       range, seen, nullptr, nullptr, 0, nullptr, 0, d_ctr, &d_ctr->any_null_rows);
+        const size_t n16 = bm_b / 16;
+        bitmap_popcount_kernel<<<(int)std::max<size_t>(1, std::min<size_t>((n16 + 255) / 256, (size_t)e.sm_count * 8)), 256, 0, e.stream>>>(
+            (const uint4*)seen, n16, &d_ctr->distinct_nonnull);
+        launches += 4;
+    }
+    TG_CUDA(cudaGetLastError());
     TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
     r.distinct = h.distinct_nonnull;
-    r.dup_keys = h.singles_minus;
+    r.dup_keys = need_singles ? h.singles_minus : 0;  // unused by the slots of this plan when !need_singles
     r.nulls = h.any_null_rows;
     return true;
 }

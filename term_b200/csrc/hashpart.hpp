@@ -18,7 +18,7 @@ bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Res
 size_t distinct64_min_rows();
 // Dense Int64 key range (max - min < 2^28 and < 32 n): exact bitmap counting, no partitioning. Returns false when
 // the column does not qualify (nothing is counted then).
-bool distinct64_dense(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches);
+bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, Distinct64Result& r, int& launches);
 
 struct Fk64Result {
     uint64_t violations = 0;           // child rows without a parent (NULL children included when not allowed)

@@ -13,7 +13,7 @@ namespace tg {
 int Plan::add_agg(Agg a) {
     for (size_t i = 0; i < aggs.size(); ++i)
         if (aggs[i].key == a.key) {
-            if (a.kind == A_NUM) aggs[i].flags |= a.flags;  // union of the statistics requested on the column
+            if (a.kind == A_NUM || a.kind == A_DISTINCT) aggs[i].flags |= a.flags;  // union of what the slots need
             return (int)i;
         }
     aggs.push_back(std::move(a));
@@ -94,9 +94,12 @@ static Agg mk_regex(const std::string& c, const std::string& pattern, bool icase
     a.text = pattern;
     return a;
 }
-static Agg mk_distinct(const std::vector<std::string>& cols) {
+// flags bit 0: some slot needs the singleton-group count (u2: GROUP BY .. HAVING COUNT(*) = 1); without it the
+// dense path can count with non-returning atomics
+static Agg mk_distinct(const std::vector<std::string>& cols, bool need_singles = false) {
     Agg a;
     a.kind = A_DISTINCT;
+    a.flags = need_singles ? 1 : 0;
     a.key = "distinct";
     for (auto& c : cols) a.key += "|" + c;
     a.cols = cols;
@@ -268,7 +271,7 @@ int plan_add_uniqueness(Plan& p, const std::vector<std::string>& cols, int kind,
     s.threshold = threshold;
     s.assertion = a;
     s.null_handling = null_handling;
-    s.aggs.push_back(p.add_agg(mk_distinct(cols)));
+    s.aggs.push_back(p.add_agg(mk_distinct(cols, kind == TG_UNIQ_UNIQUE_VALUE_RATIO)));
     p.slots.push_back(std::move(s));
     return (int)p.slots.size() - 1;
 }
