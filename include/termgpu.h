@@ -56,7 +56,9 @@ typedef enum {
     TG_UTF8 = 3,   /* Arrow Utf8: int32 offsets + value bytes */
     TG_INT32 = 4,
     TG_FLOAT32 = 5,
-    TG_BOOL = 6    /* Arrow Boolean: bit-packed values */
+    TG_BOOL = 6,   /* Arrow Boolean: bit-packed values */
+    TG_FP128 = 7   /* internal: 24-byte records {h1, h2, null flag} of a hash-shuffled Utf8 / composite key
+                      (tg_table_partition_fingerprints); only COUNT(DISTINCT ..)-type aggregates read it */
 } tg_dtype;
 
 /* ConstraintStatus (core/constraint.rs:11-20) */
@@ -253,6 +255,14 @@ TG_API tg_status tg_table_adopt_device(tg_table* t, const char* name, int32_t dt
  */
 TG_API tg_status tg_table_partition_keys(tg_engine* eng, const char* table, const char* column, int32_t n_parts,
                                          void** d_keys, int64_t* counts, int64_t* n_null_rows);
+
+/* Same for Utf8 and composite keys: every row's key tuple is reduced to its 128-bit fingerprint (the identity the
+ * single-GPU path uses too) plus a "has a NULL component" flag, and the 24-byte records {h1, h2, flag} are grouped
+ * by destination part. The receiving rank adopts them as ONE column named "tg_fp" of dtype TG_FP128 and redirects
+ * the DISTINCT aggregate to that table. (Foreign keys over Utf8 columns stay single-GPU: their violation examples
+ * need the strings.) */
+TG_API tg_status tg_table_partition_fingerprints(tg_engine* eng, const char* table, const char* const* columns,
+                                                 int32_t n_columns, int32_t n_parts, void** d_records, int64_t* counts);
 
 /* Arrow C Data Interface ingestion: `schema`/`array` are struct ArrowSchema* / struct ArrowArray* of a
  * struct-typed array (a RecordBatch). The engine copies; the caller keeps ownership and releases. */

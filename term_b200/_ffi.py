@@ -26,7 +26,7 @@ STATUS_NAMES = {
 TG_ERR_SECURITY, TG_ERR_UNSUPPORTED, TG_ERR_CUDA, TG_ERR_VALIDATION, TG_ERR_CONFIGURATION = 4, 5, 6, 10, 11
 
 # tg_dtype
-TG_INT64, TG_FLOAT64, TG_UTF8, TG_INT32, TG_FLOAT32, TG_BOOL = 1, 2, 3, 4, 5, 6
+TG_INT64, TG_FLOAT64, TG_UTF8, TG_INT32, TG_FLOAT32, TG_BOOL, TG_FP128 = 1, 2, 3, 4, 5, 6, 7
 # tg_constraint_status
 TG_SUCCESS, TG_FAILURE, TG_SKIPPED = 0, 1, 2
 
@@ -77,6 +77,7 @@ SIGNATURES = {
     "tg_table_append_host": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_adopt_device": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_append_arrow": (C.c_int, [P, P, P]),
+    "tg_table_partition_fingerprints": (C.c_int, [P, C.c_char_p, STRS, C.c_int32, C.c_int32, PP, C.POINTER(C.c_int64)]),
     "tg_table_partition_keys": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_int32, PP, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "tg_plan_create": (C.c_int, [PP]),
     "tg_plan_destroy": (None, [P]),

@@ -245,6 +245,15 @@ class SessionContext:
                                                 C.byref(nulls)))
         return int(ptr.value or 0), [int(c) for c in counts], int(nulls.value)
 
+    def partition_fingerprints(self, table: str, columns, n_parts: int):
+        """tg_table_partition_fingerprints: (device pointer to 24-byte {h1, h2, has_null} records grouped by destination
+        part, records per part)."""
+        ptr = C.c_void_p()
+        counts = (C.c_int64 * n_parts)()
+        arr, n = _strs(list(columns))
+        F.check(F.lib().tg_table_partition_fingerprints(self._h, table.encode(), arr, n, n_parts, C.byref(ptr), counts))
+        return int(ptr.value or 0), [int(c) for c in counts]
+
     def column_dtype(self, table: str, column: str) -> int:
         t = C.c_void_p()
         F.check(F.lib().tg_table_lookup(self._h, table.encode(), C.byref(t)))

@@ -28,6 +28,12 @@ struct tg_plan {
     std::string msg_scratch;
 };
 
+static std::vector<std::string> strvec(const char* const* a, int32_t n) {
+    std::vector<std::string> v;
+    for (int32_t i = 0; i < n; ++i) v.emplace_back(a[i] ? a[i] : "");
+    return v;
+}
+
 template <typename F>
 static tg_status guard(F&& f) {
     try {
@@ -156,6 +162,22 @@ tg_status tg_table_drop(tg_engine* h, const char* name) {
     });
 }
 
+tg_status tg_table_partition_fingerprints(tg_engine* h, const char* table, const char* const* columns, int32_t n_columns, int32_t n_parts,
+                                          void** d_records, int64_t* counts) {
+    return guard([&] {
+        if (!h || !table || !columns || !d_records || !counts) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        Engine& e = h->e;
+        std::lock_guard<std::mutex> g(e.mu);
+        TG_CUDA(cudaSetDevice(e.device));
+        e.sync_copies();
+        auto it = e.tables.find(table);
+        if (it == e.tables.end()) throw Error(TG_ERR_TABLE_NOT_FOUND, std::string("table '") + table + "' not found");
+        int launches = 0;
+        partition_fingerprints_by_rank(e, *it->second, strvec(columns, n_columns), n_parts, d_records, counts, launches);
+        e.launches += launches;
+    });
+}
+
 tg_status tg_table_column_dtype(const tg_table* t, const char* column, int32_t* dtype) {
     return guard([&] {
         if (!t || !column || !dtype) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
@@ -235,11 +257,6 @@ tg_status tg_plan_create(tg_plan** out) {
 void tg_plan_destroy(tg_plan* p) { delete p; }
 int32_t tg_plan_num_slots(const tg_plan* p) { return p ? (int32_t)p->p.slots.size() : 0; }
 
-static std::vector<std::string> strvec(const char* const* a, int32_t n) {
-    std::vector<std::string> v;
-    for (int32_t i = 0; i < n; ++i) v.emplace_back(a[i] ? a[i] : "");
-    return v;
-}
 
 int32_t tg_plan_add_completeness(tg_plan* p, const char* const* columns, int32_t n, double threshold, int32_t op,
                                  int32_t op_n) {

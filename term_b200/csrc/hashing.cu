@@ -329,13 +329,125 @@ static int compute_fingerprints(Engine& e, Table& t, const std::vector<Column*>&
     return launches;
 }
 
+// ---------------------------------------------------------------- fingerprint shuffle (multi-GPU, Utf8 / composite keys) ----
+struct FpRecord {
+    unsigned long long h1, h2, has_null;
+};
+constexpr int FPS_THREADS = 256, FPS_ROWS = 4, FPS_MAX_PARTS = 1024;
+
+__global__ void __launch_bounds__(FPS_THREADS) fp_rank_hist_kernel(const Fp* fp, int64_t n, uint32_t parts, unsigned long long* hist) {
+    __shared__ uint32_t s_hist[FPS_MAX_PARTS];
+    for (int i = threadIdx.x; i < (int)parts; i += FPS_THREADS) s_hist[i] = 0;
+    __syncthreads();
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x)
+        atomicAdd(&s_hist[hash_rank(fp[row].h1, parts)], 1u);
+    __syncthreads();
+    for (int i = threadIdx.x; i < (int)parts; i += FPS_THREADS)
+        if (s_hist[i]) atomicAdd(&hist[i], (unsigned long long)s_hist[i]);
+}
+__global__ void fp_prefix_kernel(const unsigned long long* hist, uint32_t parts, unsigned long long* offsets, unsigned long long* cursors) {
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        for (uint32_t i = 0; i < parts; ++i) {
+            offsets[i] = run;
+            cursors[i] = run;
+            run += hist[i];
+        }
+        offsets[parts] = run;
+    }
+}
+__global__ void __launch_bounds__(FPS_THREADS) fp_rank_scatter_kernel(const Fp* fp, const uint8_t* nullflag, int64_t n, uint32_t parts,
+                                                                      unsigned long long* cursors, FpRecord* out) {
+    __shared__ uint32_t s_cnt[FPS_MAX_PARTS];
+    __shared__ unsigned long long s_base[FPS_MAX_PARTS];
+    const int64_t tile_rows = (int64_t)FPS_THREADS * FPS_ROWS;
+    for (int64_t base = (int64_t)blockIdx.x * tile_rows; base < n; base += (int64_t)gridDim.x * tile_rows) {
+        for (int i = threadIdx.x; i < (int)parts; i += FPS_THREADS) s_cnt[i] = 0;
+        __syncthreads();
+        uint32_t part[FPS_ROWS], rank[FPS_ROWS];
+#pragma unroll
+        for (int k = 0; k < FPS_ROWS; ++k) {
+            const int64_t row = base + (int64_t)k * FPS_THREADS + threadIdx.x;
+            part[k] = 0xffffffffu;
+            if (row < n) {
+                part[k] = hash_rank(fp[row].h1, parts);
+                rank[k] = atomicAdd(&s_cnt[part[k]], 1u);
+            }
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < (int)parts; i += FPS_THREADS)
+            if (s_cnt[i]) s_base[i] = atomicAdd(&cursors[i], (unsigned long long)s_cnt[i]);
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < FPS_ROWS; ++k) {
+            const int64_t row = base + (int64_t)k * FPS_THREADS + threadIdx.x;
+            if (part[k] != 0xffffffffu) out[s_base[part[k]] + rank[k]] = FpRecord{fp[row].h1, fp[row].h2, nullflag[row] ? 1ull : 0ull};
+        }
+        __syncthreads();
+    }
+}
+__global__ void fp_unpack_kernel(const FpRecord* rec, int64_t n, Fp* fp, uint8_t* nullflag) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        fp[row] = Fp{rec[row].h1, rec[row].h2};
+        nullflag[row] = rec[row].has_null ? 1 : 0;
+    }
+}
+
+// tg_table_partition_fingerprints: records grouped by destination rank in the engine's shuffle buffer
+void partition_fingerprints_by_rank(Engine& e, Table& t, const std::vector<std::string>& names, int world, void** d_records, int64_t* counts,
+                                    int& launches) {
+    if (world < 1 || world > FPS_MAX_PARTS) throw Error(TG_ERR_INVALID_ARG, "world size must be in 1..1024");
+    std::vector<Column*> cols;
+    for (auto& nm : names) cols.push_back(need_col(t, nm));
+    if (cols.empty()) throw Error(TG_ERR_INVALID_ARG, "no key columns");
+    const int64_t n = t.n_rows;
+    const size_t rec_b = round_up((size_t)std::max<int64_t>(n, 1) * sizeof(FpRecord), 256), meta_b = round_up((size_t)(3 * (FPS_MAX_PARTS + 1)) * 8, 256);
+    const size_t need = rec_b + meta_b;
+    if (need > e.shuffle_cap) {
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        if (e.d_shuffle) TG_CUDA(cudaFree(e.d_shuffle));
+        e.d_shuffle = nullptr;
+        e.shuffle_cap = 0;
+        TG_CUDA(cudaMalloc(&e.d_shuffle, need));
+        e.shuffle_cap = need;
+    }
+    unsigned long long* hist = (unsigned long long*)(e.d_shuffle + rec_b);
+    unsigned long long* offsets = hist + (FPS_MAX_PARTS + 1);
+    unsigned long long* cursors = offsets + (FPS_MAX_PARTS + 1);
+    TG_CUDA(cudaMemsetAsync(hist, 0, meta_b, e.stream));
+    if (n > 0) {
+        const size_t fp_b = round_up((size_t)n * 16, 256), nf_b = round_up((size_t)n, 256);
+        uint8_t* scr = e.scratch(fp_b + nf_b);
+        Fp* d_fp = (Fp*)scr;
+        uint8_t* d_null = scr + fp_b;
+        launches += compute_fingerprints(e, t, cols, d_fp, d_null);
+        fp_rank_hist_kernel<<<grid_for(e, n), FPS_THREADS, 0, e.stream>>>(d_fp, n, (uint32_t)world, hist);
+        fp_prefix_kernel<<<1, 32, 0, e.stream>>>(hist, (uint32_t)world, offsets, cursors);
+        const int64_t tiles = (n + FPS_THREADS * FPS_ROWS - 1) / (FPS_THREADS * FPS_ROWS);
+        fp_rank_scatter_kernel<<<(int)std::max<int64_t>(1, std::min<int64_t>(tiles, (int64_t)e.sm_count * 8)), FPS_THREADS, 0, e.stream>>>(
+            d_fp, d_null, n, (uint32_t)world, cursors, (FpRecord*)e.d_shuffle);
+        TG_CUDA(cudaGetLastError());
+        launches += 3;
+    }
+    std::vector<unsigned long long> h((size_t)world);
+    TG_CUDA(cudaMemcpyAsync(h.data(), hist, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    for (int i = 0; i < world; ++i) counts[i] = (int64_t)h[i];
+    *d_records = e.d_shuffle;
+}
+
 void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
     Agg& a = p.aggs[agg_id];
     std::vector<Column*> cols;
-    for (auto& name : a.cols) cols.push_back(need_col(t, name));
+    // a hash-shuffled shard of a Utf8 / composite key arrives as ONE column of fingerprint records
+    Column* shard = t.find("tg_fp");
+    const bool from_records = shard && shard->dtype == TG_FP128;
+    if (from_records) cols.push_back(shard);
+    else
+        for (auto& name : a.cols) cols.push_back(need_col(t, name));
     const int64_t n = t.n_rows;
     a.u[0] = (uint64_t)n;
-    for (auto* c : cols) p.stats.bytes_scanned += col_bytes(*c, n);
+    for (auto* c : cols) p.stats.bytes_scanned += from_records ? (uint64_t)n * sizeof(FpRecord) : col_bytes(*c, n);
     if (n == 0) return;
     const bool exact64 = cols.size() == 1 && (cols[0]->dtype == TG_INT64 || cols[0]->dtype == TG_FLOAT64);
     if (exact64 && n > (1 << 20)) {
@@ -400,7 +512,12 @@ void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
     HashCounters* d_ctr = (HashCounters*)(scr + fp_b + nf_b + 2 * h_b + cnt_b);
     TG_CUDA(cudaMemsetAsync(tb.h1, 0xFF, 2 * h_b, e.stream));
     TG_CUDA(cudaMemsetAsync(tb.counts, 0, cnt_b + 256, e.stream));
-    launches += compute_fingerprints(e, t, cols, d_fp, d_null);
+    if (from_records) {
+        fp_unpack_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>((const FpRecord*)shard->values.p, n, d_fp, d_null);
+        ++launches;
+    } else {
+        launches += compute_fingerprints(e, t, cols, d_fp, d_null);
+    }
     insert128_kernel<<<grid_for(e, n), HASH_THREADS, 0, e.stream>>>(d_fp, d_null, n, tb, d_ctr);
     TG_CUDA(cudaGetLastError());
     ++launches;

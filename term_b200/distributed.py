@@ -10,7 +10,8 @@
   (constraints/uniqueness.rs:549-718, foreign_key.rs:165-172): every rank groups its keys by destination rank on
   the device (tg_table_partition_keys), one all-to-all moves them (NCCL over NVLink), the receiving rank adopts
   its keys as a table and the aggregate is redirected to it (tg_plan_redirect_aggregate). Equal keys now live on
-  exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0.
+  exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0. Utf8 and composite
+  keys travel as their 128-bit fingerprints (tg_table_partition_fingerprints), the identity the single-GPU path uses.
 """
 import os
 
@@ -215,6 +216,25 @@ def _shuffle_column(ctx, table, column, shard_name):
     _adopt_shard(ctx, shard_name, column, dtype, mine, my_nulls)
 
 
+def _shuffle_fingerprints(ctx, table, columns, shard_name):
+    """Utf8 / composite keys: every row travels as its 24-byte fingerprint record {h1, h2, has_null}; the shard is
+    adopted as one TG_FP128 column named tg_fp."""
+    world = dist.get_world_size()
+    ptr, counts = ctx.partition_fingerprints(table, columns, world)
+    total = sum(counts)
+    dev = torch.device("cuda", torch.cuda.current_device())
+    recs = _tensor_from_ptr(ptr, total * 3, dev) if total else torch.empty(0, dtype=torch.int64, device=dev)
+    mine, _ = shuffle_keys(recs, [c * 3 for c in counts], 0)
+    _adopt_fp_shard(ctx, shard_name, mine)
+
+
+def _adopt_fp_shard(ctx, name, recs: torch.Tensor):
+    n = recs.numel() // 3
+    vals = torch.zeros(n * 3 + 64, dtype=torch.int64, device=recs.device)
+    vals[: n * 3] = recs
+    ctx.register_device_table(name, {"tg_fp": dict(dtype=F.TG_FP128, n_rows=n, values=vals.data_ptr(), validity=None)}, keepalive=[vals])
+
+
 def _tensor_from_ptr(ptr, n, dev):
     class _Wrap:  # __cuda_array_interface__ v3
         pass
@@ -234,10 +254,11 @@ def execute_distributed(plan, ctx, table="data"):
         for i, (kind, key) in enumerate(plan.aggregates()):
             parts = key.split("|")
             if kind == KIND_DISTINCT:
-                if len(parts) != 2:
-                    raise NotImplementedError("multi-GPU uniqueness over composite keys is not implemented (single Int64 / Float64 key only)")
                 name = f"tg_shuffle_{i}_k"
-                _shuffle_column(ctx, table, parts[1], name)
+                if len(parts) == 2 and _column_dtype(ctx, table, parts[1]) in (F.TG_INT64, F.TG_FLOAT64):
+                    _shuffle_column(ctx, table, parts[1], name)  # exact 64-bit keys
+                else:
+                    _shuffle_fingerprints(ctx, table, parts[1:], name)  # Utf8 / composite: 128-bit fingerprints
                 temps.append(name)
                 plan.redirect(i, 0, name)
                 redirected.append((i, 0))

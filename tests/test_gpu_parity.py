@@ -655,6 +655,67 @@ def test_shuffled_shards_merge_to_single_table_answer(ctx):
             ctx.deregister_table(nm)
 
 
+@pytest.mark.parametrize("world", [2, 5])
+def test_fingerprint_shards_merge_to_single_table_answer(ctx, world):
+    """Utf8 and composite keys across GPUs: tg_table_partition_fingerprints -> one TG_FP128 shard table per rank ->
+    redirected DISTINCT aggregates -> merged states must equal the single-table evaluation (and the oracle)"""
+    import torch
+    from term_b200 import distributed as D
+    n = 120_000
+    rng = np.random.default_rng(world)
+    strs = [f"user{v}@example.com" if v % 11 else "" for v in rng.integers(0, n // 2, n)]
+    ints = rng.integers(0, 300, n)
+    flo = rng.integers(0, 50, n).astype(np.float64) / 2.0
+    t = pa.table({"s": pa.array(strs, type=pa.string(), mask=rng.random(n) < 0.03), "i": pa.array(ints, mask=rng.random(n) < 0.03),
+                  "f": pa.array(flo, mask=rng.random(n) < 0.03)})
+    ctx.register_table("fp_src", t)
+    names = []
+    try:
+        plan = T.Plan()
+        specs = []
+        for cols in (["s"], ["i", "f"], ["s", "i"]):
+            for ut, kw in ((T.UniquenessType.FullUniqueness, dict(threshold=0.5)),
+                           (T.UniquenessType.UniqueValueRatio, dict(assertion=T.Assertion.GreaterThan(0.1))),
+                           (T.UniquenessType.PrimaryKey, {})):
+                specs.append((cols, ut.name, kw, T.UniquenessConstraint(cols, ut, **kw)._add_to(plan)))
+        plan.execute(ctx, "fp_src")
+        want = [plan.result(s) for *_, s in specs]
+        aggs = plan.aggregates()
+        dev = torch.device("cuda", 0)
+        for i, (kind, key) in enumerate(aggs):
+            assert kind == 6
+            ptr, counts = ctx.partition_fingerprints("fp_src", key.split("|")[1:], world)
+            assert sum(counts) == n and min(counts) > n // (4 * world)
+            recs = D._tensor_from_ptr(ptr, sum(counts) * 3, dev).clone()
+            off = 0
+            for r in range(world):
+                nm = f"fp_{i}_{r}"
+                D._adopt_fp_shard(ctx, nm, recs[off * 3: (off + counts[r]) * 3])
+                off += counts[r]
+                names.append(nm)
+        blobs = []
+        for r in range(world):
+            for i in range(len(aggs)):
+                plan.redirect(i, 0, f"fp_{i}_{r}")
+            plan.execute_partial(ctx, "fp_src")
+            blobs.append(plan.partial_export())
+        for i in range(len(aggs)):
+            plan.redirect(i, 0, None)
+        plan.partial_reset()
+        for b in blobs:
+            plan.partial_merge(b)
+        plan.finalize()
+        for (cols, ut, kw, s), w in zip(specs, want):
+            g = plan.result(s)
+            assert (g.status, g.metric, g.message) == (w.status, w.metric, w.message), (cols, ut)
+            o = O.uniqueness(t, cols, ut, kw.get("threshold", 1.0), ("GreaterThan", 0.1) if "assertion" in kw else None)
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (cols, ut, g, o)
+    finally:
+        ctx.deregister_table("fp_src")
+        for nm in names:
+            ctx.deregister_table(nm)
+
+
 def test_grouped_completeness_matches_oracle(ctx):
     rng = np.random.default_rng(5)
     n = 100_000

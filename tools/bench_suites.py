@@ -114,6 +114,46 @@ def report(name, workload, n_rows, alg_bytes, kernel_ms, wall_ms, stats, extra=N
     print(json.dumps(line), flush=True)
 
 
+def bench_c1(ctx, dev, scale, steps):
+    """BASELINE.json configs[0]: quickstart suite on a 1 M-row users table (user_id i64, email Utf8), through the public
+    API from HOST Arrow data (register + run), and with the table resident."""
+    import numpy as np
+    import pyarrow as pa
+    n = int(1_000_000 * scale)
+    ids = np.arange(n, dtype=np.int64)
+    emails = pa.array([f"user{i}@example.com" for i in range(n)], type=pa.string())
+    table = pa.table({"user_id": pa.array(ids), "email": emails})
+    check = (T.Check.builder("quickstart").completeness("user_id", 1.0).validates_uniqueness(["email"], 1.0)
+             .validates_regex("email", "@", 1.0).build())
+    suite = T.ValidationSuite.builder("c1").table_name("users").check(check).build()
+    plan, slots = suite.build_plan()
+    ctx.register_table("users", table)
+    for _ in range(2):
+        plan.execute(ctx, "users")
+    walls = []
+    for _ in range(steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        plan.execute(ctx, "users")
+        walls.append((time.perf_counter() - t0) * 1e3)
+    st = plan.stats()
+    res = {plan.result(s).name: plan.result(s).metric for _, _, s in slots}
+    ctx.deregister_table("users")
+    e2e = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ctx.register_table("users", table)
+        plan.execute(ctx, "users")
+        _ = [plan.result(s) for _, _, s in slots]
+        ctx.deregister_table("users")
+        e2e.append((time.perf_counter() - t0) * 1e3)
+    alg = int(st["bytes_scanned"])
+    print(json.dumps({"workload": "c1_quickstart", "config": "is_complete(user_id) + is_unique(email) + has_pattern(email, '@') on 1 M rows",
+                      "rows": n, "resident_wall_ms": sum(walls) / len(walls), "gpu_ms": st["gpu_ms"], "e2e_wall_ms_from_host_arrow": sum(e2e) / len(e2e),
+                      "rows_per_s_resident": n / (sum(walls) / len(walls) / 1e3), "rows_per_s_e2e": n / (sum(e2e) / len(e2e) / 1e3),
+                      "algorithmic_bytes": alg, "launches": int(st["launches"]), "results": res}), flush=True)
+
+
 def bench_c3(ctx, dev, scale, steps):
     n = int(25_000_000 * scale)
     g = torch.Generator(device=dev)
@@ -253,7 +293,7 @@ def main():
     torch.cuda.set_device(0)
     ctx = T.SessionContext(0)
     for w in a.which:
-        {"c3": bench_c3, "c4": bench_c4, "c5": bench_c5}[w](ctx, dev, a.scale, a.steps)
+        {"c1": bench_c1, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5}[w](ctx, dev, a.scale, a.steps)
         torch.cuda.empty_cache()
     ctx.close()
 

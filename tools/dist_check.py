@@ -92,6 +92,7 @@ def main():
     A = T.Assertion
     check = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
              .validates_uniqueness(["order_key"], 0.9)
+             .validates_uniqueness(["order_key", "customer_id"], 0.5)  # composite key: fingerprint shuffle
              .foreign_key("orders.customer_id", "customers.id").build())
     suite = T.ValidationSuite.builder("dist").table_name("orders").check(check).build()
     plan, slots = suite.build_plan()
@@ -121,6 +122,7 @@ def main():
         register(ctx, "customers_all", {"id": (full["parent"], None)})
         check1 = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
                   .validates_uniqueness(["order_key"], 0.9)
+                  .validates_uniqueness(["order_key", "customer_id"], 0.5)
                   .foreign_key("orders_all.customer_id", "customers_all.id").build())
         s1 = T.ValidationSuite.builder("single").table_name("orders_all").check(check1).build()
         p1, sl1 = s1.build_plan()
