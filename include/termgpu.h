@@ -325,6 +325,14 @@ TG_API int32_t tg_plan_add_approx_count_distinct(tg_plan* plan, const char* colu
 typedef enum { TG_DT_INTEGER = 0, TG_DT_FLOAT = 1, TG_DT_BOOLEAN = 2, TG_DT_DATE = 3, TG_DT_TIMESTAMP = 4, TG_DT_STRING = 5 } tg_value_type;
 TG_API int32_t tg_plan_add_data_type(tg_plan* plan, const char* column, int32_t value_type, double threshold);
 
+/* ColumnCountConstraint::evaluate (constraints/column_count.rs:43-85): schema width of the plan's table */
+TG_API int32_t tg_plan_add_column_count(tg_plan* plan, tg_assertion assertion);
+/* HistogramAnalyzer (analyzers/advanced/histogram.rs:62-358), Float64 columns like the reference. Result through
+ * tg_plan_analyzer_result (u[0]=total_count f[0..3]=min,max,sum,sum_squared) and tg_plan_map_*: min, max, mean,
+ * std_dev, total_count, sum, sum_squared, bucket_{i}.lower / .upper / .count. Row shards merge only when their
+ * [min, max] agree (a multi-GPU histogram needs the global range first). */
+TG_API int32_t tg_plan_add_histogram(tg_plan* plan, const char* column, int32_t num_buckets);
+
 /* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
 TG_API int32_t tg_plan_add_analyzer(tg_plan* plan, int32_t analyzer_kind, const char* column,
                                     const char* column2, const char* expression);
@@ -357,7 +365,7 @@ TG_API tg_status tg_plan_partial_reset(tg_plan* plan);
 TG_API tg_status tg_plan_partial_merge(tg_plan* plan, const void* buf, size_t n_bytes);
 TG_API tg_status tg_plan_finalize(tg_plan* plan);
 /* The de-duplicated device aggregates behind the slots, in partial-blob order: kind is one of
- * 0 ROWS, 1 VALID, 2 NUM, 3 PAIR, 4 PRED, 5 REGEX, 6 DISTINCT, 7 FK, 8 KLL, 9 GROUPED, 10 SPEARMAN, 11 LENGTH; key is a
+ * 0 ROWS, 1 VALID, 2 NUM, 3 PAIR, 4 PRED, 5 REGEX, 6 DISTINCT, 7 FK, 8 KLL, 9 GROUPED, 10 SPEARMAN, 11 LENGTH, 12 HIST; key is a
  * stable textual identity such as "num|price" (valid until the plan is destroyed). Lets a host that computed a
  * shard elsewhere (another engine, a stored IncrementalAnalysisRunner state) assemble a partial blob. */
 TG_API int32_t tg_plan_num_aggregates(const tg_plan* plan);

@@ -880,6 +880,42 @@ def data_type(table, column, dtype, threshold) -> Result:
     return Result(FAILURE, ratio, f"Data type conformance {rust_f64(ratio)} is below threshold {rust_f64(threshold)}")
 
 
+def column_count(table, assertion) -> Result:
+    """constraints/column_count.rs:43-85"""
+    n = float(len(table_cols(table)))
+    if assertion_eval(assertion, n):
+        return Result(SUCCESS, n)
+    return Result(FAILURE, n, f"Column count {rust_f64(n)} does not satisfy assertion {assertion_desc(assertion)}")
+
+
+def an_histogram(table, column, num_buckets):
+    """analyzers/advanced/histogram.rs:184-358 -> dict(total_count, min, max, sum, sum_squared, mean, std_dev,
+    buckets=[(lower, upper, count)]); Float64 columns only (the reference's downcasts reject Int64)."""
+    c = table_cols(table)[column]
+    nb = min(max(int(num_buckets), 1), 1000)
+    vals = np.asarray(c.values, dtype=np.float64)[c.valid]
+    n = len(vals)
+    if n == 0:
+        return dict(total_count=0, min=0.0, max=0.0, sum=0.0, sum_squared=0.0, mean=0.0, std_dev=0.0, buckets=[])
+    mn, mx = float(vals.min()), float(vals.max())
+    s, s2 = math.fsum(vals), math.fsum(vals * vals)
+    rng = mx - mn
+    w = rng / nb if (rng > 0.0 and nb > 1) else 1.0
+    lowers = [mn + (i * w) for i in range(nb)]
+    uppers = [(mx + w * 0.001) if i == nb - 1 else mn + ((i + 1) * w) for i in range(nb)]
+    counts = [0] * nb
+    for v in vals:
+        b = nb  # ELSE {num_buckets}
+        for i in range(nb):
+            if v >= lowers[i] and v < uppers[i]:
+                b = i + 1
+                break
+        counts[b - 1] += 1
+    mean = s / n
+    std = math.sqrt(max(s2 / n - mean * mean, 0.0)) if n > 1 else 0.0
+    return dict(total_count=n, min=mn, max=mx, sum=s, sum_squared=s2, mean=mean, std_dev=std, buckets=list(zip(lowers, uppers, counts)))
+
+
 def approx_count_distinct(table, column, assertion) -> Result:
     """constraints/approx_count_distinct.rs:49-134: SELECT APPROX_DISTINCT(c) (HyperLogLog; the reference's tests only
     assert ranges). This restatement returns the exact distinct count, which every HLL error bound contains."""

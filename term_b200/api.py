@@ -614,6 +614,14 @@ class DataTypeConstraint(Constraint):  # constraints/values.rs:69-196
         return F.check_slot(F.lib().tg_plan_add_data_type(plan.handle, self.column.encode(), int(self.data_type), float(self.threshold)))
 
 
+class ColumnCountConstraint(Constraint):  # constraints/column_count.rs
+    def __init__(self, assertion: Assertion):
+        self.assertion = assertion
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_column_count(plan.handle, self.assertion.c()))
+
+
 class StatisticalConstraint(Constraint):  # constraints/statistics.rs:120-322
     def __init__(self, column, statistic: StatisticType, assertion: Assertion, percentile: float = 0.0):
         self.column, self.statistic, self.assertion, self.percentile = column, statistic, assertion, percentile
@@ -830,6 +838,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
     # core/check.rs:518-625, 1777-1786
+    def has_column_count(self, assertion): return self.constraint(ColumnCountConstraint(assertion))
     def has_approx_count_distinct(self, column, assertion): return self.constraint(ApproxCountDistinctConstraint(column, assertion))
     def has_min_length(self, column, n): return self.constraint(LengthConstraint.min(column, n))
     def has_max_length(self, column, n): return self.constraint(LengthConstraint.max(column, n))
@@ -979,6 +988,15 @@ class SizeAnalyzer(Analyzer):
 
 CompletenessAnalyzer = _mk(1, "CompletenessAnalyzer")
 DistinctnessAnalyzer = _mk(2, "DistinctnessAnalyzer")
+class HistogramAnalyzer(Analyzer):  # analyzers/advanced/histogram.rs
+    def __init__(self, column, num_buckets=10):
+        super().__init__(column)
+        self.num_buckets = num_buckets
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_histogram(plan.handle, self.column.encode(), int(self.num_buckets)))
+
+
 ApproxCountDistinctAnalyzer = _mk(14, "ApproxCountDistinctAnalyzer")  # advanced/approx_count_distinct.rs (answered exactly)
 MeanAnalyzer = _mk(3, "MeanAnalyzer")
 MinAnalyzer = _mk(4, "MinAnalyzer")

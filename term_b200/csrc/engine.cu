@@ -700,7 +700,10 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
             continue;
         }
         switch (a.kind) {
-            case A_ROWS: a.u[0] = (uint64_t)t->n_rows; break;
+            case A_ROWS:
+                a.u[0] = (uint64_t)t->n_rows;
+                a.u[1] = (uint64_t)t->cols.size();  // schema width (ColumnCountConstraint)
+                break;
             case A_VALID:
             case A_NUM:
             case A_PAIR:
@@ -733,6 +736,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
                 case A_FK: exec_fk_job(e, p, (int)i); break;
                 case A_GROUPED: exec_grouped_job(e, *t, p, (int)i); break;
                 case A_SPEARMAN: exec_spearman_job(e, *t, p, (int)i); break;
+                case A_HIST: exec_hist_job(e, *t, p, (int)i); break;
                 default: break;
             }
         } catch (Error& er) {

@@ -147,6 +147,7 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id);                               
 void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);  // sketch.cu
 void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                      // hashing.cu
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
+void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id);                         // hist.cu
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);
 

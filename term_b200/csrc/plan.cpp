@@ -564,6 +564,38 @@ int plan_add_data_type(Plan& p, const std::string& col, int data_type, double th
     return (int)p.slots.size() - 1;
 }
 
+// constraints/column_count.rs:43-85: the table's schema width against an assertion
+int plan_add_column_count(Plan& p, tg_assertion a) {
+    Slot s;
+    s.kind = SL_COLUMN_COUNT;
+    s.name = "column_count";
+    s.assertion = a;
+    s.aggs.push_back(p.add_agg(mk_rows()));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
+// analyzers/advanced/histogram.rs:62-76 (num_buckets clamped to 1..1000), :184-345
+int plan_add_histogram(Plan& p, const std::string& col, int num_buckets) {
+    validate_identifier(col);
+    Slot s;
+    s.kind = SL_HISTOGRAM;
+    s.name = "histogram";
+    s.metric_key = "histogram." + col;
+    s.columns = {col};
+    s.k = std::min(std::max(num_buckets, 1), 1000);
+    Agg num = mk_num(col, 3);  // moments + min/max
+    s.aggs.push_back(p.add_agg(std::move(num)));
+    Agg h;
+    h.kind = A_HIST;
+    h.key = "hist|" + col + "|" + std::to_string(s.k);
+    h.cols = {col};
+    h.iparam = s.k;
+    s.aggs.push_back(p.add_agg(std::move(h)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall) {
     if (groups.empty()) throw Error(TG_ERR_INVALID_ARG, "at least one grouping column is required");
@@ -668,10 +700,33 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
         }
         switch (a.kind) {
             case A_ROWS:
+                a.u[0] += u[0];
+                a.u[1] = std::max(a.u[1], u[1]);  // schema width: the same on every shard
+                break;
             case A_VALID:
             case A_REGEX:
             case A_LENGTH:
                 for (int i = 0; i < 8; ++i) a.u[i] += u[i];
+                break;
+            case A_HIST:
+                // bucket bounds come from the shard's own min / max: shards only add up when those agree
+                if (blob.empty()) break;
+                if (a.blob.empty()) {
+                    a.blob = blob;
+                    a.f[0] = f[0];
+                    a.f[1] = f[1];
+                } else if (a.f[0] == f[0] && a.f[1] == f[1] && a.blob.size() == blob.size()) {
+                    for (size_t i = 0; i + 8 <= blob.size(); i += 8) {
+                        uint64_t x, y;
+                        memcpy(&x, a.blob.data() + i, 8);
+                        memcpy(&y, blob.data() + i, 8);
+                        x += y;
+                        memcpy(a.blob.data() + i, &x, 8);
+                    }
+                } else if (a.err == TG_OK) {
+                    a.err = TG_ERR_UNSUPPORTED;
+                    a.err_msg = "histogram shards with different value ranges cannot be merged (needs a global min / max first)";
+                }
                 break;
             case A_PRED:
                 a.u[0] += u[0];
@@ -1242,6 +1297,17 @@ static void finalize_data_type(Plan& p, Slot& s) {
     else failure_metric(s, ratio, "Data type conformance " + fmt_f64(ratio) + " is below threshold " + fmt_f64(s.threshold));
 }
 
+static void finalize_column_count(Plan& p, Slot& s) {
+    const Agg& a = p.aggs[s.aggs[0]];
+    if (a.err != TG_OK) {  // column_count.rs:47-53
+        failure(s, "Constraint evaluation failed for 'column_count': Failed to access table 'data': " + a.err_msg);
+        return;
+    }
+    const double n = (double)a.u[1];
+    if (assertion_evaluate(s.assertion, n)) success_metric(s, n);
+    else failure_metric(s, n, "Column count " + fmt_f64(n) + " does not satisfy assertion " + assertion_description(s.assertion));
+}
+
 static void finalize_fk(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     if (a.err != TG_OK) {
@@ -1474,6 +1540,65 @@ static void finalize_kll(Plan& p, Slot& s) {
     }
 }
 
+// HistogramState {buckets, min_value, max_value, total_count, sum, sum_squared} and MetricValue::Histogram with
+// mean / std_dev (analyzers/advanced/histogram.rs:78-115, 300-358). Map keys: min, max, mean, std_dev, total_count,
+// sum, sum_squared, bucket_{i}.lower / .upper / .count.
+static void finalize_histogram(Plan& p, Slot& s) {
+    const Agg& num = p.aggs[s.aggs[0]];
+    const Agg& h = p.aggs[s.aggs[1]];
+    tg_analyzer_result& r = s.ares;
+    r = tg_analyzer_result{};
+    s.map.clear();
+    s.has_message = false;
+    if (num.err != TG_OK || h.err != TG_OK) {
+        analyzer_error(s, num.err != TG_OK ? num : h);
+        return;
+    }
+    if (num.u[4]) {  // MIN(Int64) is Int64: the reference fails its Float64 downcast (histogram.rs:203-208)
+        r.error = 2;
+        r.metric_kind = 3;
+        s.has_message = true;
+        s.message = "Invalid data: Expected Float64 for min";
+        return;
+    }
+    r.metric_kind = 2;
+    const uint64_t n = num.u[0];
+    r.u[0] = n;
+    if (n == 0) {  // "No data": empty bucket list, zero stats (histogram.rs:245-254)
+        for (const char* k : {"min", "max", "mean", "std_dev", "total_count", "sum", "sum_squared"}) s.map.emplace_back(k, 0.0);
+        return;
+    }
+    const double mn = num.f[3], mx = num.f[4], K = num.f[0];
+    const double sum = num.f[5];
+    const double sum_sq = num.f[2] + 2.0 * K * num.f[1] + (double)n * K * K;  // Σx² from the shifted sums
+    r.f[0] = mn;
+    r.f[1] = mx;
+    r.f[2] = sum;
+    r.f[3] = sum_sq;
+    const double mean = sum / (double)n;
+    // std_dev as the reference computes it from Σx² (histogram.rs:106-113); the shifted form avoids its cancellation
+    const double var = n > 1 ? (num.f[2] / (double)n) - (num.f[1] / (double)n) * (num.f[1] / (double)n) : 0.0;
+    s.map.emplace_back("min", mn);
+    s.map.emplace_back("max", mx);
+    s.map.emplace_back("mean", mean);
+    s.map.emplace_back("std_dev", n > 1 ? std::sqrt(var < 0 ? 0.0 : var) : 0.0);
+    s.map.emplace_back("total_count", (double)n);
+    s.map.emplace_back("sum", sum);
+    s.map.emplace_back("sum_squared", sum_sq);
+    const int nb = s.k;
+    const double range = mx - mn, width = (range > 0.0 && nb > 1) ? range / (double)nb : 1.0;
+    for (int i = 0; i < nb; ++i) {
+        const double lower = mn + ((double)i * width);
+        const double upper = i == nb - 1 ? mx + width * 0.001 : mn + ((double)(i + 1) * width);
+        uint64_t c = 0;
+        if (h.blob.size() >= (size_t)(i + 1) * 8) memcpy(&c, h.blob.data() + (size_t)i * 8, 8);
+        const std::string pre = "bucket_" + std::to_string(i);
+        s.map.emplace_back(pre + ".lower", lower);
+        s.map.emplace_back(pre + ".upper", upper);
+        s.map.emplace_back(pre + ".count", (double)c);
+    }
+}
+
 static void finalize_grouped(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     tg_analyzer_result& r = s.ares;
@@ -1568,6 +1693,8 @@ void Plan::finalize() {
             case SL_NON_NEGATIVE: finalize_value_ratio(*this, s, " values are negative"); break;
             case SL_APPROX_DISTINCT: finalize_approx_distinct(*this, s); break;
             case SL_DATA_TYPE: finalize_data_type(*this, s); break;
+            case SL_COLUMN_COUNT: finalize_column_count(*this, s); break;
+            case SL_HISTOGRAM: finalize_histogram(*this, s); break;
         }
     }
     executed = true;

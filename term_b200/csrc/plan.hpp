@@ -26,6 +26,7 @@ enum AggKind : int32_t {
     A_GROUPED = 9,   // blob = group table
     A_SPEARMAN = 10, // same layout as A_PAIR over min-ranks
     A_LENGTH = 11,   // COUNT(CASE WHEN lo <= LENGTH(c) <= hi ..)  u0 matching non-null rows u1 nulls u2 rows
+    A_HIST = 12,     // equal-width histogram over [min, max] of the column's NUM aggregate: f0 min f1 max u0 is_i64 ; blob = bucket counts
 };
 
 struct Agg {
@@ -77,6 +78,8 @@ enum SlotKind : int32_t {
     SL_NON_NEGATIVE,
     SL_APPROX_DISTINCT,
     SL_DATA_TYPE,
+    SL_COLUMN_COUNT,
+    SL_HISTOGRAM,
 };
 
 struct StatReq {
@@ -155,6 +158,8 @@ int plan_add_containment(Plan& p, const std::string& col, const std::vector<std:
 int plan_add_non_negative(Plan& p, const std::string& col);
 int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion a);
 int plan_add_data_type(Plan& p, const std::string& col, int data_type, double threshold);
+int plan_add_column_count(Plan& p, tg_assertion a);
+int plan_add_histogram(Plan& p, const std::string& col, int num_buckets);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 

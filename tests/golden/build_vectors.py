@@ -243,6 +243,22 @@ case("data_type_float", "constraints/values.rs:495-507", {"data": {"text_col": c
 case("data_type_boolean", "constraints/values.rs:509-521", {"data": {"text_col": col("str", ["true", "false", "invalid", "1"])}},
      {"kind": "data_type", "column": "text_col", "data_type": "Boolean", "threshold": 0.7}, status="success", metric=0.75)
 
+# ------------------------------------------------------------------ column count ----
+def ncols(k):
+    return {"data": {f"col_{i}": col("i64", [i, None]) for i in range(k)}}
+
+
+case("column_count_equals", "constraints/column_count.rs:138-149", ncols(5), {"kind": "column_count", "assertion": ["Equals", 5.0]},
+     status="success", metric=5.0)
+case("column_count_equals_failure", "constraints/column_count.rs:150-158", ncols(5), {"kind": "column_count", "assertion": ["Equals", 10.0]},
+     status="failure", metric=5.0, message_contains=["Column count 5 does not satisfy assertion equals 10"])
+case("column_count_greater_than", "constraints/column_count.rs:160-178", ncols(8), {"kind": "column_count", "assertion": ["GreaterThan", 10.0]},
+     status="failure", metric=8.0)
+case("column_count_between", "constraints/column_count.rs:198-215", ncols(7), {"kind": "column_count", "assertion": ["Between", 5.0, 10.0]},
+     status="success", metric=7.0)
+case("column_count_large", "constraints/column_count.rs:229-240", ncols(100), {"kind": "column_count", "assertion": ["GreaterThanOrEqual", 100.0]},
+     status="success", metric=100.0)
+
 # ------------------------------------------------------------------ approx_count_distinct ----
 case("approx_distinct_high_cardinality", "constraints/approx_count_distinct.rs:190-205",
      {"data": {"test_col": col("i64", list(range(1000)))}},

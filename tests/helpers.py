@@ -67,6 +67,8 @@ def oracle_eval(case):
         return O.approx_count_distinct(t, op["column"], tuple(op["assertion"]))
     if k == "data_type":
         return O.data_type(t, op["column"], op["data_type"], op["threshold"])
+    if k == "column_count":
+        return O.column_count(t, tuple(op["assertion"]))
     raise ValueError(k)
 
 
@@ -152,6 +154,8 @@ def build_constraint(T, op):
         return T.ApproxCountDistinctConstraint(op["column"], _assertion(T, op["assertion"]))
     if k == "data_type":
         return T.DataTypeConstraint(op["column"], T.DataType[op["data_type"]], op["threshold"])
+    if k == "column_count":
+        return T.ColumnCountConstraint(_assertion(T, op["assertion"]))
     raise ValueError(k)
 
 

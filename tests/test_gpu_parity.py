@@ -320,6 +320,59 @@ def test_length_containment_non_negative_match_oracle(ctx, n):
         ctx.deregister_table(name)
 
 
+# ---------------------------------------------------------------- histogram (§8f.1) ----
+def _check_histogram(r, want, nb):
+    assert r.error == 0 and r.metric_kind == 2
+    assert r.u[0] == want["total_count"]
+    if want["total_count"] == 0:
+        assert not any(k.startswith("bucket_") for k in r.map) and r.map["total_count"] == 0.0
+        return
+    assert r.map["min"] == want["min"] and r.map["max"] == want["max"] and r.f[0] == want["min"] and r.f[1] == want["max"]
+    assert abs(r.map["sum"] - want["sum"]) <= REL_SUM * max(1.0, abs(want["sum"]))
+    assert abs(r.map["mean"] - want["mean"]) <= REL_SUM * max(1.0, abs(want["mean"]))
+    assert abs(r.map["sum_squared"] - want["sum_squared"]) <= REL_MOMENT * max(1.0, abs(want["sum_squared"]))
+    assert abs(r.map["std_dev"] - want["std_dev"]) <= REL_MOMENT * max(1.0, abs(want["std_dev"]))
+    assert len(want["buckets"]) == nb
+    for i, (lo, hi, cnt) in enumerate(want["buckets"]):
+        assert r.map[f"bucket_{i}.lower"] == lo and r.map[f"bucket_{i}.upper"] == hi, i  # the same f64 expressions
+        assert r.map[f"bucket_{i}.count"] == cnt, (i, r.map[f"bucket_{i}.count"], cnt)
+
+
+def test_histogram_reference_fixture(ctx):
+    """analyzers/advanced/tests.rs:179-207: value = [1,2,2,3,3,3,4,5,10,NULL], 5 buckets -> total_count 9, min 1, max 10"""
+    t = pa.table({"value": pa.array([1.0, 2.0, 2.0, 3.0, 3.0, 3.0, 4.0, 5.0, 10.0, None])})
+    ctx.register_table("hist_fix", t)
+    try:
+        r = T.HistogramAnalyzer("value", 5).compute(ctx, "hist_fix")
+        assert r.u[0] == 9 and abs(r.map["min"] - 1.0) < 0.001 and abs(r.map["max"] - 10.0) < 0.001
+        assert abs(r.map["mean"] - (1.0 + 2.0 + 2.0 + 3.0 + 3.0 + 3.0 + 4.0 + 5.0 + 10.0) / 9.0) < 0.001
+        assert sum(1 for k in r.map if k.endswith(".count")) == 5
+        _check_histogram(r, O.an_histogram(t, "value", 5), 5)
+        assert [r.map[f"bucket_{i}.count"] for i in range(5)] == [3.0, 4.0, 1.0, 0.0, 1.0]
+    finally:
+        ctx.deregister_table("hist_fix")
+
+
+@pytest.mark.parametrize("n,nb", [(1, 4), (1000, 1), (5000, 10), (200_000, 1000)])
+def test_histogram_matches_oracle(ctx, n, nb):
+    rng = np.random.default_rng(n + nb)
+    vals = np.round(rng.normal(50.0, 20.0, n), 1)  # many values exactly on bucket bounds
+    if n > 10:
+        vals[:3] = [vals.min(), vals.max(), vals.max()]
+    t = pa.table({"v": pa.array(vals, mask=rng.random(n) < 0.1 if n > 1 else None), "k": pa.array(rng.integers(0, 9, n)),
+                  "allnull": pa.array(vals, mask=np.ones(n, dtype=bool)), "const": pa.array(np.full(n, 7.5))})
+    name = f"hist_{n}_{nb}"
+    ctx.register_table(name, t.to_batches(max_chunksize=4097))
+    try:
+        for col_name in ("v", "allnull", "const"):
+            r = T.HistogramAnalyzer(col_name, nb).compute(ctx, name)
+            _check_histogram(r, O.an_histogram(t, col_name, nb), min(max(nb, 1), 1000))
+        bad = T.HistogramAnalyzer("k", nb).compute(ctx, name)  # Int64: the reference's Float64 downcast fails
+        assert bad.error == 2 and bad.message == "Invalid data: Expected Float64 for min"
+    finally:
+        ctx.deregister_table(name)
+
+
 # ---------------------------------------------------------------- hash jobs: distinct / unique / FK / grouped ----
 def _uniq_all_kinds(ctx, name, t, cols):
     A = T.Assertion
