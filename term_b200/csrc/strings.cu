@@ -542,32 +542,44 @@ __global__ void __launch_bounds__(LEN_THREADS) length_kernel(const __grid_consta
             e[k] = __ldg(P.offsets + rc + 1);
             vw[k] = P.validity ? __ldg(P.validity + (rc >> 5)) : 0xffffffffu;
         }
+        // wave 2: which rows need their bytes, and the first 16 bytes of those (all loads before any counting)
+        bool live[LEN_ILP], need[LEN_ILP];
+        uint64_t w0[LEN_ILP], w1[LEN_ILP];
 #pragma unroll
         for (int k = 0; k < LEN_ILP; ++k) {
             const int64_t row = base + (int64_t)k * LEN_THREADS + threadIdx.x;
-            if (row >= P.n_rows || !((vw[k] >> (row & 31)) & 1u)) continue;
-            ++nvalid;
+            live[k] = row < P.n_rows && ((vw[k] >> (row & 31)) & 1u);
             const long long nbytes = e[k] - b[k], min_chars = (nbytes + 3) >> 2;
-            bool need_bytes = false;
+            need[k] = false;
             for (int i = 0; i < P.n_ranges; ++i) {
                 const bool surely_out = nbytes < P.lo[i] || min_chars > P.hi[i];
                 const bool surely_in = min_chars >= P.lo[i] && nbytes <= P.hi[i];
-                need_bytes |= !(surely_out || surely_in);
+                need[k] |= !(surely_out || surely_in);
             }
+            need[k] = need[k] && live[k];
+            w0[k] = need[k] && nbytes > 0 ? load_upto8(P.bytes, b[k], (int)(nbytes < 8 ? nbytes : 8)) : 0ull;
+            w1[k] = need[k] && nbytes > 8 ? load_upto8(P.bytes, b[k] + 8, (int)(nbytes - 8 < 8 ? nbytes - 8 : 8)) : 0ull;
+        }
+#pragma unroll
+        for (int k = 0; k < LEN_ILP; ++k) {
+            if (!live[k]) continue;
+            ++nvalid;
+            const long long nbytes = e[k] - b[k], min_chars = (nbytes + 3) >> 2;
+            const bool need_bytes = need[k];
             long long chars = nbytes;
             if (need_bytes) {
-                int cont = 0;
-                for (int32_t q = b[k]; q < e[k]; q += 8) {
+                // 10xxxxxx bytes are UTF-8 continuation bytes: not characters
+                int cont = __popcll(w0[k] & (~w0[k] << 1) & 0x8080808080808080ull) + __popcll(w1[k] & (~w1[k] << 1) & 0x8080808080808080ull);
+                for (int32_t q = b[k] + 16; q < e[k]; q += 8) {
                     const uint64_t w = load_upto8(P.bytes, q, min(8, e[k] - q));
-                    cont += __popcll(w & (~w << 1) & 0x8080808080808080ull);  // 10xxxxxx bytes
+                    cont += __popcll(w & (~w << 1) & 0x8080808080808080ull);
                 }
                 chars = nbytes - cont;
             }
 #pragma unroll
             for (int i = 0; i < LEN_MAX_RANGES; ++i)
                 if (i < P.n_ranges) {
-                    // when the bytes were skipped every range was decided from the bounds, and `chars = nbytes` agrees
-                    // with that decision only for surely_in / nbytes < lo; the remaining case (min_chars > hi) is out
+                    // when the bytes were skipped every range was decided from the bounds alone
                     const bool in = need_bytes ? (chars >= P.lo[i] && chars <= P.hi[i]) : (min_chars >= P.lo[i] && nbytes <= P.hi[i]);
                     cnt[i] += in;
                 }

@@ -180,6 +180,39 @@ def bench_c3(ctx, dev, scale, steps):
     ctx.deregister_table("pii")
 
 
+def bench_x(ctx, dev, scale, steps):
+    """length / data-type constraints on the C3 string column, histogram on a 125 M-row f64 column"""
+    n = int(25_000_000 * scale)
+    g = torch.Generator(device=dev)
+    g.manual_seed(42 + 3)
+    offs, data, v, cats, total = make_strings(n, g, dev)
+    ctx.register_device_table("pii", {"s": dict(dtype=F.TG_UTF8, n_rows=n, values=data.data_ptr(), offsets=offs.data_ptr(),
+                                                validity=v.data_ptr(), n_value_bytes=total)}, keepalive=[offs, data, v])
+    alg = 4 * (n + 1) + total + (n + 7) // 8
+    check = (T.Check.builder("len").has_min_length("s", 12).has_max_length("s", 40).has_length_between("s", 8, 64).is_not_empty("s").build())
+    plan, slots = T.ValidationSuite.builder("x_len").table_name("pii").check(check).build().build_plan()
+    kms, wms, st = run_plan(plan, ctx, "pii", steps, "string_ms")
+    report("x_length", "min_length + max_length + length_between + not_empty on the C3 string column (one pass)", n, alg, kms, wms, st,
+           {"results": {plan.result(s).name: plan.result(s).metric for _, _, s in slots}})
+    check = T.Check.builder("dt").constraint(T.DataTypeConstraint("s", T.DataType.Integer, 0.0)).build()
+    plan, slots = T.ValidationSuite.builder("x_dt").table_name("pii").check(check).build().build_plan()
+    kms, wms, st = run_plan(plan, ctx, "pii", steps, "string_ms")
+    report("x_data_type_integer", "DataTypeConstraint(Integer) on the C3 string column", n, alg, kms, wms, st)
+    ctx.deregister_table("pii")
+    del offs, data, v
+    m = int(125_000_000 * scale)
+    t = torch.zeros(m + 64, dtype=torch.float64, device=dev)
+    t[:m].normal_(100.0, 15.0, generator=g)
+    vv = validity(m, g, dev, 0.05)
+    ctx.register_device_table("h", {"f0": dict(dtype=F.TG_FLOAT64, n_rows=m, values=t.data_ptr(), validity=vv.data_ptr())}, keepalive=[t, vv])
+    plan = T.Plan()
+    T.HistogramAnalyzer("f0", 100)._add_to(plan)
+    kms, wms, st = run_plan(plan, ctx, "h", steps, "gpu_ms")
+    report("x_histogram", "HistogramAnalyzer(f0, 100 buckets): fused scan for min/max/moments + bucket pass (column read twice, like the reference)",
+           m, 2 * (8 * m + (m + 7) // 8), kms, wms, st)
+    ctx.deregister_table("h")
+
+
 def bench_c4(ctx, dev, scale, steps):
     n = int(125_000_000 * scale)
     g = torch.Generator(device=dev)
@@ -293,7 +326,7 @@ def main():
     torch.cuda.set_device(0)
     ctx = T.SessionContext(0)
     for w in a.which:
-        {"c1": bench_c1, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5}[w](ctx, dev, a.scale, a.steps)
+        {"c1": bench_c1, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5, "x": bench_x}[w](ctx, dev, a.scale, a.steps)
         torch.cuda.empty_cache()
     ctx.close()
 
