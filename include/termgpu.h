@@ -397,6 +397,13 @@ TG_API int32_t tg_plan_map_size(const tg_plan* plan, int32_t slot);
 TG_API tg_status tg_plan_map_entry(const tg_plan* plan, int32_t slot, int32_t i, const char** key,
                                    double* value);
 
+/* The analyzer slot's *State struct as serde_json text — what IncrementalAnalysisRunner hands to a StateStore
+ * (analyzers/incremental/runner.rs:72-80; FileSystemStateStore writes it to {partition}/{analyzer}.json,
+ * state_store.rs:153-176), so GPU-computed partitions can be mixed with CPU-computed ones. Writes
+ * NUL-terminated into buf, returns the needed length (0: this slot has no JSON state, e.g. KLL / grouped / Spearman;
+ * negative: -tg_status). */
+TG_API int32_t tg_plan_analyzer_state_json(const tg_plan* plan, int32_t slot, char* buf, int32_t cap);
+
 /* timings of the last execute, milliseconds (SURVEY §5 metrics row): h2d, scan kernels, total */
 typedef struct {
     double gpu_ms;        /* CUDA-event time of all kernels of the last execute */
@@ -430,6 +437,8 @@ TG_API const char* tg_format_pattern(int32_t format_kind, const char* arg, int32
  * same table on the device): returns 1/0 match of `pattern` (search semantics of `~`) on bytes. */
 TG_API int32_t tg_regex_host_match(const char* pattern, int32_t case_insensitive, const uint8_t* s,
                                    int64_t len, int32_t* out_match);
+/* serde_json (ryu) rendering of an f64, as in the persisted analyzer states; returns needed length */
+TG_API int32_t tg_format_f64_json(double v, char* buf, int32_t cap);
 /* Rust `{}` Display of f64, for message parity; returns needed length */
 TG_API int32_t tg_format_f64(double v, char* buf, int32_t cap);
 

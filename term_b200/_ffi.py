@@ -115,6 +115,7 @@ SIGNATURES = {
     "tg_engine_mailbox_create": (C.c_int, [P, C.c_int32, C.c_int32, C.c_size_t, P]),
     "tg_engine_mailbox_open": (C.c_int, [P, P]),
     "tg_plan_exchange_and_finalize": (C.c_int, [P, P]),
+    "tg_plan_analyzer_state_json": (C.c_int32, [P, C.c_int32, C.c_char_p, C.c_int32]),
     "tg_plan_redirect_aggregate": (C.c_int, [P, C.c_int32, C.c_int32, C.c_char_p]),
     "tg_plan_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_result)]),
     "tg_plan_analyzer_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_analyzer_result)]),
@@ -130,6 +131,7 @@ SIGNATURES = {
     "tg_format_pattern": (C.c_char_p, [C.c_int32, C.c_char_p, C.c_int32]),
     "tg_regex_host_match": (C.c_int32, [C.c_char_p, C.c_int32, P, C.c_int64, C.POINTER(C.c_int32)]),
     "tg_format_f64": (C.c_int32, [C.c_double, C.c_char_p, C.c_int32]),
+    "tg_format_f64_json": (C.c_int32, [C.c_double, C.c_char_p, C.c_int32]),
 }
 
 _lib = None

@@ -440,6 +440,13 @@ class Plan:
                               r.metric_key.decode() if r.metric_key else "",
                               r.message.decode("utf-8", "replace") if r.message else None, m)
 
+    def analyzer_state_json(self, slot: int) -> str:
+        """serde_json text of the slot's *State struct (FileSystemStateStore format); "" when it has none"""
+        n = F.check_slot(F.lib().tg_plan_analyzer_state_json(self._h, slot, None, 0))
+        buf = C.create_string_buffer(n + 1)
+        F.check_slot(F.lib().tg_plan_analyzer_state_json(self._h, slot, buf, n + 1))
+        return buf.value.decode()
+
     def stats(self):
         s = F.tg_exec_stats()
         F.check(F.lib().tg_plan_exec_stats(self._h, C.byref(s)))

@@ -419,6 +419,31 @@ tg_status tg_plan_exchange_and_finalize(tg_engine* h, tg_plan* p) {
     });
 }
 
+int32_t tg_format_f64_json(double v, char* buf, int32_t cap) {
+    const std::string s = json_f64(v);
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int32_t)s.size();
+}
+
+int32_t tg_plan_analyzer_state_json(const tg_plan* p, int32_t slot, char* buf, int32_t cap) {
+    int32_t need = -1;
+    tg_status st = guard([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        const std::string s = analyzer_state_json(p->p, slot);
+        need = (int32_t)s.size();
+        if (buf && cap > 0) {
+            const size_t n = std::min<size_t>(s.size(), (size_t)cap - 1);
+            memcpy(buf, s.data(), n);
+            buf[n] = 0;
+        }
+    });
+    return st == TG_OK ? need : -(int32_t)st;
+}
+
 tg_status tg_plan_redirect_aggregate(tg_plan* p, int32_t i, int32_t which, const char* table_name) {
     return guard([&] {
         if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");

@@ -25,6 +25,7 @@ tg_status fail(tg_status code, const std::string& msg);
 std::string fmt_f64(double v);                 // `{}` / `{v}` Display of f64
 std::string fmt_f64_prec(double v, int prec);  // `{:.N}`
 std::string fmt_i64(int64_t v);
+std::string json_f64(double v);               // serde_json / ryu rendering of an f64
 
 // ---- Assertion (constraints/assertion.rs) ----
 bool assertion_evaluate(const tg_assertion& a, double value);

@@ -59,6 +59,44 @@ std::string fmt_f64(double v) {
     return neg ? "-" + out : out;
 }
 
+// serde_json's f64 (ryu::Buffer::format_finite): shortest round-trip digits; positional for decimal exponents
+// -5 < kk <= 16 with at least ".0", otherwise d[.ddd]e[-]x; non-finite values serialise as null.
+std::string json_f64(double v) {
+    if (std::isnan(v) || std::isinf(v)) return "null";
+    if (v == 0.0) return std::signbit(v) ? "-0.0" : "0.0";
+    char buf[64];
+    auto r = std::to_chars(buf, buf + sizeof(buf), v, std::chars_format::scientific);
+    std::string sci(buf, r.ptr);
+    bool neg = false;
+    size_t i = 0;
+    if (sci[0] == '-') {
+        neg = true;
+        i = 1;
+    }
+    const size_t epos = sci.find('e');
+    std::string digits;
+    for (size_t k = i; k < epos; ++k)
+        if (sci[k] != '.') digits += sci[k];
+    while (digits.size() > 1 && digits.back() == '0') digits.pop_back();
+    const int exp10 = std::stoi(sci.substr(epos + 1));
+    const int length = (int)digits.size();
+    const int kk = exp10 + 1;          // position of the decimal point relative to the first digit
+    const int k = kk - length;         // value = digits * 10^k
+    std::string out;
+    if (0 <= k && kk <= 16) {
+        out = digits + std::string((size_t)k, '0') + ".0";
+    } else if (0 < kk && kk <= 16) {
+        out = digits.substr(0, (size_t)kk) + "." + digits.substr((size_t)kk);
+    } else if (-5 < kk && kk <= 0) {
+        out = "0." + std::string((size_t)(-kk), '0') + digits;
+    } else if (length == 1) {
+        out = digits + "e" + std::to_string(kk - 1);
+    } else {
+        out = digits.substr(0, 1) + "." + digits.substr(1) + "e" + std::to_string(kk - 1);
+    }
+    return neg ? "-" + out : out;
+}
+
 // `{:.N}`: exact decimal expansion rounded half-to-even at N places — what glibc printf does.
 std::string fmt_f64_prec(double v, int prec) {
     if (std::isnan(v)) return "NaN";

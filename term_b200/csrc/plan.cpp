@@ -1700,4 +1700,56 @@ void Plan::finalize() {
     executed = true;
 }
 
+// ---- *State structs as serde_json writes them: fields in declaration order, u64 as integers, f64 through ryu,
+// Option::None and non-finite floats as null, unit enum variants as strings ----
+std::string analyzer_state_json(const Plan& p, int slot_index) {
+    if (slot_index < 0 || slot_index >= (int)p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
+    if (!p.executed) throw Error(TG_ERR_INVALID_ARG, "plan has not been executed");
+    const Slot& s = p.slots[slot_index];
+    const tg_analyzer_result& r = s.ares;
+    auto U = [](uint64_t v) { return std::to_string(v); };
+    auto opt = [](bool has, double v) { return has ? json_f64(v) : std::string("null"); };
+    if (s.kind == SL_HISTOGRAM) {
+        // HistogramState (advanced/histogram.rs:78-91); HistogramBucket {lower_bound, upper_bound, count}
+        std::string out = "{\"buckets\":[";
+        const int nb = r.u[0] ? s.k : 0;
+        auto get = [&](const std::string& key) {
+            for (auto& kv : s.map)
+                if (kv.first == key) return kv.second;
+            return 0.0;
+        };
+        for (int i = 0; i < nb; ++i) {
+            const std::string pre = "bucket_" + std::to_string(i);
+            if (i) out += ",";
+            out += "{\"lower_bound\":" + json_f64(get(pre + ".lower")) + ",\"upper_bound\":" + json_f64(get(pre + ".upper")) +
+                   ",\"count\":" + U((uint64_t)get(pre + ".count")) + "}";
+        }
+        out += "],\"min_value\":" + json_f64(r.f[0]) + ",\"max_value\":" + json_f64(r.f[1]) + ",\"total_count\":" + U(r.u[0]) +
+               ",\"sum\":" + json_f64(r.f[2]) + ",\"sum_squared\":" + json_f64(r.f[3]) + "}";
+        return out;
+    }
+    if (s.kind != SL_ANALYZER || r.error == 2) return "";
+    switch (s.sub_kind) {
+        case TG_AN_SIZE: return "{\"count\":" + U(r.u[0]) + "}";
+        case TG_AN_COMPLETENESS: return "{\"total_count\":" + U(r.u[0]) + ",\"non_null_count\":" + U(r.u[1]) + "}";
+        case TG_AN_DISTINCTNESS: return "{\"total_count\":" + U(r.u[0]) + ",\"distinct_count\":" + U(r.u[1]) + "}";
+        case TG_AN_MEAN: return "{\"sum\":" + json_f64(r.f[0]) + ",\"count\":" + U(r.u[0]) + "}";
+        case TG_AN_MIN:
+        case TG_AN_MAX: return "{\"min\":" + opt(r.u[0] != 0, r.f[0]) + ",\"max\":" + opt(r.u[1] != 0, r.f[1]) + "}";
+        case TG_AN_SUM: return "{\"sum\":" + json_f64(r.f[0]) + ",\"has_values\":" + (r.u[0] ? "true" : "false") + "}";
+        case TG_AN_STDDEV:
+            return "{\"count\":" + U(r.u[0]) + ",\"sum\":" + json_f64(r.f[0]) + ",\"sum_squared\":" + json_f64(r.f[1]) + ",\"mean\":" +
+                   json_f64(r.f[2]) + "}";
+        case TG_AN_CORR_PEARSON:
+        case TG_AN_COVARIANCE:
+            return "{\"n\":" + U(r.u[0]) + ",\"sum_x\":" + json_f64(r.f[0]) + ",\"sum_y\":" + json_f64(r.f[1]) + ",\"sum_x2\":" +
+                   json_f64(r.f[2]) + ",\"sum_y2\":" + json_f64(r.f[3]) + ",\"sum_xy\":" + json_f64(r.f[4]) +
+                   ",\"x_ranks\":null,\"y_ranks\":null,\"correlation_type\":\"" +
+                   (s.sub_kind == TG_AN_CORR_PEARSON ? "Pearson" : "Covariance") + "\"}";
+        case TG_AN_COMPLIANCE: return "{\"compliant_count\":" + U(r.u[0]) + ",\"total_count\":" + U(r.u[1]) + "}";
+        case TG_AN_APPROX_COUNT_DISTINCT: return "{\"approx_distinct_count\":" + U(r.u[0]) + ",\"total_count\":" + U(r.u[1]) + "}";
+        default: return "";  // Spearman keeps its rank vectors on the device; KLL / grouped states are blobs
+    }
+}
+
 }  // namespace tg

@@ -163,6 +163,10 @@ int plan_add_histogram(Plan& p, const std::string& col, int num_buckets);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 
+// serde_json text of an analyzer slot's *State struct, as IncrementalAnalysisRunner / FileSystemStateStore persist it
+// (analyzers/incremental/runner.rs:72-80, state_store.rs:153-176); empty string when the slot has no such state
+std::string analyzer_state_json(const Plan& p, int slot);
+
 // KLL sketch blob helpers (kll_host.cpp)
 struct KllHost;
 void kll_blob_merge(std::vector<uint8_t>& into, const std::vector<uint8_t>& other);

@@ -195,3 +195,72 @@ def test_plan_deduplicates_aggregates(built_lib):
     assert keys.count("num|x") == 1 and keys.count("valid|x") == 1 and keys.count("valid|y") == 1
     assert sum(k.startswith("regex|s") for k in keys) == 1 and keys.count("pred|x > 1") == 1
     assert F.lib().tg_plan_num_slots(p.handle) == 9
+
+
+# ---- analyzer states as serde_json text (analyzers/incremental/runner.rs:72-80) ----
+def test_json_f64_follows_ryu_layout(built_lib):
+    import ctypes as C
+    from term_b200 import _ffi as F
+
+    def j(v):
+        buf = C.create_string_buffer(64)
+        F.lib().tg_format_f64_json(v, buf, 64)
+        return buf.value.decode()
+
+    cases = {1.0: "1.0", 0.1: "0.1", 100.0: "100.0", -2.5: "-2.5", 123456789.125: "123456789.125", 1e15: "1000000000000000.0",
+             1e16: "1e16", 1.5e16: "1.5e16", 1e21: "1e21", 1e-5: "0.00001", 1.5e-5: "0.000015", 1e-6: "1e-6", 1.234e-7: "1.234e-7",
+             0.0: "0.0", 24.3: "24.3", 5e-324: "5e-324", 1.7976931348623157e308: "1.7976931348623157e308",
+             float("nan"): "null", float("inf"): "null"}
+    for v, want in cases.items():
+        assert j(v) == want, (v, j(v), want)
+    # any finite value must parse back to the same f64 (shortest round-trip digits)
+    import json, random
+    rnd = random.Random(3)
+    for _ in range(2000):
+        v = rnd.uniform(-1, 1) * 10.0 ** rnd.randint(-30, 30)
+        assert json.loads(j(v)) == v
+
+
+def test_analyzer_state_json_matches_serde_layout(built_lib):
+    """states built from a merged partial blob (no GPU needed): field names and order of the reference's *State structs"""
+    import struct
+    import term_b200 as T
+    plan = T.Plan()
+    slots = {
+        "size": T.SizeAnalyzer()._add_to(plan), "comp": T.CompletenessAnalyzer("x")._add_to(plan),
+        "mean": T.MeanAnalyzer("x")._add_to(plan), "min": T.MinAnalyzer("x")._add_to(plan), "sum": T.SumAnalyzer("x")._add_to(plan),
+        "std": T.StandardDeviationAnalyzer("x")._add_to(plan), "corr": T.CorrelationAnalyzer.pearson("x", "y")._add_to(plan),
+        "acd": T.ApproxCountDistinctAnalyzer("x")._add_to(plan),
+    }
+    # x = [1.5, 2.5, NULL, 4.0], y = [2.0, 4.0, 6.0, NULL]
+    out = [struct.pack("<Q", len(plan.aggregates()))]
+    for kind, key in plan.aggregates():
+        u, f = [0] * 8, [0.0] * 8
+        if kind == 0:
+            u[0], u[1] = 4, 2
+        elif kind == 1:
+            u[0], u[1] = 4, 3
+        elif kind == 2:  # K = 2.5: d = [-1, 0, 1.5]
+            u[0] = 3
+            f[0], f[1], f[2], f[3], f[4], f[5] = 2.5, 0.5, 3.25, 1.5, 4.0, 8.0
+        elif kind == 3:  # pairs (1.5, 2), (2.5, 4); Kx = 1.5, Ky = 2
+            u[0] = 2
+            f[0], f[1], f[2], f[3], f[4], f[5], f[6] = 1.5, 2.0, 1.0, 2.0, 1.0, 4.0, 2.0
+        elif kind == 6:
+            u[0], u[1], u[2], u[3], u[4], u[5] = 4, 3, 3, 1, 1, 4
+        else:
+            raise AssertionError((kind, key))
+        out.append(struct.pack("<QQ", kind, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *f) + struct.pack("<QQ", 0, 0))
+    plan.partial_reset()
+    plan.partial_merge(b"".join(out))
+    plan.finalize()
+    J = plan.analyzer_state_json
+    assert J(slots["size"]) == '{"count":4}'
+    assert J(slots["comp"]) == '{"total_count":4,"non_null_count":3}'
+    assert J(slots["mean"]) == '{"sum":8.0,"count":3}'
+    assert J(slots["min"]) == '{"min":1.5,"max":4.0}'
+    assert J(slots["sum"]) == '{"sum":8.0,"has_values":true}'
+    assert J(slots["std"]) == '{"count":3,"sum":8.0,"sum_squared":24.5,"mean":2.6666666666666665}'
+    assert J(slots["corr"]) == ('{"n":2,"sum_x":4.0,"sum_y":6.0,"sum_x2":8.5,"sum_y2":20.0,"sum_xy":13.0,'
+                                '"x_ranks":null,"y_ranks":null,"correlation_type":"Pearson"}')
+    assert J(slots["acd"]) == '{"approx_distinct_count":3,"total_count":3}'
