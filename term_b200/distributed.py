@@ -140,7 +140,11 @@ def exchange_and_finalize(plan, ctx):
     are fixed-size go through the peer mailboxes (two tiny kernels + one copy over NVLink peer memory, see
     term_b200/csrc/mailbox.cu); everything else, and any platform where CUDA IPC is unavailable, takes the NCCL
     all-gather."""
-    if dist.get_backend() == "nccl" and all(k in _FIXED_KINDS for k, _ in plan.aggregates()) and _ensure_mailbox(ctx):
+    aggs = plan.aggregates()
+    # rank-independent decision (every rank must take the same path): fixed-size records only, and a slot that holds
+    # them with 4 KB to spare for error texts
+    fits = 8 + len(aggs) * 176 + 4096 <= MAILBOX_SLOT_BYTES
+    if dist.get_backend() == "nccl" and fits and all(k in _FIXED_KINDS for k, _ in aggs) and _ensure_mailbox(ctx):
         F.check(F.lib().tg_plan_exchange_and_finalize(ctx.handle, plan.handle))
         return
     merge_partials(plan, exchange_partials(plan))
