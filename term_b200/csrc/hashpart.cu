@@ -430,6 +430,34 @@ __global__ void bitmap_popcount_kernel(const uint4* __restrict__ bm, size_t n16,
     flush_counter(c, out);
 }
 
+// min / max of a strided sample (every `stride`-th row): a range GUESS that lets the bitmap job run without a full
+// min/max pass first; the job itself counts keys that fall outside and is repeated exactly when there are any
+__global__ void __launch_bounds__(PART_THREADS) sample_minmax_i64_kernel(const long long* __restrict__ values, const uint32_t* __restrict__ validity,
+                                                                         int64_t n, int64_t stride, MinMaxOut* out) {
+    long long mn = INT64_MAX, mx = INT64_MIN;
+    unsigned long long cnt = 0;
+    const int64_t m = (n + stride - 1) / stride;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i * stride;
+        if (!row_valid(validity, row)) continue;
+        const long long v = __ldg(values + row);
+        mn = min(mn, v);
+        mx = max(mx, v);
+        ++cnt;
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) {
+        mn = min(mn, __shfl_xor_sync(0xffffffffu, mn, s));
+        mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, s);
+    }
+    if ((threadIdx.x & 31) == 0 && cnt) {
+        atomicMin(&out->mn, mn);
+        atomicMax(&out->mx, mx);
+        atomicAdd(&out->n_valid, cnt);
+    }
+}
+
 // mode 0: distinct / seen-twice counting; mode 1: build the parent set (non-returning OR); mode 2: probe
 template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __restrict__ values, const uint32_t* __restrict__ validity,
@@ -437,7 +465,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
                                                              uint32_t* dup, unsigned long long* vkeys, uint64_t vmask,
                                                              unsigned long long* examples, int max_examples, HashCounters* ctr,
                                                              unsigned long long* nulls_out = nullptr) {
-    unsigned long long d = 0, dupk = 0, viol = 0, dist = 0, nulls = 0, special = 0, nulls_count = 0;
+    unsigned long long d = 0, dupk = 0, viol = 0, dist = 0, nulls = 0, special = 0, nulls_count = 0, oob = 0;
     const int64_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * PART_TILE;
@@ -460,6 +488,11 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
             nulls_count += (row < n) && !ok[k];
             const unsigned long long idx = ((unsigned long long)v[k] - (unsigned long long)lo);
             old[k] = 0;
+            if (ok[k] && MODE != 2 && idx > range) {
+                // outside the (guessed) key range: the bitmap cannot hold it; the host repeats the job with the exact range
+                ++oob;
+                ok[k] = false;
+            }
             if (ok[k]) {
                 const uint32_t bit = 1u << (idx & 31);
                 if (MODE == 0) old[k] = atomicOr(&seen[idx >> 5], bit) & bit;
@@ -511,6 +544,7 @@ __global__ void __launch_bounds__(PART_THREADS) dense_kernel(const long long* __
     }
     if (MODE != 1) flush_counter(nulls, &ctr->any_null_rows);
     if (MODE == 1 && nulls_out) flush_counter(nulls_count, nulls_out);
+    if (MODE != 2) flush_counter(oob, &ctr->overflow);
 }
 
 // ================================================================== host side ==================
@@ -746,8 +780,80 @@ static bool dense_enough(const MinMaxOut& h) {
     return range < DENSE_MAX_RANGE && range <= 32ull * h.n_valid + 4096ull;
 }
 
+// one bitmap pass over [lo, lo + range]; returns the counters (overflow = keys outside the range)
+static HashCounters dense_distinct_pass(Engine& e, const Column& c, int64_t n, bool need_singles, long long lo, unsigned long long range,
+                                        int& launches) {
+    const size_t bm_b = round_up((size_t)(range / 32 + 1) * 4, 256);
+    uint8_t* scr = e.scratch(2 * bm_b + 256);
+    uint32_t* seen = (uint32_t*)scr;
+    uint32_t* dup = (uint32_t*)(scr + bm_b);
+    HashCounters* d_ctr = (HashCounters*)(scr + 2 * bm_b);
+    if (need_singles) {
+        // one RETURNING atomicOr per key: the old bit tells first from repeated occurrence
+        fill_async(e, scr, 2 * bm_b + 256, 0u);
+        dense_kernel<0><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, lo, range,
+                                                                       seen, dup, nullptr, 0, nullptr, 0, d_ctr);
+        launches += 2;
+    } else {
+        // only COUNT(DISTINCT) is wanted: non-returning ORs (190 vs 126 G/s in L2), then count the set bits
+        fill_async(e, seen, bm_b, 0u);
+        fill_async(e, d_ctr, 256, 0u);
+        dense_kernel<1><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, lo, range,
+                                                                       seen, nullptr, nullptr, 0, nullptr, 0, d_ctr, &d_ctr->any_null_rows);
+        const size_t n16 = bm_b / 16;
+        bitmap_popcount_kernel<<<(int)std::max<size_t>(1, std::min<size_t>((n16 + 255) / 256, (size_t)e.sm_count * 8)), 256, 0, e.stream>>>(
+            (const uint4*)seen, n16, &d_ctr->distinct_nonnull);
+        launches += 4;
+    }
+    TG_CUDA(cudaGetLastError());
+    HashCounters h{};
+    TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    return h;
+}
+
 bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, Distinct64Result& r, int& launches) {
     if (c.dtype != TG_INT64 || getenv("TG_HASH_NO_DENSE")) return false;
+    auto fill_result = [&](const HashCounters& h) {
+        r.distinct = h.distinct_nonnull;
+        r.dup_keys = need_singles ? h.singles_minus : 0;  // unused by the slots of this plan when !need_singles
+        r.nulls = h.any_null_rows;
+    };
+    // 1. optimistic: guess the key range from a strided 64 K sample, padded by 1/16 of its width on both sides. For
+    //    ids / surrogate keys the guess holds and the min/max pass over the whole column is saved.
+    static const int64_t guess_min_rows = [] {
+        const char* ev = getenv("TG_HASH_GUESS_MIN_ROWS");
+        const long long x = ev ? atoll(ev) : 0;
+        return x > 0 ? (int64_t)x : (int64_t)1 << 22;
+    }();
+    if (n >= guess_min_rows && !getenv("TG_HASH_NO_GUESS")) {
+        uint8_t* scr = e.scratch(256);
+        MinMaxOut* d = (MinMaxOut*)scr;
+        MinMaxOut init{INT64_MAX, INT64_MIN, 0, 0}, g{};
+        TG_CUDA(cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, e.stream));
+        const int64_t stride = std::max<int64_t>(1, n >> 16);
+        sample_minmax_i64_kernel<<<64, PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, stride, d);
+        TG_CUDA(cudaGetLastError());
+        ++launches;
+        TG_CUDA(cudaMemcpyAsync(&g, d, sizeof(g), cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        if (g.n_valid > 0) {
+            const unsigned long long w = (unsigned long long)g.mx - (unsigned long long)g.mn;
+            const unsigned long long pad = w / 16 + 4096;
+            // keep lo / hi inside i64 (the wrap-around arithmetic of the kernel handles the rest)
+            const long long lo = g.mn < INT64_MIN + (long long)pad ? INT64_MIN : g.mn - (long long)pad;
+            const long long hi = g.mx > INT64_MAX - (long long)pad ? INT64_MAX : g.mx + (long long)pad;
+            const unsigned long long range = (unsigned long long)hi - (unsigned long long)lo;
+            if (range < DENSE_MAX_RANGE && range <= 32ull * (unsigned long long)n + 4096ull) {
+                const HashCounters h = dense_distinct_pass(e, c, n, need_singles, lo, range, launches);
+                if (h.overflow == 0) {
+                    fill_result(h);
+                    return true;
+                }
+            }
+        }
+    }
+    // 2. exact range from a full min/max pass
     MinMaxOut mm{};
     if (!minmax_i64(e, c, n, mm, launches)) {
         r = Distinct64Result{0, 0, (uint64_t)n};
@@ -755,35 +861,7 @@ bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, 
     }
     if (!dense_enough(mm)) return false;
     const unsigned long long range = (unsigned long long)mm.mx - (unsigned long long)mm.mn;
-    const size_t bm_b = round_up((size_t)(range / 32 + 1) * 4, 256);
-    uint8_t* scr = e.scratch(2 * bm_b + 256);
-    uint32_t* seen = (uint32_t*)scr;
-    uint32_t* dup = (uint32_t*)(scr + bm_b);
-    HashCounters* d_ctr = (HashCounters*)(scr + 2 * bm_b);
-    HashCounters h{};
-    if (need_singles) {
-        // one RETURNING atomicOr per key: the old bit tells first from repeated occurrence
-        fill_async(e, scr, 2 * bm_b + 256, 0u);
-        dense_kernel<0><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, mm.mn,
-                                                                       range, seen, dup, nullptr, 0, nullptr, 0, d_ctr);
-        launches += 2;
-    } else {
-        // only COUNT(DISTINCT) is wanted: non-returning ORs (190 vs 126 G/s in L2), then count the set bits
-        fill_async(e, seen, bm_b, 0u);
-        fill_async(e, d_ctr, 256, 0u);
-        dense_kernel<1><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, mm.mn,
-                                                                       range, seen, nullptr, nullptr, 0, nullptr, 0, d_ctr, &d_ctr->any_null_rows);
-        const size_t n16 = bm_b / 16;
-        bitmap_popcount_kernel<<<(int)std::max<size_t>(1, std::min<size_t>((n16 + 255) / 256, (size_t)e.sm_count * 8)), 256, 0, e.stream>>>(
-            (const uint4*)seen, n16, &d_ctr->distinct_nonnull);
-        launches += 4;
-    }
-    TG_CUDA(cudaGetLastError());
-    TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
-    TG_CUDA(cudaStreamSynchronize(e.stream));
-    r.distinct = h.distinct_nonnull;
-    r.dup_keys = need_singles ? h.singles_minus : 0;  // unused by the slots of this plan when !need_singles
-    r.nulls = h.any_null_rows;
+    fill_result(dense_distinct_pass(e, c, n, need_singles, mm.mn, range, launches));
     return true;
 }
 

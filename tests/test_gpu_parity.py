@@ -457,7 +457,7 @@ def test_uniqueness_partitioned_path_large_keys(ctx, dtype):
         ctx.deregister_table(name)
 
 
-@pytest.mark.parametrize("shape", ["all_null", "all_equal", "one_null", "two_values_sparse", "no_validity"])
+@pytest.mark.parametrize("shape", ["all_null", "all_equal", "one_null", "two_values_sparse", "no_validity", "unsampled_outliers", "sorted_ids"])
 def test_uniqueness_large_path_edge_cases(ctx, shape):
     """degenerate key columns through the dense / partitioned paths: no valid key at all, one hot key (every row in the
     same bucket), exactly one NULL (the NULL group is a singleton), two far-apart values (not dense), no bitmap"""
@@ -474,6 +474,16 @@ def test_uniqueness_large_path_edge_cases(ctx, shape):
         mask[12345] = True
     elif shape == "two_values_sparse":
         vals = np.where(rng.random(n) < 0.5, np.int64(-(2**62)), np.int64(2**62)).astype(np.int64)
+    elif shape == "unsampled_outliers":
+        # dense ids plus two far keys at rows the strided range sample (every n >> 16 = 18th row) skips: the optimistic
+        # bitmap pass must notice them and give way to the exact-range pass
+        vals = rng.integers(0, n // 2, n).astype(np.int64)
+        vals[7], vals[n - 5] = 3 * n, -2 * n
+        mask = rng.random(n) < 0.02
+        mask[7] = mask[n - 5] = False
+    elif shape == "sorted_ids":
+        vals = np.arange(n, dtype=np.int64) + 10**12
+        vals[1000] = vals[999]
     else:
         vals = rng.integers(0, n // 4, n).astype(np.int64) * 1_000_003
     arr = pa.array(vals, mask=mask) if shape != "no_validity" else pa.array(vals)
