@@ -282,7 +282,10 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
                                     : (exact ? (Sampler)kll_sample_kernel<false, true> : (Sampler)kll_sample_kernel<false, false>);
         sampler<<<grid, KLL_THREADS, 0, e.stream>>>(j.c->values.p, (const uint32_t*)j.c->validity.p, n, g, seed, v_in, w_in, max_emit, d_ctr);
         TG_CUDA(cudaGetLastError());
-        TG_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sort_b, v_in, v_out, w_in, w_out, m, 0, 64, e.stream));
+        // exact mode sorts on all 64 key bits; a sampled sketch only needs the order down to the top 32 bits (sign,
+        // exponent, 20 mantissa bits: values closer than 1e-6 relative may swap, far inside the rank-error bound),
+        // which halves the radix passes — each is launch-latency bound at this size
+        TG_CUDA(cub::DeviceRadixSort::SortPairs(d_tmp, sort_b, v_in, v_out, w_in, w_out, m, exact ? 0 : 32, 64, e.stream));
         cub::TransformInputIterator<unsigned long long, U32ToU64, const uint32_t*> w_sorted(w_out, U32ToU64());
         TG_CUDA(cub::DeviceScan::InclusiveSum(d_tmp, scan_b, w_sorted, d_cum, m, e.stream));
         kll_pick_kernel<<<(unsigned)((j.cap + 255) / 256), 256, 0, e.stream>>>(v_out, d_cum, m, d_ctr, (uint32_t)j.cap, d_pick_v, d_pick_w);
