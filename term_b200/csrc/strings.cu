@@ -387,7 +387,12 @@ static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::
     // per-warp stage: 32 rows of ~1.5x the column's mean length, so almost every block is staged by TMA
     const double mean_len = t.n_rows > 0 ? (double)c.value_bytes / (double)t.n_rows : 0.0;
     // two rows per lane once there are enough 64-row blocks to keep every warp of the grid busy several times over
-    const int R = t.n_rows >= ((int64_t)1 << 21) && !getenv("TG_STR_R1") ? 2 : 1;
+    static const int64_t r2_min_rows = [] {
+        const char* ev = getenv("TG_STR_R2_MIN_ROWS");  // tests lower it so both block shapes meet the oracle
+        const long long x = ev ? atoll(ev) : 0;
+        return x > 0 ? (int64_t)x : (int64_t)1 << 21;
+    }();
+    const int R = t.n_rows >= r2_min_rows && !getenv("TG_STR_R1") ? 2 : 1;
     size_t stage = round_up((size_t)(mean_len * 32.0 * R * (R == 2 ? 1.25 : 1.5)) + (R == 2 ? 128 : 256), 128);
     stage = std::min<size_t>(std::max<size_t>(stage, 1024), 8192);
     // warps per CTA: as many as fit beside the table (each owns a double stage + 2 mbarriers)

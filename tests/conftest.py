@@ -7,7 +7,8 @@ import pytest
 # on B200). The tests lower it so that the partitioned code is exercised against the oracle at sizes the CPU side
 # handles in seconds. Read once by libtermgpu.so, so it has to be set before the first execute.
 os.environ.setdefault("TG_HASH_BUCKET_KEYS", "262144")
-os.environ.setdefault("TG_HASH_GUESS_MIN_ROWS", "100000")  # the optimistic key-range guess of the dense path (default: 4 M rows)
+os.environ.setdefault("TG_HASH_GUESS_MIN_ROWS", "100000")
+os.environ.setdefault("TG_STR_R2_MIN_ROWS", "1000")  # string kernel: 64-row blocks (two rows per lane) from 1000 rows on (default 2 M)  # the optimistic key-range guess of the dense path (default: 4 M rows)
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
