@@ -118,6 +118,11 @@ def test_numeric_suite_matches_oracle(ctx, n, batch):
             cb.statistic(c, T.StatisticType[s], A.GreaterThan(-1e300))
         cb.has_correlation("f0", "f1", A.GreaterThan(0.5))
         cb.constraint(T.CorrelationConstraint.covariance("f0", "i0", A.LessThan(1e300)))
+        # more pairs: with the NUM / VALID / PRED aggregates this plan holds more than 16 aggregates, so the fused scan
+        # runs as two passes (one register-resident unit per consumer warp each)
+        extra_pairs = [("f1", "f2"), ("i0", "i1"), ("dense", "f0"), ("f2", "i0"), ("f1", "dense")]
+        for a, b in extra_pairs:
+            cb.has_correlation(a, b, A.GreaterThan(-2.0))
         preds = ["f2 > 0 AND i0 < 1000000", "f0 + f1 > 150", "i0 % 7 = 0 OR f2 BETWEEN 100 AND 200",
                  "NOT (f1 IS NULL) AND i0 / 3 >= -100000", "i0 IN (1, 2, 3) OR f0 IS NULL", "abs(i0) * 2 - 5 < f2 * 1000"]
         for p in preds:
@@ -156,11 +161,17 @@ def test_numeric_suite_matches_oracle(ctx, n, batch):
         o = O.correlation(t, "f0", "i0", "Covariance", ("LessThan", 1e300))
         assert abs(rs[k].metric - o.metric) <= REL_MOMENT * max(1.0, abs(o.metric)) * 1e3, (rs[k], o)
         k += 1
+        for a, b in extra_pairs:
+            o = O.correlation(t, a, b, "Pearson", ("GreaterThan", -2.0))
+            assert rs[k].status.name.lower() == o.status and abs(rs[k].metric - o.metric) <= REL_MOMENT, (a, b, rs[k], o)
+            k += 1
         for p in preds:
             o = O.custom_sql(t, p) if n <= 200_000 else None
             if o is not None:
                 assert rs[k].status.name.lower() == o.status and rs[k].metric == o.metric and rs[k].message == o.message, (p, rs[k], o)
             k += 1
+        assert k == len(rs)
+        assert suite.last_plan.stats()["launches"] >= 4  # two scan passes (kernel + finalize each)
     finally:
         ctx.deregister_table(name)
 
