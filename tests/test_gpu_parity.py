@@ -811,6 +811,30 @@ def test_grouped_completeness_matches_oracle(ctx):
         ctx.deregister_table("grp")
 
 
+def test_grouped_completeness_many_groups_spill_path(ctx):
+    """more groups (9 500, Int64 keys with NULLs, plus a Float64 key) than a CTA's 8 192-slot shared table holds: rows
+    whose group does not fit spill to the global table; counts must still be exact"""
+    rng = np.random.default_rng(17)
+    n = 300_000
+    ids = rng.integers(0, 9_500, n)
+    t = pa.table({"gid": pa.array(ids, mask=rng.random(n) < 0.01), "gf": pa.array((ids % 97).astype(np.float64) / 4.0),
+                  "v": pa.array(rng.normal(0, 1, n), mask=rng.random(n) < 0.3)})
+    ctx.register_table("grp_many", t)
+    try:
+        for groups in (["gid"], ["gid", "gf"]):
+            r = T.GroupedCompletenessAnalyzer("v", groups).compute(ctx, "grp_many")
+            want = O.grouped_completeness(t, "v", groups)
+            got = {k: v for k, v in r.map.items() if not k.startswith("__")}
+            assert len(got) == len(want)
+
+            def text(x):  # group values print like Rust's Display; NULL groups as "NULL"
+                return "NULL" if x is None else (O.rust_f64(x) if isinstance(x, float) else str(x))
+
+            assert got == {"_".join(text(x) for x in k): nn / tt for k, (tt, nn) in want.items()}
+    finally:
+        ctx.deregister_table("grp_many")
+
+
 # ---------------------------------------------------------------- quantile sketch ----
 @pytest.mark.parametrize("n,k", [(1, 50), (100, 200), (5000, 256), (3_000_000, 256)])
 def test_kll_rank_error_within_reference_bound(ctx, n, k):
