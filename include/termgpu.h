@@ -325,6 +325,15 @@ TG_API int32_t tg_plan_add_approx_count_distinct(tg_plan* plan, const char* colu
 typedef enum { TG_DT_INTEGER = 0, TG_DT_FLOAT = 1, TG_DT_BOOLEAN = 2, TG_DT_DATE = 3, TG_DT_TIMESTAMP = 4, TG_DT_STRING = 5 } tg_value_type;
 TG_API int32_t tg_plan_add_data_type(tg_plan* plan, const char* column, int32_t value_type, double threshold);
 
+/* QuantileConstraint::evaluate (constraints/quantile.rs:282-482); QuantileValidation (:83-111) as `validation`.
+ * SINGLE: one quantile + assertion (median / percentile constructors :186-203), metric = the quantile value.
+ * MULTIPLE: n quantiles each with its assertion (:206-213), no metric. MONOTONIC: n quantiles, `strict` (:102-106),
+ * assertions NULL. UNIMPLEMENTED: Distribution / Custom, which the reference answers Skipped (:474-479).
+ * APPROX_PERCENTILE_CONT (t-digest) is answered from the column's KLL sketch. */
+typedef enum { TG_QUANTILE_SINGLE = 0, TG_QUANTILE_MULTIPLE = 1, TG_QUANTILE_MONOTONIC = 2, TG_QUANTILE_UNIMPLEMENTED = 3 } tg_quantile_validation;
+TG_API int32_t tg_plan_add_quantile(tg_plan* plan, const char* column, int32_t validation, const double* quantiles,
+                                    const tg_assertion* assertions, int32_t n, int32_t strict);
+
 /* ColumnCountConstraint::evaluate (constraints/column_count.rs:43-85): schema width of the plan's table */
 TG_API int32_t tg_plan_add_column_count(tg_plan* plan, tg_assertion assertion);
 /* HistogramAnalyzer (analyzers/advanced/histogram.rs:62-358), Float64 columns like the reference. Result through

@@ -1027,3 +1027,52 @@ def rank_error(values_sorted: np.ndarray, estimate: float, q: float) -> float:
     if lo <= q <= hi:
         return 0.0
     return min(abs(lo - q), abs(hi - q))
+
+
+def kll_exact_quantile(values: np.ndarray, q: float) -> float:
+    """KllSketch::get_quantile with every item still at level 0 (weight 1), analyzers/advanced/kll_sketch.rs:246-318:
+    phi 0 / 1 => min / max, else the first sorted item whose cumulative weight reaches ceil(phi * n); NaN skipped
+    on update (:197-199)"""
+    s = np.sort(values[~np.isnan(values)])
+    if len(s) == 0:
+        return 0.0
+    if q <= 0.0:
+        return float(s[0])
+    if q >= 1.0:
+        return float(s[-1])
+    target = max(1, math.ceil(q * len(s)))
+    return float(s[min(target, len(s)) - 1])
+
+
+def quantile_constraint(table, column, mode, checks=(), quantiles=(), strict=False, quantile_fn=kll_exact_quantile) -> Result:
+    """constraints/quantile.rs:282-482. mode: "Single" [(q, assertion)], "Multiple" [(q, assertion)...],
+    "Monotonic" quantiles + strict, anything else => the catch-all Skipped arm (:474-479). The quantile VALUES come
+    from quantile_fn (APPROX_PERCENTILE_CONT in the reference — parity unpinned, SURVEY §8c; here the KLL rule);
+    a NULL aggregate (no non-null rows) is read as 0.0 (`.value(0)` without a null check, :311-316)."""
+    col = table_cols(table)[column]
+    vals = np.asarray(col.values, dtype=np.float64)[col.valid]
+
+    def qv(q):
+        return quantile_fn(vals, q) if len(vals) else 0.0
+
+    if mode == "Single":
+        q, a = checks[0]
+        v = qv(q)
+        if assertion_eval(a, v):
+            return Result(SUCCESS, v)
+        return Result(FAILURE, v, f"Quantile {rust_f64(q)} is {rust_f64(v)} which does not {assertion_desc(a)}")
+    if mode == "Multiple":
+        failures = []
+        for q, a in checks:
+            v = qv(q)
+            if not assertion_eval(a, v):
+                failures.append(f"Q{int(q * 100.0)} is {rust_f64(v)} which does not {assertion_desc(a)}")
+        return Result(SUCCESS, None) if not failures else Result(FAILURE, None, "; ".join(failures))
+    if mode == "Monotonic":
+        v = [qv(q) for q in quantiles]
+        ok = all((b > a) if strict else (b >= a) for a, b in zip(v, v[1:]))
+        if ok:
+            return Result(SUCCESS, None)
+        dbg = ", ".join(rust_f64(x) if any(c in rust_f64(x) for c in ".eN") or math.isinf(x) else rust_f64(x) + ".0" for x in v)
+        return Result(FAILURE, None, f"Quantiles are not {'strictly' if strict else ''} monotonic: [{dbg}]")
+    return Result(SKIPPED, None, "Validation type not yet implemented")

@@ -102,6 +102,8 @@ SIGNATURES = {
     "tg_plan_add_data_type": (C.c_int32, [P, C.c_char_p, C.c_int32, C.c_double]),
     "tg_plan_add_column_count": (C.c_int32, [P, tg_assertion]),
     "tg_plan_add_histogram": (C.c_int32, [P, C.c_char_p, C.c_int32]),
+    "tg_plan_add_quantile": (C.c_int32, [P, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(tg_assertion),
+                                         C.c_int32, C.c_int32]),
     "tg_plan_add_grouped_completeness": (C.c_int32, [P, C.c_char_p, STRS, C.c_int32, C.c_int32, C.c_int32]),
     "tg_plan_execute": (C.c_int, [P, P, C.c_char_p]),
     "tg_plan_execute_partial": (C.c_int, [P, P, C.c_char_p]),

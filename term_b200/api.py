@@ -669,6 +669,46 @@ class MultiStatisticalConstraint(Constraint):  # constraints/statistics.rs:385-5
         return F.check_slot(F.lib().tg_plan_add_multi_statistic(plan.handle, self.column.encode(), kinds, pcts, asr, n))
 
 
+@dataclass
+class QuantileCheck:  # constraints/quantile.rs:38-58
+    quantile: float
+    assertion: Assertion
+
+    def __post_init__(self):
+        if not (0.0 <= self.quantile <= 1.0):
+            raise F.TermGpuError(F.TG_ERR_CONFIGURATION, "Quantile must be between 0.0 and 1.0")
+
+
+class QuantileConstraint(Constraint):  # constraints/quantile.rs:147-497
+    """QuantileValidation: Single / Multiple / Monotonic evaluate; Distribution / Custom are Skipped like the
+    reference's catch-all arm (:474-479). Every quantile of a column shares the plan's one KLL sketch."""
+    SINGLE, MULTIPLE, MONOTONIC, UNIMPLEMENTED = 0, 1, 2, 3
+
+    def __init__(self, column, validation, checks=(), quantiles=(), strict=False):
+        self.column, self.validation, self.strict = column, validation, strict
+        self.checks, self.quantiles = list(checks), list(quantiles)
+        self._add_to(Plan())
+
+    @staticmethod
+    def median(column, assertion): return QuantileConstraint.percentile(column, 0.5, assertion)
+    @staticmethod
+    def percentile(column, q, assertion): return QuantileConstraint(column, QuantileConstraint.SINGLE, [QuantileCheck(q, assertion)])
+    @staticmethod
+    def multiple(column, checks): return QuantileConstraint(column, QuantileConstraint.MULTIPLE, checks)
+    @staticmethod
+    def monotonic(column, quantiles, strict): return QuantileConstraint(column, QuantileConstraint.MONOTONIC, quantiles=quantiles, strict=strict)
+    @staticmethod
+    def distribution(column, config=None): return QuantileConstraint(column, QuantileConstraint.UNIMPLEMENTED)
+
+    def _add_to(self, plan):
+        qs = [c.quantile for c in self.checks] if self.checks else self.quantiles
+        n = len(qs)
+        q = (C.c_double * max(1, n))(*qs)
+        asr = (F.tg_assertion * max(1, n))(*[c.assertion.c() for c in self.checks]) if self.checks else None
+        return F.check_slot(F.lib().tg_plan_add_quantile(plan.handle, self.column.encode(), self.validation, q, asr,
+                                                         n, int(self.strict)))
+
+
 class FormatConstraint(Constraint):  # constraints/format.rs:482-843
     def __init__(self, column, format: FormatType, threshold, options: FormatOptions = None, arg=None, flag=False):
         self.column, self.format, self.threshold = column, format, threshold
@@ -854,6 +894,8 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def is_not_empty(self, column): return self.constraint(LengthConstraint.not_empty(column))
     def length(self, column, assertion): return self.constraint(LengthConstraint(column, assertion))
     def foreign_key(self, child, parent): return self.constraint(ForeignKeyConstraint(child, parent))
+    def has_approx_quantile(self, column, q, assertion): return self.constraint(QuantileConstraint.percentile(column, q, assertion))  # core/check.rs has_approx_quantile
+    def quantile(self, c: 'QuantileConstraint'): return self.constraint(c)
 
     def build(self) -> Check:
         return self._c

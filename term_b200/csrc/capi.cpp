@@ -325,6 +325,18 @@ int32_t tg_plan_add_data_type(tg_plan* p, const char* column, int32_t data_type,
 int32_t tg_plan_add_column_count(tg_plan* p, tg_assertion a) {
     return guard_slot([&] { return plan_add_column_count(p->p, a); });
 }
+int32_t tg_plan_add_quantile(tg_plan* p, const char* column, int32_t validation, const double* quantiles,
+                             const tg_assertion* assertions, int32_t n, int32_t strict) {
+    return guard_slot([&] {
+        std::vector<double> q;
+        std::vector<tg_assertion> a;
+        for (int32_t i = 0; i < n; ++i) {
+            q.push_back(quantiles[i]);
+            if (assertions) a.push_back(assertions[i]);
+        }
+        return plan_add_quantile(p->p, column ? column : "", validation, q, a, strict);
+    });
+}
 int32_t tg_plan_add_histogram(tg_plan* p, const char* column, int32_t num_buckets) {
     return guard_slot([&] { return plan_add_histogram(p->p, column ? column : "", num_buckets); });
 }

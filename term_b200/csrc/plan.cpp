@@ -531,6 +531,38 @@ int plan_add_non_negative(Plan& p, const std::string& col) {
     return (int)p.slots.size() - 1;
 }
 
+// constraints/quantile.rs:165-224 (constructors), :282-482 (evaluate). Every quantile of a column reads the one KLL
+// sketch the plan holds for it (APPROX_PERCENTILE_CONT's t-digest in the reference; §8c "parity unpinned": the values
+// agree within the sketches' rank error, the status / message rules are the reference's).
+int plan_add_quantile(Plan& p, const std::string& col, int mode, const std::vector<double>& quantiles,
+                      const std::vector<tg_assertion>& assertions, int strict) {
+    validate_identifier(col);
+    if (mode < TG_QUANTILE_SINGLE || mode > TG_QUANTILE_UNIMPLEMENTED)
+        throw Error(TG_ERR_INVALID_ARG, "unknown quantile validation kind");
+    if (mode == TG_QUANTILE_SINGLE && quantiles.size() != 1)
+        throw Error(TG_ERR_INVALID_ARG, "a single quantile check takes exactly one quantile");
+    if (mode <= TG_QUANTILE_MULTIPLE && assertions.size() != quantiles.size())
+        throw Error(TG_ERR_INVALID_ARG, "one assertion per quantile");
+    for (double q : quantiles)  // QuantileCheck::new (:47-57)
+        if (!(q >= 0.0 && q <= 1.0)) throw Error(TG_ERR_CONFIGURATION, "Quantile must be between 0.0 and 1.0");
+    Slot s;
+    s.kind = SL_QUANTILE;
+    s.name = "quantile";
+    s.columns = {col};
+    s.sub_kind = mode;
+    s.flag = strict;
+    // should_use_exact (:244-277) counts the rows first in every mode, so an unknown table / column surfaces
+    s.aggs.push_back(p.add_agg(mk_valid(col)));
+    if (mode != TG_QUANTILE_UNIMPLEMENTED) {
+        const int kll = p.add_agg(mk_kll(col, KLL_K_FOR_PERCENTILE));
+        for (size_t i = 0; i < quantiles.size(); ++i)
+            s.stats.push_back(StatReq{TG_STAT_PERCENTILE, quantiles[i],
+                                      i < assertions.size() ? assertions[i] : tg_assertion{0, 0, 0}, kll});
+    }
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
 // constraints/approx_count_distinct.rs:40-134: SELECT APPROX_DISTINCT(c). The HyperLogLog estimate is replaced by
 // the EXACT distinct count of the hash job (error 0 <= any HLL error bound; the reference's tests assert ranges).
 int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion a) {
@@ -1069,6 +1101,70 @@ static void finalize_multistat(Plan& p, Slot& s) {
     }
     if (failures.empty()) success_metric(s, metrics.empty() ? 0.0 : metrics[0]);
     else failure(s, join(failures, "; "));
+}
+
+// `{:?}` of an f64: Display plus ".0" when Display printed an integer
+static std::string fmt_f64_debug(double v) {
+    std::string t = fmt_f64(v);
+    if (std::isfinite(v) && t.find_first_of(".e") == std::string::npos) t += ".0";
+    return t;
+}
+
+// constraints/quantile.rs:285-482. An aggregate over no rows yields one NULL row which the reference reads with
+// `.value(0)` (no null check, :311-316) => 0.0; mirrored.
+static void finalize_quantile(Plan& p, Slot& s) {
+    const Agg& rows = p.aggs[s.aggs[0]];
+    if (rows.err != TG_OK) {
+        set_error(s, rows);
+        return;
+    }
+    if (s.sub_kind == TG_QUANTILE_UNIMPLEMENTED) {  // Distribution / Custom (:474-479)
+        s.status = TG_SKIPPED;
+        s.has_message = true;
+        s.message = "Validation type not yet implemented";
+        return;
+    }
+    std::vector<double> values;
+    for (auto& r : s.stats) {
+        if (p.aggs[r.agg_kll].err != TG_OK) {
+            set_error(s, p.aggs[r.agg_kll]);
+            return;
+        }
+        double v = 0.0;
+        if (!percentile_value(p, r, &v)) v = 0.0;
+        values.push_back(v);
+    }
+    if (s.sub_kind == TG_QUANTILE_SINGLE) {
+        const StatReq& r = s.stats[0];
+        const double v = values[0];
+        if (assertion_evaluate(r.assertion, v)) success_metric(s, v);
+        else failure_metric(s, v, "Quantile " + fmt_f64(r.percentile) + " is " + fmt_f64(v) + " which does not " +
+                                      assertion_description(r.assertion));
+    } else if (s.sub_kind == TG_QUANTILE_MULTIPLE) {
+        std::vector<std::string> failures;
+        for (size_t i = 0; i < s.stats.size(); ++i)
+            if (!assertion_evaluate(s.stats[i].assertion, values[i]))
+                failures.push_back("Q" + std::to_string((int32_t)(s.stats[i].percentile * 100.0)) + " is " +
+                                   fmt_f64(values[i]) + " which does not " +
+                                   assertion_description(s.stats[i].assertion));
+        if (failures.empty()) {
+            s.status = TG_SUCCESS;
+        } else {
+            failure(s, join(failures, "; "));
+        }
+    } else {  // Monotonic (:402-472)
+        bool mono = true;
+        for (size_t i = 1; i < values.size() && mono; ++i)
+            mono = s.flag ? values[i] > values[i - 1] : values[i] >= values[i - 1];
+        if (mono) {
+            s.status = TG_SUCCESS;
+        } else {
+            std::vector<std::string> parts;
+            for (double v : values) parts.push_back(fmt_f64_debug(v));
+            failure(s, std::string("Quantiles are not ") + (s.flag ? "strictly" : "") + " monotonic: [" +
+                           join(parts, ", ") + "]");
+        }
+    }
 }
 
 static void finalize_format(Plan& p, Slot& s) {
@@ -1695,6 +1791,7 @@ void Plan::finalize() {
             case SL_DATA_TYPE: finalize_data_type(*this, s); break;
             case SL_COLUMN_COUNT: finalize_column_count(*this, s); break;
             case SL_HISTOGRAM: finalize_histogram(*this, s); break;
+            case SL_QUANTILE: finalize_quantile(*this, s); break;
         }
     }
     executed = true;

@@ -80,6 +80,7 @@ enum SlotKind : int32_t {
     SL_DATA_TYPE,
     SL_COLUMN_COUNT,
     SL_HISTOGRAM,
+    SL_QUANTILE,
 };
 
 struct StatReq {
@@ -160,6 +161,8 @@ int plan_add_approx_count_distinct(Plan& p, const std::string& col, tg_assertion
 int plan_add_data_type(Plan& p, const std::string& col, int data_type, double threshold);
 int plan_add_column_count(Plan& p, tg_assertion a);
 int plan_add_histogram(Plan& p, const std::string& col, int num_buckets);
+int plan_add_quantile(Plan& p, const std::string& col, int mode, const std::vector<double>& quantiles,
+                      const std::vector<tg_assertion>& assertions, int strict);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 

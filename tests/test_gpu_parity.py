@@ -331,6 +331,95 @@ def test_length_containment_non_negative_match_oracle(ctx, n):
         ctx.deregister_table(name)
 
 
+# ---------------------------------------------------------------- quantile constraint (§8f.3) ----
+def test_quantile_constraint_reference_cases(ctx):
+    """constraints/quantile.rs:526-592: 1..=100 — median in [45,55], p95 in [94,96], Q25/Q75, strict monotonic."""
+    t = pa.table({"value": pa.array([float(i) for i in range(1, 101)])})
+    ctx.register_table("q_ref", t)
+    try:
+        A = T.Assertion
+        cs = [T.QuantileConstraint.median("value", A.Between(45.0, 55.0)),
+              T.QuantileConstraint.percentile("value", 0.95, A.Between(94.0, 96.0)),
+              T.QuantileConstraint.multiple("value", [T.QuantileCheck(0.25, A.Between(24.0, 26.0)),
+                                                      T.QuantileCheck(0.75, A.Between(74.0, 76.0))]),
+              T.QuantileConstraint.monotonic("value", [0.1, 0.5, 0.9], True)]
+        for c in cs:
+            r = c.evaluate(ctx, "q_ref")
+            assert r.status == T.ConstraintStatus.Success and r.name == "quantile", r
+        assert cs[0].evaluate(ctx, "q_ref").metric == 50.0 and cs[1].evaluate(ctx, "q_ref").metric == 95.0
+        with pytest.raises(T.TermGpuError, match="Quantile must be between 0.0 and 1.0"):
+            T.QuantileCheck(1.5, A.LessThan(100.0))
+    finally:
+        ctx.deregister_table("q_ref")
+
+
+@pytest.mark.parametrize("n,null_p", [(0, 0.0), (1, 0.0), (64, 1.0), (777, 0.2), (4000, 0.05)])
+def test_quantile_constraint_matches_oracle(ctx, n, null_p):
+    """up to the sketch capacity (8 k items, k = 512 for constraint quantiles) the sketch holds every value at
+    weight 1, so values, statuses and messages are bit-exact against the oracle's restatement of get_quantile"""
+    rng = np.random.default_rng(n + 17)
+    x = np.round(rng.normal(100.0, 15.0, n), 1)
+    i = rng.integers(-50, 50, n)
+    t = pa.table({"x": pa.array(x, mask=rng.random(n) < null_p), "i": pa.array(i, mask=rng.random(n) < null_p)})
+    name = f"q_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=999) if n else t)
+    try:
+        A = T.Assertion
+        specs = [("x", "Single", [(0.5, A.Between(99.0, 101.0))]), ("x", "Single", [(0.99, A.LessThan(120.0))]),
+                 ("x", "Single", [(0.0, A.GreaterThan(0.0))]), ("i", "Single", [(1.0, A.Equals(49.0))]),
+                 ("x", "Multiple", [(0.25, A.Between(85.0, 95.0)), (0.5, A.GreaterThan(150.0)), (0.999, A.LessThan(100.0))]),
+                 ("i", "Multiple", [(0.1, A.LessThan(0.0)), (0.9, A.GreaterThan(0.0))]),
+                 ("x", "Monotonic", [0.1, 0.5, 0.9], True), ("i", "Monotonic", [0.5, 0.5, 0.51], False),
+                 ("i", "Monotonic", [0.5, 0.5, 0.51], True), ("x", "Monotonic", [0.9, 0.2], False), ("x", "Distribution",)]
+        cb = T.Check.builder("q")
+        for sp in specs:
+            if sp[1] == "Single":
+                cb.quantile(T.QuantileConstraint.percentile(sp[0], *sp[2][0]))
+            elif sp[1] == "Multiple":
+                cb.quantile(T.QuantileConstraint.multiple(sp[0], [T.QuantileCheck(q, a) for q, a in sp[2]]))
+            elif sp[1] == "Monotonic":
+                cb.quantile(T.QuantileConstraint.monotonic(sp[0], sp[2], sp[3]))
+            else:
+                cb.quantile(T.QuantileConstraint.distribution(sp[0]))
+        suite = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build()
+        res = suite.run(ctx)
+        rs = res.report.results
+        kll_aggs = [key for kind, key in suite.last_plan.aggregates() if kind == 8]
+        assert len(kll_aggs) == 2  # one sketch per column, however many quantiles ask
+        for sp, g in zip(specs, rs):
+            def cv(a):
+                return (T.Assertion.KINDS[a.kind], a.a, a.b) if a.kind >= 6 else (T.Assertion.KINDS[a.kind], a.a)
+            if sp[1] in ("Single", "Multiple"):
+                o = O.quantile_constraint(t, sp[0], sp[1], checks=[(q, cv(a)) for q, a in sp[2]])
+            elif sp[1] == "Monotonic":
+                o = O.quantile_constraint(t, sp[0], "Monotonic", quantiles=sp[2], strict=sp[3])
+            else:
+                o = O.quantile_constraint(t, sp[0], "Distribution")
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (sp, g, o)
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.parametrize("n", [100_000, 1_500_000])
+def test_quantile_constraint_sampled_within_rank_error(ctx, n):
+    """above the sketch capacity (resampled, 100 k rows) and above the sampler's exact-mode bound (1.5 M rows) the
+    values carry rank error: within the bound of the reference's own KLL accuracy harness
+    (tests/tpc_integration_tests.rs:533-551, 1 %)"""
+    rng = np.random.default_rng(99)
+    x = rng.lognormal(3.0, 1.0, n)
+    t = pa.table({"x": pa.array(x)})
+    ctx.register_table("q_big", t)
+    try:
+        s = np.sort(x)
+        for q in (0.01, 0.25, 0.5, 0.95, 0.999):
+            r = T.QuantileConstraint.percentile("x", q, T.Assertion.GreaterThan(0.0)).evaluate(ctx, "q_big")
+            assert r.status == T.ConstraintStatus.Success
+            assert O.rank_error(s, r.metric, q) <= 0.01, (q, r.metric)
+        assert T.QuantileConstraint.monotonic("x", [0.01, 0.1, 0.5, 0.9, 0.99], True).evaluate(ctx, "q_big").status == T.ConstraintStatus.Success
+    finally:
+        ctx.deregister_table("q_big")
+
+
 # ---------------------------------------------------------------- histogram (§8f.1) ----
 def _check_histogram(r, want, nb):
     assert r.error == 0 and r.metric_kind == 2

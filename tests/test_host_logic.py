@@ -197,6 +197,39 @@ def test_plan_deduplicates_aggregates(built_lib):
     assert F.lib().tg_plan_num_slots(p.handle) == 9
 
 
+def test_quantile_constraint_construction(built_lib):  # constraints/quantile.rs:47-57, 165-224, 595-603
+    with pytest.raises(T.TermGpuError, match="Quantile must be between 0.0 and 1.0"):
+        T.QuantileCheck(1.5, T.Assertion.LessThan(100.0))
+    with pytest.raises(T.TermGpuError, match="Quantile must be between 0.0 and 1.0"):
+        T.QuantileConstraint.monotonic("x", [0.1, -0.5], False)
+    with pytest.raises(T.TermGpuError):
+        T.QuantileConstraint.median("x; DROP TABLE t", T.Assertion.LessThan(1.0))
+    p = T.Plan()
+    T.QuantileConstraint.median("x", T.Assertion.LessThan(1.0))._add_to(p)
+    T.QuantileConstraint.multiple("x", [T.QuantileCheck(q, T.Assertion.LessThan(1.0)) for q in (0.1, 0.9)])._add_to(p)
+    T.QuantileConstraint.monotonic("x", [0.1, 0.5, 0.9], True)._add_to(p)
+    T.StatisticalConstraint.median("x", T.Assertion.LessThan(1.0))._add_to(p)
+    T.QuantileConstraint.distribution("y")._add_to(p)
+    kinds = [k for k, _ in p.aggregates()]
+    assert kinds.count(8) == 1  # every quantile of x reads one sketch; the Skipped Distribution arm asks for none
+    assert T.QuantileConstraint.median("x", T.Assertion.LessThan(1.0)).name() == "quantile"
+
+
+def test_oracle_quantile_constraint_reference_cases():  # constraints/quantile.rs:526-592
+    import pyarrow as pa
+    from oracle import term_oracle as O
+    t = pa.table({"value": pa.array([float(i) for i in range(1, 101)])})
+    assert O.quantile_constraint(t, "value", "Single", checks=[(0.5, ("Between", 45.0, 55.0))]).status == O.SUCCESS
+    assert O.quantile_constraint(t, "value", "Single", checks=[(0.95, ("Between", 94.0, 96.0))]).status == O.SUCCESS
+    assert O.quantile_constraint(t, "value", "Multiple", checks=[(0.25, ("Between", 24.0, 26.0)),
+                                                                   (0.75, ("Between", 74.0, 76.0))]).status == O.SUCCESS
+    assert O.quantile_constraint(t, "value", "Monotonic", quantiles=[0.1, 0.5, 0.9], strict=True).status == O.SUCCESS
+    r = O.quantile_constraint(t, "value", "Monotonic", quantiles=[0.9, 0.5], strict=False)
+    assert r.status == O.FAILURE and r.message == "Quantiles are not  monotonic: [90.0, 50.0]"
+    r = O.quantile_constraint(t, "value", "Multiple", checks=[(0.25, ("GreaterThan", 30.0))])
+    assert r.message == "Q25 is 25 which does not greater than 30"
+
+
 # ---- analyzer states as serde_json text (analyzers/incremental/runner.rs:72-80) ----
 def test_json_f64_follows_ryu_layout(built_lib):
     import ctypes as C
