@@ -314,13 +314,16 @@ def main():
     import torch.distributed as dist
     import term_b200 as T
     from term_b200 import _ffi as F
-    from term_b200.distributed import execute_distributed
+    from term_b200.distributed import bind_to_gpu_numa, execute_distributed
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    # N > 1: every rank stages host buffers at once; keep each rank's pinned memory on its GPU's socket. N = 1 keeps
+    # all host cores (the cpu_baseline leg uses them)
+    numa_cpus = bind_to_gpu_numa(local_rank) if world > 1 else None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
@@ -469,7 +472,9 @@ def main():
                                    "satisfies(f2 > 0 AND i0 < 1000000)) on 100M rows x 8 f64/i64 cols, 5% nulls, per GPU",
                        "rows_per_gpu": n, "columns": 8, "referenced_columns": list(SUITE_COLUMNS), "null_fraction": NULL_FRACTION,
                        "parallelism": f"row-partitioned x{world}", "l2": "inputs (3.25 GB/step) are larger than L2; no flush needed",
-                       "merge": "all-gather of partial aggregates via torch.distributed (NCCL)" if world > 1 else "single GPU"},
+                       "merge": ("fixed-size partial aggregates exchanged through peer mailboxes (P2P stores over NVLink, "
+                                 "tg_plan_exchange_and_finalize); NCCL all-gather for variable-size partials") if world > 1 else "single GPU",
+                       "numa_bound_cpus": len(numa_cpus) if numa_cpus else 0},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "wall_ms_per_step": wall / args.steps * 1e3,
             "results": [{"name": r.name, "status": r.status.name, "metric": r.metric} for r in results],

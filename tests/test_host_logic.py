@@ -297,3 +297,11 @@ def test_analyzer_state_json_matches_serde_layout(built_lib):
     assert J(slots["corr"]) == ('{"n":2,"sum_x":4.0,"sum_y":6.0,"sum_x2":8.5,"sum_y2":20.0,"sum_xy":13.0,'
                                 '"x_ranks":null,"y_ranks":null,"correlation_type":"Pearson"}')
     assert J(slots["acd"]) == '{"approx_distinct_count":3,"total_count":3}'
+
+
+def test_numa_binding_is_a_no_op_without_a_gpu():
+    import os
+    from term_b200.distributed import bind_to_gpu_numa
+    before = os.sched_getaffinity(0)
+    assert bind_to_gpu_numa(0) is None  # no device / no NVML here: nothing is changed and nothing raises
+    assert os.sched_getaffinity(0) == before
