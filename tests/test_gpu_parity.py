@@ -979,3 +979,68 @@ def test_spearman_matches_scipy_min_ranks(ctx, n):
             assert r.metric_key == f"correlation_spearman_x_{c2}"
     finally:
         ctx.deregister_table(name)
+
+
+# ---------------------------------------------------------------- concurrency (§8b threading) ----
+def test_concurrent_suites_on_one_context(ctx):
+    """tests/integration_test_suite.rs:702-745: several suites run at once against one SessionContext. ctypes drops
+    the GIL inside every C-ABI call, so the threads really contend for the engine; each must get exactly the answer
+    it gets alone, while a further thread keeps registering / dropping an unrelated table."""
+    import threading
+    n = 120_000
+    rng = np.random.default_rng(77)
+    t = pa.table({"k": pa.array(rng.integers(0, n // 2, n), mask=rng.random(n) < 0.02),
+                  "x": pa.array(rng.normal(10.0, 3.0, n), mask=rng.random(n) < 0.05),
+                  "y": pa.array(rng.normal(0.0, 1.0, n)),
+                  "s": pa.array([f"user{i}@example.com" if i % 7 else f"user{i}" for i in range(n)], type=pa.string())})
+    ctx.register_table("conc", t)
+    A = T.Assertion
+
+    def suite(i):
+        cb = T.Check.builder(f"check{i}").level(T.Level.Warning).has_size(A.GreaterThan(0.0)).completeness("x", 0.9)
+        if i % 5 == 0:
+            cb.has_mean("x", A.Between(9.0, 11.0)).has_correlation("x", "y", A.Between(-0.1, 0.1)).satisfies("x > 0 AND y < 10")
+        elif i % 5 == 1:
+            cb.validates_email("s", 0.5).validates_regex("s", "@", 0.5).has_min_length("s", 5)
+        elif i % 5 == 2:
+            cb.validates_uniqueness(["k"], 0.3).validates_unique_value_ratio(["k", "s"], A.GreaterThan(0.5))
+        elif i % 5 == 3:
+            cb.statistic("x", T.StatisticType.Median, A.Between(9.0, 11.0)).has_approx_quantile("y", 0.9, A.GreaterThan(1.0))
+        else:
+            cb.has_standard_deviation("y", A.Between(0.9, 1.1)).has_max("k", A.LessThan(float(n)))
+        return T.ValidationSuite.builder(f"concurrent_suite_{i}").table_name("conc").check(cb.build()).build()
+
+    def outcome(res):
+        return [(r.name, r.status, r.metric, r.message) for r in res.report.results]
+
+    try:
+        want = [outcome(suite(i).run(ctx)) for i in range(10)]
+        got, errors, stop = [None] * 10, [], threading.Event()
+
+        def worker(i):
+            try:
+                for _ in range(4):
+                    got[i] = outcome(suite(i).run(ctx))
+            except Exception as e:  # noqa: BLE001
+                errors.append((i, repr(e)))
+
+        def churn():
+            small = pa.table({"v": pa.array(np.arange(1000, dtype=np.int64))})
+            while not stop.is_set():
+                ctx.register_table("conc_tmp", small)
+                T.SizeConstraint(A.Equals(1000.0)).evaluate(ctx, "conc_tmp")
+                ctx.deregister_table("conc_tmp")
+
+        th = [threading.Thread(target=worker, args=(i,)) for i in range(10)]
+        ch = threading.Thread(target=churn)
+        ch.start()
+        for x in th:
+            x.start()
+        for x in th:
+            x.join(120)
+        stop.set()
+        ch.join(30)
+        assert not errors, errors
+        assert got == want
+    finally:
+        ctx.deregister_table("conc")
