@@ -222,6 +222,19 @@ TG_API tg_status tg_table_lookup(tg_engine* eng, const char* name, tg_table** ou
 TG_API int64_t tg_table_num_rows(const tg_table* t);
 /* schema lookup (SessionContext::table(..).schema().field_with_name(..).data_type()) -> tg_dtype */
 TG_API tg_status tg_table_column_dtype(const tg_table* t, const char* column, int32_t* dtype);
+/* Device addresses of a column's Arrow buffers (engine-owned, valid until the table is dropped or appended to; all
+ * pending host->device copies of the engine are complete on return). validity / offsets are NULL when the column has
+ * none. Used by the multi-GPU host code to move a column between ranks (Spearman's global ranks). */
+typedef struct tg_column_buffers {
+    int32_t dtype;
+    int64_t n_rows;
+    const void* values;
+    const void* offsets;
+    const void* validity;
+    int64_t n_value_bytes;
+    int64_t null_count;
+} tg_column_buffers;
+TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, const char* column, tg_column_buffers* out);
 
 /*
  * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity

@@ -51,6 +51,11 @@ class tg_analyzer_result(C.Structure):
                 ("metric_key", C.c_char_p), ("message", C.c_char_p)]
 
 
+class tg_column_buffers(C.Structure):
+    _fields_ = [("dtype", C.c_int32), ("n_rows", C.c_int64), ("values", C.c_void_p), ("offsets", C.c_void_p),
+                ("validity", C.c_void_p), ("n_value_bytes", C.c_int64), ("null_count", C.c_int64)]
+
+
 class tg_exec_stats(C.Structure):
     _fields_ = [("gpu_ms", C.c_double), ("scan_ms", C.c_double), ("string_ms", C.c_double),
                 ("hash_ms", C.c_double), ("sketch_ms", C.c_double), ("bytes_scanned", C.c_uint64),
@@ -74,6 +79,7 @@ SIGNATURES = {
     "tg_table_lookup": (C.c_int, [P, C.c_char_p, PP]),
     "tg_table_num_rows": (C.c_int64, [P]),
     "tg_table_column_dtype": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_int32)]),
+    "tg_table_column_buffers": (C.c_int, [P, C.c_char_p, C.c_char_p, C.POINTER(tg_column_buffers)]),
     "tg_table_append_host": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_adopt_device": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_append_arrow": (C.c_int, [P, P, P]),

@@ -261,6 +261,12 @@ class SessionContext:
         F.check(F.lib().tg_table_column_dtype(t, column.encode(), C.byref(d)))
         return int(d.value)
 
+    def column_buffers(self, table: str, column: str) -> dict:
+        """tg_table_column_buffers: device addresses of the column's Arrow buffers (engine-owned)"""
+        b = F.tg_column_buffers()
+        F.check(F.lib().tg_table_column_buffers(self._h, table.encode(), column.encode(), C.byref(b)))
+        return {k: getattr(b, k) for k, _ in F.tg_column_buffers._fields_}
+
     def num_rows(self, name: str) -> int:
         t = C.c_void_p()
         F.check(F.lib().tg_table_lookup(self._h, name.encode(), C.byref(t)))

@@ -188,6 +188,21 @@ tg_status tg_table_column_dtype(const tg_table* t, const char* column, int32_t* 
     });
 }
 
+tg_status tg_table_column_buffers(tg_engine* h, const char* table, const char* column, tg_column_buffers* out) {
+    return guard([&] {
+        if (!h || !table || !column || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        Engine& e = h->e;
+        std::lock_guard<std::mutex> g(e.mu);
+        auto it = e.tables.find(table);
+        if (it == e.tables.end())
+            throw Error(TG_ERR_TABLE_NOT_FOUND, "Error during planning: table 'datafusion.public." + std::string(table) + "' not found");
+        Column* c = it->second->find(column);
+        if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + std::string(column) + ". Valid fields are " + it->second->valid_fields() + ".");
+        e.sync_copies();
+        *out = tg_column_buffers{c->dtype, it->second->n_rows, c->values.p, c->offsets.p, c->validity.p, c->value_bytes, c->null_count};
+    });
+}
+
 tg_status tg_table_partition_keys(tg_engine* h, const char* table, const char* column, int32_t n_parts, void** d_keys,
                                   int64_t* counts, int64_t* n_null_rows) {
     return guard([&] {
@@ -460,8 +475,8 @@ tg_status tg_plan_redirect_aggregate(tg_plan* p, int32_t i, int32_t which, const
     return guard([&] {
         if (!p || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
         Agg& a = p->p.aggs[i];
-        if (which < 0 || which > 1 || (which == 1 && a.kind != A_FK) || (a.kind != A_FK && a.kind != A_DISTINCT))
-            throw Error(TG_ERR_INVALID_ARG, "only DISTINCT (which = 0) and FK (which = 0 child, 1 parent) aggregates can be redirected");
+        if (which < 0 || which > 1 || (which == 1 && a.kind != A_FK) || (a.kind != A_FK && a.kind != A_DISTINCT && a.kind != A_SPEARMAN))
+            throw Error(TG_ERR_INVALID_ARG, "only DISTINCT / SPEARMAN (which = 0) and FK (which = 0 child, 1 parent) aggregates can be redirected");
         if (table_name && *table_name) validate_identifier(table_name);
         a.redirect[which] = table_name ? table_name : "";
     });

@@ -693,7 +693,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
         Agg& a = p.aggs[i];
         if (a.err != TG_OK) continue;
         if (a.kind == A_FK) continue;  // uses its own tables
-        if (a.kind == A_DISTINCT && !a.redirect[0].empty()) continue;  // reads the hash-shuffled shard instead
+        if ((a.kind == A_DISTINCT || a.kind == A_SPEARMAN) && !a.redirect[0].empty()) continue;  // reads the shuffled / gathered table instead
         if (!t) {
             a.err = TG_ERR_TABLE_NOT_FOUND;
             a.err_msg = "Error during planning: table 'datafusion.public." + table_name + "' not found";
@@ -723,7 +723,8 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
         if (a.err != TG_OK) continue;
         try {
             switch (a.kind) {
-                case A_DISTINCT: {
+                case A_DISTINCT:
+                case A_SPEARMAN: {
                     Table* dt = t;
                     if (!a.redirect[0].empty()) {
                         auto rit = e.tables.find(a.redirect[0]);
@@ -731,11 +732,11 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
                             throw Error(TG_ERR_TABLE_NOT_FOUND, "Error during planning: table 'datafusion.public." + a.redirect[0] + "' not found");
                         dt = rit->second.get();
                     }
-                    exec_distinct_job(e, *dt, p, (int)i);
+                    if (a.kind == A_DISTINCT) exec_distinct_job(e, *dt, p, (int)i);
+                    else exec_spearman_job(e, *dt, p, (int)i);
                 } break;
                 case A_FK: exec_fk_job(e, p, (int)i); break;
                 case A_GROUPED: exec_grouped_job(e, *t, p, (int)i); break;
-                case A_SPEARMAN: exec_spearman_job(e, *t, p, (int)i); break;
                 case A_HIST: exec_hist_job(e, *t, p, (int)i); break;
                 default: break;
             }

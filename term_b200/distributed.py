@@ -12,6 +12,11 @@
   its keys as a table and the aggregate is redirected to it (tg_plan_redirect_aggregate). Equal keys now live on
   exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0. Utf8 and composite
   keys travel as their 128-bit fingerprints (tg_table_partition_fingerprints), the identity the single-GPU path uses.
+* Spearman needs GLOBAL ranks (RANK() OVER (ORDER BY ..) over the whole table, analyzers/advanced/correlation.rs:
+  334-350), so per-shard rank sums do not add up. Its two columns are reduced to their pairwise-complete rows (as
+  DOUBLE, the type the reference ranks in), gathered to rank 0 in rank order — 16 bytes per complete row, 16 GB for
+  the 1 B-row C5 table — and the one GPU that owns them computes the ranks; the other ranks contribute an empty
+  partial. "Replicas only" in SURVEY §8e's terms: exact, not faster than one GPU.
 """
 import os
 
@@ -20,7 +25,7 @@ import torch.distributed as dist
 
 from . import _ffi as F
 
-KIND_DISTINCT, KIND_FK = 6, 7
+KIND_DISTINCT, KIND_FK, KIND_SPEARMAN = 6, 7, 10
 
 
 def _device(device=None):
@@ -259,6 +264,69 @@ def _shuffle_fingerprints(ctx, table, columns, shard_name):
     _adopt_fp_shard(ctx, shard_name, mine)
 
 
+def complete_pairs(x: torch.Tensor, x_valid, y: torch.Tensor, y_valid) -> torch.Tensor:
+    """Rows where both values are non-NULL, as an (m, 2) float64 tensor (CAST(.. AS DOUBLE), row order kept).
+    x_valid / y_valid: bool masks or None (no NULLs)."""
+    xd, yd = x.to(torch.float64), y.to(torch.float64)
+    if x_valid is not None or y_valid is not None:
+        m = torch.ones(x.numel(), dtype=torch.bool, device=x.device)
+        if x_valid is not None:
+            m &= x_valid
+        if y_valid is not None:
+            m &= y_valid
+        xd, yd = xd[m], yd[m]
+    return torch.stack([xd, yd], dim=1).contiguous()
+
+
+def gather_pairs(pairs: torch.Tensor, dst: int = 0):
+    """Concatenate every rank's (m_r, 2) float64 pairs on rank `dst`, in rank order. Other ranks get an empty tensor.
+    One all-gather of the counts, then one padded gather (NCCL and gloo)."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    dev = pairs.device
+    cnt = torch.tensor([pairs.shape[0]], dtype=torch.int64, device=dev)
+    cnts = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(cnts, cnt)
+    cnts = [int(c.item()) for c in cnts]
+    cap = max(max(cnts), 1)
+    send = torch.zeros((cap, 2), dtype=torch.float64, device=dev)
+    send[: pairs.shape[0]] = pairs
+    recv = [torch.empty((cap, 2), dtype=torch.float64, device=dev) for _ in range(world)] if rank == dst else None
+    dist.gather(send, recv, dst=dst)
+    if rank != dst:
+        return torch.empty((0, 2), dtype=torch.float64, device=dev)
+    return torch.cat([r[:c] for r, c in zip(recv, cnts)], dim=0)
+
+
+def _unpack_validity(ptr, n, dev):
+    """bool mask of the first n rows of an LSB-first validity bitmap at device address ptr"""
+    bits = _tensor_from_ptr(ptr, (n + 7) // 8, dev, "|u1")
+    sh = torch.arange(8, device=dev, dtype=torch.uint8)
+    return ((bits.unsqueeze(1) >> sh) & 1).bool().view(-1)[:n]
+
+
+def _gather_spearman_columns(ctx, table, cx, cy, name):
+    """rank 0 adopts table `name` = {cx, cy} holding every rank's pairwise-complete rows; the others adopt it empty"""
+    dev = torch.device("cuda", torch.cuda.current_device())
+    cols = []
+    for c in (cx, cy):
+        b = ctx.column_buffers(table, c)
+        if b["dtype"] not in (F.TG_INT64, F.TG_FLOAT64):
+            raise NotImplementedError(f"multi-GPU Spearman over column '{table}.{c}': only Int64 / Float64 columns")
+        n = b["n_rows"]
+        v = _tensor_from_ptr(b["values"], n, dev) if n else torch.empty(0, dtype=torch.int64, device=dev)
+        if b["dtype"] == F.TG_FLOAT64:
+            v = v.view(torch.float64)
+        cols.append((v, _unpack_validity(b["validity"], n, dev) if (b["validity"] and n) else None))
+    mine = gather_pairs(complete_pairs(cols[0][0], cols[0][1], cols[1][0], cols[1][1]))
+    m = mine.shape[0]
+    xs = torch.zeros(m + 64, dtype=torch.float64, device=dev)
+    ys = torch.zeros(m + 64, dtype=torch.float64, device=dev)
+    xs[:m], ys[:m] = mine[:, 0], mine[:, 1]
+    ctx.register_device_table(name, {cx: dict(dtype=F.TG_FLOAT64, n_rows=m, values=xs.data_ptr(), validity=None),
+                                     cy: dict(dtype=F.TG_FLOAT64, n_rows=m, values=ys.data_ptr(), validity=None)},
+                              keepalive=[xs, ys])
+
+
 def _adopt_fp_shard(ctx, name, recs: torch.Tensor):
     n = recs.numel() // 3
     vals = torch.zeros(n * 3 + 64, dtype=torch.int64, device=recs.device)
@@ -266,17 +334,17 @@ def _adopt_fp_shard(ctx, name, recs: torch.Tensor):
     ctx.register_device_table(name, {"tg_fp": dict(dtype=F.TG_FP128, n_rows=n, values=vals.data_ptr(), validity=None)}, keepalive=[vals])
 
 
-def _tensor_from_ptr(ptr, n, dev):
+def _tensor_from_ptr(ptr, n, dev, typestr="<i8"):
     class _Wrap:  # __cuda_array_interface__ v3
         pass
     w = _Wrap()
-    w.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 3, "strides": None}
+    w.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 3, "strides": None}
     return torch.as_tensor(w, device=dev)
 
 
 def execute_distributed(plan, ctx, table="data"):
-    """Each rank: shuffle the keys of DISTINCT / FK aggregates, partial execute on its shard -> all-gather ->
-    ordered merge -> finalize."""
+    """Each rank: shuffle the keys of DISTINCT / FK aggregates, gather the column pairs of SPEARMAN aggregates,
+    partial execute on its shard -> exchange -> ordered merge -> finalize."""
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         plan.execute(ctx, table)
         return
@@ -303,6 +371,12 @@ def execute_distributed(plan, ctx, table="data"):
                 plan.redirect(i, 0, cname)
                 plan.redirect(i, 1, pname)
                 redirected += [(i, 0), (i, 1)]
+            elif kind == KIND_SPEARMAN:
+                name = f"tg_gather_{i}_s"
+                _gather_spearman_columns(ctx, table, parts[1], parts[2], name)  # global ranks: one GPU owns the pairs
+                temps.append(name)
+                plan.redirect(i, 0, name)
+                redirected.append((i, 0))
         plan.execute_partial(ctx, table)
         exchange_and_finalize(plan, ctx)
     finally:

@@ -226,3 +226,65 @@ def test_two_rank_gloo_hash_shuffle_uniqueness(built_lib):
     assert u == [nn, d] and md == m
     assert results[0][5] + results[1][5] == nn, "every valid key lands on exactly one rank"
     assert min(results[0][5], results[1][5]) > nn // 4, "the hash split is badly skewed"
+
+
+# ---- Spearman across ranks: global ranks need all pairwise-complete rows on one rank ----
+def spearman_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from scipy.stats import rankdata
+        import term_b200 as T
+        from term_b200.distributed import allgather_blobs, complete_pairs, gather_pairs, merge_partials
+        t = make_table()
+        # uneven shards, the last one empty: the gather pads to the largest
+        bounds = [0, N_ROWS // 3, N_ROWS, N_ROWS][: world + 1] if world == 3 else [N_ROWS * r // world for r in range(world + 1)]
+        sh = t.slice(bounds[rank], bounds[rank + 1] - bounds[rank])
+        col = lambda n: (torch.from_numpy(np.asarray(sh.column(n).fill_null(0)).copy()), torch.from_numpy(np.asarray(sh.column(n).is_valid()).copy()))  # noqa: E731
+        (x, xv), (k, kv) = col("x"), col("k")
+        pairs = gather_pairs(complete_pairs(x, xv, k, kv))  # f64 x, i64 k -> DOUBLE
+        plan = T.Plan()
+        slot = T.CorrelationAnalyzer.spearman("x", "k")._add_to(plan)
+        (kind, key), = plan.aggregates()
+        assert kind == 10 and key == "spearman|x|k"
+        u, f = [0] * 8, [0.0] * 8
+        if rank == 0:  # what exec_spearman_job computes on the gathered table: co-moments of the min-ranks
+            a = rankdata(pairs[:, 0].numpy(), method="min").astype(np.float64)
+            b = rankdata(pairs[:, 1].numpy(), method="min").astype(np.float64)
+            u[0] = len(a)
+            da, db = a - a[0], b - b[0]
+            f[0], f[1] = float(a[0]), float(b[0])
+            f[2], f[3], f[4], f[5], f[6] = math.fsum(da), math.fsum(db), math.fsum(da * da), math.fsum(db * db), math.fsum(da * db)
+        else:
+            assert pairs.shape == (0, 2)  # the other ranks hold nothing and contribute an empty partial
+        blob = struct.pack("<Q", 1) + struct.pack("<QQ", kind, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *f) + struct.pack("<QQ", 0, 0)
+        merge_partials(plan, allgather_blobs(blob))
+        r = plan.analyzer_result(slot)
+        q.put((rank, (r.u[0], r.metric_double, int(pairs.shape[0]))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_spearman_gather_gives_global_ranks(built_lib, world):
+    from oracle import term_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=spearman_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = make_table()
+    x, k = O.pair_values(t, "x", "k")
+    want = O.an_correlation(t, "x", "k", "spearman")
+    assert results[0][2] == len(x) and all(results[r][2] == 0 for r in range(1, world))
+    for r in range(world):
+        assert results[r][0] == len(x), "every rank finalizes to the global pair count"
+        assert abs(results[r][1] - want) <= 1e-9, (results[r][1], want)

@@ -86,7 +86,11 @@ def main():
     keys_valid = torch.rand(n, generator=g, device=dev) >= 0.01
     x = torch.empty(n, dtype=torch.float64, device=dev).normal_(100.0, 15.0, generator=g)
     x_valid = torch.rand(n, generator=g, device=dev) >= 0.05
-    register(ctx, "orders", {"customer_id": (child, child_valid), "order_key": (keys, keys_valid), "amount": (x, x_valid)})
+    # Int64 column correlated with amount (Spearman ~ 0.9), its own NULLs
+    score = (x * 3.0 + torch.empty(n, dtype=torch.float64, device=dev).normal_(0.0, 20.0, generator=g)).to(torch.int64)
+    score_valid = torch.rand(n, generator=g, device=dev) >= 0.03
+    register(ctx, "orders", {"customer_id": (child, child_valid), "order_key": (keys, keys_valid), "amount": (x, x_valid),
+                             "score": (score, score_valid)})
     register(ctx, "customers", {"id": (parent, None)})
 
     A = T.Assertion
@@ -110,15 +114,24 @@ def main():
     ms = (time.perf_counter() - t0) / reps * 1e3
     got = [plan.result(s) for _, _, s in slots] + [plan.result(extra)]
     got = [(r.name, r.status.name, r.metric, (r.message or "").split("Examples")[0]) for r in got]
+    # Spearman: global ranks -> the pairwise-complete rows are gathered to one GPU (distributed._gather_spearman_columns)
+    sp = T.Plan()
+    sp_slot = T.CorrelationAnalyzer.spearman("amount", "score")._add_to(sp)
+    execute_distributed(sp, ctx, "orders")
+    sp_got = sp.analyzer_result(sp_slot)
+    sp_all = [torch.zeros(2, dtype=torch.float64, device=dev) for _ in range(world)]
+    dist.all_gather(sp_all, torch.tensor([float(sp_got.u[0]), sp_got.metric_double], dtype=torch.float64, device=dev))
+    sp_agree = all(bool((v == sp_all[0]).all().item()) for v in sp_all)
 
     # reference: everything on rank 0's GPU
     full = {"customer_id": gather(child, world), "cv": gather(child_valid.to(torch.uint8), world).bool(),
             "order_key": gather(keys, world), "kv": gather(keys_valid.to(torch.uint8), world).bool(),
-            "amount": gather(x, world), "av": gather(x_valid.to(torch.uint8), world).bool(), "parent": gather(parent, world)}
+            "amount": gather(x, world), "av": gather(x_valid.to(torch.uint8), world).bool(), "parent": gather(parent, world),
+            "score": gather(score, world), "sv": gather(score_valid.to(torch.uint8), world).bool()}
     ok = True
     if rank == 0:
         register(ctx, "orders_all", {"customer_id": (full["customer_id"], full["cv"]), "order_key": (full["order_key"], full["kv"]),
-                                     "amount": (full["amount"], full["av"])})
+                                     "amount": (full["amount"], full["av"]), "score": (full["score"], full["sv"])})
         register(ctx, "customers_all", {"id": (full["parent"], None)})
         check1 = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
                   .validates_uniqueness(["order_key"], 0.9)
@@ -137,8 +150,16 @@ def main():
             ok = ok and same
             if not same:
                 print("MISMATCH", gg, ww, flush=True)
+        sp_want = T.CorrelationAnalyzer.spearman("amount", "score").compute(ctx, "orders_all")
+        sp_ok = (sp_agree and sp_got.u[0] == sp_want.u[0] and sp_got.error == 0
+                 and abs(sp_got.metric_double - sp_want.metric_double) <= 1e-9)
+        if not sp_ok:
+            print("SPEARMAN MISMATCH", sp_got.u[0], sp_got.metric_double, sp_want.u[0], sp_want.metric_double, sp_agree, flush=True)
+        ok = ok and sp_ok
         print(json.dumps({"check": "multi_gpu_parity", "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
-                          "ok": ok, "ms_per_execute": ms, "results": got}), flush=True)
+                          "ok": ok, "ms_per_execute": ms, "results": got,
+                          "spearman": {"pairs": sp_got.u[0], "rho_distributed": sp_got.metric_double, "rho_single_gpu": sp_want.metric_double,
+                                       "ranks_agree": sp_agree}}), flush=True)
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.broadcast(flag, 0)
     ctx.close()
