@@ -900,6 +900,32 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def is_not_empty(self, column): return self.constraint(LengthConstraint.not_empty(column))
     def length(self, column, assertion): return self.constraint(LengthConstraint(column, assertion))
     def foreign_key(self, child, parent): return self.constraint(ForeignKeyConstraint(child, parent))
+    # core/check.rs:2233-2298 (completeness with a logical operator over the columns)
+    def any_complete(self, columns): return self.completeness(list(columns), 1.0, LogicalOperator.Any)
+    def at_least_complete(self, n, columns, threshold): return self.completeness(list(columns), threshold, LogicalOperator.AtLeast(n))
+    def exactly_complete(self, n, columns, threshold): return self.completeness(list(columns), threshold, LogicalOperator.Exactly(n))
+    # core/check.rs:1019-1222 (format shorthands) and :1259-1410 (the same with FormatOptions)
+    def validates_phone(self, column, threshold, country=None): return self.constraint(FormatConstraint.phone(column, threshold, country))
+    def validates_postal_code(self, column, threshold, country): return self.constraint(FormatConstraint.postal_code(column, threshold, country))
+    def validates_uuid(self, column, threshold): return self.constraint(FormatConstraint.uuid(column, threshold))
+    def validates_ipv4(self, column, threshold): return self.constraint(FormatConstraint.ipv4(column, threshold))
+    def validates_ipv6(self, column, threshold): return self.constraint(FormatConstraint.ipv6(column, threshold))
+    def validates_json(self, column, threshold): return self.constraint(FormatConstraint.json(column, threshold))
+    def validates_iso8601_datetime(self, column, threshold): return self.constraint(FormatConstraint.iso8601_datetime(column, threshold))
+    def validates_email_with_options(self, column, threshold, options): return self.constraint(FormatConstraint(column, FormatType.Email, threshold, options))
+    def validates_url_with_options(self, column, threshold, allow_localhost, options): return self.constraint(FormatConstraint(column, FormatType.Url, threshold, options, flag=allow_localhost))
+    def validates_phone_with_options(self, column, threshold, country, options): return self.constraint(FormatConstraint(column, FormatType.Phone, threshold, options, arg=country))
+    def validates_regex_with_options(self, column, pattern, threshold, options): return self.constraint(FormatConstraint(column, FormatType.Regex, threshold, options, arg=pattern))
+    # core/check.rs:446-457: CorrelationConstraint::mutual_information — the reference answers Skipped (correlation.rs:340-345)
+    def has_mutual_information(self, c1, c2, assertion): return self.constraint(CorrelationConstraint(c1, c2, CorrelationType.MutualInformation, assertion))
+    # core/check.rs:1480-1500: uniqueness(columns, type, UniquenessOptions{threshold | assertion, null_handling})
+    def uniqueness(self, columns, uniqueness_type, threshold=1.0, assertion=None, null_handling=NullHandling.Exclude):
+        return self.constraint(UniquenessConstraint(columns, uniqueness_type, threshold, assertion, null_handling))
+    def with_constraint(self, c): return self.constraint(c)  # core/check.rs with_constraint
+    def constraints(self, cs):
+        for c in cs:
+            self.constraint(c)
+        return self
     def has_approx_quantile(self, column, q, assertion): return self.constraint(QuantileConstraint.percentile(column, q, assertion))  # core/check.rs has_approx_quantile
     def quantile(self, c: 'QuantileConstraint'): return self.constraint(c)
 

@@ -305,3 +305,26 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
     before = os.sched_getaffinity(0)
     assert bind_to_gpu_numa(0) is None  # no device / no NVML here: nothing is changed and nothing raises
     assert os.sched_getaffinity(0) == before
+
+
+def test_check_builder_mirrors_reference_builder_methods(built_lib):
+    """core/check.rs builder methods on the hot path; multi-table and closure-based ones
+    (cross_table_sum, join_coverage, temporal_ordering, has_histogram, has_consistent_data_type) are out of scope."""
+    names = ("level description constraint with_constraint constraints build has_size completeness any_complete at_least_complete "
+             "exactly_complete validates_uniqueness validates_distinctness validates_unique_value_ratio validates_primary_key "
+             "validates_uniqueness_with_nulls uniqueness validates_regex validates_email validates_url validates_credit_card "
+             "validates_phone validates_postal_code validates_uuid validates_ipv4 validates_ipv6 validates_json "
+             "validates_iso8601_datetime validates_email_with_options validates_url_with_options validates_phone_with_options "
+             "validates_regex_with_options has_format statistic has_min has_max has_mean has_sum has_standard_deviation has_variance "
+             "has_correlation has_mutual_information satisfies has_column_count has_approx_count_distinct has_approx_quantile "
+             "has_min_length has_max_length has_length_between has_exact_length is_not_empty length foreign_key contains_ssn").split()
+    missing = [n for n in names if not hasattr(T.CheckBuilder, n)]
+    assert not missing, missing
+    A = T.Assertion
+    c = (T.Check.builder("x").any_complete(["a", "b"]).at_least_complete(1, ["a", "b"], 0.9).exactly_complete(1, ["a", "b"], 0.9)
+         .validates_phone("s", 0.9, "US").validates_regex_with_options("s", "^a", 0.9, T.FormatOptions(trim_before_check=True))
+         .has_mutual_information("a", "b", A.GreaterThan(0.5)).uniqueness(["a"], T.UniquenessType.FullUniqueness, 0.9).build())
+    assert len(c.constraints) == 7
+    plan, slots = T.ValidationSuite.builder("s").check(c).build().build_plan()
+    keys = [k for _, k in plan.aggregates()]
+    assert keys.count("valid|a") == 1 and keys.count("valid|b") == 1  # three completeness flavours share the counts
