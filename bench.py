@@ -259,6 +259,7 @@ def run_reference_arm(args):
     sample = int(os.environ.get("TG_BENCH_CPU_ROWS", 20_000_000))
     import numpy as np  # noqa: F401
     from oracle import cpu_scan as S
+    S.use_all_host_threads()  # under torchrun every rank inherits OMP_NUM_THREADS=1
     rate, cores, _ = cpu_suite_rate(sample, repeats=1)  # warm-up incl. data generation
     times = []
     # re-use one dataset for all steps

@@ -28,6 +28,15 @@
 
 static inline int bit(const uint8_t* v, int64_t i) { return v ? (v[i >> 3] >> (i & 7)) & 1 : 1; }
 
+/* torchrun exports OMP_NUM_THREADS=1 to every rank; the baseline legs ask for the host's cores explicitly */
+void to_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int to_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

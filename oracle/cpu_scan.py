@@ -29,6 +29,7 @@ def lib():
     L = C.CDLL(out)
     P, I64, D = C.c_void_p, C.c_int64, C.c_double
     L.to_num_threads.restype = C.c_int
+    L.to_set_num_threads.argtypes = [C.c_int]
     L.to_count_valid.restype = I64
     L.to_count_valid.argtypes = [P, I64]
     L.to_min_max_f64.argtypes = [P, P, I64, C.POINTER(D), C.POINTER(D), C.POINTER(I64)]
@@ -44,6 +45,14 @@ def lib():
 
 def num_threads():
     return int(lib().to_num_threads())
+
+
+def use_all_host_threads():
+    """All the CPUs this process may run on, whatever OMP_NUM_THREADS says (torchrun sets it to 1 per rank).
+    TG_BENCH_CPU_THREADS overrides."""
+    n = int(os.environ.get("TG_BENCH_CPU_THREADS", "0")) or len(os.sched_getaffinity(0))
+    lib().to_set_num_threads(n)
+    return num_threads()
 
 
 def _p(a):
