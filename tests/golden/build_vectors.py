@@ -286,6 +286,20 @@ case("approx_distinct_all_null", "constraints/approx_count_distinct.rs:313-326",
      {"data": {"test_col": col("i64", [None, None, None, None, None])}},
      {"kind": "approx_count_distinct", "column": "test_col", "assertion": ["Equals", 0.0]}, status="success", metric=0.0)
 
+# ------------------------------------------------------------------ quantile constraint ----
+_q100 = {"data": {"value": col("f64", [float(i) for i in range(1, 101)])}}
+case("quantile_median", "constraints/quantile.rs:526-538", _q100,
+     {"kind": "quantile", "column": "value", "mode": "Single", "checks": [[0.5, ["Between", 45.0, 55.0]]]},
+     status="success", metric_gt=44.999, metric_lt=55.001)
+case("quantile_percentile_95", "constraints/quantile.rs:540-552", _q100,
+     {"kind": "quantile", "column": "value", "mode": "Single", "checks": [[0.95, ["Between", 94.0, 96.0]]]},
+     status="success", metric_gt=93.999, metric_lt=96.001)
+case("quantile_multiple", "constraints/quantile.rs:554-572", _q100,
+     {"kind": "quantile", "column": "value", "mode": "Multiple",
+      "checks": [[0.25, ["Between", 24.0, 26.0]], [0.75, ["Between", 74.0, 76.0]]]}, status="success")
+case("quantile_monotonic_strict", "constraints/quantile.rs:574-592", _q100,
+     {"kind": "quantile", "column": "value", "mode": "Monotonic", "quantiles": [0.1, 0.5, 0.9], "strict": True}, status="success")
+
 # ------------------------------------------------------------------ foreign key ----
 def fk(id, ref, parent_ids, child_ids, expect, allow_nulls=False):
     case(id, ref, {"customers": {"id": col("i64", parent_ids)}, "orders": {"customer_id": col("i64", child_ids)}},

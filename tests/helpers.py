@@ -65,6 +65,9 @@ def oracle_eval(case):
         return O.non_negative(t, op["column"])
     if k == "approx_count_distinct":
         return O.approx_count_distinct(t, op["column"], tuple(op["assertion"]))
+    if k == "quantile":
+        return O.quantile_constraint(t, op["column"], op["mode"], checks=[(q, tuple(a)) for q, a in op.get("checks", [])],
+                                     quantiles=op.get("quantiles", ()), strict=op.get("strict", False))
     if k == "data_type":
         return O.data_type(t, op["column"], op["data_type"], op["threshold"])
     if k == "column_count":
@@ -152,6 +155,11 @@ def build_constraint(T, op):
         return T.NonNegativeConstraint(op["column"])
     if k == "approx_count_distinct":
         return T.ApproxCountDistinctConstraint(op["column"], _assertion(T, op["assertion"]))
+    if k == "quantile":
+        if op["mode"] == "Monotonic":
+            return T.QuantileConstraint.monotonic(op["column"], op["quantiles"], op["strict"])
+        checks = [T.QuantileCheck(q, _assertion(T, a)) for q, a in op["checks"]]
+        return T.QuantileConstraint(op["column"], T.QuantileConstraint.SINGLE if op["mode"] == "Single" else T.QuantileConstraint.MULTIPLE, checks)
     if k == "data_type":
         return T.DataTypeConstraint(op["column"], T.DataType[op["data_type"]], op["threshold"])
     if k == "column_count":
