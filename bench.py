@@ -232,17 +232,40 @@ def build_full_suite(T, table_name):
 
 
 # ------------------------------------------------------------------------------ CPU arm ----
-def cpu_suite_rate(sample_rows, repeats=1, seed=1234):
-    """Times the oracle's C restatement (all host cores) of the literal suite on `sample_rows` rows."""
+CPU_BLOCK_ROWS = 10_000_000  # seeded block the host-side workload is tiled from (a multiple of 8: bitmaps tile bytewise)
+
+
+def make_host_table(rows, seed=1234):
+    """The C2 suite's four referenced columns on the host, `rows` rows: one seeded block of CPU_BLOCK_ROWS rows tiled
+    to length (numpy's generators are single-threaded; a scan does not care that the block repeats)."""
     import numpy as np
     from oracle import cpu_scan as S
+    blk = min(rows, CPU_BLOCK_ROWS)
+    reps = (rows + blk - 1) // blk
     rng = np.random.default_rng(seed)
-    cols = {}
-    f0 = rng.normal(100.0, 15.0, sample_rows)
-    cols["f0"] = (f0, S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
-    cols["f1"] = (0.8 * f0 + rng.normal(0.0, 9.0, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
-    cols["f2"] = (rng.uniform(0.0, 1000.0, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
-    cols["i0"] = (rng.integers(-10**6, 10**6 + 1, sample_rows), S.pack_validity(rng.random(sample_rows) >= NULL_FRACTION))
+
+    def col(values):
+        bits = np.packbits((rng.random(blk) >= NULL_FRACTION).astype(np.uint8), bitorder="little")
+        v = np.tile(values, reps)[:rows] if reps > 1 else values
+        if reps > 1 and blk % 8 == 0:
+            bm = np.tile(bits, reps)[: (rows + 7) // 8]
+            bm = np.concatenate([bm, np.zeros((-len(bm)) % 64 + 64, dtype=np.uint8)])
+        else:
+            bm = S.pack_validity(np.unpackbits(np.tile(bits, reps), bitorder="little")[:rows].astype(bool))
+        return np.ascontiguousarray(v), bm
+
+    f0 = rng.normal(100.0, 15.0, blk)
+    f1 = 0.8 * f0 + rng.normal(0.0, 9.0, blk)
+    return {"f0": col(f0), "f1": col(f1), "f2": col(rng.uniform(0.0, 1000.0, blk)),
+            "i0": col(rng.integers(-10**6, 10**6 + 1, blk))}
+
+
+def cpu_suite_rate(sample_rows, repeats=1, seed=1234, cols=None):
+    """Times the oracle's C restatement (all host cores) of the literal suite on `sample_rows` rows."""
+    from oracle import cpu_scan as S
+    S.use_all_host_threads()
+    if cols is None:
+        cols = make_host_table(sample_rows, seed)
     S.numeric_suite(cols, sample_rows)  # warm caches / thread pool
     times = []
     for _ in range(repeats):
@@ -256,37 +279,27 @@ def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    sample = int(os.environ.get("TG_BENCH_CPU_ROWS", 20_000_000))
-    import numpy as np  # noqa: F401
+    rows = int(os.environ.get("TG_BENCH_CPU_ROWS", ROWS_PER_GPU))
     from oracle import cpu_scan as S
-    S.use_all_host_threads()  # under torchrun every rank inherits OMP_NUM_THREADS=1
-    rate, cores, _ = cpu_suite_rate(sample, repeats=1)  # warm-up incl. data generation
-    times = []
-    # re-use one dataset for all steps
-    rng_rows = sample
-    import numpy as np
-    rng = np.random.default_rng(1234)
-    cols = {}
-    f0 = rng.normal(100.0, 15.0, rng_rows)
-    cols["f0"] = (f0, S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
-    cols["f1"] = (0.8 * f0 + rng.normal(0.0, 9.0, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
-    cols["f2"] = (rng.uniform(0.0, 1000.0, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
-    cols["i0"] = (rng.integers(-10**6, 10**6 + 1, rng_rows), S.pack_validity(rng.random(rng_rows) >= NULL_FRACTION))
-    for _ in range(args.warmup):
-        S.numeric_suite(cols, rng_rows)
+    cores = S.use_all_host_threads()  # under torchrun every rank inherits OMP_NUM_THREADS=1
+    cols = make_host_table(rows)
+    for _ in range(max(1, args.warmup)):
+        S.numeric_suite(cols, rows)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        S.numeric_suite(cols, rng_rows)
+        S.numeric_suite(cols, rows)
     dt = time.perf_counter() - t0
-    value = rng_rows * args.steps / dt
-    sample_desc = (f"{rng_rows} rows x 4 referenced cols per step (of the 100M-row workload), one full scan per "
-                   f"constraint as ValidationSuite::run_sequential does, OpenMP over all host cores")
+    value = rows * args.steps / dt
+    sample_desc = (f"{rows} rows x 4 referenced cols per step ({'the full' if rows == ROWS_PER_GPU else 'a sample of the'} "
+                   f"100M-row workload of one GPU), one full scan per constraint as ValidationSuite::run_sequential does, "
+                   f"OpenMP over {cores} host threads")
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "C2 numeric business-rules suite (has_size, has_min, has_mean, has_correlation, satisfies)",
-                   "rows_per_step": rng_rows, "columns": 8, "null_fraction": NULL_FRACTION},
+        "config": {"workload": "C2 numeric business-rules suite (has_size, has_min(f0), has_mean(f1), has_correlation(f0,f1), "
+                               "satisfies(f2 > 0 AND i0 < 1000000)) on 100M rows x 8 f64/i64 cols, 5% nulls",
+                   "rows_per_step": rows, "columns": 8, "referenced_columns": list(SUITE_COLUMNS), "null_fraction": NULL_FRACTION},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample_desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference's DataFusion path (oracle/cpu_scan.c); the Rust reference cannot be built in this image",
@@ -458,11 +471,12 @@ def main():
 
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        sample = int(os.environ.get("TG_BENCH_CPU_ROWS", 20_000_000))
-        rate, cores, times = cpu_suite_rate(sample, repeats=3)
+        sample = int(os.environ.get("TG_BENCH_CPU_ROWS", n))
+        rate, cores, times = cpu_suite_rate(sample, repeats=20)
         cpu_baseline = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{sample} rows of the same synthetic table, 3 repeats after warm-up; oracle/cpu_scan.c: one "
-                                  f"full scan per constraint (run_sequential schedule), OpenMP over {cores} host threads"}
+                        "sample": f"{sample} rows ({'the full per-GPU workload' if sample == n else 'a sample'}) of the same synthetic "
+                                  f"shape, 20 repeats after warm-up; oracle/cpu_scan.c: one full scan per constraint "
+                                  f"(run_sequential schedule), OpenMP over {cores} host threads"}
 
     if rank == 0:
         line = {
