@@ -237,6 +237,35 @@ typedef struct tg_column_buffers {
 TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, const char* column, tg_column_buffers* out);
 
 /*
+ * Parquet column chunk -> HBM: replaces the decode of the reference's ParquetSource
+ * (sources/parquet.rs:150-230, DataFusion ParquetExec -> Arrow RecordBatch) and the host->device copy for one
+ * column. `chunk` = the column chunk's bytes exactly as they are in the file (from the first page header,
+ * total_compressed_size bytes), `num_values` / `codec` / the physical type (as tg_dtype) / the leaf's max definition
+ * level from the file metadata. The host walks the page headers and expands the definition levels into the validity
+ * bitmap while the value bytes travel; the device scatters the densely stored non-NULL PLAIN values to their rows.
+ * Supported: INT64 / DOUBLE / INT32 / FLOAT, codec UNCOMPRESSED (0), data pages V1 / V2, PLAIN values, RLE levels,
+ * flat columns; anything else -> TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
+ * must stay readable until the next tg_plan_execute* / tg_table_column_buffers on this engine when it is pinned memory.
+ */
+TG_API tg_status tg_table_append_parquet_chunk(tg_table* t, const char* name, int32_t dtype, int32_t max_definition_level,
+                                               int32_t codec, const void* chunk, int64_t n_bytes, int64_t num_values);
+/* Host-only page walk of a column chunk (Thrift compact PageHeaders, parquet.thrift): fills up to `cap` entries and
+ * returns the number of pages, or -(tg_status). page_type: 0 DATA_PAGE, 1 INDEX_PAGE, 2 DICTIONARY_PAGE, 3 DATA_PAGE_V2 */
+typedef struct tg_parquet_page {
+    int32_t page_type, version;
+    int32_t encoding, definition_level_encoding;
+    int32_t num_values, num_nulls;
+    int32_t uncompressed_bytes, body_bytes;
+    int32_t definition_levels_bytes, repetition_levels_bytes;
+    int32_t is_compressed, reserved;
+    int64_t header_offset, body_offset;
+} tg_parquet_page;
+TG_API int32_t tg_parquet_inspect_chunk(const void* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap);
+/* Host-only: expands the definition levels of a flat optional column chunk into `out_bits` ((num_values + 7) / 8 bytes,
+ * LSB first, chunk-relative; may be NULL) and returns the non-NULL count, or -(tg_status). The bitmap the device path uses. */
+TG_API int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits);
+
+/*
  * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity
  * bitmap, LSB bit order, `bit_offset` = Arrow array offset). The call stages them through pinned
  * memory into HBM (async copies on the engine's copy stream) and returns after the copy is queued and

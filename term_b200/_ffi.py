@@ -56,6 +56,13 @@ class tg_column_buffers(C.Structure):
                 ("validity", C.c_void_p), ("n_value_bytes", C.c_int64), ("null_count", C.c_int64)]
 
 
+class tg_parquet_page(C.Structure):
+    _fields_ = [("page_type", C.c_int32), ("version", C.c_int32), ("encoding", C.c_int32), ("definition_level_encoding", C.c_int32),
+                ("num_values", C.c_int32), ("num_nulls", C.c_int32), ("uncompressed_bytes", C.c_int32), ("body_bytes", C.c_int32),
+                ("definition_levels_bytes", C.c_int32), ("repetition_levels_bytes", C.c_int32), ("is_compressed", C.c_int32),
+                ("reserved", C.c_int32), ("header_offset", C.c_int64), ("body_offset", C.c_int64)]
+
+
 class tg_exec_stats(C.Structure):
     _fields_ = [("gpu_ms", C.c_double), ("scan_ms", C.c_double), ("string_ms", C.c_double),
                 ("hash_ms", C.c_double), ("sketch_ms", C.c_double), ("bytes_scanned", C.c_uint64),
@@ -79,6 +86,9 @@ SIGNATURES = {
     "tg_table_lookup": (C.c_int, [P, C.c_char_p, PP]),
     "tg_table_num_rows": (C.c_int64, [P]),
     "tg_table_column_dtype": (C.c_int, [P, C.c_char_p, C.POINTER(C.c_int32)]),
+    "tg_table_append_parquet_chunk": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64]),
+    "tg_parquet_chunk_validity": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
+    "tg_parquet_inspect_chunk": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(tg_parquet_page), C.c_int32]),
     "tg_table_column_buffers": (C.c_int, [P, C.c_char_p, C.c_char_p, C.POINTER(tg_column_buffers)]),
     "tg_table_append_host": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),
     "tg_table_adopt_device": (C.c_int, [P, C.c_char_p, C.c_int32, C.c_int64, P, P, P, C.c_int64]),

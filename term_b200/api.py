@@ -15,6 +15,8 @@ reproduces the orchestration of `ValidationSuite::run_sequential` (core/suite.rs
 """
 import ctypes as C
 import enum
+import mmap
+import os
 import time
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence
@@ -343,6 +345,46 @@ class SessionContext:
                 C.CFUNCTYPE(None, C.c_void_p)(rel_a)(C.addressof(array_buf))
             if rel_s:
                 C.CFUNCTYPE(None, C.c_void_p)(rel_s)(C.addressof(schema_buf))
+
+    # Parquet physical type -> tg_dtype, decoded on the device (tg_table_append_parquet_chunk)
+    _PARQUET_TYPES = {"INT64": F.TG_INT64, "DOUBLE": F.TG_FLOAT64, "INT32": F.TG_INT32, "FLOAT": F.TG_FLOAT32}
+
+    def register_parquet(self, name: str, path, columns=None):
+        """ParquetSource::register (sources/parquet.rs:150-230) for the GPU path: every column chunk of every row group
+        goes to the engine as raw file bytes (tg_table_append_parquet_chunk) and is decoded into the Arrow layout in HBM.
+        The file metadata (row groups, chunk offsets, physical types) is read with pyarrow, like the Rust shim reads it
+        with the parquet crate. Unsupported encodings / codecs / types raise: there is no host decode fallback."""
+        import pyarrow.parquet as pq
+        paths = [path] if isinstance(path, (str, os.PathLike)) else list(path)
+        t = self._create(name)
+        for pth in paths:
+            pf = pq.ParquetFile(pth)
+            md, schema = pf.metadata, pf.schema
+            want = list(columns) if columns is not None else [schema.column(i).name for i in range(md.num_columns)]
+            index = {schema.column(i).path: i for i in range(md.num_columns)}
+            # the chunks are handed over as views of the mapped file: the only host copy is the engine's staging memcpy
+            with open(pth, "rb") as f, mmap.mmap(f.fileno(), 0, access=mmap.ACCESS_READ) as mm:
+                view = np.frombuffer(mm, dtype=np.uint8)
+                try:
+                    for rg in range(md.num_row_groups):
+                        for col in want:
+                            if col not in index:
+                                raise F.TermGpuError(2, f"Schema error: No field named {col}.")
+                            cm, leaf = md.row_group(rg).column(index[col]), schema.column(index[col])
+                            if cm.physical_type not in self._PARQUET_TYPES:
+                                raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': physical type {cm.physical_type} is not decoded on the device")
+                            if leaf.max_repetition_level != 0:
+                                raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}' is repeated")
+                            start = cm.dictionary_page_offset if cm.has_dictionary_page and cm.dictionary_page_offset else cm.data_page_offset
+                            chunk = view[start: start + cm.total_compressed_size]
+                            codec = 0 if cm.compression == "UNCOMPRESSED" else 1
+                            F.check(F.lib().tg_table_append_parquet_chunk(t, col.encode(), self._PARQUET_TYPES[cm.physical_type],
+                                                                          leaf.max_definition_level, codec, chunk.ctypes.data,
+                                                                          chunk.size, cm.num_values))
+                finally:
+                    chunk = None
+                    del view  # the mapping cannot close while a buffer export is alive
+        return t
 
     def register_device_table(self, name: str, columns: Dict[str, dict], keepalive=None):
         """Adopt HBM-resident Arrow buffers without copying. columns[name] = dict(dtype=TG_*, n_rows=,

@@ -10,6 +10,10 @@ const char* last_error_cstr();
 Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype);
 void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* values,
                        const int32_t* offsets, const uint8_t* validity, int64_t bit_offset);
+void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype, int32_t max_def_level, int32_t codec,
+                                const uint8_t* chunk, int64_t n_bytes, int64_t num_values);
+int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap);
+int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits);
 void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* d_values,
                         const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes);
 void table_append_arrow(Table& t, const void* schema_p, const void* array_p);
@@ -244,6 +248,25 @@ tg_status tg_table_append_host(tg_table* t, const char* name, int32_t dtype, int
         if (!t || !name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
         table_append_host(*reinterpret_cast<Table*>(t), name, dtype, n_rows, values, offsets, validity, bit_offset);
     });
+}
+
+tg_status tg_table_append_parquet_chunk(tg_table* t, const char* name, int32_t dtype, int32_t max_definition_level, int32_t codec,
+                                        const void* chunk, int64_t n_bytes, int64_t num_values) {
+    return guard([&] {
+        if (!t || !name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        table_append_parquet_chunk(*reinterpret_cast<Table*>(t), name, dtype, max_definition_level, codec, (const uint8_t*)chunk, n_bytes,
+                                   num_values);
+    });
+}
+int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits) {
+    int64_t n = 0;
+    tg_status st = guard([&] { n = parquet_chunk_validity((const uint8_t*)chunk, n_bytes, num_values, out_bits); });
+    return st == TG_OK ? n : -(int64_t)st;
+}
+int32_t tg_parquet_inspect_chunk(const void* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap) {
+    int32_t n = 0;
+    tg_status st = guard([&] { n = parquet_inspect_chunk((const uint8_t*)chunk, n_bytes, pages, cap); });
+    return st == TG_OK ? n : -(int32_t)st;
 }
 
 tg_status tg_table_adopt_device(tg_table* t, const char* name, int32_t dtype, int64_t n_rows, const void* d_values,

@@ -132,7 +132,11 @@ void Engine::h2d(void* dst, const void* src, size_t bytes) {
     }
 }
 
-void Engine::sync_copies() { TG_CUDA(cudaStreamSynchronize(copy_stream)); }
+void Engine::sync_copies() {
+    TG_CUDA(cudaStreamSynchronize(copy_stream));
+    for (auto& b : deferred_free) dev_free(b.first, b.second);
+    deferred_free.clear();
+}
 
 // ------------------------------------------------------------------ scan planning ----
 

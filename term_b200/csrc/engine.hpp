@@ -136,7 +136,14 @@ struct Engine {
     void dev_reserve(DevBuf& b, size_t need, size_t keep_bytes);
     void h2d(void* dst, const void* src, size_t bytes);  // staged through the pinned ring unless src is pinned
     void sync_copies();
+    // device blocks still read by work queued on copy_stream (Parquet staging): released by the next sync_copies()
+    std::vector<std::pair<uint8_t*, size_t>> deferred_free;
 };
+
+// tables.cu helpers shared with the Parquet path (parquet.cu)
+Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype);
+void set_pivot_host(Column& c, int32_t dtype, int64_t n, const void* values, const uint8_t* validity, int64_t bit_offset);
+void append_validity(Engine& e, Column& c, int64_t have, const uint8_t* validity, int64_t bit_offset, int64_t n);
 
 // jobs (each fills the partial state of the aggregates it owns)
 void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);   // engine.cu + scan.cu

@@ -1,0 +1,427 @@
+// Parquet column chunk -> HBM: replaces the decode half of the reference's ParquetSource
+// (sources/parquet.rs:150-230, DataFusion's ParquetExec) plus the Arrow host->device copy for one column.
+//
+// Split of work. The host walks the chunk's pages (Thrift compact PageHeaders), expands the definition levels
+// (RLE / bit-packed hybrid at bit width 1: one bit per row = n/8 bytes, cheap) into the column's validity bitmap
+// while the value bytes are already on their way to the device, and describes the value sections as blocks of up to
+// 1024 rows. The device does the part that is proportional to the data: PLAIN stores only the non-NULL values, densely,
+// so pq_expand_kernel scatters them to their row positions (Arrow layout) — one warp per block, rank of a row among
+// the block's non-NULL rows from a ballot. Pages without NULLs are copied straight into place (no kernel).
+//
+// Supported (everything else is TG_ERR_UNSUPPORTED, there is no host decode path): physical INT64 / DOUBLE /
+// INT32 / FLOAT, codec UNCOMPRESSED, data pages V1 and V2, PLAIN values, RLE definition levels, flat columns
+// (max definition level 0 or 1, no repetition levels), no dictionary page.
+#include <algorithm>
+#include <cstring>
+
+#include "engine.hpp"
+
+namespace tg {
+
+// ------------------------------------------------------------------ Thrift compact protocol (read-only) ----
+namespace {
+
+struct Thrift {
+    const uint8_t* p;
+    const uint8_t* end;
+    void need(size_t n) const {
+        if ((size_t)(end - p) < n) throw Error(TG_ERR_INVALID_ARG, "Parquet page header is truncated");
+    }
+    uint8_t byte() {
+        need(1);
+        return *p++;
+    }
+    uint64_t varint() {
+        uint64_t v = 0;
+        for (int shift = 0; shift < 64; shift += 7) {
+            const uint8_t b = byte();
+            v |= (uint64_t)(b & 0x7f) << shift;
+            if (!(b & 0x80)) return v;
+        }
+        throw Error(TG_ERR_INVALID_ARG, "Parquet page header: varint too long");
+    }
+    int64_t zigzag() {
+        const uint64_t v = varint();
+        return (int64_t)(v >> 1) ^ -(int64_t)(v & 1);
+    }
+    // returns false at STOP; type = compact wire type, id = field id
+    bool field(int& type, int& id, int& last_id) {
+        const uint8_t h = byte();
+        if (h == 0) return false;
+        type = h & 0x0f;
+        const int delta = h >> 4;
+        id = delta ? last_id + delta : (int)zigzag();
+        last_id = id;
+        return true;
+    }
+    void skip(int type, int depth = 0) {
+        if (depth > 16) throw Error(TG_ERR_INVALID_ARG, "Parquet page header: nesting too deep");
+        switch (type) {
+            case 1: case 2: break;  // bool carried by the type nibble
+            case 3: byte(); break;
+            case 4: case 5: case 6: varint(); break;
+            case 7: need(8); p += 8; break;
+            case 8: {
+                const uint64_t n = varint();
+                need(n);
+                p += n;
+            } break;
+            case 9: case 10: {
+                const uint8_t h = byte();
+                uint64_t n = h >> 4;
+                const int et = h & 0x0f;
+                if (n == 15) n = varint();
+                for (uint64_t i = 0; i < n; ++i) {
+                    if (et == 1 || et == 2) byte();  // list elements spell booleans out
+                    else skip(et, depth + 1);
+                }
+            } break;
+            case 11: {
+                const uint64_t n = varint();
+                if (n) {
+                    const uint8_t kv = byte();
+                    for (uint64_t i = 0; i < n; ++i) {
+                        skip(kv >> 4, depth + 1);
+                        skip(kv & 0x0f, depth + 1);
+                    }
+                }
+            } break;
+            case 12: {
+                int t, id, last = 0;
+                while (field(t, id, last)) skip(t, depth + 1);
+            } break;
+            default: throw Error(TG_ERR_INVALID_ARG, "Parquet page header: unknown Thrift type");
+        }
+    }
+};
+
+enum { PQ_DATA_PAGE = 0, PQ_INDEX_PAGE = 1, PQ_DICTIONARY_PAGE = 2, PQ_DATA_PAGE_V2 = 3 };
+enum { PQ_ENC_PLAIN = 0, PQ_ENC_RLE = 3 };
+
+// parquet.thrift: PageHeader {1 type, 2 uncompressed_page_size, 3 compressed_page_size, 4 crc, 5 data_page_header,
+// 6 index_page_header, 7 dictionary_page_header, 8 data_page_header_v2}; DataPageHeader {1 num_values, 2 encoding,
+// 3 definition_level_encoding, 4 repetition_level_encoding, 5 statistics}; DataPageHeaderV2 {1 num_values, 2 num_nulls,
+// 3 num_rows, 4 encoding, 5 definition_levels_byte_length, 6 repetition_levels_byte_length, 7 is_compressed, 8 statistics}
+size_t parse_page_header(const uint8_t* p, const uint8_t* end, tg_parquet_page& pg) {
+    Thrift t{p, end};
+    pg = tg_parquet_page{};
+    pg.page_type = -1;
+    pg.encoding = -1;
+    pg.definition_level_encoding = -1;
+    int type, id, last = 0;
+    while (t.field(type, id, last)) {
+        if (id == 1 && type == 5) pg.page_type = (int32_t)t.zigzag();
+        else if (id == 2 && type == 5) pg.uncompressed_bytes = (int32_t)t.zigzag();
+        else if (id == 3 && type == 5) pg.body_bytes = (int32_t)t.zigzag();
+        else if ((id == 5 || id == 8) && type == 12) {
+            const bool v2 = id == 8;
+            pg.version = v2 ? 2 : 1;
+            int ft, fid, flast = 0;
+            while (t.field(ft, fid, flast)) {
+                if (fid == 1 && ft == 5) pg.num_values = (int32_t)t.zigzag();
+                else if (!v2 && fid == 2 && ft == 5) pg.encoding = (int32_t)t.zigzag();
+                else if (!v2 && fid == 3 && ft == 5) pg.definition_level_encoding = (int32_t)t.zigzag();
+                else if (v2 && fid == 2 && ft == 5) pg.num_nulls = (int32_t)t.zigzag();
+                else if (v2 && fid == 4 && ft == 5) pg.encoding = (int32_t)t.zigzag();
+                else if (v2 && fid == 5 && ft == 5) pg.definition_levels_bytes = (int32_t)t.zigzag();
+                else if (v2 && fid == 6 && ft == 5) pg.repetition_levels_bytes = (int32_t)t.zigzag();
+                else if (v2 && fid == 7 && (ft == 1 || ft == 2)) pg.is_compressed = ft == 1;
+                else t.skip(ft);
+            }
+            if (v2) pg.definition_level_encoding = PQ_ENC_RLE;
+        } else {
+            t.skip(type);
+        }
+    }
+    if (pg.page_type < 0 || pg.body_bytes < 0) throw Error(TG_ERR_INVALID_ARG, "Parquet page header without type / size");
+    return (size_t)(t.p - p);
+}
+
+// ---- bit helpers on a chunk-relative, LSB-first bitmap ----
+void set_ones(uint8_t* bits, int64_t pos, int64_t count) {
+    while (count > 0 && (pos & 7)) {
+        bits[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+        ++pos;
+        --count;
+    }
+    const int64_t full = count / 8;
+    if (full) memset(bits + (pos >> 3), 0xFF, (size_t)full);
+    pos += full * 8;
+    count -= full * 8;
+    for (; count > 0; ++pos, --count) bits[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+}
+// copies nbits bits of src (from its bit 0) to bits[pos ..)
+void put_bits(uint8_t* bits, int64_t pos, const uint8_t* src, int64_t nbits) {
+    const int sh = (int)(pos & 7);
+    int64_t o = pos >> 3;
+    const int64_t nbytes = (nbits + 7) / 8;
+    for (int64_t i = 0; i < nbytes; ++i) {
+        uint8_t b = src[i];
+        if (i == nbytes - 1 && (nbits & 7)) b &= (uint8_t)((1u << (nbits & 7)) - 1);
+        if (sh == 0) {
+            bits[o + i] |= b;
+        } else {
+            bits[o + i] |= (uint8_t)(b << sh);
+            bits[o + i + 1] |= (uint8_t)(b >> (8 - sh));
+        }
+    }
+}
+int64_t count_ones(const uint8_t* bits, int64_t lo, int64_t hi) {
+    int64_t c = 0;
+    while (lo < hi && (lo & 63)) {
+        c += (bits[lo >> 3] >> (lo & 7)) & 1;
+        ++lo;
+    }
+    for (; lo + 64 <= hi; lo += 64) {
+        uint64_t w;
+        memcpy(&w, bits + (lo >> 3), 8);
+        c += __builtin_popcountll(w);
+    }
+    for (; lo < hi; ++lo) c += (bits[lo >> 3] >> (lo & 7)) & 1;
+    return c;
+}
+
+// RLE / bit-packed hybrid, bit width 1 (Parquet "RLE" encoding of definition levels for a flat optional column):
+// <varint header> then, header & 1 ? (header >> 1) groups of 8 values, one byte each : a run of (header >> 1) copies
+// of the value in the next byte. Writes `n` levels as bits at bits[pos ..).
+void decode_levels(const uint8_t* p, const uint8_t* end, uint8_t* bits, int64_t pos, int64_t n) {
+    Thrift t{p, end};
+    int64_t done = 0;
+    while (done < n) {
+        const uint64_t h = t.varint();
+        if (h & 1) {
+            const int64_t groups = (int64_t)(h >> 1);
+            t.need((size_t)groups);
+            const int64_t take = std::min<int64_t>(groups * 8, n - done);  // the last group may be padded
+            put_bits(bits, pos + done, t.p, take);
+            t.p += groups;
+            done += take;
+        } else {
+            const int64_t run = (int64_t)(h >> 1);
+            const uint8_t v = t.byte();
+            if (v > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: definition level > 1 (nested column)");
+            const int64_t take = std::min<int64_t>(run, n - done);
+            if (run == 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: empty RLE run in the definition levels");
+            if (v) set_ones(bits, pos + done, take);
+            done += take;
+        }
+    }
+}
+
+struct PqBlock {
+    uint64_t src_off;    // byte offset in the staging buffer of the block's first non-NULL value
+    uint32_t first_row;  // chunk-relative
+    uint32_t n_rows;     // <= PQ_BLOCK_ROWS
+};
+constexpr int PQ_BLOCK_ROWS = 1024, PQ_THREADS = 256;
+
+}  // namespace
+
+// One warp per block. Row r of the block is non-NULL iff its bit is set; its value is the (number of set bits before
+// r in the block)-th of the block's dense source values. NULL rows are written as 0 so the column is deterministic.
+template <typename V>
+__global__ void __launch_bounds__(PQ_THREADS) pq_expand_kernel(const uint8_t* __restrict__ stage, const uint8_t* __restrict__ bits,
+                                                              const PqBlock* __restrict__ blocks, int64_t n_blocks, V* __restrict__ dst) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (PQ_THREADS / 32);
+    for (int64_t b = (int64_t)blockIdx.x * (PQ_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        const PqBlock blk = blocks[b];
+        const V* src = reinterpret_cast<const V*>(stage + blk.src_off);
+        uint32_t running = 0;
+        for (uint32_t i = 0; i < blk.n_rows; i += 32) {
+            const bool in = i + lane < blk.n_rows;
+            const uint64_t r = (uint64_t)blk.first_row + i + lane;
+            const bool valid = in && ((__ldg(bits + (r >> 3)) >> (r & 7)) & 1);
+            const unsigned mask = __ballot_sync(0xffffffffu, valid);
+            const uint32_t rank = running + __popc(mask & ((1u << lane) - 1u));
+            V v = 0;
+            if (valid) v = __ldg(src + rank);
+            if (in) dst[r] = v;
+            running += __popc(mask);
+        }
+    }
+}
+
+int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap) {
+    if (!chunk || n_bytes < 0) throw Error(TG_ERR_INVALID_ARG, "NULL chunk");
+    int32_t n = 0;
+    int64_t off = 0;
+    while (off < n_bytes) {
+        tg_parquet_page pg;
+        const size_t hl = parse_page_header(chunk + off, chunk + n_bytes, pg);
+        pg.header_offset = off;
+        pg.body_offset = off + (int64_t)hl;
+        if (pg.body_offset + pg.body_bytes > n_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet page runs past the column chunk");
+        if (pages && n < cap) pages[n] = pg;
+        ++n;
+        off = pg.body_offset + pg.body_bytes;
+    }
+    return n;
+}
+
+// Host-only: the validity bitmap (chunk-relative, LSB first, (num_values + 7) / 8 bytes) a flat optional column chunk
+// decodes to, and its non-NULL count. The device path builds exactly this before it scatters the values.
+int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits) {
+    const int32_t n_pages = parquet_inspect_chunk(chunk, n_bytes, nullptr, 0);
+    std::vector<tg_parquet_page> pages((size_t)n_pages);
+    parquet_inspect_chunk(chunk, n_bytes, pages.data(), n_pages);
+    std::vector<uint8_t> bits((size_t)(num_values + 7) / 8 + 16, 0);
+    int64_t rows = 0;
+    for (auto& pg : pages) {
+        if (pg.page_type != PQ_DATA_PAGE && pg.page_type != PQ_DATA_PAGE_V2) continue;
+        if (rows + pg.num_values > num_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: more values than the chunk metadata says");
+        int64_t off = pg.body_offset, len = pg.definition_levels_bytes;
+        if (pg.version == 1) {
+            uint32_t l;
+            memcpy(&l, chunk + off, 4);
+            off += 4;
+            len = l;
+        }
+        decode_levels(chunk + off, chunk + off + len, bits.data(), rows, pg.num_values);
+        rows += pg.num_values;
+    }
+    if (out_bits) memcpy(out_bits, bits.data(), (size_t)(num_values + 7) / 8);
+    return count_ones(bits.data(), 0, rows);
+}
+
+void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype, int32_t max_def_level, int32_t codec,
+                                const uint8_t* chunk, int64_t n_bytes, int64_t num_values) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (!chunk || n_bytes <= 0 || num_values < 0) throw Error(TG_ERR_INVALID_ARG, "empty Parquet column chunk");
+    if (codec != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: only UNCOMPRESSED column chunks are decoded on the device");
+    if (max_def_level < 0 || max_def_level > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: nested columns (max definition level > 1)");
+    if (dtype != TG_INT64 && dtype != TG_FLOAT64 && dtype != TG_INT32 && dtype != TG_FLOAT32)
+        throw Error(TG_ERR_UNSUPPORTED, "Parquet: only INT64 / DOUBLE / INT32 / FLOAT columns are decoded on the device");
+    if (num_values >= ((int64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: column chunk with 2^32 or more values");
+    Column& c = *table_get_or_add(t, name, dtype);
+    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
+    const int64_t have = c.n_rows;
+    const size_t w = (size_t)c.elem_bytes();
+
+    // ---- pages ----
+    const int32_t n_pages = parquet_inspect_chunk(chunk, n_bytes, nullptr, 0);
+    std::vector<tg_parquet_page> pages((size_t)n_pages);
+    parquet_inspect_chunk(chunk, n_bytes, pages.data(), n_pages);
+    struct Section {
+        int64_t first_row, n_rows, values_off, values_bytes, levels_off, levels_bytes;
+    };
+    std::vector<Section> secs;
+    int64_t rows = 0;
+    for (auto& pg : pages) {
+        if (pg.page_type == PQ_INDEX_PAGE) continue;
+        if (pg.page_type == PQ_DICTIONARY_PAGE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: dictionary-encoded column chunk (write with use_dictionary=false)");
+        if (pg.page_type != PQ_DATA_PAGE && pg.page_type != PQ_DATA_PAGE_V2) throw Error(TG_ERR_UNSUPPORTED, "Parquet: unknown page type");
+        if (pg.encoding != PQ_ENC_PLAIN) throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) + " (only PLAIN)");
+        if (pg.version == 2 && (pg.repetition_levels_bytes != 0)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: repeated column");
+        Section s{rows, pg.num_values, pg.body_offset, pg.body_bytes, 0, 0};
+        if (max_def_level > 0) {
+            if (pg.definition_level_encoding != PQ_ENC_RLE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: definition levels not RLE-encoded");
+            if (pg.version == 1) {
+                if (pg.body_bytes < 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: data page too short");
+                uint32_t len;
+                memcpy(&len, chunk + pg.body_offset, 4);
+                s.levels_off = pg.body_offset + 4;
+                s.levels_bytes = len;
+                s.values_off = s.levels_off + len;
+                s.values_bytes = pg.body_bytes - 4 - (int64_t)len;
+            } else {
+                s.levels_off = pg.body_offset;
+                s.levels_bytes = pg.definition_levels_bytes;
+                s.values_off = s.levels_off + s.levels_bytes;
+                s.values_bytes = pg.body_bytes - s.levels_bytes;
+            }
+            if (s.values_bytes < 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
+        }
+        rows += pg.num_values;
+        secs.push_back(s);
+    }
+    if (rows != num_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: pages hold " + std::to_string(rows) + " values, the chunk metadata says " + std::to_string(num_values));
+    if (num_values == 0) {
+        t.n_rows = std::max(t.n_rows, c.n_rows);
+        return;
+    }
+
+    // ---- values on their way first: every page's value section is copied to a 16-byte aligned place in a staging
+    // block (or straight into the column when the page has no NULLs: decided after the levels are known for optional
+    // columns, immediately for required ones) ----
+    e.dev_reserve(c.values, (size_t)(have + num_values) * w, (size_t)have * w);
+    uint8_t* dst = c.values.p + (size_t)have * w;
+    std::vector<int64_t> stage_off(secs.size(), -1);
+    size_t stage_bytes = 0;
+    uint8_t* stage = nullptr;
+    if (max_def_level == 0) {
+        for (auto& s : secs) {
+            if (s.values_bytes != s.n_rows * (int64_t)w) throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page size does not match its value count");
+            e.h2d(dst + (size_t)s.first_row * w, chunk + s.values_off, (size_t)s.values_bytes);
+        }
+    } else {
+        for (size_t i = 0; i < secs.size(); ++i) {
+            stage_off[i] = (int64_t)stage_bytes;
+            stage_bytes += ((size_t)secs[i].values_bytes + 15) & ~(size_t)15;
+        }
+        stage_bytes += 64;
+        stage = e.dev_alloc(stage_bytes);
+        for (size_t i = 0; i < secs.size(); ++i)
+            e.h2d(stage + stage_off[i], chunk + secs[i].values_off, (size_t)secs[i].values_bytes);
+    }
+
+    // ---- definition levels -> chunk-relative validity bits, blocks (host work that overlaps the copies above) ----
+    std::vector<uint8_t> bits;
+    std::vector<PqBlock> blocks;
+    if (max_def_level > 0) {
+        bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
+        for (size_t i = 0; i < secs.size(); ++i) {
+            const Section& s = secs[i];
+            decode_levels(chunk + s.levels_off, chunk + s.levels_off + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
+            int64_t prefix = 0;
+            for (int64_t r = 0; r < s.n_rows; r += PQ_BLOCK_ROWS) {
+                const int64_t nr = std::min<int64_t>(PQ_BLOCK_ROWS, s.n_rows - r);
+                blocks.push_back(PqBlock{(uint64_t)stage_off[i] + (uint64_t)prefix * w, (uint32_t)(s.first_row + r), (uint32_t)nr});
+                prefix += count_ones(bits.data(), s.first_row + r, s.first_row + r + nr);
+            }
+            if (prefix * (int64_t)w != s.values_bytes)
+                throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page holds " + std::to_string(s.values_bytes) + " value bytes for " + std::to_string(prefix) + " non-null rows");
+        }
+    }
+
+    // ---- pivot of the shifted sums: from the first page's dense values ----
+    if (!c.pivot_set && !secs.empty()) {
+        const int64_t nv = std::min<int64_t>(secs[0].values_bytes / (int64_t)w, 4096);
+        if (nv > 0 && (dtype == TG_INT64 || dtype == TG_FLOAT64)) {
+            std::vector<uint64_t> head((size_t)nv);
+            memcpy(head.data(), chunk + secs[0].values_off, (size_t)nv * 8);
+            set_pivot_host(c, dtype, nv, head.data(), nullptr, 0);
+        }
+    }
+
+    // ---- validity through the common path (keeps the host mirror of a partial tail byte) ----
+    append_validity(e, c, have, max_def_level > 0 ? bits.data() : nullptr, 0, num_values);
+
+    // ---- expand ----
+    if (max_def_level > 0) {
+        const size_t bits_b = ((size_t)(num_values + 7) / 8 + 15) & ~(size_t)15, blk_b = blocks.size() * sizeof(PqBlock);
+        uint8_t* aux = e.dev_alloc(bits_b + blk_b + 64);
+        e.h2d(aux, bits.data(), (size_t)(num_values + 7) / 8);
+        e.h2d(aux + bits_b, blocks.data(), blk_b);
+        // h2d of pageable memory returns once the bytes sit in the pinned ring, so `bits` / `blocks` may go out of scope
+        const int64_t nb = (int64_t)blocks.size();
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nb + PQ_THREADS / 32 - 1) / (PQ_THREADS / 32), (int64_t)e.sm_count * 8));
+        if (w == 8)
+            pq_expand_kernel<uint64_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, aux, reinterpret_cast<const PqBlock*>(aux + bits_b), nb,
+                                                                               reinterpret_cast<uint64_t*>(dst));
+        else
+            pq_expand_kernel<uint32_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, aux, reinterpret_cast<const PqBlock*>(aux + bits_b), nb,
+                                                                               reinterpret_cast<uint32_t*>(dst));
+        TG_CUDA(cudaGetLastError());
+        e.launches += 1;
+        e.deferred_free.emplace_back(stage, stage_bytes);
+        e.deferred_free.emplace_back(aux, bits_b + blk_b + 64);
+    }
+    c.value_bytes = (have + num_values) * (int64_t)w;
+    c.n_rows = have + num_values;
+    t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+}  // namespace tg

@@ -13,8 +13,8 @@ static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Pivot K of the shifted moment sums: the median of the first (up to) five finite, valid values of the
 // column. It must be an ELEMENT of the column (the scan replaces NULL rows by K), and a typical one, so
 // that sum(x) = n*K + sum(x-K) keeps full accuracy; a median of five is robust to isolated outliers.
-static void set_pivot_host(Column& c, int32_t dtype, int64_t n, const void* values, const uint8_t* validity,
-                           int64_t bit_offset) {
+void set_pivot_host(Column& c, int32_t dtype, int64_t n, const void* values, const uint8_t* validity,
+                    int64_t bit_offset) {
     if (c.pivot_set || (dtype != TG_INT64 && dtype != TG_FLOAT64)) return;
     double cand[5];
     int64_t icand[5];
@@ -97,30 +97,9 @@ Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype) {
     return t.cols.back().get();
 }
 
-void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* values,
-                       const int32_t* offsets, const uint8_t* validity, int64_t bit_offset) {
-    Engine& e = *t.eng;
-    std::lock_guard<std::mutex> g(e.mu);
-    TG_CUDA(cudaSetDevice(e.device));
-    if (n < 0) throw Error(TG_ERR_INVALID_ARG, "negative row count");
-    Column& c = *table_get_or_add(t, name, dtype);
-    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
-    const int64_t have = c.n_rows;
-    if (n == 0) {
-        t.n_rows = std::max(t.n_rows, c.n_rows);
-        return;
-    }
-    // ---- fixed-width values first: their DMA (the bulk of the bytes) is queued before the host walks the validity
-    // bitmap below, so counting NULLs overlaps the copy instead of delaying it ----
-    const bool fixed_width = dtype == TG_INT64 || dtype == TG_FLOAT64 || dtype == TG_INT32 || dtype == TG_FLOAT32;
-    if (fixed_width) {
-        const size_t w = (size_t)c.elem_bytes();
-        e.dev_reserve(c.values, (size_t)(have + n) * w, (size_t)have * w);
-        e.h2d(c.values.p + (size_t)have * w, values, (size_t)n * w);
-        c.value_bytes = (have + n) * (int64_t)w;
-        set_pivot_host(c, dtype, n, values, validity, bit_offset);
-    }
-    // ---- validity ----
+// appends the validity of `n` rows (bitmap `validity` read from bit `bit_offset`; nullptr = no NULLs) to a column that
+// holds `have` rows; materialises the bitmap lazily the first time a NULL shows up
+void append_validity(Engine& e, Column& c, int64_t have, const uint8_t* validity, int64_t bit_offset, int64_t n) {
     bool has_nulls = false;
     bool fast_bits = false;
     int64_t zeros = 0;
@@ -163,6 +142,32 @@ void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t
         }
         c.null_count += zeros;
     }
+}
+
+void table_append_host(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* values,
+                       const int32_t* offsets, const uint8_t* validity, int64_t bit_offset) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (n < 0) throw Error(TG_ERR_INVALID_ARG, "negative row count");
+    Column& c = *table_get_or_add(t, name, dtype);
+    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
+    const int64_t have = c.n_rows;
+    if (n == 0) {
+        t.n_rows = std::max(t.n_rows, c.n_rows);
+        return;
+    }
+    // ---- fixed-width values first: their DMA (the bulk of the bytes) is queued before the host walks the validity
+    // bitmap below, so counting NULLs overlaps the copy instead of delaying it ----
+    const bool fixed_width = dtype == TG_INT64 || dtype == TG_FLOAT64 || dtype == TG_INT32 || dtype == TG_FLOAT32;
+    if (fixed_width) {
+        const size_t w = (size_t)c.elem_bytes();
+        e.dev_reserve(c.values, (size_t)(have + n) * w, (size_t)have * w);
+        e.h2d(c.values.p + (size_t)have * w, values, (size_t)n * w);
+        c.value_bytes = (have + n) * (int64_t)w;
+        set_pivot_host(c, dtype, n, values, validity, bit_offset);
+    }
+    append_validity(e, c, have, validity, bit_offset, n);
     // ---- values ----
     switch (dtype) {
         case TG_INT64:

@@ -1,0 +1,155 @@
+"""Parquet column chunk -> HBM (sources/parquet.rs in the reference). The files are written here with
+pyarrow (uncompressed, PLAIN, data pages V1 and V2, small pages so that chunks hold many), pyarrow's own reader is the
+ground truth. CPU tests: the host page walk (Thrift compact PageHeaders) and the definition-level expansion. GPU
+tests: the decoded Arrow buffers in HBM bit for bit, and a suite over the decoded table against the same suite over the
+table registered from host Arrow arrays."""
+import os
+
+import numpy as np
+import pyarrow as pa
+import pyarrow.parquet as pq
+import pytest
+
+import term_b200 as T
+from term_b200 import _ffi as F
+
+CASES = [(1, 0.0, None), (1000, 0.3, None), (300_000, 0.05, 100_000), (70_001, 1.0, None), (50_000, 0.0, None), (200_000, 0.999, None)]
+
+
+def _write(tmp_path, n, null_p, row_group, version, seed=1):
+    rng = np.random.default_rng(seed + n)
+    x, i = rng.normal(0.0, 1.0, n), rng.integers(-50, 50, n)
+    f32, i32 = rng.normal(5.0, 2.0, n).astype(np.float32), rng.integers(-9, 9, n).astype(np.int32)
+    masks = {c: rng.random(n) < null_p for c in ("x", "i", "f32", "i32")}
+    schema = pa.schema([pa.field("x", pa.float64()), pa.field("i", pa.int64()), pa.field("f32", pa.float32()), pa.field("i32", pa.int32()),
+                        pa.field("r", pa.int64(), nullable=False)])
+    t = pa.table({"x": pa.array(x, mask=masks["x"]), "i": pa.array(i, mask=masks["i"]), "f32": pa.array(f32, mask=masks["f32"]),
+                  "i32": pa.array(i32, mask=masks["i32"]), "r": pa.array(i)}, schema=schema)
+    path = os.path.join(tmp_path, f"t_{n}_{version}.parquet")
+    pq.write_table(t, path, compression="NONE", use_dictionary=False, data_page_version=version, row_group_size=row_group,
+                   data_page_size=64 * 1024)
+    return path, t
+
+
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("n,null_p,row_group", CASES)
+def test_page_walk_and_definition_levels_match_pyarrow(built_lib, tmp_path, n, null_p, row_group, version):
+    path, t = _write(str(tmp_path), n, null_p, row_group, version)
+    md = pq.ParquetFile(path).metadata
+    raw = open(path, "rb").read()
+    row0 = 0
+    for rg in range(md.num_row_groups):
+        for ci in range(md.num_columns):
+            cm = md.row_group(rg).column(ci)
+            name = cm.path_in_schema
+            chunk = np.frombuffer(raw[cm.data_page_offset: cm.data_page_offset + cm.total_compressed_size], dtype=np.uint8)
+            n_pages = F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, None, 0)
+            assert n_pages > 0, F.last_error()
+            pages = (F.tg_parquet_page * n_pages)()
+            assert F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, pages, n_pages) == n_pages
+            assert sum(p.num_values for p in pages) == cm.num_values
+            assert all(p.encoding == 0 and p.page_type == (0 if version == "1.0" else 3) for p in pages)
+            assert pages[0].header_offset == 0 and all(p.body_offset > p.header_offset for p in pages)
+            assert pages[-1].body_offset + pages[-1].body_bytes == chunk.size
+            if name != "r":
+                bits = np.zeros((cm.num_values + 7) // 8, dtype=np.uint8)
+                nn = F.lib().tg_parquet_chunk_validity(chunk.ctypes.data, chunk.size, cm.num_values, bits.ctypes.data)
+                want = np.asarray(t.column(name).slice(row0, cm.num_values).is_valid())
+                got = np.unpackbits(bits, bitorder="little")[: cm.num_values].astype(bool)
+                assert nn == int(want.sum()) and (got == want).all(), (name, rg)
+        row0 += md.row_group(rg).num_rows
+
+
+def test_truncated_and_foreign_chunks_are_rejected(built_lib, tmp_path):
+    path, _ = _write(str(tmp_path), 5000, 0.2, None, "1.0")
+    cm = pq.ParquetFile(path).metadata.row_group(0).column(0)
+    raw = open(path, "rb").read()
+    chunk = np.frombuffer(raw[cm.data_page_offset: cm.data_page_offset + cm.total_compressed_size], dtype=np.uint8)
+    cut = np.ascontiguousarray(chunk[: chunk.size // 2])
+    assert F.lib().tg_parquet_inspect_chunk(cut.ctypes.data, cut.size, None, 0) < 0  # a page runs past the chunk
+    junk = np.full(64, 0xFF, dtype=np.uint8)
+    assert F.lib().tg_parquet_inspect_chunk(junk.ctypes.data, junk.size, None, 0) < 0
+
+
+# ------------------------------------------------------------------------------------------ GPU ----
+def _device_column(ctx, table, column, np_dtype):
+    """(values ndarray, validity bool ndarray | None) read back from the column's device buffers"""
+    import torch
+    from term_b200.distributed import _tensor_from_ptr
+    b = ctx.column_buffers(table, column)
+    dev = torch.device("cuda", 0)
+    n = b["n_rows"]
+    w = np.dtype(np_dtype).itemsize
+    raw = _tensor_from_ptr(b["values"], n * w, dev, "|u1").cpu().numpy().view(np_dtype)
+    valid = None
+    if b["validity"]:
+        bits = _tensor_from_ptr(b["validity"], (n + 7) // 8, dev, "|u1").cpu().numpy()
+        valid = np.unpackbits(bits, bitorder="little")[:n].astype(bool)
+    return raw, valid, b
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("n,null_p,row_group", CASES)
+def test_parquet_chunks_decode_to_the_arrow_layout(ctx, tmp_path, n, null_p, row_group, version):
+    path, t = _write(str(tmp_path), n, null_p, row_group, version)
+    name = f"pq_{n}_{version.replace('.', '')}"
+    ctx.register_parquet(name, path)
+    try:
+        assert ctx.num_rows(name) == n
+        for col, dt in (("x", np.float64), ("i", np.int64), ("f32", np.float32), ("i32", np.int32), ("r", np.int64)):
+            vals, valid, b = _device_column(ctx, name, col, dt)
+            want_valid = np.asarray(t.column(col).is_valid())
+            want = np.asarray(t.column(col).fill_null(0)).astype(dt)
+            if valid is None:
+                assert want_valid.all(), col
+                valid = np.ones(n, dtype=bool)
+            assert (valid == want_valid).all(), col
+            assert b["null_count"] == int((~want_valid).sum())
+            assert (vals.view(np.uint8).reshape(n, -1)[valid] == want.view(np.uint8).reshape(n, -1)[valid]).all(), col  # bit for bit
+            assert (vals[~valid] == 0).all(), col  # NULL rows are written as zero
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+def test_suite_over_parquet_equals_suite_over_arrow(ctx, tmp_path):
+    path, t = _write(str(tmp_path), 300_000, 0.05, 100_000, "1.0", seed=9)
+    path2, t2 = _write(str(tmp_path), 70_001, 0.3, None, "2.0", seed=11)
+    ctx.register_parquet("pq_suite", [path2, path])  # two files appended, the second starts at an unaligned row (70 001)
+    ctx.register_table("pq_arrow", pa.concat_tables([t2, t]))
+    try:
+        A = T.Assertion
+
+        def suite(name):
+            cb = (T.Check.builder("c").has_size(A.GreaterThan(0.0)).completeness("x", 0.9).completeness(["i", "i32"], 0.5)
+                  .has_min("x", A.LessThan(0.0)).has_max("i", A.GreaterThan(0.0)).has_sum("i", A.LessThan(1e18)).has_mean("x", A.Between(-1.0, 1.0))
+                  .has_standard_deviation("x", A.Between(0.5, 2.0)).has_correlation("x", "i", A.Between(-1.0, 1.0))
+                  .satisfies("x > 0 AND i < 10").validates_uniqueness(["r"], 0.0).has_approx_quantile("x", 0.5, A.Between(-1.0, 1.0))
+                  .has_mean("f32", A.Between(4.0, 6.0)).has_max("i32", A.Equals(8.0)))
+            return T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        got, want = suite("pq_suite"), suite("pq_arrow")
+        assert [(r.name, r.status, r.metric, r.message) for r in got] == [(r.name, r.status, r.metric, r.message) for r in want]
+    finally:
+        ctx.deregister_table("pq_suite")
+        ctx.deregister_table("pq_arrow")
+
+
+@pytest.mark.gpu
+def test_unsupported_parquet_features_fail_loudly(ctx, tmp_path):
+    t = pa.table({"k": pa.array([1, 2, 3, 1, 2, 3] * 100), "s": pa.array(["a", "b", "c"] * 200)})
+    p1 = os.path.join(str(tmp_path), "dict.parquet")
+    pq.write_table(t, p1, compression="NONE", use_dictionary=True)
+    with pytest.raises(T.TermGpuError, match="dictionary"):
+        ctx.register_parquet("pq_bad", p1, columns=["k"])
+    ctx.deregister_table("pq_bad")
+    p2 = os.path.join(str(tmp_path), "snappy.parquet")
+    pq.write_table(t, p2, compression="SNAPPY", use_dictionary=False)
+    with pytest.raises(T.TermGpuError, match="UNCOMPRESSED"):
+        ctx.register_parquet("pq_bad", p2, columns=["k"])
+    ctx.deregister_table("pq_bad")
+    p3 = os.path.join(str(tmp_path), "str.parquet")
+    pq.write_table(t, p3, compression="NONE", use_dictionary=False)
+    with pytest.raises(T.TermGpuError, match="physical type"):
+        ctx.register_parquet("pq_bad", p3, columns=["s"])
+    ctx.deregister_table("pq_bad")

@@ -213,6 +213,49 @@ def bench_x(ctx, dev, scale, steps):
     ctx.deregister_table("h")
 
 
+def bench_pq(ctx, dev, scale, steps):
+    """Parquet column chunks (uncompressed, PLAIN, 5 % NULLs) -> HBM, against the same columns registered
+    from host Arrow arrays; file bytes come from the page cache. Wall time of register + first use (column_buffers
+    waits for the copies and the expand kernel)."""
+    import tempfile
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.parquet as pq
+    n = int(20_000_000 * scale)
+    rng = np.random.default_rng(42 + 8)
+    cols = {}
+    for k in range(2):
+        cols[f"f{k}"] = pa.array(rng.normal(100.0, 15.0, n), mask=rng.random(n) < 0.05)
+        cols[f"i{k}"] = pa.array(rng.integers(-10**6, 10**6, n), mask=rng.random(n) < 0.05)
+    t = pa.table(cols)
+    path = os.path.join(tempfile.gettempdir(), "tg_bench.parquet")
+    pq.write_table(t, path, compression="NONE", use_dictionary=False, row_group_size=n)
+    fbytes = os.path.getsize(path)
+    open(path, "rb").read()  # page cache
+
+    def timed(fn, name):
+        ts = []
+        for i in range(steps + 1):
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            fn()
+            for c in cols:
+                ctx.column_buffers(name, c)
+            ts.append((time.perf_counter() - t0) * 1e3)
+            ctx.deregister_table(name)
+        return sum(ts[1:]) / steps
+    launches0 = F.lib().tg_engine_launch_count(ctx.handle)
+    ms_pq = timed(lambda: ctx.register_parquet("pqb", path), "pqb")
+    launches = (F.lib().tg_engine_launch_count(ctx.handle) - launches0) // (steps + 1)
+    ms_arrow = timed(lambda: ctx.register_table("pqa", t), "pqa")
+    arrow_bytes = sum(8 * n + (n + 7) // 8 for _ in cols)
+    print(json.dumps({"workload": "x_parquet_to_hbm", "config": "4 columns (2 f64, 2 i64), 5% NULLs, uncompressed PLAIN, one row group", "rows": n,
+                      "file_bytes": fbytes, "arrow_bytes": arrow_bytes, "parquet_ms": ms_pq, "arrow_host_ms": ms_arrow,
+                      "parquet_rows_per_s": n / (ms_pq / 1e3), "arrow_rows_per_s": n / (ms_arrow / 1e3),
+                      "parquet_gbs_of_file": fbytes / (ms_pq / 1e3) / 1e9, "launches": int(launches)}), flush=True)
+    os.remove(path)
+
+
 def bench_c4(ctx, dev, scale, steps):
     n = int(125_000_000 * scale)
     g = torch.Generator(device=dev)
@@ -326,7 +369,7 @@ def main():
     torch.cuda.set_device(0)
     ctx = T.SessionContext(0)
     for w in a.which:
-        {"c1": bench_c1, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5, "x": bench_x}[w](ctx, dev, a.scale, a.steps)
+        {"c1": bench_c1, "c3": bench_c3, "c4": bench_c4, "c5": bench_c5, "x": bench_x, "pq": bench_pq}[w](ctx, dev, a.scale, a.steps)
         torch.cuda.empty_cache()
     ctx.close()
 
