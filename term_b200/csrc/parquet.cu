@@ -13,6 +13,8 @@
 // (max definition level 0 or 1, no repetition levels), no dictionary page.
 #include <algorithm>
 #include <cstring>
+#include <exception>
+#include <thread>
 
 #include "engine.hpp"
 
@@ -137,33 +139,45 @@ size_t parse_page_header(const uint8_t* p, const uint8_t* end, tg_parquet_page& 
     return (size_t)(t.p - p);
 }
 
-// ---- bit helpers on a chunk-relative, LSB-first bitmap ----
-void set_ones(uint8_t* bits, int64_t pos, int64_t count) {
-    while (count > 0 && (pos & 7)) {
-        bits[pos >> 3] |= (uint8_t)(1u << (pos & 7));
-        ++pos;
-        --count;
-    }
-    const int64_t full = count / 8;
-    if (full) memset(bits + (pos >> 3), 0xFF, (size_t)full);
-    pos += full * 8;
-    count -= full * 8;
-    for (; count > 0; ++pos, --count) bits[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+// ---- bit helpers on a chunk-relative, LSB-first bitmap (callers keep 16 bytes of slack behind it). The level streams
+// of sparse-NULL columns are millions of short runs, so both helpers work a 64-bit word at a time ----
+inline void or_word(uint8_t* bits, int64_t pos, uint64_t v) {  // v's bits land at pos ..; (pos & 7) + width(v) <= 64
+    uint64_t w;
+    memcpy(&w, bits + (pos >> 3), 8);
+    w |= v << (pos & 7);
+    memcpy(bits + (pos >> 3), &w, 8);
 }
-// copies nbits bits of src (from its bit 0) to bits[pos ..)
-void put_bits(uint8_t* bits, int64_t pos, const uint8_t* src, int64_t nbits) {
-    const int sh = (int)(pos & 7);
-    int64_t o = pos >> 3;
-    const int64_t nbytes = (nbits + 7) / 8;
-    for (int64_t i = 0; i < nbytes; ++i) {
-        uint8_t b = src[i];
-        if (i == nbytes - 1 && (nbits & 7)) b &= (uint8_t)((1u << (nbits & 7)) - 1);
-        if (sh == 0) {
-            bits[o + i] |= b;
-        } else {
-            bits[o + i] |= (uint8_t)(b << sh);
-            bits[o + i + 1] |= (uint8_t)(b >> (8 - sh));
+void set_ones(uint8_t* bits, int64_t pos, int64_t count) {
+    if (count >= 512) {  // long run: bytes in the middle
+        while (pos & 7) {
+            bits[pos >> 3] |= (uint8_t)(1u << (pos & 7));
+            ++pos;
+            --count;
         }
+        const int64_t full = count / 8;
+        memset(bits + (pos >> 3), 0xFF, (size_t)full);
+        pos += full * 8;
+        count -= full * 8;
+    }
+    while (count > 0) {
+        const int take = (int)std::min<int64_t>(count, 56);
+        or_word(bits, pos, (1ull << take) - 1ull);
+        pos += take;
+        count -= take;
+    }
+}
+// copies nbits bits of src (from its bit 0) to bits[pos ..); src_end bounds the 8-byte loads
+void put_bits(uint8_t* bits, int64_t pos, const uint8_t* src, int64_t nbits, const uint8_t* src_end) {
+    while (nbits > 0) {
+        const int take = (int)std::min<int64_t>(nbits, 56);
+        uint64_t v = 0;
+        if (src + 8 <= src_end) memcpy(&v, src, 8);
+        else memcpy(&v, src, (size_t)std::min<int64_t>((take + 7) / 8, src_end - src));
+        if (take < 64) v &= (1ull << take) - 1ull;
+        or_word(bits, pos, v);
+        pos += take;
+        nbits -= take;
+        src += 7;
     }
 }
 int64_t count_ones(const uint8_t* bits, int64_t lo, int64_t hi) {
@@ -193,7 +207,7 @@ void decode_levels(const uint8_t* p, const uint8_t* end, uint8_t* bits, int64_t 
             const int64_t groups = (int64_t)(h >> 1);
             t.need((size_t)groups);
             const int64_t take = std::min<int64_t>(groups * 8, n - done);  // the last group may be padded
-            put_bits(bits, pos + done, t.p, take);
+            put_bits(bits, pos + done, t.p, take, t.end);
             t.p += groups;
             done += take;
         } else {
@@ -242,9 +256,9 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_expand_kernel(const uint8_t* __
     }
 }
 
-int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap) {
+static std::vector<tg_parquet_page> walk_pages(const uint8_t* chunk, int64_t n_bytes) {
     if (!chunk || n_bytes < 0) throw Error(TG_ERR_INVALID_ARG, "NULL chunk");
-    int32_t n = 0;
+    std::vector<tg_parquet_page> out;
     int64_t off = 0;
     while (off < n_bytes) {
         tg_parquet_page pg;
@@ -252,19 +266,22 @@ int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_
         pg.header_offset = off;
         pg.body_offset = off + (int64_t)hl;
         if (pg.body_offset + pg.body_bytes > n_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet page runs past the column chunk");
-        if (pages && n < cap) pages[n] = pg;
-        ++n;
+        out.push_back(pg);
         off = pg.body_offset + pg.body_bytes;
     }
-    return n;
+    return out;
+}
+
+int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap) {
+    const std::vector<tg_parquet_page> v = walk_pages(chunk, n_bytes);
+    for (size_t i = 0; pages && i < v.size() && (int32_t)i < cap; ++i) pages[i] = v[i];
+    return (int32_t)v.size();
 }
 
 // Host-only: the validity bitmap (chunk-relative, LSB first, (num_values + 7) / 8 bytes) a flat optional column chunk
 // decodes to, and its non-NULL count. The device path builds exactly this before it scatters the values.
 int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits) {
-    const int32_t n_pages = parquet_inspect_chunk(chunk, n_bytes, nullptr, 0);
-    std::vector<tg_parquet_page> pages((size_t)n_pages);
-    parquet_inspect_chunk(chunk, n_bytes, pages.data(), n_pages);
+    const std::vector<tg_parquet_page> pages = walk_pages(chunk, n_bytes);
     std::vector<uint8_t> bits((size_t)(num_values + 7) / 8 + 16, 0);
     int64_t rows = 0;
     for (auto& pg : pages) {
@@ -301,9 +318,7 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
     const size_t w = (size_t)c.elem_bytes();
 
     // ---- pages ----
-    const int32_t n_pages = parquet_inspect_chunk(chunk, n_bytes, nullptr, 0);
-    std::vector<tg_parquet_page> pages((size_t)n_pages);
-    parquet_inspect_chunk(chunk, n_bytes, pages.data(), n_pages);
+    const std::vector<tg_parquet_page> pages = walk_pages(chunk, n_bytes);
     struct Section {
         int64_t first_row, n_rows, values_off, values_bytes, levels_off, levels_bytes;
     };
@@ -343,14 +358,16 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         return;
     }
 
-    // ---- values on their way first: every page's value section is copied to a 16-byte aligned place in a staging
-    // block (or straight into the column when the page has no NULLs: decided after the levels are known for optional
-    // columns, immediately for required ones) ----
+    // ---- the value sections travel while a helper thread expands the definition levels: staging a pageable source is
+    // a host memcpy into the pinned ring per piece, so the two halves of the host work run side by side. Every page's
+    // value section goes to a 16-byte aligned place in a staging block (required columns: straight into place) ----
     e.dev_reserve(c.values, (size_t)(have + num_values) * w, (size_t)have * w);
     uint8_t* dst = c.values.p + (size_t)have * w;
     std::vector<int64_t> stage_off(secs.size(), -1);
     size_t stage_bytes = 0;
     uint8_t* stage = nullptr;
+    std::vector<uint8_t> bits;
+    std::vector<PqBlock> blocks;
     if (max_def_level == 0) {
         for (auto& s : secs) {
             if (s.values_bytes != s.n_rows * (int64_t)w) throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page size does not match its value count");
@@ -362,28 +379,42 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
             stage_bytes += ((size_t)secs[i].values_bytes + 15) & ~(size_t)15;
         }
         stage_bytes += 64;
+        // definition levels -> chunk-relative validity bits + blocks
+        std::exception_ptr decode_err;
+        auto decode = [&]() {
+            try {
+                bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
+                blocks.reserve((size_t)num_values / PQ_BLOCK_ROWS + secs.size() + 1);
+                for (size_t i = 0; i < secs.size(); ++i) {
+                    const Section& s = secs[i];
+                    decode_levels(chunk + s.levels_off, chunk + s.levels_off + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
+                    int64_t prefix = 0;
+                    for (int64_t r = 0; r < s.n_rows; r += PQ_BLOCK_ROWS) {
+                        const int64_t nr = std::min<int64_t>(PQ_BLOCK_ROWS, s.n_rows - r);
+                        blocks.push_back(PqBlock{(uint64_t)stage_off[i] + (uint64_t)prefix * w, (uint32_t)(s.first_row + r), (uint32_t)nr});
+                        prefix += count_ones(bits.data(), s.first_row + r, s.first_row + r + nr);
+                    }
+                    if (prefix * (int64_t)w != s.values_bytes)
+                        throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page holds " + std::to_string(s.values_bytes) + " value bytes for " +
+                                                            std::to_string(prefix) + " non-null rows");
+                }
+            } catch (...) {
+                decode_err = std::current_exception();
+            }
+        };
+        std::thread helper(decode);
+        struct Join {
+            std::thread& t;
+            ~Join() {
+                if (t.joinable()) t.join();
+            }
+        } join{helper};
         stage = e.dev_alloc(stage_bytes);
+        e.deferred_free.emplace_back(stage, stage_bytes);  // released by the next sync_copies(), also on the error paths
         for (size_t i = 0; i < secs.size(); ++i)
             e.h2d(stage + stage_off[i], chunk + secs[i].values_off, (size_t)secs[i].values_bytes);
-    }
-
-    // ---- definition levels -> chunk-relative validity bits, blocks (host work that overlaps the copies above) ----
-    std::vector<uint8_t> bits;
-    std::vector<PqBlock> blocks;
-    if (max_def_level > 0) {
-        bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
-        for (size_t i = 0; i < secs.size(); ++i) {
-            const Section& s = secs[i];
-            decode_levels(chunk + s.levels_off, chunk + s.levels_off + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
-            int64_t prefix = 0;
-            for (int64_t r = 0; r < s.n_rows; r += PQ_BLOCK_ROWS) {
-                const int64_t nr = std::min<int64_t>(PQ_BLOCK_ROWS, s.n_rows - r);
-                blocks.push_back(PqBlock{(uint64_t)stage_off[i] + (uint64_t)prefix * w, (uint32_t)(s.first_row + r), (uint32_t)nr});
-                prefix += count_ones(bits.data(), s.first_row + r, s.first_row + r + nr);
-            }
-            if (prefix * (int64_t)w != s.values_bytes)
-                throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page holds " + std::to_string(s.values_bytes) + " value bytes for " + std::to_string(prefix) + " non-null rows");
-        }
+        helper.join();
+        if (decode_err) std::rethrow_exception(decode_err);
     }
 
     // ---- pivot of the shifted sums: from the first page's dense values ----
@@ -416,7 +447,6 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
                                                                                reinterpret_cast<uint32_t*>(dst));
         TG_CUDA(cudaGetLastError());
         e.launches += 1;
-        e.deferred_free.emplace_back(stage, stage_bytes);
         e.deferred_free.emplace_back(aux, bits_b + blk_b + 64);
     }
     c.value_bytes = (have + num_values) * (int64_t)w;
