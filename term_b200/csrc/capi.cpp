@@ -108,6 +108,8 @@ void tg_engine_destroy(tg_engine* h) {
         }
     }
     e.tables.clear();
+    for (auto& b : e.deferred_free) cudaFree(b.first);  // the device is idle (synchronised above)
+    e.deferred_free.clear();
     e.dev_trim();
     if (e.d_scratch) cudaFree(e.d_scratch);
     if (e.d_shuffle) cudaFree(e.d_shuffle);
