@@ -153,3 +153,65 @@ def test_unsupported_parquet_features_fail_loudly(ctx, tmp_path):
     with pytest.raises(T.TermGpuError, match="physical type"):
         ctx.register_parquet("pq_bad", p3, columns=["s"])
     ctx.deregister_table("pq_bad")
+
+
+# ---- hand-built pages: run structures pyarrow's writer never emits (long / tiny / unaligned runs, padded groups) ----
+def _varint(v):
+    out = bytearray()
+    while True:
+        b = v & 0x7F
+        v >>= 7
+        out.append(b | (0x80 if v else 0))
+        if not v:
+            return bytes(out)
+
+
+def _zz(v):
+    return _varint((v << 1) ^ (v >> 63))
+
+
+def _page_v1(levels: bytes, values: bytes, num_values: int) -> bytes:
+    body = len(levels).to_bytes(4, "little") + levels + values
+    dph = b"\x15" + _zz(num_values) + b"\x15" + _zz(0) + b"\x15" + _zz(3) + b"\x15" + _zz(3) + b"\x00"
+    return b"\x15" + _zz(0) + b"\x15" + _zz(len(body)) + b"\x15" + _zz(len(body)) + b"\x2c" + dph + b"\x00" + body
+
+
+def _hybrid(runs):
+    """runs: ("rle", count, bit) | ("packed", [bits...]) with len a multiple of 8 except for the stream's last run"""
+    out, bits = bytearray(), []
+    for r in runs:
+        if r[0] == "rle":
+            out += _varint(r[1] << 1) + bytes([r[2]])
+            bits += [r[2]] * r[1]
+        else:
+            b = list(r[1])
+            groups = (len(b) + 7) // 8
+            padded = b + [0] * (groups * 8 - len(b))
+            out += _varint((groups << 1) | 1) + np.packbits(np.array(padded, dtype=np.uint8), bitorder="little").tobytes()
+            bits += b
+    return bytes(out), np.array(bits, dtype=bool)
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_hybrid_level_streams_of_any_shape_expand_exactly(built_lib, seed):
+    rng = np.random.default_rng(seed)
+    pages, want_all = [], []
+    for _ in range(int(rng.integers(1, 5))):
+        runs = []
+        for k in range(int(rng.integers(1, 40))):
+            if rng.random() < 0.5:
+                runs.append(("rle", int(rng.choice([1, 2, 7, 8, 9, 55, 56, 57, 63, 64, 65, 511, 512, 513, 5000])), int(rng.integers(0, 2))))
+            else:
+                runs.append(("packed", rng.integers(0, 2, 8 * int(rng.integers(1, 70))).tolist()))
+        runs.append(("packed", rng.integers(0, 2, int(rng.integers(1, 8))).tolist()))  # padded last group
+        levels, want = _hybrid(runs)
+        pages.append(_page_v1(levels, b"\x00" * (8 * int(want.sum())), len(want)))
+        want_all.append(want)
+    want = np.concatenate(want_all)
+    chunk = np.frombuffer(b"".join(pages), dtype=np.uint8)
+    bits = np.zeros((len(want) + 7) // 8, dtype=np.uint8)
+    nn = F.lib().tg_parquet_chunk_validity(chunk.ctypes.data, chunk.size, len(want), bits.ctypes.data)
+    assert nn == int(want.sum()), F.last_error()
+    assert (np.unpackbits(bits, bitorder="little")[: len(want)].astype(bool) == want).all()
+    n_pages = F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, None, 0)
+    assert n_pages == len(pages)
