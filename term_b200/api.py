@@ -372,6 +372,8 @@ class SessionContext:
                             if col not in index:
                                 raise F.TermGpuError(2, f"Schema error: No field named {col}.")
                             cm, leaf = md.row_group(rg).column(index[col]), schema.column(index[col])
+                            if cm.num_values == 0:
+                                continue  # an empty row group holds no pages
                             if cm.physical_type not in self._PARQUET_TYPES:
                                 raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': physical type {cm.physical_type} is not decoded on the device")
                             if leaf.max_repetition_level != 0:
