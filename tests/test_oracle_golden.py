@@ -136,3 +136,44 @@ def test_oracle_property_generators(n, frac):
         assert O.stat_value(O.table_cols(t)["c"], "Max") == arr.max()
     if nn > 1:
         assert abs(O.stat_value(O.table_cols(t)["c"], "StandardDeviation") - arr.std(ddof=1)) < 1e-9  # :776-825
+
+
+# ---- second opinion on the oracle's SQL-aggregate semantics: Arrow's own compute kernels (the library DataFusion's
+# aggregates are built on; SURVEY §8c "pyarrow.compute for cross-checks") on seeded random columns ----
+@pytest.mark.parametrize("seed", range(6))
+def test_oracle_aggregates_agree_with_arrow_compute(seed):
+    import math
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from oracle import term_oracle as O
+    rng = np.random.default_rng(seed)
+    n = int(rng.integers(1, 4000))
+    f = pa.array(np.round(rng.normal(10.0, 4.0, n), 2), mask=rng.random(n) < 0.2)
+    i = pa.array(rng.integers(-40, 40, n), mask=rng.random(n) < 0.2)
+    s = pa.array([f"k{v}" for v in rng.integers(0, 30, n)], mask=rng.random(n) < 0.2)
+    t = pa.table({"f": f, "i": i, "s": s})
+    for col in ("f", "i", "s"):
+        tot, nn, _ = O.an_completeness(t, col)
+        assert (tot, nn) == (n, pc.count(t.column(col)).as_py())  # COUNT(*), COUNT(c)
+        assert O.distinct_counts(t, [col])["distinct_nonnull"] == pc.count_distinct(t.column(col), mode="only_valid").as_py()
+    cols = O.table_cols(t)
+    for col in ("f", "i"):
+        arr = t.column(col)
+        if pc.count(arr).as_py() == 0:
+            assert O.stat_value(cols[col], "Min") is None
+            continue
+        mm = pc.min_max(arr).as_py()
+        assert O.stat_value(cols[col], "Min") == float(mm["min"]) and O.stat_value(cols[col], "Max") == float(mm["max"])
+        assert abs(O.stat_value(cols[col], "Mean") - pc.mean(arr).as_py()) <= 1e-9 * max(1.0, abs(pc.mean(arr).as_py()))
+        assert abs(O.stat_value(cols[col], "Sum") - float(pc.sum(arr).as_py())) <= 1e-9 * max(1.0, abs(float(pc.sum(arr).as_py())))
+        if pc.count(arr).as_py() >= 2:  # STDDEV / VARIANCE are the sample forms (ddof = 1)
+            sd, var = pc.stddev(arr, ddof=1).as_py(), pc.variance(arr, ddof=1).as_py()
+            assert abs(O.stat_value(cols[col], "StandardDeviation") - sd) <= 1e-9 * max(1.0, sd)
+            assert abs(O.stat_value(cols[col], "Variance") - var) <= 1e-9 * max(1.0, var)
+        else:
+            assert O.stat_value(cols[col], "StandardDeviation") is None
+    # COUNT(CASE WHEN p THEN 1 END): rows where the predicate is NULL do not count
+    want = pc.sum(pc.and_kleene(pc.greater(t.column("f"), 10.0), pc.less(t.column("i"), 5)).cast(pa.int64())).as_py() or 0
+    got = O.predicate_counts(t, "f > 10 AND i < 5")
+    assert got[0] == want and math.isfinite(float(want))
