@@ -380,8 +380,8 @@ TG_API int32_t tg_plan_add_quantile(tg_plan* plan, const char* column, int32_t v
 TG_API int32_t tg_plan_add_column_count(tg_plan* plan, tg_assertion assertion);
 /* HistogramAnalyzer (analyzers/advanced/histogram.rs:62-358), Float64 columns like the reference. Result through
  * tg_plan_analyzer_result (u[0]=total_count f[0..3]=min,max,sum,sum_squared) and tg_plan_map_*: min, max, mean,
- * std_dev, total_count, sum, sum_squared, bucket_{i}.lower / .upper / .count. Row shards merge only when their
- * [min, max] agree (a multi-GPU histogram needs the global range first). */
+ * std_dev, total_count, sum, sum_squared, bucket_{i}.lower / .upper / .count. Row shards whose [min, max] differ merge through
+ * the second phase below (tg_plan_histogram_pending / _rebucket / _install). */
 TG_API int32_t tg_plan_add_histogram(tg_plan* plan, const char* column, int32_t num_buckets);
 
 /* Analyzers: column2 only for the correlation kinds; expression only for COMPLIANCE. */
@@ -435,6 +435,25 @@ TG_API tg_status tg_engine_mailbox_create(tg_engine* eng, int32_t world, int32_t
 TG_API tg_status tg_engine_mailbox_open(tg_engine* eng, const void* handles /* world x 64 bytes, rank order */);
 TG_API tg_status tg_plan_exchange_and_finalize(tg_engine* eng, tg_plan* plan);
 
+/* The sketch behind a tg_plan_add_kll / quantile slot as KllSketch's own fields (kll_sketch.rs:142-160): count / min /
+ * max come with tg_plan_analyzer_result; this returns the compactor stack. level < 0: the number of levels; otherwise
+ * the items of that level (each standing for 2^level values, ascending) are copied into items[cap] and the level's item
+ * count is returned. A shim can rebuild a reference-side KllSketch from it, or merge per level like KllSketch::merge
+ * (:327-366). */
+TG_API int32_t tg_plan_kll_levels(const tg_plan* plan, int32_t slot, int32_t level, double* items, int32_t cap);
+
+/* Two-phase histogram over row shards (analyzers/advanced/histogram.rs:184-290 derives the bucket bounds from the
+ * table-wide MIN / MAX, so shards that saw different ranges cannot add their counts). After the shards' partials were
+ * merged (tg_plan_partial_merge / tg_plan_exchange_and_finalize), tg_plan_histogram_pending lists the HIST aggregates
+ * whose shards disagreed on [min, max] (returns their number; fills up to `cap` indices). For each of them every rank
+ * calls tg_plan_histogram_rebucket, which counts ITS shard `table_name` against the merged (global) min / max of the
+ * plan's NUM aggregate into counts[n_buckets]; the host layer sums the counts over the ranks (a u64 all-reduce) and
+ * every rank installs the sums and calls tg_plan_finalize again. */
+TG_API int32_t tg_plan_histogram_pending(const tg_plan* plan, int32_t* agg_indices, int32_t cap);
+TG_API tg_status tg_plan_histogram_rebucket(tg_engine* eng, tg_plan* plan, const char* table_name, int32_t agg_index,
+                                            uint64_t* counts, int32_t n_buckets);
+TG_API tg_status tg_plan_histogram_install(tg_plan* plan, int32_t agg_index, const uint64_t* counts, int32_t n_buckets);
+
 /* Multi-GPU shuffle, step 3: aggregate i (kind 6 DISTINCT or 7 FK) reads its keys from `table_name` — the table
  * holding this rank's hash-shuffled shard (tg_table_partition_keys + all-to-all + tg_table_adopt_device) — instead
  * of the plan's table; which = 0: the DISTINCT table / the FK child table, 1: the FK parent table. NULL or ""
@@ -466,6 +485,13 @@ typedef struct {
     uint64_t launches;
 } tg_exec_stats;
 TG_API tg_status tg_plan_exec_stats(const tg_plan* plan, tg_exec_stats* out);
+
+/* Test hook (not part of the reference-facing surface): the hand-written sm_100a radix sort behind K6 (Spearman's
+ * RANK() OVER (ORDER BY ..), analyzers/advanced/correlation.rs:334-350) and K4 on its own — `n` host keys are sorted
+ * (stably) by the key bits [begin_bit, begin_bit + 8 * n_passes); out_index receives each sorted key's original
+ * position. The parity tests compare it with numpy's stable argsort. */
+TG_API tg_status tg_debug_sort_pairs(tg_engine* eng, const uint64_t* keys, int64_t n, int32_t begin_bit, int32_t n_passes,
+                                     uint64_t* out_keys, uint32_t* out_index);
 
 /* -------------------------------------------------- host-side helpers ---- */
 /* These restate O(1) reference host logic so the shim and tests can call it without a GPU. */

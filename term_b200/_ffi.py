@@ -133,6 +133,11 @@ SIGNATURES = {
     "tg_engine_mailbox_create": (C.c_int, [P, C.c_int32, C.c_int32, C.c_size_t, P]),
     "tg_engine_mailbox_open": (C.c_int, [P, P]),
     "tg_plan_exchange_and_finalize": (C.c_int, [P, P]),
+    "tg_debug_sort_pairs": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, P, P]),
+    "tg_plan_kll_levels": (C.c_int32, [P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32]),
+    "tg_plan_histogram_pending": (C.c_int32, [P, C.POINTER(C.c_int32), C.c_int32]),
+    "tg_plan_histogram_rebucket": (C.c_int, [P, P, C.c_char_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
+    "tg_plan_histogram_install": (C.c_int, [P, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),
     "tg_plan_analyzer_state_json": (C.c_int32, [P, C.c_int32, C.c_char_p, C.c_int32]),
     "tg_plan_redirect_aggregate": (C.c_int, [P, C.c_int32, C.c_int32, C.c_char_p]),
     "tg_plan_result": (C.c_int, [P, C.c_int32, C.POINTER(tg_result)]),

@@ -453,6 +453,41 @@ class Plan:
     def finalize(self):
         F.check(F.lib().tg_plan_finalize(self._h))
 
+    def kll_levels(self, slot: int):
+        """the slot's sketch as KllSketch's compactor stack: [items of level 0, items of level 1, ..] (weight 2^level)"""
+        nl = F.check_slot(F.lib().tg_plan_kll_levels(self._h, slot, -1, None, 0))
+        out = []
+        for lv in range(nl):
+            c = F.check_slot(F.lib().tg_plan_kll_levels(self._h, slot, lv, None, 0))
+            buf = (C.c_double * max(c, 1))()
+            F.check_slot(F.lib().tg_plan_kll_levels(self._h, slot, lv, buf, c))
+            out.append(list(buf[:c]))
+        return out
+
+    def histogram_pending(self):
+        """indices of HIST aggregates whose merged shards disagreed on [min, max] (second phase needed)"""
+        n = F.check_slot(F.lib().tg_plan_histogram_pending(self._h, None, 0))
+        if n == 0:
+            return []
+        idx = (C.c_int32 * n)()
+        F.check_slot(F.lib().tg_plan_histogram_pending(self._h, idx, n))
+        return list(idx)
+
+    def _hist_buckets(self, agg_index: int) -> int:
+        return int(self.aggregates()[agg_index][1].split("|")[-1])
+
+    def histogram_rebucket(self, ctx: "SessionContext", table: str, agg_index: int):
+        """this shard's bucket counts against the merged (global) min / max"""
+        nb = self._hist_buckets(agg_index)
+        counts = (C.c_uint64 * nb)()
+        F.check(F.lib().tg_plan_histogram_rebucket(ctx.handle, self._h, table.encode(), agg_index, counts, nb))
+        return list(counts)
+
+    def histogram_install(self, agg_index: int, counts):
+        nb = len(counts)
+        arr = (C.c_uint64 * nb)(*counts)
+        F.check(F.lib().tg_plan_histogram_install(self._h, agg_index, arr, nb))
+
     def redirect(self, agg_index: int, which: int, table):
         """tg_plan_redirect_aggregate: aggregate `agg_index` reads its keys from `table` (None: undo)."""
         F.check(F.lib().tg_plan_redirect_aggregate(self._h, agg_index, which, table.encode() if table else None))

@@ -3,6 +3,7 @@
 
 #include "engine.hpp"
 #include "hashpart.hpp"
+#include "radix_sort.cuh"
 #include "regex_dfa.hpp"
 
 namespace tg {
@@ -468,6 +469,86 @@ tg_status tg_plan_exchange_and_finalize(tg_engine* h, tg_plan* p) {
         p->p.reset_partials();
         for (auto& b : all) p->p.partial_merge(b.data(), b.size());
         p->p.finalize();
+    });
+}
+
+// test hook: the hand-written radix sort on its own (host keys -> device -> sort by bits [begin_bit, begin_bit + 8 *
+// n_passes) with synthesised row ids -> host)
+tg_status tg_debug_sort_pairs(tg_engine* h, const uint64_t* keys, int64_t n, int32_t begin_bit, int32_t n_passes, uint64_t* out_keys,
+                              uint32_t* out_index) {
+    return guard([&] {
+        if (!h || (n > 0 && (!keys || !out_keys || !out_index))) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        if (n < 0 || n >= ((int64_t)1 << 30) || begin_bit < 0 || n_passes < 1 || n_passes > RS_MAX_PASSES || begin_bit + 8 * n_passes > 64)
+            throw Error(TG_ERR_INVALID_ARG, "sort range out of bounds");
+        if (n == 0) return;
+        Engine& e = h->e;
+        std::lock_guard<std::mutex> g(e.mu);
+        TG_CUDA(cudaSetDevice(e.device));
+        const size_t k_b = ((size_t)n * 8 + 255) & ~(size_t)255, i_b = ((size_t)n * 4 + 255) & ~(size_t)255;
+        const size_t tmp_b = rs_temp_bytes(n, n_passes);
+        uint8_t* scr = e.scratch(2 * k_b + 2 * i_b + tmp_b + 256);
+        uint64_t* kb[2] = {(uint64_t*)scr, (uint64_t*)(scr + k_b)};
+        uint32_t* vb[2] = {(uint32_t*)(scr + 2 * k_b), (uint32_t*)(scr + 2 * k_b + i_b)};
+        const RsTemp T = rs_temp_carve(scr + 2 * k_b + 2 * i_b, n, n_passes);
+        TG_CUDA(cudaMemcpyAsync(kb[0], keys, (size_t)n * 8, cudaMemcpyHostToDevice, e.stream));
+        const int launches = rs_sort_pairs<uint32_t>(e.stream, kb, vb, n, begin_bit, n_passes, true, T, e.sm_count);
+        TG_CUDA(cudaGetLastError());
+        e.launches += launches;
+        RsControl ctl;
+        TG_CUDA(cudaMemcpyAsync(&ctl, T.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        TG_CUDA(cudaMemcpy(out_keys, kb[ctl.result], (size_t)n * 8, cudaMemcpyDeviceToHost));
+        TG_CUDA(cudaMemcpy(out_index, vb[ctl.result], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+int32_t tg_plan_kll_levels(const tg_plan* p, int32_t slot, int32_t level, double* items, int32_t cap) {
+    return guard_slot([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        if (slot < 0 || slot >= (int32_t)p->p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
+        const Slot& s = p->p.slots[slot];
+        int agg = -1;
+        for (int a : s.aggs)
+            if (p->p.aggs[a].kind == A_KLL) agg = a;
+        for (auto& r : s.stats)
+            if (r.agg_kll >= 0) agg = r.agg_kll;
+        if (agg < 0) throw Error(TG_ERR_INVALID_ARG, "slot has no quantile sketch");
+        std::vector<std::vector<double>> levels;
+        const int nl = kll_blob_levels(p->p.aggs[agg].blob, levels, nullptr);
+        if (nl < 0) return 0;
+        if (level < 0) return nl;
+        if (level >= nl) return 0;
+        const auto& l = levels[level];
+        for (size_t i = 0; items && i < l.size() && (int32_t)i < cap; ++i) items[i] = l[i];
+        return (int32_t)l.size();
+    });
+}
+
+int32_t tg_plan_histogram_pending(const tg_plan* p, int32_t* agg_indices, int32_t cap) {
+    return guard_slot([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        const std::vector<int> v = p->p.histogram_pending();
+        for (size_t i = 0; agg_indices && i < v.size() && (int32_t)i < cap; ++i) agg_indices[i] = v[i];
+        return (int32_t)v.size();
+    });
+}
+tg_status tg_plan_histogram_rebucket(tg_engine* h, tg_plan* p, const char* table_name, int32_t agg_index, uint64_t* counts, int32_t n_buckets) {
+    return guard([&] {
+        if (!h || !p || !table_name) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        Table* t = nullptr;
+        {
+            std::lock_guard<std::mutex> g(h->e.mu);
+            auto it = h->e.tables.find(table_name);
+            if (it != h->e.tables.end()) t = it->second.get();
+        }
+        if (!t) throw Error(TG_ERR_TABLE_NOT_FOUND, std::string("Error during planning: table 'datafusion.public.") + table_name + "' not found");
+        hist_rebucket(h->e, t, p->p, agg_index, counts, n_buckets);
+    });
+}
+tg_status tg_plan_histogram_install(tg_plan* p, int32_t agg_index, const uint64_t* counts, int32_t n_buckets) {
+    return guard([&] {
+        if (!p) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        p->p.histogram_install(agg_index, counts, n_buckets);
     });
 }
 

@@ -665,19 +665,46 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
         const Column* cb = b.c0 ? b.c0 : (b.pred_cols.empty() ? nullptr : b.pred_cols[0]);
         return ca < cb;
     });
+    // A pass is also bounded by the kernel's tables: SCAN_MAX_TERMS predicate terms, SCAN_MAX_COLS tile columns and
+    // SCAN_MAX_CODE predicate instructions. The reference evaluates every constraint on its own, so a suite never fails
+    // as a whole: a pass is closed before an op would overflow a table, and an op that cannot fit even alone fails
+    // only its own aggregate.
+    auto op_cols = [](const ScanOp& o, std::vector<const Column*>& out) {
+        auto add = [&](const Column* c) {
+            if (c && std::find(out.begin(), out.end(), c) == out.end()) out.push_back(c);
+        };
+        add(o.c0);
+        add(o.c1);
+        for (auto* c : o.pred_cols) add(c);
+    };
     size_t i = 0;
     while (i < ops.size()) {
         std::vector<ScanOp> pass;
-        int code = 0;
-        std::vector<Column*> cols;
+        int code = 0, terms = 0;
+        std::vector<const Column*> cols;
         while (i < ops.size() && pass.size() < (size_t)SCAN_CONSUMER_WARPS) {
-            int add_code = (int)ops[i].code.size();
-            if (code + add_code > SCAN_MAX_CODE && !pass.empty()) break;
+            const int add_code = (int)ops[i].code.size();
+            const int add_terms = ops[i].kind == UNIT_TERMS ? (int)ops[i].terms.size() : 0;
+            std::vector<const Column*> with = cols;
+            op_cols(ops[i], with);
+            if (!pass.empty() && (code + add_code > SCAN_MAX_CODE || terms + add_terms > SCAN_MAX_TERMS || with.size() > (size_t)SCAN_MAX_COLS)) break;
             code += add_code;
+            terms += add_terms;
+            cols.swap(with);
             pass.push_back(std::move(ops[i]));
             ++i;
         }
-        run_scan_pass(e, t, p, pass);
+        std::vector<int> pass_aggs;
+        for (auto& o : pass) pass_aggs.push_back(o.agg);
+        try {
+            run_scan_pass(e, t, p, pass);
+        } catch (Error& er) {
+            if (er.code == TG_ERR_CUDA) throw;
+            for (int id : pass_aggs) {
+                p.aggs[id].err = er.code;
+                p.aggs[id].err_msg = er.msg;
+            }
+        }
     }
 }
 

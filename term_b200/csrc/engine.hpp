@@ -155,6 +155,7 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
 void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                      // hashing.cu
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
 void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id);                         // hist.cu
+void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb); // hist.cu (two-phase multi-GPU histogram)
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);
 

@@ -305,11 +305,7 @@ void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id) {
     TG_CUDA(cudaMemsetAsync(P.first_row, 0x7F, h_b, e.stream));
     TG_CUDA(cudaMemsetAsync(d_n, 0, 256, e.stream));
     const size_t smem = (size_t)GRP_SLOTS * 24;
-    static bool attr = false;
-    if (!attr) {
-        TG_CUDA(cudaFuncSetAttribute(group_count_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr = true;
-    }
+    TG_CUDA(cudaFuncSetAttribute(group_count_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GRP_THREADS * GRP_ILP - 1) / (GRP_THREADS * GRP_ILP), (int64_t)e.sm_count));
     group_count_fused_kernel<<<grid, GRP_THREADS, smem, e.stream>>>(P);
     TG_CUDA(cudaGetLastError());

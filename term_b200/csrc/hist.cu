@@ -54,32 +54,20 @@ __global__ void __launch_bounds__(HIST_THREADS) hist_kernel(const double* __rest
         if (s_hist[i]) atomicAdd(&out[i], (unsigned long long)s_hist[i]);
 }
 
-void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id) {
-    Agg& a = p.aggs[agg_id];
-    Column* c = t.find(a.cols[0]);
-    if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t.valid_fields() + ".");
-    const int nb = std::min(std::max(a.iparam, 1), HIST_MAX_BUCKETS);
-    a.blob.assign((size_t)nb * 8, 0);
-    if (c->dtype != TG_FLOAT64) return;  // the slot reports the reference's Float64 downcast error from the NUM aggregate
-    const Agg* num = nullptr;
-    for (auto& o : p.aggs)
-        if (o.kind == A_NUM && o.cols.size() == 1 && o.cols[0] == a.cols[0]) num = &o;
-    if (!num || num->err != TG_OK || num->u[0] == 0 || t.n_rows == 0) return;
-    const double mn = num->f[3], mx = num->f[4];
-    a.f[0] = mn;
-    a.f[1] = mx;
+// counts of the Float64 column `c` over nb equal-width buckets of [mn, mx] -> counts[nb] (host); returns launches
+static int hist_count(Engine& e, Plan& p, const Column* c, int64_t n_rows, double mn, double mx, int nb, uint64_t* counts) {
     const double range = mx - mn, width = (range > 0.0 && nb > 1) ? range / (double)nb : 1.0;
     // algorithmic bytes: the column is read a second time (the reference scans it twice as well)
-    p.stats.bytes_scanned += (uint64_t)t.n_rows * 8 + (c->validity.p ? (uint64_t)(t.n_rows + 7) / 8 : 0);
+    p.stats.bytes_scanned += (uint64_t)n_rows * 8 + (c->validity.p ? (uint64_t)(n_rows + 7) / 8 : 0);
     uint8_t* scr = e.scratch((size_t)HIST_MAX_BUCKETS * 8 + 256);
     unsigned long long* d_out = (unsigned long long*)scr;
     TG_CUDA(cudaEventRecord(e.ev[6], e.stream));
     TG_CUDA(cudaMemsetAsync(d_out, 0, (size_t)nb * 8, e.stream));
     const int64_t per_cta = (int64_t)HIST_THREADS * HIST_ILP;
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t.n_rows + per_cta - 1) / per_cta, (int64_t)e.sm_count * 8));
-    hist_kernel<<<grid, HIST_THREADS, 0, e.stream>>>((const double*)c->values.p, (const uint32_t*)c->validity.p, t.n_rows, mn, width, nb, d_out);
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n_rows + per_cta - 1) / per_cta, (int64_t)e.sm_count * 8));
+    hist_kernel<<<grid, HIST_THREADS, 0, e.stream>>>((const double*)c->values.p, (const uint32_t*)c->validity.p, n_rows, mn, width, nb, d_out);
     TG_CUDA(cudaGetLastError());
-    TG_CUDA(cudaMemcpyAsync(a.blob.data(), d_out, (size_t)nb * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaMemcpyAsync(counts, d_out, (size_t)nb * 8, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaEventRecord(e.ev[7], e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
     float ms = 0;
@@ -88,6 +76,53 @@ void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id) {
     p.stats.gpu_ms += ms;
     p.stats.launches += 1;
     e.launches += 1;
+    return 1;
+}
+
+static const Agg* hist_num_agg(const Plan& p, const Agg& a) {
+    const Agg* num = nullptr;
+    for (auto& o : p.aggs)
+        if (o.kind == A_NUM && o.cols.size() == 1 && o.cols[0] == a.cols[0]) num = &o;
+    return num;
+}
+
+void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id) {
+    Agg& a = p.aggs[agg_id];
+    Column* c = t.find(a.cols[0]);
+    if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t.valid_fields() + ".");
+    const int nb = std::min(std::max(a.iparam, 1), HIST_MAX_BUCKETS);
+    a.blob.assign((size_t)nb * 8, 0);
+    if (c->dtype != TG_FLOAT64) return;  // the slot reports the reference's Float64 downcast error from the NUM aggregate
+    const Agg* num = hist_num_agg(p, a);
+    if (!num || num->err != TG_OK || num->u[0] == 0 || t.n_rows == 0) {
+        a.blob.clear();  // a shard without values has no range of its own: it merges into any range
+        return;
+    }
+    a.f[0] = num->f[3];
+    a.f[1] = num->f[4];
+    hist_count(e, p, c, t.n_rows, a.f[0], a.f[1], nb, (uint64_t*)a.blob.data());
+}
+
+// Second phase of a row-sharded histogram (analyzers/advanced/histogram.rs:184-290 takes the bucket bounds from the
+// table-wide MIN / MAX): after the shards' partials were merged, the plan's NUM aggregate holds the GLOBAL min / max;
+// this re-counts the LOCAL shard `t` against those bounds. The host layer sums the counts of all shards (a u64
+// all-reduce) and installs them (Plan::histogram_install).
+void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb_out) {
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    e.sync_copies();
+    if (agg_id < 0 || agg_id >= (int)p.aggs.size() || p.aggs[agg_id].kind != A_HIST) throw Error(TG_ERR_INVALID_ARG, "not a histogram aggregate");
+    Agg& a = p.aggs[agg_id];
+    const int nb = std::min(std::max(a.iparam, 1), HIST_MAX_BUCKETS);
+    if (nb_out != nb || !counts) throw Error(TG_ERR_INVALID_ARG, "histogram has " + std::to_string(nb) + " buckets");
+    for (int i = 0; i < nb; ++i) counts[i] = 0;
+    const Agg* num = hist_num_agg(p, a);
+    if (!num || num->err != TG_OK || num->u[0] == 0 || num->u[4]) return;
+    if (!t || t->n_rows == 0) return;
+    Column* c = t->find(a.cols[0]);
+    if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t->valid_fields() + ".");
+    if (c->dtype != TG_FLOAT64) return;
+    hist_count(e, p, c, t->n_rows, num->f[3], num->f[4], nb, counts);
 }
 
 }  // namespace tg

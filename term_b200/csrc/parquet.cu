@@ -266,6 +266,12 @@ static std::vector<tg_parquet_page> walk_pages(const uint8_t* chunk, int64_t n_b
         pg.header_offset = off;
         pg.body_offset = off + (int64_t)hl;
         if (pg.body_offset + pg.body_bytes > n_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet page runs past the column chunk");
+        // every count / length below comes from the file: nothing negative, no level section longer than its page
+        if (pg.num_values < 0 || pg.num_nulls < 0 || pg.uncompressed_bytes < 0)
+            throw Error(TG_ERR_INVALID_ARG, "Parquet page header: negative value count or size");
+        if (pg.definition_levels_bytes < 0 || pg.repetition_levels_bytes < 0 ||
+            (int64_t)pg.definition_levels_bytes + (int64_t)pg.repetition_levels_bytes > (int64_t)pg.body_bytes)
+            throw Error(TG_ERR_INVALID_ARG, "Parquet page header: level sections do not fit the page");
         out.push_back(pg);
         off = pg.body_offset + pg.body_bytes;
     }
@@ -289,10 +295,14 @@ int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t nu
         if (rows + pg.num_values > num_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: more values than the chunk metadata says");
         int64_t off = pg.body_offset, len = pg.definition_levels_bytes;
         if (pg.version == 1) {
+            if (pg.body_bytes < 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: data page too short");
             uint32_t l;
             memcpy(&l, chunk + off, 4);
             off += 4;
             len = l;
+            if ((int64_t)l > (int64_t)pg.body_bytes - 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
+        } else if (pg.repetition_levels_bytes != 0) {
+            throw Error(TG_ERR_UNSUPPORTED, "Parquet: repeated column");
         }
         decode_levels(chunk + off, chunk + off + len, bits.data(), rows, pg.num_values);
         rows += pg.num_values;
@@ -337,6 +347,7 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
                 if (pg.body_bytes < 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: data page too short");
                 uint32_t len;
                 memcpy(&len, chunk + pg.body_offset, 4);
+                if ((int64_t)len > (int64_t)pg.body_bytes - 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
                 s.levels_off = pg.body_offset + 4;
                 s.levels_bytes = len;
                 s.values_off = s.levels_off + len;

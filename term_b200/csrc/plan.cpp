@@ -741,13 +741,17 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
                 for (int i = 0; i < 8; ++i) a.u[i] += u[i];
                 break;
             case A_HIST:
-                // bucket bounds come from the shard's own min / max: shards only add up when those agree
-                if (blob.empty()) break;
-                if (a.blob.empty()) {
+                // bucket bounds come from the shard's own min / max: the counts only add up when those agree. Shards
+                // with different ranges leave the aggregate PENDING (u[7] = 1): the host layer then re-counts every
+                // shard against the merged (global) min / max and installs the sums (two-phase histogram,
+                // tg_plan_histogram_pending / _rebucket / _install); finalize reports an error while it is pending.
+                if (u[7]) a.u[7] = 1;
+                if (blob.empty()) break;  // that shard held no values
+                if (a.blob.empty() && !a.u[7]) {
                     a.blob = blob;
                     a.f[0] = f[0];
                     a.f[1] = f[1];
-                } else if (a.f[0] == f[0] && a.f[1] == f[1] && a.blob.size() == blob.size()) {
+                } else if (!a.u[7] && a.f[0] == f[0] && a.f[1] == f[1] && a.blob.size() == blob.size()) {
                     for (size_t i = 0; i + 8 <= blob.size(); i += 8) {
                         uint64_t x, y;
                         memcpy(&x, a.blob.data() + i, 8);
@@ -755,9 +759,9 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
                         x += y;
                         memcpy(a.blob.data() + i, &x, 8);
                     }
-                } else if (a.err == TG_OK) {
-                    a.err = TG_ERR_UNSUPPORTED;
-                    a.err_msg = "histogram shards with different value ranges cannot be merged (needs a global min / max first)";
+                } else {
+                    a.u[7] = 1;
+                    a.blob.clear();
                 }
                 break;
             case A_PRED:
@@ -839,6 +843,28 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
                 break;
         }
     }
+}
+
+// two-phase histogram: the HIST aggregates whose shards disagreed on [min, max]
+std::vector<int> Plan::histogram_pending() const {
+    std::vector<int> out;
+    for (size_t i = 0; i < aggs.size(); ++i)
+        if (aggs[i].kind == A_HIST && aggs[i].u[7] && aggs[i].err == TG_OK) out.push_back((int)i);
+    return out;
+}
+void Plan::histogram_install(int agg_id, const uint64_t* counts, int nb) {
+    if (agg_id < 0 || agg_id >= (int)aggs.size() || aggs[agg_id].kind != A_HIST) throw Error(TG_ERR_INVALID_ARG, "not a histogram aggregate");
+    Agg& a = aggs[agg_id];
+    const int want = std::min(std::max(a.iparam, 1), 1000);
+    if (nb != want || !counts) throw Error(TG_ERR_INVALID_ARG, "histogram has " + std::to_string(want) + " buckets");
+    a.blob.assign((size_t)nb * 8, 0);
+    memcpy(a.blob.data(), counts, (size_t)nb * 8);
+    for (auto& o : aggs)
+        if (o.kind == A_NUM && o.cols.size() == 1 && o.cols[0] == a.cols[0]) {
+            a.f[0] = o.f[3];
+            a.f[1] = o.f[4];
+        }
+    a.u[7] = 0;
 }
 
 // ---- grouped blob: [u64 n_groups] then per group: u32 key_len, key bytes (fields joined by \x1f), u64 total, u64 non_null
@@ -1648,6 +1674,13 @@ static void finalize_histogram(Plan& p, Slot& s) {
     s.has_message = false;
     if (num.err != TG_OK || h.err != TG_OK) {
         analyzer_error(s, num.err != TG_OK ? num : h);
+        return;
+    }
+    if (h.u[7] && !num.u[4] && num.u[0]) {
+        r.error = 2;
+        r.metric_kind = 3;
+        s.has_message = true;
+        s.message = "histogram shards with different value ranges: run the second phase (tg_plan_histogram_rebucket / _install) before finalize";
         return;
     }
     if (num.u[4]) {  // MIN(Int64) is Int64: the reference fails its Float64 downcast (histogram.rs:203-208)

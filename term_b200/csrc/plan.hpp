@@ -26,7 +26,7 @@ enum AggKind : int32_t {
     A_GROUPED = 9,   // blob = group table
     A_SPEARMAN = 10, // same layout as A_PAIR over min-ranks
     A_LENGTH = 11,   // COUNT(CASE WHEN lo <= LENGTH(c) <= hi ..)  u0 matching non-null rows u1 nulls u2 rows
-    A_HIST = 12,     // equal-width histogram over [min, max] of the column's NUM aggregate: f0 min f1 max u0 is_i64 ; blob = bucket counts
+    A_HIST = 12,     // equal-width histogram over [min, max] of the column's NUM aggregate: f0 min f1 max u0 is_i64 u7 pending (shards disagreed on the range) ; blob = bucket counts
 };
 
 struct Agg {
@@ -137,6 +137,8 @@ struct Plan {
     void partial_export(uint8_t* buf) const;
     void partial_merge(const uint8_t* buf, size_t n);  // merge another shard's partials into ours
     void finalize();                                    // slots <- aggregates
+    std::vector<int> histogram_pending() const;         // HIST aggregates waiting for the second (global-range) phase
+    void histogram_install(int agg_id, const uint64_t* counts, int nb);
 };
 
 // slot constructors (validate like the reference constructors do; throw Error)
@@ -175,6 +177,7 @@ struct KllHost;
 void kll_blob_merge(std::vector<uint8_t>& into, const std::vector<uint8_t>& other);
 bool kll_blob_query(const std::vector<uint8_t>& blob, double phi, double* out);
 void kll_blob_summary(const std::vector<uint8_t>& blob, uint64_t* n, double* mn, double* mx);
+int kll_blob_levels(const std::vector<uint8_t>& blob, std::vector<std::vector<double>>& levels, uint64_t* k);
 
 // grouped table blob helpers (plan.cpp)
 void grouped_blob_merge(std::vector<uint8_t>& into, const std::vector<uint8_t>& other);

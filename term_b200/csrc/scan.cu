@@ -1055,15 +1055,12 @@ size_t scan_smem_bytes(const ScanParams& P) {
 }
 
 cudaError_t scan_launch(const ScanParams& P, int grid, ScanAggOut* d_out, cudaStream_t stream) {
-    static bool attr_set = false;
     size_t smem = scan_smem_bytes(P);
-    if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-        if (e != cudaSuccess) return e;
-        attr_set = true;
-    }
+    // the opt-in is per device (and per context): set it before every launch, it is a host-side table write
+    cudaError_t e = cudaFuncSetAttribute(scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    if (e != cudaSuccess) return e;
     scan_kernel<<<grid, SCAN_THREADS, smem, stream>>>(P);
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     scan_finalize_kernel<<<P.n_aggs, FIN_THREADS, 0, stream>>>(P, grid, d_out);
     return cudaGetLastError();

@@ -342,6 +342,24 @@ def _tensor_from_ptr(ptr, n, dev, typestr="<i8"):
     return torch.as_tensor(w, device=dev)
 
 
+def histogram_second_phase(plan, ctx, table):
+    """Two-phase histogram (analyzers/advanced/histogram.rs:184-290: bucket bounds come from the table-wide MIN / MAX).
+    After the merge every rank holds the global min / max; aggregates whose shards disagreed on the range are
+    re-counted per shard against it, the counts are summed with one small all-reduce, installed, and the plan is
+    finalized again. The pending list is derived from the merged state, so every rank takes the same branch."""
+    pending = plan.histogram_pending()
+    if not pending:
+        return
+    dev = _device()
+    for i in pending:
+        counts = plan.histogram_rebucket(ctx, table, i)
+        # int64 on the wire (NCCL has no u64 sum in torch); counts are < 2^63
+        t = torch.tensor(counts, dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        plan.histogram_install(i, [int(x) for x in t.tolist()])
+    plan.finalize()
+
+
 def execute_distributed(plan, ctx, table="data"):
     """Each rank: shuffle the keys of DISTINCT / FK aggregates, gather the column pairs of SPEARMAN aggregates,
     partial execute on its shard -> exchange -> ordered merge -> finalize."""
@@ -379,6 +397,7 @@ def execute_distributed(plan, ctx, table="data"):
                 redirected.append((i, 0))
         plan.execute_partial(ctx, table)
         exchange_and_finalize(plan, ctx)
+        histogram_second_phase(plan, ctx, table)
     finally:
         for i, which in redirected:
             plan.redirect(i, which, None)

@@ -288,3 +288,182 @@ def test_gloo_spearman_gather_gives_global_ranks(built_lib, world):
     for r in range(world):
         assert results[r][0] == len(x), "every rank finalizes to the global pair count"
         assert abs(results[r][1] - want) <= 1e-9, (results[r][1], want)
+
+
+# ---- string / length / KLL / grouped / histogram partials across ranks (SURVEY §8e K2, K4, K5 + the two-phase histogram) ----
+M_ROWS = 6_007
+
+
+def _mixed_table():
+    rng = np.random.default_rng(21)
+    s = []
+    for i in range(M_ROWS):
+        r = rng.random()
+        s.append(None if r < 0.05 else (f"user{i}@example.com" if r < 0.6 else "x" * int(rng.integers(0, 30))))
+    v = np.round(rng.normal(10.0, 4.0, M_ROWS), 2)
+    v[:100] -= 50.0     # the global minimum lives in the first shard only
+    v[-100:] += 80.0    # .. and the maximum in the last
+    g = [f"g{int(x)}" for x in rng.integers(0, 7, M_ROWS)]
+    g[M_ROWS - 1] = "only_in_last_shard"
+    return pa.table({"s": pa.array(s, type=pa.string()), "v": pa.array(v, mask=rng.random(M_ROWS) < 0.1), "g": pa.array(g)})
+
+
+def _hist_counts(vals, mn, mx, nb):
+    """bucket rule of analyzers/advanced/histogram.rs:256-345 (first i with lower_i <= v < upper_i, else the last)"""
+    rng_ = mx - mn
+    w = rng_ / nb if (rng_ > 0.0 and nb > 1) else 1.0
+    lowers = [mn + (i * w) for i in range(nb)]
+    uppers = [(mx + w * 0.001) if i == nb - 1 else mn + ((i + 1) * w) for i in range(nb)]
+    counts = [0] * nb
+    for x in vals:
+        b = nb - 1
+        for i in range(nb):
+            if lowers[i] <= x < uppers[i]:
+                b = i
+                break
+        counts[b] += 1
+    return counts
+
+
+def mixed_shard_blob(plan, t):
+    """partial blob of a row shard for REGEX (5), KLL (8), GROUPED (9), LENGTH (11), HIST (12) (+ the NUM aggregate the
+    histogram reads its range from); layouts: term_b200/csrc/plan.hpp, kll_host.cpp, plan.cpp (grouped blob)"""
+    from oracle import term_oracle as O
+    cols = O.table_cols(t)
+    n = t.num_rows
+    out = [struct.pack("<Q", len(plan.aggregates()))]
+    for kind, key in plan.aggregates():
+        u, f, blob = [0] * 8, [0.0] * 8, b""
+        parts = key.split("|")
+        if kind == 5:
+            flags = int(parts[2])
+            m = O.regex_matches(cols[parts[1]], "|".join(parts[3:]), case_insensitive=bool(flags & 1), trim=bool(flags & 2))
+            u[0], u[1], u[2] = sum(1 for x in m if x), sum(1 for x in m if x is None), n
+        elif kind == 11:
+            lo, hi = int(parts[2]), int(parts[3])
+            c = cols[parts[1]]
+            lens = [len(x) for x, ok in zip(c.values, c.valid) if ok]
+            u[0], u[1], u[2] = sum(1 for L in lens if lo <= L <= hi), n - len(lens), n
+        elif kind == 2:
+            c = cols[parts[1]]
+            vv = np.asarray(c.values, dtype=np.float64)[c.valid]
+            u[0] = len(vv)
+            if len(vv):
+                K = float(vv[0])
+                d = vv - K
+                f[0], f[1], f[2], f[3], f[4], f[5] = K, math.fsum(d), math.fsum(d * d), float(vv.min()), float(vv.max()), math.fsum(vv)
+        elif kind == 12:
+            c = cols[parts[1]]
+            vv = np.asarray(c.values, dtype=np.float64)[c.valid]
+            nb = int(parts[2])
+            if len(vv):
+                f[0], f[1] = float(vv.min()), float(vv.max())
+                blob = struct.pack(f"<{nb}Q", *_hist_counts(vv, f[0], f[1], nb))
+        elif kind == 8:
+            c = cols[parts[1]]
+            vv = np.sort(np.asarray(c.values, dtype=np.float64)[c.valid])
+            k = int(parts[2])
+            u[0] = len(vv)
+            mn, mx = (float(vv[0]), float(vv[-1])) if len(vv) else (math.inf, -math.inf)
+            blob = struct.pack("<QddQQQ", len(vv), mn, mx, k, max(8 * k, 64), 1) + struct.pack("<Q", len(vv)) + vv.tobytes()
+        elif kind == 9:
+            tgt, gcols = cols[parts[1]], [cols[p] for p in parts[2:]]
+            groups = {}
+            for i in range(n):
+                gk = "\x1f".join(str(gc.values[i]) for gc in gcols)
+                tt, nn = groups.get(gk, (0, 0))
+                groups[gk] = (tt + 1, nn + (1 if tgt.valid[i] else 0))
+            blob = struct.pack("<Q", len(groups))
+            for gk, (tt, nn) in groups.items():
+                kb = gk.encode()
+                blob += struct.pack("<I", len(kb)) + kb + struct.pack("<QQ", tt, nn)
+        else:
+            raise AssertionError(f"unexpected aggregate {kind} {key}")
+        pad = (-len(blob)) % 8
+        out.append(struct.pack("<QQ", kind, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *f) + struct.pack("<Q", len(blob)) + blob +
+                   b"\0" * pad + struct.pack("<Q", 0))
+    return b"".join(out)
+
+
+def _mixed_plan(T):
+    cb = (T.Check.builder("c").validates_regex("s", "@", 0.5).validates_email("s", 0.5).has_min_length("s", 5).has_length_between("s", 1, 20))
+    suite = T.ValidationSuite.builder("mixed").check(cb.build()).build()
+    plan, slots = suite.build_plan()
+    kll = T.KllSketchAnalyzer("v", k=64, quantiles=[0.1, 0.5, 0.9])._add_to(plan)
+    grp = T.GroupedCompletenessAnalyzer("v", ["g"])._add_to(plan)
+    hist = T.HistogramAnalyzer("v", 12)._add_to(plan)
+    return plan, slots, kll, grp, hist
+
+
+def mixed_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import term_b200 as T
+        from term_b200.distributed import allgather_blobs, merge_partials
+        t = _mixed_table()
+        bounds = [0, M_ROWS // 3, M_ROWS // 3, M_ROWS][: world + 1] if world == 3 else [M_ROWS * r // world for r in range(world + 1)]
+        sh = t.slice(bounds[rank], bounds[rank + 1] - bounds[rank])  # world 3: the middle rank holds an EMPTY shard
+        plan, slots, kll, grp, hist = _mixed_plan(T)
+        assert sorted({k for k, _ in plan.aggregates()}) == [2, 5, 8, 9, 11, 12]
+        merge_partials(plan, allgather_blobs(mixed_shard_blob(plan, sh)))
+        # two-phase histogram: the merged NUM aggregate holds the global range; every rank re-counts its shard, the
+        # counts are all-reduced (term_b200.distributed.histogram_second_phase does this with the device re-count)
+        pending = plan.histogram_pending()
+        assert len(pending) == 1
+        assert plan.analyzer_result(hist).error == 2
+        vv = np.asarray(sh.column("v").drop_null())
+        full = np.asarray(t.column("v").drop_null())
+        mine = torch.tensor(_hist_counts(vv, float(full.min()), float(full.max()), 12), dtype=torch.int64)
+        dist.all_reduce(mine)
+        plan.histogram_install(pending[0], [int(x) for x in mine.tolist()])
+        plan.finalize()
+        res = [plan.result(s) for _, _, s in slots]
+        k, g, h = plan.analyzer_result(kll), plan.analyzer_result(grp), plan.analyzer_result(hist)
+        q.put((rank, ([(r.name, r.status.name, r.metric, r.message) for r in res], k.map, k.u[0], g.map, h.map, plan.kll_levels(kll))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_string_kll_grouped_histogram_partials_merge(built_lib, world):
+    from oracle import term_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 35500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=mixed_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for r in range(1, world):
+        assert results[r] == results[0], "ranks disagree after the ordered merge"
+    res, kmap, kn, gmap, hmap, levels = results[0]
+    t = _mixed_table()
+    want = [O.format_constraint(t, "s", "Regex", 0.5, arg="@"), O.format_constraint(t, "s", "Email", 0.5),
+            O.length_constraint(t, "s", "Min", 5), O.length_constraint(t, "s", "Between", 1, 20)]
+    for (name, status, metric, message), o in zip(res, want):
+        assert status.lower() == o.status and metric == o.metric and message == o.message, (name, metric, o)
+    # KLL: 5 400 values through a k = 64 sketch (capacity 512): compacted on merge, still inside the reference bound
+    clean = np.sort(np.asarray(t.column("v").drop_null()))
+    assert kn == len(clean) and kmap["count"] == len(clean) and kmap["min"] == clean[0] and kmap["max"] == clean[-1]
+    for qq in (0.1, 0.5, 0.9):
+        assert O.rank_error(clean, kmap["quantile_" + O.rust_f64(qq)], qq) <= 1.65 / math.sqrt(64)
+    assert sum(len(l) for l in levels) <= 512 and len(levels) >= 4, "the merged sketch is a compacted multi-level ladder"
+    total_w = sum(len(l) << i for i, l in enumerate(levels))
+    assert total_w == len(clean), "weight-preserving compaction: item weights add up to the exact count"
+    for l in levels:
+        assert l == sorted(l)
+    # grouped: a group only one rank saw survives the merge
+    gw = O.grouped_completeness(t, "v", ["g"])
+    assert {k: v for k, v in gmap.items() if not k.startswith("__")} == {k[0]: nn / tt for k, (tt, nn) in gw.items()}
+    assert "only_in_last_shard" in gmap
+    hw = O.an_histogram(t, "v", 12)
+    assert hmap["min"] == hw["min"] and hmap["max"] == hw["max"] and hmap["total_count"] == hw["total_count"]
+    for i, (lo, hi, cnt) in enumerate(hw["buckets"]):
+        assert hmap[f"bucket_{i}.lower"] == lo and hmap[f"bucket_{i}.upper"] == hi and hmap[f"bucket_{i}.count"] == cnt

@@ -215,3 +215,51 @@ def test_hybrid_level_streams_of_any_shape_expand_exactly(built_lib, seed):
     assert (np.unpackbits(bits, bitorder="little")[: len(want)].astype(bool) == want).all()
     n_pages = F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, None, 0)
     assert n_pages == len(pages)
+
+
+# ---- malformed page headers: every count / length in a page header is file-controlled ----
+def _raw_page_v1(num_values: int, levels_len_field: int, payload: bytes) -> bytes:
+    body = (levels_len_field & 0xFFFFFFFF).to_bytes(4, "little") + payload
+    dph = b"\x15" + _zz(num_values) + b"\x15" + _zz(0) + b"\x15" + _zz(3) + b"\x15" + _zz(3) + b"\x00"
+    return b"\x15" + _zz(0) + b"\x15" + _zz(len(body)) + b"\x15" + _zz(len(body)) + b"\x2c" + dph + b"\x00" + body
+
+
+def _raw_page_v2(num_values: int, num_nulls: int, def_bytes: int, rep_bytes: int, body: bytes) -> bytes:
+    # DataPageHeaderV2 {1 num_values, 2 num_nulls, 3 num_rows, 4 encoding, 5 def bytes, 6 rep bytes}: field id 8 of PageHeader
+    h2 = (b"\x15" + _zz(num_values) + b"\x15" + _zz(num_nulls) + b"\x15" + _zz(max(num_values, 0)) + b"\x15" + _zz(0) +
+          b"\x15" + _zz(def_bytes) + b"\x15" + _zz(rep_bytes) + b"\x00")
+    return b"\x15" + _zz(3) + b"\x15" + _zz(len(body)) + b"\x15" + _zz(len(body)) + b"\x5c" + h2 + b"\x00" + body
+
+
+def _validity_status(chunk_bytes: bytes, num_values: int):
+    chunk = np.frombuffer(chunk_bytes, dtype=np.uint8)
+    bits = np.zeros(max(1, (max(num_values, 0) + 7) // 8) + 64, dtype=np.uint8)
+    return F.lib().tg_parquet_chunk_validity(chunk.ctypes.data, chunk.size, num_values, bits.ctypes.data)
+
+
+def test_malformed_page_headers_are_rejected(built_lib):
+    lv8, _ = _hybrid([("rle", 8, 1)])
+    good = _page_v1(lv8, b"\x00" * 64, 8)
+    assert _validity_status(good, 8) == 8
+    # a negative value count on one page offset by a larger one on the next still sums to the chunk's count
+    neg = _raw_page_v1(-8, len(lv8), lv8 + b"\x00" * 64)
+    lv16, _ = _hybrid([("rle", 16, 1)])
+    assert _validity_status(neg + _page_v1(lv16, b"\x00" * 128, 16), 8) < 0
+    assert "negative" in F.last_error()
+    # V1 levels length larger than the page body
+    assert _validity_status(_raw_page_v1(8, 1 << 20, lv8), 8) < 0
+    assert _validity_status(_raw_page_v1(8, 0xFFFFFFF0, lv8), 8) < 0
+    # V1 page shorter than its own 4-byte length field
+    dph = b"\x15" + _zz(8) + b"\x15" + _zz(0) + b"\x15" + _zz(3) + b"\x15" + _zz(3) + b"\x00"
+    short = b"\x15" + _zz(0) + b"\x15" + _zz(2) + b"\x15" + _zz(2) + b"\x2c" + dph + b"\x00" + b"\x00\x00"
+    assert _validity_status(short, 8) < 0
+    # V2: negative / oversized level sections
+    assert _validity_status(_raw_page_v2(8, 0, -4, 0, lv8 + b"\x00" * 64), 8) < 0
+    assert _validity_status(_raw_page_v2(8, 0, 0, -4, lv8 + b"\x00" * 64), 8) < 0
+    assert _validity_status(_raw_page_v2(8, 0, 1 << 20, 0, lv8 + b"\x00" * 64), 8) < 0
+    assert _validity_status(_raw_page_v2(8, -1, len(lv8), 0, lv8 + b"\x00" * 64), 8) < 0
+    assert _validity_status(_raw_page_v2(8, 0, len(lv8), 0, lv8 + b"\x00" * 64), 8) == 8
+    # inspect agrees
+    for bad in (neg, _raw_page_v2(8, 0, -4, 0, lv8)):
+        chunk = np.frombuffer(bad, dtype=np.uint8)
+        assert F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, None, 0) < 0
