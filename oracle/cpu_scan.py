@@ -37,6 +37,7 @@ def lib():
     L.to_sum_f64.argtypes = [P, P, I64, C.POINTER(D), C.POINTER(I64)]
     L.to_var_f64.argtypes = [P, P, I64, C.POINTER(D), C.POINTER(I64)]
     L.to_corr_f64.argtypes = [P, P, P, P, I64, C.POINTER(D), C.POINTER(D), C.POINTER(I64)]
+    L.to_fused_c2.argtypes = [P, P, P, P, P, P, P, P, D, I64, I64, C.POINTER(D)]
     L.to_pred_gt_lt.restype = I64
     L.to_pred_gt_lt.argtypes = [P, P, D, P, P, I64, I64]
     _lib = L
@@ -108,6 +109,15 @@ def numeric_suite(cols, n):
     out["corr_f0_f1"] = corr_f64(cols["f0"][0], cols["f0"][1], cols["f1"][0], cols["f1"][1])[0]
     out["satisfies"] = pred_gt_lt(cols["f2"][0], cols["f2"][1], 0.0, cols["i0"][0], cols["i0"][1], 1000000) / n
     return out
+
+
+def numeric_suite_fused(cols, n):
+    """The same five constraints in ONE scan over the four referenced columns (the fused CPU variant of BASELINE.md
+    §2.2: what a working optimizer/ would hand DataFusion). Same keys as numeric_suite."""
+    out = (C.c_double * 4)()
+    lib().to_fused_c2(_p(cols["f0"][0]), _p(cols["f0"][1]), _p(cols["f1"][0]), _p(cols["f1"][1]), _p(cols["f2"][0]), _p(cols["f2"][1]),
+                      _p(cols["i0"][0]), _p(cols["i0"][1]), 0.0, 1000000, n, out)
+    return {"size": float(n), "min_f0": out[0], "mean_f1": out[1], "corr_f0_f1": out[2], "satisfies": out[3]}
 
 
 def pack_validity(mask: np.ndarray) -> np.ndarray:

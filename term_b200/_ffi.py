@@ -8,7 +8,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtermgpu.so")
+# TG_LIB selects another build of the same library (kernel-parameter sweeps on the GPU box); the product is libtermgpu.so
+LIB_PATH = os.environ.get("TG_LIB") or os.path.join(_HERE, "libtermgpu.so")
 
 
 class TermGpuError(RuntimeError):

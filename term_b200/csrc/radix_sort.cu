@@ -115,36 +115,28 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const unsigned long lo
 }
 
 // ------------------------------------------------------------------------------------------------- one pass ----
-template <typename V>
+// Shared memory of a tile. The staging buffer holds the tile's keys in tile-sorted order, then (after they have left)
+// its values: what the second write-out needs from the keys — their digit — is kept as one byte per position.
 struct RsSmem {
-    uint64_t keys[RS_TILE];
-    V vals[RS_TILE];
+    uint64_t stage[RS_TILE];               // keys, then values (V is at most 8 bytes)
+    uint8_t dig[RS_TILE];                  // digit of the key at tile-sorted position j
     uint32_t hist[RS_WARPS][RS_BINS];      // per-warp digit counts -> exclusive offsets of the warp inside the tile's bin
+    uint32_t block_hist[RS_BINS];          // the tile's digit counts (published early as the look-back aggregate)
     uint32_t digit_start[RS_BINS];         // first tile-sorted position of the bin
     long long global_base[RS_BINS];        // destination index of tile-sorted position j of bin d = global_base[d] + j
     uint32_t warp_tot[RS_BINS / 32];
     uint32_t tile;
 };
-struct RsNoVal {};
-template <>
-struct RsSmem<RsNoVal> {
-    uint64_t keys[RS_TILE];
-    uint32_t hist[RS_WARPS][RS_BINS];
-    uint32_t digit_start[RS_BINS];
-    long long global_base[RS_BINS];
-    uint32_t warp_tot[RS_BINS / 32];
-    uint32_t tile;
-};
 
-constexpr uint32_t RS_FLAG_AGG = 1u, RS_FLAG_PREFIX = 2u;
+enum : uint32_t { RS_FLAG_AGG = 1u, RS_FLAG_PREFIX = 2u };
+constexpr int RS_LOOKBACK_BATCH = 4;  // predecessor status words fetched speculatively per look-back round trip
 
 template <typename V, bool HAS_V, bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, uint64_t* k1, V* v0, V* v1, int64_t n, int shift, int pass,
-                                                             RsControl* ctl, const unsigned long long* __restrict__ bin_base,
-                                                             uint32_t* status) {
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_pass_kernel(uint64_t* k0, uint64_t* k1, V* v0, V* v1, int64_t n, int shift, int pass,
+                                                                            RsControl* ctl, const unsigned long long* __restrict__ bin_base,
+                                                                            uint32_t* status) {
     extern __shared__ __align__(16) uint8_t rs_smem_raw[];
-    using Smem = RsSmem<typename std::conditional<HAS_V, V, RsNoVal>::type>;
-    Smem& S = *reinterpret_cast<Smem*>(rs_smem_raw);
+    RsSmem& S = *reinterpret_cast<RsSmem*>(rs_smem_raw);
     if (ctl->skip[pass]) return;
     const uint32_t which = ctl->src[pass];
     const uint64_t* __restrict__ ksrc = which ? k1 : k0;
@@ -155,6 +147,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) S.tile = atomicAdd(&ctl->tile_counter[pass], 1u);
     for (int i = tid; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&S.hist[0][0])[i] = 0;
+    if (tid < RS_BINS) S.block_hist[tid] = 0;
     __syncthreads();
     const uint32_t tile = S.tile;
     const int64_t tile_base = (int64_t)tile * RS_TILE;
@@ -169,6 +162,32 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
     for (int i = 0; i < RS_ITEMS; ++i) {
         const int pos = wbase + i * 32;
         key[i] = pos < n_tile ? ksrc[tile_base + pos] : ~0ull;
+    }
+    // ---- the tile's digit counts first (plain shared atomics, no ordering needed): the aggregate the successors' look-back
+    // waits for is published before the expensive stable ranking starts
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) atomicAdd(&S.block_hist[(uint32_t)(key[i] >> shift) & (RS_BINS - 1)], 1u);
+    __syncthreads();
+    uint32_t tile_count = 0, real_count = 0;
+    volatile uint32_t* st = status + (size_t)tile * RS_BINS + tid;
+    if (tid < RS_BINS) {
+        tile_count = S.block_hist[tid];
+        // the padding keys are not data: they never leave the tile and are not counted
+        real_count = tile_count - (tid == RS_BINS - 1 ? (uint32_t)(RS_TILE - n_tile) : 0u);
+        *st = (real_count << 2) | (tile == 0 ? RS_FLAG_PREFIX : RS_FLAG_AGG);
+        // exclusive scan of tile_count over the bins -> first tile-sorted position of each bin
+        uint32_t x = tile_count;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) S.warp_tot[warp] = x;
+        // (bins live in warps 0..7 only: a named barrier over those 256 threads orders warp_tot)
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+        uint32_t pre = 0;
+        for (int i = 0; i < warp; ++i) pre += S.warp_tot[i];
+        S.digit_start[tid] = pre + x - tile_count;
     }
     // ---- stable ranking inside the warp: items with equal digits are ordered by (i, lane) = by position
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -188,8 +207,7 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
     }
     __syncthreads();
 
-    // ---- per bin (thread d): exclusive scan of the warps' counts, tile count, look-back
-    uint32_t tile_count = 0;
+    // ---- per bin (thread d): exclusive scan of the warps' counts; decoupled look-back over the predecessor tiles
     if (tid < RS_BINS) {
         uint32_t sum = 0;
 #pragma unroll
@@ -198,42 +216,30 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
             S.hist[w][tid] = sum;
             sum += t;
         }
-        tile_count = sum;
-        // the padding keys are not data: they never leave the tile and are not counted
-        uint32_t real_count = tile_count;
-        if (tid == RS_BINS - 1) real_count -= (uint32_t)(RS_TILE - n_tile);
-        volatile uint32_t* st = status + (size_t)tile * RS_BINS + tid;
-        if (tile == 0) *st = (real_count << 2) | RS_FLAG_PREFIX;
-        else *st = (real_count << 2) | RS_FLAG_AGG;
-        // exclusive scan of tile_count over the bins -> first tile-sorted position of each bin
-        uint32_t x = tile_count;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-            if (lane >= o) x += y;
-        }
-        if (lane == 31) S.warp_tot[warp] = x;
-        // (bins live in warps 0..7 only: a named barrier over those 256 threads orders warp_tot)
-        asm volatile("bar.sync 1, 256;" ::: "memory");
-        uint32_t pre = 0;
-        for (int i = 0; i < warp; ++i) pre += S.warp_tot[i];
-        const uint32_t dstart = pre + x - tile_count;
-        S.digit_start[tid] = dstart;
-        // decoupled look-back over the predecessor tiles of this bin
         unsigned long long excl = 0;
         if (tile > 0) {
             int64_t t = (int64_t)tile - 1;
-            while (true) {
-                const uint32_t v = *(volatile uint32_t*)(status + (size_t)t * RS_BINS + tid);
-                const uint32_t f = v & 3u;
-                if (f == 0) continue;  // not published yet
-                excl += v >> 2;
-                if (f & RS_FLAG_PREFIX) break;
-                --t;  // tile 0 always publishes PREFIX, so t never runs below 0
+            bool done = false;
+            while (!done) {
+                uint32_t v[RS_LOOKBACK_BATCH];
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK_BATCH; ++k)
+                    v[k] = t - k >= 0 ? *(volatile uint32_t*)(status + (size_t)(t - k) * RS_BINS + tid) : RS_FLAG_PREFIX;
+#pragma unroll
+                for (int k = 0; k < RS_LOOKBACK_BATCH; ++k) {
+                    const uint32_t f = v[k] & 3u;
+                    if (f == 0) break;  // not published yet: look again from here
+                    excl += v[k] >> 2;
+                    --t;
+                    if (f & RS_FLAG_PREFIX) {
+                        done = true;
+                        break;
+                    }
+                }
             }
             *st = ((uint32_t)(excl + real_count) << 2) | RS_FLAG_PREFIX;
         }
-        S.global_base[tid] = (long long)(bin_base[tid] + excl) - (long long)dstart;
+        S.global_base[tid] = (long long)(bin_base[tid] + excl) - (long long)S.digit_start[tid];
     }
     __syncthreads();
 
@@ -243,9 +249,18 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
         const uint32_t d = (uint32_t)(key[i] >> shift) & (RS_BINS - 1);
         const uint32_t p = S.digit_start[d] + S.hist[warp][d] + rank[i];
         rank[i] = p;
-        S.keys[p] = key[i];
+        S.stage[p] = key[i];
+    }
+    __syncthreads();
+    for (int j = tid; j < n_tile; j += RS_THREADS) {
+        const uint64_t k = S.stage[j];
+        const uint32_t d = (uint32_t)(k >> shift) & (RS_BINS - 1);
+        if constexpr (HAS_V) S.dig[j] = (uint8_t)d;
+        kdst[S.global_base[d] + j] = k;
     }
     if constexpr (HAS_V) {
+        __syncthreads();
+        V* sv = reinterpret_cast<V*>(S.stage);
         // the first executed pass of an "iota" sort synthesises the values: the positions
         const bool iota = IOTA && (uint32_t)pass == ctl->first_exec;
 #pragma unroll
@@ -253,16 +268,10 @@ __global__ void __launch_bounds__(RS_THREADS, 2) rs_pass_kernel(uint64_t* k0, ui
             const int pos = wbase + i * 32;
             V v = V();
             if (pos < n_tile) v = iota ? (V)(tile_base + pos) : vsrc[tile_base + pos];
-            S.vals[rank[i]] = v;
+            sv[rank[i]] = v;
         }
-    }
-    __syncthreads();
-    for (int j = tid; j < n_tile; j += RS_THREADS) {
-        const uint64_t k = S.keys[j];
-        const uint32_t d = (uint32_t)(k >> shift) & (RS_BINS - 1);
-        const long long g = S.global_base[d] + j;
-        kdst[g] = k;
-        if constexpr (HAS_V) vdst[g] = S.vals[j];
+        __syncthreads();
+        for (int j = tid; j < n_tile; j += RS_THREADS) vdst[S.global_base[S.dig[j]] + j] = sv[j];
     }
 }
 
@@ -288,13 +297,8 @@ int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2]
     using K = void (*)(uint64_t*, uint64_t*, V*, V*, int64_t, int, int, RsControl*, const unsigned long long*, uint32_t*);
     K kern;
     size_t smem;
-    if (!has_v) {
-        kern = rs_pass_kernel<V, false, false>;
-        smem = sizeof(RsSmem<RsNoVal>);
-    } else {
-        smem = sizeof(RsSmem<V>);
-        kern = nullptr;
-    }
+    kern = rs_pass_kernel<V, false, false>;
+    smem = sizeof(RsSmem);
     int launches = 2;
     if (has_v) kern = iota_values ? (K)rs_pass_kernel<V, true, true> : (K)rs_pass_kernel<V, true, false>;
     if (has_v && iota_values) {  // every pass trivial (all keys equal): nobody synthesises the positions

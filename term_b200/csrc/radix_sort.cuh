@@ -19,8 +19,14 @@
 namespace tg {
 
 constexpr int RS_RADIX_BITS = 8, RS_BINS = 256, RS_MAX_PASSES = 8;
-constexpr int RS_THREADS = 384, RS_WARPS = RS_THREADS / 32;
-constexpr int RS_ITEMS = 14;                       // keys per thread
+#ifndef TG_RS_THREADS
+#define TG_RS_THREADS 256
+#define TG_RS_ITEMS 14
+#define TG_RS_MIN_BLOCKS 4
+#endif
+constexpr int RS_THREADS = TG_RS_THREADS, RS_WARPS = RS_THREADS / 32;
+constexpr int RS_ITEMS = TG_RS_ITEMS;              // keys per thread
+constexpr int RS_MIN_BLOCKS = TG_RS_MIN_BLOCKS;    // resident tiles per SM the pass kernel is compiled for
 constexpr int RS_TILE = RS_THREADS * RS_ITEMS;     // 5376 keys per tile
 
 struct RsControl {

@@ -2,12 +2,19 @@
 // columns over the pairwise-complete rows, then the Pearson co-moments of the ranks
 // (analyzers/advanced/correlation.rs:334-350, metric :407-427).
 //
-// Pipeline (no library code): order-preserving 64-bit keys (rows with a NULL on either side get the maximum key and
-// sort last) -> hand-written onesweep LSD radix sort of (key, row id) (radix_sort.cu; digit positions on which every
-// key agrees — sign / exponent bytes — are skipped, the row ids of the first executed pass are synthesised) -> the
-// minimum rank of a sorted position is 1 + the position of the first key of its run: per-tile "last run head", a
-// one-block max-scan of the tile results, then an in-tile max-scan with the carry -> ranks scattered back by row id
-// -> deterministic two-level reduction of the shifted rank moments.
+// Pipeline (no library code, no random access to HBM):
+//   1. rk_count / rk_offsets / rk_compact_keys   the pairwise-complete rows, compacted in row order (deterministic),
+//                                                as order-preserving 64-bit keys (kx, ky)
+//   2. sort by kx carrying ky as the payload     hand-written onesweep LSD radix sort (radix_sort.cu); digit positions on
+//                                                which every key agrees (sign / exponent bytes) are skipped
+//   3. rk_tile_heads / rk_tile_scan / rk_rank_x  the minimum rank of a sorted position is 1 + the position of the first
+//                                                key of its run: per-tile "last run head", a one-block max-scan of the
+//                                                tile results, an in-tile max-scan with the carry. Emits (ky, rank_x).
+//   4. sort by ky carrying rank_x
+//   5. rk_tile_heads / rk_tile_scan / rk_rank_y_moments   rank_y the same way, and the shifted co-moments of
+//                                                (rank_x, rank_y) accumulated on the fly in a fixed order
+// Ranks travel with the rows through the two sorts instead of being scattered back by row id (a random 4-byte write
+// per row costs more than a whole sort pass).
 // The reference accumulates rank products in UInt64 and overflows above ~3.8M rows; here
 // ranks are exact integers carried as f64 and the sums are centred at (n+1)/2.
 #include <algorithm>
@@ -28,32 +35,106 @@ __device__ __forceinline__ uint64_t order_key(uint64_t bits, int is_i64) {
     return (bits & 0x8000000000000000ull) ? ~bits : (bits | 0x8000000000000000ull);
 }
 
-__global__ void rk_keys_kernel(const uint64_t* x, const uint32_t* vx, int x_i64, const uint64_t* y, const uint32_t* vy, int y_i64,
-                               int64_t n, uint64_t* kx, uint64_t* ky, unsigned long long* n_pairs) {
-    unsigned long long c = 0;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        const bool ok = (!vx || ((vx[r >> 5] >> (r & 31)) & 1u)) && (!vy || ((vy[r >> 5] >> (r & 31)) & 1u));
-        kx[r] = ok ? order_key(x[r], x_i64) : ~0ull;
-        ky[r] = ok ? order_key(y[r], y_i64) : ~0ull;
-        c += ok;
-    }
+// ---- 1. compaction of the pairwise-complete rows. A block owns RK_CTILE = 8192 consecutive rows: thread t the 32 rows
+// of validity word t of the tile.
+constexpr int RK_CTILE = RK_THREADS * 32;
+
+__device__ __forceinline__ uint32_t rk_pair_word(const uint32_t* __restrict__ vx, const uint32_t* __restrict__ vy, int64_t word, int64_t n) {
+    const int64_t row0 = word * 32;
+    if (row0 >= n) return 0u;
+    uint32_t w = 0xffffffffu;
+    if (vx) w &= __ldg(vx + word);
+    if (vy) w &= __ldg(vy + word);
+    if (n - row0 < 32) w &= (1u << (uint32_t)(n - row0)) - 1u;
+    return w;
+}
+
+__global__ void __launch_bounds__(RK_THREADS) rk_count_kernel(const uint32_t* __restrict__ vx, const uint32_t* __restrict__ vy, int64_t n,
+                                                              uint32_t* __restrict__ tile_count) {
+    const int64_t word = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x;
+    uint32_t c = (uint32_t)__popc(rk_pair_word(vx, vy, word, n));
+    __shared__ uint32_t red[RK_THREADS / 32];
 #pragma unroll
     for (int m = 16; m > 0; m >>= 1) c += __shfl_xor_sync(0xffffffffu, c, m);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(n_pairs, c);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t s = 0;
+        for (int w = 0; w < RK_THREADS / 32; ++w) s += red[w];
+        tile_count[blockIdx.x] = s;
+    }
 }
 
-// ---- minimum ranks from the sorted keys. A position's run head = the largest p' <= p with key[p'] != key[p' - 1]
+// one block: exclusive sum of the tile counts; total -> *n_pairs
+__global__ void __launch_bounds__(1024) rk_offsets_kernel(const uint32_t* __restrict__ tile_count, int64_t n_tiles, uint32_t* __restrict__ tile_off,
+                                                          unsigned long long* n_pairs) {
+    __shared__ unsigned long long s_part[1024];
+    const int64_t per = (n_tiles + 1023) / 1024;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
+    unsigned long long m = 0;
+    for (int64_t t = lo; t < hi; ++t) m += tile_count[t];
+    s_part[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long y = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    unsigned long long run = threadIdx.x ? s_part[threadIdx.x - 1] : 0ull;
+    for (int64_t t = lo; t < hi; ++t) {
+        tile_off[t] = (uint32_t)run;
+        run += tile_count[t];
+    }
+    if (threadIdx.x == 1023) *n_pairs = s_part[1023];
+}
+
+// warp w of the block owns validity words w*32 .. w*32+31 of the tile (1024 rows): for each word the 32 lanes read its 32
+// rows coalesced and the complete ones are written behind each other — row order is kept, so the result is deterministic
+__global__ void __launch_bounds__(RK_THREADS) rk_compact_keys_kernel(const uint64_t* __restrict__ x, const uint32_t* __restrict__ vx, int x_i64,
+                                                                     const uint64_t* __restrict__ y, const uint32_t* __restrict__ vy, int y_i64,
+                                                                     int64_t n, const uint32_t* __restrict__ tile_off,
+                                                                     uint64_t* __restrict__ kx, uint64_t* __restrict__ ky) {
+    __shared__ uint32_t s_warp[RK_THREADS / 32];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t word = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x;
+    const uint32_t w = rk_pair_word(vx, vy, word, n);
+    // exclusive scan of popc(w) over the block
+    const uint32_t c = (uint32_t)__popc(w);
+    uint32_t incl = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t base = tile_off[blockIdx.x];
+    for (int i = 0; i < warp; ++i) base += s_warp[i];
+    const uint32_t my_off = base + incl - c;  // first output slot of this lane's word
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll 4
+    for (int j = 0; j < 32; ++j) {
+        const uint32_t wj = __shfl_sync(0xffffffffu, w, j);
+        const uint32_t oj = __shfl_sync(0xffffffffu, my_off, j);
+        if (wj == 0u) continue;  // warp-uniform
+        if ((wj >> lane) & 1u) {
+            const int64_t r = (word - lane + j) * 32 + lane;
+            const uint32_t dst = oj + (uint32_t)__popc(wj & lt);
+            kx[dst] = order_key(__ldg(x + r), x_i64);
+            ky[dst] = order_key(__ldg(y + r), y_i64);
+        }
+    }
+}
+
+// ---- 3 / 5. minimum ranks from sorted keys. A position's run head = the largest p' <= p with key[p'] != key[p' - 1]
 // (p' = 0 counts); stored 1-based so that 0 means "no head in this range" and the combine is a plain max.
 constexpr int RK_ITEMS = 16, RK_TILE = RK_THREADS * RK_ITEMS;
-
-__device__ __forceinline__ const uint64_t* rk_sorted_keys(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1) {
-    return ctl->result ? k1 : k0;
-}
 
 // tile_last[t] = 1-based position of the last run head inside tile t (0: the tile starts inside a run and never leaves it)
 __global__ void __launch_bounds__(RK_THREADS) rk_tile_heads_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1, int64_t n,
                                                                    uint32_t* tile_last) {
-    const uint64_t* __restrict__ ks = rk_sorted_keys(ctl, k0, k1);
+    const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
     const int64_t base = (int64_t)blockIdx.x * RK_TILE;
     uint32_t best = 0;
 #pragma unroll 4
@@ -95,78 +176,96 @@ __global__ void __launch_bounds__(1024) rk_tile_scan_kernel(const uint32_t* __re
     }
 }
 
-// rank of every sorted position = its run head (1-based == the SQL competition rank), scattered back to its row. Keys
-// equal to the sentinel may belong to valid rows (Int64 max / an all-ones NaN): the validity bitmaps decide.
-__global__ void __launch_bounds__(RK_THREADS) rk_rank_scatter_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1,
-                                                                     const uint32_t* i0, const uint32_t* i1, int64_t n,
-                                                                     const uint32_t* __restrict__ carry, const uint32_t* __restrict__ vx,
-                                                                     const uint32_t* __restrict__ vy, uint32_t* __restrict__ rank_of_row) {
-    const uint64_t* __restrict__ ks = rk_sorted_keys(ctl, k0, k1);
-    const uint32_t* __restrict__ idx = ctl->result ? i1 : i0;
-    __shared__ uint32_t s_warp[RK_THREADS / 32];
+// the ranks of one tile of sorted keys: warp-striped positions (coalesced), run heads by comparing with the left
+// neighbour, inclusive max-scan across the warp for every item row, carried from row to row and from the earlier warps
+// (shared memory) / earlier tiles (carry). rank[i] of position warp_base + i * 32 + lane.
+struct RkTileRanks {
+    uint32_t rank[RK_ITEMS];
+};
+__device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict__ ks, int64_t n, const uint32_t* __restrict__ carry,
+                                                     uint32_t* s_warp /* [RK_THREADS / 32] */) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // blocked arrangement: thread t owns positions base + 0 .. ITEMS - 1 (a serial max-scan in registers)
-    const int64_t base = (int64_t)blockIdx.x * RK_TILE + (int64_t)threadIdx.x * RK_ITEMS;
-    uint64_t k[RK_ITEMS];
-    uint64_t prev = 0;
-    if (base > 0 && base < n) prev = ks[base - 1];
-#pragma unroll
-    for (int i = 0; i < RK_ITEMS; ++i) k[i] = base + i < n ? ks[base + i] : 0ull;
-    uint32_t head[RK_ITEMS];
-    uint32_t run = 0;
+    const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
+    RkTileRanks R;
+    uint32_t run = 0;  // last head seen so far inside this warp's range (warp-uniform after each row)
 #pragma unroll
     for (int i = 0; i < RK_ITEMS; ++i) {
-        const int64_t p = base + i;
-        if (p < n && (p == 0 || k[i] != prev)) run = (uint32_t)p + 1u;
-        head[i] = run;
-        prev = k[i];
-    }
-    // exclusive max-scan of the threads' totals
-    uint32_t x = run;
+        const int64_t p = wbase + i * 32 + lane;
+        uint32_t h = 0;
+        if (p < n) {
+            const uint64_t k = ks[p];
+            if (p == 0 || k != ks[p - 1]) h = (uint32_t)p + 1u;
+        }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
-        if (lane >= o) x = max(x, y);
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, h, o);
+            if (lane >= o) h = max(h, v);
+        }
+        h = max(h, run);
+        R.rank[i] = h;
+        run = __shfl_sync(0xffffffffu, h, 31);
     }
-    if (lane == 31) s_warp[warp] = x;
+    if (lane == 0) s_warp[warp] = run;
     __syncthreads();
     uint32_t pre = carry[blockIdx.x];
     for (int w = 0; w < warp; ++w) pre = max(pre, s_warp[w]);
-    const uint32_t up = __shfl_up_sync(0xffffffffu, x, 1);
-    if (lane > 0) pre = max(pre, up);
+#pragma unroll
+    for (int i = 0; i < RK_ITEMS; ++i) R.rank[i] = max(R.rank[i], pre);
+    return R;
+}
+
+// after the sort by kx (payload ky): emit (ky, rank_x) in the sorted-by-x order — the input of the second sort
+__global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1, const uint64_t* p0,
+                                                               const uint64_t* p1, int64_t n, const uint32_t* __restrict__ carry,
+                                                               uint64_t* __restrict__ out_key, uint32_t* __restrict__ out_rank) {
+    __shared__ uint32_t s_warp[RK_THREADS / 32];
+    const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
+    const uint64_t* __restrict__ ys = ctl->result ? p1 : p0;
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
 #pragma unroll
     for (int i = 0; i < RK_ITEMS; ++i) {
-        const int64_t p = base + i;
+        const int64_t p = wbase + i * 32 + lane;
         if (p < n) {
-            const uint32_t row = idx[p];
-            bool ok = true;
-            if (k[i] == ~0ull) ok = (!vx || ((vx[row >> 5] >> (row & 31)) & 1u)) && (!vy || ((vy[row >> 5] >> (row & 31)) & 1u));
-            if (ok) rank_of_row[row] = max(head[i], pre);
+            out_key[p] = ys[p];
+            out_rank[p] = R.rank[i];
         }
     }
 }
 
-// block partials of the shifted rank co-moments, reduced in a fixed order by rk_final_kernel
-__global__ void __launch_bounds__(RK_THREADS) rk_moments_kernel(const uint32_t* rx, const uint32_t* ry, int64_t n,
-                                                                double K, double* partial /* [grid][5] */) {
-    double s[5] = {0, 0, 0, 0, 0};
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t a = rx[r], b = ry[r];
-        if (a == 0u) continue;  // not a pairwise-complete row: its rank slots keep the memset's 0 (ranks start at 1)
-        const double dx = (double)a - K, dy = (double)b - K;
-        s[0] += dx;
-        s[1] += dy;
-        s[2] = fma(dx, dx, s[2]);
-        s[3] = fma(dy, dy, s[3]);
-        s[4] = fma(dx, dy, s[4]);
-    }
+// after the sort by ky (payload rank_x): rank_y on the fly and the block's partial sums of the shifted rank co-moments
+// (fixed tile -> block mapping, fixed reduction shape: run-to-run reproducible)
+__global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1,
+                                                                       const uint32_t* r0, const uint32_t* r1, int64_t n,
+                                                                       const uint32_t* __restrict__ carry, double K,
+                                                                       double* __restrict__ partial /* [grid][5] */) {
+    __shared__ uint32_t s_warp[RK_THREADS / 32];
     __shared__ double red[5][RK_THREADS / 32];
+    const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
+    const uint32_t* __restrict__ rxs = ctl->result ? r1 : r0;
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
+    double s[5] = {0, 0, 0, 0, 0};
+#pragma unroll
+    for (int i = 0; i < RK_ITEMS; ++i) {
+        const int64_t p = wbase + i * 32 + lane;
+        if (p < n) {
+            const double dx = (double)rxs[p] - K, dy = (double)R.rank[i] - K;
+            s[0] += dx;
+            s[1] += dy;
+            s[2] = fma(dx, dx, s[2]);
+            s[3] = fma(dy, dy, s[3]);
+            s[4] = fma(dx, dy, s[4]);
+        }
+    }
 #pragma unroll
     for (int k = 0; k < 5; ++k) {
         double v = s[k];
 #pragma unroll
         for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-        if ((threadIdx.x & 31) == 0) red[k][threadIdx.x >> 5] = v;
+        if (lane == 0) red[k][warp] = v;
     }
     __syncthreads();
     if (threadIdx.x < 5) {
@@ -175,12 +274,15 @@ __global__ void __launch_bounds__(RK_THREADS) rk_moments_kernel(const uint32_t* 
         partial[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
     }
 }
-__global__ void rk_final_kernel(const double* partial, int n_blocks, double* out) {
-    if (threadIdx.x < 5) {
-        double v = 0;
-        for (int b = 0; b < n_blocks; ++b) v += partial[(size_t)b * 5 + threadIdx.x];
-        out[threadIdx.x] = v;
-    }
+
+// fixed-order sum of the block partials: 5 warps, one per moment, lanes stride the blocks, shuffle tree at the end
+__global__ void __launch_bounds__(160) rk_final_kernel(const double* __restrict__ partial, int64_t n_blocks, double* out) {
+    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double v = 0;
+    for (int64_t b = lane; b < n_blocks; b += 32) v += partial[(size_t)b * 5 + k];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    if (lane == 0) out[k] = v;
 }
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -199,60 +301,73 @@ void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id) {
     p.stats.bytes_scanned += 2 * (uint64_t)n * 8 + (cx->validity.p ? (uint64_t)(n + 7) / 8 : 0) + (cy->validity.p ? (uint64_t)(n + 7) / 8 : 0);
     if (n == 0) return;
     if (n >= (int64_t)1 << 30) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more rows per shard");
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + RK_THREADS - 1) / RK_THREADS, (int64_t)e.sm_count * 8));
     const size_t k_b = round_up((size_t)n * 8, 256), i_b = round_up((size_t)n * 4, 256);
-    const int64_t n_tiles = (n + RK_TILE - 1) / RK_TILE;
-    const size_t t_b = round_up((size_t)n_tiles * 4, 256);
+    const int64_t c_tiles = (n + RK_CTILE - 1) / RK_CTILE;    // compaction tiles (rows)
+    const int64_t r_tiles_max = (n + RK_TILE - 1) / RK_TILE;  // rank tiles (pairs <= rows)
+    const size_t ct_b = round_up((size_t)c_tiles * 4, 256), rt_b = round_up((size_t)r_tiles_max * 4, 256);
     const size_t tmp_b = round_up(rs_temp_bytes(n, RS_MAX_PASSES), 256);
-    // kx, ky, k_alt (ping-pong partner of whichever side is being sorted), idx x2, rank_x, rank_y, tile heads / carry, sort temp, partials
-    uint8_t* scr = e.scratch(3 * k_b + 4 * i_b + 2 * t_b + tmp_b + round_up((size_t)grid * 40, 256) + 512);
+    const size_t part_b = round_up((size_t)r_tiles_max * 40, 256);
+    // A0/A1: keys of sort 1, B0/B1: its payload (ky), C: keys of sort 2 (its partner is A0), R0/R1: payload of sort 2 (rank_x)
+    uint8_t* scr = e.scratch(5 * k_b + 2 * i_b + 2 * ct_b + 2 * rt_b + tmp_b + part_b + 512);
     uint8_t* q = scr;
-    uint64_t* kx = (uint64_t*)q; q += k_b;
-    uint64_t* ky = (uint64_t*)q; q += k_b;
-    uint64_t* kalt = (uint64_t*)q; q += k_b;
-    uint32_t* idx0 = (uint32_t*)q; q += i_b;
-    uint32_t* idx1 = (uint32_t*)q; q += i_b;
-    uint32_t* rx = (uint32_t*)q; q += i_b;
-    uint32_t* ry = (uint32_t*)q; q += i_b;
-    uint32_t* tile_last = (uint32_t*)q; q += t_b;
-    uint32_t* carry = (uint32_t*)q; q += t_b;
+    uint64_t* A0 = (uint64_t*)q; q += k_b;
+    uint64_t* A1 = (uint64_t*)q; q += k_b;
+    uint64_t* B0 = (uint64_t*)q; q += k_b;
+    uint64_t* B1 = (uint64_t*)q; q += k_b;
+    uint64_t* C = (uint64_t*)q; q += k_b;
+    uint32_t* R0 = (uint32_t*)q; q += i_b;
+    uint32_t* R1 = (uint32_t*)q; q += i_b;
+    uint32_t* tile_count = (uint32_t*)q; q += ct_b;
+    uint32_t* tile_off = (uint32_t*)q; q += ct_b;
+    uint32_t* tile_last = (uint32_t*)q; q += rt_b;
+    uint32_t* carry = (uint32_t*)q; q += rt_b;
     uint8_t* d_tmp = q; q += tmp_b;
-    double* partial = (double*)q; q += round_up((size_t)grid * 40, 256);
+    double* partial = (double*)q; q += part_b;
     double* d_out = (double*)q;
     unsigned long long* d_np = (unsigned long long*)(q + 64);
     const uint32_t* vx = (const uint32_t*)cx->validity.p;
     const uint32_t* vy = (const uint32_t*)cy->validity.p;
     TG_CUDA(cudaEventRecord(e.ev[6], e.stream));
-    TG_CUDA(cudaMemsetAsync(d_np, 0, 8, e.stream));
-    TG_CUDA(cudaMemsetAsync(rx, 0, 2 * i_b, e.stream));  // rank 0 = "row is not pairwise complete"
-    rk_keys_kernel<<<grid, RK_THREADS, 0, e.stream>>>((const uint64_t*)cx->values.p, vx, cx->dtype == TG_INT64,
-                                                      (const uint64_t*)cy->values.p, vy, cy->dtype == TG_INT64, n, kx, ky, d_np);
+    rk_count_kernel<<<(unsigned)c_tiles, RK_THREADS, 0, e.stream>>>(vx, vy, n, tile_count);
+    rk_offsets_kernel<<<1, 1024, 0, e.stream>>>(tile_count, c_tiles, tile_off, d_np);
+    rk_compact_keys_kernel<<<(unsigned)c_tiles, RK_THREADS, 0, e.stream>>>((const uint64_t*)cx->values.p, vx, cx->dtype == TG_INT64,
+                                                                           (const uint64_t*)cy->values.p, vy, cy->dtype == TG_INT64, n, tile_off, A0, B0);
     TG_CUDA(cudaGetLastError());
     unsigned long long n_pairs = 0;
     TG_CUDA(cudaMemcpyAsync(&n_pairs, d_np, 8, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
-    int launches = 1;
+    int launches = 3;
     a.u[0] = n_pairs;
     const double K = ((double)n_pairs + 1.0) / 2.0;
     a.f[0] = K;
     a.f[1] = K;
     if (n_pairs >= 2) {
-        const RsTemp T = rs_temp_carve(d_tmp, n, RS_MAX_PASSES);
-        for (int side = 0; side < 2; ++side) {
-            uint64_t* keys[2] = {side ? ky : kx, kalt};
-            uint32_t* vals[2] = {idx0, idx1};
-            launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, n, 0, RS_MAX_PASSES, /*iota_values=*/true, T, e.sm_count);
+        const int64_t m = (int64_t)n_pairs;
+        const int64_t r_tiles = (m + RK_TILE - 1) / RK_TILE;
+        const RsTemp T = rs_temp_carve(d_tmp, m, RS_MAX_PASSES);
+        {
+            uint64_t* keys[2] = {A0, A1};
+            uint64_t* vals[2] = {B0, B1};
+            launches += rs_sort_pairs<uint64_t>(e.stream, keys, vals, m, 0, RS_MAX_PASSES, false, T, e.sm_count);
             TG_CUDA(cudaGetLastError());
-            rk_tile_heads_kernel<<<(unsigned)n_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, keys[0], keys[1], n, tile_last);
-            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(tile_last, n_tiles, carry);
-            rk_rank_scatter_kernel<<<(unsigned)n_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, keys[0], keys[1], idx0, idx1, n, carry, vx, vy, side ? ry : rx);
+            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, A0, A1, m, tile_last);
+            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(tile_last, r_tiles, carry);
+            rk_rank_x_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, A0, A1, B0, B1, m, carry, C, R0);
             TG_CUDA(cudaGetLastError());
             launches += 3;
         }
-        rk_moments_kernel<<<grid, RK_THREADS, 0, e.stream>>>(rx, ry, n, K, partial);
-        rk_final_kernel<<<1, 32, 0, e.stream>>>(partial, grid, d_out);
-        TG_CUDA(cudaGetLastError());
-        launches += 2;
+        {
+            uint64_t* keys[2] = {C, A0};
+            uint32_t* vals[2] = {R0, R1};
+            launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, m, 0, RS_MAX_PASSES, false, T, e.sm_count);
+            TG_CUDA(cudaGetLastError());
+            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, C, A0, m, tile_last);
+            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(tile_last, r_tiles, carry);
+            rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, C, A0, R0, R1, m, carry, K, partial);
+            rk_final_kernel<<<1, 160, 0, e.stream>>>(partial, r_tiles, d_out);
+            TG_CUDA(cudaGetLastError());
+            launches += 4;
+        }
         double h[5];
         TG_CUDA(cudaMemcpyAsync(h, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
         TG_CUDA(cudaStreamSynchronize(e.stream));

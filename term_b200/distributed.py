@@ -27,6 +27,11 @@ from . import _ffi as F
 
 KIND_DISTINCT, KIND_FK, KIND_SPEARMAN = 6, 7, 10
 
+# bench.py sets this to a dict to collect, per timed region, the bytes every rank sends through the NVLink all-to-all
+# (shuffle_bytes), the device time of those collectives (shuffle_ms, CUDA events) and the wall time of the partial-state
+# exchange (exchange_ms). None: no bookkeeping at all.
+PROFILE = None
+
 
 def _device(device=None):
     if device is not None:
@@ -201,6 +206,10 @@ def shuffle_keys(keys: torch.Tensor, counts, n_nulls: int):
     NULL count goes to rank 0. Works on NCCL (device tensors) and gloo (CPU tensors)."""
     world, rank = dist.get_world_size(), dist.get_rank()
     dev = keys.device
+    prof = PROFILE if (PROFILE is not None and dev.type == "cuda") else None
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     send = torch.tensor(list(counts), dtype=torch.int64, device=dev)
     recv = torch.zeros(world, dtype=torch.int64, device=dev)
     dist.all_to_all_single(recv, send)
@@ -209,6 +218,11 @@ def shuffle_keys(keys: torch.Tensor, counts, n_nulls: int):
     dist.all_to_all_single(out, keys[: sum(counts)].contiguous(), output_split_sizes=recv_counts, input_split_sizes=list(counts))
     nulls = torch.tensor([int(n_nulls)], dtype=torch.int64, device=dev)
     dist.all_reduce(nulls)
+    if prof is not None:
+        ev1.record()
+        ev1.synchronize()
+        prof["shuffle_ms"] += ev0.elapsed_time(ev1)
+        prof["shuffle_bytes"] += 8 * (sum(counts) - counts[rank])  # what leaves this GPU
     return out, (int(nulls.item()) if rank == 0 else 0)
 
 
@@ -396,8 +410,13 @@ def execute_distributed(plan, ctx, table="data"):
                 plan.redirect(i, 0, name)
                 redirected.append((i, 0))
         plan.execute_partial(ctx, table)
+        if PROFILE is not None:
+            import time
+            t0 = time.perf_counter()
         exchange_and_finalize(plan, ctx)
         histogram_second_phase(plan, ctx, table)
+        if PROFILE is not None:
+            PROFILE["exchange_ms"] += (time.perf_counter() - t0) * 1e3
     finally:
         for i, which in redirected:
             plan.redirect(i, which, None)
