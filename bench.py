@@ -226,6 +226,58 @@ def make_filler_columns(torch, n, seed, device):
     return cols, keep
 
 
+def make_device_table(torch, n, seed, device):
+    """(used by tests/test_gpu_full_size.py; the bench itself feeds both arms from make_host_table) Synthetic C2 table generated on the device: f0..f3 f64, i0..i3 i64, 5 % nulls, f1 = 0.8 f0 + noise.
+    Buffers carry 64 elements of slack so TMA tiles may over-read the tail."""
+    g = torch.Generator(device=device)
+    g.manual_seed(seed)
+    cols, keep = {}, []
+    pad = 64
+
+    def buf(dtype):
+        t = torch.zeros(n + pad, dtype=dtype, device=device)
+        keep.append(t)
+        return t
+
+    def validity():
+        words = (n + 63) // 64 * 8 + 64
+        bits = torch.zeros(words, dtype=torch.uint8, device=device)
+        chunk = 1 << 26
+        w = torch.tensor([1, 2, 4, 8, 16, 32, 64, 128], dtype=torch.uint8, device=device)
+        for s in range(0, n, chunk):
+            e = min(n, s + chunk)
+            m = (torch.rand(e - s, generator=g, device=device) >= NULL_FRACTION)
+            padn = (-(e - s)) % 8
+            if padn:
+                m = torch.cat([m, torch.zeros(padn, dtype=torch.bool, device=device)])
+            packed = (m.view(-1, 8).to(torch.uint8) * w).sum(dim=1, dtype=torch.int32).to(torch.uint8)
+            bits[s // 8: s // 8 + packed.numel()] = packed
+        keep.append(bits)
+        return bits
+
+    f0 = buf(torch.float64)
+    f0[:n].normal_(100.0, 15.0, generator=g)
+    f1 = buf(torch.float64)
+    f1[:n].normal_(0.0, 9.0, generator=g)
+    f1[:n].add_(f0[:n], alpha=0.8)
+    f2 = buf(torch.float64)
+    f2[:n].uniform_(0.0, 1000.0, generator=g)
+    f3 = buf(torch.float64)
+    f3[:n].normal_(0.0, 1.0, generator=g).exp_()
+    floats = {"f0": f0, "f1": f1, "f2": f2, "f3": f3}
+    ints = {}
+    for k in range(4):
+        t = buf(torch.int64)
+        t[:n].random_(-10**6, 10**6 + 1, generator=g)
+        ints[f"i{k}"] = t
+    from term_b200 import _ffi as F
+    for name, t in list(floats.items()) + list(ints.items()):
+        v = validity()
+        cols[name] = dict(dtype=F.TG_FLOAT64 if name[0] == "f" else F.TG_INT64, n_rows=n, values=t.data_ptr(),
+                          validity=v.data_ptr(), tensor=t, bits=v)
+    return cols, keep
+
+
 def build_suite(T, table_name):
     A = T.Assertion
     check = (T.Check.builder("business_rules")

@@ -719,7 +719,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
     e.sync_copies();
     auto it = e.tables.find(table_name);
     Table* t = it == e.tables.end() ? nullptr : it->second.get();
-    std::vector<int> scan_ids, string_ids, kll_ids, length_ids;
+    std::vector<int> scan_ids, string_ids, kll_ids, length_ids, grouped_ids;
     for (size_t i = 0; i < p.aggs.size(); ++i) {
         Agg& a = p.aggs[i];
         if (a.err != TG_OK) continue;
@@ -742,6 +742,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
             case A_REGEX: string_ids.push_back((int)i); break;
             case A_KLL: kll_ids.push_back((int)i); break;
             case A_LENGTH: length_ids.push_back((int)i); break;
+            case A_GROUPED: grouped_ids.push_back((int)i); break;
             default: break;
         }
     }
@@ -749,6 +750,7 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
     if (t && !string_ids.empty()) exec_string_jobs(e, *t, p, string_ids);
     if (t && !length_ids.empty()) exec_length_jobs(e, *t, p, length_ids);
     if (t && !kll_ids.empty()) exec_kll_jobs(e, *t, p, kll_ids);
+    if (t && !grouped_ids.empty()) exec_grouped_jobs(e, *t, p, grouped_ids);
     for (size_t i = 0; i < p.aggs.size(); ++i) {
         Agg& a = p.aggs[i];
         if (a.err != TG_OK) continue;
@@ -767,7 +769,6 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
                     else exec_spearman_job(e, *dt, p, (int)i);
                 } break;
                 case A_FK: exec_fk_job(e, p, (int)i); break;
-                case A_GROUPED: exec_grouped_job(e, *t, p, (int)i); break;
                 case A_HIST: exec_hist_job(e, *t, p, (int)i); break;
                 default: break;
             }

@@ -152,7 +152,7 @@ void exec_length_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_
 void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id);                     // hashing.cu
 void exec_fk_job(Engine& e, Plan& p, int agg_id);                                     // hashing.cu
 void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids);  // sketch.cu
-void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id);                      // hashing.cu
+void exec_grouped_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // grouped.cu (all groupings of a plan in one pass)
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
 void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id);                         // hist.cu
 void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb); // hist.cu (two-phase multi-GPU histogram)

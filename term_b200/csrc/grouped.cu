@@ -1,16 +1,19 @@
-// K5 — grouped completeness: GROUP BY g.. -> COUNT(*), COUNT(c) in ONE pass over the group columns.
+// K5 — grouped completeness: GROUP BY g.. -> COUNT(*), COUNT(c), ALL groupings of a plan in ONE pass over the group columns.
 //
 // Replaces  SELECT g.., COUNT(*), COUNT(c) FROM t GROUP BY g.. [ORDER BY .. LIMIT ..]
-//           (analyzers/basic/grouped_completeness.rs:131-176)
+//           (analyzers/basic/grouped_completeness.rs:131-176), one query per grouping in the reference.
 //
-// One fused kernel reads, per row, the group columns (Utf8: offsets + bytes, fixed width: the value; validity
-// bits) and the target column's validity bit — exactly the algorithmic bytes of SURVEY §8d, nothing is
-// materialised per row. The group tuple is reduced to a 128-bit fingerprint in registers and counted in a
-// per-CTA shared-memory table (the common case is a handful to a few thousand groups): a warp first agrees on
-// which lanes share a slot (__match_any_sync) so each distinct group costs one shared atomic per warp. A CTA whose
-// table fills up spills the row to the global table directly; at the end every CTA folds its table into the global
-// one. The first row of every group is kept so the host can fetch the group's key values for the report.
+// One fused kernel reads, per row, every DISTINCT group column of the batch once (Utf8: offsets + bytes, fixed width: the
+// value; validity bits) and the target columns' validity bits — exactly the algorithmic bytes of SURVEY §8d, nothing is
+// materialised per row, and a column shared by several groupings (g0, g1, (g0, g1)) is read and hashed once. A column
+// value becomes a 128-bit pair (Utf8 values of at most 8 bytes and fixed-width values carry themselves: no string
+// hashing at all); every grouping folds the pairs of its columns into its own fingerprint and counts it in its own
+// per-CTA shared-memory table (the common case is a handful to a few thousand groups): a warp first agrees on which
+// lanes share a slot (__match_any_sync) so each distinct group costs one shared atomic per warp. A CTA whose table fills
+// up spills the row to the grouping's global table directly; at the end every CTA folds its tables into the global
+// ones. The first row of every group is kept so the host can fetch the group's key values for the report.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -19,23 +22,22 @@
 
 namespace tg {
 
-constexpr int GRP_THREADS = 1024;
-constexpr int GRP_SLOTS = 8192;     // per-CTA shared table (power of two): 24 B per slot = 192 KB of dynamic shared memory
+constexpr int GRP_THREADS = 512;
+constexpr int GRP_SMEM_BYTES = 222 * 1024;  // dynamic shared memory of the fused kernel, split evenly between the batch's groupings
 constexpr int GRP_MAX_PROBE = 24;   // after this many probes the row goes to the global table
-constexpr int GRP_MAX_COLS = 8;
+constexpr int GRP_MAX_COLS = 8;     // distinct group columns per batch
+constexpr int GRP_MAX_JOBS = 4;     // groupings per batch (one kernel launch)
 
 struct GrpCol {
     const uint8_t* values;
     const int32_t* offsets;
     const uint32_t* validity;
     int32_t dtype;
-    int32_t pad;
+    uint32_t job_mask;   // groupings that contain this column
+    uint32_t first_mask; // groupings whose FIRST column this is
+    uint32_t pad;
 };
-struct GrpParams {
-    GrpCol cols[GRP_MAX_COLS];
-    int32_t n_cols;
-    int32_t pad;
-    int64_t n_rows;
+struct GrpJob {
     const uint32_t* target_validity;
     Table128 gt;  // global table (h1, h2) + parallel arrays below
     unsigned long long* totals;
@@ -43,88 +45,54 @@ struct GrpParams {
     long long* first_row;
     unsigned long long* n_groups;
 };
+struct GrpParams {
+    GrpCol cols[GRP_MAX_COLS];
+    GrpJob jobs[GRP_MAX_JOBS];
+    int32_t n_cols, n_jobs;
+    int32_t slots[GRP_MAX_JOBS];     // shared-table slots of grouping j (power of two): multi-column groupings get more
+    int32_t slot_base[GRP_MAX_JOBS]; // first slot of grouping j in the shared block (24 B per slot)
+    int64_t n_rows;
+};
 
 constexpr int GRP_ILP = 4;  // rows per thread per iteration: their loads are issued together
 
-// Fingerprints of GRP_ILP rows at once. Per group column the loads go out in waves (validity + offsets or values,
-// then the first 8 key bytes) for all rows before anything is hashed, so a thread has GRP_ILP independent memory
-// round trips in flight instead of a dependent chain per row.
-__device__ __forceinline__ void row_fingerprints(const GrpParams& P, const int64_t (&row)[GRP_ILP], const bool (&act)[GRP_ILP],
-                                                 Fp (&acc)[GRP_ILP]) {
-#pragma unroll
-    for (int k = 0; k < GRP_ILP; ++k) acc[k] = Fp{0, 0};
-    for (int i = 0; i < P.n_cols; ++i) {
-        const GrpCol& c = P.cols[i];
-        const bool first = i == 0;
-        bool valid[GRP_ILP];
-#pragma unroll
-        for (int k = 0; k < GRP_ILP; ++k) valid[k] = act[k] && row_valid(c.validity, row[k]);
-        if (c.dtype == TG_UTF8) {
-            int32_t b[GRP_ILP], e[GRP_ILP];
-            uint64_t w[GRP_ILP];
-#pragma unroll
-            for (int k = 0; k < GRP_ILP; ++k) {
-                b[k] = valid[k] ? __ldg(c.offsets + row[k]) : 0;
-                e[k] = valid[k] ? __ldg(c.offsets + row[k] + 1) : 0;
-            }
-#pragma unroll
-            for (int k = 0; k < GRP_ILP; ++k) w[k] = e[k] > b[k] ? load_upto8(c.values, b[k], min(8, e[k] - b[k])) : 0ull;
-#pragma unroll
-            for (int k = 0; k < GRP_ILP; ++k) {
-                if (!valid[k]) {
-                    fp_combine(acc[k], NULL_TAG1, NULL_TAG2, first);
-                    continue;
-                }
-                uint64_t x = 0x736f6d6570736575ull ^ (uint64_t)(e[k] - b[k]), y = 0x646f72616e646f6dull + (uint64_t)(e[k] - b[k]) * 0x100000001b3ull;
-                for (int32_t p = b[k]; p < e[k]; p += 8) {
-                    const uint64_t ww = p == b[k] ? w[k] : load_upto8(c.values, p, min(8, e[k] - p));
-                    x = (x ^ ww) * 0x9fb21c651e98df25ull;
-                    x ^= x >> 29;
-                    y = (y + ww) * 0xc2b2ae3d27d4eb4full;
-                    y ^= y >> 31;
-                }
-                fp_combine(acc[k], x, y, first);  // fp_combine applies the finalising mix
-            }
-        } else {
-            uint64_t v[GRP_ILP];
-#pragma unroll
-            for (int k = 0; k < GRP_ILP; ++k) {
-                v[k] = 0;
-                if (!valid[k]) continue;
-                const int64_t r = row[k];
-                switch (c.dtype) {
-                    case TG_INT64: v[k] = __ldg(reinterpret_cast<const unsigned long long*>(c.values) + r); break;
-                    case TG_FLOAT64: v[k] = canon_f64(__ldg(reinterpret_cast<const unsigned long long*>(c.values) + r)); break;
-                    case TG_INT32: v[k] = (uint64_t)(int64_t)__ldg(reinterpret_cast<const int32_t*>(c.values) + r); break;
-                    case TG_FLOAT32: v[k] = canon_f64((uint64_t)__double_as_longlong((double)__ldg(reinterpret_cast<const float*>(c.values) + r))); break;
-                    default: v[k] = (__ldg(reinterpret_cast<const uint32_t*>(c.values) + (r >> 5)) >> (r & 31)) & 1u; break;  // TG_BOOL
-                }
-            }
-#pragma unroll
-            for (int k = 0; k < GRP_ILP; ++k) {
-                if (valid[k]) fp_combine(acc[k], v[k], v[k] ^ 0x5851f42d4c957f2dull, first);
-                else fp_combine(acc[k], NULL_TAG1, NULL_TAG2, first);
-            }
-        }
+// The 128-bit pair a column value contributes. Values that fit carry themselves (x = the bytes, y = a small tag), so two
+// different short values can never collide; longer strings are hashed (y has the top bit set: disjoint from the tags).
+__device__ __forceinline__ void utf8_pair(const uint8_t* __restrict__ values, int32_t b, int32_t e, uint64_t w0, uint64_t& x, uint64_t& y) {
+    const int32_t len = e - b;
+    if (len <= 8) {
+        x = w0;
+        y = (uint64_t)len;
+        return;
     }
+    x = 0x736f6d6570736575ull ^ (uint64_t)len;
+    y = 0x646f72616e646f6dull + (uint64_t)len * 0x100000001b3ull;
+    for (int32_t p = b; p < e; p += 8) {
+        const uint64_t ww = p == b ? w0 : load_upto8(values, p, min(8, e - p));
+        x = (x ^ ww) * 0x9fb21c651e98df25ull;
+        x ^= x >> 29;
+        y = (y + ww) * 0xc2b2ae3d27d4eb4full;
+        y ^= y >> 31;
+    }
+    y |= 0x8000000000000000ull;
 }
 
-__device__ __noinline__ void global_count(const GrpParams& P, Fp f, unsigned long long tot, unsigned long long nn, long long first) {
+__device__ __noinline__ void global_count(const GrpJob& J, Fp f, unsigned long long tot, unsigned long long nn, long long first) {
     bool created;
-    const uint64_t slot = upsert128(P.gt, f, created);
-    if (created) atomicAdd(P.n_groups, 1ull);
-    atomicAdd(&P.totals[slot], tot);
-    if (nn) atomicAdd(&P.nonnull[slot], nn);
-    atomicMin(&P.first_row[slot], first);
+    const uint64_t slot = upsert128(J.gt, f, created);
+    if (created) atomicAdd(J.n_groups, 1ull);
+    if (tot) atomicAdd(&J.totals[slot], tot);
+    if (nn) atomicAdd(&J.nonnull[slot], nn);
+    atomicMin(&J.first_row[slot], first);
 }
 
-// find-or-insert (a, b) in the CTA's shared table; returns the slot or -1 when the probe limit is hit. Kept out of
-// line: it is called GRP_ILP times per iteration and inlining every copy overflows the instruction cache.
-__device__ __noinline__ int smem_upsert(unsigned long long* s_h1, unsigned long long* s_h2, unsigned long long a, unsigned long long b,
-                                        bool& created) {
+// find-or-insert (a, b) in a grouping's shared table; returns the slot or -1 when the probe limit is hit. Kept out of
+// line: it is called GRP_ILP x groupings times per iteration and inlining every copy overflows the instruction cache.
+__device__ __noinline__ int smem_upsert(unsigned long long* s_h1, unsigned long long* s_h2, uint32_t mask, unsigned long long a,
+                                        unsigned long long b, bool& created) {
     created = false;
-    uint32_t s = (uint32_t)(a ^ (b >> 32)) & (GRP_SLOTS - 1);
-    for (int probe = 0; probe < GRP_MAX_PROBE; ++probe, s = (s + 1) & (GRP_SLOTS - 1)) {
+    uint32_t s = (uint32_t)(a ^ (b >> 32)) & mask;
+    for (int probe = 0; probe < GRP_MAX_PROBE; ++probe, s = (s + 1) & mask) {
         unsigned long long v = s_h1[s];
         bool claimed = false;
         if (v == EMPTY64) {
@@ -144,61 +112,469 @@ __device__ __noinline__ int smem_upsert(unsigned long long* s_h1, unsigned long 
     return -1;
 }
 
-__global__ void __launch_bounds__(GRP_THREADS) group_count_fused_kernel(const __grid_constant__ GrpParams P) {
+// shared memory of grouping j: [h1: slots x 8][h2: slots x 8][tot: slots x 4][nn: slots x 4]
+template <int NJ>
+__global__ void __launch_bounds__(GRP_THREADS, 1) group_count_fused_kernel(const __grid_constant__ GrpParams P) {
     extern __shared__ __align__(16) unsigned long long grp_smem[];
-    unsigned long long* s_h1 = grp_smem;
-    unsigned long long* s_h2 = grp_smem + GRP_SLOTS;
-    uint32_t* s_tot = reinterpret_cast<uint32_t*>(grp_smem + 2 * GRP_SLOTS);
-    uint32_t* s_nn = s_tot + GRP_SLOTS;
-    for (int i = threadIdx.x; i < GRP_SLOTS; i += GRP_THREADS) {
-        s_h1[i] = EMPTY64;
-        s_h2[i] = EMPTY64;
-        s_tot[i] = 0;
-        s_nn[i] = 0;
+    unsigned long long* s_h1[NJ];
+    unsigned long long* s_h2[NJ];
+    uint32_t* s_tot[NJ];
+    uint32_t* s_nn[NJ];
+    uint32_t smask[NJ];
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        const int slots = P.slots[j];
+        unsigned long long* base = grp_smem + (size_t)P.slot_base[j] * 3;
+        s_h1[j] = base;
+        s_h2[j] = base + slots;
+        s_tot[j] = reinterpret_cast<uint32_t*>(base + 2 * slots);
+        s_nn[j] = s_tot[j] + slots;
+        smask[j] = (uint32_t)slots - 1u;
+        for (int s = threadIdx.x; s < slots; s += GRP_THREADS) {
+            s_h1[j][s] = EMPTY64;
+            s_h2[j][s] = EMPTY64;
+            s_tot[j][s] = 0;
+            s_nn[j][s] = 0;
+        }
     }
     __syncthreads();
     const int lane = threadIdx.x & 31;
     for (int64_t base0 = (int64_t)blockIdx.x * GRP_THREADS * GRP_ILP; base0 < P.n_rows; base0 += (int64_t)gridDim.x * GRP_THREADS * GRP_ILP) {
         int64_t row[GRP_ILP];
-        bool act[GRP_ILP], okv[GRP_ILP];
-        Fp fps[GRP_ILP];
+        bool act[GRP_ILP];
+        Fp fps[NJ][GRP_ILP];
 #pragma unroll
         for (int k = 0; k < GRP_ILP; ++k) {
             row[k] = base0 + (int64_t)k * GRP_THREADS + threadIdx.x;
             act[k] = row[k] < P.n_rows;
         }
 #pragma unroll
-        for (int k = 0; k < GRP_ILP; ++k) okv[k] = act[k] && row_valid(P.target_validity, row[k]);
-        row_fingerprints(P, row, act, fps);
+        for (int j = 0; j < NJ; ++j)
 #pragma unroll
-        for (int k = 0; k < GRP_ILP; ++k) {
-            const bool ok = okv[k];
-            int slot = -1;  // shared slot, or -1: not active / spilled
-            if (act[k]) {
-                // EMPTY64 is the shared table's vacancy marker in both words
-                const unsigned long long a = fps[k].h1 == EMPTY64 ? 0ull : fps[k].h1, b = fps[k].h2 == EMPTY64 ? 0ull : fps[k].h2;
-                bool created;
-                slot = smem_upsert(s_h1, s_h2, a, b, created);
-                // a new group of this CTA registers itself (and a representative row) in the global table right away;
-                // a row that finds the shared table full is counted there directly
-                if (slot < 0) global_count(P, fps[k], 1ull, ok ? 1ull : 0ull, (long long)row[k]);
-                else if (created) global_count(P, fps[k], 0ull, 0ull, (long long)row[k]);
+            for (int k = 0; k < GRP_ILP; ++k) fps[j][k] = Fp{0, 0};
+        // ---- every distinct group column once: loads of the GRP_ILP rows go out in waves (validity + offsets or values,
+        // then the first 8 key bytes) before anything is hashed; the column's pair is folded into every grouping it is in
+        for (int i = 0; i < P.n_cols; ++i) {
+            const GrpCol& c = P.cols[i];
+            bool valid[GRP_ILP];
+            uint64_t x[GRP_ILP], y[GRP_ILP];
+#pragma unroll
+            for (int k = 0; k < GRP_ILP; ++k) valid[k] = act[k] && row_valid(c.validity, row[k]);
+            if (c.dtype == TG_UTF8) {
+                int32_t b[GRP_ILP], e[GRP_ILP];
+                uint64_t w[GRP_ILP];
+#pragma unroll
+                for (int k = 0; k < GRP_ILP; ++k) {
+                    b[k] = valid[k] ? __ldg(c.offsets + row[k]) : 0;
+                    e[k] = valid[k] ? __ldg(c.offsets + row[k] + 1) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < GRP_ILP; ++k) w[k] = e[k] > b[k] ? load_upto8(c.values, b[k], min(8, e[k] - b[k])) : 0ull;
+#pragma unroll
+                for (int k = 0; k < GRP_ILP; ++k) {
+                    if (valid[k]) utf8_pair(c.values, b[k], e[k], w[k], x[k], y[k]);
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < GRP_ILP; ++k) {
+                    x[k] = 0;
+                    y[k] = 0x10ull + (uint64_t)c.dtype;  // fixed-width tag (Utf8 lengths use 0..8)
+                    if (!valid[k]) continue;
+                    const int64_t r = row[k];
+                    switch (c.dtype) {
+                        case TG_INT64: x[k] = __ldg(reinterpret_cast<const unsigned long long*>(c.values) + r); break;
+                        case TG_FLOAT64: x[k] = canon_f64(__ldg(reinterpret_cast<const unsigned long long*>(c.values) + r)); break;
+                        case TG_INT32: x[k] = (uint64_t)(int64_t)__ldg(reinterpret_cast<const int32_t*>(c.values) + r); break;
+                        case TG_FLOAT32: x[k] = canon_f64((uint64_t)__double_as_longlong((double)__ldg(reinterpret_cast<const float*>(c.values) + r))); break;
+                        default: x[k] = (__ldg(reinterpret_cast<const uint32_t*>(c.values) + (r >> 5)) >> (r & 31)) & 1u; break;  // TG_BOOL
+                    }
+                }
             }
-            // one shared atomic per distinct slot per warp
-            const unsigned peers = __match_any_sync(0xffffffffu, slot);
-            const unsigned ok_peers = __ballot_sync(0xffffffffu, ok) & peers;
-            if (slot >= 0 && lane == __ffs(peers) - 1) {
-                atomicAdd(&s_tot[slot], (uint32_t)__popc(peers));
-                const int c = __popc(ok_peers);
-                if (c) atomicAdd(&s_nn[slot], (uint32_t)c);
+#pragma unroll
+            for (int k = 0; k < GRP_ILP; ++k) {
+                if (!valid[k]) {
+                    x[k] = NULL_TAG1;
+                    y[k] = NULL_TAG2;
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < NJ; ++j) {
+                if (!((c.job_mask >> j) & 1u)) continue;
+                const bool first = (c.first_mask >> j) & 1u;
+#pragma unroll
+                for (int k = 0; k < GRP_ILP; ++k) fp_combine(fps[j][k], x[k], y[k], first);
+            }
+        }
+        // ---- count: per grouping, per row
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+            const GrpJob& J = P.jobs[j];
+#pragma unroll
+            for (int k = 0; k < GRP_ILP; ++k) {
+                const bool ok = act[k] && row_valid(J.target_validity, row[k]);
+                int slot = -1;  // shared slot, or -1: not active / spilled
+                if (act[k]) {
+                    // EMPTY64 is the shared table's vacancy marker in both words
+                    const unsigned long long a = fps[j][k].h1 == EMPTY64 ? 0ull : fps[j][k].h1, b = fps[j][k].h2 == EMPTY64 ? 0ull : fps[j][k].h2;
+                    bool created;
+                    slot = smem_upsert(s_h1[j], s_h2[j], smask[j], a, b, created);
+                    // a new group of this CTA registers itself (and a representative row) in the global table right away;
+                    // a row that finds the shared table full is counted there directly
+                    if (slot < 0) global_count(J, fps[j][k], 1ull, ok ? 1ull : 0ull, (long long)row[k]);
+                    else if (created) global_count(J, fps[j][k], 0ull, 0ull, (long long)row[k]);
+                }
+                // one shared atomic per distinct slot per warp
+                const unsigned peers = __match_any_sync(0xffffffffu, slot);
+                const unsigned ok_peers = __ballot_sync(0xffffffffu, ok) & peers;
+                if (slot >= 0 && lane == __ffs(peers) - 1) {
+                    atomicAdd(&s_tot[j][slot], (uint32_t)__popc(peers));
+                    const int c = __popc(ok_peers);
+                    if (c) atomicAdd(&s_nn[j][slot], (uint32_t)c);
+                }
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < GRP_SLOTS; i += GRP_THREADS) {
-        if (s_tot[i] == 0) continue;
-        // EMPTY64 was mapped to 0 above exactly like upsert128 maps it, so the pair can be handed over as is
-        global_count(P, Fp{s_h1[i], s_h2[i]}, s_tot[i], s_nn[i], INT64_MAX);
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) {
+        for (int i = threadIdx.x; i < P.slots[j]; i += GRP_THREADS) {
+            if (s_tot[j][i] == 0) continue;
+            // EMPTY64 was mapped to 0 above exactly like upsert128 maps it, so the pair can be handed over as is
+            global_count(P.jobs[j], Fp{s_h1[j][i], s_h2[j][i]}, s_tot[j][i], s_nn[j][i], INT64_MAX);
+        }
+    }
+}
+
+// =====================================================================================================================
+// Fast path: per-CTA column dictionaries. Group columns are low-cardinality almost by definition (the reference caps a
+// grouping at max_groups = 10 000, analyzers/grouped.rs:36), so a CTA keeps, per distinct group column, a small
+// shared-memory dictionary value -> slot. A value is identified EXACTLY: fixed-width values and Utf8 values of at most 8
+// bytes by their bits plus a tag (length / type / NULL), longer strings by a 128-bit hash pair. Per row a column costs
+// one cheap 32-bit hash and one probe; a single-column grouping counts straight into counters parallel to the
+// dictionary, a 2- / 3-column grouping keys a second shared table with the packed slot numbers (10 bits each). No
+// 64-bit multiply chains, no per-grouping string hashing. At the end a CTA publishes its dictionary entries to the
+// column's global dictionary (a 128-bit table: the global slot is the value's code), adds its counters at those codes
+// and folds its composite tables into the grouping's global table keyed by the packed global codes. A CTA whose
+// dictionary or composite table overflows raises a flag and the host re-runs the batch through the generic
+// fingerprint kernel above.
+// =====================================================================================================================
+constexpr int GD_THREADS = 1024, GD_ILP = 4;
+constexpr int GD_DICT = 1024;       // dictionary slots per column per CTA (10-bit local codes)
+constexpr int GD_MAX_COLS = 4, GD_MAX_JOBS = 4;
+constexpr int GD_PROBE = 16;
+constexpr int GD_CODE_BITS = 21;    // global dictionary slots per column <= 2^21: three codes fit one 64-bit composite key
+constexpr uint32_t GD_TAG_NULL = 0x40u, GD_TAG_LONG = 0x80u, GD_BUSY = 0xFFFFFFFFu;
+
+struct GdCol {
+    const uint8_t* values;
+    const int32_t* offsets;
+    const uint32_t* validity;
+    int32_t dtype;
+    uint32_t smem_off;     // byte offset of the column's dictionary in dynamic shared memory
+    Table128 dict;         // global dictionary (h1, h2); the slot is the value's global code
+    long long* first_row;  // a representative row per global slot
+};
+struct GdJob {
+    const uint32_t* target_validity;
+    int32_t n_cols;
+    int32_t col[3];
+    uint32_t smem_off;       // single-column: counters [tot GD_DICT][nn GD_DICT]; composite: [key S][tot S][nn S][row S]
+    uint32_t comp_slots;     // composite: S (power of two); single-column: 0
+    // global state. single-column: totals / nonnull indexed by the column's global code. composite: 64-bit key table.
+    unsigned long long* totals;
+    unsigned long long* nonnull;
+    unsigned long long* ckeys;  // composite keys (EMPTY64 = vacant)
+    long long* crow;            // composite: representative row
+    uint64_t cmask;
+};
+struct GdParams {
+    GdCol cols[GD_MAX_COLS];
+    GdJob jobs[GD_MAX_JOBS];
+    int32_t n_cols, n_jobs;
+    int64_t n_rows;
+    unsigned int* overflow;
+};
+
+// dictionary of one column in shared memory
+struct GdDict {
+    unsigned long long* x;   // [GD_DICT] value bits / first hash word
+    unsigned long long* y;   // [GD_DICT] second hash word of long strings (0 otherwise)
+    uint32_t* state;         // [GD_DICT] 0 vacant, GD_BUSY being written, else the tag (never 0)
+    uint32_t* row;           // [GD_DICT] a row holding the value; after the publish step: the global code
+};
+__device__ __forceinline__ GdDict gd_dict(uint8_t* smem, uint32_t off) {
+    GdDict d;
+    d.x = reinterpret_cast<unsigned long long*>(smem + off);
+    d.y = d.x + GD_DICT;
+    d.state = reinterpret_cast<uint32_t*>(d.y + GD_DICT);
+    d.row = d.state + GD_DICT;
+    return d;
+}
+constexpr uint32_t GD_DICT_BYTES = GD_DICT * 24;
+
+__device__ __forceinline__ uint32_t gd_hash(uint64_t x, uint32_t tag) {
+    uint32_t h = (uint32_t)x * 0x9E3779B1u ^ (uint32_t)(x >> 32) * 0x85EBCA77u ^ tag * 0xC2B2AE3Du;
+    h ^= h >> 15;
+    h *= 0x2C1B3C6Du;
+    h ^= h >> 13;
+    return h;
+}
+
+// find-or-insert; returns the slot, or -1 when the probe limit is hit (dictionary too small for this column)
+__device__ __noinline__ int gd_lookup(const GdDict d, uint64_t x, uint64_t y, uint32_t tag, uint32_t row) {
+    uint32_t s = gd_hash(x, tag) & (GD_DICT - 1);
+    for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (GD_DICT - 1)) {
+        while (true) {
+            uint32_t st = *reinterpret_cast<volatile uint32_t*>(&d.state[s]);
+            if (st == 0u) {
+                st = atomicCAS(&d.state[s], 0u, GD_BUSY);
+                if (st == 0u) {  // claimed: fill, then publish the tag
+                    d.x[s] = x;
+                    d.y[s] = y;
+                    d.row[s] = row;
+                    __threadfence_block();
+                    atomicExch(&d.state[s], tag);
+                    return (int)s;
+                }
+            }
+            if (st == GD_BUSY) continue;  // another thread is writing the entry: look again
+            if (st == tag && *reinterpret_cast<volatile unsigned long long*>(&d.x[s]) == x &&
+                *reinterpret_cast<volatile unsigned long long*>(&d.y[s]) == y)
+                return (int)s;
+            break;  // another value lives here
+        }
+    }
+    return -1;
+}
+
+__device__ __forceinline__ int gd_sel(const int (&v)[GD_MAX_COLS], int i) {
+    return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3];
+}
+
+__device__ __forceinline__ uint64_t upsert64(unsigned long long* keys, uint64_t mask, uint64_t k) {
+    uint64_t s = fmix64(k) & mask;
+    while (true) {
+        const unsigned long long prev = atomicCAS(&keys[s], EMPTY64, (unsigned long long)k);
+        if (prev == EMPTY64 || prev == k) return s;
+        s = (s + 1) & mask;
+    }
+}
+
+template <int NC>
+__global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const __grid_constant__ GdParams P) {
+    extern __shared__ __align__(16) uint8_t gd_smem[];
+    // ---- clear the dictionaries and the job tables
+    for (int c = 0; c < NC; ++c) {
+        const GdDict d = gd_dict(gd_smem, P.cols[c].smem_off);
+        for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) d.state[s] = 0u;
+    }
+    for (int j = 0; j < P.n_jobs; ++j) {
+        const GdJob& J = P.jobs[j];
+        uint32_t* base = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        if (J.comp_slots == 0) {
+            for (int s = threadIdx.x; s < 2 * GD_DICT; s += GD_THREADS) base[s] = 0u;
+        } else {
+            for (uint32_t s = threadIdx.x; s < J.comp_slots; s += GD_THREADS) {
+                base[s] = 0xFFFFFFFFu;
+                base[J.comp_slots + s] = 0u;
+                base[2 * J.comp_slots + s] = 0u;
+            }
+        }
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    bool overflow = false;
+    for (int64_t base0 = (int64_t)blockIdx.x * GD_THREADS * GD_ILP; base0 < P.n_rows; base0 += (int64_t)gridDim.x * GD_THREADS * GD_ILP) {
+        int64_t row[GD_ILP];
+        bool act[GD_ILP];
+        int slot[GD_ILP][GD_MAX_COLS];
+#pragma unroll
+        for (int k = 0; k < GD_ILP; ++k) {
+            row[k] = base0 + (int64_t)k * GD_THREADS + threadIdx.x;
+            act[k] = row[k] < P.n_rows;
+#pragma unroll
+            for (int c = 0; c < GD_MAX_COLS; ++c) slot[k][c] = -1;
+        }
+        // ---- every distinct group column once: the loads of the GD_ILP rows go out in waves, then the dictionary probes
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const GdCol& C = P.cols[c];
+            const GdDict d = gd_dict(gd_smem, C.smem_off);
+            bool valid[GD_ILP];
+            uint64_t x[GD_ILP], y[GD_ILP];
+            uint32_t tag[GD_ILP];
+#pragma unroll
+            for (int k = 0; k < GD_ILP; ++k) {
+                valid[k] = act[k] && row_valid(C.validity, row[k]);
+                y[k] = 0;
+            }
+            if (C.dtype == TG_UTF8) {
+                int32_t b[GD_ILP], e[GD_ILP];
+#pragma unroll
+                for (int k = 0; k < GD_ILP; ++k) {
+                    b[k] = valid[k] ? __ldg(C.offsets + row[k]) : 0;
+                    e[k] = valid[k] ? __ldg(C.offsets + row[k] + 1) : 0;
+                }
+#pragma unroll
+                for (int k = 0; k < GD_ILP; ++k) x[k] = e[k] > b[k] ? load_upto8(C.values, b[k], min(8, e[k] - b[k])) : 0ull;
+#pragma unroll
+                for (int k = 0; k < GD_ILP; ++k) {
+                    const int32_t len = e[k] - b[k];
+                    tag[k] = (uint32_t)len + 1u;  // 1..9
+                    if (len > 8) {
+                        uint64_t hx, hy;
+                        utf8_pair(C.values, b[k], e[k], x[k], hx, hy);
+                        x[k] = hx;
+                        y[k] = hy;
+                        tag[k] = GD_TAG_LONG;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int k = 0; k < GD_ILP; ++k) {
+                    x[k] = 0;
+                    tag[k] = 0x10u + (uint32_t)C.dtype;
+                    if (!valid[k]) continue;
+                    const int64_t r = row[k];
+                    switch (C.dtype) {
+                        case TG_INT64: x[k] = __ldg(reinterpret_cast<const unsigned long long*>(C.values) + r); break;
+                        case TG_FLOAT64: x[k] = canon_f64(__ldg(reinterpret_cast<const unsigned long long*>(C.values) + r)); break;
+                        case TG_INT32: x[k] = (uint64_t)(int64_t)__ldg(reinterpret_cast<const int32_t*>(C.values) + r); break;
+                        case TG_FLOAT32: x[k] = canon_f64((uint64_t)__double_as_longlong((double)__ldg(reinterpret_cast<const float*>(C.values) + r))); break;
+                        default: x[k] = (__ldg(reinterpret_cast<const uint32_t*>(C.values) + (r >> 5)) >> (r & 31)) & 1u; break;  // TG_BOOL
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < GD_ILP; ++k) {
+                if (!act[k]) continue;
+                if (!valid[k]) {
+                    x[k] = 0;
+                    y[k] = 0;
+                    tag[k] = GD_TAG_NULL;
+                }
+                const int s = gd_lookup(d, x[k], y[k], tag[k], (uint32_t)row[k]);
+                if (s < 0) overflow = true;
+                slot[k][c] = s;
+            }
+        }
+        // ---- count: per grouping, per row
+        for (int j = 0; j < P.n_jobs; ++j) {
+            const GdJob& J = P.jobs[j];
+            uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+#pragma unroll
+            for (int k = 0; k < GD_ILP; ++k) {
+                const bool ok = act[k] && row_valid(J.target_validity, row[k]);
+                int cs = -1;  // counter slot
+                uint32_t* tot;
+                uint32_t* nn;
+                if (J.comp_slots == 0) {
+                    cs = act[k] ? gd_sel(slot[k], J.col[0]) : -1;
+                    tot = jb;
+                    nn = jb + GD_DICT;
+                } else {
+                    const uint32_t S = J.comp_slots;
+                    tot = jb + S;
+                    nn = jb + 2 * S;
+                    if (act[k]) {
+                        const int s0 = gd_sel(slot[k], J.col[0]), s1 = gd_sel(slot[k], J.col[1]);
+                        const int s2 = J.n_cols > 2 ? gd_sel(slot[k], J.col[2]) : 0;
+                        if ((s0 | s1 | s2) >= 0) {
+                            const uint32_t key = (uint32_t)s0 | ((uint32_t)s1 << 10) | ((uint32_t)s2 << 20);
+                            uint32_t h = key * 0x9E3779B1u;
+                            h ^= h >> 15;
+                            uint32_t s = h & (S - 1);
+                            for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (S - 1)) {
+                                uint32_t v = jb[s];
+                                if (v == 0xFFFFFFFFu) {
+                                    v = atomicCAS(&jb[s], 0xFFFFFFFFu, key);
+                                    if (v == 0xFFFFFFFFu) {
+                                        jb[3 * S + s] = (uint32_t)row[k];  // representative row (read after the barrier only)
+                                        v = key;
+                                    }
+                                }
+                                if (v == key) {
+                                    cs = (int)s;
+                                    break;
+                                }
+                            }
+                            if (cs < 0) overflow = true;
+                        }
+                    }
+                }
+                // one shared atomic per distinct counter per warp (measured: plain per-lane shared atomics are 2x slower here)
+                const unsigned peers = __match_any_sync(0xffffffffu, cs);
+                const unsigned ok_peers = __ballot_sync(0xffffffffu, ok) & peers;
+                if (cs >= 0 && lane == __ffs(peers) - 1) {
+                    atomicAdd(&tot[cs], (uint32_t)__popc(peers));
+                    const int cnt = __popc(ok_peers);
+                    if (cnt) atomicAdd(&nn[cs], (uint32_t)cnt);
+                }
+            }
+        }
+    }
+    if (overflow) atomicExch(P.overflow, 1u);
+    __syncthreads();
+    // ---- publish the dictionaries: local slot -> global code (kept in d.row), representative row -> first_row
+    for (int c = 0; c < NC; ++c) {
+        const GdCol& C = P.cols[c];
+        const GdDict d = gd_dict(gd_smem, C.smem_off);
+        for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
+            const uint32_t tag = d.state[s];
+            if (tag == 0u) continue;
+            Fp f{0, 0};
+            fp_combine(f, d.x[s] ^ ((uint64_t)tag << 56), d.y[s] + tag, true);
+            // exact for short values: fp_combine(first) applies two bijections, to (x ^ tag << 56) and to (y + tag); the tag's
+            // bits 56.. can only meet value bits for 8-byte values, whose tag (9 / a type tag) is fixed per column
+            bool created;
+            const uint64_t g = upsert128(C.dict, f, created);
+            atomicMin(&C.first_row[g], (long long)d.row[s]);
+            d.row[s] = (uint32_t)g;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < P.n_jobs; ++j) {
+        const GdJob& J = P.jobs[j];
+        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        if (J.comp_slots == 0) {
+            const GdDict d = gd_dict(gd_smem, P.cols[J.col[0]].smem_off);
+            for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
+                const uint32_t t = jb[s];
+                if (!t) continue;
+                const uint32_t g = d.row[s];
+                atomicAdd(&J.totals[g], (unsigned long long)t);
+                if (jb[GD_DICT + s]) atomicAdd(&J.nonnull[g], (unsigned long long)jb[GD_DICT + s]);
+            }
+        } else {
+            const uint32_t S = J.comp_slots;
+            const GdDict d0 = gd_dict(gd_smem, P.cols[J.col[0]].smem_off), d1 = gd_dict(gd_smem, P.cols[J.col[1]].smem_off);
+            const GdDict d2 = gd_dict(gd_smem, P.cols[J.col[J.n_cols > 2 ? 2 : 0]].smem_off);
+            for (uint32_t s = threadIdx.x; s < S; s += GD_THREADS) {
+                const uint32_t key = jb[s];
+                if (key == 0xFFFFFFFFu) continue;
+                uint64_t K = (uint64_t)d0.row[key & 1023u] | ((uint64_t)d1.row[(key >> 10) & 1023u] << GD_CODE_BITS);
+                if (J.n_cols > 2) K |= (uint64_t)d2.row[(key >> 20) & 1023u] << (2 * GD_CODE_BITS);
+                const uint64_t g = upsert64(J.ckeys, J.cmask, K);
+                atomicAdd(&J.totals[g], (unsigned long long)jb[S + s]);
+                if (jb[2 * S + s]) atomicAdd(&J.nonnull[g], (unsigned long long)jb[2 * S + s]);
+                atomicMin(&J.crow[g], (long long)jb[3 * S + s]);
+            }
+        }
+    }
+}
+
+// groups of a single-column grouping: the column's global dictionary slots; of a composite grouping: its key table
+__global__ void gd_collect_kernel(const unsigned long long* present /* h1 or ckeys */, const unsigned long long* totals,
+                                  const unsigned long long* nonnull, const long long* first_row, uint64_t cap, unsigned long long* out_n,
+                                  uint64_t max_out, unsigned long long* out /* [max_out][3] = first_row, total, nonnull */) {
+    for (uint64_t s = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; s < cap; s += (uint64_t)gridDim.x * blockDim.x) {
+        if (present[s] == EMPTY64) continue;
+        const unsigned long long i = atomicAdd(out_n, 1ull);
+        if (i < max_out) {
+            out[i * 3 + 0] = (unsigned long long)first_row[s];
+            out[i * 3 + 1] = totals[s];
+            out[i * 3 + 2] = nonnull[s];
+        }
     }
 }
 
@@ -258,139 +634,393 @@ static uint64_t pow2_at_least(uint64_t x) {
     return p;
 }
 
-void exec_grouped_job(Engine& e, Table& t, Plan& p, int agg_id) {
-    Agg& a = p.aggs[agg_id];
-    auto need_col = [&](const std::string& name) -> Column* {
-        Column* c = t.find(name);
-        if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + name + ". Valid fields are " + t.valid_fields() + ".");
-        return c;
-    };
-    Column* target = need_col(a.cols[0]);
-    std::vector<Column*> gcols;
-    for (size_t i = 1; i < a.cols.size(); ++i) gcols.push_back(need_col(a.cols[i]));
-    if (gcols.size() > (size_t)GRP_MAX_COLS) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 8 grouping columns");
+struct GrpBatch {
+    std::vector<int> aggs;                   // aggregate ids
+    std::vector<Column*> dcols;              // distinct group columns
+    std::vector<std::vector<int>> job_cols;  // per job: indices into dcols, in the grouping's order
+};
+constexpr uint64_t GRP_MAX_GROUPS_DEV = 1u << 20;
+
+// global tables of the dictionary path: a column's dictionary holds at most 148 CTAs x 1024 entries (and at most n)
+static uint64_t gd_cap_dict(int64_t n) { return pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, (uint64_t)1 << 18)); }
+static uint64_t gd_cap_comp(int64_t n) { return pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, (uint64_t)1 << 22)); }
+static size_t grouped_dict_bytes(int64_t n, const GrpBatch& B) {
+    size_t need = 256 + B.dcols.size() * gd_cap_dict(n) * 24;
+    for (auto& jc : B.job_cols) need += jc.size() == 1 ? gd_cap_dict(n) * 16 : gd_cap_comp(n) * 32;
+    return need;
+}
+
+// fast path (column dictionaries): fills d_out[j] / n_groups[j]; returns false when the batch is not eligible or a CTA's
+// shared tables overflowed (the caller then runs the generic kernel)
+static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, uint8_t* scr, size_t out_b, std::vector<unsigned long long*>& d_out,
+                               std::vector<unsigned long long>& n_groups) {
     const int64_t n = t.n_rows;
-    for (auto* c : gcols) {
+    const int nj = (int)B.aggs.size(), nc = (int)B.dcols.size();
+    if (nc > GD_MAX_COLS || nj > GD_MAX_JOBS || n >= ((int64_t)1 << 32)) return false;
+    int n_comp = 0;
+    for (auto& jc : B.job_cols) {
+        if (jc.size() > 3) return false;
+        n_comp += jc.size() > 1;
+    }
+    if (getenv("TG_GROUPED_NO_DICT")) return false;
+    // shared memory: dictionaries, single-column counters, the rest split between the composite tables
+    size_t off = 0;
+    GdParams P{};
+    P.n_cols = nc;
+    P.n_jobs = nj;
+    P.n_rows = n;
+    for (int c = 0; c < nc; ++c) {
+        P.cols[c].smem_off = (uint32_t)off;
+        off += GD_DICT_BYTES;
+    }
+    for (int j = 0; j < nj; ++j)
+        if (B.job_cols[j].size() == 1) {
+            P.jobs[j].smem_off = (uint32_t)off;
+            off += (size_t)GD_DICT * 8;
+        }
+    const size_t budget = 222 * 1024;
+    if (off > budget) return false;
+    uint32_t comp_slots = 0;
+    if (n_comp) {
+        comp_slots = 8192;
+        while (comp_slots > 256 && off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
+        if (off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) return false;
+    }
+    for (int j = 0; j < nj; ++j)
+        if (B.job_cols[j].size() > 1) {
+            P.jobs[j].smem_off = (uint32_t)off;
+            P.jobs[j].comp_slots = comp_slots;
+            off += (size_t)comp_slots * 16;
+        }
+    const size_t smem = off;
+    // global state (the caller sized the scratch block with grouped_dict_bytes)
+    const uint64_t cap_d = gd_cap_dict(n), cap_c = gd_cap_comp(n);
+    const size_t dcol_b = cap_d * 8 * 3, dsingle_b = cap_d * 8 * 2, dcomp_b = cap_c * 8 * 4;
+    uint8_t* q = scr;
+    unsigned int* d_over = (unsigned int*)q; q += 256;
+    TG_CUDA(cudaMemsetAsync(d_over, 0, 256, e.stream));
+    for (int c = 0; c < nc; ++c) {
+        Column* col = B.dcols[c];
+        GdCol& C = P.cols[c];
+        C.values = col->values.p;
+        C.offsets = (const int32_t*)col->offsets.p;
+        C.validity = (const uint32_t*)col->validity.p;
+        C.dtype = col->dtype;
+        C.dict = Table128{(unsigned long long*)q, (unsigned long long*)(q + cap_d * 8), nullptr, cap_d - 1};
+        C.first_row = (long long*)(q + cap_d * 16);
+        TG_CUDA(cudaMemsetAsync(q, 0xFF, cap_d * 16, e.stream));
+        TG_CUDA(cudaMemsetAsync(q + cap_d * 16, 0x7F, cap_d * 8, e.stream));
+        q += dcol_b;
+    }
+    for (int j = 0; j < nj; ++j) {
+        GdJob& J = P.jobs[j];
+        J.target_validity = (const uint32_t*)t.find(p.aggs[B.aggs[j]].cols[0])->validity.p;
+        J.n_cols = (int)B.job_cols[j].size();
+        for (int k = 0; k < J.n_cols; ++k) J.col[k] = B.job_cols[j][k];
+        if (J.n_cols == 1) {
+            J.totals = (unsigned long long*)q;
+            J.nonnull = (unsigned long long*)(q + cap_d * 8);
+            TG_CUDA(cudaMemsetAsync(q, 0, cap_d * 16, e.stream));
+            q += dsingle_b;
+        } else {
+            J.ckeys = (unsigned long long*)q;
+            J.totals = (unsigned long long*)(q + cap_c * 8);
+            J.nonnull = (unsigned long long*)(q + cap_c * 16);
+            J.crow = (long long*)(q + cap_c * 24);
+            J.cmask = cap_c - 1;
+            TG_CUDA(cudaMemsetAsync(q, 0xFF, cap_c * 8, e.stream));
+            TG_CUDA(cudaMemsetAsync(q + cap_c * 8, 0, cap_c * 16, e.stream));
+            TG_CUDA(cudaMemsetAsync(q + cap_c * 24, 0x7F, cap_c * 8, e.stream));
+            q += dcomp_b;
+        }
+    }
+    P.overflow = d_over;
+    typedef void (*Kern)(const GdParams);
+    const Kern kern = nc == 1 ? (Kern)group_count_dict_kernel<1> : nc == 2 ? (Kern)group_count_dict_kernel<2>
+                      : nc == 3 ? (Kern)group_count_dict_kernel<3> : (Kern)group_count_dict_kernel<4>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GD_THREADS * GD_ILP - 1) / (GD_THREADS * GD_ILP), (int64_t)e.sm_count));
+    kern<<<grid, GD_THREADS, smem, e.stream>>>(P);
+    TG_CUDA(cudaGetLastError());
+    unsigned int h_over = 0;
+    TG_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    p.stats.launches += 1;
+    e.launches += 1;
+    if (h_over) return false;
+    // the groups: out triples behind the tables (the generic path's out area is not used by this path)
+    unsigned long long* d_cnt = (unsigned long long*)(d_over + 16);
+    const int cgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((std::max(cap_d, cap_c) + 255) / 256, (uint64_t)e.sm_count * 8));
+    std::vector<unsigned long long> h_cnt((size_t)nj, 0);
+    for (int j = 0; j < nj; ++j) {
+        const GdJob& J = P.jobs[j];
+        if (J.n_cols == 1) {
+            const GdCol& C = P.cols[J.col[0]];
+            gd_collect_kernel<<<cgrid, 256, 0, e.stream>>>(C.dict.h1, J.totals, J.nonnull, C.first_row, cap_d, d_cnt + j, GRP_MAX_GROUPS_DEV, d_out[j]);
+        } else {
+            gd_collect_kernel<<<cgrid, 256, 0, e.stream>>>(J.ckeys, J.totals, J.nonnull, J.crow, cap_c, d_cnt + j, GRP_MAX_GROUPS_DEV, d_out[j]);
+        }
+        TG_CUDA(cudaGetLastError());
+    }
+    TG_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)nj * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    p.stats.launches += nj;
+    e.launches += nj;
+    for (int j = 0; j < nj; ++j) n_groups[j] = h_cnt[j];
+    (void)out_b;
+    return true;
+}
+
+// generic path (128-bit fingerprints, any number of columns / groups)
+static void grouped_count_generic(Engine& e, Table& t, Plan& p, const GrpBatch& B, uint8_t* scr, size_t per_job, uint64_t cap,
+                                  std::vector<unsigned long long*>& d_out, std::vector<unsigned long long>& n_groups) {
+    const int64_t n = t.n_rows;
+    const int nj = (int)B.aggs.size();
+    const size_t h_b = cap * 8;
+    GrpParams P{};
+    P.n_cols = (int)B.dcols.size();
+    P.n_jobs = nj;
+    P.n_rows = n;
+    for (size_t i = 0; i < B.dcols.size(); ++i)
+        P.cols[i] = GrpCol{B.dcols[i]->values.p, (const int32_t*)B.dcols[i]->offsets.p, (const uint32_t*)B.dcols[i]->validity.p, B.dcols[i]->dtype, 0u, 0u, 0u};
+    std::vector<unsigned long long*> d_n(nj);
+    for (int j = 0; j < nj; ++j) {
+        uint8_t* q = scr + (size_t)j * per_job;
+        GrpJob& J = P.jobs[j];
+        J.gt = Table128{(unsigned long long*)q, (unsigned long long*)(q + h_b), nullptr, cap - 1}; q += 2 * h_b;
+        J.totals = (unsigned long long*)q; q += h_b;
+        J.nonnull = (unsigned long long*)q; q += h_b;
+        J.first_row = (long long*)q; q += h_b;
+        d_n[j] = (unsigned long long*)q;
+        J.n_groups = d_n[j];
+        J.target_validity = (const uint32_t*)t.find(p.aggs[B.aggs[j]].cols[0])->validity.p;
+        // the fingerprint folds a grouping's columns in the batch's column order; "first" = the lowest index it contains
+        int lowest = GRP_MAX_COLS;
+        for (int ci : B.job_cols[j]) {
+            P.cols[ci].job_mask |= 1u << j;
+            lowest = std::min(lowest, ci);
+        }
+        P.cols[lowest].first_mask |= 1u << j;
+        TG_CUDA(cudaMemsetAsync(J.gt.h1, 0xFF, 2 * h_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(J.totals, 0, 2 * h_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(J.first_row, 0x7F, h_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(d_n[j], 0, 256, e.stream));
+    }
+    // shared tables: a multi-column grouping has (up to) the product of its columns' cardinalities as groups, so it gets
+    // sixteen shares of the block where a single-column grouping gets one; every table a power of two, at most 8192 slots
+    int shares = 0;
+    for (int j = 0; j < nj; ++j) shares += B.job_cols[j].size() > 1 ? 16 : 1;
+    size_t smem_slots = 0;
+    for (int j = 0; j < nj; ++j) {
+        const size_t want = (size_t)GRP_SMEM_BYTES / 24 * (B.job_cols[j].size() > 1 ? 16 : 1) / (size_t)shares;
+        int sl = 512;
+        while ((size_t)sl * 2 <= want && sl < 8192) sl <<= 1;
+        P.slots[j] = sl;
+        P.slot_base[j] = (int32_t)smem_slots;
+        smem_slots += (size_t)sl;
+    }
+    const size_t smem = smem_slots * 24;
+    typedef void (*Kern)(const GrpParams);
+    const Kern kern = nj == 1 ? (Kern)group_count_fused_kernel<1> : nj == 2 ? (Kern)group_count_fused_kernel<2>
+                      : nj == 3 ? (Kern)group_count_fused_kernel<3> : (Kern)group_count_fused_kernel<4>;
+    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GRP_THREADS * GRP_ILP - 1) / (GRP_THREADS * GRP_ILP), (int64_t)e.sm_count));
+    kern<<<grid, GRP_THREADS, smem, e.stream>>>(P);
+    TG_CUDA(cudaGetLastError());
+    const int cgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((cap + 255) / 256, (uint64_t)e.sm_count * 8));
+    std::vector<unsigned long long> h_n((size_t)nj * 2, 0);
+    for (int j = 0; j < nj; ++j) {
+        const GrpJob& J = P.jobs[j];
+        group_collect_kernel<<<cgrid, 256, 0, e.stream>>>(J.gt, J.totals, J.nonnull, J.first_row, cap, d_n[j] + 1, GRP_MAX_GROUPS_DEV, d_out[j]);
+        TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaMemcpyAsync(&h_n[(size_t)j * 2], d_n[j], 16, cudaMemcpyDeviceToHost, e.stream));
+    }
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    p.stats.launches += 1 + nj;
+    e.launches += 1 + nj;
+    for (int j = 0; j < nj; ++j) n_groups[j] = h_n[(size_t)j * 2];
+}
+
+// One batch = up to GRP_MAX_JOBS groupings over up to GRP_MAX_COLS distinct group columns: one launch of a counting kernel
+// (column dictionaries when the batch is narrow and its groups are few, 128-bit fingerprints otherwise), then per
+// grouping the collection of the groups and of their key values.
+static void run_grouped_batch(Engine& e, Table& t, Plan& p, const GrpBatch& B) {
+    const std::vector<int>& batch = B.aggs;
+    const std::vector<Column*>& dcols = B.dcols;
+    const std::vector<std::vector<int>>& job_cols = B.job_cols;
+    const int64_t n = t.n_rows;
+    const int nj = (int)batch.size();
+    // algorithmic bytes: every distinct group column once, every distinct target bitmap once
+    for (auto* c : dcols) {
         uint64_t b = c->validity.p ? (uint64_t)(n + 7) / 8 : 0;
         if (c->dtype == TG_UTF8) b += (uint64_t)(n + 1) * 4 + (uint64_t)c->value_bytes;
         else if (c->dtype == TG_BOOL) b += (uint64_t)(n + 7) / 8;
         else b += (uint64_t)n * c->elem_bytes();
         p.stats.bytes_scanned += b;
     }
-    if (target->validity.p) p.stats.bytes_scanned += (uint64_t)(n + 7) / 8;
-    uint64_t zero = 0;
-    a.blob.assign((uint8_t*)&zero, (uint8_t*)&zero + 8);
-    if (n == 0) return;
-    const uint64_t max_groups_dev = 1u << 20;
-    const uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, max_groups_dev * 4));
-    const size_t h_b = cap * 8, out_b = round_up((size_t)max_groups_dev * 24, 256);
-    uint8_t* scr = e.scratch(5 * h_b + out_b + 256);
-    uint8_t* q = scr;
-    GrpParams P{};
-    P.gt = Table128{(unsigned long long*)q, (unsigned long long*)(q + h_b), nullptr, cap - 1}; q += 2 * h_b;
-    P.totals = (unsigned long long*)q; q += h_b;
-    P.nonnull = (unsigned long long*)q; q += h_b;
-    P.first_row = (long long*)q; q += h_b;
-    unsigned long long* d_out = (unsigned long long*)q; q += out_b;
-    unsigned long long* d_n = (unsigned long long*)q;
-    P.n_groups = d_n;
-    P.n_cols = (int)gcols.size();
-    P.n_rows = n;
-    P.target_validity = (const uint32_t*)target->validity.p;
-    for (size_t i = 0; i < gcols.size(); ++i)
-        P.cols[i] = GrpCol{gcols[i]->values.p, (const int32_t*)gcols[i]->offsets.p, (const uint32_t*)gcols[i]->validity.p, gcols[i]->dtype, 0};
+    {
+        std::vector<const uint8_t*> seen;
+        for (int id : batch) {
+            Column* target = t.find(p.aggs[id].cols[0]);
+            if (target->validity.p && std::find(seen.begin(), seen.end(), target->validity.p) == seen.end()) {
+                seen.push_back(target->validity.p);
+                p.stats.bytes_scanned += (uint64_t)(n + 7) / 8;
+            }
+        }
+    }
+    const uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, GRP_MAX_GROUPS_DEV * 4));
+    const size_t h_b = cap * 8, out_b = round_up((size_t)GRP_MAX_GROUPS_DEV * 24, 256);
+    const size_t per_job = 5 * h_b + 512;
+    // [tables of the counting kernel (either path)][out triples: nj x out_b]
+    const size_t tables_b = round_up(std::max(per_job * (size_t)nj, grouped_dict_bytes(n, B)), 256);
+    uint8_t* scr = e.scratch(tables_b + out_b * (size_t)nj + 1024);
+    std::vector<unsigned long long*> d_out(nj);
+    std::vector<unsigned long long> n_groups_v((size_t)nj, 0);
+    for (int j = 0; j < nj; ++j) d_out[j] = (unsigned long long*)(scr + tables_b + out_b * (size_t)j);
     cudaEventRecord(e.ev[4], e.stream);
-    TG_CUDA(cudaMemsetAsync(P.gt.h1, 0xFF, 2 * h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(P.totals, 0, 2 * h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(P.first_row, 0x7F, h_b, e.stream));
-    TG_CUDA(cudaMemsetAsync(d_n, 0, 256, e.stream));
-    const size_t smem = (size_t)GRP_SLOTS * 24;
-    TG_CUDA(cudaFuncSetAttribute(group_count_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GRP_THREADS * GRP_ILP - 1) / (GRP_THREADS * GRP_ILP), (int64_t)e.sm_count));
-    group_count_fused_kernel<<<grid, GRP_THREADS, smem, e.stream>>>(P);
-    TG_CUDA(cudaGetLastError());
-    const int cgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((cap + 255) / 256, (uint64_t)e.sm_count * 8));
-    group_collect_kernel<<<cgrid, 256, 0, e.stream>>>(P.gt, P.totals, P.nonnull, P.first_row, cap, d_n + 1, max_groups_dev, d_out);
-    TG_CUDA(cudaGetLastError());
-    unsigned long long h_n[2] = {0, 0};
-    TG_CUDA(cudaMemcpyAsync(h_n, d_n, 16, cudaMemcpyDeviceToHost, e.stream));
+    if (!grouped_count_dict(e, t, p, B, scr, out_b, d_out, n_groups_v)) grouped_count_generic(e, t, p, B, scr, per_job, cap, d_out, n_groups_v);
     cudaEventRecord(e.ev[5], e.stream);
     TG_CUDA(cudaStreamSynchronize(e.stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, e.ev[4], e.ev[5]);
     p.stats.hash_ms += ms;
     p.stats.gpu_ms += ms;
-    p.stats.launches += 2;
-    e.launches += 2;
-    const unsigned long long n_groups = h_n[0];
-    if (n_groups > max_groups_dev) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 1048576 groups");
-    // ---- key values of the groups (batched: two small kernels + two copies, however many groups) ----
-    const size_t nc = gcols.size(), n_entries = (size_t)n_groups * nc;
-    std::vector<unsigned long long> out((size_t)n_groups * 3), meta(n_entries * 3), dst_off(n_entries, 0);
-    std::vector<uint8_t> key_bytes;
-    if (n_groups) {
-        TG_CUDA(cudaMemcpy(out.data(), d_out, out.size() * 8, cudaMemcpyDeviceToHost));
-        // meta / offsets / packed bytes live in the engine's grow-only auxiliary block (no cudaMalloc per execute)
-        unsigned long long* d_meta = (unsigned long long*)e.aux(n_entries * 3 * 8 + n_entries * 8 + 256);
-        unsigned long long* d_dst = d_meta + n_entries * 3;
-        group_keys_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e.stream>>>(P, d_out, n_groups, d_meta);
-        TG_CUDA(cudaGetLastError());
-        TG_CUDA(cudaMemcpyAsync(meta.data(), d_meta, meta.size() * 8, cudaMemcpyDeviceToHost, e.stream));
-        TG_CUDA(cudaStreamSynchronize(e.stream));
-        uint64_t total = 0;
-        for (size_t i = 0; i < n_entries; ++i) {
-            dst_off[i] = total;
-            if (gcols[i % nc]->dtype == TG_UTF8 && meta[i * 3]) total += meta[i * 3 + 2];
-        }
-        key_bytes.resize((size_t)total);
-        if (total) {
-            // the packed bytes go where d_out's copy-out already happened: the scratch block (>= max_groups * 24 bytes)
-            uint8_t* d_bytes = total <= out_b ? (uint8_t*)d_out : nullptr;
-            const bool own = d_bytes == nullptr;
-            if (own) TG_CUDA(cudaMalloc(&d_bytes, (size_t)total));
-            TG_CUDA(cudaMemcpyAsync(d_dst, dst_off.data(), n_entries * 8, cudaMemcpyHostToDevice, e.stream));
-            group_key_bytes_kernel<<<(unsigned)((n_entries * 32 + 255) / 256), 256, 0, e.stream>>>(P, d_meta, d_dst, n_entries, d_bytes);
-            cudaError_t ce = cudaGetLastError();
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(key_bytes.data(), d_bytes, (size_t)total, cudaMemcpyDeviceToHost, e.stream);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
-            if (own) cudaFree(d_bytes);
-            TG_CUDA(ce);
-        }
-        p.stats.launches += 2;
-        e.launches += 2;
-    }
-    // blob: [u64 n_groups] then per group: u32 key_len, key (group column values joined by \x1f), u64 total, u64 non_null
-    a.blob.resize(8);
-    memcpy(a.blob.data(), &n_groups, 8);
-    for (unsigned long long g = 0; g < n_groups; ++g) {
-        std::string key;
-        for (size_t i = 0; i < nc; ++i) {
-            if (i) key += '\x1f';
-            const size_t en = (size_t)g * nc + i;
-            if (!meta[en * 3]) {
-                key += "NULL";
-                continue;
+
+    for (int j = 0; j < nj; ++j) {
+        Agg& a = p.aggs[batch[j]];
+        try {
+            const unsigned long long n_groups = n_groups_v[j];
+            if (n_groups > GRP_MAX_GROUPS_DEV) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 1048576 groups");
+            // ---- key values of the groups (batched: two small kernels + two copies, however many groups) ----
+            std::vector<Column*> gcols;
+            for (int ci : job_cols[j]) gcols.push_back(dcols[ci]);
+            GrpParams PK{};  // the key kernels see the grouping's own columns, in its own order
+            PK.n_cols = (int)gcols.size();
+            PK.n_rows = n;
+            for (size_t i = 0; i < gcols.size(); ++i)
+                PK.cols[i] = GrpCol{gcols[i]->values.p, (const int32_t*)gcols[i]->offsets.p, (const uint32_t*)gcols[i]->validity.p, gcols[i]->dtype, 0u, 0u, 0u};
+            const size_t nc = gcols.size(), n_entries = (size_t)n_groups * nc;
+            std::vector<unsigned long long> out((size_t)n_groups * 3), meta(n_entries * 3), dst_off(n_entries, 0);
+            std::vector<uint8_t> key_bytes;
+            if (n_groups) {
+                TG_CUDA(cudaMemcpy(out.data(), d_out[j], out.size() * 8, cudaMemcpyDeviceToHost));
+                // meta / offsets / packed bytes live in the engine's grow-only auxiliary block (no cudaMalloc per execute)
+                unsigned long long* d_meta = (unsigned long long*)e.aux(n_entries * 3 * 8 + n_entries * 8 + 256);
+                unsigned long long* d_dst = d_meta + n_entries * 3;
+                group_keys_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e.stream>>>(PK, d_out[j], n_groups, d_meta);
+                TG_CUDA(cudaGetLastError());
+                TG_CUDA(cudaMemcpyAsync(meta.data(), d_meta, meta.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+                TG_CUDA(cudaStreamSynchronize(e.stream));
+                uint64_t total = 0;
+                for (size_t i = 0; i < n_entries; ++i) {
+                    dst_off[i] = total;
+                    if (gcols[i % nc]->dtype == TG_UTF8 && meta[i * 3]) total += meta[i * 3 + 2];
+                }
+                key_bytes.resize((size_t)total);
+                if (total) {
+                    // the packed bytes go where d_out's copy-out already happened: the scratch block (>= max_groups * 24 bytes)
+                    uint8_t* d_bytes = total <= out_b ? (uint8_t*)d_out[j] : nullptr;
+                    const bool own = d_bytes == nullptr;
+                    if (own) TG_CUDA(cudaMalloc(&d_bytes, (size_t)total));
+                    TG_CUDA(cudaMemcpyAsync(d_dst, dst_off.data(), n_entries * 8, cudaMemcpyHostToDevice, e.stream));
+                    group_key_bytes_kernel<<<(unsigned)((n_entries * 32 + 255) / 256), 256, 0, e.stream>>>(PK, d_meta, d_dst, n_entries, d_bytes);
+                    cudaError_t ce = cudaGetLastError();
+                    if (ce == cudaSuccess) ce = cudaMemcpyAsync(key_bytes.data(), d_bytes, (size_t)total, cudaMemcpyDeviceToHost, e.stream);
+                    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
+                    if (own) cudaFree(d_bytes);
+                    TG_CUDA(ce);
+                }
+                p.stats.launches += 2;
+                e.launches += 2;
             }
-            const unsigned long long x = meta[en * 3 + 1];
-            switch (gcols[i]->dtype) {
-                case TG_UTF8: key.append((const char*)key_bytes.data() + dst_off[en], (size_t)meta[en * 3 + 2]); break;
-                case TG_INT64: case TG_INT32: key += fmt_i64((int64_t)x); break;
-                case TG_FLOAT64: case TG_FLOAT32: {
-                    double d;
-                    memcpy(&d, &x, 8);
-                    key += fmt_f64(d);
-                } break;
-                default: break;  // Boolean group values print as the empty string, as before
+            // blob: [u64 n_groups] then per group: u32 key_len, key (group column values joined by \x1f), u64 total, u64 non_null
+            a.blob.resize(8);
+            memcpy(a.blob.data(), &n_groups, 8);
+            for (unsigned long long g = 0; g < n_groups; ++g) {
+                std::string key;
+                for (size_t i = 0; i < nc; ++i) {
+                    if (i) key += '\x1f';
+                    const size_t en = (size_t)g * nc + i;
+                    if (!meta[en * 3]) {
+                        key += "NULL";
+                        continue;
+                    }
+                    const unsigned long long x = meta[en * 3 + 1];
+                    switch (gcols[i]->dtype) {
+                        case TG_UTF8: key.append((const char*)key_bytes.data() + dst_off[en], (size_t)meta[en * 3 + 2]); break;
+                        case TG_INT64: case TG_INT32: key += fmt_i64((int64_t)x); break;
+                        case TG_FLOAT64: case TG_FLOAT32: {
+                            double d;
+                            memcpy(&d, &x, 8);
+                            key += fmt_f64(d);
+                        } break;
+                        default: break;  // Boolean group values print as the empty string, as before
+                    }
+                }
+                uint32_t L = (uint32_t)key.size();
+                size_t o = a.blob.size();
+                a.blob.resize(o + 4 + L + 16);
+                memcpy(a.blob.data() + o, &L, 4);
+                memcpy(a.blob.data() + o + 4, key.data(), L);
+                memcpy(a.blob.data() + o + 4 + L, &out[g * 3 + 1], 8);
+                memcpy(a.blob.data() + o + 4 + L + 8, &out[g * 3 + 2], 8);
             }
+        } catch (Error& er) {
+            if (er.code == TG_ERR_CUDA) throw;
+            a.err = er.code;
+            a.err_msg = er.msg;
         }
-        uint32_t L = (uint32_t)key.size();
-        size_t o = a.blob.size();
-        a.blob.resize(o + 4 + L + 16);
-        memcpy(a.blob.data() + o, &L, 4);
-        memcpy(a.blob.data() + o + 4, key.data(), L);
-        memcpy(a.blob.data() + o + 4 + L, &out[g * 3 + 1], 8);
-        memcpy(a.blob.data() + o + 4 + L + 8, &out[g * 3 + 2], 8);
     }
+}
+
+// All grouped-completeness aggregates of a plan: bound to their columns, packed into batches that share one pass
+void exec_grouped_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids) {
+    std::vector<int> batch;
+    std::vector<Column*> dcols;
+    std::vector<std::vector<int>> job_cols;
+    auto flush = [&]() {
+        if (!batch.empty()) run_grouped_batch(e, t, p, GrpBatch{batch, dcols, job_cols});
+        batch.clear();
+        dcols.clear();
+        job_cols.clear();
+    };
+    for (int id : agg_ids) {
+        Agg& a = p.aggs[id];
+        try {
+            auto need_col = [&](const std::string& name) -> Column* {
+                Column* c = t.find(name);
+                if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + name + ". Valid fields are " + t.valid_fields() + ".");
+                return c;
+            };
+            need_col(a.cols[0]);
+            std::vector<Column*> gcols;
+            for (size_t i = 1; i < a.cols.size(); ++i) gcols.push_back(need_col(a.cols[i]));
+            if (gcols.size() > (size_t)GRP_MAX_COLS) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 8 grouping columns");
+            uint64_t zero = 0;
+            a.blob.assign((uint8_t*)&zero, (uint8_t*)&zero + 8);
+            if (t.n_rows == 0) continue;
+            // does it fit the open batch?
+            std::vector<Column*> merged = dcols;
+            for (auto* c : gcols)
+                if (std::find(merged.begin(), merged.end(), c) == merged.end()) merged.push_back(c);
+            if (batch.size() == (size_t)GRP_MAX_JOBS || merged.size() > (size_t)GRP_MAX_COLS) {
+                flush();
+                merged.clear();
+                for (auto* c : gcols)
+                    if (std::find(merged.begin(), merged.end(), c) == merged.end()) merged.push_back(c);
+            }
+            dcols = merged;
+            std::vector<int> idx;
+            for (auto* c : gcols) idx.push_back((int)(std::find(dcols.begin(), dcols.end(), c) - dcols.begin()));
+            batch.push_back(id);
+            job_cols.push_back(idx);
+        } catch (Error& er) {
+            if (er.code == TG_ERR_CUDA) throw;
+            a.err = er.code;
+            a.err_msg = er.msg;
+        }
+    }
+    flush();
 }
 
 }  // namespace tg

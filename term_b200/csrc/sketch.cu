@@ -290,9 +290,13 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
     }
     uint8_t* scr = e.scratch(per_job * jobs.size());
     uint8_t* hs = e.host_scratch(host_total);
+    // The samplers run back to back on the engine's stream at HBM speed; a column's sort / ladder / copy-out is a chain
+    // of small launch-latency-bound kernels, so it goes to a side stream and overlaps the next column's sampler.
+    e.ensure_side_streams();
     TG_CUDA(cudaEventRecord(e.ev[6], e.stream));
     for (size_t ji = 0; ji < jobs.size(); ++ji) {
         Job& j = jobs[ji];
+        cudaStream_t side = e.side[ji % 4];
         const size_t top_b = round_up((size_t)j.cap * 8, 256);
         uint8_t* q = scr + ji * per_job;
         uint64_t* kb[2];
@@ -317,19 +321,26 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
         // exact mode sorts on all 64 key bits; a sampled level only needs the order down to the top 32 bits (sign,
         // exponent, 20 mantissa bits: items closer than 1e-6 relative may swap, far inside the rank-error bound),
         // which halves the radix passes — each is launch-latency bound at this size
+        TG_CUDA(cudaEventRecord(e.side_ev[ji % 4], e.stream));
+        TG_CUDA(cudaStreamWaitEvent(side, e.side_ev[ji % 4], 0));
         const RsTemp RT = rs_temp_carve(d_tmp, m, n_passes);
         uint64_t* no_vals[2] = {nullptr, nullptr};
-        int launches = 1 + rs_sort_pairs<uint64_t>(e.stream, kb, no_vals, m, exact ? 0 : 32, n_passes, false, RT, e.sm_count);
+        int launches = 1 + rs_sort_pairs<uint64_t>(side, kb, no_vals, m, exact ? 0 : 32, n_passes, false, RT, e.sm_count);
         TG_CUDA(cudaGetLastError());
-        kll_compact_kernel<<<(unsigned)((j.cap + 255) / 256), 256, 0, e.stream>>>(RT.ctl, kb[0], kb[1], d_ctr, h0, (uint32_t)j.cap, seed, d_lad, d_top);
+        kll_compact_kernel<<<(unsigned)((j.cap + 255) / 256), 256, 0, side>>>(RT.ctl, kb[0], kb[1], d_ctr, h0, (uint32_t)j.cap, seed, d_lad, d_top);
         TG_CUDA(cudaGetLastError());
         ++launches;
-        // the D2H of the counters must not race with the H2D that initialised them from the same pinned slot: both
-        // are stream-ordered
-        TG_CUDA(cudaMemcpyAsync(hs + j.host_off, d_lad, lad_b + top_b, cudaMemcpyDeviceToHost, e.stream));
-        TG_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(KllCounters), cudaMemcpyDeviceToHost, e.stream));
+        // the D2H of the counters must not race with the H2D that initialised them from the same pinned slot: the side
+        // stream waited for the engine's stream above
+        TG_CUDA(cudaMemcpyAsync(hs + j.host_off, d_lad, lad_b + top_b, cudaMemcpyDeviceToHost, side));
+        TG_CUDA(cudaMemcpyAsync(h_ctr, d_ctr, sizeof(KllCounters), cudaMemcpyDeviceToHost, side));
         p.stats.launches += launches;
         e.launches += launches;
+    }
+    // join: the engine's stream continues only after every side chain (a side stream is reused by every 4th column in order)
+    for (int k = 0; k < 4 && k < (int)jobs.size(); ++k) {
+        TG_CUDA(cudaEventRecord(e.side_ev[k], e.side[k]));
+        TG_CUDA(cudaStreamWaitEvent(e.stream, e.side_ev[k], 0));
     }
     TG_CUDA(cudaEventRecord(e.ev[7], e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
