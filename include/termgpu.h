@@ -435,6 +435,40 @@ TG_API tg_status tg_engine_mailbox_create(tg_engine* eng, int32_t world, int32_t
 TG_API tg_status tg_engine_mailbox_open(tg_engine* eng, const void* handles /* world x 64 bytes, rank order */);
 TG_API tg_status tg_plan_exchange_and_finalize(tg_engine* eng, tg_plan* plan);
 
+/*
+ * Distributed RANK() OVER (ORDER BY ..) for the Spearman analyzer across row shards (the reference's
+ * two window functions, analyzers/advanced/correlation.rs:334-350, see every row of the table). One rank session per
+ * engine; the host layer runs a SAMPLE SORT around these stages, once per column:
+ *     tg_rank_begin          the shard's pairwise-complete rows as order-preserving keys (keys = x, payload = y)
+ *     tg_rank_local_sort     sort the shard by key (hand-written radix sort)
+ *     tg_rank_sample         up to n evenly spaced keys of the sorted shard -> host; all ranks all-gather their samples,
+ *                            sort them and take world - 1 splitters at equal steps
+ *     tg_rank_split          counts[p] = keys of this shard that belong to part p = the keys in (splitter[p-1], splitter[p]]
+ *     tg_rank_send_buffers / tg_rank_recv_buffers     device pointers for the all-to-all of keys and payload (NCCL);
+ *                            payload_bytes is 8 in the x phase (the y key) and 4 in the y phase (rank_x)
+ *     tg_rank_recv_commit    the received range becomes the session's data
+ *     tg_rank_finish_x       sort the range by x; minimum rank of a key = rank_base + position of its run's head + 1 with
+ *                            rank_base = number of keys on the lower ranks; the data becomes (keys = y, payload = rank_x)
+ *     tg_rank_finish_y       same by y; returns the range's pair count and the sums of (rank_x - c), (rank_y - c), their
+ *                            squares and their product, c = `center` = (N + 1) / 2 — the partial state of the SPEARMAN
+ *                            aggregate (tg_plan_set_aggregate_partial), which merges across ranks by addition
+ * Equal keys always meet on one rank, so ties share the global minimum rank exactly as on one GPU. tg_rank_abort drops
+ * the session. On one GPU tg_plan_execute runs the same stages back to back.
+ */
+TG_API tg_status tg_rank_begin(tg_engine* eng, const char* table, const char* column_x, const char* column_y, int64_t* n_pairs);
+TG_API tg_status tg_rank_local_sort(tg_engine* eng);
+TG_API int32_t tg_rank_sample(tg_engine* eng, int32_t n_samples, uint64_t* keys);
+TG_API tg_status tg_rank_split(tg_engine* eng, const uint64_t* splitters, int32_t n_parts, int64_t* counts);
+TG_API tg_status tg_rank_send_buffers(tg_engine* eng, const void** keys, const void** payload, int32_t* payload_bytes);
+TG_API tg_status tg_rank_recv_buffers(tg_engine* eng, int64_t n_recv, void** keys, void** payload);
+TG_API tg_status tg_rank_recv_commit(tg_engine* eng, int64_t n_recv);
+TG_API tg_status tg_rank_finish_x(tg_engine* eng, uint64_t rank_base);
+TG_API tg_status tg_rank_finish_y(tg_engine* eng, uint64_t rank_base, double center, uint64_t* n_out, double* sums5);
+TG_API tg_status tg_rank_abort(tg_engine* eng);
+/* Installs a partial state computed outside tg_plan_execute_partial for aggregate i (kind 10 SPEARMAN only): u[0] = pair
+ * count, f[0] = f[1] = center, f[2..6] = the five sums. Call it after tg_plan_execute_partial, before the exchange. */
+TG_API tg_status tg_plan_set_aggregate_partial(tg_plan* plan, int32_t i, const uint64_t* u8, const double* f8);
+
 /* The sketch behind a tg_plan_add_kll / quantile slot as KllSketch's own fields (kll_sketch.rs:142-160): count / min /
  * max come with tg_plan_analyzer_result; this returns the compactor stack. level < 0: the number of levels; otherwise
  * the items of that level (each standing for 2^level values, ascending) are copied into items[cap] and the level's item

@@ -135,6 +135,17 @@ SIGNATURES = {
     "tg_engine_mailbox_open": (C.c_int, [P, P]),
     "tg_plan_exchange_and_finalize": (C.c_int, [P, P]),
     "tg_debug_sort_pairs": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, P, P]),
+    "tg_rank_begin": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "tg_rank_local_sort": (C.c_int, [P]),
+    "tg_rank_sample": (C.c_int32, [P, C.c_int32, C.POINTER(C.c_uint64)]),
+    "tg_rank_split": (C.c_int, [P, C.POINTER(C.c_uint64), C.c_int32, C.POINTER(C.c_int64)]),
+    "tg_rank_send_buffers": (C.c_int, [P, PP, PP, C.POINTER(C.c_int32)]),
+    "tg_rank_recv_buffers": (C.c_int, [P, C.c_int64, PP, PP]),
+    "tg_rank_recv_commit": (C.c_int, [P, C.c_int64]),
+    "tg_rank_finish_x": (C.c_int, [P, C.c_uint64]),
+    "tg_rank_finish_y": (C.c_int, [P, C.c_uint64, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
+    "tg_rank_abort": (C.c_int, [P]),
+    "tg_plan_set_aggregate_partial": (C.c_int, [P, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "tg_plan_kll_levels": (C.c_int32, [P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32]),
     "tg_plan_histogram_pending": (C.c_int32, [P, C.POINTER(C.c_int32), C.c_int32]),
     "tg_plan_histogram_rebucket": (C.c_int, [P, P, C.c_char_p, C.c_int32, C.POINTER(C.c_uint64), C.c_int32]),

@@ -453,6 +453,12 @@ class Plan:
     def finalize(self):
         F.check(F.lib().tg_plan_finalize(self._h))
 
+    def set_aggregate_partial(self, agg_index: int, u, f):
+        """tg_plan_set_aggregate_partial: install an externally computed partial state (distributed Spearman)"""
+        uu = (C.c_uint64 * 8)(*[int(x) for x in u])
+        ff = (C.c_double * 8)(*[float(x) for x in f])
+        F.check(F.lib().tg_plan_set_aggregate_partial(self._h, agg_index, uu, ff))
+
     def kll_levels(self, slot: int):
         """the slot's sketch as KllSketch's compactor stack: [items of level 0, items of level 1, ..] (weight 2^level)"""
         nl = F.check_slot(F.lib().tg_plan_kll_levels(self._h, slot, -1, None, 0))

@@ -101,6 +101,7 @@ void tg_engine_destroy(tg_engine* h) {
     Engine& e = h->e;
     cudaSetDevice(e.device);
     cudaDeviceSynchronize();
+    rank_session_destroy(e);
     for (auto& kv : e.tables) {
         for (auto& c : kv.second->cols) {
             if (c->values.owned && c->values.p) cudaFree(c->values.p);
@@ -499,6 +500,80 @@ tg_status tg_debug_sort_pairs(tg_engine* h, const uint64_t* keys, int64_t n, int
         TG_CUDA(cudaStreamSynchronize(e.stream));
         TG_CUDA(cudaMemcpy(out_keys, kb[ctl.result], (size_t)n * 8, cudaMemcpyDeviceToHost));
         TG_CUDA(cudaMemcpy(out_index, vb[ctl.result], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+// ---- distributed RANK() for Spearman: the stages of ranks.cu as the host layer's sample sort sees them
+tg_status tg_rank_begin(tg_engine* h, const char* table, const char* column_x, const char* column_y, int64_t* n_pairs) {
+    return guard([&] {
+        if (!h || !table || !column_x || !column_y || !n_pairs) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        *n_pairs = rank_begin(h->e, table, column_x, column_y);
+    });
+}
+tg_status tg_rank_local_sort(tg_engine* h) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_local_sort(h->e);
+    });
+}
+int32_t tg_rank_sample(tg_engine* h, int32_t n_samples, uint64_t* keys) {
+    return guard_slot([&] {
+        if (!h || !keys) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        return rank_sample(h->e, n_samples, keys);
+    });
+}
+tg_status tg_rank_split(tg_engine* h, const uint64_t* splitters, int32_t n_parts, int64_t* counts) {
+    return guard([&] {
+        if (!h || !counts || (n_parts > 1 && !splitters)) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_split(h->e, splitters, n_parts, counts);
+    });
+}
+tg_status tg_rank_send_buffers(tg_engine* h, const void** keys, const void** payload, int32_t* payload_bytes) {
+    return guard([&] {
+        if (!h || !keys || !payload || !payload_bytes) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_send_buffers(h->e, keys, payload, payload_bytes);
+    });
+}
+tg_status tg_rank_recv_buffers(tg_engine* h, int64_t n_recv, void** keys, void** payload) {
+    return guard([&] {
+        if (!h || !keys || !payload) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_recv_buffers(h->e, n_recv, keys, payload);
+    });
+}
+tg_status tg_rank_recv_commit(tg_engine* h, int64_t n_recv) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_recv_commit(h->e, n_recv);
+    });
+}
+tg_status tg_rank_finish_x(tg_engine* h, uint64_t rank_base) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_finish_x(h->e, rank_base);
+    });
+}
+tg_status tg_rank_finish_y(tg_engine* h, uint64_t rank_base, double center, uint64_t* n_out, double* sums5) {
+    return guard([&] {
+        if (!h || !n_out || !sums5) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_finish_y(h->e, rank_base, center, n_out, sums5);
+    });
+}
+tg_status tg_rank_abort(tg_engine* h) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        rank_abort(h->e);
+    });
+}
+// a partial state computed outside tg_plan_execute_partial (the distributed rank computation): replaces aggregate i's state
+tg_status tg_plan_set_aggregate_partial(tg_plan* p, int32_t i, const uint64_t* u8, const double* f8) {
+    return guard([&] {
+        if (!p || !u8 || !f8 || i < 0 || i >= (int32_t)p->p.aggs.size()) throw Error(TG_ERR_INVALID_ARG, "aggregate index out of range");
+        Agg& a = p->p.aggs[i];
+        if (a.kind != A_SPEARMAN) throw Error(TG_ERR_INVALID_ARG, "only SPEARMAN aggregates take an externally computed partial state");
+        for (int k = 0; k < 8; ++k) {
+            a.u[k] = u8[k];
+            a.f[k] = f8[k];
+        }
     });
 }
 

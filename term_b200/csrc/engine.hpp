@@ -25,6 +25,7 @@ namespace tg {
     } while (0)
 
 struct Engine;
+struct RankSession;  // ranks.cu: state of a Spearman evaluation between its stages
 
 struct DevBuf {
     uint8_t* p = nullptr;
@@ -128,6 +129,7 @@ struct Engine {
     cudaEvent_t side_ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     void ensure_side_streams();
     Mailbox mailbox;
+    RankSession* rank_session = nullptr;
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
     size_t aux_cap = 0;
     uint8_t* aux(size_t bytes);
@@ -155,6 +157,18 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
 void exec_grouped_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids); // grouped.cu (all groupings of a plan in one pass)
 void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id);                     // ranks.cu
 void exec_hist_job(Engine& e, Table& t, Plan& p, int agg_id);                         // hist.cu
+// ranks.cu: the stages of the (distributed) rank computation behind tg_rank_*
+void rank_session_destroy(Engine& e);
+int64_t rank_begin(Engine& e, const std::string& table, const std::string& cx, const std::string& cy);
+void rank_local_sort(Engine& e);
+int32_t rank_sample(Engine& e, int32_t m, uint64_t* out);
+void rank_split(Engine& e, const uint64_t* splitters, int32_t n_parts, int64_t* counts);
+void rank_send_buffers(Engine& e, const void** keys, const void** payload, int32_t* payload_bytes);
+void rank_recv_buffers(Engine& e, int64_t n_recv, void** keys, void** payload);
+void rank_recv_commit(Engine& e, int64_t n_recv);
+void rank_finish_x(Engine& e, uint64_t rank_base);
+void rank_finish_y(Engine& e, uint64_t rank_base, double K, uint64_t* n_out, double* sums);
+void rank_abort(Engine& e);
 void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb); // hist.cu (two-phase multi-GPU histogram)
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);

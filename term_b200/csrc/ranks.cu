@@ -13,6 +13,9 @@
 //   4. sort by ky carrying rank_x
 //   5. rk_tile_heads / rk_tile_scan / rk_rank_y_moments   rank_y the same way, and the shifted co-moments of
 //                                                (rank_x, rank_y) accumulated on the fly in a fixed order
+// Across GPUs the same stages run as a sample sort: each sort is preceded by an all-to-all that brings
+// every key range to one rank (splitters from evenly spaced samples of the locally sorted shards), and the run heads
+// become GLOBAL ranks by adding the number of keys on the lower ranks (tg_rank_* entry points, distributed.py).
 // Ranks travel with the rows through the two sorts instead of being scattered back by row id (a random 4-byte write
 // per row costs more than a whole sort pass).
 // The reference accumulates rank products in UInt64 and overflows above ~3.8M rows; here
@@ -214,13 +217,17 @@ __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict_
     return R;
 }
 
-// after the sort by kx (payload ky): emit (ky, rank_x) in the sorted-by-x order — the input of the second sort
-__global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1, const uint64_t* p0,
-                                                               const uint64_t* p1, int64_t n, const uint32_t* __restrict__ carry,
-                                                               uint64_t* __restrict__ out_key, uint32_t* __restrict__ out_rank) {
+// after the sort by kx (payload ky): emit (ky, rank_base + rank_x) in the sorted-by-x order — the input of the second sort.
+// The sorted data sits in buffer ctl->result of the two ping-pong buffers; the output goes to the OTHER buffer pair
+// (keys: the 64-bit key buffer, ranks: the payload buffer reused as 32-bit words).
+__global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, uint64_t* k0, uint64_t* k1, uint64_t* p0, uint64_t* p1, int64_t n,
+                                                               const uint32_t* __restrict__ carry, uint32_t rank_base) {
     __shared__ uint32_t s_warp[RK_THREADS / 32];
-    const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
-    const uint64_t* __restrict__ ys = ctl->result ? p1 : p0;
+    const bool r = ctl->result != 0;
+    const uint64_t* __restrict__ ks = r ? k1 : k0;
+    const uint64_t* __restrict__ ys = r ? p1 : p0;
+    uint64_t* __restrict__ out_key = r ? k0 : k1;
+    uint32_t* __restrict__ out_rank = reinterpret_cast<uint32_t*>(r ? p0 : p1);
     const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
@@ -229,16 +236,16 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* 
         const int64_t p = wbase + i * 32 + lane;
         if (p < n) {
             out_key[p] = ys[p];
-            out_rank[p] = R.rank[i];
+            out_rank[p] = rank_base + R.rank[i];
         }
     }
 }
 
-// after the sort by ky (payload rank_x): rank_y on the fly and the block's partial sums of the shifted rank co-moments
-// (fixed tile -> block mapping, fixed reduction shape: run-to-run reproducible)
+// after the sort by ky (payload rank_x, 32-bit words in the payload buffers): rank_y on the fly and the block's partial
+// sums of the shifted rank co-moments (fixed tile -> block mapping, fixed reduction shape: run-to-run reproducible)
 __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1,
                                                                        const uint32_t* r0, const uint32_t* r1, int64_t n,
-                                                                       const uint32_t* __restrict__ carry, double K,
+                                                                       const uint32_t* __restrict__ carry, uint32_t rank_base, double K,
                                                                        double* __restrict__ partial /* [grid][5] */) {
     __shared__ uint32_t s_warp[RK_THREADS / 32];
     __shared__ double red[5][RK_THREADS / 32];
@@ -252,7 +259,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsC
     for (int i = 0; i < RK_ITEMS; ++i) {
         const int64_t p = wbase + i * 32 + lane;
         if (p < n) {
-            const double dx = (double)rxs[p] - K, dy = (double)R.rank[i] - K;
+            const double dx = (double)rxs[p] - K, dy = (double)(rank_base + R.rank[i]) - K;
             s[0] += dx;
             s[1] += dy;
             s[2] = fma(dx, dx, s[2]);
@@ -275,6 +282,26 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsC
     }
 }
 
+// ---- pieces of the distributed sort (sample sort): evenly spaced keys of the sorted shard, and the
+// first position behind each splitter
+__global__ void rk_sample_kernel(const uint64_t* __restrict__ sorted, int64_t n, int32_t m, uint64_t* __restrict__ out) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) out[i] = sorted[(int64_t)(((__int128)(2 * i + 1) * n) / (2 * (int64_t)m))];
+}
+__global__ void rk_split_kernel(const uint64_t* __restrict__ sorted, int64_t n, const uint64_t* __restrict__ splitters, int32_t n_split,
+                                long long* __restrict__ pos /* [n_split]: number of keys <= splitter */) {
+    const int32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_split) return;
+    const uint64_t s = splitters[i];
+    int64_t lo = 0, hi = n;  // first index with key > s
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted[mid] <= s) lo = mid + 1;
+        else hi = mid;
+    }
+    pos[i] = lo;
+}
+
 // fixed-order sum of the block partials: 5 warps, one per moment, lanes stride the blocks, shuffle tree at the end
 __global__ void __launch_bounds__(160) rk_final_kernel(const double* __restrict__ partial, int64_t n_blocks, double* out) {
     const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -287,90 +314,217 @@ __global__ void __launch_bounds__(160) rk_final_kernel(const double* __restrict_
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id) {
-    Agg& a = p.aggs[agg_id];
-    Column* cx = t.find(a.cols[0]);
-    Column* cy = t.find(a.cols[1]);
-    for (int i = 0; i < 2; ++i)
-        if (!(i ? cy : cx))
-            throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + a.cols[i] + ". Valid fields are " + t.valid_fields() + ".");
+// ---------------------------------------------------------------------------------------------------------------------
+// Rank session: the state of one Spearman evaluation between its stages. The single-GPU job runs the stages back to back;
+// the multi-GPU host layer (term_b200/distributed.py, or a Rust shim over the tg_rank_* entry points) puts a sample sort
+// between them: local sort -> splitters from evenly spaced samples of every shard -> all-to-all by key range -> the
+// receiving rank sorts its range and turns local run heads into GLOBAL minimum ranks with the number of keys on the
+// lower ranks as the offset. Equal keys always land on one rank (a key goes to the first part whose splitter is >= it).
+// ---------------------------------------------------------------------------------------------------------------------
+struct RankArena {
+    uint8_t* base = nullptr;
+    size_t bytes = 0;
+    int64_t cap = 0;
+    uint64_t* K[2] = {nullptr, nullptr};  // keys (ping-pong)
+    uint64_t* V[2] = {nullptr, nullptr};  // payload (ping-pong): 64-bit words, or 32-bit ranks in the same space
+    uint32_t* tile_last = nullptr;
+    uint32_t* carry = nullptr;
+    double* partial = nullptr;
+    uint8_t* tmp = nullptr;               // sort temp + small outputs
+    size_t tmp_bytes = 0;
+};
+struct RankSession {
+    RankArena cur, next;
+    int64_t n = 0;        // elements in cur
+    int which = 0;        // buffer of cur holding the data
+    int payload32 = 0;    // payload is 32-bit ranks (second phase)
+};
+
+static void arena_free(Engine& e, RankArena& a) {
+    if (a.base) e.dev_free(a.base, a.bytes);
+    a = RankArena{};
+}
+static void arena_alloc(Engine& e, RankArena& a, int64_t cap) {
+    arena_free(e, a);
+    cap = std::max<int64_t>(cap, 1);
+    const size_t k_b = round_up((size_t)cap * 8, 256);
+    const int64_t r_tiles = (cap + RK_TILE - 1) / RK_TILE;
+    const size_t t_b = round_up((size_t)r_tiles * 4, 256), part_b = round_up((size_t)r_tiles * 40, 256);
+    const size_t tmp_b = round_up(rs_temp_bytes(cap, RS_MAX_PASSES), 256) + 4096;
+    a.bytes = round_up(4 * k_b + 2 * t_b + part_b + tmp_b, (size_t)1 << 20);  // rounded: the block cache is keyed by size
+    a.base = e.dev_alloc(a.bytes);
+    a.cap = cap;
+    uint8_t* q = a.base;
+    a.K[0] = (uint64_t*)q; q += k_b;
+    a.K[1] = (uint64_t*)q; q += k_b;
+    a.V[0] = (uint64_t*)q; q += k_b;
+    a.V[1] = (uint64_t*)q; q += k_b;
+    a.tile_last = (uint32_t*)q; q += t_b;
+    a.carry = (uint32_t*)q; q += t_b;
+    a.partial = (double*)q; q += part_b;
+    a.tmp = q;
+    a.tmp_bytes = tmp_b;
+}
+
+static RankSession& session(Engine& e) {
+    if (!e.rank_session) e.rank_session = new RankSession();
+    return *e.rank_session;
+}
+void rank_session_destroy(Engine& e) {
+    if (!e.rank_session) return;
+    arena_free(e, e.rank_session->cur);
+    arena_free(e, e.rank_session->next);
+    delete e.rank_session;
+    e.rank_session = nullptr;
+}
+
+// stage 0: the pairwise-complete rows of (cx, cy) as order-preserving keys: keys = kx, payload = ky. Returns the pair count.
+static int64_t rank_begin_locked(Engine& e, Table& t, const std::string& nx, const std::string& ny, int* launches) {
+    Column* cx = t.find(nx);
+    Column* cy = t.find(ny);
+    if (!cx) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + nx + ". Valid fields are " + t.valid_fields() + ".");
+    if (!cy) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + ny + ". Valid fields are " + t.valid_fields() + ".");
     for (Column* c : {cx, cy})
         if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64)
             throw Error(TG_ERR_TYPE_MISMATCH, "Spearman correlation requires numeric (Int64 / Float64) columns");
     const int64_t n = t.n_rows;
-    p.stats.bytes_scanned += 2 * (uint64_t)n * 8 + (cx->validity.p ? (uint64_t)(n + 7) / 8 : 0) + (cy->validity.p ? (uint64_t)(n + 7) / 8 : 0);
-    if (n == 0) return;
     if (n >= (int64_t)1 << 30) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more rows per shard");
-    const size_t k_b = round_up((size_t)n * 8, 256), i_b = round_up((size_t)n * 4, 256);
-    const int64_t c_tiles = (n + RK_CTILE - 1) / RK_CTILE;    // compaction tiles (rows)
-    const int64_t r_tiles_max = (n + RK_TILE - 1) / RK_TILE;  // rank tiles (pairs <= rows)
-    const size_t ct_b = round_up((size_t)c_tiles * 4, 256), rt_b = round_up((size_t)r_tiles_max * 4, 256);
-    const size_t tmp_b = round_up(rs_temp_bytes(n, RS_MAX_PASSES), 256);
-    const size_t part_b = round_up((size_t)r_tiles_max * 40, 256);
-    // A0/A1: keys of sort 1, B0/B1: its payload (ky), C: keys of sort 2 (its partner is A0), R0/R1: payload of sort 2 (rank_x)
-    uint8_t* scr = e.scratch(5 * k_b + 2 * i_b + 2 * ct_b + 2 * rt_b + tmp_b + part_b + 512);
-    uint8_t* q = scr;
-    uint64_t* A0 = (uint64_t*)q; q += k_b;
-    uint64_t* A1 = (uint64_t*)q; q += k_b;
-    uint64_t* B0 = (uint64_t*)q; q += k_b;
-    uint64_t* B1 = (uint64_t*)q; q += k_b;
-    uint64_t* C = (uint64_t*)q; q += k_b;
-    uint32_t* R0 = (uint32_t*)q; q += i_b;
-    uint32_t* R1 = (uint32_t*)q; q += i_b;
-    uint32_t* tile_count = (uint32_t*)q; q += ct_b;
-    uint32_t* tile_off = (uint32_t*)q; q += ct_b;
-    uint32_t* tile_last = (uint32_t*)q; q += rt_b;
-    uint32_t* carry = (uint32_t*)q; q += rt_b;
-    uint8_t* d_tmp = q; q += tmp_b;
-    double* partial = (double*)q; q += part_b;
-    double* d_out = (double*)q;
-    unsigned long long* d_np = (unsigned long long*)(q + 64);
+    RankSession& S = session(e);
+    arena_free(e, S.next);
+    arena_alloc(e, S.cur, n);
+    S.n = 0;
+    S.which = 0;
+    S.payload32 = 0;
+    if (n == 0) return 0;
+    const int64_t c_tiles = (n + RK_CTILE - 1) / RK_CTILE;
+    // compaction scratch lives in the arena's temp area
+    uint32_t* tile_count = (uint32_t*)e.scratch(2 * round_up((size_t)c_tiles * 4, 256) + 256);
+    uint32_t* tile_off = tile_count + round_up((size_t)c_tiles * 4, 256) / 4;
+    unsigned long long* d_np = (unsigned long long*)(tile_off + round_up((size_t)c_tiles * 4, 256) / 4);
     const uint32_t* vx = (const uint32_t*)cx->validity.p;
     const uint32_t* vy = (const uint32_t*)cy->validity.p;
-    TG_CUDA(cudaEventRecord(e.ev[6], e.stream));
     rk_count_kernel<<<(unsigned)c_tiles, RK_THREADS, 0, e.stream>>>(vx, vy, n, tile_count);
     rk_offsets_kernel<<<1, 1024, 0, e.stream>>>(tile_count, c_tiles, tile_off, d_np);
     rk_compact_keys_kernel<<<(unsigned)c_tiles, RK_THREADS, 0, e.stream>>>((const uint64_t*)cx->values.p, vx, cx->dtype == TG_INT64,
-                                                                           (const uint64_t*)cy->values.p, vy, cy->dtype == TG_INT64, n, tile_off, A0, B0);
+                                                                           (const uint64_t*)cy->values.p, vy, cy->dtype == TG_INT64, n, tile_off,
+                                                                           S.cur.K[0], S.cur.V[0]);
     TG_CUDA(cudaGetLastError());
     unsigned long long n_pairs = 0;
     TG_CUDA(cudaMemcpyAsync(&n_pairs, d_np, 8, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
-    int launches = 3;
-    a.u[0] = n_pairs;
+    *launches += 3;
+    S.n = (int64_t)n_pairs;
+    return S.n;
+}
+
+// queue the sort of the session's current (keys, payload); the result buffer index is only known on the device (ctl)
+static RsTemp rank_sort_queue(Engine& e, RankSession& S, int* launches) {
+    RankArena& A = S.cur;
+    const RsTemp T = rs_temp_carve(A.tmp, std::max<int64_t>(S.n, 1), RS_MAX_PASSES);
+    uint64_t* keys[2] = {A.K[S.which], A.K[S.which ^ 1]};
+    if (S.payload32) {
+        uint32_t* vals[2] = {(uint32_t*)A.V[S.which], (uint32_t*)A.V[S.which ^ 1]};
+        *launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count);
+    } else {
+        uint64_t* vals[2] = {A.V[S.which], A.V[S.which ^ 1]};
+        *launches += rs_sort_pairs<uint64_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count);
+    }
+    TG_CUDA(cudaGetLastError());
+    return T;
+}
+// after the queued work: which physical buffer holds the result
+static void rank_sort_settle(Engine& e, RankSession& S, const RsTemp& T, bool flipped_by_consumer) {
+    RsControl ctl;
+    TG_CUDA(cudaMemcpyAsync(&ctl, T.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    int r = ctl.result ? (S.which ^ 1) : S.which;
+    if (flipped_by_consumer) r ^= 1;  // the consumer kernel wrote the next stage's data into the other buffer pair
+    S.which = r;
+}
+
+static void rank_local_sort_locked(Engine& e, int* launches) {
+    RankSession& S = session(e);
+    if (S.n <= 0) return;
+    const RsTemp T = rank_sort_queue(e, S, launches);
+    rank_sort_settle(e, S, T, false);
+}
+
+// sort the current (kx, ky), turn run heads into ranks (+ rank_base), leave (ky, rank_x) as the session's data
+static void rank_finish_x_locked(Engine& e, uint64_t rank_base, int* launches) {
+    RankSession& S = session(e);
+    if (S.payload32) throw Error(TG_ERR_INVALID_ARG, "rank session: x phase already finished");
+    if (S.n > 0) {
+        if (rank_base + (uint64_t)S.n >= ((uint64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^32 or more pairs");
+        RankArena& A = S.cur;
+        const RsTemp T = rank_sort_queue(e, S, launches);
+        const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
+        uint64_t* k0 = A.K[S.which];
+        uint64_t* k1 = A.K[S.which ^ 1];
+        uint64_t* p0 = A.V[S.which];
+        uint64_t* p1 = A.V[S.which ^ 1];
+        rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, S.n, A.tile_last);
+        rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
+        rk_rank_x_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, p0, p1, S.n, A.carry, (uint32_t)rank_base);
+        TG_CUDA(cudaGetLastError());
+        *launches += 3;
+        rank_sort_settle(e, S, T, true);
+    }
+    S.payload32 = 1;
+}
+
+// sort the current (ky, rank_x), rank_y = rank_base + run head, shifted co-moments around K -> sums[5]; ends the session
+static void rank_finish_y_locked(Engine& e, uint64_t rank_base, double K, uint64_t* n_out, double* sums, int* launches) {
+    RankSession& S = session(e);
+    if (!S.payload32) throw Error(TG_ERR_INVALID_ARG, "rank session: finish the x phase first");
+    for (int k = 0; k < 5; ++k) sums[k] = 0.0;
+    *n_out = (uint64_t)S.n;
+    if (S.n > 0) {
+        if (rank_base + (uint64_t)S.n >= ((uint64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^32 or more pairs");
+        RankArena& A = S.cur;
+        const RsTemp T = rank_sort_queue(e, S, launches);
+        const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
+        const uint64_t* k0 = A.K[S.which];
+        const uint64_t* k1 = A.K[S.which ^ 1];
+        const uint32_t* r0 = (const uint32_t*)A.V[S.which];
+        const uint32_t* r1 = (const uint32_t*)A.V[S.which ^ 1];
+        double* d_out = (double*)(A.tmp + A.tmp_bytes - 2048);
+        rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, S.n, A.tile_last);
+        rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
+        rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, r0, r1, S.n, A.carry, (uint32_t)rank_base, K, A.partial);
+        rk_final_kernel<<<1, 160, 0, e.stream>>>(A.partial, r_tiles, d_out);
+        TG_CUDA(cudaGetLastError());
+        *launches += 4;
+        TG_CUDA(cudaMemcpyAsync(sums, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+    }
+    arena_free(e, S.cur);
+    arena_free(e, S.next);
+    S.n = 0;
+}
+
+void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id) {
+    Agg& a = p.aggs[agg_id];
+    const int64_t n = t.n_rows;
+    Column* cx = t.find(a.cols[0]);
+    Column* cy = t.find(a.cols[1]);
+    if (cx && cy)
+        p.stats.bytes_scanned += 2 * (uint64_t)n * 8 + (cx->validity.p ? (uint64_t)(n + 7) / 8 : 0) + (cy->validity.p ? (uint64_t)(n + 7) / 8 : 0);
+    int launches = 0;
+    TG_CUDA(cudaEventRecord(e.ev[6], e.stream));
+    struct Cleanup {
+        Engine& e;
+        ~Cleanup() { rank_session_destroy(e); }
+    } cleanup{e};
+    const int64_t n_pairs = rank_begin_locked(e, t, a.cols[0], a.cols[1], &launches);
+    a.u[0] = (uint64_t)n_pairs;
     const double K = ((double)n_pairs + 1.0) / 2.0;
     a.f[0] = K;
     a.f[1] = K;
     if (n_pairs >= 2) {
-        const int64_t m = (int64_t)n_pairs;
-        const int64_t r_tiles = (m + RK_TILE - 1) / RK_TILE;
-        const RsTemp T = rs_temp_carve(d_tmp, m, RS_MAX_PASSES);
-        {
-            uint64_t* keys[2] = {A0, A1};
-            uint64_t* vals[2] = {B0, B1};
-            launches += rs_sort_pairs<uint64_t>(e.stream, keys, vals, m, 0, RS_MAX_PASSES, false, T, e.sm_count);
-            TG_CUDA(cudaGetLastError());
-            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, A0, A1, m, tile_last);
-            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(tile_last, r_tiles, carry);
-            rk_rank_x_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, A0, A1, B0, B1, m, carry, C, R0);
-            TG_CUDA(cudaGetLastError());
-            launches += 3;
-        }
-        {
-            uint64_t* keys[2] = {C, A0};
-            uint32_t* vals[2] = {R0, R1};
-            launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, m, 0, RS_MAX_PASSES, false, T, e.sm_count);
-            TG_CUDA(cudaGetLastError());
-            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, C, A0, m, tile_last);
-            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(tile_last, r_tiles, carry);
-            rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, C, A0, R0, R1, m, carry, K, partial);
-            rk_final_kernel<<<1, 160, 0, e.stream>>>(partial, r_tiles, d_out);
-            TG_CUDA(cudaGetLastError());
-            launches += 4;
-        }
+        rank_finish_x_locked(e, 0, &launches);
+        uint64_t n_out = 0;
         double h[5];
-        TG_CUDA(cudaMemcpyAsync(h, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
-        TG_CUDA(cudaStreamSynchronize(e.stream));
+        rank_finish_y_locked(e, 0, K, &n_out, h, &launches);
         for (int k = 0; k < 5; ++k) a.f[2 + k] = h[k];
     }
     TG_CUDA(cudaEventRecord(e.ev[7], e.stream));
@@ -381,6 +535,114 @@ void exec_spearman_job(Engine& e, Table& t, Plan& p, int agg_id) {
     p.stats.gpu_ms += ms;
     p.stats.launches += launches;
     e.launches += launches;
+}
+
+// ---- the stages as the host layer of the distributed sort sees them (capi.cpp: tg_rank_*) ----
+struct RankLock {
+    std::lock_guard<std::mutex> g;
+    explicit RankLock(Engine& e) : g(e.mu) {
+        cudaError_t ce = cudaSetDevice(e.device);
+        if (ce != cudaSuccess) throw Error(TG_ERR_CUDA, std::string("cudaSetDevice: ") + cudaGetErrorString(ce));
+    }
+};
+
+int64_t rank_begin(Engine& e, const std::string& table, const std::string& cx, const std::string& cy) {
+    RankLock l(e);
+    e.sync_copies();
+    auto it = e.tables.find(table);
+    if (it == e.tables.end()) throw Error(TG_ERR_TABLE_NOT_FOUND, "Error during planning: table 'datafusion.public." + table + "' not found");
+    int launches = 0;
+    const int64_t n = rank_begin_locked(e, *it->second, cx, cy, &launches);
+    e.launches += launches;
+    return n;
+}
+void rank_local_sort(Engine& e) {
+    RankLock l(e);
+    int launches = 0;
+    rank_local_sort_locked(e, &launches);
+    e.launches += launches;
+}
+// up to m evenly spaced keys of the sorted shard; returns how many were written
+int32_t rank_sample(Engine& e, int32_t m, uint64_t* out) {
+    RankLock l(e);
+    RankSession& S = session(e);
+    if (S.n <= 0 || m <= 0) return 0;
+    m = (int32_t)std::min<int64_t>(m, S.n);
+    uint64_t* d = (uint64_t*)e.scratch((size_t)m * 8 + 256);
+    rk_sample_kernel<<<(m + 255) / 256, 256, 0, e.stream>>>(S.cur.K[S.which], S.n, m, d);
+    TG_CUDA(cudaGetLastError());
+    TG_CUDA(cudaMemcpyAsync(out, d, (size_t)m * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    e.launches += 1;
+    return m;
+}
+// counts[p] = keys of the sorted shard that go to part p: part p takes the keys in (splitter[p-1], splitter[p]]
+void rank_split(Engine& e, const uint64_t* splitters, int32_t n_parts, int64_t* counts) {
+    RankLock l(e);
+    RankSession& S = session(e);
+    if (n_parts < 1) throw Error(TG_ERR_INVALID_ARG, "n_parts must be positive");
+    std::vector<long long> pos((size_t)n_parts, S.n);
+    if (S.n > 0 && n_parts > 1) {
+        uint8_t* scr = e.scratch((size_t)n_parts * 16 + 512);
+        uint64_t* d_s = (uint64_t*)scr;
+        long long* d_p = (long long*)(scr + round_up((size_t)n_parts * 8, 256));
+        TG_CUDA(cudaMemcpyAsync(d_s, splitters, (size_t)(n_parts - 1) * 8, cudaMemcpyHostToDevice, e.stream));
+        rk_split_kernel<<<(n_parts + 254) / 255, 256, 0, e.stream>>>(S.cur.K[S.which], S.n, d_s, n_parts - 1, d_p);
+        TG_CUDA(cudaGetLastError());
+        TG_CUDA(cudaMemcpyAsync(pos.data(), d_p, (size_t)(n_parts - 1) * 8, cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        e.launches += 1;
+    }
+    if (S.n <= 0)
+        for (auto& x : pos) x = 0;
+    long long prev = 0;
+    for (int32_t i = 0; i < n_parts; ++i) {
+        const long long hi = i == n_parts - 1 ? (long long)std::max<int64_t>(S.n, 0) : std::max(pos[i], prev);
+        counts[i] = hi - prev;
+        prev = hi;
+    }
+}
+void rank_send_buffers(Engine& e, const void** keys, const void** payload, int32_t* payload_bytes) {
+    RankLock l(e);
+    RankSession& S = session(e);
+    *keys = S.cur.K[S.which];
+    *payload = S.cur.V[S.which];
+    *payload_bytes = S.payload32 ? 4 : 8;
+}
+void rank_recv_buffers(Engine& e, int64_t n_recv, void** keys, void** payload) {
+    RankLock l(e);
+    RankSession& S = session(e);
+    if (n_recv < 0 || n_recv >= ((int64_t)1 << 30)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more keys in one rank's range");
+    arena_alloc(e, S.next, n_recv);
+    *keys = S.next.K[0];
+    *payload = S.next.V[0];
+}
+void rank_recv_commit(Engine& e, int64_t n_recv) {
+    RankLock l(e);
+    RankSession& S = session(e);
+    if (!S.next.base || n_recv > S.next.cap) throw Error(TG_ERR_INVALID_ARG, "rank session: no receive buffers of that size");
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    arena_free(e, S.cur);
+    S.cur = S.next;
+    S.next = RankArena{};
+    S.n = n_recv;
+    S.which = 0;
+}
+void rank_finish_x(Engine& e, uint64_t rank_base) {
+    RankLock l(e);
+    int launches = 0;
+    rank_finish_x_locked(e, rank_base, &launches);
+    e.launches += launches;
+}
+void rank_finish_y(Engine& e, uint64_t rank_base, double K, uint64_t* n_out, double* sums) {
+    RankLock l(e);
+    int launches = 0;
+    rank_finish_y_locked(e, rank_base, K, n_out, sums, &launches);
+    e.launches += launches;
+}
+void rank_abort(Engine& e) {
+    RankLock l(e);
+    rank_session_destroy(e);
 }
 
 }  // namespace tg

@@ -13,10 +13,14 @@
   exactly one rank, so the per-rank states add up exactly. NULL rows travel as a count to rank 0. Utf8 and composite
   keys travel as their 128-bit fingerprints (tg_table_partition_fingerprints), the identity the single-GPU path uses.
 * Spearman needs GLOBAL ranks (RANK() OVER (ORDER BY ..) over the whole table, analyzers/advanced/correlation.rs:
-  334-350), so per-shard rank sums do not add up. Its two columns are reduced to their pairwise-complete rows (as
-  DOUBLE, the type the reference ranks in), gathered to rank 0 in rank order — 16 bytes per complete row, 16 GB for
-  the 1 B-row C5 table — and the one GPU that owns them computes the ranks; the other ranks contribute an empty
-  partial. "Replicas only" in SURVEY §8e's terms: exact, not faster than one GPU.
+  334-350), so per-shard rank sums do not add up. It runs as a distributed SAMPLE SORT, once per
+  column: every rank sorts its shard's pairwise-complete rows (tg_rank_local_sort), contributes evenly spaced sample
+  keys, all ranks derive the same world - 1 splitters, one all-to-all by key range (NCCL over NVLink) brings every
+  range to its owner, which sorts it and turns local run heads into global minimum ranks by adding the number of keys
+  on the lower ranks (tg_rank_finish_x / _y). The ranks of x travel with the rows through the second sort; each rank
+  ends with the shifted rank co-moments of its y range, which merge by addition. Equal keys always meet on one rank,
+  so ties get the same global minimum rank as on one GPU. (The round-1 path — gather every pair to rank 0 — is kept
+  as gather_pairs / TG_SPEARMAN_GATHER=1 for comparison.)
 """
 import os
 
@@ -341,11 +345,181 @@ def _gather_spearman_columns(ctx, table, cx, cy, name):
                               keepalive=[xs, ys])
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# Distributed RANK() for Spearman: a sample sort around the engine's rank stages (tg_rank_*)
+# ---------------------------------------------------------------------------------------------------------------------
+RANK_SAMPLES_PER_SHARD = 2048
+
+
+class GpuRankStages:
+    """The device stages of the distributed rank computation, over the C ABI (include/termgpu.h tg_rank_*)."""
+
+    def __init__(self, ctx):
+        self.ctx, self.n, self.dev = ctx, 0, torch.device("cuda", torch.cuda.current_device())
+
+    def begin(self, table, cx, cy):
+        import ctypes as C
+        n = C.c_int64()
+        F.check(F.lib().tg_rank_begin(self.ctx.handle, table.encode(), cx.encode(), cy.encode(), C.byref(n)))
+        self.n = n.value
+        return self.n
+
+    def local_sort(self):
+        F.check(F.lib().tg_rank_local_sort(self.ctx.handle))
+
+    def sample(self, m):
+        import ctypes as C
+        import numpy as np
+        buf = (C.c_uint64 * max(m, 1))()
+        got = F.check_slot(F.lib().tg_rank_sample(self.ctx.handle, m, buf))
+        return np.frombuffer(buf, dtype=np.uint64, count=got).copy()
+
+    def split(self, splitters, world):
+        import ctypes as C
+        import numpy as np
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64)
+        counts = (C.c_int64 * world)()
+        F.check(F.lib().tg_rank_split(self.ctx.handle, sp.ctypes.data_as(C.POINTER(C.c_uint64)), world, counts))
+        return list(counts)
+
+    def _views(self, kp, pp, n, payload_bytes):
+        if n == 0:
+            return (torch.empty(0, dtype=torch.int64, device=self.dev),
+                    torch.empty(0, dtype=torch.int64 if payload_bytes == 8 else torch.int32, device=self.dev))
+        return (_tensor_from_ptr(kp, n, self.dev, "<i8"), _tensor_from_ptr(pp, n, self.dev, "<i8" if payload_bytes == 8 else "<i4"))
+
+    def send(self):
+        import ctypes as C
+        k, p, b = C.c_void_p(), C.c_void_p(), C.c_int32()
+        F.check(F.lib().tg_rank_send_buffers(self.ctx.handle, C.byref(k), C.byref(p), C.byref(b)))
+        self.payload_bytes = b.value
+        return self._views(k.value, p.value, self.n, b.value)
+
+    def recv(self, n_recv):
+        import ctypes as C
+        k, p = C.c_void_p(), C.c_void_p()
+        F.check(F.lib().tg_rank_recv_buffers(self.ctx.handle, n_recv, C.byref(k), C.byref(p)))
+        return self._views(k.value, p.value, n_recv, self.payload_bytes)
+
+    def commit(self, n_recv):
+        torch.cuda.current_stream().synchronize()  # the all-to-all wrote the receive buffers on torch's stream
+        F.check(F.lib().tg_rank_recv_commit(self.ctx.handle, n_recv))
+        self.n = n_recv
+
+    def finish_x(self, base):
+        F.check(F.lib().tg_rank_finish_x(self.ctx.handle, base))
+
+    def finish_y(self, base, center):
+        import ctypes as C
+        n, sums = C.c_uint64(), (C.c_double * 5)()
+        F.check(F.lib().tg_rank_finish_y(self.ctx.handle, base, center, C.byref(n), sums))
+        return n.value, list(sums)
+
+    def abort(self):
+        F.lib().tg_rank_abort(self.ctx.handle)
+
+
+def choose_splitters(samples, world):
+    """world - 1 splitters at equal steps of the sorted union of every shard's samples (numpy uint64). Part p takes the
+    keys in (splitter[p-1], splitter[p]]: a deterministic function of the gathered samples, identical on every rank."""
+    import numpy as np
+    s = np.sort(np.asarray(samples, dtype=np.uint64))
+    if len(s) == 0:
+        return np.zeros(world - 1, dtype=np.uint64)
+    idx = [min(len(s) - 1, max(0, (p + 1) * len(s) // world - 1)) for p in range(world - 1)]
+    return s[idx]
+
+
+def _allgather_samples(samples, cap, dev):
+    """every rank's sample keys (variable count <= cap) as one numpy uint64 array"""
+    import numpy as np
+    world = dist.get_world_size()
+    mine = torch.zeros(cap + 1, dtype=torch.int64)
+    mine[0] = len(samples)
+    if len(samples):
+        mine[1: 1 + len(samples)] = torch.from_numpy(samples.view(np.int64))
+    mine = mine.to(dev)
+    allv = [torch.zeros(cap + 1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(allv, mine)
+    out = []
+    for t in allv:
+        t = t.cpu().numpy()
+        out.append(t[1: 1 + int(t[0])].view(np.uint64))
+    return np.concatenate(out) if out else np.zeros(0, dtype=np.uint64)
+
+
+def rank_sort_exchange(stages, dev):
+    """One sample-sort exchange of the session's current (keys, payload): local sort -> splitters -> all-to-all by key
+    range. Returns (n_recv, rank_base) with rank_base = the number of keys that went to lower ranks."""
+    world, rank = dist.get_world_size(), dist.get_rank()
+    prof = PROFILE if (PROFILE is not None and dev.type == "cuda") else None
+    stages.local_sort()
+    splitters = choose_splitters(_allgather_samples(stages.sample(RANK_SAMPLES_PER_SHARD), RANK_SAMPLES_PER_SHARD, dev), world)
+    counts = stages.split(splitters, world)
+    if prof is not None:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    send = torch.tensor(counts, dtype=torch.int64, device=dev)
+    recv = torch.zeros(world, dtype=torch.int64, device=dev)
+    dist.all_to_all_single(recv, send)
+    recv_counts = [int(x) for x in recv.tolist()]
+    n_recv = sum(recv_counts)
+    k_out, p_out = stages.send()
+    k_in, p_in = stages.recv(n_recv)
+    dist.all_to_all_single(k_in, k_out, output_split_sizes=recv_counts, input_split_sizes=counts)
+    dist.all_to_all_single(p_in, p_out, output_split_sizes=recv_counts, input_split_sizes=counts)
+    totals = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(totals, torch.tensor([n_recv], dtype=torch.int64, device=dev))
+    totals = [int(t.item()) for t in totals]
+    if prof is not None:
+        ev1.record()
+        ev1.synchronize()
+        prof["shuffle_ms"] += ev0.elapsed_time(ev1)
+        prof["shuffle_bytes"] += (8 + p_out.element_size()) * (sum(counts) - counts[rank])
+    stages.commit(n_recv)
+    return n_recv, sum(totals[:rank]), sum(totals)
+
+
+def distributed_spearman(stages, table, cx, cy, dev):
+    """Global minimum ranks of both columns over every rank's pairwise-complete rows, as this rank's partial state of the
+    SPEARMAN aggregate: (u[8], f[8]) with u[0] = pairs that ended on this rank, f[0] = f[1] = (N + 1) / 2, f[2..6] = the
+    sums of the shifted ranks, their squares and their product."""
+    try:
+        stages.begin(table, cx, cy)
+        _, base, total = rank_sort_exchange(stages, dev)
+        center = (total + 1.0) / 2.0
+        stages.finish_x(base)
+        _, base, _ = rank_sort_exchange(stages, dev)
+        n, sums = stages.finish_y(base, center)
+    except Exception:
+        stages.abort()
+        raise
+    u, f = [0] * 8, [0.0] * 8
+    if total >= 2:
+        u[0], f[0], f[1] = n, center, center
+        f[2:7] = sums
+        if n == 0:  # an empty range contributes nothing (and must not carry a pivot of its own)
+            f[0] = f[1] = 0.0
+    elif rank_holds_all(n, total):
+        u[0], f[0], f[1] = n, center, center
+    return u, f
+
+
+def rank_holds_all(n, total):
+    return n == total and total > 0
+
+
 def _adopt_fp_shard(ctx, name, recs: torch.Tensor):
     n = recs.numel() // 3
     vals = torch.zeros(n * 3 + 64, dtype=torch.int64, device=recs.device)
     vals[: n * 3] = recs
     ctx.register_device_table(name, {"tg_fp": dict(dtype=F.TG_FP128, n_rows=n, values=vals.data_ptr(), validity=None)}, keepalive=[vals])
+
+
+def _register_empty_pair_table(ctx, name, cx, cy, dev):
+    z = torch.zeros(64, dtype=torch.float64, device=dev)
+    ctx.register_device_table(name, {cx: dict(dtype=F.TG_FLOAT64, n_rows=0, values=z.data_ptr(), validity=None),
+                                     cy: dict(dtype=F.TG_FLOAT64, n_rows=0, values=z.data_ptr(), validity=None)}, keepalive=[z])
 
 
 def _tensor_from_ptr(ptr, n, dev, typestr="<i8"):
@@ -380,7 +554,7 @@ def execute_distributed(plan, ctx, table="data"):
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         plan.execute(ctx, table)
         return
-    temps, redirected = [], []
+    temps, redirected, external = [], [], []
     try:
         for i, (kind, key) in enumerate(plan.aggregates()):
             parts = key.split("|")
@@ -405,11 +579,20 @@ def execute_distributed(plan, ctx, table="data"):
                 redirected += [(i, 0), (i, 1)]
             elif kind == KIND_SPEARMAN:
                 name = f"tg_gather_{i}_s"
-                _gather_spearman_columns(ctx, table, parts[1], parts[2], name)  # global ranks: one GPU owns the pairs
+                if os.environ.get("TG_SPEARMAN_GATHER"):
+                    _gather_spearman_columns(ctx, table, parts[1], parts[2], name)  # round-1 path: one GPU owns the pairs
+                else:
+                    # sample sort across the ranks; execute_partial then sees an empty table for this aggregate and the
+                    # state computed here is installed afterwards
+                    dev = torch.device("cuda", torch.cuda.current_device())
+                    external.append((i, distributed_spearman(GpuRankStages(ctx), table, parts[1], parts[2], dev)))
+                    _register_empty_pair_table(ctx, name, parts[1], parts[2], dev)
                 temps.append(name)
                 plan.redirect(i, 0, name)
                 redirected.append((i, 0))
         plan.execute_partial(ctx, table)
+        for i, (u, f) in external:
+            plan.set_aggregate_partial(i, u, f)
         if PROFILE is not None:
             import time
             t0 = time.perf_counter()

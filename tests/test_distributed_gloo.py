@@ -467,3 +467,135 @@ def test_gloo_string_kll_grouped_histogram_partials_merge(built_lib, world):
     assert hmap["min"] == hw["min"] and hmap["max"] == hw["max"] and hmap["total_count"] == hw["total_count"]
     for i, (lo, hi, cnt) in enumerate(hw["buckets"]):
         assert hmap[f"bucket_{i}.lower"] == lo and hmap[f"bucket_{i}.upper"] == hi and hmap[f"bucket_{i}.count"] == cnt
+
+
+# ---- Spearman as a distributed sample sort: the host orchestration over gloo, the device stages in numpy ----
+class NumpyRankStages:
+    """what term_b200.distributed.GpuRankStages does through tg_rank_* on the device, restated in numpy"""
+
+    def __init__(self, shard):
+        self.shard = shard
+
+    @staticmethod
+    def _key(v):
+        v = np.asarray(v, dtype=np.float64) + 0.0  # -0.0 -> +0.0
+        b = v.view(np.uint64)
+        return np.where(b >> np.uint64(63), ~b, b | np.uint64(1 << 63))
+
+    def begin(self, table, cx, cy):
+        x, y = self.shard.column(cx), self.shard.column(cy)
+        ok = np.asarray(x.is_valid()) & np.asarray(y.is_valid())
+        self.k = self._key(np.asarray(x.fill_null(0)).astype(np.float64)[ok])
+        self.p = self._key(np.asarray(y.fill_null(0)).astype(np.float64)[ok])
+        self.phase = 0
+        return len(self.k)
+
+    def local_sort(self):
+        o = np.argsort(self.k, kind="stable")
+        self.k, self.p = self.k[o], self.p[o]
+
+    def sample(self, m):
+        n = len(self.k)
+        m = min(m, n)
+        return self.k[[((2 * i + 1) * n) // (2 * m) for i in range(m)]] if m else np.zeros(0, dtype=np.uint64)
+
+    def split(self, splitters, world):
+        pos = [int(np.searchsorted(self.k, s, side="right")) for s in splitters] + [len(self.k)]
+        out, prev = [], 0
+        for q in pos:
+            q = max(q, prev)
+            out.append(q - prev)
+            prev = q
+        return out
+
+    def send(self):
+        import torch
+        pd = np.int64 if self.phase == 0 else np.int32
+        return torch.from_numpy(self.k.view(np.int64).copy()), torch.from_numpy(self.p.view(pd).copy() if self.phase == 0 else self.p.astype(np.uint32).view(np.int32).copy())
+
+    def recv(self, n_recv):
+        import torch
+        self.rk = torch.zeros(n_recv, dtype=torch.int64)
+        self.rp = torch.zeros(n_recv, dtype=torch.int64 if self.phase == 0 else torch.int32)
+        return self.rk, self.rp
+
+    def commit(self, n_recv):
+        self.k = self.rk.numpy().view(np.uint64).copy()
+        self.p = self.rp.numpy().view(np.uint64 if self.phase == 0 else np.uint32).copy()
+
+    @staticmethod
+    def _min_ranks(sorted_keys, base):
+        n = len(sorted_keys)
+        head = np.ones(n, dtype=bool)
+        head[1:] = sorted_keys[1:] != sorted_keys[:-1]
+        pos = np.where(head, np.arange(n), 0)
+        return base + np.maximum.accumulate(pos) + 1
+
+    def finish_x(self, base):
+        self.local_sort()
+        rx = self._min_ranks(self.k, base)
+        self.k, self.p, self.phase = self.p, rx.astype(np.uint32), 1
+
+    def finish_y(self, base, center):
+        self.local_sort()
+        ry = self._min_ranks(self.k, base).astype(np.float64) - center
+        rx = self.p.astype(np.float64) - center
+        return len(self.k), [math.fsum(rx), math.fsum(ry), math.fsum(rx * rx), math.fsum(ry * ry), math.fsum(rx * ry)]
+
+    def abort(self):
+        pass
+
+
+def _tie_table():
+    rng = np.random.default_rng(13)
+    n = 9_001
+    x = np.round(rng.normal(0, 3, n), 0)     # heavy ties
+    y = np.round(0.5 * x + rng.normal(0, 2, n), 1)
+    x[:50] = 7.0                              # one value that dominates a whole sample range
+    return pa.table({"x": pa.array(x, mask=rng.random(n) < 0.1), "y": pa.array(y, mask=rng.random(n) < 0.05)})
+
+
+def sample_sort_worker(rank, world, port, q):
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        import term_b200 as T
+        from term_b200.distributed import allgather_blobs, distributed_spearman, merge_partials
+        t = _tie_table()
+        n = t.num_rows
+        bounds = [0, n // 4, n // 4, n][: world + 1] if world == 3 else [n * r // world for r in range(world + 1)]
+        shard = t.slice(bounds[rank], bounds[rank + 1] - bounds[rank])  # world 3: the middle rank starts EMPTY
+        u, f = distributed_spearman(NumpyRankStages(shard), "data", "x", "y", torch.device("cpu"))
+        plan = T.Plan()
+        slot = T.CorrelationAnalyzer.spearman("x", "y")._add_to(plan)
+        blob = struct.pack("<Q", 1) + struct.pack("<QQ", 10, 0) + struct.pack("<8Q", *u) + struct.pack("<8d", *f) + struct.pack("<QQ", 0, 0)
+        merge_partials(plan, allgather_blobs(blob))
+        r = plan.analyzer_result(slot)
+        q.put((rank, (r.u[0], r.metric_double, u[0])))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_spearman_sample_sort_gives_global_ranks(built_lib, world):
+    from oracle import term_oracle as O
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 37500 + os.getpid() % 2000 + world
+    procs = [ctx.Process(target=sample_sort_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=180) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    t = _tie_table()
+    x, _ = O.pair_values(t, "x", "y")
+    want = O.an_correlation(t, "x", "y", "spearman")
+    assert sum(results[r][2] for r in range(world)) == len(x), "every pair ends on exactly one rank"
+    for r in range(world):
+        assert results[r][0] == len(x)
+        assert abs(results[r][1] - want) <= 1e-9, (results[r][1], want)

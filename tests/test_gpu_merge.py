@@ -338,3 +338,73 @@ def test_radix_sort_on_a_bit_range_is_stable(ctx):
     got_k, got_i = _gpu_sort(ctx, keys, begin_bit=8, n_passes=2)
     want_i = np.argsort((keys >> np.uint64(8)) & np.uint64(0xFFFF), kind="stable")
     assert (got_i == want_i.astype(np.uint32)).all()
+
+
+# ---------------------------------------------------------------- distributed Spearman: the device stages (tg_rank_*) ----
+@pytest.mark.parametrize("n,world", [(10, 2), (5_000, 3), (400_000, 4)])
+def test_rank_stages_sample_sort_emulated_on_one_gpu(built_lib, n, world):
+    """the sample sort of term_b200.distributed.distributed_spearman with `world` engines on ONE device standing in for the
+    ranks and device-to-device copies standing in for the NCCL all-to-all: global minimum ranks (ties, NULLs, an empty
+    shard) must reproduce scipy's rankdata(method="min") correlation"""
+    import torch
+    from term_b200.distributed import GpuRankStages, choose_splitters
+    rng = np.random.default_rng(n)
+    x = np.round(rng.normal(0, 5, n), 0 if n > 100 else 1)
+    y = np.round(0.6 * x + rng.normal(0, 3, n), 1)
+    ids = rng.integers(-50, 50, n)  # an Int64 column as the second variable of a second pair
+    t = pa.table({"x": pa.array(x, mask=rng.random(n) < 0.1), "y": pa.array(y, mask=rng.random(n) < 0.05), "k": pa.array(ids)})
+    fr = [0.0, 0.3, 0.3, 0.7, 1.0][: world] + [1.0] if world > 2 else [0.0, 0.5, 1.0]
+    cuts = [int(n * f) for f in fr]
+    ctxs = [T.SessionContext(0) for _ in range(world)]
+    try:
+        for r, c in enumerate(ctxs):
+            c.register_table("data", t.slice(cuts[r], cuts[r + 1] - cuts[r]))
+        for cx, cy in (("x", "y"), ("x", "k")):
+            st = [GpuRankStages(c) for c in ctxs]
+            total = sum(s.begin("data", cx, cy) for s in st)
+
+            def exchange():
+                for s in st:
+                    s.local_sort()
+                samples = np.concatenate([s.sample(64) for s in st])
+                sp = choose_splitters(samples, world)
+                counts = [s.split(sp, world) for s in st]  # counts[src][dst]
+                sends = [s.send() for s in st]
+                n_recv = [sum(counts[src][dst] for src in range(world)) for dst in range(world)]
+                recvs = [s.recv(n_recv[dst]) for dst, s in enumerate(st)]
+                for dst in range(world):
+                    o = 0
+                    for src in range(world):
+                        lo = sum(counts[src][:dst])
+                        c = counts[src][dst]
+                        if c:
+                            recvs[dst][0][o: o + c].copy_(sends[src][0][lo: lo + c])
+                            recvs[dst][1][o: o + c].copy_(sends[src][1][lo: lo + c])
+                        o += c
+                torch.cuda.synchronize()
+                for dst, s in enumerate(st):
+                    s.commit(n_recv[dst])
+                return [sum(n_recv[:dst]) for dst in range(world)]
+
+            bases = exchange()
+            center = (total + 1.0) / 2.0
+            for s, b in zip(st, bases):
+                s.finish_x(b)
+            bases = exchange()
+            parts = [s.finish_y(b, center) for s, b in zip(st, bases)]
+            assert sum(p[0] for p in parts) == total
+            sx, sy, sxx, syy, sxy = (sum(p[1][k] for p in parts) for k in range(5))
+            nn = float(total)
+            num = nn * sxy - sx * sy
+            den = math.sqrt((nn * sxx - sx * sx) * (nn * syy - sy * sy))
+            rho = num / den if den else 0.0
+            want = O.an_correlation(t, cx, cy, "spearman")
+            assert abs(rho - want) <= 1e-9, (cx, cy, rho, want)
+            # and the single-engine job (the same stages back to back) agrees
+            ctxs[0].register_table("whole", t)
+            one = T.CorrelationAnalyzer.spearman(cx, cy).compute(ctxs[0], "whole")
+            ctxs[0].deregister_table("whole")
+            assert one.u[0] == total and abs(one.metric_double - want) <= 1e-9
+    finally:
+        for c in ctxs:
+            c.close()
