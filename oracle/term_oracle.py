@@ -321,7 +321,11 @@ def format_description(kind, pattern, arg=None, flag=False) -> str:
 def rust_regex_to_python(pattern: str, case_insensitive: bool):
     """Rust `regex` semantics on top of Python `re`: `$` only at the very end (Python's also matches
     before a trailing newline -> rewrite unescaped `$` outside classes to `\\Z`); `\\z` -> `\\Z`;
-    `.` already excludes only \\n; Unicode classes by default for str patterns."""
+    `.` already excludes only \\n; Unicode classes by default for str patterns. Inside a multi-line group ((?m), (?ms), ..)
+    `$` keeps its multi-line meaning, which is the crate's. Patterns with Unicode properties (\\p), nested classes or class
+    set operations are compiled by the `regex` module (V1 syntax = the crate's), which Python's `re` does not parse."""
+    import re as _re
+    multiline = _re.search(r"\(\?[a-zA-Z]*m[a-zA-Z]*[):]", pattern) is not None and "(?-m" not in pattern
     out, i, in_class = [], 0, False
     while i < len(pattern):
         ch = pattern[i]
@@ -348,12 +352,16 @@ def rust_regex_to_python(pattern: str, case_insensitive: bool):
             if i + 1 < len(pattern) and pattern[i + 1] == "]":
                 out.append(r"\]")
                 i += 1
-        elif ch == "$":
+        elif ch == "$" and not multiline:
             out.append(r"\Z")
         else:
             out.append(ch)
         i += 1
-    return _rx.compile("".join(out), _rx.IGNORECASE if case_insensitive else 0)
+    py = "".join(out)
+    if _re.search(r"\\[pP]|&&|--|~~|\[\[(?!:)", pattern):
+        import regex as _regex
+        return _regex.compile(py, _regex.V1 | (_regex.IGNORECASE if case_insensitive else 0))
+    return _rx.compile(py, _rx.IGNORECASE if case_insensitive else 0)
 
 
 def regex_matches(col: Col, pattern: str, case_insensitive=False, trim=False) -> List[Optional[bool]]:

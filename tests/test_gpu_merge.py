@@ -408,3 +408,30 @@ def test_rank_stages_sample_sort_emulated_on_one_gpu(built_lib, n, world):
     finally:
         for c in ctxs:
             c.close()
+
+
+# ---------------------------------------------------------------- regex features on the device ----
+def test_word_boundaries_multiline_and_unicode_properties_on_the_device(ctx):
+    """has_pattern with \\b / (?m) / \\p{..} / class set operations: the device walks the DFA the host compiled; counts must
+    equal the oracle's (Python `re` / `regex` with the crate's semantics) on a corpus with multi-byte text and newlines"""
+    from tests.test_regex_features import HAYSTACKS
+    rng = np.random.default_rng(8)
+    vals = [HAYSTACKS[int(i)] for i in rng.integers(0, len(HAYSTACKS), 20_000)]
+    for i in range(0, len(vals), 97):
+        vals[i] = None
+    t = pa.table({"s": pa.array(vals, type=pa.string())})
+    ctx.register_table("rxf", t.to_batches(max_chunksize=3001))
+    try:
+        pats = [r"\bfoo\b", r"foo\B", r"(?m)^foo$", r"(?m)^\w+$", r"\p{Lu}\p{Ll}+", r"\p{Script=Han}", r"[a-z&&[^aeiou]]+\b", r"(?i)\bHELLO\b",
+                r"\b\d+\b", r"(?x) \b café \b"]
+        cb = T.Check.builder("rx")
+        for p in pats:
+            cb.validates_regex("s", p, 0.1)
+        cb.has_format("s", T.FormatType.Regex, 0.1, T.FormatOptions(case_sensitive=False, null_is_valid=False), arg=r"\bÉ\b")
+        rs = T.ValidationSuite.builder("s").table_name("rxf").check(cb.build()).build().run(ctx).report.results
+        want = [O.format_constraint(t, "s", "Regex", 0.1, arg=p) for p in pats]
+        want.append(O.format_constraint(t, "s", "Regex", 0.1, arg=r"\bÉ\b", case_sensitive=False, null_is_valid=False))
+        for g, o, p in zip(rs, want, pats + ["icase É"]):
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
+    finally:
+        ctx.deregister_table("rxf")

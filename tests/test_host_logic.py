@@ -173,7 +173,9 @@ def test_regex_dfa_random_fuzz(built_lib):
 
 
 def test_regex_unsupported_and_invalid_are_reported(built_lib):
-    for pat in [r"\bword\b", r"(?m)^a$", r"\p{L}+", r"[a-z&&[^b]]"]:
+    for pat in [r"\bword\b", r"(?m)^a$", r"\p{L}+", r"[a-z&&[^b]]"]:  # accepted since round 2 (tests/test_regex_features.py)
+        assert built_lib.tg_validate_regex_pattern(pat.encode()) == 0, pat
+    for pat in [r"\p{scx=Greek}", r"(?-u)a", r"(?R)a$", r"\b{start}x"]:
         assert built_lib.tg_validate_regex_pattern(pat.encode()) == F.TG_ERR_UNSUPPORTED, pat
     for pat in [r"(", r"a{2,1}", r"*a", r"[z-a]", r"\1", r"(?<!a)b", r"a{99999999}"]:
         assert built_lib.tg_validate_regex_pattern(pat.encode()) == F.TG_ERR_SECURITY, pat
