@@ -548,6 +548,9 @@ TG_API const char* tg_format_pattern(int32_t format_kind, const char* arg, int32
  * same table on the device): returns 1/0 match of `pattern` (search semantics of `~`) on bytes. */
 TG_API int32_t tg_regex_host_match(const char* pattern, int32_t case_insensitive, const uint8_t* s,
                                    int64_t len, int32_t* out_match);
+/* Size of the minimised byte DFA a pattern compiles to (states incl. DEAD / MATCH, byte classes): what the string
+ * kernel's shared-memory table holds. */
+TG_API int32_t tg_regex_dfa_size(const char* pattern, int32_t case_insensitive, uint32_t* n_states, uint32_t* n_classes);
 /* serde_json (ryu) rendering of an f64, as in the persisted analyzer states; returns needed length */
 TG_API int32_t tg_format_f64_json(double v, char* buf, int32_t cap);
 /* Rust `{}` Display of f64, for message parity; returns needed length */

@@ -165,6 +165,7 @@ SIGNATURES = {
     "tg_validate_sql_expression": (C.c_int, [C.c_char_p]),
     "tg_format_pattern": (C.c_char_p, [C.c_int32, C.c_char_p, C.c_int32]),
     "tg_regex_host_match": (C.c_int32, [C.c_char_p, C.c_int32, P, C.c_int64, C.POINTER(C.c_int32)]),
+    "tg_regex_dfa_size": (C.c_int32, [C.c_char_p, C.c_int32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]),
     "tg_format_f64": (C.c_int32, [C.c_double, C.c_char_p, C.c_int32]),
     "tg_format_f64_json": (C.c_int32, [C.c_double, C.c_char_p, C.c_int32]),
 }

@@ -763,6 +763,13 @@ int32_t tg_regex_host_match(const char* pattern, int32_t icase, const uint8_t* s
         if (out) *out = d.match(s, len) ? 1 : 0;
     });
 }
+int32_t tg_regex_dfa_size(const char* pattern, int32_t icase, uint32_t* n_states, uint32_t* n_classes) {
+    return (int32_t)guard([&] {
+        Dfa d = compile_regex(pattern ? pattern : "", icase != 0);
+        if (n_states) *n_states = d.n_states;
+        if (n_classes) *n_classes = d.n_classes;
+    });
+}
 int32_t tg_format_f64(double v, char* buf, int32_t cap) { return copy_out(fmt_f64(v), buf, cap); }
 
 }  // extern "C"

@@ -32,11 +32,14 @@ constexpr int STR_MAX_DFA = 8;          // patterns per product automaton
 constexpr int STR_MAX_WARPS = 32;       // warps per CTA (upper bound; fewer when the table is large)
 constexpr size_t STR_SMEM_MAX = 227 * 1024 - 2048;   // dynamic shared memory available beside the static tables
 constexpr size_t STR_TABLE_BUDGET = 112 * 1024;      // product tables up to this size still leave room for 32 warps
-constexpr uint32_t STR_MAX_ELEMS = 65536 - 256;      // transition entries addressable by the 16-bit row encoding
+constexpr size_t STR_SINGLE_BUDGET = 200 * 1024;     // a single pattern may take this much (fewer warps per CTA then)
+constexpr uint32_t STR_MAX_ELEMS = 131072 - 512;     // transition entries addressable by the 16-bit row encoding (rows start at even elements)
 
-// Transition table encoding (all uint16). A product state is named by the ELEMENT INDEX of its row. A row has
-// n_classes entries (next state per joint byte class) plus one END entry: the match mask if the string ends in this
-// state. Decided states (every component DEAD or MATCH) come first, so "decided" is E < n_term * (n_classes + 1);
+// Transition table encoding (all uint16). A product state is named by HALF THE ELEMENT INDEX of its row (rows are padded
+// to an even number of entries, so 16 bits name rows of tables up to 256 KB — more than shared memory holds; the big
+// automata are the ones with Unicode word boundaries). A row has n_classes entries (next state per joint byte class)
+// plus one END entry: the match mask if the string ends in this state. Decided states (every component DEAD or MATCH)
+// come first, so "decided" is E < n_term * stride / 2;
 // their rows loop to themselves. Byte 0xFF — which cannot occur in valid UTF-8 — is a class of its own that maps
 // every state to itself: the kernel pads the last 8-byte window of a string with 0xFF, so the per-byte loop has no
 // end-of-string test and no branch at all; "decided" is tested once per 8 bytes.
@@ -87,7 +90,7 @@ __device__ __forceinline__ uint32_t dfa_step8(uint32_t lo, uint32_t hi, uint32_t
     c[6] = lds_u8(__byte_perm(hi, cls_base, 0x7652));
     c[7] = lds_u8(__byte_perm(hi, cls_base, 0x7653));
 #pragma unroll
-    for (int k = 0; k < 8; ++k) E = lds_u16(tab_addr + 2u * (E + c[k]));
+    for (int k = 0; k < 8; ++k) E = lds_u16(tab_addr + 2u * (2u * E + c[k]));
     return E;
 }
 
@@ -114,7 +117,7 @@ __device__ __forceinline__ uint32_t run_dfa_smem(uint32_t stage_addr, uint32_t p
 // Same over global memory, byte loads (only blocks whose bytes exceed the stage: very long strings).
 __device__ __forceinline__ uint32_t run_dfa_gmem(const uint8_t* bytes, uint32_t p, uint32_t e, uint32_t E, uint32_t cls_base,
                                                  uint32_t tab_addr, uint32_t term_limit) {
-    for (; p < e && E >= term_limit; ++p) E = lds_u16(tab_addr + 2u * (E + lds_u8(cls_base + __ldg(bytes + p))));
+    for (; p < e && E >= term_limit; ++p) E = lds_u16(tab_addr + 2u * (2u * E + lds_u8(cls_base + __ldg(bytes + p))));
     return E;
 }
 
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_co
                     }
                     E = run_dfa_gmem(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
                 }
-                const uint32_t m = lds_u16(tab_addr + 2u * (E + n_classes));  // END entry = match mask
+                const uint32_t m = lds_u16(tab_addr + 2u * (2u * E + n_classes));  // END entry = match mask
 #pragma unroll
                 for (int i = 0; i < NDFA; ++i) cnt[i] += (m >> i) & 1u;
             }
@@ -287,7 +290,7 @@ static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_b
         }
         jclass[b] = it->second;
     }
-    const uint32_t njc = (uint32_t)rep.size(), stride = njc + 1, nop_class = jclass[0xFF];
+    const uint32_t njc = (uint32_t)rep.size(), stride = (njc + 2) & ~1u, nop_class = jclass[0xFF];  // njc entries + END, padded to even
     if (njc > 255) return pr;
     // breadth-first product construction
     typedef std::vector<uint16_t> Tuple;
@@ -332,16 +335,16 @@ static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_b
         return true;
     };
     for (uint32_t s = 0; s < ns; ++s)
-        if (decided(states[s])) enc[s] = (n_term++) * stride;
+        if (decided(states[s])) enc[s] = (n_term++) * (stride / 2);
     uint32_t row = n_term;
     for (uint32_t s = 0; s < ns; ++s)
-        if (!decided(states[s])) enc[s] = (row++) * stride;
+        if (!decided(states[s])) enc[s] = (row++) * (stride / 2);
     if ((size_t)ns * stride > max_elems) return pr;
     const size_t tab_bytes = round_up(256 + (size_t)ns * stride * 2, 16);
     pr.n_classes = njc;
     pr.n_states = ns;
     pr.n_term = n_term;
-    pr.term_limit = n_term * stride;
+    pr.term_limit = n_term * (stride / 2);
     pr.start = enc[0];
     pr.tab_bytes = (uint32_t)tab_bytes;
     pr.blob.assign(tab_bytes, 0);
@@ -353,7 +356,7 @@ static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_b
             const uint16_t x = states[s][i];
             if (x == DFA_MATCH || (x != DFA_DEAD && dfas[i]->accept_end[x])) m |= (uint8_t)(1u << i);
         }
-        uint16_t* r = tab + enc[s];
+        uint16_t* r = tab + 2 * (size_t)enc[s];
         for (uint32_t c = 0; c < njc; ++c) r[c] = (uint16_t)enc[next[(size_t)s * njc + c]];
         r[njc] = m;  // END entry
     }
@@ -486,7 +489,7 @@ void exec_string_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_
         auto flush = [&]() {
             if (pass.empty()) return;
             const Product* pr = &cached_product(pats, STR_TABLE_BUDGET);
-            if (!pr->ok && pass.size() == 1) pr = &cached_product(pats, 2 * (size_t)STR_MAX_ELEMS);
+            if (!pr->ok && pass.size() == 1) pr = &cached_product(pats, STR_SINGLE_BUDGET);  // alone it may take most of shared memory
             if (!pr->ok) {
                 for (int id : pass) {
                     p.aggs[id].err = TG_ERR_UNSUPPORTED;
