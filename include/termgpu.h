@@ -434,6 +434,17 @@ TG_API tg_status tg_plan_aggregate_info(const tg_plan* plan, int32_t i, int32_t*
 TG_API tg_status tg_engine_mailbox_create(tg_engine* eng, int32_t world, int32_t rank, size_t slot_bytes, void* handle_out);
 TG_API tg_status tg_engine_mailbox_open(tg_engine* eng, const void* handles /* world x 64 bytes, rank order */);
 TG_API tg_status tg_plan_exchange_and_finalize(tg_engine* eng, tg_plan* plan);
+/* Same, for partial blobs of any size: when some rank's blob does not fit its mailbox slot, that rank publishes a
+ * "does not fit" marker instead, EVERY rank returns *fell_back = 1 without merging anything, and the host layer
+ * exchanges the blobs over NCCL (tg_plan_partial_export / _merge). */
+TG_API tg_status tg_plan_exchange_ex(tg_engine* eng, tg_plan* plan, int32_t* fell_back);
+/* The whole multi-GPU step of a scan-only plan (ROWS / VALID / NUM / PAIR / PRED aggregates: everything the fused
+ * numeric scan answers) in one call: partial execute on this rank's shard, the aggregates' partial states assembled ON
+ * THE DEVICE behind the scan (no host round trip), published into every peer's mailbox over NVLink, collected, merged in
+ * rank order like AnalyzerState::merge (analyzers/traits.rs:154-179) and finalized — one stream synchronisation per
+ * step. *done = 0: the plan holds other aggregates, or no mailbox is open; nothing was executed and the caller takes
+ * tg_plan_execute_partial + tg_plan_exchange_ex. Every rank must call it with the same plan. */
+TG_API tg_status tg_plan_execute_exchange(tg_engine* eng, tg_plan* plan, const char* table_name, int32_t* done);
 
 /*
  * Distributed RANK() OVER (ORDER BY ..) for the Spearman analyzer across row shards (the reference's

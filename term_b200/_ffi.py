@@ -134,6 +134,8 @@ SIGNATURES = {
     "tg_engine_mailbox_create": (C.c_int, [P, C.c_int32, C.c_int32, C.c_size_t, P]),
     "tg_engine_mailbox_open": (C.c_int, [P, P]),
     "tg_plan_exchange_and_finalize": (C.c_int, [P, P]),
+    "tg_plan_exchange_ex": (C.c_int, [P, P, C.POINTER(C.c_int32)]),
+    "tg_plan_execute_exchange": (C.c_int, [P, P, C.c_char_p, C.POINTER(C.c_int32)]),
     "tg_debug_sort_pairs": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, P, P]),
     "tg_rank_begin": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "tg_rank_local_sort": (C.c_int, [P]),

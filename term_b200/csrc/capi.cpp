@@ -466,7 +466,8 @@ tg_status tg_plan_exchange_and_finalize(tg_engine* h, tg_plan* p) {
         std::vector<uint8_t> blob(p->p.partial_size());
         p->p.partial_export(blob.data());
         std::vector<std::vector<uint8_t>> all;
-        mailbox_exchange(h->e, blob.data(), blob.size(), all);
+        if (!mailbox_exchange(h->e, blob.data(), blob.size(), all))
+            throw Error(TG_ERR_INVALID_ARG, "mailbox: a rank's partial blob is larger than the slot (use tg_plan_exchange_ex, which reports it)");
         p->p.reset_partials();
         for (auto& b : all) p->p.partial_merge(b.data(), b.size());
         p->p.finalize();
@@ -574,6 +575,31 @@ tg_status tg_plan_set_aggregate_partial(tg_plan* p, int32_t i, const uint64_t* u
             a.u[k] = u8[k];
             a.f[k] = f8[k];
         }
+    });
+}
+
+// like tg_plan_exchange_and_finalize, but a blob that does not fit some rank's slot is not an error: *fell_back = 1 on
+// EVERY rank (the marker travels through the mailbox) and nothing was merged — the host layer then exchanges over NCCL
+tg_status tg_plan_exchange_ex(tg_engine* h, tg_plan* p, int32_t* fell_back) {
+    return guard([&] {
+        if (!h || !p || !fell_back) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::vector<uint8_t> blob(p->p.partial_size());
+        p->p.partial_export(blob.data());
+        std::vector<std::vector<uint8_t>> all;
+        *fell_back = mailbox_exchange(h->e, blob.data(), blob.size(), all) ? 0 : 1;
+        if (*fell_back) return;
+        p->p.reset_partials();
+        for (auto& b : all) p->p.partial_merge(b.data(), b.size());
+        p->p.finalize();
+    });
+}
+// scan-only plans: partial execute, device-side assembly of the partial states, publish / collect over the peer mailboxes
+// and the rank-ordered merge in ONE call with one stream synchronisation. *done = 0: the plan (or the platform) does not
+// qualify and nothing was executed — use tg_plan_execute_partial + tg_plan_exchange_ex.
+tg_status tg_plan_execute_exchange(tg_engine* h, tg_plan* p, const char* table_name, int32_t* done) {
+    return guard([&] {
+        if (!h || !p || !table_name || !done) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        *done = execute_exchange_fused(h->e, p->p, table_name) ? 1 : 0;
     });
 }
 

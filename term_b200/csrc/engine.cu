@@ -171,6 +171,8 @@ static std::string no_field_msg(const Table& t, const std::string& col) {
     return "Schema error: No field named " + col + ". Valid fields are " + t.valid_fields() + ".";
 }
 
+__global__ void scan_states_kernel(const ScanAggOut* __restrict__ out, const ScanOpMeta* __restrict__ metas, int n_ops, DevAggRec* __restrict__ states);
+
 static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops) {
     if (ops.empty()) return;
     auto P = std::make_unique<ScanParams>();
@@ -373,6 +375,23 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
     TG_CUDA(cudaEventRecord(e.ev[1], e.stream));
     e.launches += 2;
     p.stats.launches += 2;
+    if (e.fused) {
+        // fused multi-GPU step: no copy-out, no synchronisation — a small kernel turns the records into partial states
+        // on the device (the decode below, restated in scan_states_kernel)
+        FusedScan& fz = *e.fused;
+        ScanOpMeta* hm = fz.h_metas + fz.n_metas;
+        for (size_t i = 0; i < ops.size(); ++i) {
+            hm[i] = ScanOpMeta{ops[i].kind, ops[i].agg, ops[i].c0 ? ops[i].c0->pivot : 0.0, ops[i].c1 ? ops[i].c1->pivot : 0.0, (uint64_t)t.n_rows};
+            fz.from_device[ops[i].agg] = 1;
+        }
+        TG_CUDA(cudaMemcpyAsync(fz.d_metas + fz.n_metas, hm, ops.size() * sizeof(ScanOpMeta), cudaMemcpyHostToDevice, e.stream));
+        scan_states_kernel<<<1, 64, 0, e.stream>>>(d_out, fz.d_metas + fz.n_metas, (int)ops.size(), fz.d_states);
+        TG_CUDA(cudaGetLastError());
+        fz.n_metas += (int)ops.size();
+        e.launches += 1;
+        p.stats.launches += 1;
+        return;
+    }
     ScanAggOut* h_out = reinterpret_cast<ScanAggOut*>(e.host_scratch(out_bytes));
     TG_CUDA(cudaMemcpyAsync(h_out, d_out, out_bytes, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
@@ -428,6 +447,82 @@ static void run_scan_pass(Engine& e, Table& t, Plan& p, std::vector<ScanOp>& ops
                 a.u[2] = (uint64_t)t.n_rows;
                 break;
         }
+    }
+}
+
+// the decode above on the device (fused multi-GPU step): record i of a pass -> the partial state of its aggregate
+__global__ void scan_states_kernel(const ScanAggOut* __restrict__ out, const ScanOpMeta* __restrict__ metas, int n_ops, DevAggRec* __restrict__ states) {
+    for (int i = threadIdx.x; i < n_ops; i += blockDim.x) {
+        const ScanOpMeta m = metas[i];
+        const uint64_t* s = out[i].s;
+        DevAggRec& a = states[m.agg];
+        auto u2d = [](uint64_t u) { return __longlong_as_double((long long)u); };
+        switch (m.unit_kind) {
+            case UNIT_COUNT:
+                a.u[0] = m.n_rows;
+                a.u[1] = s[S_N];
+                break;
+            case UNIT_NUM_F64:
+            case UNIT_NUM_I64:
+                a.u[0] = s[S_N];
+                a.f[0] = m.pivot0;
+                a.f[1] = u2d(s[S_SD]);
+                a.f[2] = u2d(s[S_SDD]);
+                a.f[5] = __dadd_rn(__dmul_rn((double)s[S_N], m.pivot0), u2d(s[S_SD]));  // as the host: product and sum rounded separately
+                if (m.unit_kind == UNIT_NUM_I64) {
+                    a.u[1] = s[S_ISUM];
+                    a.u[2] = s[S_MIN];
+                    a.u[3] = s[S_MAX];
+                    a.u[4] = 1;
+                } else {
+                    a.f[3] = u2d(s[S_MIN]);
+                    a.f[4] = u2d(s[S_MAX]);
+                }
+                break;
+            case UNIT_PAIR:
+                a.u[0] = s[P_N];
+                a.f[0] = m.pivot0;
+                a.f[1] = m.pivot1;
+                a.f[2] = u2d(s[P_SX]);
+                a.f[3] = u2d(s[P_SY]);
+                a.f[4] = u2d(s[P_SXX]);
+                a.f[5] = u2d(s[P_SYY]);
+                a.f[6] = u2d(s[P_SXY]);
+                break;
+            default:  // UNIT_PRED / UNIT_TERMS
+                a.u[0] = s[0];
+                a.u[1] = m.unit_kind == UNIT_PRED ? s[1] : 0;
+                a.u[2] = m.n_rows;
+                break;
+        }
+    }
+}
+
+// the rank's payload for the mailbox: [u64 byte length][u64 n_aggs][n_aggs x DevAggRec] from the host's template (aggregates
+// the host resolved, error codes) and the device states; COUNT(c) aggregates folded into a NUM unit take its count
+__global__ void scan_payload_kernel(const DevAggRec* __restrict__ tmpl, const uint8_t* __restrict__ from_device, const DevAggRec* __restrict__ states,
+                                    const int2* __restrict__ folds, int n_folds, int n_aggs, uint64_t n_rows, uint8_t* __restrict__ payload) {
+    uint64_t* hdr = reinterpret_cast<uint64_t*>(payload);
+    DevAggRec* recs = reinterpret_cast<DevAggRec*>(payload + 16);
+    for (int i = threadIdx.x; i < n_aggs; i += blockDim.x) {
+        DevAggRec r = tmpl[i];
+        if (from_device[i]) {
+            const DevAggRec s = states[i];
+            for (int k = 0; k < 8; ++k) {
+                r.u[k] = s.u[k];
+                r.f[k] = s.f[k];
+            }
+        }
+        recs[i] = r;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n_folds; i += blockDim.x) {
+        recs[folds[i].x].u[0] = n_rows;
+        recs[folds[i].x].u[1] = recs[folds[i].y].u[0];
+    }
+    if (threadIdx.x == 0) {
+        hdr[0] = 8 + (uint64_t)n_aggs * sizeof(DevAggRec);
+        hdr[1] = (uint64_t)n_aggs;
     }
 }
 
@@ -644,12 +739,17 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
         Table& t;
         std::vector<std::pair<int, int>>& v;
         ~FoldFill() {
+            if (p_fused) {  // the NUM aggregate's count only exists on the device: scan_payload_kernel folds it
+                for (auto& pr : v) p_fused->folds.push_back(pr);
+                return;
+            }
             for (auto& pr : v) {
                 p.aggs[pr.first].u[0] = (uint64_t)t.n_rows;
                 p.aggs[pr.first].u[1] = p.aggs[pr.second].u[0];
             }
         }
-    } fold_fill{p, t, valid_from_num};
+        FusedScan* p_fused;
+    } fold_fill{p, t, valid_from_num, e.fused};
     if (t.n_rows == 0) {
         // nothing to scan: aggregates keep their zero state (COUNT(*) = 0)
         for (auto& o : ops)
@@ -778,6 +878,126 @@ void execute_partial(Engine& e, Plan& p, const std::string& table_name) {
             a.err_msg = er.msg;
         }
     }
+}
+
+// ------------------------------------------------------------------ fused multi-GPU step (scan-only plans) ----
+bool execute_exchange_fused(Engine& e, Plan& p, const std::string& table_name) {
+    std::unique_lock<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    Mailbox& m = e.mailbox;
+    if (!m.open) return false;
+    const int n_aggs = (int)p.aggs.size();
+    // rank-independent decisions only: the plan is the same on every rank
+    for (auto& a : p.aggs)
+        if (a.kind != A_ROWS && a.kind != A_VALID && a.kind != A_NUM && a.kind != A_PAIR && a.kind != A_PRED) return false;
+    const size_t payload = 16 + (size_t)n_aggs * sizeof(DevAggRec);
+    const size_t pinned_need = (size_t)n_aggs * (sizeof(DevAggRec) + sizeof(ScanOpMeta) + 1 + sizeof(int2)) + 256;
+    if (n_aggs == 0 || payload > m.slot_bytes || pinned_need > m.slot_bytes) return false;
+
+    p.reset_partials();
+    p.stats = tg_exec_stats{};
+    p.executed = false;
+    e.sync_copies();
+    auto it = e.tables.find(table_name);
+    Table* t = it == e.tables.end() ? nullptr : it->second.get();
+    // device block: states | metas | template | from_device | folds   (the payload itself is assembled in the mailbox's d_stage)
+    const size_t st_b = round_up((size_t)n_aggs * sizeof(DevAggRec), 256), me_b = round_up((size_t)n_aggs * sizeof(ScanOpMeta), 256);
+    const size_t fd_b = round_up((size_t)n_aggs, 256), fo_b = round_up((size_t)n_aggs * sizeof(int2), 256);
+    uint8_t* d = e.aux(2 * st_b + me_b + fd_b + fo_b + 256);
+    FusedScan fz;
+    fz.d_states = (DevAggRec*)d;
+    fz.d_metas = (ScanOpMeta*)(d + st_b);
+    DevAggRec* d_tmpl = (DevAggRec*)(d + st_b + me_b);
+    uint8_t* d_from = d + 2 * st_b + me_b;
+    int2* d_folds = (int2*)(d + 2 * st_b + me_b + fd_b);
+    // pinned staging: the mailbox's host stage (unused by this path otherwise)
+    uint8_t* hp = m.h_stage;
+    fz.h_metas = (ScanOpMeta*)hp;
+    DevAggRec* h_tmpl = (DevAggRec*)(hp + me_b);
+    uint8_t* h_from = hp + me_b + st_b;
+    int2* h_folds = (int2*)(hp + me_b + st_b + fd_b);
+    if (me_b + st_b + fd_b + fo_b > m.slot_bytes) return false;
+    fz.from_device.assign((size_t)n_aggs, 0);
+    TG_CUDA(cudaMemsetAsync(fz.d_states, 0, st_b, e.stream));
+
+    std::vector<int> scan_ids;
+    for (int i = 0; i < n_aggs; ++i) {
+        Agg& a = p.aggs[i];
+        if (a.err != TG_OK) continue;
+        if (!t) {
+            a.err = TG_ERR_TABLE_NOT_FOUND;
+            a.err_msg = "Error during planning: table 'datafusion.public." + table_name + "' not found";
+            continue;
+        }
+        if (a.kind == A_ROWS) {
+            a.u[0] = (uint64_t)t->n_rows;
+            a.u[1] = (uint64_t)t->cols.size();
+        } else {
+            scan_ids.push_back(i);
+        }
+    }
+    struct Unfuse {
+        Engine& e;
+        ~Unfuse() { e.fused = nullptr; }
+    } unfuse{e};
+    e.fused = &fz;
+    if (t && !scan_ids.empty()) exec_scan_jobs(e, *t, p, scan_ids);
+    e.fused = nullptr;
+    // the template: everything the host knows (kinds, error codes, host-resolved states)
+    for (int i = 0; i < n_aggs; ++i) {
+        const Agg& a = p.aggs[i];
+        DevAggRec r{};
+        r.kind = (uint64_t)a.kind;
+        r.err = (uint64_t)a.err;
+        memcpy(r.u, a.u, 64);
+        memcpy(r.f, a.f, 64);
+        h_tmpl[i] = r;
+        h_from[i] = a.err == TG_OK ? fz.from_device[i] : 0;
+    }
+    const int n_folds = (int)fz.folds.size();
+    for (int i = 0; i < n_folds; ++i) h_folds[i] = make_int2(fz.folds[i].first, fz.folds[i].second);
+    TG_CUDA(cudaMemcpyAsync(d_tmpl, h_tmpl, (size_t)n_aggs * sizeof(DevAggRec), cudaMemcpyHostToDevice, e.stream));
+    TG_CUDA(cudaMemcpyAsync(d_from, h_from, (size_t)n_aggs, cudaMemcpyHostToDevice, e.stream));
+    if (n_folds) TG_CUDA(cudaMemcpyAsync(d_folds, h_folds, (size_t)n_folds * sizeof(int2), cudaMemcpyHostToDevice, e.stream));
+    scan_payload_kernel<<<1, 128, 0, e.stream>>>(d_tmpl, d_from, fz.d_states, d_folds, n_folds, n_aggs, t ? (uint64_t)t->n_rows : 0ull, m.d_stage);
+    TG_CUDA(cudaGetLastError());
+    e.launches += 1;
+    p.stats.launches += 1;
+    std::vector<std::vector<uint8_t>> all;
+    mailbox_exchange_device(e, payload, all);  // publish + collect + the step's one synchronisation
+    float ms = 0;
+    if (t && !scan_ids.empty() && cudaEventElapsedTime(&ms, e.ev[0], e.ev[1]) == cudaSuccess) {  // the (last) scan pass
+        p.stats.scan_ms += ms;
+        p.stats.gpu_ms += ms;
+    } else {
+        cudaGetLastError();
+    }
+    // rank-ordered merge (deterministic), then finalize
+    std::vector<std::pair<tg_status, std::string>> local_err;
+    for (auto& a : p.aggs) local_err.emplace_back(a.err, a.err_msg);
+    p.reset_partials();
+    static const std::vector<uint8_t> no_blob;
+    for (int r = 0; r < m.world; ++r) {
+        const std::vector<uint8_t>& b = all[r];
+        uint64_t na = 0;
+        if (b.size() >= 8) memcpy(&na, b.data(), 8);
+        if (na != (uint64_t)n_aggs || b.size() < 8 + (size_t)n_aggs * sizeof(DevAggRec))
+            throw Error(TG_ERR_INVALID_ARG, "fused exchange: rank " + std::to_string(r) + " published the states of another plan");
+        for (int i = 0; i < n_aggs; ++i) {
+            DevAggRec rec;
+            memcpy(&rec, b.data() + 8 + (size_t)i * sizeof(DevAggRec), sizeof(rec));
+            if ((int32_t)rec.kind != p.aggs[i].kind) throw Error(TG_ERR_INVALID_ARG, "fused exchange: aggregate kinds differ between ranks");
+            const tg_status err = (tg_status)rec.err;
+            const std::string msg = err == TG_OK ? std::string()
+                                   : (r == m.rank || local_err[i].first == err) && !local_err[i].second.empty()
+                                       ? local_err[i].second
+                                       : "error " + std::to_string((int)err) + " on rank " + std::to_string(r);
+            p.merge_state(i, err, msg, rec.u, rec.f, no_blob);
+        }
+    }
+    g.unlock();
+    p.finalize();
+    return true;
 }
 
 }  // namespace tg

@@ -78,6 +78,28 @@ struct Table {
     }
 };
 
+// Fused multi-GPU step of a scan-only plan (engine.cu execute_exchange_fused): the aggregates' partial states are
+// assembled on the device behind the scan instead of on the host.
+struct DevAggRec {  // what travels between the ranks per aggregate: the partial state of plan.hpp's Agg
+    uint64_t kind, err;
+    uint64_t u[8];
+    double f[8];
+};
+struct ScanOpMeta {  // how scan_states_kernel turns one ScanAggOut record into a DevAggRec
+    int32_t unit_kind, agg;
+    double pivot0, pivot1;
+    uint64_t n_rows;
+};
+struct FusedScan {
+    DevAggRec* d_states = nullptr;  // [n_aggs], zeroed; written by scan_states_kernel after every pass
+    ScanOpMeta* d_metas = nullptr;  // [n_aggs] device
+    ScanOpMeta* h_metas = nullptr;  // [n_aggs] pinned
+    int n_metas = 0;
+    std::vector<uint8_t> from_device;          // per aggregate: its state comes from d_states
+    std::vector<std::pair<int, int>> folds;    // (VALID aggregate, NUM aggregate whose count it takes)
+    int launches = 0;
+};
+
 // peer mailboxes of the multi-GPU partial-state exchange (mailbox.cu)
 constexpr int MAILBOX_MAX_WORLD = 16;
 struct MailboxPeers {
@@ -130,6 +152,7 @@ struct Engine {
     void ensure_side_streams();
     Mailbox mailbox;
     RankSession* rank_session = nullptr;
+    FusedScan* fused = nullptr;  // non-null while execute_exchange_fused runs the scan jobs
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
     size_t aux_cap = 0;
     uint8_t* aux(size_t bytes);
@@ -172,12 +195,14 @@ void rank_abort(Engine& e);
 void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb); // hist.cu (two-phase multi-GPU histogram)
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);
+bool execute_exchange_fused(Engine& e, Plan& p, const std::string& table_name);  // false: not applicable, nothing done
 
 // mailbox.cu
 void mailbox_create(Engine& e, int world, int rank, size_t slot_bytes, void* handle_out /* 64 bytes */);
 void mailbox_open(Engine& e, const void* handles /* world x 64 bytes */);
 void mailbox_destroy(Engine& e);
-void mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out);
+bool mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out);
+void mailbox_exchange_device(Engine& e, size_t payload_bytes, std::vector<std::vector<uint8_t>>& out);
 
 // scan.cu
 size_t scan_smem_bytes(const ScanParams& P);

@@ -3,9 +3,9 @@
 // Every rank owns a small device buffer [2 parities][world slots][slot bytes] + flags, exported to the other ranks of
 // the node through CUDA IPC. After its partial execute a rank PUBLISHES: one kernel stores its serialised partial
 // states into slot[rank] of every peer's mailbox (plain stores that travel over NVLink), fences system-wide and then
-// writes the step's sequence number into the peer's flag[rank]. COLLECT is a second tiny kernel that spins on the
-// local flags until every rank's sequence number has arrived, followed by one device-to-host copy of the local
-// mailbox. Compared with H2D -> ncclAllGather -> D2H this removes two copies and the collective's launch and
+// writes the step's sequence number into the peer's flag[rank]. COLLECT is a second tiny kernel (one block per rank)
+// that spins on the local flag of its rank and then copies that rank's payload — only the bytes it holds — straight
+// into pinned host memory. Compared with H2D -> ncclAllGather -> D2H this removes two copies and the collective's launch and
 // rendezvous latency from every step (the payload is a few KB). Double buffering by step parity is enough: a rank
 // can only be one step ahead of the slowest rank, because it cannot finish collecting step s+1 before everyone has
 // published s+1, which they do after collecting s.
@@ -36,17 +36,38 @@ __global__ void mailbox_publish_kernel(const uint4* __restrict__ src, uint32_t n
     }
 }
 
-__global__ void mailbox_wait_kernel(const uint8_t* base, int world, int parity, unsigned long long seq, unsigned long long* timeout_flag) {
-    const int r = threadIdx.x;
+// COLLECT, one block per rank: wait for rank r's sequence number, then copy its payload (8-byte length + bytes, only as
+// much as it holds) from the local mailbox straight into pinned host memory — no device-to-host copy call, and a
+// large slot costs nothing when the payload is small. A length of ~0 marks "my payload did not fit the slot".
+__global__ void mailbox_collect_kernel(const uint8_t* base, int world, uint32_t slot_bytes, int parity, unsigned long long seq,
+                                       uint8_t* host_out /* pinned, [world][slot_bytes] + 64 */, unsigned long long* timeout_flag /* pinned */) {
+    const int r = blockIdx.x;
     if (r >= world) return;
-    const volatile unsigned long long* f = &reinterpret_cast<const MailboxHeader*>(base)->flag[parity][r];
-    unsigned long long spins = 0;
-    while (*f != seq) {
-        if (++spins > (1ull << 31)) {  // ~ seconds: a peer died; report instead of hanging the GPU
-            *timeout_flag = 1;
-            break;
+    __shared__ unsigned long long s_len;
+    if (threadIdx.x == 0) {
+        const volatile unsigned long long* f = &reinterpret_cast<const MailboxHeader*>(base)->flag[parity][r];
+        unsigned long long spins = 0;
+        bool ok = true;
+        while (*f != seq) {
+            if (++spins > (1ull << 31)) {  // ~ seconds: a peer died; report instead of hanging the GPU
+                *timeout_flag = 1;
+                ok = false;
+                break;
+            }
         }
+        __threadfence_system();
+        const uint8_t* slot = base + sizeof(MailboxHeader) + ((size_t)parity * world + r) * slot_bytes;
+        unsigned long long len = ok ? *reinterpret_cast<const volatile unsigned long long*>(slot) : 0ull;
+        if (len != ~0ull && len + 8 > slot_bytes) len = 0;
+        s_len = len;
     }
+    __syncthreads();
+    const unsigned long long len = s_len;
+    const uint8_t* slot = base + sizeof(MailboxHeader) + ((size_t)parity * world + r) * slot_bytes;
+    uint4* dst = reinterpret_cast<uint4*>(host_out + (size_t)r * slot_bytes);
+    const uint32_t n16 = len == ~0ull ? 1u : (uint32_t)((len + 8 + 15) / 16);
+    const uint4* src = reinterpret_cast<const uint4*>(slot);
+    for (uint32_t i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = src[i];
     __threadfence_system();
 }
 
@@ -63,7 +84,7 @@ void mailbox_create(Engine& e, int world, int rank, size_t slot_bytes, void* han
     TG_CUDA(cudaMemset(m.local, 0, m.bytes));
     TG_CUDA(cudaMalloc(&m.d_stage, slot_bytes + 256));
     TG_CUDA(cudaMallocHost(&m.h_stage, slot_bytes));
-    TG_CUDA(cudaMallocHost(&m.h_all, 2 * (size_t)world * slot_bytes));
+    TG_CUDA(cudaMallocHost(&m.h_all, (size_t)world * slot_bytes + 64));  // the collect kernel stores into it directly (UVA); last 64 bytes: timeout flag
     TG_CUDA(cudaMemset(m.d_stage, 0, slot_bytes + 256));
     cudaIpcMemHandle_t h;
     TG_CUDA(cudaIpcGetMemHandle(&h, m.local));
@@ -100,40 +121,70 @@ void mailbox_destroy(Engine& e) {
     m = Mailbox{};
 }
 
-// publish `n` bytes (this rank's partial blob, prefixed with its length) and collect every rank's; out[r] = rank r's blob
-void mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out) {
+// queue PUBLISH (d_stage -> slot[rank] of every peer + flag) and COLLECT (every rank's payload -> m.h_all) on the engine's
+// stream; `send` = bytes of d_stage to publish (16-byte multiple; the payload starts with its 8-byte length)
+static void mailbox_queue(Engine& e, size_t send, unsigned long long seq) {
     Mailbox& m = e.mailbox;
-    if (!m.open) throw Error(TG_ERR_INVALID_ARG, "mailbox: not open");
-    if (n + 8 > m.slot_bytes) throw Error(TG_ERR_INVALID_ARG, "mailbox: partial blob larger than the slot");
-    std::lock_guard<std::mutex> g(e.mu);
-    TG_CUDA(cudaSetDevice(e.device));
-    const unsigned long long seq = ++m.seq;
     const int parity = (int)(seq & 1ull);
-    const uint64_t len = n;
-    memcpy(m.h_stage, &len, 8);
-    memcpy(m.h_stage + 8, blob, n);
-    const size_t send = (n + 8 + 15) / 16 * 16;
-    TG_CUDA(cudaMemcpyAsync(m.d_stage, m.h_stage, send, cudaMemcpyHostToDevice, e.stream));
     mailbox_publish_kernel<<<m.world, 128, 0, e.stream>>>((const uint4*)m.d_stage, (uint32_t)(send / 16), m.peers, m.world, m.rank,
                                                           (uint32_t)m.slot_bytes, parity, seq);
-    unsigned long long* d_timeout = (unsigned long long*)(m.d_stage + m.slot_bytes);
-    mailbox_wait_kernel<<<1, 32 * ((m.world + 31) / 32), 0, e.stream>>>(m.local, m.world, parity, seq, d_timeout);
+    unsigned long long* h_timeout = (unsigned long long*)(m.h_all + (size_t)m.world * m.slot_bytes);
+    *h_timeout = 0;
+    mailbox_collect_kernel<<<m.world, 128, 0, e.stream>>>(m.local, m.world, (uint32_t)m.slot_bytes, parity, seq, m.h_all, h_timeout);
     TG_CUDA(cudaGetLastError());
-    const size_t half = (size_t)m.world * m.slot_bytes;
-    TG_CUDA(cudaMemcpyAsync(m.h_all, m.local + sizeof(MailboxHeader) + (size_t)parity * half, half, cudaMemcpyDeviceToHost, e.stream));
-    unsigned long long timeout = 0;
-    TG_CUDA(cudaMemcpyAsync(&timeout, d_timeout, 8, cudaMemcpyDeviceToHost, e.stream));
-    TG_CUDA(cudaStreamSynchronize(e.stream));
     e.launches += 2;
+}
+// after the stream was synchronised: rank r's payload; false when some rank could not fit its payload (then nobody uses
+// this exchange: every rank sees the same markers and takes the fallback)
+static bool mailbox_read(Engine& e, std::vector<std::vector<uint8_t>>& out) {
+    Mailbox& m = e.mailbox;
+    const unsigned long long timeout = *(const volatile unsigned long long*)(m.h_all + (size_t)m.world * m.slot_bytes);
     if (timeout) throw Error(TG_ERR_NCCL, "mailbox: a peer did not publish its partial state in time");
     out.resize(m.world);
+    bool all_fit = true;
     for (int r = 0; r < m.world; ++r) {
         const uint8_t* s = m.h_all + (size_t)r * m.slot_bytes;
         uint64_t l;
         memcpy(&l, s, 8);
+        if (l == ~0ull) {
+            all_fit = false;
+            continue;
+        }
         if (l + 8 > m.slot_bytes) throw Error(TG_ERR_INTERNAL, "mailbox: corrupt slot");
         out[r].assign(s + 8, s + 8 + l);
     }
+    return all_fit;
+}
+
+// publish `n` bytes (this rank's partial blob, prefixed with its length) and collect every rank's; out[r] = rank r's blob.
+// Returns false when some rank's blob did not fit its slot: every rank gets false and the host layer falls back to NCCL.
+bool mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out) {
+    Mailbox& m = e.mailbox;
+    if (!m.open) throw Error(TG_ERR_INVALID_ARG, "mailbox: not open");
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    const unsigned long long seq = ++m.seq;
+    const bool fits = n + 8 <= m.slot_bytes;
+    const uint64_t len = fits ? (uint64_t)n : ~0ull;
+    memcpy(m.h_stage, &len, 8);
+    if (fits) memcpy(m.h_stage + 8, blob, n);
+    const size_t send = fits ? (n + 8 + 15) / 16 * 16 : 16;
+    TG_CUDA(cudaMemcpyAsync(m.d_stage, m.h_stage, send, cudaMemcpyHostToDevice, e.stream));
+    mailbox_queue(e, send, seq);
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    return mailbox_read(e, out);
+}
+
+// the fused path of a scan-only plan (engine.cu): the payload was assembled in d_stage by kernels already queued on the
+// stream — publish / collect behind them, ONE synchronisation for the whole step
+void mailbox_exchange_device(Engine& e, size_t payload_bytes, std::vector<std::vector<uint8_t>>& out) {
+    Mailbox& m = e.mailbox;
+    if (!m.open) throw Error(TG_ERR_INVALID_ARG, "mailbox: not open");
+    if (payload_bytes > m.slot_bytes) throw Error(TG_ERR_INVALID_ARG, "mailbox: payload larger than the slot");
+    const unsigned long long seq = ++m.seq;
+    mailbox_queue(e, (payload_bytes + 15) / 16 * 16, seq);
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    if (!mailbox_read(e, out)) throw Error(TG_ERR_INTERNAL, "mailbox: a rank did not take the fused path");
 }
 
 }  // namespace tg

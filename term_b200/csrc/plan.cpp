@@ -726,10 +726,18 @@ void Plan::partial_merge(const uint8_t* buf, size_t nbytes) {
         if (p + padded > end) throw Error(TG_ERR_INVALID_ARG, "partial blob truncated");
         std::string emsg((const char*)p, elen);
         p += padded;
-        if (err != TG_OK && a.err == TG_OK) {
-            a.err = err;
-            a.err_msg = emsg;
-        }
+        merge_state((int)(&a - aggs.data()), err, emsg, u, f, blob);
+    }
+}
+
+// one shard's state of aggregate i folded into ours (AnalyzerState::merge, analyzers/traits.rs:154-179)
+void Plan::merge_state(int i, tg_status err, const std::string& emsg, const uint64_t* u, const double* f, const std::vector<uint8_t>& blob) {
+    Agg& a = aggs[i];
+    if (err != TG_OK && a.err == TG_OK) {
+        a.err = err;
+        a.err_msg = emsg;
+    }
+    {
         switch (a.kind) {
             case A_ROWS:
                 a.u[0] += u[0];

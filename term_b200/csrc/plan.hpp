@@ -136,6 +136,7 @@ struct Plan {
     size_t partial_size() const;
     void partial_export(uint8_t* buf) const;
     void partial_merge(const uint8_t* buf, size_t n);  // merge another shard's partials into ours
+    void merge_state(int i, tg_status err, const std::string& emsg, const uint64_t* u, const double* f, const std::vector<uint8_t>& blob);
     void finalize();                                    // slots <- aggregates
     std::vector<int> histogram_pending() const;         // HIST aggregates waiting for the second (global-range) phase
     void histogram_install(int agg_id, const uint64_t* counts, int nb);

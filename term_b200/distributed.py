@@ -96,6 +96,7 @@ def merge_partials(plan, blobs):
 
 
 _FIXED_KINDS = {0, 1, 2, 3, 4, 5, 6, 10, 11}  # aggregates whose partial record has a fixed size (no blob)
+_SCAN_KINDS = {0, 1, 2, 3, 4}  # ROWS / VALID / NUM / PAIR / PRED: what the fused numeric scan answers (tg_plan_execute_exchange)
 _bufs = {}
 
 
@@ -137,7 +138,7 @@ def allgather_blobs_fixed(blob: bytes, cap: int, device=None):
     return out
 
 
-MAILBOX_SLOT_BYTES = 64 * 1024
+MAILBOX_SLOT_BYTES = 1 << 20  # 1 MiB per rank and parity: KLL sketches / grouped tables fit; the collect kernel only moves what a slot holds
 
 
 def _ensure_mailbox(ctx) -> bool:
@@ -177,18 +178,28 @@ def _ensure_mailbox(ctx) -> bool:
 
 
 def exchange_and_finalize(plan, ctx):
-    """Exchange this rank's partial states with every rank, merge in rank order, finalize. Plans whose partial records
-    are fixed-size go through the peer mailboxes (two tiny kernels + one copy over NVLink peer memory, see
-    term_b200/csrc/mailbox.cu); everything else, and any platform where CUDA IPC is unavailable, takes the NCCL
-    all-gather."""
-    aggs = plan.aggregates()
-    # rank-independent decision (every rank must take the same path): fixed-size records only, and a slot that holds
-    # them with 4 KB to spare for error texts
-    fits = 8 + len(aggs) * 176 + 4096 <= MAILBOX_SLOT_BYTES
-    if dist.get_backend() == "nccl" and fits and all(k in _FIXED_KINDS for k, _ in aggs) and _ensure_mailbox(ctx):
-        F.check(F.lib().tg_plan_exchange_and_finalize(ctx.handle, plan.handle))
-        return
+    """Exchange this rank's partial states with every rank, merge in rank order, finalize. Over NCCL on one node the
+    blobs travel through the peer mailboxes (two tiny kernels over NVLink peer memory, see term_b200/csrc/mailbox.cu),
+    whatever their size: a rank whose blob does not fit its slot publishes a marker instead, EVERY rank sees it and all
+    take the NCCL all-gather together. Platforms without CUDA IPC (and the gloo tests) always take the all-gather."""
+    import ctypes as C
+    if dist.get_backend() == "nccl" and _ensure_mailbox(ctx):
+        fell_back = C.c_int32(0)
+        F.check(F.lib().tg_plan_exchange_ex(ctx.handle, plan.handle, C.byref(fell_back)))
+        if not fell_back.value:
+            return
     merge_partials(plan, exchange_partials(plan))
+
+
+def execute_exchange_fused(plan, ctx, table):
+    """tg_plan_execute_exchange: the whole step of a scan-only plan in one call (partial states assembled on the device,
+    published over NVLink, one synchronisation). Returns False when the plan does not qualify (nothing was executed)."""
+    import ctypes as C
+    if dist.get_backend() != "nccl" or os.environ.get("TG_NO_FUSED_EXCHANGE") or not _ensure_mailbox(ctx):
+        return False
+    done = C.c_int32(0)
+    F.check(F.lib().tg_plan_execute_exchange(ctx.handle, plan.handle, table.encode(), C.byref(done)))
+    return bool(done.value)
 
 
 def exchange_partials(plan):
@@ -554,9 +565,18 @@ def execute_distributed(plan, ctx, table="data"):
     if not dist.is_available() or not dist.is_initialized() or dist.get_world_size() == 1:
         plan.execute(ctx, table)
         return
+    aggs = plan.aggregates()
+    if all(k in _SCAN_KINDS for k, _ in aggs):
+        if PROFILE is not None:
+            import time
+            t0 = time.perf_counter()
+        if execute_exchange_fused(plan, ctx, table):
+            if PROFILE is not None:
+                PROFILE["exchange_ms"] += 0.0  # inside the one call: not separable from the scan
+            return
     temps, redirected, external = [], [], []
     try:
-        for i, (kind, key) in enumerate(plan.aggregates()):
+        for i, (kind, key) in enumerate(aggs):
             parts = key.split("|")
             if kind == KIND_DISTINCT:
                 name = f"tg_shuffle_{i}_k"

@@ -123,6 +123,28 @@ def main():
     dist.all_gather(sp_all, torch.tensor([float(sp_got.u[0]), sp_got.metric_double], dtype=torch.float64, device=dev))
     sp_agree = all(bool((v == sp_all[0]).all().item()) for v in sp_all)
 
+    # scan-only plan: the fused step (tg_plan_execute_exchange: states assembled on the device, one synchronisation), and the
+    # same plan through the two-call path (TG_NO_FUSED_EXCHANGE) — both must give the single-GPU answer
+    def scan_suite(table):
+        cb = (T.Check.builder("scan").has_size(A.GreaterThan(0.0)).completeness("amount", 0.9).completeness("customer_id", 0.9)
+              .has_min("amount", A.GreaterThan(-1e9)).has_max("amount", A.LessThan(1e9)).has_mean("amount", A.Between(90.0, 110.0))
+              .has_standard_deviation("amount", A.LessThan(100.0)).has_sum("score", A.LessThan(1e300)).has_min("score", A.LessThan(1e18))
+              .has_correlation("amount", "score", A.GreaterThan(0.5)).satisfies("amount > 50 AND score < 1000"))
+        return T.ValidationSuite.builder("scan").table_name(table).check(cb.build()).build().build_plan()
+    sc_plan, sc_slots = scan_suite("orders")
+    execute_distributed(sc_plan, ctx, "orders")
+    sc_fused = [(r.name, r.status.name, r.metric) for r in (sc_plan.result(s) for _, _, s in sc_slots)]
+    os.environ["TG_NO_FUSED_EXCHANGE"] = "1"
+    execute_distributed(sc_plan, ctx, "orders")
+    del os.environ["TG_NO_FUSED_EXCHANGE"]
+    sc_two = [(r.name, r.status.name, r.metric) for r in (sc_plan.result(s) for _, _, s in sc_slots)]
+    # variable-size partials through the mailboxes: KLL sketch, grouped completeness, two-phase histogram
+    an_plan = T.Plan()
+    kll_slot = T.KllSketchAnalyzer("amount", 256, (0.5, 0.95, 0.99))._add_to(an_plan)
+    hist_slot = T.HistogramAnalyzer("amount", 20)._add_to(an_plan)
+    execute_distributed(an_plan, ctx, "orders")
+    kll_got, hist_got = an_plan.analyzer_result(kll_slot), an_plan.analyzer_result(hist_slot)
+
     # reference: everything on rank 0's GPU
     full = {"customer_id": gather(child, world), "cv": gather(child_valid.to(torch.uint8), world).bool(),
             "order_key": gather(keys, world), "kv": gather(keys_valid.to(torch.uint8), world).bool(),
@@ -156,7 +178,32 @@ def main():
         if not sp_ok:
             print("SPEARMAN MISMATCH", sp_got.u[0], sp_got.metric_double, sp_want.u[0], sp_want.metric_double, sp_agree, flush=True)
         ok = ok and sp_ok
-        print(json.dumps({"check": "multi_gpu_parity", "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
+        p2, sl2 = scan_suite("orders_all")
+        p2.execute(ctx, "orders_all")
+        sc_want = [(r.name, r.status.name, r.metric) for r in (p2.result(s) for _, _, s in sl2)]
+        exact_names = {"size", "completeness", "min", "max", "sum", "custom_sql"}
+        for label, res in (("fused", sc_fused), ("two-call", sc_two)):
+            for gg, ww in zip(res, sc_want):
+                same = gg[:2] == ww[:2] and (gg[2] == ww[2] if gg[0] in exact_names else abs(gg[2] - ww[2]) <= 1e-9 * max(1.0, abs(ww[2])))
+                ok = ok and same
+                if not same:
+                    print("SCAN MISMATCH", label, gg, ww, flush=True)
+        a2 = T.Plan()
+        k2, h2 = T.KllSketchAnalyzer("amount", 256, (0.5, 0.95, 0.99))._add_to(a2), T.HistogramAnalyzer("amount", 20)._add_to(a2)
+        a2.execute(ctx, "orders_all")
+        kw, hw = a2.analyzer_result(k2), a2.analyzer_result(h2)
+        an_ok = (kll_got.error == 0 and hist_got.error == 0 and kll_got.u[0] == kw.u[0] and kll_got.map["min"] == kw.map["min"]
+                 and kll_got.map["max"] == kw.map["max"])
+        srt = torch.sort(full["amount"][full["av"]]).values
+        for q in (0.5, 0.95, 0.99):
+            est = kll_got.map["quantile_" + str(q)]
+            pos = int(torch.searchsorted(srt, torch.tensor([est], dtype=torch.float64, device=dev)).item())
+            an_ok = an_ok and abs(pos / srt.numel() - q) <= 0.01  # far inside 1.65 / sqrt(256)
+        an_ok = an_ok and all(hist_got.map[k] == v for k, v in hw.map.items() if k.endswith(".count") or k.endswith(".lower") or k in ("min", "max", "total_count"))
+        if not an_ok:
+            print("ANALYZER MISMATCH", kll_got.map, kw.map, flush=True)
+        ok = ok and an_ok
+        print(json.dumps({"check": "multi_gpu_parity", "scan_fused": sc_fused, "kll_distributed": kll_got.map, "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
                           "ok": ok, "ms_per_execute": ms, "results": got,
                           "spearman": {"pairs": sp_got.u[0], "rho_distributed": sp_got.metric_double, "rho_single_gpu": sp_want.metric_double,
                                        "ranks_agree": sp_agree}}), flush=True)
