@@ -306,6 +306,26 @@ TG_API tg_status tg_table_partition_keys(tg_engine* eng, const char* table, cons
 TG_API tg_status tg_table_partition_fingerprints(tg_engine* eng, const char* table, const char* const* columns,
                                                  int32_t n_columns, int32_t n_parts, void** d_records, int64_t* counts);
 
+/*
+ * The shuffle as ONE call, NCCL inside the library (libnccl.so.2 is bound at run time, so single-GPU hosts never load it).
+ * One communicator per engine: rank 0 calls tg_comm_unique_id, the host carries the 128 bytes to every rank (any
+ * transport), every rank calls tg_comm_init (collective, like ncclCommInitRank). tg_table_shuffle_column then does, for
+ * one Int64 / Float64 key column: partition the valid keys by destination rank on the device, all-gather the counts,
+ * ncclSend / ncclRecv every part (one group) straight into the value buffer of a NEW engine-owned table `shard_table`
+ * (same column name; the NULL rows of every rank become trailing NULL rows of rank 0's shard) — what
+ * tg_table_partition_keys + a host-side all-to-all + tg_table_adopt_device do in three steps. The aggregate is then
+ * redirected to the shard (tg_plan_redirect_aggregate) and the shard dropped with tg_table_drop after the step.
+ * tg_table_shuffle_fingerprints: the same for Utf8 / composite keys (24-byte records, column "tg_fp", dtype TG_FP128).
+ * tg_comm_bytes_sent: bytes this rank has sent to other ranks through these calls (bench bookkeeping).
+ */
+TG_API tg_status tg_comm_unique_id(void* id128);
+TG_API tg_status tg_comm_init(tg_engine* eng, const void* id128, int32_t world, int32_t rank);
+TG_API tg_status tg_comm_destroy(tg_engine* eng);
+TG_API uint64_t tg_comm_bytes_sent(const tg_engine* eng);
+TG_API tg_status tg_table_shuffle_column(tg_engine* eng, const char* table, const char* column, const char* shard_table, int64_t* n_rows);
+TG_API tg_status tg_table_shuffle_fingerprints(tg_engine* eng, const char* table, const char* const* columns, int32_t n_columns,
+                                               const char* shard_table, int64_t* n_rows);
+
 /* Arrow C Data Interface ingestion: `schema`/`array` are struct ArrowSchema* / struct ArrowArray* of a
  * struct-typed array (a RecordBatch). The engine copies; the caller keeps ownership and releases. */
 TG_API tg_status tg_table_append_arrow(tg_table* t, const void* arrow_schema, const void* arrow_array);

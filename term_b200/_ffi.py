@@ -137,6 +137,12 @@ SIGNATURES = {
     "tg_plan_exchange_ex": (C.c_int, [P, P, C.POINTER(C.c_int32)]),
     "tg_plan_execute_exchange": (C.c_int, [P, P, C.c_char_p, C.POINTER(C.c_int32)]),
     "tg_debug_sort_pairs": (C.c_int, [P, P, C.c_int64, C.c_int32, C.c_int32, P, P]),
+    "tg_comm_unique_id": (C.c_int, [P]),
+    "tg_comm_init": (C.c_int, [P, P, C.c_int32, C.c_int32]),
+    "tg_comm_destroy": (C.c_int, [P]),
+    "tg_comm_bytes_sent": (C.c_uint64, [P]),
+    "tg_table_shuffle_column": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "tg_table_shuffle_fingerprints": (C.c_int, [P, C.c_char_p, STRS, C.c_int32, C.c_char_p, C.POINTER(C.c_int64)]),
     "tg_rank_begin": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "tg_rank_local_sort": (C.c_int, [P]),
     "tg_rank_sample": (C.c_int32, [P, C.c_int32, C.POINTER(C.c_uint64)]),

@@ -102,6 +102,10 @@ void tg_engine_destroy(tg_engine* h) {
     cudaSetDevice(e.device);
     cudaDeviceSynchronize();
     rank_session_destroy(e);
+    try {
+        comm_destroy(e);
+    } catch (...) {
+    }
     for (auto& kv : e.tables) {
         for (auto& c : kv.second->cols) {
             if (c->values.owned && c->values.p) cudaFree(c->values.p);
@@ -501,6 +505,46 @@ tg_status tg_debug_sort_pairs(tg_engine* h, const uint64_t* keys, int64_t n, int
         TG_CUDA(cudaStreamSynchronize(e.stream));
         TG_CUDA(cudaMemcpy(out_keys, kb[ctl.result], (size_t)n * 8, cudaMemcpyDeviceToHost));
         TG_CUDA(cudaMemcpy(out_index, vb[ctl.result], (size_t)n * 4, cudaMemcpyDeviceToHost));
+    });
+}
+
+// ---- NCCL behind the C ABI (comm.cpp)
+tg_status tg_comm_unique_id(void* id128) {
+    return guard([&] {
+        if (!id128) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        comm_unique_id(id128);
+    });
+}
+tg_status tg_comm_init(tg_engine* h, const void* id128, int32_t world, int32_t rank) {
+    return guard([&] {
+        if (!h || !id128) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        comm_init(h->e, id128, world, rank);
+    });
+}
+tg_status tg_comm_destroy(tg_engine* h) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        cudaSetDevice(h->e.device);
+        comm_destroy(h->e);
+    });
+}
+uint64_t tg_comm_bytes_sent(const tg_engine* h) { return h ? h->e.comm_bytes_sent : 0; }
+tg_status tg_table_shuffle_column(tg_engine* h, const char* table, const char* column, const char* shard_table, int64_t* n_rows) {
+    return guard([&] {
+        if (!h || !table || !column || !shard_table) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        validate_identifier(shard_table);
+        const int64_t n = comm_shuffle_column(h->e, table, column, shard_table);
+        if (n_rows) *n_rows = n;
+    });
+}
+tg_status tg_table_shuffle_fingerprints(tg_engine* h, const char* table, const char* const* columns, int32_t n_columns, const char* shard_table,
+                                        int64_t* n_rows) {
+    return guard([&] {
+        if (!h || !table || !columns || n_columns < 1 || !shard_table) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        validate_identifier(shard_table);
+        const int64_t n = comm_shuffle_fingerprints(h->e, table, strvec(columns, n_columns), shard_table);
+        if (n_rows) *n_rows = n;
     });
 }
 

@@ -152,6 +152,11 @@ struct Engine {
     void ensure_side_streams();
     Mailbox mailbox;
     RankSession* rank_session = nullptr;
+    // NCCL communicator of the hash shuffle behind the C ABI (comm.cpp; libnccl bound at run time)
+    void* comm = nullptr;
+    int comm_world = 0, comm_rank = 0;
+    uint8_t* d_comm_counts = nullptr;
+    uint64_t comm_bytes_sent = 0;  // bytes this rank sent to OTHER ranks through tg_table_shuffle_* since creation
     FusedScan* fused = nullptr;  // non-null while execute_exchange_fused runs the scan jobs
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)
     size_t aux_cap = 0;
@@ -203,6 +208,13 @@ void mailbox_open(Engine& e, const void* handles /* world x 64 bytes */);
 void mailbox_destroy(Engine& e);
 bool mailbox_exchange(Engine& e, const uint8_t* blob, size_t n, std::vector<std::vector<uint8_t>>& out);
 void mailbox_exchange_device(Engine& e, size_t payload_bytes, std::vector<std::vector<uint8_t>>& out);
+
+// comm.cpp
+void comm_unique_id(void* id128);
+void comm_init(Engine& e, const void* id128, int world, int rank);
+void comm_destroy(Engine& e);
+int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name);
+int64_t comm_shuffle_fingerprints(Engine& e, const std::string& table, const std::vector<std::string>& columns, const std::string& shard_name);
 
 // scan.cu
 size_t scan_smem_bytes(const ScanParams& P);

@@ -263,8 +263,59 @@ def _column_dtype(ctx, table, column):
     return ctx.column_dtype(table, column)
 
 
+def _ensure_comm(ctx) -> bool:
+    """One-time setup of the library's own NCCL communicator (tg_comm_*): rank 0 draws the ncclUniqueId, torch.distributed
+    carries its 128 bytes, every rank joins. Returns False (and remembers it) when the platform refuses or
+    TG_NO_CABI_SHUFFLE is set: the shuffle then runs through torch.distributed's all_to_all_single."""
+    import ctypes as C
+    state = getattr(ctx, "_comm_state", None)
+    world, rank = dist.get_world_size(), dist.get_rank()
+    if state is not None:
+        return state == ("ok", world)
+    ok = dist.get_backend() == "nccl" and not os.environ.get("TG_NO_CABI_SHUFFLE")
+    dev = _device()
+    buf = C.create_string_buffer(128)
+    if ok and rank == 0:
+        try:
+            F.check(F.lib().tg_comm_unique_id(buf))
+        except Exception:
+            ok = False
+    idt = torch.frombuffer(bytearray(buf.raw), dtype=torch.uint8).to(dev)
+    dist.broadcast(idt, 0)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    ok = bool(flag.item())
+    if ok:
+        try:
+            F.check(F.lib().tg_comm_init(ctx.handle, bytes(idt.cpu().numpy().tobytes()), world, rank))
+        except Exception:
+            ok = False  # a rank that fails here would leave the others inside ncclCommInitRank: NCCL reports it there
+        flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        ok = bool(flag.item())
+    ctx._comm_state = ("ok", world) if ok else ("failed", world)
+    return ok
+
+
+def _cabi_shuffle(ctx, call, *args):
+    """one tg_table_shuffle_* call with the PROFILE bookkeeping around it"""
+    import ctypes as C
+    import time
+    n = C.c_int64()
+    sent0 = F.lib().tg_comm_bytes_sent(ctx.handle)
+    t0 = time.perf_counter()
+    F.check(call(ctx.handle, *args, C.byref(n)))
+    if PROFILE is not None:
+        PROFILE["shuffle_ms"] += (time.perf_counter() - t0) * 1e3  # partition + counts + NCCL group + sync, one call
+        PROFILE["shuffle_bytes"] += F.lib().tg_comm_bytes_sent(ctx.handle) - sent0
+    return n.value
+
+
 def _shuffle_column(ctx, table, column, shard_name):
     """partition -> all-to-all -> adopt as table `shard_name` (column keeps its name)."""
+    if _ensure_comm(ctx):  # NCCL inside the library: one call, parts land in the shard's own column buffer
+        _cabi_shuffle(ctx, F.lib().tg_table_shuffle_column, table.encode(), column.encode(), shard_name.encode())
+        return
     world = dist.get_world_size()
     dtype = _column_dtype(ctx, table, column)
     if dtype not in (F.TG_INT64, F.TG_FLOAT64):
@@ -284,6 +335,11 @@ def _shuffle_column(ctx, table, column, shard_name):
 def _shuffle_fingerprints(ctx, table, columns, shard_name):
     """Utf8 / composite keys: every row travels as its 24-byte fingerprint record {h1, h2, has_null}; the shard is
     adopted as one TG_FP128 column named tg_fp."""
+    if _ensure_comm(ctx):
+        import ctypes as C
+        arr = (C.c_char_p * len(columns))(*[c.encode() for c in columns])
+        _cabi_shuffle(ctx, F.lib().tg_table_shuffle_fingerprints, table.encode(), arr, len(columns), shard_name.encode())
+        return
     world = dist.get_world_size()
     ptr, counts = ctx.partition_fingerprints(table, columns, world)
     total = sum(counts)
