@@ -9,6 +9,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 
 #include "engine.hpp"
@@ -81,7 +82,10 @@ void comm_unique_id(void* id128) {
     memcpy(id128, &id, sizeof(id));
 }
 
+void comm_push_destroy(Engine& e);
+
 void comm_destroy(Engine& e) {
+    comm_push_destroy(e);
     if (e.comm) {
         nccl().CommDestroy((ncclComm_t)e.comm);
         e.comm = nullptr;
@@ -179,6 +183,185 @@ static int64_t exchange_into_table(Engine& e, const uint8_t* d_send, const int64
     return n_rows;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Push shuffle: partition and all-to-all as ONE kernel. Every rank owns receive buffers that all peers of the node have
+// mapped through CUDA IPC; after the ranks have exchanged their per-destination counts (a (world + 1)-number all-gather)
+// each rank knows where its part for rank d starts in d's buffer, and the partition's scatter kernel writes every part
+// straight there — the coalesced runs leave the SM as NVLink stores, the transfer overlaps the partition tile by tile and
+// no intermediate copy of the keys exists anywhere. A second tiny collective is the barrier after which a rank may read
+// its buffer. Falls back to partition + ncclSend / ncclRecv when peer mapping is not available (TG_NO_PUSH_SHUFFLE).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int PUSH_SLOTS = 2;  // shards alive at the same time (a foreign key shuffles the child and the parent column)
+
+struct PushSlot {
+    uint8_t* local = nullptr;
+    size_t cap = 0;
+    std::vector<uint8_t*> peers;      // every rank's buffer as seen from this device
+    uint64_t** d_ptrs = nullptr;      // the same as a device array (argument of the scatter kernel)
+    std::string user;                 // shard table living in the buffer
+};
+struct PushState {
+    PushSlot slot[PUSH_SLOTS];
+    bool disabled = false;
+};
+
+static void push_slot_release(Engine& e, PushSlot& s) {
+    for (size_t r = 0; r < s.peers.size(); ++r)
+        if ((int)r != e.comm_rank && s.peers[r]) cudaIpcCloseMemHandle(s.peers[r]);
+    if (s.local) cudaFree(s.local);
+    if (s.d_ptrs) cudaFree(s.d_ptrs);
+    s = PushSlot{};
+}
+void comm_push_destroy(Engine& e) {
+    if (!e.push) return;
+    PushState* ps = (PushState*)e.push;
+    for (auto& s : ps->slot) push_slot_release(e, s);
+    delete ps;
+    e.push = nullptr;
+}
+
+// (re)allocate slot `s` with `cap` bytes on every rank and map the peers' buffers: collective
+static void push_slot_grow(Engine& e, PushSlot& s, size_t cap) {
+    const int world = e.comm_world, rank = e.comm_rank;
+    ncclComm_t comm = (ncclComm_t)e.comm;
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    push_slot_release(e, s);
+    TG_CUDA(cudaMalloc(&s.local, cap));
+    s.cap = cap;
+    cudaIpcMemHandle_t mine;
+    TG_CUDA(cudaIpcGetMemHandle(&mine, s.local));
+    uint8_t* d_mine = e.d_comm_counts;  // staging: (world + 1) x 64 bytes fit ((world + 1)^2 x 8 + 256 were allocated; world >= 7 ... checked below)
+    uint8_t* d_all = nullptr;
+    TG_CUDA(cudaMalloc(&d_all, (size_t)(world + 1) * 64));
+    std::vector<cudaIpcMemHandle_t> all((size_t)world);
+    try {
+        TG_CUDA(cudaMemcpyAsync(d_all + (size_t)world * 64, &mine, 64, cudaMemcpyHostToDevice, e.stream));
+        TG_NCCL(nccl().AllGather(d_all + (size_t)world * 64, d_all, 64, NCCL_UINT8, comm, e.stream));
+        TG_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)world * 64, cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+    } catch (...) {
+        cudaFree(d_all);
+        throw;
+    }
+    cudaFree(d_all);
+    (void)d_mine;
+    s.peers.assign((size_t)world, nullptr);
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) {
+            s.peers[r] = s.local;
+            continue;
+        }
+        void* p = nullptr;
+        TG_CUDA(cudaIpcOpenMemHandle(&p, all[r], cudaIpcMemLazyEnablePeerAccess));
+        s.peers[r] = (uint8_t*)p;
+    }
+    TG_CUDA(cudaMalloc(&s.d_ptrs, (size_t)world * 8));
+    TG_CUDA(cudaMemcpy(s.d_ptrs, s.peers.data(), (size_t)world * 8, cudaMemcpyHostToDevice));
+}
+
+// returns -1 when the push path is not available (the caller then takes the send / recv path)
+static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::string& shard_name) {
+    static const bool off = getenv("TG_NO_PUSH_SHUFFLE") != nullptr;
+    if (off) return -1;
+    if (!e.push) e.push = new PushState();
+    PushState& ps = *(PushState*)e.push;
+    if (ps.disabled) return -1;
+    const int world = e.comm_world, rank = e.comm_rank;
+    ncclComm_t comm = (ncclComm_t)e.comm;
+    if (e.tables.count(shard_name)) throw Error(TG_ERR_INVALID_ARG, "table '" + shard_name + "' already exists");
+    // a free slot: one whose shard table is gone (the same choice on every rank: the call sequences are the same)
+    int si = -1;
+    for (int i = 0; i < PUSH_SLOTS && si < 0; ++i)
+        if (ps.slot[i].user.empty() || !e.tables.count(ps.slot[i].user)) si = i;
+    if (si < 0) return -1;
+    PushSlot& s = ps.slot[si];
+    s.user.clear();
+    // ---- counts
+    std::vector<int64_t> counts((size_t)world, 0);
+    int64_t nulls = 0;
+    int launches = 0;
+    push_partition_hist(e, c, t.n_rows, world, counts.data(), &nulls, launches);
+    const int w1 = world + 1;
+    std::vector<long long> mine((size_t)w1), all((size_t)w1 * world);
+    for (int r = 0; r < world; ++r) mine[r] = counts[r];
+    mine[world] = nulls;
+    long long* d_mine = (long long*)e.d_comm_counts;
+    long long* d_all = d_mine + w1;
+    TG_CUDA(cudaMemcpyAsync(d_mine, mine.data(), (size_t)w1 * 8, cudaMemcpyHostToDevice, e.stream));
+    TG_NCCL(nccl().AllGather(d_mine, d_all, (size_t)w1, NCCL_INT64, comm, e.stream));
+    TG_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)w1 * world * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    int64_t nulls_total = 0, max_rows = 0, n_recv = 0;
+    std::vector<unsigned long long> first((size_t)world, 0);  // where my part starts in rank d's buffer
+    for (int sr = 0; sr < world; ++sr) nulls_total += all[(size_t)sr * w1 + world];
+    for (int d = 0; d < world; ++d) {
+        int64_t tot = 0;
+        for (int sr = 0; sr < world; ++sr) {
+            if (sr == rank) first[d] = (unsigned long long)tot;
+            tot += all[(size_t)sr * w1 + d];
+        }
+        if (d == rank) n_recv = tot;
+        max_rows = std::max(max_rows, tot + (d == 0 ? nulls_total : 0));
+    }
+    const int64_t my_nulls = rank == 0 ? nulls_total : 0;
+    const int64_t n_rows = n_recv + my_nulls;
+    // ---- capacity: the same decision on every rank (everyone holds the whole matrix)
+    const size_t need = round_up((size_t)std::max<int64_t>(max_rows, 1) * 8 + 512, 256);
+    if (need > s.cap) {
+        try {
+            push_slot_grow(e, s, round_up(need + need / 8, (size_t)1 << 20));
+        } catch (Error&) {
+            // peer mapping refused (no IPC / no P2P): NOT rank-consistent in general, but CUDA IPC availability is a
+            // property of the node, so every rank lands here together; remember it and use send / recv from now on
+            ps.disabled = true;
+            cudaGetLastError();
+            push_slot_release(e, s);
+            return -2;  // the counts collective was consumed: tell the caller to rerun the fallback from the start
+        }
+    }
+    // ---- the scatter IS the all-to-all
+    push_partition_scatter(e, c, t.n_rows, world, first.data(), (uint64_t* const*)s.d_ptrs, launches);
+    // tail padding + NULL rows of my own buffer (nobody else writes behind n_recv)
+    TG_CUDA(cudaMemsetAsync(s.local + (size_t)n_recv * 8, 0, std::min(s.cap - (size_t)n_recv * 8, (size_t)my_nulls * 8 + 512), e.stream));
+    // ---- barrier: every rank's scatter has completed (kernel completion makes its peer stores visible) before anyone reads
+    TG_NCCL(nccl().AllGather(d_mine, d_all, 1, NCCL_INT64, comm, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    e.launches += launches;
+    // ---- the shard table lives in the receive buffer
+    auto tab = std::make_unique<Table>();
+    tab->eng = &e;
+    tab->name = shard_name;
+    Column* sc = table_get_or_add(*tab, c.name, c.dtype);
+    sc->n_rows = n_rows;
+    tab->n_rows = n_rows;
+    sc->values.p = s.local;
+    sc->values.cap = 0;
+    sc->values.owned = false;
+    sc->adopted = true;
+    sc->value_bytes = n_rows * 8;
+    sc->null_count = my_nulls;
+    if (my_nulls) {
+        const size_t bits_b = round_up((size_t)(n_rows + 7) / 8 + 256, 256);
+        sc->validity.p = e.dev_alloc(bits_b);
+        sc->validity.cap = bits_b;
+        sc->validity.owned = true;
+        TG_CUDA(cudaMemsetAsync(sc->validity.p, 0, bits_b, e.stream));
+        TG_CUDA(cudaMemsetAsync(sc->validity.p, 0xFF, (size_t)(n_recv / 8), e.stream));
+        if (n_recv % 8) {
+            const uint8_t last = (uint8_t)((1u << (n_recv % 8)) - 1u);
+            TG_CUDA(cudaMemcpyAsync(sc->validity.p + n_recv / 8, &last, 1, cudaMemcpyHostToDevice, e.stream));
+        }
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+    }
+    e.tables[shard_name] = std::move(tab);
+    s.user = shard_name;
+    int64_t sent = 0;
+    for (int d = 0; d < world; ++d)
+        if (d != rank) sent += counts[d];
+    e.comm_bytes_sent += (uint64_t)sent * 8;
+    return n_rows;
+}
+
 int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name) {
     std::lock_guard<std::mutex> g(e.mu);
     TG_CUDA(cudaSetDevice(e.device));
@@ -190,6 +373,10 @@ int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::stri
     Column* c = t.find(column);
     if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + column + ". Valid fields are " + t.valid_fields() + ".");
     if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64) throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports Int64 / Float64 key columns");
+    {
+        const int64_t pushed = push_shuffle_column(e, t, *c, shard_name);
+        if (pushed >= 0) return pushed;
+    }
     uint64_t* keys = nullptr;
     std::vector<int64_t> counts((size_t)e.comm_world, 0);
     int64_t nulls = 0;

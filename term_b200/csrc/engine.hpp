@@ -156,6 +156,7 @@ struct Engine {
     void* comm = nullptr;
     int comm_world = 0, comm_rank = 0;
     uint8_t* d_comm_counts = nullptr;
+    void* push = nullptr;          // comm.cpp PushState: IPC-mapped receive buffers of the push shuffle
     uint64_t comm_bytes_sent = 0;  // bytes this rank sent to OTHER ranks through tg_table_shuffle_* since creation
     FusedScan* fused = nullptr;  // non-null while execute_exchange_fused runs the scan jobs
     uint8_t* d_aux = nullptr;  // small grow-only device block for result post-processing (group keys, ..)

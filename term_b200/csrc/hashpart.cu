@@ -145,7 +145,7 @@ __global__ void part_prefix_kernel(const unsigned long long* hist, uint32_t part
 template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64_t* __restrict__ values, const uint32_t* __restrict__ validity,
                                                                     int64_t n, int is_f64, uint32_t parts, unsigned long long* cursors,
-                                                                    uint64_t* __restrict__ out) {
+                                                                    uint64_t* __restrict__ out, uint64_t* const* __restrict__ outs) {
     __shared__ uint64_t s_keys[PART_TILE];
     __shared__ uint16_t s_part[PART_TILE];
     __shared__ uint32_t s_cnt[PART_MAX], s_off[PART_MAX];
@@ -207,9 +207,12 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64
         __syncthreads();
         uint32_t total = 0;
         for (int w = 0; w < PART_THREADS / 32; ++w) total += s_warp_tot[w];
+        // outs != nullptr: every part has its own destination buffer — the peer GPU's receive buffer, mapped through CUDA
+        // IPC: the partition's output IS the all-to-all (the runs leave the SM as NVLink stores)
         for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
             const uint32_t b = s_part[i];
-            out[s_gbase[b] + (i - s_off[b])] = s_keys[i];
+            uint64_t* dst = outs ? outs[b] : out;
+            dst[s_gbase[b] + (i - s_off[b])] = s_keys[i];
         }
         __syncthreads();
     }
@@ -595,9 +598,52 @@ static int partition_column(Engine& e, const Column& c, int64_t n, uint32_t part
                                                                parts, m.hist, m.ctr);
     part_prefix_kernel<<<1, PART_MAX, 0, e.stream>>>(m.hist, parts, m.offsets, m.cursors);
     part_scatter_kernel<MODE><<<grid, PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n, is_f64,
-                                                                  parts, m.cursors, out);
+                                                                  parts, m.cursors, out, nullptr);
     TG_CUDA(cudaGetLastError());
     return 3;
+}
+
+// The two halves of the partition as the push shuffle (comm.cpp) uses them: the histogram first — the ranks exchange the
+// counts and derive where each part goes in its destination's receive buffer — then the scatter with those positions as
+// cursors and one destination pointer per part (peer memory).
+void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches) {
+    if (world < 1 || world > PART_MAX) throw Error(TG_ERR_INVALID_ARG, "world size must be in 1..1024");
+    const size_t need = PartMeta::bytes() + 256;
+    if (need > e.shuffle_cap) {
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        if (e.d_shuffle) TG_CUDA(cudaFree(e.d_shuffle));
+        e.d_shuffle = nullptr;
+        e.shuffle_cap = 0;
+        TG_CUDA(cudaMalloc(&e.d_shuffle, need));
+        e.shuffle_cap = need;
+    }
+    PartMeta m;
+    m.bind(e.d_shuffle);
+    TG_CUDA(cudaMemsetAsync(m.hist, 0, PartMeta::bytes(), e.stream));
+    if (n > 0) {
+        part_hist_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
+                                                                                  c.dtype == TG_FLOAT64, (uint32_t)world, m.hist, m.ctr);
+        TG_CUDA(cudaGetLastError());
+        launches += 1;
+    }
+    std::vector<unsigned long long> h((size_t)world);
+    PartCounters pc{};
+    TG_CUDA(cudaMemcpyAsync(h.data(), m.hist, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaMemcpyAsync(&pc, m.ctr, sizeof(pc), cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    for (int i = 0; i < world; ++i) counts[i] = (int64_t)h[i];
+    *n_nulls = (int64_t)pc.nulls;
+}
+void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, const unsigned long long* first_index /* host, [world] */,
+                            uint64_t* const* d_outs /* device array of world pointers */, int& launches) {
+    if (n <= 0) return;
+    PartMeta m;
+    m.bind(e.d_shuffle);
+    TG_CUDA(cudaMemcpyAsync(m.cursors, first_index, (size_t)world * 8, cudaMemcpyHostToDevice, e.stream));
+    part_scatter_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
+                                                                                 c.dtype == TG_FLOAT64, (uint32_t)world, m.cursors, nullptr, d_outs);
+    TG_CUDA(cudaGetLastError());
+    launches += 1;
 }
 
 bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches) {

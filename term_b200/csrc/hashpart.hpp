@@ -37,6 +37,12 @@ bool fk64_dense(Engine& e, const Column& child, int64_t nc, const Column& parent
 void partition_keys_by_rank(Engine& e, const Column& c, int64_t n, int world, uint64_t** d_keys, int64_t* counts,
                             int64_t* n_nulls, int& launches);
 
+// the same partition in two halves for the push shuffle (comm.cpp): counts first, then the scatter straight into the
+// destination ranks' receive buffers (one pointer per part, peer memory)
+void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches);
+void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, const unsigned long long* first_index, uint64_t* const* d_outs,
+                            int& launches);
+
 // hashing.cu: same for Utf8 / composite keys, as 24-byte fingerprint records {h1, h2, has_null}
 void partition_fingerprints_by_rank(Engine& e, Table& t, const std::vector<std::string>& names, int world, void** d_records, int64_t* counts,
                                     int& launches);
