@@ -314,7 +314,9 @@ TG_API tg_status tg_table_partition_fingerprints(tg_engine* eng, const char* tab
  * ncclSend / ncclRecv every part (one group) straight into the value buffer of a NEW engine-owned table `shard_table`
  * (same column name; the NULL rows of every rank become trailing NULL rows of rank 0's shard) — what
  * tg_table_partition_keys + a host-side all-to-all + tg_table_adopt_device do in three steps. The aggregate is then
- * redirected to the shard (tg_plan_redirect_aggregate) and the shard dropped with tg_table_drop after the step.
+ * redirected to the shard (tg_plan_redirect_aggregate) and the shard dropped with tg_table_drop after the step. On one
+ * node the transfer is not even a separate step: the ranks' receive buffers are mapped into every peer through CUDA IPC
+ * and the partition's scatter kernel writes each part straight into its destination over NVLink ("push shuffle").
  * tg_table_shuffle_fingerprints: the same for Utf8 / composite keys (24-byte records, column "tg_fp", dtype TG_FP128).
  * tg_comm_bytes_sent: bytes this rank has sent to other ranks through these calls (bench bookkeeping).
  */
@@ -322,7 +324,11 @@ TG_API tg_status tg_comm_unique_id(void* id128);
 TG_API tg_status tg_comm_init(tg_engine* eng, const void* id128, int32_t world, int32_t rank);
 TG_API tg_status tg_comm_destroy(tg_engine* eng);
 TG_API uint64_t tg_comm_bytes_sent(const tg_engine* eng);
-TG_API tg_status tg_table_shuffle_column(tg_engine* eng, const char* table, const char* column, const char* shard_table, int64_t* n_rows);
+/* partition: 0 = by hash (the only choice for a foreign key: both sides must use the same function); 1 = by value range when
+ * the Int64 keys are globally dense (decided from the all-gathered min / max / count, abandoned when the slices come
+ * out unbalanced), by hash otherwise — a rank's slice of a dense key space de-duplicates on the L2-resident bitmap path. */
+TG_API tg_status tg_table_shuffle_column(tg_engine* eng, const char* table, const char* column, const char* shard_table,
+                                         int32_t partition, int64_t* n_rows);
 TG_API tg_status tg_table_shuffle_fingerprints(tg_engine* eng, const char* table, const char* const* columns, int32_t n_columns,
                                                const char* shard_table, int64_t* n_rows);
 

@@ -141,7 +141,7 @@ SIGNATURES = {
     "tg_comm_init": (C.c_int, [P, P, C.c_int32, C.c_int32]),
     "tg_comm_destroy": (C.c_int, [P]),
     "tg_comm_bytes_sent": (C.c_uint64, [P]),
-    "tg_table_shuffle_column": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
+    "tg_table_shuffle_column": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.c_int32, C.POINTER(C.c_int64)]),
     "tg_table_shuffle_fingerprints": (C.c_int, [P, C.c_char_p, STRS, C.c_int32, C.c_char_p, C.POINTER(C.c_int64)]),
     "tg_rank_begin": (C.c_int, [P, C.c_char_p, C.c_char_p, C.c_char_p, C.POINTER(C.c_int64)]),
     "tg_rank_local_sort": (C.c_int, [P]),

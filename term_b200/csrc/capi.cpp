@@ -530,11 +530,11 @@ tg_status tg_comm_destroy(tg_engine* h) {
     });
 }
 uint64_t tg_comm_bytes_sent(const tg_engine* h) { return h ? h->e.comm_bytes_sent : 0; }
-tg_status tg_table_shuffle_column(tg_engine* h, const char* table, const char* column, const char* shard_table, int64_t* n_rows) {
+tg_status tg_table_shuffle_column(tg_engine* h, const char* table, const char* column, const char* shard_table, int32_t partition, int64_t* n_rows) {
     return guard([&] {
         if (!h || !table || !column || !shard_table) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
         validate_identifier(shard_table);
-        const int64_t n = comm_shuffle_column(h->e, table, column, shard_table);
+        const int64_t n = comm_shuffle_column(h->e, table, column, shard_table, partition == 1);
         if (n_rows) *n_rows = n;
     });
 }

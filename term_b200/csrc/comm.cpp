@@ -260,7 +260,7 @@ static void push_slot_grow(Engine& e, PushSlot& s, size_t cap) {
 }
 
 // returns -1 when the push path is not available (the caller then takes the send / recv path)
-static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::string& shard_name) {
+static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::string& shard_name, bool allow_range) {
     static const bool off = getenv("TG_NO_PUSH_SHUFFLE") != nullptr;
     if (off) return -1;
     if (!e.push) e.push = new PushState();
@@ -276,21 +276,68 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
     if (si < 0) return -1;
     PushSlot& s = ps.slot[si];
     s.user.clear();
-    // ---- counts
     std::vector<int64_t> counts((size_t)world, 0);
     int64_t nulls = 0;
     int launches = 0;
-    push_partition_hist(e, c, t.n_rows, world, counts.data(), &nulls, launches);
     const int w1 = world + 1;
     std::vector<long long> mine((size_t)w1), all((size_t)w1 * world);
-    for (int r = 0; r < world; ++r) mine[r] = counts[r];
-    mine[world] = nulls;
     long long* d_mine = (long long*)e.d_comm_counts;
     long long* d_all = d_mine + w1;
-    TG_CUDA(cudaMemcpyAsync(d_mine, mine.data(), (size_t)w1 * 8, cudaMemcpyHostToDevice, e.stream));
-    TG_NCCL(nccl().AllGather(d_mine, d_all, (size_t)w1, NCCL_INT64, comm, e.stream));
-    TG_CUDA(cudaMemcpyAsync(all.data(), d_all, (size_t)w1 * world * 8, cudaMemcpyDeviceToHost, e.stream));
-    TG_CUDA(cudaStreamSynchronize(e.stream));
+    auto gather = [&](size_t n_words) {  // `mine` -> `all` on every rank
+        TG_CUDA(cudaMemcpyAsync(d_mine, mine.data(), n_words * 8, cudaMemcpyHostToDevice, e.stream));
+        TG_NCCL(nccl().AllGather(d_mine, d_all, n_words, NCCL_INT64, comm, e.stream));
+        TG_CUDA(cudaMemcpyAsync(all.data(), d_all, n_words * world * 8, cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+    };
+    // ---- dense Int64 keys (the 1 B-key permutation of C4, surrogate ids): split by VALUE RANGE, so that every rank gets a
+    // contiguous slice of the key space and its de-duplication runs on the L2-resident bitmap path instead of hash tables.
+    // Decided from the global min / max / count — the same numbers, hence the same decision, on every rank.
+    bool by_range = false;
+    long long range_min = 0;
+    unsigned long long range_span = 1;
+    if (allow_range && c.dtype == TG_INT64 && !getenv("TG_NO_RANGE_SHUFFLE")) {
+        long long mn = 0, mx = 0;
+        unsigned long long nv = 0;
+        column_minmax_i64(e, c, t.n_rows, &mn, &mx, &nv, launches);
+        mine[0] = mn;
+        mine[1] = mx;
+        mine[2] = (long long)nv;
+        gather(3);
+        long long gmn = INT64_MAX, gmx = INT64_MIN;
+        unsigned long long gn = 0;
+        for (int r = 0; r < world; ++r) {
+            if (all[(size_t)r * 3 + 2] == 0) continue;
+            gmn = std::min<long long>(gmn, all[(size_t)r * 3]);
+            gmx = std::max<long long>(gmx, all[(size_t)r * 3 + 1]);
+            gn += (unsigned long long)all[(size_t)r * 3 + 2];
+        }
+        if (gn > 0) {
+            const unsigned long long range = (unsigned long long)gmx - (unsigned long long)gmn;
+            const unsigned long long span = range / (unsigned long long)world + 1;
+            if (range <= 32ull * gn && span < (1ull << 28)) {
+                by_range = true;
+                range_min = gmn;
+                range_span = span;
+            }
+        }
+    }
+    // ---- counts (a value-range split that turns out badly balanced is abandoned for the hash split)
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        push_partition_hist(e, c, t.n_rows, world, counts.data(), &nulls, launches, by_range ? &range_min : nullptr, range_span);
+        for (int r = 0; r < world; ++r) mine[r] = counts[r];
+        mine[world] = nulls;
+        gather((size_t)w1);
+        if (!by_range) break;
+        long long total = 0, worst = 0;
+        for (int d = 0; d < world; ++d) {
+            long long tot = 0;
+            for (int sr = 0; sr < world; ++sr) tot += all[(size_t)sr * w1 + d];
+            total += tot;
+            worst = std::max(worst, tot);
+        }
+        if (worst <= 2 * (total / world) + 4096) break;
+        by_range = false;
+    }
     int64_t nulls_total = 0, max_rows = 0, n_recv = 0;
     std::vector<unsigned long long> first((size_t)world, 0);  // where my part starts in rank d's buffer
     for (int sr = 0; sr < world; ++sr) nulls_total += all[(size_t)sr * w1 + world];
@@ -320,7 +367,7 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
         }
     }
     // ---- the scatter IS the all-to-all
-    push_partition_scatter(e, c, t.n_rows, world, first.data(), (uint64_t* const*)s.d_ptrs, launches);
+    push_partition_scatter(e, c, t.n_rows, world, first.data(), (uint64_t* const*)s.d_ptrs, launches, by_range ? &range_min : nullptr, range_span);
     // tail padding + NULL rows of my own buffer (nobody else writes behind n_recv)
     TG_CUDA(cudaMemsetAsync(s.local + (size_t)n_recv * 8, 0, std::min(s.cap - (size_t)n_recv * 8, (size_t)my_nulls * 8 + 512), e.stream));
     // ---- barrier: every rank's scatter has completed (kernel completion makes its peer stores visible) before anyone reads
@@ -362,7 +409,7 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
     return n_rows;
 }
 
-int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name) {
+int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name, bool allow_range) {
     std::lock_guard<std::mutex> g(e.mu);
     TG_CUDA(cudaSetDevice(e.device));
     if (!e.comm) throw Error(TG_ERR_NCCL, "no communicator: call tg_comm_init first");
@@ -374,7 +421,7 @@ int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::stri
     if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + column + ". Valid fields are " + t.valid_fields() + ".");
     if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64) throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports Int64 / Float64 key columns");
     {
-        const int64_t pushed = push_shuffle_column(e, t, *c, shard_name);
+        const int64_t pushed = push_shuffle_column(e, t, *c, shard_name, allow_range);
         if (pushed >= 0) return pushed;
     }
     uint64_t* keys = nullptr;

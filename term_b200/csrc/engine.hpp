@@ -214,7 +214,7 @@ void mailbox_exchange_device(Engine& e, size_t payload_bytes, std::vector<std::v
 void comm_unique_id(void* id128);
 void comm_init(Engine& e, const void* id128, int world, int rank);
 void comm_destroy(Engine& e);
-int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name);
+int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name, bool allow_range);
 int64_t comm_shuffle_fingerprints(Engine& e, const std::string& table, const std::vector<std::string>& columns, const std::string& shard_name);
 
 // scan.cu

@@ -54,7 +54,13 @@ struct PartCounters {
 
 // MODE 0: local radix bucket (hash bits 32..), EMPTY-sentinel keys and NULLs are counted and skipped
 // MODE 1: destination rank of the shuffle, every valid key is kept (raw bits)
-enum { PM_BUCKET = 0, PM_RANK = 1 };
+// MODE 2: destination rank by VALUE RANGE (Int64 keys known to be dense): part = (key - range_min) / range_span, so every
+//         rank receives a contiguous slice of the key space and de-duplicates it with the bitmap path
+enum { PM_BUCKET = 0, PM_RANK = 1, PM_RANGE = 2 };
+struct RangeSplit {
+    long long min;
+    unsigned long long span;
+};
 
 // Loads the PART_KEYS_PER_THREAD keys of this thread's tile slots up front (independent, predicated loads: all in
 // flight together) and classifies them from registers: part >= 0, -1 NULL / past the end, -2 the EMPTY sentinel
@@ -62,7 +68,7 @@ enum { PM_BUCKET = 0, PM_RANK = 1 };
 template <int MODE>
 __device__ __forceinline__ void load_classify(const uint64_t* __restrict__ values, const uint32_t* __restrict__ validity, int64_t base,
                                               int64_t n, int is_f64, uint32_t parts, uint64_t (&key)[PART_KEYS_PER_THREAD],
-                                              int (&part)[PART_KEYS_PER_THREAD]) {
+                                              int (&part)[PART_KEYS_PER_THREAD], RangeSplit rs = RangeSplit{0, 1}) {
     uint64_t raw[PART_KEYS_PER_THREAD];
     uint32_t vw[PART_KEYS_PER_THREAD];
 #pragma unroll
@@ -81,9 +87,13 @@ __device__ __forceinline__ void load_classify(const uint64_t* __restrict__ value
         if (MODE == PM_BUCKET) {
             key[k] = ck;
             part[k] = !valid ? -1 : (ck == EMPTY64 ? -2 : (int)hash_bucket(h, parts - 1));
-        } else {
+        } else if (MODE == PM_RANK) {
             key[k] = raw[k];
             part[k] = !valid ? -1 : (int)hash_rank(h, parts);
+        } else {
+            key[k] = raw[k];
+            const unsigned long long d = ((unsigned long long)raw[k] - (unsigned long long)rs.min) / rs.span;
+            part[k] = !valid ? -1 : (int)(d < parts ? d : parts - 1);
         }
     }
 }
@@ -91,7 +101,7 @@ __device__ __forceinline__ void load_classify(const uint64_t* __restrict__ value
 template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint64_t* __restrict__ values, const uint32_t* __restrict__ validity,
                                                                  int64_t n, int is_f64, uint32_t parts, unsigned long long* hist,
-                                                                 PartCounters* ctr) {
+                                                                 PartCounters* ctr, RangeSplit rs = RangeSplit{0, 1}) {
     // `copies` private histograms (one per group of warps) keep same-address shared atomics rare for small `parts`
     __shared__ uint32_t s_hist[PART_MAX];
     const uint32_t copies = parts <= PART_MAX / 8 ? 8u : 1u;
@@ -104,7 +114,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint64_t*
         const int64_t base = tile * PART_TILE;
         uint64_t key[PART_KEYS_PER_THREAD];
         int part[PART_KEYS_PER_THREAD];
-        load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part);
+        load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part, rs);
 #pragma unroll
         for (int k = 0; k < PART_KEYS_PER_THREAD; ++k) {
             if (part[k] >= 0) atomicAdd(&my_hist[part[k]], 1u);
@@ -145,7 +155,8 @@ __global__ void part_prefix_kernel(const unsigned long long* hist, uint32_t part
 template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64_t* __restrict__ values, const uint32_t* __restrict__ validity,
                                                                     int64_t n, int is_f64, uint32_t parts, unsigned long long* cursors,
-                                                                    uint64_t* __restrict__ out, uint64_t* const* __restrict__ outs) {
+                                                                    uint64_t* __restrict__ out, uint64_t* const* __restrict__ outs,
+                                                                    RangeSplit rs = RangeSplit{0, 1}) {
     __shared__ uint64_t s_keys[PART_TILE];
     __shared__ uint16_t s_part[PART_TILE];
     __shared__ uint32_t s_cnt[PART_MAX], s_off[PART_MAX];
@@ -160,7 +171,7 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64
         uint64_t key[PART_KEYS_PER_THREAD];
         int part[PART_KEYS_PER_THREAD];
         uint32_t rank[PART_KEYS_PER_THREAD];
-        load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part);
+        load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part, rs);
 #pragma unroll
         for (int k = 0; k < PART_KEYS_PER_THREAD; ++k)
             if (part[k] >= 0) rank[k] = atomicAdd(&s_cnt[part[k]], 1u);
@@ -603,10 +614,14 @@ static int partition_column(Engine& e, const Column& c, int64_t n, uint32_t part
     return 3;
 }
 
+struct MinMaxOut;
+static bool minmax_i64(Engine& e, const Column& c, int64_t n, MinMaxOut& h, int& launches);
+
 // The two halves of the partition as the push shuffle (comm.cpp) uses them: the histogram first — the ranks exchange the
 // counts and derive where each part goes in its destination's receive buffer — then the scatter with those positions as
 // cursors and one destination pointer per part (peer memory).
-void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches) {
+void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches,
+                         const long long* range_min, unsigned long long range_span) {
     if (world < 1 || world > PART_MAX) throw Error(TG_ERR_INVALID_ARG, "world size must be in 1..1024");
     const size_t need = PartMeta::bytes() + 256;
     if (need > e.shuffle_cap) {
@@ -621,8 +636,12 @@ void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64
     m.bind(e.d_shuffle);
     TG_CUDA(cudaMemsetAsync(m.hist, 0, PartMeta::bytes(), e.stream));
     if (n > 0) {
-        part_hist_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
-                                                                                  c.dtype == TG_FLOAT64, (uint32_t)world, m.hist, m.ctr);
+        if (range_min)
+            part_hist_kernel<PM_RANGE><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n, 0,
+                                                                                       (uint32_t)world, m.hist, m.ctr, RangeSplit{*range_min, range_span});
+        else
+            part_hist_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
+                                                                                      c.dtype == TG_FLOAT64, (uint32_t)world, m.hist, m.ctr);
         TG_CUDA(cudaGetLastError());
         launches += 1;
     }
@@ -635,15 +654,30 @@ void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64
     *n_nulls = (int64_t)pc.nulls;
 }
 void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, const unsigned long long* first_index /* host, [world] */,
-                            uint64_t* const* d_outs /* device array of world pointers */, int& launches) {
+                            uint64_t* const* d_outs /* device array of world pointers */, int& launches, const long long* range_min,
+                            unsigned long long range_span) {
     if (n <= 0) return;
     PartMeta m;
     m.bind(e.d_shuffle);
     TG_CUDA(cudaMemcpyAsync(m.cursors, first_index, (size_t)world * 8, cudaMemcpyHostToDevice, e.stream));
-    part_scatter_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
-                                                                                 c.dtype == TG_FLOAT64, (uint32_t)world, m.cursors, nullptr, d_outs);
+    if (range_min)
+        part_scatter_kernel<PM_RANGE><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n, 0,
+                                                                                      (uint32_t)world, m.cursors, nullptr, d_outs,
+                                                                                      RangeSplit{*range_min, range_span});
+    else
+        part_scatter_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
+                                                                                     c.dtype == TG_FLOAT64, (uint32_t)world, m.cursors, nullptr, d_outs);
     TG_CUDA(cudaGetLastError());
     launches += 1;
+}
+// min / max / valid count of an Int64 key column (the dense test of the range-partitioned shuffle)
+bool column_minmax_i64(Engine& e, const Column& c, int64_t n, long long* mn, long long* mx, unsigned long long* n_valid, int& launches) {
+    MinMaxOut h{};
+    const bool any = minmax_i64(e, c, n, h, launches);
+    *mn = h.mn;
+    *mx = h.mx;
+    *n_valid = h.n_valid;
+    return any;
 }
 
 bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches) {

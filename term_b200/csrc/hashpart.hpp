@@ -39,9 +39,12 @@ void partition_keys_by_rank(Engine& e, const Column& c, int64_t n, int world, ui
 
 // the same partition in two halves for the push shuffle (comm.cpp): counts first, then the scatter straight into the
 // destination ranks' receive buffers (one pointer per part, peer memory)
-void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches);
+// range_min != nullptr: partition by value range, part = (key - *range_min) / range_span (dense Int64 keys)
+void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64_t* counts, int64_t* n_nulls, int& launches,
+                         const long long* range_min = nullptr, unsigned long long range_span = 1);
 void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, const unsigned long long* first_index, uint64_t* const* d_outs,
-                            int& launches);
+                            int& launches, const long long* range_min = nullptr, unsigned long long range_span = 1);
+bool column_minmax_i64(Engine& e, const Column& c, int64_t n, long long* mn, long long* mx, unsigned long long* n_valid, int& launches);
 
 // hashing.cu: same for Utf8 / composite keys, as 24-byte fingerprint records {h1, h2, has_null}
 void partition_fingerprints_by_rank(Engine& e, Table& t, const std::vector<std::string>& names, int world, void** d_records, int64_t* counts,

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cmath>
 #include <map>
+#include <unordered_map>
 #include <set>
 
 namespace tg {
@@ -875,43 +876,68 @@ void Plan::histogram_install(int agg_id, const uint64_t* counts, int nb) {
     a.u[7] = 0;
 }
 
-// ---- grouped blob: [u64 n_groups] then per group: u32 key_len, key bytes (fields joined by \x1f), u64 total, u64 non_null
-void grouped_blob_merge(std::vector<uint8_t>& into, const std::vector<uint8_t>& other) {
-    auto parse = [](const std::vector<uint8_t>& b, std::map<std::string, std::pair<uint64_t, uint64_t>>& m) {
-        if (b.size() < 8) return;
-        uint64_t n;
-        memcpy(&n, b.data(), 8);
-        const uint8_t* p = b.data() + 8;
-        for (uint64_t i = 0; i < n; ++i) {
-            uint32_t L;
-            memcpy(&L, p, 4);
-            p += 4;
-            std::string k((const char*)p, L);
-            p += L;
-            uint64_t t, nn;
-            memcpy(&t, p, 8);
-            memcpy(&nn, p + 8, 8);
-            p += 16;
-            m[k].first += t;
-            m[k].second += nn;
-        }
+// ---- grouped blob: [u64 n_entries] then per entry: u32 key_len, key bytes (fields joined by \x1f), u64 total, u64 non_null.
+// Merging appends the other shard's entries (GroupedCompletenessState::merge adds the counts of equal keys,
+// grouped_completeness.rs:37-84; here equal keys are summed when the state is read — grouped_blob_compact — so that merging
+// 8 shards costs 8 appends, not 8 rebuilds of a string-keyed map).
+void grouped_blob_compact(std::vector<uint8_t>& b) {
+    if (b.size() < 8) return;
+    uint64_t n;
+    memcpy(&n, b.data(), 8);
+    struct Ent {
+        const uint8_t* key;
+        uint32_t len;
+        uint64_t total, nn;
     };
-    std::map<std::string, std::pair<uint64_t, uint64_t>> m;
-    parse(into, m);
-    parse(other, m);
-    into.clear();
-    uint64_t n = m.size();
-    into.resize(8);
-    memcpy(into.data(), &n, 8);
-    for (auto& kv : m) {
-        uint32_t L = (uint32_t)kv.first.size();
-        size_t o = into.size();
-        into.resize(o + 4 + L + 16);
-        memcpy(into.data() + o, &L, 4);
-        memcpy(into.data() + o + 4, kv.first.data(), L);
-        memcpy(into.data() + o + 4 + L, &kv.second.first, 8);
-        memcpy(into.data() + o + 4 + L + 8, &kv.second.second, 8);
+    std::unordered_map<std::string, size_t> idx;
+    idx.reserve((size_t)n * 2);
+    std::vector<Ent> ents;
+    const uint8_t* p = b.data() + 8;
+    bool dup = false;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t L;
+        memcpy(&L, p, 4);
+        p += 4;
+        uint64_t t, nn;
+        memcpy(&t, p + L, 8);
+        memcpy(&nn, p + L + 8, 8);
+        auto ins = idx.emplace(std::string((const char*)p, L), ents.size());
+        if (ins.second) ents.push_back(Ent{p, L, t, nn});
+        else {
+            ents[ins.first->second].total += t;
+            ents[ins.first->second].nn += nn;
+            dup = true;
+        }
+        p += L + 16;
     }
+    if (!dup) return;
+    std::vector<uint8_t> out(8);
+    const uint64_t m = ents.size();
+    memcpy(out.data(), &m, 8);
+    for (auto& e : ents) {
+        const size_t o = out.size();
+        out.resize(o + 4 + e.len + 16);
+        memcpy(out.data() + o, &e.len, 4);
+        memcpy(out.data() + o + 4, e.key, e.len);
+        memcpy(out.data() + o + 4 + e.len, &e.total, 8);
+        memcpy(out.data() + o + 4 + e.len + 8, &e.nn, 8);
+    }
+    b.swap(out);
+}
+
+void grouped_blob_merge(std::vector<uint8_t>& into, const std::vector<uint8_t>& other) {
+    if (other.size() < 8) return;
+    if (into.size() < 8) {
+        into = other;
+        return;
+    }
+    uint64_t a, b;
+    memcpy(&a, into.data(), 8);
+    memcpy(&b, other.data(), 8);
+    a += b;
+    memcpy(into.data(), &a, 8);
+    into.insert(into.end(), other.begin() + 8, other.end());
+    if (into.size() > ((size_t)8 << 20)) grouped_blob_compact(into);  // long merge chains (incremental runs) stay bounded
 }
 
 // ------------------------------------------------------------------ finalize ----
@@ -1753,10 +1779,12 @@ static void finalize_grouped(Plan& p, Slot& s) {
         uint64_t total, nn;
     };
     std::vector<G> gs;
-    if (a.blob.size() >= 8) {
+    std::vector<uint8_t> state = a.blob;
+    grouped_blob_compact(state);  // entries of equal keys (one per merged shard) add up
+    if (state.size() >= 8) {
         uint64_t n;
-        memcpy(&n, a.blob.data(), 8);
-        const uint8_t* q = a.blob.data() + 8;
+        memcpy(&n, state.data(), 8);
+        const uint8_t* q = state.data() + 8;
         for (uint64_t i = 0; i < n; ++i) {
             uint32_t L;
             memcpy(&L, q, 4);

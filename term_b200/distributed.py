@@ -311,10 +311,11 @@ def _cabi_shuffle(ctx, call, *args):
     return n.value
 
 
-def _shuffle_column(ctx, table, column, shard_name):
-    """partition -> all-to-all -> adopt as table `shard_name` (column keeps its name)."""
+def _shuffle_column(ctx, table, column, shard_name, by_range_if_dense=False):
+    """partition -> all-to-all -> adopt as table `shard_name` (column keeps its name). by_range_if_dense: a DISTINCT
+    aggregate may split dense Int64 keys by value range (a foreign key may not: both sides must agree on the function)."""
     if _ensure_comm(ctx):  # NCCL inside the library: one call, parts land in the shard's own column buffer
-        _cabi_shuffle(ctx, F.lib().tg_table_shuffle_column, table.encode(), column.encode(), shard_name.encode())
+        _cabi_shuffle(ctx, F.lib().tg_table_shuffle_column, table.encode(), column.encode(), shard_name.encode(), 1 if by_range_if_dense else 0)
         return
     world = dist.get_world_size()
     dtype = _column_dtype(ctx, table, column)
@@ -637,7 +638,7 @@ def execute_distributed(plan, ctx, table="data"):
             if kind == KIND_DISTINCT:
                 name = f"tg_shuffle_{i}_k"
                 if len(parts) == 2 and _column_dtype(ctx, table, parts[1]) in (F.TG_INT64, F.TG_FLOAT64):
-                    _shuffle_column(ctx, table, parts[1], name)  # exact 64-bit keys
+                    _shuffle_column(ctx, table, parts[1], name, by_range_if_dense=True)  # exact 64-bit keys
                 else:
                     _shuffle_fingerprints(ctx, table, parts[1:], name)  # Utf8 / composite: 128-bit fingerprints
                 temps.append(name)
