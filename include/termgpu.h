@@ -502,6 +502,13 @@ TG_API tg_status tg_rank_recv_commit(tg_engine* eng, int64_t n_recv);
 TG_API tg_status tg_rank_finish_x(tg_engine* eng, uint64_t rank_base);
 TG_API tg_status tg_rank_finish_y(tg_engine* eng, uint64_t rank_base, double center, uint64_t* n_out, double* sums5);
 TG_API tg_status tg_rank_abort(tg_engine* eng);
+/* The exchange between tg_rank_begin / tg_rank_finish_x / tg_rank_finish_y done by the library itself (needs tg_comm_init):
+ * samples all-gathered over NCCL, splitters, then the session's (key, payload) pairs are PUSHED to the ranks that own
+ * their key ranges by the partition's scatter kernel — NVLink peer stores into IPC-mapped receive buffers, no local
+ * pre-sort and no separate all-to-all. Returns the rows this rank now holds, the number of keys on the lower ranks
+ * (rank_base of the finish calls) and the global pair count. *done = 0: peer mapping is unavailable, nothing happened;
+ * run tg_rank_local_sort / _sample / _split and an all-to-all of your own instead. */
+TG_API tg_status tg_rank_exchange(tg_engine* eng, int64_t* n_recv, uint64_t* rank_base, uint64_t* total, int32_t* done);
 /* Installs a partial state computed outside tg_plan_execute_partial for aggregate i (kind 10 SPEARMAN only): u[0] = pair
  * count, f[0] = f[1] = center, f[2..6] = the five sums. Call it after tg_plan_execute_partial, before the exchange. */
 TG_API tg_status tg_plan_set_aggregate_partial(tg_plan* plan, int32_t i, const uint64_t* u8, const double* f8);

@@ -153,6 +153,7 @@ SIGNATURES = {
     "tg_rank_finish_x": (C.c_int, [P, C.c_uint64]),
     "tg_rank_finish_y": (C.c_int, [P, C.c_uint64, C.c_double, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "tg_rank_abort": (C.c_int, [P]),
+    "tg_rank_exchange": (C.c_int, [P, C.POINTER(C.c_int64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_int32)]),
     "tg_plan_set_aggregate_partial": (C.c_int, [P, C.c_int32, C.POINTER(C.c_uint64), C.POINTER(C.c_double)]),
     "tg_plan_kll_levels": (C.c_int32, [P, C.c_int32, C.c_int32, C.POINTER(C.c_double), C.c_int32]),
     "tg_plan_histogram_pending": (C.c_int32, [P, C.POINTER(C.c_int32), C.c_int32]),

@@ -603,6 +603,12 @@ tg_status tg_rank_finish_y(tg_engine* h, uint64_t rank_base, double center, uint
         rank_finish_y(h->e, rank_base, center, n_out, sums5);
     });
 }
+tg_status tg_rank_exchange(tg_engine* h, int64_t* n_recv, uint64_t* rank_base, uint64_t* total, int32_t* done) {
+    return guard([&] {
+        if (!h || !n_recv || !rank_base || !total || !done) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        *done = comm_rank_exchange(h->e, n_recv, rank_base, total) ? 1 : 0;
+    });
+}
 tg_status tg_rank_abort(tg_engine* h) {
     return guard([&] {
         if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");

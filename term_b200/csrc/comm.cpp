@@ -92,6 +92,8 @@ void comm_destroy(Engine& e) {
     }
     if (e.d_comm_counts) cudaFree(e.d_comm_counts);
     e.d_comm_counts = nullptr;
+    if (e.d_comm_samples) cudaFree(e.d_comm_samples);
+    e.d_comm_samples = nullptr;
     e.comm_world = 0;
 }
 
@@ -191,7 +193,8 @@ static int64_t exchange_into_table(Engine& e, const uint8_t* d_send, const int64
 // no intermediate copy of the keys exists anywhere. A second tiny collective is the barrier after which a rank may read
 // its buffer. Falls back to partition + ncclSend / ncclRecv when peer mapping is not available (TG_NO_PUSH_SHUFFLE).
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int PUSH_SLOTS = 2;  // shards alive at the same time (a foreign key shuffles the child and the parent column)
+constexpr int PUSH_SHUFFLE_SLOTS = 2;  // shards alive at the same time (a foreign key shuffles the child and the parent column)
+constexpr int PUSH_SLOTS = PUSH_SHUFFLE_SLOTS + 4;  // + keys / payload receive buffers of the two phases of the distributed sort
 
 struct PushSlot {
     uint8_t* local = nullptr;
@@ -271,7 +274,7 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
     if (e.tables.count(shard_name)) throw Error(TG_ERR_INVALID_ARG, "table '" + shard_name + "' already exists");
     // a free slot: one whose shard table is gone (the same choice on every rank: the call sequences are the same)
     int si = -1;
-    for (int i = 0; i < PUSH_SLOTS && si < 0; ++i)
+    for (int i = 0; i < PUSH_SHUFFLE_SLOTS && si < 0; ++i)
         if (ps.slot[i].user.empty() || !e.tables.count(ps.slot[i].user)) si = i;
     if (si < 0) return -1;
     PushSlot& s = ps.slot[si];
@@ -431,6 +434,112 @@ int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::stri
     partition_keys_by_rank(e, *c, t.n_rows, e.comm_world, &keys, counts.data(), &nulls, launches);
     e.launches += launches;
     return exchange_into_table(e, (const uint8_t*)keys, counts.data(), nulls, 8, shard_name, column, c->dtype);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The exchange of the distributed sort (Spearman's global ranks, ranks.cu) inside the library: evenly spaced sample keys of
+// every rank -> the same world - 1 splitters everywhere -> the session's (key, payload) pairs pushed to the rank whose
+// key range holds them by the partition's scatter kernel (NVLink peer stores, as in the key shuffle above). The receiving
+// rank then sorts its range (rank_finish_x / _y). Returns false when peer mapping is unavailable: the host layer then
+// runs the same exchange with tg_rank_sample / tg_rank_split and its own all-to-all.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int RANK_SAMPLES = 2048;
+
+bool comm_rank_exchange(Engine& e, int64_t* n_recv_out, uint64_t* rank_base, uint64_t* total_out) {
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (!e.comm) return false;
+    static const bool off = getenv("TG_NO_PUSH_SHUFFLE") != nullptr;
+    if (off) return false;
+    if (!e.push) e.push = new PushState();
+    PushState& ps = *(PushState*)e.push;
+    if (ps.disabled) return false;
+    const int world = e.comm_world, rank = e.comm_rank;
+    if (world > 64) return false;
+    ncclComm_t comm = (ncclComm_t)e.comm;
+    const uint64_t* keys = nullptr;
+    const void* payload = nullptr;
+    int pay_bytes = 8;
+    int64_t n = 0;
+    rank_current_unlocked(e, &keys, &payload, &pay_bytes, &n);
+    int launches = 0;
+    // ---- samples -> splitters (identical on every rank)
+    const size_t sw = RANK_SAMPLES + 1;
+    if (!e.d_comm_samples) TG_CUDA(cudaMalloc(&e.d_comm_samples, sw * 8 * (size_t)(world + 1) + 1024));
+    std::vector<uint64_t> mine(sw, 0), all(sw * (size_t)world);
+    mine[0] = (uint64_t)rank_sample_unlocked(e, RANK_SAMPLES, mine.data() + 1);
+    uint64_t* d_mine = (uint64_t*)e.d_comm_samples;
+    uint64_t* d_all = d_mine + sw;
+    TG_CUDA(cudaMemcpyAsync(d_mine, mine.data(), sw * 8, cudaMemcpyHostToDevice, e.stream));
+    TG_NCCL(nccl().AllGather(d_mine, d_all, sw, NCCL_INT64, comm, e.stream));
+    TG_CUDA(cudaMemcpyAsync(all.data(), d_all, sw * world * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    std::vector<uint64_t> samples;
+    for (int r = 0; r < world; ++r) {
+        const uint64_t c = std::min<uint64_t>(all[(size_t)r * sw], RANK_SAMPLES);
+        samples.insert(samples.end(), all.begin() + (size_t)r * sw + 1, all.begin() + (size_t)r * sw + 1 + c);
+    }
+    std::sort(samples.begin(), samples.end());
+    std::vector<uint64_t> splitters((size_t)std::max(world - 1, 1), 0);
+    for (int p = 0; p + 1 < world && !samples.empty(); ++p) {
+        const size_t L = samples.size();
+        const size_t idx = std::min(L - 1, (size_t)std::max<long long>(0, (long long)((size_t)(p + 1) * L / (size_t)world) - 1));
+        splitters[p] = samples[idx];
+    }
+    uint64_t* d_split = d_all + sw * world;  // behind the gathered samples (1 KB of slack was allocated: world <= 64 splitters)
+    TG_CUDA(cudaMemcpyAsync(d_split, splitters.data(), splitters.size() * 8, cudaMemcpyHostToDevice, e.stream));
+    // ---- counts
+    std::vector<int64_t> counts((size_t)world, 0);
+    split_partition_hist(e, keys, n, world, d_split, counts.data(), launches);
+    std::vector<long long> cm((size_t)world), call((size_t)world * world);
+    for (int r = 0; r < world; ++r) cm[r] = counts[r];
+    long long* dc_mine = (long long*)e.d_comm_counts;
+    long long* dc_all = dc_mine + (world + 1);
+    TG_CUDA(cudaMemcpyAsync(dc_mine, cm.data(), (size_t)world * 8, cudaMemcpyHostToDevice, e.stream));
+    TG_NCCL(nccl().AllGather(dc_mine, dc_all, (size_t)world, NCCL_INT64, comm, e.stream));
+    TG_CUDA(cudaMemcpyAsync(call.data(), dc_all, (size_t)world * world * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    std::vector<unsigned long long> first((size_t)world, 0);
+    int64_t n_recv = 0, max_rows = 0;
+    uint64_t base = 0, total = 0;
+    for (int d = 0; d < world; ++d) {
+        int64_t tot = 0;
+        for (int sr = 0; sr < world; ++sr) {
+            if (sr == rank) first[d] = (unsigned long long)tot;
+            tot += call[(size_t)sr * world + d];
+        }
+        if (d == rank) n_recv = tot;
+        if (d < rank) base += (uint64_t)tot;
+        total += (uint64_t)tot;
+        max_rows = std::max(max_rows, tot);
+    }
+    if (max_rows >= ((int64_t)1 << 30)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more keys in one rank's range");
+    // ---- receive buffers of this phase (keys, payload), grown collectively
+    const int phase = rank_phase_unlocked(e);
+    PushSlot& sk = ps.slot[PUSH_SHUFFLE_SLOTS + 2 * phase];
+    PushSlot& sp = ps.slot[PUSH_SHUFFLE_SLOTS + 2 * phase + 1];
+    const size_t need = round_up((size_t)std::max<int64_t>(max_rows, 1) * 8 + 512, 256);
+    try {
+        if (need > sk.cap) push_slot_grow(e, sk, round_up(need + need / 8, (size_t)1 << 20));
+        if (need > sp.cap) push_slot_grow(e, sp, round_up(need + need / 8, (size_t)1 << 20));
+    } catch (Error&) {
+        ps.disabled = true;
+        cudaGetLastError();
+        push_slot_release(e, sk);
+        push_slot_release(e, sp);
+        return false;  // every rank of the node fails alike (IPC is a property of the node) and takes the host-layer path
+    }
+    // ---- the scatter is the exchange
+    split_partition_scatter(e, keys, payload, pay_bytes, n, world, d_split, first.data(), (uint64_t* const*)sk.d_ptrs, (uint8_t* const*)sp.d_ptrs, launches);
+    TG_NCCL(nccl().AllGather(dc_mine, dc_all, 1, NCCL_INT64, comm, e.stream));  // barrier: every rank's stores have landed
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    e.launches += launches;
+    e.comm_bytes_sent += (uint64_t)(n - counts[rank]) * (uint64_t)(8 + pay_bytes);
+    rank_adopt_received_unlocked(e, (uint64_t*)sk.local, sp.local, n_recv);
+    *n_recv_out = n_recv;
+    *rank_base = base;
+    *total_out = total;
+    return true;
 }
 
 int64_t comm_shuffle_fingerprints(Engine& e, const std::string& table, const std::vector<std::string>& columns, const std::string& shard_name) {

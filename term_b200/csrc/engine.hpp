@@ -156,6 +156,7 @@ struct Engine {
     void* comm = nullptr;
     int comm_world = 0, comm_rank = 0;
     uint8_t* d_comm_counts = nullptr;
+    uint8_t* d_comm_samples = nullptr;
     void* push = nullptr;          // comm.cpp PushState: IPC-mapped receive buffers of the push shuffle
     uint64_t comm_bytes_sent = 0;  // bytes this rank sent to OTHER ranks through tg_table_shuffle_* since creation
     FusedScan* fused = nullptr;  // non-null while execute_exchange_fused runs the scan jobs
@@ -198,6 +199,10 @@ void rank_recv_commit(Engine& e, int64_t n_recv);
 void rank_finish_x(Engine& e, uint64_t rank_base);
 void rank_finish_y(Engine& e, uint64_t rank_base, double K, uint64_t* n_out, double* sums);
 void rank_abort(Engine& e);
+void rank_current_unlocked(Engine& e, const uint64_t** keys, const void** payload, int* pay_bytes, int64_t* n);
+int32_t rank_sample_unlocked(Engine& e, int32_t m, uint64_t* out);
+void rank_adopt_received_unlocked(Engine& e, uint64_t* keys, void* payload, int64_t n_recv);
+int rank_phase_unlocked(Engine& e);
 void hist_rebucket(Engine& e, Table* t, Plan& p, int agg_id, uint64_t* counts, int nb); // hist.cu (two-phase multi-GPU histogram)
 
 void execute_partial(Engine& e, Plan& p, const std::string& table_name);
@@ -215,6 +220,7 @@ void comm_unique_id(void* id128);
 void comm_init(Engine& e, const void* id128, int world, int rank);
 void comm_destroy(Engine& e);
 int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::string& column, const std::string& shard_name, bool allow_range);
+bool comm_rank_exchange(Engine& e, int64_t* n_recv, uint64_t* rank_base, uint64_t* total);  // false: push exchange unavailable
 int64_t comm_shuffle_fingerprints(Engine& e, const std::string& table, const std::vector<std::string>& columns, const std::string& shard_name);
 
 // scan.cu

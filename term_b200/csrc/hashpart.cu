@@ -56,10 +56,13 @@ struct PartCounters {
 // MODE 1: destination rank of the shuffle, every valid key is kept (raw bits)
 // MODE 2: destination rank by VALUE RANGE (Int64 keys known to be dense): part = (key - range_min) / range_span, so every
 //         rank receives a contiguous slice of the key space and de-duplicates it with the bitmap path
-enum { PM_BUCKET = 0, PM_RANK = 1, PM_RANGE = 2 };
+// MODE 3: destination rank by SPLITTERS (the distributed sort of K6): part = number of splitters < key, so part p holds
+//         the keys in (splitter[p-1], splitter[p]] and equal keys meet on one rank; an optional payload travels along
+enum { PM_BUCKET = 0, PM_RANK = 1, PM_RANGE = 2, PM_SPLIT = 3 };
 struct RangeSplit {
     long long min;
     unsigned long long span;
+    const uint64_t* splitters = nullptr;  // PM_SPLIT: parts - 1 ascending keys (device)
 };
 
 // Loads the PART_KEYS_PER_THREAD keys of this thread's tile slots up front (independent, predicated loads: all in
@@ -90,10 +93,19 @@ __device__ __forceinline__ void load_classify(const uint64_t* __restrict__ value
         } else if (MODE == PM_RANK) {
             key[k] = raw[k];
             part[k] = !valid ? -1 : (int)hash_rank(h, parts);
-        } else {
+        } else if (MODE == PM_RANGE) {
             key[k] = raw[k];
             const unsigned long long d = ((unsigned long long)raw[k] - (unsigned long long)rs.min) / rs.span;
             part[k] = !valid ? -1 : (int)(d < parts ? d : parts - 1);
+        } else {
+            key[k] = raw[k];
+            int lo = 0, hi = (int)parts - 1;  // first splitter >= key (lower bound) = number of splitters < key
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (__ldg(rs.splitters + mid) < raw[k]) lo = mid + 1;
+                else hi = mid;
+            }
+            part[k] = !valid ? -1 : lo;
         }
     }
 }
@@ -156,11 +168,14 @@ template <int MODE>
 __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64_t* __restrict__ values, const uint32_t* __restrict__ validity,
                                                                     int64_t n, int is_f64, uint32_t parts, unsigned long long* cursors,
                                                                     uint64_t* __restrict__ out, uint64_t* const* __restrict__ outs,
-                                                                    RangeSplit rs = RangeSplit{0, 1}) {
+                                                                    RangeSplit rs = RangeSplit{0, 1}, const uint8_t* __restrict__ pay_in = nullptr,
+                                                                    uint8_t* const* __restrict__ pay_outs = nullptr, int pay_bytes = 0) {
     __shared__ uint64_t s_keys[PART_TILE];
+    __shared__ uint64_t s_pay[MODE == PM_SPLIT ? PART_TILE : 1];
     __shared__ uint16_t s_part[PART_TILE];
-    __shared__ uint32_t s_cnt[PART_MAX], s_off[PART_MAX];
-    __shared__ unsigned long long s_gbase[PART_MAX];
+    constexpr int NP = MODE == PM_SPLIT ? 64 : PART_MAX;  // the distributed sort has at most 64 destinations
+    __shared__ uint32_t s_cnt[NP], s_off[NP];
+    __shared__ unsigned long long s_gbase[NP];
     __shared__ uint32_t s_warp_tot[PART_THREADS / 32];
     const int64_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
     const int per_thread = (int)(parts + PART_THREADS - 1) / PART_THREADS;  // buckets per thread in the scan (<= 4)
@@ -214,6 +229,11 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64
                 const uint32_t pos = s_off[part[k]] + rank[k];
                 s_keys[pos] = key[k];
                 s_part[pos] = (uint16_t)part[k];
+                if (MODE == PM_SPLIT && pay_bytes) {  // the payload of the same row travels with its key
+                    const int64_t row = base + k * PART_THREADS + threadIdx.x;
+                    s_pay[pos] = pay_bytes == 8 ? __ldg(reinterpret_cast<const unsigned long long*>(pay_in) + row)
+                                                : (uint64_t)__ldg(reinterpret_cast<const uint32_t*>(pay_in) + row);
+                }
             }
         __syncthreads();
         uint32_t total = 0;
@@ -223,7 +243,12 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64
         for (uint32_t i = threadIdx.x; i < total; i += PART_THREADS) {
             const uint32_t b = s_part[i];
             uint64_t* dst = outs ? outs[b] : out;
-            dst[s_gbase[b] + (i - s_off[b])] = s_keys[i];
+            const unsigned long long gi = s_gbase[b] + (i - s_off[b]);
+            dst[gi] = s_keys[i];
+            if (MODE == PM_SPLIT && pay_bytes) {
+                if (pay_bytes == 8) reinterpret_cast<uint64_t*>(pay_outs[b])[gi] = s_pay[i];
+                else reinterpret_cast<uint32_t*>(pay_outs[b])[gi] = (uint32_t)s_pay[i];
+            }
         }
         __syncthreads();
     }
@@ -670,6 +695,46 @@ void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, co
     TG_CUDA(cudaGetLastError());
     launches += 1;
 }
+// The distributed sort's exchange (ranks.cu / comm.cpp): raw 64-bit keys (no validity), destination = number of splitters
+// below the key. d_splitters: world - 1 ascending keys on the device.
+void split_partition_hist(Engine& e, const uint64_t* d_keys, int64_t n, int world, const uint64_t* d_splitters, int64_t* counts, int& launches) {
+    const size_t need = PartMeta::bytes() + 256;
+    if (need > e.shuffle_cap) {
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        if (e.d_shuffle) TG_CUDA(cudaFree(e.d_shuffle));
+        e.d_shuffle = nullptr;
+        e.shuffle_cap = 0;
+        TG_CUDA(cudaMalloc(&e.d_shuffle, need));
+        e.shuffle_cap = need;
+    }
+    PartMeta m;
+    m.bind(e.d_shuffle);
+    TG_CUDA(cudaMemsetAsync(m.hist, 0, PartMeta::bytes(), e.stream));
+    if (n > 0) {
+        part_hist_kernel<PM_SPLIT><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>(d_keys, nullptr, n, 0, (uint32_t)world, m.hist, m.ctr,
+                                                                                   RangeSplit{0, 1, d_splitters});
+        TG_CUDA(cudaGetLastError());
+        launches += 1;
+    }
+    std::vector<unsigned long long> h((size_t)world);
+    TG_CUDA(cudaMemcpyAsync(h.data(), m.hist, h.size() * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    for (int i = 0; i < world; ++i) counts[i] = (int64_t)h[i];
+}
+void split_partition_scatter(Engine& e, const uint64_t* d_keys, const void* d_payload, int pay_bytes, int64_t n, int world,
+                             const uint64_t* d_splitters, const unsigned long long* first_index, uint64_t* const* d_key_outs,
+                             uint8_t* const* d_pay_outs, int& launches) {
+    if (n <= 0) return;
+    PartMeta m;
+    m.bind(e.d_shuffle);
+    TG_CUDA(cudaMemcpyAsync(m.cursors, first_index, (size_t)world * 8, cudaMemcpyHostToDevice, e.stream));
+    part_scatter_kernel<PM_SPLIT><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>(d_keys, nullptr, n, 0, (uint32_t)world, m.cursors, nullptr, d_key_outs,
+                                                                                  RangeSplit{0, 1, d_splitters}, (const uint8_t*)d_payload, d_pay_outs,
+                                                                                  pay_bytes);
+    TG_CUDA(cudaGetLastError());
+    launches += 1;
+}
+
 // min / max / valid count of an Int64 key column (the dense test of the range-partitioned shuffle)
 bool column_minmax_i64(Engine& e, const Column& c, int64_t n, long long* mn, long long* mx, unsigned long long* n_valid, int& launches) {
     MinMaxOut h{};

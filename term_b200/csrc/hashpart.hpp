@@ -44,6 +44,11 @@ void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64
                          const long long* range_min = nullptr, unsigned long long range_span = 1);
 void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, const unsigned long long* first_index, uint64_t* const* d_outs,
                             int& launches, const long long* range_min = nullptr, unsigned long long range_span = 1);
+// the exchange of the distributed sort: raw keys (+ payload of 4 / 8 bytes) to the rank whose key range holds them
+void split_partition_hist(Engine& e, const uint64_t* d_keys, int64_t n, int world, const uint64_t* d_splitters, int64_t* counts, int& launches);
+void split_partition_scatter(Engine& e, const uint64_t* d_keys, const void* d_payload, int pay_bytes, int64_t n, int world,
+                             const uint64_t* d_splitters, const unsigned long long* first_index, uint64_t* const* d_key_outs,
+                             uint8_t* const* d_pay_outs, int& launches);
 bool column_minmax_i64(Engine& e, const Column& c, int64_t n, long long* mn, long long* mx, unsigned long long* n_valid, int& launches);
 
 // hashing.cu: same for Utf8 / composite keys, as 24-byte fingerprint records {h1, h2, has_null}

@@ -640,6 +640,43 @@ void rank_finish_y(Engine& e, uint64_t rank_base, double K, uint64_t* n_out, dou
     rank_finish_y_locked(e, rank_base, K, n_out, sums, &launches);
     e.launches += launches;
 }
+// ---- hooks of the in-library exchange (comm.cpp rank_exchange; the caller holds the engine's lock)
+void rank_current_unlocked(Engine& e, const uint64_t** keys, const void** payload, int* pay_bytes, int64_t* n) {
+    RankSession& S = session(e);
+    *keys = S.cur.K[S.which];
+    *payload = S.cur.V[S.which];
+    *pay_bytes = S.payload32 ? 4 : 8;
+    *n = S.n;
+}
+int32_t rank_sample_unlocked(Engine& e, int32_t m, uint64_t* out) {
+    RankSession& S = session(e);
+    if (S.n <= 0 || m <= 0) return 0;
+    m = (int32_t)std::min<int64_t>(m, S.n);
+    uint64_t* d = (uint64_t*)e.scratch((size_t)m * 8 + 256);
+    rk_sample_kernel<<<(m + 255) / 256, 256, 0, e.stream>>>(S.cur.K[S.which], S.n, m, d);
+    TG_CUDA(cudaGetLastError());
+    TG_CUDA(cudaMemcpyAsync(out, d, (size_t)m * 8, cudaMemcpyDeviceToHost, e.stream));
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    e.launches += 1;
+    return m;
+}
+// the session's data now lives in external buffers (this rank's receive buffers of the push exchange, capacity >= n_recv
+// elements); a fresh arena supplies the ping-pong partners
+void rank_adopt_received_unlocked(Engine& e, uint64_t* keys, void* payload, int64_t n_recv) {
+    RankSession& S = session(e);
+    if (n_recv < 0 || n_recv >= ((int64_t)1 << 30)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more keys in one rank's range");
+    TG_CUDA(cudaStreamSynchronize(e.stream));
+    arena_alloc(e, S.next, n_recv);
+    arena_free(e, S.cur);
+    S.cur = S.next;
+    S.next = RankArena{};
+    S.cur.K[0] = keys;
+    S.cur.V[0] = (uint64_t*)payload;
+    S.n = n_recv;
+    S.which = 0;
+}
+int rank_phase_unlocked(Engine& e) { return session(e).payload32 ? 1 : 0; }
+
 void rank_abort(Engine& e) {
     RankLock l(e);
     rank_session_destroy(e);

@@ -483,6 +483,22 @@ class GpuRankStages:
         F.check(F.lib().tg_rank_finish_y(self.ctx.handle, base, center, C.byref(n), sums))
         return n.value, list(sums)
 
+    def exchange_in_library(self):
+        """tg_rank_exchange; None when the library cannot do it (no peer mapping): the caller runs the host-layer exchange"""
+        import ctypes as C
+        import time
+        n, base, total, done = C.c_int64(), C.c_uint64(), C.c_uint64(), C.c_int32()
+        sent0 = F.lib().tg_comm_bytes_sent(self.ctx.handle)
+        t0 = time.perf_counter()
+        F.check(F.lib().tg_rank_exchange(self.ctx.handle, C.byref(n), C.byref(base), C.byref(total), C.byref(done)))
+        if not done.value:
+            return None
+        if PROFILE is not None:
+            PROFILE["shuffle_ms"] += (time.perf_counter() - t0) * 1e3
+            PROFILE["shuffle_bytes"] += F.lib().tg_comm_bytes_sent(self.ctx.handle) - sent0
+        self.n = n.value
+        return n.value, base.value, total.value
+
     def abort(self):
         F.lib().tg_rank_abort(self.ctx.handle)
 
@@ -521,6 +537,10 @@ def rank_sort_exchange(stages, dev):
     range. Returns (n_recv, rank_base) with rank_base = the number of keys that went to lower ranks."""
     world, rank = dist.get_world_size(), dist.get_rank()
     prof = PROFILE if (PROFILE is not None and dev.type == "cuda") else None
+    if isinstance(stages, GpuRankStages) and _ensure_comm(stages.ctx):
+        got = stages.exchange_in_library()  # samples, splitters and the push of every pair to its range's owner: one call
+        if got is not None:
+            return got
     stages.local_sort()
     splitters = choose_splitters(_allgather_samples(stages.sample(RANK_SAMPLES_PER_SHARD), RANK_SAMPLES_PER_SHARD, dev), world)
     counts = stages.split(splitters, world)
