@@ -209,6 +209,9 @@ TG_API const char* tg_last_error(void);
 TG_API const char* tg_version(void);
 /* number of kernels this library has launched on this engine since creation (bench `gpu_launches`) */
 TG_API uint64_t tg_engine_launch_count(const tg_engine* eng);
+/* Waits until every host->device copy queued by tg_table_append_* has completed: after it returns the caller may free or
+ * reuse the pinned host buffers it appended from. */
+TG_API tg_status tg_engine_sync_copies(tg_engine* eng);
 /* raw CUDA stream (cudaStream_t) the engine launches scan kernels on; for event timing by the harness */
 TG_API void* tg_engine_stream(tg_engine* eng);
 

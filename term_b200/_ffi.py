@@ -82,6 +82,7 @@ SIGNATURES = {
     "tg_version": (C.c_char_p, []),
     "tg_engine_launch_count": (C.c_uint64, [P]),
     "tg_engine_stream": (C.c_void_p, [P]),
+    "tg_engine_sync_copies": (C.c_int, [P]),
     "tg_table_create": (C.c_int, [P, C.c_char_p, PP]),
     "tg_table_drop": (C.c_int, [P, C.c_char_p]),
     "tg_table_lookup": (C.c_int, [P, C.c_char_p, PP]),

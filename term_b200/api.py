@@ -225,6 +225,10 @@ class SessionContext:
     def launch_count(self) -> int:
         return int(F.lib().tg_engine_launch_count(self._h))
 
+    def sync_copies(self):
+        """tg_engine_sync_copies: pinned host buffers appended from may be freed / reused after this returns"""
+        F.check(F.lib().tg_engine_sync_copies(self._h))
+
     def stream(self) -> int:
         return int(F.lib().tg_engine_stream(self._h) or 0)
 
@@ -357,6 +361,27 @@ class SessionContext:
         import pyarrow.parquet as pq
         paths = [path] if isinstance(path, (str, os.PathLike)) else list(path)
         t = self._create(name)
+        try:
+            return self._register_parquet(t, paths, columns)
+        except Exception:
+            F.lib().tg_table_drop(self._h, name.encode())  # like register_table: no half-registered table stays behind
+            raise
+
+    @staticmethod
+    def _check_parquet_logical_type(col, leaf):
+        """The device path delivers the PHYSICAL values. Annotated columns whose Arrow type is not the plain signed integer /
+        float of that width (DECIMAL, DATE, TIME, TIMESTAMP, unsigned or narrow INT) would be silently wrong: refuse them,
+        the reference's ParquetSource yields their logical Arrow types (sources/parquet.rs:150-230)."""
+        lt = str(getattr(leaf, "logical_type", "NONE") or "NONE").upper()
+        ct = str(getattr(leaf, "converted_type", "NONE") or "NONE").upper()
+        ok_logical = lt in ("NONE", "NULL") or lt.startswith("INT(BITWIDTH=64, ISSIGNED=TRUE") or lt.startswith("INT(BITWIDTH=32, ISSIGNED=TRUE")
+        ok_converted = ct in ("NONE", "INT_64", "INT_32")
+        if not (ok_logical and ok_converted):
+            raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': logical type {lt} / {ct} is not decoded on the device "
+                                                        "(only plain signed INT32 / INT64 and FLOAT / DOUBLE columns)")
+
+    def _register_parquet(self, t, paths, columns):
+        import pyarrow.parquet as pq
         for pth in paths:
             pf = pq.ParquetFile(pth)
             md, schema = pf.metadata, pf.schema
@@ -378,6 +403,7 @@ class SessionContext:
                                 raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': physical type {cm.physical_type} is not decoded on the device")
                             if leaf.max_repetition_level != 0:
                                 raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}' is repeated")
+                            self._check_parquet_logical_type(col, leaf)
                             start = cm.dictionary_page_offset if cm.has_dictionary_page and cm.dictionary_page_offset else cm.data_page_offset
                             chunk = view[start: start + cm.total_compressed_size]
                             codec = 0 if cm.compression == "UNCOMPRESSED" else 1

@@ -141,6 +141,15 @@ uint64_t tg_engine_launch_count(const tg_engine* h) { return h ? h->e.launches :
 void* tg_engine_stream(tg_engine* h) { return h ? (void*)h->e.stream : nullptr; }
 
 // tables are owned by the engine's registry; tg_table* is a borrowed handle
+tg_status tg_engine_sync_copies(tg_engine* h) {
+    return guard([&] {
+        if (!h) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
+        std::lock_guard<std::mutex> g(h->e.mu);
+        TG_CUDA(cudaSetDevice(h->e.device));
+        h->e.sync_copies();
+    });
+}
+
 tg_status tg_table_create(tg_engine* h, const char* name, tg_table** out) {
     return guard([&] {
         if (!h || !name || !out) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
