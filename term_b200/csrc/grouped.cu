@@ -258,7 +258,11 @@ __global__ void __launch_bounds__(GRP_THREADS, 1) group_count_fused_kernel(const
 // dictionary or composite table overflows raises a flag and the host re-runs the batch through the generic
 // fingerprint kernel above.
 // =====================================================================================================================
-constexpr int GD_THREADS = 1024, GD_ILP = 4;
+#ifndef TG_GD_THREADS
+#define TG_GD_THREADS 1024
+#define TG_GD_ILP 2
+#endif
+constexpr int GD_THREADS = TG_GD_THREADS, GD_ILP = TG_GD_ILP;
 constexpr int GD_DICT = 1024;       // dictionary slots per column per CTA (10-bit local codes)
 constexpr int GD_MAX_COLS = 4, GD_MAX_JOBS = 4;
 constexpr int GD_PROBE = 16;
