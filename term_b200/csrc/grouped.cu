@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(GRP_THREADS, 1) group_count_fused_kernel(const
 // =====================================================================================================================
 #ifndef TG_GD_THREADS
 #define TG_GD_THREADS 1024
-#define TG_GD_ILP 2
+#define TG_GD_ILP 4
 #endif
 constexpr int GD_THREADS = TG_GD_THREADS, GD_ILP = TG_GD_ILP;
 constexpr int GD_DICT = 1024;       // dictionary slots per column per CTA (10-bit local codes)
@@ -284,6 +284,8 @@ struct GdJob {
     int32_t col[3];
     uint32_t smem_off;       // single-column: counters [tot GD_DICT][nn GD_DICT]; composite: [key S][tot S][nn S][row S]
     uint32_t comp_slots;     // composite: S (power of two); single-column: 0
+    int32_t derived_from;    // >= 0: this single-column grouping is a marginal of that composite job (same target): not
+    int32_t derived_pos;     // counted per row; its column's code sits at bits [10 * derived_pos ..) of the composite key
     // global state. single-column: totals / nonnull indexed by the column's global code. composite: 64-bit key table.
     unsigned long long* totals;
     unsigned long long* nonnull;
@@ -299,19 +301,17 @@ struct GdParams {
     unsigned int* overflow;
 };
 
-// dictionary of one column in shared memory
+// dictionary of one column in shared memory: 16-byte entries {x.lo, x.hi, state, row} — a probe is ONE 128-bit shared
+// load — and the second hash word of long strings in a parallel array (only read for entries tagged GD_TAG_LONG)
 struct GdDict {
-    unsigned long long* x;   // [GD_DICT] value bits / first hash word
+    uint4* ent;              // [GD_DICT] .x/.y value bits (first hash word), .z state: 0 vacant, GD_BUSY being written, else
+                             // the tag (never 0), .w a row holding the value; after the publish step: the global code
     unsigned long long* y;   // [GD_DICT] second hash word of long strings (0 otherwise)
-    uint32_t* state;         // [GD_DICT] 0 vacant, GD_BUSY being written, else the tag (never 0)
-    uint32_t* row;           // [GD_DICT] a row holding the value; after the publish step: the global code
 };
 __device__ __forceinline__ GdDict gd_dict(uint8_t* smem, uint32_t off) {
     GdDict d;
-    d.x = reinterpret_cast<unsigned long long*>(smem + off);
-    d.y = d.x + GD_DICT;
-    d.state = reinterpret_cast<uint32_t*>(d.y + GD_DICT);
-    d.row = d.state + GD_DICT;
+    d.ent = reinterpret_cast<uint4*>(smem + off);
+    d.y = reinterpret_cast<unsigned long long*>(smem + off + GD_DICT * 16);
     return d;
 }
 constexpr uint32_t GD_DICT_BYTES = GD_DICT * 24;
@@ -319,31 +319,41 @@ constexpr uint32_t GD_DICT_BYTES = GD_DICT * 24;
 __device__ __forceinline__ uint32_t gd_hash(uint64_t x, uint32_t tag) {
     uint32_t h = (uint32_t)x * 0x9E3779B1u ^ (uint32_t)(x >> 32) * 0x85EBCA77u ^ tag * 0xC2B2AE3Du;
     h ^= h >> 15;
-    h *= 0x2C1B3C6Du;
-    h ^= h >> 13;
-    return h;
+    return (h * 0x2C1B3C6Du) >> 22;  // GD_DICT = 1024 slots
+}
+static_assert(GD_DICT == 1024, "gd_hash keeps the top 10 bits");
+
+__device__ __forceinline__ uint4 lds128_volatile(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "r"((uint32_t)__cvta_generic_to_shared(p)));
+    return r;
 }
 
-// find-or-insert; returns the slot, or -1 when the probe limit is hit (dictionary too small for this column)
-__device__ __noinline__ int gd_lookup(const GdDict d, uint64_t x, uint64_t y, uint32_t tag, uint32_t row) {
-    uint32_t s = gd_hash(x, tag) & (GD_DICT - 1);
+// find-or-insert, the general case (first-probe hits are answered inline by the caller); returns the slot, or -1 when the
+// probe limit is hit (dictionary too small for this column)
+__device__ __noinline__ int gd_lookup_slow(const GdDict d, uint32_t s, uint64_t x, uint64_t y, uint32_t tag, uint32_t row) {
     for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (GD_DICT - 1)) {
+        uint32_t* state = &d.ent[s].z;
         while (true) {
-            uint32_t st = *reinterpret_cast<volatile uint32_t*>(&d.state[s]);
+            uint32_t st = *reinterpret_cast<volatile uint32_t*>(state);
             if (st == 0u) {
-                st = atomicCAS(&d.state[s], 0u, GD_BUSY);
+                st = atomicCAS(state, 0u, GD_BUSY);
                 if (st == 0u) {  // claimed: fill, then publish the tag
-                    d.x[s] = x;
+                    d.ent[s].x = (uint32_t)x;
+                    d.ent[s].y = (uint32_t)(x >> 32);
+                    d.ent[s].w = row;
                     d.y[s] = y;
-                    d.row[s] = row;
                     __threadfence_block();
-                    atomicExch(&d.state[s], tag);
+                    atomicExch(state, tag);
                     return (int)s;
                 }
             }
             if (st == GD_BUSY) continue;  // another thread is writing the entry: look again
-            if (st == tag && *reinterpret_cast<volatile unsigned long long*>(&d.x[s]) == x &&
-                *reinterpret_cast<volatile unsigned long long*>(&d.y[s]) == y)
+            const uint4 e = lds128_volatile(&d.ent[s]);
+            if (st == tag && e.x == (uint32_t)x && e.y == (uint32_t)(x >> 32) &&
+                (tag != GD_TAG_LONG || *reinterpret_cast<volatile unsigned long long*>(&d.y[s]) == y))
                 return (int)s;
             break;  // another value lives here
         }
@@ -351,8 +361,20 @@ __device__ __noinline__ int gd_lookup(const GdDict d, uint64_t x, uint64_t y, ui
     return -1;
 }
 
-__device__ __forceinline__ int gd_sel(const int (&v)[GD_MAX_COLS], int i) {
-    return i == 0 ? v[0] : i == 1 ? v[1] : i == 2 ? v[2] : v[3];
+// find-or-insert of a packed composite key in a job's shared table [key S][tot S][nul S][row S]
+__device__ __noinline__ int gd_comp_slow(uint32_t* jb, uint32_t S, uint32_t s, uint32_t key, uint32_t row) {
+    for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (S - 1)) {
+        uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
+        if (v == 0xFFFFFFFFu) {
+            v = atomicCAS(&jb[s], 0xFFFFFFFFu, key);
+            if (v == 0xFFFFFFFFu) {
+                jb[3 * S + s] = row;  // representative row (read after the barrier only)
+                return (int)s;
+            }
+        }
+        if (v == key) return (int)s;
+    }
+    return -1;
 }
 
 __device__ __forceinline__ uint64_t upsert64(unsigned long long* keys, uint64_t mask, uint64_t k) {
@@ -364,13 +386,20 @@ __device__ __forceinline__ uint64_t upsert64(unsigned long long* keys, uint64_t 
     }
 }
 
+// A warp owns 32 * GD_ILP consecutive rows per iteration (lane l: rows l, 32 + l, ...): validity words are one broadcast
+// load per 32 rows, offsets and string bytes are read coalesced, and the GD_ILP independent rows of a lane keep that many
+// dependent load chains (offset -> bytes -> dictionary) in flight. Per row: one inline first-probe hit per distinct group
+// column (a 128-bit shared load and a compare), the local codes of the row packed 10 bits per column, one counter update
+// per COUNTED grouping (a single-column grouping that is a marginal of a composite grouping over the same target is not
+// counted per row: the CTA derives it from the composite table before folding), NULL targets counted instead of non-NULL
+// ones (they are the rare case).
 template <int NC>
 __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const __grid_constant__ GdParams P) {
     extern __shared__ __align__(16) uint8_t gd_smem[];
     // ---- clear the dictionaries and the job tables
     for (int c = 0; c < NC; ++c) {
         const GdDict d = gd_dict(gd_smem, P.cols[c].smem_off);
-        for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) d.state[s] = 0u;
+        for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) d.ent[s].z = 0u;
     }
     for (int j = 0; j < P.n_jobs; ++j) {
         const GdJob& J = P.jobs[j];
@@ -386,20 +415,23 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
         }
     }
     __syncthreads();
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     bool overflow = false;
     for (int64_t base0 = (int64_t)blockIdx.x * GD_THREADS * GD_ILP; base0 < P.n_rows; base0 += (int64_t)gridDim.x * GD_THREADS * GD_ILP) {
-        int64_t row[GD_ILP];
+        const int64_t wrow0 = base0 + (int64_t)warp * 32 * GD_ILP;  // first row of the warp (a multiple of 32)
+        if (wrow0 >= P.n_rows) continue;
+        uint32_t row[GD_ILP];  // n_rows < 2^32 (checked by the host)
         bool act[GD_ILP];
-        int slot[GD_ILP][GD_MAX_COLS];
+        uint32_t packed[GD_ILP];  // local code of column c in bits [8c .. ) — see below: 10 bits per column, <= 3 columns; the
+        uint32_t packed3[GD_ILP]; // 4th column's code apart
 #pragma unroll
         for (int k = 0; k < GD_ILP; ++k) {
-            row[k] = base0 + (int64_t)k * GD_THREADS + threadIdx.x;
-            act[k] = row[k] < P.n_rows;
-#pragma unroll
-            for (int c = 0; c < GD_MAX_COLS; ++c) slot[k][c] = -1;
+            row[k] = (uint32_t)(wrow0 + k * 32 + lane);
+            act[k] = (int64_t)row[k] < P.n_rows;
+            packed[k] = 0;
+            packed3[k] = 0;
         }
-        // ---- every distinct group column once: the loads of the GD_ILP rows go out in waves, then the dictionary probes
+        // ---- every distinct group column once
 #pragma unroll
         for (int c = 0; c < NC; ++c) {
             const GdCol& C = P.cols[c];
@@ -409,7 +441,9 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             uint32_t tag[GD_ILP];
 #pragma unroll
             for (int k = 0; k < GD_ILP; ++k) {
-                valid[k] = act[k] && row_valid(C.validity, row[k]);
+                const int64_t w = (wrow0 >> 5) + k;  // warp-uniform validity word
+                const uint32_t vw = (C.validity && w * 32 < P.n_rows) ? __ldg(C.validity + w) : 0xffffffffu;
+                valid[k] = act[k] && ((vw >> lane) & 1u);
                 y[k] = 0;
             }
             if (C.dtype == TG_UTF8) {
@@ -451,89 +485,113 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             }
 #pragma unroll
             for (int k = 0; k < GD_ILP; ++k) {
-                if (!act[k]) continue;
                 if (!valid[k]) {
                     x[k] = 0;
                     y[k] = 0;
                     tag[k] = GD_TAG_NULL;
                 }
-                const int s = gd_lookup(d, x[k], y[k], tag[k], (uint32_t)row[k]);
-                if (s < 0) overflow = true;
-                slot[k][c] = s;
-            }
-        }
-        // ---- count: per grouping, per row
-        for (int j = 0; j < P.n_jobs; ++j) {
-            const GdJob& J = P.jobs[j];
-            uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
-#pragma unroll
-            for (int k = 0; k < GD_ILP; ++k) {
-                const bool ok = act[k] && row_valid(J.target_validity, row[k]);
-                int cs = -1;  // counter slot
-                uint32_t* tot;
-                uint32_t* nn;
-                if (J.comp_slots == 0) {
-                    cs = act[k] ? gd_sel(slot[k], J.col[0]) : -1;
-                    tot = jb;
-                    nn = jb + GD_DICT;
-                } else {
-                    const uint32_t S = J.comp_slots;
-                    tot = jb + S;
-                    nn = jb + 2 * S;
-                    if (act[k]) {
-                        const int s0 = gd_sel(slot[k], J.col[0]), s1 = gd_sel(slot[k], J.col[1]);
-                        const int s2 = J.n_cols > 2 ? gd_sel(slot[k], J.col[2]) : 0;
-                        if ((s0 | s1 | s2) >= 0) {
-                            const uint32_t key = (uint32_t)s0 | ((uint32_t)s1 << 10) | ((uint32_t)s2 << 20);
-                            uint32_t h = key * 0x9E3779B1u;
-                            h ^= h >> 15;
-                            uint32_t s = h & (S - 1);
-                            for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (S - 1)) {
-                                uint32_t v = jb[s];
-                                if (v == 0xFFFFFFFFu) {
-                                    v = atomicCAS(&jb[s], 0xFFFFFFFFu, key);
-                                    if (v == 0xFFFFFFFFu) {
-                                        jb[3 * S + s] = (uint32_t)row[k];  // representative row (read after the barrier only)
-                                        v = key;
-                                    }
-                                }
-                                if (v == key) {
-                                    cs = (int)s;
-                                    break;
-                                }
-                            }
-                            if (cs < 0) overflow = true;
-                        }
+                int s = (int)gd_hash(x[k], tag[k]);
+                if (act[k]) {
+                    // hits are answered inline (linear probing at a load of <= 20 %: one or two probes); vacant or busy
+                    // entries and long strings (second hash word) go through the out-of-line find-or-insert
+                    bool hit = false;
+#pragma unroll 1
+                    for (int probe = 0; probe < GD_PROBE; ++probe) {
+                        const uint4 en = lds128_volatile(&d.ent[s]);
+                        hit = en.z == tag[k] && en.x == (uint32_t)x[k] && en.y == (uint32_t)(x[k] >> 32);
+                        if (hit || en.z == 0u || en.z == GD_BUSY) break;
+                        s = (s + 1) & (GD_DICT - 1);
+                    }
+                    if (!hit || tag[k] == GD_TAG_LONG) s = gd_lookup_slow(d, (uint32_t)s, x[k], y[k], tag[k], row[k]);
+                    if (s < 0) {
+                        overflow = true;
+                        s = 0;
                     }
                 }
+                if (c < 3) packed[k] |= (uint32_t)s << (10 * c);
+                else packed3[k] = (uint32_t)s;
+            }
+        }
+        // ---- count: per counted grouping, per row
+        for (int j = 0; j < P.n_jobs; ++j) {
+            const GdJob& J = P.jobs[j];
+            if (J.derived_from >= 0) continue;
+            uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+            const uint32_t S = J.comp_slots;
+            uint32_t* tot = S ? jb + S : jb;
+            uint32_t* nul = S ? jb + 2 * S : jb + GD_DICT;
+            const int c0 = J.col[0], c1 = J.col[1], c2 = J.col[2];
+#pragma unroll
+            for (int k = 0; k < GD_ILP; ++k) {
+                const int64_t w = (wrow0 >> 5) + k;
+                const uint32_t tw = (J.target_validity && w * 32 < P.n_rows) ? __ldg(J.target_validity + w) : 0xffffffffu;
+                const uint32_t s0 = c0 < 3 ? (packed[k] >> (10 * c0)) & 1023u : packed3[k];
+                int cs = (int)s0;
+                if (S) {
+                    const uint32_t s1 = c1 < 3 ? (packed[k] >> (10 * c1)) & 1023u : packed3[k];
+                    const uint32_t s2 = J.n_cols > 2 ? (c2 < 3 ? (packed[k] >> (10 * c2)) & 1023u : packed3[k]) : 0u;
+                    const uint32_t key = s0 | (s1 << 10) | (s2 << 20);
+                    uint32_t h = key * 0x9E3779B1u;
+                    h ^= h >> 15;
+                    uint32_t s = h & (S - 1);
+                    if (act[k]) {
+                        bool hit = false;
+#pragma unroll 1
+                        for (int probe = 0; probe < GD_PROBE; ++probe) {
+                            const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
+                            hit = v == key;
+                            if (hit || v == 0xFFFFFFFFu) break;
+                            s = (s + 1) & (S - 1);
+                        }
+                        cs = hit ? (int)s : gd_comp_slow(jb, S, s, key, row[k]);
+                        if (cs < 0) overflow = true;
+                    }
+                }
+                if (!act[k]) cs = -1;
                 // one shared atomic per distinct counter per warp (measured: plain per-lane shared atomics are 2x slower here)
                 const unsigned peers = __match_any_sync(0xffffffffu, cs);
-                const unsigned ok_peers = __ballot_sync(0xffffffffu, ok) & peers;
-                if (cs >= 0 && lane == __ffs(peers) - 1) {
-                    atomicAdd(&tot[cs], (uint32_t)__popc(peers));
-                    const int cnt = __popc(ok_peers);
-                    if (cnt) atomicAdd(&nn[cs], (uint32_t)cnt);
+                if (cs >= 0) {
+                    if (lane == __ffs(peers) - 1) atomicAdd(&tot[cs], (uint32_t)__popc(peers));
+                    if (!((tw >> lane) & 1u)) atomicAdd(&nul[cs], 1u);
                 }
             }
         }
     }
     if (overflow) atomicExch(P.overflow, 1u);
     __syncthreads();
-    // ---- publish the dictionaries: local slot -> global code (kept in d.row), representative row -> first_row
+    // ---- marginals: a derived single-column grouping gets its counters from the composite table it is a marginal of
+    for (int j = 0; j < P.n_jobs; ++j) {
+        const GdJob& J = P.jobs[j];
+        if (J.derived_from < 0) continue;
+        const GdJob& Q = P.jobs[J.derived_from];
+        const uint32_t* qb = reinterpret_cast<const uint32_t*>(gd_smem + Q.smem_off);
+        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        const uint32_t S = Q.comp_slots;
+        for (uint32_t s = threadIdx.x; s < S; s += GD_THREADS) {
+            const uint32_t key = qb[s];
+            if (key == 0xFFFFFFFFu) continue;
+            const uint32_t code = (key >> (10 * J.derived_pos)) & 1023u;
+            atomicAdd(&jb[code], qb[S + s]);
+            if (qb[2 * S + s]) atomicAdd(&jb[GD_DICT + code], qb[2 * S + s]);
+        }
+    }
+    // ---- publish the dictionaries: local slot -> global code (kept in ent.w), representative row -> first_row
     for (int c = 0; c < NC; ++c) {
         const GdCol& C = P.cols[c];
         const GdDict d = gd_dict(gd_smem, C.smem_off);
         for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
-            const uint32_t tag = d.state[s];
+            const uint4 en = d.ent[s];
+            const uint32_t tag = en.z;
             if (tag == 0u) continue;
+            const uint64_t x = (uint64_t)en.x | ((uint64_t)en.y << 32);
             Fp f{0, 0};
-            fp_combine(f, d.x[s] ^ ((uint64_t)tag << 56), d.y[s] + tag, true);
+            fp_combine(f, x ^ ((uint64_t)tag << 56), d.y[s] + tag, true);
             // exact for short values: fp_combine(first) applies two bijections, to (x ^ tag << 56) and to (y + tag); the tag's
             // bits 56.. can only meet value bits for 8-byte values, whose tag (9 / a type tag) is fixed per column
             bool created;
             const uint64_t g = upsert128(C.dict, f, created);
-            atomicMin(&C.first_row[g], (long long)d.row[s]);
-            d.row[s] = (uint32_t)g;
+            atomicMin(&C.first_row[g], (long long)en.w);
+            d.ent[s].w = (uint32_t)g;
         }
     }
     __syncthreads();
@@ -545,9 +603,9 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
                 const uint32_t t = jb[s];
                 if (!t) continue;
-                const uint32_t g = d.row[s];
+                const uint32_t g = d.ent[s].w;
                 atomicAdd(&J.totals[g], (unsigned long long)t);
-                if (jb[GD_DICT + s]) atomicAdd(&J.nonnull[g], (unsigned long long)jb[GD_DICT + s]);
+                if (t != jb[GD_DICT + s]) atomicAdd(&J.nonnull[g], (unsigned long long)(t - jb[GD_DICT + s]));
             }
         } else {
             const uint32_t S = J.comp_slots;
@@ -556,11 +614,12 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             for (uint32_t s = threadIdx.x; s < S; s += GD_THREADS) {
                 const uint32_t key = jb[s];
                 if (key == 0xFFFFFFFFu) continue;
-                uint64_t K = (uint64_t)d0.row[key & 1023u] | ((uint64_t)d1.row[(key >> 10) & 1023u] << GD_CODE_BITS);
-                if (J.n_cols > 2) K |= (uint64_t)d2.row[(key >> 20) & 1023u] << (2 * GD_CODE_BITS);
+                uint64_t K = (uint64_t)d0.ent[key & 1023u].w | ((uint64_t)d1.ent[(key >> 10) & 1023u].w << GD_CODE_BITS);
+                if (J.n_cols > 2) K |= (uint64_t)d2.ent[(key >> 20) & 1023u].w << (2 * GD_CODE_BITS);
                 const uint64_t g = upsert64(J.ckeys, J.cmask, K);
-                atomicAdd(&J.totals[g], (unsigned long long)jb[S + s]);
-                if (jb[2 * S + s]) atomicAdd(&J.nonnull[g], (unsigned long long)jb[2 * S + s]);
+                const uint32_t t = jb[S + s], nl = jb[2 * S + s];
+                atomicAdd(&J.totals[g], (unsigned long long)t);
+                if (t != nl) atomicAdd(&J.nonnull[g], (unsigned long long)(t - nl));
                 atomicMin(&J.crow[g], (long long)jb[3 * S + s]);
             }
         }
@@ -738,6 +797,23 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
             q += dcomp_b;
         }
     }
+    // marginals: a single-column grouping whose column is part of a composite grouping over the same target column is
+    // summed out of that grouping's per-CTA table instead of being counted per row
+    for (int j = 0; j < nj; ++j) {
+        P.jobs[j].derived_from = -1;
+        if (P.jobs[j].n_cols != 1 || getenv("TG_GROUPED_NO_MARGINALS")) continue;
+        for (int q2 = 0; q2 < nj && P.jobs[j].derived_from < 0; ++q2) {
+            if (P.jobs[q2].n_cols < 2 || P.jobs[q2].target_validity != P.jobs[j].target_validity ||
+                p.aggs[B.aggs[q2]].cols[0] != p.aggs[B.aggs[j]].cols[0])
+                continue;
+            for (int k = 0; k < P.jobs[q2].n_cols; ++k)
+                if (P.jobs[q2].col[k] == P.jobs[j].col[0]) {
+                    P.jobs[j].derived_from = q2;
+                    P.jobs[j].derived_pos = k;
+                    break;
+                }
+        }
+    }
     P.overflow = d_over;
     typedef void (*Kern)(const GdParams);
     const Kern kern = nc == 1 ? (Kern)group_count_dict_kernel<1> : nc == 2 ? (Kern)group_count_dict_kernel<2>
@@ -746,16 +822,11 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
     const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GD_THREADS * GD_ILP - 1) / (GD_THREADS * GD_ILP), (int64_t)e.sm_count));
     kern<<<grid, GD_THREADS, smem, e.stream>>>(P);
     TG_CUDA(cudaGetLastError());
-    unsigned int h_over = 0;
-    TG_CUDA(cudaMemcpyAsync(&h_over, d_over, 4, cudaMemcpyDeviceToHost, e.stream));
-    TG_CUDA(cudaStreamSynchronize(e.stream));
-    p.stats.launches += 1;
-    e.launches += 1;
-    if (h_over) return false;
+    // the overflow flag is read together with the group counts (ONE synchronisation): the collection kernels are cheap
+    // enough to run speculatively
     // the groups: out triples behind the tables (the generic path's out area is not used by this path)
     unsigned long long* d_cnt = (unsigned long long*)(d_over + 16);
     const int cgrid = (int)std::max<uint64_t>(1, std::min<uint64_t>((std::max(cap_d, cap_c) + 255) / 256, (uint64_t)e.sm_count * 8));
-    std::vector<unsigned long long> h_cnt((size_t)nj, 0);
     for (int j = 0; j < nj; ++j) {
         const GdJob& J = P.jobs[j];
         if (J.n_cols == 1) {
@@ -766,11 +837,14 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
         }
         TG_CUDA(cudaGetLastError());
     }
-    TG_CUDA(cudaMemcpyAsync(h_cnt.data(), d_cnt, (size_t)nj * 8, cudaMemcpyDeviceToHost, e.stream));
+    // d_over (4 bytes) and d_cnt (64 bytes behind it) come back in one pinned copy
+    unsigned long long* h_cnt = (unsigned long long*)e.host_scratch(256);
+    TG_CUDA(cudaMemcpyAsync(h_cnt, d_over, 64 + GD_MAX_JOBS * 8, cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
-    p.stats.launches += nj;
-    e.launches += nj;
-    for (int j = 0; j < nj; ++j) n_groups[j] = h_cnt[j];
+    p.stats.launches += 1 + nj;
+    e.launches += 1 + nj;
+    if (*(const unsigned int*)h_cnt) return false;
+    for (int j = 0; j < nj; ++j) n_groups[j] = h_cnt[8 + j];
     (void)out_b;
     return true;
 }
@@ -890,89 +964,151 @@ static void run_grouped_batch(Engine& e, Table& t, Plan& p, const GrpBatch& B) {
     p.stats.hash_ms += ms;
     p.stats.gpu_ms += ms;
 
+    // ---- key values of the groups, all groupings of the batch together: three waves of small kernels / copies through
+    // pinned memory and ONE synchronisation per wave, however many groupings and groups there are ----
+    struct Fetch {
+        std::vector<Column*> gcols;
+        GrpParams PK{};
+        size_t nc = 0, n_entries = 0;
+        unsigned long long ng = 0;
+        bool live = false;
+        std::vector<unsigned long long> out, meta, dst_off;
+        std::vector<uint8_t> key_bytes;
+        unsigned long long *d_meta = nullptr, *d_dst = nullptr;
+        uint8_t* d_bytes = nullptr;
+        bool own_bytes = false;
+        uint64_t total = 0;
+        size_t h_off = 0;
+    };
+    std::vector<Fetch> F((size_t)nj);
+    size_t aux_b = 0, host_b = 0;
     for (int j = 0; j < nj; ++j) {
+        Fetch& f = F[j];
         Agg& a = p.aggs[batch[j]];
-        try {
-            const unsigned long long n_groups = n_groups_v[j];
-            if (n_groups > GRP_MAX_GROUPS_DEV) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 1048576 groups");
-            // ---- key values of the groups (batched: two small kernels + two copies, however many groups) ----
-            std::vector<Column*> gcols;
-            for (int ci : job_cols[j]) gcols.push_back(dcols[ci]);
-            GrpParams PK{};  // the key kernels see the grouping's own columns, in its own order
-            PK.n_cols = (int)gcols.size();
-            PK.n_rows = n;
-            for (size_t i = 0; i < gcols.size(); ++i)
-                PK.cols[i] = GrpCol{gcols[i]->values.p, (const int32_t*)gcols[i]->offsets.p, (const uint32_t*)gcols[i]->validity.p, gcols[i]->dtype, 0u, 0u, 0u};
-            const size_t nc = gcols.size(), n_entries = (size_t)n_groups * nc;
-            std::vector<unsigned long long> out((size_t)n_groups * 3), meta(n_entries * 3), dst_off(n_entries, 0);
-            std::vector<uint8_t> key_bytes;
-            if (n_groups) {
-                TG_CUDA(cudaMemcpy(out.data(), d_out[j], out.size() * 8, cudaMemcpyDeviceToHost));
-                // meta / offsets / packed bytes live in the engine's grow-only auxiliary block (no cudaMalloc per execute)
-                unsigned long long* d_meta = (unsigned long long*)e.aux(n_entries * 3 * 8 + n_entries * 8 + 256);
-                unsigned long long* d_dst = d_meta + n_entries * 3;
-                group_keys_kernel<<<(unsigned)((n_entries + 255) / 256), 256, 0, e.stream>>>(PK, d_out[j], n_groups, d_meta);
-                TG_CUDA(cudaGetLastError());
-                TG_CUDA(cudaMemcpyAsync(meta.data(), d_meta, meta.size() * 8, cudaMemcpyDeviceToHost, e.stream));
-                TG_CUDA(cudaStreamSynchronize(e.stream));
-                uint64_t total = 0;
-                for (size_t i = 0; i < n_entries; ++i) {
-                    dst_off[i] = total;
-                    if (gcols[i % nc]->dtype == TG_UTF8 && meta[i * 3]) total += meta[i * 3 + 2];
-                }
-                key_bytes.resize((size_t)total);
-                if (total) {
-                    // the packed bytes go where d_out's copy-out already happened: the scratch block (>= max_groups * 24 bytes)
-                    uint8_t* d_bytes = total <= out_b ? (uint8_t*)d_out[j] : nullptr;
-                    const bool own = d_bytes == nullptr;
-                    if (own) TG_CUDA(cudaMalloc(&d_bytes, (size_t)total));
-                    TG_CUDA(cudaMemcpyAsync(d_dst, dst_off.data(), n_entries * 8, cudaMemcpyHostToDevice, e.stream));
-                    group_key_bytes_kernel<<<(unsigned)((n_entries * 32 + 255) / 256), 256, 0, e.stream>>>(PK, d_meta, d_dst, n_entries, d_bytes);
-                    cudaError_t ce = cudaGetLastError();
-                    if (ce == cudaSuccess) ce = cudaMemcpyAsync(key_bytes.data(), d_bytes, (size_t)total, cudaMemcpyDeviceToHost, e.stream);
-                    if (ce == cudaSuccess) ce = cudaStreamSynchronize(e.stream);
-                    if (own) cudaFree(d_bytes);
-                    TG_CUDA(ce);
-                }
-                p.stats.launches += 2;
-                e.launches += 2;
+        f.ng = n_groups_v[j];
+        if (f.ng > GRP_MAX_GROUPS_DEV) {
+            a.err = TG_ERR_UNSUPPORTED;
+            a.err_msg = "grouped completeness: more than 1048576 groups";
+            continue;
+        }
+        f.live = true;
+        for (int ci : job_cols[j]) f.gcols.push_back(dcols[ci]);
+        f.PK.n_cols = (int)f.gcols.size();  // the key kernels see the grouping's own columns, in its own order
+        f.PK.n_rows = n;
+        for (size_t i = 0; i < f.gcols.size(); ++i)
+            f.PK.cols[i] = GrpCol{f.gcols[i]->values.p, (const int32_t*)f.gcols[i]->offsets.p, (const uint32_t*)f.gcols[i]->validity.p, f.gcols[i]->dtype, 0u, 0u, 0u};
+        f.nc = f.gcols.size();
+        f.n_entries = (size_t)f.ng * f.nc;
+        f.h_off = host_b;
+        host_b += round_up((size_t)f.ng * 24 + f.n_entries * 24, 256);
+        aux_b += round_up(f.n_entries * 32, 256);
+    }
+    // wave 1: group triples + key metadata
+    if (host_b) {
+        uint8_t* d_auxp = e.aux(aux_b + 256);  // grow-only auxiliary block (no cudaMalloc per execute)
+        uint8_t* h = e.host_scratch(host_b);
+        for (int j = 0; j < nj; ++j) {
+            Fetch& f = F[j];
+            if (!f.live || !f.ng) continue;
+            f.d_meta = (unsigned long long*)d_auxp;
+            f.d_dst = f.d_meta + f.n_entries * 3;
+            d_auxp += round_up(f.n_entries * 32, 256);
+            TG_CUDA(cudaMemcpyAsync(h + f.h_off, d_out[j], (size_t)f.ng * 24, cudaMemcpyDeviceToHost, e.stream));
+            group_keys_kernel<<<(unsigned)((f.n_entries + 255) / 256), 256, 0, e.stream>>>(f.PK, d_out[j], f.ng, f.d_meta);
+            TG_CUDA(cudaGetLastError());
+            TG_CUDA(cudaMemcpyAsync(h + f.h_off + (size_t)f.ng * 24, f.d_meta, f.n_entries * 24, cudaMemcpyDeviceToHost, e.stream));
+            p.stats.launches += 1;
+            e.launches += 1;
+        }
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        for (int j = 0; j < nj; ++j) {
+            Fetch& f = F[j];
+            if (!f.live || !f.ng) continue;
+            const unsigned long long* ho = (const unsigned long long*)(h + f.h_off);
+            f.out.assign(ho, ho + (size_t)f.ng * 3);
+            f.meta.assign(ho + (size_t)f.ng * 3, ho + (size_t)f.ng * 3 + f.n_entries * 3);
+            f.dst_off.assign(f.n_entries, 0);
+            for (size_t i = 0; i < f.n_entries; ++i) {
+                f.dst_off[i] = f.total;
+                if (f.gcols[i % f.nc]->dtype == TG_UTF8 && f.meta[i * 3]) f.total += f.meta[i * 3 + 2];
             }
-            // blob: [u64 n_groups] then per group: u32 key_len, key (group column values joined by \x1f), u64 total, u64 non_null
-            a.blob.resize(8);
-            memcpy(a.blob.data(), &n_groups, 8);
-            for (unsigned long long g = 0; g < n_groups; ++g) {
-                std::string key;
-                for (size_t i = 0; i < nc; ++i) {
-                    if (i) key += '\x1f';
-                    const size_t en = (size_t)g * nc + i;
-                    if (!meta[en * 3]) {
-                        key += "NULL";
-                        continue;
-                    }
-                    const unsigned long long x = meta[en * 3 + 1];
-                    switch (gcols[i]->dtype) {
-                        case TG_UTF8: key.append((const char*)key_bytes.data() + dst_off[en], (size_t)meta[en * 3 + 2]); break;
-                        case TG_INT64: case TG_INT32: key += fmt_i64((int64_t)x); break;
-                        case TG_FLOAT64: case TG_FLOAT32: {
-                            double d;
-                            memcpy(&d, &x, 8);
-                            key += fmt_f64(d);
-                        } break;
-                        default: break;  // Boolean group values print as the empty string, as before
-                    }
-                }
-                uint32_t L = (uint32_t)key.size();
-                size_t o = a.blob.size();
-                a.blob.resize(o + 4 + L + 16);
-                memcpy(a.blob.data() + o, &L, 4);
-                memcpy(a.blob.data() + o + 4, key.data(), L);
-                memcpy(a.blob.data() + o + 4 + L, &out[g * 3 + 1], 8);
-                memcpy(a.blob.data() + o + 4 + L + 8, &out[g * 3 + 2], 8);
+        }
+        // wave 2: the Utf8 key bytes, packed per grouping where its triples were (the scratch block, >= max_groups * 24 bytes)
+        size_t hb = 0;
+        for (int j = 0; j < nj; ++j) {
+            Fetch& f = F[j];
+            if (f.total) {
+                f.h_off = hb;
+                hb += round_up(f.n_entries * 8, 256) + round_up((size_t)f.total, 256);
             }
-        } catch (Error& er) {
-            if (er.code == TG_ERR_CUDA) throw;
-            a.err = er.code;
-            a.err_msg = er.msg;
+        }
+        if (hb) {
+            h = e.host_scratch(hb);
+            cudaError_t ce = cudaSuccess;
+            for (int j = 0; j < nj && ce == cudaSuccess; ++j) {
+                Fetch& f = F[j];
+                if (!f.total) continue;
+                f.d_bytes = f.total <= out_b ? (uint8_t*)d_out[j] : nullptr;
+                f.own_bytes = f.d_bytes == nullptr;
+                if (f.own_bytes) ce = cudaMalloc(&f.d_bytes, (size_t)f.total);
+                if (ce != cudaSuccess) break;
+                memcpy(h + f.h_off, f.dst_off.data(), f.n_entries * 8);
+                ce = cudaMemcpyAsync(f.d_dst, h + f.h_off, f.n_entries * 8, cudaMemcpyHostToDevice, e.stream);
+                if (ce != cudaSuccess) break;
+                group_key_bytes_kernel<<<(unsigned)((f.n_entries * 32 + 255) / 256), 256, 0, e.stream>>>(f.PK, f.d_meta, f.d_dst, f.n_entries, f.d_bytes);
+                ce = cudaGetLastError();
+                if (ce == cudaSuccess)
+                    ce = cudaMemcpyAsync(h + f.h_off + round_up(f.n_entries * 8, 256), f.d_bytes, (size_t)f.total, cudaMemcpyDeviceToHost, e.stream);
+                p.stats.launches += 1;
+                e.launches += 1;
+            }
+            const cudaError_t se = cudaStreamSynchronize(e.stream);
+            if (ce == cudaSuccess) ce = se;
+            for (auto& f : F)
+                if (f.own_bytes && f.d_bytes) cudaFree(f.d_bytes);
+            TG_CUDA(ce);
+            for (auto& f : F)
+                if (f.total) f.key_bytes.assign(h + f.h_off + round_up(f.n_entries * 8, 256), h + f.h_off + round_up(f.n_entries * 8, 256) + f.total);
+        }
+    }
+    for (int j = 0; j < nj; ++j) {
+        Fetch& f = F[j];
+        if (!f.live) continue;
+        Agg& a = p.aggs[batch[j]];
+        const unsigned long long n_groups = f.ng;
+        const size_t nc = f.nc;
+        // blob: [u64 n_groups] then per group: u32 key_len, key (group column values joined by \x1f), u64 total, u64 non_null
+        a.blob.resize(8);
+        memcpy(a.blob.data(), &n_groups, 8);
+        std::string key;
+        for (unsigned long long g = 0; g < n_groups; ++g) {
+            key.clear();
+            for (size_t i = 0; i < nc; ++i) {
+                if (i) key += '\x1f';
+                const size_t en = (size_t)g * nc + i;
+                if (!f.meta[en * 3]) {
+                    key += "NULL";
+                    continue;
+                }
+                const unsigned long long x = f.meta[en * 3 + 1];
+                switch (f.gcols[i]->dtype) {
+                    case TG_UTF8: key.append((const char*)f.key_bytes.data() + f.dst_off[en], (size_t)f.meta[en * 3 + 2]); break;
+                    case TG_INT64: case TG_INT32: key += fmt_i64((int64_t)x); break;
+                    case TG_FLOAT64: case TG_FLOAT32: {
+                        double d;
+                        memcpy(&d, &x, 8);
+                        key += fmt_f64(d);
+                    } break;
+                    default: break;  // Boolean group values print as the empty string, as before
+                }
+            }
+            uint32_t L = (uint32_t)key.size();
+            size_t o = a.blob.size();
+            a.blob.resize(o + 4 + L + 16);
+            memcpy(a.blob.data() + o, &L, 4);
+            memcpy(a.blob.data() + o + 4, key.data(), L);
+            memcpy(a.blob.data() + o + 4 + L, &f.out[g * 3 + 1], 8);
+            memcpy(a.blob.data() + o + 4 + L + 8, &f.out[g * 3 + 2], 8);
         }
     }
 }
