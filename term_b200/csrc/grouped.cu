@@ -293,12 +293,24 @@ struct GdJob {
     long long* crow;            // composite: representative row
     uint64_t cmask;
 };
+// staging ring of the tile kernel: per stage, per column the pieces below (byte offsets inside a stage; 0xFFFFFFFF = none)
+struct GdStageCol {
+    uint32_t main_off;   // Utf8: offsets of the tile's rows (+1); fixed width: the values
+    uint32_t bytes_off;  // Utf8: the tile's string bytes, from the 16-byte boundary below its first byte
+    uint32_t bytes_cap;  // Utf8: room for them (a tile with more is read from global memory)
+    uint32_t val_off;    // validity words
+};
 struct GdParams {
     GdCol cols[GD_MAX_COLS];
     GdJob jobs[GD_MAX_JOBS];
     int32_t n_cols, n_jobs;
     int64_t n_rows;
     unsigned int* overflow;
+    // tile kernel only
+    GdStageCol st[GD_MAX_COLS];
+    uint32_t st_target[GD_MAX_JOBS];  // target validity words of job j inside a stage (shared by jobs with one target)
+    uint32_t ring_off, stage_bytes, n_stages;
+    uint32_t tv_copy_mask;            // bit j: job j is the first user of its target piece (the producer copies it once)
 };
 
 // dictionary of one column in shared memory: 16-byte entries {x.lo, x.hi, state, row} — a probe is ONE 128-bit shared
@@ -329,6 +341,12 @@ __device__ __forceinline__ uint4 lds128_volatile(const uint4* p) {
                  : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
                  : "r"((uint32_t)__cvta_generic_to_shared(p)));
     return r;
+}
+
+__device__ __noinline__ ulonglong2 gd_long_pair(const uint8_t* __restrict__ values, int32_t b, int32_t e, uint64_t w0) {
+    uint64_t hx, hy;
+    utf8_pair(values, b, e, w0, hx, hy);
+    return make_ulonglong2(hx, hy);
 }
 
 // find-or-insert, the general case (first-probe hits are answered inline by the caller); returns the slot, or -1 when the
@@ -386,6 +404,90 @@ __device__ __forceinline__ uint64_t upsert64(unsigned long long* keys, uint64_t 
     }
 }
 
+// End of a counting kernel (either variant): marginal groupings summed out of the composite tables, local dictionary
+// slots published as global codes, counters folded into the global tables. `late_zero`: the derived groupings' counters
+// alias memory the main loop used (the staging ring) and are cleared here first.
+template <int NC>
+__device__ __forceinline__ void gd_fold(const GdParams& P, uint8_t* gd_smem, bool overflow, bool late_zero) {
+    const int GDT = blockDim.x;
+    if (overflow) atomicExch(P.overflow, 1u);
+    __syncthreads();
+    if (late_zero) {
+        for (int j = 0; j < P.n_jobs; ++j) {
+            const GdJob& J = P.jobs[j];
+            if (J.derived_from < 0) continue;
+            uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+            for (int s = threadIdx.x; s < 2 * GD_DICT; s += GDT) jb[s] = 0u;
+        }
+        __syncthreads();
+    }
+    // ---- marginals: a derived single-column grouping gets its counters from the composite table it is a marginal of
+    for (int j = 0; j < P.n_jobs; ++j) {
+        const GdJob& J = P.jobs[j];
+        if (J.derived_from < 0) continue;
+        const GdJob& Q = P.jobs[J.derived_from];
+        const uint32_t* qb = reinterpret_cast<const uint32_t*>(gd_smem + Q.smem_off);
+        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        const uint32_t S = Q.comp_slots;
+        for (uint32_t s = threadIdx.x; s < S; s += GDT) {
+            const uint32_t key = qb[s];
+            if (key == 0xFFFFFFFFu) continue;
+            const uint32_t code = (key >> (10 * J.derived_pos)) & 1023u;
+            atomicAdd(&jb[code], qb[S + s]);
+            if (qb[2 * S + s]) atomicAdd(&jb[GD_DICT + code], qb[2 * S + s]);
+        }
+    }
+    // ---- publish the dictionaries: local slot -> global code (kept in ent.w), representative row -> first_row
+    for (int c = 0; c < NC; ++c) {
+        const GdCol& C = P.cols[c];
+        const GdDict d = gd_dict(gd_smem, C.smem_off);
+        for (int s = threadIdx.x; s < GD_DICT; s += GDT) {
+            const uint4 en = d.ent[s];
+            const uint32_t tag = en.z;
+            if (tag == 0u) continue;
+            const uint64_t x = (uint64_t)en.x | ((uint64_t)en.y << 32);
+            Fp f{0, 0};
+            fp_combine(f, x ^ ((uint64_t)tag << 56), d.y[s] + tag, true);
+            // exact for short values: fp_combine(first) applies two bijections, to (x ^ tag << 56) and to (y + tag); the tag's
+            // bits 56.. can only meet value bits for 8-byte values, whose tag (9 / a type tag) is fixed per column
+            bool created;
+            const uint64_t g = upsert128(C.dict, f, created);
+            atomicMin(&C.first_row[g], (long long)en.w);
+            d.ent[s].w = (uint32_t)g;
+        }
+    }
+    __syncthreads();
+    for (int j = 0; j < P.n_jobs; ++j) {
+        const GdJob& J = P.jobs[j];
+        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        if (J.comp_slots == 0) {
+            const GdDict d = gd_dict(gd_smem, P.cols[J.col[0]].smem_off);
+            for (int s = threadIdx.x; s < GD_DICT; s += GDT) {
+                const uint32_t t = jb[s];
+                if (!t || d.ent[s].z == 0u) continue;  // (a counter without an entry: rows parked at slot 0 after an overflow)
+                const uint32_t g = d.ent[s].w;
+                atomicAdd(&J.totals[g], (unsigned long long)t);
+                if (t != jb[GD_DICT + s]) atomicAdd(&J.nonnull[g], (unsigned long long)(t - jb[GD_DICT + s]));
+            }
+        } else {
+            const uint32_t S = J.comp_slots;
+            const GdDict d0 = gd_dict(gd_smem, P.cols[J.col[0]].smem_off), d1 = gd_dict(gd_smem, P.cols[J.col[1]].smem_off);
+            const GdDict d2 = gd_dict(gd_smem, P.cols[J.col[J.n_cols > 2 ? 2 : 0]].smem_off);
+            for (uint32_t s = threadIdx.x; s < S; s += GDT) {
+                const uint32_t key = jb[s];
+                if (key == 0xFFFFFFFFu) continue;
+                uint64_t K = (uint64_t)d0.ent[key & 1023u].w | ((uint64_t)d1.ent[(key >> 10) & 1023u].w << GD_CODE_BITS);
+                if (J.n_cols > 2) K |= (uint64_t)d2.ent[(key >> 20) & 1023u].w << (2 * GD_CODE_BITS);
+                const uint64_t g = upsert64(J.ckeys, J.cmask, K);
+                const uint32_t t = jb[S + s], nl = jb[2 * S + s];
+                atomicAdd(&J.totals[g], (unsigned long long)t);
+                if (t != nl) atomicAdd(&J.nonnull[g], (unsigned long long)(t - nl));
+                atomicMin(&J.crow[g], (long long)jb[3 * S + s]);
+            }
+        }
+    }
+}
+
 // A warp owns 32 * GD_ILP consecutive rows per iteration (lane l: rows l, 32 + l, ...): validity words are one broadcast
 // load per 32 rows, offsets and string bytes are read coalesced, and the GD_ILP independent rows of a lane keep that many
 // dependent load chains (offset -> bytes -> dictionary) in flight. Per row: one inline first-probe hit per distinct group
@@ -420,14 +522,16 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
     for (int64_t base0 = (int64_t)blockIdx.x * GD_THREADS * GD_ILP; base0 < P.n_rows; base0 += (int64_t)gridDim.x * GD_THREADS * GD_ILP) {
         const int64_t wrow0 = base0 + (int64_t)warp * 32 * GD_ILP;  // first row of the warp (a multiple of 32)
         if (wrow0 >= P.n_rows) continue;
+        // Rows past the end are clamped to the last row for every load (in bounds, branch-free) and dropped at the counters.
         uint32_t row[GD_ILP];  // n_rows < 2^32 (checked by the host)
-        bool act[GD_ILP];
-        uint32_t packed[GD_ILP];  // local code of column c in bits [8c .. ) — see below: 10 bits per column, <= 3 columns; the
-        uint32_t packed3[GD_ILP]; // 4th column's code apart
+        uint32_t packed[GD_ILP];   // local code of column c in bits [10c ..), c < 3;
+        uint32_t packed3[GD_ILP];  // the 4th column's code apart
+        const uint32_t last_row = (uint32_t)(P.n_rows - 1);
+        const int64_t word0 = wrow0 >> 5;                       // warp-uniform validity word of k = 0
+        const int64_t last_word = (P.n_rows - 1) >> 5;
 #pragma unroll
         for (int k = 0; k < GD_ILP; ++k) {
-            row[k] = (uint32_t)(wrow0 + k * 32 + lane);
-            act[k] = (int64_t)row[k] < P.n_rows;
+            row[k] = min((uint32_t)(wrow0 + k * 32 + lane), last_row);
             packed[k] = 0;
             packed3[k] = 0;
         }
@@ -436,43 +540,61 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
         for (int c = 0; c < NC; ++c) {
             const GdCol& C = P.cols[c];
             const GdDict d = gd_dict(gd_smem, C.smem_off);
-            bool valid[GD_ILP];
+            uint32_t vbit[GD_ILP];
             uint64_t x[GD_ILP], y[GD_ILP];
             uint32_t tag[GD_ILP];
 #pragma unroll
             for (int k = 0; k < GD_ILP; ++k) {
-                const int64_t w = (wrow0 >> 5) + k;  // warp-uniform validity word
-                const uint32_t vw = (C.validity && w * 32 < P.n_rows) ? __ldg(C.validity + w) : 0xffffffffu;
-                valid[k] = act[k] && ((vw >> lane) & 1u);
+                const uint32_t vw = C.validity ? __ldg(C.validity + min(word0 + k, last_word)) : 0xffffffffu;
+                vbit[k] = (vw >> (row[k] & 31u)) & 1u;
                 y[k] = 0;
             }
             if (C.dtype == TG_UTF8) {
-                int32_t b[GD_ILP], e[GD_ILP];
+                // branch-free for strings of at most 8 bytes: both offsets, the two aligned 8-byte words around the start (the
+                // value buffer is padded: the over-read stays in bounds), a 128-bit funnel shift and a length mask
+                int32_t b[GD_ILP], len[GD_ILP];
+                uint2 w0[GD_ILP], w1[GD_ILP];
 #pragma unroll
                 for (int k = 0; k < GD_ILP; ++k) {
-                    b[k] = valid[k] ? __ldg(C.offsets + row[k]) : 0;
-                    e[k] = valid[k] ? __ldg(C.offsets + row[k] + 1) : 0;
+                    const int32_t* op = C.offsets + row[k];
+                    b[k] = __ldg(op);
+                    len[k] = __ldg(op + 1) - b[k];
                 }
 #pragma unroll
-                for (int k = 0; k < GD_ILP; ++k) x[k] = e[k] > b[k] ? load_upto8(C.values, b[k], min(8, e[k] - b[k])) : 0ull;
+                for (int k = 0; k < GD_ILP; ++k) {
+                    const uint2* vp = reinterpret_cast<const uint2*>(C.values + ((uint32_t)b[k] & ~7u));
+                    w0[k] = __ldg(vp);
+                    w1[k] = __ldg(vp + 1);
+                }
+                bool any_long = false;
 #pragma unroll
                 for (int k = 0; k < GD_ILP; ++k) {
-                    const int32_t len = e[k] - b[k];
-                    tag[k] = (uint32_t)len + 1u;  // 1..9
-                    if (len > 8) {
-                        uint64_t hx, hy;
-                        utf8_pair(C.values, b[k], e[k], x[k], hx, hy);
-                        x[k] = hx;
-                        y[k] = hy;
-                        tag[k] = GD_TAG_LONG;
+                    const uint32_t sh = ((uint32_t)b[k] & 7u) * 8u, sl = sh & 31u;
+                    const bool up = sh >= 32u;
+                    const uint32_t A = up ? w0[k].y : w0[k].x, Bw = up ? w1[k].x : w0[k].y, Cw = up ? w1[k].y : w1[k].x;
+                    const uint32_t lo = __funnelshift_r(A, Bw, sl), hi = __funnelshift_r(Bw, Cw, sl);
+                    const uint32_t nb = (uint32_t)min(len[k], 8) * 8u;  // bits kept
+                    const uint32_t mlo = nb >= 32u ? 0xffffffffu : ((1u << nb) - 1u);
+                    const uint32_t mhi = nb >= 64u ? 0xffffffffu : (nb > 32u ? ((1u << (nb - 32u)) - 1u) : 0u);
+                    x[k] = (uint64_t)(lo & mlo) | ((uint64_t)(hi & mhi) << 32);
+                    tag[k] = (uint32_t)len[k] + 1u;  // 1..9
+                    any_long |= len[k] > 8 && vbit[k];
+                }
+                if (__any_sync(0xffffffffu, any_long)) {  // longer strings: identified by a 128-bit hash pair
+#pragma unroll
+                    for (int k = 0; k < GD_ILP; ++k) {
+                        if (len[k] > 8 && vbit[k]) {
+                            const ulonglong2 h2 = gd_long_pair(C.values, b[k], b[k] + len[k], x[k]);
+                            x[k] = h2.x;
+                            y[k] = h2.y;
+                            tag[k] = GD_TAG_LONG;
+                        }
                     }
                 }
             } else {
 #pragma unroll
                 for (int k = 0; k < GD_ILP; ++k) {
-                    x[k] = 0;
                     tag[k] = 0x10u + (uint32_t)C.dtype;
-                    if (!valid[k]) continue;
                     const int64_t r = row[k];
                     switch (C.dtype) {
                         case TG_INT64: x[k] = __ldg(reinterpret_cast<const unsigned long long*>(C.values) + r); break;
@@ -485,28 +607,26 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             }
 #pragma unroll
             for (int k = 0; k < GD_ILP; ++k) {
-                if (!valid[k]) {
+                if (!vbit[k]) {
                     x[k] = 0;
                     y[k] = 0;
                     tag[k] = GD_TAG_NULL;
                 }
                 int s = (int)gd_hash(x[k], tag[k]);
-                if (act[k]) {
-                    // hits are answered inline (linear probing at a load of <= 20 %: one or two probes); vacant or busy
-                    // entries and long strings (second hash word) go through the out-of-line find-or-insert
-                    bool hit = false;
+                // hits are answered inline (linear probing at a load of <= 20 %: one or two probes); vacant or busy entries
+                // and long strings (second hash word) go through the out-of-line find-or-insert
+                bool hit = false;
 #pragma unroll 1
-                    for (int probe = 0; probe < GD_PROBE; ++probe) {
-                        const uint4 en = lds128_volatile(&d.ent[s]);
-                        hit = en.z == tag[k] && en.x == (uint32_t)x[k] && en.y == (uint32_t)(x[k] >> 32);
-                        if (hit || en.z == 0u || en.z == GD_BUSY) break;
-                        s = (s + 1) & (GD_DICT - 1);
-                    }
-                    if (!hit || tag[k] == GD_TAG_LONG) s = gd_lookup_slow(d, (uint32_t)s, x[k], y[k], tag[k], row[k]);
-                    if (s < 0) {
-                        overflow = true;
-                        s = 0;
-                    }
+                for (int probe = 0; probe < GD_PROBE; ++probe) {
+                    const uint4 en = lds128_volatile(&d.ent[s]);
+                    hit = en.z == tag[k] && en.x == (uint32_t)x[k] && en.y == (uint32_t)(x[k] >> 32);
+                    if (hit || en.z == 0u || en.z == GD_BUSY) break;
+                    s = (s + 1) & (GD_DICT - 1);
+                }
+                if (!hit || tag[k] == GD_TAG_LONG) s = gd_lookup_slow(d, (uint32_t)s, x[k], y[k], tag[k], row[k]);
+                if (s < 0) {
+                    overflow = true;
+                    s = 0;
                 }
                 if (c < 3) packed[k] |= (uint32_t)s << (10 * c);
                 else packed3[k] = (uint32_t)s;
@@ -523,8 +643,7 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             const int c0 = J.col[0], c1 = J.col[1], c2 = J.col[2];
 #pragma unroll
             for (int k = 0; k < GD_ILP; ++k) {
-                const int64_t w = (wrow0 >> 5) + k;
-                const uint32_t tw = (J.target_validity && w * 32 < P.n_rows) ? __ldg(J.target_validity + w) : 0xffffffffu;
+                const uint32_t tw = J.target_validity ? __ldg(J.target_validity + min(word0 + k, last_word)) : 0xffffffffu;
                 const uint32_t s0 = c0 < 3 ? (packed[k] >> (10 * c0)) & 1023u : packed3[k];
                 int cs = (int)s0;
                 if (S) {
@@ -534,20 +653,18 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
                     uint32_t h = key * 0x9E3779B1u;
                     h ^= h >> 15;
                     uint32_t s = h & (S - 1);
-                    if (act[k]) {
-                        bool hit = false;
+                    bool hit = false;
 #pragma unroll 1
-                        for (int probe = 0; probe < GD_PROBE; ++probe) {
-                            const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
-                            hit = v == key;
-                            if (hit || v == 0xFFFFFFFFu) break;
-                            s = (s + 1) & (S - 1);
-                        }
-                        cs = hit ? (int)s : gd_comp_slow(jb, S, s, key, row[k]);
-                        if (cs < 0) overflow = true;
+                    for (int probe = 0; probe < GD_PROBE; ++probe) {
+                        const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
+                        hit = v == key;
+                        if (hit || v == 0xFFFFFFFFu) break;
+                        s = (s + 1) & (S - 1);
                     }
+                    cs = hit ? (int)s : gd_comp_slow(jb, S, s, key, row[k]);
+                    if (cs < 0) overflow = true;
                 }
-                if (!act[k]) cs = -1;
+                if (wrow0 + k * 32 + lane >= P.n_rows) cs = -1;  // a clamped row past the end
                 // one shared atomic per distinct counter per warp (measured: plain per-lane shared atomics are 2x slower here)
                 const unsigned peers = __match_any_sync(0xffffffffu, cs);
                 if (cs >= 0) {
@@ -557,73 +674,261 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
             }
         }
     }
-    if (overflow) atomicExch(P.overflow, 1u);
-    __syncthreads();
-    // ---- marginals: a derived single-column grouping gets its counters from the composite table it is a marginal of
-    for (int j = 0; j < P.n_jobs; ++j) {
-        const GdJob& J = P.jobs[j];
-        if (J.derived_from < 0) continue;
-        const GdJob& Q = P.jobs[J.derived_from];
-        const uint32_t* qb = reinterpret_cast<const uint32_t*>(gd_smem + Q.smem_off);
-        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
-        const uint32_t S = Q.comp_slots;
-        for (uint32_t s = threadIdx.x; s < S; s += GD_THREADS) {
-            const uint32_t key = qb[s];
-            if (key == 0xFFFFFFFFu) continue;
-            const uint32_t code = (key >> (10 * J.derived_pos)) & 1023u;
-            atomicAdd(&jb[code], qb[S + s]);
-            if (qb[2 * S + s]) atomicAdd(&jb[GD_DICT + code], qb[2 * S + s]);
-        }
-    }
-    // ---- publish the dictionaries: local slot -> global code (kept in ent.w), representative row -> first_row
+    gd_fold<NC>(P, gd_smem, overflow, false);
+}
+
+// =====================================================================================================================
+// Tile variant of the dictionary kernel (the one that normally runs): a producer warp stages every tile of GT_ROWS rows —
+// offsets, the tile's string bytes, fixed-width values, validity words of the group columns and of the targets — in a
+// shared-memory ring with TMA bulk copies (cp.async.bulk + mbarrier complete_tx), 24 consumer warps take one row per
+// lane from shared memory. A row's dependent chain offset -> bytes -> dictionary runs at shared-memory latency, nothing
+// is unrolled (small code, no register pressure), and every byte crosses HBM -> SM once. CTAs own contiguous tile
+// ranges so a tile's last offset is the next tile's first; the producer fetches 32 tile boundaries per round trip.
+// =====================================================================================================================
+constexpr int GT_CONSUMER_WARPS = 24, GT_THREADS = (GT_CONSUMER_WARPS + 1) * 32, GT_ROWS = GT_CONSUMER_WARPS * 32;
+constexpr int GT_MAX_STAGES = 4;
+
+template <int NC>
+__global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const __grid_constant__ GdParams P) {
+    extern __shared__ __align__(16) uint8_t gd_smem[];
+    __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
+    __shared__ uint32_t s_byte_base[GT_MAX_STAGES][GD_MAX_COLS];  // absolute byte offset staged at bytes_off; 0xFFFFFFFF: not staged
     for (int c = 0; c < NC; ++c) {
-        const GdCol& C = P.cols[c];
-        const GdDict d = gd_dict(gd_smem, C.smem_off);
-        for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
-            const uint4 en = d.ent[s];
-            const uint32_t tag = en.z;
-            if (tag == 0u) continue;
-            const uint64_t x = (uint64_t)en.x | ((uint64_t)en.y << 32);
-            Fp f{0, 0};
-            fp_combine(f, x ^ ((uint64_t)tag << 56), d.y[s] + tag, true);
-            // exact for short values: fp_combine(first) applies two bijections, to (x ^ tag << 56) and to (y + tag); the tag's
-            // bits 56.. can only meet value bits for 8-byte values, whose tag (9 / a type tag) is fixed per column
-            bool created;
-            const uint64_t g = upsert128(C.dict, f, created);
-            atomicMin(&C.first_row[g], (long long)en.w);
-            d.ent[s].w = (uint32_t)g;
-        }
+        const GdDict d = gd_dict(gd_smem, P.cols[c].smem_off);
+        for (int s = threadIdx.x; s < GD_DICT; s += GT_THREADS) d.ent[s].z = 0u;
     }
-    __syncthreads();
     for (int j = 0; j < P.n_jobs; ++j) {
         const GdJob& J = P.jobs[j];
-        uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+        if (J.derived_from >= 0) continue;  // cleared by the fold (their counters alias the ring)
+        uint32_t* base = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
         if (J.comp_slots == 0) {
-            const GdDict d = gd_dict(gd_smem, P.cols[J.col[0]].smem_off);
-            for (int s = threadIdx.x; s < GD_DICT; s += GD_THREADS) {
-                const uint32_t t = jb[s];
-                if (!t) continue;
-                const uint32_t g = d.ent[s].w;
-                atomicAdd(&J.totals[g], (unsigned long long)t);
-                if (t != jb[GD_DICT + s]) atomicAdd(&J.nonnull[g], (unsigned long long)(t - jb[GD_DICT + s]));
-            }
+            for (int s = threadIdx.x; s < 2 * GD_DICT; s += GT_THREADS) base[s] = 0u;
         } else {
-            const uint32_t S = J.comp_slots;
-            const GdDict d0 = gd_dict(gd_smem, P.cols[J.col[0]].smem_off), d1 = gd_dict(gd_smem, P.cols[J.col[1]].smem_off);
-            const GdDict d2 = gd_dict(gd_smem, P.cols[J.col[J.n_cols > 2 ? 2 : 0]].smem_off);
-            for (uint32_t s = threadIdx.x; s < S; s += GD_THREADS) {
-                const uint32_t key = jb[s];
-                if (key == 0xFFFFFFFFu) continue;
-                uint64_t K = (uint64_t)d0.ent[key & 1023u].w | ((uint64_t)d1.ent[(key >> 10) & 1023u].w << GD_CODE_BITS);
-                if (J.n_cols > 2) K |= (uint64_t)d2.ent[(key >> 20) & 1023u].w << (2 * GD_CODE_BITS);
-                const uint64_t g = upsert64(J.ckeys, J.cmask, K);
-                const uint32_t t = jb[S + s], nl = jb[2 * S + s];
-                atomicAdd(&J.totals[g], (unsigned long long)t);
-                if (t != nl) atomicAdd(&J.nonnull[g], (unsigned long long)(t - nl));
-                atomicMin(&J.crow[g], (long long)jb[3 * S + s]);
+            for (uint32_t s = threadIdx.x; s < J.comp_slots; s += GT_THREADS) {
+                base[s] = 0xFFFFFFFFu;
+                base[J.comp_slots + s] = 0u;
+                base[2 * J.comp_slots + s] = 0u;
             }
         }
     }
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < P.n_stages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], GT_CONSUMER_WARPS);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n_tiles = (P.n_rows + GT_ROWS - 1) / GT_ROWS;
+    const int64_t t_begin = n_tiles * blockIdx.x / gridDim.x, t_end = n_tiles * (blockIdx.x + 1) / gridDim.x;
+    uint8_t* ring = gd_smem + P.ring_off;
+    bool overflow = false;
+    if (warp == GT_CONSUMER_WARPS) {
+        // ---------------- producer ----------------
+        int32_t b0[NC], bnd[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            b0[c] = 0;
+            if (P.cols[c].dtype == TG_UTF8 && t_begin < t_end) b0[c] = __ldg(P.cols[c].offsets + t_begin * GT_ROWS);
+        }
+        uint32_t s = 0, ph = 0;
+        for (int64_t tb = t_begin; tb < t_end; tb += 32) {
+            // lane l: the end boundary of tile tb + l
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                bnd[c] = 0;
+                if (P.cols[c].dtype == TG_UTF8) {
+                    const int64_t r1 = min((tb + lane + 1) * (int64_t)GT_ROWS, P.n_rows);
+                    bnd[c] = __ldg(P.cols[c].offsets + r1);
+                }
+            }
+            const int n_here = (int)min((int64_t)32, t_end - tb);
+            for (int i = 0; i < n_here; ++i) {
+                const int64_t t = tb + i, r0 = t * GT_ROWS;
+                const uint32_t rows = (uint32_t)min((int64_t)GT_ROWS, P.n_rows - r0);
+                int32_t b1[NC];
+#pragma unroll
+                for (int c = 0; c < NC; ++c) b1[c] = __shfl_sync(0xffffffffu, bnd[c], i);
+                if (lane == 0) {
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    uint8_t* stage = ring + (size_t)s * P.stage_bytes;
+                    const uint32_t vbytes = ((rows + 7) / 8 + 15) & ~15u;
+                    uint32_t total = 0;
+                    // sizes first (expect_tx precedes the copies)
+                    uint32_t src_lo[NC], nbytes[NC];
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const GdCol& C = P.cols[c];
+                        if (C.validity) total += vbytes;
+                        src_lo[c] = 0;
+                        nbytes[c] = 0;
+                        if (C.dtype == TG_UTF8) {
+                            total += ((rows + 1) * 4 + 15) & ~15u;
+                            src_lo[c] = (uint32_t)b0[c] & ~15u;
+                            nbytes[c] = (((uint32_t)b1[c] + 15u) & ~15u) - src_lo[c];
+                            if (nbytes[c] > P.st[c].bytes_cap) nbytes[c] = 0;  // does not fit: consumers read global memory
+                            s_byte_base[s][c] = nbytes[c] ? src_lo[c] : 0xFFFFFFFFu;
+                            total += nbytes[c];
+                        } else {
+                            nbytes[c] = C.dtype == TG_BOOL ? vbytes : C.dtype == TG_INT32 || C.dtype == TG_FLOAT32 ? (rows * 4 + 15) & ~15u : (rows * 8 + 15) & ~15u;
+                            total += nbytes[c];
+                        }
+                    }
+                    for (int j = 0; j < P.n_jobs; ++j)
+                        if ((P.tv_copy_mask >> j) & 1u) total += vbytes;
+                    mbar_arrive_expect_tx(&full[s], total);
+#pragma unroll
+                    for (int c = 0; c < NC; ++c) {
+                        const GdCol& C = P.cols[c];
+                        if (C.validity) bulk_g2s(stage + P.st[c].val_off, reinterpret_cast<const uint8_t*>(C.validity) + r0 / 8, vbytes, &full[s]);
+                        if (C.dtype == TG_UTF8) {
+                            bulk_g2s(stage + P.st[c].main_off, C.offsets + r0, ((rows + 1) * 4 + 15) & ~15u, &full[s]);
+                            if (nbytes[c]) bulk_g2s(stage + P.st[c].bytes_off, C.values + src_lo[c], nbytes[c], &full[s]);
+                        } else {
+                            const uint8_t* src = C.dtype == TG_BOOL ? C.values + r0 / 8
+                                                 : C.dtype == TG_INT32 || C.dtype == TG_FLOAT32 ? C.values + r0 * 4 : C.values + r0 * 8;
+                            bulk_g2s(stage + P.st[c].main_off, src, nbytes[c], &full[s]);
+                        }
+                    }
+                    for (int j = 0; j < P.n_jobs; ++j)
+                        if ((P.tv_copy_mask >> j) & 1u)
+                            bulk_g2s(stage + P.st_target[j], reinterpret_cast<const uint8_t*>(P.jobs[j].target_validity) + r0 / 8, vbytes, &full[s]);
+                }
+#pragma unroll
+                for (int c = 0; c < NC; ++c) b0[c] = b1[c];
+                if (++s == P.n_stages) {
+                    s = 0;
+                    ph ^= 1u;
+                }
+            }
+        }
+    } else {
+        // ---------------- consumers: one row per lane per tile ----------------
+        uint32_t s = 0, ph = 0;
+        const uint32_t rt0 = (uint32_t)warp * 32u + (uint32_t)lane;
+        for (int64_t t = t_begin; t < t_end; ++t) {
+            const int64_t r0 = t * GT_ROWS;
+            const uint32_t rows = (uint32_t)min((int64_t)GT_ROWS, P.n_rows - r0);
+            const uint32_t rt = min(rt0, rows - 1u);  // rows past the end: clamped for the loads, dropped at the counters
+            const uint32_t row = (uint32_t)r0 + rt;
+            mbar_wait(&full[s], ph);
+            const uint8_t* stage = ring + (size_t)s * P.stage_bytes;
+            uint32_t packed = 0, packed3 = 0;
+#pragma unroll
+            for (int c = 0; c < NC; ++c) {
+                const GdCol& C = P.cols[c];
+                const GdDict d = gd_dict(gd_smem, C.smem_off);
+                uint32_t vbit = 1u;
+                if (C.validity) vbit = (reinterpret_cast<const uint32_t*>(stage + P.st[c].val_off)[rt >> 5] >> (rt & 31u)) & 1u;
+                uint64_t x, y = 0;
+                uint32_t tag;
+                if (C.dtype == TG_UTF8) {
+                    const int32_t* so = reinterpret_cast<const int32_t*>(stage + P.st[c].main_off) + rt;
+                    const int32_t b = so[0], len = so[1] - b;
+                    const uint32_t base = s_byte_base[s][c];
+                    if (base != 0xFFFFFFFFu) {
+                        // the two aligned 8-byte words around the start, a 128-bit funnel shift, a length mask
+                        const uint32_t pb = (uint32_t)b - base;
+                        const uint2* vp = reinterpret_cast<const uint2*>(stage + P.st[c].bytes_off + (pb & ~7u));
+                        const uint2 w0 = vp[0], w1 = vp[1];
+                        const uint32_t sh = (pb & 7u) * 8u, sl = sh & 31u;
+                        const bool up = sh >= 32u;
+                        const uint32_t A = up ? w0.y : w0.x, Bw = up ? w1.x : w0.y, Cw = up ? w1.y : w1.x;
+                        const uint32_t lo = __funnelshift_r(A, Bw, sl), hi = __funnelshift_r(Bw, Cw, sl);
+                        const uint32_t nb = (uint32_t)min(len, 8) * 8u;  // bits kept
+                        const uint32_t mlo = nb >= 32u ? 0xffffffffu : ((1u << nb) - 1u);
+                        const uint32_t mhi = nb >= 64u ? 0xffffffffu : (nb > 32u ? ((1u << (nb - 32u)) - 1u) : 0u);
+                        x = (uint64_t)(lo & mlo) | ((uint64_t)(hi & mhi) << 32);
+                    } else {
+                        x = len > 0 ? load_upto8(C.values, b, min(8, len)) : 0ull;
+                    }
+                    tag = (uint32_t)len + 1u;  // 1..9
+                    if (len > 8 && vbit) {  // longer strings: identified by a 128-bit hash pair
+                        const ulonglong2 h2 = gd_long_pair(C.values, b, b + len, x);
+                        x = h2.x;
+                        y = h2.y;
+                        tag = GD_TAG_LONG;
+                    }
+                } else {
+                    tag = 0x10u + (uint32_t)C.dtype;
+                    const uint8_t* sv = stage + P.st[c].main_off;
+                    switch (C.dtype) {
+                        case TG_INT64: x = reinterpret_cast<const unsigned long long*>(sv)[rt]; break;
+                        case TG_FLOAT64: x = canon_f64(reinterpret_cast<const unsigned long long*>(sv)[rt]); break;
+                        case TG_INT32: x = (uint64_t)(int64_t) reinterpret_cast<const int32_t*>(sv)[rt]; break;
+                        case TG_FLOAT32: x = canon_f64((uint64_t)__double_as_longlong((double)reinterpret_cast<const float*>(sv)[rt])); break;
+                        default: x = (reinterpret_cast<const uint32_t*>(sv)[rt >> 5] >> (rt & 31u)) & 1u; break;  // TG_BOOL
+                    }
+                }
+                if (!vbit) {
+                    x = 0;
+                    y = 0;
+                    tag = GD_TAG_NULL;
+                }
+                int sl2 = (int)gd_hash(x, tag);
+                bool hit = false;
+#pragma unroll 1
+                for (int probe = 0; probe < GD_PROBE; ++probe) {
+                    const uint4 en = lds128_volatile(&d.ent[sl2]);
+                    hit = en.z == tag && en.x == (uint32_t)x && en.y == (uint32_t)(x >> 32);
+                    if (hit || en.z == 0u || en.z == GD_BUSY) break;
+                    sl2 = (sl2 + 1) & (GD_DICT - 1);
+                }
+                if (!hit || tag == GD_TAG_LONG) sl2 = gd_lookup_slow(d, (uint32_t)sl2, x, y, tag, row);
+                if (sl2 < 0) {
+                    overflow = true;
+                    sl2 = 0;
+                }
+                if (c < 3) packed |= (uint32_t)sl2 << (10 * c);
+                else packed3 = (uint32_t)sl2;
+            }
+            for (int j = 0; j < P.n_jobs; ++j) {
+                const GdJob& J = P.jobs[j];
+                if (J.derived_from >= 0) continue;
+                uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
+                const uint32_t S = J.comp_slots;
+                uint32_t* tot = S ? jb + S : jb;
+                uint32_t* nul = S ? jb + 2 * S : jb + GD_DICT;
+                const int c0 = J.col[0], c1 = J.col[1], c2 = J.col[2];
+                uint32_t tbit = 1u;
+                if (P.st_target[j] != 0xFFFFFFFFu) tbit = (reinterpret_cast<const uint32_t*>(stage + P.st_target[j])[rt >> 5] >> (rt & 31u)) & 1u;
+                const uint32_t s0 = c0 < 3 ? (packed >> (10 * c0)) & 1023u : packed3;
+                int cs = (int)s0;
+                if (S) {
+                    const uint32_t s1 = c1 < 3 ? (packed >> (10 * c1)) & 1023u : packed3;
+                    const uint32_t s2 = J.n_cols > 2 ? (c2 < 3 ? (packed >> (10 * c2)) & 1023u : packed3) : 0u;
+                    const uint32_t key = s0 | (s1 << 10) | (s2 << 20);
+                    uint32_t h = key * 0x9E3779B1u;
+                    h ^= h >> 15;
+                    uint32_t sq = h & (S - 1);
+                    bool hit = false;
+#pragma unroll 1
+                    for (int probe = 0; probe < GD_PROBE; ++probe) {
+                        const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[sq]);
+                        hit = v == key;
+                        if (hit || v == 0xFFFFFFFFu) break;
+                        sq = (sq + 1) & (S - 1);
+                    }
+                    cs = hit ? (int)sq : gd_comp_slow(jb, S, sq, key, row);
+                    if (cs < 0) overflow = true;
+                }
+                if (rt0 >= rows) cs = -1;  // a clamped row past the end
+                const unsigned peers = __match_any_sync(0xffffffffu, cs);
+                if (cs >= 0) {
+                    if (lane == __ffs(peers) - 1) atomicAdd(&tot[cs], (uint32_t)__popc(peers));
+                    if (!tbit) atomicAdd(&nul[cs], 1u);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+            if (++s == P.n_stages) {
+                s = 0;
+                ph ^= 1u;
+            }
+        }
+    }
+    gd_fold<NC>(P, gd_smem, overflow, true);
 }
 
 // groups of a single-column grouping: the column's global dictionary slots; of a composite grouping: its key table
@@ -719,43 +1024,144 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
                                std::vector<unsigned long long>& n_groups) {
     const int64_t n = t.n_rows;
     const int nj = (int)B.aggs.size(), nc = (int)B.dcols.size();
-    if (nc > GD_MAX_COLS || nj > GD_MAX_JOBS || n >= ((int64_t)1 << 32)) return false;
+    if (nc > GD_MAX_COLS || nj > GD_MAX_JOBS || n >= ((int64_t)1 << 31) || n <= 0) return false;
     int n_comp = 0;
     for (auto& jc : B.job_cols) {
         if (jc.size() > 3) return false;
         n_comp += jc.size() > 1;
     }
     if (getenv("TG_GROUPED_NO_DICT")) return false;
-    // shared memory: dictionaries, single-column counters, the rest split between the composite tables
-    size_t off = 0;
     GdParams P{};
     P.n_cols = nc;
     P.n_jobs = nj;
     P.n_rows = n;
-    for (int c = 0; c < nc; ++c) {
-        P.cols[c].smem_off = (uint32_t)off;
-        off += GD_DICT_BYTES;
+    for (int j = 0; j < nj; ++j) {
+        GdJob& J = P.jobs[j];
+        J.target_validity = (const uint32_t*)t.find(p.aggs[B.aggs[j]].cols[0])->validity.p;
+        J.n_cols = (int)B.job_cols[j].size();
+        for (int k = 0; k < J.n_cols; ++k) J.col[k] = B.job_cols[j][k];
+        J.derived_from = -1;
     }
-    for (int j = 0; j < nj; ++j)
-        if (B.job_cols[j].size() == 1) {
-            P.jobs[j].smem_off = (uint32_t)off;
-            off += (size_t)GD_DICT * 8;
+    // marginals: a single-column grouping whose column is part of a composite grouping over the same target column is
+    // summed out of that grouping's per-CTA table instead of being counted per row
+    int n_derived = 0;
+    for (int j = 0; j < nj; ++j) {
+        if (P.jobs[j].n_cols != 1 || getenv("TG_GROUPED_NO_MARGINALS")) continue;
+        for (int q2 = 0; q2 < nj && P.jobs[j].derived_from < 0; ++q2) {
+            if (P.jobs[q2].n_cols < 2 || p.aggs[B.aggs[q2]].cols[0] != p.aggs[B.aggs[j]].cols[0]) continue;
+            for (int k = 0; k < P.jobs[q2].n_cols; ++k)
+                if (P.jobs[q2].col[k] == P.jobs[j].col[0]) {
+                    P.jobs[j].derived_from = q2;
+                    P.jobs[j].derived_pos = k;
+                    ++n_derived;
+                    break;
+                }
         }
+    }
+    // ---- shared memory. Persistent part: dictionaries, counters of the counted single-column groupings, composite tables.
     const size_t budget = 222 * 1024;
-    if (off > budget) return false;
-    uint32_t comp_slots = 0;
-    if (n_comp) {
-        comp_slots = 8192;
-        while (comp_slots > 256 && off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
-        if (off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) return false;
-    }
-    for (int j = 0; j < nj; ++j)
-        if (B.job_cols[j].size() > 1) {
-            P.jobs[j].smem_off = (uint32_t)off;
-            P.jobs[j].comp_slots = comp_slots;
-            off += (size_t)comp_slots * 16;
+    size_t stage_b = 0;
+    uint32_t tv_off[GD_MAX_JOBS];
+    {
+        // one stage of the tile kernel's ring
+        const size_t vb = round_up((size_t)(GT_ROWS + 7) / 8, 16);
+        for (int c = 0; c < nc; ++c) {
+            Column* col = B.dcols[c];
+            GdStageCol& S = P.st[c];
+            S.main_off = S.bytes_off = S.val_off = 0xFFFFFFFFu;
+            S.bytes_cap = 0;
+            if (col->validity.p) {
+                S.val_off = (uint32_t)stage_b;
+                stage_b += vb;
+            }
+            S.main_off = (uint32_t)stage_b;
+            if (col->dtype == TG_UTF8) {
+                stage_b += round_up((size_t)(GT_ROWS + 1) * 4, 16);
+                // room for 1.5x the average tile plus slack (a tile with more bytes is read from global memory)
+                const double avg = (double)col->value_bytes / (double)n;
+                S.bytes_cap = (uint32_t)round_up((size_t)std::min(std::max(avg * GT_ROWS * 1.5 + 512.0, 2048.0), 24576.0), 16);
+                S.bytes_off = (uint32_t)stage_b;
+                stage_b += S.bytes_cap + 16;  // the funnel shift over-reads up to 16 bytes
+            } else {
+                stage_b += round_up((size_t)GT_ROWS * 8, 16);
+            }
         }
-    const size_t smem = off;
+        for (int j = 0; j < nj; ++j) {
+            tv_off[j] = 0xFFFFFFFFu;
+            if (!P.jobs[j].target_validity) continue;
+            for (int q2 = 0; q2 < j; ++q2)
+                if (P.jobs[q2].target_validity == P.jobs[j].target_validity) tv_off[j] = tv_off[q2];
+            if (tv_off[j] == 0xFFFFFFFFu) {
+                tv_off[j] = (uint32_t)stage_b;
+                stage_b += vb;
+            }
+        }
+    }
+    bool tile = !getenv("TG_GROUPED_NO_TILE");
+    uint32_t comp_slots = 0;
+    size_t smem = 0;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        size_t off = 0;
+        for (int c = 0; c < nc; ++c) {
+            P.cols[c].smem_off = (uint32_t)off;
+            off += GD_DICT_BYTES;
+        }
+        for (int j = 0; j < nj; ++j)
+            if (P.jobs[j].n_cols == 1 && !(tile && P.jobs[j].derived_from >= 0)) {
+                P.jobs[j].smem_off = (uint32_t)off;
+                off += (size_t)GD_DICT * 8;
+            }
+        // the tile kernel keeps >= 2 stages of its ring (which also hosts the derived groupings' counters at the end)
+        const size_t ring_min = tile ? std::max(2 * stage_b, (size_t)n_derived * GD_DICT * 8) : 0;
+        if (off + ring_min > budget) {
+            if (tile) {
+                tile = false;
+                continue;
+            }
+            return false;
+        }
+        comp_slots = 0;
+        if (n_comp) {
+            comp_slots = 8192;
+            while (comp_slots > 2048 && off + ring_min + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
+            if (off + ring_min + (size_t)comp_slots * 16 * (size_t)n_comp > budget) {
+                if (tile) {
+                    tile = false;
+                    continue;
+                }
+                while (comp_slots > 256 && off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
+                if (off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) return false;
+            }
+        }
+        for (int j = 0; j < nj; ++j)
+            if (P.jobs[j].n_cols > 1) {
+                P.jobs[j].smem_off = (uint32_t)off;
+                P.jobs[j].comp_slots = comp_slots;
+                off += (size_t)comp_slots * 16;
+            }
+        if (tile) {
+            P.ring_off = (uint32_t)off;
+            P.stage_bytes = (uint32_t)stage_b;
+            P.n_stages = (uint32_t)std::min<size_t>(GT_MAX_STAGES, (budget - off) / stage_b);
+            size_t ring_b = (size_t)P.n_stages * stage_b, dq = 0;
+            for (int j = 0; j < nj; ++j)
+                if (P.jobs[j].n_cols == 1 && P.jobs[j].derived_from >= 0) {
+                    P.jobs[j].smem_off = (uint32_t)(off + dq);
+                    dq += (size_t)GD_DICT * 8;
+                }
+            ring_b = std::max(ring_b, dq);
+            off += ring_b;
+            for (int j = 0; j < nj; ++j) P.st_target[j] = tv_off[j];
+            P.tv_copy_mask = 0;
+            for (int j = 0; j < nj; ++j) {
+                bool first = tv_off[j] != 0xFFFFFFFFu;
+                for (int q2 = 0; q2 < j; ++q2) first = first && tv_off[q2] != tv_off[j];
+                if (first) P.tv_copy_mask |= 1u << j;
+            }
+        }
+        smem = off;
+        break;
+    }
     // global state (the caller sized the scratch block with grouped_dict_bytes)
     const uint64_t cap_d = gd_cap_dict(n), cap_c = gd_cap_comp(n);
     const size_t dcol_b = cap_d * 8 * 3, dsingle_b = cap_d * 8 * 2, dcomp_b = cap_c * 8 * 4;
@@ -777,9 +1183,6 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
     }
     for (int j = 0; j < nj; ++j) {
         GdJob& J = P.jobs[j];
-        J.target_validity = (const uint32_t*)t.find(p.aggs[B.aggs[j]].cols[0])->validity.p;
-        J.n_cols = (int)B.job_cols[j].size();
-        for (int k = 0; k < J.n_cols; ++k) J.col[k] = B.job_cols[j][k];
         if (J.n_cols == 1) {
             J.totals = (unsigned long long*)q;
             J.nonnull = (unsigned long long*)(q + cap_d * 8);
@@ -797,30 +1200,22 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
             q += dcomp_b;
         }
     }
-    // marginals: a single-column grouping whose column is part of a composite grouping over the same target column is
-    // summed out of that grouping's per-CTA table instead of being counted per row
-    for (int j = 0; j < nj; ++j) {
-        P.jobs[j].derived_from = -1;
-        if (P.jobs[j].n_cols != 1 || getenv("TG_GROUPED_NO_MARGINALS")) continue;
-        for (int q2 = 0; q2 < nj && P.jobs[j].derived_from < 0; ++q2) {
-            if (P.jobs[q2].n_cols < 2 || P.jobs[q2].target_validity != P.jobs[j].target_validity ||
-                p.aggs[B.aggs[q2]].cols[0] != p.aggs[B.aggs[j]].cols[0])
-                continue;
-            for (int k = 0; k < P.jobs[q2].n_cols; ++k)
-                if (P.jobs[q2].col[k] == P.jobs[j].col[0]) {
-                    P.jobs[j].derived_from = q2;
-                    P.jobs[j].derived_pos = k;
-                    break;
-                }
-        }
-    }
     P.overflow = d_over;
     typedef void (*Kern)(const GdParams);
-    const Kern kern = nc == 1 ? (Kern)group_count_dict_kernel<1> : nc == 2 ? (Kern)group_count_dict_kernel<2>
-                      : nc == 3 ? (Kern)group_count_dict_kernel<3> : (Kern)group_count_dict_kernel<4>;
-    TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
-    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GD_THREADS * GD_ILP - 1) / (GD_THREADS * GD_ILP), (int64_t)e.sm_count));
-    kern<<<grid, GD_THREADS, smem, e.stream>>>(P);
+    if (tile) {
+        const Kern kern = nc == 1 ? (Kern)group_count_tile_kernel<1> : nc == 2 ? (Kern)group_count_tile_kernel<2>
+                          : nc == 3 ? (Kern)group_count_tile_kernel<3> : (Kern)group_count_tile_kernel<4>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+        const int64_t n_tiles = (n + GT_ROWS - 1) / GT_ROWS;
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)e.sm_count));
+        kern<<<grid, GT_THREADS, smem, e.stream>>>(P);
+    } else {
+        const Kern kern = nc == 1 ? (Kern)group_count_dict_kernel<1> : nc == 2 ? (Kern)group_count_dict_kernel<2>
+                          : nc == 3 ? (Kern)group_count_dict_kernel<3> : (Kern)group_count_dict_kernel<4>;
+        TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((n + GD_THREADS * GD_ILP - 1) / (GD_THREADS * GD_ILP), (int64_t)e.sm_count));
+        kern<<<grid, GD_THREADS, smem, e.stream>>>(P);
+    }
     TG_CUDA(cudaGetLastError());
     // the overflow flag is read together with the group counts (ONE synchronisation): the collection kernels are cheap
     // enough to run speculatively
@@ -945,6 +1340,12 @@ static void run_grouped_batch(Engine& e, Table& t, Plan& p, const GrpBatch& B) {
                 p.stats.bytes_scanned += (uint64_t)(n + 7) / 8;
             }
         }
+    }
+    if (n == 0) {  // an empty shard: no groups
+        for (int id : batch) {
+            p.aggs[id].blob.assign(8, 0);
+        }
+        return;
     }
     const uint64_t cap = pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, GRP_MAX_GROUPS_DEV * 4));
     const size_t h_b = cap * 8, out_b = round_up((size_t)GRP_MAX_GROUPS_DEV * 24, 256);

@@ -889,9 +889,13 @@ void grouped_blob_compact(std::vector<uint8_t>& b) {
         uint32_t len;
         uint64_t total, nn;
     };
-    std::unordered_map<std::string, size_t> idx;
-    idx.reserve((size_t)n * 2);
+    // open-addressing index over the entries (FNV-1a of the key bytes): no per-entry allocation — a state read costs
+    // microseconds even with thousands of groups
+    size_t cap = 16;
+    while (cap < (size_t)n * 2) cap <<= 1;
+    std::vector<uint32_t> slot(cap, 0xFFFFFFFFu);
     std::vector<Ent> ents;
+    ents.reserve((size_t)n);
     const uint8_t* p = b.data() + 8;
     bool dup = false;
     for (uint64_t i = 0; i < n; ++i) {
@@ -901,12 +905,23 @@ void grouped_blob_compact(std::vector<uint8_t>& b) {
         uint64_t t, nn;
         memcpy(&t, p + L, 8);
         memcpy(&nn, p + L + 8, 8);
-        auto ins = idx.emplace(std::string((const char*)p, L), ents.size());
-        if (ins.second) ents.push_back(Ent{p, L, t, nn});
-        else {
-            ents[ins.first->second].total += t;
-            ents[ins.first->second].nn += nn;
-            dup = true;
+        uint64_t h = 0xcbf29ce484222325ull;
+        for (uint32_t k = 0; k < L; ++k) h = (h ^ p[k]) * 0x100000001b3ull;
+        size_t q = (size_t)(h ^ (h >> 29)) & (cap - 1);
+        while (true) {
+            const uint32_t at = slot[q];
+            if (at == 0xFFFFFFFFu) {
+                slot[q] = (uint32_t)ents.size();
+                ents.push_back(Ent{p, L, t, nn});
+                break;
+            }
+            if (ents[at].len == L && memcmp(ents[at].key, p, L) == 0) {
+                ents[at].total += t;
+                ents[at].nn += nn;
+                dup = true;
+                break;
+            }
+            q = (q + 1) & (cap - 1);
         }
         p += L + 16;
     }
@@ -914,6 +929,7 @@ void grouped_blob_compact(std::vector<uint8_t>& b) {
     std::vector<uint8_t> out(8);
     const uint64_t m = ents.size();
     memcpy(out.data(), &m, 8);
+    out.reserve(b.size());
     for (auto& e : ents) {
         const size_t o = out.size();
         out.resize(o + 4 + e.len + 16);
@@ -1775,8 +1791,10 @@ static void finalize_grouped(Plan& p, Slot& s) {
     // groups sorted by completeness DESC, LIMIT max_groups+1 (grouped_completeness.rs:131-139), then the
     // first max_groups kept; overall = sum over the kept groups (:191-194)
     struct G {
-        std::string key;
+        const uint8_t* key;
+        uint32_t len;
         uint64_t total, nn;
+        double ratio;
     };
     std::vector<G> gs;
     std::vector<uint8_t> state = a.blob;
@@ -1784,35 +1802,39 @@ static void finalize_grouped(Plan& p, Slot& s) {
     if (state.size() >= 8) {
         uint64_t n;
         memcpy(&n, state.data(), 8);
+        gs.reserve((size_t)n);
         const uint8_t* q = state.data() + 8;
         for (uint64_t i = 0; i < n; ++i) {
             uint32_t L;
             memcpy(&L, q, 4);
             q += 4;
             G g;
-            g.key.assign((const char*)q, L);
+            g.key = q;
+            g.len = L;
             q += L;
             memcpy(&g.total, q, 8);
             memcpy(&g.nn, q + 8, 8);
+            g.ratio = (double)g.nn * 1.0 / (double)g.total;
             q += 16;
             gs.push_back(g);
         }
     }
     std::stable_sort(gs.begin(), gs.end(), [](const G& x, const G& y) {
-        double cx = (double)x.nn * 1.0 / (double)x.total, cy = (double)y.nn * 1.0 / (double)y.total;
-        if (cx != cy) return cx > cy;
-        return x.key < y.key;
+        if (x.ratio != y.ratio) return x.ratio > y.ratio;
+        const int c = memcmp(x.key, y.key, std::min(x.len, y.len));  // std::string's order: unsigned bytes, then length
+        return c != 0 ? c < 0 : x.len < y.len;
     });
     const size_t total_groups = gs.size();
     const bool truncated = gs.size() > (size_t)s.max_groups;
     if (truncated) gs.resize(s.max_groups);
     uint64_t ot = 0, on = 0;
     r.metric_kind = 2;
+    s.map.reserve(gs.size() + 3);
     for (auto& g : gs) {
-        std::string k = g.key;
+        std::string k((const char*)g.key, g.len);
         for (auto& ch : k)
             if (ch == '\x1f') ch = '_';  // GroupedMetrics::to_metric_value joins key parts with '_' (grouped.rs:135-156)
-        s.map.emplace_back(k, g.total == 0 ? 1.0 : (double)g.nn / (double)g.total);
+        s.map.emplace_back(std::move(k), g.total == 0 ? 1.0 : (double)g.nn / (double)g.total);
         ot += g.total;
         on += g.nn;
     }
