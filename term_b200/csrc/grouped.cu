@@ -267,6 +267,7 @@ constexpr int GD_DICT = 1024;       // dictionary slots per column per CTA (10-b
 constexpr int GD_MAX_COLS = 4, GD_MAX_JOBS = 4;
 constexpr int GD_PROBE = 16;
 constexpr int GD_CODE_BITS = 21;    // global dictionary slots per column <= 2^21: three codes fit one 64-bit composite key
+constexpr size_t GD_CTA_ROWS_BYTES = (size_t)256 * 8192 * 4;  // per composite grouping: up to 256 CTAs x 8192 slots x 4 bytes
 constexpr uint32_t GD_TAG_NULL = 0x40u, GD_TAG_LONG = 0x80u, GD_BUSY = 0xFFFFFFFFu;
 
 struct GdCol {
@@ -282,7 +283,7 @@ struct GdJob {
     const uint32_t* target_validity;
     int32_t n_cols;
     int32_t col[3];
-    uint32_t smem_off;       // single-column: counters [tot GD_DICT][nn GD_DICT]; composite: [key S][tot S][nn S][row S]
+    uint32_t smem_off;       // single-column: counters [tot GD_DICT][nul GD_DICT]; composite: [key S][tot S][nul S]
     uint32_t comp_slots;     // composite: S (power of two); single-column: 0
     int32_t derived_from;    // >= 0: this single-column grouping is a marginal of that composite job (same target): not
     int32_t derived_pos;     // counted per row; its column's code sits at bits [10 * derived_pos ..) of the composite key
@@ -291,6 +292,7 @@ struct GdJob {
     unsigned long long* nonnull;
     unsigned long long* ckeys;  // composite keys (EMPTY64 = vacant)
     long long* crow;            // composite: representative row
+    uint32_t* cta_rows;         // composite: [CTA][comp_slots] representative row of the CTA's table entry (kept out of shared memory)
     uint64_t cmask;
 };
 // staging ring of the tile kernel: per stage, per column the pieces below (byte offsets inside a stage; 0xFFFFFFFF = none)
@@ -379,14 +381,14 @@ __device__ __noinline__ int gd_lookup_slow(const GdDict d, uint32_t s, uint64_t 
     return -1;
 }
 
-// find-or-insert of a packed composite key in a job's shared table [key S][tot S][nul S][row S]
-__device__ __noinline__ int gd_comp_slow(uint32_t* jb, uint32_t S, uint32_t s, uint32_t key, uint32_t row) {
+// find-or-insert of a packed composite key in a job's shared table [key S][tot S][nul S] (+ the entry's row in global memory)
+__device__ __noinline__ int gd_comp_slow(uint32_t* jb, uint32_t* cta_rows, uint32_t S, uint32_t s, uint32_t key, uint32_t row) {
     for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (S - 1)) {
         uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
         if (v == 0xFFFFFFFFu) {
             v = atomicCAS(&jb[s], 0xFFFFFFFFu, key);
             if (v == 0xFFFFFFFFu) {
-                jb[3 * S + s] = row;  // representative row (read after the barrier only)
+                cta_rows[s] = row;  // representative row, the CTA's own slice (read by this CTA after a barrier only)
                 return (int)s;
             }
         }
@@ -482,7 +484,7 @@ __device__ __forceinline__ void gd_fold(const GdParams& P, uint8_t* gd_smem, boo
                 const uint32_t t = jb[S + s], nl = jb[2 * S + s];
                 atomicAdd(&J.totals[g], (unsigned long long)t);
                 if (t != nl) atomicAdd(&J.nonnull[g], (unsigned long long)(t - nl));
-                atomicMin(&J.crow[g], (long long)jb[3 * S + s]);
+                atomicMin(&J.crow[g], (long long)J.cta_rows[(size_t)blockIdx.x * S + s]);
             }
         }
     }
@@ -661,7 +663,7 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
                         if (hit || v == 0xFFFFFFFFu) break;
                         s = (s + 1) & (S - 1);
                     }
-                    cs = hit ? (int)s : gd_comp_slow(jb, S, s, key, row[k]);
+                    cs = hit ? (int)s : gd_comp_slow(jb, J.cta_rows + (size_t)blockIdx.x * S, S, s, key, row[k]);
                     if (cs < 0) overflow = true;
                 }
                 if (wrow0 + k * 32 + lane >= P.n_rows) cs = -1;  // a clamped row past the end
@@ -805,6 +807,20 @@ __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const _
         }
     } else {
         // ---------------- consumers: one row per lane per tile ----------------
+        // the counted groupings' descriptors live in registers (the loops over them are unrolled): table address, slots,
+        // where the codes of their columns sit in `packed` (a two-column grouping reads its third code from bits 30..: 0)
+        uint32_t j_tab[GD_MAX_JOBS], j_slots[GD_MAX_JOBS], j_shifts[GD_MAX_JOBS], j_tv[GD_MAX_JOBS];
+        uint32_t* j_rows[GD_MAX_JOBS];
+#pragma unroll
+        for (int j = 0; j < GD_MAX_JOBS; ++j) {
+            const GdJob& J = P.jobs[j];
+            const bool counted = j < P.n_jobs && J.derived_from < 0;
+            j_tab[j] = counted ? smem_u32(gd_smem + J.smem_off) : 0u;
+            j_slots[j] = J.comp_slots;
+            j_shifts[j] = (uint32_t)(10 * J.col[0]) | ((uint32_t)(10 * J.col[1]) << 8) | ((uint32_t)(J.n_cols > 2 ? 10 * J.col[2] : 30) << 16);
+            j_tv[j] = P.st_target[j];
+            j_rows[j] = J.cta_rows + (size_t)blockIdx.x * J.comp_slots;
+        }
         uint32_t s = 0, ph = 0;
         const uint32_t rt0 = (uint32_t)warp * 32u + (uint32_t)lane;
         for (int64_t t = t_begin; t < t_end; ++t) {
@@ -814,7 +830,7 @@ __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const _
             const uint32_t row = (uint32_t)r0 + rt;
             mbar_wait(&full[s], ph);
             const uint8_t* stage = ring + (size_t)s * P.stage_bytes;
-            uint32_t packed = 0, packed3 = 0;
+            uint32_t packed = 0;  // local code of column c in bits [10c ..) (NC <= 3)
 #pragma unroll
             for (int c = 0; c < NC; ++c) {
                 const GdCol& C = P.cols[c];
@@ -880,44 +896,43 @@ __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const _
                     overflow = true;
                     sl2 = 0;
                 }
-                if (c < 3) packed |= (uint32_t)sl2 << (10 * c);
-                else packed3 = (uint32_t)sl2;
+                packed |= (uint32_t)sl2 << (10 * c);
             }
-            for (int j = 0; j < P.n_jobs; ++j) {
-                const GdJob& J = P.jobs[j];
-                if (J.derived_from >= 0) continue;
-                uint32_t* jb = reinterpret_cast<uint32_t*>(gd_smem + J.smem_off);
-                const uint32_t S = J.comp_slots;
-                uint32_t* tot = S ? jb + S : jb;
-                uint32_t* nul = S ? jb + 2 * S : jb + GD_DICT;
-                const int c0 = J.col[0], c1 = J.col[1], c2 = J.col[2];
+#pragma unroll
+            for (int j = 0; j < GD_MAX_JOBS; ++j) {
+                if (j_tab[j] == 0u) continue;  // absent or derived (warp-uniform)
+                const uint32_t S = j_slots[j];
                 uint32_t tbit = 1u;
-                if (P.st_target[j] != 0xFFFFFFFFu) tbit = (reinterpret_cast<const uint32_t*>(stage + P.st_target[j])[rt >> 5] >> (rt & 31u)) & 1u;
-                const uint32_t s0 = c0 < 3 ? (packed >> (10 * c0)) & 1023u : packed3;
-                int cs = (int)s0;
+                if (j_tv[j] != 0xFFFFFFFFu) tbit = (reinterpret_cast<const uint32_t*>(stage + j_tv[j])[rt >> 5] >> (rt & 31u)) & 1u;
+                int cs = (int)((packed >> (j_shifts[j] & 255u)) & 1023u);
+                uint32_t tot_a = j_tab[j], nul_a = j_tab[j] + GD_DICT * 4;  // shared-window addresses of the counters
                 if (S) {
-                    const uint32_t s1 = c1 < 3 ? (packed >> (10 * c1)) & 1023u : packed3;
-                    const uint32_t s2 = J.n_cols > 2 ? (c2 < 3 ? (packed >> (10 * c2)) & 1023u : packed3) : 0u;
-                    const uint32_t key = s0 | (s1 << 10) | (s2 << 20);
+                    const uint32_t key = (uint32_t)cs | (((packed >> ((j_shifts[j] >> 8) & 255u)) & 1023u) << 10) |
+                                         (((packed >> (j_shifts[j] >> 16)) & 1023u) << 20);
                     uint32_t h = key * 0x9E3779B1u;
                     h ^= h >> 15;
                     uint32_t sq = h & (S - 1);
                     bool hit = false;
 #pragma unroll 1
                     for (int probe = 0; probe < GD_PROBE; ++probe) {
-                        const uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[sq]);
+                        uint32_t v;
+                        asm volatile("ld.volatile.shared.u32 %0, [%1];" : "=r"(v) : "r"(j_tab[j] + sq * 4u));
                         hit = v == key;
                         if (hit || v == 0xFFFFFFFFu) break;
                         sq = (sq + 1) & (S - 1);
                     }
-                    cs = hit ? (int)sq : gd_comp_slow(jb, S, sq, key, row);
+                    cs = hit ? (int)sq : gd_comp_slow(reinterpret_cast<uint32_t*>(gd_smem + P.jobs[j].smem_off), j_rows[j], S, sq, key, row);
                     if (cs < 0) overflow = true;
+                    tot_a = j_tab[j] + S * 4u;
+                    nul_a = j_tab[j] + S * 8u;
                 }
                 if (rt0 >= rows) cs = -1;  // a clamped row past the end
+                // one shared atomic per distinct counter per warp (measured: plain per-lane shared atomics are 2x slower here)
                 const unsigned peers = __match_any_sync(0xffffffffu, cs);
                 if (cs >= 0) {
-                    if (lane == __ffs(peers) - 1) atomicAdd(&tot[cs], (uint32_t)__popc(peers));
-                    if (!tbit) atomicAdd(&nul[cs], 1u);
+                    if (lane == __ffs(peers) - 1)
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tot_a + (uint32_t)cs * 4u), "r"((uint32_t)__popc(peers)) : "memory");
+                    if (!tbit) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(nul_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
                 }
             }
             __syncwarp();
@@ -1014,7 +1029,7 @@ static uint64_t gd_cap_dict(int64_t n) { return pow2_at_least(std::min<uint64_t>
 static uint64_t gd_cap_comp(int64_t n) { return pow2_at_least(std::min<uint64_t>((uint64_t)n * 2, (uint64_t)1 << 22)); }
 static size_t grouped_dict_bytes(int64_t n, const GrpBatch& B) {
     size_t need = 256 + B.dcols.size() * gd_cap_dict(n) * 24;
-    for (auto& jc : B.job_cols) need += jc.size() == 1 ? gd_cap_dict(n) * 16 : gd_cap_comp(n) * 32;
+    for (auto& jc : B.job_cols) need += jc.size() == 1 ? gd_cap_dict(n) * 16 : gd_cap_comp(n) * 32 + (size_t)GD_CTA_ROWS_BYTES;
     return need;
 }
 
@@ -1097,7 +1112,7 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
             }
         }
     }
-    bool tile = !getenv("TG_GROUPED_NO_TILE");
+    bool tile = nc <= 3 && !getenv("TG_GROUPED_NO_TILE");
     uint32_t comp_slots = 0;
     size_t smem = 0;
     for (int attempt = 0; attempt < 2; ++attempt) {
@@ -1112,7 +1127,7 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
                 off += (size_t)GD_DICT * 8;
             }
         // the tile kernel keeps >= 2 stages of its ring (which also hosts the derived groupings' counters at the end)
-        const size_t ring_min = tile ? std::max(2 * stage_b, (size_t)n_derived * GD_DICT * 8) : 0;
+        const size_t ring_min = tile ? std::max(3 * stage_b, (size_t)n_derived * GD_DICT * 8) : 0;
         if (off + ring_min > budget) {
             if (tile) {
                 tile = false;
@@ -1123,21 +1138,21 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
         comp_slots = 0;
         if (n_comp) {
             comp_slots = 8192;
-            while (comp_slots > 2048 && off + ring_min + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
-            if (off + ring_min + (size_t)comp_slots * 16 * (size_t)n_comp > budget) {
+            while (comp_slots > 2048 && off + ring_min + (size_t)comp_slots * 12 * (size_t)n_comp > budget) comp_slots >>= 1;
+            if (off + ring_min + (size_t)comp_slots * 12 * (size_t)n_comp > budget) {
                 if (tile) {
                     tile = false;
                     continue;
                 }
-                while (comp_slots > 256 && off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) comp_slots >>= 1;
-                if (off + (size_t)comp_slots * 16 * (size_t)n_comp > budget) return false;
+                while (comp_slots > 256 && off + (size_t)comp_slots * 12 * (size_t)n_comp > budget) comp_slots >>= 1;
+                if (off + (size_t)comp_slots * 12 * (size_t)n_comp > budget) return false;
             }
         }
         for (int j = 0; j < nj; ++j)
             if (P.jobs[j].n_cols > 1) {
                 P.jobs[j].smem_off = (uint32_t)off;
                 P.jobs[j].comp_slots = comp_slots;
-                off += (size_t)comp_slots * 16;
+                off += (size_t)comp_slots * 12;
             }
         if (tile) {
             P.ring_off = (uint32_t)off;
@@ -1193,18 +1208,18 @@ static bool grouped_count_dict(Engine& e, Table& t, Plan& p, const GrpBatch& B, 
             J.totals = (unsigned long long*)(q + cap_c * 8);
             J.nonnull = (unsigned long long*)(q + cap_c * 16);
             J.crow = (long long*)(q + cap_c * 24);
+            J.cta_rows = (uint32_t*)(q + dcomp_b);
             J.cmask = cap_c - 1;
             TG_CUDA(cudaMemsetAsync(q, 0xFF, cap_c * 8, e.stream));
             TG_CUDA(cudaMemsetAsync(q + cap_c * 8, 0, cap_c * 16, e.stream));
             TG_CUDA(cudaMemsetAsync(q + cap_c * 24, 0x7F, cap_c * 8, e.stream));
-            q += dcomp_b;
+            q += dcomp_b + GD_CTA_ROWS_BYTES;
         }
     }
     P.overflow = d_over;
     typedef void (*Kern)(const GdParams);
     if (tile) {
-        const Kern kern = nc == 1 ? (Kern)group_count_tile_kernel<1> : nc == 2 ? (Kern)group_count_tile_kernel<2>
-                          : nc == 3 ? (Kern)group_count_tile_kernel<3> : (Kern)group_count_tile_kernel<4>;
+        const Kern kern = nc == 1 ? (Kern)group_count_tile_kernel<1> : nc == 2 ? (Kern)group_count_tile_kernel<2> : (Kern)group_count_tile_kernel<3>;
         TG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));  // per device
         const int64_t n_tiles = (n + GT_ROWS - 1) / GT_ROWS;
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(n_tiles, (int64_t)e.sm_count));

@@ -50,6 +50,11 @@ __device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, u
         : "memory");
 }
 
+// Bulk prefetch of a global range into L2 (no destination, no completion to wait for). 16-byte aligned, multiple of 16.
+__device__ __forceinline__ void l2_prefetch(const void* gmem_src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
+
 // Streaming (read-once) 128-bit global load that does not allocate in L1.
 __device__ __forceinline__ uint4 ld_stream_u4(const void* p) {
     uint4 r;
