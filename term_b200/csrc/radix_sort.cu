@@ -34,9 +34,12 @@ constexpr int RSH_THREADS = 512;
 
 // One read of the keys, all digit positions at once. A digit that is the same across the warp (the sign / exponent
 // bytes of a numeric column, the high bytes of small integers) costs ONE shared atomic instead of a 32-way conflict.
+template <bool QUANT>
 __global__ void __launch_bounds__(RSH_THREADS) rs_hist_kernel(const uint64_t* __restrict__ keys, int64_t n, int begin_bit, int n_passes,
-                                                              unsigned long long* __restrict__ hist) {
+                                                              unsigned long long* __restrict__ hist, const RsQuant* __restrict__ quant) {
     __shared__ uint32_t s_hist[RS_MAX_PASSES][RS_BINS];
+    RsQuant Q{};
+    if constexpr (QUANT) Q = *quant;
     for (int i = threadIdx.x; i < RS_MAX_PASSES * RS_BINS; i += RSH_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
     const int lane = threadIdx.x & 31;
@@ -47,9 +50,10 @@ __global__ void __launch_bounds__(RSH_THREADS) rs_hist_kernel(const uint64_t* __
         for (int64_t r0 = c0 + (int64_t)(threadIdx.x & ~31); r0 < c1; r0 += RSH_THREADS) {
             const int64_t r = r0 + lane;
             const bool in = r < c1;
-            const uint64_t k = in ? __ldg(keys + r) : 0ull;
+            uint64_t k = in ? __ldg(keys + r) : 0ull;
             const unsigned live = __ballot_sync(0xffffffffu, in);
             if (!in) continue;
+            if constexpr (QUANT) k = rs_quant(Q, k);
             const int leader = __ffs(live) - 1;
             for (int p = 0; p < n_passes; ++p) {
                 const uint32_t d = (uint32_t)(k >> (begin_bit + p * RS_RADIX_BITS)) & (RS_BINS - 1);
@@ -75,7 +79,7 @@ __global__ void __launch_bounds__(RSH_THREADS) rs_hist_kernel(const uint64_t* __
 
 // hist -> exclusive bin bases per pass; trivial passes; ping-pong parity
 __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const unsigned long long* __restrict__ hist, unsigned long long* __restrict__ base,
-                                                          int64_t n, int n_passes, RsControl* ctl) {
+                                                          int64_t n, int n_passes, RsControl* ctl, uint32_t quantised) {
     __shared__ unsigned long long s_warp[RS_BINS / 32];
     __shared__ uint32_t s_trivial[RS_MAX_PASSES];
     const int d = threadIdx.x, lane = d & 31, w = d >> 5;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(RS_BINS) rs_scan_kernel(const unsigned long lo
         __syncthreads();
     }
     if (d == 0) {
+        ctl->quantised = quantised;
         uint32_t cur = 0, first = (uint32_t)n_passes;
         for (int p = 0; p < n_passes; ++p) {
             ctl->skip[p] = s_trivial[p];
@@ -131,10 +136,10 @@ struct RsSmem {
 enum : uint32_t { RS_FLAG_AGG = 1u, RS_FLAG_PREFIX = 2u };
 constexpr int RS_LOOKBACK_BATCH = 4;  // predecessor status words fetched speculatively per look-back round trip
 
-template <typename V, bool HAS_V, bool IOTA>
+template <typename V, bool HAS_V, bool IOTA, bool QUANT>
 __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_pass_kernel(uint64_t* k0, uint64_t* k1, V* v0, V* v1, int64_t n, int shift, int pass,
                                                                             RsControl* ctl, const unsigned long long* __restrict__ bin_base,
-                                                                            uint32_t* status) {
+                                                                            uint32_t* status, const RsQuant* __restrict__ quant) {
     extern __shared__ __align__(16) uint8_t rs_smem_raw[];
     RsSmem& S = *reinterpret_cast<RsSmem*>(rs_smem_raw);
     if (ctl->skip[pass]) return;
@@ -157,16 +162,31 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_pass_kernel(uint
     // Positions past the end are padded with the maximum key: they rank behind every real key of bin 255.
     uint64_t key[RS_ITEMS];
     uint32_t rank[RS_ITEMS];
+    uint32_t dg[(RS_ITEMS + 3) / 4];  // the items' digits, computed once, four to a register
     const int wbase = warp * 32 * RS_ITEMS + lane;
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const int pos = wbase + i * 32;
         key[i] = pos < n_tile ? ksrc[tile_base + pos] : ~0ull;
     }
+    {
+        RsQuant Q{};
+        if constexpr (QUANT) Q = *quant;
+#pragma unroll
+        for (int i = 0; i < (RS_ITEMS + 3) / 4; ++i) dg[i] = 0;
+#pragma unroll
+        for (int i = 0; i < RS_ITEMS; ++i) {
+            uint32_t d;
+            if constexpr (QUANT) d = wbase + i * 32 < n_tile ? (rs_quant(Q, key[i]) >> shift) & (RS_BINS - 1) : (uint32_t)(RS_BINS - 1);
+            else d = (uint32_t)(key[i] >> shift) & (RS_BINS - 1);
+            dg[i >> 2] |= d << (8 * (i & 3));
+        }
+    }
+#define RS_DIGIT(i) ((dg[(i) >> 2] >> (8 * ((i)&3))) & 255u)
     // ---- the tile's digit counts first (plain shared atomics, no ordering needed): the aggregate the successors' look-back
     // waits for is published before the expensive stable ranking starts
 #pragma unroll
-    for (int i = 0; i < RS_ITEMS; ++i) atomicAdd(&S.block_hist[(uint32_t)(key[i] >> shift) & (RS_BINS - 1)], 1u);
+    for (int i = 0; i < RS_ITEMS; ++i) atomicAdd(&S.block_hist[RS_DIGIT(i)], 1u);
     __syncthreads();
     uint32_t tile_count = 0, real_count = 0;
     volatile uint32_t* st = status + (size_t)tile * RS_BINS + tid;
@@ -193,7 +213,7 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_pass_kernel(uint
     const unsigned lt_mask = (1u << lane) - 1u;
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t d = (uint32_t)(key[i] >> shift) & (RS_BINS - 1);
+        const uint32_t d = RS_DIGIT(i);
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t pre = 0;
@@ -246,16 +266,22 @@ __global__ void __launch_bounds__(RS_THREADS, RS_MIN_BLOCKS) rs_pass_kernel(uint
     // ---- reorder the tile in shared memory (tile-sorted order), then every bin's run is written contiguously
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
-        const uint32_t d = (uint32_t)(key[i] >> shift) & (RS_BINS - 1);
+        const uint32_t d = RS_DIGIT(i);
         const uint32_t p = S.digit_start[d] + S.hist[warp][d] + rank[i];
         rank[i] = p;
         S.stage[p] = key[i];
+        if constexpr (QUANT) S.dig[p] = (uint8_t)d;  // (plain sorts read the digit back from the staged key)
     }
+#undef RS_DIGIT
     __syncthreads();
     for (int j = tid; j < n_tile; j += RS_THREADS) {
         const uint64_t k = S.stage[j];
-        const uint32_t d = (uint32_t)(k >> shift) & (RS_BINS - 1);
-        if constexpr (HAS_V) S.dig[j] = (uint8_t)d;
+        uint32_t d;
+        if constexpr (QUANT) d = S.dig[j];
+        else {
+            d = (uint32_t)(k >> shift) & (RS_BINS - 1);
+            if constexpr (HAS_V) S.dig[j] = (uint8_t)d;
+        }
         kdst[S.global_base[d] + j] = k;
     }
     if constexpr (HAS_V) {
@@ -281,9 +307,45 @@ __global__ void rs_iota_if_unsorted_kernel(V* vals, int64_t n, const RsControl* 
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) vals[i] = (V)i;
 }
 
+__global__ void rs_quant_setup_kernel(const unsigned long long* __restrict__ minmax, int is_i64, RsQuant* q) {
+    const uint64_t kmin = minmax[0], kmax = minmax[1];
+    RsQuant r{};
+    r.mode = 0;
+    r.kmin = kmin;
+    if (kmax >= kmin) {
+        if (is_i64) {
+            const uint64_t range = kmax - kmin;
+            const int bits = 64 - __clzll((long long)range);  // 0 when range == 0
+            r.mode = 1;
+            r.shift = bits > 32 ? (uint32_t)(bits - 32) : 0u;
+        } else {
+            auto value = [](uint64_t k) {
+                const uint64_t bits = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+                return __longlong_as_double((long long)bits);
+            };
+            const double lo = value(kmin), hi = value(kmax), range = hi - lo;
+            // NaN / infinite ends or an overflowing range: the raw prefix (mode 0) and, most likely, the full-sort fallback
+            if (isfinite(lo) && isfinite(hi) && isfinite(range)) {
+                r.mode = 2;
+                r.xmin = lo;
+                r.scale = range > 0.0 ? 4294967295.0 / range : 0.0;
+                if (!isfinite(r.scale)) r.scale = 0.0;
+            }
+        }
+    }
+    *q = r;
+}
+void rs_quant_setup(cudaStream_t stream, const unsigned long long* minmax, int is_i64, RsQuant* q) {
+    rs_quant_setup_kernel<<<1, 1, 0, stream>>>(minmax, is_i64, q);
+}
+
 template <typename V>
 int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2], int64_t n, int begin_bit, int n_passes,
-                  bool iota_values, const RsTemp& T, int sm_count) {
+                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant) {
+    if (quant) {
+        begin_bit = 0;
+        n_passes = 4;
+    }
     if (n_passes > RS_MAX_PASSES) n_passes = RS_MAX_PASSES;
     const int64_t tiles = rs_tiles(n);
     cudaMemsetAsync(T.ctl, 0, sizeof(RsControl), stream);
@@ -291,31 +353,30 @@ int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2]
     if (n <= 0 || n_passes <= 0) return 0;
     cudaMemsetAsync(T.status, 0, T.status_words_per_pass * 4 * (size_t)n_passes, stream);
     const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + ((int64_t)1 << 16) - 1) >> 16, (int64_t)sm_count * 4));
-    rs_hist_kernel<<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist);
-    rs_scan_kernel<<<1, RS_BINS, 0, stream>>>(T.hist, T.base, n, n_passes, T.ctl);
+    if (quant) rs_hist_kernel<true><<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist, quant);
+    else rs_hist_kernel<false><<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist, nullptr);
+    rs_scan_kernel<<<1, RS_BINS, 0, stream>>>(T.hist, T.base, n, n_passes, T.ctl, quant ? 1u : 0u);
     const bool has_v = vals[0] != nullptr || vals[1] != nullptr;
-    using K = void (*)(uint64_t*, uint64_t*, V*, V*, int64_t, int, int, RsControl*, const unsigned long long*, uint32_t*);
+    using K = void (*)(uint64_t*, uint64_t*, V*, V*, int64_t, int, int, RsControl*, const unsigned long long*, uint32_t*, const RsQuant*);
     K kern;
-    size_t smem;
-    kern = rs_pass_kernel<V, false, false>;
-    smem = sizeof(RsSmem);
+    const size_t smem = sizeof(RsSmem);
+    if (quant) kern = !has_v ? (K)rs_pass_kernel<V, false, false, true> : iota_values ? (K)rs_pass_kernel<V, true, true, true> : (K)rs_pass_kernel<V, true, false, true>;
+    else kern = !has_v ? (K)rs_pass_kernel<V, false, false, false> : iota_values ? (K)rs_pass_kernel<V, true, true, false> : (K)rs_pass_kernel<V, true, false, false>;
     int launches = 2;
-    if (has_v) kern = iota_values ? (K)rs_pass_kernel<V, true, true> : (K)rs_pass_kernel<V, true, false>;
     if (has_v && iota_values) {  // every pass trivial (all keys equal): nobody synthesises the positions
         rs_iota_if_unsorted_kernel<V><<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count * 8)), 256, 0, stream>>>(vals[0], n, T.ctl);
         ++launches;
     }
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     for (int p = 0; p < n_passes; ++p) {
-        K k = kern;
-        cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<(unsigned)tiles, RS_THREADS, smem, stream>>>(keys[0], keys[1], vals[0], vals[1], n, begin_bit + p * RS_RADIX_BITS, p, T.ctl,
-                                                         T.base + (size_t)p * RS_BINS, T.status + (size_t)p * T.status_words_per_pass);
+        kern<<<(unsigned)tiles, RS_THREADS, smem, stream>>>(keys[0], keys[1], vals[0], vals[1], n, begin_bit + p * RS_RADIX_BITS, p, T.ctl,
+                                                            T.base + (size_t)p * RS_BINS, T.status + (size_t)p * T.status_words_per_pass, quant);
         ++launches;
     }
     return launches;
 }
 
-template int rs_sort_pairs<uint32_t>(cudaStream_t, uint64_t* const[2], uint32_t* const[2], int64_t, int, int, bool, const RsTemp&, int);
-template int rs_sort_pairs<uint64_t>(cudaStream_t, uint64_t* const[2], uint64_t* const[2], int64_t, int, int, bool, const RsTemp&, int);
+template int rs_sort_pairs<uint32_t>(cudaStream_t, uint64_t* const[2], uint32_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*);
+template int rs_sort_pairs<uint64_t>(cudaStream_t, uint64_t* const[2], uint64_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*);
 
 }  // namespace tg

@@ -36,8 +36,33 @@ struct RsControl {
     uint32_t n_passes;
     uint32_t tile_counter[RS_MAX_PASSES];
     uint32_t first_exec;               // first non-trivial pass (== n_passes when every pass is trivial)
-    uint32_t pad[4];
+    uint32_t quantised;                // the data ends up sorted by rs_quant(key) only (0: by the key bits)
+    uint32_t fallback;                 // raised by a consumer of a quantised result that needs the full order after all
+    uint32_t pad[2];
 };
+
+// "Quantised" sorts order the data by a 32-bit monotone function Q of the key instead of the key's own bits: for numeric
+// columns Q is LINEAR IN THE VALUE between the column's minimum and maximum, so its 32 bits are spent evenly over the
+// value range (the raw bits of a double spend 11 of them on the exponent: a column that spans zero collapses whole binades
+// into one prefix). Q is monotone (every step is a monotone floating-point / integer operation), so the result is ordered
+// by Q with equal Q in input order; the consumer orders the short runs of equal Q by the full keys (ranks.cu).
+struct RsQuant {       // device-resident, written by rs_quant_setup
+    uint32_t mode;     // 0: Q = key >> 32; 1: integer keys, Q = (key - kmin) >> shift; 2: f64 order keys, Q = (x - xmin) * scale
+    uint32_t shift;
+    uint64_t kmin;
+    double xmin, scale;
+};
+__device__ __forceinline__ uint32_t rs_quant(const RsQuant& q, uint64_t k) {
+    if (q.mode == 2) {
+        const uint64_t bits = (k & 0x8000000000000000ull) ? (k ^ 0x8000000000000000ull) : ~k;
+        const double x = __longlong_as_double((long long)bits);
+        return __double2uint_rz((x - q.xmin) * q.scale);  // saturating; the keys lie inside [xmin, xmax]
+    }
+    if (q.mode == 1) return (uint32_t)((k - q.kmin) >> q.shift);
+    return (uint32_t)(k >> 32);
+}
+// minmax[0] / [1]: smallest / largest key (order-preserving u64 keys of an Int64 (is_i64) or Float64 column)
+void rs_quant_setup(cudaStream_t stream, const unsigned long long* minmax, int is_i64, RsQuant* q);
 
 struct RsTemp {
     RsControl* ctl;
@@ -55,8 +80,9 @@ RsTemp rs_temp_carve(uint8_t* temp, int64_t n, int n_passes);
 // the other ping-pong buffer. vals may be {nullptr, nullptr} (keys only). iota_values: the values of the input are the
 // positions 0..n-1 and vals[0] is never read (it is filled with them when every pass turns out trivial). n < 2^30. Returns the number of kernels launched; the buffer index of the
 // result is T.ctl->result (device memory).
+// quant != nullptr: a quantised sort (4 passes over the 32 bits of rs_quant(*quant, key); begin_bit / n_passes ignored).
 template <typename V>
 int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2], int64_t n, int begin_bit, int n_passes,
-                  bool iota_values, const RsTemp& T, int sm_count);
+                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant = nullptr);
 
 }  // namespace tg

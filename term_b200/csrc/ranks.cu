@@ -25,6 +25,7 @@
 #include <cstring>
 
 #include "engine.hpp"
+#include "ptx.cuh"
 #include "radix_sort.cuh"
 
 namespace tg {
@@ -135,15 +136,26 @@ __global__ void __launch_bounds__(RK_THREADS) rk_compact_keys_kernel(const uint6
 constexpr int RK_ITEMS = 16, RK_TILE = RK_THREADS * RK_ITEMS;
 
 // tile_last[t] = 1-based position of the last run head inside tile t (0: the tile starts inside a run and never leaves it)
-__global__ void __launch_bounds__(RK_THREADS) rk_tile_heads_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1, int64_t n,
-                                                                   uint32_t* tile_last) {
+// what the runs are runs of: the whole key after a full sort, rs_quant(key) after a quantised one
+struct RkRunKey {
+    bool quantised;
+    RsQuant Q;
+    __device__ __forceinline__ RkRunKey(const RsControl* ctl, const RsQuant* quant) : quantised(ctl->quantised != 0), Q{} {
+        if (quantised) Q = *quant;
+    }
+    __device__ __forceinline__ uint64_t operator()(uint64_t k) const { return quantised ? (uint64_t)rs_quant(Q, k) : k; }
+};
+
+__global__ void __launch_bounds__(RK_THREADS) rk_tile_heads_kernel(const RsControl* ctl, const RsQuant* quant, const uint64_t* k0, const uint64_t* k1,
+                                                                   int64_t n, uint32_t* tile_last) {
     const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
+    const RkRunKey rk(ctl, quant);
     const int64_t base = (int64_t)blockIdx.x * RK_TILE;
     uint32_t best = 0;
 #pragma unroll 4
     for (int i = 0; i < RK_ITEMS; ++i) {
         const int64_t p = base + (int64_t)i * RK_THREADS + threadIdx.x;
-        if (p < n && (p == 0 || ks[p] != ks[p - 1])) best = (uint32_t)p + 1u;  // positions grow with i
+        if (p < n && (p == 0 || rk(ks[p]) != rk(ks[p - 1]))) best = (uint32_t)p + 1u;  // positions grow with i
     }
     __shared__ uint32_t red[RK_THREADS / 32];
 #pragma unroll
@@ -185,8 +197,16 @@ __global__ void __launch_bounds__(1024) rk_tile_scan_kernel(const uint32_t* __re
 struct RkTileRanks {
     uint32_t rank[RK_ITEMS];
 };
+// After a QUANTISED sort (RsControl::quantised) the runs are runs of equal rs_quant(key), inside which the keys are in
+// input order: the minimum rank of a key is then (run head) + (keys of its run that are smaller). Runs are short when
+// the 32-bit quantisation nearly identifies the key (continuous data: one or two keys), so every position simply walks its run from
+// the head: up to RK_RUN_LIMIT keys, neighbours in sorted order (cache hits). A longer run is fine when all its keys are
+// equal (duplicates); a position of a longer run that sees a key different from its own within the first RK_RUN_LIMIT keys
+// raises *fallback and the host repeats the phase with a full sort (every impure run contains such a position: one whose
+// key differs from the run's first key).
+constexpr int RK_RUN_LIMIT = 32;
 __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict__ ks, int64_t n, const uint32_t* __restrict__ carry,
-                                                     uint32_t* s_warp /* [RK_THREADS / 32] */) {
+                                                     uint32_t* s_warp /* [RK_THREADS / 32] */, const RkRunKey& rk, uint32_t* fallback) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
     RkTileRanks R;
@@ -197,7 +217,7 @@ __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict_
         uint32_t h = 0;
         if (p < n) {
             const uint64_t k = ks[p];
-            if (p == 0 || k != ks[p - 1]) h = (uint32_t)p + 1u;
+            if (p == 0 || rk(k) != rk(ks[p - 1])) h = (uint32_t)p + 1u;
         }
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -214,21 +234,44 @@ __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict_
     for (int w = 0; w < warp; ++w) pre = max(pre, s_warp[w]);
 #pragma unroll
     for (int i = 0; i < RK_ITEMS; ++i) R.rank[i] = max(R.rank[i], pre);
+    if (rk.quantised) {
+        bool bad = false;
+#pragma unroll
+        for (int i = 0; i < RK_ITEMS; ++i) {
+            const int64_t p = wbase + i * 32 + lane;
+            if (p >= n) continue;
+            const uint64_t k = ks[p], q = rk(k);
+            const int64_t head = (int64_t)R.rank[i] - 1;  // 0-based first position of the run
+            uint32_t less = 0;
+            bool differ = false;
+            int64_t j = head;
+            for (int s = 0; s < RK_RUN_LIMIT && j < n; ++s, ++j) {
+                const uint64_t kj = j == p ? k : ks[j];
+                if (rk(kj) != q) break;
+                less += kj < k;
+                differ |= kj != k;
+            }
+            const bool ended = j >= n || rk(ks[j]) != q;
+            if (!ended && differ) bad = true;  // a long run with different keys: the prefix order is not enough
+            R.rank[i] += less;                   // (long runs of equal keys: less == 0)
+        }
+        if (bad) atomicExch(fallback, 1u);
+    }
     return R;
 }
 
 // after the sort by kx (payload ky): emit (ky, rank_base + rank_x) in the sorted-by-x order — the input of the second sort.
 // The sorted data sits in buffer ctl->result of the two ping-pong buffers; the output goes to the OTHER buffer pair
 // (keys: the 64-bit key buffer, ranks: the payload buffer reused as 32-bit words).
-__global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, uint64_t* k0, uint64_t* k1, uint64_t* p0, uint64_t* p1, int64_t n,
-                                                               const uint32_t* __restrict__ carry, uint32_t rank_base) {
+__global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, const RsQuant* quant, uint64_t* k0, uint64_t* k1, uint64_t* p0,
+                                                               uint64_t* p1, int64_t n, const uint32_t* __restrict__ carry, uint32_t rank_base) {
     __shared__ uint32_t s_warp[RK_THREADS / 32];
     const bool r = ctl->result != 0;
     const uint64_t* __restrict__ ks = r ? k1 : k0;
     const uint64_t* __restrict__ ys = r ? p1 : p0;
     uint64_t* __restrict__ out_key = r ? k0 : k1;
     uint32_t* __restrict__ out_rank = reinterpret_cast<uint32_t*>(r ? p0 : p1);
-    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp);
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
 #pragma unroll
@@ -243,7 +286,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* 
 
 // after the sort by ky (payload rank_x, 32-bit words in the payload buffers): rank_y on the fly and the block's partial
 // sums of the shifted rank co-moments (fixed tile -> block mapping, fixed reduction shape: run-to-run reproducible)
-__global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsControl* ctl, const uint64_t* k0, const uint64_t* k1,
+__global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsControl* ctl, const RsQuant* quant, const uint64_t* k0, const uint64_t* k1,
                                                                        const uint32_t* r0, const uint32_t* r1, int64_t n,
                                                                        const uint32_t* __restrict__ carry, uint32_t rank_base, double K,
                                                                        double* __restrict__ partial /* [grid][5] */) {
@@ -251,7 +294,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsC
     __shared__ double red[5][RK_THREADS / 32];
     const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
     const uint32_t* __restrict__ rxs = ctl->result ? r1 : r0;
-    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp);
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
     double s[5] = {0, 0, 0, 0, 0};
@@ -279,6 +322,26 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsC
         double v = 0;
         for (int w = 0; w < RK_THREADS / 32; ++w) v += red[threadIdx.x][w];
         partial[(size_t)blockIdx.x * 5 + threadIdx.x] = v;
+    }
+}
+
+// smallest / largest key (out = {~0, 0} before): the range the quantised sort spreads its 32 bits over
+__global__ void __launch_bounds__(RK_THREADS) rk_minmax_kernel(const uint64_t* __restrict__ keys, int64_t n, unsigned long long* out) {
+    uint64_t lo = ~0ull, hi = 0ull;
+    for (int64_t i = (int64_t)blockIdx.x * RK_THREADS + threadIdx.x; i < n; i += (int64_t)gridDim.x * RK_THREADS) {
+        const uint64_t k = __ldg(keys + i);
+        lo = k < lo ? k : lo;
+        hi = k > hi ? k : hi;
+    }
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) {
+        const uint64_t a = shfl_xor_u64(lo, m), b = shfl_xor_u64(hi, m);
+        lo = a < lo ? a : lo;
+        hi = b > hi ? b : hi;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(out, (unsigned long long)lo);
+        atomicMax(out + 1, (unsigned long long)hi);
     }
 }
 
@@ -338,6 +401,7 @@ struct RankSession {
     int64_t n = 0;        // elements in cur
     int which = 0;        // buffer of cur holding the data
     int payload32 = 0;    // payload is 32-bit ranks (second phase)
+    int x_i64 = 0, y_i64 = 0;  // the columns' types (how their order keys map back to values)
 };
 
 static void arena_free(Engine& e, RankArena& a) {
@@ -395,6 +459,8 @@ static int64_t rank_begin_locked(Engine& e, Table& t, const std::string& nx, con
     S.n = 0;
     S.which = 0;
     S.payload32 = 0;
+    S.x_i64 = cx->dtype == TG_INT64;
+    S.y_i64 = cy->dtype == TG_INT64;
     if (n == 0) return 0;
     const int64_t c_tiles = (n + RK_CTILE - 1) / RK_CTILE;
     // compaction scratch lives in the arena's temp area
@@ -418,28 +484,51 @@ static int64_t rank_begin_locked(Engine& e, Table& t, const std::string& nx, con
 }
 
 // queue the sort of the session's current (keys, payload); the result buffer index is only known on the device (ctl)
-static RsTemp rank_sort_queue(Engine& e, RankSession& S, int* launches) {
+// where the quantisation of the session's current sort lives (the arena's temp area, behind the sort's own pieces)
+static RsQuant* rank_quant(RankArena& A) { return (RsQuant*)(A.tmp + A.tmp_bytes - 1024); }
+
+// quantised: finish_x / finish_y sort 32 value-linear bits (4 passes instead of 8), then fix the short runs of equal
+// quantised keys; key_is_i64 says how the keys of this phase came about (the x / y column's type)
+static RsTemp rank_sort_queue(Engine& e, RankSession& S, int* launches, bool quantised = false, int key_is_i64 = 0) {
     RankArena& A = S.cur;
     const RsTemp T = rs_temp_carve(A.tmp, std::max<int64_t>(S.n, 1), RS_MAX_PASSES);
     uint64_t* keys[2] = {A.K[S.which], A.K[S.which ^ 1]};
+    const RsQuant* quant = nullptr;
+    if (quantised) {
+        unsigned long long* mm = (unsigned long long*)(A.tmp + A.tmp_bytes - 512);
+        TG_CUDA(cudaMemsetAsync(mm, 0xFF, 8, e.stream));
+        TG_CUDA(cudaMemsetAsync(mm + 1, 0, 8, e.stream));
+        rk_minmax_kernel<<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((S.n + RK_THREADS * 8 - 1) / (RK_THREADS * 8), (int64_t)e.sm_count * 8)), RK_THREADS, 0,
+                           e.stream>>>(keys[0], S.n, mm);
+        rs_quant_setup(e.stream, mm, key_is_i64, rank_quant(A));
+        *launches += 2;
+        quant = rank_quant(A);
+    }
     if (S.payload32) {
         uint32_t* vals[2] = {(uint32_t*)A.V[S.which], (uint32_t*)A.V[S.which ^ 1]};
-        *launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count);
+        *launches += rs_sort_pairs<uint32_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count, quant);
     } else {
         uint64_t* vals[2] = {A.V[S.which], A.V[S.which ^ 1]};
-        *launches += rs_sort_pairs<uint64_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count);
+        *launches += rs_sort_pairs<uint64_t>(e.stream, keys, vals, S.n, 0, RS_MAX_PASSES, false, T, e.sm_count, quant);
     }
     TG_CUDA(cudaGetLastError());
     return T;
 }
 // after the queued work: which physical buffer holds the result
-static void rank_sort_settle(Engine& e, RankSession& S, const RsTemp& T, bool flipped_by_consumer) {
+// Returns false when the consumer of a prefix-sorted result asked for the full order (S.which then names the buffer that
+// holds the prefix-sorted input, untouched by the consumer: the caller repeats the phase with a full sort).
+static bool rank_sort_settle(Engine& e, RankSession& S, const RsTemp& T, bool flipped_by_consumer) {
     RsControl ctl;
     TG_CUDA(cudaMemcpyAsync(&ctl, T.ctl, sizeof(ctl), cudaMemcpyDeviceToHost, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
     int r = ctl.result ? (S.which ^ 1) : S.which;
+    if (ctl.fallback) {
+        S.which = r;
+        return false;
+    }
     if (flipped_by_consumer) r ^= 1;  // the consumer kernel wrote the next stage's data into the other buffer pair
     S.which = r;
+    return true;
 }
 
 static void rank_local_sort_locked(Engine& e, int* launches) {
@@ -456,18 +545,20 @@ static void rank_finish_x_locked(Engine& e, uint64_t rank_base, int* launches) {
     if (S.n > 0) {
         if (rank_base + (uint64_t)S.n >= ((uint64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^32 or more pairs");
         RankArena& A = S.cur;
-        const RsTemp T = rank_sort_queue(e, S, launches);
-        const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
-        uint64_t* k0 = A.K[S.which];
-        uint64_t* k1 = A.K[S.which ^ 1];
-        uint64_t* p0 = A.V[S.which];
-        uint64_t* p1 = A.V[S.which ^ 1];
-        rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, S.n, A.tile_last);
-        rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
-        rk_rank_x_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, p0, p1, S.n, A.carry, (uint32_t)rank_base);
-        TG_CUDA(cudaGetLastError());
-        *launches += 3;
-        rank_sort_settle(e, S, T, true);
+        for (int prefix = getenv("TG_RANK_FULL_SORT") ? 0 : 1;; prefix = 0) {
+            const RsTemp T = rank_sort_queue(e, S, launches, prefix != 0, S.x_i64);
+            const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
+            uint64_t* k0 = A.K[S.which];
+            uint64_t* k1 = A.K[S.which ^ 1];
+            uint64_t* p0 = A.V[S.which];
+            uint64_t* p1 = A.V[S.which ^ 1];
+            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, S.n, A.tile_last);
+            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
+            rk_rank_x_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, p0, p1, S.n, A.carry, (uint32_t)rank_base);
+            TG_CUDA(cudaGetLastError());
+            *launches += 3;
+            if (rank_sort_settle(e, S, T, true) || prefix == 0) break;  // else: long runs of different keys — full sort
+        }
     }
     S.payload32 = 1;
 }
@@ -481,21 +572,25 @@ static void rank_finish_y_locked(Engine& e, uint64_t rank_base, double K, uint64
     if (S.n > 0) {
         if (rank_base + (uint64_t)S.n >= ((uint64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^32 or more pairs");
         RankArena& A = S.cur;
-        const RsTemp T = rank_sort_queue(e, S, launches);
-        const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
-        const uint64_t* k0 = A.K[S.which];
-        const uint64_t* k1 = A.K[S.which ^ 1];
-        const uint32_t* r0 = (const uint32_t*)A.V[S.which];
-        const uint32_t* r1 = (const uint32_t*)A.V[S.which ^ 1];
-        double* d_out = (double*)(A.tmp + A.tmp_bytes - 2048);
-        rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, S.n, A.tile_last);
-        rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
-        rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, k0, k1, r0, r1, S.n, A.carry, (uint32_t)rank_base, K, A.partial);
-        rk_final_kernel<<<1, 160, 0, e.stream>>>(A.partial, r_tiles, d_out);
-        TG_CUDA(cudaGetLastError());
-        *launches += 4;
-        TG_CUDA(cudaMemcpyAsync(sums, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
-        TG_CUDA(cudaStreamSynchronize(e.stream));
+        double* h_sums = (double*)e.host_scratch(256);
+        for (int prefix = getenv("TG_RANK_FULL_SORT") ? 0 : 1;; prefix = 0) {
+            const RsTemp T = rank_sort_queue(e, S, launches, prefix != 0, S.y_i64);
+            const int64_t r_tiles = (S.n + RK_TILE - 1) / RK_TILE;
+            const uint64_t* k0 = A.K[S.which];
+            const uint64_t* k1 = A.K[S.which ^ 1];
+            const uint32_t* r0 = (const uint32_t*)A.V[S.which];
+            const uint32_t* r1 = (const uint32_t*)A.V[S.which ^ 1];
+            double* d_out = (double*)(A.tmp + A.tmp_bytes - 2048);
+            rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, S.n, A.tile_last);
+            rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
+            rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, r0, r1, S.n, A.carry, (uint32_t)rank_base, K, A.partial);
+            rk_final_kernel<<<1, 160, 0, e.stream>>>(A.partial, r_tiles, d_out);
+            TG_CUDA(cudaGetLastError());
+            *launches += 4;
+            TG_CUDA(cudaMemcpyAsync(h_sums, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
+            if (rank_sort_settle(e, S, T, false) || prefix == 0) break;  // (the settle synchronises the stream)
+        }
+        for (int k = 0; k < 5; ++k) sums[k] = h_sums[k];
     }
     arena_free(e, S.cur);
     arena_free(e, S.next);

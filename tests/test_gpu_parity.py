@@ -981,6 +981,48 @@ def test_spearman_matches_scipy_min_ranks(ctx, n):
         ctx.deregister_table(name)
 
 
+def _spearman_cases(n, rng):
+    """columns that steer the rank kernels through every branch of the prefix sort (ranks.cu): keys that differ only below
+    the sorted 32-bit prefix (short runs of different keys -> fixed in place), long runs of equal keys (duplicates), long
+    runs of DIFFERENT keys under one prefix (an outlier stretches the range -> the full-sort fallback)"""
+    base = rng.normal(100.0, 15.0, n)
+    tiny = base.view(np.int64).copy()
+    tiny[: n // 2] = tiny[n // 2: 2 * (n // 2)] ^ rng.integers(0, 1 << 12, n // 2)  # pairs equal down to the last 12 mantissa bits
+    ids = rng.integers(0, 1_000_000, n)
+    ids_out = ids.copy()
+    ids_out[0] = 1 << 60                                                             # every other key shares the top 32 bits
+    return {
+        "cont": base,
+        "tiny": tiny.view(np.float64),
+        "dups": rng.integers(0, 7, n).astype(np.float64),
+        "ids": ids,
+        "ids_outlier": ids_out,
+        "mixed": np.where(rng.random(n) < 0.5, 3.25, base),                          # one value repeated n/2 times among distinct ones
+    }
+
+
+@pytest.mark.parametrize("n", [70_000, 1_500_000])
+def test_spearman_prefix_sort_paths(ctx, n):
+    from scipy.stats import rankdata
+    rng = np.random.default_rng(1000 + n)
+    cols = _spearman_cases(n, rng)
+    y = 0.3 * cols["cont"] + rng.normal(0, 20.0, n)
+    t = pa.table({**{k: pa.array(v, mask=rng.random(n) < 0.03) for k, v in cols.items()}, "y": pa.array(y, mask=rng.random(n) < 0.03)})
+    name = f"spear_paths_{n}"
+    ctx.register_table(name, t)
+    try:
+        for c in cols:
+            for a, b in ((c, "y"), ("y", c)):
+                r = T.CorrelationAnalyzer.spearman(a, b).compute(ctx, name)
+                va, vb = t[a].to_numpy(zero_copy_only=False), t[b].to_numpy(zero_copy_only=False)
+                ok = ~(np.isnan(va.astype(np.float64)) | np.isnan(vb.astype(np.float64)))
+                ra, rb = rankdata(va[ok], method="min"), rankdata(vb[ok], method="min")
+                want = float(np.corrcoef(ra, rb)[0, 1])
+                assert abs(r.metric_double - want) <= 1e-9, (a, b, r.metric_double, want)
+    finally:
+        ctx.deregister_table(name)
+
+
 # ---------------------------------------------------------------- concurrency (§8b threading) ----
 def test_concurrent_suites_on_one_context(ctx):
     """tests/integration_test_suite.rs:702-745: several suites run at once against one SessionContext. ctypes drops
