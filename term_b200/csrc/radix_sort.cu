@@ -324,8 +324,16 @@ __global__ void rs_quant_setup_kernel(const unsigned long long* __restrict__ min
                 return __longlong_as_double((long long)bits);
             };
             const double lo = value(kmin), hi = value(kmax), range = hi - lo;
-            // NaN / infinite ends or an overflowing range: the raw prefix (mode 0) and, most likely, the full-sort fallback
-            if (isfinite(lo) && isfinite(hi) && isfinite(range)) {
+            // One sign and at most 64 binades: the order keys themselves are value-linear inside a binade and every binade
+            // gets >= 2^26 of the 2^32 levels — integer arithmetic only (the fp64 chain below costs the pass kernel ~25 %).
+            const bool same_sign = ((kmin ^ kmax) >> 63) == 0;
+            if (same_sign && (kmax >> 52) - (kmin >> 52) < 64 && isfinite(lo) && isfinite(hi)) {
+                const uint64_t r2 = kmax - kmin;
+                const int bits = 64 - __clzll((long long)r2);
+                r.mode = 1;
+                r.shift = bits > 32 ? (uint32_t)(bits - 32) : 0u;
+            } else if (isfinite(lo) && isfinite(hi) && isfinite(range)) {
+                // NaN / infinite ends or an overflowing range: the raw prefix (mode 0) and, most likely, the full-sort fallback
                 r.mode = 2;
                 r.xmin = lo;
                 r.scale = range > 0.0 ? 4294967295.0 / range : 0.0;

@@ -47,7 +47,8 @@ struct RsControl {
 // into one prefix). Q is monotone (every step is a monotone floating-point / integer operation), so the result is ordered
 // by Q with equal Q in input order; the consumer orders the short runs of equal Q by the full keys (ranks.cu).
 struct RsQuant {       // device-resident, written by rs_quant_setup
-    uint32_t mode;     // 0: Q = key >> 32; 1: integer keys, Q = (key - kmin) >> shift; 2: f64 order keys, Q = (x - xmin) * scale
+    uint32_t mode;     // 0: Q = key >> 32; 1: Q = (key - kmin) >> shift (integer keys; f64 keys of one sign within 64 binades);
+                       // 2: f64 order keys, Q = (x - xmin) * scale
     uint32_t shift;
     uint64_t kmin;
     double xmin, scale;
