@@ -8,6 +8,9 @@
 // the one that resolves. The host layer only has to carry the 128-byte ncclUniqueId from rank 0 to the other ranks.
 #include <dlfcn.h>
 
+#include <chrono>
+#include <cstdio>
+
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
@@ -282,6 +285,15 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
     std::vector<int64_t> counts((size_t)world, 0);
     int64_t nulls = 0;
     int launches = 0;
+    // TG_SHUFFLE_TRACE=1: wall-clock milestones of one shuffle on stderr (every milestone follows a stream synchronisation)
+    static const bool trace = getenv("TG_SHUFFLE_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace || rank != 0) return;
+        cudaStreamSynchronize(e.stream);
+        fprintf(stderr, "[shuffle %s] %-14s +%.3f ms\n", c.name.c_str(), what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     const int w1 = world + 1;
     std::vector<long long> mine((size_t)w1), all((size_t)w1 * world);
     long long* d_mine = (long long*)e.d_comm_counts;
@@ -302,10 +314,12 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
         long long mn = 0, mx = 0;
         unsigned long long nv = 0;
         column_minmax_i64(e, c, t.n_rows, &mn, &mx, &nv, launches);
+        mark("minmax");
         mine[0] = mn;
         mine[1] = mx;
         mine[2] = (long long)nv;
         gather(3);
+        mark("gather minmax");
         long long gmn = INT64_MAX, gmx = INT64_MIN;
         unsigned long long gn = 0;
         for (int r = 0; r < world; ++r) {
@@ -315,9 +329,16 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
             gn += (unsigned long long)all[(size_t)r * 3 + 2];
         }
         if (gn > 0) {
+            // the ends come from samples on large columns: pad them (1/64 of the width) so that practically every key lies
+            // inside; the few that do not go to the first / last rank (still one rank per key value)
+            const unsigned long long w0 = (unsigned long long)gmx - (unsigned long long)gmn, pad = w0 / 64 + 4096;
+            if (gmn >= INT64_MIN + (long long)pad && gmx <= INT64_MAX - (long long)pad) {
+                gmn -= (long long)pad;
+                gmx += (long long)pad;
+            }
             const unsigned long long range = (unsigned long long)gmx - (unsigned long long)gmn;
             const unsigned long long span = range / (unsigned long long)world + 1;
-            if (range <= 32ull * gn && span < (1ull << 28)) {
+            if (range <= 32ull * gn + 8192ull && span < (1ull << 28)) {
                 by_range = true;
                 range_min = gmn;
                 range_span = span;
@@ -327,9 +348,11 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
     // ---- counts (a value-range split that turns out badly balanced is abandoned for the hash split)
     for (int attempt = 0; attempt < 2; ++attempt) {
         push_partition_hist(e, c, t.n_rows, world, counts.data(), &nulls, launches, by_range ? &range_min : nullptr, range_span);
+        mark("hist");
         for (int r = 0; r < world; ++r) mine[r] = counts[r];
         mine[world] = nulls;
         gather((size_t)w1);
+        mark("gather counts");
         if (!by_range) break;
         long long total = 0, worst = 0;
         for (int d = 0; d < world; ++d) {
@@ -369,13 +392,16 @@ static int64_t push_shuffle_column(Engine& e, Table& t, Column& c, const std::st
             return -2;  // the counts collective was consumed: tell the caller to rerun the fallback from the start
         }
     }
+    mark("slot");
     // ---- the scatter IS the all-to-all
     push_partition_scatter(e, c, t.n_rows, world, first.data(), (uint64_t* const*)s.d_ptrs, launches, by_range ? &range_min : nullptr, range_span);
+    mark("scatter");
     // tail padding + NULL rows of my own buffer (nobody else writes behind n_recv)
     TG_CUDA(cudaMemsetAsync(s.local + (size_t)n_recv * 8, 0, std::min(s.cap - (size_t)n_recv * 8, (size_t)my_nulls * 8 + 512), e.stream));
     // ---- barrier: every rank's scatter has completed (kernel completion makes its peer stores visible) before anyone reads
     TG_NCCL(nccl().AllGather(d_mine, d_all, 1, NCCL_INT64, comm, e.stream));
     TG_CUDA(cudaStreamSynchronize(e.stream));
+    mark("barrier");
     e.launches += launches;
     // ---- the shard table lives in the receive buffer
     auto tab = std::make_unique<Table>();

@@ -63,6 +63,14 @@ struct RangeSplit {
     long long min;
     unsigned long long span;
     const uint64_t* splitters = nullptr;  // PM_SPLIT: parts - 1 ascending keys (device)
+    // PM_RANGE: part = mulhi(key - min, inv), inv = min(2^64 - 1, ceil(2^64 / span)) — monotone in the key and within one
+    // of the exact quotient, which is all a partition needs (a 64-bit division per key tripled the histogram pass)
+    unsigned long long inv = 0;
+    static RangeSplit range(long long mn, unsigned long long span) {
+        RangeSplit r{mn, span};
+        r.inv = span <= 1 ? ~0ull : (unsigned long long)((((unsigned __int128)1 << 64) + span - 1) / span);
+        return r;
+    }
 };
 
 // Loads the PART_KEYS_PER_THREAD keys of this thread's tile slots up front (independent, predicated loads: all in
@@ -95,7 +103,8 @@ __device__ __forceinline__ void load_classify(const uint64_t* __restrict__ value
             part[k] = !valid ? -1 : (int)hash_rank(h, parts);
         } else if (MODE == PM_RANGE) {
             key[k] = raw[k];
-            const unsigned long long d = ((unsigned long long)raw[k] - (unsigned long long)rs.min) / rs.span;
+            const unsigned long long d = (long long)raw[k] < rs.min ? 0ull  // (below a sampled minimum: the first part)
+                                                                    : __umul64hi((unsigned long long)raw[k] - (unsigned long long)rs.min, rs.inv);
             part[k] = !valid ? -1 : (int)(d < parts ? d : parts - 1);
         } else {
             key[k] = raw[k];
@@ -127,11 +136,19 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint64_t*
         uint64_t key[PART_KEYS_PER_THREAD];
         int part[PART_KEYS_PER_THREAD];
         load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part, rs);
+        // few parts (the ranks of a shuffle): the lanes of a warp that agree on the part add once (a per-key shared atomic
+        // on 2 .. 8 addresses serialises 4- to 16-fold)
+        const bool few = parts <= 64;
 #pragma unroll
         for (int k = 0; k < PART_KEYS_PER_THREAD; ++k) {
-            if (part[k] >= 0) atomicAdd(&my_hist[part[k]], 1u);
-            else if (part[k] == -2) ++special;
-            else if (base + k * PART_THREADS + threadIdx.x < n) ++nulls;
+            if (few) {
+                const unsigned peers = __match_any_sync(0xffffffffu, part[k]);
+                if (part[k] >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&my_hist[part[k]], (uint32_t)__popc(peers));
+            } else if (part[k] >= 0) {
+                atomicAdd(&my_hist[part[k]], 1u);
+            }
+            if (part[k] == -2) ++special;
+            else if (part[k] == -1 && base + k * PART_THREADS + threadIdx.x < n) ++nulls;
         }
     }
     __syncthreads();
@@ -187,9 +204,22 @@ __global__ void __launch_bounds__(PART_THREADS) part_scatter_kernel(const uint64
         int part[PART_KEYS_PER_THREAD];
         uint32_t rank[PART_KEYS_PER_THREAD];
         load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part, rs);
+        // position inside the tile's run of its part. Few parts (the ranks of a shuffle): one returning shared atomic per
+        // distinct part per warp instead of one per key
+        const bool few = parts <= 64;
 #pragma unroll
-        for (int k = 0; k < PART_KEYS_PER_THREAD; ++k)
-            if (part[k] >= 0) rank[k] = atomicAdd(&s_cnt[part[k]], 1u);
+        for (int k = 0; k < PART_KEYS_PER_THREAD; ++k) {
+            if (few) {
+                const unsigned peers = __match_any_sync(0xffffffffu, part[k]);
+                const int leader = __ffs(peers) - 1;
+                uint32_t b0 = 0;
+                if (part[k] >= 0 && (int)(threadIdx.x & 31) == leader) b0 = atomicAdd(&s_cnt[part[k]], (uint32_t)__popc(peers));
+                b0 = __shfl_sync(0xffffffffu, b0, leader);
+                rank[k] = b0 + (uint32_t)__popc(peers & ((1u << (threadIdx.x & 31)) - 1u));
+            } else if (part[k] >= 0) {
+                rank[k] = atomicAdd(&s_cnt[part[k]], 1u);
+            }
+        }
         __syncthreads();
         // exclusive scan of s_cnt over the buckets (thread t owns buckets t*per_thread ..), and one global
         // atomicAdd per non-empty bucket reserves this tile's run in the output
@@ -663,7 +693,7 @@ void push_partition_hist(Engine& e, const Column& c, int64_t n, int world, int64
     if (n > 0) {
         if (range_min)
             part_hist_kernel<PM_RANGE><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n, 0,
-                                                                                       (uint32_t)world, m.hist, m.ctr, RangeSplit{*range_min, range_span});
+                                                                                       (uint32_t)world, m.hist, m.ctr, RangeSplit::range(*range_min, range_span));
         else
             part_hist_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
                                                                                       c.dtype == TG_FLOAT64, (uint32_t)world, m.hist, m.ctr);
@@ -688,7 +718,7 @@ void push_partition_scatter(Engine& e, const Column& c, int64_t n, int world, co
     if (range_min)
         part_scatter_kernel<PM_RANGE><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n, 0,
                                                                                       (uint32_t)world, m.cursors, nullptr, d_outs,
-                                                                                      RangeSplit{*range_min, range_span});
+                                                                                      RangeSplit::range(*range_min, range_span));
     else
         part_scatter_kernel<PM_RANK><<<part_grid(e, n), PART_THREADS, 0, e.stream>>>((const uint64_t*)c.values.p, (const uint32_t*)c.validity.p, n,
                                                                                      c.dtype == TG_FLOAT64, (uint32_t)world, m.cursors, nullptr, d_outs);
@@ -736,8 +766,26 @@ void split_partition_scatter(Engine& e, const uint64_t* d_keys, const void* d_pa
 }
 
 // min / max / valid count of an Int64 key column (the dense test of the range-partitioned shuffle)
+// (large columns: from a strided 64 K-row sample — a partition only needs boundaries every rank agrees on; keys outside the
+// sampled range go to the first / last rank, and the valid count is scaled up from the sample)
 bool column_minmax_i64(Engine& e, const Column& c, int64_t n, long long* mn, long long* mx, unsigned long long* n_valid, int& launches) {
     MinMaxOut h{};
+    if (n >= ((int64_t)1 << 22) && !getenv("TG_HASH_NO_GUESS")) {
+        uint8_t* scr = e.scratch(256);
+        MinMaxOut* d = (MinMaxOut*)scr;
+        MinMaxOut init{INT64_MAX, INT64_MIN, 0, 0};
+        TG_CUDA(cudaMemcpyAsync(d, &init, sizeof(init), cudaMemcpyHostToDevice, e.stream));
+        const int64_t stride = std::max<int64_t>(1, n >> 16);
+        sample_minmax_i64_kernel<<<64, PART_THREADS, 0, e.stream>>>((const long long*)c.values.p, (const uint32_t*)c.validity.p, n, stride, d);
+        TG_CUDA(cudaGetLastError());
+        ++launches;
+        TG_CUDA(cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
+        TG_CUDA(cudaStreamSynchronize(e.stream));
+        *mn = h.mn;
+        *mx = h.mx;
+        *n_valid = h.n_valid * (unsigned long long)stride;
+        return h.n_valid > 0;
+    }
     const bool any = minmax_i64(e, c, n, h, launches);
     *mn = h.mn;
     *mx = h.mx;
