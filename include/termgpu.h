@@ -245,9 +245,12 @@ TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, cons
  * column. `chunk` = the column chunk's bytes exactly as they are in the file (from the first page header,
  * total_compressed_size bytes), `num_values` / `codec` / the physical type (as tg_dtype) / the leaf's max definition
  * level from the file metadata. The host walks the page headers and expands the definition levels into the validity
- * bitmap while the value bytes travel; the device scatters the densely stored non-NULL PLAIN values to their rows.
- * Supported: INT64 / DOUBLE / INT32 / FLOAT, codec UNCOMPRESSED (0), data pages V1 / V2, PLAIN values, RLE levels,
- * flat columns; anything else -> TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
+ * bitmap while the value bytes travel; Snappy pages are decompressed on the host; the device scatters the densely stored
+ * non-NULL values to their rows, looking dictionary-encoded ones up through the page's index stream (RLE / bit-packed
+ * hybrid, only its run headers are walked on the host) and the chunk's dictionary.
+ * Supported: INT64 / DOUBLE / INT32 / FLOAT, codec UNCOMPRESSED (0) / SNAPPY (1) (parquet.thrift CompressionCodec), data
+ * pages V1 / V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values, RLE levels, flat columns; anything else ->
+ * TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
  * must stay readable until the next tg_plan_execute* / tg_table_column_buffers on this engine when it is pinned memory.
  */
 TG_API tg_status tg_table_append_parquet_chunk(tg_table* t, const char* name, int32_t dtype, int32_t max_definition_level,
@@ -267,6 +270,9 @@ TG_API int32_t tg_parquet_inspect_chunk(const void* chunk, int64_t n_bytes, tg_p
 /* Host-only: expands the definition levels of a flat optional column chunk into `out_bits` ((num_values + 7) / 8 bytes,
  * LSB first, chunk-relative; may be NULL) and returns the non-NULL count, or -(tg_status). The bitmap the device path uses. */
 TG_API int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits);
+/* Host-only: the Snappy raw-format decoder the chunk path applies to compressed pages (parquet-format Compression.md);
+ * returns the uncompressed size, or -(tg_status) for a corrupt stream / a stream larger than `cap`. */
+TG_API int64_t tg_parquet_snappy_decompress(const void* src, int64_t n_bytes, void* dst, int64_t cap);
 
 /*
  * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity

@@ -353,6 +353,8 @@ class SessionContext:
     # Parquet physical type -> tg_dtype, decoded on the device (tg_table_append_parquet_chunk)
     _PARQUET_TYPES = {"INT64": F.TG_INT64, "DOUBLE": F.TG_FLOAT64, "INT32": F.TG_INT32, "FLOAT": F.TG_FLOAT32}
 
+    _PARQUET_CODECS = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZO": 3, "BROTLI": 4, "LZ4": 5, "ZSTD": 6, "LZ4_RAW": 7}
+
     def register_parquet(self, name: str, path, columns=None):
         """ParquetSource::register (sources/parquet.rs:150-230) for the GPU path: every column chunk of every row group
         goes to the engine as raw file bytes (tg_table_append_parquet_chunk) and is decoded into the Arrow layout in HBM.
@@ -406,7 +408,7 @@ class SessionContext:
                             self._check_parquet_logical_type(col, leaf)
                             start = cm.dictionary_page_offset if cm.has_dictionary_page and cm.dictionary_page_offset else cm.data_page_offset
                             chunk = view[start: start + cm.total_compressed_size]
-                            codec = 0 if cm.compression == "UNCOMPRESSED" else 1
+                            codec = self._PARQUET_CODECS.get(cm.compression, 99)  # parquet.thrift CompressionCodec; unknown -> refused
                             F.check(F.lib().tg_table_append_parquet_chunk(t, col.encode(), self._PARQUET_TYPES[cm.physical_type],
                                                                           leaf.max_definition_level, codec, chunk.ctypes.data,
                                                                           chunk.size, cm.num_values))

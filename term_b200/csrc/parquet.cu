@@ -8,9 +8,17 @@
 // so pq_expand_kernel scatters them to their row positions (Arrow layout) — one warp per block, rank of a row among
 // the block's non-NULL rows from a ballot. Pages without NULLs are copied straight into place (no kernel).
 //
+// Dictionary-encoded chunks (what writers produce by default): the dictionary page's PLAIN values and the data pages'
+// index streams (RLE / bit-packed hybrid) travel as they are; the host only walks the RUN HEADERS of the index streams (one
+// varint per run, not per value) into a run table, and pq_expand_kernel looks every row's index up on the device — binary
+// search of its run, bit extraction, dictionary gather — in the same pass that scatters the values to their rows.
+// Snappy-compressed pages are decompressed on the host into the staging source (the raw format's tag stream is serial
+// by construction); the levels of V2 pages are never compressed.
+//
 // Supported (everything else is TG_ERR_UNSUPPORTED, there is no host decode path): physical INT64 / DOUBLE /
-// INT32 / FLOAT, codec UNCOMPRESSED, data pages V1 and V2, PLAIN values, RLE definition levels, flat columns
-// (max definition level 0 or 1, no repetition levels), no dictionary page.
+// INT32 / FLOAT, codecs UNCOMPRESSED and SNAPPY, data pages V1 and V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values
+// (a chunk may mix them: writers fall back to PLAIN when the dictionary grows too large), RLE definition levels, flat
+// columns (max definition level 0 or 1, no repetition levels).
 #include <algorithm>
 #include <cstring>
 #include <exception>
@@ -98,7 +106,8 @@ struct Thrift {
 };
 
 enum { PQ_DATA_PAGE = 0, PQ_INDEX_PAGE = 1, PQ_DICTIONARY_PAGE = 2, PQ_DATA_PAGE_V2 = 3 };
-enum { PQ_ENC_PLAIN = 0, PQ_ENC_RLE = 3 };
+enum { PQ_ENC_PLAIN = 0, PQ_ENC_PLAIN_DICTIONARY = 2, PQ_ENC_RLE = 3, PQ_ENC_RLE_DICTIONARY = 8 };
+enum { PQ_CODEC_UNCOMPRESSED = 0, PQ_CODEC_SNAPPY = 1 };
 
 // parquet.thrift: PageHeader {1 type, 2 uncompressed_page_size, 3 compressed_page_size, 4 crc, 5 data_page_header,
 // 6 index_page_header, 7 dictionary_page_header, 8 data_page_header_v2}; DataPageHeader {1 num_values, 2 encoding,
@@ -131,6 +140,13 @@ size_t parse_page_header(const uint8_t* p, const uint8_t* end, tg_parquet_page& 
                 else t.skip(ft);
             }
             if (v2) pg.definition_level_encoding = PQ_ENC_RLE;
+        } else if (id == 7 && type == 12) {
+            int ft, fid, flast = 0;
+            while (t.field(ft, fid, flast)) {
+                if (fid == 1 && ft == 5) pg.num_values = (int32_t)t.zigzag();
+                else if (fid == 2 && ft == 5) pg.encoding = (int32_t)t.zigzag();
+                else t.skip(ft);
+            }
         } else {
             t.skip(type);
         }
@@ -222,20 +238,138 @@ void decode_levels(const uint8_t* p, const uint8_t* end, uint8_t* bits, int64_t 
     }
 }
 
+// Snappy raw format (format_description.txt): varint uncompressed length, then elements tagged by their low two bits:
+// 00 literal (length - 1 in the upper six bits, 60..63: that many extra length bytes), 01 copy with an 11-bit offset and
+// a 4..11 byte length, 10 copy with a 16-bit offset, 11 copy with a 32-bit offset (length - 1 in the upper six bits).
+// Copies may overlap their own output (run-length expansion), so they move byte by byte when offset < length.
+size_t snappy_uncompressed_length(const uint8_t* src, size_t n, size_t* header_bytes) {
+    uint64_t v = 0;
+    size_t i = 0;
+    for (int shift = 0; shift < 35; shift += 7) {
+        if (i >= n) throw Error(TG_ERR_INVALID_ARG, "Parquet: truncated Snappy stream");
+        const uint8_t b = src[i++];
+        v |= (uint64_t)(b & 0x7f) << shift;
+        if (!(b & 0x80)) {
+            *header_bytes = i;
+            return (size_t)v;
+        }
+    }
+    throw Error(TG_ERR_INVALID_ARG, "Parquet: bad Snappy length");
+}
+size_t snappy_decompress(const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    size_t ip = 0;
+    const size_t total = snappy_uncompressed_length(src, n, &ip);
+    if (total > cap) throw Error(TG_ERR_INVALID_ARG, "Parquet: Snappy page larger than its header says");
+    size_t op = 0;
+    auto bad = []() { throw Error(TG_ERR_INVALID_ARG, "Parquet: corrupt Snappy stream"); };
+    while (ip < n) {
+        const uint8_t tag = src[ip++];
+        size_t len, off = 0;
+        if ((tag & 3) == 0) {
+            len = (size_t)(tag >> 2) + 1;
+            if (len > 60) {
+                const size_t extra = len - 60;
+                if (ip + extra > n) bad();
+                len = 0;
+                for (size_t k = 0; k < extra; ++k) len |= (size_t)src[ip + k] << (8 * k);
+                len += 1;
+                ip += extra;
+            }
+            if (ip + len > n || op + len > total) bad();
+            memcpy(dst + op, src + ip, len);
+            ip += len;
+            op += len;
+            continue;
+        }
+        if ((tag & 3) == 1) {
+            if (ip + 1 > n) bad();
+            len = (size_t)((tag >> 2) & 7) + 4;
+            off = ((size_t)(tag >> 5) << 8) | src[ip];
+            ip += 1;
+        } else if ((tag & 3) == 2) {
+            if (ip + 2 > n) bad();
+            len = (size_t)(tag >> 2) + 1;
+            off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8);
+            ip += 2;
+        } else {
+            if (ip + 4 > n) bad();
+            len = (size_t)(tag >> 2) + 1;
+            off = (size_t)src[ip] | ((size_t)src[ip + 1] << 8) | ((size_t)src[ip + 2] << 16) | ((size_t)src[ip + 3] << 24);
+            ip += 4;
+        }
+        if (off == 0 || off > op || op + len > total) bad();
+        if (off >= len) memcpy(dst + op, dst + op - off, len);
+        else
+            for (size_t k = 0; k < len; ++k) dst[op + k] = dst[op + k - off];
+        op += len;
+    }
+    if (op != total) bad();
+    return total;
+}
+
+// One run of a dictionary-index stream (RLE / bit-packed hybrid at the page's bit width)
+struct PqRun {
+    uint32_t start;   // dense index (among the section's non-NULL values) of the run's first value
+    uint32_t count;
+    uint64_t data;    // RLE: the repeated index; bit-packed: byte offset of the packed groups in the staging buffer
+    uint32_t bw;      // bit width of the page (0..32)
+    uint32_t packed;  // 1: bit-packed, 0: RLE
+};
+// Walks the run headers of an index stream: p[0] = bit width, then <varint header> (header & 1 ? bit-packed groups of 8
+// : RLE run) until `n_values` are covered. `stage_off` = where p[0] sits in the staging buffer.
+void parse_index_runs(const uint8_t* p, const uint8_t* end, int64_t n_values, uint64_t stage_off, std::vector<PqRun>& runs) {
+    if (n_values == 0) return;
+    if (p >= end) throw Error(TG_ERR_INVALID_ARG, "Parquet: empty dictionary-index section");
+    const uint32_t bw = p[0];
+    if (bw > 32) throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary index bit width > 32");
+    Thrift t{p + 1, end};
+    int64_t done = 0;
+    while (done < n_values) {
+        const uint64_t h = t.varint();
+        if (h & 1) {
+            const uint64_t groups = h >> 1;
+            const uint64_t bytes = groups * bw;
+            if (groups == 0 || groups > ((uint64_t)1 << 40)) throw Error(TG_ERR_INVALID_ARG, "Parquet: bad bit-packed run");
+            t.need((size_t)bytes);
+            const int64_t take = std::min<int64_t>((int64_t)groups * 8, n_values - done);
+            runs.push_back(PqRun{(uint32_t)done, (uint32_t)take, stage_off + (uint64_t)(t.p - p), bw, 1u});
+            t.p += bytes;
+            done += take;
+        } else {
+            const uint64_t run = h >> 1;
+            if (run == 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: empty RLE run in the dictionary indices");
+            const int vb = (int)(bw + 7) / 8;
+            t.need((size_t)vb);
+            uint64_t v = 0;
+            for (int k = 0; k < vb; ++k) v |= (uint64_t)t.p[k] << (8 * k);
+            t.p += vb;
+            const int64_t take = std::min<int64_t>((int64_t)run, n_values - done);
+            runs.push_back(PqRun{(uint32_t)done, (uint32_t)take, v, bw, 0u});
+            done += take;
+        }
+    }
+}
+
 struct PqBlock {
-    uint64_t src_off;    // byte offset in the staging buffer of the block's first non-NULL value
-    uint32_t first_row;  // chunk-relative
-    uint32_t n_rows;     // <= PQ_BLOCK_ROWS
+    uint64_t src_off;     // PLAIN: byte offset in the staging buffer of the block's first non-NULL value
+    uint32_t first_row;   // chunk-relative
+    uint32_t n_rows;      // <= PQ_BLOCK_ROWS
+    uint32_t first_dense; // dictionary: dense index (inside the block's section) of the block's first non-NULL value
+    uint32_t run_lo, run_hi;  // dictionary: the section's runs [run_lo, run_hi) in the run table; run_hi == 0: a PLAIN block
+    uint32_t pad;
 };
 constexpr int PQ_BLOCK_ROWS = 1024, PQ_THREADS = 256;
 
 }  // namespace
 
-// One warp per block. Row r of the block is non-NULL iff its bit is set; its value is the (number of set bits before
-// r in the block)-th of the block's dense source values. NULL rows are written as 0 so the column is deterministic.
+// One warp per block. Row r of the block is non-NULL iff its bit is set (bits == nullptr: a required column, every row
+// is); its value is the (number of set bits before r in the block)-th of the block's dense source values — read directly
+// (PLAIN) or through the section's index stream and the chunk's dictionary. NULL rows are written as 0 so the column is
+// deterministic. Indices past the dictionary (a corrupt file) read its last entry: memory-safe, never out of bounds.
 template <typename V>
 __global__ void __launch_bounds__(PQ_THREADS) pq_expand_kernel(const uint8_t* __restrict__ stage, const uint8_t* __restrict__ bits,
-                                                              const PqBlock* __restrict__ blocks, int64_t n_blocks, V* __restrict__ dst) {
+                                                              const PqBlock* __restrict__ blocks, int64_t n_blocks, V* __restrict__ dst,
+                                                              const PqRun* __restrict__ runs, const V* __restrict__ dict, uint32_t dict_count) {
     const int lane = threadIdx.x & 31;
     const int64_t warps = (int64_t)gridDim.x * (PQ_THREADS / 32);
     for (int64_t b = (int64_t)blockIdx.x * (PQ_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
@@ -245,11 +379,35 @@ __global__ void __launch_bounds__(PQ_THREADS) pq_expand_kernel(const uint8_t* __
         for (uint32_t i = 0; i < blk.n_rows; i += 32) {
             const bool in = i + lane < blk.n_rows;
             const uint64_t r = (uint64_t)blk.first_row + i + lane;
-            const bool valid = in && ((__ldg(bits + (r >> 3)) >> (r & 7)) & 1);
+            const bool valid = in && (!bits || ((__ldg(bits + (r >> 3)) >> (r & 7)) & 1));
             const unsigned mask = __ballot_sync(0xffffffffu, valid);
             const uint32_t rank = running + __popc(mask & ((1u << lane) - 1u));
             V v = 0;
-            if (valid) v = __ldg(src + rank);
+            if (valid) {
+                if (blk.run_hi == 0) {
+                    v = __ldg(src + rank);
+                } else {
+                    const uint32_t d = blk.first_dense + rank;
+                    uint32_t lo = blk.run_lo, hi = blk.run_hi;  // the last run with start <= d
+                    while (hi - lo > 1) {
+                        const uint32_t mid = (lo + hi) >> 1;
+                        if (__ldg(&runs[mid].start) <= d) lo = mid;
+                        else hi = mid;
+                    }
+                    const PqRun run = runs[lo];
+                    uint64_t idx = run.data;
+                    if (run.packed) {
+                        const uint64_t bit = (uint64_t)(d - run.start) * run.bw;
+                        const uint64_t byte = run.data + (bit >> 3);
+                        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (byte & ~(uint64_t)3));
+                        const uint64_t w = (uint64_t)__ldg(wp) | ((uint64_t)__ldg(wp + 1) << 32);
+                        const uint32_t sh = (uint32_t)((byte & 3) * 8 + (bit & 7));
+                        idx = run.bw ? ((w >> sh) & (((uint64_t)1 << run.bw) - 1ull)) : 0ull;
+                    }
+                    if (idx >= dict_count) idx = dict_count - 1;
+                    v = __ldg(dict + idx);
+                }
+            }
             if (in) dst[r] = v;
             running += __popc(mask);
         }
@@ -317,7 +475,8 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
     std::lock_guard<std::mutex> g(e.mu);
     TG_CUDA(cudaSetDevice(e.device));
     if (!chunk || n_bytes <= 0 || num_values < 0) throw Error(TG_ERR_INVALID_ARG, "empty Parquet column chunk");
-    if (codec != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: only UNCOMPRESSED column chunks are decoded on the device");
+    if (codec != PQ_CODEC_UNCOMPRESSED && codec != PQ_CODEC_SNAPPY)
+        throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " (only UNCOMPRESSED and SNAPPY chunks are decoded)");
     if (max_def_level < 0 || max_def_level > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: nested columns (max definition level > 1)");
     if (dtype != TG_INT64 && dtype != TG_FLOAT64 && dtype != TG_INT32 && dtype != TG_FLOAT32)
         throw Error(TG_ERR_UNSUPPORTED, "Parquet: only INT64 / DOUBLE / INT32 / FLOAT columns are decoded on the device");
@@ -327,38 +486,84 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
     const int64_t have = c.n_rows;
     const size_t w = (size_t)c.elem_bytes();
 
-    // ---- pages ----
+    // ---- pages: every page body as UNCOMPRESSED bytes (a view of the chunk, or of `inflated` for Snappy pages) ----
     const std::vector<tg_parquet_page> pages = walk_pages(chunk, n_bytes);
     struct Section {
-        int64_t first_row, n_rows, values_off, values_bytes, levels_off, levels_bytes;
+        int64_t first_row, n_rows;
+        const uint8_t* values;
+        int64_t values_bytes;
+        const uint8_t* levels;
+        int64_t levels_bytes;
+        bool dict;
     };
     std::vector<Section> secs;
+    std::vector<uint8_t> inflated;
+    {
+        size_t need = 0;
+        for (auto& pg : pages)
+            if (codec == PQ_CODEC_SNAPPY && pg.page_type != PQ_INDEX_PAGE) need += (size_t)pg.uncompressed_bytes + 16;
+        inflated.resize(need);
+    }
+    size_t inflated_used = 0;
+    const uint8_t* dict_values = nullptr;
+    int64_t dict_count = 0;
     int64_t rows = 0;
     for (auto& pg : pages) {
         if (pg.page_type == PQ_INDEX_PAGE) continue;
-        if (pg.page_type == PQ_DICTIONARY_PAGE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: dictionary-encoded column chunk (write with use_dictionary=false)");
-        if (pg.page_type != PQ_DATA_PAGE && pg.page_type != PQ_DATA_PAGE_V2) throw Error(TG_ERR_UNSUPPORTED, "Parquet: unknown page type");
-        if (pg.encoding != PQ_ENC_PLAIN) throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) + " (only PLAIN)");
+        if (pg.page_type != PQ_DATA_PAGE && pg.page_type != PQ_DATA_PAGE_V2 && pg.page_type != PQ_DICTIONARY_PAGE)
+            throw Error(TG_ERR_UNSUPPORTED, "Parquet: unknown page type");
         if (pg.version == 2 && (pg.repetition_levels_bytes != 0)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: repeated column");
-        Section s{rows, pg.num_values, pg.body_offset, pg.body_bytes, 0, 0};
+        // the uncompressed body: V1 and dictionary pages are compressed as a whole, V2 keeps its level sections plain
+        const uint8_t* body = chunk + pg.body_offset;
+        int64_t body_bytes = pg.body_bytes;
+        const int64_t plain_head = pg.page_type == PQ_DATA_PAGE_V2 ? (int64_t)pg.definition_levels_bytes + pg.repetition_levels_bytes : 0;
+        const bool compressed = codec == PQ_CODEC_SNAPPY && (pg.page_type != PQ_DATA_PAGE_V2 || pg.is_compressed);
+        if (compressed) {
+            if ((int64_t)pg.uncompressed_bytes < plain_head) throw Error(TG_ERR_INVALID_ARG, "Parquet: page sizes do not fit its level sections");
+            uint8_t* out = inflated.data() + inflated_used;
+            memcpy(out, body, (size_t)plain_head);
+            const size_t got = pg.body_bytes > plain_head
+                                   ? snappy_decompress(body + plain_head, (size_t)(pg.body_bytes - plain_head), out + plain_head,
+                                                       (size_t)(pg.uncompressed_bytes - plain_head))
+                                   : 0;
+            body = out;
+            body_bytes = plain_head + (int64_t)got;
+            inflated_used += (size_t)pg.uncompressed_bytes + 16;
+        }
+        if (pg.page_type == PQ_DICTIONARY_PAGE) {
+            if (pg.encoding != PQ_ENC_PLAIN && pg.encoding != PQ_ENC_PLAIN_DICTIONARY)
+                throw Error(TG_ERR_UNSUPPORTED, "Parquet: dictionary page encoding " + std::to_string(pg.encoding));
+            if (dict_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: more than one dictionary page in a column chunk");
+            if ((int64_t)pg.num_values * (int64_t)w > body_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary page shorter than its value count");
+            dict_values = body;
+            dict_count = pg.num_values;
+            continue;
+        }
+        const bool is_dict = pg.encoding == PQ_ENC_RLE_DICTIONARY || pg.encoding == PQ_ENC_PLAIN_DICTIONARY;
+        if (!is_dict && pg.encoding != PQ_ENC_PLAIN)
+            throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) + " (PLAIN and dictionary encodings only)");
+        Section s{rows, pg.num_values, body, body_bytes, nullptr, 0, is_dict};
         if (max_def_level > 0) {
             if (pg.definition_level_encoding != PQ_ENC_RLE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: definition levels not RLE-encoded");
             if (pg.version == 1) {
-                if (pg.body_bytes < 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: data page too short");
+                if (body_bytes < 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: data page too short");
                 uint32_t len;
-                memcpy(&len, chunk + pg.body_offset, 4);
-                if ((int64_t)len > (int64_t)pg.body_bytes - 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
-                s.levels_off = pg.body_offset + 4;
+                memcpy(&len, body, 4);
+                if ((int64_t)len > body_bytes - 4) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
+                s.levels = body + 4;
                 s.levels_bytes = len;
-                s.values_off = s.levels_off + len;
-                s.values_bytes = pg.body_bytes - 4 - (int64_t)len;
+                s.values = s.levels + len;
+                s.values_bytes = body_bytes - 4 - (int64_t)len;
             } else {
-                s.levels_off = pg.body_offset;
+                s.levels = body;
                 s.levels_bytes = pg.definition_levels_bytes;
-                s.values_off = s.levels_off + s.levels_bytes;
-                s.values_bytes = pg.body_bytes - s.levels_bytes;
+                s.values = s.levels + s.levels_bytes;
+                s.values_bytes = body_bytes - s.levels_bytes;
             }
             if (s.values_bytes < 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: definition levels run past the page");
+        } else if (pg.version == 2 && pg.definition_levels_bytes) {
+            s.values = body + pg.definition_levels_bytes;
+            s.values_bytes = body_bytes - pg.definition_levels_bytes;
         }
         rows += pg.num_values;
         secs.push_back(s);
@@ -368,10 +573,14 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         t.n_rows = std::max(t.n_rows, c.n_rows);
         return;
     }
+    bool any_dict = false;
+    for (auto& s : secs) any_dict = any_dict || s.dict;
+    if (!dict_values) dict_count = 0;  // (a dictionary-encoded page needs one unless all its rows are NULL: checked with the levels)
 
     // ---- the value sections travel while a helper thread expands the definition levels: staging a pageable source is
     // a host memcpy into the pinned ring per piece, so the two halves of the host work run side by side. Every page's
-    // value section goes to a 16-byte aligned place in a staging block (required columns: straight into place) ----
+    // value section goes to a 16-byte aligned place in a staging block (PLAIN pages of required columns: straight into
+    // place); the dictionary's values sit in the same block ----
     e.dev_reserve(c.values, (size_t)(have + num_values) * w, (size_t)have * w);
     uint8_t* dst = c.values.p + (size_t)have * w;
     std::vector<int64_t> stage_off(secs.size(), -1);
@@ -379,35 +588,50 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
     uint8_t* stage = nullptr;
     std::vector<uint8_t> bits;
     std::vector<PqBlock> blocks;
-    if (max_def_level == 0) {
+    std::vector<PqRun> runs;
+    const bool direct = max_def_level == 0 && !any_dict;
+    if (direct) {
         for (auto& s : secs) {
             if (s.values_bytes != s.n_rows * (int64_t)w) throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page size does not match its value count");
-            e.h2d(dst + (size_t)s.first_row * w, chunk + s.values_off, (size_t)s.values_bytes);
+            e.h2d(dst + (size_t)s.first_row * w, s.values, (size_t)s.values_bytes);
         }
     } else {
         for (size_t i = 0; i < secs.size(); ++i) {
             stage_off[i] = (int64_t)stage_bytes;
             stage_bytes += ((size_t)secs[i].values_bytes + 15) & ~(size_t)15;
         }
+        const size_t dict_off = stage_bytes;
+        stage_bytes += (((size_t)dict_count * w) + 15) & ~(size_t)15;
         stage_bytes += 64;
-        // definition levels -> chunk-relative validity bits + blocks
+        // definition levels -> chunk-relative validity bits + blocks (+ the run tables of dictionary-index sections)
         std::exception_ptr decode_err;
         auto decode = [&]() {
             try {
-                bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
+                if (max_def_level > 0) bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
                 blocks.reserve((size_t)num_values / PQ_BLOCK_ROWS + secs.size() + 1);
                 for (size_t i = 0; i < secs.size(); ++i) {
                     const Section& s = secs[i];
-                    decode_levels(chunk + s.levels_off, chunk + s.levels_off + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
+                    if (max_def_level > 0) decode_levels(s.levels, s.levels + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
+                    const uint32_t run_lo = (uint32_t)runs.size();
+                    const size_t blk_lo = blocks.size();
                     int64_t prefix = 0;
                     for (int64_t r = 0; r < s.n_rows; r += PQ_BLOCK_ROWS) {
                         const int64_t nr = std::min<int64_t>(PQ_BLOCK_ROWS, s.n_rows - r);
-                        blocks.push_back(PqBlock{(uint64_t)stage_off[i] + (uint64_t)prefix * w, (uint32_t)(s.first_row + r), (uint32_t)nr});
-                        prefix += count_ones(bits.data(), s.first_row + r, s.first_row + r + nr);
+                        blocks.push_back(PqBlock{(uint64_t)stage_off[i] + (uint64_t)prefix * w, (uint32_t)(s.first_row + r), (uint32_t)nr, (uint32_t)prefix, 0u, 0u, 0u});
+                        prefix += max_def_level > 0 ? count_ones(bits.data(), s.first_row + r, s.first_row + r + nr) : nr;
                     }
-                    if (prefix * (int64_t)w != s.values_bytes)
+                    if (s.dict) {
+                        if (prefix > 0 && dict_count <= 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary-encoded page without a dictionary page");
+                        parse_index_runs(s.values, s.values + s.values_bytes, prefix, (uint64_t)stage_off[i], runs);
+                        const uint32_t run_hi = (uint32_t)runs.size();
+                        for (size_t k = blk_lo; k < blocks.size(); ++k) {
+                            blocks[k].run_lo = run_lo;
+                            blocks[k].run_hi = run_hi > run_lo ? run_hi : run_lo + 1;  // (an all-NULL section has no runs: never looked up)
+                        }
+                    } else if (prefix * (int64_t)w != s.values_bytes) {
                         throw Error(TG_ERR_INVALID_ARG, "Parquet: PLAIN page holds " + std::to_string(s.values_bytes) + " value bytes for " +
                                                             std::to_string(prefix) + " non-null rows");
+                    }
                 }
             } catch (...) {
                 decode_err = std::current_exception();
@@ -423,46 +647,67 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         stage = e.dev_alloc(stage_bytes);
         e.deferred_free.emplace_back(stage, stage_bytes);  // released by the next sync_copies(), also on the error paths
         for (size_t i = 0; i < secs.size(); ++i)
-            e.h2d(stage + stage_off[i], chunk + secs[i].values_off, (size_t)secs[i].values_bytes);
+            if (secs[i].values_bytes) e.h2d(stage + stage_off[i], secs[i].values, (size_t)secs[i].values_bytes);
+        if (dict_count > 0) e.h2d(stage + dict_off, dict_values, (size_t)dict_count * w);
         helper.join();
         if (decode_err) std::rethrow_exception(decode_err);
-    }
 
-    // ---- pivot of the shifted sums: from the first page's dense values ----
-    if (!c.pivot_set && !secs.empty()) {
-        const int64_t nv = std::min<int64_t>(secs[0].values_bytes / (int64_t)w, 4096);
-        if (nv > 0 && (dtype == TG_INT64 || dtype == TG_FLOAT64)) {
-            std::vector<uint64_t> head((size_t)nv);
-            memcpy(head.data(), chunk + secs[0].values_off, (size_t)nv * 8);
-            set_pivot_host(c, dtype, nv, head.data(), nullptr, 0);
+        // ---- pivot of the shifted sums: from the dictionary / the first PLAIN page's dense values ----
+        if (!c.pivot_set && (dtype == TG_INT64 || dtype == TG_FLOAT64)) {
+            const uint8_t* src = dict_count > 0 ? dict_values : (!secs.empty() && !secs[0].dict ? secs[0].values : nullptr);
+            const int64_t nv = std::min<int64_t>(dict_count > 0 ? dict_count : (secs.empty() ? 0 : secs[0].values_bytes / (int64_t)w), 4096);
+            if (src && nv > 0) {
+                std::vector<uint64_t> head((size_t)nv);
+                memcpy(head.data(), src, (size_t)nv * 8);
+                set_pivot_host(c, dtype, nv, head.data(), nullptr, 0);
+            }
         }
-    }
+        // ---- validity through the common path (keeps the host mirror of a partial tail byte) ----
+        append_validity(e, c, have, max_def_level > 0 ? bits.data() : nullptr, 0, num_values);
 
-    // ---- validity through the common path (keeps the host mirror of a partial tail byte) ----
-    append_validity(e, c, have, max_def_level > 0 ? bits.data() : nullptr, 0, num_values);
-
-    // ---- expand ----
-    if (max_def_level > 0) {
-        const size_t bits_b = ((size_t)(num_values + 7) / 8 + 15) & ~(size_t)15, blk_b = blocks.size() * sizeof(PqBlock);
-        uint8_t* aux = e.dev_alloc(bits_b + blk_b + 64);
-        e.h2d(aux, bits.data(), (size_t)(num_values + 7) / 8);
-        e.h2d(aux + bits_b, blocks.data(), blk_b);
-        // h2d of pageable memory returns once the bytes sit in the pinned ring, so `bits` / `blocks` may go out of scope
+        // ---- expand ----
+        const size_t bits_b = max_def_level > 0 ? (((size_t)(num_values + 7) / 8 + 15) & ~(size_t)15) : 0;
+        const size_t blk_b = (blocks.size() * sizeof(PqBlock) + 15) & ~(size_t)15, run_b = runs.size() * sizeof(PqRun);
+        uint8_t* aux = e.dev_alloc(bits_b + blk_b + run_b + 64);
+        if (bits_b) e.h2d(aux, bits.data(), (size_t)(num_values + 7) / 8);
+        e.h2d(aux + bits_b, blocks.data(), blocks.size() * sizeof(PqBlock));
+        if (run_b) e.h2d(aux + bits_b + blk_b, runs.data(), run_b);
+        // h2d of pageable memory returns once the bytes sit in the pinned ring, so `bits` / `blocks` / `inflated` may go out of scope
         const int64_t nb = (int64_t)blocks.size();
         const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nb + PQ_THREADS / 32 - 1) / (PQ_THREADS / 32), (int64_t)e.sm_count * 8));
+        const uint8_t* d_bits = bits_b ? aux : nullptr;
+        const PqBlock* d_blocks = reinterpret_cast<const PqBlock*>(aux + bits_b);
+        const PqRun* d_runs = reinterpret_cast<const PqRun*>(aux + bits_b + blk_b);
         if (w == 8)
-            pq_expand_kernel<uint64_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, aux, reinterpret_cast<const PqBlock*>(aux + bits_b), nb,
-                                                                               reinterpret_cast<uint64_t*>(dst));
+            pq_expand_kernel<uint64_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, d_bits, d_blocks, nb, reinterpret_cast<uint64_t*>(dst), d_runs,
+                                                                               reinterpret_cast<const uint64_t*>(stage + dict_off), (uint32_t)dict_count);
         else
-            pq_expand_kernel<uint32_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, aux, reinterpret_cast<const PqBlock*>(aux + bits_b), nb,
-                                                                               reinterpret_cast<uint32_t*>(dst));
+            pq_expand_kernel<uint32_t><<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, d_bits, d_blocks, nb, reinterpret_cast<uint32_t*>(dst), d_runs,
+                                                                               reinterpret_cast<const uint32_t*>(stage + dict_off), (uint32_t)dict_count);
         TG_CUDA(cudaGetLastError());
         e.launches += 1;
-        e.deferred_free.emplace_back(aux, bits_b + blk_b + 64);
+        e.deferred_free.emplace_back(aux, bits_b + blk_b + run_b + 64);
+    }
+    if (direct) {
+        if (!c.pivot_set && !secs.empty() && (dtype == TG_INT64 || dtype == TG_FLOAT64)) {
+            const int64_t nv = std::min<int64_t>(secs[0].values_bytes / (int64_t)w, 4096);
+            if (nv > 0) {
+                std::vector<uint64_t> head((size_t)nv);
+                memcpy(head.data(), secs[0].values, (size_t)nv * 8);
+                set_pivot_host(c, dtype, nv, head.data(), nullptr, 0);
+            }
+        }
+        append_validity(e, c, have, nullptr, 0, num_values);
     }
     c.value_bytes = (have + num_values) * (int64_t)w;
     c.n_rows = have + num_values;
     t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+// host-only (tests): Snappy raw-format decompression as the Parquet path uses it; returns the uncompressed size
+int64_t parquet_snappy_decompress(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+    if (!src || n <= 0 || !dst || cap < 0) throw Error(TG_ERR_INVALID_ARG, "NULL Snappy buffers");
+    return (int64_t)snappy_decompress(src, (size_t)n, dst, (size_t)cap);
 }
 
 }  // namespace tg

@@ -1,6 +1,6 @@
 """Parquet column chunk -> HBM (sources/parquet.rs in the reference). The files are written here with
-pyarrow (uncompressed, PLAIN, data pages V1 and V2, small pages so that chunks hold many), pyarrow's own reader is the
-ground truth. CPU tests: the host page walk (Thrift compact PageHeaders) and the definition-level expansion. GPU
+pyarrow (uncompressed / Snappy, PLAIN / dictionary-encoded, data pages V1 and V2, small pages so that chunks hold many),
+pyarrow's own reader is the ground truth. CPU tests: the host page walk (Thrift compact PageHeaders) and the definition-level expansion. GPU
 tests: the decoded Arrow buffers in HBM bit for bit, and a suite over the decoded table against the same suite over the
 table registered from host Arrow arrays."""
 import os
@@ -135,18 +135,131 @@ def test_suite_over_parquet_equals_suite_over_arrow(ctx, tmp_path):
         ctx.deregister_table("pq_arrow")
 
 
+def _write_encoded(tmp_path, n, null_p, version, compression, seed=3, dict_limit=None):
+    """low-cardinality columns (dictionary pages + RLE / bit-packed index streams), a constant column (bit width 0), a
+    sorted one (long RLE runs), a high-cardinality one (the writer falls back to PLAIN when the dictionary outgrows
+    `dict_limit`), nullable and required, 4- and 8-byte types"""
+    rng = np.random.default_rng(seed + n)
+    cols = {
+        "cat": rng.integers(0, 37, n).astype(np.int64) * 1_000_003,
+        "const": np.full(n, 42, dtype=np.int64),
+        "runs": np.sort(rng.integers(0, 9, n)).astype(np.float64) * 0.5,
+        "wide": rng.integers(0, 1 << 40, n).astype(np.int64),
+        "f32": rng.integers(0, 5, n).astype(np.float32) * 1.25,
+        "i32": rng.integers(-3, 3, n).astype(np.int32),
+    }
+    masks = {c: rng.random(n) < null_p for c in cols}
+    fields = [pa.field(c, pa.from_numpy_dtype(v.dtype)) for c, v in cols.items()] + [pa.field("req", pa.int64(), nullable=False)]
+    arrays = {c: pa.array(v, mask=masks[c]) for c, v in cols.items()}
+    arrays["req"] = pa.array(cols["cat"])
+    t = pa.table(arrays, schema=pa.schema(fields))
+    path = os.path.join(tmp_path, f"enc_{n}_{version}_{compression}.parquet")
+    kw = dict(dictionary_pagesize_limit=dict_limit) if dict_limit else {}
+    pq.write_table(t, path, compression=compression, use_dictionary=True, data_page_version=version, row_group_size=max(1, n // 2 + 1),
+                   data_page_size=32 * 1024, **kw)
+    return path, t
+
+
+def test_snappy_decoder_matches_pyarrow(built_lib):
+    rng = np.random.default_rng(5)
+    codec = pa.Codec("snappy")
+    samples = [b"", b"a", b"abc" * 1000, bytes(rng.integers(0, 256, 70_000, dtype=np.uint8)), bytes(rng.integers(0, 4, 300_000, dtype=np.uint8)),
+               np.sort(rng.integers(0, 1 << 20, 50_000)).astype(np.int64).tobytes(), b"\x00" * 200_000, bytes(range(256)) * 300]
+    for raw in samples:
+        comp = np.frombuffer(codec.compress(raw, asbytes=True), dtype=np.uint8).copy()
+        out = np.zeros(len(raw) + 8, dtype=np.uint8)
+        got = F.lib().tg_parquet_snappy_decompress(comp.ctypes.data, comp.size, out.ctypes.data, len(raw))
+        assert got == len(raw), F.last_error()
+        assert out[: len(raw)].tobytes() == raw
+        if len(raw) > 64:
+            # a stream that claims more than the room it is given, and a truncated one
+            assert F.lib().tg_parquet_snappy_decompress(comp.ctypes.data, comp.size, out.ctypes.data, len(raw) - 1) < 0
+            assert F.lib().tg_parquet_snappy_decompress(comp.ctypes.data, comp.size // 2, out.ctypes.data, len(raw)) < 0
+    # copies that reach before the start of the output
+    bad = np.frombuffer(b"\x08" + b"\x01\xff" + b"\x00" * 8, dtype=np.uint8).copy()
+    out = np.zeros(64, dtype=np.uint8)
+    assert F.lib().tg_parquet_snappy_decompress(bad.ctypes.data, bad.size, out.ctypes.data, 64) < 0
+
+
+@pytest.mark.parametrize("compression", ["NONE", "SNAPPY"])
+def test_page_walk_sees_dictionary_pages(built_lib, tmp_path, compression):
+    path, t = _write_encoded(str(tmp_path), 20_000, 0.1, "1.0", compression)
+    md = pq.ParquetFile(path).metadata
+    raw = open(path, "rb").read()
+    cm = md.row_group(0).column(0)
+    assert cm.has_dictionary_page
+    start = cm.dictionary_page_offset
+    chunk = np.frombuffer(raw[start: start + cm.total_compressed_size], dtype=np.uint8)
+    n_pages = F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, None, 0)
+    pages = (F.tg_parquet_page * n_pages)()
+    assert F.lib().tg_parquet_inspect_chunk(chunk.ctypes.data, chunk.size, pages, n_pages) == n_pages
+    assert pages[0].page_type == 2 and pages[0].num_values == 37 and pages[0].encoding in (0, 2)
+    assert all(p.page_type == 0 and p.encoding in (2, 8) for p in pages[1:])
+    assert sum(p.num_values for p in pages[1:]) == cm.num_values
+    if compression == "SNAPPY":
+        assert pages[0].uncompressed_bytes == 37 * 8
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("compression", ["NONE", "SNAPPY"])
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("n,null_p,dict_limit", [(1, 0.0, None), (1000, 0.3, None), (300_000, 0.05, None), (70_001, 1.0, None), (250_000, 0.02, 4096),
+                                                  (120_000, 0.999, None)])
+def test_dictionary_and_snappy_chunks_decode_to_the_arrow_layout(ctx, tmp_path, n, null_p, dict_limit, version, compression):
+    path, t = _write_encoded(str(tmp_path), n, null_p, version, compression, dict_limit=dict_limit)
+    name = f"pqe_{n}_{version.replace('.', '')}_{compression}"
+    ctx.register_parquet(name, path)
+    try:
+        assert ctx.num_rows(name) == n
+        for col in t.column_names:
+            dt = t.schema.field(col).type.to_pandas_dtype()
+            vals, valid, b = _device_column(ctx, name, col, dt)
+            want_valid = np.asarray(t.column(col).is_valid())
+            want = np.asarray(t.column(col).fill_null(0)).astype(dt)
+            if valid is None:
+                assert want_valid.all(), col
+                valid = np.ones(n, dtype=bool)
+            assert (valid == want_valid).all(), col
+            assert b["null_count"] == int((~want_valid).sum())
+            assert (vals.view(np.uint8).reshape(n, -1)[valid] == want.view(np.uint8).reshape(n, -1)[valid]).all(), col  # bit for bit
+            assert (vals[~valid] == 0).all(), col
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+def test_suite_over_encoded_parquet_equals_suite_over_arrow(ctx, tmp_path):
+    path, t = _write_encoded(str(tmp_path), 200_000, 0.05, "1.0", "SNAPPY", seed=21, dict_limit=8192)
+    ctx.register_parquet("pqe_suite", path)
+    ctx.register_table("pqe_arrow", t)
+    try:
+        A = T.Assertion
+
+        def suite(name):
+            cb = (T.Check.builder("c").has_size(A.GreaterThan(0.0)).completeness("cat", 0.9).has_min("runs", A.LessThan(1.0))
+                  .has_max("wide", A.GreaterThan(0.0)).has_sum("cat", A.LessThan(1e18)).has_mean("runs", A.Between(0.0, 5.0))
+                  .has_standard_deviation("wide", A.GreaterThan(0.0)).has_correlation("cat", "wide", A.Between(-1.0, 1.0))
+                  .satisfies("const = 42").validates_uniqueness(["wide"], 0.0).has_approx_quantile("runs", 0.5, A.Between(0.0, 5.0)))
+            return T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        got, want = suite("pqe_suite"), suite("pqe_arrow")
+        assert [(r.name, r.status, r.metric, r.message) for r in got] == [(r.name, r.status, r.metric, r.message) for r in want]
+    finally:
+        ctx.deregister_table("pqe_suite")
+        ctx.deregister_table("pqe_arrow")
+
+
 @pytest.mark.gpu
 def test_unsupported_parquet_features_fail_loudly(ctx, tmp_path):
     t = pa.table({"k": pa.array([1, 2, 3, 1, 2, 3] * 100), "s": pa.array(["a", "b", "c"] * 200)})
-    p1 = os.path.join(str(tmp_path), "dict.parquet")
-    pq.write_table(t, p1, compression="NONE", use_dictionary=True)
-    with pytest.raises(T.TermGpuError, match="dictionary"):
+    p1 = os.path.join(str(tmp_path), "delta.parquet")
+    pq.write_table(t, p1, compression="NONE", use_dictionary=False, column_encoding={"k": "DELTA_BINARY_PACKED", "s": "PLAIN"})
+    with pytest.raises(T.TermGpuError, match="encoding"):
         ctx.register_parquet("pq_bad", p1, columns=["k"])
     with pytest.raises(T.TermGpuError):  # a failed registration leaves no half-built table behind
         ctx.num_rows("pq_bad")
-    p2 = os.path.join(str(tmp_path), "snappy.parquet")
-    pq.write_table(t, p2, compression="SNAPPY", use_dictionary=False)
-    with pytest.raises(T.TermGpuError, match="UNCOMPRESSED"):
+    p2 = os.path.join(str(tmp_path), "gzip.parquet")
+    pq.write_table(t, p2, compression="GZIP", use_dictionary=False)
+    with pytest.raises(T.TermGpuError, match="codec"):
         ctx.register_parquet("pq_bad", p2, columns=["k"])
     p3 = os.path.join(str(tmp_path), "str.parquet")
     pq.write_table(t, p3, compression="NONE", use_dictionary=False)
