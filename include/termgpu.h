@@ -248,7 +248,9 @@ TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, cons
  * bitmap while the value bytes travel; Snappy pages are decompressed on the host; the device scatters the densely stored
  * non-NULL values to their rows, looking dictionary-encoded ones up through the page's index stream (RLE / bit-packed
  * hybrid, only its run headers are walked on the host) and the chunk's dictionary.
- * Supported: INT64 / DOUBLE / INT32 / FLOAT, codec UNCOMPRESSED (0) / SNAPPY (1) (parquet.thrift CompressionCodec), data
+ * BYTE_ARRAY strings (dtype TG_UTF8) become int32 offsets + concatenated bytes: the device locates every row's bytes
+ * (dictionary entry or PLAIN value), scans the lengths and copies; the host walks the PLAIN pages' length prefixes.
+ * Supported: INT64 / DOUBLE / INT32 / FLOAT / BYTE_ARRAY (Utf8), codec UNCOMPRESSED (0) / SNAPPY (1) (parquet.thrift CompressionCodec), data
  * pages V1 / V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values, RLE levels, flat columns; anything else ->
  * TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
  * must stay readable until the next tg_plan_execute* / tg_table_column_buffers on this engine when it is pinned memory.

@@ -351,7 +351,7 @@ class SessionContext:
                 C.CFUNCTYPE(None, C.c_void_p)(rel_s)(C.addressof(schema_buf))
 
     # Parquet physical type -> tg_dtype, decoded on the device (tg_table_append_parquet_chunk)
-    _PARQUET_TYPES = {"INT64": F.TG_INT64, "DOUBLE": F.TG_FLOAT64, "INT32": F.TG_INT32, "FLOAT": F.TG_FLOAT32}
+    _PARQUET_TYPES = {"INT64": F.TG_INT64, "DOUBLE": F.TG_FLOAT64, "INT32": F.TG_INT32, "FLOAT": F.TG_FLOAT32, "BYTE_ARRAY": F.TG_UTF8}
 
     _PARQUET_CODECS = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZO": 3, "BROTLI": 4, "LZ4": 5, "ZSTD": 6, "LZ4_RAW": 7}
 
@@ -376,6 +376,11 @@ class SessionContext:
         the reference's ParquetSource yields their logical Arrow types (sources/parquet.rs:150-230)."""
         lt = str(getattr(leaf, "logical_type", "NONE") or "NONE").upper()
         ct = str(getattr(leaf, "converted_type", "NONE") or "NONE").upper()
+        if str(leaf.physical_type) == "BYTE_ARRAY":
+            # strings only: the string kernels rely on valid UTF-8 (Arrow's Utf8 contract); raw binary is refused
+            if lt == "STRING" or ct == "UTF8":
+                return
+            raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': BYTE_ARRAY with logical type {lt} / {ct} (only STRING columns)")
         ok_logical = lt in ("NONE", "NULL") or lt.startswith("INT(BITWIDTH=64, ISSIGNED=TRUE") or lt.startswith("INT(BITWIDTH=32, ISSIGNED=TRUE")
         ok_converted = ct in ("NONE", "INT_64", "INT_32")
         if not (ok_logical and ok_converted):

@@ -16,7 +16,7 @@
 // by construction); the levels of V2 pages are never compressed.
 //
 // Supported (everything else is TG_ERR_UNSUPPORTED, there is no host decode path): physical INT64 / DOUBLE /
-// INT32 / FLOAT, codecs UNCOMPRESSED and SNAPPY, data pages V1 and V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values
+// INT32 / FLOAT and BYTE_ARRAY strings (below), codecs UNCOMPRESSED and SNAPPY, data pages V1 and V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values
 // (a chunk may mix them: writers fall back to PLAIN when the dictionary grows too large), RLE definition levels, flat
 // columns (max definition level 0 or 1, no repetition levels).
 #include <algorithm>
@@ -469,44 +469,33 @@ int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t nu
     return count_ones(bits.data(), 0, rows);
 }
 
-void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype, int32_t max_def_level, int32_t codec,
-                                const uint8_t* chunk, int64_t n_bytes, int64_t num_values) {
-    Engine& e = *t.eng;
-    std::lock_guard<std::mutex> g(e.mu);
-    TG_CUDA(cudaSetDevice(e.device));
-    if (!chunk || n_bytes <= 0 || num_values < 0) throw Error(TG_ERR_INVALID_ARG, "empty Parquet column chunk");
-    if (codec != PQ_CODEC_UNCOMPRESSED && codec != PQ_CODEC_SNAPPY)
-        throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " (only UNCOMPRESSED and SNAPPY chunks are decoded)");
-    if (max_def_level < 0 || max_def_level > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: nested columns (max definition level > 1)");
-    if (dtype != TG_INT64 && dtype != TG_FLOAT64 && dtype != TG_INT32 && dtype != TG_FLOAT32)
-        throw Error(TG_ERR_UNSUPPORTED, "Parquet: only INT64 / DOUBLE / INT32 / FLOAT columns are decoded on the device");
-    if (num_values >= ((int64_t)1 << 32)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: column chunk with 2^32 or more values");
-    Column& c = *table_get_or_add(t, name, dtype);
-    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
-    const int64_t have = c.n_rows;
-    const size_t w = (size_t)c.elem_bytes();
-
-    // ---- pages: every page body as UNCOMPRESSED bytes (a view of the chunk, or of `inflated` for Snappy pages) ----
+namespace {
+struct PqSection {
+    int64_t first_row, n_rows;
+    const uint8_t* values;
+    int64_t values_bytes;
+    const uint8_t* levels;
+    int64_t levels_bytes;
+    bool dict;
+};
+struct PqChunk {
+    std::vector<PqSection> secs;
+    std::vector<uint8_t> inflated;       // the uncompressed bodies of Snappy pages (sections point into it)
+    const uint8_t* dict_values = nullptr;
+    int64_t dict_bytes = 0, dict_count = 0;
+    bool any_dict = false;
+};
+// Every page body as UNCOMPRESSED bytes (a view of the chunk, or of `inflated` for Snappy pages), cut into its level and
+// value sections. elem_w: width of a fixed-width value (0: BYTE_ARRAY).
+void collect_sections(const uint8_t* chunk, int64_t n_bytes, int32_t codec, int32_t max_def_level, int64_t num_values, size_t elem_w, PqChunk& out) {
     const std::vector<tg_parquet_page> pages = walk_pages(chunk, n_bytes);
-    struct Section {
-        int64_t first_row, n_rows;
-        const uint8_t* values;
-        int64_t values_bytes;
-        const uint8_t* levels;
-        int64_t levels_bytes;
-        bool dict;
-    };
-    std::vector<Section> secs;
-    std::vector<uint8_t> inflated;
     {
         size_t need = 0;
         for (auto& pg : pages)
             if (codec == PQ_CODEC_SNAPPY && pg.page_type != PQ_INDEX_PAGE) need += (size_t)pg.uncompressed_bytes + 16;
-        inflated.resize(need);
+        out.inflated.resize(need);
     }
     size_t inflated_used = 0;
-    const uint8_t* dict_values = nullptr;
-    int64_t dict_count = 0;
     int64_t rows = 0;
     for (auto& pg : pages) {
         if (pg.page_type == PQ_INDEX_PAGE) continue;
@@ -520,29 +509,31 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         const bool compressed = codec == PQ_CODEC_SNAPPY && (pg.page_type != PQ_DATA_PAGE_V2 || pg.is_compressed);
         if (compressed) {
             if ((int64_t)pg.uncompressed_bytes < plain_head) throw Error(TG_ERR_INVALID_ARG, "Parquet: page sizes do not fit its level sections");
-            uint8_t* out = inflated.data() + inflated_used;
-            memcpy(out, body, (size_t)plain_head);
+            uint8_t* o = out.inflated.data() + inflated_used;
+            memcpy(o, body, (size_t)plain_head);
             const size_t got = pg.body_bytes > plain_head
-                                   ? snappy_decompress(body + plain_head, (size_t)(pg.body_bytes - plain_head), out + plain_head,
+                                   ? snappy_decompress(body + plain_head, (size_t)(pg.body_bytes - plain_head), o + plain_head,
                                                        (size_t)(pg.uncompressed_bytes - plain_head))
                                    : 0;
-            body = out;
+            body = o;
             body_bytes = plain_head + (int64_t)got;
             inflated_used += (size_t)pg.uncompressed_bytes + 16;
         }
         if (pg.page_type == PQ_DICTIONARY_PAGE) {
             if (pg.encoding != PQ_ENC_PLAIN && pg.encoding != PQ_ENC_PLAIN_DICTIONARY)
                 throw Error(TG_ERR_UNSUPPORTED, "Parquet: dictionary page encoding " + std::to_string(pg.encoding));
-            if (dict_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: more than one dictionary page in a column chunk");
-            if ((int64_t)pg.num_values * (int64_t)w > body_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary page shorter than its value count");
-            dict_values = body;
-            dict_count = pg.num_values;
+            if (out.dict_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: more than one dictionary page in a column chunk");
+            if (elem_w && (int64_t)pg.num_values * (int64_t)elem_w > body_bytes)
+                throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary page shorter than its value count");
+            out.dict_values = body;
+            out.dict_bytes = body_bytes;
+            out.dict_count = pg.num_values;
             continue;
         }
         const bool is_dict = pg.encoding == PQ_ENC_RLE_DICTIONARY || pg.encoding == PQ_ENC_PLAIN_DICTIONARY;
         if (!is_dict && pg.encoding != PQ_ENC_PLAIN)
             throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) + " (PLAIN and dictionary encodings only)");
-        Section s{rows, pg.num_values, body, body_bytes, nullptr, 0, is_dict};
+        PqSection s{rows, pg.num_values, body, body_bytes, nullptr, 0, is_dict};
         if (max_def_level > 0) {
             if (pg.definition_level_encoding != PQ_ENC_RLE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: definition levels not RLE-encoded");
             if (pg.version == 1) {
@@ -566,16 +557,49 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
             s.values_bytes = body_bytes - pg.definition_levels_bytes;
         }
         rows += pg.num_values;
-        secs.push_back(s);
+        out.any_dict = out.any_dict || is_dict;
+        out.secs.push_back(s);
     }
     if (rows != num_values) throw Error(TG_ERR_INVALID_ARG, "Parquet: pages hold " + std::to_string(rows) + " values, the chunk metadata says " + std::to_string(num_values));
+    if (!out.dict_values) out.dict_count = 0;  // (a dictionary-encoded page needs one unless all its rows are NULL: checked with the levels)
+}
+}  // namespace
+
+static void append_parquet_utf8(Table& t, const std::string& name, int32_t max_def_level, int32_t codec, const uint8_t* chunk, int64_t n_bytes,
+                                int64_t num_values);
+
+void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype, int32_t max_def_level, int32_t codec,
+                                const uint8_t* chunk, int64_t n_bytes, int64_t num_values) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    TG_CUDA(cudaSetDevice(e.device));
+    if (!chunk || n_bytes <= 0 || num_values < 0) throw Error(TG_ERR_INVALID_ARG, "empty Parquet column chunk");
+    if (codec != PQ_CODEC_UNCOMPRESSED && codec != PQ_CODEC_SNAPPY)
+        throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " (only UNCOMPRESSED and SNAPPY chunks are decoded)");
+    if (max_def_level < 0 || max_def_level > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: nested columns (max definition level > 1)");
+    if (num_values >= ((int64_t)1 << 31)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: column chunk with 2^31 or more values");
+    if (dtype == TG_UTF8) {
+        append_parquet_utf8(t, name, max_def_level, codec, chunk, n_bytes, num_values);
+        return;
+    }
+    if (dtype != TG_INT64 && dtype != TG_FLOAT64 && dtype != TG_INT32 && dtype != TG_FLOAT32)
+        throw Error(TG_ERR_UNSUPPORTED, "Parquet: only INT64 / DOUBLE / INT32 / FLOAT / BYTE_ARRAY (Utf8) columns are decoded on the device");
+    Column& c = *table_get_or_add(t, name, dtype);
+    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
+    const int64_t have = c.n_rows;
+    const size_t w = (size_t)c.elem_bytes();
+
+    PqChunk pc;
+    collect_sections(chunk, n_bytes, codec, max_def_level, num_values, w, pc);
+    using Section = PqSection;
+    std::vector<PqSection>& secs = pc.secs;
+    const uint8_t* dict_values = pc.dict_values;
+    int64_t dict_count = pc.dict_count;
     if (num_values == 0) {
         t.n_rows = std::max(t.n_rows, c.n_rows);
         return;
     }
-    bool any_dict = false;
-    for (auto& s : secs) any_dict = any_dict || s.dict;
-    if (!dict_values) dict_count = 0;  // (a dictionary-encoded page needs one unless all its rows are NULL: checked with the levels)
+    const bool any_dict = pc.any_dict;
 
     // ---- the value sections travel while a helper thread expands the definition levels: staging a pageable source is
     // a host memcpy into the pinned ring per piece, so the two halves of the host work run side by side. Every page's
@@ -700,6 +724,281 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         append_validity(e, c, have, nullptr, 0, num_values);
     }
     c.value_bytes = (have + num_values) * (int64_t)w;
+    c.n_rows = have + num_values;
+    t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BYTE_ARRAY (Utf8) chunks. A value is a 4-byte length followed by its bytes (PLAIN) or an index into a dictionary of such
+// values; the Arrow layout wants int32 offsets (one more than rows) and the concatenated bytes. Three device steps:
+//   pq_str_locate_kernel  per row: where its bytes sit in the staging buffer and how long they are — through the
+//                         dictionary (index stream as for fixed-width columns) or the PLAIN section's entry table — and
+//                         the byte total of every 1024-row block
+//   pq_block_scan_kernel  exclusive scan of the block totals (one CTA)
+//   pq_str_write_kernel   in-block scan of the lengths -> offsets, bytes copied to their place
+// The host walks what is serial by construction: page headers, run headers, and the interleaved length prefixes of PLAIN
+// pages (one entry {staging offset, length} per value); the dictionary page's own entries likewise (it is small).
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+// {byte offset in the staging buffer : 40 bits | length : 24 bits}; strings of 16 MiB or more are refused
+inline uint64_t pq_str_ent(uint64_t off, uint32_t len) { return off | ((uint64_t)len << 40); }
+constexpr uint32_t PQ_STR_MAX_LEN = (1u << 24) - 1u;
+
+// walks `count` PLAIN BYTE_ARRAY values at p (length prefixes interleaved) into entries; stage_off = where p sits in staging
+void walk_plain_strings(const uint8_t* p, int64_t n_bytes, int64_t count, uint64_t stage_off, std::vector<uint64_t>& ents) {
+    int64_t pos = 0;
+    for (int64_t i = 0; i < count; ++i) {
+        if (pos + 4 > n_bytes) throw Error(TG_ERR_INVALID_ARG, "Parquet: BYTE_ARRAY page is truncated");
+        uint32_t len;
+        memcpy(&len, p + pos, 4);
+        pos += 4;
+        if ((int64_t)len > n_bytes - pos) throw Error(TG_ERR_INVALID_ARG, "Parquet: BYTE_ARRAY value runs past its page");
+        if (len > PQ_STR_MAX_LEN) throw Error(TG_ERR_UNSUPPORTED, "Parquet: string value of 16 MiB or more");
+        ents.push_back(pq_str_ent(stage_off + (uint64_t)pos, len));
+        pos += len;
+    }
+}
+}  // namespace
+
+__device__ __forceinline__ uint64_t pq_row_entry(const PqBlock& blk, uint32_t rank, const uint8_t* __restrict__ stage,
+                                                 const PqRun* __restrict__ runs, const uint64_t* __restrict__ plain_ents,
+                                                 const uint64_t* __restrict__ dict_ents, uint32_t dict_count) {
+    if (blk.run_hi == 0) return __ldg(plain_ents + blk.src_off + rank);  // PLAIN: src_off = the block's first entry
+    const uint32_t d = blk.first_dense + rank;
+    uint32_t lo = blk.run_lo, hi = blk.run_hi;
+    while (hi - lo > 1) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (__ldg(&runs[mid].start) <= d) lo = mid;
+        else hi = mid;
+    }
+    const PqRun run = runs[lo];
+    uint64_t idx = run.data;
+    if (run.packed) {
+        const uint64_t bit = (uint64_t)(d - run.start) * run.bw;
+        const uint64_t byte = run.data + (bit >> 3);
+        const uint32_t* wp = reinterpret_cast<const uint32_t*>(stage + (byte & ~(uint64_t)3));
+        const uint64_t w = (uint64_t)__ldg(wp) | ((uint64_t)__ldg(wp + 1) << 32);
+        const uint32_t sh = (uint32_t)((byte & 3) * 8 + (bit & 7));
+        idx = run.bw ? ((w >> sh) & (((uint64_t)1 << run.bw) - 1ull)) : 0ull;
+    }
+    if (idx >= dict_count) idx = dict_count - 1;
+    return __ldg(dict_ents + idx);
+}
+
+__global__ void __launch_bounds__(PQ_THREADS) pq_str_locate_kernel(const uint8_t* __restrict__ stage, const uint8_t* __restrict__ bits,
+                                                                  const PqBlock* __restrict__ blocks, int64_t n_blocks,
+                                                                  const PqRun* __restrict__ runs, const uint64_t* __restrict__ plain_ents,
+                                                                  const uint64_t* __restrict__ dict_ents, uint32_t dict_count,
+                                                                  uint64_t* __restrict__ row_ent, unsigned long long* __restrict__ block_bytes) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (PQ_THREADS / 32);
+    for (int64_t b = (int64_t)blockIdx.x * (PQ_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        const PqBlock blk = blocks[b];
+        uint32_t running = 0;
+        unsigned long long total = 0;
+        for (uint32_t i = 0; i < blk.n_rows; i += 32) {
+            const bool in = i + lane < blk.n_rows;
+            const uint64_t r = (uint64_t)blk.first_row + i + lane;
+            const bool valid = in && (!bits || ((__ldg(bits + (r >> 3)) >> (r & 7)) & 1));
+            const unsigned mask = __ballot_sync(0xffffffffu, valid);
+            const uint32_t rank = running + __popc(mask & ((1u << lane) - 1u));
+            uint64_t ent = 0;
+            if (valid) ent = pq_row_entry(blk, rank, stage, runs, plain_ents, dict_ents, dict_count);
+            if (in) row_ent[r] = ent;
+            total += ent >> 40;
+            running += __popc(mask);
+        }
+#pragma unroll
+        for (int m = 16; m > 0; m >>= 1) total += __shfl_xor_sync(0xffffffffu, total, m);
+        if (lane == 0) block_bytes[b] = total;
+    }
+}
+
+// one CTA: exclusive scan of the block totals; out[n] = the grand total
+__global__ void __launch_bounds__(1024) pq_block_scan_kernel(const unsigned long long* __restrict__ in, int64_t n, unsigned long long* __restrict__ out) {
+    __shared__ unsigned long long s_part[1024];
+    const int64_t per = (n + 1023) / 1024;
+    const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n ? lo + per : n;
+    unsigned long long m = 0;
+    for (int64_t t = lo; t < hi; ++t) m += in[t];
+    s_part[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 1; o < 1024; o <<= 1) {
+        const unsigned long long y = (int)threadIdx.x >= o ? s_part[threadIdx.x - o] : 0ull;
+        __syncthreads();
+        s_part[threadIdx.x] += y;
+        __syncthreads();
+    }
+    unsigned long long run = threadIdx.x ? s_part[threadIdx.x - 1] : 0ull;
+    for (int64_t t = lo; t < hi; ++t) {
+        out[t] = run;
+        run += in[t];
+    }
+    if (threadIdx.x == 1023) out[n] = s_part[1023];
+}
+
+__global__ void __launch_bounds__(PQ_THREADS) pq_str_write_kernel(const uint8_t* __restrict__ stage, const PqBlock* __restrict__ blocks, int64_t n_blocks,
+                                                                 const uint64_t* __restrict__ row_ent, const unsigned long long* __restrict__ block_base,
+                                                                 int32_t* __restrict__ offsets /* at the chunk's first row */, uint8_t* __restrict__ values,
+                                                                 int64_t byte_base, int64_t num_values) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = (int64_t)gridDim.x * (PQ_THREADS / 32);
+    for (int64_t b = (int64_t)blockIdx.x * (PQ_THREADS / 32) + (threadIdx.x >> 5); b < n_blocks; b += warps) {
+        const PqBlock blk = blocks[b];
+        unsigned long long running = (unsigned long long)byte_base + block_base[b];
+        for (uint32_t i = 0; i < blk.n_rows; i += 32) {
+            const bool in = i + lane < blk.n_rows;
+            const uint64_t r = (uint64_t)blk.first_row + i + lane;
+            const uint64_t ent = in ? row_ent[r] : 0ull;
+            const uint32_t len = (uint32_t)(ent >> 40);
+            uint32_t incl = len;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
+            }
+            const unsigned long long start = running + incl - len;
+            if (in) {
+                offsets[r] = (int32_t)start;
+                if (r + 1 == (uint64_t)num_values) offsets[r + 1] = (int32_t)(start + len);
+                const uint8_t* src = stage + (ent & ((1ull << 40) - 1ull));
+                uint8_t* dst = values + start;
+                for (uint32_t k = 0; k < len; ++k) dst[k] = __ldg(src + k);
+            }
+            running += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+}
+
+static void append_parquet_utf8(Table& t, const std::string& name, int32_t max_def_level, int32_t codec, const uint8_t* chunk, int64_t n_bytes,
+                                int64_t num_values) {
+    Engine& e = *t.eng;  // (the caller holds the engine's lock)
+    Column& c = *table_get_or_add(t, name, TG_UTF8);
+    if (c.adopted) throw Error(TG_ERR_INVALID_ARG, "cannot append to an adopted device column");
+    const int64_t have = c.n_rows;
+    PqChunk pc;
+    collect_sections(chunk, n_bytes, codec, max_def_level, num_values, 0, pc);
+    std::vector<PqSection>& secs = pc.secs;
+    if (num_values == 0) {
+        t.n_rows = std::max(t.n_rows, c.n_rows);
+        return;
+    }
+    // ---- staging layout: every section's value bytes as they are, then the dictionary page's body
+    std::vector<int64_t> stage_off(secs.size(), 0);
+    size_t stage_bytes = 0;
+    for (size_t i = 0; i < secs.size(); ++i) {
+        stage_off[i] = (int64_t)stage_bytes;
+        stage_bytes += ((size_t)secs[i].values_bytes + 15) & ~(size_t)15;
+    }
+    const size_t dict_off = stage_bytes;
+    stage_bytes += ((size_t)pc.dict_bytes + 15) & ~(size_t)15;
+    stage_bytes += 64;
+    if (stage_bytes >= ((size_t)1 << 40)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: column chunk of 1 TiB or more");
+    std::vector<uint8_t> bits;
+    std::vector<PqBlock> blocks;
+    std::vector<PqRun> runs;
+    std::vector<uint64_t> plain_ents, dict_ents;
+    if (pc.dict_count > 0) {
+        dict_ents.reserve((size_t)pc.dict_count);
+        walk_plain_strings(pc.dict_values, pc.dict_bytes, pc.dict_count, (uint64_t)dict_off, dict_ents);
+    }
+    std::exception_ptr decode_err;
+    auto decode = [&]() {
+        try {
+            if (max_def_level > 0) bits.assign((size_t)(num_values + 7) / 8 + 16, 0);
+            blocks.reserve((size_t)num_values / PQ_BLOCK_ROWS + secs.size() + 1);
+            for (size_t i = 0; i < secs.size(); ++i) {
+                const PqSection& s = secs[i];
+                if (max_def_level > 0) decode_levels(s.levels, s.levels + s.levels_bytes, bits.data(), s.first_row, s.n_rows);
+                const uint32_t run_lo = (uint32_t)runs.size();
+                const size_t blk_lo = blocks.size();
+                const uint64_t ent_lo = (uint64_t)plain_ents.size();
+                int64_t prefix = 0;
+                for (int64_t r = 0; r < s.n_rows; r += PQ_BLOCK_ROWS) {
+                    const int64_t nr = std::min<int64_t>(PQ_BLOCK_ROWS, s.n_rows - r);
+                    blocks.push_back(PqBlock{ent_lo + (uint64_t)prefix, (uint32_t)(s.first_row + r), (uint32_t)nr, (uint32_t)prefix, 0u, 0u, 0u});
+                    prefix += max_def_level > 0 ? count_ones(bits.data(), s.first_row + r, s.first_row + r + nr) : nr;
+                }
+                if (s.dict) {
+                    if (prefix > 0 && pc.dict_count <= 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: dictionary-encoded page without a dictionary page");
+                    parse_index_runs(s.values, s.values + s.values_bytes, prefix, (uint64_t)stage_off[i], runs);
+                    const uint32_t run_hi = (uint32_t)runs.size();
+                    for (size_t k = blk_lo; k < blocks.size(); ++k) {
+                        blocks[k].run_lo = run_lo;
+                        blocks[k].run_hi = run_hi > run_lo ? run_hi : run_lo + 1;
+                    }
+                } else {
+                    walk_plain_strings(s.values, s.values_bytes, prefix, (uint64_t)stage_off[i], plain_ents);
+                }
+            }
+        } catch (...) {
+            decode_err = std::current_exception();
+        }
+    };
+    std::thread helper(decode);
+    struct Join {
+        std::thread& t;
+        ~Join() {
+            if (t.joinable()) t.join();
+        }
+    } join{helper};
+    uint8_t* stage = e.dev_alloc(stage_bytes);
+    e.deferred_free.emplace_back(stage, stage_bytes);
+    for (size_t i = 0; i < secs.size(); ++i)
+        if (secs[i].values_bytes) e.h2d(stage + stage_off[i], secs[i].values, (size_t)secs[i].values_bytes);
+    if (pc.dict_bytes > 0) e.h2d(stage + dict_off, pc.dict_values, (size_t)pc.dict_bytes);
+    helper.join();
+    if (decode_err) std::rethrow_exception(decode_err);
+
+    append_validity(e, c, have, max_def_level > 0 ? bits.data() : nullptr, 0, num_values);
+
+    // ---- device tables: bits | blocks | runs | plain entries | dictionary entries | per-row entries | block totals + bases
+    const int64_t nb = (int64_t)blocks.size();
+    auto r16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t bits_b = max_def_level > 0 ? r16((size_t)(num_values + 7) / 8) : 0, blk_b = r16(blocks.size() * sizeof(PqBlock));
+    const size_t run_b = r16(runs.size() * sizeof(PqRun)), pe_b = r16(plain_ents.size() * 8), de_b = r16(dict_ents.size() * 8);
+    const size_t re_b = r16((size_t)num_values * 8), bb_b = r16((size_t)(nb + 1) * 8);
+    const size_t aux_b = bits_b + blk_b + run_b + pe_b + de_b + re_b + 2 * bb_b + 64;
+    uint8_t* aux = e.dev_alloc(aux_b);
+    e.deferred_free.emplace_back(aux, aux_b);
+    uint8_t* q = aux;
+    const uint8_t* d_bits = bits_b ? q : nullptr;
+    if (bits_b) e.h2d(q, bits.data(), (size_t)(num_values + 7) / 8);
+    q += bits_b;
+    const PqBlock* d_blocks = (const PqBlock*)q;
+    e.h2d(q, blocks.data(), blocks.size() * sizeof(PqBlock));
+    q += blk_b;
+    const PqRun* d_runs = (const PqRun*)q;
+    if (!runs.empty()) e.h2d(q, runs.data(), runs.size() * sizeof(PqRun));
+    q += run_b;
+    const uint64_t* d_pe = (const uint64_t*)q;
+    if (!plain_ents.empty()) e.h2d(q, plain_ents.data(), plain_ents.size() * 8);
+    q += pe_b;
+    const uint64_t* d_de = (const uint64_t*)q;
+    if (!dict_ents.empty()) e.h2d(q, dict_ents.data(), dict_ents.size() * 8);
+    q += de_b;
+    uint64_t* d_row = (uint64_t*)q;
+    q += re_b;
+    unsigned long long* d_tot = (unsigned long long*)q;
+    q += bb_b;
+    unsigned long long* d_base = (unsigned long long*)q;
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((nb + PQ_THREADS / 32 - 1) / (PQ_THREADS / 32), (int64_t)e.sm_count * 8));
+    pq_str_locate_kernel<<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, d_bits, d_blocks, nb, d_runs, d_pe, d_de, (uint32_t)pc.dict_count, d_row, d_tot);
+    pq_block_scan_kernel<<<1, 1024, 0, e.copy_stream>>>(d_tot, nb, d_base);
+    TG_CUDA(cudaGetLastError());
+    unsigned long long total = 0;
+    TG_CUDA(cudaMemcpyAsync(&total, d_base + nb, 8, cudaMemcpyDeviceToHost, e.copy_stream));
+    TG_CUDA(cudaStreamSynchronize(e.copy_stream));  // the byte total decides the value buffer's size
+    if ((unsigned long long)c.value_bytes + total > (unsigned long long)INT32_MAX)
+        throw Error(TG_ERR_UNSUPPORTED, "Utf8 column exceeds 2 GiB of value bytes (32-bit offsets)");
+    e.dev_reserve(c.values, (size_t)(c.value_bytes + (int64_t)total), (size_t)c.value_bytes);
+    e.dev_reserve(c.offsets, (size_t)(have + num_values + 1) * 4, have ? (size_t)(have + 1) * 4 : 0);
+    pq_str_write_kernel<<<grid, PQ_THREADS, 0, e.copy_stream>>>(stage, d_blocks, nb, d_row, d_base, reinterpret_cast<int32_t*>(c.offsets.p) + have, c.values.p,
+                                                               c.value_bytes, num_values);
+    TG_CUDA(cudaGetLastError());
+    e.launches += 3;
+    c.value_bytes += (int64_t)total;
+    c.last_offset = (int32_t)c.value_bytes;
     c.n_rows = have + num_values;
     t.n_rows = std::max(t.n_rows, c.n_rows);
 }

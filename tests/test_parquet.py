@@ -88,6 +88,34 @@ def _device_column(ctx, table, column, np_dtype):
     return raw, valid, b
 
 
+def _check_string_column(ctx, table, column, want_col):
+    """offsets / bytes / validity of a decoded Utf8 column against the Arrow array pyarrow reads"""
+    import torch
+    from term_b200.distributed import _tensor_from_ptr
+    b = ctx.column_buffers(table, column)
+    dev = torch.device("cuda", 0)
+    n = b["n_rows"]
+    want = want_col.combine_chunks()
+    assert n == len(want)
+    offs = _tensor_from_ptr(b["offsets"], (n + 1) * 4, dev, "|u1").cpu().numpy().view(np.int32)
+    data = _tensor_from_ptr(b["values"], max(int(offs[-1]), 1), dev, "|u1").cpu().numpy()[: int(offs[-1])]
+    want_valid = np.asarray(want.is_valid())
+    if b["validity"]:
+        bits = _tensor_from_ptr(b["validity"], (n + 7) // 8, dev, "|u1").cpu().numpy()
+        valid = np.unpackbits(bits, bitorder="little")[:n].astype(bool)
+    else:
+        valid = np.ones(n, dtype=bool)
+    assert (valid == want_valid).all(), column
+    assert b["null_count"] == int((~want_valid).sum())
+    assert offs[0] == 0 and (np.diff(offs) >= 0).all()
+    filled = want.fill_null("")
+    w_offs = np.frombuffer(filled.buffers()[1], dtype=np.int32)[filled.offset: filled.offset + n + 1]
+    w_data = np.frombuffer(filled.buffers()[2], dtype=np.uint8) if filled.buffers()[2] is not None else np.zeros(0, dtype=np.uint8)
+    assert (np.diff(offs) == np.diff(w_offs)).all(), column          # NULL rows are empty
+    assert data.tobytes() == w_data[int(w_offs[0]): int(w_offs[-1])].tobytes(), column
+    assert b["n_value_bytes"] == int(offs[-1])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("version", ["1.0", "2.0"])
 @pytest.mark.parametrize("n,null_p,row_group", CASES)
@@ -152,6 +180,14 @@ def _write_encoded(tmp_path, n, null_p, version, compression, seed=3, dict_limit
     fields = [pa.field(c, pa.from_numpy_dtype(v.dtype)) for c, v in cols.items()] + [pa.field("req", pa.int64(), nullable=False)]
     arrays = {c: pa.array(v, mask=masks[c]) for c, v in cols.items()}
     arrays["req"] = pa.array(cols["cat"])
+    # strings: a low-cardinality column (dictionary), a high-cardinality one with multi-byte characters and empty strings
+    # (dictionary overflow -> PLAIN when dict_limit is small), a required one
+    words = np.array(["", "a", "bb", "région", "naïve café", "x" * 40, "日本語のテキスト", "tail"], dtype=object)
+    smask, umask = rng.random(n) < null_p, rng.random(n) < null_p
+    arrays["scat"] = pa.array(words[rng.integers(0, len(words), n)].tolist(), type=pa.string(), mask=smask)
+    arrays["suniq"] = pa.array([f"user{v}@exämple.com" if v % 7 else "" for v in rng.integers(0, 1 << 30, n)], type=pa.string(), mask=umask)
+    arrays["sreq"] = pa.array(words[rng.integers(0, len(words), n)].tolist(), type=pa.string())
+    fields += [pa.field("scat", pa.string()), pa.field("suniq", pa.string()), pa.field("sreq", pa.string(), nullable=False)]
     t = pa.table(arrays, schema=pa.schema(fields))
     path = os.path.join(tmp_path, f"enc_{n}_{version}_{compression}.parquet")
     kw = dict(dictionary_pagesize_limit=dict_limit) if dict_limit else {}
@@ -212,6 +248,9 @@ def test_dictionary_and_snappy_chunks_decode_to_the_arrow_layout(ctx, tmp_path, 
     try:
         assert ctx.num_rows(name) == n
         for col in t.column_names:
+            if pa.types.is_string(t.schema.field(col).type):
+                _check_string_column(ctx, name, col, t.column(col))
+                continue
             dt = t.schema.field(col).type.to_pandas_dtype()
             vals, valid, b = _device_column(ctx, name, col, dt)
             want_valid = np.asarray(t.column(col).is_valid())
@@ -239,7 +278,9 @@ def test_suite_over_encoded_parquet_equals_suite_over_arrow(ctx, tmp_path):
             cb = (T.Check.builder("c").has_size(A.GreaterThan(0.0)).completeness("cat", 0.9).has_min("runs", A.LessThan(1.0))
                   .has_max("wide", A.GreaterThan(0.0)).has_sum("cat", A.LessThan(1e18)).has_mean("runs", A.Between(0.0, 5.0))
                   .has_standard_deviation("wide", A.GreaterThan(0.0)).has_correlation("cat", "wide", A.Between(-1.0, 1.0))
-                  .satisfies("const = 42").validates_uniqueness(["wide"], 0.0).has_approx_quantile("runs", 0.5, A.Between(0.0, 5.0)))
+                  .satisfies("const = 42").validates_uniqueness(["wide"], 0.0).has_approx_quantile("runs", 0.5, A.Between(0.0, 5.0))
+                  .completeness("suniq", 0.5).validates_email("suniq", 0.1).validates_regex("scat", "é", 0.01).validates_uniqueness(["suniq"], 0.1)
+                  .has_min_length("sreq", 0).has_max_length("scat", 100))
             return T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
         got, want = suite("pqe_suite"), suite("pqe_arrow")
         assert [(r.name, r.status, r.metric, r.message) for r in got] == [(r.name, r.status, r.metric, r.message) for r in want]
@@ -261,10 +302,10 @@ def test_unsupported_parquet_features_fail_loudly(ctx, tmp_path):
     pq.write_table(t, p2, compression="GZIP", use_dictionary=False)
     with pytest.raises(T.TermGpuError, match="codec"):
         ctx.register_parquet("pq_bad", p2, columns=["k"])
-    p3 = os.path.join(str(tmp_path), "str.parquet")
-    pq.write_table(t, p3, compression="NONE", use_dictionary=False)
-    with pytest.raises(T.TermGpuError, match="physical type"):
-        ctx.register_parquet("pq_bad", p3, columns=["s"])
+    p3 = os.path.join(str(tmp_path), "bin.parquet")
+    pq.write_table(pa.table({"b": pa.array([b"\xff\x00", b"x"] * 10, type=pa.binary())}), p3, compression="NONE", use_dictionary=False)
+    with pytest.raises(T.TermGpuError, match="STRING"):
+        ctx.register_parquet("pq_bad", p3, columns=["b"])
     # annotated integer columns would be delivered as raw physical values: refused (the reference yields the logical types)
     import decimal
     t2 = pa.table({"ts": pa.array([1, 2, 3], pa.timestamp("us")), "u": pa.array([1, 2, 3], pa.uint32()), "dt": pa.array([1, 2, 3], pa.date32()),
