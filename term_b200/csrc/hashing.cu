@@ -568,12 +568,16 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
     };
     Table& ct = find_table(a.redirect[0].empty() ? a.cols[0] : a.redirect[0]);
     Table& pt = find_table(a.redirect[1].empty() ? a.cols[2] : a.redirect[1]);
-    Column* cc = need_col(ct, a.cols[1]);
-    Column* pc = need_col(pt, a.cols[3]);
+    // hash-shuffled shards of Utf8 key columns (multi-GPU) arrive as ONE column of fingerprint records on both sides
+    Column* cshard = a.redirect[0].empty() ? nullptr : ct.find("tg_fp");
+    Column* pshard = a.redirect[1].empty() ? nullptr : pt.find("tg_fp");
+    const bool from_records = cshard && pshard && cshard->dtype == TG_FP128 && pshard->dtype == TG_FP128;
+    Column* cc = from_records ? cshard : need_col(ct, a.cols[1]);
+    Column* pc = from_records ? pshard : need_col(pt, a.cols[3]);
     if (cc->dtype != pc->dtype)
         throw Error(TG_ERR_TYPE_MISMATCH, "foreign key columns have different types");
     const int64_t nc = ct.n_rows, np = pt.n_rows;
-    p.stats.bytes_scanned += col_bytes(*cc, nc) + col_bytes(*pc, np);
+    p.stats.bytes_scanned += from_records ? (uint64_t)(nc + np) * sizeof(FpRecord) : col_bytes(*cc, nc) + col_bytes(*pc, np);
     const int allow_nulls = a.flags, max_examples = std::max(0, a.iparam);
     if (nc == 0) return;
     const bool exact64 = cc->dtype == TG_INT64 || cc->dtype == TG_FLOAT64;
@@ -677,7 +681,7 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
             ex_rows.resize(ne);
             if (ne) TG_CUDA(cudaMemcpy(ex_rows.data(), d_ex, ne * 8, cudaMemcpyDeviceToHost));
         }
-    } else if (cc->dtype == TG_UTF8) {
+    } else if (cc->dtype == TG_UTF8 || from_records) {
         const size_t cfp_b = round_up((size_t)nc * 16, 256), cnf_b = round_up((size_t)nc, 256);
         const size_t pfp_b = round_up((size_t)std::max<int64_t>(np, 1) * 16, 256), pnf_b = round_up((size_t)std::max<int64_t>(np, 1), 256);
         const size_t ph_b = pcap * 8;
@@ -696,9 +700,19 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
         TG_CUDA(cudaMemsetAsync(ptab.h1, 0xFF, 2 * ph_b, e.stream));
         TG_CUDA(cudaMemsetAsync(vtab.h1, 0xFF, 2 * vh_b, e.stream));
         TG_CUDA(cudaMemsetAsync(vtab.counts, 0, vc_b + ex_b + 512, e.stream));
-        launches += compute_fingerprints(e, ct, {cc}, cfp, cnf);
+        if (from_records) {
+            fp_unpack_kernel<<<grid_for(e, nc), HASH_THREADS, 0, e.stream>>>((const FpRecord*)cc->values.p, nc, cfp, cnf);
+            ++launches;
+        } else {
+            launches += compute_fingerprints(e, ct, {cc}, cfp, cnf);
+        }
         if (np > 0) {
-            launches += compute_fingerprints(e, pt, {pc}, pfp, pnf);
+            if (from_records) {
+                fp_unpack_kernel<<<grid_for(e, np), HASH_THREADS, 0, e.stream>>>((const FpRecord*)pc->values.p, np, pfp, pnf);
+                ++launches;
+            } else {
+                launches += compute_fingerprints(e, pt, {pc}, pfp, pnf);
+            }
             build_set128_kernel<<<grid_for(e, np), HASH_THREADS, 0, e.stream>>>(pfp, pnf, np, ptab);
             ++launches;
         }
@@ -707,7 +721,8 @@ void exec_fk_job(Engine& e, Plan& p, int agg_id) {
         ++launches;
         TG_CUDA(cudaMemcpyAsync(&h, d_ctr, sizeof(h), cudaMemcpyDeviceToHost, e.stream));
         TG_CUDA(cudaStreamSynchronize(e.stream));
-        const size_t ne = (size_t)std::min<uint64_t>(h.n_examples, (uint64_t)max_examples);
+        // (a shard of fingerprint records has no strings to show: counts only, the examples stay empty)
+        const size_t ne = from_records ? 0 : (size_t)std::min<uint64_t>(h.n_examples, (uint64_t)max_examples);
         ex_rows.resize(ne);
         if (ne) TG_CUDA(cudaMemcpy(ex_rows.data(), d_ex, ne * 8, cudaMemcpyDeviceToHost));
     } else {

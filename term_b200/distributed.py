@@ -667,10 +667,18 @@ def execute_distributed(plan, ctx, table="data"):
             elif kind == KIND_FK:
                 (ct, cc), (pt, pc) = parts[1].split("."), parts[2].split(".")
                 cname, pname = f"tg_shuffle_{i}_c", f"tg_shuffle_{i}_p"
-                _shuffle_column(ctx, ct, cc, cname)
-                temps.append(cname)
-                _shuffle_column(ctx, pt, pc, pname)
-                temps.append(pname)
+                if _column_dtype(ctx, ct, cc) in (F.TG_INT64, F.TG_FLOAT64):
+                    _shuffle_column(ctx, ct, cc, cname)
+                    temps.append(cname)
+                    _shuffle_column(ctx, pt, pc, pname)
+                    temps.append(pname)
+                else:
+                    # Utf8 keys: both sides travel as 128-bit fingerprint records (the identity the single-GPU path uses);
+                    # counts are exact, the violation EXAMPLES (strings) are not reported across GPUs
+                    _shuffle_fingerprints(ctx, ct, [cc], cname)
+                    temps.append(cname)
+                    _shuffle_fingerprints(ctx, pt, [pc], pname)
+                    temps.append(pname)
                 plan.redirect(i, 0, cname)
                 plan.redirect(i, 1, pname)
                 redirected += [(i, 0), (i, 1)]

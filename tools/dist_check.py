@@ -47,7 +47,27 @@ def register(ctx, name, cols):
         keep += [v, b]
         spec[c] = dict(dtype=F.TG_FLOAT64 if vals.dtype == torch.float64 else F.TG_INT64, n_rows=vals.numel(), values=v.data_ptr(),
                        validity=b.data_ptr() if b is not None else None)
+    torch.cuda.synchronize()  # the engine runs on its own stream: the tensors must be complete before it reads them
     ctx.register_device_table(name, spec, keepalive=keep)
+
+
+def register_strings(ctx, name, col, ids, valid, width=10):
+    """a Utf8 column "k" + zero-padded decimal of ids (width digits, 1 + width bytes per row), built on the device"""
+    n = ids.numel()
+    dev = ids.device
+    digits = torch.empty((n, width + 1), dtype=torch.uint8, device=dev)
+    digits[:, 0] = ord("k")
+    rem = ids.clone()
+    for d in range(width, 0, -1):
+        digits[:, d] = (rem % 10 + ord("0")).to(torch.uint8)
+        rem //= 10
+    data = torch.cat([digits.reshape(-1), torch.zeros(256, dtype=torch.uint8, device=dev)])
+    offs = torch.cat([torch.arange(n + 1, dtype=torch.int32, device=dev) * (width + 1), torch.zeros(64, dtype=torch.int32, device=dev)])
+    b = bitmap(valid) if valid is not None else None
+    torch.cuda.synchronize()  # the engine runs on its own stream: the tensors must be complete before it reads them
+    ctx.register_device_table(name, {col: dict(dtype=F.TG_UTF8, n_rows=n, values=data.data_ptr(), offsets=offs.data_ptr(),
+                                               validity=b.data_ptr() if b is not None else None, n_value_bytes=n * (width + 1))},
+                              keepalive=[data, offs, b])
 
 
 def gather(t, world):
@@ -145,11 +165,21 @@ def main():
     execute_distributed(an_plan, ctx, "orders")
     kll_got, hist_got = an_plan.analyzer_result(kll_slot), an_plan.analyzer_result(hist_slot)
 
+    # foreign key over Utf8 columns: both sides travel as fingerprint records (counts exact, no examples across GPUs)
+    ns = min(n, 2_000_000)
+    register_strings(ctx, "s_orders", "cid", child[:ns], child_valid[:ns])
+    register_strings(ctx, "s_customers", "id", parent, None)
+    fk_check = T.Check.builder("sfk").foreign_key("s_orders.cid", "s_customers.id").build()
+    fk_plan, fk_slots = T.ValidationSuite.builder("sfk").table_name("s_orders").check(fk_check).build().build_plan()
+    execute_distributed(fk_plan, ctx, "s_orders")
+    fk_got = [(r.status.name, r.metric, (r.message or "").split(". Examples")[0]) for r in (fk_plan.result(s) for _, _, s in fk_slots)]
+
     # reference: everything on rank 0's GPU
     full = {"customer_id": gather(child, world), "cv": gather(child_valid.to(torch.uint8), world).bool(),
             "order_key": gather(keys, world), "kv": gather(keys_valid.to(torch.uint8), world).bool(),
             "amount": gather(x, world), "av": gather(x_valid.to(torch.uint8), world).bool(), "parent": gather(parent, world),
             "score": gather(score, world), "sv": gather(score_valid.to(torch.uint8), world).bool()}
+    gather_done = {"child": gather(child[:ns].contiguous(), world), "cv": gather(child_valid[:ns].to(torch.uint8).contiguous(), world).bool()}
     ok = True
     if rank == 0:
         register(ctx, "orders_all", {"customer_id": (full["customer_id"], full["cv"]), "order_key": (full["order_key"], full["kv"]),
@@ -203,7 +233,19 @@ def main():
         if not an_ok:
             print("ANALYZER MISMATCH", kll_got.map, kw.map, flush=True)
         ok = ok and an_ok
-        print(json.dumps({"check": "multi_gpu_parity", "scan_fused": sc_fused, "kll_distributed": kll_got.map, "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
+        register_strings(ctx, "s_orders_all", "cid", gather_done["child"], gather_done["cv"])
+        register_strings(ctx, "s_customers_all", "id", full["parent"], None)
+        fk1 = T.Check.builder("sfk").foreign_key("s_orders_all.cid", "s_customers_all.id").build()
+        fp1, fs1 = T.ValidationSuite.builder("sfk").table_name("s_orders_all").check(fk1).build().build_plan()
+        fp1.execute(ctx, "s_orders_all")
+        fk_want = [(r.status.name, r.metric, (r.message or "").split(". Examples")[0].replace("s_orders_all", "s_orders").replace("s_customers_all", "s_customers"))
+                   for r in (fp1.result(s) for _, _, s in fs1)]
+        if fk_got != fk_want:
+            exp = int((~torch.isin(gather_done["child"], full["parent"]) & gather_done["cv"]).sum().item()) + int((~gather_done["cv"]).sum().item())
+            print("UTF8 FK MISMATCH", fk_got, fk_want, "torch says", exp, "child", gather_done["child"].numel(), "parents", full["parent"].numel(),
+                  ctx.num_rows("s_orders_all"), ctx.num_rows("s_customers_all"), flush=True)
+            ok = False
+        print(json.dumps({"check": "multi_gpu_parity", "utf8_foreign_key": fk_got, "scan_fused": sc_fused, "kll_distributed": kll_got.map, "world": world, "rows_per_gpu": n, "parents_per_gpu": m, "sparse_keys": a.sparse,
                           "ok": ok, "ms_per_execute": ms, "results": got,
                           "spearman": {"pairs": sp_got.u[0], "rho_distributed": sp_got.metric_double, "rho_single_gpu": sp_want.metric_double,
                                        "ranks_agree": sp_agree}}), flush=True)
