@@ -489,6 +489,14 @@ bool comm_rank_exchange(Engine& e, int64_t* n_recv_out, uint64_t* rank_base, uin
     int64_t n = 0;
     rank_current_unlocked(e, &keys, &payload, &pay_bytes, &n);
     int launches = 0;
+    static const bool trace = getenv("TG_SHUFFLE_TRACE") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    auto mark = [&](const char* what) {
+        if (!trace || rank != 0) return;
+        cudaStreamSynchronize(e.stream);
+        fprintf(stderr, "[rank exchange %d] %-14s +%.3f ms\n", pay_bytes, what,
+                std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_start).count());
+    };
     // ---- samples -> splitters (identical on every rank)
     const size_t sw = RANK_SAMPLES + 1;
     if (!e.d_comm_samples) TG_CUDA(cudaMalloc(&e.d_comm_samples, sw * 8 * (size_t)(world + 1) + 1024));
@@ -514,9 +522,11 @@ bool comm_rank_exchange(Engine& e, int64_t* n_recv_out, uint64_t* rank_base, uin
     }
     uint64_t* d_split = d_all + sw * world;  // behind the gathered samples (1 KB of slack was allocated: world <= 64 splitters)
     TG_CUDA(cudaMemcpyAsync(d_split, splitters.data(), splitters.size() * 8, cudaMemcpyHostToDevice, e.stream));
+    mark("splitters");
     // ---- counts
     std::vector<int64_t> counts((size_t)world, 0);
     split_partition_hist(e, keys, n, world, d_split, counts.data(), launches);
+    mark("hist");
     std::vector<long long> cm((size_t)world), call((size_t)world * world);
     for (int r = 0; r < world; ++r) cm[r] = counts[r];
     long long* dc_mine = (long long*)e.d_comm_counts;
@@ -555,13 +565,16 @@ bool comm_rank_exchange(Engine& e, int64_t* n_recv_out, uint64_t* rank_base, uin
         push_slot_release(e, sp);
         return false;  // every rank of the node fails alike (IPC is a property of the node) and takes the host-layer path
     }
+    mark("counts+slots");
     // ---- the scatter is the exchange
     split_partition_scatter(e, keys, payload, pay_bytes, n, world, d_split, first.data(), (uint64_t* const*)sk.d_ptrs, (uint8_t* const*)sp.d_ptrs, launches);
     TG_NCCL(nccl().AllGather(dc_mine, dc_all, 1, NCCL_INT64, comm, e.stream));  // barrier: every rank's stores have landed
     TG_CUDA(cudaStreamSynchronize(e.stream));
+    mark("scatter+barrier");
     e.launches += launches;
     e.comm_bytes_sent += (uint64_t)(n - counts[rank]) * (uint64_t)(8 + pay_bytes);
     rank_adopt_received_unlocked(e, (uint64_t*)sk.local, sp.local, n_recv);
+    mark("adopt");
     *n_recv_out = n_recv;
     *rank_base = base;
     *total_out = total;

@@ -152,6 +152,7 @@ struct Engine {
     void ensure_side_streams();
     Mailbox mailbox;
     RankSession* rank_session = nullptr;
+    int64_t rank_cap_hint = 0;  // largest rank arena so far: later arenas take that size and hit the device-block cache
     // NCCL communicator of the hash shuffle behind the C ABI (comm.cpp; libnccl bound at run time)
     void* comm = nullptr;
     int comm_world = 0, comm_rank = 0;
