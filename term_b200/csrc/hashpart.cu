@@ -131,31 +131,25 @@ __global__ void __launch_bounds__(PART_THREADS) part_hist_kernel(const uint64_t*
     uint32_t* my_hist = s_hist + ((threadIdx.x >> 5) % copies) * parts;
     unsigned long long nulls = 0, special = 0;
     const int64_t n_tiles = (n + PART_TILE - 1) / PART_TILE;
-    // two tiles per iteration: 16 independent key loads per thread in flight (the pass is a pure read: with 8 it sat at
-    // 2.6 TB/s on load latency). A second tile past the end classifies nothing.
-    for (int64_t tile = (int64_t)blockIdx.x * 2; tile < n_tiles; tile += (int64_t)gridDim.x * 2) {
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int64_t base = tile * PART_TILE;
-        uint64_t key[2][PART_KEYS_PER_THREAD];
-        int part[2][PART_KEYS_PER_THREAD];
-        load_classify<MODE>(values, validity, base, n, is_f64, parts, key[0], part[0], rs);
-        load_classify<MODE>(values, validity, base + PART_TILE, n, is_f64, parts, key[1], part[1], rs);
+        uint64_t key[PART_KEYS_PER_THREAD];
+        int part[PART_KEYS_PER_THREAD];
+        load_classify<MODE>(values, validity, base, n, is_f64, parts, key, part, rs);
         // few parts (the ranks of a shuffle): the lanes of a warp that agree on the part add once (a per-key shared atomic
-        // on 2 .. 8 addresses serialises 4- to 16-fold)
+        // on 2 .. 8 addresses serialises 4- to 16-fold). (Tried: two tiles per iteration for more loads in flight — slower,
+        // 0.62 vs 0.35 ms per GB: the registers cost more occupancy than the extra loads bring.)
         const bool few = parts <= 64;
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-#pragma unroll
-            for (int k = 0; k < PART_KEYS_PER_THREAD; ++k) {
-                const int pk = part[h][k];
-                if (few) {
-                    const unsigned peers = __match_any_sync(0xffffffffu, pk);
-                    if (pk >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&my_hist[pk], (uint32_t)__popc(peers));
-                } else if (pk >= 0) {
-                    atomicAdd(&my_hist[pk], 1u);
-                }
-                if (pk == -2) ++special;
-                else if (pk == -1 && base + h * PART_TILE + k * PART_THREADS + threadIdx.x < n) ++nulls;
+        for (int k = 0; k < PART_KEYS_PER_THREAD; ++k) {
+            if (few) {
+                const unsigned peers = __match_any_sync(0xffffffffu, part[k]);
+                if (part[k] >= 0 && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&my_hist[part[k]], (uint32_t)__popc(peers));
+            } else if (part[k] >= 0) {
+                atomicAdd(&my_hist[part[k]], 1u);
             }
+            if (part[k] == -2) ++special;
+            else if (part[k] == -1 && base + k * PART_THREADS + threadIdx.x < n) ++nulls;
         }
     }
     __syncthreads();
