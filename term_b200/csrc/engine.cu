@@ -760,11 +760,24 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
     // state stays in registers; beyond that the kernel keeps per-lane state in shared memory and runs ~3x slower
     // (measured: 80 % -> 26 % of the HBM peak on the full numeric set), so re-reading a column in a second fast pass
     // is the better deal. Aggregates are ordered by their first column so a column's aggregates share a pass.
-    std::stable_sort(ops.begin(), ops.end(), [](const ScanOp& a, const ScanOp& b) {
-        const Column* ca = a.c0 ? a.c0 : (a.pred_cols.empty() ? nullptr : a.pred_cols[0]);
-        const Column* cb = b.c0 ? b.c0 : (b.pred_cols.empty() ? nullptr : b.pred_cols[0]);
-        return ca < cb;
-    });
+    // (by the column's ORDINAL in the table, never its address: the unit layout — and with it the order of the
+    // floating-point sums — must not depend on where the heap put the Column objects)
+    auto ordinal = [&](const ScanOp& o) {
+        const Column* c = o.c0 ? o.c0 : (o.pred_cols.empty() ? nullptr : o.pred_cols[0]);
+        if (!c) return -1;
+        for (size_t i = 0; i < t.cols.size(); ++i)
+            if (t.cols[i].get() == c) return (int)i;
+        return (int)t.cols.size();
+    };
+    std::vector<std::pair<int, size_t>> op_key(ops.size());
+    for (size_t i = 0; i < ops.size(); ++i) op_key[i] = {ordinal(ops[i]), i};
+    std::stable_sort(op_key.begin(), op_key.end(), [](const std::pair<int, size_t>& a, const std::pair<int, size_t>& b) { return a.first < b.first; });
+    {
+        std::vector<ScanOp> sorted;
+        sorted.reserve(ops.size());
+        for (auto& k : op_key) sorted.push_back(std::move(ops[k.second]));
+        ops.swap(sorted);
+    }
     // A pass is also bounded by the kernel's tables: SCAN_MAX_TERMS predicate terms, SCAN_MAX_COLS tile columns and
     // SCAN_MAX_CODE predicate instructions. The reference evaluates every constraint on its own, so a suite never fails
     // as a whole: a pass is closed before an op would overflow a table, and an op that cannot fit even alone fails

@@ -350,6 +350,44 @@ void parse_index_runs(const uint8_t* p, const uint8_t* end, int64_t n_values, ui
     }
 }
 
+// the first `want` indices of an index stream, decoded on the host (the column's pivot is chosen from its first values)
+void decode_first_indices(const uint8_t* p, const uint8_t* end, int64_t n_values, int64_t want, std::vector<uint32_t>& out) {
+    if (n_values <= 0 || p >= end) return;
+    const uint32_t bw = p[0];
+    if (bw > 32) return;
+    Thrift t{p + 1, end};
+    int64_t done = 0;
+    const int64_t target = std::min(n_values, want);  // (n_values may count NULL rows too: the stream simply ends earlier)
+    while (done < target && t.p < t.end) {
+        const uint64_t h = t.varint();
+        if (h & 1) {
+            const uint64_t groups = h >> 1;
+            if (groups * bw > (uint64_t)(t.end - t.p)) return;
+            const int64_t take = std::min<int64_t>((int64_t)groups * 8, target - done);
+            for (int64_t i = 0; i < take; ++i) {
+                const uint64_t bit = (uint64_t)i * bw;
+                uint64_t w = 0;
+                const size_t byte = (size_t)(bit >> 3), avail = (size_t)(t.end - t.p) - byte;
+                memcpy(&w, t.p + byte, std::min<size_t>(8, avail));
+                out.push_back(bw ? (uint32_t)((w >> (bit & 7)) & (((uint64_t)1 << bw) - 1ull)) : 0u);
+            }
+            t.p += groups * bw;
+            done += take;
+        } else {
+            const uint64_t run = h >> 1;
+            if (run == 0) return;
+            const int vb = (int)(bw + 7) / 8;
+            if (vb > t.end - t.p) return;
+            uint32_t v = 0;
+            for (int k = 0; k < vb; ++k) v |= (uint32_t)t.p[k] << (8 * k);
+            t.p += vb;
+            const int64_t take = std::min<int64_t>((int64_t)run, target - done);
+            for (int64_t i = 0; i < take; ++i) out.push_back(v);
+            done += take;
+        }
+    }
+}
+
 struct PqBlock {
     uint64_t src_off;     // PLAIN: byte offset in the staging buffer of the block's first non-NULL value
     uint32_t first_row;   // chunk-relative
@@ -676,14 +714,32 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
         helper.join();
         if (decode_err) std::rethrow_exception(decode_err);
 
-        // ---- pivot of the shifted sums: from the dictionary / the first PLAIN page's dense values ----
+        // ---- pivot of the shifted sums: from the column's FIRST values, like the Arrow path (same K, bit-identical sums):
+        // the first PLAIN page's dense values, or the dictionary entries the first page's first indices name ----
         if (!c.pivot_set && (dtype == TG_INT64 || dtype == TG_FLOAT64)) {
-            const uint8_t* src = dict_count > 0 ? dict_values : (!secs.empty() && !secs[0].dict ? secs[0].values : nullptr);
-            const int64_t nv = std::min<int64_t>(dict_count > 0 ? dict_count : (secs.empty() ? 0 : secs[0].values_bytes / (int64_t)w), 4096);
-            if (src && nv > 0) {
-                std::vector<uint64_t> head((size_t)nv);
-                memcpy(head.data(), src, (size_t)nv * 8);
-                set_pivot_host(c, dtype, nv, head.data(), nullptr, 0);
+            for (auto& s0 : secs) {
+                if (s0.n_rows == 0) continue;
+                std::vector<uint64_t> head;
+                if (!s0.dict) {
+                    const int64_t nv = std::min<int64_t>(s0.values_bytes / (int64_t)w, 4096);
+                    head.resize((size_t)nv);
+                    memcpy(head.data(), s0.values, (size_t)nv * 8);
+                } else if (dict_count > 0) {
+                    std::vector<uint32_t> idx;
+                    try {
+                        decode_first_indices(s0.values, s0.values + s0.values_bytes, s0.n_rows, 256, idx);
+                    } catch (Error&) {  // (a malformed stream is reported by the run walk below, with its own message)
+                    }
+                    for (uint32_t k : idx) {
+                        uint64_t v;
+                        memcpy(&v, dict_values + (size_t)std::min<int64_t>(k, dict_count - 1) * 8, 8);
+                        head.push_back(v);
+                    }
+                }
+                if (!head.empty()) {
+                    set_pivot_host(c, dtype, (int64_t)head.size(), head.data(), nullptr, 0);
+                    break;
+                }
             }
         }
         // ---- validity through the common path (keeps the host mirror of a partial tail byte) ----

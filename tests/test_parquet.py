@@ -283,7 +283,8 @@ def test_suite_over_encoded_parquet_equals_suite_over_arrow(ctx, tmp_path):
                   .has_min_length("sreq", 0).has_max_length("scat", 100))
             return T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
         got, want = suite("pqe_suite"), suite("pqe_arrow")
-        assert [(r.name, r.status, r.metric, r.message) for r in got] == [(r.name, r.status, r.metric, r.message) for r in want]
+        g2, w2 = [(r.name, r.status, r.metric, r.message) for r in got], [(r.name, r.status, r.metric, r.message) for r in want]
+        assert g2 == w2, [(a, b) for a, b in zip(g2, w2) if a != b]
     finally:
         ctx.deregister_table("pqe_suite")
         ctx.deregister_table("pqe_arrow")
