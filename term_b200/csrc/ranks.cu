@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(RK_THREADS) rk_compact_keys_kernel(const uint6
 
 // ---- 3 / 5. minimum ranks from sorted keys. A position's run head = the largest p' <= p with key[p'] != key[p' - 1]
 // (p' = 0 counts); stored 1-based so that 0 means "no head in this range" and the combine is a plain max.
-constexpr int RK_ITEMS = 16, RK_TILE = RK_THREADS * RK_ITEMS;
+constexpr int RK_ITEMS = 8, RK_TILE = RK_THREADS * RK_ITEMS;
 
 // tile_last[t] = 1-based position of the last run head inside tile t (0: the tile starts inside a run and never leaves it)
 // what the runs are runs of: the whole key after a full sort, rs_quant(key) after a quantised one
@@ -205,53 +205,85 @@ struct RkTileRanks {
 // raises *fallback and the host repeats the phase with a full sort (every impure run contains such a position: one whose
 // key differs from the run's first key).
 constexpr int RK_RUN_LIMIT = 32;
+// The tile's keys and their quantised values are staged ONCE in shared memory, with RK_RUN_LIMIT positions of halo on
+// both sides: the head test, the singleton test (the common case of continuous data: a run of one) and the run walk read
+// the staged copy; only a run that reaches further than the halo (long runs of duplicates) goes back to global memory.
+constexpr int RK_HALO = RK_RUN_LIMIT, RK_WIN = RK_TILE + 2 * RK_HALO;
+struct RkStage {
+    uint64_t k[RK_WIN];
+    uint32_t q[RK_WIN];
+    uint32_t warp_last[RK_THREADS / 32];
+};
 __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict__ ks, int64_t n, const uint32_t* __restrict__ carry,
-                                                     uint32_t* s_warp /* [RK_THREADS / 32] */, const RkRunKey& rk, uint32_t* fallback) {
+                                                     RkStage& S, const RkRunKey& rk, uint32_t* fallback) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
+    const int64_t win0 = (int64_t)blockIdx.x * RK_TILE - RK_HALO;  // global position of S.k[0]
+    const bool quantised = rk.quantised;
+    for (int o = threadIdx.x; o < RK_WIN; o += RK_THREADS) {
+        const int64_t j = win0 + o;
+        if (j >= 0 && j < n) {
+            const uint64_t k = ks[j];
+            S.k[o] = k;
+            if (quantised) S.q[o] = rs_quant(rk.Q, k);
+        }
+    }
+    __syncthreads();
+    const int obase = RK_HALO + warp * 32 * RK_ITEMS + lane;  // window index of item 0
     RkTileRanks R;
     uint32_t run = 0;  // last head seen so far inside this warp's range (warp-uniform after each row)
 #pragma unroll
     for (int i = 0; i < RK_ITEMS; ++i) {
-        const int64_t p = wbase + i * 32 + lane;
+        const int o = obase + i * 32;
+        const int64_t p = win0 + o;
         uint32_t h = 0;
         if (p < n) {
-            const uint64_t k = ks[p];
-            if (p == 0 || rk(k) != rk(ks[p - 1])) h = (uint32_t)p + 1u;
+            const bool head = p == 0 || (quantised ? S.q[o] != S.q[o - 1] : S.k[o] != S.k[o - 1]);
+            if (head) h = (uint32_t)p + 1u;
         }
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(0xffffffffu, h, o);
-            if (lane >= o) h = max(h, v);
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, h, d);
+            if (lane >= d) h = max(h, v);
         }
         h = max(h, run);
         R.rank[i] = h;
         run = __shfl_sync(0xffffffffu, h, 31);
     }
-    if (lane == 0) s_warp[warp] = run;
+    if (lane == 0) S.warp_last[warp] = run;
     __syncthreads();
     uint32_t pre = carry[blockIdx.x];
-    for (int w = 0; w < warp; ++w) pre = max(pre, s_warp[w]);
+    for (int w = 0; w < warp; ++w) pre = max(pre, S.warp_last[w]);
 #pragma unroll
     for (int i = 0; i < RK_ITEMS; ++i) R.rank[i] = max(R.rank[i], pre);
-    if (rk.quantised) {
+    if (quantised) {
         bool bad = false;
+        auto key_at = [&](int64_t j) {
+            const int64_t o = j - win0;
+            return o >= 0 && o < RK_WIN ? S.k[o] : ks[j];
+        };
+        auto quant_at = [&](int64_t j) {
+            const int64_t o = j - win0;
+            return o >= 0 && o < RK_WIN ? S.q[o] : rs_quant(rk.Q, ks[j]);
+        };
 #pragma unroll
         for (int i = 0; i < RK_ITEMS; ++i) {
-            const int64_t p = wbase + i * 32 + lane;
+            const int o = obase + i * 32;
+            const int64_t p = win0 + o;
             if (p >= n) continue;
-            const uint64_t k = ks[p], q = rk(k);
             const int64_t head = (int64_t)R.rank[i] - 1;  // 0-based first position of the run
+            const uint32_t q = S.q[o];
+            if (head == p && (p + 1 >= n || S.q[o + 1] != q)) continue;  // a run of one
+            const uint64_t k = S.k[o];
             uint32_t less = 0;
             bool differ = false;
             int64_t j = head;
             for (int s = 0; s < RK_RUN_LIMIT && j < n; ++s, ++j) {
-                const uint64_t kj = j == p ? k : ks[j];
-                if (rk(kj) != q) break;
+                if (quant_at(j) != q) break;
+                const uint64_t kj = key_at(j);
                 less += kj < k;
                 differ |= kj != k;
             }
-            const bool ended = j >= n || rk(ks[j]) != q;
+            const bool ended = j >= n || quant_at(j) != q;
             if (!ended && differ) bad = true;  // a long run with different keys: the prefix order is not enough
             R.rank[i] += less;                   // (long runs of equal keys: less == 0)
         }
@@ -265,13 +297,13 @@ __device__ __forceinline__ RkTileRanks rk_tile_ranks(const uint64_t* __restrict_
 // (keys: the 64-bit key buffer, ranks: the payload buffer reused as 32-bit words).
 __global__ void __launch_bounds__(RK_THREADS) rk_rank_x_kernel(const RsControl* ctl, const RsQuant* quant, uint64_t* k0, uint64_t* k1, uint64_t* p0,
                                                                uint64_t* p1, int64_t n, const uint32_t* __restrict__ carry, uint32_t rank_base) {
-    __shared__ uint32_t s_warp[RK_THREADS / 32];
+    __shared__ RkStage S;
     const bool r = ctl->result != 0;
     const uint64_t* __restrict__ ks = r ? k1 : k0;
     const uint64_t* __restrict__ ys = r ? p1 : p0;
     uint64_t* __restrict__ out_key = r ? k0 : k1;
     uint32_t* __restrict__ out_rank = reinterpret_cast<uint32_t*>(r ? p0 : p1);
-    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, S, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
 #pragma unroll
@@ -290,11 +322,11 @@ __global__ void __launch_bounds__(RK_THREADS) rk_rank_y_moments_kernel(const RsC
                                                                        const uint32_t* r0, const uint32_t* r1, int64_t n,
                                                                        const uint32_t* __restrict__ carry, uint32_t rank_base, double K,
                                                                        double* __restrict__ partial /* [grid][5] */) {
-    __shared__ uint32_t s_warp[RK_THREADS / 32];
+    __shared__ RkStage S;
     __shared__ double red[5][RK_THREADS / 32];
     const uint64_t* __restrict__ ks = ctl->result ? k1 : k0;
     const uint32_t* __restrict__ rxs = ctl->result ? r1 : r0;
-    const RkTileRanks R = rk_tile_ranks(ks, n, carry, s_warp, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
+    const RkTileRanks R = rk_tile_ranks(ks, n, carry, S, RkRunKey(ctl, quant), const_cast<uint32_t*>(&ctl->fallback));
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t wbase = (int64_t)blockIdx.x * RK_TILE + (int64_t)warp * 32 * RK_ITEMS;
     double s[5] = {0, 0, 0, 0, 0};
