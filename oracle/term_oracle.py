@@ -121,8 +121,11 @@ def logical_desc(op) -> str:
 class Col:
     """values: numpy array (numeric) or list of str; valid: bool mask; kind: 'i64' | 'f64' | 'str' | 'bool'"""
 
-    def __init__(self, values, valid, kind):
+    def __init__(self, values, valid, kind, narrow=None):
         self.values, self.valid, self.kind = values, np.asarray(valid, dtype=bool), kind
+        # Arrow name of a 4-byte numeric source type ("Int32" / "Float32"): DataFusion's MIN / MAX keep that type and the
+        # reference's Int64 / Float64 downcasts fail (constraints/statistics.rs:278-308, analyzers/basic/min_max.rs:112-131)
+        self.narrow = narrow
 
     def __len__(self):
         return len(self.valid)
@@ -136,10 +139,10 @@ def col_from_arrow(arr) -> Col:
     t = arr.type
     if pa.types.is_integer(t):
         vals = np.asarray(arr.fill_null(0)).astype(np.int64)
-        return Col(vals, valid, "i64")
+        return Col(vals, valid, "i64", "Int32" if pa.types.is_int32(t) else None)
     if pa.types.is_floating(t):
         vals = np.asarray(arr.fill_null(0.0)).astype(np.float64)
-        return Col(vals, valid, "f64")
+        return Col(vals, valid, "f64", "Float32" if pa.types.is_float32(t) else None)
     if pa.types.is_boolean(t):
         return Col(np.asarray(arr.fill_null(False)), valid, "bool")
     return Col(arr.to_pylist(), valid, "str")
@@ -241,6 +244,8 @@ def stat_value(col: Col, stat: str) -> Optional[float]:
 def statistic(table, column, stat, assertion) -> Result:
     """constraints/statistics.rs:254-322"""
     col = table_cols(table)[column]
+    if col.narrow and stat in ("Min", "Max"):  # the result array is Int32 / Float32: `Err(TermError::Internal(..))` (:303-307)
+        return Result(FAILURE, None, "Error evaluating constraint: Internal error: Failed to extract statistic value")
     v = stat_value(col, stat)
     name = STAT_NAMES[stat]
     if v is None:
@@ -255,8 +260,11 @@ def multi_statistic(table, column, stats) -> Result:
     col = table_cols(table)[column]
     failures, metrics = [], []
     for stat, a in stats:
-        v = stat_value(col, stat)
         name = STAT_NAMES[stat]
+        if col.narrow and stat in ("Min", "Max"):  # :481-485
+            failures.append(f"Failed to compute {name}")
+            continue
+        v = stat_value(col, stat)
         if v is None:
             failures.append(f"{name} is null")
             continue

@@ -112,6 +112,7 @@ void tg_engine_destroy(tg_engine* h) {
             if (c->values.owned && c->values.p) cudaFree(c->values.p);
             if (c->offsets.owned && c->offsets.p) cudaFree(c->offsets.p);
             if (c->validity.owned && c->validity.p) cudaFree(c->validity.p);
+            if (c->wide && c->wide->values.owned && c->wide->values.p) cudaFree(c->wide->values.p);
         }
     }
     e.tables.clear();
@@ -175,11 +176,7 @@ tg_status tg_table_drop(tg_engine* h, const char* name) {
         cudaSetDevice(h->e.device);
         cudaStreamSynchronize(h->e.copy_stream);
         cudaStreamSynchronize(h->e.stream);
-        for (auto& c : it->second->cols) {
-            if (c->values.owned) h->e.dev_free(c->values.p, c->values.cap);
-            if (c->offsets.owned) h->e.dev_free(c->offsets.p, c->offsets.cap);
-            if (c->validity.owned) h->e.dev_free(c->validity.p, c->validity.cap);
-        }
+        for (auto& c : it->second->cols) column_free(h->e, *c);
         h->e.tables.erase(it);
     });
 }
@@ -238,8 +235,8 @@ tg_status tg_table_partition_keys(tg_engine* h, const char* table, const char* c
         Table& t = *it->second;
         Column* c = t.find(column);
         if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + std::string(column) + ". Valid fields are " + t.valid_fields() + ".");
-        if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64)
-            throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports Int64 / Float64 key columns");
+        c = numeric_view(e, c);  // (Int32 / Float32 keys travel as their exactly widened values)
+        if (!c) throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports numeric key columns (strings travel as fingerprints)");
         uint64_t* keys = nullptr;
         int launches = 0;
         partition_keys_by_rank(e, *c, t.n_rows, n_parts, &keys, counts, n_null_rows, launches);

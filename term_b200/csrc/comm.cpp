@@ -448,7 +448,8 @@ int64_t comm_shuffle_column(Engine& e, const std::string& table, const std::stri
     Table& t = *it->second;
     Column* c = t.find(column);
     if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + column + ". Valid fields are " + t.valid_fields() + ".");
-    if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64) throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports Int64 / Float64 key columns");
+    c = numeric_view(e, c);  // (Int32 / Float32 keys travel as their exactly widened values)
+    if (!c) throw Error(TG_ERR_TYPE_MISMATCH, "the multi-GPU key shuffle supports numeric key columns (strings travel as fingerprints)");
     {
         const int64_t pushed = push_shuffle_column(e, t, *c, shard_name, allow_range);
         if (pushed >= 0) return pushed;

@@ -546,6 +546,61 @@ __global__ void str_eq_kernel(const int32_t* offsets, const uint8_t* bytes, int6
     }
 }
 
+// ---- Int32 / Float32 columns ------------------------------------------------------------------------
+// SUM / AVG / STDDEV / CORR and predicates over a 4-byte column are defined by DataFusion on the value widened to Int64 /
+// Float64 (both exact), so the 8-byte kernels serve them through a widened shadow column: values converted on the device
+// (the 4-byte data crossed PCIe once), validity shared with the source column.
+__global__ void widen_kernel(const uint32_t* __restrict__ src, uint64_t* __restrict__ dst, int64_t n, int is_float) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t v = __ldg(src + i);
+        dst[i] = is_float ? (uint64_t)__double_as_longlong((double)__uint_as_float(v)) : (uint64_t)(int64_t)(int32_t)v;
+    }
+}
+
+Column* numeric_view(Engine& e, Column* c) {
+    if (!c) return nullptr;
+    if (c->dtype == TG_INT64 || c->dtype == TG_FLOAT64) return c;
+    if (c->dtype != TG_INT32 && c->dtype != TG_FLOAT32) return nullptr;
+    if (!c->wide) c->wide = std::make_unique<Column>();
+    Column& w = *c->wide;
+    if (w.n_rows != c->n_rows || !w.values.p) {
+        e.sync_copies();  // the 4-byte values may still be in flight on the copy stream
+        w.name = c->name;
+        w.dtype = c->dtype == TG_INT32 ? TG_INT64 : TG_FLOAT64;
+        e.dev_reserve(w.values, (size_t)c->n_rows * 8, 0);
+        if (c->n_rows > 0) {
+            const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((c->n_rows + 255) / 256, (int64_t)e.sm_count * 16));
+            widen_kernel<<<grid, 256, 0, e.stream>>>(reinterpret_cast<const uint32_t*>(c->values.p), reinterpret_cast<uint64_t*>(w.values.p),
+                                                     c->n_rows, c->dtype == TG_FLOAT32 ? 1 : 0);
+            TG_CUDA(cudaGetLastError());
+            e.launches += 1;
+            // pivot of the shifted sums: from the first values, like every 8-byte column
+            const int64_t head = std::min<int64_t>(c->n_rows, 65536);
+            std::vector<uint8_t> hv((size_t)head * 8), hb((size_t)(head + 7) / 8);
+            TG_CUDA(cudaMemcpyAsync(hv.data(), w.values.p, hv.size(), cudaMemcpyDeviceToHost, e.stream));
+            if (c->validity.p) TG_CUDA(cudaMemcpyAsync(hb.data(), c->validity.p, hb.size(), cudaMemcpyDeviceToHost, e.stream));
+            TG_CUDA(cudaStreamSynchronize(e.stream));
+            w.pivot_set = false;
+            set_pivot_host(w, w.dtype, head, hv.data(), c->validity.p ? hb.data() : nullptr, 0);
+        }
+        w.n_rows = c->n_rows;
+        w.value_bytes = c->n_rows * 8;
+    }
+    w.validity.p = c->validity.p;  // (may have been reallocated by an append: refreshed on every use)
+    w.validity.cap = 0;
+    w.validity.owned = false;
+    w.null_count = c->null_count;
+    return &w;
+}
+
+void column_free(Engine& e, Column& c) {
+    if (c.values.owned && c.values.p) e.dev_free(c.values.p, c.values.cap);
+    if (c.offsets.owned && c.offsets.p) e.dev_free(c.offsets.p, c.offsets.cap);
+    if (c.validity.owned && c.validity.p) e.dev_free(c.validity.p, c.validity.cap);
+    if (c.wide && c.wide->values.owned && c.wide->values.p) e.dev_free(c.wide->values.p, c.wide->values.cap);
+    c.wide.reset();
+}
+
 struct VirtualCols {
     Engine& e;
     std::vector<std::unique_ptr<Column>> cols;
@@ -647,8 +702,12 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
             }
             return c;
         };
-        auto numeric = [&](Column* c) {
-            if (c->dtype == TG_INT64 || c->dtype == TG_FLOAT64) return true;
+        auto numeric = [&](Column*& c) {  // (Int32 / Float32: replaced by the widened shadow)
+            if (Column* v = numeric_view(e, c)) {
+                if (v != c) a.narrow = c->dtype == TG_INT32 ? 1 : 2;
+                c = v;
+                return true;
+            }
             a.err = TG_ERR_TYPE_MISMATCH;
             a.err_msg = "Error during planning: numeric aggregate is not supported for column '" + c->name +
                         "' of this type";
@@ -706,6 +765,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
                             for (auto& v : virtuals.cols)
                                 if (v->name == name) c = v.get();
                         if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, no_field_msg(t, name));
+                        if (c->dtype == TG_INT32 || c->dtype == TG_FLOAT32) c = numeric_view(e, c);
                         for (size_t i = 0; i < o.pred_cols.size(); ++i)
                             if (o.pred_cols[i] == c) return ColumnBinding{(int)i, c->dtype};
                         o.pred_cols.push_back(c);
@@ -766,7 +826,7 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
         const Column* c = o.c0 ? o.c0 : (o.pred_cols.empty() ? nullptr : o.pred_cols[0]);
         if (!c) return -1;
         for (size_t i = 0; i < t.cols.size(); ++i)
-            if (t.cols[i].get() == c) return (int)i;
+            if (t.cols[i].get() == c || t.cols[i]->wide.get() == c) return (int)i;
         return (int)t.cols.size();
     };
     std::vector<std::pair<int, size_t>> op_key(ops.size());

@@ -49,6 +49,9 @@ struct Column {
     double pivot = 0.0;           // shift K of the moment sums (== (double)ipivot for Int64 columns)
     int64_t ipivot = 0;
     bool adopted = false;
+    // Int32 / Float32 columns: the exact 8-byte (Int64 / Float64) shadow the numeric aggregates, predicates, sketches and
+    // rank sorts read (numeric_view, engine.cu): built on the device on first use, rebuilt when rows were appended since
+    std::unique_ptr<Column> wide;
     int elem_bytes() const {
         switch (dtype) {
             case TG_INT64: case TG_FLOAT64: return 8;
@@ -172,6 +175,10 @@ struct Engine {
     // device blocks still read by work queued on copy_stream (Parquet staging): released by the next sync_copies()
     std::vector<std::pair<uint8_t*, size_t>> deferred_free;
 };
+
+// the column itself when it is Int64 / Float64, the widened shadow of an Int32 / Float32 column, nullptr for other types
+Column* numeric_view(Engine& e, Column* c);
+void column_free(Engine& e, Column& c);
 
 // tables.cu helpers shared with the Parquet path (parquet.cu)
 Column* table_get_or_add(Table& t, const std::string& name, int32_t dtype);

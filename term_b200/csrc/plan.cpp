@@ -1127,6 +1127,12 @@ static bool percentile_value(Plan& p, const StatReq& r, double* out) {
     return kll_blob_query(k.blob, r.percentile, out);
 }
 
+// DataFusion result typing for Int32 / Float32 columns: MIN / MAX / APPROX_PERCENTILE_CONT keep the column's type (the
+// reference then fails its Int64 / Float64 downcasts), SUM widens to Int64 / Float64, AVG / STDDEV / VAR are Float64
+static bool narrow_result(const Agg& a, int kind) {
+    return a.narrow != 0 && (kind == TG_STAT_MIN || kind == TG_STAT_MAX || kind == TG_STAT_MEDIAN || kind == TG_STAT_PERCENTILE);
+}
+
 static void finalize_stat(Plan& p, Slot& s) {
     const Agg& a = p.aggs[s.aggs[0]];
     if (a.err != TG_OK) {
@@ -1134,6 +1140,12 @@ static void finalize_stat(Plan& p, Slot& s) {
         return;
     }
     const StatReq& r = s.stats[0];
+    if (narrow_result(a, r.kind)) {  // an Int32 / Float32 result array: neither downcast succeeds (statistics.rs:278-308)
+        Agg er = a;
+        er.err_msg = "Internal error: Failed to extract statistic value";
+        set_error(s, er);
+        return;
+    }
     double v;
     bool ok;
     if (r.kind == TG_STAT_MEDIAN || r.kind == TG_STAT_PERCENTILE) {
@@ -1163,6 +1175,10 @@ static void finalize_multistat(Plan& p, Slot& s) {
     std::vector<std::string> failures;
     std::vector<double> metrics;
     for (auto& r : s.stats) {
+        if (narrow_result(a, r.kind)) {  // statistics.rs:481-485
+            failures.push_back(std::string("Failed to compute ") + stat_name(r.kind, r.percentile));
+            continue;
+        }
         double v;
         bool ok = (r.kind == TG_STAT_MEDIAN || r.kind == TG_STAT_PERCENTILE) ? percentile_value(p, r, &v)
                                                                              : stat_value(a, r.kind, &v);
@@ -1584,6 +1600,14 @@ static void finalize_analyzer(Plan& p, Slot& s) {
             break;
         case TG_AN_MIN:
         case TG_AN_MAX: {
+            if (a.narrow) {  // min_max.rs:112-131: neither Float64 nor Int64
+                r.error = 2;
+                r.metric_kind = 3;
+                s.has_message = true;
+                s.message = std::string("Invalid data: Expected numeric array for ") + (s.sub_kind == TG_AN_MIN ? "min" : "max") + ", got " +
+                            (a.narrow == 1 ? "Int32" : "Float32");
+                break;
+            }
             const bool has = a.u[0] > 0;
             r.u[0] = r.u[1] = has;
             r.f[0] = a.u[4] ? (double)(int64_t)a.u[2] : a.f[3];

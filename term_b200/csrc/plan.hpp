@@ -47,6 +47,7 @@ struct Agg {
     // ---- bind status of the last execute ----
     tg_status err = TG_OK;
     std::string err_msg;
+    int32_t narrow = 0;              // the (first) column is Int32 (1) / Float32 (2): the SQL result keeps DataFusion's typing
     // ---- partial state ----
     uint64_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -57,6 +58,7 @@ struct Agg {
         blob.clear();
         err = ctor_err;
         err_msg = ctor_err_msg;
+        narrow = 0;
     }
 };
 

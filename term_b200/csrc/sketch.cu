@@ -247,9 +247,10 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
             a.err_msg = "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t.valid_fields() + ".";
             continue;
         }
-        if (c->dtype != TG_INT64 && c->dtype != TG_FLOAT64) {
+        c = numeric_view(e, c);  // (Int32 / Float32: the widened shadow)
+        if (!c) {
             a.err = TG_ERR_TYPE_MISMATCH;
-            a.err_msg = "quantile sketch requires a numeric (Int64 / Float64) column";
+            a.err_msg = "quantile sketch requires a numeric column";
             continue;
         }
         // sketch capacity: 8k items in total (k = the reference's accuracy parameter)

@@ -1086,3 +1086,87 @@ def test_concurrent_suites_on_one_context(ctx):
         assert got == want
     finally:
         ctx.deregister_table("conc")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 777, 150_001])
+def test_int32_float32_columns_follow_datafusion_result_typing(ctx, n):
+    """Int32 / Float32 columns: SUM / AVG / STDDEV / VAR / CORR / predicates / Spearman / KLL are computed on the exactly
+    widened values (DataFusion: SUM(Int32) is Int64, the others Float64); MIN / MAX keep the column's 4-byte type, which the
+    reference's Int64 / Float64 downcasts reject (constraints/statistics.rs:278-308,481-485, analyzers/basic/min_max.rs:112-131)."""
+    rng = np.random.default_rng(n)
+    i32 = rng.integers(-2**31, 2**31, n).astype(np.int32)
+    f32 = rng.normal(50.0, 20.0, n).astype(np.float32)
+    small = rng.integers(-1000, 1000, n).astype(np.int32)
+    f64 = f32.astype(np.float64) * 0.5 + rng.normal(0, 3.0, n)
+    t = pa.table({"i32": pa.array(i32, mask=rng.random(n) < 0.1), "f32": pa.array(f32, mask=rng.random(n) < 0.1),
+                  "small": pa.array(small), "f64": pa.array(f64)})
+    name = f"narrow_{n}"
+    ctx.register_table(name, t)
+    try:
+        A = T.Assertion
+        stats = [(c, s) for c in ("i32", "f32", "small") for s in ("Min", "Max", "Mean", "Sum", "StandardDeviation", "Variance")]
+        cb = T.Check.builder("narrow")
+        for c, s in stats:
+            cb.statistic(c, T.StatisticType[s], A.GreaterThan(-1e300))
+        cb.has_correlation("f32", "f64", A.GreaterThan(-2.0)).has_correlation("small", "i32", A.GreaterThan(-2.0))
+        preds = ["small >= 0 AND f32 > 40", "i32 % 3 = 0 OR f32 IS NULL", "small * 2 + 1 < f64"]
+        for p in preds:
+            cb.satisfies(p)
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        k = 0
+        for c, s in stats:
+            o, g = O.statistic(t, c, s, ("GreaterThan", -1e300)), rs[k]
+            assert g.status.name.lower() == o.status, (c, s, g, o)
+            if o.metric is None:
+                assert g.metric is None and g.message == o.message, (c, s, g.message, o.message)
+            elif s == "Sum" and c != "f32":
+                assert g.metric == o.metric, (c, s, g.metric, o.metric)  # Int64 sum: bit-exact
+            else:
+                tol = REL_SUM if s in ("Mean", "Sum") else REL_MOMENT
+                scale = max(abs(o.metric), 1e-300)
+                if s in ("Mean", "Sum"):
+                    col = O.table_cols(t)[c]
+                    scale = max(scale, float(np.abs(col.values[col.valid]).sum()) * (1e-3 if s == "Sum" else 1e-3 / max(1, int(col.valid.sum()))))
+                assert abs(g.metric - o.metric) <= tol * scale, (c, s, g.metric, o.metric)
+            k += 1
+        for a, b in (("f32", "f64"), ("small", "i32")):
+            o = O.correlation(t, a, b, "Pearson", ("GreaterThan", -2.0))
+            assert rs[k].status.name.lower() == o.status, (rs[k], o)
+            if o.metric is not None:
+                assert abs(rs[k].metric - o.metric) <= REL_MOMENT, (rs[k], o)
+            k += 1
+        for p in preds:
+            o = O.custom_sql(t, p)
+            assert rs[k].status.name.lower() == o.status and rs[k].metric == o.metric, (p, rs[k], o)
+            k += 1
+        # multi-statistic: the MIN / MAX entries fail on their own (statistics.rs:481-485)
+        ms = T.MultiStatisticalConstraint("f32", [(T.StatisticType.Min, A.GreaterThan(-1e300)), (T.StatisticType.Mean, A.GreaterThan(-1e300))])
+        g = T.ValidationSuite.builder("m").table_name(name).check(T.Check.builder("m").constraint(ms).build()).build().run(ctx).report.results[0]
+        o = O.multi_statistic(t, "f32", [("Min", ("GreaterThan", -1e300)), ("Mean", ("GreaterThan", -1e300))])
+        assert g.status.name.lower() == o.status and g.message == o.message, (g, o)
+        # analyzers
+        r = T.MinAnalyzer("i32").compute(ctx, name)
+        assert r.error == 2 and r.message == "Invalid data: Expected numeric array for min, got Int32"
+        r = T.MaxAnalyzer("f32").compute(ctx, name)
+        assert r.error == 2 and r.message == "Invalid data: Expected numeric array for max, got Float32"
+        r = T.SumAnalyzer("small").compute(ctx, name)
+        assert r.metric == float(small.astype(np.int64).sum())
+        if n >= 2:
+            from scipy import stats as SS
+            both = np.asarray(t.column("f32").is_valid())
+            rho = T.CorrelationAnalyzer.spearman("f32", "f64").compute(ctx, name)
+            want = None
+            if both.sum() >= 2:
+                rx, ry = SS.rankdata(f32[both].astype(np.float64), method="min"), SS.rankdata(f64[both], method="min")
+                if rx.std() > 0 and ry.std() > 0:
+                    want = float(np.corrcoef(rx, ry)[0, 1])
+            if want is not None:
+                assert abs(rho.metric - want) <= 1e-9, (rho.metric, want)
+        kll = T.KllSketchAnalyzer("f32", 256, (0.5,)).compute(ctx, name)
+        v = np.sort(f32[np.asarray(t.column("f32").is_valid())].astype(np.float64))
+        if len(v):
+            assert kll.map["min"] == v[0] and kll.map["max"] == v[-1] and kll.map["count"] == float(len(v))
+            assert O.rank_error(v, kll.map["quantile_0.5"], 0.5) <= 1.65 / math.sqrt(256) + 1.0 / len(v)
+    finally:
+        ctx.deregister_table(name)
