@@ -245,12 +245,14 @@ TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, cons
  * column. `chunk` = the column chunk's bytes exactly as they are in the file (from the first page header,
  * total_compressed_size bytes), `num_values` / `codec` / the physical type (as tg_dtype) / the leaf's max definition
  * level from the file metadata. The host walks the page headers and expands the definition levels into the validity
- * bitmap while the value bytes travel; Snappy pages are decompressed on the host; the device scatters the densely stored
+ * bitmap while the value bytes travel; compressed pages are inflated on the host (Snappy by the library's own decoder, GZIP /
+ * BROTLI / ZSTD / LZ4_RAW by the host's codec libraries, bound at run time); the device scatters the densely stored
  * non-NULL values to their rows, looking dictionary-encoded ones up through the page's index stream (RLE / bit-packed
  * hybrid, only its run headers are walked on the host) and the chunk's dictionary.
  * BYTE_ARRAY strings (dtype TG_UTF8) become int32 offsets + concatenated bytes: the device locates every row's bytes
  * (dictionary entry or PLAIN value), scans the lengths and copies; the host walks the PLAIN pages' length prefixes.
- * Supported: INT64 / DOUBLE / INT32 / FLOAT / BYTE_ARRAY (Utf8), codec UNCOMPRESSED (0) / SNAPPY (1) (parquet.thrift CompressionCodec), data
+ * Supported: INT64 / DOUBLE / INT32 / FLOAT / BYTE_ARRAY (Utf8), codec UNCOMPRESSED (0) / SNAPPY (1) / GZIP (2) / BROTLI (4) / ZSTD (6) /
+ * LZ4_RAW (7) (parquet.thrift CompressionCodec numbers; LZO and the deprecated hadoop-framed LZ4 are refused), data
  * pages V1 / V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values, RLE levels, flat columns; anything else ->
  * TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
  * must stay readable until the next tg_plan_execute* / tg_table_column_buffers on this engine when it is pinned memory.
@@ -275,6 +277,10 @@ TG_API int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int
 /* Host-only: the Snappy raw-format decoder the chunk path applies to compressed pages (parquet-format Compression.md);
  * returns the uncompressed size, or -(tg_status) for a corrupt stream / a stream larger than `cap`. */
 TG_API int64_t tg_parquet_snappy_decompress(const void* src, int64_t n_bytes, void* dst, int64_t cap);
+/* Host-only: one compressed page body of codec `codec` (parquet.thrift numbers, see above) -> dst; returns the uncompressed
+ * size, or -(tg_status): TG_ERR_UNSUPPORTED for a codec without a decoder (or whose library this host lacks),
+ * TG_ERR_INVALID_ARG for a corrupt stream / one larger than `cap`. What the chunk path applies to every compressed page. */
+TG_API int64_t tg_parquet_page_decompress(int32_t codec, const void* src, int64_t n_bytes, void* dst, int64_t cap);
 
 /*
  * Append `n_rows` rows to column `name` from HOST Arrow buffers (values / int32 offsets / validity

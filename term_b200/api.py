@@ -353,7 +353,9 @@ class SessionContext:
     # Parquet physical type -> tg_dtype, decoded on the device (tg_table_append_parquet_chunk)
     _PARQUET_TYPES = {"INT64": F.TG_INT64, "DOUBLE": F.TG_FLOAT64, "INT32": F.TG_INT32, "FLOAT": F.TG_FLOAT32, "BYTE_ARRAY": F.TG_UTF8}
 
-    _PARQUET_CODECS = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZO": 3, "BROTLI": 4, "LZ4": 5, "ZSTD": 6, "LZ4_RAW": 7}
+    # parquet.thrift CompressionCodec numbers by pyarrow's names: its "LZ4" is the raw block format (thrift LZ4_RAW = 7; the
+    # deprecated hadoop-framed thrift LZ4 = 5 reads back as "LZ4_HADOOP")
+    _PARQUET_CODECS = {"UNCOMPRESSED": 0, "SNAPPY": 1, "GZIP": 2, "LZO": 3, "BROTLI": 4, "LZ4_HADOOP": 5, "ZSTD": 6, "LZ4": 7, "LZ4_RAW": 7}
 
     def register_parquet(self, name: str, path, columns=None):
         """ParquetSource::register (sources/parquet.rs:150-230) for the GPU path: every column chunk of every row group

@@ -16,6 +16,7 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
 int32_t parquet_inspect_chunk(const uint8_t* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap);
 int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t num_values, uint8_t* out_bits);
 int64_t parquet_snappy_decompress(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
+int64_t parquet_page_decompress(int32_t codec, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
 void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* d_values,
                         const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes);
 void table_append_arrow(Table& t, const void* schema_p, const void* array_p);
@@ -281,6 +282,11 @@ int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int64_t nu
 int64_t tg_parquet_snappy_decompress(const void* src, int64_t n_bytes, void* dst, int64_t cap) {
     int64_t n = 0;
     tg_status st = guard([&] { n = parquet_snappy_decompress((const uint8_t*)src, n_bytes, (uint8_t*)dst, cap); });
+    return st == TG_OK ? n : -(int64_t)st;
+}
+int64_t tg_parquet_page_decompress(int32_t codec, const void* src, int64_t n_bytes, void* dst, int64_t cap) {
+    int64_t n = 0;
+    tg_status st = guard([&] { n = parquet_page_decompress(codec, (const uint8_t*)src, n_bytes, (uint8_t*)dst, cap); });
     return st == TG_OK ? n : -(int64_t)st;
 }
 int32_t tg_parquet_inspect_chunk(const void* chunk, int64_t n_bytes, tg_parquet_page* pages, int32_t cap) {

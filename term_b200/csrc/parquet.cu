@@ -19,7 +19,10 @@
 // INT32 / FLOAT and BYTE_ARRAY strings (below), codecs UNCOMPRESSED and SNAPPY, data pages V1 and V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values
 // (a chunk may mix them: writers fall back to PLAIN when the dictionary grows too large), RLE definition levels, flat
 // columns (max definition level 0 or 1, no repetition levels).
+#include <dlfcn.h>
+
 #include <algorithm>
+#include <mutex>
 #include <cstring>
 #include <exception>
 #include <thread>
@@ -107,7 +110,7 @@ struct Thrift {
 
 enum { PQ_DATA_PAGE = 0, PQ_INDEX_PAGE = 1, PQ_DICTIONARY_PAGE = 2, PQ_DATA_PAGE_V2 = 3 };
 enum { PQ_ENC_PLAIN = 0, PQ_ENC_PLAIN_DICTIONARY = 2, PQ_ENC_RLE = 3, PQ_ENC_RLE_DICTIONARY = 8 };
-enum { PQ_CODEC_UNCOMPRESSED = 0, PQ_CODEC_SNAPPY = 1 };
+enum { PQ_CODEC_UNCOMPRESSED = 0, PQ_CODEC_SNAPPY = 1, PQ_CODEC_GZIP = 2, PQ_CODEC_BROTLI = 4, PQ_CODEC_ZSTD = 6, PQ_CODEC_LZ4_RAW = 7 };
 
 // parquet.thrift: PageHeader {1 type, 2 uncompressed_page_size, 3 compressed_page_size, 4 crc, 5 data_page_header,
 // 6 index_page_header, 7 dictionary_page_header, 8 data_page_header_v2}; DataPageHeader {1 num_values, 2 encoding,
@@ -388,6 +391,107 @@ void decode_first_indices(const uint8_t* p, const uint8_t* end, int64_t n_values
     }
 }
 
+// ---- GZIP / ZSTD / LZ4_RAW / BROTLI pages: inflated on the host by the system's own codec libraries, bound at run time the first
+// time a chunk needs one (dlopen, like libnccl: libtermgpu.so keeps no link-time dependency); Snappy stays hand-written above.
+struct PqCodecLibs {
+    std::mutex mu;
+    bool tried[8] = {};
+    // zlib
+    struct ZStream {  // z_stream of zlib 1.x on LP64
+        const uint8_t* next_in; unsigned avail_in; unsigned long total_in;
+        uint8_t* next_out; unsigned avail_out; unsigned long total_out;
+        const char* msg; void* state; void* zalloc; void* zfree; void* opaque; int data_type; unsigned long adler; unsigned long reserved;
+    };
+    int (*inflateInit2_)(ZStream*, int, const char*, int) = nullptr;
+    int (*inflate)(ZStream*, int) = nullptr;
+    int (*inflateEnd)(ZStream*) = nullptr;
+    size_t (*ZSTD_decompress)(void*, size_t, const void*, size_t) = nullptr;
+    unsigned (*ZSTD_isError)(size_t) = nullptr;
+    int (*LZ4_decompress_safe)(const char*, char*, int, int) = nullptr;
+    int (*BrotliDecoderDecompress)(size_t, const uint8_t*, size_t*, uint8_t*) = nullptr;
+    static void* open_first(std::initializer_list<const char*> names) {
+        for (const char* n : names)
+            if (void* h = dlopen(n, RTLD_NOW | RTLD_LOCAL)) return h;
+        return nullptr;
+    }
+    void bind(int codec) {
+        std::lock_guard<std::mutex> g(mu);
+        if (tried[codec]) return;
+        tried[codec] = true;
+        if (codec == PQ_CODEC_GZIP) {
+            if (void* h = open_first({"libz.so.1", "libz.so"})) {
+                inflateInit2_ = (decltype(inflateInit2_))dlsym(h, "inflateInit2_");
+                inflate = (decltype(inflate))dlsym(h, "inflate");
+                inflateEnd = (decltype(inflateEnd))dlsym(h, "inflateEnd");
+            }
+        } else if (codec == PQ_CODEC_ZSTD) {
+            if (void* h = open_first({"libzstd.so.1", "libzstd.so"})) {
+                ZSTD_decompress = (decltype(ZSTD_decompress))dlsym(h, "ZSTD_decompress");
+                ZSTD_isError = (decltype(ZSTD_isError))dlsym(h, "ZSTD_isError");
+            }
+        } else if (codec == PQ_CODEC_LZ4_RAW) {
+            if (void* h = open_first({"liblz4.so.1", "liblz4.so"})) LZ4_decompress_safe = (decltype(LZ4_decompress_safe))dlsym(h, "LZ4_decompress_safe");
+        } else if (codec == PQ_CODEC_BROTLI) {
+            if (void* h = open_first({"libbrotlidec.so.1", "libbrotlidec.so"}))
+                BrotliDecoderDecompress = (decltype(BrotliDecoderDecompress))dlsym(h, "BrotliDecoderDecompress");
+        }
+    }
+};
+PqCodecLibs g_codecs;
+
+bool codec_supported(int32_t codec) {
+    return codec == PQ_CODEC_UNCOMPRESSED || codec == PQ_CODEC_SNAPPY || codec == PQ_CODEC_GZIP || codec == PQ_CODEC_ZSTD ||
+           codec == PQ_CODEC_LZ4_RAW || codec == PQ_CODEC_BROTLI;
+}
+
+// one page body -> dst[0, cap): returns the uncompressed size (which must not exceed what the page header announced)
+size_t page_decompress(int32_t codec, const uint8_t* src, size_t n, uint8_t* dst, size_t cap) {
+    if (codec == PQ_CODEC_SNAPPY) return snappy_decompress(src, n, dst, cap);
+    g_codecs.bind(codec);
+    if (n > 0x7fffffffull || cap > 0x7fffffffull) throw Error(TG_ERR_UNSUPPORTED, "Parquet: page of 2 GiB or more");
+    switch (codec) {
+        case PQ_CODEC_GZIP: {
+            if (!g_codecs.inflateInit2_ || !g_codecs.inflate || !g_codecs.inflateEnd)
+                throw Error(TG_ERR_UNSUPPORTED, "Parquet: GZIP pages need libz.so.1, which this host does not have");
+            PqCodecLibs::ZStream z;
+            memset(&z, 0, sizeof z);
+            // window bits 15 + 32: zlib and gzip wrappers are both accepted (parquet-mr writes gzip members)
+            if (g_codecs.inflateInit2_(&z, 15 + 32, "1.2.11", (int)sizeof z) != 0) throw Error(TG_ERR_INTERNAL, "Parquet: inflateInit2 failed");
+            z.next_in = src;
+            z.avail_in = (unsigned)n;
+            z.next_out = dst;
+            z.avail_out = (unsigned)cap;
+            const int rc = g_codecs.inflate(&z, 4 /* Z_FINISH */);
+            const size_t got = (size_t)z.total_out;
+            g_codecs.inflateEnd(&z);
+            if (rc != 1 /* Z_STREAM_END */) throw Error(TG_ERR_INVALID_ARG, "Parquet: corrupt GZIP page (or larger than its header says)");
+            return got;
+        }
+        case PQ_CODEC_ZSTD: {
+            if (!g_codecs.ZSTD_decompress || !g_codecs.ZSTD_isError)
+                throw Error(TG_ERR_UNSUPPORTED, "Parquet: ZSTD pages need libzstd.so.1, which this host does not have");
+            const size_t got = g_codecs.ZSTD_decompress(dst, cap, src, n);
+            if (g_codecs.ZSTD_isError(got)) throw Error(TG_ERR_INVALID_ARG, "Parquet: corrupt ZSTD page (or larger than its header says)");
+            return got;
+        }
+        case PQ_CODEC_LZ4_RAW: {
+            if (!g_codecs.LZ4_decompress_safe) throw Error(TG_ERR_UNSUPPORTED, "Parquet: LZ4_RAW pages need liblz4.so.1, which this host does not have");
+            const int got = g_codecs.LZ4_decompress_safe((const char*)src, (char*)dst, (int)n, (int)cap);
+            if (got < 0) throw Error(TG_ERR_INVALID_ARG, "Parquet: corrupt LZ4 page (or larger than its header says)");
+            return (size_t)got;
+        }
+        case PQ_CODEC_BROTLI: {
+            if (!g_codecs.BrotliDecoderDecompress)
+                throw Error(TG_ERR_UNSUPPORTED, "Parquet: BROTLI pages need libbrotlidec.so.1, which this host does not have");
+            size_t got = cap;
+            if (g_codecs.BrotliDecoderDecompress(n, src, &got, dst) != 1 /* BROTLI_DECODER_RESULT_SUCCESS */)
+                throw Error(TG_ERR_INVALID_ARG, "Parquet: corrupt BROTLI page (or larger than its header says)");
+            return got;
+        }
+    }
+    throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec));
+}
+
 struct PqBlock {
     uint64_t src_off;     // PLAIN: byte offset in the staging buffer of the block's first non-NULL value
     uint32_t first_row;   // chunk-relative
@@ -530,7 +634,7 @@ void collect_sections(const uint8_t* chunk, int64_t n_bytes, int32_t codec, int3
     {
         size_t need = 0;
         for (auto& pg : pages)
-            if (codec == PQ_CODEC_SNAPPY && pg.page_type != PQ_INDEX_PAGE) need += (size_t)pg.uncompressed_bytes + 16;
+            if (codec != PQ_CODEC_UNCOMPRESSED && pg.page_type != PQ_INDEX_PAGE) need += (size_t)pg.uncompressed_bytes + 16;
         out.inflated.resize(need);
     }
     size_t inflated_used = 0;
@@ -544,14 +648,14 @@ void collect_sections(const uint8_t* chunk, int64_t n_bytes, int32_t codec, int3
         const uint8_t* body = chunk + pg.body_offset;
         int64_t body_bytes = pg.body_bytes;
         const int64_t plain_head = pg.page_type == PQ_DATA_PAGE_V2 ? (int64_t)pg.definition_levels_bytes + pg.repetition_levels_bytes : 0;
-        const bool compressed = codec == PQ_CODEC_SNAPPY && (pg.page_type != PQ_DATA_PAGE_V2 || pg.is_compressed);
+        const bool compressed = codec != PQ_CODEC_UNCOMPRESSED && (pg.page_type != PQ_DATA_PAGE_V2 || pg.is_compressed);
         if (compressed) {
             if ((int64_t)pg.uncompressed_bytes < plain_head) throw Error(TG_ERR_INVALID_ARG, "Parquet: page sizes do not fit its level sections");
             uint8_t* o = out.inflated.data() + inflated_used;
             memcpy(o, body, (size_t)plain_head);
             const size_t got = pg.body_bytes > plain_head
-                                   ? snappy_decompress(body + plain_head, (size_t)(pg.body_bytes - plain_head), o + plain_head,
-                                                       (size_t)(pg.uncompressed_bytes - plain_head))
+                                   ? page_decompress(codec, body + plain_head, (size_t)(pg.body_bytes - plain_head), o + plain_head,
+                                                     (size_t)(pg.uncompressed_bytes - plain_head))
                                    : 0;
             body = o;
             body_bytes = plain_head + (int64_t)got;
@@ -612,8 +716,8 @@ void table_append_parquet_chunk(Table& t, const std::string& name, int32_t dtype
     std::lock_guard<std::mutex> g(e.mu);
     TG_CUDA(cudaSetDevice(e.device));
     if (!chunk || n_bytes <= 0 || num_values < 0) throw Error(TG_ERR_INVALID_ARG, "empty Parquet column chunk");
-    if (codec != PQ_CODEC_UNCOMPRESSED && codec != PQ_CODEC_SNAPPY)
-        throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " (only UNCOMPRESSED and SNAPPY chunks are decoded)");
+    if (!codec_supported(codec))
+        throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " (UNCOMPRESSED, SNAPPY, GZIP, BROTLI, ZSTD and LZ4_RAW chunks are decoded)");
     if (max_def_level < 0 || max_def_level > 1) throw Error(TG_ERR_UNSUPPORTED, "Parquet: nested columns (max definition level > 1)");
     if (num_values >= ((int64_t)1 << 31)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: column chunk with 2^31 or more values");
     if (dtype == TG_UTF8) {
@@ -1057,6 +1161,13 @@ static void append_parquet_utf8(Table& t, const std::string& name, int32_t max_d
     c.last_offset = (int32_t)c.value_bytes;
     c.n_rows = have + num_values;
     t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+// host-only (tests): one page body through the codec dispatch of the chunk path
+int64_t parquet_page_decompress(int32_t codec, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap) {
+    if (!src || n < 0 || !dst || cap < 0) throw Error(TG_ERR_INVALID_ARG, "NULL page buffers");
+    if (codec == PQ_CODEC_UNCOMPRESSED || !codec_supported(codec)) throw Error(TG_ERR_UNSUPPORTED, "Parquet: codec " + std::to_string(codec) + " has no decoder");
+    return (int64_t)page_decompress(codec, src, (size_t)n, dst, (size_t)cap);
 }
 
 // host-only (tests): Snappy raw-format decompression as the Parquet path uses it; returns the uncompressed size

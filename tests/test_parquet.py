@@ -217,6 +217,29 @@ def test_snappy_decoder_matches_pyarrow(built_lib):
     assert F.lib().tg_parquet_snappy_decompress(bad.ctypes.data, bad.size, out.ctypes.data, 64) < 0
 
 
+@pytest.mark.parametrize("name,number", [("gzip", 2), ("brotli", 4), ("zstd", 6), ("lz4_raw", 7), ("snappy", 1)])
+def test_page_codecs_match_pyarrow(built_lib, name, number):
+    """GZIP / BROTLI / ZSTD / LZ4_RAW page bodies through the host's codec libraries (bound at run time), Snappy through
+    the library's own decoder: the same dispatch the chunk path applies to compressed pages"""
+    if not pa.Codec.is_available(name):
+        pytest.skip(f"pyarrow has no {name} codec here")
+    rng = np.random.default_rng(11)
+    codec = pa.Codec(name)
+    samples = [b"a", b"abc" * 1000, bytes(rng.integers(0, 256, 70_000, dtype=np.uint8)), bytes(rng.integers(0, 4, 300_000, dtype=np.uint8)),
+               np.sort(rng.integers(0, 1 << 20, 50_000)).astype(np.int64).tobytes(), b"\x00" * 200_000]
+    for raw in samples:
+        comp = np.frombuffer(codec.compress(raw, asbytes=True), dtype=np.uint8).copy()
+        out = np.zeros(len(raw) + 8, dtype=np.uint8)
+        got = F.lib().tg_parquet_page_decompress(number, comp.ctypes.data, comp.size, out.ctypes.data, len(raw))
+        assert got == len(raw), F.last_error()
+        assert out[: len(raw)].tobytes() == raw
+        if len(raw) > 64:  # a stream larger than the room its page header announced, and a truncated one
+            assert F.lib().tg_parquet_page_decompress(number, comp.ctypes.data, comp.size, out.ctypes.data, len(raw) - 1) < 0
+            assert F.lib().tg_parquet_page_decompress(number, comp.ctypes.data, comp.size // 2, out.ctypes.data, len(raw)) < 0
+    for bad in (0, 3, 5, 99):  # UNCOMPRESSED is not a page codec; LZO / hadoop LZ4 / unknown numbers have no decoder
+        assert F.lib().tg_parquet_page_decompress(bad, comp.ctypes.data, comp.size, out.ctypes.data, len(raw)) == -F.TG_ERR_UNSUPPORTED
+
+
 @pytest.mark.parametrize("compression", ["NONE", "SNAPPY"])
 def test_page_walk_sees_dictionary_pages(built_lib, tmp_path, compression):
     path, t = _write_encoded(str(tmp_path), 20_000, 0.1, "1.0", compression)
@@ -267,6 +290,15 @@ def test_dictionary_and_snappy_chunks_decode_to_the_arrow_layout(ctx, tmp_path, 
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("compression", ["ZSTD", "GZIP", "LZ4", "BROTLI"])
+@pytest.mark.parametrize("version", ["1.0", "2.0"])
+@pytest.mark.parametrize("n,null_p,dict_limit", [(1000, 0.3, None), (250_000, 0.02, 4096)])
+def test_system_codec_chunks_decode_to_the_arrow_layout(ctx, tmp_path, n, null_p, dict_limit, version, compression):
+    """GZIP / ZSTD / LZ4_RAW / BROTLI pages (inflated by the host's own codec libraries, bound at run time)"""
+    test_dictionary_and_snappy_chunks_decode_to_the_arrow_layout(ctx, tmp_path, n, null_p, dict_limit, version, compression)
+
+
+@pytest.mark.gpu
 def test_suite_over_encoded_parquet_equals_suite_over_arrow(ctx, tmp_path):
     path, t = _write_encoded(str(tmp_path), 200_000, 0.05, "1.0", "SNAPPY", seed=21, dict_limit=8192)
     ctx.register_parquet("pqe_suite", path)
@@ -299,10 +331,16 @@ def test_unsupported_parquet_features_fail_loudly(ctx, tmp_path):
         ctx.register_parquet("pq_bad", p1, columns=["k"])
     with pytest.raises(T.TermGpuError):  # a failed registration leaves no half-built table behind
         ctx.num_rows("pq_bad")
-    p2 = os.path.join(str(tmp_path), "gzip.parquet")
-    pq.write_table(t, p2, compression="GZIP", use_dictionary=False)
-    with pytest.raises(T.TermGpuError, match="codec"):
-        ctx.register_parquet("pq_bad", p2, columns=["k"])
+    # LZO / hadoop-framed LZ4 chunks: no decoder (pyarrow cannot write them: the C ABI is called with the codec number)
+    from term_b200 import _ffi as F
+    tab = ctx._create("pq_codec")
+    try:
+        chunk = np.zeros(64, dtype=np.uint8)
+        for codec in (3, 5, 99):
+            with pytest.raises(T.TermGpuError, match="codec"):
+                F.check(F.lib().tg_table_append_parquet_chunk(tab, b"k", F.TG_INT64, 0, codec, chunk.ctypes.data, chunk.size, 1))
+    finally:
+        ctx.deregister_table("pq_codec")
     p3 = os.path.join(str(tmp_path), "bin.parquet")
     pq.write_table(pa.table({"b": pa.array([b"\xff\x00", b"x"] * 10, type=pa.binary())}), p3, compression="NONE", use_dictionary=False)
     with pytest.raises(T.TermGpuError, match="STRING"):
