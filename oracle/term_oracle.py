@@ -553,7 +553,7 @@ def _tokenize(s):
         elif m.group(5) is not None:
             w = m.group(5)
             up = w.upper()
-            if up in ("AND", "OR", "NOT", "IS", "NULL", "TRUE", "FALSE", "BETWEEN", "IN"):
+            if up in ("AND", "OR", "NOT", "IS", "NULL", "TRUE", "FALSE", "BETWEEN", "IN", "LIKE"):
                 out.append(("k", up))
             else:
                 out.append(("c", w.lower().split(".")[-1]))
@@ -616,6 +616,14 @@ class _P:
                     neg = True
                 w = self.eat("k")
                 l = ("is", w, neg, l)
+            elif self.is_("k", "LIKE") or (self.is_("k", "NOT") and self.t[self.i + 1] == ("k", "LIKE")):
+                neg = False
+                if self.is_("k", "NOT"):
+                    self.eat()
+                    neg = True
+                self.eat("k", "LIKE")
+                e = ("like", l, self.add())
+                l = ("not", e) if neg else e
             elif self.is_("k", "BETWEEN") or (self.is_("k", "NOT") and self.t[self.i + 1] in (("k", "BETWEEN"), ("k", "IN"))):
                 neg = False
                 if self.is_("k", "NOT"):
@@ -727,7 +735,29 @@ def _ev(e, row):
         if e[1] == "ABS":
             v = _ev(e[2][0], row)
             return None if v is None else abs(v)
+        if e[1] in ("LENGTH", "CHAR_LENGTH", "CHARACTER_LENGTH", "OCTET_LENGTH"):  # DataFusion: characters / bytes of a Utf8 value
+            v = _ev(e[2][0], row)
+            return None if v is None else (len(v.encode("utf-8")) if e[1] == "OCTET_LENGTH" else len(v))
         raise ValueError(e[1])
+    if k == "like":
+        # arrow-string `like`: `%` any sequence, `_` exactly one character, backslash takes the next character literally
+        v, pat = _ev(e[1], row), _ev(e[2], row)
+        if v is None or pat is None:
+            return None
+        rx, i = [], 0
+        while i < len(pat):
+            ch = pat[i]
+            if ch == "\\" and i + 1 < len(pat):
+                i += 1
+                rx.append(re.escape(pat[i]))
+            elif ch == "%":
+                rx.append(".*")
+            elif ch == "_":
+                rx.append(".")
+            else:
+                rx.append(re.escape(ch))
+            i += 1
+        return re.fullmatch("".join(rx), v, re.DOTALL) is not None
     if k == "ar":
         a, b = _ev(e[2], row), _ev(e[3], row)
         if a is None or b is None:

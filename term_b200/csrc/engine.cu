@@ -612,46 +612,237 @@ struct VirtualCols {
     }
 };
 
+// ---- the other string sub-expressions of a predicate, materialised the same way ----
+// comparisons (byte-wise, the order DataFusion gives Utf8: UTF-8 preserves code-point order) of a Utf8 column with a
+// literal or with another Utf8 column; op: 0 =, 1 <>, 2 <, 3 <=, 4 >, 5 >=. out_valid (column-column only) = both valid.
+__device__ __forceinline__ int str_bytes_cmp(const uint8_t* a, int32_t la, const uint8_t* b, int32_t lb) {
+    const int32_t m = la < lb ? la : lb;
+    for (int32_t k = 0; k < m; ++k)
+        if (a[k] != b[k]) return a[k] < b[k] ? -1 : 1;
+    return la < lb ? -1 : (la > lb ? 1 : 0);
+}
+__global__ void str_cmp_kernel(const int32_t* offs_a, const uint8_t* bytes_a, const int32_t* offs_b, const uint8_t* bytes_b, int32_t lit_len,
+                               const uint32_t* valid_a, const uint32_t* valid_b, int64_t n, int op, uint32_t* out_bits, uint32_t* out_valid) {
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = base + (threadIdx.x & 31);
+        bool r = false;
+        if (row < n) {
+            const int32_t a0 = offs_a[row], a1 = offs_a[row + 1];
+            const uint8_t* pb = bytes_b;
+            int32_t lb = lit_len;
+            if (offs_b) {
+                pb = bytes_b + offs_b[row];
+                lb = offs_b[row + 1] - offs_b[row];
+            }
+            const int c = str_bytes_cmp(bytes_a + a0, a1 - a0, pb, lb);
+            r = op == 0 ? c == 0 : op == 1 ? c != 0 : op == 2 ? c < 0 : op == 3 ? c <= 0 : op == 4 ? c > 0 : c >= 0;
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, r);
+        if ((threadIdx.x & 31) == 0) {
+            out_bits[base >> 5] = w;
+            if (out_valid) out_valid[base >> 5] = (valid_a ? valid_a[base >> 5] : 0xffffffffu) & (valid_b ? valid_b[base >> 5] : 0xffffffffu);
+        }
+    }
+}
+// LENGTH / CHAR_LENGTH / CHARACTER_LENGTH (characters: bytes that are not UTF-8 continuation bytes) and OCTET_LENGTH
+__global__ void str_length_kernel(const int32_t* offsets, const uint8_t* bytes, int64_t n, int octets, int64_t* out) {
+    for (int64_t row = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; row < n; row += (int64_t)gridDim.x * blockDim.x) {
+        const int32_t b = offsets[row], e = offsets[row + 1];
+        int64_t c = e - b;
+        if (!octets) {
+            c = 0;
+            for (int32_t k = b; k < e; ++k) c += (bytes[k] & 0xC0) != 0x80;
+        }
+        out[row] = c;
+    }
+}
+// LIKE: the pattern as tokens (kind 0: this byte, 1: `_` one character, 2: `%` any sequence); greedy match with
+// backtracking to the last `%`, stepping whole UTF-8 characters
+__global__ void str_like_kernel(const int32_t* offsets, const uint8_t* bytes, int64_t n, const uint8_t* tok_kind, const uint8_t* tok_byte, int32_t m,
+                                uint32_t* out_bits) {
+    for (int64_t base = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) & ~31ll; base < n; base += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = base + (threadIdx.x & 31);
+        bool ok = false;
+        if (row < n) {
+            const uint8_t* str = bytes + offsets[row];
+            const int32_t len = offsets[row + 1] - offsets[row];
+            auto next_char = [&](int32_t i) {
+                ++i;
+                while (i < len && (str[i] & 0xC0) == 0x80) ++i;
+                return i;
+            };
+            int32_t si = 0, pi = 0, star_p = -1, star_s = 0;
+            bool fail = false;
+            while (si < len) {
+                if (pi < m && tok_kind[pi] == 0 && str[si] == tok_byte[pi]) {
+                    ++si;
+                    ++pi;
+                } else if (pi < m && tok_kind[pi] == 1) {
+                    si = next_char(si);
+                    ++pi;
+                } else if (pi < m && tok_kind[pi] == 2) {
+                    star_p = pi++;
+                    star_s = si;
+                } else if (star_p >= 0) {
+                    pi = star_p + 1;
+                    star_s = next_char(star_s);
+                    si = star_s;
+                } else {
+                    fail = true;
+                    break;
+                }
+            }
+            while (!fail && pi < m && tok_kind[pi] == 2) ++pi;
+            ok = !fail && pi == m;
+        }
+        const uint32_t w = __ballot_sync(0xffffffffu, ok);
+        if ((threadIdx.x & 31) == 0) out_bits[base >> 5] = w;
+    }
+}
+
 static ExprP rewrite_string_compares(const ExprP& ex, Engine& e, Table& t, Plan& p, VirtualCols& vc) {
     if (!ex) return ex;
-    if (ex->kind == Expr::BINARY && (ex->s == "=" || ex->s == "<>")) {
-        ExprP c = ex->args[0], l = ex->args[1];
-        if (c->kind != Expr::COL) std::swap(c, l);
-        if (c->kind == Expr::COL && l->kind == Expr::LIT_S) {
-            Column* col = t.find(c->s);
-            if (col && col->dtype == TG_UTF8) {
-                auto v = std::make_unique<Column>();
-                v->name = std::string("\x01str") + std::to_string(vc.cols.size());
-                v->dtype = TG_BOOL;
-                v->n_rows = t.n_rows;
+    auto utf8_col = [&](const ExprP& x) -> Column* {
+        if (!x || x->kind != Expr::COL) return nullptr;
+        Column* c = t.find(x->s);
+        return c && c->dtype == TG_UTF8 ? c : nullptr;
+    };
+    // a virtual column of `value_bytes` value bytes followed by `extra` more device bytes (literals, a combined validity)
+    auto make_virtual = [&](int32_t dtype, size_t value_bytes, size_t extra, uint8_t** d_extra) -> Column* {
+        auto v = std::make_unique<Column>();
+        v->name = std::string("\x01str") + std::to_string(vc.cols.size());
+        v->dtype = dtype;
+        v->n_rows = t.n_rows;
+        const size_t bytes = round_up(value_bytes + PAD, PAD), ex_b = round_up(extra + PAD, PAD);
+        TG_CUDA(cudaMalloc(&v->values.p, bytes + ex_b));
+        TG_CUDA(cudaMemsetAsync(v->values.p, 0, bytes + ex_b, e.stream));
+        v->values.cap = bytes + ex_b;
+        v->value_bytes = (int64_t)value_bytes;
+        *d_extra = v->values.p + bytes;
+        vc.cols.push_back(std::move(v));
+        return vc.cols.back().get();
+    };
+    auto col_node = [](const Column* v) {
+        auto node = std::make_shared<Expr>();
+        node->kind = Expr::COL;
+        node->s = v->name;
+        return node;
+    };
+    auto launched = [&]() {
+        TG_CUDA(cudaGetLastError());
+        e.launches += 1;
+        p.stats.launches += 1;
+    };
+    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t.n_rows + 255) / 256, (int64_t)e.sm_count * 8));
+    const size_t words = (size_t)(t.n_rows + 31) / 32;
+    static const char* const kCmp[6] = {"=", "<>", "<", "<=", ">", ">="};
+    static const int kFlip[6] = {0, 1, 4, 5, 2, 3};  // literal on the left: `'a' < c` is `c > 'a'`
+    if (ex->kind == Expr::BINARY) {
+        int op = -1;
+        for (int k = 0; k < 6; ++k)
+            if (ex->s == kCmp[k]) op = k;
+        if (op >= 0) {
+            Column* ca = utf8_col(ex->args[0]);
+            Column* cb = utf8_col(ex->args[1]);
+            const ExprP& la = ex->args[0];
+            const ExprP& lb = ex->args[1];
+            if ((ca && lb->kind == Expr::LIT_S) || (cb && la->kind == Expr::LIT_S)) {
+                Column* col = ca ? ca : cb;
+                const std::string& lit = ca ? lb->s : la->s;
+                if (!ca) op = kFlip[op];
+                uint8_t* d_lit = nullptr;
+                Column* v = make_virtual(TG_BOOL, words * 4, lit.size() + 1, &d_lit);
                 v->validity = col->validity;
                 v->validity.owned = false;
-                const size_t words = (size_t)(t.n_rows + 31) / 32;
-                const size_t bytes = round_up(words * 4 + PAD, PAD), lit_b = round_up(l->s.size() + 1, 256);
-                TG_CUDA(cudaMalloc(&v->values.p, bytes + lit_b));
-                TG_CUDA(cudaMemsetAsync(v->values.p, 0, bytes + lit_b, e.stream));
-                uint8_t* d_lit = v->values.p + bytes;
-                if (!l->s.empty()) TG_CUDA(cudaMemcpyAsync(d_lit, l->s.data(), l->s.size(), cudaMemcpyHostToDevice, e.stream));
+                if (!lit.empty()) TG_CUDA(cudaMemcpyAsync(d_lit, lit.data(), lit.size(), cudaMemcpyHostToDevice, e.stream));
                 if (t.n_rows > 0) {
-                    const int grid = (int)std::max<int64_t>(1, std::min<int64_t>((t.n_rows + 255) / 256, (int64_t)e.sm_count * 8));
-                    str_eq_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, t.n_rows, d_lit,
-                                                              (int32_t)l->s.size(), (uint32_t*)v->values.p);
-                    TG_CUDA(cudaGetLastError());
-                    e.launches += 1;
-                    p.stats.launches += 1;
+                    if (op == 0)  // (equality keeps its own kernel: length test first)
+                        str_eq_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, t.n_rows, d_lit, (int32_t)lit.size(),
+                                                                  (uint32_t*)v->values.p);
+                    else
+                        str_cmp_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, nullptr, d_lit, (int32_t)lit.size(), nullptr,
+                                                                   nullptr, t.n_rows, op, (uint32_t*)v->values.p, nullptr);
+                    launched();
                 }
                 p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)col->value_bytes;
-                auto node = std::make_shared<Expr>();
-                node->kind = Expr::COL;
-                node->s = v->name;
-                vc.cols.push_back(std::move(v));
-                if (ex->s == "=") return node;
-                auto neg = std::make_shared<Expr>();
-                neg->kind = Expr::UNARY;
-                neg->s = "NOT";
-                neg->args = {node};
-                return neg;
+                return col_node(v);
             }
+            if (ca && cb) {
+                uint8_t* d_valid = nullptr;
+                const bool any_nulls = ca->validity.p || cb->validity.p;
+                Column* v = make_virtual(TG_BOOL, words * 4, any_nulls ? words * 4 : 0, &d_valid);
+                if (any_nulls) {
+                    v->validity.p = d_valid;
+                    v->validity.owned = false;
+                    v->null_count = -1;
+                }
+                if (t.n_rows > 0) {
+                    str_cmp_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)ca->offsets.p, ca->values.p, (const int32_t*)cb->offsets.p, cb->values.p, 0,
+                                                               (const uint32_t*)ca->validity.p, (const uint32_t*)cb->validity.p, t.n_rows, op,
+                                                               (uint32_t*)v->values.p, any_nulls ? (uint32_t*)d_valid : nullptr);
+                    launched();
+                }
+                p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 8 + (uint64_t)ca->value_bytes + (uint64_t)cb->value_bytes;
+                return col_node(v);
+            }
+        }
+    }
+    if (ex->kind == Expr::FUNC && ex->args.size() == 1 &&
+        (ex->s == "LENGTH" || ex->s == "CHAR_LENGTH" || ex->s == "CHARACTER_LENGTH" || ex->s == "OCTET_LENGTH")) {
+        if (Column* col = utf8_col(ex->args[0])) {
+            uint8_t* unused = nullptr;
+            Column* v = make_virtual(TG_INT64, (size_t)t.n_rows * 8, 0, &unused);
+            v->validity = col->validity;
+            v->validity.owned = false;
+            if (t.n_rows > 0) {
+                str_length_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, t.n_rows, ex->s == "OCTET_LENGTH" ? 1 : 0,
+                                                              (int64_t*)v->values.p);
+                launched();
+            }
+            p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (ex->s == "OCTET_LENGTH" ? 0 : (uint64_t)col->value_bytes);
+            return col_node(v);
+        }
+    }
+    if (ex->kind == Expr::FUNC && ex->s == "LIKE" && ex->args.size() == 2 && ex->args[1]->kind == Expr::LIT_S) {
+        if (Column* col = utf8_col(ex->args[0])) {
+            // `%` any sequence, `_` one character, `\` takes the next character literally (DataFusion / arrow-string `like`)
+            std::string kind, byte;
+            const std::string& pat = ex->args[1]->s;
+            for (size_t i = 0; i < pat.size(); ++i) {
+                const char ch = pat[i];
+                if (ch == '\\' && i + 1 < pat.size()) {
+                    kind.push_back(0);
+                    byte.push_back(pat[++i]);
+                } else if (ch == '%') {
+                    if (kind.empty() || kind.back() != 2) {
+                        kind.push_back(2);
+                        byte.push_back(0);
+                    }
+                } else if (ch == '_') {
+                    kind.push_back(1);
+                    byte.push_back(0);
+                } else {
+                    kind.push_back(0);
+                    byte.push_back(ch);
+                }
+            }
+            const size_t m = kind.size();
+            uint8_t* d_tok = nullptr;
+            Column* v = make_virtual(TG_BOOL, words * 4, 2 * m + 2, &d_tok);
+            v->validity = col->validity;
+            v->validity.owned = false;
+            if (m) {
+                TG_CUDA(cudaMemcpyAsync(d_tok, kind.data(), m, cudaMemcpyHostToDevice, e.stream));
+                TG_CUDA(cudaMemcpyAsync(d_tok + m, byte.data(), m, cudaMemcpyHostToDevice, e.stream));
+                TG_CUDA(cudaStreamSynchronize(e.stream));  // (the token strings are locals)
+            }
+            if (t.n_rows > 0) {
+                str_like_kernel<<<grid, 256, 0, e.stream>>>((const int32_t*)col->offsets.p, col->values.p, t.n_rows, d_tok, d_tok + m, (int32_t)m,
+                                                            (uint32_t*)v->values.p);
+                launched();
+            }
+            p.stats.bytes_scanned += (uint64_t)(t.n_rows + 1) * 4 + (uint64_t)col->value_bytes;
+            return col_node(v);
         }
     }
     auto copy = std::make_shared<Expr>(*ex);

@@ -221,12 +221,22 @@ struct Parser {
                 size_t save_p = lx.p;
                 Tok save = cur;
                 adv();
-                if (is_kw("BETWEEN") || is_kw("IN")) neg = true;
+                if (is_kw("BETWEEN") || is_kw("IN") || is_kw("LIKE")) neg = true;
                 else {
                     lx.p = save_p;
                     cur = save;
                     break;
                 }
+            }
+            if (is_kw("LIKE")) {  // pattern: a string literal (`%`, `_`, backslash escape); evaluated as a virtual column
+                adv();
+                ExprP pat = parse_add();
+                if (pat->kind != Expr::LIT_S) err("the LIKE pattern must be a string literal");
+                auto e = mk(Expr::FUNC);
+                e->s = "LIKE";
+                e->args = {l, pat};
+                l = neg ? un("NOT", e) : ExprP(e);
+                continue;
             }
             if (is_kw("BETWEEN")) {
                 adv();

@@ -1,7 +1,9 @@
 // Predicate grammar for `satisfies` / ComplianceAnalyzer: parser + compiler to the scan kernel's
 // 3-address code. Declared subset of SQL (SURVEY §7 hard part d): column refs, numeric / boolean /
 // NULL literals, + - * / %, unary -, comparisons, AND / OR / NOT, IS [NOT] NULL, IS [NOT] TRUE|FALSE,
-// [NOT] BETWEEN, [NOT] IN (...), ABS(). Anything else -> TG_ERR_UNSUPPORTED.
+// [NOT] BETWEEN, [NOT] IN (...), ABS(); over Utf8 columns: the six comparisons with a string literal or another Utf8
+// column, [NOT] LIKE 'pattern', LENGTH / CHAR_LENGTH / CHARACTER_LENGTH / OCTET_LENGTH (materialised as virtual columns
+// by the engine before the scan, engine.cu rewrite_string_compares). Anything else -> TG_ERR_UNSUPPORTED.
 #pragma once
 #include <functional>
 #include <memory>

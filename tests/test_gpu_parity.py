@@ -1170,3 +1170,33 @@ def test_int32_float32_columns_follow_datafusion_result_typing(ctx, n):
             assert O.rank_error(v, kll.map["quantile_0.5"], 0.5) <= 1.65 / math.sqrt(256) + 1.0 / len(v)
     finally:
         ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 31, 1000, 70_001])
+def test_string_predicates_match_oracle(ctx, n):
+    """`satisfies` over Utf8 columns: the six comparisons with a literal (either side) or another Utf8 column, [NOT] LIKE,
+    LENGTH / CHAR_LENGTH / OCTET_LENGTH — mixed with numeric terms, NULLs on both sides, multi-byte characters"""
+    rng = np.random.default_rng(n + 17)
+    alphabet = list("ab_%c ") + ["é", "你", "🦀"]
+    mk = lambda: ["".join(rng.choice(alphabet, rng.integers(0, 7))) for _ in range(n)]
+    t = pa.table({"s": pa.array(mk(), type=pa.string(), mask=rng.random(n) < 0.15), "u": pa.array(mk(), type=pa.string(), mask=rng.random(n) < 0.15),
+                  "req": pa.array(mk(), type=pa.string()), "x": pa.array(rng.integers(-5, 9, n), mask=rng.random(n) < 0.1)})
+    name = f"strpred_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=997))
+    preds = ["s LIKE 'a%'", "s NOT LIKE '%a'", "s LIKE '%a%b%'", "s LIKE '_'", "req LIKE '__%'", "s LIKE '%'", "s LIKE ''", "s LIKE 'a\\%%'",
+             "s LIKE '%\\_%'", "s LIKE '_é%' OR x > 3", "req LIKE '%🦀'", "s LIKE '%你_' AND x IS NOT NULL", "LENGTH(s) >= 3", "CHAR_LENGTH(req) = 0",
+             "CHARACTER_LENGTH(s) < x", "OCTET_LENGTH(s) > LENGTH(s)", "LENGTH(s) + LENGTH(u) BETWEEN 4 AND 8", "s = u", "s <> u", "s < u", "s <= u",
+             "s > u", "req >= u", "s > 'b'", "s <= 'ab'", "'b' >= s", "'a_' < req", "s >= '' AND u < 'é'", "NOT (s < u) OR x = 0",
+             "s IN ('a', 'ab', '') OR s LIKE 'c%'"]
+    try:
+        cb = T.Check.builder("strpred")
+        for p in preds:
+            cb.satisfies(p)
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        assert len(rs) == len(preds)
+        for p, g in zip(preds, rs):
+            o = O.custom_sql(t, p)
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
+    finally:
+        ctx.deregister_table(name)

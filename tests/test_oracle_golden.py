@@ -177,3 +177,37 @@ def test_oracle_aggregates_agree_with_arrow_compute(seed):
     want = pc.sum(pc.and_kleene(pc.greater(t.column("f"), 10.0), pc.less(t.column("i"), 5)).cast(pa.int64())).as_py() or 0
     got = O.predicate_counts(t, "f > 10 AND i < 5")
     assert got[0] == want and math.isfinite(float(want))
+
+
+# ---- string sub-expressions of `satisfies` predicates: Arrow's own string kernels as the second opinion (DataFusion's LIKE,
+# character_length and Utf8 comparisons are these kernels' Rust siblings: `%` / `_` / backslash escape, characters not bytes,
+# byte-wise order) ----
+@pytest.mark.parametrize("seed", range(4))
+def test_oracle_string_predicates_agree_with_arrow_compute(seed):
+    import numpy as np
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from oracle import term_oracle as O
+    rng = np.random.default_rng(100 + seed)
+    n = 600
+    alphabet = list("ab_%c ") + ["é", "你", "🦀"]
+    mk = lambda: ["".join(rng.choice(alphabet, rng.integers(0, 7))) for _ in range(n)]
+    s = pa.array(mk(), type=pa.string(), mask=rng.random(n) < 0.15)
+    u = pa.array(mk(), type=pa.string(), mask=rng.random(n) < 0.15)
+    t = pa.table({"s": s, "u": u})
+
+    def count_true(arr):
+        return pc.sum(pc.fill_null(arr, False).cast(pa.int64())).as_py() or 0
+
+    for pat in ["a%", "%a", "%a%b%", "_", "__%", "%", "", "a\\%%", "%\\_%", "_é%", "%🦀", "ab c", "%你_"]:
+        want = count_true(pc.match_like(s, pat))
+        assert O.predicate_counts(t, f"s LIKE '{pat}'") == (want, n), pat
+        want_not = count_true(pc.invert(pc.match_like(s, pat)))
+        assert O.predicate_counts(t, f"s NOT LIKE '{pat}'") == (want_not, n), pat
+    for k in (0, 1, 3, 6):
+        assert O.predicate_counts(t, f"LENGTH(s) >= {k}")[0] == count_true(pc.greater_equal(pc.utf8_length(s), k))
+        assert O.predicate_counts(t, f"OCTET_LENGTH(s) = {k}")[0] == count_true(pc.equal(pc.binary_length(s), k))
+    for op, fn in (("=", pc.equal), ("<>", pc.not_equal), ("<", pc.less), ("<=", pc.less_equal), (">", pc.greater), (">=", pc.greater_equal)):
+        assert O.predicate_counts(t, f"s {op} u")[0] == count_true(fn(s.cast(pa.binary()), u.cast(pa.binary()))), op
+        assert O.predicate_counts(t, f"s {op} 'b'")[0] == count_true(fn(s.cast(pa.binary()), pa.scalar(b"b"))), op
+        assert O.predicate_counts(t, f"'b' {op} s")[0] == count_true(fn(pa.scalar(b"b"), s.cast(pa.binary()))), op
