@@ -121,8 +121,9 @@ def logical_desc(op) -> str:
 class Col:
     """values: numpy array (numeric) or list of str; valid: bool mask; kind: 'i64' | 'f64' | 'str' | 'bool'"""
 
-    def __init__(self, values, valid, kind, narrow=None):
+    def __init__(self, values, valid, kind, narrow=None, unsigned=False):
         self.values, self.valid, self.kind = values, np.asarray(valid, dtype=bool), kind
+        self.unsigned = unsigned  # SUM of an unsigned column is UInt64: the reference's downcasts fail on it as well
         # Arrow name of a 4-byte numeric source type ("Int32" / "Float32"): DataFusion's MIN / MAX keep that type and the
         # reference's Int64 / Float64 downcasts fail (constraints/statistics.rs:278-308, analyzers/basic/min_max.rs:112-131)
         self.narrow = narrow
@@ -137,9 +138,14 @@ def col_from_arrow(arr) -> Col:
         arr = arr.combine_chunks()
     valid = np.asarray(arr.is_valid())
     t = arr.type
+    if pa.types.is_temporal(t):  # dates / times / timestamps / durations: their integer representation (comparisons only)
+        ints = arr.cast(pa.int32() if t.bit_width == 32 else pa.int64())
+        return Col(np.asarray(ints.fill_null(0)).astype(np.int64), valid, "i64", str(t))
     if pa.types.is_integer(t):
         vals = np.asarray(arr.fill_null(0)).astype(np.int64)
-        return Col(vals, valid, "i64", "Int32" if pa.types.is_int32(t) else None)
+        names = {pa.int8(): "Int8", pa.int16(): "Int16", pa.int32(): "Int32", pa.uint8(): "UInt8", pa.uint16(): "UInt16", pa.uint32(): "UInt32",
+                 pa.uint64(): "UInt64"}
+        return Col(vals, valid, "i64", names.get(t), pa.types.is_unsigned_integer(t))
     if pa.types.is_floating(t):
         vals = np.asarray(arr.fill_null(0.0)).astype(np.float64)
         return Col(vals, valid, "f64", "Float32" if pa.types.is_float32(t) else None)
@@ -244,7 +250,7 @@ def stat_value(col: Col, stat: str) -> Optional[float]:
 def statistic(table, column, stat, assertion) -> Result:
     """constraints/statistics.rs:254-322"""
     col = table_cols(table)[column]
-    if col.narrow and stat in ("Min", "Max"):  # the result array is Int32 / Float32: `Err(TermError::Internal(..))` (:303-307)
+    if (col.narrow and stat in ("Min", "Max")) or (col.unsigned and stat == "Sum"):  # the result array is neither Int64 nor Float64: `Err(TermError::Internal(..))` (:303-307)
         return Result(FAILURE, None, "Error evaluating constraint: Internal error: Failed to extract statistic value")
     v = stat_value(col, stat)
     name = STAT_NAMES[stat]
@@ -261,7 +267,7 @@ def multi_statistic(table, column, stats) -> Result:
     failures, metrics = [], []
     for stat, a in stats:
         name = STAT_NAMES[stat]
-        if col.narrow and stat in ("Min", "Max"):  # :481-485
+        if (col.narrow and stat in ("Min", "Max")) or (col.unsigned and stat == "Sum"):  # :481-485
             failures.append(f"Failed to compute {name}")
             continue
         v = stat_value(col, stat)

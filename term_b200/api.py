@@ -310,9 +310,6 @@ class SessionContext:
             return self._append_batch_c(t, batch)
         for col_name, arr in zip(batch.schema.names, batch.columns):
             typ = arr.type
-            if pa.types.is_large_string(typ):
-                arr = arr.cast(pa.string())
-                typ = arr.type
             bufs = arr.buffers()
             validity = bufs[0].address if (bufs[0] is not None and arr.null_count > 0) else None
             n, off = len(arr), arr.offset
@@ -332,7 +329,10 @@ class SessionContext:
                 vals = bufs[1].address if bufs[1] is not None else None
                 F.check(F.lib().tg_table_append_host(t, col_name.encode(), F.TG_BOOL, n, vals, None, validity, off))
             else:
-                raise TypeError(f"column {col_name}: unsupported Arrow type {typ}")
+                # Int8 .. UInt64, Date / Time / Timestamp / Duration, LargeUtf8: the Arrow C Data Interface entry point widens /
+                # narrows them on the host and records the delivered type (DataFusion types MIN / MAX / SUM after it);
+                # anything it does not know either (decimals, nested types, ..) raises TG_ERR_UNSUPPORTED
+                self._append_batch_c(t, pa.record_batch([arr], names=[col_name]))
 
     def _append_batch_c(self, t, batch):
         # Arrow C Data Interface: export the batch as a struct array, hand the two structs to the engine

@@ -894,8 +894,11 @@ void exec_scan_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_id
             return c;
         };
         auto numeric = [&](Column*& c) {  // (Int32 / Float32: replaced by the widened shadow)
-            if (Column* v = numeric_view(e, c)) {
-                if (v != c) a.narrow = c->dtype == TG_INT32 ? 1 : 2;
+            if (Column* v = c->temporal ? nullptr : numeric_view(e, c)) {
+                if (v != c || c->src_type) {
+                    a.narrow = 1 | (c->src_unsigned ? 2 : 0);
+                    a.narrow_name = c->src_type ? c->src_type : (c->dtype == TG_INT32 ? "Int32" : "Float32");
+                }
                 c = v;
                 return true;
             }

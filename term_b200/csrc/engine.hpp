@@ -52,6 +52,11 @@ struct Column {
     // Int32 / Float32 columns: the exact 8-byte (Int64 / Float64) shadow the numeric aggregates, predicates, sketches and
     // rank sorts read (numeric_view, engine.cu): built on the device on first use, rebuilt when rows were appended since
     std::unique_ptr<Column> wide;
+    // Arrow type the column was delivered as when it is not the stored one (Int8 .. UInt64 / Date / Timestamp / Time /
+    // Duration columns are stored as Int32 / Int64): DataFusion types MIN / MAX (and SUM of unsigned columns) after it
+    const char* src_type = nullptr;  // static string ("UInt16", "Date32", "Timestamp(Microsecond, None)", ..)
+    bool src_unsigned = false;
+    bool temporal = false;           // comparisons / completeness / uniqueness / grouping only: no numeric aggregates
     int elem_bytes() const {
         switch (dtype) {
             case TG_INT64: case TG_FLOAT64: return 8;

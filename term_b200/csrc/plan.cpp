@@ -1130,7 +1130,8 @@ static bool percentile_value(Plan& p, const StatReq& r, double* out) {
 // DataFusion result typing for Int32 / Float32 columns: MIN / MAX / APPROX_PERCENTILE_CONT keep the column's type (the
 // reference then fails its Int64 / Float64 downcasts), SUM widens to Int64 / Float64, AVG / STDDEV / VAR are Float64
 static bool narrow_result(const Agg& a, int kind) {
-    return a.narrow != 0 && (kind == TG_STAT_MIN || kind == TG_STAT_MAX || kind == TG_STAT_MEDIAN || kind == TG_STAT_PERCENTILE);
+    if ((a.narrow & 1) && (kind == TG_STAT_MIN || kind == TG_STAT_MAX || kind == TG_STAT_MEDIAN || kind == TG_STAT_PERCENTILE)) return true;
+    return (a.narrow & 2) && kind == TG_STAT_SUM;  // SUM(UInt*) is UInt64
 }
 
 static void finalize_stat(Plan& p, Slot& s) {
@@ -1600,12 +1601,12 @@ static void finalize_analyzer(Plan& p, Slot& s) {
             break;
         case TG_AN_MIN:
         case TG_AN_MAX: {
-            if (a.narrow) {  // min_max.rs:112-131: neither Float64 nor Int64
+            if (a.narrow & 1) {  // min_max.rs:112-131: neither Float64 nor Int64
                 r.error = 2;
                 r.metric_kind = 3;
                 s.has_message = true;
                 s.message = std::string("Invalid data: Expected numeric array for ") + (s.sub_kind == TG_AN_MIN ? "min" : "max") + ", got " +
-                            (a.narrow == 1 ? "Int32" : "Float32");
+                            a.narrow_name;
                 break;
             }
             const bool has = a.u[0] > 0;

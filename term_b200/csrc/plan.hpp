@@ -47,7 +47,10 @@ struct Agg {
     // ---- bind status of the last execute ----
     tg_status err = TG_OK;
     std::string err_msg;
-    int32_t narrow = 0;              // the (first) column is Int32 (1) / Float32 (2): the SQL result keeps DataFusion's typing
+    // DataFusion result typing of the (first) column's aggregates: bit 0: MIN / MAX / APPROX_PERCENTILE_CONT keep a type that
+    // is neither Int64 nor Float64 (Int8..Int32, UInt*, Float32); bit 1: SUM is UInt64 (unsigned columns). narrow_name: that type
+    int32_t narrow = 0;
+    const char* narrow_name = "";
     // ---- partial state ----
     uint64_t u[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     double f[8] = {0, 0, 0, 0, 0, 0, 0, 0};

@@ -485,8 +485,8 @@ static int64_t rank_begin_locked(Engine& e, Table& t, const std::string& nx, con
     Column* cy = t.find(ny);
     if (!cx) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + nx + ". Valid fields are " + t.valid_fields() + ".");
     if (!cy) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + ny + ". Valid fields are " + t.valid_fields() + ".");
-    cx = numeric_view(e, cx);  // (Int32 / Float32: the widened shadows)
-    cy = numeric_view(e, cy);
+    cx = cx->temporal ? nullptr : numeric_view(e, cx);  // (Int32 / Float32: the widened shadows)
+    cy = cy->temporal ? nullptr : numeric_view(e, cy);
     if (!cx || !cy) throw Error(TG_ERR_TYPE_MISMATCH, "Spearman correlation requires numeric columns");
     const int64_t n = t.n_rows;
     if (n >= (int64_t)1 << 30) throw Error(TG_ERR_UNSUPPORTED, "Spearman: 2^30 or more rows per shard");

@@ -247,7 +247,7 @@ void exec_kll_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg_ids
             a.err_msg = "Schema error: No field named " + a.cols[0] + ". Valid fields are " + t.valid_fields() + ".";
             continue;
         }
-        c = numeric_view(e, c);  // (Int32 / Float32: the widened shadow)
+        c = c->temporal ? nullptr : numeric_view(e, c);  // (Int32 / Float32: the widened shadow)
         if (!c) {
             a.err = TG_ERR_TYPE_MISMATCH;
             a.err_msg = "quantile sketch requires a numeric column";

@@ -266,26 +266,94 @@ void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
         const ArrowSchema* cs = sc->children[i];
         const ArrowArray* ca = ar->children[i];
         const std::string fmt = cs->format;
+        // stored type; width / signedness of the delivered values when they are widened on the host; DataFusion's name of the type
         int32_t dtype;
+        int src_w = 0;
+        bool src_unsigned = false, temporal = false, large_offsets = false;
+        const char* src_type = nullptr;
+        auto starts = [&](const char* pre) { return fmt.compare(0, strlen(pre), pre) == 0; };
         if (fmt == "l") dtype = TG_INT64;
         else if (fmt == "g") dtype = TG_FLOAT64;
         else if (fmt == "u") dtype = TG_UTF8;
+        else if (fmt == "U") dtype = TG_UTF8, large_offsets = true;
         else if (fmt == "i") dtype = TG_INT32;
         else if (fmt == "f") dtype = TG_FLOAT32;
         else if (fmt == "b") dtype = TG_BOOL;
+        else if (fmt == "c") dtype = TG_INT32, src_w = 1, src_type = "Int8";
+        else if (fmt == "C") dtype = TG_INT32, src_w = 1, src_unsigned = true, src_type = "UInt8";
+        else if (fmt == "s") dtype = TG_INT32, src_w = 2, src_type = "Int16";
+        else if (fmt == "S") dtype = TG_INT32, src_w = 2, src_unsigned = true, src_type = "UInt16";
+        else if (fmt == "I") dtype = TG_INT64, src_w = 4, src_unsigned = true, src_type = "UInt32";
+        else if (fmt == "L") dtype = TG_INT64, src_w = 8, src_unsigned = true, src_type = "UInt64";
+        else if (fmt == "tdD") dtype = TG_INT32, temporal = true, src_type = "Date32";
+        else if (fmt == "tdm") dtype = TG_INT64, temporal = true, src_type = "Date64";
+        else if (fmt == "tts" || fmt == "ttm") dtype = TG_INT32, temporal = true, src_type = "Time32";
+        else if (fmt == "ttu" || fmt == "ttn") dtype = TG_INT64, temporal = true, src_type = "Time64";
+        else if (starts("tss:") || starts("tsm:") || starts("tsu:") || starts("tsn:")) dtype = TG_INT64, temporal = true, src_type = "Timestamp";
+        else if (fmt == "tDs" || fmt == "tDm" || fmt == "tDu" || fmt == "tDn") dtype = TG_INT64, temporal = true, src_type = "Duration";
         else throw Error(TG_ERR_UNSUPPORTED, std::string("Arrow format '") + fmt + "' of column '" + cs->name + "' is not supported");
         const uint8_t* validity = (const uint8_t*)ca->buffers[0];
         if (ca->null_count == 0) validity = nullptr;
         const int64_t off = ca->offset, n = ca->length;
-        if (dtype == TG_UTF8) {
+        if (src_type) {  // (checked before anything is appended: a column keeps one delivered type)
+            Column* have = t.find(cs->name);
+            if (have && (have->src_type == nullptr || strcmp(have->src_type, src_type) != 0))
+                throw Error(TG_ERR_TYPE_MISMATCH, std::string("column '") + cs->name + "' was registered with a different type");
+        }
+        if (dtype == TG_UTF8 && large_offsets) {
+            // LargeUtf8: 64-bit offsets narrowed on the host (a batch of 2 GiB or more of string bytes does not fit Utf8)
+            const int64_t* o64 = (const int64_t*)ca->buffers[1] + off;
+            std::vector<int32_t> o32((size_t)n + 1);
+            const int64_t base = n > 0 || ca->buffers[1] ? o64[0] : 0;
+            for (int64_t r = 0; r <= n; ++r) {
+                const int64_t d = (ca->buffers[1] ? o64[r] : 0) - base;
+                if (d > 0x7fffffffll) throw Error(TG_ERR_UNSUPPORTED, std::string("LargeUtf8 column '") + cs->name + "': a batch holds 2 GiB or more of string bytes");
+                o32[(size_t)r] = (int32_t)d;
+            }
+            table_append_host(t, cs->name, dtype, n, (const uint8_t*)ca->buffers[2] + base, o32.data(), validity, off);
+        } else if (dtype == TG_UTF8) {
             const int32_t* offs = (const int32_t*)ca->buffers[1] + off;
             table_append_host(t, cs->name, dtype, n, ca->buffers[2], offs, validity, off);
         } else if (dtype == TG_BOOL) {
             // values bitmap shares the array offset; append_bits takes one bit offset for both
             table_append_host(t, cs->name, dtype, n, ca->buffers[1], nullptr, validity, off);
+        } else if (src_w && src_w != (dtype == TG_INT64 ? 8 : 4)) {
+            // Int8 / Int16 / UInt8 / UInt16 -> Int32, UInt32 -> Int64: widened exactly on the host
+            const uint8_t* src = (const uint8_t*)ca->buffers[1] + off * src_w;
+            std::vector<uint8_t> wide((size_t)n * (dtype == TG_INT64 ? 8 : 4));
+            for (int64_t r = 0; r < n; ++r) {
+                if (src_w == 1) {
+                    const int32_t v = src_unsigned ? (int32_t)src[r] : (int32_t)(int8_t)src[r];
+                    memcpy(wide.data() + r * 4, &v, 4);
+                } else if (src_w == 2) {
+                    uint16_t u;
+                    memcpy(&u, src + r * 2, 2);
+                    const int32_t v = src_unsigned ? (int32_t)u : (int32_t)(int16_t)u;
+                    memcpy(wide.data() + r * 4, &v, 4);
+                } else {
+                    uint32_t u;
+                    memcpy(&u, src + r * 4, 4);
+                    const int64_t v = (int64_t)u;
+                    memcpy(wide.data() + r * 8, &v, 8);
+                }
+            }
+            table_append_host(t, cs->name, dtype, n, wide.data(), nullptr, validity, off);
         } else {
             const int w = dtype == TG_INT64 || dtype == TG_FLOAT64 ? 8 : 4;
-            table_append_host(t, cs->name, dtype, n, (const uint8_t*)ca->buffers[1] + off * w, nullptr, validity, off);
+            const uint8_t* vals = (const uint8_t*)ca->buffers[1] + off * w;
+            if (src_unsigned && src_w == 8) {  // UInt64: representable as Int64 unless a valid value has the top bit set
+                for (int64_t r = 0; r < n; ++r) {
+                    if (validity && !((validity[(off + r) >> 3] >> ((off + r) & 7)) & 1)) continue;
+                    if (vals[r * 8 + 7] & 0x80) throw Error(TG_ERR_UNSUPPORTED, std::string("UInt64 column '") + cs->name + "' holds values above the Int64 range");
+                }
+            }
+            table_append_host(t, cs->name, dtype, n, vals, nullptr, validity, off);
+        }
+        if (src_type) {
+            Column* c = t.find(cs->name);
+            c->src_type = src_type;
+            c->src_unsigned = src_unsigned;
+            c->temporal = temporal;
         }
     }
 }

@@ -1200,3 +1200,80 @@ def test_string_predicates_match_oracle(ctx, n):
             assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
     finally:
         ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 3000])
+def test_small_integer_unsigned_temporal_and_large_string_columns(ctx, n):
+    """Arrow types a reference user's RecordBatches hold beyond Int64 / Float64 / Utf8: Int8 .. UInt64 are widened exactly
+    (MIN / MAX — and SUM of unsigned columns — keep DataFusion's result type, which the reference's downcasts reject),
+    Date32 / Timestamp columns serve comparisons / completeness / uniqueness, LargeUtf8 is narrowed to Utf8"""
+    rng = np.random.default_rng(n + 3)
+    t = pa.table({
+        "i8": pa.array(rng.integers(-128, 128, n).astype(np.int8), mask=rng.random(n) < 0.1),
+        "u8": pa.array(rng.integers(0, 256, n).astype(np.uint8)),
+        "i16": pa.array(rng.integers(-2**15, 2**15, n).astype(np.int16), mask=rng.random(n) < 0.1),
+        "u16": pa.array(rng.integers(0, 2**16, n).astype(np.uint16)),
+        "u32": pa.array(rng.integers(0, 2**32, n).astype(np.uint32), mask=rng.random(n) < 0.1),
+        "u64": pa.array(rng.integers(0, 2**62, n).astype(np.uint64)),
+        "d": pa.array(rng.integers(19000, 19100, n).astype(np.int32), type=pa.date32(), mask=rng.random(n) < 0.1),
+        "ts0": pa.array(rng.integers(0, 10**6, n), type=pa.timestamp("us"), mask=rng.random(n) < 0.1),
+        "ts1": pa.array(rng.integers(0, 10**6, n), type=pa.timestamp("us")),
+        "ls": pa.array([f"k{v}" for v in rng.integers(0, 50, n)], type=pa.large_string(), mask=rng.random(n) < 0.1),
+    })
+    name = f"arrowtypes_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=701))
+    try:
+        A = T.Assertion
+        stats = [(c, s) for c in ("i8", "u8", "i16", "u16", "u32", "u64") for s in ("Min", "Max", "Mean", "Sum", "StandardDeviation")]
+        preds = ["i8 > 0 AND u8 < 200", "i16 + u16 > 1000 OR u32 % 2 = 0", "u64 / 2 >= u32", "ts0 <= ts1", "ts0 <> ts1 OR d IS NULL",
+                 "ls = 'k7' OR ls LIKE 'k1_'", "LENGTH(ls) = 2"]
+        cb = T.Check.builder("types")
+        for c in t.column_names:
+            cb.completeness(c, 0.8)
+        for c, s in stats:
+            cb.statistic(c, T.StatisticType[s], A.GreaterThan(-1e300))
+        for p in preds:
+            cb.satisfies(p)
+        cb.validates_uniqueness(["d"], 0.0).validates_uniqueness(["ls"], 0.0).validates_uniqueness(["u16"], 0.0)
+        cb.has_correlation("i8", "u16", A.GreaterThan(-2.0))
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        k = 0
+        for c in t.column_names:
+            o = O.completeness(t, c, 0.8)
+            assert rs[k].status.name.lower() == o.status and rs[k].metric == o.metric, (c, rs[k], o)
+            k += 1
+        for c, s in stats:
+            o, g = O.statistic(t, c, s, ("GreaterThan", -1e300)), rs[k]
+            assert g.status.name.lower() == o.status, (c, s, g, o)
+            if o.metric is None:
+                assert g.metric is None and g.message == o.message, (c, s, g.message, o.message)
+            elif s == "Sum":
+                assert g.metric == o.metric, (c, s, g.metric, o.metric)
+            else:
+                assert abs(g.metric - o.metric) <= REL_MOMENT * max(abs(o.metric), 1e-300), (c, s, g.metric, o.metric)
+            k += 1
+        for p in preds:
+            o = O.custom_sql(t, p)
+            assert rs[k].status.name.lower() == o.status and rs[k].metric == o.metric, (p, rs[k], o)
+            k += 1
+        for c in ("d", "ls", "u16"):
+            o = O.uniqueness(t, [c], "FullUniqueness", 0.0)
+            assert rs[k].status.name.lower() == o.status and rs[k].metric == o.metric, (c, rs[k], o)
+            k += 1
+        o = O.correlation(t, "i8", "u16", "Pearson", ("GreaterThan", -2.0))
+        assert rs[k].status.name.lower() == o.status, (rs[k], o)
+        if o.metric is not None:
+            assert abs(rs[k].metric - o.metric) <= REL_MOMENT, (rs[k], o)
+        # numeric aggregates over a temporal column are refused (DataFusion has no AVG(Timestamp)); a UInt64 value above the
+        # Int64 range and a decimal column fail the registration loudly
+        g = T.ValidationSuite.builder("m").table_name(name).check(T.Check.builder("m").has_mean("ts0", A.GreaterThan(0.0)).build()).build().run(ctx).report.results[0]
+        assert g.status.name == "Failure" and "not supported" in g.message
+        import decimal
+        for bad in (pa.table({"x": pa.array([2**63 + 5], type=pa.uint64())}), pa.table({"x": pa.array([decimal.Decimal("1.5")])})):
+            with pytest.raises(T.TermGpuError):
+                ctx.register_table("arrowtypes_bad", bad)
+            with pytest.raises(T.TermGpuError):
+                ctx.num_rows("arrowtypes_bad")
+    finally:
+        ctx.deregister_table(name)
