@@ -259,6 +259,13 @@ TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, cons
  */
 TG_API tg_status tg_table_append_parquet_chunk(tg_table* t, const char* name, int32_t dtype, int32_t max_definition_level,
                                                int32_t codec, const void* chunk, int64_t n_bytes, int64_t num_values);
+/* Declares the Arrow type (C Data Interface format string) that a stored Int32 / Int64 column stands for when its values
+ * arrived already in the stored representation — Parquet chunks annotated DATE ("tdD"), TIME ("ttm" / "ttu" / "ttn"),
+ * TIMESTAMP ("tsm:" / "tsu:" / "tsn:"), INT(8|16, signed) ("c" / "s"), INT(8|16, unsigned) ("C" / "S"): the physical values are
+ * the Arrow values. The column then follows the typing rules of tg_table_append_arrow for that type (temporal columns:
+ * comparisons / completeness / uniqueness / grouping; MIN / MAX / SUM result types as DataFusion's, sources/parquet.rs:150-230
+ * yields these logical Arrow types). UInt32 / UInt64 need converted values and are refused here. */
+TG_API tg_status tg_table_set_column_arrow_type(tg_table* t, const char* column, const char* arrow_format);
 /* Host-only page walk of a column chunk (Thrift compact PageHeaders, parquet.thrift): fills up to `cap` entries and
  * returns the number of pages, or -(tg_status). page_type: 0 DATA_PAGE, 1 INDEX_PAGE, 2 DICTIONARY_PAGE, 3 DATA_PAGE_V2 */
 typedef struct tg_parquet_page {

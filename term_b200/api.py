@@ -373,24 +373,51 @@ class SessionContext:
 
     @staticmethod
     def _check_parquet_logical_type(col, leaf):
-        """The device path delivers the PHYSICAL values. Annotated columns whose Arrow type is not the plain signed integer /
-        float of that width (DECIMAL, DATE, TIME, TIMESTAMP, unsigned or narrow INT) would be silently wrong: refuse them,
-        the reference's ParquetSource yields their logical Arrow types (sources/parquet.rs:150-230)."""
+        """The device path delivers the PHYSICAL values. Returns the Arrow C-Data format string to declare on the column
+        (tg_table_set_column_arrow_type) when the annotation names a type whose Arrow values ARE the physical values — DATE,
+        TIME, TIMESTAMP, INT(8|16) — or None for plain columns. Annotations that would need converted values (DECIMAL,
+        UINT_32 / UINT_64, raw BYTE_ARRAY) are refused: the reference's ParquetSource yields their logical Arrow types
+        (sources/parquet.rs:150-230) and the physical values would be silently wrong."""
         lt = str(getattr(leaf, "logical_type", "NONE") or "NONE").upper()
         ct = str(getattr(leaf, "converted_type", "NONE") or "NONE").upper()
-        if str(leaf.physical_type) == "BYTE_ARRAY":
+        phys = str(leaf.physical_type)
+        if phys == "BYTE_ARRAY":
             # strings only: the string kernels rely on valid UTF-8 (Arrow's Utf8 contract); raw binary is refused
             if lt == "STRING" or ct == "UTF8":
-                return
+                return None
             raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': BYTE_ARRAY with logical type {lt} / {ct} (only STRING columns)")
-        ok_logical = lt in ("NONE", "NULL") or lt.startswith("INT(BITWIDTH=64, ISSIGNED=TRUE") or lt.startswith("INT(BITWIDTH=32, ISSIGNED=TRUE")
-        ok_converted = ct in ("NONE", "INT_64", "INT_32")
-        if not (ok_logical and ok_converted):
-            raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': logical type {lt} / {ct} is not decoded on the device "
-                                                        "(only plain signed INT32 / INT64 and FLOAT / DOUBLE columns)")
+        if phys in ("FLOAT", "DOUBLE"):
+            if lt in ("NONE", "NULL") and ct == "NONE":
+                return None
+        elif lt in ("NONE", "NULL") and ct in ("NONE", "INT_64", "INT_32"):
+            return None
+        elif lt.startswith("INT(BITWIDTH=64, ISSIGNED=TRUE") or lt.startswith("INT(BITWIDTH=32, ISSIGNED=TRUE"):
+            return None
+        elif phys == "INT32" and (lt == "DATE" or ct == "DATE"):
+            return "tdD"
+        elif phys == "INT32" and lt.startswith("INT(BITWIDTH=8,") or ct in ("INT_8", "UINT_8"):
+            return "c" if ("ISSIGNED=TRUE" in lt or ct == "INT_8") else "C"
+        elif phys == "INT32" and lt.startswith("INT(BITWIDTH=16,") or ct in ("INT_16", "UINT_16"):
+            return "s" if ("ISSIGNED=TRUE" in lt or ct == "INT_16") else "S"
+        elif lt.startswith("TIMESTAMP(") and phys == "INT64":
+            unit = "m" if "MILLISECONDS" in lt else "u" if "MICROSECONDS" in lt else "n" if "NANOSECONDS" in lt else None
+            if unit:
+                return f"ts{unit}:" + ("UTC" if "ISADJUSTEDTOUTC=TRUE" in lt else "")
+        elif ct in ("TIMESTAMP_MILLIS", "TIMESTAMP_MICROS") and phys == "INT64":
+            return "tsm:" if ct == "TIMESTAMP_MILLIS" else "tsu:"
+        elif lt.startswith("TIME(") or ct in ("TIME_MILLIS", "TIME_MICROS"):
+            if phys == "INT32" and ("MILLISECONDS" in lt or ct == "TIME_MILLIS"):
+                return "ttm"
+            if phys == "INT64" and ("MICROSECONDS" in lt or ct == "TIME_MICROS"):
+                return "ttu"
+            if phys == "INT64" and "NANOSECONDS" in lt:
+                return "ttn"
+        raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': logical type {lt} / {ct} is not decoded on the device "
+                                                    "(plain and DATE / TIME / TIMESTAMP / INT(8|16) annotated INT32 / INT64, FLOAT / DOUBLE, STRING)")
 
     def _register_parquet(self, t, paths, columns):
         import pyarrow.parquet as pq
+        declared = {}
         for pth in paths:
             pf = pq.ParquetFile(pth)
             md, schema = pf.metadata, pf.schema
@@ -412,7 +439,7 @@ class SessionContext:
                                 raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}': physical type {cm.physical_type} is not decoded on the device")
                             if leaf.max_repetition_level != 0:
                                 raise F.TermGpuError(F.TG_ERR_UNSUPPORTED, f"Parquet column '{col}' is repeated")
-                            self._check_parquet_logical_type(col, leaf)
+                            declared[col] = self._check_parquet_logical_type(col, leaf)
                             start = cm.dictionary_page_offset if cm.has_dictionary_page and cm.dictionary_page_offset else cm.data_page_offset
                             chunk = view[start: start + cm.total_compressed_size]
                             codec = self._PARQUET_CODECS.get(cm.compression, 99)  # parquet.thrift CompressionCodec; unknown -> refused
@@ -422,6 +449,9 @@ class SessionContext:
                 finally:
                     chunk = None
                     del view  # the mapping cannot close while a buffer export is alive
+        for col, fmt in declared.items():
+            if fmt is not None:
+                F.check(F.lib().tg_table_set_column_arrow_type(t, col.encode(), fmt.encode()))
         return t
 
     def register_device_table(self, name: str, columns: Dict[str, dict], keepalive=None):

@@ -256,6 +256,57 @@ struct ArrowArray {
     void* private_data;
 };
 
+// Arrow C Data Interface format string -> the stored type; width / signedness of the delivered values when they are widened
+// on the host; DataFusion's name of the delivered type (nullptr: it is the stored type)
+struct ArrowFormat {
+    int32_t dtype = 0;
+    int src_w = 0;
+    bool src_unsigned = false, temporal = false, large_offsets = false;
+    const char* src_type = nullptr;
+};
+static ArrowFormat arrow_format(const std::string& fmt, const char* column) {
+    ArrowFormat f;
+    auto starts = [&](const char* pre) { return fmt.compare(0, strlen(pre), pre) == 0; };
+    if (fmt == "l") f.dtype = TG_INT64;
+    else if (fmt == "g") f.dtype = TG_FLOAT64;
+    else if (fmt == "u") f.dtype = TG_UTF8;
+    else if (fmt == "U") f.dtype = TG_UTF8, f.large_offsets = true;
+    else if (fmt == "i") f.dtype = TG_INT32;
+    else if (fmt == "f") f.dtype = TG_FLOAT32;
+    else if (fmt == "b") f.dtype = TG_BOOL;
+    else if (fmt == "c") f.dtype = TG_INT32, f.src_w = 1, f.src_type = "Int8";
+    else if (fmt == "C") f.dtype = TG_INT32, f.src_w = 1, f.src_unsigned = true, f.src_type = "UInt8";
+    else if (fmt == "s") f.dtype = TG_INT32, f.src_w = 2, f.src_type = "Int16";
+    else if (fmt == "S") f.dtype = TG_INT32, f.src_w = 2, f.src_unsigned = true, f.src_type = "UInt16";
+    else if (fmt == "I") f.dtype = TG_INT64, f.src_w = 4, f.src_unsigned = true, f.src_type = "UInt32";
+    else if (fmt == "L") f.dtype = TG_INT64, f.src_w = 8, f.src_unsigned = true, f.src_type = "UInt64";
+    else if (fmt == "tdD") f.dtype = TG_INT32, f.temporal = true, f.src_type = "Date32";
+    else if (fmt == "tdm") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Date64";
+    else if (fmt == "tts" || fmt == "ttm") f.dtype = TG_INT32, f.temporal = true, f.src_type = "Time32";
+    else if (fmt == "ttu" || fmt == "ttn") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Time64";
+    else if (starts("tss:") || starts("tsm:") || starts("tsu:") || starts("tsn:")) f.dtype = TG_INT64, f.temporal = true, f.src_type = "Timestamp";
+    else if (fmt == "tDs" || fmt == "tDm" || fmt == "tDu" || fmt == "tDn") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Duration";
+    else throw Error(TG_ERR_UNSUPPORTED, std::string("Arrow format '") + fmt + "' of column '" + column + "' is not supported");
+    return f;
+}
+
+// Declares the Arrow type a stored Int32 / Int64 column stands for when its values arrived already in the stored
+// representation (Parquet chunks annotated DATE / TIME / TIMESTAMP / INT(8|16): the physical INT32 / INT64 values ARE the
+// Arrow values): the typing rules of table_append_arrow then apply to it.
+void table_set_column_arrow_type(Table& t, const std::string& name, const std::string& fmt) {
+    Engine& e = *t.eng;
+    std::lock_guard<std::mutex> g(e.mu);
+    Column* c = t.find(name);
+    if (!c) throw Error(TG_ERR_COLUMN_NOT_FOUND, "Schema error: No field named " + name + ". Valid fields are " + t.valid_fields() + ".");
+    const ArrowFormat f = arrow_format(fmt, name.c_str());
+    if (f.dtype != c->dtype || f.large_offsets) throw Error(TG_ERR_TYPE_MISMATCH, "column '" + name + "' does not store Arrow format '" + fmt + "'");
+    if (f.src_w == 4 || f.src_w == 8)  // UInt32 / UInt64 need a conversion of the stored values, not a label
+        throw Error(TG_ERR_UNSUPPORTED, "column '" + name + "': Arrow format '" + fmt + "' cannot be declared on stored values");
+    c->src_type = f.src_type;
+    c->src_unsigned = f.src_unsigned;
+    c->temporal = f.temporal;
+}
+
 void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
     const ArrowSchema* sc = (const ArrowSchema*)schema_p;
     const ArrowArray* ar = (const ArrowArray*)array_p;
@@ -266,32 +317,11 @@ void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
         const ArrowSchema* cs = sc->children[i];
         const ArrowArray* ca = ar->children[i];
         const std::string fmt = cs->format;
-        // stored type; width / signedness of the delivered values when they are widened on the host; DataFusion's name of the type
-        int32_t dtype;
-        int src_w = 0;
-        bool src_unsigned = false, temporal = false, large_offsets = false;
-        const char* src_type = nullptr;
-        auto starts = [&](const char* pre) { return fmt.compare(0, strlen(pre), pre) == 0; };
-        if (fmt == "l") dtype = TG_INT64;
-        else if (fmt == "g") dtype = TG_FLOAT64;
-        else if (fmt == "u") dtype = TG_UTF8;
-        else if (fmt == "U") dtype = TG_UTF8, large_offsets = true;
-        else if (fmt == "i") dtype = TG_INT32;
-        else if (fmt == "f") dtype = TG_FLOAT32;
-        else if (fmt == "b") dtype = TG_BOOL;
-        else if (fmt == "c") dtype = TG_INT32, src_w = 1, src_type = "Int8";
-        else if (fmt == "C") dtype = TG_INT32, src_w = 1, src_unsigned = true, src_type = "UInt8";
-        else if (fmt == "s") dtype = TG_INT32, src_w = 2, src_type = "Int16";
-        else if (fmt == "S") dtype = TG_INT32, src_w = 2, src_unsigned = true, src_type = "UInt16";
-        else if (fmt == "I") dtype = TG_INT64, src_w = 4, src_unsigned = true, src_type = "UInt32";
-        else if (fmt == "L") dtype = TG_INT64, src_w = 8, src_unsigned = true, src_type = "UInt64";
-        else if (fmt == "tdD") dtype = TG_INT32, temporal = true, src_type = "Date32";
-        else if (fmt == "tdm") dtype = TG_INT64, temporal = true, src_type = "Date64";
-        else if (fmt == "tts" || fmt == "ttm") dtype = TG_INT32, temporal = true, src_type = "Time32";
-        else if (fmt == "ttu" || fmt == "ttn") dtype = TG_INT64, temporal = true, src_type = "Time64";
-        else if (starts("tss:") || starts("tsm:") || starts("tsu:") || starts("tsn:")) dtype = TG_INT64, temporal = true, src_type = "Timestamp";
-        else if (fmt == "tDs" || fmt == "tDm" || fmt == "tDu" || fmt == "tDn") dtype = TG_INT64, temporal = true, src_type = "Duration";
-        else throw Error(TG_ERR_UNSUPPORTED, std::string("Arrow format '") + fmt + "' of column '" + cs->name + "' is not supported");
+        const ArrowFormat F = arrow_format(fmt, cs->name);
+        const int32_t dtype = F.dtype;
+        const int src_w = F.src_w;
+        const bool src_unsigned = F.src_unsigned, temporal = F.temporal, large_offsets = F.large_offsets;
+        const char* src_type = F.src_type;
         const uint8_t* validity = (const uint8_t*)ca->buffers[0];
         if (ca->null_count == 0) validity = nullptr;
         const int64_t off = ca->offset, n = ca->length;
