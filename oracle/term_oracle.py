@@ -559,7 +559,7 @@ def _tokenize(s):
         elif m.group(5) is not None:
             w = m.group(5)
             up = w.upper()
-            if up in ("AND", "OR", "NOT", "IS", "NULL", "TRUE", "FALSE", "BETWEEN", "IN", "LIKE"):
+            if up in ("AND", "OR", "NOT", "IS", "NULL", "TRUE", "FALSE", "BETWEEN", "IN", "LIKE", "CASE", "WHEN", "THEN", "ELSE", "END", "AS"):
                 out.append(("k", up))
             else:
                 out.append(("c", w.lower().split(".")[-1]))
@@ -706,6 +706,34 @@ class _P:
             e = self.or_()
             self.eat("o", ")")
             return e
+        if k == "k" and v == "CASE":
+            # CASE [operand] WHEN c THEN x .. [ELSE y] END; the simple form compares the operand with each WHEN value
+            self.eat()
+            operand = None if self.is_("k", "WHEN") else self.or_()
+            arms = []
+            while self.is_("k", "WHEN"):
+                self.eat()
+                c = self.or_()
+                if operand is not None:
+                    c = ("cmp", "=", operand, c)
+                self.eat("k", "THEN")
+                arms.append((c, self.or_()))
+            other = None
+            if self.is_("k", "ELSE"):
+                self.eat()
+                other = self.or_()
+            self.eat("k", "END")
+            return ("case", arms, other)
+        if k == "c" and v == "cast" and self.t[self.i + 1] == ("o", "("):
+            self.eat()
+            self.eat("o", "(")
+            e = self.or_()
+            self.eat("k", "AS")
+            ty = self.eat("c").upper()
+            if ty == "DOUBLE" and self.is_("c", "precision"):
+                self.eat()
+            self.eat("o", ")")
+            return ("cast", "f" if ty in ("DOUBLE", "FLOAT", "REAL", "FLOAT8", "FLOAT4") else "i", e)
         if k == "c":
             self.eat()
             if self.is_("o", "("):
@@ -728,6 +756,60 @@ class DivideByZero(Exception):
     pass
 
 
+def _static_type(e, kinds):
+    """'i' | 'f' | 'b' | 's' | None (a NULL literal) — the SQL type of an expression given the columns' kinds: DataFusion
+    coerces the arms of CASE / COALESCE to a common type (Int64 with Float64 -> Float64) before evaluating them"""
+    k = e[0]
+    if k == "lit":
+        v = e[1]
+        return None if v is None else "b" if isinstance(v, bool) else "i" if isinstance(v, int) else "f" if isinstance(v, float) else "s"
+    if k == "col":
+        return {"i64": "i", "f64": "f", "bool": "b", "str": "s"}[kinds[e[1]]]
+    if k == "neg":
+        return _static_type(e[1], kinds)
+    if k == "fn":
+        if e[1] == "ABS":
+            return _static_type(e[2][0], kinds)
+        if e[1] == "COALESCE":
+            return _unify([_static_type(a, kinds) for a in e[2]])
+        return "i"  # the length functions
+    if k == "ar":
+        a, b = _static_type(e[2], kinds), _static_type(e[3], kinds)
+        return None if a is None or b is None else ("f" if "f" in (a, b) else "i")
+    if k == "case":
+        return _unify([_static_type(x, kinds) for _, x in e[1]] + ([_static_type(e[2], kinds)] if e[2] is not None else []))
+    if k == "cast":
+        return e[1]
+    return "b"
+
+
+def _unify(types):
+    ts = {t for t in types if t is not None}
+    if not ts:
+        return None
+    return "f" if ts == {"i", "f"} else next(iter(ts))
+
+
+def _annotate(e, kinds):
+    """CASE / COALESCE nodes get their coerced result type appended"""
+    if not isinstance(e, tuple):
+        return e
+    if e[0] == "case":
+        arms = [(_annotate(c, kinds), _annotate(x, kinds)) for c, x in e[1]]
+        return ("case", arms, _annotate(e[2], kinds) if e[2] is not None else None, _static_type(e, kinds))
+    if e[0] == "fn" and e[1] == "COALESCE":
+        return ("fn", "COALESCE", [_annotate(a, kinds) for a in e[2]], _static_type(e, kinds))
+    if e[0] == "fn":
+        return ("fn", e[1], [_annotate(a, kinds) for a in e[2]])
+    if e[0] == "lit" or e[0] == "col":
+        return e
+    return tuple(_annotate(x, kinds) if isinstance(x, tuple) else x for x in e)
+
+
+def _coerce(v, ty):
+    return float(v) if (ty == "f" and v is not None and not isinstance(v, bool)) else v
+
+
 def _ev(e, row):
     k = e[0]
     if k == "lit":
@@ -744,7 +826,27 @@ def _ev(e, row):
         if e[1] in ("LENGTH", "CHAR_LENGTH", "CHARACTER_LENGTH", "OCTET_LENGTH"):  # DataFusion: characters / bytes of a Utf8 value
             v = _ev(e[2][0], row)
             return None if v is None else (len(v.encode("utf-8")) if e[1] == "OCTET_LENGTH" else len(v))
+        if e[1] == "COALESCE":  # the first non-NULL argument, coerced to the common type
+            for a in e[2]:
+                v = _ev(a, row)
+                if v is not None:
+                    return _coerce(v, e[3])
+            return None
         raise ValueError(e[1])
+    if k == "case":  # the first arm whose condition is TRUE (NULL is not), else ELSE, else NULL
+        for c, x in e[1]:
+            if _ev(c, row) is True:
+                return _coerce(_ev(x, row), e[3])
+        return _coerce(_ev(e[2], row), e[3]) if e[2] is not None else None
+    if k == "cast":
+        v = _ev(e[2], row)
+        if v is None:
+            return None
+        if e[1] == "f":
+            return float(v)
+        if isinstance(v, float):
+            raise ValueError("CAST of a floating point value to an integer")
+        return v
     if k == "like":
         # arrow-string `like`: `%` any sequence, `_` exactly one character, backslash takes the next character literally
         v, pat = _ev(e[1], row), _ev(e[2], row)
@@ -825,7 +927,7 @@ def predicate_counts(table, expression):
     """COUNT(CASE WHEN expr THEN 1 END), COUNT(*) — rows where expr is NULL are not counted
     (constraints/custom_sql.rs:203-209)"""
     cols = table_cols(table)
-    ast = _P(_tokenize(expression)).or_()
+    ast = _annotate(_P(_tokenize(expression)).or_(), {nm: c.kind for nm, c in cols.items()})
     n = n_rows(cols)
     names = list(cols)
     sat = 0

@@ -591,7 +591,9 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
                             case PO_MUL_I: o = (uint64_t)ai * (uint64_t)bi; break;
                             case PO_DIV_I:
                             case PO_MOD_I: {
-                                const uint32_t z = __ballot_sync(0xffffffffu, bi == 0) & ~nm;
+                                // (rows past the end of the table are zero padding: a column without a validity bitmap has
+                                // no NULL bits to hide them, so they are masked here like in the final count)
+                                const uint32_t z = __ballot_sync(0xffffffffu, bi == 0) & ~nm & tail_mask(u.row0 + 32 * (j + g), rows_in_tile);
                                 div0 |= z;
                                 nm |= z;
                                 const int64_t sb = bi == 0 ? 1 : bi;
@@ -601,6 +603,10 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
                             case PO_NEG_I: o = (uint64_t)0 - (uint64_t)ai; break;
                             case PO_ABS_I: o = ai < 0 ? (uint64_t)0 - (uint64_t)ai : (uint64_t)ai; break;
                             case PO_I2F: o = d2u((double)ai); break;
+                            case PO_COALESCE_N:
+                                o = ((a.nul[g] >> lane) & 1u) ? b.v[g] : a.v[g];
+                                nm = a.nul[g] & b.nul[g];
+                                break;
                             default: break;
                         }
                         r.v[g] = o;
@@ -651,6 +657,16 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k == ins.dst) bt[k] = r;
+            } else if (ins.op == PO_KEEPIF_N) {
+                NumVal a;
+                BoolVal b;
+                fetch_num(P, stage, ins.a_kind, ins.a_idx, ins.imm, nt, row, a);
+                fetch_bool(P, stage, ins.b_kind, ins.b_idx, ins.imm, bt, row, b);
+#pragma unroll
+                for (int g = 0; g < PG; ++g) a.nul[g] |= ~b.t[g];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (k == ins.dst) nt[k] = a;
             } else {
                 BoolVal a, b, r;
                 fetch_bool(P, stage, ins.a_kind, ins.a_idx, ins.imm, bt, row, a);

@@ -1,5 +1,6 @@
 #include "sqlexpr.hpp"
 
+#include <algorithm>
 #include <cmath>
 #include <cstdlib>
 
@@ -310,6 +311,54 @@ struct Parser {
         }
         return parse_primary();
     }
+    // CASE [operand] WHEN c THEN x [WHEN ..] [ELSE y] END -> FUNC "CASE", args = c1, x1, .., cn, xn [, y]; i = 1 when ELSE is there.
+    // The simple form compares the operand with every WHEN value.
+    ExprP parse_case() {
+        ExprP operand;
+        if (!is_kw("WHEN")) operand = parse_or();
+        auto e = mk(Expr::FUNC);
+        e->s = "CASE";
+        if (!is_kw("WHEN")) err("expected WHEN after CASE");
+        while (is_kw("WHEN")) {
+            adv();
+            ExprP c = parse_or();
+            if (operand) c = bin("=", operand, c);
+            if (!is_kw("THEN")) err("expected THEN");
+            adv();
+            e->args.push_back(c);
+            e->args.push_back(parse_or());
+        }
+        if (is_kw("ELSE")) {
+            adv();
+            e->args.push_back(parse_or());
+            e->i = 1;
+        }
+        if (!is_kw("END")) err("expected END of CASE");
+        adv();
+        return e;
+    }
+    // CAST(x AS type): the floating-point types and the integer types (of an integer operand)
+    ExprP parse_cast() {
+        adv();  // (
+        auto e = mk(Expr::FUNC);
+        e->args.push_back(parse_or());
+        if (!is_kw("AS")) err("expected AS in CAST");
+        adv();
+        if (cur.k != Tok::IDENT) err("expected a type name in CAST");
+        const std::string ty = upper(cur.s);
+        adv();
+        if (ty == "DOUBLE" && is_kw("PRECISION")) adv();
+        if (cur.k == Tok::LP) {  // (precision [, scale])
+            while (cur.k != Tok::RP && cur.k != Tok::END) adv();
+            if (cur.k == Tok::RP) adv();
+        }
+        if (ty == "DOUBLE" || ty == "FLOAT" || ty == "REAL" || ty == "FLOAT8" || ty == "FLOAT4") e->s = "CAST_F64";
+        else if (ty == "BIGINT" || ty == "INT" || ty == "INTEGER" || ty == "SMALLINT" || ty == "TINYINT" || ty == "INT8" || ty == "INT4") e->s = "CAST_I64";
+        else err("CAST to " + ty + " is not supported");
+        if (cur.k != Tok::RP) err("expected ) after CAST");
+        adv();
+        return e;
+    }
     ExprP parse_primary() {
         if (cur.k == Tok::NUM_I) {
             auto e = mk(Expr::LIT_I);
@@ -355,6 +404,8 @@ struct Parser {
                 return mk(Expr::LIT_NULL);
             }
             adv();
+            if (up == "CASE") return parse_case();
+            if (up == "CAST" && cur.k == Tok::LP) return parse_cast();
             if (cur.k == Tok::LP) {
                 adv();
                 auto e = mk(Expr::FUNC);
@@ -459,6 +510,74 @@ struct Compiler {
         return o;
     }
 
+    // static type of an expression (what gen() will produce), needed before the arms of CASE / COALESCE are generated
+    static PredType unify(PredType a, PredType b) {
+        if (a == PT_NULL) return b;
+        if (b == PT_NULL) return a;
+        if (a == PT_BOOL || b == PT_BOOL) {
+            if (a != b) throw Error(TG_ERR_TYPE_MISMATCH, "CASE / COALESCE arms mix boolean and numeric values");
+            return PT_BOOL;
+        }
+        return a == PT_F64 || b == PT_F64 ? PT_F64 : PT_I64;
+    }
+    PredType type_of(const ExprP& e) {
+        switch (e->kind) {
+            case Expr::LIT_I: return PT_I64;
+            case Expr::LIT_F: return PT_F64;
+            case Expr::LIT_B: return PT_BOOL;
+            case Expr::LIT_NULL: return PT_NULL;
+            case Expr::LIT_S: throw Error(TG_ERR_UNSUPPORTED, "string literals are only supported in comparisons with a Utf8 column");
+            case Expr::COL: {
+                const ColumnBinding b = resolve(e->s);
+                if (b.dtype == TG_INT64) return PT_I64;
+                if (b.dtype == TG_FLOAT64) return PT_F64;
+                if (b.dtype == TG_BOOL) return PT_BOOL;
+                throw Error(TG_ERR_UNSUPPORTED, "column '" + e->s + "' has a type the predicate engine does not support");
+            }
+            case Expr::UNARY: return e->s == "NOT" ? PT_BOOL : type_of(e->args[0]);
+            case Expr::IS: return PT_BOOL;
+            case Expr::BINARY: {
+                const std::string& op = e->s;
+                if (!(op == "+" || op == "-" || op == "*" || op == "/" || op == "%")) return PT_BOOL;
+                const PredType a = type_of(e->args[0]), b = type_of(e->args[1]);
+                if (a == PT_NULL || b == PT_NULL) return PT_NULL;
+                return a == PT_F64 || b == PT_F64 ? PT_F64 : PT_I64;
+            }
+            case Expr::FUNC: {
+                if (e->s == "ABS" && e->args.size() == 1) return type_of(e->args[0]);
+                if (e->s == "CAST_F64") return PT_F64;
+                if (e->s == "CAST_I64") return PT_I64;
+                if (e->s == "COALESCE" || e->s == "CASE") {
+                    PredType t = PT_NULL;
+                    const size_t n_arm = e->s == "CASE" ? (e->args.size() - (size_t)e->i) / 2 : 0;
+                    for (size_t k = 0; k < e->args.size(); ++k) {
+                        if (e->s == "CASE" && k < 2 * n_arm && k % 2 == 0) continue;  // a WHEN condition
+                        t = unify(t, type_of(e->args[k]));
+                    }
+                    return t;
+                }
+                throw Error(TG_ERR_UNSUPPORTED, "function " + e->s + " is not supported by the predicate engine");
+            }
+        }
+        throw Error(TG_ERR_INTERNAL, "bad expression node");
+    }
+    static int height(const ExprP& e) {
+        int h = 0;
+        for (auto& a : e->args) h = std::max(h, height(a));
+        return h + 1;
+    }
+    Operand as_num(Operand o, PredType t) {
+        if (o.type == PT_BOOL) throw Error(TG_ERR_TYPE_MISMATCH, "expected a numeric operand");
+        return t == PT_F64 ? to_f64(o) : o;
+    }
+    static ExprP node(Expr::Kind k, const std::string& s, std::vector<ExprP> args) {
+        auto e = std::make_shared<Expr>();
+        e->kind = k;
+        e->s = s;
+        e->args = std::move(args);
+        return e;
+    }
+
     Operand gen(const ExprP& e) {
         switch (e->kind) {
             case Expr::LIT_I: return Operand{PK_IMM, 0, (uint64_t)e->i, PT_I64};
@@ -501,17 +620,77 @@ struct Compiler {
                     if (a.type == PT_NULL) return a;
                     throw Error(TG_ERR_TYPE_MISMATCH, "ABS requires a numeric operand");
                 }
+                if (e->s == "CAST_F64" && e->args.size() == 1) return to_f64(gen(e->args[0]));
+                if (e->s == "CAST_I64" && e->args.size() == 1) {
+                    Operand a = gen(e->args[0]);
+                    if (a.type == PT_I64 || a.type == PT_NULL) return a;
+                    throw Error(TG_ERR_UNSUPPORTED, "CAST to an integer type is supported for integer operands only");
+                }
+                if (e->s == "COALESCE" && !e->args.empty()) {
+                    const PredType t = type_of(e);
+                    if (t == PT_BOOL) throw Error(TG_ERR_UNSUPPORTED, "COALESCE over boolean operands is not supported");
+                    if (t == PT_NULL) return null_num();
+                    Operand r = as_num(gen(e->args[0]), t);
+                    for (size_t k = 1; k < e->args.size(); ++k) {
+                        Operand b = as_num(gen(e->args[k]), t);
+                        r = emit(PO_COALESCE_N, r, b, t);
+                    }
+                    return r;
+                }
+                if (e->s == "CASE" && e->args.size() >= 2) {
+                    const size_t n_arm = (e->args.size() - (size_t)e->i) / 2;
+                    const PredType t = type_of(e);
+                    auto is_true = [&](const ExprP& c) { return node(Expr::IS, "TRUE", {c}); };
+                    if (t == PT_BOOL || t == PT_NULL) {
+                        // (c IS TRUE AND x) OR (NOT (c IS TRUE) AND rest): three-valued AND / OR give exactly the arm's value
+                        ExprP rest = e->i ? e->args.back() : node(Expr::LIT_NULL, "", {});
+                        for (size_t k = n_arm; k-- > 0;) {
+                            const ExprP c = is_true(e->args[2 * k]);
+                            rest = node(Expr::BINARY, "OR", {node(Expr::BINARY, "AND", {c, e->args[2 * k + 1]}),
+                                                             node(Expr::BINARY, "AND", {node(Expr::UNARY, "NOT", {c}), rest})});
+                        }
+                        return as_bool(gen(rest));
+                    }
+                    // numeric arms: COALESCE(x where c IS TRUE, rest where NOT (c IS TRUE)); a NULL arm stays NULL because the
+                    // other side is masked out on the same rows
+                    Operand rest = e->i ? as_num(gen(e->args.back()), t) : null_num();
+                    for (size_t k = n_arm; k-- > 0;) {
+                        const ExprP c = is_true(e->args[2 * k]);
+                        Operand cv = gen(c);
+                        Operand x = as_num(gen(e->args[2 * k + 1]), t);
+                        Operand keep_x = emit(PO_KEEPIF_N, x, cv, t);
+                        Operand ncv = gen(node(Expr::UNARY, "NOT", {c}));
+                        Operand keep_r = emit(PO_KEEPIF_N, rest, ncv, t);
+                        rest = emit(PO_COALESCE_N, keep_x, keep_r, t);
+                    }
+                    return rest;
+                }
                 throw Error(TG_ERR_UNSUPPORTED, "function " + e->s + " is not supported by the predicate engine");
             }
             case Expr::BINARY: {
                 const std::string& op = e->s;
+                // the taller operand first (Sethi-Ullman order): its result then occupies ONE temporary while the other is
+                // generated — right-leaning chains (desugared CASE / IN lists) stay within the four temporaries
+                const bool right_first = height(e->args[1]) > height(e->args[0]);
                 if (op == "AND" || op == "OR") {
-                    Operand a = as_bool(gen(e->args[0]));
-                    Operand b = as_bool(gen(e->args[1]));
+                    Operand a, b;
+                    if (right_first) {
+                        b = as_bool(gen(e->args[1]));
+                        a = as_bool(gen(e->args[0]));
+                    } else {
+                        a = as_bool(gen(e->args[0]));
+                        b = as_bool(gen(e->args[1]));
+                    }
                     return emit(op == "AND" ? PO_AND : PO_OR, a, b, PT_BOOL);
                 }
-                Operand a = gen(e->args[0]);
-                Operand b = gen(e->args[1]);
+                Operand a, b;
+                if (right_first) {
+                    b = gen(e->args[1]);
+                    a = gen(e->args[0]);
+                } else {
+                    a = gen(e->args[0]);
+                    b = gen(e->args[1]);
+                }
                 const bool arith = op == "+" || op == "-" || op == "*" || op == "/" || op == "%";
                 if (a.type == PT_NULL || b.type == PT_NULL) {
                     release(a);

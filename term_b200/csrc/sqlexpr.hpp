@@ -3,7 +3,9 @@
 // NULL literals, + - * / %, unary -, comparisons, AND / OR / NOT, IS [NOT] NULL, IS [NOT] TRUE|FALSE,
 // [NOT] BETWEEN, [NOT] IN (...), ABS(); over Utf8 columns: the six comparisons with a string literal or another Utf8
 // column, [NOT] LIKE 'pattern', LENGTH / CHAR_LENGTH / CHARACTER_LENGTH / OCTET_LENGTH (materialised as virtual columns
-// by the engine before the scan, engine.cu rewrite_string_compares). Anything else -> TG_ERR_UNSUPPORTED.
+// by the engine before the scan, engine.cu rewrite_string_compares); CASE (searched and simple form; boolean arms desugar to
+// three-valued AND / OR, numeric arms use PO_KEEPIF_N + PO_COALESCE_N), COALESCE over numeric operands, CAST to the
+// floating-point types (and to integer types of integer operands). Anything else -> TG_ERR_UNSUPPORTED.
 #pragma once
 #include <functional>
 #include <memory>

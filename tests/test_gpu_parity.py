@@ -1277,3 +1277,35 @@ def test_small_integer_unsigned_temporal_and_large_string_columns(ctx, n):
                 ctx.num_rows("arrowtypes_bad")
     finally:
         ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", [1, 65, 50_003])
+def test_case_coalesce_cast_predicates_match_oracle(ctx, n):
+    """CASE (searched and simple form, boolean and numeric arms, with and without ELSE), COALESCE and CAST inside `satisfies`:
+    three-valued logic, Int64 / Float64 arms coerced to Float64, NULL arms"""
+    rng = np.random.default_rng(n + 23)
+    t = pa.table({"s": pa.array([["a", "b", "c", ""][v] for v in rng.integers(0, 4, n)], mask=rng.random(n) < 0.2),
+                  "i": pa.array(rng.integers(-5, 9, n), mask=rng.random(n) < 0.2), "j": pa.array(rng.integers(-5, 9, n)),
+                  "f": pa.array(np.round(rng.normal(1.0, 3.0, n), 2), mask=rng.random(n) < 0.2)})
+    name = f"casepred_{n}"
+    ctx.register_table(name, t.to_batches(max_chunksize=991))
+    preds = ["CASE WHEN s = 'a' THEN i > 0 ELSE TRUE END", "CASE WHEN s = 'a' THEN i > 0 END", "CASE WHEN i > 2 THEN f > 0 WHEN i < 0 THEN f < 0 ELSE j = 0 END",
+             "COALESCE(i, 0) >= 1", "COALESCE(i, f, 7) / 2 > 1.9", "COALESCE(f, 0.0) + COALESCE(i, j) > 2",
+             "CASE s WHEN 'a' THEN 1 WHEN 'b' THEN 2.5 ELSE 0 END / 2 >= 0.5", "CAST(i AS DOUBLE) / 3 > 1", "CAST(j AS BIGINT) % 2 = 0",
+             "CASE WHEN f > 0 THEN i ELSE 10 END > 3", "CASE WHEN i IS NULL THEN f WHEN i > 3 THEN 100 END > 2",
+             "CASE WHEN f IS NULL THEN NULL ELSE j END IS NULL", "NOT CASE WHEN j > 0 THEN i > j ELSE FALSE END",
+             "CASE WHEN j > 0 THEN CASE WHEN i > 0 THEN 1 ELSE 2 END ELSE 3 END = 2", "COALESCE(i, j) / j > 0 OR j = 0",
+             # a divisor column WITHOUT a validity bitmap and a ragged row count: the zero padding past the last row must not
+             # raise DataFusion's "Divide by zero" (it did before the tail mask was applied to the division flags)
+             "i / (j * j + 1) >= 0 OR i < 0", "j % (j * j + 1) < 9"]
+    try:
+        cb = T.Check.builder("casepred")
+        for p in preds:
+            cb.satisfies(p)
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        for p, g in zip(preds, rs):
+            o = O.custom_sql(t, p)
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
+    finally:
+        ctx.deregister_table(name)
