@@ -253,7 +253,8 @@ TG_API tg_status tg_table_column_buffers(tg_engine* eng, const char* table, cons
  * (dictionary entry or PLAIN value), scans the lengths and copies; the host walks the PLAIN pages' length prefixes.
  * Supported: INT64 / DOUBLE / INT32 / FLOAT / BYTE_ARRAY (Utf8), codec UNCOMPRESSED (0) / SNAPPY (1) / GZIP (2) / BROTLI (4) / ZSTD (6) /
  * LZ4_RAW (7) (parquet.thrift CompressionCodec numbers; LZO and the deprecated hadoop-framed LZ4 are refused), data
- * pages V1 / V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values, RLE levels, flat columns; anything else ->
+ * pages V1 / V2, PLAIN / PLAIN_DICTIONARY / RLE_DICTIONARY values (on the device) and DELTA_BINARY_PACKED / DELTA_LENGTH_BYTE_ARRAY /
+ * DELTA_BYTE_ARRAY / BYTE_STREAM_SPLIT values (serial streams: rewritten to PLAIN on the host), RLE levels, flat columns; anything else ->
  * TG_ERR_UNSUPPORTED (there is no host decode path). Appends num_values rows; `chunk`
  * must stay readable until the next tg_plan_execute* / tg_table_column_buffers on this engine when it is pinned memory.
  */
@@ -284,6 +285,12 @@ TG_API int64_t tg_parquet_chunk_validity(const void* chunk, int64_t n_bytes, int
 /* Host-only: the Snappy raw-format decoder the chunk path applies to compressed pages (parquet-format Compression.md);
  * returns the uncompressed size, or -(tg_status) for a corrupt stream / a stream larger than `cap`. */
 TG_API int64_t tg_parquet_snappy_decompress(const void* src, int64_t n_bytes, void* dst, int64_t cap);
+/* Host-only: the value section of one data page (n_values non-NULL values) encoded DELTA_BINARY_PACKED (5), DELTA_LENGTH_BYTE_ARRAY
+ * (6), DELTA_BYTE_ARRAY (7) or BYTE_STREAM_SPLIT (9) (parquet.thrift Encoding numbers) rewritten into the PLAIN layout
+ * (elem_width 4 / 8: little-endian values; 0: BYTE_ARRAY as 4-byte length + bytes) — what the chunk path does on the host for
+ * such pages before the common PLAIN path stages them. Returns the PLAIN size, or -(tg_status). */
+TG_API int64_t tg_parquet_decode_to_plain(int32_t encoding, int32_t elem_width, const void* src, int64_t n_bytes, int64_t n_values, void* dst,
+                                          int64_t cap);
 /* Host-only: one compressed page body of codec `codec` (parquet.thrift numbers, see above) -> dst; returns the uncompressed
  * size, or -(tg_status): TG_ERR_UNSUPPORTED for a codec without a decoder (or whose library this host lacks),
  * TG_ERR_INVALID_ARG for a corrupt stream / one larger than `cap`. What the chunk path applies to every compressed page. */

@@ -92,6 +92,7 @@ SIGNATURES = {
     "tg_parquet_chunk_validity": (C.c_int64, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p]),
     "tg_parquet_snappy_decompress": (C.c_int64, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "tg_table_set_column_arrow_type": (C.c_int32, [C.c_void_p, C.c_char_p, C.c_char_p]),
+    "tg_parquet_decode_to_plain": (C.c_int64, [C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64]),
     "tg_parquet_page_decompress": (C.c_int64, [C.c_int32, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64]),
     "tg_parquet_inspect_chunk": (C.c_int32, [C.c_void_p, C.c_int64, C.POINTER(tg_parquet_page), C.c_int32]),
     "tg_table_column_buffers": (C.c_int, [P, C.c_char_p, C.c_char_p, C.POINTER(tg_column_buffers)]),

@@ -18,6 +18,7 @@ int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t nu
 int64_t parquet_snappy_decompress(const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
 int64_t parquet_page_decompress(int32_t codec, const uint8_t* src, int64_t n, uint8_t* dst, int64_t cap);
 void table_set_column_arrow_type(Table& t, const std::string& name, const std::string& fmt);
+int64_t parquet_decode_to_plain(int32_t encoding, int32_t elem_width, const uint8_t* src, int64_t n, int64_t n_values, uint8_t* dst, int64_t cap);
 void table_adopt_device(Table& t, const std::string& name, int32_t dtype, int64_t n, const void* d_values,
                         const int32_t* d_offsets, const uint8_t* d_validity, int64_t n_value_bytes);
 void table_append_arrow(Table& t, const void* schema_p, const void* array_p);
@@ -290,6 +291,11 @@ tg_status tg_table_set_column_arrow_type(tg_table* t, const char* column, const 
         if (!t || !column || !arrow_format) throw Error(TG_ERR_INVALID_ARG, "NULL argument");
         table_set_column_arrow_type(*reinterpret_cast<Table*>(t), column, arrow_format);
     });
+}
+int64_t tg_parquet_decode_to_plain(int32_t encoding, int32_t elem_width, const void* src, int64_t n_bytes, int64_t n_values, void* dst, int64_t cap) {
+    int64_t n = 0;
+    tg_status st = guard([&] { n = parquet_decode_to_plain(encoding, elem_width, (const uint8_t*)src, n_bytes, n_values, (uint8_t*)dst, cap); });
+    return st == TG_OK ? n : -(int64_t)st;
 }
 int64_t tg_parquet_page_decompress(int32_t codec, const void* src, int64_t n_bytes, void* dst, int64_t cap) {
     int64_t n = 0;

@@ -22,6 +22,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <memory>
 #include <mutex>
 #include <cstring>
 #include <exception>
@@ -109,7 +110,8 @@ struct Thrift {
 };
 
 enum { PQ_DATA_PAGE = 0, PQ_INDEX_PAGE = 1, PQ_DICTIONARY_PAGE = 2, PQ_DATA_PAGE_V2 = 3 };
-enum { PQ_ENC_PLAIN = 0, PQ_ENC_PLAIN_DICTIONARY = 2, PQ_ENC_RLE = 3, PQ_ENC_RLE_DICTIONARY = 8 };
+enum { PQ_ENC_PLAIN = 0, PQ_ENC_PLAIN_DICTIONARY = 2, PQ_ENC_RLE = 3, PQ_ENC_DELTA_BINARY_PACKED = 5, PQ_ENC_DELTA_LENGTH_BYTE_ARRAY = 6,
+       PQ_ENC_DELTA_BYTE_ARRAY = 7, PQ_ENC_RLE_DICTIONARY = 8, PQ_ENC_BYTE_STREAM_SPLIT = 9 };
 enum { PQ_CODEC_UNCOMPRESSED = 0, PQ_CODEC_SNAPPY = 1, PQ_CODEC_GZIP = 2, PQ_CODEC_BROTLI = 4, PQ_CODEC_ZSTD = 6, PQ_CODEC_LZ4_RAW = 7 };
 
 // parquet.thrift: PageHeader {1 type, 2 uncompressed_page_size, 3 compressed_page_size, 4 crc, 5 data_page_header,
@@ -612,6 +614,132 @@ int64_t parquet_chunk_validity(const uint8_t* chunk, int64_t n_bytes, int64_t nu
 }
 
 namespace {
+// the number of non-NULL rows among the `n` definition levels of one page
+int64_t count_levels_set(const uint8_t* p, const uint8_t* end, int64_t n) {
+    if (n <= 0) return 0;
+    std::vector<uint8_t> bits((size_t)(n + 7) / 8 + 8, 0);
+    decode_levels(p, end, bits.data(), 0, n);
+    return count_ones(bits.data(), 0, n);
+}
+
+// ---- DELTA_BINARY_PACKED / DELTA_LENGTH_BYTE_ARRAY / DELTA_BYTE_ARRAY / BYTE_STREAM_SPLIT pages (parquet-format Encodings.md):
+// their value streams are serial prefix sums / byte transposes; the host rewrites them into the PLAIN layout of the page
+// (fixed width: little-endian values; BYTE_ARRAY: 4-byte length + bytes) and the common PLAIN path takes it from there.
+// Decodes one DELTA_BINARY_PACKED stream: <block size> <miniblocks per block> <total count> <first value (zigzag)>, then per
+// block <min delta (zigzag)> <bit widths> <miniblocks>; values wrap in 64 bits (INT32 columns keep the low 32). Returns the
+// end of the stream.
+const uint8_t* delta_binary_unpack(const uint8_t* p, const uint8_t* end, std::vector<int64_t>& out) {
+    Thrift t{p, end};
+    const uint64_t block = t.varint(), minis = t.varint(), total = t.varint();
+    uint64_t last = (uint64_t)t.zigzag();
+    if (block == 0 || block % 128 != 0 || minis == 0 || block % minis != 0 || (block / minis) % 32 != 0 || minis > 512)
+        throw Error(TG_ERR_INVALID_ARG, "Parquet: malformed DELTA_BINARY_PACKED header");
+    if (total > (uint64_t)(end - p) * 64 + 1) throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_BINARY_PACKED count does not fit the page");
+    const uint64_t per_mini = block / minis;
+    out.clear();
+    out.reserve((size_t)total);
+    if (total > 0) out.push_back((int64_t)last);
+    while (out.size() < total) {
+        const uint64_t min_delta = (uint64_t)t.zigzag();
+        t.need((size_t)minis);
+        const uint8_t* widths = t.p;
+        t.p += minis;
+        for (uint64_t m = 0; m < minis && out.size() < total; ++m) {
+            const uint32_t bw = widths[m];
+            if (bw > 64) throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_BINARY_PACKED bit width above 64");
+            const size_t bytes = (size_t)(per_mini * bw / 8);
+            t.need(bytes);
+            for (uint64_t i = 0; i < per_mini && out.size() < total; ++i) {
+                uint64_t d = 0;
+                if (bw) {
+                    const uint64_t bit = i * bw;
+                    const size_t byte = (size_t)(bit >> 3);
+                    const uint32_t sh = (uint32_t)(bit & 7);
+                    uint8_t buf[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+                    memcpy(buf, t.p + byte, std::min<size_t>(9, bytes - byte));
+                    uint64_t lo;
+                    memcpy(&lo, buf, 8);
+                    d = lo >> sh;
+                    if (sh && bw + sh > 64) d |= (uint64_t)buf[8] << (64 - sh);
+                    if (bw < 64) d &= ((uint64_t)1 << bw) - 1;
+                }
+                last = last + min_delta + d;
+                out.push_back((int64_t)last);
+            }
+            t.p += bytes;
+        }
+    }
+    return t.p;
+}
+
+// one page's value section (n_present non-NULL values) of `encoding` -> PLAIN layout appended to `out`
+void decode_to_plain(int32_t encoding, size_t elem_w, const uint8_t* p, int64_t n_bytes, int64_t n_present, std::vector<uint8_t>& out) {
+    const uint8_t* end = p + n_bytes;
+    std::vector<int64_t> a, b;
+    auto need_count = [&](size_t got) {
+        if ((int64_t)got != n_present) throw Error(TG_ERR_INVALID_ARG, "Parquet: page holds " + std::to_string(got) + " encoded values, its levels say " + std::to_string(n_present));
+    };
+    switch (encoding) {
+        case PQ_ENC_DELTA_BINARY_PACKED: {
+            if (elem_w != 4 && elem_w != 8) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_BINARY_PACKED on a non-integer column");
+            if (n_present == 0) return;
+            delta_binary_unpack(p, end, a);
+            need_count(a.size());
+            const size_t at = out.size();
+            out.resize(at + a.size() * elem_w);
+            for (size_t i = 0; i < a.size(); ++i) memcpy(out.data() + at + i * elem_w, &a[i], elem_w);  // (little endian: the low bytes)
+        } break;
+        case PQ_ENC_BYTE_STREAM_SPLIT: {
+            if (elem_w != 4 && elem_w != 8) throw Error(TG_ERR_UNSUPPORTED, "Parquet: BYTE_STREAM_SPLIT on a variable-width column");
+            if (n_bytes != n_present * (int64_t)elem_w) throw Error(TG_ERR_INVALID_ARG, "Parquet: BYTE_STREAM_SPLIT page size does not match its value count");
+            const size_t at = out.size();
+            out.resize(at + (size_t)n_bytes);
+            for (size_t k = 0; k < elem_w; ++k)
+                for (int64_t i = 0; i < n_present; ++i) out[at + (size_t)i * elem_w + k] = p[k * (size_t)n_present + (size_t)i];
+        } break;
+        case PQ_ENC_DELTA_LENGTH_BYTE_ARRAY: {
+            if (elem_w != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_LENGTH_BYTE_ARRAY on a fixed-width column");
+            if (n_present == 0) return;
+            const uint8_t* q = delta_binary_unpack(p, end, a);
+            need_count(a.size());
+            for (int64_t len : a) {
+                if (len < 0 || len > end - q) throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_LENGTH_BYTE_ARRAY value runs past the page");
+                const uint32_t l32 = (uint32_t)len;
+                out.insert(out.end(), (const uint8_t*)&l32, (const uint8_t*)&l32 + 4);
+                out.insert(out.end(), q, q + len);
+                q += len;
+            }
+        } break;
+        case PQ_ENC_DELTA_BYTE_ARRAY: {
+            if (elem_w != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_BYTE_ARRAY on a fixed-width column");
+            if (n_present == 0) return;
+            const uint8_t* q = delta_binary_unpack(p, end, a);  // prefix lengths
+            q = delta_binary_unpack(q, end, b);                 // suffix lengths, then the suffix bytes
+            need_count(a.size());
+            need_count(b.size());
+            size_t prev_at = 0, prev_len = 0;  // the previous value inside `out` (after its length prefix)
+            for (size_t i = 0; i < a.size(); ++i) {
+                const int64_t pre = a[i], suf = b[i];
+                if (pre < 0 || (size_t)pre > prev_len || suf < 0 || suf > end - q || pre + suf > 0x7fffffffll)
+                    throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_BYTE_ARRAY value runs past the page or its predecessor");
+                const uint32_t l32 = (uint32_t)(pre + suf);
+                const size_t at = out.size();
+                out.resize(at + 4 + (size_t)l32);
+                memcpy(out.data() + at, &l32, 4);
+                if (pre) memmove(out.data() + at + 4, out.data() + prev_at, (size_t)pre);
+                memcpy(out.data() + at + 4 + pre, q, (size_t)suf);
+                q += suf;
+                prev_at = at + 4;
+                prev_len = l32;
+            }
+        } break;
+        default: throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(encoding));
+    }
+}
+bool encoding_rewritten_on_host(int32_t enc) {
+    return enc == PQ_ENC_DELTA_BINARY_PACKED || enc == PQ_ENC_DELTA_LENGTH_BYTE_ARRAY || enc == PQ_ENC_DELTA_BYTE_ARRAY || enc == PQ_ENC_BYTE_STREAM_SPLIT;
+}
+
 struct PqSection {
     int64_t first_row, n_rows;
     const uint8_t* values;
@@ -623,6 +751,7 @@ struct PqSection {
 struct PqChunk {
     std::vector<PqSection> secs;
     std::vector<uint8_t> inflated;       // the uncompressed bodies of Snappy pages (sections point into it)
+    std::vector<std::unique_ptr<std::vector<uint8_t>>> rewritten;  // PLAIN rewrites of DELTA / BYTE_STREAM_SPLIT value sections
     const uint8_t* dict_values = nullptr;
     int64_t dict_bytes = 0, dict_count = 0;
     bool any_dict = false;
@@ -673,8 +802,9 @@ void collect_sections(const uint8_t* chunk, int64_t n_bytes, int32_t codec, int3
             continue;
         }
         const bool is_dict = pg.encoding == PQ_ENC_RLE_DICTIONARY || pg.encoding == PQ_ENC_PLAIN_DICTIONARY;
-        if (!is_dict && pg.encoding != PQ_ENC_PLAIN)
-            throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) + " (PLAIN and dictionary encodings only)");
+        if (!is_dict && pg.encoding != PQ_ENC_PLAIN && !encoding_rewritten_on_host(pg.encoding))
+            throw Error(TG_ERR_UNSUPPORTED, "Parquet: value encoding " + std::to_string(pg.encoding) +
+                                                " (PLAIN, dictionary, DELTA_* and BYTE_STREAM_SPLIT encodings only)");
         PqSection s{rows, pg.num_values, body, body_bytes, nullptr, 0, is_dict};
         if (max_def_level > 0) {
             if (pg.definition_level_encoding != PQ_ENC_RLE) throw Error(TG_ERR_UNSUPPORTED, "Parquet: definition levels not RLE-encoded");
@@ -697,6 +827,18 @@ void collect_sections(const uint8_t* chunk, int64_t n_bytes, int32_t codec, int3
         } else if (pg.version == 2 && pg.definition_levels_bytes) {
             s.values = body + pg.definition_levels_bytes;
             s.values_bytes = body_bytes - pg.definition_levels_bytes;
+        }
+        if (encoding_rewritten_on_host(pg.encoding)) {
+            // the number of values present = the page's rows minus its NULLs (counted from the levels when the header has no count)
+            int64_t present = pg.num_values;
+            if (max_def_level > 0) {
+                if (pg.version == 2) present -= pg.num_nulls;
+                else present = count_levels_set(s.levels, s.levels + s.levels_bytes, pg.num_values);
+            }
+            out.rewritten.push_back(std::make_unique<std::vector<uint8_t>>());
+            decode_to_plain(pg.encoding, elem_w, s.values, s.values_bytes, present, *out.rewritten.back());
+            s.values = out.rewritten.back()->data();
+            s.values_bytes = (int64_t)out.rewritten.back()->size();
         }
         rows += pg.num_values;
         out.any_dict = out.any_dict || is_dict;
@@ -1161,6 +1303,17 @@ static void append_parquet_utf8(Table& t, const std::string& name, int32_t max_d
     c.last_offset = (int32_t)c.value_bytes;
     c.n_rows = have + num_values;
     t.n_rows = std::max(t.n_rows, c.n_rows);
+}
+
+// host-only (tests): one page's value section of a DELTA_* / BYTE_STREAM_SPLIT encoding rewritten to the PLAIN layout
+int64_t parquet_decode_to_plain(int32_t encoding, int32_t elem_width, const uint8_t* src, int64_t n, int64_t n_values, uint8_t* dst, int64_t cap) {
+    if (!src || n < 0 || n_values < 0 || (!dst && cap > 0) || cap < 0) throw Error(TG_ERR_INVALID_ARG, "NULL value buffers");
+    if (elem_width != 0 && elem_width != 4 && elem_width != 8) throw Error(TG_ERR_INVALID_ARG, "element width must be 0 (BYTE_ARRAY), 4 or 8");
+    std::vector<uint8_t> out;
+    decode_to_plain(encoding, (size_t)elem_width, src, n, n_values, out);
+    if ((int64_t)out.size() > cap) throw Error(TG_ERR_INVALID_ARG, "PLAIN rewrite larger than the output buffer");
+    if (!out.empty()) memcpy(dst, out.data(), out.size());
+    return (int64_t)out.size();
 }
 
 // host-only (tests): one page body through the codec dispatch of the chunk path

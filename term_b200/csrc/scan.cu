@@ -546,6 +546,31 @@ __device__ __forceinline__ void fetch_bool(const ScanTables& P, const uint8_t* s
     }
 }
 
+// the two select-type instructions of numeric CASE / COALESCE, kept out of line: the evaluator's common instructions (and
+// with them the register allocation of the scan kernel that calls it) stay exactly what they were without them
+__device__ __noinline__ void pred_select(const ScanTables& P, const uint8_t* stage, const PredInstr& ins, NumVal (&nt)[4], const BoolVal (&bt)[4],
+                                         int row, int lane) {
+    NumVal a;
+    fetch_num(P, stage, ins.a_kind, ins.a_idx, ins.imm, nt, row, a);
+    if (ins.op == PO_KEEPIF_N) {
+        BoolVal b;
+        fetch_bool(P, stage, ins.b_kind, ins.b_idx, ins.imm, bt, row, b);
+#pragma unroll
+        for (int g = 0; g < PG; ++g) a.nul[g] |= ~b.t[g];
+    } else {
+        NumVal b;
+        fetch_num(P, stage, ins.b_kind, ins.b_idx, ins.imm, nt, row, b);
+#pragma unroll
+        for (int g = 0; g < PG; ++g) {
+            if ((a.nul[g] >> lane) & 1u) a.v[g] = b.v[g];
+            a.nul[g] &= b.nul[g];
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        if (k == ins.dst) nt[k] = a;
+}
+
 __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& u, const uint8_t* stage, int lane,
                                        int rows_in_tile, uint64_t* cnt_out, uint64_t* div0_out) {
     uint64_t cnt = 0;
@@ -603,10 +628,6 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
                             case PO_NEG_I: o = (uint64_t)0 - (uint64_t)ai; break;
                             case PO_ABS_I: o = ai < 0 ? (uint64_t)0 - (uint64_t)ai : (uint64_t)ai; break;
                             case PO_I2F: o = d2u((double)ai); break;
-                            case PO_COALESCE_N:
-                                o = ((a.nul[g] >> lane) & 1u) ? b.v[g] : a.v[g];
-                                nm = a.nul[g] & b.nul[g];
-                                break;
                             default: break;
                         }
                         r.v[g] = o;
@@ -657,16 +678,8 @@ __device__ __noinline__ void unit_pred(const ScanTables& P, const ScanUnitDesc& 
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     if (k == ins.dst) bt[k] = r;
-            } else if (ins.op == PO_KEEPIF_N) {
-                NumVal a;
-                BoolVal b;
-                fetch_num(P, stage, ins.a_kind, ins.a_idx, ins.imm, nt, row, a);
-                fetch_bool(P, stage, ins.b_kind, ins.b_idx, ins.imm, bt, row, b);
-#pragma unroll
-                for (int g = 0; g < PG; ++g) a.nul[g] |= ~b.t[g];
-#pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (k == ins.dst) nt[k] = a;
+            } else if (ins.op >= PO_KEEPIF_N) {
+                pred_select(P, stage, ins, nt, bt, row, lane);
             } else {
                 BoolVal a, b, r;
                 fetch_bool(P, stage, ins.a_kind, ins.a_idx, ins.imm, bt, row, a);

@@ -97,7 +97,6 @@ enum : uint8_t {
     PO_ADD_F, PO_SUB_F, PO_MUL_F, PO_DIV_F, PO_NEG_F, PO_ABS_F,
     PO_ADD_I, PO_SUB_I, PO_MUL_I, PO_DIV_I, PO_MOD_I, PO_NEG_I, PO_ABS_I,
     PO_I2F,
-    PO_COALESCE_N,  // a unless it is NULL, else b (same numeric type on both sides)
     // numeric -> boolean
     PO_EQ_F, PO_NE_F, PO_LT_F, PO_LE_F, PO_GT_F, PO_GE_F,
     PO_EQ_I, PO_NE_I, PO_LT_I, PO_LE_I, PO_GT_I, PO_GE_I,
@@ -106,6 +105,8 @@ enum : uint8_t {
     PO_MOVB, PO_AND, PO_OR, PO_NOT, PO_ISNULL_B, PO_ISNOTNULL_B, PO_ISTRUE, PO_ISFALSE, PO_EQ_B, PO_NE_B,
     // (numeric a, boolean b) -> numeric: a where b is TRUE, NULL elsewhere (the arms of a numeric CASE)
     PO_KEEPIF_N,
+    // (numeric a, numeric b) -> numeric: a unless it is NULL, else b (same numeric type on both sides)
+    PO_COALESCE_N,
 };
 struct PredInstr {
     uint8_t op;
