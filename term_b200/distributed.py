@@ -311,6 +311,14 @@ def _cabi_shuffle(ctx, call, *args):
     return n.value
 
 
+def _exact_shuffle_key(ctx, dtype):
+    """the column travels as its own 64-bit values: Int64 / Float64 always; Int32 / Float32 when the library does the shuffle
+    (tg_table_shuffle_column reads them through the exactly widened shadow) — otherwise as 128-bit fingerprints"""
+    if dtype in (F.TG_INT64, F.TG_FLOAT64):
+        return True
+    return dtype in (F.TG_INT32, F.TG_FLOAT32) and _ensure_comm(ctx)
+
+
 def _shuffle_column(ctx, table, column, shard_name, by_range_if_dense=False):
     """partition -> all-to-all -> adopt as table `shard_name` (column keeps its name). by_range_if_dense: a DISTINCT
     aggregate may split dense Int64 keys by value range (a foreign key may not: both sides must agree on the function)."""
@@ -657,7 +665,7 @@ def execute_distributed(plan, ctx, table="data"):
             parts = key.split("|")
             if kind == KIND_DISTINCT:
                 name = f"tg_shuffle_{i}_k"
-                if len(parts) == 2 and _column_dtype(ctx, table, parts[1]) in (F.TG_INT64, F.TG_FLOAT64):
+                if len(parts) == 2 and _exact_shuffle_key(ctx, _column_dtype(ctx, table, parts[1])):
                     _shuffle_column(ctx, table, parts[1], name, by_range_if_dense=True)  # exact 64-bit keys
                 else:
                     _shuffle_fingerprints(ctx, table, parts[1:], name)  # Utf8 / composite: 128-bit fingerprints
@@ -667,7 +675,7 @@ def execute_distributed(plan, ctx, table="data"):
             elif kind == KIND_FK:
                 (ct, cc), (pt, pc) = parts[1].split("."), parts[2].split(".")
                 cname, pname = f"tg_shuffle_{i}_c", f"tg_shuffle_{i}_p"
-                if _column_dtype(ctx, ct, cc) in (F.TG_INT64, F.TG_FLOAT64):
+                if _exact_shuffle_key(ctx, _column_dtype(ctx, ct, cc)) and _exact_shuffle_key(ctx, _column_dtype(ctx, pt, pc)):
                     _shuffle_column(ctx, ct, cc, cname)
                     temps.append(cname)
                     _shuffle_column(ctx, pt, pc, pname)

@@ -45,7 +45,8 @@ def register(ctx, name, cols):
         v = pad(vals)
         b = bitmap(valid) if valid is not None else None
         keep += [v, b]
-        spec[c] = dict(dtype=F.TG_FLOAT64 if vals.dtype == torch.float64 else F.TG_INT64, n_rows=vals.numel(), values=v.data_ptr(),
+        dt = {torch.float64: F.TG_FLOAT64, torch.int64: F.TG_INT64, torch.int32: F.TG_INT32, torch.float32: F.TG_FLOAT32}[vals.dtype]
+        spec[c] = dict(dtype=dt, n_rows=vals.numel(), values=v.data_ptr(),
                        validity=b.data_ptr() if b is not None else None)
     torch.cuda.synchronize()  # the engine runs on its own stream: the tensors must be complete before it reads them
     ctx.register_device_table(name, spec, keepalive=keep)
@@ -109,15 +110,19 @@ def main():
     # Int64 column correlated with amount (Spearman ~ 0.9), its own NULLs
     score = (x * 3.0 + torch.empty(n, dtype=torch.float64, device=dev).normal_(0.0, 20.0, generator=g)).to(torch.int64)
     score_valid = torch.rand(n, generator=g, device=dev) >= 0.03
+    # an Int32 key column (travels through the shuffle as its exactly widened values) and a Float32 measure
+    region = (keys % 100_003).to(torch.int32)
+    price = x.to(torch.float32)
     register(ctx, "orders", {"customer_id": (child, child_valid), "order_key": (keys, keys_valid), "amount": (x, x_valid),
-                             "score": (score, score_valid)})
+                             "score": (score, score_valid), "region": (region, keys_valid), "price": (price, x_valid)})
     register(ctx, "customers", {"id": (parent, None)})
 
     A = T.Assertion
     check = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
              .validates_uniqueness(["order_key"], 0.9)
              .validates_uniqueness(["order_key", "customer_id"], 0.5)  # composite key: fingerprint shuffle
-             .foreign_key("orders.customer_id", "customers.id").build())
+             .foreign_key("orders.customer_id", "customers.id")
+             .validates_uniqueness(["region"], 0.0).has_standard_deviation("price", A.GreaterThan(0.0)).build())
     suite = T.ValidationSuite.builder("dist").table_name("orders").check(check).build()
     plan, slots = suite.build_plan()
     extra = T.UniquenessConstraint(["order_key"], T.UniquenessType.UniqueValueRatio, assertion=A.GreaterThan(0.0))._add_to(plan)
@@ -178,17 +183,20 @@ def main():
     full = {"customer_id": gather(child, world), "cv": gather(child_valid.to(torch.uint8), world).bool(),
             "order_key": gather(keys, world), "kv": gather(keys_valid.to(torch.uint8), world).bool(),
             "amount": gather(x, world), "av": gather(x_valid.to(torch.uint8), world).bool(), "parent": gather(parent, world),
-            "score": gather(score, world), "sv": gather(score_valid.to(torch.uint8), world).bool()}
+            "score": gather(score, world), "sv": gather(score_valid.to(torch.uint8), world).bool(),
+            "region": gather(region, world), "price": gather(price, world)}
     gather_done = {"child": gather(child[:ns].contiguous(), world), "cv": gather(child_valid[:ns].to(torch.uint8).contiguous(), world).bool()}
     ok = True
     if rank == 0:
         register(ctx, "orders_all", {"customer_id": (full["customer_id"], full["cv"]), "order_key": (full["order_key"], full["kv"]),
-                                     "amount": (full["amount"], full["av"]), "score": (full["score"], full["sv"])})
+                                     "amount": (full["amount"], full["av"]), "score": (full["score"], full["sv"]),
+                                     "region": (full["region"], full["kv"]), "price": (full["price"], full["av"])})
         register(ctx, "customers_all", {"id": (full["parent"], None)})
         check1 = (T.Check.builder("integrity").has_size(A.GreaterThan(0.0)).has_mean("amount", A.Between(90.0, 110.0))
                   .validates_uniqueness(["order_key"], 0.9)
                   .validates_uniqueness(["order_key", "customer_id"], 0.5)
-                  .foreign_key("orders_all.customer_id", "customers_all.id").build())
+                  .foreign_key("orders_all.customer_id", "customers_all.id")
+                  .validates_uniqueness(["region"], 0.0).has_standard_deviation("price", A.GreaterThan(0.0)).build())
         s1 = T.ValidationSuite.builder("single").table_name("orders_all").check(check1).build()
         p1, sl1 = s1.build_plan()
         e1 = T.UniquenessConstraint(["order_key"], T.UniquenessType.UniqueValueRatio, assertion=A.GreaterThan(0.0))._add_to(p1)
@@ -197,7 +205,7 @@ def main():
         want = [(r.name, r.status.name, r.metric, (r.message or "").split("Examples")[0].replace("orders_all", "orders").replace("customers_all", "customers"))
                 for r in want]
         for gg, ww in zip(got, want):
-            exact = gg[0] != "mean"
+            exact = gg[0] not in ("mean", "standard_deviation")
             same = gg[1] == ww[1] and gg[3] == ww[3] and (gg[2] == ww[2] if exact else abs(gg[2] - ww[2]) <= 1e-9 * abs(ww[2]))
             ok = ok and same
             if not same:
