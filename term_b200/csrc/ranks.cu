@@ -175,6 +175,7 @@ __global__ void __launch_bounds__(1024) rk_tile_scan_kernel(const uint32_t* __re
     const int64_t per = (n_tiles + 1023) / 1024;
     const int64_t lo = (int64_t)threadIdx.x * per, hi = lo + per < n_tiles ? lo + per : n_tiles;
     uint32_t m = 0;
+#pragma unroll 8
     for (int64_t t = lo; t < hi; ++t) m = max(m, tile_last[t]);
     s_part[threadIdx.x] = m;
     __syncthreads();
@@ -185,6 +186,7 @@ __global__ void __launch_bounds__(1024) rk_tile_scan_kernel(const uint32_t* __re
         __syncthreads();
     }
     uint32_t run = threadIdx.x ? s_part[threadIdx.x - 1] : 0u;
+#pragma unroll 8
     for (int64_t t = lo; t < hi; ++t) {
         carry[t] = run;
         run = max(run, tile_last[t]);
@@ -397,14 +399,27 @@ __global__ void rk_split_kernel(const uint64_t* __restrict__ sorted, int64_t n, 
     pos[i] = lo;
 }
 
-// fixed-order sum of the block partials: 5 warps, one per moment, lanes stride the blocks, shuffle tree at the end
-__global__ void __launch_bounds__(160) rk_final_kernel(const double* __restrict__ partial, int64_t n_blocks, double* out) {
-    const int k = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double v = 0;
-    for (int64_t b = lane; b < n_blocks; b += 32) v += partial[(size_t)b * 5 + k];
-#pragma unroll
-    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
-    if (lane == 0) out[k] = v;
+// fixed-order sum of the block partials: one block per moment, thread t sums the blocks t, t + 1024, .. (four independent
+// chains), then a fixed shared-memory tree — the same order on every run
+__global__ void __launch_bounds__(1024) rk_final_kernel(const double* __restrict__ partial, int64_t n_blocks, double* out) {
+    __shared__ double s_sum[1024];
+    const int k = blockIdx.x;
+    double v0 = 0, v1 = 0, v2 = 0, v3 = 0;
+    int64_t b = threadIdx.x;
+    for (; b + 3 * 1024 < n_blocks; b += 4 * 1024) {
+        v0 += partial[(size_t)b * 5 + k];
+        v1 += partial[(size_t)(b + 1024) * 5 + k];
+        v2 += partial[(size_t)(b + 2048) * 5 + k];
+        v3 += partial[(size_t)(b + 3072) * 5 + k];
+    }
+    for (; b < n_blocks; b += 1024) v0 += partial[(size_t)b * 5 + k];
+    s_sum[threadIdx.x] = (v0 + v1) + (v2 + v3);
+    __syncthreads();
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s_sum[threadIdx.x] += s_sum[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[k] = s_sum[0];
 }
 
 static size_t round_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
@@ -621,7 +636,7 @@ static void rank_finish_y_locked(Engine& e, uint64_t rank_base, double K, uint64
             rk_tile_heads_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, S.n, A.tile_last);
             rk_tile_scan_kernel<<<1, 1024, 0, e.stream>>>(A.tile_last, r_tiles, A.carry);
             rk_rank_y_moments_kernel<<<(unsigned)r_tiles, RK_THREADS, 0, e.stream>>>(T.ctl, rank_quant(A), k0, k1, r0, r1, S.n, A.carry, (uint32_t)rank_base, K, A.partial);
-            rk_final_kernel<<<1, 160, 0, e.stream>>>(A.partial, r_tiles, d_out);
+            rk_final_kernel<<<5, 1024, 0, e.stream>>>(A.partial, r_tiles, d_out);
             TG_CUDA(cudaGetLastError());
             *launches += 4;
             TG_CUDA(cudaMemcpyAsync(h_sums, d_out, 40, cudaMemcpyDeviceToHost, e.stream));
