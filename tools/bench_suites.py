@@ -277,6 +277,19 @@ def bench_c4(ctx, dev, scale, steps):
            kms, wms, st, {"metric": r.metric})
     ctx.deregister_table("keys")
     del keys, v
+    # the same check over SPARSE keys (64-bit ids spread over the whole range: no bitmap, the radix-partitioned hash path)
+    keys = torch.cat([(torch.randperm(n, generator=g, device=dev, dtype=torch.int64) * 1_000_003) ^ 0x5DEECE66D, pad])
+    keys[torch.randint(0, n, (ndup,), generator=g, device=dev)] = keys[torch.randint(0, n, (ndup,), generator=g, device=dev)]
+    v = validity(n, g, dev, 0.01)
+    ctx.register_device_table("keys", {"k": dict(dtype=F.TG_INT64, n_rows=n, values=keys.data_ptr(), validity=v.data_ptr())},
+                              keepalive=[keys, v])
+    plan, slots = suite.build_plan()
+    kms, wms, st = run_plan(plan, ctx, "keys", steps, "hash_ms")
+    r = plan.result(slots[0][2])
+    report("c4_is_unique_sparse", "validates_uniqueness on sparse i64 keys (ids spread over 64 bits, 1e-6 duplicates, 1% null)", n, 8 * n + (n + 7) // 8,
+           kms, wms, st, {"metric": r.metric})
+    ctx.deregister_table("keys")
+    del keys, v
     # foreign key: child n rows -> parent n/10 rows
     m = max(1000, n // 10)
     parent = torch.cat([torch.randperm(m, generator=g, device=dev, dtype=torch.int64), pad])
