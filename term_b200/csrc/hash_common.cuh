@@ -55,6 +55,23 @@ __device__ __forceinline__ void flush_counter(unsigned long long v, unsigned lon
     if ((threadIdx.x & 31) == 0 && v) atomicAdd(dst, v);
 }
 
+// the same with ONE global atomic per block (every thread of the block must call it): the bucket kernels are launched per
+// bucket with ~1000 blocks each, and a warp-granular flush made thousands of same-address atomics the tail of every launch
+__device__ __forceinline__ void flush_counter_block(unsigned long long v, unsigned long long* dst) {
+    __shared__ unsigned long long s_part[32];
+#pragma unroll
+    for (int m = 16; m > 0; m >>= 1) v += __shfl_xor_sync(0xffffffffu, v, m);
+    const int warp = threadIdx.x >> 5, n_warps = (blockDim.x + 31) >> 5;
+    __syncthreads();  // (s_part may still be read by the previous counter's flush)
+    if ((threadIdx.x & 31) == 0) s_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long t = 0;
+        for (int w = 0; w < n_warps; ++w) t += s_part[w];
+        if (t) atomicAdd(dst, t);
+    }
+}
+
 // ---- 128-bit fingerprints of Utf8 / composite keys ----
 struct Fp {
     uint64_t h1, h2;

@@ -348,9 +348,9 @@ __global__ void __launch_bounds__(HASH_THREADS) insert_bucket_kernel(const uint6
             }
         }
     }
-    flush_counter(d, &ctr->distinct_nonnull);
-    flush_counter(dup, &ctr->singles_minus);
-    flush_counter(ovf, &ctr->overflow);
+    flush_counter_block(d, &ctr->distinct_nonnull);
+    flush_counter_block(dup, &ctr->singles_minus);
+    flush_counter_block(ovf, &ctr->overflow);
 }
 
 // FK: build the parent bucket's key set, then probe the child bucket

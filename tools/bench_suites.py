@@ -570,6 +570,20 @@ def suite_c4(ctx, dev, world, rank, peak_gbs, steps):
                  n, 8 * n + (n + 7) // 8, world, peak_gbs, tm, {"metric": plan.result(slots[0][2]).metric})]
     ctx.deregister_table("keys")
     del keys, v
+    # the same check over SPARSE keys (ids spread over 64 bits: no bitmap; the radix-partitioned hash tables on one GPU, the hash
+    # shuffle instead of the range shuffle across GPUs) — the unfriendly case of the same configuration
+    keys = torch.cat([((torch.randperm(n, generator=g, device=dev, dtype=torch.int64) + rank * n) * 1_000_003) ^ 0x5DEECE66D, pad])
+    keys[torch.randint(0, n, (ndup,), generator=g, device=dev)] = keys[torch.randint(0, n, (ndup,), generator=g, device=dev)]
+    v = validity(n, g, dev, 0.01)
+    ctx.register_device_table("keys", {"k": dict(dtype=F.TG_INT64, n_rows=n, values=keys.data_ptr(), validity=v.data_ptr())}, keepalive=[keys, v])
+    plan, slots = (T.ValidationSuite.builder("c4s").table_name("keys")
+                   .check(T.Check.builder("u").validates_uniqueness(["k"], 0.9).build()).build().build_plan())
+    tm = _timed(plan, ctx, "keys", steps, world, dev, "hash_ms")
+    out.append(_line("c4_is_unique_sparse", "C4 with sparse keys: validates_uniqueness on 125 M i64 ids per GPU spread over 64 bits (1e-6 duplicates, 1% null): "
+                                            "radix-partitioned L2-resident hash tables; N > 1: hash shuffle over NVLink",
+                     n, 8 * n + (n + 7) // 8, world, peak_gbs, tm, {"metric": plan.result(slots[0][2]).metric}))
+    ctx.deregister_table("keys")
+    del keys, v
     m = n // 10
     parent = torch.cat([torch.randperm(m, generator=g, device=dev, dtype=torch.int64) + rank * m, pad])
     child = torch.cat([torch.randint(0, int(m * world * (1 + 1e-4)), (n,), generator=g, device=dev, dtype=torch.int64), pad])
