@@ -124,6 +124,7 @@ class Col:
     def __init__(self, values, valid, kind, narrow=None, unsigned=False):
         self.values, self.valid, self.kind = values, np.asarray(valid, dtype=bool), kind
         self.unsigned = unsigned  # SUM of an unsigned column is UInt64: the reference's downcasts fail on it as well
+        self.temporal_unit = None  # 'D' (Date32 days) / 's' / 'm' / 'u' / 'n': string literals compared with the column are cast to it
         # Arrow name of a 4-byte numeric source type ("Int32" / "Float32"): DataFusion's MIN / MAX keep that type and the
         # reference's Int64 / Float64 downcasts fail (constraints/statistics.rs:278-308, analyzers/basic/min_max.rs:112-131)
         self.narrow = narrow
@@ -140,7 +141,14 @@ def col_from_arrow(arr) -> Col:
     t = arr.type
     if pa.types.is_temporal(t):  # dates / times / timestamps / durations: their integer representation (comparisons only)
         ints = arr.cast(pa.int32() if t.bit_width == 32 else pa.int64())
-        return Col(np.asarray(ints.fill_null(0)).astype(np.int64), valid, "i64", str(t))
+        c = Col(np.asarray(ints.fill_null(0)).astype(np.int64), valid, "i64", str(t))
+        if pa.types.is_date32(t):
+            c.temporal_unit = "D"
+        elif pa.types.is_date64(t):
+            c.temporal_unit = "m"
+        elif pa.types.is_timestamp(t):
+            c.temporal_unit = {"s": "s", "ms": "m", "us": "u", "ns": "n"}[t.unit]
+        return c
     if pa.types.is_integer(t):
         vals = np.asarray(arr.fill_null(0)).astype(np.int64)
         names = {pa.int8(): "Int8", pa.int16(): "Int16", pa.int32(): "Int32", pa.uint8(): "UInt8", pa.uint16(): "UInt16", pa.uint32(): "UInt32",
@@ -724,6 +732,9 @@ class _P:
                 other = self.or_()
             self.eat("k", "END")
             return ("case", arms, other)
+        if k == "c" and v in ("date", "timestamp") and self.t[self.i + 1][0] == "s":  # DATE '..' / TIMESTAMP '..'
+            self.eat()
+            return ("lit", self.eat("s"))
         if k == "c" and v == "cast" and self.t[self.i + 1] == ("o", "("):
             self.eat()
             self.eat("o", "(")
@@ -790,20 +801,51 @@ def _unify(types):
     return "f" if ts == {"i", "f"} else next(iter(ts))
 
 
-def _annotate(e, kinds):
-    """CASE / COALESCE nodes get their coerced result type appended"""
+def temporal_literal(text: str, unit: str) -> int:
+    """DataFusion's cast of a string literal to the type of the date / timestamp column it is compared with: 'YYYY-MM-DD' for
+    Date32 (days since the epoch); 'YYYY-MM-DD[( |T)hh:mm[:ss[.f]]][Z|+hh:mm]' for timestamps (naive = UTC), in the column's unit"""
+    import datetime as _dt
+    if unit == "D":
+        d = _dt.date.fromisoformat(text)
+        return (d - _dt.date(1970, 1, 1)).days
+    m = re.fullmatch(r"(\d{4}-\d{2}-\d{2})(?:[ Tt](\d{2}):(\d{2})(?::(\d{2})(?:\.(\d+))?)?)?([Zz]|[+-]\d{2}:?\d{2})?", text)
+    if not m:
+        raise ValueError(f"Cannot cast string '{text}'")
+    d = _dt.date.fromisoformat(m.group(1))
+    if int(m.group(2) or 0) > 23 or int(m.group(3) or 0) > 59 or int(m.group(4) or 0) > 59:
+        raise ValueError(f"Cannot cast string '{text}'")
+    secs = (d - _dt.date(1970, 1, 1)).days * 86400 + int(m.group(2) or 0) * 3600 + int(m.group(3) or 0) * 60 + int(m.group(4) or 0)
+    frac_ns = int((m.group(5) or "0")[:9].ljust(9, "0"))
+    tz = m.group(6)
+    if tz and tz not in "Zz":
+        sign = -1 if tz[0] == "-" else 1
+        digits = tz[1:].replace(":", "")
+        secs -= sign * (int(digits[:2]) * 3600 + int(digits[2:4]) * 60)
+    return {"s": secs, "m": secs * 1000 + frac_ns // 1_000_000, "u": secs * 1_000_000 + frac_ns // 1000, "n": secs * 1_000_000_000 + frac_ns}[unit]
+
+
+def _annotate(e, kinds, temporal=None):
+    """CASE / COALESCE nodes get their coerced result type appended; string literals compared with a date / timestamp column
+    become that column's integer"""
+    temporal = temporal or {}
     if not isinstance(e, tuple):
         return e
+    if e[0] == "cmp":
+        a, b = e[2], e[3]
+        for col, lit, flip in ((a, b, False), (b, a, True)):
+            if col[0] == "col" and temporal.get(col[1]) and lit[0] == "lit" and isinstance(lit[1], str):
+                v = ("lit", temporal_literal(lit[1], temporal[col[1]]))
+                return ("cmp", e[1], v, col) if flip else ("cmp", e[1], col, v)
     if e[0] == "case":
-        arms = [(_annotate(c, kinds), _annotate(x, kinds)) for c, x in e[1]]
-        return ("case", arms, _annotate(e[2], kinds) if e[2] is not None else None, _static_type(e, kinds))
+        arms = [(_annotate(c, kinds, temporal), _annotate(x, kinds, temporal)) for c, x in e[1]]
+        return ("case", arms, _annotate(e[2], kinds, temporal) if e[2] is not None else None, _static_type(e, kinds))
     if e[0] == "fn" and e[1] == "COALESCE":
-        return ("fn", "COALESCE", [_annotate(a, kinds) for a in e[2]], _static_type(e, kinds))
+        return ("fn", "COALESCE", [_annotate(a, kinds, temporal) for a in e[2]], _static_type(e, kinds))
     if e[0] == "fn":
-        return ("fn", e[1], [_annotate(a, kinds) for a in e[2]])
+        return ("fn", e[1], [_annotate(a, kinds, temporal) for a in e[2]])
     if e[0] == "lit" or e[0] == "col":
         return e
-    return tuple(_annotate(x, kinds) if isinstance(x, tuple) else x for x in e)
+    return tuple(_annotate(x, kinds, temporal) if isinstance(x, tuple) else x for x in e)
 
 
 def _coerce(v, ty):
@@ -927,7 +969,8 @@ def predicate_counts(table, expression):
     """COUNT(CASE WHEN expr THEN 1 END), COUNT(*) — rows where expr is NULL are not counted
     (constraints/custom_sql.rs:203-209)"""
     cols = table_cols(table)
-    ast = _annotate(_P(_tokenize(expression)).or_(), {nm: c.kind for nm, c in cols.items()})
+    ast = _annotate(_P(_tokenize(expression)).or_(), {nm: c.kind for nm, c in cols.items()},
+                    {nm: c.temporal_unit for nm, c in cols.items() if c.temporal_unit})
     n = n_rows(cols)
     names = list(cols)
     sat = 0

@@ -700,8 +700,112 @@ __global__ void str_like_kernel(const int32_t* offsets, const uint8_t* bytes, in
     }
 }
 
+// ---- date / timestamp literals ----------------------------------------------------------------------
+// `date_col >= '2024-01-31'`, `ts_col < '2024-01-31 10:11:12.5'` (also with a T separator, Z / +hh:mm offsets and the typed forms
+// DATE '..' / TIMESTAMP '..'): DataFusion casts the string to the column's type; here the literal becomes the column's integer
+// (days for Date32, the timestamp unit otherwise; naive literals are UTC). Returns false when the text is not a date / timestamp.
+static int64_t days_from_civil(int64_t y, unsigned m, unsigned d) {  // proleptic Gregorian, days since 1970-01-01
+    y -= m <= 2;
+    const int64_t era = (y >= 0 ? y : y - 399) / 400;
+    const unsigned yoe = (unsigned)(y - era * 400);
+    const unsigned doy = (153 * (m + (m > 2 ? -3 : 9)) + 2) / 5 + d - 1;
+    const unsigned doe = yoe * 365 + yoe / 4 - yoe / 100 + doy;
+    return era * 146097 + (int64_t)doe - 719468;
+}
+static bool parse_temporal_literal(const std::string& text, char unit, int64_t* out) {
+    size_t i = 0;
+    auto digits = [&](int n, int64_t* v) {
+        if (i + (size_t)n > text.size()) return false;
+        int64_t x = 0;
+        for (int k = 0; k < n; ++k) {
+            if (!isdigit((unsigned char)text[i + k])) return false;
+            x = x * 10 + (text[i + k] - '0');
+        }
+        i += (size_t)n;
+        *v = x;
+        return true;
+    };
+    int64_t Y, M, D, h = 0, mi = 0, sec = 0, frac_ns = 0, off_s = 0;
+    if (!digits(4, &Y) || i >= text.size() || text[i++] != '-' || !digits(2, &M) || i >= text.size() || text[i++] != '-' || !digits(2, &D)) return false;
+    static const int mdays[12] = {31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+    if (M < 1 || M > 12 || D < 1 || D > mdays[M - 1]) return false;
+    if (M == 2 && D == 29 && !((Y % 4 == 0 && Y % 100 != 0) || Y % 400 == 0)) return false;
+    bool has_time = false;
+    if (i < text.size()) {
+        if (text[i] != ' ' && text[i] != 'T' && text[i] != 't') return false;
+        ++i;
+        has_time = true;
+        if (!digits(2, &h) || i >= text.size() || text[i++] != ':' || !digits(2, &mi)) return false;
+        if (i < text.size() && text[i] == ':') {
+            ++i;
+            if (!digits(2, &sec)) return false;
+            if (i < text.size() && text[i] == '.') {
+                ++i;
+                int n = 0;
+                int64_t f = 0;
+                while (i < text.size() && isdigit((unsigned char)text[i])) {
+                    if (n < 9) {
+                        f = f * 10 + (text[i] - '0');
+                        ++n;
+                    }
+                    ++i;
+                }
+                if (n == 0) return false;
+                while (n++ < 9) f *= 10;
+                frac_ns = f;
+            }
+        }
+        if (h > 23 || mi > 59 || sec > 59) return false;
+        if (i < text.size() && (text[i] == 'Z' || text[i] == 'z')) ++i;
+        else if (i < text.size() && (text[i] == '+' || text[i] == '-')) {
+            const int sign = text[i++] == '-' ? -1 : 1;
+            int64_t oh, om = 0;
+            if (!digits(2, &oh)) return false;
+            if (i < text.size() && text[i] == ':') ++i;
+            if (i < text.size() && !digits(2, &om)) return false;
+            off_s = sign * (oh * 3600 + om * 60);
+        }
+        if (i != text.size()) return false;
+    }
+    const int64_t days = days_from_civil(Y, (unsigned)M, (unsigned)D);
+    if (unit == 'D') {
+        if (has_time) return false;  // (a Date32 cast takes a plain date)
+        *out = days;
+        return true;
+    }
+    const int64_t secs = days * 86400 + h * 3600 + mi * 60 + sec - off_s;
+    switch (unit) {
+        case 's': *out = secs; return true;
+        case 'm': *out = secs * 1000 + frac_ns / 1000000; return true;
+        case 'u': *out = secs * 1000000 + frac_ns / 1000; return true;
+        case 'n': *out = secs * 1000000000 + frac_ns; return true;
+    }
+    return false;
+}
+
 static ExprP rewrite_string_compares(const ExprP& ex, Engine& e, Table& t, Plan& p, VirtualCols& vc) {
     if (!ex) return ex;
+    // typed literals DATE '..' / TIMESTAMP '..' parse as a function-less pair: the parser hands them over as FUNC nodes
+    if (ex->kind == Expr::BINARY && (ex->s == "=" || ex->s == "<>" || ex->s == "<" || ex->s == "<=" || ex->s == ">" || ex->s == ">=")) {
+        for (int side = 0; side < 2; ++side) {
+            const ExprP& c = ex->args[side];
+            ExprP l = ex->args[1 - side];
+            if (l->kind == Expr::FUNC && (l->s == "DATE_LITERAL" || l->s == "TIMESTAMP_LITERAL") && l->args.size() == 1) l = l->args[0];
+            if (c->kind != Expr::COL || l->kind != Expr::LIT_S) continue;
+            Column* col = t.find(c->s);
+            if (!col || !col->temporal) continue;
+            int64_t v = 0;
+            if (!col->temporal_unit || !parse_temporal_literal(l->s, col->temporal_unit, &v))
+                throw Error(TG_ERR_INVALID_ARG, "Arrow error: Cast error: Cannot cast string '" + l->s + "' to value of " +
+                                                    std::string(col->src_type ? col->src_type : "temporal") + " type");
+            auto lit = std::make_shared<Expr>();
+            lit->kind = Expr::LIT_I;
+            lit->i = v;
+            auto copy = std::make_shared<Expr>(*ex);
+            copy->args[1 - side] = lit;
+            return copy;
+        }
+    }
     auto utf8_col = [&](const ExprP& x) -> Column* {
         if (!x || x->kind != Expr::COL) return nullptr;
         Column* c = t.find(x->s);

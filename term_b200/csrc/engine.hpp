@@ -57,6 +57,7 @@ struct Column {
     const char* src_type = nullptr;  // static string ("UInt16", "Date32", "Timestamp(Microsecond, None)", ..)
     bool src_unsigned = false;
     bool temporal = false;           // comparisons / completeness / uniqueness / grouping only: no numeric aggregates
+    char temporal_unit = 0;          // 'D' days (Date32), 's' / 'm' / 'u' / 'n' (Date64 is 'm', Timestamp by unit); 0: times, durations
     int elem_bytes() const {
         switch (dtype) {
             case TG_INT64: case TG_FLOAT64: return 8;

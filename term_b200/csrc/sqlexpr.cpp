@@ -404,6 +404,15 @@ struct Parser {
                 return mk(Expr::LIT_NULL);
             }
             adv();
+            if ((up == "DATE" || up == "TIMESTAMP") && cur.k == Tok::STR) {  // typed literal: resolved against the column it meets
+                auto e = mk(Expr::FUNC);
+                e->s = up + "_LITERAL";
+                auto lit = mk(Expr::LIT_S);
+                lit->s = cur.s;
+                e->args.push_back(lit);
+                adv();
+                return e;
+            }
             if (up == "CASE") return parse_case();
             if (up == "CAST" && cur.k == Tok::LP) return parse_cast();
             if (cur.k == Tok::LP) {

@@ -5,7 +5,8 @@
 // column, [NOT] LIKE 'pattern', LENGTH / CHAR_LENGTH / CHARACTER_LENGTH / OCTET_LENGTH (materialised as virtual columns
 // by the engine before the scan, engine.cu rewrite_string_compares); CASE (searched and simple form; boolean arms desugar to
 // three-valued AND / OR, numeric arms use PO_KEEPIF_N + PO_COALESCE_N), COALESCE over numeric operands, CAST to the
-// floating-point types (and to integer types of integer operands). Anything else -> TG_ERR_UNSUPPORTED.
+// floating-point types (and to integer types of integer operands); string / DATE '..' / TIMESTAMP '..' literals compared with a
+// date or timestamp column are cast to the column's type by the engine (engine.cu). Anything else -> TG_ERR_UNSUPPORTED.
 #pragma once
 #include <functional>
 #include <memory>

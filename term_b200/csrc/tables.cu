@@ -263,6 +263,7 @@ struct ArrowFormat {
     int src_w = 0;
     bool src_unsigned = false, temporal = false, large_offsets = false;
     const char* src_type = nullptr;
+    char temporal_unit = 0;
 };
 static ArrowFormat arrow_format(const std::string& fmt, const char* column) {
     ArrowFormat f;
@@ -280,11 +281,12 @@ static ArrowFormat arrow_format(const std::string& fmt, const char* column) {
     else if (fmt == "S") f.dtype = TG_INT32, f.src_w = 2, f.src_unsigned = true, f.src_type = "UInt16";
     else if (fmt == "I") f.dtype = TG_INT64, f.src_w = 4, f.src_unsigned = true, f.src_type = "UInt32";
     else if (fmt == "L") f.dtype = TG_INT64, f.src_w = 8, f.src_unsigned = true, f.src_type = "UInt64";
-    else if (fmt == "tdD") f.dtype = TG_INT32, f.temporal = true, f.src_type = "Date32";
-    else if (fmt == "tdm") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Date64";
+    else if (fmt == "tdD") f.dtype = TG_INT32, f.temporal = true, f.src_type = "Date32", f.temporal_unit = 'D';
+    else if (fmt == "tdm") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Date64", f.temporal_unit = 'm';
     else if (fmt == "tts" || fmt == "ttm") f.dtype = TG_INT32, f.temporal = true, f.src_type = "Time32";
     else if (fmt == "ttu" || fmt == "ttn") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Time64";
-    else if (starts("tss:") || starts("tsm:") || starts("tsu:") || starts("tsn:")) f.dtype = TG_INT64, f.temporal = true, f.src_type = "Timestamp";
+    else if (starts("tss:") || starts("tsm:") || starts("tsu:") || starts("tsn:"))
+        f.dtype = TG_INT64, f.temporal = true, f.src_type = "Timestamp", f.temporal_unit = fmt[2];
     else if (fmt == "tDs" || fmt == "tDm" || fmt == "tDu" || fmt == "tDn") f.dtype = TG_INT64, f.temporal = true, f.src_type = "Duration";
     else throw Error(TG_ERR_UNSUPPORTED, std::string("Arrow format '") + fmt + "' of column '" + column + "' is not supported");
     return f;
@@ -305,6 +307,7 @@ void table_set_column_arrow_type(Table& t, const std::string& name, const std::s
     c->src_type = f.src_type;
     c->src_unsigned = f.src_unsigned;
     c->temporal = f.temporal;
+    c->temporal_unit = f.temporal_unit;
 }
 
 void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
@@ -384,6 +387,7 @@ void table_append_arrow(Table& t, const void* schema_p, const void* array_p) {
             c->src_type = src_type;
             c->src_unsigned = src_unsigned;
             c->temporal = temporal;
+            c->temporal_unit = F.temporal_unit;
         }
     }
 }

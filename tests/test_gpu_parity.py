@@ -1309,3 +1309,35 @@ def test_case_coalesce_cast_predicates_match_oracle(ctx, n):
             assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
     finally:
         ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unit", ["s", "ms", "us", "ns"])
+def test_date_and_timestamp_literals_in_predicates(ctx, unit):
+    """`date_col >= '2024-01-31'`, `ts_col < '2024-01-31 10:11:12.5'`, typed DATE / TIMESTAMP literals, BETWEEN / IN lists, zone
+    offsets: the literal is cast to the column's type (days / the timestamp unit) like DataFusion's coercion does"""
+    import datetime as dt
+    rng = np.random.default_rng(31)
+    n = 20_000
+    base = int(dt.datetime(2024, 1, 31, 10, 11, 12, tzinfo=dt.timezone.utc).timestamp())
+    per_s = {"s": 1, "ms": 10**3, "us": 10**6, "ns": 10**9}[unit]
+    ts = (base + rng.integers(-5, 6, n)) * per_s + rng.integers(0, per_s, n) * (rng.random(n) < 0.5)
+    t = pa.table({"d": pa.array(rng.integers(19750, 19760, n).astype(np.int32), type=pa.date32(), mask=rng.random(n) < 0.1),
+                  "ts": pa.array(ts, type=pa.timestamp(unit), mask=rng.random(n) < 0.1), "x": pa.array(rng.integers(0, 5, n))})
+    name = f"temporal_{unit}"
+    ctx.register_table(name, t.to_batches(max_chunksize=3000))
+    preds = ["d >= '2024-01-31'", "d < DATE '2024-02-02' AND x > 1", "d BETWEEN '2024-01-28' AND '2024-02-01'", "d IN ('2024-01-31', '2024-02-03')",
+             "'2024-02-01' > d OR d IS NULL", "ts < '2024-01-31 10:11:12.5'", "ts >= TIMESTAMP '2024-01-31T10:11:12'", "ts = '2024-01-31 10:11:12'",
+             "ts > '2024-01-31T12:11:10+02:00'", "ts <= '2024-01-31T10:11:14Z' AND d <> '2024-01-31'", "ts BETWEEN '2024-01-31' AND '2024-01-31 10:11:12.25'"]
+    try:
+        cb = T.Check.builder("temporal")
+        for p in preds:
+            cb.satisfies(p)
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        for p, g in zip(preds, rs):
+            o = O.custom_sql(t, p)
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
+        bad = T.ValidationSuite.builder("b").table_name(name).check(T.Check.builder("b").satisfies("d > 'yesterday'").build()).build().run(ctx).report.results[0]
+        assert bad.status.name == "Failure" and "Cannot cast string 'yesterday' to value of Date32 type" in bad.message
+    finally:
+        ctx.deregister_table(name)

@@ -211,3 +211,28 @@ def test_oracle_string_predicates_agree_with_arrow_compute(seed):
         assert O.predicate_counts(t, f"s {op} u")[0] == count_true(fn(s.cast(pa.binary()), u.cast(pa.binary()))), op
         assert O.predicate_counts(t, f"s {op} 'b'")[0] == count_true(fn(s.cast(pa.binary()), pa.scalar(b"b"))), op
         assert O.predicate_counts(t, f"'b' {op} s")[0] == count_true(fn(pa.scalar(b"b"), s.cast(pa.binary()))), op
+
+
+def test_oracle_temporal_literals_agree_with_arrow_casts():
+    """string literals compared with date / timestamp columns: the oracle's cast against Arrow's own string -> Date32 / Timestamp casts"""
+    import pyarrow as pa
+    import pyarrow.compute as pc
+    from oracle import term_oracle as O
+    dates = ["1970-01-01", "2024-01-31", "2024-02-29", "1969-12-31", "1999-12-31", "2100-03-01", "0001-01-01"]
+    want = pc.cast(pa.array(dates), pa.date32()).cast(pa.int32()).to_pylist()
+    assert [O.temporal_literal(d, "D") for d in dates] == want
+    stamps = ["2024-01-31", "2024-01-31 10:11:12", "2024-01-31T10:11:12", "2024-01-31 10:11:12.5", "2024-01-31T10:11:12.123456789",
+              "1969-12-31 23:59:59.25", "2024-01-31T10:11:12Z", "2024-01-31T12:11:12+02:00", "2024-01-31 05:41:12.5-04:30", "2024-01-31 10:11"]
+    for unit, u in (("s", "s"), ("ms", "m"), ("us", "u"), ("ns", "n")):
+        for text in stamps:
+            # (Arrow refuses to drop sub-unit digits on a safe cast: the literal path truncates like DataFusion's cast to the column type)
+            got = O.temporal_literal(text, u)
+            has_zone = text.endswith("Z") or "+" in text or "-" in text[11:]
+            ref = pc.cast(pa.array([text]), pa.timestamp("ns", tz="UTC") if has_zone else pa.timestamp("ns"))
+            ref_ns = ref.cast(pa.int64()).to_pylist()[0]
+            div = {"s": 10**9, "m": 10**6, "u": 10**3, "n": 1}[u]
+            assert got == ref_ns // div, (text, unit, got, ref_ns)
+    for bad in ("2024-13-01", "2024-02-30", "31/01/2024", "2024-01-31 25:00:00", "abc", ""):
+        for u in ("D", "u"):
+            with pytest.raises(ValueError):
+                O.temporal_literal(bad, u)
