@@ -451,12 +451,14 @@ void exec_distinct_job(Engine& e, Table& t, Plan& p, int agg_id) {
     if (n == 0) return;
     const bool exact64 = cols.size() == 1 && (cols[0]->dtype == TG_INT64 || cols[0]->dtype == TG_FLOAT64);
     if (exact64 && n > (1 << 20)) {
-        // large key column (hashpart.cu): dense Int64 ranges are counted in bitmaps; anything else is radix-
-        // partitioned and deduplicated bucket by bucket in an L2-resident table
+        // large key column: dense Int64 ranges are counted in bitmaps (hashpart.cu); anything else is hashed, radix-sorted by
+        // its low hash bits and de-duplicated in shared memory (hashsort.cu) — or, for hot keys, radix-partitioned and
+        // de-duplicated bucket by bucket in an L2-resident table (hashpart.cu)
         Distinct64Result r;
         Timer tm(e, p);
         int launches = 0;
         bool ok = distinct64_dense(e, *cols[0], n, (a.flags & 1) != 0, r, launches);
+        if (!ok && (size_t)n > distinct64_min_rows()) ok = distinct64_sorted(e, *cols[0], n, r, launches);
         if (!ok && (size_t)n > distinct64_min_rows()) ok = distinct64_partitioned(e, *cols[0], n, r, launches);
         tm.stop(launches);
         if (ok) {

@@ -1026,6 +1026,9 @@ bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, 
         TG_CUDA(cudaStreamSynchronize(e.stream));
         if (g.n_valid > 0) {
             const unsigned long long w = (unsigned long long)g.mx - (unsigned long long)g.mn;
+            // the column's range is at least the sample's and it holds at most n valid keys: a sample that is not dense
+            // settles it without the min/max pass over the whole column
+            if (w >= DENSE_MAX_RANGE || w > 32ull * (unsigned long long)n + 4096ull) return false;
             const unsigned long long pad = w / 16 + 4096;
             // keep lo / hi inside i64 (the wrap-around arithmetic of the kernel handles the rest)
             const long long lo = g.mn < INT64_MIN + (long long)pad ? INT64_MIN : g.mn - (long long)pad;

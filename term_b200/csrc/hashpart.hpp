@@ -16,6 +16,10 @@ struct Distinct64Result {
 // table overflowed (pathologically skewed hash): the caller falls back to the single-table path.
 bool distinct64_partitioned(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches);
 size_t distinct64_min_rows();
+// The same counts for sparse keys without a global atomic (hashsort.cu): hashes of the valid keys, two or three radix passes
+// over their low bits, shared-memory de-duplication of the contiguous hash buckets. Returns false (nothing counted) on a
+// hot key / skewed bucket or for n >= 2^30: the caller takes the partitioned path.
+bool distinct64_sorted(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches);
 // Dense Int64 key range (max - min < 2^28 and < 32 n): exact bitmap counting, no partitioning. Returns false when
 // the column does not qualify (nothing is counted then).
 bool distinct64_dense(Engine& e, const Column& c, int64_t n, bool need_singles, Distinct64Result& r, int& launches);

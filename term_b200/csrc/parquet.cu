@@ -628,12 +628,16 @@ int64_t count_levels_set(const uint8_t* p, const uint8_t* end, int64_t n) {
 // Decodes one DELTA_BINARY_PACKED stream: <block size> <miniblocks per block> <total count> <first value (zigzag)>, then per
 // block <min delta (zigzag)> <bit widths> <miniblocks>; values wrap in 64 bits (INT32 columns keep the low 32). Returns the
 // end of the stream.
-const uint8_t* delta_binary_unpack(const uint8_t* p, const uint8_t* end, std::vector<int64_t>& out) {
+// `expect` >= 0: the count the page's levels announce — a stream that disagrees is refused before anything is allocated.
+const uint8_t* delta_binary_unpack(const uint8_t* p, const uint8_t* end, std::vector<int64_t>& out, int64_t expect = -1) {
     Thrift t{p, end};
     const uint64_t block = t.varint(), minis = t.varint(), total = t.varint();
     uint64_t last = (uint64_t)t.zigzag();
-    if (block == 0 || block % 128 != 0 || minis == 0 || block % minis != 0 || (block / minis) % 32 != 0 || minis > 512)
+    // (block sizes are 128 .. a few thousand in every writer; the bound keeps per_mini * bit width far from 64-bit overflow)
+    if (block == 0 || block % 128 != 0 || block > ((uint64_t)1 << 24) || minis == 0 || block % minis != 0 || (block / minis) % 32 != 0 || minis > 512)
         throw Error(TG_ERR_INVALID_ARG, "Parquet: malformed DELTA_BINARY_PACKED header");
+    if (expect >= 0 && total != (uint64_t)expect)
+        throw Error(TG_ERR_INVALID_ARG, "Parquet: page holds " + std::to_string(total) + " encoded values, its levels say " + std::to_string(expect));
     if (total > (uint64_t)(end - p) * 64 + 1) throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_BINARY_PACKED count does not fit the page");
     const uint64_t per_mini = block / minis;
     out.clear();
@@ -683,7 +687,7 @@ void decode_to_plain(int32_t encoding, size_t elem_w, const uint8_t* p, int64_t 
         case PQ_ENC_DELTA_BINARY_PACKED: {
             if (elem_w != 4 && elem_w != 8) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_BINARY_PACKED on a non-integer column");
             if (n_present == 0) return;
-            delta_binary_unpack(p, end, a);
+            delta_binary_unpack(p, end, a, n_present);
             need_count(a.size());
             const size_t at = out.size();
             out.resize(at + a.size() * elem_w);
@@ -700,7 +704,7 @@ void decode_to_plain(int32_t encoding, size_t elem_w, const uint8_t* p, int64_t 
         case PQ_ENC_DELTA_LENGTH_BYTE_ARRAY: {
             if (elem_w != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_LENGTH_BYTE_ARRAY on a fixed-width column");
             if (n_present == 0) return;
-            const uint8_t* q = delta_binary_unpack(p, end, a);
+            const uint8_t* q = delta_binary_unpack(p, end, a, n_present);
             need_count(a.size());
             for (int64_t len : a) {
                 if (len < 0 || len > end - q) throw Error(TG_ERR_INVALID_ARG, "Parquet: DELTA_LENGTH_BYTE_ARRAY value runs past the page");
@@ -713,8 +717,8 @@ void decode_to_plain(int32_t encoding, size_t elem_w, const uint8_t* p, int64_t 
         case PQ_ENC_DELTA_BYTE_ARRAY: {
             if (elem_w != 0) throw Error(TG_ERR_UNSUPPORTED, "Parquet: DELTA_BYTE_ARRAY on a fixed-width column");
             if (n_present == 0) return;
-            const uint8_t* q = delta_binary_unpack(p, end, a);  // prefix lengths
-            q = delta_binary_unpack(q, end, b);                 // suffix lengths, then the suffix bytes
+            const uint8_t* q = delta_binary_unpack(p, end, a, n_present);  // prefix lengths
+            q = delta_binary_unpack(q, end, b, n_present);                 // suffix lengths, then the suffix bytes
             need_count(a.size());
             need_count(b.size());
             size_t prev_at = 0, prev_len = 0;  // the previous value inside `out` (after its length prefix)

@@ -349,7 +349,7 @@ void rs_quant_setup(cudaStream_t stream, const unsigned long long* minmax, int i
 
 template <typename V>
 int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2], int64_t n, int begin_bit, int n_passes,
-                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant) {
+                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant, bool hist_ready) {
     if (quant) {
         begin_bit = 0;
         n_passes = 4;
@@ -357,11 +357,12 @@ int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2]
     if (n_passes > RS_MAX_PASSES) n_passes = RS_MAX_PASSES;
     const int64_t tiles = rs_tiles(n);
     cudaMemsetAsync(T.ctl, 0, sizeof(RsControl), stream);
-    cudaMemsetAsync(T.hist, 0, (size_t)RS_MAX_PASSES * RS_BINS * 8, stream);
+    if (!hist_ready) cudaMemsetAsync(T.hist, 0, (size_t)RS_MAX_PASSES * RS_BINS * 8, stream);
     if (n <= 0 || n_passes <= 0) return 0;
     cudaMemsetAsync(T.status, 0, T.status_words_per_pass * 4 * (size_t)n_passes, stream);
     const int hgrid = (int)std::max<int64_t>(1, std::min<int64_t>((n + ((int64_t)1 << 16) - 1) >> 16, (int64_t)sm_count * 4));
-    if (quant) rs_hist_kernel<true><<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist, quant);
+    if (hist_ready) {
+    } else if (quant) rs_hist_kernel<true><<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist, quant);
     else rs_hist_kernel<false><<<hgrid, RSH_THREADS, 0, stream>>>(keys[0], n, begin_bit, n_passes, T.hist, nullptr);
     rs_scan_kernel<<<1, RS_BINS, 0, stream>>>(T.hist, T.base, n, n_passes, T.ctl, quant ? 1u : 0u);
     const bool has_v = vals[0] != nullptr || vals[1] != nullptr;
@@ -370,7 +371,7 @@ int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2]
     const size_t smem = sizeof(RsSmem);
     if (quant) kern = !has_v ? (K)rs_pass_kernel<V, false, false, true> : iota_values ? (K)rs_pass_kernel<V, true, true, true> : (K)rs_pass_kernel<V, true, false, true>;
     else kern = !has_v ? (K)rs_pass_kernel<V, false, false, false> : iota_values ? (K)rs_pass_kernel<V, true, true, false> : (K)rs_pass_kernel<V, true, false, false>;
-    int launches = 2;
+    int launches = hist_ready ? 1 : 2;
     if (has_v && iota_values) {  // every pass trivial (all keys equal): nobody synthesises the positions
         rs_iota_if_unsorted_kernel<V><<<(unsigned)std::max<int64_t>(1, std::min<int64_t>((n + 255) / 256, (int64_t)sm_count * 8)), 256, 0, stream>>>(vals[0], n, T.ctl);
         ++launches;
@@ -384,7 +385,7 @@ int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2]
     return launches;
 }
 
-template int rs_sort_pairs<uint32_t>(cudaStream_t, uint64_t* const[2], uint32_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*);
-template int rs_sort_pairs<uint64_t>(cudaStream_t, uint64_t* const[2], uint64_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*);
+template int rs_sort_pairs<uint32_t>(cudaStream_t, uint64_t* const[2], uint32_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*, bool);
+template int rs_sort_pairs<uint64_t>(cudaStream_t, uint64_t* const[2], uint64_t* const[2], int64_t, int, int, bool, const RsTemp&, int, const RsQuant*, bool);
 
 }  // namespace tg

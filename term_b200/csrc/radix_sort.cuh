@@ -82,8 +82,10 @@ RsTemp rs_temp_carve(uint8_t* temp, int64_t n, int n_passes);
 // positions 0..n-1 and vals[0] is never read (it is filled with them when every pass turns out trivial). n < 2^30. Returns the number of kernels launched; the buffer index of the
 // result is T.ctl->result (device memory).
 // quant != nullptr: a quantised sort (4 passes over the 32 bits of rs_quant(*quant, key); begin_bit / n_passes ignored).
+// hist_ready: the producer of keys[0] has already counted the digits into T.hist ([pass][256], zeroed by the caller before):
+// no histogram pass over the keys.
 template <typename V>
 int rs_sort_pairs(cudaStream_t stream, uint64_t* const keys[2], V* const vals[2], int64_t n, int begin_bit, int n_passes,
-                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant = nullptr);
+                  bool iota_values, const RsTemp& T, int sm_count, const RsQuant* quant = nullptr, bool hist_ready = false);
 
 }  // namespace tg

@@ -608,6 +608,48 @@ def test_uniqueness_large_path_edge_cases(ctx, shape):
         ctx.deregister_table(name)
 
 
+@pytest.mark.parametrize("path", ["sorted", "partitioned"])
+@pytest.mark.parametrize("shape", ["triples", "warm_key", "hot_key", "f64_mixed"])
+def test_uniqueness_sparse_paths(ctx, shape, path, monkeypatch):
+    """sparse keys through BOTH large-column paths: the sorted-bucket path (hashsort.cu: hash, two radix passes over the low
+    hash bits, shared-memory de-duplication) and the partitioned path it falls back to (hashpart.cu; forced here with
+    TG_HASH_NO_SORTED). warm_key: 60 K copies of one key stay below the skew limit (one CTA streams the bucket's tail);
+    hot_key: 400 K copies exceed it and the sorted path hands over to the partitioned one. Counts bit-exact vs np.unique."""
+    if path == "partitioned":
+        monkeypatch.setenv("TG_HASH_NO_SORTED", "1")
+    else:
+        monkeypatch.delenv("TG_HASH_NO_SORTED", raising=False)
+    n = 2_500_000
+    rng = np.random.default_rng(31)
+    if shape == "f64_mixed":
+        vals = np.round(rng.normal(0.0, 1e6, n), 1)
+        vals[rng.random(n) < 0.001] = -0.0
+        vals[rng.random(n) < 0.001] = 0.0
+        vals[rng.random(n) < 0.0005] = np.nan
+    else:
+        vals = rng.integers(0, n // 3, n).astype(np.int64) * 1_000_003 - 2**40
+        vals[rng.random(n) < 0.0005] = -1  # fmix64 and the table sentinels must not care
+        if shape == "warm_key":
+            vals[rng.choice(n, 60_000, replace=False)] = 123_456_789_012
+        elif shape == "hot_key":
+            vals[rng.choice(n, 400_000, replace=False)] = 123_456_789_012
+    mask = rng.random(n) < 0.01
+    name = f"uniq_sparse_{shape}_{path}"
+    ctx.register_table(name, pa.table({"k": pa.array(vals, mask=mask)}))
+    try:
+        kept = vals[~mask]
+        if shape == "f64_mixed":
+            kept = kept + 0.0  # -0.0 groups with +0.0; np.unique (equal_nan) groups the NaNs like the canonical key does
+        _, counts = np.unique(kept, return_counts=True)
+        distinct, singles, nulls = len(counts), int((counts == 1).sum()), int(mask.sum())
+        a = T.DistinctnessAnalyzer("k").compute(ctx, name)
+        assert a.u[:2] == [n - nulls, distinct]
+        g = H.build_constraint(T, dict(kind="uniqueness", columns=["k"], uniqueness="UniqueValueRatio", assertion=["GreaterThanOrEqual", 0.0])).evaluate(ctx, name)
+        assert g.metric == (singles + (1 if nulls == 1 else 0)) / n
+    finally:
+        ctx.deregister_table(name)
+
+
 @pytest.mark.parametrize("shape", ["empty_parent", "all_null_children", "parent_with_nulls_sparse"])
 def test_foreign_key_large_path_edge_cases(ctx, shape):
     n_child = 1_200_000
