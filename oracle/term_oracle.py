@@ -735,6 +735,15 @@ class _P:
         if k == "c" and v in ("date", "timestamp") and self.t[self.i + 1][0] == "s":  # DATE '..' / TIMESTAMP '..'
             self.eat()
             return ("lit", self.eat("s"))
+        if k == "c" and v == "interval" and self.t[self.i + 1][0] == "s":  # INTERVAL '1 day' / INTERVAL '1' DAY
+            self.eat()
+            text = self.eat("s")
+            if self.peek()[0] == "c" and self.peek()[1].rstrip("s") in _INTERVAL_UNITS:
+                text += " " + self.eat("c")
+            return ("interval", text)
+        if k == "c" and v in ("current_timestamp", "current_date") and self.t[self.i + 1] != ("o", "("):
+            self.eat()
+            return ("fn", v.upper(), [])
         if k == "c" and v == "cast" and self.t[self.i + 1] == ("o", "("):
             self.eat()
             self.eat("o", "(")
@@ -824,6 +833,74 @@ def temporal_literal(text: str, unit: str) -> int:
     return {"s": secs, "m": secs * 1000 + frac_ns // 1_000_000, "u": secs * 1_000_000 + frac_ns // 1000, "n": secs * 1_000_000_000 + frac_ns}[unit]
 
 
+_INTERVAL_UNITS = {"year": None, "month": None, "week": 7 * 86400 * 10**9, "day": 86400 * 10**9, "hour": 3600 * 10**9, "minute": 60 * 10**9,
+                   "second": 10**9, "millisecond": 10**6, "microsecond": 10**3, "nanosecond": 1}
+
+
+def query_now_ns() -> int:
+    """now() is the query's start time (DataFusion folds it at planning time); TG_FIXED_NOW_NS pins it for the parity tests"""
+    import os as _os
+    import time as _time
+    return int(_os.environ["TG_FIXED_NOW_NS"]) if "TG_FIXED_NOW_NS" in _os.environ else _time.time_ns()
+
+
+def interval_literal(text: str):
+    """'N unit [N unit ..]' -> (months, nanoseconds of the day-time part as an exact Fraction-free integer)"""
+    from fractions import Fraction
+    months, nanos = 0, Fraction(0)
+    parts = re.findall(r"\s*([+-]?\d+(?:\.\d+)?)\s*([A-Za-z]*)", text)
+    if not parts or "".join(a + b for a, b in parts).replace(" ", "") != text.replace(" ", ""):
+        raise ValueError(f"bad interval {text!r}")
+    for num, unit in parts:
+        u = (unit.lower() or "second")
+        u = u[:-1] if len(u) > 1 and u.endswith("s") else u
+        if u in ("year", "month"):
+            months += int(num) * (12 if u == "year" else 1)
+        else:
+            nanos += Fraction(num) * _INTERVAL_UNITS[u]
+    return months, int(round(nanos))
+
+
+def _add_interval(ns: int, months: int, nanos: int, sign: int) -> int:
+    """timestamp (ns since the epoch) +/- interval: calendar months first (day clamped to the month's length), then the rest"""
+    import calendar
+    import datetime as _dt
+    if months:
+        day_ns = 86400 * 10**9
+        days, tod = divmod(ns, day_ns)
+        d = _dt.date(1970, 1, 1) + _dt.timedelta(days=days)
+        mm = d.year * 12 + (d.month - 1) + sign * months
+        y, m = divmod(mm, 12)
+        d = _dt.date(y, m + 1, min(d.day, calendar.monthrange(y, m + 1)[1]))
+        ns = (d - _dt.date(1970, 1, 1)).days * day_ns + tod
+    return ns + sign * nanos
+
+
+def _has_temporal_fn(e) -> bool:
+    if e[0] == "interval" or (e[0] == "fn" and e[1] in ("NOW", "CURRENT_TIMESTAMP", "CURRENT_DATE", "TODAY")):
+        return True
+    return e[0] == "ar" and e[1] in "+-" and (_has_temporal_fn(e[2]) or _has_temporal_fn(e[3]))
+
+
+def temporal_const_ns(e, now_ns: int) -> int:
+    """a constant instant: string / DATE / TIMESTAMP literal, now() / current_timestamp / current_date / today(), +/- intervals"""
+    if e[0] == "lit" and isinstance(e[1], str):
+        return temporal_literal(e[1], "n")
+    if e[0] == "fn" and e[1] in ("NOW", "CURRENT_TIMESTAMP") and not e[2]:
+        return now_ns
+    if e[0] == "fn" and e[1] in ("CURRENT_DATE", "TODAY") and not e[2]:
+        return now_ns - now_ns % (86400 * 10**9)
+    if e[0] == "ar" and e[1] in "+-":
+        if e[3][0] == "interval":
+            return _add_interval(temporal_const_ns(e[2], now_ns), *interval_literal(e[3][1]), 1 if e[1] == "+" else -1)
+        if e[1] == "+" and e[2][0] == "interval":
+            return _add_interval(temporal_const_ns(e[3], now_ns), *interval_literal(e[2][1]), 1)
+    raise ValueError("unsupported date / timestamp arithmetic")
+
+
+_UNIT_NS = {"D": 86400 * 10**9, "s": 10**9, "m": 10**6, "u": 10**3, "n": 1}
+
+
 def _annotate(e, kinds, temporal=None):
     """CASE / COALESCE nodes get their coerced result type appended; string literals compared with a date / timestamp column
     become that column's integer"""
@@ -833,6 +910,11 @@ def _annotate(e, kinds, temporal=None):
     if e[0] == "cmp":
         a, b = e[2], e[3]
         for col, lit, flip in ((a, b, False), (b, a, True)):
+            if col[0] == "col" and temporal.get(col[1]) and _has_temporal_fn(lit):
+                # both sides as exact nanoseconds (DataFusion coerces the coarser side up): no rounding to the column's unit
+                x = ("lit", temporal_const_ns(lit, query_now_ns()))
+                scaled = ("tscale", col, _UNIT_NS[temporal[col[1]]])
+                return ("cmp", e[1], x, scaled) if flip else ("cmp", e[1], scaled, x)
             if col[0] == "col" and temporal.get(col[1]) and lit[0] == "lit" and isinstance(lit[1], str):
                 v = ("lit", temporal_literal(lit[1], temporal[col[1]]))
                 return ("cmp", e[1], v, col) if flip else ("cmp", e[1], col, v)
@@ -934,6 +1016,9 @@ def _ev(e, row):
             if b == 0:
                 raise DivideByZero()
             return int(math.fmod(a, b))
+    if k == "tscale":  # a date / timestamp value in nanoseconds (Python integers: exact)
+        v = _ev(e[1], row)
+        return None if v is None else v * e[2]
     if k == "cmp":
         a, b = _ev(e[2], row), _ev(e[3], row)
         if a is None or b is None:

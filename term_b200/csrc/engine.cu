@@ -4,7 +4,9 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
+#include <ctime>
 
 namespace tg {
 
@@ -783,8 +785,183 @@ static bool parse_temporal_literal(const std::string& text, char unit, int64_t* 
     return false;
 }
 
+// ---- constant date / timestamp arithmetic: now() / current_timestamp / current_date / today(), DATE / TIMESTAMP literals and
+// `+ / - INTERVAL '..'` (README.md:75 of the reference: `created_at > now() - interval '1 day'`). DataFusion folds these at
+// planning time (now() is the query's start time); here they fold on the host to a count of nanoseconds since the epoch
+// and the comparison is rewritten in the column's own unit. TG_FIXED_NOW_NS pins now() (tests).
+struct IntervalMDN {
+    int64_t months = 0, days = 0, nanos = 0;
+};
+// 'N unit [N unit ..]' with unit = year | month | week | day | hour | minute | second | millisecond | microsecond | nanosecond
+// (singular / plural, any case); N an integer, or a decimal for the units of a week and below
+static bool parse_interval_literal(const std::string& text, IntervalMDN* out) {
+    size_t i = 0;
+    const size_t n = text.size();
+    IntervalMDN iv;
+    bool any = false;
+    while (true) {
+        while (i < n && isspace((unsigned char)text[i])) ++i;
+        if (i == n) break;
+        size_t j = i;
+        if (j < n && (text[j] == '-' || text[j] == '+')) ++j;
+        bool digit = false, dot = false;
+        while (j < n && (isdigit((unsigned char)text[j]) || (text[j] == '.' && !dot))) {
+            if (text[j] == '.') dot = true;
+            else digit = true;
+            ++j;
+        }
+        if (!digit) return false;
+        const std::string num = text.substr(i, j - i);
+        i = j;
+        while (i < n && isspace((unsigned char)text[i])) ++i;
+        j = i;
+        while (j < n && isalpha((unsigned char)text[j])) ++j;
+        std::string u = text.substr(i, j - i);
+        for (auto& ch : u) ch = (char)tolower((unsigned char)ch);
+        if (u.size() > 1 && u.back() == 's') u.pop_back();
+        i = j;
+        if (u.empty()) u = "second";  // (a bare number counts seconds)
+        const double x = atof(num.c_str());
+        const long long whole = atoll(num.c_str());
+        if (u == "year" || u == "month") {
+            if (dot) return false;
+            iv.months += whole * (u == "year" ? 12 : 1);
+        } else if (u == "week" || u == "day") {
+            const double d = x * (u == "week" ? 7.0 : 1.0);
+            const double fl = floor(d);
+            iv.days += (int64_t)fl;
+            iv.nanos += (int64_t)llround((d - fl) * 86400e9);
+        } else {
+            const double per = u == "hour" ? 3600e9 : u == "minute" ? 60e9 : u == "second" ? 1e9 : u == "millisecond" ? 1e6 : u == "microsecond" ? 1e3
+                               : u == "nanosecond" ? 1.0 : 0.0;
+            if (per == 0.0) return false;
+            iv.nanos += dot ? (int64_t)llround(x * per) : whole * (int64_t)per;
+        }
+        any = true;
+    }
+    *out = iv;
+    return any;
+}
+static void civil_from_days(int64_t z, int64_t* y, unsigned* m, unsigned* d) {
+    z += 719468;
+    const int64_t era = (z >= 0 ? z : z - 146096) / 146097;
+    const unsigned doe = (unsigned)(z - era * 146097);
+    const unsigned yoe = (doe - doe / 1460 + doe / 36524 - doe / 146096) / 365;
+    const unsigned doy = doe - (365 * yoe + yoe / 4 - yoe / 100);
+    const unsigned mp = (5 * doy + 2) / 153;
+    *d = doy - (153 * mp + 2) / 5 + 1;
+    *m = mp < 10 ? mp + 3 : mp - 9;
+    *y = (int64_t)yoe + era * 400 + (*m <= 2);
+}
+constexpr int64_t DAY_NS = 86400ll * 1000000000ll;
+static int64_t floor_div(int64_t a, int64_t b) { return a / b - ((a % b != 0) && ((a < 0) != (b < 0))); }
+// months first (the day of the month clamped to the target month's length), then days, then the sub-day part
+static int64_t add_interval(int64_t ns, const IntervalMDN& iv, int sign) {
+    int64_t days = floor_div(ns, DAY_NS);
+    const int64_t tod = ns - days * DAY_NS;
+    if (iv.months) {
+        int64_t y;
+        unsigned m, d;
+        civil_from_days(days, &y, &m, &d);
+        const int64_t mm = y * 12 + (int64_t)(m - 1) + sign * iv.months;
+        y = floor_div(mm, 12);
+        m = (unsigned)(mm - y * 12) + 1;
+        static const unsigned mdays[12] = {31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31};
+        const bool leap = (y % 4 == 0 && y % 100 != 0) || y % 400 == 0;
+        const unsigned last = m == 2 && leap ? 29 : mdays[m - 1];
+        days = days_from_civil(y, m, d < last ? d : last);
+    }
+    return (days + sign * iv.days) * DAY_NS + tod + sign * iv.nanos;
+}
+static bool is_fn(const ExprP& x, const char* name, size_t n_args) { return x->kind == Expr::FUNC && x->s == name && x->args.size() == n_args; }
+static bool eval_interval(const ExprP& x, IntervalMDN* iv) {
+    return is_fn(x, "INTERVAL_LITERAL", 1) && x->args[0]->kind == Expr::LIT_S && parse_interval_literal(x->args[0]->s, iv);
+}
+// does the tree hold anything only the folding below understands?
+static bool has_temporal_fn(const ExprP& x) {
+    if (!x) return false;
+    if (x->kind == Expr::FUNC && (x->s == "NOW" || x->s == "CURRENT_TIMESTAMP" || x->s == "CURRENT_DATE" || x->s == "TODAY" || x->s == "INTERVAL_LITERAL"))
+        return true;
+    if (x->kind == Expr::BINARY && (x->s == "+" || x->s == "-")) return has_temporal_fn(x->args[0]) || has_temporal_fn(x->args[1]);
+    return false;
+}
+static bool eval_temporal_const(const ExprP& x, int64_t now_ns, int64_t* ns) {
+    if (x->kind == Expr::LIT_S) return parse_temporal_literal(x->s, 'n', ns);
+    if ((is_fn(x, "DATE_LITERAL", 1) || is_fn(x, "TIMESTAMP_LITERAL", 1)) && x->args[0]->kind == Expr::LIT_S)
+        return parse_temporal_literal(x->args[0]->s, 'n', ns);
+    if (is_fn(x, "NOW", 0) || is_fn(x, "CURRENT_TIMESTAMP", 0)) {
+        *ns = now_ns;
+        return true;
+    }
+    if (is_fn(x, "CURRENT_DATE", 0) || is_fn(x, "TODAY", 0)) {
+        *ns = floor_div(now_ns, DAY_NS) * DAY_NS;
+        return true;
+    }
+    if (x->kind == Expr::BINARY && (x->s == "+" || x->s == "-") && x->args.size() == 2) {
+        IntervalMDN iv;
+        int64_t base;
+        if (eval_temporal_const(x->args[0], now_ns, &base) && eval_interval(x->args[1], &iv)) {
+            *ns = add_interval(base, iv, x->s == "+" ? 1 : -1);
+            return true;
+        }
+        if (x->s == "+" && eval_interval(x->args[0], &iv) && eval_temporal_const(x->args[1], now_ns, &base)) {
+            *ns = add_interval(base, iv, 1);
+            return true;
+        }
+    }
+    return false;
+}
+static int64_t query_now_ns() {
+    if (const char* f = getenv("TG_FIXED_NOW_NS")) return (int64_t)atoll(f);
+    timespec ts{};
+    clock_gettime(CLOCK_REALTIME, &ts);
+    return (int64_t)ts.tv_sec * 1000000000ll + ts.tv_nsec;
+}
+// `col OP x` for a date / timestamp column and a constant instant x (nanoseconds): the same comparison in the column's unit.
+// An x between two ticks of a coarser column (days against a time of day) keeps the comparison exact by moving to the tick
+// below: col > x <=> col >= x <=> col > q, col < x <=> col <= x <=> col <= q, col = x never, col <> x always (NULL rows stay NULL).
+static ExprP temporal_compare(const ExprP& col_node, const Column& col, const std::string& op_from_col, int64_t x_ns) {
+    const int64_t unit = col.temporal_unit == 'D' ? DAY_NS : col.temporal_unit == 's' ? 1000000000ll : col.temporal_unit == 'm' ? 1000000ll
+                         : col.temporal_unit == 'u' ? 1000ll : 1ll;
+    const int64_t q = floor_div(x_ns, unit);
+    const bool exact = q * unit == x_ns;
+    auto node = std::make_shared<Expr>();
+    node->kind = Expr::BINARY;
+    auto lit = std::make_shared<Expr>();
+    lit->kind = Expr::LIT_I;
+    lit->i = q;
+    node->args = {col_node, lit};
+    if (exact) node->s = op_from_col;
+    else if (op_from_col == ">" || op_from_col == ">=") node->s = ">";
+    else if (op_from_col == "<" || op_from_col == "<=") node->s = "<=";
+    else {
+        node->s = op_from_col == "=" ? "<>" : "=";
+        node->args[1] = col_node;
+    }
+    return node;
+}
+
 static ExprP rewrite_string_compares(const ExprP& ex, Engine& e, Table& t, Plan& p, VirtualCols& vc) {
     if (!ex) return ex;
+    if (ex->kind == Expr::BINARY && ex->args.size() == 2 && (ex->s == "=" || ex->s == "<>" || ex->s == "<" || ex->s == "<=" || ex->s == ">" || ex->s == ">=")) {
+        static const char* const kOps[6] = {"=", "<>", "<", "<=", ">", ">="};
+        static const char* const kFlipped[6] = {"=", "<>", ">", ">=", "<", "<="};
+        for (int side = 0; side < 2; ++side) {
+            const ExprP& c = ex->args[side];
+            const ExprP& k = ex->args[1 - side];
+            if (c->kind != Expr::COL || !has_temporal_fn(k)) continue;
+            Column* col = t.find(c->s);
+            if (!col || !col->temporal || !col->temporal_unit) continue;
+            int64_t x_ns = 0;
+            if (!eval_temporal_const(k, query_now_ns(), &x_ns))
+                throw Error(TG_ERR_UNSUPPORTED, "This feature is not implemented: date / timestamp arithmetic beyond <constant> +/- INTERVAL '..'");
+            std::string op = ex->s;
+            if (side == 1)
+                for (int q = 0; q < 6; ++q)
+                    if (ex->s == kOps[q]) op = kFlipped[q];
+            return temporal_compare(c, *col, op, x_ns);
+        }
+    }
     // typed literals DATE '..' / TIMESTAMP '..' parse as a function-less pair: the parser hands them over as FUNC nodes
     if (ex->kind == Expr::BINARY && (ex->s == "=" || ex->s == "<>" || ex->s == "<" || ex->s == "<=" || ex->s == ">" || ex->s == ">=")) {
         for (int side = 0; side < 2; ++side) {

@@ -413,6 +413,29 @@ struct Parser {
                 adv();
                 return e;
             }
+            if (up == "INTERVAL" && cur.k == Tok::STR) {  // INTERVAL '1 day' / INTERVAL '1' DAY: folded with the constant it meets
+                auto e = mk(Expr::FUNC);
+                e->s = "INTERVAL_LITERAL";
+                auto lit = mk(Expr::LIT_S);
+                lit->s = cur.s;
+                adv();
+                if (cur.k == Tok::IDENT) {
+                    std::string u = upper(cur.s);
+                    if (!u.empty() && u.back() == 'S') u.pop_back();
+                    if (u == "YEAR" || u == "MONTH" || u == "WEEK" || u == "DAY" || u == "HOUR" || u == "MINUTE" || u == "SECOND" ||
+                        u == "MILLISECOND" || u == "MICROSECOND" || u == "NANOSECOND") {
+                        lit->s += " " + cur.s;
+                        adv();
+                    }
+                }
+                e->args.push_back(lit);
+                return e;
+            }
+            if ((up == "CURRENT_TIMESTAMP" || up == "CURRENT_DATE") && cur.k != Tok::LP) {  // (SQL spells these without parentheses)
+                auto e = mk(Expr::FUNC);
+                e->s = up;
+                return e;
+            }
             if (up == "CASE") return parse_case();
             if (up == "CAST" && cur.k == Tok::LP) return parse_cast();
             if (cur.k == Tok::LP) {

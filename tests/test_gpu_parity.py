@@ -1355,6 +1355,50 @@ def test_case_coalesce_cast_predicates_match_oracle(ctx, n):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("unit", ["s", "ms", "us", "ns"])
+def test_now_and_interval_arithmetic_in_predicates(ctx, unit, monkeypatch):
+    """`created_at > now() - interval '1 day'` (the reference's README.md:75) and its relatives: now() / current_timestamp /
+    current_date / today(), DATE / TIMESTAMP literals +/- INTERVAL (calendar months, day-time units, `INTERVAL '2' MONTH`) fold on
+    the host and the comparison runs in the column's unit; an instant between two ticks of a coarser column (now() with a
+    fraction of a second against seconds, a time of day against Date32) must not round the comparison. The oracle compares
+    exact nanoseconds instead. now() is pinned with TG_FIXED_NOW_NS for both."""
+    import datetime as dt
+    rng = np.random.default_rng(32)
+    n = 20_000
+    base = int(dt.datetime(2024, 1, 31, 10, 11, 12, tzinfo=dt.timezone.utc).timestamp())
+    monkeypatch.setenv("TG_FIXED_NOW_NS", str(base * 10**9 + 500_000_000))
+    per_s = {"s": 1, "ms": 10**3, "us": 10**6, "ns": 10**9}[unit]
+    ts = (base + rng.integers(-5, 6, n)) * per_s + rng.integers(0, per_s, n) * (rng.random(n) < 0.5)
+    ts[rng.random(n) < 0.2] -= 86400 * per_s  # a day earlier: on both sides of now() - 1 day
+    t = pa.table({"d": pa.array(rng.integers(19690, 19760, n).astype(np.int32), type=pa.date32(), mask=rng.random(n) < 0.1),
+                  "ts": pa.array(ts, type=pa.timestamp(unit), mask=rng.random(n) < 0.1), "x": pa.array(rng.integers(0, 5, n))})
+    name = f"temporal_now_{unit}"
+    ctx.register_table(name, t.to_batches(max_chunksize=3000))
+    preds = ["ts > now() - interval '1 day'", "ts <= current_timestamp", "ts >= CURRENT_TIMESTAMP - INTERVAL '86400 seconds' AND x > 1",
+             "now() - interval '1 day 2 seconds' < ts", "ts = now()", "ts <> now() OR x = 0", "ts < now() + interval '1.5 seconds'",
+             "ts < TIMESTAMP '2024-01-31 10:11:12' + INTERVAL '2 seconds 500 milliseconds'", "ts >= DATE '2024-03-31' - INTERVAL '2' MONTH",
+             "ts > TIMESTAMP '2024-03-30 10:11:13' - interval '1 month 29 days'", "interval '1 hour' + TIMESTAMP '2024-01-31 09:11:10' <= ts",
+             "d >= current_date - interval '3 days'", "d < now()", "d >= now()", "d = current_date", "d = now()", "d <> now()",
+             "d > today() - interval '1 month'", "d <= DATE '2023-12-31' + interval '1 month 1 day'", "d < current_date + interval '1 week' AND ts IS NOT NULL",
+             "d BETWEEN current_date - interval '2 days' AND now()"]
+    try:
+        cb = T.Check.builder("temporal")
+        for p in preds:
+            cb.satisfies(p)
+        rs = T.ValidationSuite.builder("s").table_name(name).check(cb.build()).build().run(ctx).report.results
+        seen = set()
+        for p, g in zip(preds, rs):
+            o = O.custom_sql(t, p)
+            assert g.status.name.lower() == o.status and g.metric == o.metric and g.message == o.message, (p, g, o)
+            seen.add(g.metric)
+        assert len(seen) > 8  # the predicates cut the data at different places
+        bad = T.ValidationSuite.builder("b").table_name(name).check(T.Check.builder("b").satisfies("ts > now() * 2").build()).build().run(ctx).report.results[0]
+        assert bad.status.name == "Failure"
+    finally:
+        ctx.deregister_table(name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("unit", ["s", "ms", "us", "ns"])
 def test_date_and_timestamp_literals_in_predicates(ctx, unit):
     """`date_col >= '2024-01-31'`, `ts_col < '2024-01-31 10:11:12.5'`, typed DATE / TIMESTAMP literals, BETWEEN / IN lists, zone
     offsets: the literal is cast to the column's type (days / the timestamp unit) like DataFusion's coercion does"""
