@@ -454,6 +454,15 @@ TG_API int32_t tg_plan_add_grouped_completeness(tg_plan* plan, const char* colum
                                                 const char* const* group_columns, int32_t n_group_columns,
                                                 int32_t max_groups, int32_t include_overall);
 
+/* HistogramConstraint (constraints/histogram.rs:208-413): value frequencies of `column` (GROUP BY CAST(column AS VARCHAR) over
+ * the non-NULL rows, ORDER BY count DESC, value). After execute: tg_plan_result gives Skipped("No data to analyze") when no
+ * row is non-NULL, otherwise a provisional Success whose metric is the histogram's entropy; tg_plan_map_entry(slot, i) walks
+ * the buckets in order (key = value, value = count) and tg_plan_analyzer_result's u[0..2] = {total_count, null_count,
+ * distinct_count}. The HistogramAssertion is a closure: the host applies it to the buckets and, when it fails, builds the
+ * reference's message (histogram.rs:371-381). Utf8, integer and Boolean columns; floating-point and temporal columns are
+ * TG_ERR_UNSUPPORTED (Arrow's CAST(.. AS VARCHAR) formatting of those is not restated). At most 2^20 distinct values. */
+TG_API int32_t tg_plan_add_value_histogram(tg_plan* plan, const char* column);
+
 /*
  * Evaluate every slot against table `table_name` (the reference's task-local
  * ValidationContext::table_name, core/validation_context.rs:71-82; default "data"). Blocking.

@@ -1170,6 +1170,68 @@ def column_count(table, assertion) -> Result:
     return Result(FAILURE, n, f"Column count {rust_f64(n)} does not satisfy assertion {assertion_desc(assertion)}")
 
 
+class OHistogram:
+    """constraints/histogram.rs:25-127 — buckets [(value, count, ratio)] ordered by count DESC, value ASC"""
+
+    def __init__(self, buckets, total_count, null_count):
+        self.buckets, self.total_count, self.null_count, self.distinct_count = buckets, total_count, null_count, len(buckets)
+
+    def most_common_ratio(self): return self.buckets[0][2] if self.buckets else 0.0
+    def least_common_ratio(self): return self.buckets[-1][2] if self.buckets else 0.0
+    def bucket_count(self): return len(self.buckets)
+    def top_n(self, n): return [(v, r) for v, _, r in self.buckets[:n]]
+    def get_value_ratio(self, value): return next((r for v, _, r in self.buckets if v == value), None)
+    def null_ratio(self): return 0.0 if self.total_count == 0 else self.null_count / self.total_count
+    def follows_power_law(self, top_n, threshold): return sum((r for _, _, r in self.buckets[:top_n]), 0.0) >= threshold
+
+    def is_roughly_uniform(self, threshold):
+        if not self.buckets:
+            return True
+        return False if self.least_common_ratio() == 0.0 else self.most_common_ratio() / self.least_common_ratio() <= threshold
+
+    def entropy(self):
+        e = 0.0
+        for _, _, r in self.buckets:
+            if r > 0.0:
+                e += -r * math.log(r)
+        return e
+
+
+def histogram_of(table, column) -> OHistogram:
+    """the query of constraints/histogram.rs:214-241: GROUP BY CAST(c AS VARCHAR) over the non-NULL rows, ratio = count * 1.0 /
+    (total - nulls), ORDER BY count DESC, value (VARCHAR: byte order). Utf8, integer and Boolean columns."""
+    c = table_cols(table)[column]
+    counts = {}
+    nulls = 0
+    for v, ok in zip(c.values, c.valid):
+        if not ok:
+            nulls += 1
+            continue
+        if c.kind == "bool":
+            k = "true" if v else "false"
+        elif c.kind == "str":
+            k = v
+        elif c.kind == "i64":
+            k = str(int(v))
+        else:
+            raise ValueError("histogram of a floating-point column: CAST AS VARCHAR formatting is not restated")
+        counts[k] = counts.get(k, 0) + 1
+    total = len(c.values)
+    items = sorted(counts.items(), key=lambda kv: (-kv[1], kv[0].encode("utf-8")))
+    return OHistogram([(k, n, n * 1.0 / (total - nulls)) for k, n in items], total, nulls)
+
+
+def histogram_constraint(table, column, assertion, description="custom assertion") -> Result:
+    """constraints/histogram.rs:208-413: Skipped without a non-NULL row; metric = entropy; the failure message at :371-381"""
+    h = histogram_of(table, column)
+    if not h.buckets:
+        return Result(SKIPPED, None, "No data to analyze")
+    if assertion(h):
+        return Result(SUCCESS, h.entropy())
+    return Result(FAILURE, h.entropy(), f"Histogram assertion '{description}' failed for column '{column}'. Distribution: {h.distinct_count} distinct values, "
+                                        f"most common ratio: {h.most_common_ratio() * 100.0:.2f}%, null ratio: {h.null_ratio() * 100.0:.2f}%")
+
+
 def an_histogram(table, column, num_buckets):
     """analyzers/advanced/histogram.rs:184-358 -> dict(total_count, min, max, sum, sum_squared, mean, std_dev,
     buckets=[(lower, upper, count)]); Float64 columns only (the reference's downcasts reject Int64)."""

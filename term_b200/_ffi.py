@@ -127,6 +127,7 @@ SIGNATURES = {
     "tg_plan_add_quantile": (C.c_int32, [P, C.c_char_p, C.c_int32, C.POINTER(C.c_double), C.POINTER(tg_assertion),
                                          C.c_int32, C.c_int32]),
     "tg_plan_add_grouped_completeness": (C.c_int32, [P, C.c_char_p, STRS, C.c_int32, C.c_int32, C.c_int32]),
+    "tg_plan_add_value_histogram": (C.c_int32, [P, C.c_char_p]),
     "tg_plan_execute": (C.c_int, [P, P, C.c_char_p]),
     "tg_plan_execute_partial": (C.c_int, [P, P, C.c_char_p]),
     "tg_plan_partial_size": (C.c_int, [P, C.POINTER(C.c_size_t)]),

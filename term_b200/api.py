@@ -15,11 +15,12 @@ reproduces the orchestration of `ValidationSuite::run_sequential` (core/suite.rs
 """
 import ctypes as C
 import enum
+import math
 import mmap
 import os
 import time
 from dataclasses import dataclass, field
-from typing import Dict, List, Optional, Sequence
+from typing import Callable, Dict, List, Optional, Sequence
 
 import numpy as np
 
@@ -645,11 +646,15 @@ class Constraint:
     def _add_to(self, plan: Plan) -> int:
         raise NotImplementedError
 
+    def _result(self, plan: Plan, slot: int) -> ConstraintResult:
+        """the slot's result; constraints whose assertion is a host closure (HistogramConstraint) finish it here"""
+        return plan.result(slot)
+
     def evaluate(self, ctx: SessionContext, table: str = "data") -> ConstraintResult:
         plan = Plan()
         slot = self._add_to(plan)
         plan.execute(ctx, table)
-        return plan.result(slot)
+        return self._result(plan, slot)
 
     def name(self):
         plan = Plan()
@@ -992,6 +997,79 @@ class ForeignKeyConstraint(Constraint):  # constraints/foreign_key.rs
 
 # ----------------------------------------------------------------------------- Check / Suite ----
 @dataclass
+class HistogramBucket:  # constraints/histogram.rs:14-22
+    value: str
+    count: int
+    ratio: float
+
+
+class Histogram:  # constraints/histogram.rs:25-127
+    def __init__(self, buckets, total_count, null_count):
+        self.buckets, self.total_count, self.null_count = list(buckets), total_count, null_count
+        self.distinct_count = len(self.buckets)
+
+    def most_common_ratio(self): return self.buckets[0].ratio if self.buckets else 0.0
+    def least_common_ratio(self): return self.buckets[-1].ratio if self.buckets else 0.0
+    def bucket_count(self): return len(self.buckets)
+    def top_n(self, n): return [(b.value, b.ratio) for b in self.buckets[:n]]
+
+    def is_roughly_uniform(self, threshold):
+        if not self.buckets:
+            return True
+        lo = self.least_common_ratio()
+        return False if lo == 0.0 else self.most_common_ratio() / lo <= threshold
+
+    def get_value_ratio(self, value):
+        return next((b.ratio for b in self.buckets if b.value == value), None)
+
+    def entropy(self):
+        e = 0.0
+        for b in self.buckets:
+            if b.ratio > 0.0:
+                e += -b.ratio * math.log(b.ratio)
+        return e
+
+    def follows_power_law(self, top_n, threshold):
+        s = 0.0
+        for b in self.buckets[:top_n]:
+            s += b.ratio
+        return s >= threshold
+
+    def null_ratio(self): return 0.0 if self.total_count == 0 else self.null_count / self.total_count
+
+
+class HistogramConstraint(Constraint):  # constraints/histogram.rs:129-413
+    """The value frequencies come from the GPU (tg_plan_add_value_histogram: the grouped-count kernel over the column itself);
+    the assertion is a host closure over the Histogram, as in the reference."""
+
+    def __init__(self, column, assertion: Callable[[Histogram], bool], description="custom assertion"):
+        self.column, self.assertion, self.assertion_description = column, assertion, description
+
+    @staticmethod
+    def new_with_description(column, assertion, description): return HistogramConstraint(column, assertion, description)
+
+    def _add_to(self, plan):
+        return F.check_slot(F.lib().tg_plan_add_value_histogram(plan.handle, self.column.encode()))
+
+    def histogram(self, plan, slot) -> Histogram:
+        a = plan.analyzer_result(slot)
+        total, nulls = a.u[0], a.u[1]
+        return Histogram([HistogramBucket(k, int(v), int(v) * 1.0 / (total - nulls)) for k, v in a.map.items()], total, nulls)
+
+    def _result(self, plan, slot):
+        r = plan.result(slot)
+        if r.status is not ConstraintStatus.Success:  # Skipped("No data to analyze") / an evaluation error
+            return r
+        h = self.histogram(plan, slot)
+        if self.assertion(h):
+            return r
+        r.status = ConstraintStatus.Failure
+        r.message = (f"Histogram assertion '{self.assertion_description}' failed for column '{self.column}'. Distribution: {h.distinct_count} "
+                     f"distinct values, most common ratio: {h.most_common_ratio() * 100.0:.2f}%, null ratio: {h.null_ratio() * 100.0:.2f}%")
+        return r
+
+
+@dataclass
 class Check:  # core/check.rs
     name: str
     level: Level = Level.Error
@@ -1041,6 +1119,9 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_variance(self, column, assertion): return self.statistic(column, StatisticType.Variance, assertion)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
+    # core/check.rs has_histogram / has_histogram_with_description
+    def has_histogram(self, column, assertion): return self.constraint(HistogramConstraint(column, assertion))
+    def has_histogram_with_description(self, column, assertion, description): return self.constraint(HistogramConstraint(column, assertion, description))
     # core/check.rs:518-625, 1777-1786
     def has_column_count(self, assertion): return self.constraint(ColumnCountConstraint(assertion))
     def has_approx_count_distinct(self, column, assertion): return self.constraint(ApproxCountDistinctConstraint(column, assertion))
@@ -1152,7 +1233,7 @@ class ValidationSuite:  # core/suite.rs
         m = report.metrics
         has_errors = False
         for check, c, slot in slots:
-            r = plan.result(slot)
+            r = c._result(plan, slot)
             report.results.append(r)
             m.total_checks += 1
             if r.status is ConstraintStatus.Success:

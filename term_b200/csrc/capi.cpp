@@ -417,6 +417,9 @@ int32_t tg_plan_add_quantile(tg_plan* p, const char* column, int32_t validation,
 int32_t tg_plan_add_histogram(tg_plan* p, const char* column, int32_t num_buckets) {
     return guard_slot([&] { return plan_add_histogram(p->p, column ? column : "", num_buckets); });
 }
+int32_t tg_plan_add_value_histogram(tg_plan* p, const char* column) {
+    return guard_slot([&] { return plan_add_value_histogram(p->p, column ? column : ""); });
+}
 int32_t tg_plan_add_grouped_completeness(tg_plan* p, const char* column, const char* const* groups, int32_t n,
                                          int32_t max_groups, int32_t include_overall) {
     return guard_slot([&] {
@@ -794,7 +797,7 @@ tg_status tg_plan_analyzer_result(const tg_plan* p, int32_t slot, tg_analyzer_re
         if (slot < 0 || slot >= (int32_t)p->p.slots.size()) throw Error(TG_ERR_INVALID_ARG, "slot out of range");
         if (!p->p.executed) throw Error(TG_ERR_INVALID_ARG, "plan has not been executed");
         const Slot& s = p->p.slots[slot];
-        if (s.kind != SL_ANALYZER && s.kind != SL_KLL && s.kind != SL_GROUPED && s.kind != SL_HISTOGRAM)
+        if (s.kind != SL_ANALYZER && s.kind != SL_KLL && s.kind != SL_GROUPED && s.kind != SL_HISTOGRAM && s.kind != SL_VALUE_HIST)
             throw Error(TG_ERR_INVALID_ARG, "slot is not an analyzer");
         *out = s.ares;
         out->metric_key = s.metric_key.c_str();

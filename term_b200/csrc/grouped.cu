@@ -1515,7 +1515,9 @@ static void run_grouped_batch(Engine& e, Table& t, Plan& p, const GrpBatch& B) {
                         memcpy(&d, &x, 8);
                         key += fmt_f64(d);
                     } break;
-                    default: break;  // Boolean group values print as the empty string, as before
+                    default:  // Boolean group values print as the empty string, as before; a value histogram casts them to VARCHAR
+                        if (a.flags & 2) key += x ? "true" : "false";
+                        break;
                 }
             }
             uint32_t L = (uint32_t)key.size();
@@ -1552,6 +1554,8 @@ void exec_grouped_jobs(Engine& e, Table& t, Plan& p, const std::vector<int>& agg
             std::vector<Column*> gcols;
             for (size_t i = 1; i < a.cols.size(); ++i) gcols.push_back(need_col(a.cols[i]));
             if (gcols.size() > (size_t)GRP_MAX_COLS) throw Error(TG_ERR_UNSUPPORTED, "grouped completeness: more than 8 grouping columns");
+            if ((a.flags & 2) && (gcols[0]->dtype == TG_FLOAT64 || gcols[0]->dtype == TG_FLOAT32 || gcols[0]->temporal))
+                throw Error(TG_ERR_UNSUPPORTED, "histogram of a floating-point / temporal column: CAST(" + a.cols[1] + " AS VARCHAR) formatting is not restated");
             uint64_t zero = 0;
             a.blob.assign((uint8_t*)&zero, (uint8_t*)&zero + 8);
             if (t.n_rows == 0) continue;

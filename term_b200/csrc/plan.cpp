@@ -653,6 +653,22 @@ int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::ve
     return (int)p.slots.size() - 1;
 }
 
+int plan_add_value_histogram(Plan& p, const std::string& col) {
+    Slot s;
+    s.kind = SL_VALUE_HIST;
+    s.name = "histogram";
+    s.metric_key = "histogram." + col;
+    s.columns = {col};
+    Agg a;
+    a.kind = A_GROUPED;
+    a.key = "vhist|" + col;
+    a.cols = {col, col};  // target and grouping column: a group's non-NULL count is its size, the NULL group counts the NULLs
+    a.flags = 2;
+    s.aggs.push_back(p.add_agg(std::move(a)));
+    p.slots.push_back(std::move(s));
+    return (int)p.slots.size() - 1;
+}
+
 // ---- partial (de)serialisation: [u64 n_aggs] then per agg: kind, err, u[8], f[8], blob_len, blob, err_len, err ----
 size_t Plan::partial_size() const {
     size_t n = 8;
@@ -1872,6 +1888,76 @@ static void finalize_grouped(Plan& p, Slot& s) {
     r.metric_double = ot == 0 ? 1.0 : (double)on / (double)ot;
 }
 
+// HistogramConstraint::evaluate (constraints/histogram.rs:208-413): buckets = the non-NULL values with their counts, ordered by
+// count DESC, value ASC; metric = the entropy of the ratios count / (total - nulls), summed in that order; no bucket at all =>
+// Skipped("No data to analyze"). The assertion is a closure over the Histogram: it stays on the host side of the boundary,
+// which reads the buckets through tg_plan_map_entry (value -> count) and u[0..2] = {total_count, null_count, distinct_count}.
+static void finalize_value_hist(Plan& p, Slot& s) {
+    const Agg& a = p.aggs[s.aggs[0]];
+    tg_analyzer_result& r = s.ares;
+    r = tg_analyzer_result{};
+    s.map.clear();
+    if (a.err != TG_OK) {
+        set_error(s, a);
+        return;
+    }
+    struct G {
+        const uint8_t* key;
+        uint32_t len;
+        uint64_t count;
+    };
+    std::vector<G> gs;
+    std::vector<uint8_t> state = a.blob;
+    grouped_blob_compact(state);
+    uint64_t total = 0, nulls = 0;
+    if (state.size() >= 8) {
+        uint64_t n;
+        memcpy(&n, state.data(), 8);
+        const uint8_t* q = state.data() + 8;
+        for (uint64_t i = 0; i < n; ++i) {
+            uint32_t L;
+            memcpy(&L, q, 4);
+            q += 4;
+            G g{q, L, 0};
+            q += L;
+            uint64_t tot, nn;
+            memcpy(&tot, q, 8);
+            memcpy(&nn, q + 8, 8);
+            q += 16;
+            total += tot;
+            if (nn == 0) {  // the NULL group (the target IS the grouping column: every other group has nn == tot > 0)
+                nulls += tot;
+                continue;
+            }
+            g.count = tot;
+            gs.push_back(g);
+        }
+    }
+    std::stable_sort(gs.begin(), gs.end(), [](const G& x, const G& y) {
+        if (x.count != y.count) return x.count > y.count;
+        const int c = memcmp(x.key, y.key, std::min(x.len, y.len));
+        return c != 0 ? c < 0 : x.len < y.len;
+    });
+    r.metric_kind = 2;
+    r.u[0] = total;
+    r.u[1] = nulls;
+    r.u[2] = gs.size();
+    if (gs.empty()) {
+        skipped(s, "No data to analyze");
+        return;
+    }
+    double entropy = 0.0;
+    const double denom = (double)(int64_t)(total - nulls);
+    s.map.reserve(gs.size());
+    for (auto& g : gs) {
+        const double ratio = (double)(int64_t)g.count * 1.0 / denom;
+        if (ratio > 0.0) entropy += -ratio * log(ratio);
+        s.map.emplace_back(std::string((const char*)g.key, g.len), (double)g.count);
+    }
+    r.metric_double = entropy;
+    success_metric(s, entropy);  // provisional: the host applies the assertion closure
+}
+
 void Plan::finalize() {
     for (auto& s : slots) {
         s.has_message = false;
@@ -1900,6 +1986,7 @@ void Plan::finalize() {
             case SL_ANALYZER: finalize_analyzer(*this, s); break;
             case SL_KLL: finalize_kll(*this, s); break;
             case SL_GROUPED: finalize_grouped(*this, s); break;
+            case SL_VALUE_HIST: finalize_value_hist(*this, s); break;
             case SL_LENGTH: finalize_length(*this, s); break;
             case SL_CONTAINMENT: finalize_value_ratio(*this, s, " values are not in the allowed set"); break;
             case SL_NON_NEGATIVE: finalize_value_ratio(*this, s, " values are negative"); break;

@@ -34,7 +34,8 @@ struct Agg {
     std::string key;                 // de-duplication key
     std::vector<std::string> cols;   // for A_FK: child table, child col, parent table, parent col
     std::string text;                // predicate / regex pattern
-    int32_t flags = 0;               // regex: bit0 case-insensitive, bit1 trim ; distinct: see hash job
+    int32_t flags = 0;               // regex: bit0 case-insensitive, bit1 trim ; distinct: see hash job ; grouped: bit1 = value histogram
+                                     // (keys print as CAST(.. AS VARCHAR): booleans true / false, no floating point)
     int32_t iparam = 0;              // KLL k / FK max examples / grouped max_groups
     int64_t lo = 0, hi = 0;          // A_LENGTH: inclusive character-count range
     ExprP expr;                      // parsed predicate
@@ -86,6 +87,7 @@ enum SlotKind : int32_t {
     SL_COLUMN_COUNT,
     SL_HISTOGRAM,
     SL_QUANTILE,
+    SL_VALUE_HIST,
 };
 
 struct StatReq {
@@ -171,6 +173,8 @@ int plan_add_column_count(Plan& p, tg_assertion a);
 int plan_add_histogram(Plan& p, const std::string& col, int num_buckets);
 int plan_add_quantile(Plan& p, const std::string& col, int mode, const std::vector<double>& quantiles,
                       const std::vector<tg_assertion>& assertions, int strict);
+// HistogramConstraint (constraints/histogram.rs:208-244): value frequencies of one column, as a grouped count of the column by itself
+int plan_add_value_histogram(Plan& p, const std::string& col);
 int plan_add_grouped_completeness(Plan& p, const std::string& col, const std::vector<std::string>& groups,
                                   int max_groups, int include_overall);
 
