@@ -1170,6 +1170,29 @@ def column_count(table, assertion) -> Result:
     return Result(FAILURE, n, f"Column count {rust_f64(n)} does not satisfy assertion {assertion_desc(assertion)}")
 
 
+def unified_data_type(table, column, kind, predicate=None, description="", threshold=None, expected=None, actual_type=None) -> Result:
+    """constraints/datatype.rs:296-431 (the unified DataTypeConstraint): SpecificType compares the schema's `{:?}`; Consistency is
+    the reference's placeholder (0.95); the other validations count `predicate` over the non-NULL rows:
+    SELECT COUNT(*), SUM(CASE WHEN pred THEN 1 ELSE 0 END) FROM t WHERE col IS NOT NULL — Success iff every one satisfies it."""
+    cols = table_cols(table)
+    if column not in cols:
+        raise KeyError(column)
+    if kind == "specific":
+        if actual_type == expected:
+            return Result(SUCCESS, 1.0, f"Column '{column}' has expected type {expected}")
+        return Result(FAILURE, 0.0, f"Column '{column}' has type {actual_type}, expected {expected}")
+    if kind == "consistency":
+        ok = 0.95 >= threshold
+        return Result(SUCCESS if ok else FAILURE, 0.95, f"Type consistency {95.0:.1f}% {'meets' if ok else 'below'} threshold {threshold * 100.0:.1f}%")
+    c = cols[column]
+    # (WHERE col IS NOT NULL filters first: a predicate that ignores the column must not count its NULL rows)
+    sat_nn, _ = predicate_counts(table, f'"{column}" IS NOT NULL AND ({predicate})')
+    total = int(np.count_nonzero(c.valid))
+    rate = sat_nn / total if total else float("nan")
+    pct = "NaN" if rate != rate else f"{rate * 100.0:.1f}"
+    return Result(SUCCESS if rate >= 1.0 else FAILURE, rate, f"{pct}% of values satisfy {description}")
+
+
 class OHistogram:
     """constraints/histogram.rs:25-127 — buckets [(value, count, ratio)] ordered by count DESC, value ASC"""
 

@@ -284,6 +284,11 @@ class SessionContext:
         column -> numpy array | (numpy array, validity bool mask) | list of str/None."""
         t = self._create(name)
         try:
+            sch = data.schema if pa is not None and isinstance(data, (pa.Table, pa.RecordBatch)) else (
+                data[0].schema if isinstance(data, list) and data and pa is not None and isinstance(data[0], pa.RecordBatch) else None)
+            if not hasattr(self, "_schemas"):
+                self._schemas = {}
+            self._schemas[name] = sch
             if pa is not None and isinstance(data, (pa.Table, pa.RecordBatch)):
                 batches = data.to_batches() if isinstance(data, pa.Table) else [data]
                 if isinstance(data, pa.Table) and not batches:
@@ -498,6 +503,7 @@ class Plan:
         return self._h
 
     def execute(self, ctx: SessionContext, table: str = "data"):
+        self._ctx_schema = getattr(ctx, "_schemas", {}).get(table)  # (schema-only constraints read it, as the reference reads df.schema())
         F.check(F.lib().tg_plan_execute(ctx.handle, self._h, table.encode()))
 
     def execute_partial(self, ctx: SessionContext, table: str = "data"):
@@ -1069,6 +1075,117 @@ class HistogramConstraint(Constraint):  # constraints/histogram.rs:129-413
         return r
 
 
+def arrow_type_debug(t) -> str:
+    """`{:?}` of the arrow-rs DataType a pyarrow type corresponds to (what DataTypeConstraint::specific_type compares with)"""
+    simple = {"int8": "Int8", "int16": "Int16", "int32": "Int32", "int64": "Int64", "uint8": "UInt8", "uint16": "UInt16", "uint32": "UInt32",
+              "uint64": "UInt64", "float": "Float32", "double": "Float64", "halffloat": "Float16", "bool": "Boolean", "string": "Utf8",
+              "large_string": "LargeUtf8", "binary": "Binary", "large_binary": "LargeBinary", "date32[day]": "Date32", "date64[ms]": "Date64", "null": "Null"}
+    k = str(t)
+    if k in simple:
+        return simple[k]
+    units = {"s": "Second", "ms": "Millisecond", "us": "Microsecond", "ns": "Nanosecond"}
+    if pa.types.is_timestamp(t):
+        return f"Timestamp({units[t.unit]}, " + ("None" if t.tz is None else f'Some("{t.tz}")') + ")"
+    if pa.types.is_duration(t):
+        return f"Duration({units[t.unit]})"
+    if pa.types.is_time(t):
+        return f"Time{t.bit_width}({units[t.unit]})"
+    return k
+
+
+class UnifiedDataTypeConstraint(Constraint):  # constraints/datatype.rs:236-445 (the reference's second DataTypeConstraint)
+    """SpecificType reads the schema; Consistency is the reference's placeholder (column must exist, consistency = 0.95);
+    every other validation is a predicate counted over the non-NULL rows — here the non-NULL count (K1 validity popcount)
+    and the count of rows where `col IS NOT NULL AND (predicate)` holds (K1 predicate unit), fused into one scan."""
+
+    def __init__(self, column, kind, predicate=None, description="", threshold=None, expected=None):
+        F.check(F.lib().tg_validate_identifier(column.encode()))
+        if kind == "consistency" and not (0.0 <= threshold <= 1.0):
+            raise ValueError("Threshold must be between 0.0 and 1.0")
+        self.column, self.kind, self.predicate, self.description, self.threshold, self.expected = column, kind, predicate, description, threshold, expected
+
+    @staticmethod
+    def _esc(column): return '"' + column.replace('"', '""') + '"'
+
+    @classmethod
+    def specific_type(cls, column, data_type): return cls(column, "specific", expected=data_type, description=f"type is {data_type}")
+    @classmethod
+    def type_consistency(cls, column, threshold): return cls(column, "consistency", threshold=threshold)
+    @classmethod
+    def _pred(cls, column, template, description): return cls(column, "predicate", template.replace("{c}", cls._esc(column)), description)
+    @classmethod
+    def non_negative(cls, column): return cls._pred(column, "{c} >= 0", "non-negative values")
+    @classmethod
+    def positive(cls, column): return cls._pred(column, "{c} > 0", "positive values")
+    @classmethod
+    def integer(cls, column): return cls._pred(column, "{c} = CAST({c} AS INT)", "integer values")
+    @classmethod
+    def range(cls, column, lo, hi): return cls._pred(column, "{c} BETWEEN " + _rust_num(lo) + " AND " + _rust_num(hi), f"values between {_rust_num(lo)} and {_rust_num(hi)}")
+    @classmethod
+    def not_empty(cls, column): return cls._pred(column, "LENGTH({c}) > 0", "non-empty strings")
+    @classmethod
+    def valid_utf8(cls, column): return cls._pred(column, "{c} IS NOT NULL", "valid UTF-8 strings")
+    @classmethod
+    def max_bytes(cls, column, n): return cls._pred(column, "OCTET_LENGTH({c}) <= " + str(int(n)), f"strings with max {int(n)} bytes")
+    @classmethod
+    def past_date(cls, column): return cls._pred(column, "{c} < CURRENT_DATE", "past dates")
+    @classmethod
+    def future_date(cls, column): return cls._pred(column, "{c} > CURRENT_DATE", "future dates")
+    @classmethod
+    def date_range(cls, column, start, end): return cls._pred(column, "{c} BETWEEN '" + start + "' AND '" + end + "'", f"dates between {start} and {end}")
+    @classmethod
+    def valid_timezone(cls, column): return cls._pred(column, "{c} IS NOT NULL", "valid timezone")
+
+    @classmethod
+    def custom(cls, column, sql_predicate):
+        if ";" in sql_predicate or "drop" in sql_predicate.lower():  # datatype.rs:219-225
+            raise ValueError("Potentially unsafe SQL predicate")
+        return cls(column, "predicate", sql_predicate.replace("{column}", cls._esc(column)), f"custom validation: {sql_predicate}")
+
+    def _add_to(self, plan):
+        # slot = the non-NULL count of the column (also what makes a missing column an error); the predicate count rides behind it
+        self._count_slot = None
+        s = CompletenessAnalyzer(self.column)._add_to(plan)
+        if self.kind == "predicate":
+            self._count_slot = ComplianceAnalyzer("datatype", f"{self._esc(self.column)} IS NOT NULL AND ({self.predicate})")._add_to(plan)
+        return s
+
+    def _result(self, plan, slot):
+        a = plan.analyzer_result(slot)
+        if a.error == 2:
+            return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: " + (a.message or ""), "datatype")
+        if self.kind == "specific":
+            sch = getattr(plan, "_ctx_schema", None)
+            actual = arrow_type_debug(sch.field(self.column).type) if sch is not None else None
+            if actual is None:
+                return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: the table's Arrow schema is not known to this context", "datatype")
+            if actual == self.expected:
+                return ConstraintResult(ConstraintStatus.Success, 1.0, f"Column '{self.column}' has expected type {self.expected}", "datatype")
+            return ConstraintResult(ConstraintStatus.Failure, 0.0, f"Column '{self.column}' has type {actual}, expected {self.expected}", "datatype")
+        if self.kind == "consistency":
+            consistency = 0.95  # the reference's placeholder (datatype.rs:357-359)
+            ok = consistency >= self.threshold
+            return ConstraintResult(ConstraintStatus.Success if ok else ConstraintStatus.Failure, consistency,
+                                    f"Type consistency {consistency * 100.0:.1f}% {'meets' if ok else 'below'} threshold {self.threshold * 100.0:.1f}%", "datatype")
+        c = plan.analyzer_result(self._count_slot)
+        if c.error == 2:
+            return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: " + (c.message or ""), "datatype")
+        total, valid = a.u[1], c.u[0]   # CompletenessAnalyzer: u = [rows, non-NULL rows]; ComplianceAnalyzer: u = [satisfied, rows]
+        rate = valid / total if total else float("nan")   # SUM over no rows is NULL, read as 0: 0 / 0
+        return ConstraintResult(ConstraintStatus.Success if rate >= 1.0 else ConstraintStatus.Failure, rate,
+                                f"{_rust_fixed1(rate * 100.0)}% of values satisfy {self.description}", "datatype")
+
+
+def _rust_num(x) -> str:
+    """`{}` of an f64 (Range { min, max } are f64 in the reference): integral values print without a fraction"""
+    x = float(x)
+    return str(int(x)) if x == int(x) and abs(x) < 1e15 else repr(x)
+
+
+def _rust_fixed1(x: float) -> str:
+    return "NaN" if x != x else f"{x:.1f}"
+
+
 @dataclass
 class Check:  # core/check.rs
     name: str
@@ -1119,6 +1236,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_variance(self, column, assertion): return self.statistic(column, StatisticType.Variance, assertion)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
+    def has_consistent_data_type(self, column, threshold): return self.constraint(UnifiedDataTypeConstraint.type_consistency(column, threshold))  # core/check.rs:651-657
     # core/check.rs has_histogram / has_histogram_with_description
     def has_histogram(self, column, assertion): return self.constraint(HistogramConstraint(column, assertion))
     def has_histogram_with_description(self, column, assertion, description): return self.constraint(HistogramConstraint(column, assertion, description))
