@@ -26,13 +26,19 @@
 
 namespace tg {
 
-constexpr int HS_THREADS = 512, HS_WARPS = HS_THREADS / 32;
-constexpr int HS_KEYS = 8;                       // rows per thread per tile of the prep kernel
+#ifndef TG_HS_THREADS
+#define TG_HS_THREADS 512
+#define TG_HS_CHUNK 2048
+#define TG_HS_SLOTS 8192
+#define TG_HS_SPEC 5
+#endif
+constexpr int HS_THREADS = TG_HS_THREADS, HS_WARPS = HS_THREADS / 32;
+constexpr int HS_KEYS = 4096 / HS_THREADS;       // rows per thread per tile of the prep kernel (128 (row group, warp) counts per tile)
 constexpr int HS_TILE = HS_THREADS * HS_KEYS;
-constexpr int HS_CHUNK = 2048;                   // nominal keys per chunk of the dedup kernel
-constexpr int HS_SLOTS = 8192;                   // shared table: chunk + the tail of its last bucket at load <= ~0.5
-constexpr int HS_SPEC = 5;                       // rounds of HS_THREADS keys past the chunk that are loaded speculatively
-constexpr int HS_MAX_TAIL_ROUNDS = 256;          // a bucket that runs > 128 K keys past its chunk is not a hash bucket: skew
+constexpr int HS_CHUNK = TG_HS_CHUNK;            // nominal keys per chunk of the dedup kernel
+constexpr int HS_SLOTS = TG_HS_SLOTS;            // shared table: chunk + the tail of its last bucket at load <= ~0.5
+constexpr int HS_SPEC = TG_HS_SPEC;              // rounds of HS_THREADS keys past the chunk that are loaded speculatively
+constexpr int HS_MAX_TAIL_ROUNDS = (128 << 10) / HS_THREADS;  // a bucket that runs > 128 K keys past its chunk is not a hash bucket: skew
 
 struct HsCounters {
     unsigned long long n_valid;   // keys written by the prep kernel
@@ -249,7 +255,9 @@ bool distinct64_sorted(Engine& e, const Column& c, int64_t n, Distinct64Result& 
         const size_t smem = (size_t)HS_SLOTS * 8 + HS_SLOTS / 8;
         TG_CUDA(cudaFuncSetAttribute(hs_dedup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int64_t n_chunks = (nv + HS_CHUNK - 1) / HS_CHUNK;
-        const int dgrid = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)e.sm_count * 3));
+        int per_sm = 1;
+        TG_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, hs_dedup_kernel, HS_THREADS, smem));
+        const int dgrid = (int)std::max<int64_t>(1, std::min<int64_t>(n_chunks, (int64_t)e.sm_count * std::max(per_sm, 1)));
         hs_dedup_kernel<<<dgrid, HS_THREADS, smem, e.stream>>>(bufs[0], bufs[1], T.ctl, nv, ((uint64_t)1 << (8 * n_passes)) - 1, 8 * n_passes, d_ctr);
         TG_CUDA(cudaGetLastError());
         ++launches;
