@@ -229,7 +229,8 @@ __global__ void __launch_bounds__(HS_THREADS) hs_dedup_kernel(const uint64_t* __
 
 bool distinct64_sorted(Engine& e, const Column& c, int64_t n, Distinct64Result& r, int& launches) {
     if (n <= 0 || n >= ((int64_t)1 << 30) || getenv("TG_HASH_NO_SORTED")) return false;
-    const int n_passes = n > ((int64_t)1 << 27) ? 3 : 2;
+    int n_passes = n > ((int64_t)1 << 27) ? 3 : 2;
+    if (const char* f = getenv("TG_HS_PASSES")) n_passes = atoi(f) == 3 ? 3 : n_passes;  // (tests reach the 24-bit bucket mode without 2^27 rows)
     const size_t keys_b = hs_round_up((size_t)n * 8, 256), tmp_b = hs_round_up(rs_temp_bytes(n, n_passes), 256);
     uint8_t* scr = e.scratch(2 * keys_b + tmp_b + 256);
     uint64_t* bufs[2] = {(uint64_t*)scr, (uint64_t*)(scr + keys_b)};

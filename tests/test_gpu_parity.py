@@ -608,7 +608,7 @@ def test_uniqueness_large_path_edge_cases(ctx, shape):
         ctx.deregister_table(name)
 
 
-@pytest.mark.parametrize("path", ["sorted", "partitioned"])
+@pytest.mark.parametrize("path", ["sorted", "sorted24", "partitioned"])
 @pytest.mark.parametrize("shape", ["triples", "warm_key", "hot_key", "f64_mixed"])
 def test_uniqueness_sparse_paths(ctx, shape, path, monkeypatch):
     """sparse keys through BOTH large-column paths: the sorted-bucket path (hashsort.cu: hash, two radix passes over the low
@@ -619,6 +619,10 @@ def test_uniqueness_sparse_paths(ctx, shape, path, monkeypatch):
         monkeypatch.setenv("TG_HASH_NO_SORTED", "1")
     else:
         monkeypatch.delenv("TG_HASH_NO_SORTED", raising=False)
+    if path == "sorted24":  # three radix passes / 2^24 buckets: the mode of columns above 2^27 rows
+        monkeypatch.setenv("TG_HS_PASSES", "3")
+    else:
+        monkeypatch.delenv("TG_HS_PASSES", raising=False)
     n = 2_500_000
     rng = np.random.default_rng(31)
     if shape == "f64_mixed":
