@@ -79,22 +79,34 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
 
 // 8 automaton steps over the bytes of (lo, hi). cls_base = shared address of the class map (256-byte aligned, so
 // "base + byte" is one PRMT); the 8 class lookups do not depend on the state and issue ahead of the chain.
+// DIRECT: the table's rows are indexed by the BYTE itself (small automata: rows of 256 + END entries fit shared memory), so a
+// byte costs ONE shared load instead of two — the kernel is bound by the shared-memory pipe.
+template <bool DIRECT>
 __device__ __forceinline__ uint32_t dfa_step8(uint32_t lo, uint32_t hi, uint32_t E, uint32_t cls_base, uint32_t tab_addr) {
     uint32_t c[8];
-    c[0] = lds_u8(__byte_perm(lo, cls_base, 0x7650));
-    c[1] = lds_u8(__byte_perm(lo, cls_base, 0x7651));
-    c[2] = lds_u8(__byte_perm(lo, cls_base, 0x7652));
-    c[3] = lds_u8(__byte_perm(lo, cls_base, 0x7653));
-    c[4] = lds_u8(__byte_perm(hi, cls_base, 0x7650));
-    c[5] = lds_u8(__byte_perm(hi, cls_base, 0x7651));
-    c[6] = lds_u8(__byte_perm(hi, cls_base, 0x7652));
-    c[7] = lds_u8(__byte_perm(hi, cls_base, 0x7653));
+    if constexpr (DIRECT) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            c[k] = (lo >> (8 * k)) & 255u;
+            c[4 + k] = (hi >> (8 * k)) & 255u;
+        }
+    } else {
+        c[0] = lds_u8(__byte_perm(lo, cls_base, 0x7650));
+        c[1] = lds_u8(__byte_perm(lo, cls_base, 0x7651));
+        c[2] = lds_u8(__byte_perm(lo, cls_base, 0x7652));
+        c[3] = lds_u8(__byte_perm(lo, cls_base, 0x7653));
+        c[4] = lds_u8(__byte_perm(hi, cls_base, 0x7650));
+        c[5] = lds_u8(__byte_perm(hi, cls_base, 0x7651));
+        c[6] = lds_u8(__byte_perm(hi, cls_base, 0x7652));
+        c[7] = lds_u8(__byte_perm(hi, cls_base, 0x7653));
+    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) E = lds_u16(tab_addr + 2u * (2u * E + c[k]));
     return E;
 }
 
 // Runs the product automaton over bytes [p, e) of the warp's stage (shared address stage_addr).
+template <bool DIRECT>
 __device__ __forceinline__ uint32_t run_dfa_smem(uint32_t stage_addr, uint32_t p, uint32_t e, uint32_t E, uint32_t cls_base,
                                                  uint32_t tab_addr, uint32_t term_limit) {
     while (p < e) {
@@ -108,23 +120,27 @@ __device__ __forceinline__ uint32_t run_dfa_smem(uint32_t stage_addr, uint32_t p
             lo |= (uint32_t)m;
             hi |= (uint32_t)(m >> 32);
         }
-        E = dfa_step8(lo, hi, E, cls_base, tab_addr);
+        E = dfa_step8<DIRECT>(lo, hi, E, cls_base, tab_addr);
         p += 8u;
         if (E < term_limit) break;
     }
     return E;
 }
 // Same over global memory, byte loads (only blocks whose bytes exceed the stage: very long strings).
+template <bool DIRECT>
 __device__ __forceinline__ uint32_t run_dfa_gmem(const uint8_t* bytes, uint32_t p, uint32_t e, uint32_t E, uint32_t cls_base,
                                                  uint32_t tab_addr, uint32_t term_limit) {
-    for (; p < e && E >= term_limit; ++p) E = lds_u16(tab_addr + 2u * (2u * E + lds_u8(cls_base + __ldg(bytes + p))));
+    for (; p < e && E >= term_limit; ++p) {
+        const uint32_t b = __ldg(bytes + p);
+        E = lds_u16(tab_addr + 2u * (2u * E + (DIRECT ? b : lds_u8(cls_base + b))));
+    }
     return E;
 }
 
 // R = rows per lane per block: a warp's block is 32*R consecutive rows (lane l owns rows base + j*32 + l, j < R).
 // R = 2 halves the per-block bookkeeping (offset prefetch, TMA issue, mbarrier wait) per string and evens out the
 // string-length imbalance between lanes; R = 1 keeps small inputs spread over all SMs.
-template <int NDFA, int R>
+template <int NDFA, int R, bool DIRECT>
 __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_constant__ StrParams P) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
     // ---- stage class map + transition table ----
@@ -226,14 +242,14 @@ __global__ void __launch_bounds__(STR_MAX_WARPS * 32) dfa_kernel(const __grid_co
                         while (p < e && base[p] == ' ') ++p;
                         while (e > p && base[e - 1] == ' ') --e;
                     }
-                    E = run_dfa_smem(stage_addr + buf * stage_bytes, p, e, P.start, cls_base, tab_addr, term_limit);
+                    E = run_dfa_smem<DIRECT>(stage_addr + buf * stage_bytes, p, e, P.start, cls_base, tab_addr, term_limit);
                 } else {
                     uint32_t p = c0.o[j], e = c0.oe[j];
                     if (P.trim) {
                         while (p < e && P.bytes[p] == ' ') ++p;
                         while (e > p && P.bytes[e - 1] == ' ') --e;
                     }
-                    E = run_dfa_gmem(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
+                    E = run_dfa_gmem<DIRECT>(P.bytes, p, e, P.start, cls_base, tab_addr, term_limit);
                 }
                 const uint32_t m = lds_u16(tab_addr + 2u * (2u * E + n_classes));  // END entry = match mask
 #pragma unroll
@@ -270,9 +286,10 @@ struct Product {
     uint32_t n_classes = 0, n_states = 0, n_term = 0, term_limit = 0, start = 0, tab_bytes = 0;
     std::vector<uint8_t> blob;  // device image, see StrParams::g_blob
     bool ok = false;            // false: exceeded the state / size limits
+    bool direct = false;        // rows indexed by the byte (n_classes == 256): dfa_kernel<.., DIRECT = true>
 };
 
-static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_budget) {
+static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_budget, bool allow_direct) {
     Product pr;
     const size_t nd = dfas.size();
     // joint byte classes
@@ -340,6 +357,40 @@ static Product build_product(const std::vector<const Dfa*>& dfas, size_t table_b
     for (uint32_t s = 0; s < ns; ++s)
         if (!decided(states[s])) enc[s] = (row++) * (stride / 2);
     if ((size_t)ns * stride > max_elems) return pr;
+    // small automata: rows indexed by the byte itself (256 entries + END, padded to 258), when that table still fits the budget
+    // (and the 16-bit row names: E = row * 129)
+    if (allow_direct && (size_t)ns * 258 * 2 + 256 <= table_budget && (size_t)ns * 129 < 65536) {
+        const uint32_t dstride = 258;
+        uint32_t nt = 0;
+        for (uint32_t s = 0; s < ns; ++s)
+            if (decided(states[s])) enc[s] = (nt++) * (dstride / 2);
+        uint32_t drow = nt;
+        for (uint32_t s = 0; s < ns; ++s)
+            if (!decided(states[s])) enc[s] = (drow++) * (dstride / 2);
+        const size_t tb = round_up(256 + (size_t)ns * dstride * 2, 16);
+        pr.n_classes = 256;
+        pr.n_states = ns;
+        pr.n_term = nt;
+        pr.term_limit = nt * (dstride / 2);
+        pr.start = enc[0];
+        pr.tab_bytes = (uint32_t)tb;
+        pr.blob.assign(tb, 0);
+        for (int b = 0; b < 256; ++b) pr.blob[b] = (uint8_t)jclass[b];  // (unused by the direct kernel)
+        uint16_t* dtab = reinterpret_cast<uint16_t*>(pr.blob.data() + 256);
+        for (uint32_t s = 0; s < ns; ++s) {
+            uint8_t m = 0;
+            for (size_t i = 0; i < nd; ++i) {
+                const uint16_t x = states[s][i];
+                if (x == DFA_MATCH || (x != DFA_DEAD && dfas[i]->accept_end[x])) m |= (uint8_t)(1u << i);
+            }
+            uint16_t* r = dtab + 2 * (size_t)enc[s];
+            for (int b = 0; b < 256; ++b) r[b] = (uint16_t)enc[next[(size_t)s * njc + jclass[b]]];
+            r[256] = m;  // END entry (index n_classes)
+        }
+        pr.direct = true;
+        pr.ok = true;
+        return pr;
+    }
     const size_t tab_bytes = round_up(256 + (size_t)ns * stride * 2, 16);
     pr.n_classes = njc;
     pr.n_states = ns;
@@ -369,14 +420,15 @@ static const Product& cached_product(const std::vector<std::pair<std::string, bo
     static std::mutex mu;
     static std::map<std::pair<std::vector<std::pair<std::string, bool>>, size_t>, Product> cache;
     std::lock_guard<std::mutex> g(mu);
-    auto key = std::make_pair(pats, budget);
+    const bool allow_direct = getenv("TG_STR_NO_DIRECT") == nullptr;  // (tests run both table layouts against the oracle)
+    auto key = std::make_pair(pats, budget * 2 + (allow_direct ? 1 : 0));
     auto it = cache.find(key);
     if (it != cache.end()) return it->second;
     std::vector<Dfa> dfas;
     for (auto& p : pats) dfas.push_back(compile_regex(p.first, p.second));
     std::vector<const Dfa*> ptrs;
     for (auto& d : dfas) ptrs.push_back(&d);
-    return cache.emplace(key, build_product(ptrs, budget)).first->second;
+    return cache.emplace(key, build_product(ptrs, budget, allow_direct)).first->second;
 }
 
 static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::vector<int>& ids, const Product& pr, bool trim) {
@@ -420,9 +472,11 @@ static void run_string_pass(Engine& e, Table& t, Plan& p, Column& c, const std::
     P.n_rows = t.n_rows;
     P.n_blocks = (t.n_rows + 32 * R - 1) / (32 * R);
     typedef void (*Kernel)(const StrParams);
-    const Kernel k1 = nd <= 1 ? (Kernel)dfa_kernel<1, 1> : nd <= 2 ? (Kernel)dfa_kernel<2, 1> : nd <= 4 ? (Kernel)dfa_kernel<4, 1> : (Kernel)dfa_kernel<8, 1>;
-    const Kernel k2 = nd <= 1 ? (Kernel)dfa_kernel<1, 2> : nd <= 2 ? (Kernel)dfa_kernel<2, 2> : nd <= 4 ? (Kernel)dfa_kernel<4, 2> : (Kernel)dfa_kernel<8, 2>;
-    const Kernel kernel = R == 2 ? k2 : k1;
+    const Kernel k1 = nd <= 1 ? (Kernel)dfa_kernel<1, 1, false> : nd <= 2 ? (Kernel)dfa_kernel<2, 1, false> : nd <= 4 ? (Kernel)dfa_kernel<4, 1, false> : (Kernel)dfa_kernel<8, 1, false>;
+    const Kernel k2 = nd <= 1 ? (Kernel)dfa_kernel<1, 2, false> : nd <= 2 ? (Kernel)dfa_kernel<2, 2, false> : nd <= 4 ? (Kernel)dfa_kernel<4, 2, false> : (Kernel)dfa_kernel<8, 2, false>;
+    const Kernel d1 = nd <= 1 ? (Kernel)dfa_kernel<1, 1, true> : nd <= 2 ? (Kernel)dfa_kernel<2, 1, true> : nd <= 4 ? (Kernel)dfa_kernel<4, 1, true> : (Kernel)dfa_kernel<8, 1, true>;
+    const Kernel d2 = nd <= 1 ? (Kernel)dfa_kernel<1, 2, true> : nd <= 2 ? (Kernel)dfa_kernel<2, 2, true> : nd <= 4 ? (Kernel)dfa_kernel<4, 2, true> : (Kernel)dfa_kernel<8, 2, true>;
+    const Kernel kernel = pr.direct ? (R == 2 ? d2 : d1) : (R == 2 ? k2 : k1);
     TG_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)STR_SMEM_MAX));
     const int threads = warps * 32;
     int per_sm = 1;

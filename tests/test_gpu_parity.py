@@ -215,7 +215,17 @@ def test_error_paths_become_failed_constraints(ctx):
         ctx.deregister_table("errs")
 
 
-def test_unicode_and_long_strings(ctx):
+@pytest.fixture(params=["direct_tables", "class_tables"])
+def dfa_layout(request, monkeypatch):
+    """the string kernel's two table layouts: rows indexed by the byte (small automata, the default) or by joint byte classes"""
+    if request.param == "class_tables":
+        monkeypatch.setenv("TG_STR_NO_DIRECT", "1")
+    else:
+        monkeypatch.delenv("TG_STR_NO_DIRECT", raising=False)
+    return request.param
+
+
+def test_unicode_and_long_strings(ctx, dfa_layout):
     vals = ["héllo@exämple.com", "日本語", "a" * 5000 + "@x.io", "", None, "x@y.z", "٣٤٥", "ſ", "K", "tab\there", "nl\n"]
     t = pa.table({"s": pa.array(vals, type=pa.string())})
     ctx.register_table("uni", t)
@@ -258,10 +268,10 @@ def _random_strings(n, seed):
 
 
 @pytest.mark.parametrize("n", [1, 255, 256, 257, 50_000])
-def test_string_suite_matches_oracle(ctx, n):
+def test_string_suite_matches_oracle(ctx, n, dfa_layout):
     vals = _random_strings(n, seed=n)
     t = pa.table({"s": pa.array(vals, type=pa.string())})
-    name = f"str_{n}"
+    name = f"str_{n}_{dfa_layout}"
     ctx.register_table(name, t.to_batches(max_chunksize=4099))
     try:
         cb = (T.Check.builder("pii").validates_regex("s", "@", 0.5).validates_email("s", 0.5).contains_ssn("s", 0.1)
