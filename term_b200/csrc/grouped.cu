@@ -382,13 +382,15 @@ __device__ __noinline__ int gd_lookup_slow(const GdDict d, uint32_t s, uint64_t 
 }
 
 // find-or-insert of a packed composite key in a job's shared table [key S][tot S][nul S] (+ the entry's row in global memory)
-__device__ __noinline__ int gd_comp_slow(uint32_t* jb, uint32_t* cta_rows, uint32_t S, uint32_t s, uint32_t key, uint32_t row) {
+__device__ __noinline__ int gd_comp_slow(uint32_t* jb, uint32_t* cta_rows, uint32_t S, uint32_t s, uint32_t key, uint32_t row,
+                                         uint32_t* n_entries = nullptr) {
     for (int probe = 0; probe < GD_PROBE; ++probe, s = (s + 1) & (S - 1)) {
         uint32_t v = *reinterpret_cast<volatile uint32_t*>(&jb[s]);
         if (v == 0xFFFFFFFFu) {
             v = atomicCAS(&jb[s], 0xFFFFFFFFu, key);
             if (v == 0xFFFFFFFFu) {
                 cta_rows[s] = row;  // representative row, the CTA's own slice (read by this CTA after a barrier only)
+                if (n_entries) atomicAdd(n_entries, 1u);
                 return (int)s;
             }
         }
@@ -689,12 +691,18 @@ __global__ void __launch_bounds__(GD_THREADS, 1) group_count_dict_kernel(const _
 // =====================================================================================================================
 constexpr int GT_CONSUMER_WARPS = 24, GT_THREADS = (GT_CONSUMER_WARPS + 1) * 32, GT_ROWS = GT_CONSUMER_WARPS * 32;
 constexpr int GT_MAX_STAGES = 4;
+#ifndef TG_GT_DIRECT_GROUPS
+#define TG_GT_DIRECT_GROUPS 256
+#endif
+constexpr uint32_t GT_DIRECT_GROUPS = TG_GT_DIRECT_GROUPS;  // composite groups in the CTA's table from which the counters are bumped per lane
 
 template <int NC>
 __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const __grid_constant__ GdParams P) {
     extern __shared__ __align__(16) uint8_t gd_smem[];
     __shared__ __align__(8) uint64_t full[GT_MAX_STAGES], empty[GT_MAX_STAGES];
     __shared__ uint32_t s_byte_base[GT_MAX_STAGES][GD_MAX_COLS];  // absolute byte offset staged at bytes_off; 0xFFFFFFFF: not staged
+    __shared__ uint32_t s_comp_entries[GD_MAX_JOBS];              // composite groups this CTA has met so far
+    if (threadIdx.x < GD_MAX_JOBS) s_comp_entries[threadIdx.x] = 0u;
     for (int c = 0; c < NC; ++c) {
         const GdDict d = gd_dict(gd_smem, P.cols[c].smem_off);
         for (int s = threadIdx.x; s < GD_DICT; s += GT_THREADS) d.ent[s].z = 0u;
@@ -921,18 +929,33 @@ __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const _
                         if (hit || v == 0xFFFFFFFFu) break;
                         sq = (sq + 1) & (S - 1);
                     }
-                    cs = hit ? (int)sq : gd_comp_slow(reinterpret_cast<uint32_t*>(gd_smem + P.jobs[j].smem_off), j_rows[j], S, sq, key, row);
+                    cs = hit ? (int)sq : gd_comp_slow(reinterpret_cast<uint32_t*>(gd_smem + P.jobs[j].smem_off), j_rows[j], S, sq, key, row, &s_comp_entries[j]);
                     if (cs < 0) overflow = true;
                     tot_a = j_tab[j] + S * 4u;
                     nul_a = j_tab[j] + S * 8u;
                 }
                 if (rt0 >= rows) cs = -1;  // a clamped row past the end
-                // one shared atomic per distinct counter per warp (measured: plain per-lane shared atomics are 2x slower here)
-                const unsigned peers = __match_any_sync(0xffffffffu, cs);
-                if (cs >= 0) {
-                    if (lane == __ffs(peers) - 1)
-                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tot_a + (uint32_t)cs * 4u), "r"((uint32_t)__popc(peers)) : "memory");
-                    if (!tbit) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(nul_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
+                // Few groups: one shared atomic per distinct counter per warp (plain per-lane shared atomics are 2x slower: the 32
+                // lanes collide on a handful of counters). A composite table that already holds hundreds of groups spreads the lanes
+                // over as many counters: two lanes rarely meet, and MATCH.ANY + the leader election cost more than the collisions.
+                // (the lanes that took the slow path above may not have rejoined the others yet: the decision is read by one lane
+                // after the warp has reconverged, so that every lane takes the same branch — the other one holds a full-mask MATCH)
+                __syncwarp();
+                uint32_t n_met = 0;
+                if (S && lane == 0) n_met = *reinterpret_cast<volatile uint32_t*>(&s_comp_entries[j]);
+                n_met = __shfl_sync(0xffffffffu, n_met, 0);
+                if (n_met >= GT_DIRECT_GROUPS) {
+                    if (cs >= 0) {
+                        asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tot_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
+                        if (!tbit) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(nul_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
+                    }
+                } else {
+                    const unsigned peers = __match_any_sync(0xffffffffu, cs);
+                    if (cs >= 0) {
+                        if (lane == __ffs(peers) - 1)
+                            asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tot_a + (uint32_t)cs * 4u), "r"((uint32_t)__popc(peers)) : "memory");
+                        if (!tbit) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(nul_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
+                    }
                 }
             }
             __syncwarp();

@@ -2,8 +2,8 @@
 # full single-GPU check: every GPU test, then the bench line (with suites) and the reference arm
 TAG=${1:-f}
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -x -q 2>&1 | tail -6
-python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
+timeout 420 python -m pytest tests -m gpu -x -q 2>&1 | tail -6
+timeout 240 python bench.py > gpurun_out/bench_$TAG.json 2> gpurun_out/bench_$TAG.err
 tail -2 gpurun_out/bench_$TAG.err
 python - <<PY
 import json
