@@ -940,11 +940,15 @@ __global__ void __launch_bounds__(GT_THREADS, 1) group_count_tile_kernel(const _
                 // over as many counters: two lanes rarely meet, and MATCH.ANY + the leader election cost more than the collisions.
                 // (the lanes that took the slow path above may not have rejoined the others yet: the decision is read by one lane
                 // after the warp has reconverged, so that every lane takes the same branch — the other one holds a full-mask MATCH)
-                __syncwarp();
-                uint32_t n_met = 0;
-                if (S && lane == 0) n_met = *reinterpret_cast<volatile uint32_t*>(&s_comp_entries[j]);
-                n_met = __shfl_sync(0xffffffffu, n_met, 0);
-                if (n_met >= GT_DIRECT_GROUPS) {
+                // — composite groupings only (S is warp-uniform): a single-column grouping pays nothing for the test)
+                bool per_lane = false;
+                if (S) {
+                    __syncwarp();
+                    uint32_t n_met = 0;
+                    if (lane == 0) n_met = *reinterpret_cast<volatile uint32_t*>(&s_comp_entries[j]);
+                    per_lane = __shfl_sync(0xffffffffu, n_met, 0) >= GT_DIRECT_GROUPS;
+                }
+                if (per_lane) {
                     if (cs >= 0) {
                         asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(tot_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
                         if (!tbit) asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(nul_a + (uint32_t)cs * 4u), "r"(1u) : "memory");
