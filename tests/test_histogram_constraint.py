@@ -128,3 +128,34 @@ def test_gpu_histogram_all_null_column_is_skipped(ctx):
         assert g.status.name == "Skipped" and g.message == "No data to analyze" and g.metric is None
     finally:
         ctx.deregister_table("hist_null")
+
+
+@pytest.mark.parametrize("kind", ["utf8", "int64", "bool"])
+def test_oracle_histogram_matches_arrow_value_counts(kind):
+    """the oracle's buckets against Arrow's value_counts kernel (counts), with the reference query's order (count DESC, value ASC)
+    and ratio (count / non-NULL rows) checked independently"""
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(9)
+    n = 20_000
+    mask = rng.random(n) < 0.1
+    if kind == "utf8":
+        arr = pa.array(np.array(["x", "yy", "", "Zeta", "émile", "zz top"], dtype=object)[rng.zipf(1.5, n) % 6], type=pa.string(), mask=mask)
+    elif kind == "int64":
+        arr = pa.array(rng.integers(-20, 20, n), mask=mask)
+    else:
+        arr = pa.array(rng.random(n) < 0.7, mask=mask)
+    t = pa.table({"c": arr})
+    h = O.histogram_of(t, "c")
+    vc = {}
+    for e in pc.value_counts(arr).to_pylist():
+        if e["values"] is None:
+            continue
+        v = e["values"]
+        key = ("true" if v else "false") if kind == "bool" else str(v)
+        vc[key] = e["counts"]
+    assert {v: c for v, c, _ in h.buckets} == vc
+    assert h.total_count == n and h.null_count == int(mask.sum())
+    keys = [(-c, v.encode()) for v, c, _ in h.buckets]
+    assert keys == sorted(keys)
+    assert all(r == c / (n - h.null_count) for _, c, r in h.buckets)
+    assert abs(sum(r for _, _, r in h.buckets) - 1.0) < 1e-12

@@ -61,3 +61,32 @@ def test_now_and_current_date(monkeypatch):
     for p, k in want.items():
         r = O.custom_sql(t, p)
         assert r.metric == k / 3, (p, r)
+
+
+def test_month_arithmetic_matches_pandas_dateoffset():
+    """calendar-month addition (day of month clamped to the target month's length) cross-checked against pandas' DateOffset on
+    random instants, both directions, across leap years and the epoch"""
+    pd = pytest.importorskip("pandas")
+    rng = np.random.default_rng(3)
+    for _ in range(400):
+        secs = int(rng.integers(-2_000_000_000, 4_000_000_000))
+        months = int(rng.integers(0, 40))
+        sign = 1 if rng.random() < 0.5 else -1
+        ts = pd.Timestamp(secs, unit="s", tz="UTC")
+        want = ts + pd.DateOffset(months=sign * months)
+        got = O._add_interval(secs * 10**9, months, 0, sign)
+        assert got == int(want.value), (ts, months, sign)
+
+
+def test_day_time_arithmetic_matches_arrow_compute():
+    """timestamp +/- a day-time interval against Arrow's own timestamp + duration kernel"""
+    import pyarrow.compute as pc
+    rng = np.random.default_rng(4)
+    base = rng.integers(-10**9, 2 * 10**9, 200)
+    ts = pa.array(base * 10**9, type=pa.timestamp("ns"))
+    for text, ns in (("1 day", 86400 * 10**9), ("90 minutes", 5400 * 10**9), ("2 weeks 3 hours", (14 * 86400 + 10800) * 10**9), ("250 milliseconds", 250 * 10**6)):
+        months, nanos = O.interval_literal(text)
+        assert (months, nanos) == (0, ns)
+        want = pc.add(ts, pa.scalar(ns, type=pa.duration("ns"))).cast(pa.int64()).to_pylist()
+        got = [O._add_interval(int(b) * 10**9, 0, nanos, 1) for b in base]
+        assert got == want
