@@ -1193,6 +1193,57 @@ def unified_data_type(table, column, kind, predicate=None, description="", thres
     return Result(SUCCESS if rate >= 1.0 else FAILURE, rate, f"{pct}% of values satisfy {description}")
 
 
+def temporal_ordering(table, kind, args, allow_nulls=False, tolerance_seconds=0) -> Result:
+    """constraints/temporal_ordering.rs:336-600 on the raw Arrow arrays (no SQL evaluator): total_rows = rows the WHERE clause
+    keeps, violations = those whose comparison is not TRUE (NULL counts as a violation when NULLs are allowed through).
+    kind: 'before_after' (before, after, allow_equal) — compares with `>` when allow_equal, `>=` otherwise, as the reference
+    does —, 'date_range' (column, min, max), 'business_hours' (column, 'HH:MM', 'HH:MM', weekdays_only); timestamps are naive UTC."""
+    import pyarrow as pa
+    units = {"s": 10**9, "ms": 10**6, "us": 10**3, "ns": 1}
+
+    def ns_of(name):
+        a = table.column(name).combine_chunks()
+        u = units[a.type.unit]
+        return [None if v is None else v * u for v in a.cast(pa.int64()).to_pylist()]
+
+    day = 86400 * 10**9
+    if kind == "before_after":
+        b, a, allow_equal = args
+        before, after = ns_of(b), ns_of(a)
+        rows = [(x, y) for x, y in zip(before, after) if allow_nulls or (x is not None and y is not None)]
+        tol = tolerance_seconds * 10**9 if tolerance_seconds > 0 else 0
+        good = sum(1 for x, y in rows if x is not None and y is not None and (y > x + tol if allow_equal else y >= x + tol))
+        what = f"Temporal ordering violation: {{v}} records where '{b}' is not before '{a}'"
+    elif kind == "date_range":
+        c, lo, hi = args
+        vals = ns_of(c)
+        lo_ns = temporal_literal(lo, "n") if lo is not None else None
+        hi_ns = temporal_literal(hi, "n") if hi is not None else None
+        rows = [v for v in vals if allow_nulls or v is not None]
+        good = sum(1 for v in rows if v is not None and (lo_ns is None or v >= lo_ns) and (hi_ns is None or v <= hi_ns))
+        what = f"Date range violation: {{v}} records with '{c}' outside valid range"
+    else:
+        c, start, end, weekdays = args
+        vals = ns_of(c)
+        sec = lambda hhmm: (int(hhmm[:2]) * 3600 + int(hhmm[3:5]) * 60) * 10**9
+        rows = []
+        for v in vals:
+            if v is None:
+                if allow_nulls and not weekdays:  # EXTRACT(DOW FROM NULL) BETWEEN .. is NULL: the WHERE clause drops the row
+                    rows.append(v)
+                continue
+            if weekdays and not 1 <= ((v // day) + 4) % 7 <= 5:   # Sunday = 0; 1970-01-01 was a Thursday
+                continue
+            rows.append(v)
+        good = sum(1 for v in rows if v is not None and sec(start) <= v % day <= sec(end))
+        what = f"Business hours violation: {{v}} records with '{c}' outside business hours"
+    total, violations = len(rows), len(rows) - good
+    if violations == 0:
+        return Result(SUCCESS, 1.0)
+    rate = (total - violations) / total if total > 0 else 1.0
+    return Result(FAILURE, rate, what.format(v=violations) + f" ({rate * 100.0:.2f}% compliance)")
+
+
 class OHistogram:
     """constraints/histogram.rs:25-127 — buckets [(value, count, ratio)] ordered by count DESC, value ASC"""
 

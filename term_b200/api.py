@@ -504,6 +504,7 @@ class Plan:
 
     def execute(self, ctx: SessionContext, table: str = "data"):
         self._ctx_schema = getattr(ctx, "_schemas", {}).get(table)  # (schema-only constraints read it, as the reference reads df.schema())
+        self._ctx = ctx  # (constraints that name their own table — TemporalOrderingConstraint — evaluate against it from _result)
         F.check(F.lib().tg_plan_execute(ctx.handle, self._h, table.encode()))
 
     def execute_partial(self, ctx: SessionContext, table: str = "data"):
@@ -1176,6 +1177,140 @@ class UnifiedDataTypeConstraint(Constraint):  # constraints/datatype.rs:236-445 
                                 f"{_rust_fixed1(rate * 100.0)}% of values satisfy {self.description}", "datatype")
 
 
+class TemporalOrderingConstraint(Constraint):  # constraints/temporal_ordering.rs:56-600
+    """before_after / before_or_equal (with tolerance_seconds), date_range and business_hours (UTC) over the timestamp columns
+    of ONE table, as counts of the reference's own comparisons (K1 predicate units): total_rows = the rows its WHERE clause
+    keeps, violations = those for which the comparison is not TRUE. The reference's quirk is kept: before_or_equal compares
+    with `>` and before_after with `>=` (temporal_ordering.rs:351-367). max_time_gap (LAG window), event sequences and
+    business hours in a named time zone are not built: an error result."""
+    _UNITS = {"s": 1, "ms": 10**3, "us": 10**6, "ns": 10**9}
+
+    def __init__(self, table_name):
+        self.table_name, self.kind, self.args = table_name, "before_after", ("", "", False)
+        self._allow_nulls, self._tolerance = False, 0
+
+    def before_after(self, before, after):
+        self.kind, self.args = "before_after", (before, after, False)
+        return self
+
+    def before_or_equal(self, before, after):
+        self.kind, self.args = "before_after", (before, after, True)
+        return self
+
+    def business_hours(self, column, start, end):
+        self.kind, self.args = "business_hours", [column, start, end, False, None]
+        return self
+
+    def weekdays_only(self, flag):
+        if self.kind == "business_hours":
+            self.args[3] = bool(flag)
+        return self
+
+    def with_timezone(self, tz):
+        if self.kind == "business_hours":
+            self.args[4] = tz
+        return self
+
+    def date_range(self, column, min_date=None, max_date=None):
+        self.kind, self.args = "date_range", (column, min_date, max_date)
+        return self
+
+    def max_time_gap(self, column, max_gap_seconds):
+        self.kind, self.args = "max_time_gap", (column, max_gap_seconds)
+        return self
+
+    def allow_nulls(self, allow):
+        self._allow_nulls = bool(allow)
+        return self
+
+    def tolerance_seconds(self, seconds):
+        self._tolerance = int(seconds)
+        return self
+
+    @staticmethod
+    def _q(c): return '"' + c.replace('"', '""') + '"'
+
+    def _unit(self, ctx, column):
+        sch = getattr(ctx, "_schemas", {}).get(self.table_name)
+        if sch is None or column not in sch.names or not pa.types.is_timestamp(sch.field(column).type):
+            raise ValueError(f"'{column}' of table '{self.table_name}' is not a timestamp column known to this context")
+        return self._UNITS[sch.field(column).type.unit]
+
+    def _queries(self, ctx):
+        """(WHERE clause or None, comparison) — both in the declared predicate grammar"""
+        for name in [self.table_name] + (list(self.args[:2]) if self.kind == "before_after" else [self.args[0]]):
+            F.check(F.lib().tg_validate_identifier(name.encode()))
+        if self.kind == "before_after":
+            b, a, allow_equal = self.args
+            qb, qa = self._q(b), self._q(a)
+            op = ">" if allow_equal else ">="   # (sic: temporal_ordering.rs:351-367)
+            rhs = qb
+            if self._tolerance > 0:
+                ub, ua = self._unit(ctx, b), self._unit(ctx, a)
+                if ub != ua:
+                    raise ValueError("tolerance_seconds needs both columns in the same timestamp unit")
+                rhs = f"{qb} + {self._tolerance * ub}"
+            where = None if self._allow_nulls else f"{qb} IS NOT NULL AND {qa} IS NOT NULL"
+            return where, f"{qa} {op} {rhs}"
+        if self.kind == "date_range":
+            c, lo, hi = self.args
+            qc = self._q(c)
+            conds = ([f"{qc} >= TIMESTAMP '{lo}'"] if lo is not None else []) + ([f"{qc} <= TIMESTAMP '{hi}'"] if hi is not None else [])
+            if not conds:
+                raise ValueError("DateRange validation requires at least min_date or max_date")
+            return (None if self._allow_nulls else f"{qc} IS NOT NULL"), " AND ".join(conds)
+        if self.kind == "business_hours":
+            c, start, end, weekdays, tz = self.args
+            if tz is not None:
+                raise ValueError("business hours in a named time zone are not supported (UTC only)")
+            u = self._unit(ctx, c)
+            qc, day = self._q(c), 86400 * u
+            tod = f"((({qc} % {day}) + {day}) % {day})"   # CAST(ts AS TIME) of a naive timestamp, in the column's unit
+            sec = lambda hhmm: (int(hhmm.split(":")[0]) * 3600 + int(hhmm.split(":")[1]) * 60) * u
+            check = f"{tod} BETWEEN {sec(start)} AND {sec(end)}"
+            clauses = []
+            if weekdays:  # EXTRACT(DOW ..): Sunday = 0; 1970-01-01 was a Thursday
+                clauses.append(f"((((({qc} - {tod}) / {day}) % 7) + 11) % 7) BETWEEN 1 AND 5")
+            if not self._allow_nulls:
+                clauses.append(f"{qc} IS NOT NULL")
+            return (" AND ".join(clauses) if clauses else None), check
+        raise ValueError(f"temporal validation '{self.kind}' is not supported (window functions)")
+
+    def _add_to(self, plan):
+        return SizeConstraint(Assertion.GreaterThanOrEqual(0.0))._add_to(plan)  # placeholder slot: the constraint names its own table
+
+    def evaluate(self, ctx, table=None):
+        try:
+            where, cmp_ = self._queries(ctx)
+        except (ValueError, F.TermGpuError) as ex:
+            return ConstraintResult(ConstraintStatus.Failure, None, f"Error evaluating constraint: {ex}", "temporal_ordering")
+        plan = Plan()
+        s_ok = ComplianceAnalyzer("ok", f"({where}) AND ({cmp_})" if where else cmp_)._add_to(plan)
+        s_tot = ComplianceAnalyzer("total", where)._add_to(plan) if where else None
+        plan.execute(ctx, self.table_name)
+        ok = plan.analyzer_result(s_ok)
+        tot = plan.analyzer_result(s_tot) if s_tot is not None else None
+        for a in (ok, tot):
+            if a is not None and a.error == 2:
+                return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: " + (a.message or ""), "temporal_ordering")
+        total_rows = tot.u[0] if tot is not None else ok.u[1]
+        violations = total_rows - ok.u[0]
+        if violations == 0:
+            return ConstraintResult(ConstraintStatus.Success, 1.0, None, "temporal_ordering")
+        rate = (total_rows - violations) / total_rows if total_rows > 0 else 1.0
+        pct = f"{rate * 100.0:.2f}"
+        if self.kind == "before_after":
+            msg = f"Temporal ordering violation: {violations} records where '{self.args[0]}' is not before '{self.args[1]}' ({pct}% compliance)"
+        elif self.kind == "business_hours":
+            msg = f"Business hours violation: {violations} records with '{self.args[0]}' outside business hours ({pct}% compliance)"
+        else:
+            msg = f"Date range violation: {violations} records with '{self.args[0]}' outside valid range ({pct}% compliance)"
+        return ConstraintResult(ConstraintStatus.Failure, rate, msg, "temporal_ordering")
+
+    def _result(self, plan, slot):
+        return self.evaluate(plan._ctx)
+
+
 def _rust_num(x) -> str:
     """`{}` of an f64 (Range { min, max } are f64 in the reference): integral values print without a fraction"""
     x = float(x)
@@ -1237,6 +1372,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
     def has_consistent_data_type(self, column, threshold): return self.constraint(UnifiedDataTypeConstraint.type_consistency(column, threshold))  # core/check.rs:651-657
+    def temporal_ordering(self, table_name): return self.constraint(TemporalOrderingConstraint(table_name))  # core/check.rs:2174-2179
     # core/check.rs has_histogram / has_histogram_with_description
     def has_histogram(self, column, assertion): return self.constraint(HistogramConstraint(column, assertion))
     def has_histogram_with_description(self, column, assertion, description): return self.constraint(HistogramConstraint(column, assertion, description))
