@@ -1244,6 +1244,25 @@ def temporal_ordering(table, kind, args, allow_nulls=False, tolerance_seconds=0)
     return Result(FAILURE, rate, what.format(v=violations) + f" ({rate * 100.0:.2f}% compliance)")
 
 
+def cross_table_sum(left_table, left_col, right_table, right_col, left_name, right_name, tolerance=0.0, max_violations=100) -> Result:
+    """constraints/cross_table_sum.rs:196-215, 560-628 (no grouping): COALESCE(SUM(l), 0.0) vs COALESCE(SUM(r), 0.0); Success with
+    the absolute difference as the metric when it is within the tolerance. Sums with math.fsum (exactly rounded)."""
+    def total(table, col):
+        c = table_cols(table)[col]
+        vals = [float(v) for v, ok in zip(c.values, c.valid) if ok]
+        return math.fsum(vals) if vals else 0.0
+    left, right = total(left_table, left_col), total(right_table, right_col)
+    diff = abs(left - right)
+    if not diff > tolerance:
+        return Result(SUCCESS, diff)
+    tol = f" (tolerance: {tolerance:.4f})" if tolerance > 0.0 else " (exact match required)"
+    if max_violations > 0:
+        ex = f"Group 'ALL': {left_name} = {left:.4f}, {right_name} = {right:.4f} (diff: {diff:.4f})"
+        return Result(FAILURE, diff, f"Cross-table sum mismatch: 1/1 overall totals failed validation{tol}. Examples: [{ex}]")
+    return Result(FAILURE, diff, f"Cross-table sum mismatch: 1/1 overall totals failed validation{tol}, total sums: {rust_f64(left)} vs {rust_f64(right)} "
+                                 f"(max diff: {diff:.4f})")
+
+
 class OHistogram:
     """constraints/histogram.rs:25-127 — buckets [(value, count, ratio)] ordered by count DESC, value ASC"""
 

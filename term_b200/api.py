@@ -1311,6 +1311,76 @@ class TemporalOrderingConstraint(Constraint):  # constraints/temporal_ordering.r
         return self.evaluate(plan._ctx)
 
 
+class CrossTableSumConstraint(Constraint):  # constraints/cross_table_sum.rs:60-630
+    """SUM(left_table.col) against SUM(right_table.col) within a tolerance: two K1 sum aggregates, one plan per table, compared on the
+    host like the reference's scalar query (:200-215). The grouped form (GROUP BY + FULL OUTER JOIN of per-group sums) is not
+    built: an error result. The failure message carries the reference's 'ALL' example row (:296-312, :452-460)."""
+
+    def __init__(self, left_column, right_column):
+        self.left_column, self.right_column = left_column, right_column
+        self.group_by_columns, self._tolerance, self._max_violations = [], 0.0, 100
+
+    def group_by(self, columns):
+        self.group_by_columns = list(columns)
+        return self
+
+    def tolerance(self, t):
+        self._tolerance = abs(float(t))
+        return self
+
+    def max_violations_reported(self, n):
+        self._max_violations = int(n)
+        return self
+
+    @staticmethod
+    def parse_qualified_column(q):
+        parts = q.split(".")
+        if len(parts) != 2:
+            raise ValueError(f"Column must be qualified (table.column): '{q}'")
+        for part in parts:
+            F.check(F.lib().tg_validate_identifier(part.encode()))
+        return parts[0], parts[1]
+
+    @staticmethod
+    def _sum(ctx, table, column):
+        plan = Plan()
+        slot = StatisticalConstraint(column, StatisticType.Sum, Assertion.GreaterThanOrEqual(float("-inf")))._add_to(plan)
+        plan.execute(ctx, table)
+        r = plan.result(slot)
+        if r.error_code:
+            raise ValueError(r.message or "sum failed")
+        return 0.0 if r.metric is None else float(r.metric)   # COALESCE(SUM(..), 0.0): no non-NULL row
+
+    def _add_to(self, plan):
+        return SizeConstraint(Assertion.GreaterThanOrEqual(0.0))._add_to(plan)  # placeholder slot: the constraint names its own tables
+
+    def evaluate(self, ctx, table=None):
+        try:
+            lt, lc = self.parse_qualified_column(self.left_column)
+            rt, rc = self.parse_qualified_column(self.right_column)
+            for g in self.group_by_columns:
+                F.check(F.lib().tg_validate_identifier(g.encode()))
+            if self.group_by_columns:
+                raise ValueError("grouped cross-table sums are not supported (per-group sums + FULL OUTER JOIN)")
+            left, right = self._sum(ctx, lt, lc), self._sum(ctx, rt, rc)
+        except (ValueError, F.TermGpuError) as ex:
+            return ConstraintResult(ConstraintStatus.Failure, None, f"Error evaluating constraint: {ex}", "cross_table_sum")
+        diff = abs(left - right)
+        if not diff > self._tolerance:
+            return ConstraintResult(ConstraintStatus.Success, diff, None, "cross_table_sum")
+        tol = f" (tolerance: {self._tolerance:.4f})" if self._tolerance > 0.0 else " (exact match required)"
+        if self._max_violations > 0:
+            ex = f"Group 'ALL': {self.left_column} = {left:.4f}, {self.right_column} = {right:.4f} (diff: {diff:.4f})"
+            msg = f"Cross-table sum mismatch: 1/1 overall totals failed validation{tol}. Examples: [{ex}]"
+        else:
+            msg = (f"Cross-table sum mismatch: 1/1 overall totals failed validation{tol}, total sums: {_rust_num(left)} vs {_rust_num(right)} "
+                   f"(max diff: {diff:.4f})")
+        return ConstraintResult(ConstraintStatus.Failure, diff, msg, "cross_table_sum")
+
+    def _result(self, plan, slot):
+        return self.evaluate(plan._ctx)
+
+
 def _rust_num(x) -> str:
     """`{}` of an f64 (Range { min, max } are f64 in the reference): integral values print without a fraction"""
     x = float(x)
@@ -1372,6 +1442,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def has_correlation(self, c1, c2, assertion): return self.constraint(CorrelationConstraint.pearson(c1, c2, assertion))
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
     def has_consistent_data_type(self, column, threshold): return self.constraint(UnifiedDataTypeConstraint.type_consistency(column, threshold))  # core/check.rs:651-657
+    def cross_table_sum(self, left_column, right_column): return self.constraint(CrossTableSumConstraint(left_column, right_column))  # core/check.rs
     def temporal_ordering(self, table_name): return self.constraint(TemporalOrderingConstraint(table_name))  # core/check.rs:2174-2179
     # core/check.rs has_histogram / has_histogram_with_description
     def has_histogram(self, column, assertion): return self.constraint(HistogramConstraint(column, assertion))
