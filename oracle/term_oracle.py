@@ -1263,6 +1263,44 @@ def cross_table_sum(left_table, left_col, right_table, right_col, left_name, rig
                                  f"(max diff: {diff:.4f})")
 
 
+def join_coverage(left, lk, right, rk, left_name, right_name, expected=1.0, coverage="Left", distinct_only=False, max_examples=100) -> Result:
+    """constraints/join_coverage.rs:186-426 with the joins spelled out (any key multiplicities): LEFT JOIN rows = every left row once
+    per matching right row (once when there is none); matched = those with a partner. distinct_only divides the matched ROWS by
+    COUNT(DISTINCT left key), as the reference's query does. NULL keys never match."""
+    from collections import Counter
+
+    def keys(table, col):
+        c = table_cols(table)[col]
+        return [v if ok else None for v, ok in zip(c.values, c.valid)]
+
+    L, R = keys(left, lk), keys(right, rk)
+    cl, cr = Counter(k for k in L if k is not None), Counter(k for k in R if k is not None)
+
+    def one_way(rows, other):  # (join rows, matched join rows) of `rows` OUTER JOIN other
+        total = sum(max(other.get(k, 0), 1) if k is not None else 1 for k in rows)
+        matched = sum(other.get(k, 0) for k in rows if k is not None)
+        return total, matched
+
+    div = lambda a, b: a / b if b else float("nan")
+    tl, ml = one_way(L, cr)
+    tr, mr = one_way(R, cl)
+    if coverage == "Left":
+        rate = div(ml, len(cl) if distinct_only else tl)
+    elif coverage == "Right":
+        rate = div(mr, tr)
+    else:
+        a, b = div(ml, tl), div(mr, tr)
+        rate = float("nan") if (a != a or b != b) else min(a, b)
+    if rate >= expected:
+        return Result(SUCCESS, rate)
+    unmatched = {k for k in L if k is None or k not in cr}
+    shown = min(len(unmatched), max_examples)
+    ex = f" ({shown} unmatched examples found)" if max_examples > 0 and shown > 0 else ""
+    arrow = {"Left": "->", "Right": "<-", "Bidirectional": "<->"}[coverage]
+    pct = lambda x: "NaN" if x != x else f"{x * 100.0:.2f}"
+    return Result(FAILURE, rate, f"Join coverage constraint failed: {left_name} {arrow} {right_name} coverage is {pct(rate)}% (expected: {pct(expected)}%){ex}")
+
+
 class OHistogram:
     """constraints/histogram.rs:25-127 — buckets [(value, count, ratio)] ordered by count DESC, value ASC"""
 

@@ -1381,6 +1381,124 @@ class CrossTableSumConstraint(Constraint):  # constraints/cross_table_sum.rs:60-
         return self.evaluate(plan._ctx)
 
 
+class CoverageType(enum.Enum):  # constraints/join_coverage.rs:72-79
+    LeftCoverage = 0
+    RightCoverage = 1
+    BidirectionalCoverage = 2
+
+
+class JoinCoverageConstraint(Constraint):  # constraints/join_coverage.rs:61-426
+    """Share of the rows of one table whose join key finds a partner in the other: the foreign-key kernels (K3 build / probe) give
+    the unmatched rows, the uniqueness kernels verify the precondition under which a LEFT / RIGHT JOIN's row count is the
+    table's own — the probed side's keys must be unique (a duplicated key multiplies the join's rows: that needs a counting
+    hash join, which is not built: an error result, like composite keys). distinct_only keeps the reference's arithmetic
+    (matched ROWS over COUNT(DISTINCT left key)). The count in "(N unmatched examples found)" is the reference's first result
+    batch of a DISTINCT .. LIMIT query: here min(distinct unmatched keys, max_examples_reported) — unpinned (it depends on how
+    DataFusion partitions the aggregate's output)."""
+
+    def __init__(self, left_table, right_table):
+        self.left_table, self.right_table, self.join_keys = left_table, right_table, []
+        self.expected_match_rate, self._coverage, self._distinct_only, self._max_examples = 1.0, CoverageType.LeftCoverage, False, 100
+
+    def on(self, left_column, right_column):
+        self.join_keys = [(left_column, right_column)]
+        return self
+
+    def on_multiple(self, keys):
+        self.join_keys = [(l, r) for l, r in keys]
+        return self
+
+    def expect_match_rate(self, rate):
+        self.expected_match_rate = min(max(float(rate), 0.0), 1.0)
+        return self
+
+    def coverage_type(self, t):
+        self._coverage = t
+        return self
+
+    def distinct_only(self, flag):
+        self._distinct_only = bool(flag)
+        return self
+
+    def max_examples_reported(self, n):
+        self._max_examples = int(n)
+        return self
+
+    def _add_to(self, plan):
+        return SizeConstraint(Assertion.GreaterThanOrEqual(0.0))._add_to(plan)  # placeholder slot: the constraint names its own tables
+
+    @staticmethod
+    def _side(ctx, table, key):
+        """(rows, non-NULL keys, distinct keys) of one side"""
+        d = DistinctnessAnalyzer(key).compute(ctx, table)
+        if d.error == 2:
+            raise ValueError(d.message or "join key not readable")
+        c = CompletenessAnalyzer(key).compute(ctx, table)
+        return c.u[0], c.u[1], d.u[1]
+
+    @staticmethod
+    def _unmatched(ctx, child_table, child_key, parent_table, parent_key):
+        """(rows of `child` whose non-NULL key has no partner in `parent`, distinct such keys)"""
+        r = ForeignKeyConstraint(f"{child_table}.{child_key}", f"{parent_table}.{parent_key}").allow_nulls(True).evaluate(ctx)
+        if r.error_code:
+            raise ValueError(r.message or "foreign key job failed")
+        if r.status is ConstraintStatus.Success:
+            return 0, 0
+        uniq = int(r.message.split("unique: ")[1].split(")")[0])
+        return int(r.metric), uniq
+
+    def evaluate(self, ctx, table=None):
+        try:
+            for name in [self.left_table, self.right_table] + [c for pair in self.join_keys for c in pair]:
+                F.check(F.lib().tg_validate_identifier(name.encode()))
+            if not self.join_keys:
+                raise ValueError("No join keys specified. Use .on() or .on_multiple() to set join keys")
+            if len(self.join_keys) > 1:
+                raise ValueError("composite join keys are not supported")
+            lk, rk = self.join_keys[0]
+            n_l, nn_l, d_l = self._side(ctx, self.left_table, lk)
+            n_r, nn_r, d_r = self._side(ctx, self.right_table, rk)
+            need_right_unique = self._coverage in (CoverageType.LeftCoverage, CoverageType.BidirectionalCoverage)
+            need_left_unique = self._coverage in (CoverageType.RightCoverage, CoverageType.BidirectionalCoverage)
+            if (need_right_unique and d_r != nn_r) or (need_left_unique and d_l != nn_l):
+                raise ValueError("join coverage over a duplicated key on the probed side is not supported (the join multiplies its rows)")
+            if self._distinct_only and self._coverage is not CoverageType.LeftCoverage:
+                raise ValueError("distinct_only is supported for LeftCoverage only")
+            div = lambda a, b: a / b if b else float("nan")
+            examples = 0
+            if self._coverage is CoverageType.LeftCoverage:
+                orphans, uniq = self._unmatched(ctx, self.left_table, lk, self.right_table, rk)
+                matched = nn_l - orphans
+                rate = div(matched, d_l if self._distinct_only else n_l)
+                examples = uniq + (1 if n_l > nn_l else 0)
+            elif self._coverage is CoverageType.RightCoverage:
+                orphans, _ = self._unmatched(ctx, self.right_table, rk, self.left_table, lk)
+                rate = div(nn_r - orphans, n_r)
+            else:
+                lo, uniq = self._unmatched(ctx, self.left_table, lk, self.right_table, rk)
+                ro, _ = self._unmatched(ctx, self.right_table, rk, self.left_table, lk)
+                a, b = div(nn_l - lo, n_l), div(nn_r - ro, n_r)
+                rate = float("nan") if (a != a or b != b) else min(a, b)
+                examples = uniq + (1 if n_l > nn_l else 0)
+            if self._coverage is CoverageType.RightCoverage:  # (the unmatched query is always the LEFT JOIN one: join_coverage.rs:288-324)
+                _, uniq = self._unmatched(ctx, self.left_table, lk, self.right_table, rk)
+                examples = uniq + (1 if n_l > nn_l else 0)
+        except (ValueError, F.TermGpuError) as ex:
+            return ConstraintResult(ConstraintStatus.Failure, None, f"Error evaluating constraint: {ex}", "join_coverage")
+        if rate >= self.expected_match_rate:
+            return ConstraintResult(ConstraintStatus.Success, rate, None, "join_coverage")
+        arrow = {CoverageType.LeftCoverage: "->", CoverageType.RightCoverage: "<-", CoverageType.BidirectionalCoverage: "<->"}[self._coverage]
+        shown = min(examples, self._max_examples)
+        ex_msg = f" ({shown} unmatched examples found)" if self._max_examples > 0 and shown > 0 else ""
+        pct = lambda x: "NaN" if x != x else f"{x * 100.0:.2f}"
+        return ConstraintResult(ConstraintStatus.Failure, rate,
+                                f"Join coverage constraint failed: {self.left_table} {arrow} {self.right_table} coverage is {pct(rate)}% "
+                                f"(expected: {pct(self.expected_match_rate)}%){ex_msg}", "join_coverage")
+
+    def _result(self, plan, slot):
+        return self.evaluate(plan._ctx)
+
+
 def _rust_num(x) -> str:
     """`{}` of an f64 (Range { min, max } are f64 in the reference): integral values print without a fraction"""
     x = float(x)
@@ -1443,6 +1561,7 @@ class CheckBuilder:  # core/check.rs (builder methods listed in SURVEY §0.1)
     def satisfies(self, expression, hint=None): return self.constraint(CustomSqlConstraint(expression, hint))
     def has_consistent_data_type(self, column, threshold): return self.constraint(UnifiedDataTypeConstraint.type_consistency(column, threshold))  # core/check.rs:651-657
     def cross_table_sum(self, left_column, right_column): return self.constraint(CrossTableSumConstraint(left_column, right_column))  # core/check.rs
+    def join_coverage(self, left_table, right_table): return self.constraint(JoinCoverageConstraint(left_table, right_table))  # core/check.rs
     def temporal_ordering(self, table_name): return self.constraint(TemporalOrderingConstraint(table_name))  # core/check.rs:2174-2179
     # core/check.rs has_histogram / has_histogram_with_description
     def has_histogram(self, column, assertion): return self.constraint(HistogramConstraint(column, assertion))

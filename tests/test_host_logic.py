@@ -311,7 +311,7 @@ def test_numa_binding_is_a_no_op_without_a_gpu():
 
 def test_check_builder_mirrors_reference_builder_methods(built_lib):
     """core/check.rs builder methods on the hot path and has_histogram (closure over the GPU's value frequencies); the
-    join_coverage and the grouped cross_table_sum are out of scope."""
+    the grouped cross_table_sum and join_coverage over duplicated keys are error results."""
     names = ("level description constraint with_constraint constraints build has_size completeness any_complete at_least_complete "
              "exactly_complete validates_uniqueness validates_distinctness validates_unique_value_ratio validates_primary_key "
              "validates_uniqueness_with_nulls uniqueness validates_regex validates_email validates_url validates_credit_card "
@@ -320,7 +320,7 @@ def test_check_builder_mirrors_reference_builder_methods(built_lib):
              "validates_regex_with_options has_format statistic has_min has_max has_mean has_sum has_standard_deviation has_variance "
              "has_correlation has_mutual_information satisfies has_column_count has_approx_count_distinct has_approx_quantile "
              "has_min_length has_max_length has_length_between has_exact_length is_not_empty length foreign_key contains_ssn "
-             "has_histogram has_histogram_with_description has_consistent_data_type temporal_ordering cross_table_sum").split()
+             "has_histogram has_histogram_with_description has_consistent_data_type temporal_ordering cross_table_sum join_coverage").split()
     missing = [n for n in names if not hasattr(T.CheckBuilder, n)]
     assert not missing, missing
     A = T.Assertion
