@@ -508,6 +508,8 @@ class Plan:
         F.check(F.lib().tg_plan_execute(ctx.handle, self._h, table.encode()))
 
     def execute_partial(self, ctx: SessionContext, table: str = "data"):
+        self._ctx_schema = getattr(ctx, "_schemas", {}).get(table)
+        self._ctx = ctx
         F.check(F.lib().tg_plan_execute_partial(ctx.handle, self._h, table.encode()))
 
     def partial_export(self) -> bytes:
@@ -1308,7 +1310,10 @@ class TemporalOrderingConstraint(Constraint):  # constraints/temporal_ordering.r
         return ConstraintResult(ConstraintStatus.Failure, rate, msg, "temporal_ordering")
 
     def _result(self, plan, slot):
-        return self.evaluate(plan._ctx)
+        ctx = getattr(plan, "_ctx", None)
+        if ctx is None:  # (a plan driven through execute_partial / the distributed path by hand: evaluate the constraint directly)
+            return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: this constraint names its own tables; call evaluate(ctx)", self.__class__.__name__)
+        return self.evaluate(ctx)
 
 
 class CrossTableSumConstraint(Constraint):  # constraints/cross_table_sum.rs:60-630
@@ -1378,7 +1383,10 @@ class CrossTableSumConstraint(Constraint):  # constraints/cross_table_sum.rs:60-
         return ConstraintResult(ConstraintStatus.Failure, diff, msg, "cross_table_sum")
 
     def _result(self, plan, slot):
-        return self.evaluate(plan._ctx)
+        ctx = getattr(plan, "_ctx", None)
+        if ctx is None:  # (a plan driven through execute_partial / the distributed path by hand: evaluate the constraint directly)
+            return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: this constraint names its own tables; call evaluate(ctx)", self.__class__.__name__)
+        return self.evaluate(ctx)
 
 
 class CoverageType(enum.Enum):  # constraints/join_coverage.rs:72-79
@@ -1496,7 +1504,10 @@ class JoinCoverageConstraint(Constraint):  # constraints/join_coverage.rs:61-426
                                 f"(expected: {pct(self.expected_match_rate)}%){ex_msg}", "join_coverage")
 
     def _result(self, plan, slot):
-        return self.evaluate(plan._ctx)
+        ctx = getattr(plan, "_ctx", None)
+        if ctx is None:  # (a plan driven through execute_partial / the distributed path by hand: evaluate the constraint directly)
+            return ConstraintResult(ConstraintStatus.Failure, None, "Error evaluating constraint: this constraint names its own tables; call evaluate(ctx)", self.__class__.__name__)
+        return self.evaluate(ctx)
 
 
 def _rust_num(x) -> str:
