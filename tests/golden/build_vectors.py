@@ -323,6 +323,14 @@ case("size_failure_message", "constraints/size.rs:101-116", tbl(id=col("i64", [1
      {"kind": "size", "assertion": ["GreaterThan", 10.0]}, status="failure", metric=3.0,
      message_contains=["Size 3 does not greater than 10"])
 
+# the constraint's own tests: value = 0 .. n-1 (constraints/size.rs:147-167)
+for nm, src, n, assertion, status in (("size_rs_equals", "constraints/size.rs:169-179", 100, ["Equals", 100.0], "success"),
+                                      ("size_rs_greater_than", "constraints/size.rs:181-191", 50, ["GreaterThan", 25.0], "success"),
+                                      ("size_rs_between", "constraints/size.rs:193-203", 75, ["Between", 50.0, 100.0], "success"),
+                                      ("size_rs_failure", "constraints/size.rs:205-215", 10, ["GreaterThan", 50.0], "failure"),
+                                      ("size_rs_empty", "constraints/size.rs:217-227", 0, ["Equals", 0.0], "success")):
+    case(nm, src, tbl(value=col("i64", list(range(n)))), {"kind": "size", "assertion": assertion}, status=status, metric=float(n))
+
 # ------------------------------------------------------------------ analyzers ----
 an_tbl = tbl(id=col("i64", [1, 2, 3, 4, None]), value=col("f64", [10.0, 20.0, None, 30.0, 40.0]),
              name=col("str", ["a", "b", "a", None, "c"]))
