@@ -580,7 +580,7 @@ def suite_c4(ctx, dev, world, rank, peak_gbs, steps):
                    .check(T.Check.builder("u").validates_uniqueness(["k"], 0.9).build()).build().build_plan())
     tm = _timed(plan, ctx, "keys", steps, world, dev, "hash_ms")
     out.append(_line("c4_is_unique_sparse", "C4 with sparse keys: validates_uniqueness on 125 M i64 ids per GPU spread over 64 bits (1e-6 duplicates, 1% null): "
-                                            "radix-partitioned L2-resident hash tables; N > 1: hash shuffle over NVLink",
+                                            "hashes radix-sorted into 2^16 buckets + shared-memory de-duplication (hashsort.cu); N > 1: hash shuffle over NVLink",
                      n, 8 * n + (n + 7) // 8, world, peak_gbs, tm, {"metric": plan.result(slots[0][2]).metric}))
     ctx.deregister_table("keys")
     del keys, v
