@@ -1530,7 +1530,9 @@ static void run_grouped_batch(Engine& e, Table& t, Plan& p, const GrpBatch& B) {
                 if (i) key += '\x1f';
                 const size_t en = (size_t)g * nc + i;
                 if (!f.meta[en * 3]) {
-                    key += "NULL";
+                    // (a value histogram must tell the NULL group from the string 'NULL' when shard states are merged by key:
+                    // its NULL key starts with a byte no valid UTF-8 value holds)
+                    key += (a.flags & 2) ? "\xFFNULL" : "NULL";
                     continue;
                 }
                 const unsigned long long x = f.meta[en * 3 + 1];

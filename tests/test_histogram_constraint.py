@@ -80,7 +80,7 @@ def test_gpu_histogram_matches_oracle_on_random_columns(ctx, kind):
     n = 50_000
     mask = rng.random(n) < 0.07
     if kind == "utf8":
-        vals = np.array(["alpha", "beta", "gamma", "", "δέλτα", "a much longer category name than eight bytes"], dtype=object)[rng.integers(0, 6, n)]
+        vals = np.array(["alpha", "beta", "gamma", "", "δέλτα", "a much longer category name than eight bytes", "NULL"], dtype=object)[rng.integers(0, 7, n)]
         arr = pa.array(vals, type=pa.string(), mask=mask)
     elif kind == "utf8_many":
         vals = np.array([f"k{int(x):05d}" for x in rng.zipf(1.3, n) % 3000], dtype=object)
@@ -159,3 +159,44 @@ def test_oracle_histogram_matches_arrow_value_counts(kind):
     assert keys == sorted(keys)
     assert all(r == c / (n - h.null_count) for _, c, r in h.buckets)
     assert abs(sum(r for _, _, r in h.buckets) - 1.0) < 1e-12
+
+
+def _grouped_partial(plan, values):
+    """partial blob of one row shard of a value-histogram plan, built on the CPU: the grouped state is [u64 n] then per group
+    {u32 key_len, key, u64 rows, u64 non-NULL rows} (term_b200/csrc/plan.cpp: grouped blob; the NULL group has 0 non-NULL rows
+    and, in a value histogram, a key that no string value can equal — the column below holds the string 'NULL' too)"""
+    import struct
+    from collections import Counter
+    (kind, _key), = plan.aggregates()
+    counts = Counter(b"\xffNULL" if v is None else str(v).encode() for v in values)  # the NULL group's key is not valid UTF-8
+    blob = struct.pack("<Q", len(counts))
+    for kb, c in counts.items():
+        blob += struct.pack("<I", len(kb)) + kb + struct.pack("<QQ", c, 0 if kb == b"\xffNULL" else c)
+    pad = (-len(blob)) % 8
+    rec = struct.pack("<QQ", kind, 0) + struct.pack("<8Q", len(values), 0, 0, 0, 0, 0, 0, 0) + struct.pack("<8d", *([0.0] * 8))
+    rec += struct.pack("<Q", len(blob)) + blob + bytes(pad) + struct.pack("<Q", 0)
+    return struct.pack("<Q", 1) + rec
+
+
+@pytest.mark.parametrize("n_shards", [1, 3])
+def test_value_histogram_finalize_and_shard_merge_on_cpu(built_lib, n_shards):
+    """the host half of the histogram constraint without a GPU: shard states (here built by hand in the documented layout) merge
+    through tg_plan_partial_merge, finalize orders the buckets (count DESC, value ASC), computes the entropy and leaves the
+    assertion to the host closure — equal to the oracle on the whole column"""
+    import term_b200.api as T
+    rng = np.random.default_rng(2)
+    vals = [None if rng.random() < 0.1 else ["b", "a", "cc", "", "NULL"][int(rng.integers(0, 5))] for _ in range(3000)]
+    t = pa.table({"c": pa.array(vals, type=pa.string())})
+    cons = T.HistogramConstraint.new_with_description("c", lambda h: h.bucket_count() == 4, "four categories")
+    plan = T.Plan()
+    slot = cons._add_to(plan)
+    plan.partial_reset()
+    for s in range(n_shards):
+        plan.partial_merge(_grouped_partial(plan, vals[len(vals) * s // n_shards: len(vals) * (s + 1) // n_shards]))
+    plan.finalize()
+    h, oh = cons.histogram(plan, slot), O.histogram_of(t, "c")
+    assert [(b.value, b.count, b.ratio) for b in h.buckets] == oh.buckets
+    assert (h.total_count, h.null_count, h.distinct_count) == (oh.total_count, oh.null_count, 5)
+    g = cons._result(plan, slot)
+    o = O.histogram_constraint(t, "c", lambda hh: hh.bucket_count() == 4, "four categories")
+    assert (g.status.name.lower(), g.metric, g.message) == (o.status, o.metric, o.message) and g.status.name == "Failure"
